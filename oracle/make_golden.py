@@ -1,0 +1,191 @@
+"""TEST INFRASTRUCTURE ONLY -- generate tests/golden/*.npz from the REAL reference (container only).
+
+Run:  python -m oracle.make_golden          (needs /root/reference; see oracle/ref_loader.py)
+
+Every fixture stores seeded inputs, the reference-layout state_dict and the outputs of the unmodified
+reference code (one documented GN patch, see ref_loader).  The fixtures travel to the GPU box, where
+``/root/reference`` does not exist; tests compare both the oracle port and the CUDA engine against them.
+Fixtures are kept small (few 100 KB each).
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import json
+import os
+
+import numpy as np
+import torch
+
+from oracle import ref_loader
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+# (name, arch, ctor kwargs, batch) -- small versions of the BASELINE configs + block-order / norm variants
+MODEL_CASES = [
+    ("resunet3d_gn_silu", "resunet", dict(image_shape=(16, 16, 16, 2), activation="silu", feature_maps=[16, 32],
+                                           drop_values=[0, 0], normalization="gn", k_size=3, yx_down=[2], z_down=[2],
+                                           isotropy=[True] * 2, larger_io=False, conv_layers=[2] * 2, output_channels=[1]), 2),
+    ("resunet3d_gn_deep", "resunet", dict(image_shape=(16, 16, 16, 2), activation="silu", feature_maps=[8, 16, 32],
+                                           drop_values=[0, 0, 0], normalization="gn", k_size=3, yx_down=[2, 2], z_down=[2, 2],
+                                           isotropy=[True] * 3, larger_io=False, conv_layers=[2] * 3, output_channels=[1]), 1),
+    ("resunet3d_preact_in", "resunet", dict(image_shape=(8, 16, 16, 1), activation="relu", feature_maps=[8, 16],
+                                             drop_values=[0, 0], normalization="in", k_size=3, yx_down=[2], z_down=[1],
+                                             isotropy=[False, True], larger_io=True, conv_layers=[2, 3], output_channels=[2],
+                                             conv_block_order="norm_act_conv"), 1),
+    ("unet2d_in_elu", "unet", dict(image_shape=(32, 32, 1), activation="elu", feature_maps=[8, 16, 32],
+                                    drop_values=[0, 0, 0], normalization="in", k_size=3, yx_down=[2, 2], z_down=[2, 2],
+                                    isotropy=[True] * 3, larger_io=False, conv_layers=[2] * 3, output_channels=[1]), 2),
+    ("unet2d_gn_3ch", "unet", dict(image_shape=(32, 32, 3), activation="silu", feature_maps=[16, 32],
+                                    drop_values=[0, 0], normalization="gn", k_size=3, yx_down=[2], z_down=[2],
+                                    isotropy=[True] * 2, larger_io=False, conv_layers=[2] * 2, output_channels=[2]), 2),
+    ("attunet3d_in_elu", "attention_unet", dict(image_shape=(16, 16, 16, 1), activation="elu", feature_maps=[8, 16, 32],
+                                                 drop_values=[0, 0, 0], normalization="in", k_size=3, yx_down=[2, 2], z_down=[2, 2],
+                                                 isotropy=[True] * 3, larger_io=False, conv_layers=[2] * 3, output_channels=[1]), 2),
+    ("unet3d_none_relu_upsampling", "unet", dict(image_shape=(8, 8, 8, 2), activation="relu", feature_maps=[8, 16],
+                                                  drop_values=[0, 0], normalization="none", k_size=3, yx_down=[2], z_down=[2],
+                                                  isotropy=[True] * 2, larger_io=False, conv_layers=[1, 2], output_channels=[1, 1],
+                                                  output_channel_info=["A", "B"], upsample_layer="upsampling"), 1),
+    ("resunet3d_none_relu", "resunet", dict(image_shape=(8, 8, 8, 1), activation="relu", feature_maps=[8, 16],
+                                             drop_values=[0, 0], normalization="none", k_size=3, yx_down=[2], z_down=[2],
+                                             isotropy=[True] * 2, larger_io=False, conv_layers=[2, 2], output_channels=[1]), 1),
+]
+
+STITCH_3D = [
+    # (name, vol shape, patch, overlap, padding, pad_type)
+    ("s3d_a", (24, 28, 20, 2), (12, 12, 12, 2), (0.25, 0.25, 0.25), (0, 0, 0), "reflect"),
+    ("s3d_b", (21, 25, 19, 1), (8, 12, 10, 1), (0.1, 0.3, 0.5), (1, 0, 2), "reflect"),
+    ("s3d_c", (14, 16, 14, 1), (8, 10, 8, 1), (0, 0, 0), (2, 2, 2), "zeros"),
+    ("s3d_dup", (12, 14, 12, 1), (12, 8, 12, 1), (0.25, 0.5, 0.25), (0, 0, 0), "reflect"),   # axis == patch, ov>0
+    ("s3d_hi", (26, 8, 8, 1), (10, 8, 8, 1), (0.7, 0, 0), (0, 0, 0), "symmetric"),
+]
+STITCH_2D = [
+    ("s2d_a", (2, 50, 60, 3), (24, 24, 3), (0.25, 0.25), (0, 0), "reflect"),
+    ("s2d_b", (1, 44, 38, 1), (20, 16, 1), (0.5, 0.1), (4, 2), "reflect"),
+]
+# index-only known answers (no tensors): shape, patch, overlap, padding -> n patches + per-axis starts
+GRID_CASES_3D = [
+    ((512, 512, 512), (128, 128, 128), (0.25, 0.25, 0.25), (0, 0, 0)),
+    ((165, 768, 1024), (80, 80, 80), (0.5, 0.5, 0.5), (0, 0, 0)),
+    ((165, 768, 1024), (80, 80, 80), (0, 0, 0), (0, 0, 0)),
+    ((165, 768, 1024), (80, 80, 80), (0, 0, 0), (10, 10, 10)),
+    ((100, 120, 90), (40, 40, 40), (0, 0, 0), (0, 0, 0)),
+    ((100, 120, 90), (40, 40, 40), (0, 0, 0), (6, 6, 6)),
+    ((100, 120, 90), (40, 40, 40), (0.25, 0.25, 0.25), (6, 6, 6)),
+    ((97, 113, 89), (32, 48, 40), (0.1, 0.3, 0.5), (4, 0, 8)),
+    ((64, 64, 64), (64, 64, 64), (0.25, 0.25, 0.25), (0, 0, 0)),
+    ((200, 150, 100), (50, 100, 96), (0.9, 0.7, 0.35), (0, 0, 0)),
+]
+GRID_CASES_2D = [
+    ((2048, 2048), (512, 512), (0.25, 0.25), (0, 0)),
+    ((768, 1024), (256, 256), (0, 0), (0, 0)),
+    ((768, 1024), (256, 256), (0.5, 0.5), (0, 0)),
+    ((768, 1024), (256, 256), (0, 0), (64, 64)),
+    ((300, 500), (128, 96), (0.33, 0.8), (16, 8)),
+]
+
+
+def _quiet():
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+def make_models(R):
+    for name, arch, kw, batch in MODEL_CASES:
+        cls = {"unet": R.unet.U_Net, "resunet": R.resunet.ResUNet, "attention_unet": R.attention_unet.Attention_U_Net}[arch]
+        torch.manual_seed(0)
+        with _quiet():
+            m = cls(**kw)
+        # non-trivial affine / bias values so that every parameter matters
+        g = torch.Generator().manual_seed(1)
+        with torch.no_grad():
+            for k, p in m.named_parameters():
+                if p.ndim == 1:
+                    p.add_(0.2 * torch.randn(p.shape, generator=g))
+        m.train()  # exercise the training-mode graph (norm layers here carry no running stats)
+        shape = kw["image_shape"]
+        x = torch.randn((batch, shape[-1]) + tuple(shape[:-1]), generator=g)
+        x.requires_grad_(True)
+        y = m(x)
+        gy = torch.randn(y.shape, generator=g)
+        (y * gy).sum().backward()
+        out = {"x": x.detach().numpy(), "y": y.detach().numpy(), "gy": gy.numpy(), "gx": x.grad.numpy(),
+               "kwargs_json": np.array(json.dumps(kw)), "arch": np.array(arch)}
+        for k, v in m.state_dict().items():
+            out["sd." + k] = v.numpy()
+        for k, p in m.named_parameters():
+            out["grad." + k] = p.grad.numpy()
+        np.savez_compressed(os.path.join(OUT, f"model_{name}.npz"), **out)
+        print("model", name, tuple(y.shape), "params", sum(p.numel() for p in m.parameters()))
+
+
+def make_stitch(R):
+    rng = np.random.default_rng(7)
+    for name, vshape, patch, ov, pad, pad_type in STITCH_3D:
+        vol = rng.standard_normal(vshape).astype(np.float32)
+        patches, coords = R.d3.crop_3D_data_with_overlap(vol, patch, overlap=ov, padding=pad, verbose=False, pad_type=pad_type)
+        starts = np.array([[c.z_start, c.y_start, c.x_start] for c in coords], dtype=np.int64)
+        pred = patches * 0.5 + rng.standard_normal(patches.shape).astype(np.float32)
+        merged = R.d3.merge_3D_data_with_overlap(pred, vshape, overlap=ov, padding=pad, verbose=False)
+        merged16 = R.d3.merge_3D_data_with_overlap(pred.astype(np.float16), vshape, overlap=ov, padding=pad, verbose=False)
+        roundtrip = R.d3.merge_3D_data_with_overlap(patches, vshape, overlap=ov, padding=pad, verbose=False)
+        np.savez_compressed(os.path.join(OUT, f"stitch_{name}.npz"), vol=vol, patches_crc=np.array(_crc(patches)),
+                            starts=starts, pred=pred, merged=merged, merged16=merged16, roundtrip=roundtrip,
+                            meta=np.array(json.dumps(dict(vshape=vshape, patch=patch, overlap=ov, padding=pad, pad_type=pad_type))))
+        print("stitch", name, patches.shape, "roundtrip err", float(np.abs(roundtrip - vol).max()))
+    for name, dshape, patch, ov, pad, pad_type in STITCH_2D:
+        img = rng.standard_normal(dshape).astype(np.float32)
+        patches, coords = R.d2.crop_data_with_overlap(img, patch, overlap=ov, padding=pad, verbose=False, pad_type=pad_type)
+        starts = np.array([[c.y_start, c.x_start] for c in coords], dtype=np.int64)
+        pred = patches * 0.5 + rng.standard_normal(patches.shape).astype(np.float32)
+        merged = R.d2.merge_data_with_overlap(pred, dshape, overlap=ov, padding=pad, verbose=False)
+        np.savez_compressed(os.path.join(OUT, f"stitch_{name}.npz"), vol=img, patches_crc=np.array(_crc(patches)),
+                            starts=starts, pred=pred, merged=merged,
+                            meta=np.array(json.dumps(dict(vshape=dshape, patch=patch, overlap=ov, padding=pad, pad_type=pad_type))))
+        print("stitch", name, patches.shape)
+
+
+def _crc(a: np.ndarray) -> int:
+    import zlib
+    return zlib.crc32(np.ascontiguousarray(a).tobytes())
+
+
+def make_grids(R):
+    grids = {"3d": [], "2d": []}
+    for shape, patch, ov, pad in GRID_CASES_3D:
+        dummy = np.broadcast_to(np.zeros((1,), np.uint8), shape + (1,))
+        coords = R.d3.crop_3D_data_with_overlap(dummy, patch + (1,), overlap=ov, padding=pad, verbose=False, load_data=False)
+        z = sorted({c.z_start for c in coords}); y = sorted({c.y_start for c in coords}); x = sorted({c.x_start for c in coords})
+        first = [[c.z_start, c.y_start, c.x_start] for c in coords[:3]] + [[c.z_start, c.y_start, c.x_start] for c in coords[-3:]]
+        import zlib
+        allc = np.array([[c.z_start, c.z_end, c.y_start, c.y_end, c.x_start, c.x_end] for c in coords], dtype=np.int64)
+        grids["3d"].append(dict(shape=shape, patch=patch, overlap=ov, padding=pad, n=len(coords), z=z, y=y, x=x,
+                                edge_coords=first, crc=zlib.crc32(allc.tobytes())))
+        print("grid3d", shape, patch, ov, pad, "->", len(coords))
+    for shape, patch, ov, pad in GRID_CASES_2D:
+        dummy = np.broadcast_to(np.zeros((1,), np.uint8), (1,) + shape + (1,))
+        coords = R.d2.crop_data_with_overlap(dummy, patch + (1,), overlap=ov, padding=pad, verbose=False, load_data=False)
+        y = sorted({c.y_start for c in coords}); x = sorted({c.x_start for c in coords})
+        import zlib
+        allc = np.array([[c.y_start, c.y_end, c.x_start, c.x_end] for c in coords], dtype=np.int64)
+        grids["2d"].append(dict(shape=shape, patch=patch, overlap=ov, padding=pad, n=len(coords), y=y, x=x,
+                                crc=zlib.crc32(allc.tobytes())))
+        print("grid2d", shape, patch, ov, pad, "->", len(coords))
+    # float-truncation probes (SURVEY 8a addendum)
+    grids["trunc"] = [dict(P=P, ov=ov, step=int(P * (1 - ov))) for P, ov in [(50, 0.9), (100, 0.7), (96, 0.35), (128, 0.25), (80, 0.5)]]
+    with open(os.path.join(OUT, "grids.json"), "w") as f:
+        json.dump(grids, f, indent=0)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    R = ref_loader.load()
+    make_grids(R)
+    make_stitch(R)
+    make_models(R)
+    with open(os.path.join(OUT, "PROVENANCE.txt"), "w") as f:
+        f.write("generated by oracle/make_golden.py from /root/reference (BiaPy 3.7.0 @ 29539acd), "
+                f"torch {torch.__version__}, numpy {np.__version__}; GN call patched as documented in oracle/ref_loader.py\n")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,109 @@
+"""TEST INFRASTRUCTURE ONLY -- loads the *real* BiaPy reference modules for the hot path.
+
+This module imports the reference's own files from ``/root/reference`` by file path, behind stub
+parent packages, so that the oracle restatement in ``oracle/port_*.py`` can be validated against the
+reference itself and golden vectors can be generated (``oracle/make_golden.py``).
+
+It only works in the build container (``/root/reference`` does not exist on the GPU box); nothing in
+``biapy_b200`` may import it.  Recipe follows SURVEY.md section 8c:
+
+* stub packages ``biapy``, ``biapy.models``, ``biapy.data``, ``biapy.utils`` and stub modules
+  ``h5py``, ``zarr``, ``biapy.utils.misc`` (only ``is_main_process`` is needed by the hot functions);
+* one documented patch: ``get_norm_3d/2d('gn', C)`` raise ``TypeError`` in the reference
+  (``biapy/models/blocks.py:2124-2125`` and ``:2162-2163`` pass ``num_groups`` twice).  The intended
+  semantics ``GroupNorm(8, C)`` (3D) / ``GroupNorm(16, C)`` (2D) are patched in *before* the model files
+  bind the names.  Everything else is the unmodified reference code.
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("BIAPY_REFERENCE_ROOT", "/root/reference")
+
+_loaded = None
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "biapy", "models", "blocks.py"))
+
+
+def _stub(name: str, **attrs) -> types.ModuleType:
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    m.__path__ = []  # behave like a package
+    sys.modules[name] = m
+    return m
+
+
+def _load(modname: str, relpath: str) -> types.ModuleType:
+    path = os.path.join(REFERENCE_ROOT, relpath)
+    spec = importlib.util.spec_from_file_location(modname, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[modname] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def load():
+    """Return a namespace with the reference modules (blocks, unet, resunet, attention_unet, d2, d3, dataset)."""
+    global _loaded
+    if _loaded is not None:
+        return _loaded
+    if not available():
+        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+    import torch.nn as nn
+
+    saved = {k: sys.modules.get(k) for k in list(sys.modules) if k == "biapy" or k.startswith("biapy.")}
+    for k in saved:
+        del sys.modules[k]
+    try:
+        _stub("biapy")
+        _stub("biapy.models")
+        _stub("biapy.data")
+        _stub("biapy.utils")
+        _stub("biapy.utils.misc", is_main_process=lambda: True)
+        if "h5py" not in sys.modules:
+            _stub("h5py", File=type("File", (), {}), Dataset=type("Dataset", (), {}), Group=type("Group", (), {}))
+        if "zarr" not in sys.modules:
+            _stub("zarr", Array=type("Array", (), {}), Group=type("Group", (), {}))
+
+        blocks = _load("biapy.models.blocks", "biapy/models/blocks.py")
+
+        # --- the one documented patch (reference defect, see module docstring) -------------------------
+        _orig3, _orig2 = blocks.get_norm_3d, blocks.get_norm_2d
+
+        def get_norm_3d(norm, out_channels, bn_momentum=0.1):
+            if norm == "gn":
+                return nn.GroupNorm(8, out_channels)
+            return _orig3(norm, out_channels, bn_momentum)
+
+        def get_norm_2d(norm, out_channels, bn_momentum=0.1):
+            if norm == "gn":
+                return nn.GroupNorm(16, out_channels)
+            return _orig2(norm, out_channels, bn_momentum)
+
+        blocks.get_norm_3d, blocks.get_norm_2d = get_norm_3d, get_norm_2d
+        # -----------------------------------------------------------------------------------------------
+        heads = _load("biapy.models.heads", "biapy/models/heads.py")
+        unet = _load("biapy.models.unet", "biapy/models/unet.py")
+        resunet = _load("biapy.models.resunet", "biapy/models/resunet.py")
+        attention_unet = _load("biapy.models.attention_unet", "biapy/models/attention_unet.py")
+        dataset = _load("biapy.data.dataset", "biapy/data/dataset.py")
+        d2 = _load("biapy.data.data_2D_manipulation", "biapy/data/data_2D_manipulation.py")
+        d3 = _load("biapy.data.data_3D_manipulation", "biapy/data/data_3D_manipulation.py")
+        ns = types.SimpleNamespace(
+            blocks=blocks, heads=heads, unet=unet, resunet=resunet, attention_unet=attention_unet,
+            dataset=dataset, d2=d2, d3=d3,
+        )
+    finally:
+        # do not leave the stub `biapy` package in sys.modules (a real install may coexist)
+        for k in [k for k in sys.modules if k == "biapy" or k.startswith("biapy.")]:
+            del sys.modules[k]
+        for k, v in saved.items():
+            if v is not None:
+                sys.modules[k] = v
+    _loaded = ns
+    return ns

@@ -1,0 +1,113 @@
+"""CPU tests: the oracle restatement (oracle/port_*.py) against the golden vectors produced by the real
+reference (oracle/make_golden.py).  Index bookkeeping must be bit-exact, merge output bit-exact (same numpy
+operations in the same order), model outputs within 1e-5 (same ATen kernels, different graph plumbing)."""
+import glob
+import json
+import os
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import port_models, port_stitch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _grids():
+    with open(os.path.join(GOLDEN, "grids.json")) as f:
+        return json.load(f)
+
+
+def test_grid_known_answers_3d():
+    g = _grids()
+    for case in g["3d"]:
+        plans, starts = port_stitch.crop_grid(case["shape"], case["patch"], case["overlap"], case["padding"])
+        assert starts.shape[0] == case["n"]
+        for ax, key in enumerate("zyx"):
+            got = sorted({pl for pl in starts[:, ax].tolist()})
+            assert got == case[key], (case, key)
+        allc = np.stack([starts[:, 0], starts[:, 0] + case["patch"][0], starts[:, 1], starts[:, 1] + case["patch"][1],
+                         starts[:, 2], starts[:, 2] + case["patch"][2]], axis=1).astype(np.int64)
+        assert zlib.crc32(allc.tobytes()) == case["crc"]
+
+
+def test_grid_docstring_counts():
+    # reference docstring known answers: data_3D_manipulation.py:425-447, data_2D_manipulation.py:124-171
+    n = lambda *a: port_stitch.crop_grid(*a)[1].shape[0]
+    assert n((165, 768, 1024), (80, 80, 80), (0.5, 0.5, 0.5), (0, 0, 0)) == 2600
+    assert n((165, 768, 1024), (80, 80, 80), (0, 0, 0), (0, 0, 0)) == 390
+    assert n((512, 512, 512), (128, 128, 128), (0.25,) * 3, (0, 0, 0)) == 216
+    # 2D: 165 images of 768x1024, 256x256 crops
+    assert 165 * n((768, 1024), (256, 256), (0, 0), (0, 0)) == 1980
+    assert 165 * n((768, 1024), (256, 256), (0.5, 0.5), (0, 0)) == 7920
+
+
+def test_grid_known_answers_2d():
+    g = _grids()
+    for case in g["2d"]:
+        plans, starts = port_stitch.crop_grid(case["shape"], case["patch"], case["overlap"], case["padding"])
+        assert starts.shape[0] == case["n"]
+        allc = np.stack([starts[:, 0], starts[:, 0] + case["patch"][0], starts[:, 1], starts[:, 1] + case["patch"][1]],
+                        axis=1).astype(np.int64)
+        assert zlib.crc32(allc.tobytes()) == case["crc"]
+
+
+def test_float_truncation():
+    for t in _grids()["trunc"]:
+        assert port_stitch.AxisPlan(10 * t["P"], t["P"], 0, t["ov"]).step <= t["step"]
+        assert int(t["P"] * (1 - t["ov"])) == t["step"]
+    assert int(50 * (1 - 0.9)) == 4
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "stitch_s3d_*.npz"))))
+def test_stitch_3d(path):
+    z = np.load(path)
+    meta = json.loads(str(z["meta"]))
+    patches, starts = port_stitch.crop_3d(z["vol"], meta["patch"], meta["overlap"], meta["padding"], meta["pad_type"])
+    assert np.array_equal(starts, z["starts"])
+    assert zlib.crc32(np.ascontiguousarray(patches).tobytes()) == int(z["patches_crc"])
+    merged = port_stitch.merge_3d(z["pred"], meta["vshape"], meta["overlap"], meta["padding"])
+    assert merged.dtype == np.float32 and np.array_equal(merged, z["merged"])
+    merged16 = port_stitch.merge_3d(z["pred"].astype(np.float16), meta["vshape"], meta["overlap"], meta["padding"])
+    assert merged16.dtype == np.float16 and np.array_equal(merged16, z["merged16"])
+    rt = port_stitch.merge_3d(patches, meta["vshape"], meta["overlap"], meta["padding"])
+    assert np.array_equal(rt, z["roundtrip"])
+    assert np.abs(rt - z["vol"]).max() < 2e-6       # crop -> merge is the identity
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "stitch_s2d_*.npz"))))
+def test_stitch_2d(path):
+    z = np.load(path)
+    meta = json.loads(str(z["meta"]))
+    patches, starts = port_stitch.crop_2d(z["vol"], meta["patch"], meta["overlap"], meta["padding"], meta["pad_type"])
+    assert np.array_equal(starts, z["starts"])
+    assert zlib.crc32(np.ascontiguousarray(patches).tobytes()) == int(z["patches_crc"])
+    merged = port_stitch.merge_2d(z["pred"], meta["vshape"], meta["overlap"], meta["padding"])
+    assert np.array_equal(merged, z["merged"])
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "model_*.npz"))))
+def test_model_port(path):
+    z = np.load(path)
+    kw = json.loads(str(z["kwargs_json"]))
+    arch = str(z["arch"])
+    sd = {k[3:]: torch.from_numpy(z[k]).requires_grad_(z[k].dtype == np.float32) for k in z.files if k.startswith("sd.")}
+    x = torch.from_numpy(z["x"]).requires_grad_(True)
+    y = port_models.forward(arch, sd, x, training=True, **kw)
+    ref = torch.from_numpy(z["y"])
+    assert y.shape == ref.shape
+    assert (y - ref).abs().max() <= 1e-5 * max(1.0, ref.abs().max().item())
+    (y * torch.from_numpy(z["gy"])).sum().backward()
+    gx = torch.from_numpy(z["gx"])
+    assert (x.grad - gx).abs().max() <= 1e-4 * max(1.0, gx.abs().max().item())
+    # parameters in front of a norm layer have mathematically-zero gradients (pure rounding noise), so the
+    # tolerance is tied to the largest gradient of the model, not to each tensor's own magnitude
+    scale = max(float(np.abs(z[k]).max()) for k in z.files if k.startswith("grad."))
+    for k in z.files:
+        if k.startswith("grad."):
+            g = torch.from_numpy(z[k])
+            got = sd[k[5:]].grad
+            assert got is not None, k
+            assert (got - g).abs().max() <= 1e-4 * max(1.0, scale), k
