@@ -1,0 +1,350 @@
+// CUDA-core (FFMA, fp32 accumulate) convolution kernels: the exact-precision path (fp32 storage) and the
+// fallback for shapes the tcgen05 kernels do not take (odd channel counts, first layer Cin=1..3, 1-channel
+// heads, 5x5x5 "larger_io" kernels, 2D).  Same C ABI and packed-weight layout as the tensor-core path.
+//   fprop : y[n,z,y,x,co] = b[co] + sum_{tap,ci} x[n,z+dz,y+dy,x+dx,ci] * w[co][tap][ci]     (+ residual)
+//   dgrad : the same kernel with the flipped/transposed packing of the weights
+//   wgrad : dw[co][tap][ci] += sum_vox dy[vox][co] * x[vox+tap][ci]
+#include "common.cuh"
+
+namespace b200 {
+
+struct ConvGeom {
+  int n, d, h, w, cin, cout;
+  int kd, kh, kw;
+  int64_t ldx, ldy, ldr;
+};
+
+constexpr int kTW = 32;   // tile width (x), one lane per column
+constexpr int kTH = 4;    // rows (y) per thread
+constexpr int kTN = 32;   // output channels per block (4 warps x 8)
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+conv_fprop_simt_kernel(const T* __restrict__ x, const T* __restrict__ wp, const float* __restrict__ bias,
+                       const T* __restrict__ res, T* __restrict__ y, ConvGeom g, int accumulate, int CK) {
+  extern __shared__ float smem[];
+  const int taps = g.kd * g.kh * g.kw;
+  const int HW = kTW + g.kw - 1, HH = kTH + g.kh - 1;
+  const int plane = g.kd * HH * HW;               // halo elements per input channel
+  float* s_in = smem;                              // [CK][kd][HH][HW]
+  float* s_w = smem + (size_t)CK * plane;          // [taps][CK][kTN]
+
+  const int tiles_x = (g.w + kTW - 1) / kTW;
+  const int x0 = (blockIdx.x % tiles_x) * kTW;
+  const int y0 = (blockIdx.x / tiles_x) * kTH;
+  const int z0 = blockIdx.y % g.d;
+  const int n = blockIdx.y / g.d;
+  const int co0 = blockIdx.z * kTN;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int pd = g.kd / 2, ph = g.kh / 2, pw = g.kw / 2;
+
+  float acc[kTH][8];
+#pragma unroll
+  for (int r = 0; r < kTH; ++r)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[r][j] = 0.f;
+
+  for (int ci0 = 0; ci0 < g.cin; ci0 += CK) {
+    __syncthreads();
+    // ---- input halo (channel fastest in global memory)
+    for (int i = tid; i < plane * CK; i += blockDim.x) {
+      int ck = i % CK;
+      int p = i / CK;
+      int xx = p % HW;
+      int yy = (p / HW) % HH;
+      int dz = p / (HW * HH);
+      int gz = z0 + dz - pd, gy = y0 + yy - ph, gx = x0 + xx - pw, c = ci0 + ck;
+      float v = 0.f;
+      if (gz >= 0 && gz < g.d && gy >= 0 && gy < g.h && gx >= 0 && gx < g.w && c < g.cin)
+        v = to_f<T>(x[((((int64_t)n * g.d + gz) * g.h + gy) * g.w + gx) * g.ldx + c]);
+      s_in[(size_t)ck * plane + p] = v;
+    }
+    // ---- weights [tap][ck][n]
+    for (int i = tid; i < taps * CK * kTN; i += blockDim.x) {
+      int ck = i % CK;
+      int t = (i / CK) % taps;
+      int nn = i / (CK * taps);
+      int co = co0 + nn, c = ci0 + ck;
+      float v = 0.f;
+      if (co < g.cout && c < g.cin) v = to_f<T>(wp[((int64_t)co * taps + t) * g.cin + c]);
+      s_w[((size_t)t * CK + ck) * kTN + nn] = v;
+    }
+    __syncthreads();
+    for (int dz = 0; dz < g.kd; ++dz)
+      for (int dy = 0; dy < g.kh; ++dy)
+        for (int dx = 0; dx < g.kw; ++dx) {
+          const int t = (dz * g.kh + dy) * g.kw + dx;
+          for (int ck = 0; ck < CK; ++ck) {
+            const float4 w0 = *reinterpret_cast<const float4*>(&s_w[((size_t)t * CK + ck) * kTN + warp * 8]);
+            const float4 w1 = *reinterpret_cast<const float4*>(&s_w[((size_t)t * CK + ck) * kTN + warp * 8 + 4]);
+            const float* src = s_in + (size_t)ck * plane + ((size_t)dz * HH + dy) * HW + lane + dx;
+#pragma unroll
+            for (int r = 0; r < kTH; ++r) {
+              const float a = src[r * HW];
+              acc[r][0] = fmaf(a, w0.x, acc[r][0]);
+              acc[r][1] = fmaf(a, w0.y, acc[r][1]);
+              acc[r][2] = fmaf(a, w0.z, acc[r][2]);
+              acc[r][3] = fmaf(a, w0.w, acc[r][3]);
+              acc[r][4] = fmaf(a, w1.x, acc[r][4]);
+              acc[r][5] = fmaf(a, w1.y, acc[r][5]);
+              acc[r][6] = fmaf(a, w1.z, acc[r][6]);
+              acc[r][7] = fmaf(a, w1.w, acc[r][7]);
+            }
+          }
+        }
+  }
+  // ---- epilogue
+  const int gx = x0 + lane;
+  if (gx < g.w) {
+#pragma unroll
+    for (int r = 0; r < kTH; ++r) {
+      const int gy = y0 + r;
+      if (gy >= g.h) continue;
+      const int64_t vox = (((int64_t)n * g.d + z0) * g.h + gy) * g.w + gx;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int co = co0 + warp * 8 + j;
+        if (co >= g.cout) continue;
+        float v = acc[r][j];
+        if (bias) v += bias[co];
+        if (res) v += to_f<T>(res[vox * g.ldr + co]);
+        T* o = y + vox * g.ldy + co;
+        if (accumulate) v += to_f<T>(*o);
+        *o = from_f<T>(v);
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------------- wgrad
+constexpr int kWgTile = 16;   // ci x co tile per block
+constexpr int kWgVox = 32;    // voxels (along x) per step
+constexpr int kWgTaps = 27;   // taps kept in registers per thread
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv_wgrad_simt_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw,
+                       float* __restrict__ dbias, ConvGeom g, int taps_per_chunk, int64_t units) {
+  extern __shared__ float smem[];
+  const int taps = g.kd * g.kh * g.kw;
+  const int HW = kWgVox + g.kw - 1;
+  const int t0 = blockIdx.z * taps_per_chunk;
+  const int ntaps = min(taps_per_chunk, taps - t0);
+  float* s_dy = smem;                                   // [kWgVox][16]
+  float* s_x = smem + kWgVox * kWgTile;                  // [kd][kh][HW][16]
+  __shared__ int s_off[kWgTaps];
+  const int tid = threadIdx.x;
+  const int ci_l = tid / kWgTile, co_l = tid % kWgTile;
+  const int tiles_co = (g.cout + kWgTile - 1) / kWgTile;
+  const int co0 = (blockIdx.y % tiles_co) * kWgTile;
+  const int ci0 = (blockIdx.y / tiles_co) * kWgTile;
+  const int pd = g.kd / 2, ph = g.kh / 2, pw = g.kw / 2;
+  if (tid < kWgTaps) {
+    int t = t0 + tid;
+    int off = 0;
+    if (tid < ntaps) {
+      int dx = t % g.kw, dyy = (t / g.kw) % g.kh, dz = t / (g.kw * g.kh);
+      off = ((dz * g.kh + dyy) * HW + dx) * kWgTile;
+    }
+    s_off[tid] = off;
+  }
+  float acc[kWgTaps];
+#pragma unroll
+  for (int t = 0; t < kWgTaps; ++t) acc[t] = 0.f;
+  float bacc = 0.f;
+  const int segs = (g.w + kWgVox - 1) / kWgVox;
+  const int rows_x = g.kd * g.kh * HW;
+
+  for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+    int seg = (int)(u % segs);
+    int64_t r = u / segs;
+    int yy = (int)(r % g.h); r /= g.h;
+    int zz = (int)(r % g.d);
+    int n = (int)(r / g.d);
+    int x0 = seg * kWgVox;
+    __syncthreads();
+    for (int i = tid; i < kWgVox * kWgTile; i += blockDim.x) {
+      int c = i % kWgTile, v = i / kWgTile;
+      float val = 0.f;
+      if (x0 + v < g.w && co0 + c < g.cout)
+        val = to_f<T>(dy[((((int64_t)n * g.d + zz) * g.h + yy) * g.w + x0 + v) * g.ldy + co0 + c]);
+      s_dy[i] = val;
+    }
+    for (int i = tid; i < rows_x * kWgTile; i += blockDim.x) {
+      int c = i % kWgTile;
+      int p = i / kWgTile;
+      int xx = p % HW;
+      int dyy = (p / HW) % g.kh;
+      int dz = p / (HW * g.kh);
+      int gz = zz + dz - pd, gy = yy + dyy - ph, gx = x0 + xx - pw;
+      float val = 0.f;
+      if (gz >= 0 && gz < g.d && gy >= 0 && gy < g.h && gx >= 0 && gx < g.w && ci0 + c < g.cin)
+        val = to_f<T>(x[((((int64_t)n * g.d + gz) * g.h + gy) * g.w + gx) * g.ldx + ci0 + c]);
+      s_x[i] = val;
+    }
+    __syncthreads();
+    for (int v = 0; v < kWgVox; ++v) {
+      const float d = s_dy[v * kWgTile + co_l];
+      const float* xb = s_x + v * kWgTile + ci_l;
+      bacc += d;
+#pragma unroll
+      for (int t = 0; t < kWgTaps; ++t)
+        if (t < ntaps) acc[t] = fmaf(d, xb[s_off[t]], acc[t]);
+    }
+  }
+  const int co = co0 + co_l, ci = ci0 + ci_l;
+  if (co < g.cout && ci < g.cin) {
+#pragma unroll
+    for (int t = 0; t < kWgTaps; ++t)
+      if (t < ntaps) atomicAdd(&dw[((int64_t)co * taps + t0 + t) * g.cin + ci], acc[t]);
+  }
+  if (dbias && ci0 == 0 && ci_l == 0 && blockIdx.z == 0 && co < g.cout) atomicAdd(&dbias[co], bacc);
+}
+
+template <typename T>
+__global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ p, int cout, int cin, int taps, int flip) {
+  const int64_t total = (int64_t)cout * cin * taps;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int t = (int)(i % taps);
+    int ci = (int)((i / taps) % cin);
+    int co = (int)(i / ((int64_t)taps * cin));
+    float v = w[i];
+    int64_t o = flip ? (((int64_t)ci * taps + (taps - 1 - t)) * cout + co) : (((int64_t)co * taps + t) * cin + ci);
+    p[o] = from_f<T>(v);
+  }
+}
+
+__global__ void unpack_wgrad_kernel(const float* __restrict__ p, float* __restrict__ dw, int cout, int cin, int taps,
+                                    int accumulate) {
+  const int64_t total = (int64_t)cout * cin * taps;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int t = (int)(i % taps);
+    int ci = (int)((i / taps) % cin);
+    int co = (int)(i / ((int64_t)taps * cin));
+    float v = p[((int64_t)co * taps + t) * cin + ci];
+    dw[i] = accumulate ? dw[i] + v : v;
+  }
+}
+
+int conv_fprop_simt(const b200_tensor* x, const void* w, const float* bias, const b200_tensor* res, const b200_tensor* y,
+                    int kd, int kh, int kw, int accumulate, cudaStream_t st) {
+  ConvGeom g{x->n, x->d, x->h, x->w, x->c, y->c, kd, kh, kw, x->ld, y->ld, res ? res->ld : 0};
+  const int taps = kd * kh * kw;
+  const size_t per_ck = ((size_t)kd * (kTH + kh - 1) * (kTW + kw - 1) + (size_t)taps * kTN) * sizeof(float);
+  int CK = (int)(96 * 1024 / per_ck);
+  if (CK > 8) CK = 8;
+  if (CK > x->c) CK = x->c;
+  B200_CHECK_ARG(CK >= 1, "conv_fprop(simt): kernel %dx%dx%d too large", kd, kh, kw);
+  const size_t smem = per_ck * CK;
+  dim3 grid((unsigned)(ceil_div(x->w, kTW) * ceil_div(x->h, kTH)), (unsigned)(x->d * x->n), (unsigned)ceil_div(y->c, kTN));
+  B200_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "conv_fprop(simt): grid too large");
+  B200_DISPATCH_DTYPE(x->dtype, T, {
+    auto kern = conv_fprop_simt_kernel<T>;
+    if (smem > 48 * 1024) B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 128, smem, st>>>((const T*)x->data, (const T*)w, bias, res ? (const T*)res->data : nullptr, (T*)y->data, g,
+                                  accumulate, CK);
+  });
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+int conv_wgrad_simt(const b200_tensor* x, const b200_tensor* dy, float* dw, float* dbias, int kd, int kh, int kw,
+                    cudaStream_t st) {
+  ConvGeom g{x->n, x->d, x->h, x->w, x->c, dy->c, kd, kh, kw, x->ld, dy->ld, 0};
+  const int taps = kd * kh * kw;
+  int tpc = taps <= kWgTaps ? taps : kh * kw;
+  B200_CHECK_ARG(tpc <= kWgTaps, "conv_wgrad(simt): kernel plane %dx%d too large", kh, kw);
+  const int chunks = (int)ceil_div(taps, tpc);
+  const size_t smem = ((size_t)kWgVox * kWgTile + (size_t)kd * kh * (kWgVox + kw - 1) * kWgTile) * sizeof(float);
+  const int64_t units = (int64_t)x->n * x->d * x->h * ceil_div(x->w, kWgVox);
+  const int tiles = (int)(ceil_div(x->c, kWgTile) * ceil_div(dy->c, kWgTile));
+  int64_t bx = ceil_div((int64_t)sm_count() * 4, (int64_t)tiles * chunks);
+  if (bx > units) bx = units;
+  if (bx < 1) bx = 1;
+  dim3 grid((unsigned)bx, (unsigned)tiles, (unsigned)chunks);
+  B200_CHECK_ARG(grid.y <= 65535, "conv_wgrad(simt): too many channel tiles");
+  B200_DISPATCH_DTYPE(x->dtype, T, {
+    auto kern = conv_wgrad_simt_kernel<T>;
+    if (smem > 48 * 1024) B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 256, smem, st>>>((const T*)x->data, (const T*)dy->data, dw, dbias, g, tpc, units);
+  });
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+// implemented in conv_umma.cu
+int conv_fprop_umma(const b200_tensor* x, const void* w, const float* bias, const b200_tensor* res, const b200_tensor* y,
+                    int kd, int kh, int kw, int accumulate, cudaStream_t st);
+bool conv_fprop_umma_supported(const b200_tensor* x, const b200_tensor* res, const b200_tensor* y, int kd, int kh, int kw);
+int conv_wgrad_umma(const b200_tensor* x, const b200_tensor* dy, float* dw, float* dbias, int kd, int kh, int kw,
+                    cudaStream_t st);
+bool conv_wgrad_umma_supported(const b200_tensor* x, const b200_tensor* dy, int kd, int kh, int kw);
+
+}  // namespace b200
+
+using namespace b200;
+
+B200_EXPORT int b200_pack_conv_weight(const float* w, void* packed, int32_t dtype, int32_t cout, int32_t cin, int32_t kd,
+                                      int32_t kh, int32_t kw, int32_t flip_transpose, void* stream) {
+  B200_CHECK_ARG(w && packed && cout > 0 && cin > 0 && kd > 0 && kh > 0 && kw > 0, "pack_conv_weight: bad args");
+  const int taps = kd * kh * kw;
+  int64_t total = (int64_t)cout * cin * taps;
+  unsigned blocks = (unsigned)(ceil_div(total, 256) < 4096 ? ceil_div(total, 256) : 4096);
+  B200_DISPATCH_DTYPE(dtype, T, (pack_weight_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (T*)packed, cout, cin, taps,
+                                                                                              flip_transpose)));
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+B200_EXPORT int b200_unpack_conv_wgrad(const float* dw_packed, float* dw, int32_t cout, int32_t cin, int32_t taps,
+                                       int32_t accumulate, void* stream) {
+  B200_CHECK_ARG(dw_packed && dw && cout > 0 && cin > 0 && taps > 0, "unpack_conv_wgrad: bad args");
+  int64_t total = (int64_t)cout * cin * taps;
+  unsigned blocks = (unsigned)(ceil_div(total, 256) < 4096 ? ceil_div(total, 256) : 4096);
+  unpack_wgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dw_packed, dw, cout, cin, taps, accumulate);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+static int check_conv(const b200_tensor* x, const b200_tensor* y, int kd, int kh, int kw, const char* who) {
+  B200_CHECK_ARG(check_tensor(x, who) && check_tensor(y, who), "%s", b200_last_error());
+  B200_CHECK_ARG(same_spatial(x, y) && x->dtype == y->dtype, "%s: x/y spatial shape or dtype mismatch", who);
+  B200_CHECK_ARG(kd > 0 && kh > 0 && kw > 0 && (kd & 1) && (kh & 1) && (kw & 1), "%s: kernel sizes must be odd ('same' padding)", who);
+  return B200_OK;
+}
+
+B200_EXPORT int b200_conv_fprop(const b200_tensor* x, const void* w_packed, const float* bias, const b200_tensor* residual,
+                                const b200_tensor* y, int32_t kd, int32_t kh, int32_t kw, int32_t accumulate, int32_t impl,
+                                void* stream) {
+  int st = check_conv(x, y, kd, kh, kw, "conv_fprop");
+  if (st) return st;
+  B200_CHECK_ARG(w_packed != nullptr, "conv_fprop: null weights");
+  if (residual)
+    B200_CHECK_ARG(check_tensor(residual, "conv_fprop.residual") && same_spatial(residual, y) && residual->c == y->c &&
+                       residual->dtype == y->dtype, "conv_fprop: residual mismatch");
+  cudaStream_t s = (cudaStream_t)stream;
+  bool umma_ok = conv_fprop_umma_supported(x, residual, y, kd, kh, kw);
+  if (impl == B200_IMPL_UMMA && !umma_ok) {
+    set_error("conv_fprop: shape not supported by the tcgen05 kernel (cin=%d cout=%d k=%dx%dx%d dtype=%d)", x->c, y->c, kd, kh,
+              kw, x->dtype);
+    return B200_ERR_UNSUPPORTED;
+  }
+  if (impl == B200_IMPL_UMMA || (impl == B200_IMPL_AUTO && umma_ok))
+    return conv_fprop_umma(x, w_packed, bias, residual, y, kd, kh, kw, accumulate, s);
+  return conv_fprop_simt(x, w_packed, bias, residual, y, kd, kh, kw, accumulate, s);
+}
+
+B200_EXPORT int b200_conv_wgrad(const b200_tensor* x, const b200_tensor* dy, float* dw_packed, float* dbias, int32_t kd,
+                                int32_t kh, int32_t kw, int32_t impl, void* stream) {
+  int st = check_conv(x, dy, kd, kh, kw, "conv_wgrad");
+  if (st) return st;
+  B200_CHECK_ARG(dw_packed != nullptr, "conv_wgrad: null output");
+  cudaStream_t s = (cudaStream_t)stream;
+  bool umma_ok = conv_wgrad_umma_supported(x, dy, kd, kh, kw);
+  if (impl == B200_IMPL_UMMA && !umma_ok) {
+    set_error("conv_wgrad: shape not supported by the tcgen05 kernel");
+    return B200_ERR_UNSUPPORTED;
+  }
+  if (impl == B200_IMPL_UMMA || (impl == B200_IMPL_AUTO && umma_ok)) return conv_wgrad_umma(x, dy, dw_packed, dbias, kd, kh, kw, s);
+  return conv_wgrad_simt(x, dy, dw_packed, dbias, kd, kh, kw, s);
+}

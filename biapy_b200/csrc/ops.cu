@@ -1,0 +1,912 @@
+// HBM-bound kernels of the U-Net path: normalisation statistics / apply / backward, activations, max-pool,
+// element-wise glue, losses and the optimiser step.  All tensors are channels-last with a voxel pitch `ld`.
+// Reference call sites are listed next to each entry point in include/biapy_b200.h.
+#include "common.cuh"
+
+namespace b200 {
+
+// View used inside kernels
+template <typename T>
+struct View {
+  T* p;
+  int64_t ld;
+  int c;
+  int64_t vox;      // n*d*h*w
+  int64_t spatial;  // d*h*w
+};
+template <typename T>
+static View<T> view(const b200_tensor* t) {
+  return View<T>{(T*)t->data, t->ld, t->c, voxels(t), (int64_t)t->d * t->h * t->w};
+}
+
+static inline bool vec_ok(const b200_tensor* t, int vec) {
+  return t->c % vec == 0 && t->ld % vec == 0 && ((uintptr_t)t->data % 16) == 0;
+}
+
+static inline unsigned grid_for(int64_t work, int threads, int waves = 8) {
+  int64_t b = ceil_div(work, threads);
+  int64_t cap = (int64_t)sm_count() * waves;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+template <typename T, int VEC>
+__device__ __forceinline__ void load_vec(const T* p, float (&f)[VEC]) {
+  Pack<T, VEC> v = *reinterpret_cast<const Pack<T, VEC>*>(p);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) f[i] = to_f<T>(v.v[i]);
+}
+template <typename T, int VEC>
+__device__ __forceinline__ void store_vec(T* p, const float (&f)[VEC]) {
+  Pack<T, VEC> v;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) v.v[i] = from_f<T>(f[i]);
+  *reinterpret_cast<Pack<T, VEC>*>(p) = v;
+}
+
+// ------------------------------------------------------------------------------------------ channel sums
+// grid = (chunks, N).  Block = rows x CV threads (CV = C/VEC channel vectors); every thread owns one channel
+// vector and strides over the voxels of its chunk.  fp32 partials are flushed into fp64 every 32 voxels, the
+// block result is reduced through shared memory and added to sums[n][c][0..1] with one fp64 atomic each.
+template <typename T, int VEC>
+__global__ void channel_sums_kernel(View<const T> x, double* __restrict__ sums, int cv_count, int rows) {
+  extern __shared__ double s_red[];  // rows * cv_count * VEC * 2
+  const int n = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int cv = tid % cv_count;
+  const int row = tid / cv_count;
+  double acc[VEC], acc2[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[i] = acc2[i] = 0.0;
+  if (row < rows) {
+    const int64_t chunk = (x.spatial + gridDim.x - 1) / gridDim.x;
+    const int64_t v0 = (int64_t)blockIdx.x * chunk;
+    int64_t v1 = v0 + chunk;
+    if (v1 > x.spatial) v1 = x.spatial;
+    const T* base = x.p + (int64_t)n * x.spatial * x.ld + (int64_t)cv * VEC;
+    float f[VEC], s[VEC], s2[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) s[i] = s2[i] = 0.f;
+    int cnt = 0;
+    for (int64_t v = v0 + row; v < v1; v += rows) {
+      load_vec<T, VEC>(base + v * x.ld, f);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        s[i] += f[i];
+        s2[i] = fmaf(f[i], f[i], s2[i]);
+      }
+      if (++cnt == 32) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          acc[i] += (double)s[i];
+          acc2[i] += (double)s2[i];
+          s[i] = s2[i] = 0.f;
+        }
+        cnt = 0;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      acc[i] += (double)s[i];
+      acc2[i] += (double)s2[i];
+    }
+    double* dst = s_red + ((int64_t)row * cv_count + cv) * VEC * 2;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      dst[2 * i] = acc[i];
+      dst[2 * i + 1] = acc2[i];
+    }
+  }
+  __syncthreads();
+  // first `cv_count*VEC*2` threads reduce over rows
+  const int items = cv_count * VEC * 2;
+  for (int it = tid; it < items; it += blockDim.x) {
+    double t = 0.0;
+    for (int r = 0; r < rows; ++r) t += s_red[(int64_t)r * items + it];
+    atomicAdd(&sums[((int64_t)n * x.c) * 2 + it], t);
+  }
+}
+
+template <typename T>
+static int launch_channel_sums(const b200_tensor* x, double* sums, cudaStream_t st) {
+  constexpr int V = VecOf<T>::n;
+  View<const T> xv{(const T*)x->data, x->ld, x->c, voxels(x), (int64_t)x->d * x->h * x->w};
+  int64_t chunks = ceil_div(xv.spatial, 2048);
+  int64_t cap = ceil_div((int64_t)sm_count() * 8, x->n);
+  if (chunks > cap) chunks = cap;
+  if (chunks < 1) chunks = 1;
+  dim3 grid((unsigned)chunks, x->n);
+  if (vec_ok(x, V) && x->c / V <= 256) {
+    int cvn = x->c / V;
+    int rows = 256 / cvn;
+    if (rows > 32) rows = 32;
+    int threads = ((rows * cvn + 31) / 32) * 32;
+    size_t smem = sizeof(double) * rows * cvn * V * 2;
+    channel_sums_kernel<T, V><<<grid, threads, smem, st>>>(xv, sums, cvn, rows);
+  } else {
+    B200_CHECK_ARG(x->c <= 1024, "channel_sums: too many channels (%d)", x->c);
+    int cvn = x->c;
+    int rows = 256 / cvn;
+    if (rows < 1) rows = 1;
+    if (rows > 32) rows = 32;
+    int threads = ((rows * cvn + 31) / 32) * 32;
+    size_t smem = sizeof(double) * rows * cvn * 2;
+    channel_sums_kernel<T, 1><<<grid, threads, smem, st>>>(xv, sums, cvn, rows);
+  }
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+// ----------------------------------------------------------------------------------------- norm finalize
+__global__ void norm_finalize_kernel(const double* __restrict__ sums, int n, int c, int groups, int64_t spatial,
+                                     int batch_stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     float eps, float* __restrict__ mean, float* __restrict__ rstd,
+                                     float* __restrict__ scale, float* __restrict__ shift) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (n, g)
+  if (idx >= n * groups) return;
+  int ni = idx / groups, g = idx % groups;
+  int cpg = c / groups;
+  double s = 0.0, s2 = 0.0;
+  int n0 = batch_stats ? 0 : ni, n1 = batch_stats ? n : ni + 1;
+  for (int nn = n0; nn < n1; ++nn)
+    for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) {
+      s += sums[((int64_t)nn * c + cc) * 2];
+      s2 += sums[((int64_t)nn * c + cc) * 2 + 1];
+    }
+  double m = (double)spatial * cpg * (n1 - n0);
+  double mu = s / m;
+  double var = s2 / m - mu * mu;
+  if (var < 0.0) var = 0.0;
+  float r = 1.0f / sqrtf((float)var + eps);
+  mean[idx] = (float)mu;
+  rstd[idx] = r;
+  for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) {
+    float ga = gamma ? gamma[cc] : 1.f, be = beta ? beta[cc] : 0.f;
+    float sc = r * ga;
+    scale[(int64_t)ni * c + cc] = sc;
+    shift[(int64_t)ni * c + cc] = be - (float)mu * sc;
+  }
+}
+
+// ----------------------------------------------------------------------------------- scale-shift-activation
+template <typename TI, typename TO, int VEC>
+__global__ void scale_shift_act_kernel(View<const TI> x, View<TO> y, const float* __restrict__ scale,
+                                       const float* __restrict__ shift, int act) {
+  const int cvn = x.c / VEC;
+  const int64_t total = x.vox * cvn;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t vox = i / cvn;
+    int cv = (int)(i % cvn);
+    int n = (int)(vox / x.spatial);
+    float f[VEC];
+    load_vec<TI, VEC>(x.p + vox * x.ld + cv * VEC, f);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      float v = f[k];
+      if (scale) v = fmaf(v, scale[(int64_t)n * x.c + cv * VEC + k], shift[(int64_t)n * x.c + cv * VEC + k]);
+      f[k] = act_fwd(act, v);
+    }
+    store_vec<TO, VEC>(y.p + vox * y.ld + cv * VEC, f);
+  }
+}
+
+// -------------------------------------------------------------------------------- norm+act backward, pass 1
+// same thread layout as channel_sums; accumulates (sum g, sum g*xhat) per (n,c)
+template <typename T, int VEC>
+__global__ void norm_act_bwd_reduce_kernel(View<const T> x, View<const T> dy, const float* __restrict__ mean,
+                                           const float* __restrict__ rstd, int groups,
+                                           const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+                                           double* __restrict__ red, int cv_count, int rows) {
+  extern __shared__ double s_red[];
+  const int n = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int cv = tid % cv_count;
+  const int row = tid / cv_count;
+  const int cpg = x.c / groups;
+  if (row < rows) {
+    double acc[VEC], acc2[VEC];
+    float mu[VEC], rs[VEC], ga[VEC], be[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      acc[i] = acc2[i] = 0.0;
+      int c = cv * VEC + i;
+      int g = c / cpg;
+      mu[i] = mean[(int64_t)n * groups + g];
+      rs[i] = rstd[(int64_t)n * groups + g];
+      ga[i] = gamma ? gamma[c] : 1.f;
+      be[i] = beta ? beta[c] : 0.f;
+    }
+    const int64_t chunk = (x.spatial + gridDim.x - 1) / gridDim.x;
+    const int64_t v0 = (int64_t)blockIdx.x * chunk;
+    int64_t v1 = v0 + chunk;
+    if (v1 > x.spatial) v1 = x.spatial;
+    const T* xb = x.p + (int64_t)n * x.spatial * x.ld + (int64_t)cv * VEC;
+    const T* db = dy.p + (int64_t)n * x.spatial * dy.ld + (int64_t)cv * VEC;
+    float fx[VEC], fd[VEC], s[VEC], s2[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) s[i] = s2[i] = 0.f;
+    int cnt = 0;
+    for (int64_t v = v0 + row; v < v1; v += rows) {
+      load_vec<T, VEC>(xb + v * x.ld, fx);
+      load_vec<T, VEC>(db + v * dy.ld, fd);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        float xh = (fx[i] - mu[i]) * rs[i];
+        float g = fd[i] * act_grad(act, fmaf(xh, ga[i], be[i]));
+        s[i] += g;
+        s2[i] = fmaf(g, xh, s2[i]);
+      }
+      if (++cnt == 32) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          acc[i] += (double)s[i];
+          acc2[i] += (double)s2[i];
+          s[i] = s2[i] = 0.f;
+        }
+        cnt = 0;
+      }
+    }
+    double* dst = s_red + ((int64_t)row * cv_count + cv) * VEC * 2;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      dst[2 * i] = acc[i] + (double)s[i];
+      dst[2 * i + 1] = acc2[i] + (double)s2[i];
+    }
+  }
+  __syncthreads();
+  const int items = cv_count * VEC * 2;
+  for (int it = tid; it < items; it += blockDim.x) {
+    double t = 0.0;
+    for (int r = 0; r < rows; ++r) t += s_red[(int64_t)r * items + it];
+    atomicAdd(&red[((int64_t)n * x.c) * 2 + it], t);
+  }
+}
+
+// tiny: per (n, g) coefficients + dgamma/dbeta
+__global__ void norm_bwd_finalize_kernel(const double* __restrict__ red, const float* __restrict__ rstd,
+                                         const float* __restrict__ gamma, int n, int c, int groups, int64_t spatial,
+                                         int batch_stats, float* __restrict__ coef, float* __restrict__ dgamma,
+                                         float* __restrict__ dbeta) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  int cpg = c / groups;
+  if (idx < n * groups) {
+    int ni = idx / groups, g = idx % groups;
+    int n0 = batch_stats ? 0 : ni, n1 = batch_stats ? n : ni + 1;
+    double a = 0.0, b = 0.0;
+    for (int nn = n0; nn < n1; ++nn)
+      for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) {
+        double ga = gamma ? (double)gamma[cc] : 1.0;
+        a += ga * red[((int64_t)nn * c + cc) * 2];
+        b += ga * red[((int64_t)nn * c + cc) * 2 + 1];
+      }
+    double m = (double)spatial * cpg * (n1 - n0);
+    float r = rstd[idx];
+    for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) {
+      float ga = gamma ? gamma[cc] : 1.f;
+      float* o = coef + ((int64_t)ni * c + cc) * 3;
+      o[0] = r * ga;
+      o[1] = (float)(r * (a / m));
+      o[2] = (float)(r * (b / m));
+    }
+  }
+  if (idx < c) {
+    double sg = 0.0, sb = 0.0;
+    for (int nn = 0; nn < n; ++nn) {
+      sb += red[((int64_t)nn * c + idx) * 2];
+      sg += red[((int64_t)nn * c + idx) * 2 + 1];
+    }
+    if (dgamma) dgamma[idx] += (float)sg;
+    if (dbeta) dbeta[idx] += (float)sb;
+  }
+}
+
+template <typename T, int VEC>
+__global__ void norm_act_bwd_apply_kernel(View<const T> x, View<const T> dy, View<T> dx, const float* __restrict__ mean,
+                                          const float* __restrict__ rstd, int groups, const float* __restrict__ gamma,
+                                          const float* __restrict__ beta, int act, const float* __restrict__ coef,
+                                          int accumulate) {
+  const int cvn = x.c / VEC;
+  const int cpg = x.c / groups;
+  const int64_t total = x.vox * cvn;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t vox = i / cvn;
+    int cv = (int)(i % cvn);
+    int n = (int)(vox / x.spatial);
+    float fx[VEC], fd[VEC], fo[VEC];
+    load_vec<T, VEC>(x.p + vox * x.ld + cv * VEC, fx);
+    load_vec<T, VEC>(dy.p + vox * dy.ld + cv * VEC, fd);
+    if (accumulate) load_vec<T, VEC>(dx.p + vox * dx.ld + cv * VEC, fo);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      int c = cv * VEC + k;
+      int g = c / cpg;
+      float mu = mean[(int64_t)n * groups + g], rs = rstd[(int64_t)n * groups + g];
+      float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+      float xh = (fx[k] - mu) * rs;
+      float gg = fd[k] * act_grad(act, fmaf(xh, ga, be));
+      const float* cf = coef + ((int64_t)n * x.c + c) * 3;
+      float r = gg * cf[0] - cf[1] - xh * cf[2];
+      fo[k] = accumulate ? fo[k] + r : r;
+    }
+    store_vec<T, VEC>(dx.p + vox * dx.ld + cv * VEC, fo);
+  }
+}
+
+template <typename T, int VEC>
+__global__ void act_bwd_kernel(View<const T> x, View<const T> dy, View<T> dx, int act, int accumulate) {
+  const int cvn = x.c / VEC;
+  const int64_t total = x.vox * cvn;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t vox = i / cvn;
+    int cv = (int)(i % cvn);
+    float fx[VEC], fd[VEC], fo[VEC];
+    load_vec<T, VEC>(x.p + vox * x.ld + cv * VEC, fx);
+    load_vec<T, VEC>(dy.p + vox * dy.ld + cv * VEC, fd);
+    if (accumulate) load_vec<T, VEC>(dx.p + vox * dx.ld + cv * VEC, fo);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      float r = fd[k] * act_grad(act, fx[k]);
+      fo[k] = accumulate ? fo[k] + r : r;
+    }
+    store_vec<T, VEC>(dx.p + vox * dx.ld + cv * VEC, fo);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ max-pool
+struct PoolGeom {
+  int n, d, h, w, c;     // input
+  int od, oh, ow;        // output
+  int pd, ph, pw;
+};
+
+template <typename T>
+__global__ void maxpool_fwd_kernel(const T* __restrict__ x, int64_t ldx, T* __restrict__ y, int64_t ldy, PoolGeom g) {
+  const int64_t total = (int64_t)g.n * g.od * g.oh * g.ow * g.c;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = i;
+    int c = (int)(t % g.c); t /= g.c;
+    int ox = (int)(t % g.ow); t /= g.ow;
+    int oy = (int)(t % g.oh); t /= g.oh;
+    int oz = (int)(t % g.od); t /= g.od;
+    int n = (int)t;
+    float m = -INFINITY;
+    for (int a = 0; a < g.pd; ++a)
+      for (int b = 0; b < g.ph; ++b)
+        for (int e = 0; e < g.pw; ++e) {
+          int64_t vox = (((int64_t)n * g.d + oz * g.pd + a) * g.h + oy * g.ph + b) * g.w + ox * g.pw + e;
+          float v = to_f<T>(x[vox * ldx + c]);
+          if (v > m || v != v) m = v;
+        }
+    int64_t ov = (((int64_t)n * g.od + oz) * g.oh + oy) * g.ow + ox;
+    y[ov * ldy + c] = from_f<T>(m);
+  }
+}
+
+// one thread per INPUT element: finds the first maximum of its window in (d,h,w) scan order
+template <typename T>
+__global__ void maxpool_bwd_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy, int64_t lddy,
+                                   T* __restrict__ dx, int64_t lddx, PoolGeom g, int accumulate) {
+  const int64_t total = (int64_t)g.n * g.d * g.h * g.w * g.c;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = i;
+    int c = (int)(t % g.c); t /= g.c;
+    int xx = (int)(t % g.w); t /= g.w;
+    int yy = (int)(t % g.h); t /= g.h;
+    int zz = (int)(t % g.d); t /= g.d;
+    int n = (int)t;
+    int oz = zz / g.pd, oy = yy / g.ph, ox = xx / g.pw;
+    float r = 0.f;
+    if (oz < g.od && oy < g.oh && ox < g.ow) {
+      float m = -INFINITY;
+      int arg = 0, k = 0;
+      for (int a = 0; a < g.pd; ++a)
+        for (int b = 0; b < g.ph; ++b)
+          for (int e = 0; e < g.pw; ++e, ++k) {
+            int64_t vox = (((int64_t)n * g.d + oz * g.pd + a) * g.h + oy * g.ph + b) * g.w + ox * g.pw + e;
+            float v = to_f<T>(x[vox * ldx + c]);
+            if (v > m || v != v) { m = v; arg = k; }
+          }
+      int mine = ((zz - oz * g.pd) * g.ph + (yy - oy * g.ph)) * g.pw + (xx - ox * g.pw);
+      if (mine == arg) {
+        int64_t ov = (((int64_t)n * g.od + oz) * g.oh + oy) * g.ow + ox;
+        r = to_f<T>(dy[ov * lddy + c]);
+      }
+    }
+    int64_t iv = (((int64_t)n * g.d + zz) * g.h + yy) * g.w + xx;
+    T* o = dx + iv * lddx + c;
+    *o = from_f<T>(accumulate ? to_f<T>(*o) + r : r);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------- binary ops
+template <typename TA, typename TB, typename TY>
+__global__ void binary_kernel(View<const TA> a, View<const TB> b, View<TY> y, int op, int b_bcast) {
+  const int64_t total = a.vox * a.c;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t vox = i / a.c;
+    int c = (int)(i % a.c);
+    float va = to_f<TA>(a.p[vox * a.ld + c]);
+    float vb = 0.f;
+    if (op != 3 && op != 4) vb = to_f<TB>(b.p[vox * b.ld + (b_bcast ? 0 : c)]);
+    float r;
+    switch (op) {
+      case 0: r = va + vb; break;
+      case 1: r = va * vb; break;
+      case 2: r = fmaxf(va + vb, 0.f); break;
+      case 3: r = va; break;
+      default: r = 1.f / (1.f + expf(-va)); break;
+    }
+    y.p[vox * y.ld + c] = from_f<TY>(r);
+  }
+}
+
+// out = psi * x (psi has 1 channel): dpsi[vox] = sum_c dout*x ; dx (+)= dout*psi
+template <typename T>
+__global__ void gate_bwd_kernel(View<const T> x, View<const T> psi, View<const T> dout, View<T> dpsi, View<T> dx,
+                                int accumulate) {
+  for (int64_t vox = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; vox < x.vox; vox += (int64_t)gridDim.x * blockDim.x) {
+    float p = to_f<T>(psi.p[vox * psi.ld]);
+    float s = 0.f;
+    for (int c = 0; c < x.c; ++c) {
+      float d = to_f<T>(dout.p[vox * dout.ld + c]);
+      s = fmaf(d, to_f<T>(x.p[vox * x.ld + c]), s);
+      T* o = dx.p + vox * dx.ld + c;
+      float r = d * p;
+      *o = from_f<T>(accumulate ? to_f<T>(*o) + r : r);
+    }
+    dpsi.p[vox * dpsi.ld] = from_f<T>(s);
+  }
+}
+
+template <typename T>
+__global__ void relu_mask_bwd_kernel(View<const T> y, View<const T> dy, View<T> da) {
+  const int64_t total = y.vox * y.c;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t vox = i / y.c;
+    int c = (int)(i % y.c);
+    float v = to_f<T>(y.p[vox * y.ld + c]);
+    float d = to_f<T>(dy.p[vox * dy.ld + c]);
+    da.p[vox * da.ld + c] = from_f<T>(v > 0.f ? d : 0.f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------- losses
+__device__ __forceinline__ void block_atomic_add(double v, double* dst) {
+  __shared__ double s_w[32];
+  v = warp_sum(v);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) s_w[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    double t = (lane < (int)((blockDim.x + 31) / 32)) ? s_w[lane] : 0.0;
+    t = warp_sum(t);
+    if (lane == 0) atomicAdd(dst, t);
+  }
+  __syncthreads();
+}
+
+template <typename T>
+__global__ void bce_logits_kernel(View<const T> z, const float* __restrict__ target, double* __restrict__ loss_sum,
+                                  View<T> dz, float grad_scale) {
+  const int64_t total = z.vox * z.c;
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t vox = i / z.c;
+    int c = (int)(i % z.c);
+    float v = to_f<T>(z.p[vox * z.ld + c]);
+    float t = target[i];
+    // max(z,0) - z*t + log1p(exp(-|z|))
+    float l = fmaxf(v, 0.f) - v * t + log1pf(expf(-fabsf(v)));
+    acc += (double)l;
+    if (dz.p) {
+      float s = 1.f / (1.f + expf(-v));
+      dz.p[vox * dz.ld + c] = from_f<T>((s - t) * grad_scale);
+    }
+  }
+  block_atomic_add(acc, loss_sum);
+}
+
+// target dense (vox, 2C): first C = target, last C = mask
+template <typename T>
+__global__ void n2v_mse_kernel(View<const T> y, const float* __restrict__ target, double* __restrict__ sums,
+                               View<T> dy, float grad_scale, int mode) {
+  const int64_t total = y.vox * y.c;
+  double a = 0.0, b = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t vox = i / y.c;
+    int c = (int)(i % y.c);
+    float v = to_f<T>(y.p[vox * y.ld + c]);
+    float t = target[vox * 2 * y.c + c];
+    float m = target[vox * 2 * y.c + y.c + c];
+    float e = t - v * m;
+    if (mode == 0) {
+      a += (double)e * e;
+      b += (double)m;
+    } else {
+      dy.p[vox * dy.ld + c] = from_f<T>(-2.f * e * m * grad_scale);
+    }
+  }
+  if (mode == 0) {
+    block_atomic_add(a, sums);
+    block_atomic_add(b, sums + 1);
+  }
+}
+
+// softmax CE over channels; one thread per voxel
+template <typename T>
+__global__ void softmax_ce_kernel(View<const T> z, const int64_t* __restrict__ target, double* __restrict__ sums,
+                                  View<T> dz, float grad_scale) {
+  double acc = 0.0;
+  for (int64_t vox = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; vox < z.vox; vox += (int64_t)gridDim.x * blockDim.x) {
+    const T* p = z.p + vox * z.ld;
+    float mx = -INFINITY;
+    for (int c = 0; c < z.c; ++c) mx = fmaxf(mx, to_f<T>(p[c]));
+    float se = 0.f;
+    for (int c = 0; c < z.c; ++c) se += expf(to_f<T>(p[c]) - mx);
+    float lse = mx + logf(se);
+    int t = (int)target[vox];
+    acc += (double)(lse - to_f<T>(p[t]));
+    if (dz.p) {
+      T* o = dz.p + vox * dz.ld;
+      for (int c = 0; c < z.c; ++c) {
+        float sm = expf(to_f<T>(p[c]) - lse);
+        o[c] = from_f<T>((sm - (c == t ? 1.f : 0.f)) * grad_scale);
+      }
+    }
+  }
+  block_atomic_add(acc, sums);
+}
+
+template <typename TI, typename TO>
+__global__ void softmax_channels_kernel(View<const TI> x, View<TO> y, int c0, int c1) {
+  for (int64_t vox = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; vox < x.vox; vox += (int64_t)gridDim.x * blockDim.x) {
+    const TI* p = x.p + vox * x.ld;
+    float mx = -INFINITY;
+    for (int c = c0; c < c1; ++c) mx = fmaxf(mx, to_f<TI>(p[c]));
+    float se = 0.f;
+    for (int c = c0; c < c1; ++c) se += expf(to_f<TI>(p[c]) - mx);
+    float inv = 1.f / se;
+    TO* o = y.p + vox * y.ld;
+    for (int c = c0; c < c1; ++c) o[c] = from_f<TO>(expf(to_f<TI>(p[c]) - mx) * inv);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ optimiser
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps, float wd,
+                             float bc1, float bc2_sqrt, float grad_scale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * grad_scale;
+    float pi = p[i] * (1.f - lr * wd);
+    float mi = m[i] + (1.f - b1) * (gi - m[i]);          // torch: exp_avg.lerp_(grad, 1 - beta1)
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi -= (lr / bc1) * (mi / denom);
+    p[i] = pi; m[i] = mi; v[i] = vi;
+  }
+}
+
+__global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mom, int64_t n,
+                           float lr, float momentum, float wd, int first, float grad_scale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * grad_scale + wd * p[i];
+    if (momentum != 0.f) {
+      float b = first ? gi : momentum * mom[i] + gi;
+      mom[i] = b;
+      gi = b;
+    }
+    p[i] -= lr * gi;
+  }
+}
+
+__global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ out) {
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    acc += (double)g[i] * g[i];
+  block_atomic_add(acc, out);
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+// ================================================================================================ C ABI
+B200_EXPORT int b200_channel_sums(const b200_tensor* x, double* sums, void* stream) {
+  B200_CHECK_ARG(check_tensor(x, "channel_sums.x") && sums, "%s", b200_last_error());
+  B200_DISPATCH_DTYPE(x->dtype, T, return launch_channel_sums<T>(x, sums, (cudaStream_t)stream));
+  return B200_OK;
+}
+
+B200_EXPORT int b200_norm_finalize(const double* sums, int32_t n, int32_t c, int32_t groups, int64_t spatial,
+                                   int32_t batch_stats, const float* gamma, const float* beta, float eps,
+                                   float* mean, float* rstd, float* scale, float* shift, void* stream) {
+  B200_CHECK_ARG(sums && mean && rstd && scale && shift, "norm_finalize: null pointer");
+  B200_CHECK_ARG(groups > 0 && c % groups == 0, "norm_finalize: channels %d not divisible by groups %d", c, groups);
+  int total = n * groups;
+  norm_finalize_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, n, c, groups, spatial, batch_stats,
+                                                                             gamma, beta, eps, mean, rstd, scale, shift);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+B200_EXPORT int b200_scale_shift_act(const b200_tensor* x, const float* scale, const float* shift, int32_t act,
+                                     const b200_tensor* y, void* stream) {
+  B200_CHECK_ARG(check_tensor(x, "scale_shift_act.x") && check_tensor(y, "scale_shift_act.y"), "%s", b200_last_error());
+  B200_CHECK_ARG(same_spatial(x, y) && x->c == y->c, "scale_shift_act: shape mismatch");
+  B200_CHECK_ARG((scale == nullptr) == (shift == nullptr), "scale_shift_act: scale/shift must both be given");
+  cudaStream_t st = (cudaStream_t)stream;
+#define SSA(TI, TO)                                                                                              \
+  {                                                                                                              \
+    constexpr int V = VecOf<TI>::n < VecOf<TO>::n ? VecOf<TI>::n : VecOf<TO>::n;                                  \
+    View<const TI> xv{(const TI*)x->data, x->ld, x->c, voxels(x), (int64_t)x->d * x->h * x->w};                    \
+    View<TO> yv{(TO*)y->data, y->ld, y->c, voxels(y), (int64_t)y->d * y->h * y->w};                                \
+    if (vec_ok(x, V) && vec_ok(y, V) && sizeof(TI) == sizeof(TO))                                                 \
+      scale_shift_act_kernel<TI, TO, V><<<grid_for(xv.vox * (x->c / V), 256), 256, 0, st>>>(xv, yv, scale, shift, act); \
+    else                                                                                                         \
+      scale_shift_act_kernel<TI, TO, 1><<<grid_for(xv.vox * x->c, 256), 256, 0, st>>>(xv, yv, scale, shift, act);  \
+  }
+  if (x->dtype == y->dtype) {
+    B200_DISPATCH_DTYPE(x->dtype, T, SSA(T, T));
+  } else if (x->dtype == B200_F32 && y->dtype == B200_BF16) SSA(float, __nv_bfloat16)
+  else if (x->dtype == B200_F32 && y->dtype == B200_F16) SSA(float, __half)
+  else if (x->dtype == B200_BF16 && y->dtype == B200_F32) SSA(__nv_bfloat16, float)
+  else if (x->dtype == B200_F16 && y->dtype == B200_F32) SSA(__half, float)
+  else { set_error("scale_shift_act: unsupported dtype pair"); return B200_ERR_UNSUPPORTED; }
+#undef SSA
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+B200_EXPORT int b200_convert(const b200_tensor* src, const b200_tensor* dst, void* stream) {
+  return b200_scale_shift_act(src, nullptr, nullptr, B200_ACT_NONE, dst, stream);
+}
+
+B200_EXPORT int b200_norm_act_bwd_reduce(const b200_tensor* x, const b200_tensor* dy, const float* mean,
+                                         const float* rstd, int32_t groups, const float* gamma, const float* beta,
+                                         int32_t act, double* red, void* stream) {
+  B200_CHECK_ARG(check_tensor(x, "bwd_reduce.x") && check_tensor(dy, "bwd_reduce.dy") && mean && rstd && red, "%s",
+                 b200_last_error());
+  B200_CHECK_ARG(same_spatial(x, dy) && x->c == dy->c && x->dtype == dy->dtype, "bwd_reduce: shape/dtype mismatch");
+  B200_CHECK_ARG(groups > 0 && x->c % groups == 0, "bwd_reduce: bad groups");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t spatial = (int64_t)x->d * x->h * x->w;
+  int64_t chunks = ceil_div(spatial, 2048);
+  int64_t cap = ceil_div((int64_t)sm_count() * 8, x->n);
+  if (chunks > cap) chunks = cap;
+  if (chunks < 1) chunks = 1;
+  dim3 grid((unsigned)chunks, x->n);
+  B200_DISPATCH_DTYPE(x->dtype, T, {
+    constexpr int V = VecOf<T>::n;
+    View<const T> xv{(const T*)x->data, x->ld, x->c, voxels(x), spatial};
+    View<const T> dv{(const T*)dy->data, dy->ld, dy->c, voxels(dy), spatial};
+    if (vec_ok(x, V) && vec_ok(dy, V) && x->c / V <= 256) {
+      int cvn = x->c / V, rows = 256 / cvn;
+      if (rows > 32) rows = 32;
+      int threads = ((rows * cvn + 31) / 32) * 32;
+      norm_act_bwd_reduce_kernel<T, V><<<grid, threads, sizeof(double) * rows * cvn * V * 2, st>>>(
+          xv, dv, mean, rstd, groups, gamma, beta, act, red, cvn, rows);
+    } else {
+      B200_CHECK_ARG(x->c <= 1024, "bwd_reduce: too many channels");
+      int cvn = x->c, rows = 256 / cvn;
+      if (rows < 1) rows = 1;
+      if (rows > 32) rows = 32;
+      int threads = ((rows * cvn + 31) / 32) * 32;
+      norm_act_bwd_reduce_kernel<T, 1><<<grid, threads, sizeof(double) * rows * cvn * 2, st>>>(
+          xv, dv, mean, rstd, groups, gamma, beta, act, red, cvn, rows);
+    }
+  });
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+B200_EXPORT int b200_norm_bwd_finalize(const double* red, const float* rstd, const float* gamma, int32_t n, int32_t c,
+                                       int32_t groups, int64_t spatial, int32_t batch_stats, float* coef, float* dgamma,
+                                       float* dbeta, void* stream) {
+  B200_CHECK_ARG(red && rstd && coef, "norm_bwd_finalize: null pointer");
+  int total = n * groups > c ? n * groups : c;
+  norm_bwd_finalize_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(red, rstd, gamma, n, c, groups, spatial,
+                                                                                 batch_stats, coef, dgamma, dbeta);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+B200_EXPORT int b200_norm_act_bwd_apply(const b200_tensor* x, const b200_tensor* dy, const float* mean, const float* rstd,
+                                        int32_t groups, const float* gamma, const float* beta, int32_t act,
+                                        const float* coef, const b200_tensor* dx, int32_t accumulate, void* stream) {
+  B200_CHECK_ARG(check_tensor(x, "bwd_apply.x") && check_tensor(dy, "bwd_apply.dy") && check_tensor(dx, "bwd_apply.dx"),
+                 "%s", b200_last_error());
+  B200_CHECK_ARG(same_spatial(x, dy) && same_spatial(x, dx) && x->c == dy->c && x->c == dx->c &&
+                     x->dtype == dy->dtype && x->dtype == dx->dtype, "bwd_apply: shape/dtype mismatch");
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_DISPATCH_DTYPE(x->dtype, T, {
+    constexpr int V = VecOf<T>::n;
+    View<const T> xv = view<const T>(x);
+    View<const T> dv = view<const T>(dy);
+    View<T> ov = view<T>(dx);
+    if (vec_ok(x, V) && vec_ok(dy, V) && vec_ok(dx, V))
+      norm_act_bwd_apply_kernel<T, V><<<grid_for(xv.vox * (x->c / V), 256), 256, 0, st>>>(xv, dv, ov, mean, rstd, groups,
+                                                                                         gamma, beta, act, coef, accumulate);
+    else
+      norm_act_bwd_apply_kernel<T, 1><<<grid_for(xv.vox * x->c, 256), 256, 0, st>>>(xv, dv, ov, mean, rstd, groups, gamma,
+                                                                                   beta, act, coef, accumulate);
+  });
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+B200_EXPORT int b200_act_bwd(const b200_tensor* x, const b200_tensor* dy, int32_t act, const b200_tensor* dx,
+                             int32_t accumulate, void* stream) {
+  B200_CHECK_ARG(check_tensor(x, "act_bwd.x") && check_tensor(dy, "act_bwd.dy") && check_tensor(dx, "act_bwd.dx"), "%s",
+                 b200_last_error());
+  B200_CHECK_ARG(same_spatial(x, dy) && same_spatial(x, dx) && x->c == dy->c && x->c == dx->c &&
+                     x->dtype == dy->dtype && x->dtype == dx->dtype, "act_bwd: shape/dtype mismatch");
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_DISPATCH_DTYPE(x->dtype, T, {
+    constexpr int V = VecOf<T>::n;
+    View<const T> xv = view<const T>(x);
+    View<const T> dv = view<const T>(dy);
+    View<T> ov = view<T>(dx);
+    if (vec_ok(x, V) && vec_ok(dy, V) && vec_ok(dx, V))
+      act_bwd_kernel<T, V><<<grid_for(xv.vox * (x->c / V), 256), 256, 0, st>>>(xv, dv, ov, act, accumulate);
+    else
+      act_bwd_kernel<T, 1><<<grid_for(xv.vox * x->c, 256), 256, 0, st>>>(xv, dv, ov, act, accumulate);
+  });
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+static int pool_geom(const b200_tensor* x, const b200_tensor* y, int pd, int ph, int pw, PoolGeom* g) {
+  B200_CHECK_ARG(pd > 0 && ph > 0 && pw > 0, "maxpool: bad window");
+  B200_CHECK_ARG(y->n == x->n && y->c == x->c && y->d == x->d / pd && y->h == x->h / ph && y->w == x->w / pw,
+                 "maxpool: output shape (%d,%d,%d,%d,%d) does not match floor(input/window)", y->n, y->d, y->h, y->w, y->c);
+  *g = PoolGeom{x->n, x->d, x->h, x->w, x->c, y->d, y->h, y->w, pd, ph, pw};
+  return B200_OK;
+}
+
+B200_EXPORT int b200_maxpool_fwd(const b200_tensor* x, const b200_tensor* y, int32_t pd, int32_t ph, int32_t pw,
+                                 void* stream) {
+  B200_CHECK_ARG(check_tensor(x, "maxpool.x") && check_tensor(y, "maxpool.y") && x->dtype == y->dtype, "%s",
+                 b200_last_error());
+  PoolGeom g;
+  int st = pool_geom(x, y, pd, ph, pw, &g);
+  if (st) return st;
+  int64_t total = voxels(y) * y->c;
+  B200_DISPATCH_DTYPE(x->dtype, T, (maxpool_fwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                                       (const T*)x->data, x->ld, (T*)y->data, y->ld, g)));
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+B200_EXPORT int b200_maxpool_bwd(const b200_tensor* x, const b200_tensor* y, const b200_tensor* dy, const b200_tensor* dx,
+                                 int32_t pd, int32_t ph, int32_t pw, int32_t accumulate, void* stream) {
+  B200_CHECK_ARG(check_tensor(x, "maxpool_bwd.x") && check_tensor(dy, "maxpool_bwd.dy") && check_tensor(dx, "maxpool_bwd.dx"),
+                 "%s", b200_last_error());
+  B200_CHECK_ARG(x->dtype == dy->dtype && x->dtype == dx->dtype && same_spatial(x, dx) && x->c == dx->c,
+                 "maxpool_bwd: shape/dtype mismatch");
+  PoolGeom g;
+  int st = pool_geom(x, dy, pd, ph, pw, &g);
+  if (st) return st;
+  (void)y;
+  int64_t total = voxels(x) * x->c;
+  B200_DISPATCH_DTYPE(x->dtype, T, (maxpool_bwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                                       (const T*)x->data, x->ld, (const T*)dy->data, dy->ld, (T*)dx->data, dx->ld, g,
+                                       accumulate)));
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+B200_EXPORT int b200_binary(const b200_tensor* a, const b200_tensor* b, const b200_tensor* y, int32_t op, void* stream) {
+  B200_CHECK_ARG(check_tensor(a, "binary.a") && check_tensor(y, "binary.y"), "%s", b200_last_error());
+  B200_CHECK_ARG(op >= 0 && op <= 4, "binary: bad op");
+  const bool needs_b = (op != 3 && op != 4);
+  if (needs_b) B200_CHECK_ARG(check_tensor(b, "binary.b") && same_spatial(a, b) && (b->c == a->c || b->c == 1) &&
+                                  b->dtype == a->dtype, "binary: operand mismatch");
+  B200_CHECK_ARG(same_spatial(a, y) && a->c == y->c && a->dtype == y->dtype, "binary: output mismatch");
+  cudaStream_t st = (cudaStream_t)stream;
+  const b200_tensor* bb = needs_b ? b : a;
+  int bcast = needs_b && b->c == 1 && a->c != 1;
+  B200_DISPATCH_DTYPE(a->dtype, T, (binary_kernel<T, T, T><<<grid_for(voxels(a) * a->c, 256), 256, 0, st>>>(
+                                       view<const T>(a), view<const T>(bb), view<T>(y), op, bcast)));
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+B200_EXPORT int b200_gate_bwd(const b200_tensor* x, const b200_tensor* psi, const b200_tensor* dout,
+                              const b200_tensor* dpsi, const b200_tensor* dx, int32_t accumulate, void* stream) {
+  B200_CHECK_ARG(check_tensor(x, "gate.x") && check_tensor(psi, "gate.psi") && check_tensor(dout, "gate.dout") &&
+                     check_tensor(dpsi, "gate.dpsi") && check_tensor(dx, "gate.dx"), "%s", b200_last_error());
+  B200_CHECK_ARG(psi->c == 1 && dpsi->c == 1 && x->c == dout->c && x->c == dx->c && same_spatial(x, psi) &&
+                     same_spatial(x, dout) && same_spatial(x, dpsi) && same_spatial(x, dx), "gate_bwd: shape mismatch");
+  B200_DISPATCH_DTYPE(x->dtype, T, (gate_bwd_kernel<T><<<grid_for(voxels(x), 128), 128, 0, (cudaStream_t)stream>>>(
+                                       view<const T>(x), view<const T>(psi), view<const T>(dout), view<T>(dpsi), view<T>(dx),
+                                       accumulate)));
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+B200_EXPORT int b200_relu_mask_bwd(const b200_tensor* y, const b200_tensor* dy, const b200_tensor* da, void* stream) {
+  B200_CHECK_ARG(check_tensor(y, "relu_mask.y") && check_tensor(dy, "relu_mask.dy") && check_tensor(da, "relu_mask.da"),
+                 "%s", b200_last_error());
+  B200_CHECK_ARG(same_spatial(y, dy) && same_spatial(y, da) && y->c == dy->c && y->c == da->c, "relu_mask_bwd: mismatch");
+  B200_DISPATCH_DTYPE(y->dtype, T, (relu_mask_bwd_kernel<T><<<grid_for(voxels(y) * y->c, 256), 256, 0, (cudaStream_t)stream>>>(
+                                       view<const T>(y), view<const T>(dy), view<T>(da))));
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+B200_EXPORT int b200_bce_logits(const b200_tensor* logits, const float* target, double* loss_sum,
+                                const b200_tensor* dlogits, float grad_scale, void* stream) {
+  B200_CHECK_ARG(check_tensor(logits, "bce.logits") && target && loss_sum, "%s", b200_last_error());
+  if (dlogits) B200_CHECK_ARG(check_tensor(dlogits, "bce.dlogits") && same_spatial(logits, dlogits) &&
+                                  logits->c == dlogits->c && logits->dtype == dlogits->dtype, "bce: dlogits mismatch");
+  B200_DISPATCH_DTYPE(logits->dtype, T, {
+    View<T> dv{dlogits ? (T*)dlogits->data : nullptr, dlogits ? dlogits->ld : 0, logits->c, voxels(logits), 0};
+    bce_logits_kernel<T><<<grid_for(voxels(logits) * logits->c, 256, 4), 256, 0, (cudaStream_t)stream>>>(
+        view<const T>(logits), target, loss_sum, dv, grad_scale);
+  });
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+B200_EXPORT int b200_n2v_mse(const b200_tensor* pred, const float* target, double* sums, const b200_tensor* dpred,
+                             float grad_scale, int32_t mode, void* stream) {
+  B200_CHECK_ARG(check_tensor(pred, "n2v.pred") && target, "%s", b200_last_error());
+  B200_CHECK_ARG(mode == 0 ? sums != nullptr : (dpred && check_tensor(dpred, "n2v.dpred")), "n2v: missing output");
+  B200_DISPATCH_DTYPE(pred->dtype, T, {
+    View<T> dv{dpred ? (T*)dpred->data : nullptr, dpred ? dpred->ld : 0, pred->c, voxels(pred), 0};
+    n2v_mse_kernel<T><<<grid_for(voxels(pred) * pred->c, 256, 4), 256, 0, (cudaStream_t)stream>>>(
+        view<const T>(pred), target, sums, dv, grad_scale, mode);
+  });
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+B200_EXPORT int b200_softmax_ce(const b200_tensor* logits, const int64_t* target, double* sums,
+                                const b200_tensor* dlogits, float grad_scale, void* stream) {
+  B200_CHECK_ARG(check_tensor(logits, "ce.logits") && target && sums, "%s", b200_last_error());
+  B200_DISPATCH_DTYPE(logits->dtype, T, {
+    View<T> dv{dlogits ? (T*)dlogits->data : nullptr, dlogits ? dlogits->ld : 0, logits->c, voxels(logits), 0};
+    softmax_ce_kernel<T><<<grid_for(voxels(logits), 128, 4), 128, 0, (cudaStream_t)stream>>>(view<const T>(logits), target,
+                                                                                          sums, dv, grad_scale);
+  });
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+B200_EXPORT int b200_softmax_channels(const b200_tensor* x, const b200_tensor* y, int32_t c0, int32_t c1, void* stream) {
+  B200_CHECK_ARG(check_tensor(x, "softmax.x") && check_tensor(y, "softmax.y") && same_spatial(x, y) && x->c == y->c &&
+                     x->dtype == y->dtype, "%s", b200_last_error());
+  B200_CHECK_ARG(0 <= c0 && c0 < c1 && c1 <= x->c, "softmax: bad channel range");
+  B200_DISPATCH_DTYPE(x->dtype, T, (softmax_channels_kernel<T, T><<<grid_for(voxels(x), 128), 128, 0, (cudaStream_t)stream>>>(
+                                       view<const T>(x), view<T>(y), c0, c1)));
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+B200_EXPORT int b200_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                                float beta2, float eps, float weight_decay, int64_t step, float grad_scale, void* stream) {
+  B200_CHECK_ARG(p && g && m && v && n > 0 && step > 0, "adamw: bad args");
+  float bc1 = 1.f - powf(beta1, (float)step);
+  float bc2 = sqrtf(1.f - powf(beta2, (float)step));
+  adamw_kernel<<<grid_for(n, 256, 4), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay,
+                                                                     bc1, bc2, grad_scale);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+B200_EXPORT int b200_sgd_step(float* p, const float* g, float* mom, int64_t n, float lr, float momentum,
+                              float weight_decay, int32_t first_step, float grad_scale, void* stream) {
+  B200_CHECK_ARG(p && g && n > 0 && (momentum == 0.f || mom), "sgd: bad args");
+  sgd_kernel<<<grid_for(n, 256, 4), 256, 0, (cudaStream_t)stream>>>(p, g, mom, n, lr, momentum, weight_decay, first_step,
+                                                                   grad_scale);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+B200_EXPORT int b200_sumsq(const float* g, int64_t n, double* out, void* stream) {
+  B200_CHECK_ARG(g && out && n > 0, "sumsq: bad args");
+  sumsq_kernel<<<grid_for(n, 256, 4), 256, 0, (cudaStream_t)stream>>>(g, n, out);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}

@@ -1,0 +1,288 @@
+// Sliding-window bookkeeping and stitching: bit-exact patch-grid planner (host), crop gather and
+// spline-weighted overlap-add gather (device).  Mirrors biapy/data/data_3D_manipulation.py:353-859 and the 2D
+// twins in biapy/data/data_2D_manipulation.py:54-533 (see include/biapy_b200.h for the per-function map).
+#include "common.cuh"
+
+
+namespace b200 {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace b200
+
+B200_EXPORT const char* b200_last_error(void) { return b200::g_err; }
+B200_EXPORT int b200_version(void) { return 100; }
+
+B200_EXPORT int b200_device_info(int device, int* sm_count, int* cc, int64_t* total_mem) {
+  cudaDeviceProp p;
+  B200_CUDA(cudaGetDeviceProperties(&p, device));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc) *cc = p.major * 10 + p.minor;
+  if (total_mem) *total_mem = (int64_t)p.totalGlobalMem;
+  return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ planner
+static inline int64_t floordiv(int64_t a, int64_t b) {
+  int64_t q = a / b, r = a % b;
+  return (r != 0 && ((r < 0) != (b < 0))) ? q - 1 : q;
+}
+
+B200_EXPORT int b200_plan_axis(int64_t dim, int64_t patch, int64_t pad, double overlap, b200_axis_plan* out) {
+  B200_CHECK_ARG(out != nullptr, "plan_axis: null output");
+  B200_CHECK_ARG(dim > 0 && patch > 0 && pad >= 0, "plan_axis: bad sizes dim=%lld patch=%lld pad=%lld",
+                 (long long)dim, (long long)patch, (long long)pad);
+  B200_CHECK_ARG(!(overlap >= 1.0 || overlap < 0.0), "'overlap' values must be floats between range [0, 1)");
+  const int64_t core = patch - 2 * pad;
+  // data_3D_manipulation.py:537-542 -- Python: int((P - 2p) * (1 - ov)); IEEE double product, truncation.
+  // volatile keeps the compiler from contracting / re-associating the two double operations.
+  volatile double keep = (overlap == 0.0) ? 1.0 : 1.0 - overlap;
+  volatile double prod = (double)core * keep;
+  int64_t step = (int64_t)prod;
+  B200_CHECK_ARG(step != 0, "division by zero (step == 0 for patch=%lld pad=%lld overlap=%g)", (long long)patch,
+                 (long long)pad, overlap);
+  volatile double q = (double)dim / (double)step;                 // :543 math.ceil(dim / step)
+  int64_t n = (int64_t)ceil(q);
+  int64_t last = (n == 1) ? 0 : ((n - 1) * step + patch) - (dim + 2 * pad);   // :544
+  int64_t per_block = (n > 1) ? floordiv(last, n - 1) : 0;        // :545
+  step -= per_block;                                              // :546
+  last -= per_block * (n - 1);                                    // :547
+  out->dim = dim; out->patch = patch; out->pad = pad;
+  out->step = step; out->n = n; out->last = last;
+  out->core = core; out->ov_px = core - step;                     // :814-816
+  return B200_OK;
+}
+
+B200_EXPORT int64_t b200_axis_start(const b200_axis_plan* p, int64_t i, int frame) {
+  if (frame == 0) {  // crop: data_3D_manipulation.py:596-606 (padded frame, full patch extent)
+    int64_t d = ((i * p->step + p->patch) < (p->dim + 2 * p->pad)) ? 0 : p->last;
+    return i * p->step - d;
+  }
+  // merge: data_3D_manipulation.py:826-835 (original frame, core extent)
+  int64_t d = ((i * p->step + p->core) < p->dim) ? 0 : p->last;
+  return i * p->step - d;
+}
+
+B200_EXPORT int b200_spline_window_1d(int64_t size, int64_t ov_px, float* out) {
+  B200_CHECK_ARG(size > 0 && out, "spline_window_1d: bad args");
+  for (int64_t i = 0; i < size; ++i) out[i] = 1.0f;
+  if (ov_px > 0) {
+    int64_t ov = ov_px < size / 2 ? ov_px : size / 2;   // min(ov_pixels, size // 2)
+    if (ov > 0) {
+      // np.linspace(0, 1, ov + 2)[1:-1]: y_i = i * (1.0 / (ov + 1))     (numpy: arange * step + start)
+      volatile double step = 1.0 / (double)(ov + 1);
+      for (int64_t j = 0; j < ov; ++j) {
+        volatile double x = (double)(j + 1) * step;
+        volatile double x2 = x * x;                       // x ** 2
+        volatile double omx = 1.0 - x;
+        volatile double o2 = omx * omx;
+        volatile double den = x2 + o2;
+        den = den + 1e-8;
+        volatile double t = x2 / den;
+        float tf = (float)t;
+        out[j] = tf;                                      // wind[:ov] = taper
+        out[size - 1 - j] = tf;                           // wind[-ov:] = taper[::-1]
+      }
+    }
+  }
+  return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------- crop gather
+namespace b200 {
+
+__device__ __forceinline__ int64_t pad_src(int64_t j, int64_t dim, int mode) {
+  // j is the coordinate in the un-padded frame (may be out of range); returns -1 for "constant zero"
+  if (j >= 0 && j < dim) return j;
+  switch (mode) {
+    case B200_PAD_ZEROS: return -1;
+    case B200_PAD_EDGE: return j < 0 ? 0 : dim - 1;
+    case B200_PAD_REFLECT: {
+      if (dim == 1) return 0;
+      int64_t period = 2 * (dim - 1);
+      int64_t m = j % period;
+      if (m < 0) m += period;
+      return m < dim ? m : period - m;
+    }
+    case B200_PAD_SYMMETRIC: {
+      int64_t period = 2 * dim;
+      int64_t m = j % period;
+      if (m < 0) m += period;
+      return m < dim ? m : period - 1 - m;
+    }
+    default: {  // wrap
+      int64_t m = j % dim;
+      if (m < 0) m += dim;
+      return m;
+    }
+  }
+}
+
+struct CropParams {
+  int64_t D, H, W, C, pd, ph, pw, nz, ny, nx, pad_z, pad_y, pad_x, total;
+  int mode;
+};
+
+constexpr int kMaxAxisPatches = 1024;
+
+template <typename U>
+__global__ void crop_gather_kernel(const U* __restrict__ src, U* __restrict__ dst, CropParams p,
+                                   const int64_t* __restrict__ sz, const int64_t* __restrict__ sy,
+                                   const int64_t* __restrict__ sx) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < p.total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = idx;
+    int64_t ch = t % p.C; t /= p.C;
+    int64_t lx = t % p.pw; t /= p.pw;
+    int64_t ly = t % p.ph; t /= p.ph;
+    int64_t lz = t % p.pd; t /= p.pd;
+    int64_t ix = t % p.nx; t /= p.nx;
+    int64_t iy = t % p.ny; t /= p.ny;
+    int64_t iz = t;
+    int64_t z = pad_src(sz[iz] + lz - p.pad_z, p.D, p.mode);
+    int64_t y = pad_src(sy[iy] + ly - p.pad_y, p.H, p.mode);
+    int64_t x = pad_src(sx[ix] + lx - p.pad_x, p.W, p.mode);
+    U v = 0;
+    if (z >= 0 && y >= 0 && x >= 0) v = src[((z * p.H + y) * p.W + x) * p.C + ch];
+    dst[idx] = v;
+  }
+}
+
+}  // namespace b200
+
+B200_EXPORT int b200_crop_gather(const void* src, int32_t dtype, int64_t D, int64_t H, int64_t W, int64_t C,
+                                 void* dst, int64_t pd, int64_t ph, int64_t pw,
+                                 const int64_t* starts_z, int64_t nz, const int64_t* starts_y, int64_t ny,
+                                 const int64_t* starts_x, int64_t nx,
+                                 int64_t pad_z, int64_t pad_y, int64_t pad_x, int32_t pad_mode, void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(src && dst && starts_z && starts_y && starts_x, "crop_gather: null pointer");
+  B200_CHECK_ARG(valid_dtype(dtype) || dtype == 3, "crop_gather: bad dtype");
+  B200_CHECK_ARG(nz > 0 && ny > 0 && nx > 0 && nz <= kMaxAxisPatches && ny <= kMaxAxisPatches && nx <= kMaxAxisPatches,
+                 "crop_gather: patches per axis must be in [1, %d]", kMaxAxisPatches);
+  B200_CHECK_ARG(pad_mode >= 0 && pad_mode <= 4, "crop_gather: bad pad mode");
+  cudaStream_t st = (cudaStream_t)stream;
+  CropParams p{D, H, W, C, pd, ph, pw, nz, ny, nx, pad_z, pad_y, pad_x, nz * ny * nx * pd * ph * pw * C, pad_mode};
+  int threads = 256;
+  int64_t blocks = ceil_div(p.total, threads);
+  int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (dtype == 3)
+    crop_gather_kernel<uint8_t><<<(unsigned)blocks, threads, 0, st>>>((const uint8_t*)src, (uint8_t*)dst, p,
+                                                                     starts_z, starts_y, starts_x);
+  else if (dtype == B200_F32)
+    crop_gather_kernel<uint32_t><<<(unsigned)blocks, threads, 0, st>>>((const uint32_t*)src, (uint32_t*)dst, p,
+                                                                      starts_z, starts_y, starts_x);
+  else
+    crop_gather_kernel<uint16_t><<<(unsigned)blocks, threads, 0, st>>>((const uint16_t*)src, (uint16_t*)dst, p,
+                                                                      starts_z, starts_y, starts_x);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------ overlap-add
+namespace b200 {
+
+struct MergeParams {
+  int64_t D, H, W, C, pz, py, px, pad_z, pad_y, pad_x, cz, cy, cx, nz, ny, nx, total;
+};
+
+// One thread per output element.  For every covering patch, in increasing patch index (z-major, then y,
+// then x -- the order of the reference's triple loop, data_3D_manipulation.py:822-845):
+//     acc  = acc  + (float(patch) * w)        w = (wz * wy) * wx   (float32, numpy left-to-right)
+//     wsum = wsum + w
+// and finally out = acc / (wsum + 1e-18f) cast to the output dtype (:849).  The explicit _rn intrinsics
+// forbid FMA contraction, so float32 results are bit-identical to numpy's.
+template <typename TI, typename TO>
+__global__ void overlap_add_kernel(const TI* __restrict__ patches, TO* __restrict__ out, MergeParams p,
+                                   const int64_t* __restrict__ sz, const int64_t* __restrict__ sy,
+                                   const int64_t* __restrict__ sx, const float* __restrict__ wz,
+                                   const float* __restrict__ wy, const float* __restrict__ wx) {
+  extern __shared__ int64_t s_starts[];  // nz + ny + nx
+  int64_t* s_z = s_starts;
+  int64_t* s_y = s_z + p.nz;
+  int64_t* s_x = s_y + p.ny;
+  for (int i = threadIdx.x; i < p.nz; i += blockDim.x) s_z[i] = sz[i];
+  for (int i = threadIdx.x; i < p.ny; i += blockDim.x) s_y[i] = sy[i];
+  for (int i = threadIdx.x; i < p.nx; i += blockDim.x) s_x[i] = sx[i];
+  __syncthreads();
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < p.total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = idx;
+    int64_t ch = t % p.C; t /= p.C;
+    int64_t x = t % p.W; t /= p.W;
+    int64_t y = t % p.H; t /= p.H;
+    int64_t z = t;
+    float acc = 0.f, wsum = 0.f;
+    for (int64_t iz = 0; iz < p.nz; ++iz) {
+      int64_t lz = z - s_z[iz];
+      if (lz < 0 || lz >= p.cz) continue;
+      float fz = wz[lz];
+      for (int64_t iy = 0; iy < p.ny; ++iy) {
+        int64_t ly = y - s_y[iy];
+        if (ly < 0 || ly >= p.cy) continue;
+        float fzy = __fmul_rn(fz, wy[ly]);
+        for (int64_t ix = 0; ix < p.nx; ++ix) {
+          int64_t lx = x - s_x[ix];
+          if (lx < 0 || lx >= p.cx) continue;
+          float w = __fmul_rn(fzy, wx[lx]);
+          int64_t c = (iz * p.ny + iy) * p.nx + ix;
+          int64_t off = (((c * p.pz + lz + p.pad_z) * p.py + ly + p.pad_y) * p.px + lx + p.pad_x) * p.C + ch;
+          float v = to_f<TI>(patches[off]);
+          acc = __fadd_rn(acc, __fmul_rn(v, w));
+          wsum = __fadd_rn(wsum, w);
+        }
+      }
+    }
+    out[idx] = from_f<TO>(__fdiv_rn(acc, __fadd_rn(wsum, 1e-18f)));
+  }
+}
+
+template <typename TI, typename TO>
+static int launch_overlap_add(const void* patches, void* out, const MergeParams& p, const int64_t* sz,
+                              const int64_t* sy, const int64_t* sx, const float* wz, const float* wy,
+                              const float* wx, cudaStream_t st) {
+  int threads = 256;
+  int64_t blocks = ceil_div(p.total, threads);
+  int64_t cap = (int64_t)sm_count() * 32;
+  if (blocks > cap) blocks = cap;
+  size_t smem = sizeof(int64_t) * (p.nz + p.ny + p.nx);
+  overlap_add_kernel<TI, TO><<<(unsigned)blocks, threads, smem, st>>>((const TI*)patches, (TO*)out, p, sz, sy, sx,
+                                                                     wz, wy, wx);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+}  // namespace b200
+
+B200_EXPORT int b200_overlap_add(const void* patches, int32_t dtype_in, void* out, int32_t dtype_out,
+                                 int64_t D, int64_t H, int64_t W, int64_t C,
+                                 int64_t pz, int64_t py, int64_t px, int64_t pad_z, int64_t pad_y, int64_t pad_x,
+                                 const int64_t* starts_z, int64_t nz, const int64_t* starts_y, int64_t ny,
+                                 const int64_t* starts_x, int64_t nx,
+                                 const float* win_z, const float* win_y, const float* win_x, void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(patches && out && starts_z && starts_y && starts_x && win_z && win_y && win_x,
+                 "overlap_add: null pointer");
+  B200_CHECK_ARG(valid_dtype(dtype_in) && valid_dtype(dtype_out), "overlap_add: bad dtype");
+  B200_CHECK_ARG(nz > 0 && ny > 0 && nx > 0 && nz + ny + nx <= 4096, "overlap_add: bad patch counts");
+  B200_CHECK_ARG(pz > 2 * pad_z && py > 2 * pad_y && px > 2 * pad_x, "overlap_add: padding too large");
+  MergeParams p{D, H, W, C, pz, py, px, pad_z, pad_y, pad_x, pz - 2 * pad_z, py - 2 * pad_y, px - 2 * pad_x,
+                nz, ny, nx, D * H * W * C};
+  cudaStream_t st = (cudaStream_t)stream;
+#define OA(TI, TO) return launch_overlap_add<TI, TO>(patches, out, p, starts_z, starts_y, starts_x, win_z, win_y, win_x, st)
+  if (dtype_in == B200_F32 && dtype_out == B200_F32) OA(float, float);
+  if (dtype_in == B200_F16 && dtype_out == B200_F16) OA(__half, __half);
+  if (dtype_in == B200_F16 && dtype_out == B200_F32) OA(__half, float);
+  if (dtype_in == B200_BF16 && dtype_out == B200_BF16) OA(__nv_bfloat16, __nv_bfloat16);
+  if (dtype_in == B200_BF16 && dtype_out == B200_F32) OA(__nv_bfloat16, float);
+  if (dtype_in == B200_F32 && dtype_out == B200_F16) OA(float, __half);
+  if (dtype_in == B200_F32 && dtype_out == B200_BF16) OA(float, __nv_bfloat16);
+#undef OA
+  set_error("overlap_add: unsupported dtype pair %d -> %d", dtype_in, dtype_out);
+  return B200_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,116 @@
+"""Device implementation shared by the 2D / 3D crop and merge mirrors.
+
+The integer bookkeeping runs in the C planner (``b200_plan_axis`` / ``b200_axis_start``, host code, bit-exact
+with the reference's Python float/int arithmetic); the data movement runs in two CUDA gather kernels
+(``b200_crop_gather``, ``b200_overlap_add``).  2D stacks are handled as volumes whose z axis is the image
+index with a z-patch of 1, so one kernel pair serves both families.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+from .. import _lib
+
+
+class Axis:
+    """One axis of the patch grid (a thin view over the C planner's ``b200_axis_plan``)."""
+
+    def __init__(self, dim: int, patch: int, pad: int, overlap: float):
+        self.c = _lib.AxisPlan()
+        st = _lib.lib().b200_plan_axis(int(dim), int(patch), int(pad), float(overlap), C.byref(self.c))
+        if st != 0:
+            msg = _lib.lib().b200_last_error().decode()
+            if "division by zero" in msg:
+                raise ZeroDivisionError("division by zero")          # what the reference raises (math.ceil(dim / 0))
+            raise ValueError(msg)
+
+    step = property(lambda s: s.c.step)
+    n = property(lambda s: s.c.n)
+    last = property(lambda s: s.c.last)
+    core = property(lambda s: s.c.core)
+    ov_px = property(lambda s: s.c.ov_px)
+    patch = property(lambda s: s.c.patch)
+    pad = property(lambda s: s.c.pad)
+    dim = property(lambda s: s.c.dim)
+
+    def starts(self, frame: int) -> np.ndarray:
+        f = _lib.lib().b200_axis_start
+        return np.array([f(C.byref(self.c), i, frame) for i in range(self.c.n)], dtype=np.int64)
+
+    def window(self) -> np.ndarray:
+        out = np.empty(self.core, dtype=np.float32)
+        _lib.call("b200_spline_window_1d", self.core, self.ov_px, out.ctypes.data_as(C.POINTER(C.c_float)))
+        return out
+
+
+def identity_axis(n: int) -> Tuple[np.ndarray, np.ndarray]:
+    """z axis of a 2D stack: one 'patch' of extent 1 per image, no taper."""
+    return np.arange(n, dtype=np.int64), np.ones(1, dtype=np.float32)
+
+
+def _dev(a: np.ndarray, device):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device)
+
+
+def crop_device(vol, patch: Sequence[int], starts: Sequence[np.ndarray], pads: Sequence[int], pad_mode: str):
+    """vol: CUDA tensor (D,H,W,C) dense.  Returns (n_patches, pd, ph, pw, C) on the same device."""
+    import torch
+    _lib.require_cuda(vol, "crop input")
+    vol = vol.contiguous()
+    D, H, W, Cc = vol.shape
+    pd, ph, pw = (int(p) for p in patch)
+    if pad_mode not in _lib.PAD_MODE:
+        raise ValueError(f"unsupported pad_type {pad_mode!r}")
+    n = len(starts[0]) * len(starts[1]) * len(starts[2])
+    out = torch.empty((n, pd, ph, pw, Cc), dtype=vol.dtype, device=vol.device)
+    tabs = [_dev(s, vol.device) for s in starts]
+    _lib.call("b200_crop_gather", vol.data_ptr(), _lib.torch_dtype_code(vol.dtype), D, H, W, Cc, out.data_ptr(),
+              pd, ph, pw, tabs[0].data_ptr(), len(starts[0]), tabs[1].data_ptr(), len(starts[1]),
+              tabs[2].data_ptr(), len(starts[2]), int(pads[0]), int(pads[1]), int(pads[2]),
+              _lib.PAD_MODE[pad_mode], _lib.stream_ptr())
+    return out
+
+
+def merge_device(patches, out_shape: Sequence[int], starts: Sequence[np.ndarray], windows: Sequence[np.ndarray],
+                 pads: Sequence[int], out_dtype=None):
+    """patches: CUDA tensor (n, pz, py, px, C) dense incl. padding border.  Returns (D,H,W,C)."""
+    import torch
+    _lib.require_cuda(patches, "merge input")
+    patches = patches.contiguous()
+    n, pz, py, px, Cc = patches.shape
+    D, H, W = (int(v) for v in out_shape[:3])
+    assert n == len(starts[0]) * len(starts[1]) * len(starts[2]), (n, [len(s) for s in starts])
+    out_dtype = out_dtype or patches.dtype
+    out = torch.empty((D, H, W, Cc), dtype=out_dtype, device=patches.device)
+    tabs = [_dev(s, patches.device) for s in starts]
+    wins = [_dev(w, patches.device) for w in windows]
+    _lib.call("b200_overlap_add", patches.data_ptr(), _lib.torch_dtype_code(patches.dtype), out.data_ptr(),
+              _lib.torch_dtype_code(out_dtype), D, H, W, Cc, pz, py, px, int(pads[0]), int(pads[1]), int(pads[2]),
+              tabs[0].data_ptr(), len(starts[0]), tabs[1].data_ptr(), len(starts[1]), tabs[2].data_ptr(),
+              len(starts[2]), wins[0].data_ptr(), wins[1].data_ptr(), wins[2].data_ptr(), _lib.stream_ptr())
+    return out
+
+
+_FLOAT_OK = ("float32", "float16")
+
+
+def to_device(a, device=None):
+    """numpy / torch -> CUDA tensor (no dtype change).  Fails loudly without a GPU."""
+    import torch
+    if isinstance(a, torch.Tensor):
+        _lib.require_cuda(a)
+        return a
+    if not torch.cuda.is_available():
+        raise _lib.B200Error("no CUDA device: biapy_b200 has no CPU path for crop/merge")
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device or "cuda")
+
+
+def like_input(result, template):
+    """Return `result` (CUDA tensor) as numpy if the caller passed numpy, else as a tensor."""
+    if isinstance(template, np.ndarray):
+        return result.cpu().numpy()
+    return result

@@ -1,0 +1,208 @@
+/*
+ * biapy_b200 -- C ABI of the B200-native engine for BiaPy's patch U-Net hot path.
+ *
+ * This is the drop-in boundary: plain C, raw device pointers + sizes + cudaStream_t
+ * (passed as void*), int status codes (0 = OK, <0 = error, text via b200_last_error()).  No allocation happens
+ * inside any call: outputs and workspaces are caller-owned.  Calls are thread-compatible (no hidden global
+ * state except the per-thread last-error string and a cache of TMA descriptors keyed by their arguments).
+ *
+ * The reference (BiaPy 3.7.0, 100% Python) has no FFI for this path: the "interface each entry point
+ * replaces" is therefore the Python/torch call cited next to it (paths relative to the reference root).
+ * INTEGRATION.md shows the ctypes binding a BiaPy maintainer would add.
+ *
+ * Tensors are channels-last: (N, D, H, W, C) with C contiguous -- the layout BiaPy's host arrays already
+ * have (biapy/utils/misc.py:689-713 only permutes a (N,Z,Y,X,C) numpy array).  2D data uses D == 1.
+ * `ld` is the voxel pitch in elements (>= C); it lets a tensor be a channel slice of a wider buffer so that
+ * torch.cat([up, skip], 1) (biapy/models/blocks.py:664-666, 1653) is never materialised.
+ */
+#ifndef BIAPY_B200_H
+#define BIAPY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_ERR_ARG -1
+#define B200_ERR_CUDA -2
+#define B200_ERR_UNSUPPORTED -3
+
+enum b200_dtype { B200_F32 = 0, B200_BF16 = 1, B200_F16 = 2, B200_U8 = 3 /* crop only */ };
+enum b200_act {
+  B200_ACT_NONE = 0, B200_ACT_RELU = 1, B200_ACT_ELU = 2, B200_ACT_SILU = 3, B200_ACT_LEAKY_RELU = 4,
+  B200_ACT_GELU = 5, B200_ACT_TANH = 6, B200_ACT_SIGMOID = 7, B200_ACT_SOFTPLUS = 8
+};
+enum b200_pad_mode { B200_PAD_ZEROS = 0, B200_PAD_REFLECT = 1, B200_PAD_SYMMETRIC = 2, B200_PAD_EDGE = 3, B200_PAD_WRAP = 4 };
+enum b200_conv_impl { B200_IMPL_AUTO = 0, B200_IMPL_SIMT = 1, B200_IMPL_UMMA = 2 };
+
+typedef struct b200_tensor {
+  void* data;      /* device pointer */
+  int32_t dtype;   /* enum b200_dtype */
+  int32_t n, d, h, w, c;
+  int64_t ld;      /* voxel pitch in elements (>= c) */
+} b200_tensor;
+
+/* ------------------------------------------------------------------------------------------------ runtime */
+const char* b200_last_error(void);
+int b200_version(void);
+/* sm count, compute capability major*10+minor, total global memory; any pointer may be NULL */
+int b200_device_info(int device, int* sm_count, int* cc, int64_t* total_mem);
+
+/* ------------------------------------------------------------------------------------- patch-grid planner
+ * Bit-exact restatement (IEEE double + int64) of the per-axis grid arithmetic of
+ *   crop_3D_data_with_overlap   biapy/data/data_3D_manipulation.py:536-563, 596-606  (frame = 0)
+ *   merge_3D_data_with_overlap  biapy/data/data_3D_manipulation.py:777-816, 826-835  (frame = 1)
+ * and their 2D twins biapy/data/data_2D_manipulation.py:226-243 / 464-484.  Host-only, no CUDA.          */
+typedef struct b200_axis_plan {
+  int64_t dim, patch, pad;   /* inputs */
+  int64_t step, n, last;     /* step after the per-block overlap adjustment, patches on this axis, last-tile shift */
+  int64_t core, ov_px;       /* patch - 2*pad; core - step (spline taper length of the merge) */
+} b200_axis_plan;
+/* returns B200_ERR_ARG with "division by zero" if int((patch-2*pad)*(1-overlap)) == 0 (the reference raises
+ * ZeroDivisionError there) */
+int b200_plan_axis(int64_t dim, int64_t patch, int64_t pad, double overlap, b200_axis_plan* out);
+/* start of patch i: frame 0 = crop (padded frame), frame 1 = merge (original frame) */
+int64_t b200_axis_start(const b200_axis_plan* plan, int64_t i, int frame);
+/* 1-D spline taper, float32 (data_3D_manipulation.py:664-672): out[size] */
+int b200_spline_window_1d(int64_t size, int64_t ov_px, float* out);
+
+/* --------------------------------------------------------------------------------------- crop (device gather)
+ * Replaces np.pad + the strided copies of crop_3D_data_with_overlap (data_3D_manipulation.py:505-516, 591-623).
+ * src: one volume (D,H,W,C) dense, any of the three dtypes; dst: (n_patches, pd, ph, pw, C) dense, same dtype.
+ * starts_{z,y,x}: per-axis patch starts in the padded frame (DEVICE int64 arrays of length n_{z,y,x});
+ * patches are emitted in C order over (z,y,x), exactly the reference's `c` counter.                        */
+int b200_crop_gather(const void* src, int32_t dtype, int64_t D, int64_t H, int64_t W, int64_t C,
+                     void* dst, int64_t pd, int64_t ph, int64_t pw,
+                     const int64_t* starts_z, int64_t nz, const int64_t* starts_y, int64_t ny,
+                     const int64_t* starts_x, int64_t nx,
+                     int64_t pad_z, int64_t pad_y, int64_t pad_x, int32_t pad_mode, void* stream);
+
+/* ------------------------------------------------------------------------ overlap-add merge (device gather)
+ * Replaces the accumulate + normalise loop of merge_3D_data_with_overlap (data_3D_manipulation.py:822-849).
+ * Gather formulation: one thread per output element walks the covering patches in increasing patch index
+ * and reproduces the reference's float32 operation order (multiply, add, add, divide) -- results are
+ * bit-identical to numpy for float32 / float16 patches.
+ * patches: (n_patches, pz, py, px, C) dense INCLUDING the `pad` border (it is skipped, :748-755);
+ * out: (D,H,W,C) dense, dtype_out (f32 / bf16 / f16; the reference casts to the patch dtype).
+ * win_{z,y,x}: device float32 1-D windows of the core size; starts_*: device int64 merge starts (orig frame). */
+int b200_overlap_add(const void* patches, int32_t dtype_in, void* out, int32_t dtype_out,
+                     int64_t D, int64_t H, int64_t W, int64_t C,
+                     int64_t pz, int64_t py, int64_t px, int64_t pad_z, int64_t pad_y, int64_t pad_x,
+                     const int64_t* starts_z, int64_t nz, const int64_t* starts_y, int64_t ny,
+                     const int64_t* starts_x, int64_t nx,
+                     const float* win_z, const float* win_y, const float* win_x, void* stream);
+
+/* ---------------------------------------------------------------------------------------------- convolution
+ * nn.Conv3d / nn.Conv2d, stride 1, padding='same', bias (biapy/models/blocks.py:154,157,1372; unet.py:347).
+ * Weights are packed once per step from the PyTorch layout (Cout,Cin,kd,kh,kw) fp32:
+ *   flip_transpose = 0 : [Cout][tap][Cin]          (fprop operand, K = tap*Cin + ci contiguous)
+ *   flip_transpose = 1 : [Cin][flipped tap][Cout]  (dgrad operand: dX = conv(dY, W'))                     */
+int b200_pack_conv_weight(const float* w, void* packed, int32_t dtype, int32_t cout, int32_t cin,
+                          int32_t kd, int32_t kh, int32_t kw, int32_t flip_transpose, void* stream);
+/* y = conv(x, w) + bias (+ residual) ; if accumulate != 0: y += ... (used by dgrad into a shared gradient) */
+int b200_conv_fprop(const b200_tensor* x, const void* w_packed, const float* bias, const b200_tensor* residual,
+                    const b200_tensor* y, int32_t kd, int32_t kh, int32_t kw, int32_t accumulate, int32_t impl,
+                    void* stream);
+/* dw_packed[Cout][tap][Cin] (fp32) += sum_vox dy[vox][co] * x[vox+tap][ci] ; dbias[Cout] += sum_vox dy.
+ * Both outputs must be zero-initialised by the caller (they are accumulated with atomics).                  */
+int b200_conv_wgrad(const b200_tensor* x, const b200_tensor* dy, float* dw_packed, float* dbias,
+                    int32_t kd, int32_t kh, int32_t kw, int32_t impl, void* stream);
+/* dw (Cout,Cin,kd,kh,kw) fp32 (+)= dw_packed[Cout][tap][Cin] */
+int b200_unpack_conv_wgrad(const float* dw_packed, float* dw, int32_t cout, int32_t cin, int32_t taps,
+                           int32_t accumulate, void* stream);
+
+/* -------------------------------------------------------------------------- transposed convolution (k == s)
+ * nn.ConvTranspose3d(kernel_size=s, stride=s) (biapy/models/blocks.py:603, 1607).  w: PyTorch layout
+ * (Cin,Cout,sd,sh,sw) fp32, read directly.                                                                   */
+int b200_convT_fprop(const b200_tensor* x, const float* w, const float* bias, const b200_tensor* y,
+                     int32_t sd, int32_t sh, int32_t sw, void* stream);
+int b200_convT_dgrad(const b200_tensor* dy, const float* w, const b200_tensor* dx,
+                     int32_t sd, int32_t sh, int32_t sw, int32_t accumulate, void* stream);
+/* dw (Cin,Cout,sd,sh,sw), dbias (Cout): zero-initialised by the caller, accumulated with atomics */
+int b200_convT_wgrad(const b200_tensor* x, const b200_tensor* dy, float* dw, float* dbias,
+                     int32_t sd, int32_t sh, int32_t sw, void* stream);
+
+/* -------------------------------------------------------------------------------------------------- pooling
+ * nn.MaxPool3d / MaxPool2d with kernel == stride (unet.py:255-256).  Backward recomputes the arg-max from
+ * (x, y): the first maximum in (d,h,w) scan order receives the gradient, as ATen's max_pool backward.       */
+int b200_maxpool_fwd(const b200_tensor* x, const b200_tensor* y, int32_t pd, int32_t ph, int32_t pw, void* stream);
+int b200_maxpool_bwd(const b200_tensor* x, const b200_tensor* y, const b200_tensor* dy, const b200_tensor* dx,
+                     int32_t pd, int32_t ph, int32_t pw, int32_t accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------ normalisation + activation
+ * GroupNorm(8|16, C) / InstanceNorm(affine) / BatchNorm (biapy/models/blocks.py:2092-2165) as
+ * (1) per-(n,c) sums, (2) finalize to per-(n,c) scale/shift, (3) fused scale-shift-activation.
+ * sums: double [N][C][2] = (sum x, sum x^2), zero-initialised by the caller.                                  */
+int b200_channel_sums(const b200_tensor* x, double* sums, void* stream);
+/* groups: G channels groups per sample (G == C -> instance norm). batch_stats != 0: statistics are pooled over
+ * the batch as well (BatchNorm training).  Writes mean[N][G], rstd[N][G], scale[N][C], shift[N][C] (fp32).   */
+int b200_norm_finalize(const double* sums, int32_t n, int32_t c, int32_t groups, int64_t spatial, int32_t batch_stats,
+                       const float* gamma, const float* beta, float eps,
+                       float* mean, float* rstd, float* scale, float* shift, void* stream);
+/* y = act(x * scale[n,c] + shift[n,c]);  scale/shift may be NULL (pure activation)                           */
+int b200_scale_shift_act(const b200_tensor* x, const float* scale, const float* shift, int32_t act,
+                         const b200_tensor* y, void* stream);
+/* backward, pass 1: with xhat = (x-mean)*rstd, ypre = xhat*gamma+beta, g = dy*act'(ypre):
+ *   red[N][C][2] (double, zero-initialised) += (sum g, sum g*xhat)                                            */
+int b200_norm_act_bwd_reduce(const b200_tensor* x, const b200_tensor* dy, const float* mean, const float* rstd,
+                             int32_t groups, const float* gamma, const float* beta, int32_t act,
+                             double* red, void* stream);
+/* tiny: coef[N][C][3] = (rstd*gamma, rstd*a_g, rstd*b_g); dgamma[C] += sum_n S2, dbeta[C] += sum_n S1         */
+int b200_norm_bwd_finalize(const double* red, const float* rstd, const float* gamma, int32_t n, int32_t c,
+                           int32_t groups, int64_t spatial, int32_t batch_stats,
+                           float* coef, float* dgamma, float* dbeta, void* stream);
+/* pass 2: dx (+)= g*coef0 - coef1 - xhat*coef2                                                                 */
+int b200_norm_act_bwd_apply(const b200_tensor* x, const b200_tensor* dy, const float* mean, const float* rstd,
+                            int32_t groups, const float* gamma, const float* beta, int32_t act,
+                            const float* coef, const b200_tensor* dx, int32_t accumulate, void* stream);
+/* activation only (norm == 'none'): dx (+)= dy * act'(x) */
+int b200_act_bwd(const b200_tensor* x, const b200_tensor* dy, int32_t act, const b200_tensor* dx,
+                 int32_t accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------- element-wise
+ * op: 0 y=a+b, 1 y=a*b, 2 y=relu(a+b), 3 y=copy(a), 4 y=sigmoid(a); b may have c == 1 (broadcast over channels) */
+int b200_binary(const b200_tensor* a, const b200_tensor* b, const b200_tensor* y, int32_t op, void* stream);
+/* attention gate backward helpers (biapy/models/blocks.py:1112-1116):
+ *   out = psi * x : dpsi[vox] = sum_c dout*x ; dx (+)= dout*psi                                                */
+int b200_gate_bwd(const b200_tensor* x, const b200_tensor* psi, const b200_tensor* dout,
+                  const b200_tensor* dpsi, const b200_tensor* dx, int32_t accumulate, void* stream);
+/* dy -> da: (a+b) relu'd : da = dy * (y > 0) */
+int b200_relu_mask_bwd(const b200_tensor* y, const b200_tensor* dy, const b200_tensor* da, void* stream);
+/* dtype conversion / strided copy between tensor views */
+int b200_convert(const b200_tensor* src, const b200_tensor* dst, void* stream);
+
+/* ------------------------------------------------------------------------------------------------- losses
+ * BCEWithLogits mean (biapy/engine/metrics.py:544-546, 577-580): loss_sum[0] (double, zeroed by caller) +=
+ * sum of per-element losses; dlogits = (sigmoid(z) - t) * grad_scale.  target is float32 dense.                */
+int b200_bce_logits(const b200_tensor* logits, const float* target, double* loss_sum, const b200_tensor* dlogits,
+                    float grad_scale, void* stream);
+/* N2V masked MSE (metrics.py:2265-2286): sums[0] += sum((t - y*m)^2), sums[1] += sum(m); second call computes
+ * dlogits = -2*(t - y*m)*m * grad_scale (grad_scale = upstream / sum(m)).  target dense (N,...,2C) float32.     */
+int b200_n2v_mse(const b200_tensor* pred, const float* target, double* sums, const b200_tensor* dpred,
+                 float grad_scale, int32_t mode, void* stream);
+/* softmax cross-entropy over channels (metrics.py:581-586): target int64 class per voxel; ignore_index < 0 = none */
+int b200_softmax_ce(const b200_tensor* logits, const int64_t* target, double* sums, const b200_tensor* dlogits,
+                    float grad_scale, void* stream);
+/* head activations (biapy/engine/base_workflow.py:1367-1470): sigmoid per channel or softmax over [c0, c1) */
+int b200_softmax_channels(const b200_tensor* x, const b200_tensor* y, int32_t c0, int32_t c1, void* stream);
+
+/* --------------------------------------------------------------------------------------------- optimiser
+ * AdamW / SGD on a flat fp32 buffer (replaces timm create_optimizer_v2 -> torch.optim, engine/__init__.py:62-68). */
+int b200_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                    float eps, float weight_decay, int64_t step, float grad_scale, void* stream);
+int b200_sgd_step(float* p, const float* g, float* mom, int64_t n, float lr, float momentum, float weight_decay,
+                  int32_t first_step, float grad_scale, void* stream);
+/* sum of squares of a flat fp32 buffer (for clip_grad_norm_, train_engine.py:174-176): out[0] (double) += ...   */
+int b200_sumsq(const float* g, int64_t n, double* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------ self tests (GPU)
+ * tcgen05 / TMA plumbing check: runs one small GEMM through every descriptor mode the conv kernels use and
+ * compares against a SIMT reference on device.  Returns the number of mismatching modes (0 = all good).       */
+int b200_umma_selftest(int32_t verbose, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIAPY_B200_H */
