@@ -1,0 +1,297 @@
+"""Define-by-run executor for the U-Net family on the B200 kernels.
+
+The model classes (``biapy_b200.models``) walk their reference-shaped module tree and call the methods of a
+:class:`Tape`; each method launches the forward kernels immediately and, in training mode, records a closure
+that launches the matching backward kernels.  :meth:`Tape.backward` replays the closures in reverse.
+
+Design points (B200-first):
+
+* activations are channels-last ``(N, D, H, W, C)`` in the engine dtype (bf16 by default, fp32 for the exact path);
+* ``torch.cat([up, skip], 1)`` never happens: producers write straight into channel slices of a pre-allocated
+  buffer (:meth:`Tape.new` + :meth:`TT.slice`) and gradients are read back through the same slices;
+* the residual ``block(x) + shortcut(x)`` is an accumulate-in-place epilogue of the last convolution, so the
+  incoming gradient of the sum is consumed by both producers without an extra pass;
+* gradient buffers are allocated on first write; later writers accumulate in their own epilogue.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from .. import _lib, ops
+
+
+class TT:
+    """A tensor on the tape: data + lazily allocated gradient; may be a channel slice of a parent buffer."""
+
+    __slots__ = ("data", "_grad", "_ready", "parent", "off", "requires_grad")
+
+    def __init__(self, data: torch.Tensor, requires_grad: bool = True, parent: "Optional[TT]" = None, off: int = 0):
+        self.data = data
+        self._grad = None
+        self._ready = False
+        self.parent = parent
+        self.off = off
+        self.requires_grad = requires_grad
+
+    @property
+    def shape(self):
+        return self.data.shape
+
+    @property
+    def c(self) -> int:
+        return self.data.shape[-1]
+
+    def slice(self, off: int, c: int) -> "TT":
+        return TT(self.data[..., off:off + c], self.requires_grad, parent=self, off=off)
+
+    # -- gradient plumbing -----------------------------------------------------------------------------
+    @property
+    def grad_ready(self) -> bool:
+        return self.parent.grad_ready if self.parent is not None else self._ready
+
+    def grad(self) -> torch.Tensor:
+        """Gradient buffer (allocated on first use).  For slices: a view into the parent's gradient."""
+        if self.parent is not None:
+            return self.parent.grad()[..., self.off:self.off + self.c]
+        if self._grad is None:
+            self._grad = torch.empty_like(self.data)
+        return self._grad
+
+    def mark_written(self):
+        if self.parent is not None:
+            # a slice can only be written first if the whole parent is zero-filled before; keep it simple: the
+            # parent buffer is zero-initialised once, then every writer accumulates.
+            self.parent.mark_written()
+        else:
+            self._ready = True
+
+    def prepare_accumulate(self) -> bool:
+        """Return the `accumulate` flag for a kernel about to write this gradient, and mark it written."""
+        if self.parent is not None:
+            root = self.parent
+            while root.parent is not None:
+                root = root.parent
+            if not root._ready:
+                root.grad().zero_()
+                root._ready = True
+            return True
+        acc = self._ready
+        self._ready = True
+        return acc
+
+
+class Tape:
+    def __init__(self, dtype: torch.dtype, device, training: bool, conv_impl: int = _lib.IMPL_AUTO):
+        self.dtype = dtype
+        self.device = device
+        self.training = training
+        self.impl = conv_impl
+        self.steps: List[Callable[[], None]] = []
+        self.param_grads: Dict[torch.nn.Parameter, torch.Tensor] = {}
+        self._packed: Dict[Tuple[int, bool], torch.Tensor] = {}
+
+    # ------------------------------------------------------------------------------------------ helpers
+    def new(self, like: torch.Tensor, channels: int, spatial: Optional[Sequence[int]] = None) -> TT:
+        n = like.shape[0]
+        sp = tuple(spatial) if spatial is not None else tuple(like.shape[1:4])
+        return TT(torch.empty((n,) + sp + (channels,), dtype=self.dtype, device=self.device))
+
+    def _pgrad(self, p: torch.nn.Parameter) -> torch.Tensor:
+        g = self.param_grads.get(p)
+        if g is None:
+            g = torch.zeros(p.shape, dtype=torch.float32, device=self.device)
+            self.param_grads[p] = g
+        return g
+
+    def _pack(self, w: torch.nn.Parameter, flip: bool) -> torch.Tensor:
+        key = (id(w), flip)
+        t = self._packed.get(key)
+        if t is None:
+            t = ops.pack_conv_weight(w, self.dtype, flip)
+            self._packed[key] = t
+        return t
+
+    @staticmethod
+    def _k3(k) -> Tuple[int, int, int]:
+        k = tuple(int(v) for v in k)
+        return k if len(k) == 3 else (1,) + k
+
+    def _f32(self, p):
+        if p is None:
+            return None
+        t = p.detach()
+        return t if t.dtype == torch.float32 else t.float()
+
+    # --------------------------------------------------------------------------------------------- ops
+    def conv(self, x: TT, mod: torch.nn.Module, out: Optional[TT] = None, accumulate: bool = False) -> TT:
+        """y = conv(x) + bias, stride 1, 'same' padding.  `accumulate` adds into `out` (residual epilogue)."""
+        w, b = mod.weight, mod.bias
+        k = self._k3(w.shape[2:])
+        cout, cin = w.shape[0], w.shape[1]
+        assert x.c == cin, (x.c, cin)
+        if out is None:
+            out = self.new(x.data, cout)
+        ops.conv_fprop(x.data, self._pack(w, False), self._f32(b), out.data, k, accumulate=accumulate, impl=self.impl)
+        if self.training:
+            def bwd(x=x, out=out, w=w, b=b, k=k, cout=cout, cin=cin):
+                dy = out.grad()
+                assert out.grad_ready, "conv output gradient was never produced"
+                if w.requires_grad:
+                    gb = self._pgrad(b) if (b is not None and b.requires_grad) else None
+                    first = w not in self.param_grads
+                    ops.conv_wgrad(x.data, dy, cout, cin, k, self._pgrad(w), gb, accumulate=not first, impl=self.impl)
+                if x.requires_grad:
+                    acc = x.prepare_accumulate()
+                    ops.conv_fprop(dy, self._pack(w, True), None, x.grad(), k, accumulate=acc, impl=self.impl)
+            self.steps.append(bwd)
+        return out
+
+    def convT(self, x: TT, mod: torch.nn.Module, out: Optional[TT] = None) -> TT:
+        w, b = mod.weight, mod.bias          # (Cin, Cout, *s)
+        s = self._k3(w.shape[2:])
+        cin, cout = w.shape[0], w.shape[1]
+        assert x.c == cin
+        if out is None:
+            sp = (x.shape[1] * s[0], x.shape[2] * s[1], x.shape[3] * s[2])
+            out = self.new(x.data, cout, sp)
+        wf = self._f32(w).contiguous()
+        ops.convT_fprop(x.data, wf, self._f32(b), out.data, s)
+        if self.training:
+            def bwd(x=x, out=out, w=w, b=b, s=s, wf=wf):
+                dy = out.grad()
+                assert out.grad_ready
+                if w.requires_grad:
+                    gb = self._pgrad(b) if (b is not None and b.requires_grad) else None
+                    ops.convT_wgrad(x.data, dy, self._pgrad(w), gb, s)
+                if x.requires_grad:
+                    acc = x.prepare_accumulate()
+                    ops.convT_dgrad(dy, wf, x.grad(), s, accumulate=acc)
+            self.steps.append(bwd)
+        return out
+
+    def norm_act(self, x: TT, norm: Optional[torch.nn.Module], act: Optional[str], out: Optional[TT] = None) -> TT:
+        """out = act(norm(x)).  norm: GroupNorm / InstanceNorm(affine) parameter holder or None."""
+        act = (act or "none").lower()
+        if norm is None and act in ("none", "linear"):
+            return x
+        if out is None:
+            out = self.new(x.data, x.c)
+        if norm is None:
+            ops.scale_shift_act(x.data, None, None, act, out.data)
+            if self.training:
+                def bwd(x=x, out=out, act=act):
+                    assert out.grad_ready
+                    if x.requires_grad:
+                        acc = x.prepare_accumulate()
+                        ops.act_bwd(x.data, out.grad(), act, x.grad(), accumulate=acc)
+                self.steps.append(bwd)
+            return out
+        groups = norm_groups(norm, x.c)
+        gamma, beta = getattr(norm, "weight", None), getattr(norm, "bias", None)
+        g32, b32 = self._f32(gamma), self._f32(beta)
+        st = ops.norm_stats(x.data, groups, g32, b32, eps=float(norm.eps))
+        ops.scale_shift_act(x.data, st.scale, st.shift, act, out.data)
+        if self.training:
+            def bwd(x=x, out=out, st=st, gamma=gamma, beta=beta, g32=g32, b32=b32, act=act):
+                assert out.grad_ready
+                dg = self._pgrad(gamma) if (gamma is not None and gamma.requires_grad) else None
+                db = self._pgrad(beta) if (beta is not None and beta.requires_grad) else None
+                dx, acc = None, False
+                if x.requires_grad:
+                    acc = x.prepare_accumulate()
+                    dx = x.grad()
+                ops.norm_act_bwd(x.data, out.grad(), st, g32, b32, act, dx, dg, db, accumulate=acc)
+            self.steps.append(bwd)
+        return out
+
+    def maxpool(self, x: TT, window: Sequence[int]) -> TT:
+        p = self._k3(window)
+        sp = (x.shape[1] // p[0], x.shape[2] // p[1], x.shape[3] // p[2])
+        out = self.new(x.data, x.c, sp)
+        ops.maxpool_fwd(x.data, out.data, p)
+        if self.training:
+            def bwd(x=x, out=out, p=p):
+                assert out.grad_ready
+                if x.requires_grad:
+                    acc = x.prepare_accumulate()
+                    ops.maxpool_bwd(x.data, out.data, out.grad(), x.grad(), p, accumulate=acc)
+            self.steps.append(bwd)
+        return out
+
+    def _route_grad(self, t: TT, d: torch.Tensor):
+        """Add (or copy) a finished gradient tensor `d` into t's gradient."""
+        if not t.requires_grad:
+            return
+        if t.prepare_accumulate():
+            ops.binary(t.grad(), d, t.grad(), ops.OP_ADD)
+        else:
+            ops.binary(d, None, t.grad(), ops.OP_COPY)
+
+    def add(self, a: TT, b: TT, out: Optional[TT] = None) -> TT:
+        """out = a + b (out may be `b` itself: in-place residual add)."""
+        if out is None:
+            out = self.new(a.data, a.c)
+        ops.binary(a.data, b.data, out.data, ops.OP_ADD)
+        if self.training:
+            def bwd(a=a, b=b, out=out):
+                assert out.grad_ready
+                for t in (a, b):
+                    if t is not out:
+                        self._route_grad(t, out.grad())
+            self.steps.append(bwd)
+        return out
+
+    def copy_into(self, src: TT, dst: TT) -> TT:
+        """dst = src (used when a skip tensor must be replicated into several concat buffers)."""
+        ops.binary(src.data, None, dst.data, ops.OP_COPY)
+        if self.training:
+            def bwd(src=src, dst=dst):
+                assert dst.grad_ready
+                self._route_grad(src, dst.grad())
+            self.steps.append(bwd)
+        return dst
+
+    def add_relu(self, a: TT, b: TT) -> TT:
+        out = self.new(a.data, a.c)
+        ops.binary(a.data, b.data, out.data, ops.OP_ADD_RELU)
+        if self.training:
+            def bwd(a=a, b=b, out=out):
+                assert out.grad_ready
+                d = torch.empty_like(out.data)
+                ops.relu_mask_bwd(out.data, out.grad(), d)
+                for t in (a, b):
+                    self._route_grad(t, d)
+            self.steps.append(bwd)
+        return out
+
+    def gate(self, psi: TT, x: TT, out: Optional[TT] = None) -> TT:
+        """out = psi * x with a single-channel psi (attention gate, blocks.py:1116)."""
+        if out is None:
+            out = self.new(x.data, x.c)
+        ops.binary(x.data, psi.data, out.data, ops.OP_MUL)
+        if self.training:
+            def bwd(psi=psi, x=x, out=out):
+                assert out.grad_ready
+                acc_x = x.prepare_accumulate()
+                dpsi = torch.empty_like(psi.data)
+                ops.gate_bwd(x.data, psi.data, out.grad(), dpsi, x.grad(), accumulate=acc_x)
+                self._route_grad(psi, dpsi)
+            self.steps.append(bwd)
+        return out
+
+    # ------------------------------------------------------------------------------------------ backward
+    def backward(self):
+        for step in reversed(self.steps):
+            step()
+        self.steps = []
+
+
+def norm_groups(norm: torch.nn.Module, channels: int) -> int:
+    if isinstance(norm, torch.nn.GroupNorm):
+        return norm.num_groups
+    if isinstance(norm, (torch.nn.InstanceNorm2d, torch.nn.InstanceNorm3d)):
+        return channels
+    raise NotImplementedError(f"normalization layer {type(norm).__name__} is not supported by the B200 engine "
+                              "(supported: 'gn', 'in', 'none')")

@@ -1,0 +1,200 @@
+"""Thin torch-tensor front end over the C ABI (``include/biapy_b200.h``).
+
+Every function takes channels-last CUDA tensors ``(N, D, H, W, C)`` (a channel slice of a wider buffer is fine)
+and launches hand-written CUDA on the current torch stream.  PyTorch is used for memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ACT, as_tensor, call, stream_ptr
+
+# kernel launch counter (bench.py reports it as `gpu_launches`)
+LAUNCHES = 0
+
+
+def _launch(name, *args):
+    global LAUNCHES
+    LAUNCHES += 1
+    call(name, *args)
+
+
+def _ref(t):
+    return C.byref(as_tensor(t)) if t is not None else None
+
+
+def _ptr(t) -> C.c_void_p:
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def empty_like_cl(t: torch.Tensor, channels: Optional[int] = None, dtype=None) -> torch.Tensor:
+    shp = list(t.shape)
+    if channels is not None:
+        shp[-1] = channels
+    return torch.empty(shp, dtype=dtype or t.dtype, device=t.device)
+
+
+# ---------------------------------------------------------------------------------------------- convolution
+def pack_conv_weight(w: torch.Tensor, dtype: torch.dtype, flip_transpose: bool) -> torch.Tensor:
+    """w: (Cout, Cin, *k) fp32 parameter -> packed [Cout][tap][Cin] (or [Cin][flipped tap][Cout])."""
+    w = w.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    cout, cin = w.shape[:2]
+    k = tuple(w.shape[2:])
+    if len(k) == 2:
+        k = (1,) + k
+    out = torch.empty(w.numel(), dtype=dtype, device=w.device)
+    _launch("b200_pack_conv_weight", _ptr(w), _ptr(out), _lib.torch_dtype_code(dtype), cout, cin, k[0], k[1], k[2],
+            1 if flip_transpose else 0, stream_ptr())
+    return out
+
+
+def conv_fprop(x, w_packed, bias, y, k: Sequence[int], residual=None, accumulate=False, impl=_lib.IMPL_AUTO):
+    _launch("b200_conv_fprop", _ref(x), _ptr(w_packed), _ptr(bias), _ref(residual), _ref(y), k[0], k[1], k[2],
+            1 if accumulate else 0, impl, stream_ptr())
+    return y
+
+
+def conv_wgrad(x, dy, cout: int, cin: int, k: Sequence[int], dw_out: torch.Tensor, dbias_out: Optional[torch.Tensor],
+               accumulate=False, impl=_lib.IMPL_AUTO):
+    """dw_out: (Cout, Cin, *k) fp32; dbias_out: (Cout,) fp32, must be zero-initialised unless accumulate."""
+    taps = k[0] * k[1] * k[2]
+    packed = torch.zeros(cout * taps * cin, dtype=torch.float32, device=x.device)
+    _launch("b200_conv_wgrad", _ref(x), _ref(dy), _ptr(packed), _ptr(dbias_out), k[0], k[1], k[2], impl, stream_ptr())
+    _launch("b200_unpack_conv_wgrad", _ptr(packed), _ptr(dw_out), cout, cin, taps, 1 if accumulate else 0, stream_ptr())
+
+
+def convT_fprop(x, w, bias, y, s: Sequence[int]):
+    _launch("b200_convT_fprop", _ref(x), _ptr(w), _ptr(bias), _ref(y), s[0], s[1], s[2], stream_ptr())
+    return y
+
+
+def convT_dgrad(dy, w, dx, s: Sequence[int], accumulate=False):
+    _launch("b200_convT_dgrad", _ref(dy), _ptr(w), _ref(dx), s[0], s[1], s[2], 1 if accumulate else 0, stream_ptr())
+
+
+def convT_wgrad(x, dy, dw, dbias, s: Sequence[int]):
+    _launch("b200_convT_wgrad", _ref(x), _ref(dy), _ptr(dw), _ptr(dbias), s[0], s[1], s[2], stream_ptr())
+
+
+# ------------------------------------------------------------------------------------------------- pooling
+def maxpool_fwd(x, y, p: Sequence[int]):
+    _launch("b200_maxpool_fwd", _ref(x), _ref(y), p[0], p[1], p[2], stream_ptr())
+    return y
+
+
+def maxpool_bwd(x, y, dy, dx, p: Sequence[int], accumulate=False):
+    _launch("b200_maxpool_bwd", _ref(x), _ref(y), _ref(dy), _ref(dx), p[0], p[1], p[2], 1 if accumulate else 0, stream_ptr())
+
+
+# ------------------------------------------------------------------------------------- normalisation / act
+class NormStats:
+    __slots__ = ("mean", "rstd", "scale", "shift", "groups", "batch_stats")
+
+
+def norm_stats(x, groups: int, gamma, beta, eps: float = 1e-5, batch_stats: bool = False) -> NormStats:
+    n, d, h, w, c = x.shape
+    sums = torch.zeros(n * c * 2, dtype=torch.float64, device=x.device)
+    _launch("b200_channel_sums", _ref(x), _ptr(sums), stream_ptr())
+    st = NormStats()
+    st.groups, st.batch_stats = groups, batch_stats
+    buf = torch.empty(2 * n * groups + 2 * n * c, dtype=torch.float32, device=x.device)
+    st.mean, st.rstd = buf[: n * groups], buf[n * groups: 2 * n * groups]
+    st.scale, st.shift = buf[2 * n * groups: 2 * n * groups + n * c], buf[2 * n * groups + n * c:]
+    _launch("b200_norm_finalize", _ptr(sums), n, c, groups, d * h * w, 1 if batch_stats else 0, _ptr(gamma), _ptr(beta),
+            eps, _ptr(st.mean), _ptr(st.rstd), _ptr(st.scale), _ptr(st.shift), stream_ptr())
+    return st
+
+
+def scale_shift_act(x, scale, shift, act: str, y):
+    _launch("b200_scale_shift_act", _ref(x), _ptr(scale), _ptr(shift), ACT[act], _ref(y), stream_ptr())
+    return y
+
+
+def norm_act_bwd(x, dy, st: NormStats, gamma, beta, act: str, dx, dgamma, dbeta, accumulate=False):
+    n, d, h, w, c = x.shape
+    red = torch.zeros(n * c * 2, dtype=torch.float64, device=x.device)
+    _launch("b200_norm_act_bwd_reduce", _ref(x), _ref(dy), _ptr(st.mean), _ptr(st.rstd), st.groups, _ptr(gamma), _ptr(beta),
+            ACT[act], _ptr(red), stream_ptr())
+    coef = torch.empty(n * c * 3, dtype=torch.float32, device=x.device)
+    _launch("b200_norm_bwd_finalize", _ptr(red), _ptr(st.rstd), _ptr(gamma), n, c, st.groups, d * h * w,
+            1 if st.batch_stats else 0, _ptr(coef), _ptr(dgamma), _ptr(dbeta), stream_ptr())
+    if dx is not None:
+        _launch("b200_norm_act_bwd_apply", _ref(x), _ref(dy), _ptr(st.mean), _ptr(st.rstd), st.groups, _ptr(gamma), _ptr(beta),
+                ACT[act], _ptr(coef), _ref(dx), 1 if accumulate else 0, stream_ptr())
+
+
+def act_bwd(x, dy, act: str, dx, accumulate=False):
+    _launch("b200_act_bwd", _ref(x), _ref(dy), ACT[act], _ref(dx), 1 if accumulate else 0, stream_ptr())
+
+
+# --------------------------------------------------------------------------------------------- element-wise
+OP_ADD, OP_MUL, OP_ADD_RELU, OP_COPY, OP_SIGMOID = 0, 1, 2, 3, 4
+
+
+def binary(a, b, y, op: int):
+    _launch("b200_binary", _ref(a), _ref(b), _ref(y), op, stream_ptr())
+    return y
+
+
+def gate_bwd(x, psi, dout, dpsi, dx, accumulate=False):
+    _launch("b200_gate_bwd", _ref(x), _ref(psi), _ref(dout), _ref(dpsi), _ref(dx), 1 if accumulate else 0, stream_ptr())
+
+
+def relu_mask_bwd(y, dy, da):
+    _launch("b200_relu_mask_bwd", _ref(y), _ref(dy), _ref(da), stream_ptr())
+
+
+def convert(src, dst):
+    _launch("b200_convert", _ref(src), _ref(dst), stream_ptr())
+    return dst
+
+
+def softmax_channels(x, y, c0: int, c1: int):
+    _launch("b200_softmax_channels", _ref(x), _ref(y), c0, c1, stream_ptr())
+
+
+# --------------------------------------------------------------------------------------------------- losses
+def bce_logits(logits, target_f32, dlogits=None, grad_scale: float = 1.0) -> torch.Tensor:
+    """Returns the SUM of the per-element losses as a 1-element float64 tensor (device)."""
+    out = torch.zeros(1, dtype=torch.float64, device=logits.device)
+    _launch("b200_bce_logits", _ref(logits), _ptr(target_f32), _ptr(out), _ref(dlogits), float(grad_scale), stream_ptr())
+    return out
+
+
+def n2v_mse_sums(pred, target_f32) -> torch.Tensor:
+    out = torch.zeros(2, dtype=torch.float64, device=pred.device)
+    _launch("b200_n2v_mse", _ref(pred), _ptr(target_f32), _ptr(out), None, 1.0, 0, stream_ptr())
+    return out
+
+
+def n2v_mse_bwd(pred, target_f32, dpred, grad_scale: float):
+    _launch("b200_n2v_mse", _ref(pred), _ptr(target_f32), None, _ref(dpred), float(grad_scale), 1, stream_ptr())
+
+
+def softmax_ce(logits, target_i64, dlogits=None, grad_scale: float = 1.0) -> torch.Tensor:
+    out = torch.zeros(1, dtype=torch.float64, device=logits.device)
+    _launch("b200_softmax_ce", _ref(logits), _ptr(target_i64), _ptr(out), _ref(dlogits), float(grad_scale), stream_ptr())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ optimiser
+def adamw_step(p, g, m, v, lr, beta1, beta2, eps, wd, step: int, grad_scale: float = 1.0):
+    _launch("b200_adamw_step", _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), lr, beta1, beta2, eps, wd, step, grad_scale,
+            stream_ptr())
+
+
+def sgd_step(p, g, mom, lr, momentum, wd, first: bool, grad_scale: float = 1.0):
+    _launch("b200_sgd_step", _ptr(p), _ptr(g), _ptr(mom), p.numel(), lr, momentum, wd, 1 if first else 0, grad_scale,
+            stream_ptr())
+
+
+def sumsq(g) -> torch.Tensor:
+    out = torch.zeros(1, dtype=torch.float64, device=g.device)
+    _launch("b200_sumsq", _ptr(g), g.numel(), _ptr(out), stream_ptr())
+    return out

@@ -1,0 +1,77 @@
+"""CPU tests of the host-side model mirror: constructor surface, state_dict layout (checkpoint compatibility with
+the reference classes, via the golden fixtures) and loud failure without a GPU."""
+import contextlib
+import glob
+import io
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from biapy_b200 import _lib
+from biapy_b200.models import build_model
+from biapy_b200.models.attention_unet import Attention_U_Net
+from biapy_b200.models.resunet import ResUNet
+from biapy_b200.models.unet import U_Net
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CLS = {"unet": U_Net, "resunet": ResUNet, "attention_unet": Attention_U_Net}
+
+
+def _build(arch, kw):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return CLS[arch](**kw)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "model_*.npz"))))
+def test_state_dict_matches_reference_layout(path):
+    z = np.load(path)
+    kw = json.loads(str(z["kwargs_json"]))
+    if kw.get("upsample_layer") == "upsampling":
+        with pytest.raises(NotImplementedError):
+            _build(str(z["arch"]), kw)
+        return
+    m = _build(str(z["arch"]), kw)
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    m.load_state_dict(sd, strict=True)          # same keys, same shapes as the reference class
+    assert list(m.state_dict().keys()) == list(sd.keys())   # and the same order
+
+
+def test_cfg2_model_has_reference_parameter_count():
+    m = _build("resunet", dict(image_shape=(128, 128, 128, 2), activation="silu", feature_maps=[16, 32, 64, 128, 256],
+                               drop_values=[0] * 5, normalization="gn", k_size=3, yx_down=[2] * 4, z_down=[2] * 4,
+                               isotropy=[True] * 5, larger_io=False, conv_layers=[2] * 5, output_channels=[1]))
+    assert sum(p.numel() for p in m.parameters()) == 6_694_065 or abs(sum(p.numel() for p in m.parameters()) - 6.694e6) < 2e3
+    keys = list(m.state_dict().keys())
+    assert keys[0] == "down_path.0.block.0.block.0.weight"
+    assert "up_paths.0.3.conv_block.shortcut.0.weight" in keys and "heads.0.bias" in keys
+    assert tuple(m.state_dict()["up_paths.0.0.up.weight"].shape) == (256, 256, 2, 2, 2)
+
+
+def test_cpu_input_fails_loudly():
+    m = _build("unet", dict(image_shape=(16, 16, 1), activation="elu", feature_maps=[8, 16], drop_values=[0, 0],
+                            normalization="in", yx_down=[2], z_down=[2], isotropy=True, larger_io=False,
+                            conv_layers=[2, 2], output_channels=[1]))
+    with pytest.raises(_lib.B200Error):
+        m(torch.zeros(1, 1, 16, 16))
+
+
+def test_build_model_from_cfg_dict():
+    cfg = {"PROBLEM": {"NDIM": "3D"}, "DATA": {"PATCH_SIZE": (32, 32, 32, 2)},
+           "MODEL": {"ARCHITECTURE": "resunet", "FEATURE_MAPS": [16, 32], "NORMALIZATION": "gn", "ACTIVATION": "SiLU",
+                     "DROPOUT_VALUES": [0, 0], "Z_DOWN": [0], "YX_DOWN": [0], "ISOTROPY": [True, True], "CONV_LAYERS": [2, 2]}}
+    with contextlib.redirect_stdout(io.StringIO()):
+        model, name, srcs, imports, files, args, stride = build_model(cfg, [1], ["F"], ["ce_sigmoid"], "cpu")
+    assert name == "ResUNet" and stride == [1, 1, 1]
+    assert args["z_down"] == [2] and args["activation"] == "silu"
+    with pytest.raises(NotImplementedError):
+        build_model({"PROBLEM": {"NDIM": "2D"}, "DATA": {"PATCH_SIZE": (32, 32, 1)}, "MODEL": {"ARCHITECTURE": "unetr"}},
+                    [1], ["F"], ["ce_sigmoid"], "cpu")
+
+
+def test_unsupported_options_fail_loudly():
+    with pytest.raises(NotImplementedError):
+        _build("unet", dict(image_shape=(16, 16, 1), feature_maps=[8, 16], drop_values=[0, 0], normalization="bn",
+                            yx_down=[2], z_down=[2], larger_io=False, conv_layers=[2, 2]))
