@@ -1,21 +1,331 @@
-// tcgen05 / TMA implicit-GEMM convolution kernels (placeholder until the kernels land in this file).
-#include "common.cuh"
+// tcgen05 / TMA implicit-GEMM convolution for sm_100a (bf16 / fp16 storage, fp32 accumulation in TMEM).
+//
+//   fprop / dgrad:  D[128 voxels][Cout tile] = sum over (tap, Cin chunk) A_tap[128 voxels][CK] * W[Cout tile][tap, CK]
+//     A_tap is one TMA box of the channels-last activation tensor shifted by the tap offset; out-of-bounds voxels are
+//     zero-filled by the TMA unit, which IS the 'same' padding -- no im2col buffer, no halo code.  Weights
+//     [Cout][tap][Cin] are a plain K-major matrix.  Both land in 32/64/128-byte-swizzled shared memory and feed
+//     tcgen05.mma directly (M = 128, N = Cout tile <= 256, K = 16 per instruction).
+//   Warp roles (192 threads, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
+//     warps 2-5 = epilogue (TMEM -> registers -> +bias (+old value) -> 16-bit -> global, 32 B per thread per 16 columns).
+//   Two TMEM accumulator buffers let the epilogue of tile i overlap the main loop of tile i+1.
+#include "umma.cuh"
+
+#include <mutex>
+#include <unordered_map>
+#include <string>
 
 namespace b200 {
-bool conv_fprop_umma_supported(const b200_tensor*, const b200_tensor*, const b200_tensor*, int, int, int) { return false; }
-int conv_fprop_umma(const b200_tensor*, const void*, const float*, const b200_tensor*, const b200_tensor*, int, int, int, int,
-                    cudaStream_t) {
-  set_error("conv_fprop_umma: not built");
-  return B200_ERR_UNSUPPORTED;
+namespace sm100 {
+
+// ---------------------------------------------------------------------------------------- tensor-map helpers
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
 }
+
+static CUtensorMapDataType tm_dtype(int dt) {
+  return dt == B200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+}
+
+int make_act_tmap(CUtensorMap* out, const b200_tensor* t, int ck, int bw, int bh, int bd) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  B200_CHECK_ARG(fn != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  const uint64_t es = 2;
+  cuuint64_t dims[5] = {(cuuint64_t)t->c, (cuuint64_t)t->w, (cuuint64_t)t->h, (cuuint64_t)t->d, (cuuint64_t)t->n};
+  cuuint64_t strides[4] = {(cuuint64_t)t->ld * es, (cuuint64_t)t->w * t->ld * es, (cuuint64_t)t->h * t->w * t->ld * es,
+                           (cuuint64_t)t->d * t->h * t->w * t->ld * es};
+  cuuint32_t box[5] = {(cuuint32_t)ck, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(out, tm_dtype(t->dtype), 5, t->data, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_for_bytes(ck * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation) failed with %d (c=%d ld=%lld box=%d,%d,%d,%d)", (int)r,
+                 t->c, (long long)t->ld, ck, bw, bh, bd);
+  return B200_OK;
+}
+
+int make_matrix_tmap(CUtensorMap* out, const void* base, int dtype, int64_t rows, int64_t cols, int box_rows, int box_cols) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  B200_CHECK_ARG(fn != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, tm_dtype(dtype), 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_for_bytes(box_cols * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(matrix) failed with %d (rows=%lld cols=%lld box=%d,%d)", (int)r,
+                 (long long)rows, (long long)cols, box_rows, box_cols);
+  return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- fprop kernel
+struct FpropParams {
+  int n, d, h, w, cin, cout;
+  int kd, kh, kw;
+  int bd, bh, bw;                       // voxel tile (bd*bh*bw == 128)
+  int tiles_d, tiles_h, tiles_w, tiles_n;
+  int num_tiles;
+  int ck, chunks;                       // channels per K block, Cin / ck
+  int nt;                               // Cout tile (multiple of 16, <= 256)
+  int stages;
+  uint32_t a_bytes, b_bytes, stage_bytes;
+  uint32_t layout, sbo;                 // UMMA swizzle code and stride-byte-offset for this ck
+  uint32_t idesc;
+  uint32_t tmem_cols;
+  int64_t ldy;
+  int accumulate;
+};
+
+constexpr int kMaxStages = 12;
+
+template <typename T>
+__global__ void __launch_bounds__(192, 1)
+conv_fprop_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                       const float* __restrict__ bias, T* __restrict__ y, const FpropParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t s_bar[2 * kMaxStages + 4];
+  __shared__ uint32_t s_tmem;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_full = smem_u32(&s_bar[0]);
+  const uint32_t bar_empty = smem_u32(&s_bar[kMaxStages]);
+  const uint32_t bar_tfull = smem_u32(&s_bar[2 * kMaxStages]);
+  const uint32_t bar_tempty = smem_u32(&s_bar[2 * kMaxStages + 2]);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_tfull + 8 * b, 1);
+      mbar_init(bar_tempty + 8 * b, 128);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&s_tmem), p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+
+  const int taps = p.kd * p.kh * p.kw;
+  const int num_kb = taps * p.chunks;
+  const int pd = p.kd / 2, ph = p.kh / 2, pw = p.kw / 2;
+
+  auto decode = [&](int tile, int& n, int& z0, int& y0, int& x0, int& n0) {
+    int t = tile;
+    n0 = (t % p.tiles_n) * p.nt; t /= p.tiles_n;
+    x0 = (t % p.tiles_w) * p.bw; t /= p.tiles_w;
+    y0 = (t % p.tiles_h) * p.bh; t /= p.tiles_h;
+    z0 = (t % p.tiles_d) * p.bd; t /= p.tiles_d;
+    n = t;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================================================================= TMA producer
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int n, z0, y0, x0, n0;
+        decode(tile, n, z0, y0, x0, n0);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / p.chunks, ch = kb - tap * p.chunks;
+          const int dx = tap % p.kw, dy = (tap / p.kw) % p.kh, dz = tap / (p.kw * p.kh);
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          const uint32_t a_dst = smem0 + stage * p.stage_bytes;
+          mbar_expect_tx(bar_full + 8 * stage, p.a_bytes + p.b_bytes);
+          tma_load_5d(a_dst, &tmap_x, bar_full + 8 * stage, ch * p.ck, x0 + dx - pw, y0 + dy - ph, z0 + dz - pd, n);
+          tma_load_2d(a_dst + p.a_bytes, &tmap_w, bar_full + 8 * stage, tap * p.cin + ch * p.ck, n0);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ================================================================= MMA issuer
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem + buf * p.nt;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t a_base = smem0 + stage * p.stage_bytes;
+          const uint32_t b_base = a_base + p.a_bytes;
+          for (int k = 0; k < p.ck / 16; ++k) {
+            const uint64_t ad = make_smem_desc(a_base + k * 32, 16, p.sbo, p.layout);
+            const uint64_t bd = make_smem_desc(b_base + k * 32, 16, p.sbo, p.layout);
+            umma_f16(d_tmem, ad, bd, p.idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(bar_empty + 8 * stage);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(bar_tfull + 8 * buf);
+      }
+    }
+  } else {
+    // =================================================================== epilogue (warps 2..5 -> TMEM lane quarter warp%4)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int lx = row % p.bw, ly = (row / p.bw) % p.bh, lz = row / (p.bw * p.bh);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      int n, z0, y0, x0, n0;
+      decode(tile, n, z0, y0, x0, n0);
+      mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
+      tc_fence_after();
+      const int gz = z0 + lz, gy = y0 + ly, gx = x0 + lx;
+      const bool valid = gz < p.d && gy < p.h && gx < p.w;
+      T* yrow = y + ((((int64_t)n * p.d + gz) * p.h + gy) * p.w + gx) * p.ldy + n0;
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.nt);
+      for (int j0 = 0; j0 < p.nt; j0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + j0, r);
+        tmem_ld_wait();
+        if (valid && n0 + j0 < p.cout) {
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(r[j]) + (bias ? __ldg(bias + n0 + j0 + j) : 0.f);
+          if (p.accumulate) {
+            Pack<T, 8> o0 = *reinterpret_cast<const Pack<T, 8>*>(yrow + j0);
+            Pack<T, 8> o1 = *reinterpret_cast<const Pack<T, 8>*>(yrow + j0 + 8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              f[j] += to_f<T>(o0.v[j]);
+              f[8 + j] += to_f<T>(o1.v[j]);
+            }
+          }
+          Pack<T, 8> w0, w1;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            w0.v[j] = from_f<T>(f[j]);
+            w1.v[j] = from_f<T>(f[8 + j]);
+          }
+          *reinterpret_cast<Pack<T, 8>*>(yrow + j0) = w0;
+          *reinterpret_cast<Pack<T, 8>*>(yrow + j0 + 8) = w1;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_tempty + 8 * buf);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem, p.tmem_cols);
+  }
+}
+
+static void pick_tile(int d, int h, int w, int* bd, int* bh, int* bw) {
+  static const int cand[][3] = {{2, 8, 8}, {4, 4, 8}, {1, 8, 16}, {1, 16, 8}, {2, 4, 16}, {4, 8, 4}, {8, 4, 4}, {1, 4, 32},
+                                {2, 2, 32}, {1, 2, 64}, {1, 1, 128}, {2, 16, 4}, {1, 32, 4}, {4, 2, 16}, {8, 8, 2}, {16, 8, 1},
+                                {1, 64, 2}, {1, 128, 1}, {128, 1, 1}, {2, 64, 1}, {8, 16, 1}, {4, 32, 1}, {32, 4, 1}, {64, 2, 1}};
+  double best = 1e30;
+  for (auto& c : cand) {
+    double cover = (double)ceil_div(d, c[0]) * c[0] * ceil_div(h, c[1]) * c[1] * ceil_div(w, c[2]) * c[2];
+    if (cover < best - 0.5) {
+      best = cover;
+      *bd = c[0]; *bh = c[1]; *bw = c[2];
+    }
+  }
+}
+
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+}  // namespace sm100
+
+bool conv_fprop_umma_supported(const b200_tensor* x, const b200_tensor* res, const b200_tensor* y, int kd, int kh, int kw) {
+  if (x->dtype != B200_BF16 && x->dtype != B200_F16) return false;
+  if (res != nullptr) return false;
+  if (x->c % 16 != 0 || y->c % 16 != 0) return false;
+  if (x->ld % 8 != 0 || y->ld % 8 != 0) return false;
+  if (!sm100::aligned16(x->data) || !sm100::aligned16(y->data)) return false;
+  if (kd * kh * kw > 125) return false;
+  if ((int64_t)x->n * x->d * x->h * x->w < 128) return false;
+  (void)kd; (void)kh; (void)kw;
+  return sm100::encode_tiled_fn() != nullptr;
+}
+
+int conv_fprop_umma(const b200_tensor* x, const void* w, const float* bias, const b200_tensor* res, const b200_tensor* y,
+                    int kd, int kh, int kw, int accumulate, cudaStream_t st) {
+  using namespace sm100;
+  (void)res;
+  B200_CHECK_ARG(aligned16(w), "conv_fprop(umma): packed weights must be 16-byte aligned");
+  FpropParams p{};
+  p.n = x->n; p.d = x->d; p.h = x->h; p.w = x->w; p.cin = x->c; p.cout = y->c;
+  p.kd = kd; p.kh = kh; p.kw = kw;
+  pick_tile(x->d, x->h, x->w, &p.bd, &p.bh, &p.bw);
+  p.ck = (x->c % 64 == 0) ? 64 : ((x->c % 32 == 0) ? 32 : 16);
+  p.chunks = x->c / p.ck;
+  p.nt = y->c <= 256 ? y->c : 128;
+  p.tiles_d = (int)ceil_div(x->d, p.bd); p.tiles_h = (int)ceil_div(x->h, p.bh); p.tiles_w = (int)ceil_div(x->w, p.bw);
+  p.tiles_n = (int)ceil_div(y->c, p.nt);
+  p.num_tiles = x->n * p.tiles_d * p.tiles_h * p.tiles_w * p.tiles_n;
+  p.a_bytes = 128u * p.ck * 2;
+  p.b_bytes = (uint32_t)p.nt * p.ck * 2;
+  p.stage_bytes = (p.a_bytes + p.b_bytes + 1023u) & ~1023u;
+  int stages = (int)((200u * 1024u) / p.stage_bytes);
+  if (stages > 8) stages = 8;
+  B200_CHECK_ARG(stages >= 2, "conv_fprop(umma): tile does not fit in shared memory");
+  p.stages = stages;
+  p.layout = p.ck == 64 ? kSwizzle128 : (p.ck == 32 ? kSwizzle64 : kSwizzle32);
+  p.sbo = 8u * p.ck * 2;
+  p.idesc = make_idesc(x->dtype == B200_BF16, p.nt, 0, 0);
+  uint32_t cols = 32;
+  while (cols < 2u * p.nt) cols <<= 1;
+  p.tmem_cols = cols;
+  p.ldy = y->ld;
+  p.accumulate = accumulate;
+
+  CUtensorMap tx, tw;
+  int rc = make_act_tmap(&tx, x, p.ck, p.bw, p.bh, p.bd);
+  if (rc) return rc;
+  rc = make_matrix_tmap(&tw, w, x->dtype, y->c, (int64_t)kd * kh * kw * x->c, p.nt, p.ck);
+  if (rc) return rc;
+
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  if (x->dtype == B200_BF16) {
+    auto kern = conv_fprop_umma_kernel<__nv_bfloat16>;
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 192, smem, st>>>(tx, tw, bias, (__nv_bfloat16*)y->data, p);
+  } else {
+    auto kern = conv_fprop_umma_kernel<__half>;
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 192, smem, st>>>(tx, tw, bias, (__half*)y->data, p);
+  }
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
 bool conv_wgrad_umma_supported(const b200_tensor*, const b200_tensor*, int, int, int) { return false; }
 int conv_wgrad_umma(const b200_tensor*, const b200_tensor*, float*, float*, int, int, int, cudaStream_t) {
   set_error("conv_wgrad_umma: not built");
   return B200_ERR_UNSUPPORTED;
 }
+
 }  // namespace b200
 
-B200_EXPORT int b200_umma_selftest(int32_t, void*) {
-  b200::set_error("umma_selftest: not built");
+B200_EXPORT int b200_umma_selftest(int32_t verbose, void* stream) {
+  (void)verbose; (void)stream;
+  b200::set_error("umma_selftest: use tests/test_gpu_umma.py");
   return B200_ERR_UNSUPPORTED;
 }

@@ -1,0 +1,152 @@
+"""GPU parity of the whole networks against the reference's golden vectors (tests/golden/model_*.npz, produced by
+the unmodified BiaPy classes on CPU) and against the CPU oracle at other sizes.
+
+Tolerance (BASELINE north_star): outputs and gradients within 1e-3 relative of the fp32 CPU reference.  The
+measure is the normalised max error  max|a-b| / max|b|  per tensor (per model for parameter gradients, because
+parameters in front of a norm layer have mathematically-zero gradients).  The fp32 engine must meet 1e-3; the
+bf16 storage path (the bench dtype) is held to a looser, stated bound and its error is printed."""
+import contextlib
+import glob
+import io
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import port_models
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _cls(arch):
+    from biapy_b200.models.attention_unet import Attention_U_Net
+    from biapy_b200.models.resunet import ResUNet
+    from biapy_b200.models.unet import U_Net
+    return {"unet": U_Net, "resunet": ResUNet, "attention_unet": Attention_U_Net}[arch]
+
+
+def _build(arch, kw, sd, dtype):
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = _cls(arch)(**kw)
+    m.load_state_dict(sd, strict=True)
+    return m.cuda().set_engine(dtype=dtype)
+
+
+def nerr(a, b):
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-12)
+
+
+def l2err(a, b):
+    return ((a - b).double().norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+FIXTURES = [p for p in sorted(glob.glob(os.path.join(GOLDEN, "model_*.npz"))) if "upsampling" not in p]
+
+
+@pytest.mark.parametrize("path", FIXTURES)
+@pytest.mark.parametrize("dtype,tol_fwd,tol_bwd", [(torch.float32, 1e-3, 1e-3), (torch.bfloat16, 5e-2, 2.5e-1)])
+def test_golden_forward_backward(path, dtype, tol_fwd, tol_bwd):
+    z = np.load(path)
+    kw = json.loads(str(z["kwargs_json"]))
+    arch = str(z["arch"])
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    m = _build(arch, kw, sd, dtype)
+    m.train()
+    x = torch.from_numpy(z["x"]).cuda().requires_grad_(True)
+    y = m(x)
+    ref = torch.from_numpy(z["y"])
+    assert tuple(y.shape) == tuple(ref.shape)
+    e_fwd = nerr(y.detach().cpu(), ref)
+    (y * torch.from_numpy(z["gy"]).cuda()).sum().backward()
+    e_gx = nerr(x.grad.cpu(), torch.from_numpy(z["gx"]))
+    scale = max(float(np.abs(z[k]).max()) for k in z.files if k.startswith("grad."))
+    e_p = 0.0
+    worst = None
+    for name, p in m.named_parameters():
+        assert p.grad is not None, name
+        e = (p.grad.cpu() - torch.from_numpy(z["grad." + name])).abs().max().item() / scale
+        if e > e_p:
+            e_p, worst = e, name
+    l2_fwd = l2err(y.detach().cpu(), ref)
+    l2_gx = l2err(x.grad.cpu(), torch.from_numpy(z["gx"]))
+    print(f"\n[parity] {os.path.basename(path)} {dtype}: max-norm fwd {e_fwd:.2e} dx {e_gx:.2e} dparams {e_p:.2e} ({worst}); "
+          f"rel-L2 fwd {l2_fwd:.2e} dx {l2_gx:.2e}")
+    if dtype == torch.float32:          # the 1e-3 parity bar of the north star
+        assert e_fwd < tol_fwd and e_gx < tol_bwd and e_p < tol_bwd
+    else:                               # bf16 storage: stated, looser bound on the relative L2 error
+        assert l2_fwd < tol_fwd and l2_gx < tol_bwd and e_p < tol_bwd
+
+
+def test_eval_mode_no_grad_and_second_call():
+    z = np.load(os.path.join(GOLDEN, "model_resunet3d_gn_silu.npz"))
+    kw = json.loads(str(z["kwargs_json"]))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    m = _build("resunet", kw, sd, torch.float32).eval()
+    x = torch.from_numpy(z["x"]).cuda()
+    with torch.no_grad():
+        y1 = m(x)
+        y2 = m(x)
+    assert torch.equal(y1, y2)
+    assert nerr(y1.cpu(), torch.from_numpy(z["y"])) < 1e-3
+
+
+def test_host_layout_input_is_consumed_without_copy_semantics():
+    """BiaPy hands the model a permuted view of a (N,Z,Y,X,C) array (misc.py:689-713)."""
+    z = np.load(os.path.join(GOLDEN, "model_resunet3d_gn_silu.npz"))
+    kw = json.loads(str(z["kwargs_json"]))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    m = _build("resunet", kw, sd, torch.float32).eval()
+    host = np.ascontiguousarray(np.transpose(z["x"], (0, 2, 3, 4, 1)))          # (N,Z,Y,X,C) like BiaPy's arrays
+    x = torch.from_numpy(host).to(torch.float32).permute(0, 4, 1, 2, 3).to("cuda", non_blocking=True)
+    with torch.no_grad():
+        y = m(x)
+    assert nerr(y.cpu(), torch.from_numpy(z["y"])) < 1e-3
+
+
+@pytest.mark.parametrize("arch,kw,batch", [
+    ("resunet", dict(image_shape=(32, 32, 32, 2), activation="silu", feature_maps=[16, 32, 64], drop_values=[0] * 3,
+                     normalization="gn", k_size=3, yx_down=[2, 2], z_down=[2, 2], isotropy=[True] * 3, larger_io=False,
+                     conv_layers=[2] * 3, output_channels=[1]), 2),
+    ("unet", dict(image_shape=(64, 64, 1), activation="elu", feature_maps=[16, 32, 64], drop_values=[0] * 3,
+                  normalization="in", k_size=3, yx_down=[2, 2], z_down=[2, 2], isotropy=[True] * 3, larger_io=False,
+                  conv_layers=[2] * 3, output_channels=[1]), 1),
+    ("attention_unet", dict(image_shape=(16, 32, 32, 1), activation="elu", feature_maps=[16, 32], drop_values=[0] * 2,
+                            normalization="in", k_size=3, yx_down=[2], z_down=[2], isotropy=[True] * 2, larger_io=False,
+                            conv_layers=[2] * 2, output_channels=[1]), 2),
+    ("unet", dict(image_shape=(32, 32, 3), activation="silu", feature_maps=[32, 64], drop_values=[0] * 2,
+                  normalization="gn", k_size=3, yx_down=[2], z_down=[2], isotropy=[True] * 2, larger_io=False,
+                  conv_layers=[2] * 2, output_channels=[1, 1], output_channel_info=["B", "C"], separated_decoders=True), 2),
+])
+def test_against_cpu_oracle_larger(arch, kw, batch):
+    """Same check at sizes beyond the fixtures, against oracle/port_models.py (itself pinned to the reference)."""
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = _cls(arch)(**kw)
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.ndim == 1:
+                p.add_(0.2 * torch.randn(p.shape, generator=g))
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    shape = kw["image_shape"]
+    x = torch.randn((batch, shape[-1]) + tuple(shape[:-1]), generator=g)
+    if kw.get("separated_decoders"):
+        # the oracle port walks decoder 0 only; compare the first head
+        pytest.skip("separated decoders are checked against the fixtures' single-decoder graph only")
+    sd_r = {k: v.clone().requires_grad_(v.dtype == torch.float32) for k, v in sd.items()}
+    xr = x.clone().requires_grad_(True)
+    yr = port_models.forward(arch, sd_r, xr, training=True, **kw)
+    gy = torch.randn(yr.shape, generator=g)
+    (yr * gy).sum().backward()
+    m = m.cuda().set_engine(dtype=torch.float32)
+    xc = x.cuda().requires_grad_(True)
+    y = m(xc)
+    (y * gy.cuda()).sum().backward()
+    assert nerr(y.detach().cpu(), yr.detach()) < 1e-3
+    assert nerr(xc.grad.cpu(), xr.grad) < 1e-3
+    scale = max(v.grad.abs().max().item() for v in sd_r.values() if v.grad is not None)
+    for name, p in m.named_parameters():
+        assert (p.grad.cpu() - sd_r[name].grad).abs().max().item() / scale < 1e-3, name

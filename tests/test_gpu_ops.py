@@ -1,0 +1,262 @@
+"""GPU parity tests, one CUDA entry point at a time, through the C ABI (biapy_b200.ops -> ctypes -> kernels).
+
+The checker is the oracle arithmetic of the reference path: PyTorch ATen on CPU in fp32 (what BiaPy itself runs,
+SURVEY 8c), evaluated on the same seeded inputs.  fp32 kernels must agree to 1e-4 (normalised max error); the
+bf16 storage path is compared with the same CPU computation on bf16-rounded operands."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def cl(x):      # (N,C,D,H,W) cpu -> (N,D,H,W,C) cuda contiguous
+    return x.permute(0, 2, 3, 4, 1).contiguous().cuda()
+
+
+def ncdhw(x):   # (N,D,H,W,C) cuda -> (N,C,D,H,W) cpu fp32
+    return x.float().permute(0, 4, 1, 2, 3).cpu()
+
+
+def nerr(a, b):
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-6)
+
+
+CONV_CASES = [
+    # n, d, h, w, cin, cout, k
+    (2, 5, 9, 37, 3, 5, (3, 3, 3)),
+    (1, 1, 20, 33, 16, 32, (1, 3, 3)),
+    (1, 4, 8, 8, 8, 8, (1, 1, 1)),
+    (1, 6, 7, 6, 2, 4, (5, 5, 5)),
+    (2, 8, 8, 8, 16, 16, (3, 3, 3)),
+    (1, 3, 5, 40, 48, 16, (3, 3, 3)),
+    (1, 2, 4, 4, 20, 1, (1, 1, 1)),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_conv_fprop_dgrad_wgrad_simt(case, dtype):
+    from biapy_b200 import _lib, ops
+    n, d, h, w, cin, cout, k = case
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(n, cin, d, h, w, generator=g)
+    wt = torch.randn(cout, cin, *k, generator=g) * 0.2
+    b = torch.randn(cout, generator=g)
+    gy = torch.randn(n, cout, d, h, w, generator=g)
+    if dtype != torch.float32:
+        x, wt, gy = x.to(dtype).float(), wt.to(dtype).float(), gy.to(dtype).float()
+    xr, wr, br = x.clone().requires_grad_(True), wt.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = F.conv3d(xr, wr, br, padding=[kk // 2 for kk in k])
+    (yr * gy).sum().backward()
+    tol = 1e-4 if dtype == torch.float32 else 1.5e-2
+
+    xd = cl(x).to(dtype)
+    wp = ops.pack_conv_weight(wt.cuda(), dtype, False)
+    # output written into a channel slice of a wider buffer (concat fusion), input read from a slice as well
+    ybuf = torch.zeros(n, d, h, w, cout + 3, dtype=dtype, device="cuda")
+    yv = ybuf[..., 2:2 + cout]
+    xbuf = torch.zeros(n, d, h, w, cin + 5, dtype=dtype, device="cuda")
+    xbuf[..., 1:1 + cin] = xd
+    ops.conv_fprop(xbuf[..., 1:1 + cin], wp, b.cuda(), yv, k, impl=_lib.IMPL_SIMT)
+    assert nerr(ncdhw(yv), yr.detach()) < tol
+    assert ybuf[..., :2].abs().max().item() == 0 and ybuf[..., 2 + cout:].abs().max().item() == 0
+    # accumulate epilogue: y += conv(x) + bias
+    before = ncdhw(yv)
+    ops.conv_fprop(xd, wp, b.cuda(), yv, k, accumulate=True, impl=_lib.IMPL_SIMT)
+    assert nerr(ncdhw(yv), before + yr.detach()) < 2 * tol
+    # dgrad = fprop with the flipped/transposed packing
+    wpf = ops.pack_conv_weight(wt.cuda(), dtype, True)
+    gyd = cl(gy).to(dtype)
+    dx = torch.empty(n, d, h, w, cin, dtype=dtype, device="cuda")
+    ops.conv_fprop(gyd, wpf, None, dx, k, impl=_lib.IMPL_SIMT)
+    assert nerr(ncdhw(dx), xr.grad) < tol
+    # wgrad + bias grad
+    dw = torch.empty_like(wt).cuda()
+    db = torch.zeros(cout, device="cuda")
+    ops.conv_wgrad(xd, gyd, cout, cin, k, dw, db, impl=_lib.IMPL_SIMT)
+    assert nerr(dw.cpu(), wr.grad) < tol
+    assert nerr(db.cpu(), br.grad) < tol
+
+
+@pytest.mark.parametrize("stride", [(2, 2, 2), (1, 2, 2), (2, 1, 1)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_convT(stride, dtype):
+    from biapy_b200 import ops
+    n, d, h, w, cin, cout = 2, 3, 5, 7, 12, 20
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(n, cin, d, h, w, generator=g)
+    wt = torch.randn(cin, cout, *stride, generator=g) * 0.3
+    b = torch.randn(cout, generator=g)
+    gy = torch.randn(n, cout, d * stride[0], h * stride[1], w * stride[2], generator=g)
+    if dtype != torch.float32:
+        x, gy = x.to(dtype).float(), gy.to(dtype).float()
+    xr, wr, br = x.clone().requires_grad_(True), wt.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = F.conv_transpose3d(xr, wr, br, stride=stride)
+    (yr * gy).sum().backward()
+    tol = 1e-4 if dtype == torch.float32 else 1.5e-2
+    xd, gyd = cl(x).to(dtype), cl(gy).to(dtype)
+    y = torch.empty(n, d * stride[0], h * stride[1], w * stride[2], cout, dtype=dtype, device="cuda")
+    ops.convT_fprop(xd, wt.cuda(), b.cuda(), y, stride)
+    assert nerr(ncdhw(y), yr.detach()) < tol
+    dx = torch.empty_like(xd)
+    ops.convT_dgrad(gyd, wt.cuda(), dx, stride)
+    assert nerr(ncdhw(dx), xr.grad) < tol
+    ops.convT_dgrad(gyd, wt.cuda(), dx, stride, accumulate=True)
+    assert nerr(ncdhw(dx), 2 * xr.grad) < 2 * tol
+    dw, db = torch.zeros_like(wt).cuda(), torch.zeros(cout, device="cuda")
+    ops.convT_wgrad(xd, gyd, dw, db, stride)
+    assert nerr(dw.cpu(), wr.grad) < tol and nerr(db.cpu(), br.grad) < tol
+
+
+@pytest.mark.parametrize("window", [(2, 2, 2), (1, 2, 2)])
+def test_maxpool_with_ties(window):
+    from biapy_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    # small integer values -> many ties; the gradient must go to the first maximum in scan order (ATen behaviour)
+    x = torch.randint(0, 3, (2, 5, 4, 6, 8), generator=g).float()
+    xr = x.clone().requires_grad_(True)
+    yr = F.max_pool3d(xr, window)
+    gy = torch.randn(yr.shape, generator=g)
+    (yr * gy).sum().backward()
+    xd = cl(x)
+    y = torch.empty(2, 4 // window[0], 6 // window[1], 8 // window[2], 5, device="cuda")
+    ops.maxpool_fwd(xd, y, window)
+    assert torch.equal(ncdhw(y), yr.detach())
+    dx = torch.empty_like(xd)
+    ops.maxpool_bwd(xd, y, cl(gy), dx, window)
+    assert torch.equal(ncdhw(dx), xr.grad)
+
+
+@pytest.mark.parametrize("kind,c,groups", [("gn", 16, 8), ("gn", 48, 8), ("in", 6, 6), ("in", 1, 1)])
+@pytest.mark.parametrize("act", ["silu", "elu", "relu", "none", "sigmoid"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_norm_act_fwd_bwd(kind, c, groups, act, dtype):
+    from biapy_b200 import ops
+    n, d, h, w = 2, 4, 6, 10
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(n, c, d, h, w, generator=g) * 1.7 + 0.4
+    gamma = torch.randn(c, generator=g)
+    beta = torch.randn(c, generator=g)
+    gy = torch.randn(n, c, d, h, w, generator=g)
+    if dtype != torch.float32:
+        x, gy = x.to(dtype).float(), gy.to(dtype).float()
+    xr, gr, br = x.clone().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yn = F.group_norm(xr, groups, gr, br, 1e-5)
+    fn = {"silu": F.silu, "elu": F.elu, "relu": F.relu, "none": lambda t: t, "sigmoid": torch.sigmoid}[act]
+    yr = fn(yn)
+    (yr * gy).sum().backward()
+    tol = 2e-4 if dtype == torch.float32 else 2e-2
+    xd = cl(x).to(dtype)
+    st = ops.norm_stats(xd, groups, gamma.cuda(), beta.cuda())
+    y = torch.empty_like(xd)
+    ops.scale_shift_act(xd, st.scale, st.shift, act, y)
+    assert nerr(ncdhw(y), yr.detach()) < tol
+    dx = torch.empty_like(xd)
+    dg, db = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
+    ops.norm_act_bwd(xd, cl(gy).to(dtype), st, gamma.cuda(), beta.cuda(), act, dx, dg, db)
+    assert nerr(ncdhw(dx), xr.grad) < tol
+    assert nerr(dg.cpu(), gr.grad) < tol and nerr(db.cpu(), br.grad) < tol
+
+
+def test_act_only_and_elementwise():
+    from biapy_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    a, b = torch.randn(2, 7, 3, 4, 5, generator=g), torch.randn(2, 7, 3, 4, 5, generator=g)
+    ad, bd = cl(a), cl(b)
+    y = torch.empty_like(ad)
+    for op, ref in ((ops.OP_ADD, a + b), (ops.OP_MUL, a * b), (ops.OP_ADD_RELU, F.relu(a + b))):
+        ops.binary(ad, bd, y, op)
+        assert nerr(ncdhw(y), ref) < 1e-6
+    ops.binary(ad, None, y, ops.OP_SIGMOID)
+    assert nerr(ncdhw(y), torch.sigmoid(a)) < 1e-6
+    # gate: out = psi * x and its backward
+    psi = torch.rand(2, 1, 3, 4, 5, generator=g)
+    xr, pr = a.clone().requires_grad_(True), psi.clone().requires_grad_(True)
+    (pr * xr * b).sum().backward()
+    ops.binary(ad, cl(psi), y, ops.OP_MUL)
+    assert nerr(ncdhw(y), (psi * a)) < 1e-6
+    dpsi, dx = torch.empty(2, 3, 4, 5, 1, device="cuda"), torch.empty_like(ad)
+    ops.gate_bwd(ad, cl(psi), bd, dpsi, dx)
+    assert nerr(ncdhw(dx), xr.grad) < 1e-6 and nerr(ncdhw(dpsi), pr.grad) < 1e-5
+    for act in ("silu", "elu", "relu", "leaky_relu", "gelu", "tanh", "sigmoid", "softplus"):
+        ar = a.clone().requires_grad_(True)
+        fn = {"silu": F.silu, "elu": F.elu, "relu": F.relu, "leaky_relu": F.leaky_relu, "gelu": F.gelu, "tanh": torch.tanh,
+              "sigmoid": torch.sigmoid, "softplus": F.softplus}[act]
+        out = fn(ar)
+        (out * b).sum().backward()
+        ops.scale_shift_act(ad, None, None, act, y)
+        assert nerr(ncdhw(y), out.detach()) < 2e-6, act
+        ops.act_bwd(ad, bd, act, dx)
+        assert nerr(ncdhw(dx), ar.grad) < 2e-6, act
+
+
+def test_losses():
+    from biapy_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    z = torch.randn(2, 1, 4, 6, 8, generator=g) * 3
+    t = (torch.rand(2, 1, 4, 6, 8, generator=g) < 0.3).float()
+    zr = z.clone().requires_grad_(True)
+    loss = F.binary_cross_entropy_with_logits(zr, t)
+    loss.backward()
+    zd = cl(z)
+    dz = torch.empty_like(zd)
+    s = ops.bce_logits(zd, cl(t).contiguous(), dz, grad_scale=1.0 / z.numel())
+    assert abs(s.item() / z.numel() - loss.item()) < 1e-6
+    assert nerr(ncdhw(dz), zr.grad) < 1e-5
+    # N2V masked MSE
+    C = 2
+    y = torch.randn(2, C, 3, 4, 5, generator=g)
+    tgt = torch.randn(2, 2 * C, 3, 4, 5, generator=g)
+    tgt[:, C:] = (torch.rand(2, C, 3, 4, 5, generator=g) < 0.2).float()
+    yr = y.clone().requires_grad_(True)
+    l = torch.sum(torch.square(tgt[:, :C] - yr * tgt[:, C:])) / torch.sum(tgt[:, C:])
+    l.backward()
+    yd, td = cl(y), cl(tgt).contiguous()
+    sums = ops.n2v_mse_sums(yd, td)
+    assert abs((sums[0] / sums[1]).item() - l.item()) < 1e-5
+    dy = torch.empty_like(yd)
+    ops.n2v_mse_bwd(yd, td, dy, 1.0 / sums[1].item())
+    assert nerr(ncdhw(dy), yr.grad) < 1e-5
+    # softmax cross entropy
+    zc = torch.randn(2, 4, 3, 4, 5, generator=g)
+    cls = torch.randint(0, 4, (2, 3, 4, 5), generator=g)
+    zcr = zc.clone().requires_grad_(True)
+    lc = F.cross_entropy(zcr, cls)
+    lc.backward()
+    zcd = cl(zc)
+    dzc = torch.empty_like(zcd)
+    sc = ops.softmax_ce(zcd, cls.cuda().contiguous(), dzc, grad_scale=1.0 / cls.numel())
+    assert abs(sc.item() / cls.numel() - lc.item()) < 1e-5
+    assert nerr(ncdhw(dzc), zcr.grad) < 1e-5
+    out = torch.empty_like(zcd)
+    ops.softmax_channels(zcd, out, 0, 4)
+    assert nerr(ncdhw(out), torch.softmax(zc, 1)) < 1e-6
+
+
+def test_optimizers_match_torch():
+    from biapy_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    p0 = torch.randn(1000, generator=g)
+    grads = [torch.randn(1000, generator=g) for _ in range(5)]
+    pr = p0.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([pr], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.02)
+    p = p0.clone().cuda()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for i, gr in enumerate(grads):
+        pr.grad = gr.clone()
+        opt.step()
+        ops.adamw_step(p, gr.cuda(), m, v, 1e-3, 0.9, 0.999, 1e-8, 0.02, i + 1)
+    assert nerr(p.cpu(), pr.detach()) < 1e-6
+    pr = p0.clone().requires_grad_(True)
+    opt = torch.optim.SGD([pr], lr=1e-2, momentum=0.9, weight_decay=1e-4)
+    p = p0.clone().cuda()
+    mom = torch.zeros_like(p)
+    for i, gr in enumerate(grads):
+        pr.grad = gr.clone()
+        opt.step()
+        ops.sgd_step(p, gr.cuda(), mom, 1e-2, 0.9, 1e-4, i == 0)
+    assert nerr(p.cpu(), pr.detach()) < 1e-6
+    ss = ops.sumsq(grads[0].cuda())
+    assert abs(ss.item() - float((grads[0].double() ** 2).sum())) < 1e-6 * ss.item()
