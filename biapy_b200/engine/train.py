@@ -1,0 +1,156 @@
+"""Training step of the U-Net path on the B200 engine: forward, loss, backward, gradient all-reduce, optimiser.
+
+Mirrors the hot loop of ``biapy/engine/train_engine.py:106-203`` (``model_call_func(is_train=True)`` ->
+``loss_function`` -> ``loss.backward()`` -> optional ``clip_grad_norm_`` -> ``optimizer.step()``) for the two
+workflows of the hot path:
+
+* semantic segmentation: ``BCEWithLogits`` for ``N_CLASSES <= 2`` / ``CrossEntropy`` otherwise
+  (``biapy/engine/metrics.py:544-546, 577-586``);
+* denoising: Noise2Void masked MSE (``metrics.py:2265-2286``).
+
+B200-first choices: parameters, gradients and Adam moments live in three flat fp32 buffers (the ``nn.Parameter``
+objects become views, so ``state_dict`` and checkpoints are unchanged); one fused optimiser kernel updates all
+6.7 M parameters; data parallelism is ONE ``all_reduce`` over the flat gradient buffer on NCCL/NVLink instead of
+DDP's bucketed hooks (``base_workflow.py:951-958``); nothing in the step synchronises the host (the reference
+calls ``.item()`` twice and ``synchronize()`` once per step, ``train_engine.py:159,183,187``).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from .. import _lib, ops
+from .tape import TT, Tape
+
+
+class FlatParams:
+    """Re-home every parameter of `model` into one contiguous fp32 buffer (views keep the module API intact)."""
+
+    def __init__(self, model: torch.nn.Module):
+        params = [p for p in model.parameters() if p.requires_grad]
+        if not params:
+            raise ValueError("model has no trainable parameters")
+        dev = params[0].device
+        _lib.require_cuda(params[0], "model parameters")
+        sizes = [p.numel() for p in params]
+        # keep every parameter 16-byte aligned inside the flat buffer
+        offs, total = [], 0
+        for s in sizes:
+            offs.append(total)
+            total += (s + 3) // 4 * 4
+        self.params = params
+        self.offsets = offs
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        for p, o in zip(params, offs):
+            v = self.flat[o:o + p.numel()].view(p.shape)
+            v.copy_(p.data)
+            p.data = v
+        self.grad_views: Dict[torch.nn.Parameter, torch.Tensor] = {
+            p: self.grad[o:o + p.numel()].view(p.shape) for p, o in zip(params, offs)}
+
+
+class Trainer:
+    """One object = model + loss + optimiser state; ``step(x, target)`` runs one training iteration.
+
+    x: ``(N, [Z,] Y, X, C)`` channels-last host (numpy / pinned torch) or device tensor -- BiaPy's batch layout.
+    target: same layout; float mask for ``bce``, class indices in channel 0 for ``ce``, ``target||mask`` for ``n2v_mse``.
+    """
+
+    def __init__(self, model, loss: str = "bce", optimizer: str = "adamw", lr: float = 1e-3, betas=(0.9, 0.999),
+                 eps: float = 1e-8, weight_decay: float = 0.0, momentum: float = 0.0, clip_norm: float = 0.0,
+                 process_group=None):
+        self.model = model
+        self.loss_kind = loss.lower()
+        assert self.loss_kind in ("bce", "ce", "n2v_mse"), loss
+        self.opt_kind = optimizer.lower()
+        assert self.opt_kind in ("adamw", "sgd"), optimizer
+        self.lr, self.betas, self.eps, self.wd, self.momentum = lr, betas, eps, weight_decay, momentum
+        self.clip_norm = clip_norm
+        self.fp = FlatParams(model)
+        self.m = torch.zeros_like(self.fp.flat)
+        self.v = torch.zeros_like(self.fp.flat) if self.opt_kind == "adamw" else None
+        self.t = 0
+        self.pg = process_group
+        self.world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size(process_group)
+        self.device = self.fp.flat.device
+        self.ndim = model.ndim
+
+    # ------------------------------------------------------------------------------------------------- data
+    def _to_device_cl(self, a, dtype=None) -> torch.Tensor:
+        """host/device array in BiaPy layout -> (N, D, H, W, C) CUDA tensor (async copy from pinned memory)."""
+        if not isinstance(a, torch.Tensor):
+            a = torch.from_numpy(a)
+        if not a.is_cuda:
+            a = a.to(self.device, non_blocking=True)
+        if self.ndim == 2:
+            a = a.unsqueeze(1)
+        return a
+
+    # ------------------------------------------------------------------------------------------------- step
+    def step(self, x, target) -> torch.Tensor:
+        """Returns the (mean) loss as a 1-element float64 CUDA tensor; no host synchronisation."""
+        model = self.model
+        xd = self._to_device_cl(x)
+        td = self._to_device_cl(target)
+        tape = Tape(model.engine_dtype, self.device, training=True, conv_impl=model.conv_impl)
+        tape.param_grads = dict(self.fp.grad_views)           # gradients land directly in the flat buffer
+        self.fp.grad.zero_()
+        if xd.dtype == model.engine_dtype and xd.is_contiguous():
+            x_tt = TT(xd, requires_grad=False)
+        else:
+            if xd.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+                xd = xd.float()
+            x_tt = TT(torch.empty(xd.shape, dtype=model.engine_dtype, device=self.device), requires_grad=False)
+            ops.convert(xd.contiguous(), x_tt.data)
+        pred, cls = model._run(tape, x_tt)
+        assert cls is None, "class heads are not part of the semantic-seg / denoising training step"
+        loss = self._loss_and_grad(pred, td)
+        pred.mark_written()
+        tape.backward()
+        self._reduce_and_update()
+        return loss
+
+    def _loss_and_grad(self, pred: TT, td: torch.Tensor) -> torch.Tensor:
+        numel = pred.data.numel()
+        if self.loss_kind == "bce":
+            t32 = td if td.dtype == torch.float32 and td.is_contiguous() else self._as_f32(td)
+            s = ops.bce_logits(pred.data, t32, pred.grad(), grad_scale=1.0 / numel)
+            return s / numel
+        if self.loss_kind == "ce":
+            cls = td[..., 0].long().contiguous()
+            nvox = cls.numel()
+            s = ops.softmax_ce(pred.data, cls, pred.grad(), grad_scale=1.0 / nvox)
+            return s / nvox
+        t32 = td if td.dtype == torch.float32 and td.is_contiguous() else self._as_f32(td)
+        sums = ops.n2v_mse_sums(pred.data, t32)
+        # grad_scale = 1 / sum(mask): one host read of a scalar (the reference reads the loss here anyway)
+        ops.n2v_mse_bwd(pred.data, t32, pred.grad(), 1.0 / float(sums[1].item()))
+        return sums[0:1] / sums[1:2]
+
+    def _as_f32(self, t: torch.Tensor) -> torch.Tensor:
+        if t.dtype in (torch.float16, torch.bfloat16):
+            out = torch.empty(t.shape, dtype=torch.float32, device=t.device)
+            ops.convert(t.contiguous(), out)
+            return out
+        return t.float().contiguous()
+
+    def _reduce_and_update(self):
+        g = self.fp.grad
+        scale = 1.0
+        if self.world > 1:
+            torch.distributed.all_reduce(g, group=self.pg)       # one NCCL all-reduce over NVLink
+            scale = 1.0 / self.world
+        if self.clip_norm and self.clip_norm > 0:
+            total = math.sqrt(float(ops.sumsq(g).item())) * scale
+            scale *= min(1.0, self.clip_norm / (total + 1e-6))
+        self.t += 1
+        if self.opt_kind == "adamw":
+            ops.adamw_step(self.fp.flat, g, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.t,
+                           grad_scale=scale)
+        else:
+            ops.sgd_step(self.fp.flat, g, self.m, self.lr, self.momentum, self.wd, self.t == 1, grad_scale=scale)
