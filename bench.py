@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""Headline benchmark: 3D patches/s of the 128^3 x 2ch bf16 Residual U-Net training step (BASELINE config[1]).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun for N > 1)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port), rank 0 only
+    python bench.py --workload infer                         # BASELINE config[2]: 512^3 sliding-window inference
+
+A step = forward + BCEWithLogits + backward + gradient all-reduce + AdamW on one batch of 4 synthetic patches per
+GPU (weak scaling).  `value` is measured with the batch resident in HBM; `e2e` runs the same step through the
+public Trainer API from pinned host fp16 buffers (H2D inside the timed region, loss read back every step).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import io
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+CFG2 = dict(image_shape=(128, 128, 128, 2), activation="silu", feature_maps=[16, 32, 64, 128, 256], drop_values=[0] * 5,
+            normalization="gn", k_size=3, yx_down=[2] * 4, z_down=[2] * 4, isotropy=[True] * 5, larger_io=False,
+            conv_layers=[2] * 5, output_channels=[1])
+BATCH = 4
+FWD_GFLOP_PER_PATCH = 305.61      # conv + convT, 2*MAC
+STEP_GFLOP_PER_PATCH = 913.08     # fwd + dgrad + wgrad minus dgrad of the two input-fed layers
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [v.strip() for v in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_model(dtype):
+    from biapy_b200.models.resunet import ResUNet
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = ResUNet(**CFG2)
+    return m.cuda().set_engine(dtype=dtype)
+
+
+def synth_batch(seed, n=BATCH):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, 128, 128, 128, 2, generator=g).to(torch.float16)         # synthetic fp16 volume patches
+    t = (torch.rand(n, 128, 128, 128, 1, generator=g) < 0.3).to(torch.float16)  # Bernoulli(0.3) mask
+    return x, t
+
+
+def dist_setup(n_gpus):
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    return rank, world, local
+
+
+def timed(fn, steps, world):
+    """barrier + synchronize on both sides, CUDA events on the launching stream, max over ranks -> ms per step"""
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        torch.distributed.barrier()
+        ms = t.item()
+    return ms / steps
+
+
+def cpu_step_time(threads, reps=1, patch=128):
+    """One training step (fwd + BCE + bwd + AdamW) of the reference path on the host cores, batch 1, fp32,
+    through the oracle port (the reference's own Python cannot travel to this box)."""
+    from oracle import port_models
+    from biapy_b200.models.resunet import ResUNet
+    torch.set_num_threads(threads)
+    kw = dict(CFG2)
+    kw["image_shape"] = (patch, patch, patch, 2)
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = ResUNet(**kw)
+    sd = {k: v.clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    opt = torch.optim.AdamW(list(sd.values()), lr=1e-3, weight_decay=0.02)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, 2, patch, patch, patch, generator=g)
+    t = (torch.rand(1, 1, patch, patch, patch, generator=g) < 0.3).float()
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        y = port_models.forward("resunet", sd, x, training=True, **kw)
+        loss = port_models.bce_with_logits_loss(y, t)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        times.append(time.perf_counter() - t0)
+    return min(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    threads = cores
+    torch.set_num_threads(threads)
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_step_time(threads)
+    ts = [cpu_step_time(threads) for _ in range(max(1, args.steps))]
+    sec = sum(ts) / len(ts)
+    v = 1.0 / sec
+    out = {"impl": "reference", "metric": "3D patches/sec (128^3x2ch ResU-Net training step)", "value": v, "unit": "patches/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "ResUNet fm[16,32,64,128,256] gn/silu 128^3x2ch training step (fwd+BCE+bwd+AdamW)",
+                      "sample": "batch 1 per step (the B200 arm runs batch 4 per GPU)"},
+           "cpu_baseline": {"value": v, "unit": "patches/s", "cores": threads, "kind": "port",
+                            "sample": "one 128^3x2 patch per step, fwd+bwd+AdamW, torch CPU fp32 via oracle/port_models.py"},
+           "e2e": {"value": v, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def run_train(args):
+    from biapy_b200 import ops
+    from biapy_b200.engine.train import Trainer
+    rank, world, local = dist_setup(args.gpus)
+    peaks = load_peaks()
+    dtype = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[args.dtype]
+    model = build_model(dtype)
+    trainer = Trainer(model, loss="bce", optimizer="adamw", lr=1e-3, weight_decay=0.02)
+    xh, th = synth_batch(100 + rank)
+    xh, th = xh.pin_memory(), th.pin_memory()
+    xd, td = xh.cuda(), th.cuda()
+    loss_host = torch.zeros(1, dtype=torch.float64).pin_memory()
+
+    def dev_step(i):
+        trainer.step(xd, td)
+
+    def e2e_step(i):
+        loss = trainer.step(xh, th)                      # pinned host -> device copies happen inside
+        loss_host.copy_(loss, non_blocking=True)
+
+    for i in range(args.warmup):
+        dev_step(i)
+    torch.cuda.synchronize()
+    n0 = ops.LAUNCHES
+    sampler = ClockSampler(local)
+    sampler.start()
+    ops.PROFILE = {} if rank == 0 else None
+    ms = timed(dev_step, args.steps, world)
+    prof, ops.PROFILE = ops.PROFILE, None
+    clocks = sampler.stop()
+    launches = (ops.LAUNCHES - n0)
+    for i in range(min(args.warmup, 2)):
+        e2e_step(i)
+    ms_e2e = timed(e2e_step, args.steps, world)
+    torch.cuda.synchronize()
+    final_loss = float(loss_host.item())
+
+    if rank != 0:
+        return
+    patches = BATCH * world
+    value = patches / (ms / 1e3)
+    # ---- roofline of the dominant kernel class (by summed device time inside the timed region)
+    roof = None
+    if prof:
+        agg = {}
+        for name, recs in prof.items():
+            t = sum(a.elapsed_time(b) for a, b, _, _ in recs)
+            agg[name] = (t, sum(r[2] for r in recs), sum(r[3] for r in recs), len(recs))
+        top = max(agg, key=lambda k: agg[k][0])
+        t, fl, by, cnt = agg[top]
+        ach = fl / (t / 1e3) / 1e12
+        roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
+                "frac": ach / peaks["tf_sust"], "traffic": None, "launches": cnt, "ms_in_step": t / args.steps,
+                "peak_source": peaks["src"] + ", sustained figure (kernel timed inside a long step)",
+                "all": {k: {"ms_per_step": v[0] / args.steps, "TFLOP/s": v[1] / (v[0] / 1e3) / 1e12, "launches": v[3]}
+                        for k, v in sorted(agg.items())}}
+    cpu = None
+    if args.cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        sec = cpu_step_time(cores)
+        cpu = {"value": 1.0 / sec, "unit": "patches/s", "cores": cores, "kind": "port",
+               "sample": "one training step on one 128^3x2 patch (batch 1), fp32, torch CPU via oracle/port_models.py"}
+    out = {
+        "metric": "3D patches/sec (128^3x2ch bf16 ResU-Net training step)", "value": value, "unit": "patches/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": "BASELINE config[1]: 3D Residual U-Net fm[16,32,64,128,256] gn/silu, 128^3x2ch, batch 4 per GPU, "
+                               "training step = fwd + BCEWithLogits + bwd + grad all-reduce + AdamW(lr 1e-3, wd 0.02)",
+                   "global_batch": patches, "parallelism": f"dp{world}",
+                   "l2": "per-step working set (activations + gradients, several GB) >> 126 MB L2; no explicit flush",
+                   "algorithmic_gflop_per_step": STEP_GFLOP_PER_PATCH * BATCH},
+        "e2e": {"value": patches / (ms_e2e / 1e3), "unit": "patches/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": xh.numel() * xh.element_size() + th.numel() * th.element_size(), "d2h_bytes_per_step": 8,
+                "api": "biapy_b200.engine.train.Trainer.step(host fp16 batch, host fp16 target)"},
+        "gpu_launches": launches, "step_tflops": STEP_GFLOP_PER_PATCH * BATCH / ms, "final_loss": final_loss,
+        "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def run_infer(args):
+    """BASELINE config[2]: 512^3 volume, 128^3 patches, 25% overlap -> 216 patches, sigmoid head, device-resident."""
+    from biapy_b200 import ops
+    from biapy_b200.engine.inference import predict_volume
+    rank, world, local = dist_setup(args.gpus)
+    model = build_model(torch.bfloat16).eval()
+    g = torch.Generator().manual_seed(1)
+    vol_h = torch.randn(512, 512, 512, 2, generator=g).to(torch.float16).pin_memory()
+    vol_d = vol_h.cuda()
+
+    def step(i):
+        predict_volume(model, vol_d, (128, 128, 128, 2), overlap=(0.25,) * 3, padding=(0, 0, 0), batch_size=4,
+                       head_activations=["ce_sigmoid"])
+
+    for i in range(max(1, args.warmup // 2)):
+        step(i)
+    n0 = ops.LAUNCHES
+    ms = timed(step, args.steps, world)
+    if rank == 0:
+        print(json.dumps({"metric": "3D patches/sec (sliding-window inference, 512^3 volume)", "value": 216 * world / (ms / 1e3),
+                          "unit": "patches/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                          "config": {"workload": "BASELINE config[2]: crop 512^3 -> 216x128^3 (25% overlap) -> ResUNet fwd -> "
+                                                 "sigmoid -> spline overlap-add, one volume per GPU"},
+                          "gpu_launches": ops.LAUNCHES - n0}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="train", choices=["train", "infer"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (biapy_b200 has no CPU path); use --impl reference for the CPU arm")
+    if args.workload == "infer":
+        return run_infer(args)
+    return run_train(args)
+
+
+if __name__ == "__main__":
+    main()

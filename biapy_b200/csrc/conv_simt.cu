@@ -348,3 +348,10 @@ B200_EXPORT int b200_conv_wgrad(const b200_tensor* x, const b200_tensor* dy, flo
   if (impl == B200_IMPL_UMMA || (impl == B200_IMPL_AUTO && umma_ok)) return conv_wgrad_umma(x, dy, dw_packed, dbias, kd, kh, kw, s);
   return conv_wgrad_simt(x, dy, dw_packed, dbias, kd, kh, kw, s);
 }
+
+B200_EXPORT int b200_conv_impl_query(const b200_tensor* x, const b200_tensor* y, int32_t kd, int32_t kh, int32_t kw,
+                                     int32_t wgrad) {
+  if (!x || !y) return B200_IMPL_SIMT;
+  bool ok = wgrad ? conv_wgrad_umma_supported(x, y, kd, kh, kw) : conv_fprop_umma_supported(x, nullptr, y, kd, kh, kw);
+  return ok ? B200_IMPL_UMMA : B200_IMPL_SIMT;
+}

@@ -17,10 +17,31 @@ from ._lib import ACT, as_tensor, call, stream_ptr
 LAUNCHES = 0
 
 
+# optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline):
+# PROFILE = {} enables it; entries are name -> [(start_event, end_event, flops, bytes)]
+PROFILE = None
+
+
 def _launch(name, *args):
     global LAUNCHES
     LAUNCHES += 1
     call(name, *args)
+
+
+def _launch_timed(label, flops, nbytes, name, *args):
+    if PROFILE is None:
+        return _launch(name, *args)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _launch(name, *args)
+    e1.record()
+    PROFILE.setdefault(label, []).append((e0, e1, flops, nbytes))
+
+
+def _impl_name(x, y, k, wgrad, impl):
+    if impl == _lib.IMPL_AUTO:
+        impl = _lib.lib().b200_conv_impl_query(_ref(x), _ref(y), k[0], k[1], k[2], 1 if wgrad else 0)
+    return "umma" if impl == _lib.IMPL_UMMA else "simt"
 
 
 def _ref(t):
@@ -55,7 +76,13 @@ def pack_conv_weight(w: torch.Tensor, dtype: torch.dtype, flip_transpose: bool) 
 
 
 def conv_fprop(x, w_packed, bias, y, k: Sequence[int], residual=None, accumulate=False, impl=_lib.IMPL_AUTO):
-    _launch("b200_conv_fprop", _ref(x), _ptr(w_packed), _ptr(bias), _ref(residual), _ref(y), k[0], k[1], k[2],
+    label = flops = nbytes = None
+    if PROFILE is not None:
+        vox = x.shape[0] * x.shape[1] * x.shape[2] * x.shape[3]
+        flops = 2.0 * vox * x.shape[-1] * y.shape[-1] * k[0] * k[1] * k[2]
+        nbytes = vox * (x.shape[-1] + y.shape[-1] * (2 if accumulate else 1)) * x.element_size()
+        label = "conv_fprop_" + _impl_name(x, y, k, False, impl)
+    _launch_timed(label, flops, nbytes, "b200_conv_fprop", _ref(x), _ptr(w_packed), _ptr(bias), _ref(residual), _ref(y), k[0], k[1], k[2],
             1 if accumulate else 0, impl, stream_ptr())
     return y
 
@@ -65,7 +92,13 @@ def conv_wgrad(x, dy, cout: int, cin: int, k: Sequence[int], dw_out: torch.Tenso
     """dw_out: (Cout, Cin, *k) fp32; dbias_out: (Cout,) fp32, must be zero-initialised unless accumulate."""
     taps = k[0] * k[1] * k[2]
     packed = torch.zeros(cout * taps * cin, dtype=torch.float32, device=x.device)
-    _launch("b200_conv_wgrad", _ref(x), _ref(dy), _ptr(packed), _ptr(dbias_out), k[0], k[1], k[2], impl, stream_ptr())
+    label = flops = nbytes = None
+    if PROFILE is not None:
+        vox = x.shape[0] * x.shape[1] * x.shape[2] * x.shape[3]
+        flops = 2.0 * vox * cin * cout * taps
+        nbytes = vox * (cin + cout) * x.element_size()
+        label = "conv_wgrad_" + _impl_name(x, dy, k, True, impl)
+    _launch_timed(label, flops, nbytes, "b200_conv_wgrad", _ref(x), _ref(dy), _ptr(packed), _ptr(dbias_out), k[0], k[1], k[2], impl, stream_ptr())
     _launch("b200_unpack_conv_wgrad", _ptr(packed), _ptr(dw_out), cout, cin, taps, 1 if accumulate else 0, stream_ptr())
 
 

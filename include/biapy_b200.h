@@ -109,6 +109,9 @@ int b200_conv_fprop(const b200_tensor* x, const void* w_packed, const float* bia
  * Both outputs must be zero-initialised by the caller (they are accumulated with atomics).                  */
 int b200_conv_wgrad(const b200_tensor* x, const b200_tensor* dy, float* dw_packed, float* dbias,
                     int32_t kd, int32_t kh, int32_t kw, int32_t impl, void* stream);
+/* which kernel family B200_IMPL_AUTO picks for these operands: returns B200_IMPL_UMMA or B200_IMPL_SIMT
+ * (wgrad != 0: for b200_conv_wgrad with y = dy) */
+int b200_conv_impl_query(const b200_tensor* x, const b200_tensor* y, int32_t kd, int32_t kh, int32_t kw, int32_t wgrad);
 /* dw (Cout,Cin,kd,kh,kw) fp32 (+)= dw_packed[Cout][tap][Cin] */
 int b200_unpack_conv_wgrad(const float* dw_packed, float* dw, int32_t cout, int32_t cin, int32_t taps,
                            int32_t accumulate, void* stream);
