@@ -201,6 +201,36 @@ conv_wgrad_simt_kernel(const T* __restrict__ x, const T* __restrict__ dy, float*
   if (dbias && ci0 == 0 && ci_l == 0 && blockIdx.z == 0 && co < g.cout) atomicAdd(&dbias[co], bacc);
 }
 
+// dbias[co] += sum_vox dy[vox][co]: block-level partial sums, one fp32 atomic per (block, channel)
+template <typename T>
+__global__ void bias_grad_kernel(const T* __restrict__ dy, int64_t ld, int c, int64_t nvox, float* __restrict__ dbias) {
+  extern __shared__ float s_part[];   // [rows][c]
+  const int rows = blockDim.x / c;
+  const int row = threadIdx.x / c, ch = threadIdx.x % c;
+  float acc = 0.f;
+  if (row < rows)
+    for (int64_t v = (int64_t)blockIdx.x * rows + row; v < nvox; v += (int64_t)gridDim.x * rows) acc += to_f<T>(dy[v * ld + ch]);
+  if (row < rows) s_part[row * c + ch] = acc;
+  __syncthreads();
+  if (threadIdx.x < c) {
+    float t = 0.f;
+    for (int r = 0; r < rows; ++r) t += s_part[r * c + threadIdx.x];
+    atomicAdd(&dbias[threadIdx.x], t);
+  }
+}
+
+int conv_bias_grad(const b200_tensor* dy, float* dbias, cudaStream_t st) {
+  B200_CHECK_ARG(dy->c <= 1024, "conv_bias_grad: too many channels");
+  int threads = dy->c <= 256 ? 256 : 1024;
+  threads = (threads / dy->c) * dy->c;
+  int64_t nvox = voxels(dy);
+  int blocks = (int)(ceil_div(nvox, threads / dy->c) < (int64_t)sm_count() * 8 ? ceil_div(nvox, threads / dy->c) : (int64_t)sm_count() * 8);
+  B200_DISPATCH_DTYPE(dy->dtype, T, (bias_grad_kernel<T><<<blocks, threads, threads * sizeof(float), st>>>((const T*)dy->data, dy->ld, dy->c,
+                                                                                                       nvox, dbias)));
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
 template <typename T>
 __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ p, int cout, int cin, int taps, int flip) {
   const int64_t total = (int64_t)cout * cin * taps;

@@ -15,6 +15,8 @@
 #include <string>
 
 namespace b200 {
+int conv_bias_grad(const b200_tensor* dy, float* dbias, cudaStream_t st);   // conv_simt.cu
+
 namespace sm100 {
 
 // ---------------------------------------------------------------------------------------- tensor-map helpers
@@ -316,10 +318,247 @@ int conv_fprop_umma(const b200_tensor* x, const void* w, const float* bias, cons
   return B200_OK;
 }
 
-bool conv_wgrad_umma_supported(const b200_tensor*, const b200_tensor*, int, int, int) { return false; }
-int conv_wgrad_umma(const b200_tensor*, const b200_tensor*, float*, float*, int, int, int, cudaStream_t) {
-  set_error("conv_wgrad_umma: not built");
-  return B200_ERR_UNSUPPORTED;
+// ================================================================================================== wgrad
+// dW[co][tap][ci] += sum_vox dY[vox][co] * X[vox + off(tap)][ci]  as  D[(tap, ci)][co] = A^T B with K = voxels:
+//   A  = shifted activation tiles [128 voxels][16 ch]  (TMA, 32-byte rows, SWIZZLE_32B)  -> M-major operand
+//   B  = gradient tile           [128 voxels][Cout]    (TMA, 32/64/128-byte rows)        -> N-major operand
+// The same bytes the fprop kernel reads K-major are consumed here MN-major (instruction-descriptor major bits = 1):
+// channels are the contiguous dimension and the voxel index is K.  Eight (tap, 16-channel) chunks form one M = 128
+// block (LBO = 4 KB chunk tile, SBO = 256 B per 8 voxels); each CTA owns `g` M-blocks whose fp32 accumulators stay
+// in TMEM (g * Cout <= 512 columns) across ALL voxel tiles it visits, and are added to dw with fp32 atomics once.
+namespace sm100 {
+
+struct WgradParams {
+  int n, d, h, w, cin, cout;
+  int kd, kh, kw;
+  int bd, bh, bw;
+  int tiles_d, tiles_h, tiles_w, num_vtiles;
+  int chunks16;            // cin / 16
+  int q_total;             // taps * chunks16
+  int mb_total;            // ceil(q_total / 8)
+  int g;                   // M-blocks per CTA
+  int a_stages, b_stages;
+  uint32_t b_bytes, b_box_c, b_boxes, b_layout, b_sbo, b_lbo, b_kstep;
+  uint32_t idesc, tmem_cols;
+  uint32_t a_off;          // byte offset of the A ring inside dynamic smem (after the B ring)
+};
+
+constexpr uint32_t kChunkBytes = 128u * 16u * 2u;   // one [128 voxels][16 ch] tile
+constexpr uint32_t kBlockBytes = 8u * kChunkBytes;   // one M-block of A
+constexpr int kMaxAStages = 6, kMaxBStages = 3;
+
+template <typename T>
+__global__ void __launch_bounds__(192, 1)
+conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
+                       float* __restrict__ dw, const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t s_bar[2 * kMaxAStages + 2 * kMaxBStages + 1];
+  __shared__ uint32_t s_tmem;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_afull = smem_u32(&s_bar[0]);
+  const uint32_t bar_aempty = smem_u32(&s_bar[kMaxAStages]);
+  const uint32_t bar_bfull = smem_u32(&s_bar[2 * kMaxAStages]);
+  const uint32_t bar_bempty = smem_u32(&s_bar[2 * kMaxAStages + kMaxBStages]);
+  const uint32_t bar_done = smem_u32(&s_bar[2 * kMaxAStages + 2 * kMaxBStages]);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1); }
+    for (int s = 0; s < p.b_stages; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); }
+    mbar_init(bar_done, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_dy);
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&s_tmem), p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+
+  const int pd = p.kd / 2, ph = p.kh / 2, pw = p.kw / 2;
+  const int mb0 = blockIdx.y * p.g;
+  const int mb1 = min(mb0 + p.g, p.mb_total);
+
+  auto decode = [&](int vt, int& n, int& z0, int& y0, int& x0) {
+    int t = vt;
+    x0 = (t % p.tiles_w) * p.bw; t /= p.tiles_w;
+    y0 = (t % p.tiles_h) * p.bh; t /= p.tiles_h;
+    z0 = (t % p.tiles_d) * p.bd; t /= p.tiles_d;
+    n = t;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================================================================= TMA producer
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int vt = blockIdx.x; vt < p.num_vtiles; vt += gridDim.x) {
+        int n, z0, y0, x0;
+        decode(vt, n, z0, y0, x0);
+        mbar_wait(bar_bempty + 8 * bs, bph ^ 1);
+        const uint32_t b_dst = smem0 + bs * p.b_bytes;
+        mbar_expect_tx(bar_bfull + 8 * bs, p.b_bytes);
+        for (uint32_t i = 0; i < p.b_boxes; ++i)
+          tma_load_5d(b_dst + i * 128u * p.b_box_c * 2u, &tmap_dy, bar_bfull + 8 * bs, (int)(i * p.b_box_c), x0, y0, z0, n);
+        if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+        for (int mb = mb0; mb < mb1; ++mb) {
+          mbar_wait(bar_aempty + 8 * as, aph ^ 1);
+          const uint32_t a_dst = smem0 + p.a_off + as * kBlockBytes;
+          const int nq = min(8, p.q_total - mb * 8);
+          mbar_expect_tx(bar_afull + 8 * as, (uint32_t)nq * kChunkBytes);
+          for (int j = 0; j < nq; ++j) {
+            const int q = mb * 8 + j;
+            const int tap = q / p.chunks16, cc = q - tap * p.chunks16;
+            const int dx = tap % p.kw, dy = (tap / p.kw) % p.kh, dz = tap / (p.kw * p.kh);
+            tma_load_5d(a_dst + j * kChunkBytes, &tmap_x, bar_afull + 8 * as, cc * 16, x0 + dx - pw, y0 + dy - ph,
+                        z0 + dz - pd, n);
+          }
+          if (++as == p.a_stages) { as = 0; aph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ================================================================= MMA issuer
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      bool first = true;
+      for (int vt = blockIdx.x; vt < p.num_vtiles; vt += gridDim.x) {
+        mbar_wait(bar_bfull + 8 * bs, bph);
+        tc_fence_after();
+        const uint32_t b_base = smem0 + bs * p.b_bytes;
+        for (int mb = mb0; mb < mb1; ++mb) {
+          mbar_wait(bar_afull + 8 * as, aph);
+          tc_fence_after();
+          const uint32_t a_base = smem0 + p.a_off + as * kBlockBytes;
+          const uint32_t d_tmem = tmem + (uint32_t)((mb - mb0) * p.cout);
+#pragma unroll 1
+          for (int ks = 0; ks < 8; ++ks) {
+            // A: M-major, SWIZZLE_32B: 16 voxels (K) per instruction = 512 bytes of every chunk tile
+            const uint64_t ad = make_smem_desc(a_base + ks * 512u, kChunkBytes, 256u, kSwizzle32);
+            const uint64_t bd = make_smem_desc(b_base + ks * p.b_kstep, p.b_lbo, p.b_sbo, p.b_layout);
+            umma_f16(d_tmem, ad, bd, p.idesc, (first && ks == 0) ? 0u : 1u);
+          }
+          umma_commit(bar_aempty + 8 * as);
+          if (++as == p.a_stages) { as = 0; aph ^= 1; }
+        }
+        umma_commit(bar_bempty + 8 * bs);
+        if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+        first = false;
+      }
+      umma_commit(bar_done);
+    }
+  } else {
+    // =================================================================== epilogue: TMEM -> fp32 atomics into dw
+    const int q4 = warp & 3;
+    const int row = q4 * 32 + lane;
+    const int taps = p.kd * p.kh * p.kw;
+    if ((int)blockIdx.x < p.num_vtiles) {
+      mbar_wait(bar_done, 0);
+      tc_fence_after();
+      for (int mb = mb0; mb < mb1; ++mb) {
+        const int q = mb * 8 + row / 16;
+        const bool valid = q < p.q_total;
+        const int tap = valid ? q / p.chunks16 : 0;
+        const int ci = valid ? (q - tap * p.chunks16) * 16 + (row & 15) : 0;
+        const uint32_t taddr = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)((mb - mb0) * p.cout);
+        for (int j0 = 0; j0 < p.cout; j0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + j0, r);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              atomicAdd(dw + ((int64_t)(j0 + j) * taps + tap) * p.cin + ci, __uint_as_float(r[j]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem, p.tmem_cols);
+  }
+}
+
+}  // namespace sm100
+
+bool conv_wgrad_umma_supported(const b200_tensor* x, const b200_tensor* dy, int kd, int kh, int kw) {
+  if (x->dtype != B200_BF16 && x->dtype != B200_F16) return false;
+  if (x->c % 16 != 0 || x->ld % 8 != 0 || dy->ld % 8 != 0) return false;
+  const int co = dy->c;
+  if (!(co == 16 || co == 32 || co == 64 || co == 128 || co == 256)) return false;
+  if (!sm100::aligned16(x->data) || !sm100::aligned16(dy->data)) return false;
+  if (kd * kh * kw > 125) return false;
+  if ((int64_t)x->n * x->d * x->h * x->w < 128) return false;
+  return sm100::encode_tiled_fn() != nullptr;
+}
+
+int conv_wgrad_umma(const b200_tensor* x, const b200_tensor* dy, float* dw, float* dbias, int kd, int kh, int kw,
+                    cudaStream_t st) {
+  using namespace sm100;
+  WgradParams p{};
+  p.n = x->n; p.d = x->d; p.h = x->h; p.w = x->w; p.cin = x->c; p.cout = dy->c;
+  p.kd = kd; p.kh = kh; p.kw = kw;
+  pick_tile(x->d, x->h, x->w, &p.bd, &p.bh, &p.bw);
+  p.tiles_d = (int)ceil_div(x->d, p.bd); p.tiles_h = (int)ceil_div(x->h, p.bh); p.tiles_w = (int)ceil_div(x->w, p.bw);
+  p.num_vtiles = x->n * p.tiles_d * p.tiles_h * p.tiles_w;
+  p.chunks16 = x->c / 16;
+  p.q_total = kd * kh * kw * p.chunks16;
+  p.mb_total = (int)ceil_div(p.q_total, 8);
+  p.g = 512 / p.cout;
+  if (p.g > p.mb_total) p.g = p.mb_total;
+  const int groups = (int)ceil_div(p.mb_total, p.g);
+  // B operand (dy tile): channels per TMA box = min(cout, 64); N-major atoms of that width
+  p.b_box_c = p.cout < 64 ? (uint32_t)p.cout : 64u;
+  p.b_boxes = (uint32_t)p.cout / p.b_box_c;
+  const uint32_t rp = p.b_box_c * 2;                  // row pitch in bytes = swizzle width
+  p.b_layout = rp == 128 ? kSwizzle128 : (rp == 64 ? kSwizzle64 : kSwizzle32);
+  p.b_sbo = 8u * rp;
+  p.b_lbo = 128u * rp;
+  p.b_kstep = 16u * rp;
+  p.b_bytes = 128u * (uint32_t)p.cout * 2u;
+  p.b_stages = 2;
+  p.a_off = p.b_stages * p.b_bytes;
+  int a_st = (int)((200u * 1024u - p.a_off) / kBlockBytes);
+  if (a_st > 4) a_st = 4;
+  B200_CHECK_ARG(a_st >= 2, "conv_wgrad(umma): tiles do not fit in shared memory");
+  p.a_stages = a_st;
+  p.idesc = make_idesc(x->dtype == B200_BF16, p.cout, 1, 1);
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(p.g * p.cout)) cols <<= 1;
+  p.tmem_cols = cols;
+
+  CUtensorMap tx, tdy;
+  int rc = make_act_tmap(&tx, x, 16, p.bw, p.bh, p.bd);
+  if (rc) return rc;
+  rc = make_act_tmap(&tdy, dy, (int)p.b_box_c, p.bw, p.bh, p.bd);
+  if (rc) return rc;
+
+  int vsplit = sm_count() / groups;
+  if (vsplit < 1) vsplit = 1;
+  if (vsplit > p.num_vtiles) vsplit = p.num_vtiles;
+  dim3 grid((unsigned)vsplit, (unsigned)groups);
+  const size_t smem = (size_t)p.a_off + (size_t)p.a_stages * kBlockBytes + 1024;
+  if (x->dtype == B200_BF16) {
+    auto kern = conv_wgrad_umma_kernel<__nv_bfloat16>;
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 192, smem, st>>>(tx, tdy, dw, p);
+  } else {
+    auto kern = conv_wgrad_umma_kernel<__half>;
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 192, smem, st>>>(tx, tdy, dw, p);
+  }
+  B200_LAUNCH_CHECK();
+  if (dbias) {
+    int rc2 = conv_bias_grad(dy, dbias, st);
+    if (rc2) return rc2;
+  }
+  return B200_OK;
 }
 
 }  // namespace b200

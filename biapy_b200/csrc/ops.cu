@@ -646,13 +646,7 @@ B200_EXPORT int b200_scale_shift_act(const b200_tensor* x, const float* scale, c
     else                                                                                                         \
       scale_shift_act_kernel<TI, TO, 1><<<grid_for(xv.vox * x->c, 256), 256, 0, st>>>(xv, yv, scale, shift, act);  \
   }
-  if (x->dtype == y->dtype) {
-    B200_DISPATCH_DTYPE(x->dtype, T, SSA(T, T));
-  } else if (x->dtype == B200_F32 && y->dtype == B200_BF16) SSA(float, __nv_bfloat16)
-  else if (x->dtype == B200_F32 && y->dtype == B200_F16) SSA(float, __half)
-  else if (x->dtype == B200_BF16 && y->dtype == B200_F32) SSA(__nv_bfloat16, float)
-  else if (x->dtype == B200_F16 && y->dtype == B200_F32) SSA(__half, float)
-  else { set_error("scale_shift_act: unsupported dtype pair"); return B200_ERR_UNSUPPORTED; }
+  B200_DISPATCH_DTYPE(x->dtype, TI_, { B200_DISPATCH_DTYPE(y->dtype, TO_, SSA(TI_, TO_)); });
 #undef SSA
   B200_LAUNCH_CHECK();
   return B200_OK;

@@ -78,3 +78,37 @@ def test_conv_dgrad_umma(case):
     dx = torch.empty(n, d, h, w, cin, dtype=dtype, device="cuda")
     ops.conv_fprop(cl(gy).to(dtype), wpf, None, dx, k, impl=_lib.IMPL_UMMA)
     assert nerr(ncdhw(dx), x.grad) < 1.5e-2
+
+
+WGRAD_CASES = [
+    (1, 8, 8, 8, 16, 16, (3, 3, 3)),       # B: SWIZZLE_32B, one M-group of 4 blocks (27 chunks -> 5 dummy slots)
+    (2, 8, 16, 16, 32, 32, (3, 3, 3)),     # B: SWIZZLE_64B
+    (1, 8, 8, 16, 64, 64, (3, 3, 3)),      # B: SWIZZLE_128B, several M-groups
+    (1, 4, 8, 8, 48, 16, (3, 3, 3)),       # decoder concat shape
+    (1, 8, 8, 8, 128, 256, (3, 3, 3)),     # N = 256 (4 boxes), g = 2
+    (1, 8, 8, 8, 32, 128, (3, 3, 3)),      # N = 128 (2 boxes)
+    (1, 5, 9, 11, 16, 16, (3, 3, 3)),      # partial tiles
+    (2, 1, 24, 40, 32, 16, (1, 3, 3)),     # 2D
+    (1, 4, 8, 8, 64, 32, (1, 1, 1)),       # pointwise
+    (3, 16, 16, 16, 16, 32, (3, 3, 3)),    # many voxel tiles per CTA
+    (1, 32, 32, 32, 96, 32, (3, 3, 3)),
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES)
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_conv_wgrad_umma(case, dtype):
+    from biapy_b200 import _lib, ops
+    n, d, h, w, cin, cout, k = case
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(n, cin, d, h, w, generator=g).to(dtype).float()
+    wt = torch.zeros(cout, cin, *k, requires_grad=True)
+    b = torch.zeros(cout, requires_grad=True)
+    gy = torch.randn(n, cout, d, h, w, generator=g).to(dtype).float()
+    F.conv3d(x, wt, b, padding=[kk // 2 for kk in k]).backward(gy)
+    dw = torch.empty(cout, cin, *k, device="cuda")
+    db = torch.zeros(cout, device="cuda")
+    ops.conv_wgrad(cl(x).to(dtype), cl(gy).to(dtype), cout, cin, k, dw, db, impl=_lib.IMPL_UMMA)
+    torch.cuda.synchronize()
+    assert nerr(dw.cpu(), wt.grad) < 2e-3          # same bf16 operands, fp32 accumulation on both sides
+    assert nerr(db.cpu(), b.grad) < 2e-3
