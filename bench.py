@@ -218,6 +218,7 @@ def run_train(args):
     sampler = ClockSampler(local)
     sampler.start()
     ops.PROFILE = {} if rank == 0 else None
+    ops.PROFILE_SHAPES = args.detail
     ms = timed(dev_step, args.steps, world)
     prof, ops.PROFILE = ops.PROFILE, None
     clocks = sampler.stop()
@@ -239,14 +240,14 @@ def run_train(args):
         for name, recs in prof.items():
             t = sum(a.elapsed_time(b) for a, b, _, _ in recs)
             agg[name] = (t, sum(r[2] for r in recs), sum(r[3] for r in recs), len(recs))
-        top = max(agg, key=lambda k: agg[k][0])
+        top = max((k for k in agg if agg[k][1] > 0), key=lambda k: agg[k][0])
         t, fl, by, cnt = agg[top]
         ach = fl / (t / 1e3) / 1e12
         roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
                 "frac": ach / peaks["tf_sust"], "traffic": None, "launches": cnt, "ms_in_step": t / args.steps,
                 "peak_source": peaks["src"] + ", sustained figure (kernel timed inside a long step)",
-                "all": {k: {"ms_per_step": v[0] / args.steps, "TFLOP/s": v[1] / (v[0] / 1e3) / 1e12, "launches": v[3]}
-                        for k, v in sorted(agg.items())}}
+                "all": {k: {"ms_per_step": round(v[0] / args.steps, 3), "TFLOP/s": round(v[1] / (v[0] / 1e3) / 1e12, 1),
+                            "launches": v[3] // args.steps} for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}}
     cpu = None
     if args.cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
@@ -307,6 +308,7 @@ def main():
     ap.add_argument("--workload", default="train", choices=["train", "infer"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--detail", action="store_true", help="per-layer-shape kernel table in roofline.all")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -15,6 +15,7 @@ import torch
 
 from .. import _lib, ops
 from ..data import _stitch
+from .dist import deal_patches, gather_patch_predictions
 
 
 def apply_head_activations(pred_cl: torch.Tensor, head_activations: Sequence[str], out: torch.Tensor) -> torch.Tensor:
@@ -59,7 +60,7 @@ def predict_volume(model, vol, patch_shape: Sequence[int], overlap=(0, 0, 0), pa
     c_out = sum(model.output_channels)
     acts = head_activations or ["linear"] * c_out
     pred = torch.empty((n,) + tuple(patches.shape[1:4]) + (c_out,), dtype=out_dtype, device=patches.device)
-    mine = list(range(rank, n, world)) if world > 1 else None
+    mine = deal_patches(n, rank, world) if world > 1 else None
     idx = range(0, n, batch_size) if world == 1 else range(0, len(mine), batch_size)
     for k in idx:
         if world == 1:
@@ -78,15 +79,7 @@ def predict_volume(model, vol, patch_shape: Sequence[int], overlap=(0, 0, 0), pa
             apply_head_activations(ycl, acts, tmp)
             pred.index_copy_(0, sel, tmp)
     if world > 1:
-        # patches were dealt round-robin: gather every rank's predictions (one NCCL exchange), then merge locally
-        per = (n + world - 1) // world
-        send = torch.zeros((per,) + tuple(pred.shape[1:]), dtype=pred.dtype, device=pred.device)
-        send[: len(mine)] = pred[mine]
-        gathered = [torch.empty_like(send) for _ in range(world)]
-        torch.distributed.all_gather(gathered, send)
-        for r in range(world):
-            ids = list(range(r, n, world))
-            pred[ids] = gathered[r][: len(ids)]
+        gather_patch_predictions(pred, n)          # one NCCL all_gather, then every rank merges locally
     axes_m = [_stitch.Axis(dev_vol.shape[i], patch_shape[i], padding[i], overlap[i]) for i in range(3)]
     merged = _stitch.merge_device(pred, (Z, Y, X), [a.starts(1) for a in axes_m], [a.window() for a in axes_m], padding)
     return merged.cpu().numpy() if is_np else merged

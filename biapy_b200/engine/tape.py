@@ -25,7 +25,7 @@ from .. import _lib, ops
 class TT:
     """A tensor on the tape: data + lazily allocated gradient; may be a channel slice of a parent buffer."""
 
-    __slots__ = ("data", "_grad", "_ready", "parent", "off", "requires_grad")
+    __slots__ = ("data", "_grad", "_ready", "parent", "off", "requires_grad", "padded")
 
     def __init__(self, data: torch.Tensor, requires_grad: bool = True, parent: "Optional[TT]" = None, off: int = 0):
         self.data = data
@@ -34,6 +34,7 @@ class TT:
         self.parent = parent
         self.off = off
         self.requires_grad = requires_grad
+        self.padded = None          # zero-padded 16-channel copy (network inputs with < 16 channels, see Tape.conv)
 
     @property
     def shape(self):
@@ -133,6 +134,9 @@ class Tape:
         assert x.c == cin, (x.c, cin)
         if out is None:
             out = self.new(x.data, cout)
+        if (cin < 16 and cout % 16 == 0 and not x.requires_grad and self.dtype != torch.float32
+                and self.impl != _lib.IMPL_SIMT):
+            return self._conv_padded_input(x, mod, out, accumulate, k, cout, cin)
         ops.conv_fprop(x.data, self._pack(w, False), self._f32(b), out.data, k, accumulate=accumulate, impl=self.impl)
         if self.training:
             def bwd(x=x, out=out, w=w, b=b, k=k, cout=cout, cin=cin):
@@ -145,6 +149,33 @@ class Tape:
                 if x.requires_grad:
                     acc = x.prepare_accumulate()
                     ops.conv_fprop(dy, self._pack(w, True), None, x.grad(), k, accumulate=acc, impl=self.impl)
+            self.steps.append(bwd)
+        return out
+
+    def _conv_padded_input(self, x: TT, mod, out: TT, accumulate: bool, k, cout: int, cin: int) -> TT:
+        """Image-fed convolutions (Cin = 1..3) run on the tensor cores by zero-padding the input and the weights to
+        16 channels (K = taps*16 instead of a CUDA-core kernel); the padded gradient columns are discarded."""
+        w, b = mod.weight, mod.bias
+        if x.padded is None:
+            buf = torch.zeros(tuple(x.shape[:4]) + (16,), dtype=self.dtype, device=self.device)
+            ops.convert(x.data, buf[..., :cin])
+            x.padded = buf
+        key = (id(w), "pad16")
+        wp = self._packed.get(key)
+        if wp is None:
+            w16 = torch.zeros((cout, 16) + tuple(w.shape[2:]), dtype=torch.float32, device=self.device)
+            w16[:, :cin] = w.detach()
+            wp = ops.pack_conv_weight(w16, self.dtype, False)
+            self._packed[key] = wp
+        ops.conv_fprop(x.padded, wp, self._f32(b), out.data, k, accumulate=accumulate, impl=self.impl)
+        if self.training:
+            def bwd(x=x, out=out, w=w, b=b, k=k, cout=cout, cin=cin):
+                assert out.grad_ready, "conv output gradient was never produced"
+                if w.requires_grad:
+                    gb = self._pgrad(b) if (b is not None and b.requires_grad) else None
+                    dw16 = torch.empty((cout, 16) + tuple(w.shape[2:]), dtype=torch.float32, device=self.device)
+                    ops.conv_wgrad(x.padded, out.grad(), cout, 16, k, dw16, gb, accumulate=False, impl=self.impl)
+                    self._pgrad(w).add_(dw16[:, :cin])
             self.steps.append(bwd)
         return out
 

@@ -22,6 +22,7 @@ from typing import Dict, Optional, Sequence
 import torch
 
 from .. import _lib, ops
+from .dist import allreduce_mean_
 from .tape import TT, Tape
 
 
@@ -141,10 +142,7 @@ class Trainer:
 
     def _reduce_and_update(self):
         g = self.fp.grad
-        scale = 1.0
-        if self.world > 1:
-            torch.distributed.all_reduce(g, group=self.pg)       # one NCCL all-reduce over NVLink
-            scale = 1.0 / self.world
+        scale = allreduce_mean_(g, self.pg)                      # one NCCL all-reduce over NVLink (no-op for 1 rank)
         if self.clip_norm and self.clip_norm > 0:
             total = math.sqrt(float(ops.sumsq(g).item())) * scale
             scale *= min(1.0, self.clip_norm / (total + 1e-6))

@@ -20,22 +20,31 @@ LAUNCHES = 0
 # optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline):
 # PROFILE = {} enables it; entries are name -> [(start_event, end_event, flops, bytes)]
 PROFILE = None
+PROFILE_SHAPES = False     # append the layer shape to the conv labels (bench.py --detail)
+
+
+def _timed_call(label, flops, nbytes, name, *args):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    call(name, *args)
+    e1.record()
+    PROFILE.setdefault(label, []).append((e0, e1, flops, nbytes))
 
 
 def _launch(name, *args):
     global LAUNCHES
     LAUNCHES += 1
-    call(name, *args)
+    if PROFILE is None:
+        return call(name, *args)
+    _timed_call(name[5:], 0.0, 0.0, name, *args)
 
 
 def _launch_timed(label, flops, nbytes, name, *args):
+    global LAUNCHES
+    LAUNCHES += 1
     if PROFILE is None:
-        return _launch(name, *args)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    _launch(name, *args)
-    e1.record()
-    PROFILE.setdefault(label, []).append((e0, e1, flops, nbytes))
+        return call(name, *args)
+    _timed_call(label, flops, nbytes, name, *args)
 
 
 def _impl_name(x, y, k, wgrad, impl):
@@ -82,6 +91,8 @@ def conv_fprop(x, w_packed, bias, y, k: Sequence[int], residual=None, accumulate
         flops = 2.0 * vox * x.shape[-1] * y.shape[-1] * k[0] * k[1] * k[2]
         nbytes = vox * (x.shape[-1] + y.shape[-1] * (2 if accumulate else 1)) * x.element_size()
         label = "conv_fprop_" + _impl_name(x, y, k, False, impl)
+        if PROFILE_SHAPES:
+            label += f" {x.shape[-1]}->{y.shape[-1]} k{k[0]}{k[1]}{k[2]} @{x.shape[1]}x{x.shape[2]}x{x.shape[3]}"
     _launch_timed(label, flops, nbytes, "b200_conv_fprop", _ref(x), _ptr(w_packed), _ptr(bias), _ref(residual), _ref(y), k[0], k[1], k[2],
             1 if accumulate else 0, impl, stream_ptr())
     return y
@@ -98,6 +109,8 @@ def conv_wgrad(x, dy, cout: int, cin: int, k: Sequence[int], dw_out: torch.Tenso
         flops = 2.0 * vox * cin * cout * taps
         nbytes = vox * (cin + cout) * x.element_size()
         label = "conv_wgrad_" + _impl_name(x, dy, k, True, impl)
+        if PROFILE_SHAPES:
+            label += f" {cin}->{cout} k{k[0]}{k[1]}{k[2]} @{x.shape[1]}x{x.shape[2]}x{x.shape[3]}"
     _launch_timed(label, flops, nbytes, "b200_conv_wgrad", _ref(x), _ref(dy), _ptr(packed), _ptr(dbias_out), k[0], k[1], k[2], impl, stream_ptr())
     _launch("b200_unpack_conv_wgrad", _ptr(packed), _ptr(dw_out), cout, cin, taps, 1 if accumulate else 0, stream_ptr())
 
