@@ -59,6 +59,12 @@ SIGNATURES = {
     "b200_convT_fprop": (_I, [_T, _P, _P, _T, _I, _I, _I, _P]),
     "b200_convT_dgrad": (_I, [_T, _P, _T, _I, _I, _I, _I, _P]),
     "b200_convT_wgrad": (_I, [_T, _T, _P, _P, _I, _I, _I, _P]),
+    "b200_convT_tc_supported": (_I, [_T, _T, _I, _I, _I]),
+    "b200_pack_convT_weight": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "b200_convT_fprop_tc": (_I, [_T, _P, _P, _T, _I, _I, _I, _P]),
+    "b200_convT_dgrad_tc": (_I, [_T, _P, _T, _I, _I, _I, _I, _P]),
+    "b200_convT_wgrad_tc": (_I, [_T, _T, _P, _P, _I, _I, _I, _P]),
+    "b200_unpack_convT_wgrad": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "b200_maxpool_fwd": (_I, [_T, _T, _I, _I, _I, _P]),
     "b200_maxpool_bwd": (_I, [_T, _T, _T, _T, _I, _I, _I, _I, _P]),
     "b200_channel_sums": (_I, [_T, _P, _P]),

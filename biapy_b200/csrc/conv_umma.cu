@@ -37,19 +37,18 @@ static CUtensorMapDataType tm_dtype(int dt) {
   return dt == B200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
 }
 
-int make_act_tmap(CUtensorMap* out, const b200_tensor* t, int ck, int bw, int bh, int bd) {
+int make_act_tmap(CUtensorMap* out, const ActView& t, int ck, int bw, int bh, int bd) {
   EncodeTiledFn fn = encode_tiled_fn();
   B200_CHECK_ARG(fn != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
   const uint64_t es = 2;
-  cuuint64_t dims[5] = {(cuuint64_t)t->c, (cuuint64_t)t->w, (cuuint64_t)t->h, (cuuint64_t)t->d, (cuuint64_t)t->n};
-  cuuint64_t strides[4] = {(cuuint64_t)t->ld * es, (cuuint64_t)t->w * t->ld * es, (cuuint64_t)t->h * t->w * t->ld * es,
-                           (cuuint64_t)t->d * t->h * t->w * t->ld * es};
+  cuuint64_t dims[5] = {(cuuint64_t)t.c, (cuuint64_t)t.w, (cuuint64_t)t.h, (cuuint64_t)t.d, (cuuint64_t)t.n};
+  cuuint64_t strides[4] = {(cuuint64_t)t.sw * es, (cuuint64_t)t.sh * es, (cuuint64_t)t.sd * es, (cuuint64_t)t.sn * es};
   cuuint32_t box[5] = {(cuuint32_t)ck, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(out, tm_dtype(t->dtype), 5, t->data, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = fn(out, tm_dtype(t.dtype), 5, t.data, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   swizzle_for_bytes(ck * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  B200_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation) failed with %d (c=%d ld=%lld box=%d,%d,%d,%d)", (int)r,
-                 t->c, (long long)t->ld, ck, bw, bh, bd);
+  B200_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation) failed with %d (c=%d sw=%lld box=%d,%d,%d,%d)", (int)r,
+                 t.c, (long long)t.sw, ck, bw, bh, bd);
   return B200_OK;
 }
 
@@ -81,7 +80,7 @@ struct FpropParams {
   uint32_t layout, sbo;                 // UMMA swizzle code and stride-byte-offset for this ck
   uint32_t idesc;
   uint32_t tmem_cols;
-  int64_t ldy;
+  int64_t ysw, ysh, ysd, ysn;           // output element strides (x, y, z, batch)
   int accumulate;
 };
 
@@ -194,7 +193,7 @@ conv_fprop_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
       tc_fence_after();
       const int gz = z0 + lz, gy = y0 + ly, gx = x0 + lx;
       const bool valid = gz < p.d && gy < p.h && gx < p.w;
-      T* yrow = y + ((((int64_t)n * p.d + gz) * p.h + gy) * p.w + gx) * p.ldy + n0;
+      T* yrow = y + (int64_t)n * p.ysn + (int64_t)gz * p.ysd + (int64_t)gy * p.ysh + (int64_t)gx * p.ysw + n0;
       const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.nt);
       for (int j0 = 0; j0 < p.nt; j0 += 16) {
         uint32_t r[16];
@@ -252,6 +251,10 @@ static void pick_tile(int d, int h, int w, int* bd, int* bh, int* bw) {
 
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
+int conv_fprop_umma_v(const ActView& x, const void* w, const float* bias, const ActView& y, int kd, int kh, int kw,
+                      int accumulate, cudaStream_t st);
+int conv_wgrad_umma_v(const ActView& x, const ActView& dy, float* dw, int kd, int kh, int kw, cudaStream_t st);
+
 }  // namespace sm100
 
 bool conv_fprop_umma_supported(const b200_tensor* x, const b200_tensor* res, const b200_tensor* y, int kd, int kh, int kw) {
@@ -268,8 +271,15 @@ bool conv_fprop_umma_supported(const b200_tensor* x, const b200_tensor* res, con
 
 int conv_fprop_umma(const b200_tensor* x, const void* w, const float* bias, const b200_tensor* res, const b200_tensor* y,
                     int kd, int kh, int kw, int accumulate, cudaStream_t st) {
-  using namespace sm100;
   (void)res;
+  return sm100::conv_fprop_umma_v(sm100::view_of(x), w, bias, sm100::view_of(y), kd, kh, kw, accumulate, st);
+}
+
+namespace sm100 {
+int conv_fprop_umma_v(const ActView& xv, const void* w, const float* bias, const ActView& yv, int kd, int kh, int kw,
+                      int accumulate, cudaStream_t st) {
+  const ActView* x = &xv;
+  const ActView* y = &yv;
   B200_CHECK_ARG(aligned16(w), "conv_fprop(umma): packed weights must be 16-byte aligned");
   FpropParams p{};
   p.n = x->n; p.d = x->d; p.h = x->h; p.w = x->w; p.cin = x->c; p.cout = y->c;
@@ -294,11 +304,11 @@ int conv_fprop_umma(const b200_tensor* x, const void* w, const float* bias, cons
   uint32_t cols = 32;
   while (cols < 2u * p.nt) cols <<= 1;
   p.tmem_cols = cols;
-  p.ldy = y->ld;
+  p.ysw = y->sw; p.ysh = y->sh; p.ysd = y->sd; p.ysn = y->sn;
   p.accumulate = accumulate;
 
   CUtensorMap tx, tw;
-  int rc = make_act_tmap(&tx, x, p.ck, p.bw, p.bh, p.bd);
+  int rc = make_act_tmap(&tx, *x, p.ck, p.bw, p.bh, p.bd);
   if (rc) return rc;
   rc = make_matrix_tmap(&tw, w, x->dtype, y->c, (int64_t)kd * kh * kw * x->c, p.nt, p.ck);
   if (rc) return rc;
@@ -317,6 +327,7 @@ int conv_fprop_umma(const b200_tensor* x, const void* w, const float* bias, cons
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
+}  // namespace sm100
 
 // ================================================================================================== wgrad
 // dW[co][tap][ci] += sum_vox dY[vox][co] * X[vox + off(tap)][ci]  as  D[(tap, ci)][co] = A^T B with K = voxels:
@@ -500,7 +511,16 @@ bool conv_wgrad_umma_supported(const b200_tensor* x, const b200_tensor* dy, int 
 
 int conv_wgrad_umma(const b200_tensor* x, const b200_tensor* dy, float* dw, float* dbias, int kd, int kh, int kw,
                     cudaStream_t st) {
-  using namespace sm100;
+  int rc = sm100::conv_wgrad_umma_v(sm100::view_of(x), sm100::view_of(dy), dw, kd, kh, kw, st);
+  if (rc) return rc;
+  if (dbias) return conv_bias_grad(dy, dbias, st);
+  return B200_OK;
+}
+
+namespace sm100 {
+int conv_wgrad_umma_v(const ActView& xv, const ActView& dyv, float* dw, int kd, int kh, int kw, cudaStream_t st) {
+  const ActView* x = &xv;
+  const ActView* dy = &dyv;
   WgradParams p{};
   p.n = x->n; p.d = x->d; p.h = x->h; p.w = x->w; p.cin = x->c; p.cout = dy->c;
   p.kd = kd; p.kh = kh; p.kw = kw;
@@ -534,9 +554,9 @@ int conv_wgrad_umma(const b200_tensor* x, const b200_tensor* dy, float* dw, floa
   p.tmem_cols = cols;
 
   CUtensorMap tx, tdy;
-  int rc = make_act_tmap(&tx, x, 16, p.bw, p.bh, p.bd);
+  int rc = make_act_tmap(&tx, *x, 16, p.bw, p.bh, p.bd);
   if (rc) return rc;
-  rc = make_act_tmap(&tdy, dy, (int)p.b_box_c, p.bw, p.bh, p.bd);
+  rc = make_act_tmap(&tdy, *dy, (int)p.b_box_c, p.bw, p.bh, p.bd);
   if (rc) return rc;
 
   int vsplit = sm_count() / groups;
@@ -554,14 +574,148 @@ int conv_wgrad_umma(const b200_tensor* x, const b200_tensor* dy, float* dw, floa
     kern<<<grid, 192, smem, st>>>(tx, tdy, dw, p);
   }
   B200_LAUNCH_CHECK();
-  if (dbias) {
-    int rc2 = conv_bias_grad(dy, dbias, st);
-    if (rc2) return rc2;
+  return B200_OK;
+}
+}  // namespace sm100
+
+}  // namespace b200
+
+// ============================================================================== transposed convolution (k == s)
+// Each of the s^3 output phases is a pointwise convolution between the coarse tensor and a strided sub-lattice view
+// of the fine tensor, so the three passes reuse the kernels above with ActView strides:
+//   fprop : for every phase t   Y_t   = X . W_t^T + b         (conv_fprop_umma_v, k = 1, strided epilogue)
+//   dgrad : dX = sum_t dY_t . W_t                             (k = 1, TMA reads the strided view, accumulate epilogue)
+//   wgrad : dW_t = X^T . dY_t                                 (conv_wgrad_umma_v, k = 1)
+namespace b200 {
+namespace sm100 {
+
+template <typename T>
+__global__ void pack_convT_weight_kernel(const float* __restrict__ w, T* __restrict__ p, int cin, int cout, int taps, int for_dgrad) {
+  const int64_t total = (int64_t)cin * cout * taps;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int t = (int)(i % taps);
+    int co = (int)((i / taps) % cout);
+    int ci = (int)(i / ((int64_t)taps * cout));
+    int64_t o = for_dgrad ? (((int64_t)t * cin + ci) * cout + co) : (((int64_t)t * cout + co) * cin + ci);
+    p[o] = from_f<T>(w[i]);
   }
+}
+
+__global__ void unpack_convT_wgrad_kernel(const float* __restrict__ p, float* __restrict__ dw, int cin, int cout, int taps,
+                                          int accumulate) {
+  const int64_t total = (int64_t)cin * cout * taps;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int t = (int)(i % taps);
+    int co = (int)((i / taps) % cout);
+    int ci = (int)(i / ((int64_t)taps * cout));
+    float v = p[((int64_t)t * cout + co) * cin + ci];
+    dw[i] = accumulate ? dw[i] + v : v;
+  }
+}
+
+static bool convT_tc_ok(const b200_tensor* x, const b200_tensor* y, int sd, int sh, int sw) {
+  if (x->dtype != B200_BF16 && x->dtype != B200_F16) return false;
+  if (y->dtype != x->dtype) return false;
+  if (x->c % 16 != 0 || y->c % 16 != 0 || x->ld % 8 != 0 || y->ld % 8 != 0) return false;
+  const int co = y->c;
+  if (!(co == 16 || co == 32 || co == 64 || co == 128 || co == 256)) return false;   // wgrad N tile
+  if (x->c > 256) return false;                                                      // dgrad N tile
+  if (!aligned16(x->data) || !aligned16(y->data)) return false;
+  if (y->d != x->d * sd || y->h != x->h * sh || y->w != x->w * sw) return false;
+  if ((int64_t)x->n * x->d * x->h * x->w < 128) return false;
+  return encode_tiled_fn() != nullptr;
+}
+
+}  // namespace sm100
+}  // namespace b200
+
+using namespace b200;
+using namespace b200::sm100;
+
+B200_EXPORT int b200_convT_tc_supported(const b200_tensor* x, const b200_tensor* y, int32_t sd, int32_t sh, int32_t sw) {
+  if (!x || !y) return 0;
+  return convT_tc_ok(x, y, sd, sh, sw) ? 1 : 0;
+}
+
+B200_EXPORT int b200_pack_convT_weight(const float* w, void* packed, int32_t dtype, int32_t cin, int32_t cout, int32_t taps,
+                                       int32_t for_dgrad, void* stream) {
+  B200_CHECK_ARG(w && packed && cin > 0 && cout > 0 && taps > 0, "pack_convT_weight: bad args");
+  int64_t total = (int64_t)cin * cout * taps;
+  unsigned blocks = (unsigned)(ceil_div(total, 256) < 4096 ? ceil_div(total, 256) : 4096);
+  if (dtype == B200_BF16)
+    pack_convT_weight_kernel<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)packed, cin, cout, taps, for_dgrad);
+  else if (dtype == B200_F16)
+    pack_convT_weight_kernel<__half><<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__half*)packed, cin, cout, taps, for_dgrad);
+  else {
+    set_error("pack_convT_weight: 16-bit dtypes only");
+    return B200_ERR_ARG;
+  }
+  B200_LAUNCH_CHECK();
   return B200_OK;
 }
 
-}  // namespace b200
+B200_EXPORT int b200_unpack_convT_wgrad(const float* dw_packed, float* dw, int32_t cin, int32_t cout, int32_t taps,
+                                        int32_t accumulate, void* stream) {
+  B200_CHECK_ARG(dw_packed && dw, "unpack_convT_wgrad: null pointer");
+  int64_t total = (int64_t)cin * cout * taps;
+  unsigned blocks = (unsigned)(ceil_div(total, 256) < 4096 ? ceil_div(total, 256) : 4096);
+  unpack_convT_wgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dw_packed, dw, cin, cout, taps, accumulate);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+B200_EXPORT int b200_convT_fprop_tc(const b200_tensor* x, const void* w_packed, const float* bias, const b200_tensor* y,
+                                    int32_t sd, int32_t sh, int32_t sw, void* stream) {
+  B200_CHECK_ARG(check_tensor(x, "convT_fprop_tc.x") && check_tensor(y, "convT_fprop_tc.y") && w_packed, "%s", b200_last_error());
+  B200_CHECK_ARG(convT_tc_ok(x, y, sd, sh, sw), "convT_fprop_tc: unsupported operands (query b200_convT_tc_supported first)");
+  const ActView xv = view_of(x);
+  int t = 0;
+  for (int a = 0; a < sd; ++a)
+    for (int b = 0; b < sh; ++b)
+      for (int c = 0; c < sw; ++c, ++t) {
+        const ActView yv = phase_view(y, sd, sh, sw, a, b, c);
+        const char* wt = (const char*)w_packed + (size_t)t * y->c * x->c * 2;
+        int rc = conv_fprop_umma_v(xv, wt, bias, yv, 1, 1, 1, 0, (cudaStream_t)stream);
+        if (rc) return rc;
+      }
+  return B200_OK;
+}
+
+B200_EXPORT int b200_convT_dgrad_tc(const b200_tensor* dy, const void* w_packed_t, const b200_tensor* dx, int32_t sd,
+                                    int32_t sh, int32_t sw, int32_t accumulate, void* stream) {
+  B200_CHECK_ARG(check_tensor(dy, "convT_dgrad_tc.dy") && check_tensor(dx, "convT_dgrad_tc.dx") && w_packed_t, "%s",
+                 b200_last_error());
+  B200_CHECK_ARG(convT_tc_ok(dx, dy, sd, sh, sw), "convT_dgrad_tc: unsupported operands");
+  const ActView xv = view_of(dx);
+  int t = 0;
+  for (int a = 0; a < sd; ++a)
+    for (int b = 0; b < sh; ++b)
+      for (int c = 0; c < sw; ++c, ++t) {
+        const ActView yv = phase_view(dy, sd, sh, sw, a, b, c);
+        const char* wt = (const char*)w_packed_t + (size_t)t * dy->c * dx->c * 2;     // [Cin][Cout] for this phase
+        int rc = conv_fprop_umma_v(yv, wt, nullptr, xv, 1, 1, 1, (accumulate || t > 0) ? 1 : 0, (cudaStream_t)stream);
+        if (rc) return rc;
+      }
+  return B200_OK;
+}
+
+B200_EXPORT int b200_convT_wgrad_tc(const b200_tensor* x, const b200_tensor* dy, float* dw_packed, float* dbias, int32_t sd,
+                                    int32_t sh, int32_t sw, void* stream) {
+  B200_CHECK_ARG(check_tensor(x, "convT_wgrad_tc.x") && check_tensor(dy, "convT_wgrad_tc.dy") && dw_packed, "%s",
+                 b200_last_error());
+  B200_CHECK_ARG(convT_tc_ok(x, dy, sd, sh, sw), "convT_wgrad_tc: unsupported operands");
+  const ActView xv = view_of(x);
+  int t = 0;
+  for (int a = 0; a < sd; ++a)
+    for (int b = 0; b < sh; ++b)
+      for (int c = 0; c < sw; ++c, ++t) {
+        const ActView yv = phase_view(dy, sd, sh, sw, a, b, c);
+        int rc = conv_wgrad_umma_v(xv, yv, dw_packed + (size_t)t * dy->c * x->c, 1, 1, 1, (cudaStream_t)stream);
+        if (rc) return rc;
+      }
+  if (dbias) return conv_bias_grad(dy, dbias, (cudaStream_t)stream);
+  return B200_OK;
+}
 
 B200_EXPORT int b200_umma_selftest(int32_t verbose, void* stream) {
   (void)verbose; (void)stream;

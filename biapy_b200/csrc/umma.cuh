@@ -142,8 +142,28 @@ inline CUtensorMapSwizzle swizzle_for_bytes(int inner_bytes) {
   return inner_bytes >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (inner_bytes >= 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
-// channels-last activation view (N,D,H,W,C) with voxel pitch ld: rank-5 map (C, W, H, D, N), box (ck, bw, bh, bd, 1)
-int make_act_tmap(CUtensorMap* out, const b200_tensor* t, int ck, int bw, int bh, int bd);
+// Channels-last activation view with explicit element strides per spatial axis; lets a stride-s sub-lattice of a
+// tensor (the s^3 output phases of a transposed convolution) be addressed as an ordinary tensor by TMA and epilogues.
+struct ActView {
+  void* data;
+  int dtype;
+  int n, d, h, w, c;
+  int64_t sw, sh, sd, sn;   // element strides of x, y, z, batch
+};
+inline ActView view_of(const b200_tensor* t) {
+  return ActView{t->data, t->dtype, t->n, t->d, t->h, t->w, t->c, t->ld, (int64_t)t->w * t->ld, (int64_t)t->h * t->w * t->ld,
+                 (int64_t)t->d * t->h * t->w * t->ld};
+}
+// phase (a, b, c) of the (sd, sh, sw)-strided sub-lattice of `fine`: dims = fine dims / stride
+inline ActView phase_view(const b200_tensor* fine, int sd, int sh, int sw, int a, int b, int c) {
+  ActView v = view_of(fine);
+  v.data = (char*)fine->data + (((int64_t)a * fine->h + b) * fine->w + c) * fine->ld * 2;
+  v.d = fine->d / sd; v.h = fine->h / sh; v.w = fine->w / sw;
+  v.sw *= sw; v.sh *= sh; v.sd *= sd;
+  return v;
+}
+// rank-5 map (C, W, H, D, N), box (ck, bw, bh, bd, 1)
+int make_act_tmap(CUtensorMap* out, const ActView& t, int ck, int bw, int bh, int bd);
 // row-major matrix [rows][cols] of 16-bit elements: rank-2 map (cols, rows), box (box_cols, box_rows)
 int make_matrix_tmap(CUtensorMap* out, const void* base, int dtype, int64_t rows, int64_t cols, int box_rows, int box_cols);
 

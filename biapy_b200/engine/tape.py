@@ -188,17 +188,35 @@ class Tape:
             sp = (x.shape[1] * s[0], x.shape[2] * s[1], x.shape[3] * s[2])
             out = self.new(x.data, cout, sp)
         wf = self._f32(w).contiguous()
-        ops.convT_fprop(x.data, wf, self._f32(b), out.data, s)
+        tc = self.dtype != torch.float32 and self.impl != _lib.IMPL_SIMT and ops.convT_tc_supported(x.data, out.data, s)
+        if tc:
+            key = (id(w), "convT")
+            wp = self._packed.get(key)
+            if wp is None:
+                wp = self._packed[key] = ops.pack_convT_weight(wf, self.dtype, False)
+            ops.convT_fprop_tc(x.data, wp, self._f32(b), out.data, s)
+        else:
+            ops.convT_fprop(x.data, wf, self._f32(b), out.data, s)
         if self.training:
-            def bwd(x=x, out=out, w=w, b=b, s=s, wf=wf):
+            def bwd(x=x, out=out, w=w, b=b, s=s, wf=wf, tc=tc):
                 dy = out.grad()
                 assert out.grad_ready
                 if w.requires_grad:
                     gb = self._pgrad(b) if (b is not None and b.requires_grad) else None
-                    ops.convT_wgrad(x.data, dy, self._pgrad(w), gb, s)
+                    if tc:
+                        ops.convT_wgrad_tc(x.data, dy, self._pgrad(w), gb, s, accumulate=True)
+                    else:
+                        ops.convT_wgrad(x.data, dy, self._pgrad(w), gb, s)
                 if x.requires_grad:
                     acc = x.prepare_accumulate()
-                    ops.convT_dgrad(dy, wf, x.grad(), s, accumulate=acc)
+                    if tc:
+                        key = (id(w), "convT_d")
+                        wpt = self._packed.get(key)
+                        if wpt is None:
+                            wpt = self._packed[key] = ops.pack_convT_weight(wf, self.dtype, True)
+                        ops.convT_dgrad_tc(dy, wpt, x.grad(), s, accumulate=acc)
+                    else:
+                        ops.convT_dgrad(dy, wf, x.grad(), s, accumulate=acc)
             self.steps.append(bwd)
         return out
 

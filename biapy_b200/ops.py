@@ -128,6 +128,49 @@ def convT_wgrad(x, dy, dw, dbias, s: Sequence[int]):
     _launch("b200_convT_wgrad", _ref(x), _ref(dy), _ptr(dw), _ptr(dbias), s[0], s[1], s[2], stream_ptr())
 
 
+def convT_tc_supported(x, y, s: Sequence[int]) -> bool:
+    return bool(_lib.lib().b200_convT_tc_supported(_ref(x), _ref(y), s[0], s[1], s[2]))
+
+
+def pack_convT_weight(w: torch.Tensor, dtype: torch.dtype, for_dgrad: bool) -> torch.Tensor:
+    """w: (Cin, Cout, *s) fp32 -> [tap][Cout][Cin] (fprop) or [tap][Cin][Cout] (dgrad) in the engine dtype."""
+    w = w.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    cin, cout = w.shape[:2]
+    taps = w[0, 0].numel()
+    out = torch.empty(w.numel(), dtype=dtype, device=w.device)
+    _launch("b200_pack_convT_weight", _ptr(w), _ptr(out), _lib.torch_dtype_code(dtype), cin, cout, taps, 1 if for_dgrad else 0,
+            stream_ptr())
+    return out
+
+
+def _convT_work(x, cout, s):
+    vox = x.shape[0] * x.shape[1] * x.shape[2] * x.shape[3]
+    return 2.0 * vox * x.shape[-1] * cout * s[0] * s[1] * s[2]
+
+
+def convT_fprop_tc(x, w_packed, bias, y, s: Sequence[int]):
+    _launch_timed("convT_fprop_tc", _convT_work(x, y.shape[-1], s) if PROFILE is not None else 0, 0,
+                  "b200_convT_fprop_tc", _ref(x), _ptr(w_packed), _ptr(bias), _ref(y), s[0], s[1], s[2], stream_ptr())
+    return y
+
+
+def convT_dgrad_tc(dy, w_packed_t, dx, s: Sequence[int], accumulate=False):
+    _launch_timed("convT_dgrad_tc", _convT_work(dx, dy.shape[-1], s) if PROFILE is not None else 0, 0,
+                  "b200_convT_dgrad_tc", _ref(dy), _ptr(w_packed_t), _ref(dx), s[0], s[1], s[2], 1 if accumulate else 0, stream_ptr())
+
+
+def convT_wgrad_tc(x, dy, dw: torch.Tensor, dbias, s: Sequence[int], accumulate=False):
+    """dw: (Cin, Cout, *s) fp32 parameter-layout gradient."""
+    cin, cout = x.shape[-1], dy.shape[-1]
+    taps = s[0] * s[1] * s[2]
+    packed = torch.zeros(taps * cout * cin, dtype=torch.float32, device=x.device)
+    _launch_timed("convT_wgrad_tc", _convT_work(x, cout, s) if PROFILE is not None else 0, 0,
+                  "b200_convT_wgrad_tc", _ref(x), _ref(dy), _ptr(packed), _ptr(dbias), s[0], s[1], s[2], stream_ptr())
+    _launch("b200_unpack_convT_wgrad", _ptr(packed), _ptr(dw), cin, cout, taps, 1 if accumulate else 0, stream_ptr())
+
+
 # ------------------------------------------------------------------------------------------------- pooling
 def maxpool_fwd(x, y, p: Sequence[int]):
     _launch("b200_maxpool_fwd", _ref(x), _ref(y), p[0], p[1], p[2], stream_ptr())

@@ -127,6 +127,22 @@ int b200_convT_dgrad(const b200_tensor* dy, const float* w, const b200_tensor* d
 int b200_convT_wgrad(const b200_tensor* x, const b200_tensor* dy, float* dw, float* dbias,
                      int32_t sd, int32_t sh, int32_t sw, void* stream);
 
+/* Tensor-core route of the same three passes (16-bit dtypes, Cin/Cout multiples of 16): each of the s^3 output phases
+ * is a pointwise tcgen05 GEMM over a strided sub-lattice view of the fine tensor.  Weights are packed per step:
+ *   for_dgrad = 0: [tap][Cout][Cin] (fprop)        for_dgrad = 1: [tap][Cin][Cout] (dgrad)
+ * dw_packed of the wgrad is fp32 [tap][Cout][Cin], zero-initialised by the caller.                                   */
+int b200_convT_tc_supported(const b200_tensor* x, const b200_tensor* y, int32_t sd, int32_t sh, int32_t sw);
+int b200_pack_convT_weight(const float* w, void* packed, int32_t dtype, int32_t cin, int32_t cout, int32_t taps,
+                           int32_t for_dgrad, void* stream);
+int b200_convT_fprop_tc(const b200_tensor* x, const void* w_packed, const float* bias, const b200_tensor* y,
+                        int32_t sd, int32_t sh, int32_t sw, void* stream);
+int b200_convT_dgrad_tc(const b200_tensor* dy, const void* w_packed_t, const b200_tensor* dx,
+                        int32_t sd, int32_t sh, int32_t sw, int32_t accumulate, void* stream);
+int b200_convT_wgrad_tc(const b200_tensor* x, const b200_tensor* dy, float* dw_packed, float* dbias,
+                        int32_t sd, int32_t sh, int32_t sw, void* stream);
+int b200_unpack_convT_wgrad(const float* dw_packed, float* dw, int32_t cin, int32_t cout, int32_t taps,
+                            int32_t accumulate, void* stream);
+
 /* -------------------------------------------------------------------------------------------------- pooling
  * nn.MaxPool3d / MaxPool2d with kernel == stride (unet.py:255-256).  Backward recomputes the arg-max from
  * (x, y): the first maximum in (d,h,w) scan order receives the gradient, as ATen's max_pool backward.       */

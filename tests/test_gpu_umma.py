@@ -112,3 +112,35 @@ def test_conv_wgrad_umma(case, dtype):
     torch.cuda.synchronize()
     assert nerr(dw.cpu(), wt.grad) < 2e-3          # same bf16 operands, fp32 accumulation on both sides
     assert nerr(db.cpu(), b.grad) < 2e-3
+
+
+@pytest.mark.parametrize("shape", [(2, 4, 8, 8, 32, 32), (1, 8, 8, 8, 256, 256), (1, 4, 4, 16, 64, 64), (1, 3, 5, 12, 32, 16)])
+@pytest.mark.parametrize("stride", [(2, 2, 2), (1, 2, 2)])
+def test_convT_tensor_core_route(shape, stride):
+    """ConvTranspose(k = s): fprop / dgrad / wgrad through the tcgen05 kernels on strided sub-lattice views."""
+    from biapy_b200 import ops
+    n, d, h, w, cin, cout = shape
+    dtype = torch.bfloat16
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(n, cin, d, h, w, generator=g).to(dtype).float().requires_grad_(True)
+    wt = (torch.randn(cin, cout, *stride, generator=g) * 0.2).to(dtype).float().requires_grad_(True)
+    b = torch.randn(cout, generator=g).requires_grad_(True)
+    gy = torch.randn(n, cout, d * stride[0], h * stride[1], w * stride[2], generator=g).to(dtype).float()
+    yr = F.conv_transpose3d(x, wt, b, stride=stride)
+    yr.backward(gy)
+    xd, gyd = cl(x.detach()).to(dtype), cl(gy).to(dtype)
+    ybuf = torch.zeros(n, d * stride[0], h * stride[1], w * stride[2], cout + 16, dtype=dtype, device="cuda")
+    y = ybuf[..., :cout]                       # first slice of a concat buffer, as the decoder uses it
+    assert ops.convT_tc_supported(xd, y, stride)
+    wp = ops.pack_convT_weight(wt.detach().cuda(), dtype, False)
+    ops.convT_fprop_tc(xd, wp, b.detach().cuda(), y, stride)
+    torch.cuda.synchronize()
+    assert nerr(ncdhw(y), yr.detach()) < 1.5e-2
+    assert ybuf[..., cout:].abs().max().item() == 0
+    wpt = ops.pack_convT_weight(wt.detach().cuda(), dtype, True)
+    dx = torch.empty_like(xd)
+    ops.convT_dgrad_tc(gyd, wpt, dx, stride)
+    assert nerr(ncdhw(dx), x.grad) < 1.5e-2
+    dw, db = torch.zeros_like(wt).cuda(), torch.zeros(cout, device="cuda")
+    ops.convT_wgrad_tc(xd, gyd, dw, db, stride)
+    assert nerr(dw.cpu(), wt.grad) < 2e-3 and nerr(db.cpu(), b.grad) < 2e-3
