@@ -71,8 +71,8 @@ SIGNATURES = {
     "b200_norm_finalize": (_I, [_P, _I, _I, _I, _L, _I, _P, _P, _F, _P, _P, _P, _P, _P]),
     "b200_scale_shift_act": (_I, [_T, _P, _P, _I, _T, _P]),
     "b200_norm_act_bwd_reduce": (_I, [_T, _T, _P, _P, _I, _P, _P, _I, _P, _P]),
-    "b200_norm_bwd_finalize": (_I, [_P, _P, _P, _I, _I, _I, _L, _I, _P, _P, _P, _P]),
-    "b200_norm_act_bwd_apply": (_I, [_T, _T, _P, _P, _I, _P, _P, _I, _P, _T, _I, _P]),
+    "b200_norm_bwd_finalize": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _L, _I, _P, _P, _P, _P]),
+    "b200_norm_act_bwd_apply": (_I, [_T, _T, _I, _P, _T, _I, _P]),
     "b200_act_bwd": (_I, [_T, _T, _I, _T, _I, _P]),
     "b200_binary": (_I, [_T, _T, _T, _I, _P]),
     "b200_gate_bwd": (_I, [_T, _T, _T, _T, _T, _I, _P]),

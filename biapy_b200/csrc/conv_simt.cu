@@ -256,8 +256,110 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ p, float* __restri
   }
 }
 
+// ---------------------------------------------------------------------------------------- small pointwise convs
+// k = 1 layers with a handful of channels on one side (segmentation heads 16->1, attention psi 8->1 and their
+// gradients) are pure HBM streams: one thread per voxel, weights in shared memory, fp32 accumulation.
+constexpr int kSmallMax = 8;
+
+// y[vox][co] = b[co] + sum_ci x[vox][ci] * w[co][ci]   for cout <= 8 (any cin)
+template <typename T>
+__global__ void conv1x1_small_cout_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ wp, const float* __restrict__ bias,
+                                          T* __restrict__ y, int64_t ldy, int cin, int cout, int64_t nvox, int accumulate) {
+  extern __shared__ float s_w[];   // [cout][cin]
+  for (int i = threadIdx.x; i < cin * cout; i += blockDim.x) s_w[i] = to_f<T>(wp[i]);
+  __syncthreads();
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (int64_t)gridDim.x * blockDim.x) {
+    float acc[kSmallMax];
+#pragma unroll
+    for (int j = 0; j < kSmallMax; ++j) acc[j] = (bias && j < cout) ? bias[j] : 0.f;
+    const T* xr = x + v * ldx;
+    for (int ci = 0; ci < cin; ++ci) {
+      float a = to_f<T>(xr[ci]);
+#pragma unroll
+      for (int j = 0; j < kSmallMax; ++j)
+        if (j < cout) acc[j] = fmaf(a, s_w[j * cin + ci], acc[j]);
+    }
+    T* yr = y + v * ldy;
+#pragma unroll
+    for (int j = 0; j < kSmallMax; ++j)
+      if (j < cout) yr[j] = from_f<T>(accumulate ? to_f<T>(yr[j]) + acc[j] : acc[j]);
+  }
+}
+
+// y[vox][co] = b[co] + sum_{ci < cin <= 8} x[vox][ci] * w[co][ci]   for cin <= 8 (any cout)
+template <typename T>
+__global__ void conv1x1_small_cin_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ wp, const float* __restrict__ bias,
+                                         T* __restrict__ y, int64_t ldy, int cin, int cout, int64_t nvox, int accumulate) {
+  extern __shared__ float s_w[];   // [cout][cin]
+  for (int i = threadIdx.x; i < cin * cout; i += blockDim.x) s_w[i] = to_f<T>(wp[i]);
+  __syncthreads();
+  const int64_t total = nvox * cout;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t v = i / cout;
+    int co = (int)(i % cout);
+    float acc = bias ? bias[co] : 0.f;
+    for (int ci = 0; ci < cin; ++ci) acc = fmaf(to_f<T>(x[v * ldx + ci]), s_w[co * cin + ci], acc);
+    T* o = y + v * ldy + co;
+    *o = from_f<T>(accumulate ? to_f<T>(*o) + acc : acc);
+  }
+}
+
+// dw[co][ci] += sum_vox dy[vox][co] * x[vox][ci], dbias[co] += sum dy   for cin*cout <= 128 with min(cin,cout) <= 8
+template <typename T>
+__global__ void conv1x1_small_wgrad_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy, int64_t lddy,
+                                           float* __restrict__ dw, float* __restrict__ dbias, int cin, int cout, int64_t nvox) {
+  // thread = (pair p = co*cin+ci) x voxel lane; 128 pairs max
+  extern __shared__ float s_red[];
+  const int pairs = cin * cout;
+  const int lanes = blockDim.x / pairs;
+  const int p = threadIdx.x % pairs, lane = threadIdx.x / pairs;
+  const int co = p / cin, ci = p % cin;
+  float acc = 0.f, bacc = 0.f;
+  if (lane < lanes)
+    for (int64_t v = (int64_t)blockIdx.x * lanes + lane; v < nvox; v += (int64_t)gridDim.x * lanes) {
+      float d = to_f<T>(dy[v * lddy + co]);
+      acc = fmaf(d, to_f<T>(x[v * ldx + ci]), acc);
+      bacc += d;
+    }
+  s_red[threadIdx.x] = (lane < lanes) ? acc : 0.f;
+  s_red[blockDim.x + threadIdx.x] = (lane < lanes) ? bacc : 0.f;
+  __syncthreads();
+  if (threadIdx.x < pairs) {
+    float t = 0.f, tb = 0.f;
+    for (int l = 0; l < lanes; ++l) {
+      t += s_red[l * pairs + threadIdx.x];
+      tb += s_red[blockDim.x + l * pairs + threadIdx.x];
+    }
+    atomicAdd(&dw[(int64_t)co * cin + ci], t);
+    if (dbias && ci == 0) atomicAdd(&dbias[co], tb);
+  }
+}
+
+static bool small_pointwise(const b200_tensor* x, const b200_tensor* y, int kd, int kh, int kw) {
+  return kd == 1 && kh == 1 && kw == 1 && (x->c <= kSmallMax || y->c <= kSmallMax) && x->c * y->c <= 128;
+}
+
 int conv_fprop_simt(const b200_tensor* x, const void* w, const float* bias, const b200_tensor* res, const b200_tensor* y,
                     int kd, int kh, int kw, int accumulate, cudaStream_t st) {
+  if (!res && small_pointwise(x, y, kd, kh, kw)) {
+    const int64_t nvox = voxels(x);
+    const size_t smem = sizeof(float) * x->c * y->c;
+    B200_DISPATCH_DTYPE(x->dtype, T, {
+      if (y->c <= kSmallMax) {
+        int64_t blocks = ceil_div(nvox, 256);
+        if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
+        conv1x1_small_cout_kernel<T><<<(unsigned)blocks, 256, smem, st>>>((const T*)x->data, x->ld, (const T*)w, bias, (T*)y->data,
+                                                                        y->ld, x->c, y->c, nvox, accumulate);
+      } else {
+        int64_t blocks = ceil_div(nvox * y->c, 256);
+        if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
+        conv1x1_small_cin_kernel<T><<<(unsigned)blocks, 256, smem, st>>>((const T*)x->data, x->ld, (const T*)w, bias, (T*)y->data,
+                                                                       y->ld, x->c, y->c, nvox, accumulate);
+      }
+    });
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+  }
   ConvGeom g{x->n, x->d, x->h, x->w, x->c, y->c, kd, kh, kw, x->ld, y->ld, res ? res->ld : 0};
   const int taps = kd * kh * kw;
   const size_t per_ck = ((size_t)kd * (kTH + kh - 1) * (kTW + kw - 1) + (size_t)taps * kTN) * sizeof(float);
@@ -280,6 +382,18 @@ int conv_fprop_simt(const b200_tensor* x, const void* w, const float* bias, cons
 
 int conv_wgrad_simt(const b200_tensor* x, const b200_tensor* dy, float* dw, float* dbias, int kd, int kh, int kw,
                     cudaStream_t st) {
+  if (small_pointwise(x, dy, kd, kh, kw)) {
+    const int64_t nvox = voxels(x);
+    const int pairs = x->c * dy->c;
+    const int threads = (256 / pairs) * pairs >= pairs ? (256 / pairs) * pairs : pairs;
+    int64_t blocks = ceil_div(nvox, (int64_t)(threads / pairs) * 16);
+    if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
+    if (blocks < 1) blocks = 1;
+    B200_DISPATCH_DTYPE(x->dtype, T, (conv1x1_small_wgrad_kernel<T><<<(unsigned)blocks, threads, 2 * threads * sizeof(float), st>>>(
+                                         (const T*)x->data, x->ld, (const T*)dy->data, dy->ld, dw, dbias, x->c, dy->c, nvox)));
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+  }
   ConvGeom g{x->n, x->d, x->h, x->w, x->c, dy->c, kd, kh, kw, x->ld, dy->ld, 0};
   const int taps = kd * kh * kw;
   int tpc = taps <= kWgTaps ? taps : kh * kw;

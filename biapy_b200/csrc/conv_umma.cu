@@ -11,6 +11,8 @@
 #include "umma.cuh"
 
 #include <mutex>
+#include <cstdlib>
+#include <cstring>
 #include <unordered_map>
 #include <string>
 
@@ -235,6 +237,211 @@ conv_fprop_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   }
 }
 
+// ------------------------------------------------------------------------------------- fprop kernel, cp.async-fed
+// Same GEMM and epilogue as conv_fprop_umma_kernel, but the operands are brought in by four loader warps with
+// 16-byte cp.async (zero-fill for padding) straight into the swizzled K-major layout the UMMA descriptors expect.
+// Measured reason (profiles/README.md): a TMA box is fetched one innermost row at a time (~6 cycles per row,
+// independent of the row size), so the 32..64-byte channel rows of the C <= 32 layers ran at ~6 B/clk/SM; the LSU path
+// moves the same bytes with a handful of instructions per thread and lets one pipeline stage carry all kw taps.
+// Warp roles (288 threads): warp 0 = MMA issuer + TMEM owner, warps 1-4 = epilogue, warps 5-8 = loaders.
+struct FpropParams2 {
+  int n, d, h, w, cin, cout;
+  int kd, kh, kw;
+  int bd, bh, bw;
+  int tiles_d, tiles_h, tiles_w, tiles_n;
+  int num_tiles;
+  int ck, chunks;
+  int nt;
+  int tg;                               // taps per pipeline stage (kw or 1)
+  int stages;
+  uint32_t a_bytes, b_bytes, stage_bytes;   // per tap / per tap / per stage (tg taps)
+  uint32_t layout, sbo;
+  uint32_t idesc;
+  uint32_t tmem_cols;
+  int64_t xsw, xsh, xsd, xsn;           // input element strides
+  int64_t ysw, ysh, ysd, ysn;           // output element strides
+  int accumulate;
+};
+
+__device__ __forceinline__ uint32_t swz_chunk(uint32_t row, uint32_t j, int ck) {
+  // 16-byte chunk j of row `row` inside a K-major tile with ck*2-byte rows (Swizzle<1|2|3,4,3> of the byte offset)
+  return ck == 64 ? (j ^ (row & 7u)) : (ck == 32 ? (j ^ ((row >> 1) & 3u)) : (j ^ ((row >> 2) & 1u)));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(288, 1)
+conv_fprop_umma2_kernel(const T* __restrict__ x, const T* __restrict__ wp, const float* __restrict__ bias, T* __restrict__ y,
+                        const FpropParams2 p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t s_bar[2 * kMaxStages + 4];
+  __shared__ uint32_t s_tmem;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_full = smem_u32(&s_bar[0]);
+  const uint32_t bar_empty = smem_u32(&s_bar[kMaxStages]);
+  const uint32_t bar_tfull = smem_u32(&s_bar[2 * kMaxStages]);
+  const uint32_t bar_tempty = smem_u32(&s_bar[2 * kMaxStages + 2]);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(bar_full + 8 * s, 128);     // one asynchronous arrival per loader thread
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_tfull + 8 * b, 1);
+      mbar_init(bar_tempty + 8 * b, 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&s_tmem), p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+
+  const int taps = p.kd * p.kh * p.kw;
+  const int groups = taps / p.tg;                 // tap groups (tg divides kw)
+  const int num_kb = groups * p.chunks;
+  const int pd = p.kd / 2, ph = p.kh / 2, pw = p.kw / 2;
+
+  auto decode = [&](int tile, int& n, int& z0, int& y0, int& x0, int& n0) {
+    int t = tile;
+    n0 = (t % p.tiles_n) * p.nt; t /= p.tiles_n;
+    x0 = (t % p.tiles_w) * p.bw; t /= p.tiles_w;
+    y0 = (t % p.tiles_h) * p.bh; t /= p.tiles_h;
+    z0 = (t % p.tiles_d) * p.bd; t /= p.tiles_d;
+    n = t;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================================================================= MMA issuer
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem + buf * p.nt;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          fence_proxy_async();
+          tc_fence_after();
+          const uint32_t s_base = smem0 + stage * p.stage_bytes;
+          for (int t = 0; t < p.tg; ++t) {
+            const uint32_t a_base = s_base + t * (p.a_bytes + p.b_bytes);
+            const uint32_t b_base = a_base + p.a_bytes;
+            for (int k = 0; k < p.ck / 16; ++k) {
+              const uint64_t ad = make_smem_desc(a_base + k * 32, 16, p.sbo, p.layout);
+              const uint64_t bd = make_smem_desc(b_base + k * 32, 16, p.sbo, p.layout);
+              umma_f16(d_tmem, ad, bd, p.idesc, (kb | t | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(bar_empty + 8 * stage);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(bar_tfull + 8 * buf);
+      }
+    }
+  } else if (warp <= 4) {
+    // =================================================================== epilogue (TMEM lane quarter = warp % 4)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int lx = row % p.bw, ly = (row / p.bw) % p.bh, lz = row / (p.bw * p.bh);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      int n, z0, y0, x0, n0;
+      decode(tile, n, z0, y0, x0, n0);
+      mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
+      tc_fence_after();
+      const int gz = z0 + lz, gy = y0 + ly, gx = x0 + lx;
+      const bool valid = gz < p.d && gy < p.h && gx < p.w;
+      T* yrow = y + (int64_t)n * p.ysn + (int64_t)gz * p.ysd + (int64_t)gy * p.ysh + (int64_t)gx * p.ysw + n0;
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.nt);
+      for (int j0 = 0; j0 < p.nt; j0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + j0, r);
+        tmem_ld_wait();
+        if (valid && n0 + j0 < p.cout) {
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(r[j]) + (bias ? __ldg(bias + n0 + j0 + j) : 0.f);
+          if (p.accumulate) {
+            Pack<T, 8> o0 = *reinterpret_cast<const Pack<T, 8>*>(yrow + j0);
+            Pack<T, 8> o1 = *reinterpret_cast<const Pack<T, 8>*>(yrow + j0 + 8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              f[j] += to_f<T>(o0.v[j]);
+              f[8 + j] += to_f<T>(o1.v[j]);
+            }
+          }
+          Pack<T, 8> w0, w1;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            w0.v[j] = from_f<T>(f[j]);
+            w1.v[j] = from_f<T>(f[8 + j]);
+          }
+          *reinterpret_cast<Pack<T, 8>*>(yrow + j0) = w0;
+          *reinterpret_cast<Pack<T, 8>*>(yrow + j0 + 8) = w1;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_tempty + 8 * buf);
+    }
+  } else {
+    // =================================================================== loaders (128 threads, one A row each)
+    const int r = threadIdx.x - 160;
+    const int lx = r % p.bw, ly = (r / p.bw) % p.bh, lz = r / (p.bw * p.bh);
+    const int cpr = p.ck / 8;                       // 16-byte chunks per row
+    const int b_chunks = p.nt * cpr;                // 16-byte chunks of one weight tile
+    const int64_t wrow = (int64_t)taps * p.cin;     // packed weight row length (elements)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int n, z0, y0, x0, n0;
+      decode(tile, n, z0, y0, x0, n0);
+      const int gz = z0 + lz, gy = y0 + ly, gx = x0 + lx;
+      const T* xrow = x + (int64_t)n * p.xsn + (int64_t)gz * p.xsd + (int64_t)gy * p.xsh + (int64_t)gx * p.xsw;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int grp = kb / p.chunks, ch = kb - grp * p.chunks;
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        const uint32_t s_base = smem0 + stage * p.stage_bytes;
+        for (int t = 0; t < p.tg; ++t) {
+          const int tap = grp * p.tg + t;
+          const int dx = tap % p.kw, dy = (tap / p.kw) % p.kh, dz = tap / (p.kw * p.kh);
+          const int iz = gz + dz - pd, iy = gy + dy - ph, ix = gx + dx - pw;
+          const bool ok = iz >= 0 && iz < p.d && iy >= 0 && iy < p.h && ix >= 0 && ix < p.w;
+          const T* src = ok ? xrow + (int64_t)(dz - pd) * p.xsd + (int64_t)(dy - ph) * p.xsh + (int64_t)(dx - pw) * p.xsw + ch * p.ck
+                            : x;
+          const uint32_t a_base = s_base + t * (p.a_bytes + p.b_bytes);
+          const uint32_t arow = a_base + (uint32_t)r * (uint32_t)(p.ck * 2);
+          for (int j = 0; j < cpr; ++j) cp_async16(arow + (swz_chunk((uint32_t)r, (uint32_t)j, p.ck) << 4), src + j * 8, ok ? 16u : 0u);
+          // weight tile [nt][ck] of this tap / chunk
+          const uint32_t b_base = a_base + p.a_bytes;
+          for (int c = r; c < b_chunks; c += 128) {
+            const int brow = c / cpr, j = c - brow * cpr;
+            const bool bok = n0 + brow < p.cout;
+            const T* bsrc = bok ? wp + (int64_t)(n0 + brow) * wrow + (int64_t)tap * p.cin + ch * p.ck + j * 8 : wp;
+            cp_async16(b_base + (uint32_t)brow * (uint32_t)(p.ck * 2) + (swz_chunk((uint32_t)brow, (uint32_t)j, p.ck) << 4), bsrc,
+                       bok ? 16u : 0u);
+          }
+        }
+        cp_async_arrive_noinc(bar_full + 8 * stage);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem, p.tmem_cols);
+  }
+}
+
 static void pick_tile(int d, int h, int w, int* bd, int* bh, int* bw) {
   static const int cand[][3] = {{2, 8, 8}, {4, 4, 8}, {1, 8, 16}, {1, 16, 8}, {2, 4, 16}, {4, 8, 4}, {8, 4, 4}, {1, 4, 32},
                                 {2, 2, 32}, {1, 2, 64}, {1, 1, 128}, {2, 16, 4}, {1, 32, 4}, {4, 2, 16}, {8, 8, 2}, {16, 8, 1},
@@ -250,6 +457,15 @@ static void pick_tile(int d, int h, int w, int* bd, int* bh, int* bw) {
 }
 
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+static int loader_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("B200_CONV_LOADER");
+    mode = (e && strcmp(e, "tma") == 0) ? 0 : 1;       // default: cp.async loaders
+  }
+  return mode;
+}
 
 int conv_fprop_umma_v(const ActView& x, const void* w, const float* bias, const ActView& y, int kd, int kh, int kw,
                       int accumulate, cudaStream_t st);
@@ -276,8 +492,53 @@ int conv_fprop_umma(const b200_tensor* x, const void* w, const float* bias, cons
 }
 
 namespace sm100 {
+static int conv_fprop_umma2_v(const ActView& x, const void* w, const float* bias, const ActView& y, int kd, int kh, int kw,
+                              int accumulate, cudaStream_t st) {
+  FpropParams2 p{};
+  p.n = x.n; p.d = x.d; p.h = x.h; p.w = x.w; p.cin = x.c; p.cout = y.c;
+  p.kd = kd; p.kh = kh; p.kw = kw;
+  pick_tile(x.d, x.h, x.w, &p.bd, &p.bh, &p.bw);
+  p.ck = (x.c % 64 == 0) ? 64 : ((x.c % 32 == 0) ? 32 : 16);
+  p.chunks = x.c / p.ck;
+  p.nt = y.c <= 256 ? y.c : 128;
+  p.tiles_d = (int)ceil_div(x.d, p.bd); p.tiles_h = (int)ceil_div(x.h, p.bh); p.tiles_w = (int)ceil_div(x.w, p.bw);
+  p.tiles_n = (int)ceil_div(y.c, p.nt);
+  p.num_tiles = x.n * p.tiles_d * p.tiles_h * p.tiles_w * p.tiles_n;
+  p.a_bytes = 128u * p.ck * 2;
+  p.b_bytes = (((uint32_t)p.nt * p.ck * 2) + 1023u) & ~1023u;       // keep every operand tile 1 KB aligned
+  p.tg = (kw > 1 && (uint32_t)kw * (p.a_bytes + p.b_bytes) <= 24u * 1024u) ? kw : 1;
+  p.stage_bytes = (uint32_t)p.tg * (p.a_bytes + p.b_bytes);
+  int stages = (int)((200u * 1024u) / p.stage_bytes);
+  if (stages > 8) stages = 8;
+  B200_CHECK_ARG(stages >= 2, "conv_fprop(umma): tile does not fit in shared memory");
+  p.stages = stages;
+  p.layout = p.ck == 64 ? kSwizzle128 : (p.ck == 32 ? kSwizzle64 : kSwizzle32);
+  p.sbo = 8u * p.ck * 2;
+  p.idesc = make_idesc(x.dtype == B200_BF16, p.nt, 0, 0);
+  uint32_t cols = 32;
+  while (cols < 2u * p.nt) cols <<= 1;
+  p.tmem_cols = cols;
+  p.xsw = x.sw; p.xsh = x.sh; p.xsd = x.sd; p.xsn = x.sn;
+  p.ysw = y.sw; p.ysh = y.sh; p.ysd = y.sd; p.ysn = y.sn;
+  p.accumulate = accumulate;
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  if (x.dtype == B200_BF16) {
+    auto kern = conv_fprop_umma2_kernel<__nv_bfloat16>;
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 288, smem, st>>>((const __nv_bfloat16*)x.data, (const __nv_bfloat16*)w, bias, (__nv_bfloat16*)y.data, p);
+  } else {
+    auto kern = conv_fprop_umma2_kernel<__half>;
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 288, smem, st>>>((const __half*)x.data, (const __half*)w, bias, (__half*)y.data, p);
+  }
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
 int conv_fprop_umma_v(const ActView& xv, const void* w, const float* bias, const ActView& yv, int kd, int kh, int kw,
                       int accumulate, cudaStream_t st) {
+  if (loader_mode() == 1) return conv_fprop_umma2_v(xv, w, bias, yv, kd, kh, kw, accumulate, st);
   const ActView* x = &xv;
   const ActView* y = &yv;
   B200_CHECK_ARG(aligned16(w), "conv_fprop(umma): packed weights must be 16-byte aligned");
@@ -496,6 +757,171 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   }
 }
 
+// ---------------------------------------------------------------------------------------- wgrad, cp.async-fed
+// Same decomposition as conv_wgrad_umma_kernel; operands are written by four loader warps (thread r <-> voxel row r)
+// with cp.async into the 32-byte-swizzled chunk tiles (A) and the 32/64/128-byte-swizzled dY tile (B).
+// Warp roles (288 threads): warp 0 = MMA issuer + TMEM owner, warps 1-4 = epilogue (once, at the end), 5-8 = loaders.
+struct WgradParams2 {
+  WgradParams base;
+  int64_t xsw, xsh, xsd, xsn;
+  int64_t ysw, ysh, ysd, ysn;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(288, 1)
+conv_wgrad_umma2_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw, const WgradParams2 pp) {
+  const WgradParams& p = pp.base;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t s_bar[2 * kMaxAStages + 2 * kMaxBStages + 1];
+  __shared__ uint32_t s_tmem;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_afull = smem_u32(&s_bar[0]);
+  const uint32_t bar_aempty = smem_u32(&s_bar[kMaxAStages]);
+  const uint32_t bar_bfull = smem_u32(&s_bar[2 * kMaxAStages]);
+  const uint32_t bar_bempty = smem_u32(&s_bar[2 * kMaxAStages + kMaxBStages]);
+  const uint32_t bar_done = smem_u32(&s_bar[2 * kMaxAStages + 2 * kMaxBStages]);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(bar_afull + 8 * s, 128); mbar_init(bar_aempty + 8 * s, 1); }
+    for (int s = 0; s < p.b_stages; ++s) { mbar_init(bar_bfull + 8 * s, 128); mbar_init(bar_bempty + 8 * s, 1); }
+    mbar_init(bar_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&s_tmem), p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+
+  const int pd = p.kd / 2, ph = p.kh / 2, pw = p.kw / 2;
+  const int mb0 = blockIdx.y * p.g;
+  const int mb1 = min(mb0 + p.g, p.mb_total);
+
+  auto decode = [&](int vt, int& n, int& z0, int& y0, int& x0) {
+    int t = vt;
+    x0 = (t % p.tiles_w) * p.bw; t /= p.tiles_w;
+    y0 = (t % p.tiles_h) * p.bh; t /= p.tiles_h;
+    z0 = (t % p.tiles_d) * p.bd; t /= p.tiles_d;
+    n = t;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================================================================= MMA issuer
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      bool first = true;
+      for (int vt = blockIdx.x; vt < p.num_vtiles; vt += gridDim.x) {
+        mbar_wait(bar_bfull + 8 * bs, bph);
+        fence_proxy_async();
+        tc_fence_after();
+        const uint32_t b_base = smem0 + bs * p.b_bytes;
+        for (int mb = mb0; mb < mb1; ++mb) {
+          mbar_wait(bar_afull + 8 * as, aph);
+          fence_proxy_async();
+          tc_fence_after();
+          const uint32_t a_base = smem0 + p.a_off + as * kBlockBytes;
+          const uint32_t d_tmem = tmem + (uint32_t)((mb - mb0) * p.cout);
+#pragma unroll 1
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t ad = make_smem_desc(a_base + ks * 512u, kChunkBytes, 256u, kSwizzle32);
+            const uint64_t bd = make_smem_desc(b_base + ks * p.b_kstep, p.b_lbo, p.b_sbo, p.b_layout);
+            umma_f16(d_tmem, ad, bd, p.idesc, (first && ks == 0) ? 0u : 1u);
+          }
+          umma_commit(bar_aempty + 8 * as);
+          if (++as == p.a_stages) { as = 0; aph ^= 1; }
+        }
+        umma_commit(bar_bempty + 8 * bs);
+        if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+        first = false;
+      }
+      umma_commit(bar_done);
+    }
+  } else if (warp <= 4) {
+    // =================================================================== epilogue: TMEM -> fp32 atomics into dw
+    const int q4 = warp & 3;
+    const int row = q4 * 32 + lane;
+    const int taps = p.kd * p.kh * p.kw;
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+    for (int mb = mb0; mb < mb1; ++mb) {
+      const int q = mb * 8 + row / 16;
+      const bool valid = q < p.q_total;
+      const int tap = valid ? q / p.chunks16 : 0;
+      const int ci = valid ? (q - tap * p.chunks16) * 16 + (row & 15) : 0;
+      const uint32_t taddr = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)((mb - mb0) * p.cout);
+      for (int j0 = 0; j0 < p.cout; j0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + j0, r);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) atomicAdd(dw + ((int64_t)(j0 + j) * taps + tap) * p.cin + ci, __uint_as_float(r[j]));
+        }
+      }
+    }
+  } else {
+    // =================================================================== loaders
+    const int r = threadIdx.x - 160;
+    const int lx = r % p.bw, ly = (r / p.bw) % p.bh, lz = r / (p.bw * p.bh);
+    const uint32_t rp = p.b_box_c * 2;                 // dY row pitch inside one box tile
+    const int bcpr = (int)(p.b_box_c / 8);             // 16-byte chunks per dY box row
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
+    for (int vt = blockIdx.x; vt < p.num_vtiles; vt += gridDim.x) {
+      int n, z0, y0, x0;
+      decode(vt, n, z0, y0, x0);
+      const int gz = z0 + lz, gy = y0 + ly, gx = x0 + lx;
+      const bool inside = gz < p.d && gy < p.h && gx < p.w;
+      // ---- dY tile (B operand)
+      mbar_wait(bar_bempty + 8 * bs, bph ^ 1);
+      {
+        const uint32_t b_dst = smem0 + bs * p.b_bytes;
+        const T* yrow = inside ? dy + (int64_t)n * pp.ysn + (int64_t)gz * pp.ysd + (int64_t)gy * pp.ysh + (int64_t)gx * pp.ysw : dy;
+        for (uint32_t i = 0; i < p.b_boxes; ++i) {
+          const uint32_t rowaddr = b_dst + i * 128u * rp + (uint32_t)r * rp;
+          for (int j = 0; j < bcpr; ++j) {
+            const uint32_t sj = rp == 128 ? ((uint32_t)j ^ ((uint32_t)r & 7u))
+                                          : (rp == 64 ? ((uint32_t)j ^ (((uint32_t)r >> 1) & 3u)) : ((uint32_t)j ^ (((uint32_t)r >> 2) & 1u)));
+            cp_async16(rowaddr + (sj << 4), yrow + i * p.b_box_c + j * 8, inside ? 16u : 0u);
+          }
+        }
+        cp_async_arrive_noinc(bar_bfull + 8 * bs);
+        if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+      }
+      // ---- activation chunk tiles (A operand), 8 per M-block
+      const T* xrow = x + (int64_t)n * pp.xsn + (int64_t)gz * pp.xsd + (int64_t)gy * pp.xsh + (int64_t)gx * pp.xsw;
+      for (int mb = mb0; mb < mb1; ++mb) {
+        mbar_wait(bar_aempty + 8 * as, aph ^ 1);
+        const uint32_t a_dst = smem0 + p.a_off + as * kBlockBytes;
+        const int nq = min(8, p.q_total - mb * 8);
+        for (int j = 0; j < nq; ++j) {
+          const int q = mb * 8 + j;
+          const int tap = q / p.chunks16, cc = q - tap * p.chunks16;
+          const int dx = tap % p.kw, dyy = (tap / p.kw) % p.kh, dz = tap / (p.kw * p.kh);
+          const int iz = gz + dz - pd, iy = gy + dyy - ph, ix = gx + dx - pw;
+          const bool ok = iz >= 0 && iz < p.d && iy >= 0 && iy < p.h && ix >= 0 && ix < p.w;
+          const T* src = ok ? xrow + (int64_t)(dz - pd) * pp.xsd + (int64_t)(dyy - ph) * pp.xsh + (int64_t)(dx - pw) * pp.xsw + cc * 16 : x;
+          const uint32_t rowaddr = a_dst + (uint32_t)j * kChunkBytes + (uint32_t)r * 32u;
+          const uint32_t sw = ((uint32_t)r >> 2) & 1u;
+          cp_async16(rowaddr + ((0u ^ sw) << 4), src, ok ? 16u : 0u);
+          cp_async16(rowaddr + ((1u ^ sw) << 4), src + 8, ok ? 16u : 0u);
+        }
+        cp_async_arrive_noinc(bar_afull + 8 * as);
+        if (++as == p.a_stages) { as = 0; aph ^= 1; }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem, p.tmem_cols);
+  }
+}
+
 }  // namespace sm100
 
 bool conv_wgrad_umma_supported(const b200_tensor* x, const b200_tensor* dy, int kd, int kh, int kw) {
@@ -553,17 +979,30 @@ int conv_wgrad_umma_v(const ActView& xv, const ActView& dyv, float* dw, int kd, 
   while (cols < (uint32_t)(p.g * p.cout)) cols <<= 1;
   p.tmem_cols = cols;
 
-  CUtensorMap tx, tdy;
-  int rc = make_act_tmap(&tx, *x, 16, p.bw, p.bh, p.bd);
-  if (rc) return rc;
-  rc = make_act_tmap(&tdy, *dy, (int)p.b_box_c, p.bw, p.bh, p.bd);
-  if (rc) return rc;
-
   int vsplit = sm_count() / groups;
   if (vsplit < 1) vsplit = 1;
   if (vsplit > p.num_vtiles) vsplit = p.num_vtiles;
   dim3 grid((unsigned)vsplit, (unsigned)groups);
   const size_t smem = (size_t)p.a_off + (size_t)p.a_stages * kBlockBytes + 1024;
+  if (loader_mode() == 1) {
+    WgradParams2 pp{p, x->sw, x->sh, x->sd, x->sn, dy->sw, dy->sh, dy->sd, dy->sn};
+    if (x->dtype == B200_BF16) {
+      auto kern = conv_wgrad_umma2_kernel<__nv_bfloat16>;
+      B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<grid, 288, smem, st>>>((const __nv_bfloat16*)x->data, (const __nv_bfloat16*)dy->data, dw, pp);
+    } else {
+      auto kern = conv_wgrad_umma2_kernel<__half>;
+      B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<grid, 288, smem, st>>>((const __half*)x->data, (const __half*)dy->data, dw, pp);
+    }
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+  }
+  CUtensorMap tx, tdy;
+  int rc = make_act_tmap(&tx, *x, 16, p.bw, p.bh, p.bd);
+  if (rc) return rc;
+  rc = make_act_tmap(&tdy, *dy, (int)p.b_box_c, p.bw, p.bh, p.bd);
+  if (rc) return rc;
   if (x->dtype == B200_BF16) {
     auto kern = conv_wgrad_umma_kernel<__nv_bfloat16>;
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

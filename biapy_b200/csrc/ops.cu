@@ -3,6 +3,8 @@
 // Reference call sites are listed next to each entry point in include/biapy_b200.h.
 #include "common.cuh"
 
+#include <type_traits>
+
 namespace b200 {
 
 // View used inside kernels
@@ -69,14 +71,21 @@ __global__ void channel_sums_kernel(View<const T> x, double* __restrict__ sums, 
 #pragma unroll
     for (int i = 0; i < VEC; ++i) s[i] = s2[i] = 0.f;
     int cnt = 0;
-    for (int64_t v = v0 + row; v < v1; v += rows) {
+    float f2[VEC];
+    for (int64_t v = v0 + row; v < v1; v += 2 * rows) {
+      const bool two = v + rows < v1;
       load_vec<T, VEC>(base + v * x.ld, f);
+      if (two) load_vec<T, VEC>(base + (v + rows) * x.ld, f2);
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
         s[i] += f[i];
         s2[i] = fmaf(f[i], f[i], s2[i]);
+        if (two) {
+          s[i] += f2[i];
+          s2[i] = fmaf(f2[i], f2[i], s2[i]);
+        }
       }
-      if (++cnt == 32) {
+      if (++cnt == 16) {
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
           acc[i] += (double)s[i];
@@ -112,15 +121,14 @@ template <typename T>
 static int launch_channel_sums(const b200_tensor* x, double* sums, cudaStream_t st) {
   constexpr int V = VecOf<T>::n;
   View<const T> xv{(const T*)x->data, x->ld, x->c, voxels(x), (int64_t)x->d * x->h * x->w};
-  int64_t chunks = ceil_div(xv.spatial, 2048);
-  int64_t cap = ceil_div((int64_t)sm_count() * 8, x->n);
+  int64_t chunks = ceil_div(xv.spatial, 4096);
+  int64_t cap = ceil_div((int64_t)sm_count() * 6, x->n);
   if (chunks > cap) chunks = cap;
   if (chunks < 1) chunks = 1;
   dim3 grid((unsigned)chunks, x->n);
   if (vec_ok(x, V) && x->c / V <= 256) {
     int cvn = x->c / V;
     int rows = 256 / cvn;
-    if (rows > 32) rows = 32;
     int threads = ((rows * cvn + 31) / 32) * 32;
     size_t smem = sizeof(double) * rows * cvn * V * 2;
     channel_sums_kernel<T, V><<<grid, threads, smem, st>>>(xv, sums, cvn, rows);
@@ -227,17 +235,29 @@ __global__ void norm_act_bwd_reduce_kernel(View<const T> x, View<const T> dy, co
 #pragma unroll
     for (int i = 0; i < VEC; ++i) s[i] = s2[i] = 0.f;
     int cnt = 0;
-    for (int64_t v = v0 + row; v < v1; v += rows) {
+    float fx2[VEC], fd2[VEC];
+    for (int64_t v = v0 + row; v < v1; v += 2 * rows) {
+      const bool two = v + rows < v1;
       load_vec<T, VEC>(xb + v * x.ld, fx);
       load_vec<T, VEC>(db + v * dy.ld, fd);
+      if (two) {
+        load_vec<T, VEC>(xb + (v + rows) * x.ld, fx2);
+        load_vec<T, VEC>(db + (v + rows) * dy.ld, fd2);
+      }
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
         float xh = (fx[i] - mu[i]) * rs[i];
         float g = fd[i] * act_grad(act, fmaf(xh, ga[i], be[i]));
         s[i] += g;
         s2[i] = fmaf(g, xh, s2[i]);
+        if (two) {
+          float xh2 = (fx2[i] - mu[i]) * rs[i];
+          float g2 = fd2[i] * act_grad(act, fmaf(xh2, ga[i], be[i]));
+          s[i] += g2;
+          s2[i] = fmaf(g2, xh2, s2[i]);
+        }
       }
-      if (++cnt == 32) {
+      if (++cnt == 16) {
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
           acc[i] += (double)s[i];
@@ -264,8 +284,9 @@ __global__ void norm_act_bwd_reduce_kernel(View<const T> x, View<const T> dy, co
 }
 
 // tiny: per (n, g) coefficients + dgamma/dbeta
-__global__ void norm_bwd_finalize_kernel(const double* __restrict__ red, const float* __restrict__ rstd,
-                                         const float* __restrict__ gamma, int n, int c, int groups, int64_t spatial,
+__global__ void norm_bwd_finalize_kernel(const double* __restrict__ red, const float* __restrict__ mean,
+                                         const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                         const float* __restrict__ beta, int n, int c, int groups, int64_t spatial,
                                          int batch_stats, float* __restrict__ coef, float* __restrict__ dgamma,
                                          float* __restrict__ dbeta) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -281,13 +302,16 @@ __global__ void norm_bwd_finalize_kernel(const double* __restrict__ red, const f
         b += ga * red[((int64_t)nn * c + cc) * 2 + 1];
       }
     double m = (double)spatial * cpg * (n1 - n0);
-    float r = rstd[idx];
+    // with ypre = x*k0 + B and g = dy*act'(ypre):  dx = g*k0 - x*P - Q
+    float r = rstd[idx], mu = mean[idx];
+    float k1 = (float)(r * (a / m)), k2 = (float)(r * (b / m));
     for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) {
-      float ga = gamma ? gamma[cc] : 1.f;
-      float* o = coef + ((int64_t)ni * c + cc) * 3;
+      float ga = gamma ? gamma[cc] : 1.f, be = beta ? beta[cc] : 0.f;
+      float* o = coef + ((int64_t)ni * c + cc) * 4;
       o[0] = r * ga;
-      o[1] = (float)(r * (a / m));
-      o[2] = (float)(r * (b / m));
+      o[1] = be - mu * r * ga;
+      o[2] = r * k2;
+      o[3] = k1 - mu * r * k2;
     }
   }
   if (idx < c) {
@@ -301,35 +325,76 @@ __global__ void norm_bwd_finalize_kernel(const double* __restrict__ red, const f
   }
 }
 
-template <typename T, int VEC>
-__global__ void norm_act_bwd_apply_kernel(View<const T> x, View<const T> dy, View<T> dx, const float* __restrict__ mean,
-                                          const float* __restrict__ rstd, int groups, const float* __restrict__ gamma,
-                                          const float* __restrict__ beta, int act, const float* __restrict__ coef,
+// element-wise fallback (any channel count): coefficients re-read per element
+template <typename T>
+__global__ void norm_act_bwd_apply_kernel(View<const T> x, View<const T> dy, View<T> dx, int act, const float* __restrict__ coef,
                                           int accumulate) {
-  const int cvn = x.c / VEC;
-  const int cpg = x.c / groups;
-  const int64_t total = x.vox * cvn;
+  const int64_t total = x.vox * x.c;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t vox = i / cvn;
-    int cv = (int)(i % cvn);
+    int64_t vox = i / x.c;
+    int c = (int)(i % x.c);
     int n = (int)(vox / x.spatial);
-    float fx[VEC], fd[VEC], fo[VEC];
-    load_vec<T, VEC>(x.p + vox * x.ld + cv * VEC, fx);
-    load_vec<T, VEC>(dy.p + vox * dy.ld + cv * VEC, fd);
-    if (accumulate) load_vec<T, VEC>(dx.p + vox * dx.ld + cv * VEC, fo);
+    const float* cf = coef + ((int64_t)n * x.c + c) * 4;
+    float xv = to_f<T>(x.p[vox * x.ld + c]);
+    float g = to_f<T>(dy.p[vox * dy.ld + c]) * act_grad(act, fmaf(xv, cf[0], cf[1]));
+    float r = g * cf[0] - xv * cf[2] - cf[3];
+    T* o = dx.p + vox * dx.ld + c;
+    *o = from_f<T>(accumulate ? to_f<T>(*o) + r : r);
+  }
+}
+
+// vectorised: grid = (chunks, N), block = rows x cvn threads; every thread keeps the coefficients of its 8 (4) channels
+// in registers, so the loop body is 2-3 16-byte loads, the activation derivative and one 16-byte store
+template <typename T, int VEC>
+__global__ void norm_act_bwd_apply_rows_kernel(View<const T> x, View<const T> dy, View<T> dx, int act,
+                                               const float* __restrict__ coef, int accumulate, int cvn, int rows) {
+  const int n = blockIdx.y;
+  const int cv = threadIdx.x % cvn, row = threadIdx.x / cvn;
+  if (row >= rows) return;
+  float k0[VEC], kb[VEC], kp[VEC], kq[VEC];
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-      int c = cv * VEC + k;
-      int g = c / cpg;
-      float mu = mean[(int64_t)n * groups + g], rs = rstd[(int64_t)n * groups + g];
-      float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
-      float xh = (fx[k] - mu) * rs;
-      float gg = fd[k] * act_grad(act, fmaf(xh, ga, be));
-      const float* cf = coef + ((int64_t)n * x.c + c) * 3;
-      float r = gg * cf[0] - cf[1] - xh * cf[2];
-      fo[k] = accumulate ? fo[k] + r : r;
+  for (int i = 0; i < VEC; ++i) {
+    const float* cf = coef + ((int64_t)n * x.c + cv * VEC + i) * 4;
+    k0[i] = cf[0]; kb[i] = cf[1]; kp[i] = cf[2]; kq[i] = cf[3];
+  }
+  const T* xb = x.p + (int64_t)n * x.spatial * x.ld + cv * VEC;
+  const T* db = dy.p + (int64_t)n * x.spatial * dy.ld + cv * VEC;
+  T* ob = dx.p + (int64_t)n * x.spatial * dx.ld + cv * VEC;
+  for (int64_t v = (int64_t)blockIdx.x * rows + row; v < x.spatial; v += (int64_t)gridDim.x * rows) {
+    float fx[VEC], fd[VEC], fo[VEC];
+    load_vec<T, VEC>(xb + v * x.ld, fx);
+    load_vec<T, VEC>(db + v * dy.ld, fd);
+    if (accumulate) load_vec<T, VEC>(ob + v * dx.ld, fo);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      float g = fd[i] * act_grad(act, fmaf(fx[i], k0[i], kb[i]));
+      float r = g * k0[i] - fx[i] * kp[i] - kq[i];
+      fo[i] = accumulate ? fo[i] + r : r;
     }
-    store_vec<T, VEC>(dx.p + vox * dx.ld + cv * VEC, fo);
+    store_vec<T, VEC>(ob + v * dx.ld, fo);
+  }
+}
+
+template <typename T, int VEC>
+__global__ void scale_shift_act_rows_kernel(View<const T> x, View<T> y, const float* __restrict__ scale,
+                                            const float* __restrict__ shift, int act, int cvn, int rows) {
+  const int n = blockIdx.y;
+  const int cv = threadIdx.x % cvn, row = threadIdx.x / cvn;
+  if (row >= rows) return;
+  float sc[VEC], sh[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    sc[i] = scale[(int64_t)n * x.c + cv * VEC + i];
+    sh[i] = shift[(int64_t)n * x.c + cv * VEC + i];
+  }
+  const T* xb = x.p + (int64_t)n * x.spatial * x.ld + cv * VEC;
+  T* yb = y.p + (int64_t)n * x.spatial * y.ld + cv * VEC;
+  for (int64_t v = (int64_t)blockIdx.x * rows + row; v < x.spatial; v += (int64_t)gridDim.x * rows) {
+    float f[VEC];
+    load_vec<T, VEC>(xb + v * x.ld, f);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) f[i] = act_fwd(act, fmaf(f[i], sc[i], sh[i]));
+    store_vec<T, VEC>(yb + v * y.ld, f);
   }
 }
 
@@ -416,6 +481,85 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ x, int64_t ldx, const T
     int64_t iv = (((int64_t)n * g.d + zz) * g.h + yy) * g.w + xx;
     T* o = dx + iv * lddx + c;
     *o = from_f<T>(accumulate ? to_f<T>(*o) + r : r);
+  }
+}
+
+// Vectorised pooling: one thread per pooled voxel and channel vector; every input element is read once and every
+// gradient element written once (the scalar kernels above stay as the fallback for odd shapes / channel counts).
+template <typename T, int VEC>
+__global__ void maxpool_fwd_vec_kernel(const T* __restrict__ x, int64_t ldx, T* __restrict__ y, int64_t ldy, PoolGeom g) {
+  const int cvn = g.c / VEC;
+  const int64_t total = (int64_t)g.n * g.od * g.oh * g.ow * cvn;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = i;
+    int cv = (int)(t % cvn); t /= cvn;
+    int ox = (int)(t % g.ow); t /= g.ow;
+    int oy = (int)(t % g.oh); t /= g.oh;
+    int oz = (int)(t % g.od); t /= g.od;
+    int n = (int)t;
+    float m[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) m[k] = -INFINITY;
+    for (int a = 0; a < g.pd; ++a)
+      for (int b = 0; b < g.ph; ++b)
+        for (int e = 0; e < g.pw; ++e) {
+          int64_t vox = (((int64_t)n * g.d + oz * g.pd + a) * g.h + oy * g.ph + b) * g.w + ox * g.pw + e;
+          float f[VEC];
+          load_vec<T, VEC>(x + vox * ldx + cv * VEC, f);
+#pragma unroll
+          for (int k = 0; k < VEC; ++k)
+            if (f[k] > m[k] || f[k] != f[k]) m[k] = f[k];
+        }
+    int64_t ov = (((int64_t)n * g.od + oz) * g.oh + oy) * g.ow + ox;
+    store_vec<T, VEC>(y + ov * ldy + cv * VEC, m);
+  }
+}
+
+template <typename T, int VEC, int MAXW>
+__global__ void maxpool_bwd_vec_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy, int64_t lddy,
+                                       T* __restrict__ dx, int64_t lddx, PoolGeom g, int accumulate) {
+  const int cvn = g.c / VEC;
+  const int64_t total = (int64_t)g.n * g.od * g.oh * g.ow * cvn;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = i;
+    int cv = (int)(t % cvn); t /= cvn;
+    int ox = (int)(t % g.ow); t /= g.ow;
+    int oy = (int)(t % g.oh); t /= g.oh;
+    int oz = (int)(t % g.od); t /= g.od;
+    int n = (int)t;
+    float m[VEC];
+    int arg[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) { m[k] = -INFINITY; arg[k] = 0; }
+    int w = 0;
+    for (int a = 0; a < g.pd; ++a)
+      for (int b = 0; b < g.ph; ++b)
+        for (int e = 0; e < g.pw; ++e, ++w) {
+          int64_t vox = (((int64_t)n * g.d + oz * g.pd + a) * g.h + oy * g.ph + b) * g.w + ox * g.pw + e;
+          float f[VEC];
+          load_vec<T, VEC>(x + vox * ldx + cv * VEC, f);
+#pragma unroll
+          for (int k = 0; k < VEC; ++k)
+            if (f[k] > m[k] || f[k] != f[k]) { m[k] = f[k]; arg[k] = w; }
+        }
+    int64_t ov = (((int64_t)n * g.od + oz) * g.oh + oy) * g.ow + ox;
+    float gy[VEC];
+    load_vec<T, VEC>(dy + ov * lddy + cv * VEC, gy);
+    w = 0;
+    for (int a = 0; a < g.pd; ++a)
+      for (int b = 0; b < g.ph; ++b)
+        for (int e = 0; e < g.pw; ++e, ++w) {
+          int64_t vox = (((int64_t)n * g.d + oz * g.pd + a) * g.h + oy * g.ph + b) * g.w + ox * g.pw + e;
+          T* o = dx + vox * lddx + cv * VEC;
+          float r[VEC];
+          if (accumulate) load_vec<T, VEC>(o, r);
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) {
+            float v = (arg[k] == w) ? gy[k] : 0.f;
+            r[k] = accumulate ? r[k] + v : v;
+          }
+          store_vec<T, VEC>(o, r);
+        }
   }
 }
 
@@ -611,6 +755,14 @@ __global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, double* __r
 
 using namespace b200;
 
+static inline unsigned rows_grid(int64_t spatial, int rows, int n) {
+  int64_t b = ceil_div(spatial, (int64_t)rows * 4);
+  int64_t cap = ceil_div((int64_t)sm_count() * 8, n);
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
 // ================================================================================================ C ABI
 B200_EXPORT int b200_channel_sums(const b200_tensor* x, double* sums, void* stream) {
   B200_CHECK_ARG(check_tensor(x, "channel_sums.x") && sums, "%s", b200_last_error());
@@ -641,7 +793,14 @@ B200_EXPORT int b200_scale_shift_act(const b200_tensor* x, const float* scale, c
     constexpr int V = VecOf<TI>::n < VecOf<TO>::n ? VecOf<TI>::n : VecOf<TO>::n;                                  \
     View<const TI> xv{(const TI*)x->data, x->ld, x->c, voxels(x), (int64_t)x->d * x->h * x->w};                    \
     View<TO> yv{(TO*)y->data, y->ld, y->c, voxels(y), (int64_t)y->d * y->h * y->w};                                \
-    if (vec_ok(x, V) && vec_ok(y, V) && sizeof(TI) == sizeof(TO))                                                 \
+    if (scale && std::is_same<TI, TO>::value && vec_ok(x, VecOf<TI>::n) && vec_ok(y, VecOf<TI>::n) &&             \
+        x->c / VecOf<TI>::n <= 256) {                                                                             \
+      constexpr int VV = VecOf<TI>::n;                                                                            \
+      int cvn = x->c / VV, rows = 256 / cvn;                                                                      \
+      dim3 grid(rows_grid(xv.spatial, rows, x->n), x->n);                                                         \
+      View<TI> yv2{(TI*)y->data, y->ld, y->c, voxels(y), (int64_t)y->d * y->h * y->w};                              \
+      scale_shift_act_rows_kernel<TI, VV><<<grid, 256, 0, st>>>(xv, yv2, scale, shift, act, cvn, rows);           \
+    } else if (vec_ok(x, V) && vec_ok(y, V) && sizeof(TI) == sizeof(TO))                                          \
       scale_shift_act_kernel<TI, TO, V><<<grid_for(xv.vox * (x->c / V), 256), 256, 0, st>>>(xv, yv, scale, shift, act); \
     else                                                                                                         \
       scale_shift_act_kernel<TI, TO, 1><<<grid_for(xv.vox * x->c, 256), 256, 0, st>>>(xv, yv, scale, shift, act);  \
@@ -665,8 +824,8 @@ B200_EXPORT int b200_norm_act_bwd_reduce(const b200_tensor* x, const b200_tensor
   B200_CHECK_ARG(groups > 0 && x->c % groups == 0, "bwd_reduce: bad groups");
   cudaStream_t st = (cudaStream_t)stream;
   int64_t spatial = (int64_t)x->d * x->h * x->w;
-  int64_t chunks = ceil_div(spatial, 2048);
-  int64_t cap = ceil_div((int64_t)sm_count() * 8, x->n);
+  int64_t chunks = ceil_div(spatial, 4096);
+  int64_t cap = ceil_div((int64_t)sm_count() * 6, x->n);
   if (chunks > cap) chunks = cap;
   if (chunks < 1) chunks = 1;
   dim3 grid((unsigned)chunks, x->n);
@@ -676,7 +835,6 @@ B200_EXPORT int b200_norm_act_bwd_reduce(const b200_tensor* x, const b200_tensor
     View<const T> dv{(const T*)dy->data, dy->ld, dy->c, voxels(dy), spatial};
     if (vec_ok(x, V) && vec_ok(dy, V) && x->c / V <= 256) {
       int cvn = x->c / V, rows = 256 / cvn;
-      if (rows > 32) rows = 32;
       int threads = ((rows * cvn + 31) / 32) * 32;
       norm_act_bwd_reduce_kernel<T, V><<<grid, threads, sizeof(double) * rows * cvn * V * 2, st>>>(
           xv, dv, mean, rstd, groups, gamma, beta, act, red, cvn, rows);
@@ -694,21 +852,20 @@ B200_EXPORT int b200_norm_act_bwd_reduce(const b200_tensor* x, const b200_tensor
   return B200_OK;
 }
 
-B200_EXPORT int b200_norm_bwd_finalize(const double* red, const float* rstd, const float* gamma, int32_t n, int32_t c,
-                                       int32_t groups, int64_t spatial, int32_t batch_stats, float* coef, float* dgamma,
-                                       float* dbeta, void* stream) {
-  B200_CHECK_ARG(red && rstd && coef, "norm_bwd_finalize: null pointer");
+B200_EXPORT int b200_norm_bwd_finalize(const double* red, const float* mean, const float* rstd, const float* gamma,
+                                       const float* beta, int32_t n, int32_t c, int32_t groups, int64_t spatial,
+                                       int32_t batch_stats, float* coef, float* dgamma, float* dbeta, void* stream) {
+  B200_CHECK_ARG(red && mean && rstd && coef, "norm_bwd_finalize: null pointer");
   int total = n * groups > c ? n * groups : c;
-  norm_bwd_finalize_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(red, rstd, gamma, n, c, groups, spatial,
-                                                                                 batch_stats, coef, dgamma, dbeta);
+  norm_bwd_finalize_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(red, mean, rstd, gamma, beta, n, c, groups,
+                                                                                 spatial, batch_stats, coef, dgamma, dbeta);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
 
-B200_EXPORT int b200_norm_act_bwd_apply(const b200_tensor* x, const b200_tensor* dy, const float* mean, const float* rstd,
-                                        int32_t groups, const float* gamma, const float* beta, int32_t act,
-                                        const float* coef, const b200_tensor* dx, int32_t accumulate, void* stream) {
-  B200_CHECK_ARG(check_tensor(x, "bwd_apply.x") && check_tensor(dy, "bwd_apply.dy") && check_tensor(dx, "bwd_apply.dx"),
+B200_EXPORT int b200_norm_act_bwd_apply(const b200_tensor* x, const b200_tensor* dy, int32_t act, const float* coef,
+                                        const b200_tensor* dx, int32_t accumulate, void* stream) {
+  B200_CHECK_ARG(check_tensor(x, "bwd_apply.x") && check_tensor(dy, "bwd_apply.dy") && check_tensor(dx, "bwd_apply.dx") && coef,
                  "%s", b200_last_error());
   B200_CHECK_ARG(same_spatial(x, dy) && same_spatial(x, dx) && x->c == dy->c && x->c == dx->c &&
                      x->dtype == dy->dtype && x->dtype == dx->dtype, "bwd_apply: shape/dtype mismatch");
@@ -718,12 +875,13 @@ B200_EXPORT int b200_norm_act_bwd_apply(const b200_tensor* x, const b200_tensor*
     View<const T> xv = view<const T>(x);
     View<const T> dv = view<const T>(dy);
     View<T> ov = view<T>(dx);
-    if (vec_ok(x, V) && vec_ok(dy, V) && vec_ok(dx, V))
-      norm_act_bwd_apply_kernel<T, V><<<grid_for(xv.vox * (x->c / V), 256), 256, 0, st>>>(xv, dv, ov, mean, rstd, groups,
-                                                                                         gamma, beta, act, coef, accumulate);
-    else
-      norm_act_bwd_apply_kernel<T, 1><<<grid_for(xv.vox * x->c, 256), 256, 0, st>>>(xv, dv, ov, mean, rstd, groups, gamma,
-                                                                                   beta, act, coef, accumulate);
+    if (vec_ok(x, V) && vec_ok(dy, V) && vec_ok(dx, V) && x->c / V <= 256) {
+      int cvn = x->c / V, rows = 256 / cvn;
+      dim3 grid(rows_grid(xv.spatial, rows, x->n), x->n);
+      norm_act_bwd_apply_rows_kernel<T, V><<<grid, 256, 0, st>>>(xv, dv, ov, act, coef, accumulate, cvn, rows);
+    } else {
+      norm_act_bwd_apply_kernel<T><<<grid_for(xv.vox * x->c, 256), 256, 0, st>>>(xv, dv, ov, act, coef, accumulate);
+    }
   });
   B200_LAUNCH_CHECK();
   return B200_OK;
@@ -766,8 +924,14 @@ B200_EXPORT int b200_maxpool_fwd(const b200_tensor* x, const b200_tensor* y, int
   int st = pool_geom(x, y, pd, ph, pw, &g);
   if (st) return st;
   int64_t total = voxels(y) * y->c;
-  B200_DISPATCH_DTYPE(x->dtype, T, (maxpool_fwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-                                       (const T*)x->data, x->ld, (T*)y->data, y->ld, g)));
+  B200_DISPATCH_DTYPE(x->dtype, T, {
+    constexpr int V = VecOf<T>::n;
+    if (vec_ok(x, V) && vec_ok(y, V))
+      maxpool_fwd_vec_kernel<T, V><<<grid_for(total / V, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x->data, x->ld, (T*)y->data,
+                                                                                             y->ld, g);
+    else
+      maxpool_fwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x->data, x->ld, (T*)y->data, y->ld, g);
+  });
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
@@ -783,9 +947,16 @@ B200_EXPORT int b200_maxpool_bwd(const b200_tensor* x, const b200_tensor* y, con
   if (st) return st;
   (void)y;
   int64_t total = voxels(x) * x->c;
-  B200_DISPATCH_DTYPE(x->dtype, T, (maxpool_bwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-                                       (const T*)x->data, x->ld, (const T*)dy->data, dy->ld, (T*)dx->data, dx->ld, g,
-                                       accumulate)));
+  const bool divisible = x->d % pd == 0 && x->h % ph == 0 && x->w % pw == 0;
+  B200_DISPATCH_DTYPE(x->dtype, T, {
+    constexpr int V = VecOf<T>::n;
+    if (divisible && vec_ok(x, V) && vec_ok(dy, V) && vec_ok(dx, V))
+      maxpool_bwd_vec_kernel<T, V, 8><<<grid_for(voxels(dy) * (x->c / V), 256), 256, 0, (cudaStream_t)stream>>>(
+          (const T*)x->data, x->ld, (const T*)dy->data, dy->ld, (T*)dx->data, dx->ld, g, accumulate);
+    else
+      maxpool_bwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x->data, x->ld, (const T*)dy->data,
+                                                                                  dy->ld, (T*)dx->data, dx->ld, g, accumulate);
+  });
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

@@ -210,12 +210,12 @@ def norm_act_bwd(x, dy, st: NormStats, gamma, beta, act: str, dx, dgamma, dbeta,
     red = torch.zeros(n * c * 2, dtype=torch.float64, device=x.device)
     _launch("b200_norm_act_bwd_reduce", _ref(x), _ref(dy), _ptr(st.mean), _ptr(st.rstd), st.groups, _ptr(gamma), _ptr(beta),
             ACT[act], _ptr(red), stream_ptr())
-    coef = torch.empty(n * c * 3, dtype=torch.float32, device=x.device)
-    _launch("b200_norm_bwd_finalize", _ptr(red), _ptr(st.rstd), _ptr(gamma), n, c, st.groups, d * h * w,
-            1 if st.batch_stats else 0, _ptr(coef), _ptr(dgamma), _ptr(dbeta), stream_ptr())
+    coef = torch.empty(n * c * 4, dtype=torch.float32, device=x.device)
+    _launch("b200_norm_bwd_finalize", _ptr(red), _ptr(st.mean), _ptr(st.rstd), _ptr(gamma), _ptr(beta), n, c, st.groups,
+            d * h * w, 1 if st.batch_stats else 0, _ptr(coef), _ptr(dgamma), _ptr(dbeta), stream_ptr())
     if dx is not None:
-        _launch("b200_norm_act_bwd_apply", _ref(x), _ref(dy), _ptr(st.mean), _ptr(st.rstd), st.groups, _ptr(gamma), _ptr(beta),
-                ACT[act], _ptr(coef), _ref(dx), 1 if accumulate else 0, stream_ptr())
+        _launch("b200_norm_act_bwd_apply", _ref(x), _ref(dy), ACT[act], _ptr(coef), _ref(dx), 1 if accumulate else 0,
+                stream_ptr())
 
 
 def act_bwd(x, dy, act: str, dx, accumulate=False):

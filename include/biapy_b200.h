@@ -168,14 +168,14 @@ int b200_scale_shift_act(const b200_tensor* x, const float* scale, const float* 
 int b200_norm_act_bwd_reduce(const b200_tensor* x, const b200_tensor* dy, const float* mean, const float* rstd,
                              int32_t groups, const float* gamma, const float* beta, int32_t act,
                              double* red, void* stream);
-/* tiny: coef[N][C][3] = (rstd*gamma, rstd*a_g, rstd*b_g); dgamma[C] += sum_n S2, dbeta[C] += sum_n S1         */
-int b200_norm_bwd_finalize(const double* red, const float* rstd, const float* gamma, int32_t n, int32_t c,
-                           int32_t groups, int64_t spatial, int32_t batch_stats,
+/* tiny: coef[N][C][4] = (k0, B, P, Q) such that, with ypre = x*k0 + B and g = dy*act'(ypre), dx = g*k0 - x*P - Q;
+ * dgamma[C] += sum_n S2, dbeta[C] += sum_n S1                                                                  */
+int b200_norm_bwd_finalize(const double* red, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                           int32_t n, int32_t c, int32_t groups, int64_t spatial, int32_t batch_stats,
                            float* coef, float* dgamma, float* dbeta, void* stream);
-/* pass 2: dx (+)= g*coef0 - coef1 - xhat*coef2                                                                 */
-int b200_norm_act_bwd_apply(const b200_tensor* x, const b200_tensor* dy, const float* mean, const float* rstd,
-                            int32_t groups, const float* gamma, const float* beta, int32_t act,
-                            const float* coef, const b200_tensor* dx, int32_t accumulate, void* stream);
+/* pass 2: dx (+)= g*k0 - x*P - Q                                                                               */
+int b200_norm_act_bwd_apply(const b200_tensor* x, const b200_tensor* dy, int32_t act, const float* coef,
+                            const b200_tensor* dx, int32_t accumulate, void* stream);
 /* activation only (norm == 'none'): dx (+)= dy * act'(x) */
 int b200_act_bwd(const b200_tensor* x, const b200_tensor* dy, int32_t act, const b200_tensor* dx,
                  int32_t accumulate, void* stream);
