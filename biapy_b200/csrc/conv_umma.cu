@@ -142,16 +142,20 @@ conv_fprop_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         int n, z0, y0, x0, n0;
         decode(tile, n, z0, y0, x0, n0);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          const int tap = kb / p.chunks, ch = kb - tap * p.chunks;
-          const int dx = tap % p.kw, dy = (tap / p.kw) % p.kh, dz = tap / (p.kw * p.kh);
-          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-          const uint32_t a_dst = smem0 + stage * p.stage_bytes;
-          mbar_expect_tx(bar_full + 8 * stage, p.a_bytes + p.b_bytes);
-          tma_load_5d(a_dst, &tmap_x, bar_full + 8 * stage, ch * p.ck, x0 + dx - pw, y0 + dy - ph, z0 + dz - pd, n);
-          tma_load_2d(a_dst + p.a_bytes, &tmap_w, bar_full + 8 * stage, tap * p.cin + ch * p.ck, n0);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
-        }
+        // nested tap loops: the single producer lane must not spend its issue slots on integer division
+        int kcol = 0;
+        for (int dz = 0; dz < p.kd; ++dz)
+          for (int dy = 0; dy < p.kh; ++dy)
+            for (int dx = 0; dx < p.kw; ++dx)
+              for (int ch = 0; ch < p.chunks; ++ch, kcol += p.ck) {
+                mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                const uint32_t a_dst = smem0 + stage * p.stage_bytes;
+                const uint32_t fb = bar_full + 8 * stage;
+                mbar_expect_tx(fb, p.a_bytes + p.b_bytes);
+                tma_load_5d(a_dst, &tmap_x, fb, ch * p.ck, x0 + dx - pw, y0 + dy - ph, z0 + dz - pd, n);
+                tma_load_2d(a_dst + p.a_bytes, &tmap_w, fb, kcol, n0);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+              }
       }
     }
   } else if (warp == 1) {
@@ -394,7 +398,8 @@ conv_fprop_umma2_kernel(const T* __restrict__ x, const T* __restrict__ wp, const
     // =================================================================== loaders (128 threads, one A row each)
     const int r = threadIdx.x - 160;
     const int lx = r % p.bw, ly = (r / p.bw) % p.bh, lz = r / (p.bw * p.bh);
-    const int cpr = p.ck / 8;                       // 16-byte chunks per row
+    const int cpr = p.ck / 8;                       // 16-byte chunks per row (2, 4 or 8)
+    const int cpr_shift = p.ck == 16 ? 1 : (p.ck == 32 ? 2 : 3);
     const int b_chunks = p.nt * cpr;                // 16-byte chunks of one weight tile
     const int64_t wrow = (int64_t)taps * p.cin;     // packed weight row length (elements)
     int stage = 0;
@@ -404,32 +409,48 @@ conv_fprop_umma2_kernel(const T* __restrict__ x, const T* __restrict__ wp, const
       decode(tile, n, z0, y0, x0, n0);
       const int gz = z0 + lz, gy = y0 + ly, gx = x0 + lx;
       const T* xrow = x + (int64_t)n * p.xsn + (int64_t)gz * p.xsd + (int64_t)gy * p.xsh + (int64_t)gx * p.xsw;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int grp = kb / p.chunks, ch = kb - grp * p.chunks;
-        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-        const uint32_t s_base = smem0 + stage * p.stage_bytes;
-        for (int t = 0; t < p.tg; ++t) {
-          const int tap = grp * p.tg + t;
-          const int dx = tap % p.kw, dy = (tap / p.kw) % p.kh, dz = tap / (p.kw * p.kh);
-          const int iz = gz + dz - pd, iy = gy + dy - ph, ix = gx + dx - pw;
-          const bool ok = iz >= 0 && iz < p.d && iy >= 0 && iy < p.h && ix >= 0 && ix < p.w;
-          const T* src = ok ? xrow + (int64_t)(dz - pd) * p.xsd + (int64_t)(dy - ph) * p.xsh + (int64_t)(dx - pw) * p.xsw + ch * p.ck
-                            : x;
-          const uint32_t a_base = s_base + t * (p.a_bytes + p.b_bytes);
-          const uint32_t arow = a_base + (uint32_t)r * (uint32_t)(p.ck * 2);
-          for (int j = 0; j < cpr; ++j) cp_async16(arow + (swz_chunk((uint32_t)r, (uint32_t)j, p.ck) << 4), src + j * 8, ok ? 16u : 0u);
-          // weight tile [nt][ck] of this tap / chunk
-          const uint32_t b_base = a_base + p.a_bytes;
-          for (int c = r; c < b_chunks; c += 128) {
-            const int brow = c / cpr, j = c - brow * cpr;
-            const bool bok = n0 + brow < p.cout;
-            const T* bsrc = bok ? wp + (int64_t)(n0 + brow) * wrow + (int64_t)tap * p.cin + ch * p.ck + j * 8 : wp;
-            cp_async16(b_base + (uint32_t)brow * (uint32_t)(p.ck * 2) + (swz_chunk((uint32_t)brow, (uint32_t)j, p.ck) << 4), bsrc,
-                       bok ? 16u : 0u);
-          }
+      const uint32_t row_off = (uint32_t)r * (uint32_t)(p.ck * 2);
+      // stage = one (dz, dy) pair x `tg` consecutive dx taps x one channel chunk
+      for (int dz = 0; dz < p.kd; ++dz) {
+        const int iz = gz + dz - pd;
+        const bool okz = iz >= 0 && iz < p.d;
+        for (int dy = 0; dy < p.kh; ++dy) {
+          const int iy = gy + dy - ph;
+          const bool okzy = okz && iy >= 0 && iy < p.h;
+          const T* line = xrow + (int64_t)(dz - pd) * p.xsd + (int64_t)(dy - ph) * p.xsh;
+          const int tap0 = (dz * p.kh + dy) * p.kw;
+          for (int dx0 = 0; dx0 < p.kw; dx0 += p.tg)
+            for (int ch = 0; ch < p.chunks; ++ch) {
+              mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+              uint32_t a_base = smem0 + stage * p.stage_bytes;
+              for (int t = 0; t < p.tg; ++t, a_base += p.a_bytes + p.b_bytes) {
+                const int dx = dx0 + t;
+                const int ix = gx + dx - pw;
+                const bool ok = okzy && ix >= 0 && ix < p.w;
+                const T* src = ok ? line + (int64_t)(dx - pw) * p.xsw + ch * p.ck : x;
+                const uint32_t arow = a_base + row_off;
+                const uint32_t nb = ok ? 16u : 0u;
+                if (p.ck == 16) {
+                  const uint32_t sw = ((uint32_t)r >> 2) & 1u;
+                  cp_async16(arow + (sw << 4), src, nb);
+                  cp_async16(arow + ((sw ^ 1u) << 4), src + 8, nb);
+                } else {
+                  for (int j = 0; j < cpr; ++j) cp_async16(arow + (swz_chunk((uint32_t)r, (uint32_t)j, p.ck) << 4), src + j * 8, nb);
+                }
+                // weight tile [nt][ck] of this tap / chunk: 16-byte chunk c -> (row c / cpr, chunk c % cpr)
+                const uint32_t b_base = a_base + p.a_bytes;
+                const T* wt = wp + (int64_t)(tap0 + dx) * p.cin + ch * p.ck;
+                for (int c = r; c < b_chunks; c += 128) {
+                  const int brow = c >> cpr_shift, j = c & (cpr - 1);
+                  const bool bok = n0 + brow < p.cout;
+                  cp_async16(b_base + (uint32_t)brow * (uint32_t)(p.ck * 2) + (swz_chunk((uint32_t)brow, (uint32_t)j, p.ck) << 4),
+                             bok ? wt + (int64_t)(n0 + brow) * wrow + j * 8 : wp, bok ? 16u : 0u);
+                }
+              }
+              cp_async_arrive_noinc(bar_full + 8 * stage);
+              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
         }
-        cp_async_arrive_noinc(bar_full + 8 * stage);
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   }
@@ -674,17 +695,23 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
         for (uint32_t i = 0; i < p.b_boxes; ++i)
           tma_load_5d(b_dst + i * 128u * p.b_box_c * 2u, &tmap_dy, bar_bfull + 8 * bs, (int)(i * p.b_box_c), x0, y0, z0, n);
         if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+        // first chunk of this CTA's M-group, then advanced incrementally (no division per chunk)
+        int cc, dx, dy, dz;
+        {
+          const int q = mb0 * 8;
+          const int tap = q / p.chunks16;
+          cc = q - tap * p.chunks16;
+          dx = tap % p.kw; dy = (tap / p.kw) % p.kh; dz = tap / (p.kw * p.kh);
+        }
         for (int mb = mb0; mb < mb1; ++mb) {
           mbar_wait(bar_aempty + 8 * as, aph ^ 1);
           const uint32_t a_dst = smem0 + p.a_off + as * kBlockBytes;
           const int nq = min(8, p.q_total - mb * 8);
           mbar_expect_tx(bar_afull + 8 * as, (uint32_t)nq * kChunkBytes);
           for (int j = 0; j < nq; ++j) {
-            const int q = mb * 8 + j;
-            const int tap = q / p.chunks16, cc = q - tap * p.chunks16;
-            const int dx = tap % p.kw, dy = (tap / p.kw) % p.kh, dz = tap / (p.kw * p.kh);
             tma_load_5d(a_dst + j * kChunkBytes, &tmap_x, bar_afull + 8 * as, cc * 16, x0 + dx - pw, y0 + dy - ph,
                         z0 + dz - pd, n);
+            if (++cc == p.chunks16) { cc = 0; if (++dx == p.kw) { dx = 0; if (++dy == p.kh) { dy = 0; ++dz; } } }
           }
           if (++as == p.a_stages) { as = 0; aph ^= 1; }
         }
@@ -892,21 +919,26 @@ conv_wgrad_umma2_kernel(const T* __restrict__ x, const T* __restrict__ dy, float
       }
       // ---- activation chunk tiles (A operand), 8 per M-block
       const T* xrow = x + (int64_t)n * pp.xsn + (int64_t)gz * pp.xsd + (int64_t)gy * pp.xsh + (int64_t)gx * pp.xsw;
+      int cc, dx, dyy, dz;
+      {
+        const int q = mb0 * 8;
+        const int tap = q / p.chunks16;
+        cc = q - tap * p.chunks16;
+        dx = tap % p.kw; dyy = (tap / p.kw) % p.kh; dz = tap / (p.kw * p.kh);
+      }
+      const uint32_t sw = ((uint32_t)r >> 2) & 1u;
       for (int mb = mb0; mb < mb1; ++mb) {
         mbar_wait(bar_aempty + 8 * as, aph ^ 1);
         const uint32_t a_dst = smem0 + p.a_off + as * kBlockBytes;
         const int nq = min(8, p.q_total - mb * 8);
-        for (int j = 0; j < nq; ++j) {
-          const int q = mb * 8 + j;
-          const int tap = q / p.chunks16, cc = q - tap * p.chunks16;
-          const int dx = tap % p.kw, dyy = (tap / p.kw) % p.kh, dz = tap / (p.kw * p.kh);
+        uint32_t rowaddr = a_dst + (uint32_t)r * 32u;
+        for (int j = 0; j < nq; ++j, rowaddr += kChunkBytes) {
           const int iz = gz + dz - pd, iy = gy + dyy - ph, ix = gx + dx - pw;
           const bool ok = iz >= 0 && iz < p.d && iy >= 0 && iy < p.h && ix >= 0 && ix < p.w;
           const T* src = ok ? xrow + (int64_t)(dz - pd) * pp.xsd + (int64_t)(dyy - ph) * pp.xsh + (int64_t)(dx - pw) * pp.xsw + cc * 16 : x;
-          const uint32_t rowaddr = a_dst + (uint32_t)j * kChunkBytes + (uint32_t)r * 32u;
-          const uint32_t sw = ((uint32_t)r >> 2) & 1u;
-          cp_async16(rowaddr + ((0u ^ sw) << 4), src, ok ? 16u : 0u);
-          cp_async16(rowaddr + ((1u ^ sw) << 4), src + 8, ok ? 16u : 0u);
+          cp_async16(rowaddr + (sw << 4), src, ok ? 16u : 0u);
+          cp_async16(rowaddr + ((sw ^ 1u) << 4), src + 8, ok ? 16u : 0u);
+          if (++cc == p.chunks16) { cc = 0; if (++dx == p.kw) { dx = 0; if (++dyy == p.kh) { dyy = 0; ++dz; } } }
         }
         cp_async_arrive_noinc(bar_afull + 8 * as);
         if (++as == p.a_stages) { as = 0; aph ^= 1; }

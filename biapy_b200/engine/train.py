@@ -80,6 +80,8 @@ class Trainer:
             self.world = torch.distributed.get_world_size(process_group)
         self.device = self.fp.flat.device
         self.ndim = model.ndim
+        self._graph = None
+        self.graph_launches = 0
 
     # ------------------------------------------------------------------------------------------------- data
     def _to_device_cl(self, a, dtype=None) -> torch.Tensor:
@@ -95,9 +97,60 @@ class Trainer:
     # ------------------------------------------------------------------------------------------------- step
     def step(self, x, target) -> torch.Tensor:
         """Returns the (mean) loss as a 1-element float64 CUDA tensor; no host synchronisation."""
-        model = self.model
+        if self._graph is not None:
+            return self._step_graphed(x, target)
         xd = self._to_device_cl(x)
         td = self._to_device_cl(target)
+        loss = self._forward_backward(xd, td)
+        self._reduce_and_update()
+        return loss
+
+    # ---------------------------------------------------------------------------------------- CUDA graph mode
+    def enable_cuda_graph(self, x_example, t_example):
+        """Capture forward + loss + backward (~900 kernel launches of fixed shape) into one CUDA graph; the gradient
+        all-reduce and the optimiser kernel stay eager (NCCL call, step-dependent bias correction).  Inputs are staged
+        through static device buffers; H2D copies stay outside the graph on the same stream."""
+        if self.loss_kind == "n2v_mse":
+            raise NotImplementedError("n2v_mse reads a scalar on the host and cannot be captured")
+        xs = self._to_device_cl(x_example)
+        ts = self._to_device_cl(t_example)
+        self._x_static = torch.empty_like(xs)
+        self._t_static = torch.empty_like(ts)
+        self._x_static.copy_(xs)
+        self._t_static.copy_(ts)
+        prof, ops.PROFILE = ops.PROFILE, None
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):                                   # warm-up: allocator, cudaFuncSetAttribute, caches
+                self._forward_backward(self._x_static, self._t_static)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        n0 = ops.LAUNCHES
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._loss_static = self._forward_backward(self._x_static, self._t_static)
+        self.graph_launches = ops.LAUNCHES - n0
+        self._graph = g
+        ops.PROFILE = prof
+        return self
+
+    def _step_graphed(self, x, target) -> torch.Tensor:
+        xs = x if isinstance(x, torch.Tensor) else torch.from_numpy(x)
+        ts = target if isinstance(target, torch.Tensor) else torch.from_numpy(target)
+        if self.ndim == 2:
+            xs, ts = xs.unsqueeze(1), ts.unsqueeze(1)
+        if xs.data_ptr() != self._x_static.data_ptr():
+            self._x_static.copy_(xs, non_blocking=True)
+        if ts.data_ptr() != self._t_static.data_ptr():
+            self._t_static.copy_(ts, non_blocking=True)
+        self._graph.replay()
+        ops.LAUNCHES += self.graph_launches
+        self._reduce_and_update()
+        return self._loss_static
+
+    def _forward_backward(self, xd: torch.Tensor, td: torch.Tensor) -> torch.Tensor:
+        model = self.model
         tape = Tape(model.engine_dtype, self.device, training=True, conv_impl=model.conv_impl)
         tape.param_grads = dict(self.fp.grad_views)           # gradients land directly in the flat buffer
         self.fp.grad.zero_()
@@ -113,7 +166,6 @@ class Trainer:
         loss = self._loss_and_grad(pred, td)
         pred.mark_written()
         tape.backward()
-        self._reduce_and_update()
         return loss
 
     def _loss_and_grad(self, pred: TT, td: torch.Tensor) -> torch.Tensor:

@@ -31,12 +31,15 @@ def _timed_call(label, flops, nbytes, name, *args):
     PROFILE.setdefault(label, []).append((e0, e1, flops, nbytes))
 
 
-def _launch(name, *args):
+def _launch(name, *args, shape=None):
     global LAUNCHES
     LAUNCHES += 1
     if PROFILE is None:
         return call(name, *args)
-    _timed_call(name[5:], 0.0, 0.0, name, *args)
+    label = name[5:]
+    if PROFILE_SHAPES and shape is not None:
+        label += f" c{shape[-1]} @{shape[1]}x{shape[2]}x{shape[3]}"
+    _timed_call(label, 0.0, 0.0, name, *args)
 
 
 def _launch_timed(label, flops, nbytes, name, *args):
@@ -189,7 +192,7 @@ class NormStats:
 def norm_stats(x, groups: int, gamma, beta, eps: float = 1e-5, batch_stats: bool = False) -> NormStats:
     n, d, h, w, c = x.shape
     sums = torch.zeros(n * c * 2, dtype=torch.float64, device=x.device)
-    _launch("b200_channel_sums", _ref(x), _ptr(sums), stream_ptr())
+    _launch("b200_channel_sums", _ref(x), _ptr(sums), stream_ptr(), shape=x.shape)
     st = NormStats()
     st.groups, st.batch_stats = groups, batch_stats
     buf = torch.empty(2 * n * groups + 2 * n * c, dtype=torch.float32, device=x.device)
@@ -201,7 +204,7 @@ def norm_stats(x, groups: int, gamma, beta, eps: float = 1e-5, batch_stats: bool
 
 
 def scale_shift_act(x, scale, shift, act: str, y):
-    _launch("b200_scale_shift_act", _ref(x), _ptr(scale), _ptr(shift), ACT[act], _ref(y), stream_ptr())
+    _launch("b200_scale_shift_act", _ref(x), _ptr(scale), _ptr(shift), ACT[act], _ref(y), stream_ptr(), shape=x.shape)
     return y
 
 
@@ -209,13 +212,13 @@ def norm_act_bwd(x, dy, st: NormStats, gamma, beta, act: str, dx, dgamma, dbeta,
     n, d, h, w, c = x.shape
     red = torch.zeros(n * c * 2, dtype=torch.float64, device=x.device)
     _launch("b200_norm_act_bwd_reduce", _ref(x), _ref(dy), _ptr(st.mean), _ptr(st.rstd), st.groups, _ptr(gamma), _ptr(beta),
-            ACT[act], _ptr(red), stream_ptr())
+            ACT[act], _ptr(red), stream_ptr(), shape=x.shape)
     coef = torch.empty(n * c * 4, dtype=torch.float32, device=x.device)
     _launch("b200_norm_bwd_finalize", _ptr(red), _ptr(st.mean), _ptr(st.rstd), _ptr(gamma), _ptr(beta), n, c, st.groups,
             d * h * w, 1 if st.batch_stats else 0, _ptr(coef), _ptr(dgamma), _ptr(dbeta), stream_ptr())
     if dx is not None:
         _launch("b200_norm_act_bwd_apply", _ref(x), _ref(dy), ACT[act], _ptr(coef), _ref(dx), 1 if accumulate else 0,
-                stream_ptr())
+                stream_ptr(), shape=x.shape)
 
 
 def act_bwd(x, dy, act: str, dx, accumulate=False):
