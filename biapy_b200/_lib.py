@@ -15,7 +15,7 @@ F32, BF16, F16, U8 = 0, 1, 2, 3
 ACT = {None: 0, "none": 0, "linear": 0, "relu": 1, "elu": 2, "silu": 3, "leaky_relu": 4, "gelu": 5, "tanh": 6,
        "sigmoid": 7, "softplus": 8}
 PAD_MODE = {"zeros": 0, "constant": 0, "reflect": 1, "symmetric": 2, "edge": 3, "wrap": 4}
-IMPL_AUTO, IMPL_SIMT, IMPL_UMMA = 0, 1, 2
+IMPL_AUTO, IMPL_SIMT, IMPL_UMMA, IMPL_XFOLD = 0, 1, 2, 3
 
 
 class Tensor(C.Structure):
@@ -54,6 +54,7 @@ SIGNATURES = {
     "b200_pack_conv_weight": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "b200_conv_fprop": (_I, [_T, _P, _P, _T, _T, _I, _I, _I, _I, _I, _P]),
     "b200_conv_wgrad": (_I, [_T, _T, _P, _P, _I, _I, _I, _I, _P]),
+    "b200_pack_conv_weight_xfold": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "b200_conv_impl_query": (_I, [_T, _T, _I, _I, _I, _I]),
     "b200_unpack_conv_wgrad": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "b200_convT_fprop": (_I, [_T, _P, _P, _T, _I, _I, _I, _P]),

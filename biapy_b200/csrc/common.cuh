@@ -72,7 +72,7 @@ __device__ __forceinline__ float act_fwd(int act, float x) {
   switch (act) {
     case B200_ACT_RELU: return x > 0.f ? x : 0.f;
     case B200_ACT_ELU: return x > 0.f ? x : expm1f(x);
-    case B200_ACT_SILU: return x / (1.f + expf(-x));
+    case B200_ACT_SILU: return __fdividef(x, 1.f + __expf(-x));
     case B200_ACT_LEAKY_RELU: return x > 0.f ? x : 0.01f * x;
     case B200_ACT_GELU: return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
     case B200_ACT_TANH: return tanhf(x);
@@ -88,7 +88,7 @@ __device__ __forceinline__ float act_grad(int act, float x) {
     case B200_ACT_RELU: return x > 0.f ? 1.f : 0.f;
     case B200_ACT_ELU: return x > 0.f ? 1.f : expf(x);
     case B200_ACT_SILU: {
-      float s = 1.f / (1.f + expf(-x));
+      float s = __fdividef(1.f, 1.f + __expf(-x));
       return s * (1.f + x * (1.f - s));
     }
     case B200_ACT_LEAKY_RELU: return x > 0.f ? 1.f : 0.01f;

@@ -241,6 +241,225 @@ conv_fprop_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   }
 }
 
+// ------------------------------------------------------------------------------------------- x-folded fprop kernel
+// For the small-channel layers (Cin <= 96 at 64^3..128^3, 60 % of the model FLOPs) one TMA box row of the direct kernel
+// carries only 32..64 bytes and the TMA unit, not L2 or the tensor pipe, limits throughput (profiles/README.md).
+// Folding 4 consecutive x-voxels into ONE GEMM row makes the rows fat and the instruction N large:
+//     D[(y,z) row][ (j, co) ] = sum_{dz,dy} sum_{xi<6, ci} X[z+dz, y+dy, 4g-1+xi, ci] * Wt[(j,co)][(dz,dy,xi,ci)]
+// with the block-Toeplitz weights Wt[(j,co)][(dz,dy,xi,ci)] = W[co][ci][dz][dy][xi-j] for 0 <= xi-j <= 2, else 0.
+// The 6 input voxels of a row are 6*Cin contiguous elements (dense channels-last), fetched as 128-byte (64 el) and
+// 64-byte (32 el) boxes of a rank-4 map (W*C, H, D, N): per output voxel the TMA moves 4.5 rows (Cin = 16) instead of 27,
+// the MMA runs with N = 4*Cout (64..256) instead of 16..64, and each thread of the epilogue stores 4 voxels.
+// Half of the issued MACs hit Toeplitz zeros; the tensor pipe is not the bottleneck of these layers.
+struct XfoldParams {
+  int n, d, h, w, cin, cout;
+  int kd, kh;                           // kw == 3
+  int bh, bd;                           // rows of a tile: bh * bd == 128 (y fastest)
+  int groups_x, tiles_h, tiles_d, num_tiles;
+  int kx;                               // 6 * cin
+  int boxes64, has32;                   // K boxes per (dz, dy): boxes64 of 64 elements, then one of 32 if has32
+  int nt;                               // 4 * cout
+  int stages;
+  uint32_t a_bytes, stage_bytes;        // A tile of a 64-element box; stage = A + B (max box)
+  uint32_t idesc, tmem_cols;
+  int64_t ysw, ysh, ysd, ysn;
+  int accumulate;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(192, 1)
+conv_fprop_xfold_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid_constant__ CUtensorMap tmx32,
+                        const __grid_constant__ CUtensorMap tmw64, const __grid_constant__ CUtensorMap tmw32,
+                        const float* __restrict__ bias, T* __restrict__ y, const XfoldParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t s_bar[2 * kMaxStages + 4];
+  __shared__ uint32_t s_tmem;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_full = smem_u32(&s_bar[0]);
+  const uint32_t bar_empty = smem_u32(&s_bar[kMaxStages]);
+  const uint32_t bar_tfull = smem_u32(&s_bar[2 * kMaxStages]);
+  const uint32_t bar_tempty = smem_u32(&s_bar[2 * kMaxStages + 2]);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_tfull + 8 * b, 1);
+      mbar_init(bar_tempty + 8 * b, 128);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmx64); tma_prefetch_desc(&tmx32); tma_prefetch_desc(&tmw64); tma_prefetch_desc(&tmw32);
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&s_tmem), p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  const int pd = p.kd / 2, ph = p.kh / 2;
+  const int nboxes = p.boxes64 + p.has32;
+
+  auto decode = [&](int tile, int& n, int& z0, int& y0, int& g) {
+    int t = tile;
+    g = t % p.groups_x; t /= p.groups_x;
+    y0 = (t % p.tiles_h) * p.bh; t /= p.tiles_h;
+    z0 = (t % p.tiles_d) * p.bd; t /= p.tiles_d;
+    n = t;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================================================================= TMA producer
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int n, z0, y0, g;
+        decode(tile, n, z0, y0, g);
+        const int e0 = (4 * g - 1) * p.cin;              // first element of the 6-voxel window (may be negative)
+        int kcol = 0;
+        for (int dz = 0; dz < p.kd; ++dz)
+          for (int dy = 0; dy < p.kh; ++dy)
+            for (int b = 0; b < nboxes; ++b) {
+              const bool wide = b < p.boxes64;
+              mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+              const uint32_t a_dst = smem0 + stage * p.stage_bytes;
+              const uint32_t fb = bar_full + 8 * stage;
+              const uint32_t wbytes = wide ? 128u : 64u;
+              mbar_expect_tx(fb, 128u * wbytes + (uint32_t)p.nt * wbytes);
+              asm volatile(
+                  "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                  ::"r"(a_dst), "l"((uint64_t)(wide ? &tmx64 : &tmx32)), "r"(fb), "r"(e0 + b * 64), "r"(y0 + dy - ph),
+                    "r"(z0 + dz - pd), "r"(n)
+                  : "memory");
+              tma_load_2d(a_dst + p.a_bytes, wide ? &tmw64 : &tmw32, fb, kcol, 0);
+              kcol += wide ? 64 : 32;
+              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ================================================================= MMA issuer
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      const int nkb = p.kd * p.kh * nboxes;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem + buf * p.nt;
+        int b = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const bool wide = b < p.boxes64;
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t a_base = smem0 + stage * p.stage_bytes;
+          const uint32_t b_base = a_base + p.a_bytes;
+          const uint32_t layout = wide ? kSwizzle128 : kSwizzle64;
+          const uint32_t sbo = wide ? 1024u : 512u;
+          const int ksteps = wide ? 4 : 2;
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t ad = make_smem_desc(a_base + k * 32, 16, sbo, layout);
+            const uint64_t bd = make_smem_desc(b_base + k * 32, 16, sbo, layout);
+            umma_f16(d_tmem, ad, bd, p.idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(bar_empty + 8 * stage);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          if (++b == nboxes) b = 0;
+        }
+        umma_commit(bar_tfull + 8 * buf);
+      }
+    }
+  } else {
+    // =================================================================== epilogue
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int ly = row % p.bh, lz = row / p.bh;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      int n, z0, y0, g;
+      decode(tile, n, z0, y0, g);
+      mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
+      tc_fence_after();
+      const int gz = z0 + lz, gy = y0 + ly;
+      const bool valid = gz < p.d && gy < p.h;
+      T* ybase = y + (int64_t)n * p.ysn + (int64_t)gz * p.ysd + (int64_t)gy * p.ysh + (int64_t)(4 * g) * p.ysw;
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.nt);
+      int j = 0, co = 0;                               // column = j * cout + co
+      for (int c0 = 0; c0 < p.nt; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c0, r);
+        tmem_ld_wait();
+        if (valid && 4 * g + j < p.w) {
+          T* yrow = ybase + (int64_t)j * p.ysw + co;
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(r[i]) + (bias ? __ldg(bias + co + i) : 0.f);
+          if (p.accumulate) {
+            Pack<T, 8> o0 = *reinterpret_cast<const Pack<T, 8>*>(yrow);
+            Pack<T, 8> o1 = *reinterpret_cast<const Pack<T, 8>*>(yrow + 8);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              f[i] += to_f<T>(o0.v[i]);
+              f[8 + i] += to_f<T>(o1.v[i]);
+            }
+          }
+          Pack<T, 8> w0, w1;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            w0.v[i] = from_f<T>(f[i]);
+            w1.v[i] = from_f<T>(f[8 + i]);
+          }
+          *reinterpret_cast<Pack<T, 8>*>(yrow) = w0;
+          *reinterpret_cast<Pack<T, 8>*>(yrow + 8) = w1;
+        }
+        co += 16;
+        if (co == p.cout) { co = 0; ++j; }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_tempty + 8 * buf);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem, p.tmem_cols);
+  }
+}
+
+// Toeplitz packing: out[(j, co)][(dz, dy, xi, ci)] from w (Cout, Cin, kd, kh, 3) fp32; flip_transpose builds the dgrad
+// operand (roles of Cin/Cout swapped, taps mirrored) directly.
+template <typename T>
+__global__ void pack_weight_xfold_kernel(const float* __restrict__ w, T* __restrict__ out, int cout, int cin, int kd, int kh,
+                                         int flip) {
+  // logical conv: co_l in [0, CO), ci_l in [0, CI) with CO = flip ? cin : cout, CI = flip ? cout : cin
+  const int CO = flip ? cin : cout, CI = flip ? cout : cin;
+  const int64_t ktot = (int64_t)kd * kh * 6 * CI;
+  const int64_t total = (int64_t)4 * CO * ktot;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = i;
+    const int ci = (int)(t % CI); t /= CI;
+    const int xi = (int)(t % 6); t /= 6;
+    const int dy = (int)(t % kh); t /= kh;
+    const int dz = (int)(t % kd); t /= kd;
+    const int co = (int)(t % CO);
+    const int j = (int)(t / CO);
+    const int kx = xi - j;
+    float v = 0.f;
+    if (kx >= 0 && kx <= 2) {
+      if (!flip) v = w[((((int64_t)co * cin + ci) * kd + dz) * kh + dy) * 3 + kx];
+      else v = w[((((int64_t)ci * cin + co) * kd + (kd - 1 - dz)) * kh + (kh - 1 - dy)) * 3 + (2 - kx)];
+    }
+    out[i] = from_f<T>(v);
+  }
+}
+
 // ------------------------------------------------------------------------------------- fprop kernel, cp.async-fed
 // Same GEMM and epilogue as conv_fprop_umma_kernel, but the operands are brought in by four loader warps with
 // 16-byte cp.async (zero-fill for padding) straight into the swizzled K-major layout the UMMA descriptors expect.
@@ -483,7 +702,7 @@ static int loader_mode() {
   static int mode = -1;
   if (mode < 0) {
     const char* e = getenv("B200_CONV_LOADER");
-    mode = (e && strcmp(e, "tma") == 0) ? 0 : 1;       // default: cp.async loaders
+    mode = (e && strcmp(e, "cpasync") == 0) ? 1 : 0;   // default: TMA (measured faster, profiles/README.md)
   }
   return mode;
 }
@@ -610,6 +829,118 @@ int conv_fprop_umma_v(const ActView& xv, const void* w, const float* bias, const
   return B200_OK;
 }
 }  // namespace sm100
+
+namespace sm100 {
+
+static int make_tmap4(CUtensorMap* out, const void* base, int dtype, const cuuint64_t dims[4], const cuuint64_t strides_b[3],
+                      const cuuint32_t box[4]) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  B200_CHECK_ARG(fn != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, tm_dtype(dtype), 4, const_cast<void*>(base), dims, strides_b, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_for_bytes((int)box[0] * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(rank 4) failed with %d", (int)r);
+  return B200_OK;
+}
+
+bool conv_xfold_ok(const ActView& x, const ActView& y, int kd, int kh, int kw) {
+  if (x.dtype != B200_BF16 && x.dtype != B200_F16) return false;
+  if (kw != 3 || kd > 5 || kh > 5) return false;
+  if (x.c % 16 != 0 || y.c % 16 != 0 || y.c > 64 || x.c > 96) return false;
+  if (x.sw != x.c || x.sh != (int64_t)x.w * x.c) return false;              // dense rows: 6 voxels are contiguous
+  if (x.w % 4 != 0 || x.w < 8) return false;
+  if (y.sw % 8 != 0 || !aligned16(x.data) || !aligned16(y.data)) return false;
+  if ((int64_t)x.d * x.h < 128) return false;
+  return encode_tiled_fn() != nullptr;
+}
+
+int conv_fprop_xfold_v(const ActView& x, const void* w, const float* bias, const ActView& y, int kd, int kh, int accumulate,
+                       cudaStream_t st) {
+  B200_CHECK_ARG(conv_xfold_ok(x, y, kd, kh, 3), "conv_fprop(xfold): unsupported operands");
+  XfoldParams p{};
+  p.n = x.n; p.d = x.d; p.h = x.h; p.w = x.w; p.cin = x.c; p.cout = y.c;
+  p.kd = kd; p.kh = kh;
+  {  // rows of a tile = bh x bd positions in (y, z)
+    static const int cand[][2] = {{16, 8}, {8, 16}, {32, 4}, {4, 32}, {64, 2}, {2, 64}, {128, 1}, {1, 128}};
+    double best = 1e30;
+    for (auto& c : cand) {
+      double cover = (double)ceil_div(x.h, c[0]) * c[0] * ceil_div(x.d, c[1]) * c[1];
+      if (cover < best - 0.5) { best = cover; p.bh = c[0]; p.bd = c[1]; }
+    }
+  }
+  p.groups_x = x.w / 4;
+  p.tiles_h = (int)ceil_div(x.h, p.bh); p.tiles_d = (int)ceil_div(x.d, p.bd);
+  p.num_tiles = x.n * p.tiles_d * p.tiles_h * p.groups_x;
+  p.kx = 6 * x.c;
+  p.boxes64 = p.kx / 64; p.has32 = (p.kx % 64) ? 1 : 0;
+  p.nt = 4 * y.c;
+  p.a_bytes = 128u * 128u;
+  p.stage_bytes = p.a_bytes + (((uint32_t)p.nt * 128u + 1023u) & ~1023u);
+  int stages = (int)((200u * 1024u) / p.stage_bytes);
+  if (stages > 8) stages = 8;
+  B200_CHECK_ARG(stages >= 2, "conv_fprop(xfold): tile does not fit in shared memory");
+  p.stages = stages;
+  p.idesc = make_idesc(x.dtype == B200_BF16, p.nt, 0, 0);
+  uint32_t cols = 32;
+  while (cols < 2u * p.nt) cols <<= 1;
+  p.tmem_cols = cols;
+  p.ysw = y.sw; p.ysh = y.sh; p.ysd = y.sd; p.ysn = y.sn;
+  p.accumulate = accumulate;
+
+  CUtensorMap tx64, tx32, tw64, tw32;
+  const cuuint64_t xd[4] = {(cuuint64_t)x.w * x.c, (cuuint64_t)x.h, (cuuint64_t)x.d, (cuuint64_t)x.n};
+  const cuuint64_t xs[3] = {(cuuint64_t)x.sh * 2, (cuuint64_t)x.sd * 2, (cuuint64_t)x.sn * 2};
+  const cuuint32_t b64[4] = {64, (cuuint32_t)p.bh, (cuuint32_t)p.bd, 1};
+  const cuuint32_t b32[4] = {32, (cuuint32_t)p.bh, (cuuint32_t)p.bd, 1};
+  int rc = make_tmap4(&tx64, x.data, x.dtype, xd, xs, b64);
+  if (rc) return rc;
+  rc = make_tmap4(&tx32, x.data, x.dtype, xd, xs, b32);
+  if (rc) return rc;
+  const int64_t ktot = (int64_t)kd * kh * p.kx;
+  rc = make_matrix_tmap(&tw64, w, x.dtype, p.nt, ktot, p.nt, 64);
+  if (rc) return rc;
+  rc = make_matrix_tmap(&tw32, w, x.dtype, p.nt, ktot, p.nt, 32);
+  if (rc) return rc;
+
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  if (x.dtype == B200_BF16) {
+    auto kern = conv_fprop_xfold_kernel<__nv_bfloat16>;
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 192, smem, st>>>(tx64, tx32, tw64, tw32, bias, (__nv_bfloat16*)y.data, p);
+  } else {
+    auto kern = conv_fprop_xfold_kernel<__half>;
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 192, smem, st>>>(tx64, tx32, tw64, tw32, bias, (__half*)y.data, p);
+  }
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+}  // namespace sm100
+
+bool conv_fprop_xfold_supported(const b200_tensor* x, const b200_tensor* y, int kd, int kh, int kw) {
+  return sm100::conv_xfold_ok(sm100::view_of(x), sm100::view_of(y), kd, kh, kw);
+}
+int conv_fprop_xfold(const b200_tensor* x, const void* w, const float* bias, const b200_tensor* y, int kd, int kh, int accumulate,
+                     cudaStream_t st) {
+  return sm100::conv_fprop_xfold_v(sm100::view_of(x), w, bias, sm100::view_of(y), kd, kh, accumulate, st);
+}
+int pack_weight_xfold(const float* w, void* packed, int dtype, int cout, int cin, int kd, int kh, int flip, cudaStream_t st) {
+  const int CO = flip ? cin : cout, CI = flip ? cout : cin;
+  int64_t total = (int64_t)4 * CO * kd * kh * 6 * CI;
+  unsigned blocks = (unsigned)(ceil_div(total, 256) < 8192 ? ceil_div(total, 256) : 8192);
+  if (dtype == B200_BF16)
+    sm100::pack_weight_xfold_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w, (__nv_bfloat16*)packed, cout, cin, kd, kh, flip);
+  else if (dtype == B200_F16)
+    sm100::pack_weight_xfold_kernel<__half><<<blocks, 256, 0, st>>>(w, (__half*)packed, cout, cin, kd, kh, flip);
+  else {
+    set_error("pack_weight_xfold: 16-bit dtypes only");
+    return B200_ERR_ARG;
+  }
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
 
 // ================================================================================================== wgrad
 // dW[co][tap][ci] += sum_vox dY[vox][co] * X[vox + off(tap)][ci]  as  D[(tap, ci)][co] = A^T B with K = voxels:

@@ -121,18 +121,22 @@ template <typename T>
 static int launch_channel_sums(const b200_tensor* x, double* sums, cudaStream_t st) {
   constexpr int V = VecOf<T>::n;
   View<const T> xv{(const T*)x->data, x->ld, x->c, voxels(x), (int64_t)x->d * x->h * x->w};
-  int64_t chunks = ceil_div(xv.spatial, 4096);
-  int64_t cap = ceil_div((int64_t)sm_count() * 6, x->n);
-  if (chunks > cap) chunks = cap;
-  if (chunks < 1) chunks = 1;
-  dim3 grid((unsigned)chunks, x->n);
-  if (vec_ok(x, V) && x->c / V <= 256) {
-    int cvn = x->c / V;
+  auto grid_of = [&](int rows) {
+    int64_t chunks = ceil_div(xv.spatial, (int64_t)rows * 16);
+    int64_t cap = ceil_div((int64_t)sm_count() * 8, x->n);
+    if (chunks > cap) chunks = cap;
+    if (chunks < 1) chunks = 1;
+    return dim3((unsigned)chunks, x->n);
+  };
+  constexpr int VH = V / 2 > 0 ? V / 2 : 1;      // half-width vectors: ~60 registers -> 4 blocks per SM
+  if (vec_ok(x, V) && x->c / VH <= 256) {
+    int cvn = x->c / VH;
     int rows = 256 / cvn;
     int threads = ((rows * cvn + 31) / 32) * 32;
-    size_t smem = sizeof(double) * rows * cvn * V * 2;
-    channel_sums_kernel<T, V><<<grid, threads, smem, st>>>(xv, sums, cvn, rows);
+    size_t smem = sizeof(double) * rows * cvn * VH * 2;
+    channel_sums_kernel<T, VH><<<grid_of(rows), threads, smem, st>>>(xv, sums, cvn, rows);
   } else {
+    dim3 grid = grid_of(1);
     B200_CHECK_ARG(x->c <= 1024, "channel_sums: too many channels (%d)", x->c);
     int cvn = x->c;
     int rows = 256 / cvn;
@@ -824,21 +828,25 @@ B200_EXPORT int b200_norm_act_bwd_reduce(const b200_tensor* x, const b200_tensor
   B200_CHECK_ARG(groups > 0 && x->c % groups == 0, "bwd_reduce: bad groups");
   cudaStream_t st = (cudaStream_t)stream;
   int64_t spatial = (int64_t)x->d * x->h * x->w;
-  int64_t chunks = ceil_div(spatial, 4096);
-  int64_t cap = ceil_div((int64_t)sm_count() * 6, x->n);
-  if (chunks > cap) chunks = cap;
-  if (chunks < 1) chunks = 1;
-  dim3 grid((unsigned)chunks, x->n);
+  auto grid_of = [&](int rows) {
+    int64_t chunks = ceil_div(spatial, (int64_t)rows * 16);
+    int64_t cap = ceil_div((int64_t)sm_count() * 8, x->n);
+    if (chunks > cap) chunks = cap;
+    if (chunks < 1) chunks = 1;
+    return dim3((unsigned)chunks, x->n);
+  };
   B200_DISPATCH_DTYPE(x->dtype, T, {
     constexpr int V = VecOf<T>::n;
+    constexpr int VH = V / 2;
     View<const T> xv{(const T*)x->data, x->ld, x->c, voxels(x), spatial};
     View<const T> dv{(const T*)dy->data, dy->ld, dy->c, voxels(dy), spatial};
-    if (vec_ok(x, V) && vec_ok(dy, V) && x->c / V <= 256) {
-      int cvn = x->c / V, rows = 256 / cvn;
+    if (vec_ok(x, V) && vec_ok(dy, V) && x->c / VH <= 256) {
+      int cvn = x->c / VH, rows = 256 / cvn;
       int threads = ((rows * cvn + 31) / 32) * 32;
-      norm_act_bwd_reduce_kernel<T, V><<<grid, threads, sizeof(double) * rows * cvn * V * 2, st>>>(
+      norm_act_bwd_reduce_kernel<T, VH><<<grid_of(rows), threads, sizeof(double) * rows * cvn * VH * 2, st>>>(
           xv, dv, mean, rstd, groups, gamma, beta, act, red, cvn, rows);
     } else {
+      dim3 grid = grid_of(1);
       B200_CHECK_ARG(x->c <= 1024, "bwd_reduce: too many channels");
       int cvn = x->c, rows = 256 / cvn;
       if (rows < 1) rows = 1;

@@ -129,26 +129,30 @@ struct CropParams {
 
 constexpr int kMaxAxisPatches = 1024;
 
+// grid = (chunks of ph*pw*C, pd, n_patches): only 32-bit index arithmetic per element
 template <typename U>
 __global__ void crop_gather_kernel(const U* __restrict__ src, U* __restrict__ dst, CropParams p,
                                    const int64_t* __restrict__ sz, const int64_t* __restrict__ sy,
                                    const int64_t* __restrict__ sx) {
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < p.total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    int64_t t = idx;
-    int64_t ch = t % p.C; t /= p.C;
-    int64_t lx = t % p.pw; t /= p.pw;
-    int64_t ly = t % p.ph; t /= p.ph;
-    int64_t lz = t % p.pd; t /= p.pd;
-    int64_t ix = t % p.nx; t /= p.nx;
-    int64_t iy = t % p.ny; t /= p.ny;
-    int64_t iz = t;
-    int64_t z = pad_src(sz[iz] + lz - p.pad_z, p.D, p.mode);
-    int64_t y = pad_src(sy[iy] + ly - p.pad_y, p.H, p.mode);
-    int64_t x = pad_src(sx[ix] + lx - p.pad_x, p.W, p.mode);
+  const int patch = blockIdx.z;
+  const int lz = blockIdx.y;
+  const int ix = patch % (int)p.nx;
+  const int iy = (patch / (int)p.nx) % (int)p.ny;
+  const int iz = patch / (int)(p.nx * p.ny);
+  const int64_t z = pad_src(sz[iz] + lz - p.pad_z, p.D, p.mode);
+  const int64_t y0 = sy[iy] - p.pad_y, x0 = sx[ix] - p.pad_x;
+  const int plane = (int)(p.ph * p.pw * p.C);
+  U* out = dst + ((int64_t)patch * p.pd + lz) * plane;
+  const int C = (int)p.C, pw = (int)p.pw;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += gridDim.x * blockDim.x) {
+    const int ch = i % C;
+    const int t = i / C;
+    const int lx = t % pw, ly = t / pw;
+    const int64_t y = pad_src(y0 + ly, p.H, p.mode);
+    const int64_t x = pad_src(x0 + lx, p.W, p.mode);
     U v = 0;
     if (z >= 0 && y >= 0 && x >= 0) v = src[((z * p.H + y) * p.W + x) * p.C + ch];
-    dst[idx] = v;
+    out[i] = v;
   }
 }
 
@@ -168,17 +172,19 @@ B200_EXPORT int b200_crop_gather(const void* src, int32_t dtype, int64_t D, int6
   cudaStream_t st = (cudaStream_t)stream;
   CropParams p{D, H, W, C, pd, ph, pw, nz, ny, nx, pad_z, pad_y, pad_x, nz * ny * nx * pd * ph * pw * C, pad_mode};
   int threads = 256;
-  int64_t blocks = ceil_div(p.total, threads);
-  int64_t cap = (int64_t)sm_count() * 16;
-  if (blocks > cap) blocks = cap;
+  B200_CHECK_ARG(ph * pw * C < (1LL << 30) && nz * ny * nx <= 65535 * 32 && pd <= 65535, "crop_gather: patch too large");
+  int64_t bx = ceil_div(ph * pw * C, threads);
+  if (bx > 64) bx = 64;
+  B200_CHECK_ARG(nz * ny * nx <= 65535, "crop_gather: more than 65535 patches per call");
+  dim3 blocks((unsigned)bx, (unsigned)pd, (unsigned)(nz * ny * nx));
   if (dtype == 3)
-    crop_gather_kernel<uint8_t><<<(unsigned)blocks, threads, 0, st>>>((const uint8_t*)src, (uint8_t*)dst, p,
+    crop_gather_kernel<uint8_t><<<blocks, threads, 0, st>>>((const uint8_t*)src, (uint8_t*)dst, p,
                                                                      starts_z, starts_y, starts_x);
   else if (dtype == B200_F32)
-    crop_gather_kernel<uint32_t><<<(unsigned)blocks, threads, 0, st>>>((const uint32_t*)src, (uint32_t*)dst, p,
+    crop_gather_kernel<uint32_t><<<blocks, threads, 0, st>>>((const uint32_t*)src, (uint32_t*)dst, p,
                                                                       starts_z, starts_y, starts_x);
   else
-    crop_gather_kernel<uint16_t><<<(unsigned)blocks, threads, 0, st>>>((const uint16_t*)src, (uint16_t*)dst, p,
+    crop_gather_kernel<uint16_t><<<blocks, threads, 0, st>>>((const uint16_t*)src, (uint16_t*)dst, p,
                                                                       starts_z, starts_y, starts_x);
   B200_LAUNCH_CHECK();
   return B200_OK;
@@ -210,13 +216,14 @@ __global__ void overlap_add_kernel(const TI* __restrict__ patches, TO* __restric
   for (int i = threadIdx.x; i < p.ny; i += blockDim.x) s_y[i] = sy[i];
   for (int i = threadIdx.x; i < p.nx; i += blockDim.x) s_x[i] = sx[i];
   __syncthreads();
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < p.total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    int64_t t = idx;
-    int64_t ch = t % p.C; t /= p.C;
-    int64_t x = t % p.W; t /= p.W;
-    int64_t y = t % p.H; t /= p.H;
-    int64_t z = t;
+  const int plane = (int)(p.H * p.W * p.C);
+  const int C = (int)p.C, Wd = (int)p.W;
+  for (int64_t z = blockIdx.y; z < p.D; z += gridDim.y)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += gridDim.x * blockDim.x) {
+    const int ch = i % C;
+    const int tq = i / C;
+    const int64_t x = tq % Wd, y = tq / Wd;
+    const int64_t idx = z * plane + i;
     float acc = 0.f, wsum = 0.f;
     for (int64_t iz = 0; iz < p.nz; ++iz) {
       int64_t lz = z - s_z[iz];
@@ -247,11 +254,12 @@ static int launch_overlap_add(const void* patches, void* out, const MergeParams&
                               const int64_t* sy, const int64_t* sx, const float* wz, const float* wy,
                               const float* wx, cudaStream_t st) {
   int threads = 256;
-  int64_t blocks = ceil_div(p.total, threads);
-  int64_t cap = (int64_t)sm_count() * 32;
-  if (blocks > cap) blocks = cap;
+  B200_CHECK_ARG(p.H * p.W * p.C < (1LL << 31), "overlap_add: plane too large");
+  int64_t bx = ceil_div(p.H * p.W * p.C, threads);
+  if (bx > 1024) bx = 1024;
+  dim3 blocks((unsigned)bx, (unsigned)(p.D < 65535 ? p.D : 65535));
   size_t smem = sizeof(int64_t) * (p.nz + p.ny + p.nx);
-  overlap_add_kernel<TI, TO><<<(unsigned)blocks, threads, smem, st>>>((const TI*)patches, (TO*)out, p, sz, sy, sx,
+  overlap_add_kernel<TI, TO><<<blocks, threads, smem, st>>>((const TI*)patches, (TO*)out, p, sz, sy, sx,
                                                                      wz, wy, wx);
   B200_LAUNCH_CHECK();
   return B200_OK;

@@ -15,6 +15,7 @@ Design points (B200-first):
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -90,6 +91,7 @@ class Tape:
         self.training = training
         self.impl = conv_impl
         self.steps: List[Callable[[], None]] = []
+        self.use_xfold = os.environ.get("B200_XFOLD", "1") != "0"
         self.param_grads: Dict[torch.nn.Parameter, torch.Tensor] = {}
         self._packed: Dict[Tuple[int, bool], torch.Tensor] = {}
 
@@ -106,13 +108,21 @@ class Tape:
             self.param_grads[p] = g
         return g
 
-    def _pack(self, w: torch.nn.Parameter, flip: bool) -> torch.Tensor:
-        key = (id(w), flip)
+    def _pack(self, w: torch.nn.Parameter, flip: bool, xfold: bool = False) -> torch.Tensor:
+        key = (id(w), flip, xfold)
         t = self._packed.get(key)
         if t is None:
-            t = ops.pack_conv_weight(w, self.dtype, flip)
+            t = ops.pack_conv_weight_xfold(w, self.dtype, flip) if xfold else ops.pack_conv_weight(w, self.dtype, flip)
             self._packed[key] = t
         return t
+
+    def _conv_launch(self, x: torch.Tensor, w, flip: bool, bias, y: torch.Tensor, k, accumulate: bool):
+        """Pick the kernel family for (x -> y) and launch it with the matching weight packing."""
+        impl = self.impl
+        if impl == _lib.IMPL_AUTO and self.dtype != torch.float32 and self.use_xfold:
+            if ops.conv_impl_query(x, y, k) == _lib.IMPL_XFOLD:
+                impl = _lib.IMPL_XFOLD
+        ops.conv_fprop(x, self._pack(w, flip, impl == _lib.IMPL_XFOLD), bias, y, k, accumulate=accumulate, impl=impl)
 
     @staticmethod
     def _k3(k) -> Tuple[int, int, int]:
@@ -137,7 +147,7 @@ class Tape:
         if (cin < 16 and cout % 16 == 0 and not x.requires_grad and self.dtype != torch.float32
                 and self.impl != _lib.IMPL_SIMT):
             return self._conv_padded_input(x, mod, out, accumulate, k, cout, cin)
-        ops.conv_fprop(x.data, self._pack(w, False), self._f32(b), out.data, k, accumulate=accumulate, impl=self.impl)
+        self._conv_launch(x.data, w, False, self._f32(b), out.data, k, accumulate)
         if self.training:
             def bwd(x=x, out=out, w=w, b=b, k=k, cout=cout, cin=cin):
                 dy = out.grad()
@@ -148,7 +158,7 @@ class Tape:
                     ops.conv_wgrad(x.data, dy, cout, cin, k, self._pgrad(w), gb, accumulate=not first, impl=self.impl)
                 if x.requires_grad:
                     acc = x.prepare_accumulate()
-                    ops.conv_fprop(dy, self._pack(w, True), None, x.grad(), k, accumulate=acc, impl=self.impl)
+                    self._conv_launch(dy, w, True, None, x.grad(), k, acc)
             self.steps.append(bwd)
         return out
 

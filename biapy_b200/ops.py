@@ -50,10 +50,17 @@ def _launch_timed(label, flops, nbytes, name, *args):
     _timed_call(label, flops, nbytes, name, *args)
 
 
+def conv_impl_query(x, y, k, wgrad=False) -> int:
+    """Best kernel family for these operands: IMPL_XFOLD / IMPL_UMMA / IMPL_SIMT."""
+    return _lib.lib().b200_conv_impl_query(_ref(x), _ref(y), k[0], k[1], k[2], 1 if wgrad else 0)
+
+
 def _impl_name(x, y, k, wgrad, impl):
     if impl == _lib.IMPL_AUTO:
-        impl = _lib.lib().b200_conv_impl_query(_ref(x), _ref(y), k[0], k[1], k[2], 1 if wgrad else 0)
-    return "umma" if impl == _lib.IMPL_UMMA else "simt"
+        impl = conv_impl_query(x, y, k, wgrad)
+        if impl == _lib.IMPL_XFOLD:
+            impl = _lib.IMPL_UMMA        # AUTO never selects the x-folded kernel (different weight packing)
+    return {_lib.IMPL_UMMA: "umma", _lib.IMPL_XFOLD: "xfold"}.get(impl, "simt")
 
 
 def _ref(t):
@@ -83,6 +90,23 @@ def pack_conv_weight(w: torch.Tensor, dtype: torch.dtype, flip_transpose: bool) 
         k = (1,) + k
     out = torch.empty(w.numel(), dtype=dtype, device=w.device)
     _launch("b200_pack_conv_weight", _ptr(w), _ptr(out), _lib.torch_dtype_code(dtype), cout, cin, k[0], k[1], k[2],
+            1 if flip_transpose else 0, stream_ptr())
+    return out
+
+
+def pack_conv_weight_xfold(w: torch.Tensor, dtype: torch.dtype, flip_transpose: bool) -> torch.Tensor:
+    """w: (Cout, Cin, kd, kh, 3) or (Cout, Cin, kh, 3) fp32 -> block-Toeplitz packing of the x-folded kernel."""
+    w = w.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    cout, cin = w.shape[:2]
+    k = tuple(w.shape[2:])
+    if len(k) == 2:
+        k = (1,) + k
+    assert k[2] == 3
+    co_l, ci_l = (cin, cout) if flip_transpose else (cout, cin)
+    out = torch.empty(4 * co_l * k[0] * k[1] * 6 * ci_l, dtype=dtype, device=w.device)
+    _launch("b200_pack_conv_weight_xfold", _ptr(w), _ptr(out), _lib.torch_dtype_code(dtype), cout, cin, k[0], k[1],
             1 if flip_transpose else 0, stream_ptr())
     return out
 

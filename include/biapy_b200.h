@@ -35,7 +35,7 @@ enum b200_act {
   B200_ACT_GELU = 5, B200_ACT_TANH = 6, B200_ACT_SIGMOID = 7, B200_ACT_SOFTPLUS = 8
 };
 enum b200_pad_mode { B200_PAD_ZEROS = 0, B200_PAD_REFLECT = 1, B200_PAD_SYMMETRIC = 2, B200_PAD_EDGE = 3, B200_PAD_WRAP = 4 };
-enum b200_conv_impl { B200_IMPL_AUTO = 0, B200_IMPL_SIMT = 1, B200_IMPL_UMMA = 2 };
+enum b200_conv_impl { B200_IMPL_AUTO = 0, B200_IMPL_SIMT = 1, B200_IMPL_UMMA = 2, B200_IMPL_XFOLD = 3 };
 
 typedef struct b200_tensor {
   void* data;      /* device pointer */
@@ -109,8 +109,14 @@ int b200_conv_fprop(const b200_tensor* x, const void* w_packed, const float* bia
  * Both outputs must be zero-initialised by the caller (they are accumulated with atomics).                  */
 int b200_conv_wgrad(const b200_tensor* x, const b200_tensor* dy, float* dw_packed, float* dbias,
                     int32_t kd, int32_t kh, int32_t kw, int32_t impl, void* stream);
-/* which kernel family B200_IMPL_AUTO picks for these operands: returns B200_IMPL_UMMA or B200_IMPL_SIMT
- * (wgrad != 0: for b200_conv_wgrad with y = dy) */
+/* x-folded tensor-core kernel for small-channel 3x3(x3) layers (see csrc/conv_umma.cu): block-Toeplitz packing
+ *   [(j, co)][(dz, dy, xi, ci)], j < 4, xi < 6  -- 8x the plain packing; elements = 4*Cout' * kd*kh*6*Cin'
+ * where (Cout', Cin') = (Cout, Cin), or (Cin, Cout) when flip_transpose (dgrad operand).  Used with impl =
+ * B200_IMPL_XFOLD in b200_conv_fprop; B200_IMPL_AUTO never selects it (the packing differs). */
+int b200_pack_conv_weight_xfold(const float* w, void* packed, int32_t dtype, int32_t cout, int32_t cin, int32_t kd,
+                                int32_t kh, int32_t flip_transpose, void* stream);
+/* best kernel family for these operands: B200_IMPL_XFOLD, B200_IMPL_UMMA or B200_IMPL_SIMT
+ * (wgrad != 0: for b200_conv_wgrad with y = dy; never XFOLD) */
 int b200_conv_impl_query(const b200_tensor* x, const b200_tensor* y, int32_t kd, int32_t kh, int32_t kw, int32_t wgrad);
 /* dw (Cout,Cin,kd,kh,kw) fp32 (+)= dw_packed[Cout][tap][Cin] */
 int b200_unpack_conv_wgrad(const float* dw_packed, float* dw, int32_t cout, int32_t cin, int32_t taps,

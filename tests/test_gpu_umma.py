@@ -144,3 +144,50 @@ def test_convT_tensor_core_route(shape, stride):
     dw, db = torch.zeros_like(wt).cuda(), torch.zeros(cout, device="cuda")
     ops.convT_wgrad_tc(xd, gyd, dw, db, stride)
     assert nerr(dw.cpu(), wt.grad) < 2e-3 and nerr(db.cpu(), b.grad) < 2e-3
+
+
+XFOLD_CASES = [
+    # n, d, h, w, cin, cout, k
+    (1, 8, 16, 16, 16, 16, (3, 3, 3)),     # K row = 96 el: one 64-box + one 32-box, N = 64
+    (2, 16, 16, 32, 32, 32, (3, 3, 3)),    # 192 el: three 64-boxes, N = 128
+    (1, 8, 16, 8, 48, 16, (3, 3, 3)),      # decoder: 288 el = 4 x 64 + 32
+    (1, 8, 16, 16, 16, 48, (3, 3, 3)),     # dgrad of the decoder conv: N = 192
+    (1, 16, 8, 12, 96, 32, (3, 3, 3)),     # 576 el = 9 boxes
+    (1, 9, 20, 12, 16, 16, (3, 3, 3)),     # partial tiles in y and z
+    (3, 1, 128, 16, 32, 16, (1, 3, 3)),    # 2D (kd = 1)
+    (1, 32, 32, 32, 16, 64, (3, 3, 3)),    # N = 256, more tiles than SMs
+]
+
+
+@pytest.mark.parametrize("case", XFOLD_CASES)
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_conv_fprop_xfold(case, dtype):
+    """x-folded kernel (4 x-voxels per GEMM row, block-Toeplitz weights) vs the CPU oracle arithmetic, fprop + dgrad."""
+    from biapy_b200 import _lib, ops
+    n, d, h, w, cin, cout, k = case
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(n, cin, d, h, w, generator=g).to(dtype).float().requires_grad_(True)
+    wt = (torch.randn(cout, cin, *k, generator=g) * 0.1).to(dtype).float()
+    b = torch.randn(cout, generator=g)
+    gy = torch.randn(n, cout, d, h, w, generator=g).to(dtype).float()
+    yr = F.conv3d(x, wt, b, padding=[kk // 2 for kk in k])
+    yr.backward(gy)
+    xd = cl(x.detach()).to(dtype)
+    ybuf = torch.zeros(n, d, h, w, cout + 16, dtype=dtype, device="cuda")
+    yv = ybuf[..., 8:8 + cout]
+    assert ops.conv_impl_query(xd, yv, k) == _lib.IMPL_XFOLD
+    wp = ops.pack_conv_weight_xfold(wt.cuda(), dtype, False)
+    ops.conv_fprop(xd, wp, b.cuda(), yv, k, impl=_lib.IMPL_XFOLD)
+    torch.cuda.synchronize()
+    assert nerr(ncdhw(yv), yr.detach()) < 1.5e-2
+    assert ybuf[..., :8].abs().max().item() == 0 and ybuf[..., 8 + cout:].abs().max().item() == 0
+    before = ncdhw(yv)
+    ops.conv_fprop(xd, wp, b.cuda(), yv, k, accumulate=True, impl=_lib.IMPL_XFOLD)
+    assert nerr(ncdhw(yv), before + yr.detach()) < 3e-2
+    # dgrad through the same kernel with the flipped / transposed Toeplitz packing (when the roles fit: Cout <= 96, Cin <= 64)
+    gyd = cl(gy).to(dtype)
+    dx = torch.empty(n, d, h, w, cin, dtype=dtype, device="cuda")
+    if ops.conv_impl_query(gyd, dx, k) == _lib.IMPL_XFOLD:
+        wpf = ops.pack_conv_weight_xfold(wt.cuda(), dtype, True)
+        ops.conv_fprop(gyd, wpf, None, dx, k, impl=_lib.IMPL_XFOLD)
+        assert nerr(ncdhw(dx), x.grad) < 1.5e-2
