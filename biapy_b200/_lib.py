@@ -54,7 +54,7 @@ SIGNATURES = {
     "b200_pack_conv_weight": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "b200_conv_fprop": (_I, [_T, _P, _P, _T, _T, _I, _I, _I, _I, _I, _P]),
     "b200_conv_wgrad": (_I, [_T, _T, _P, _P, _I, _I, _I, _I, _P]),
-    "b200_pack_conv_weight_xfold": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "b200_pack_conv_weight_xfold": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "b200_conv_impl_query": (_I, [_T, _T, _I, _I, _I, _I]),
     "b200_unpack_conv_wgrad": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "b200_convT_fprop": (_I, [_T, _P, _P, _T, _I, _I, _I, _P]),

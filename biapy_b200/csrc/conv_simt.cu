@@ -424,9 +424,10 @@ int conv_wgrad_umma(const b200_tensor* x, const b200_tensor* dy, float* dw, floa
                     cudaStream_t st);
 bool conv_wgrad_umma_supported(const b200_tensor* x, const b200_tensor* dy, int kd, int kh, int kw);
 bool conv_fprop_xfold_supported(const b200_tensor* x, const b200_tensor* y, int kd, int kh, int kw);
-int conv_fprop_xfold(const b200_tensor* x, const void* w, const float* bias, const b200_tensor* y, int kd, int kh, int accumulate,
-                     cudaStream_t st);
-int pack_weight_xfold(const float* w, void* packed, int dtype, int cout, int cin, int kd, int kh, int flip, cudaStream_t st);
+int conv_fprop_xfold(const b200_tensor* x, const void* w, const float* bias, const b200_tensor* y, int kd, int kh, int kw,
+                     int accumulate, cudaStream_t st);
+int pack_weight_xfold(const float* w, void* packed, int dtype, int cout, int cin, int kd, int kh, int kw, int flip,
+                      cudaStream_t st);
 
 }  // namespace b200
 
@@ -474,7 +475,7 @@ B200_EXPORT int b200_conv_fprop(const b200_tensor* x, const void* w_packed, cons
   if (impl == B200_IMPL_XFOLD) {   // weights must have been packed with b200_pack_conv_weight_xfold
     B200_CHECK_ARG(residual == nullptr && conv_fprop_xfold_supported(x, y, kd, kh, kw),
                    "conv_fprop: operands not supported by the x-folded kernel (query b200_conv_impl_query)");
-    return conv_fprop_xfold(x, w_packed, bias, y, kd, kh, accumulate, s);
+    return conv_fprop_xfold(x, w_packed, bias, y, kd, kh, kw, accumulate, s);
   }
   bool umma_ok = conv_fprop_umma_supported(x, residual, y, kd, kh, kw);
   if (impl == B200_IMPL_UMMA && !umma_ok) {
@@ -511,7 +512,7 @@ B200_EXPORT int b200_conv_impl_query(const b200_tensor* x, const b200_tensor* y,
 }
 
 B200_EXPORT int b200_pack_conv_weight_xfold(const float* w, void* packed, int32_t dtype, int32_t cout, int32_t cin, int32_t kd,
-                                            int32_t kh, int32_t flip_transpose, void* stream) {
-  B200_CHECK_ARG(w && packed && cout > 0 && cin > 0 && kd > 0 && kh > 0, "pack_conv_weight_xfold: bad args");
-  return pack_weight_xfold(w, packed, dtype, cout, cin, kd, kh, flip_transpose, (cudaStream_t)stream);
+                                            int32_t kh, int32_t kw, int32_t flip_transpose, void* stream) {
+  B200_CHECK_ARG(w && packed && cout > 0 && cin > 0 && kd > 0 && kh > 0 && (kw == 1 || kw == 3), "pack_conv_weight_xfold: bad args");
+  return pack_weight_xfold(w, packed, dtype, cout, cin, kd, kh, kw, flip_transpose, (cudaStream_t)stream);
 }

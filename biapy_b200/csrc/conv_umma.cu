@@ -253,10 +253,10 @@ conv_fprop_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
 // Half of the issued MACs hit Toeplitz zeros; the tensor pipe is not the bottleneck of these layers.
 struct XfoldParams {
   int n, d, h, w, cin, cout;
-  int kd, kh;                           // kw == 3
+  int kd, kh, kw;                       // kw in {1, 3}; a GEMM row covers win = 3 + kw input voxels
   int bh, bd;                           // rows of a tile: bh * bd == 128 (y fastest)
   int groups_x, tiles_h, tiles_d, num_tiles;
-  int kx;                               // 6 * cin
+  int kx;                               // win * cin
   int boxes64, has32;                   // K boxes per (dz, dy): boxes64 of 64 elements, then one of 32 if has32
   int nt;                               // 4 * cout
   int stages;
@@ -317,7 +317,7 @@ conv_fprop_xfold_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid_
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         int n, z0, y0, g;
         decode(tile, n, z0, y0, g);
-        const int e0 = (4 * g - 1) * p.cin;              // first element of the 6-voxel window (may be negative)
+        const int e0 = (4 * g - p.kw / 2) * p.cin;       // first element of the input window (may be negative)
         int kcol = 0;
         for (int dz = 0; dz < p.kd; ++dz)
           for (int dy = 0; dy < p.kh; ++dy)
@@ -437,24 +437,25 @@ conv_fprop_xfold_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid_
 // operand (roles of Cin/Cout swapped, taps mirrored) directly.
 template <typename T>
 __global__ void pack_weight_xfold_kernel(const float* __restrict__ w, T* __restrict__ out, int cout, int cin, int kd, int kh,
-                                         int flip) {
+                                         int kw, int flip) {
   // logical conv: co_l in [0, CO), ci_l in [0, CI) with CO = flip ? cin : cout, CI = flip ? cout : cin
   const int CO = flip ? cin : cout, CI = flip ? cout : cin;
-  const int64_t ktot = (int64_t)kd * kh * 6 * CI;
+  const int win = 3 + kw;
+  const int64_t ktot = (int64_t)kd * kh * win * CI;
   const int64_t total = (int64_t)4 * CO * ktot;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t t = i;
     const int ci = (int)(t % CI); t /= CI;
-    const int xi = (int)(t % 6); t /= 6;
+    const int xi = (int)(t % win); t /= win;
     const int dy = (int)(t % kh); t /= kh;
     const int dz = (int)(t % kd); t /= kd;
     const int co = (int)(t % CO);
     const int j = (int)(t / CO);
     const int kx = xi - j;
     float v = 0.f;
-    if (kx >= 0 && kx <= 2) {
-      if (!flip) v = w[((((int64_t)co * cin + ci) * kd + dz) * kh + dy) * 3 + kx];
-      else v = w[((((int64_t)ci * cin + co) * kd + (kd - 1 - dz)) * kh + (kh - 1 - dy)) * 3 + (2 - kx)];
+    if (kx >= 0 && kx < kw) {
+      if (!flip) v = w[((((int64_t)co * cin + ci) * kd + dz) * kh + dy) * kw + kx];
+      else v = w[((((int64_t)ci * cin + co) * kd + (kd - 1 - dz)) * kh + (kh - 1 - dy)) * kw + (kw - 1 - kx)];
     }
     out[i] = from_f<T>(v);
   }
@@ -710,6 +711,8 @@ static int loader_mode() {
 int conv_fprop_umma_v(const ActView& x, const void* w, const float* bias, const ActView& y, int kd, int kh, int kw,
                       int accumulate, cudaStream_t st);
 int conv_wgrad_umma_v(const ActView& x, const ActView& dy, float* dw, int kd, int kh, int kw, cudaStream_t st);
+bool conv_wgrad_xfold_ok(const ActView& x, const ActView& dy, int kd, int kh, int kw);
+int conv_wgrad_xfold_v(const ActView& x, const ActView& dy, float* dw, int kd, int kh, int kw, cudaStream_t st);
 
 }  // namespace sm100
 
@@ -845,7 +848,7 @@ static int make_tmap4(CUtensorMap* out, const void* base, int dtype, const cuuin
 
 bool conv_xfold_ok(const ActView& x, const ActView& y, int kd, int kh, int kw) {
   if (x.dtype != B200_BF16 && x.dtype != B200_F16) return false;
-  if (kw != 3 || kd > 5 || kh > 5) return false;
+  if ((kw != 3 && kw != 1) || kd > 5 || kh > 5) return false;
   if (x.c % 16 != 0 || y.c % 16 != 0 || y.c > 64 || x.c > 96) return false;
   if (x.sw != x.c || x.sh != (int64_t)x.w * x.c) return false;              // dense rows: 6 voxels are contiguous
   if (x.w % 4 != 0 || x.w < 8) return false;
@@ -854,12 +857,12 @@ bool conv_xfold_ok(const ActView& x, const ActView& y, int kd, int kh, int kw) {
   return encode_tiled_fn() != nullptr;
 }
 
-int conv_fprop_xfold_v(const ActView& x, const void* w, const float* bias, const ActView& y, int kd, int kh, int accumulate,
-                       cudaStream_t st) {
-  B200_CHECK_ARG(conv_xfold_ok(x, y, kd, kh, 3), "conv_fprop(xfold): unsupported operands");
+int conv_fprop_xfold_v(const ActView& x, const void* w, const float* bias, const ActView& y, int kd, int kh, int kw,
+                       int accumulate, cudaStream_t st) {
+  B200_CHECK_ARG(conv_xfold_ok(x, y, kd, kh, kw), "conv_fprop(xfold): unsupported operands");
   XfoldParams p{};
   p.n = x.n; p.d = x.d; p.h = x.h; p.w = x.w; p.cin = x.c; p.cout = y.c;
-  p.kd = kd; p.kh = kh;
+  p.kd = kd; p.kh = kh; p.kw = kw;
   {  // rows of a tile = bh x bd positions in (y, z)
     static const int cand[][2] = {{16, 8}, {8, 16}, {32, 4}, {4, 32}, {64, 2}, {2, 64}, {128, 1}, {1, 128}};
     double best = 1e30;
@@ -871,7 +874,7 @@ int conv_fprop_xfold_v(const ActView& x, const void* w, const float* bias, const
   p.groups_x = x.w / 4;
   p.tiles_h = (int)ceil_div(x.h, p.bh); p.tiles_d = (int)ceil_div(x.d, p.bd);
   p.num_tiles = x.n * p.tiles_d * p.tiles_h * p.groups_x;
-  p.kx = 6 * x.c;
+  p.kx = (3 + kw) * x.c;
   p.boxes64 = p.kx / 64; p.has32 = (p.kx % 64) ? 1 : 0;
   p.nt = 4 * y.c;
   p.a_bytes = 128u * 128u;
@@ -922,18 +925,19 @@ int conv_fprop_xfold_v(const ActView& x, const void* w, const float* bias, const
 bool conv_fprop_xfold_supported(const b200_tensor* x, const b200_tensor* y, int kd, int kh, int kw) {
   return sm100::conv_xfold_ok(sm100::view_of(x), sm100::view_of(y), kd, kh, kw);
 }
-int conv_fprop_xfold(const b200_tensor* x, const void* w, const float* bias, const b200_tensor* y, int kd, int kh, int accumulate,
-                     cudaStream_t st) {
-  return sm100::conv_fprop_xfold_v(sm100::view_of(x), w, bias, sm100::view_of(y), kd, kh, accumulate, st);
+int conv_fprop_xfold(const b200_tensor* x, const void* w, const float* bias, const b200_tensor* y, int kd, int kh, int kw,
+                     int accumulate, cudaStream_t st) {
+  return sm100::conv_fprop_xfold_v(sm100::view_of(x), w, bias, sm100::view_of(y), kd, kh, kw, accumulate, st);
 }
-int pack_weight_xfold(const float* w, void* packed, int dtype, int cout, int cin, int kd, int kh, int flip, cudaStream_t st) {
+int pack_weight_xfold(const float* w, void* packed, int dtype, int cout, int cin, int kd, int kh, int kw, int flip,
+                      cudaStream_t st) {
   const int CO = flip ? cin : cout, CI = flip ? cout : cin;
-  int64_t total = (int64_t)4 * CO * kd * kh * 6 * CI;
+  int64_t total = (int64_t)4 * CO * kd * kh * (3 + kw) * CI;
   unsigned blocks = (unsigned)(ceil_div(total, 256) < 8192 ? ceil_div(total, 256) : 8192);
   if (dtype == B200_BF16)
-    sm100::pack_weight_xfold_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w, (__nv_bfloat16*)packed, cout, cin, kd, kh, flip);
+    sm100::pack_weight_xfold_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w, (__nv_bfloat16*)packed, cout, cin, kd, kh, kw, flip);
   else if (dtype == B200_F16)
-    sm100::pack_weight_xfold_kernel<__half><<<blocks, 256, 0, st>>>(w, (__half*)packed, cout, cin, kd, kh, flip);
+    sm100::pack_weight_xfold_kernel<__half><<<blocks, 256, 0, st>>>(w, (__half*)packed, cout, cin, kd, kh, kw, flip);
   else {
     set_error("pack_weight_xfold: 16-bit dtypes only");
     return B200_ERR_ARG;
@@ -1103,6 +1107,185 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
               atomicAdd(dw + ((int64_t)(j0 + j) * taps + tap) * p.cin + ci, __uint_as_float(r[j]));
           }
         }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ x-folded wgrad
+// Weight gradient of the small-channel layers in the x-folded formulation (see conv_fprop_xfold_kernel):
+//     dWt[(dz,dy,xi,ci)][(j,co)] = sum over rows (n,z,y) and x-groups g of  X[z+dz, y+dy, 4g-pw+xi, ci] * dY[z, y, 4g+j, co]
+// GEMM rows (K) are (y,z) positions; the A operand is the input window (win*Cin contiguous elements per row) fetched as
+// 32-element / 64-byte TMA boxes = M-major SWIZZLE_64B atoms (4 atoms = one M = 128 block), the B operand is the dY row
+// (4 voxels x Cout contiguous elements) as N-major SWIZZLE_128B atoms of 64 elements.  The epilogue folds the Toeplitz
+// diagonals straight into dw[co][tap][ci] with fp32 atomics (kx = xi - j; entries outside [0, kw) are structural zeros).
+struct WgradXParams {
+  int n, d, h, w, cin, cout;
+  int kd, kh, kw, win;
+  int bh, bd, groups_x, tiles_h, tiles_d, num_vtiles;
+  int atoms_per_slab;      // win * cin / 32
+  int q_total;             // kd * kh * atoms_per_slab
+  int mb_total, g;         // M-blocks of 4 atoms; M-blocks per CTA
+  int a_stages, b_stages;
+  int nt;                  // 4 * cout
+  uint32_t b_boxes, b_bytes, a_off;
+  uint32_t idesc, tmem_cols;
+};
+
+constexpr uint32_t kXAtomBytes = 128u * 64u;          // [128 rows][32 el]
+constexpr uint32_t kXBlockBytes = 4u * kXAtomBytes;    // one M-block of A
+
+template <typename T>
+__global__ void __launch_bounds__(192, 1)
+conv_wgrad_xfold_kernel(const __grid_constant__ CUtensorMap tmx32, const __grid_constant__ CUtensorMap tmy64,
+                        float* __restrict__ dw, const WgradXParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t s_bar[2 * kMaxAStages + 2 * kMaxBStages + 1];
+  __shared__ uint32_t s_tmem;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_afull = smem_u32(&s_bar[0]);
+  const uint32_t bar_aempty = smem_u32(&s_bar[kMaxAStages]);
+  const uint32_t bar_bfull = smem_u32(&s_bar[2 * kMaxAStages]);
+  const uint32_t bar_bempty = smem_u32(&s_bar[2 * kMaxAStages + kMaxBStages]);
+  const uint32_t bar_done = smem_u32(&s_bar[2 * kMaxAStages + 2 * kMaxBStages]);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1); }
+    for (int s = 0; s < p.b_stages; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); }
+    mbar_init(bar_done, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmx32);
+    tma_prefetch_desc(&tmy64);
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&s_tmem), p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+
+  const int pd = p.kd / 2, ph = p.kh / 2, pw = p.kw / 2;
+  const int mb0 = blockIdx.y * p.g;
+  const int mb1 = min(mb0 + p.g, p.mb_total);
+
+  auto decode = [&](int vt, int& n, int& z0, int& y0, int& g) {
+    int t = vt;
+    g = t % p.groups_x; t /= p.groups_x;
+    y0 = (t % p.tiles_h) * p.bh; t /= p.tiles_h;
+    z0 = (t % p.tiles_d) * p.bd; t /= p.tiles_d;
+    n = t;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================================================================= TMA producer
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int vt = blockIdx.x; vt < p.num_vtiles; vt += gridDim.x) {
+        int n, z0, y0, g;
+        decode(vt, n, z0, y0, g);
+        mbar_wait(bar_bempty + 8 * bs, bph ^ 1);
+        const uint32_t b_dst = smem0 + bs * p.b_bytes;
+        mbar_expect_tx(bar_bfull + 8 * bs, p.b_bytes);
+        for (uint32_t i = 0; i < p.b_boxes; ++i)
+          asm volatile(
+              "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+              ::"r"(b_dst + i * 128u * 128u), "l"((uint64_t)&tmy64), "r"(bar_bfull + 8 * bs), "r"(4 * g * p.cout + (int)i * 64),
+                "r"(y0), "r"(z0), "r"(n)
+              : "memory");
+        if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+        // first atom of this CTA's M-group, then advanced incrementally
+        int at, dy, dz;
+        {
+          const int q = mb0 * 4;
+          const int slab = q / p.atoms_per_slab;
+          at = q - slab * p.atoms_per_slab;
+          dy = slab % p.kh; dz = slab / p.kh;
+        }
+        const int e0 = (4 * g - pw) * p.cin;
+        for (int mb = mb0; mb < mb1; ++mb) {
+          mbar_wait(bar_aempty + 8 * as, aph ^ 1);
+          const uint32_t a_dst = smem0 + p.a_off + as * kXBlockBytes;
+          const int nq = min(4, p.q_total - mb * 4);
+          mbar_expect_tx(bar_afull + 8 * as, (uint32_t)nq * kXAtomBytes);
+          for (int j = 0; j < nq; ++j) {
+            asm volatile(
+                "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                ::"r"(a_dst + j * kXAtomBytes), "l"((uint64_t)&tmx32), "r"(bar_afull + 8 * as), "r"(e0 + at * 32),
+                  "r"(y0 + dy - ph), "r"(z0 + dz - pd), "r"(n)
+                : "memory");
+            if (++at == p.atoms_per_slab) { at = 0; if (++dy == p.kh) { dy = 0; ++dz; } }
+          }
+          if (++as == p.a_stages) { as = 0; aph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ================================================================= MMA issuer
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      bool first = true;
+      for (int vt = blockIdx.x; vt < p.num_vtiles; vt += gridDim.x) {
+        mbar_wait(bar_bfull + 8 * bs, bph);
+        tc_fence_after();
+        const uint32_t b_base = smem0 + bs * p.b_bytes;
+        for (int mb = mb0; mb < mb1; ++mb) {
+          mbar_wait(bar_afull + 8 * as, aph);
+          tc_fence_after();
+          const uint32_t a_base = smem0 + p.a_off + as * kXBlockBytes;
+          const uint32_t d_tmem = tmem + (uint32_t)((mb - mb0) * p.nt);
+#pragma unroll 1
+          for (int ks = 0; ks < 8; ++ks) {
+            // A: M-major SWIZZLE_64B atoms (32 el), 16 K rows = 1024 B; B: N-major SWIZZLE_128B atoms (64 el), 16 rows = 2048 B
+            const uint64_t ad = make_smem_desc(a_base + ks * 1024u, kXAtomBytes, 512u, kSwizzle64);
+            const uint64_t bd = make_smem_desc(b_base + ks * 2048u, 128u * 128u, 1024u, kSwizzle128);
+            umma_f16(d_tmem, ad, bd, p.idesc, (first && ks == 0) ? 0u : 1u);
+          }
+          umma_commit(bar_aempty + 8 * as);
+          if (++as == p.a_stages) { as = 0; aph ^= 1; }
+        }
+        umma_commit(bar_bempty + 8 * bs);
+        if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+        first = false;
+      }
+      umma_commit(bar_done);
+    }
+  } else {
+    // =================================================================== epilogue: fold Toeplitz diagonals into dw
+    const int q4 = warp & 3;
+    const int row = q4 * 32 + lane;
+    const int taps = p.kd * p.kh * p.kw;
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+    for (int mb = mb0; mb < mb1; ++mb) {
+      const int q = mb * 4 + row / 32;                  // atom index
+      const bool valid = q < p.q_total;
+      const int slab = valid ? q / p.atoms_per_slab : 0;
+      const int e = valid ? (q - slab * p.atoms_per_slab) * 32 + (row & 31) : 0;      // element inside the window
+      const int xi = e / p.cin, ci = e - xi * p.cin;
+      const uint32_t taddr = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)((mb - mb0) * p.nt);
+      int j = 0, co = 0;
+      for (int c0 = 0; c0 < p.nt; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c0, r);
+        tmem_ld_wait();
+        const int kx = xi - j;
+        if (valid && kx >= 0 && kx < p.kw) {
+          const int tap = slab * p.kw + kx;
+          float* dst = dw + ((int64_t)co * taps + tap) * p.cin + ci;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) atomicAdd(dst + (int64_t)i * taps * p.cin, __uint_as_float(r[i]));
+        }
+        co += 16;
+        if (co == p.cout) { co = 0; ++j; }
       }
     }
   }
@@ -1285,6 +1468,85 @@ conv_wgrad_umma2_kernel(const T* __restrict__ x, const T* __restrict__ dy, float
   }
 }
 
+bool conv_wgrad_xfold_ok(const ActView& x, const ActView& dy, int kd, int kh, int kw) {
+  if (x.dtype != B200_BF16 && x.dtype != B200_F16) return false;
+  if ((kw != 3 && kw != 1) || kd > 5 || kh > 5) return false;
+  if (x.c % 16 != 0 || x.c > 96 || ((3 + kw) * x.c) % 32 != 0) return false;
+  if (!(dy.c == 16 || dy.c == 32 || dy.c == 64)) return false;
+  if (x.sw != x.c || x.sh != (int64_t)x.w * x.c) return false;
+  if (dy.sw != dy.c || dy.sh != (int64_t)dy.w * dy.c) return false;
+  if (x.w % 4 != 0 || x.w < 8) return false;
+  if (!aligned16(x.data) || !aligned16(dy.data)) return false;
+  if ((int64_t)x.d * x.h < 128) return false;
+  return encode_tiled_fn() != nullptr;
+}
+
+int conv_wgrad_xfold_v(const ActView& x, const ActView& dy, float* dw, int kd, int kh, int kw, cudaStream_t st) {
+  B200_CHECK_ARG(conv_wgrad_xfold_ok(x, dy, kd, kh, kw), "conv_wgrad(xfold): unsupported operands");
+  WgradXParams p{};
+  p.n = x.n; p.d = x.d; p.h = x.h; p.w = x.w; p.cin = x.c; p.cout = dy.c;
+  p.kd = kd; p.kh = kh; p.kw = kw; p.win = 3 + kw;
+  {
+    static const int cand[][2] = {{16, 8}, {8, 16}, {32, 4}, {4, 32}, {64, 2}, {2, 64}, {128, 1}, {1, 128}};
+    double best = 1e30;
+    for (auto& c : cand) {
+      double cover = (double)ceil_div(x.h, c[0]) * c[0] * ceil_div(x.d, c[1]) * c[1];
+      if (cover < best - 0.5) { best = cover; p.bh = c[0]; p.bd = c[1]; }
+    }
+  }
+  p.groups_x = x.w / 4;
+  p.tiles_h = (int)ceil_div(x.h, p.bh); p.tiles_d = (int)ceil_div(x.d, p.bd);
+  p.num_vtiles = x.n * p.tiles_d * p.tiles_h * p.groups_x;
+  p.atoms_per_slab = p.win * x.c / 32;
+  p.q_total = kd * kh * p.atoms_per_slab;
+  p.mb_total = (int)ceil_div(p.q_total, 4);
+  p.nt = 4 * dy.c;
+  p.g = 512 / p.nt;
+  if (p.g > p.mb_total) p.g = p.mb_total;
+  const int groups = (int)ceil_div(p.mb_total, p.g);
+  p.b_boxes = (uint32_t)p.nt / 64u;
+  p.b_bytes = 128u * (uint32_t)p.nt * 2u;
+  p.b_stages = 2;
+  p.a_off = p.b_stages * p.b_bytes;
+  int a_st = (int)((200u * 1024u - p.a_off) / kXBlockBytes);
+  if (a_st > 4) a_st = 4;
+  B200_CHECK_ARG(a_st >= 2, "conv_wgrad(xfold): tiles do not fit in shared memory");
+  p.a_stages = a_st;
+  p.idesc = make_idesc(x.dtype == B200_BF16, p.nt, 1, 1);
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(p.g * p.nt)) cols <<= 1;
+  p.tmem_cols = cols;
+
+  CUtensorMap tx, ty;
+  const cuuint64_t xd[4] = {(cuuint64_t)x.w * x.c, (cuuint64_t)x.h, (cuuint64_t)x.d, (cuuint64_t)x.n};
+  const cuuint64_t xs[3] = {(cuuint64_t)x.sh * 2, (cuuint64_t)x.sd * 2, (cuuint64_t)x.sn * 2};
+  const cuuint32_t bx[4] = {32, (cuuint32_t)p.bh, (cuuint32_t)p.bd, 1};
+  int rc = make_tmap4(&tx, x.data, x.dtype, xd, xs, bx);
+  if (rc) return rc;
+  const cuuint64_t yd[4] = {(cuuint64_t)dy.w * dy.c, (cuuint64_t)dy.h, (cuuint64_t)dy.d, (cuuint64_t)dy.n};
+  const cuuint64_t ys[3] = {(cuuint64_t)dy.sh * 2, (cuuint64_t)dy.sd * 2, (cuuint64_t)dy.sn * 2};
+  const cuuint32_t by[4] = {64, (cuuint32_t)p.bh, (cuuint32_t)p.bd, 1};
+  rc = make_tmap4(&ty, dy.data, dy.dtype, yd, ys, by);
+  if (rc) return rc;
+
+  int vsplit = sm_count() / groups;
+  if (vsplit < 1) vsplit = 1;
+  if (vsplit > p.num_vtiles) vsplit = p.num_vtiles;
+  dim3 grid((unsigned)vsplit, (unsigned)groups);
+  const size_t smem = (size_t)p.a_off + (size_t)p.a_stages * kXBlockBytes + 1024;
+  if (x.dtype == B200_BF16) {
+    auto kern = conv_wgrad_xfold_kernel<__nv_bfloat16>;
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 192, smem, st>>>(tx, ty, dw, p);
+  } else {
+    auto kern = conv_wgrad_xfold_kernel<__half>;
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 192, smem, st>>>(tx, ty, dw, p);
+  }
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
 }  // namespace sm100
 
 bool conv_wgrad_umma_supported(const b200_tensor* x, const b200_tensor* dy, int kd, int kh, int kw) {
@@ -1298,9 +1560,21 @@ bool conv_wgrad_umma_supported(const b200_tensor* x, const b200_tensor* dy, int 
   return sm100::encode_tiled_fn() != nullptr;
 }
 
+static int wgrad_xfold_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("B200_XFOLD");
+    mode = (e && strcmp(e, "0") == 0) ? 0 : 1;
+  }
+  return mode;
+}
+
 int conv_wgrad_umma(const b200_tensor* x, const b200_tensor* dy, float* dw, float* dbias, int kd, int kh, int kw,
                     cudaStream_t st) {
-  int rc = sm100::conv_wgrad_umma_v(sm100::view_of(x), sm100::view_of(dy), dw, kd, kh, kw, st);
+  const sm100::ActView xv = sm100::view_of(x), dv = sm100::view_of(dy);
+  int rc = (wgrad_xfold_mode() && sm100::conv_wgrad_xfold_ok(xv, dv, kd, kh, kw))
+               ? sm100::conv_wgrad_xfold_v(xv, dv, dw, kd, kh, kw, st)
+               : sm100::conv_wgrad_umma_v(xv, dv, dw, kd, kh, kw, st);
   if (rc) return rc;
   if (dbias) return conv_bias_grad(dy, dbias, st);
   return B200_OK;

@@ -58,20 +58,17 @@ __global__ void channel_sums_kernel(View<const T> x, double* __restrict__ sums, 
   const int tid = threadIdx.x;
   const int cv = tid % cv_count;
   const int row = tid / cv_count;
-  double acc[VEC], acc2[VEC];
-#pragma unroll
-  for (int i = 0; i < VEC; ++i) acc[i] = acc2[i] = 0.0;
   if (row < rows) {
+    // fp32 partials per thread (a few hundred voxels at most), fp64 across threads / blocks
+    float s[VEC], s2[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) s[i] = s2[i] = 0.f;
     const int64_t chunk = (x.spatial + gridDim.x - 1) / gridDim.x;
     const int64_t v0 = (int64_t)blockIdx.x * chunk;
     int64_t v1 = v0 + chunk;
     if (v1 > x.spatial) v1 = x.spatial;
     const T* base = x.p + (int64_t)n * x.spatial * x.ld + (int64_t)cv * VEC;
-    float f[VEC], s[VEC], s2[VEC];
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) s[i] = s2[i] = 0.f;
-    int cnt = 0;
-    float f2[VEC];
+    float f[VEC], f2[VEC];
     for (int64_t v = v0 + row; v < v1; v += 2 * rows) {
       const bool two = v + rows < v1;
       load_vec<T, VEC>(base + v * x.ld, f);
@@ -85,30 +82,15 @@ __global__ void channel_sums_kernel(View<const T> x, double* __restrict__ sums, 
           s2[i] = fmaf(f2[i], f2[i], s2[i]);
         }
       }
-      if (++cnt == 16) {
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-          acc[i] += (double)s[i];
-          acc2[i] += (double)s2[i];
-          s[i] = s2[i] = 0.f;
-        }
-        cnt = 0;
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      acc[i] += (double)s[i];
-      acc2[i] += (double)s2[i];
     }
     double* dst = s_red + ((int64_t)row * cv_count + cv) * VEC * 2;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      dst[2 * i] = acc[i];
-      dst[2 * i + 1] = acc2[i];
+      dst[2 * i] = (double)s[i];
+      dst[2 * i + 1] = (double)s2[i];
     }
   }
   __syncthreads();
-  // first `cv_count*VEC*2` threads reduce over rows
   const int items = cv_count * VEC * 2;
   for (int it = tid; it < items; it += blockDim.x) {
     double t = 0.0;
@@ -122,13 +104,13 @@ static int launch_channel_sums(const b200_tensor* x, double* sums, cudaStream_t 
   constexpr int V = VecOf<T>::n;
   View<const T> xv{(const T*)x->data, x->ld, x->c, voxels(x), (int64_t)x->d * x->h * x->w};
   auto grid_of = [&](int rows) {
-    int64_t chunks = ceil_div(xv.spatial, (int64_t)rows * 16);
-    int64_t cap = ceil_div((int64_t)sm_count() * 8, x->n);
+    int64_t chunks = ceil_div(xv.spatial, (int64_t)rows * 64);
+    int64_t cap = ceil_div((int64_t)sm_count() * 16, x->n);
     if (chunks > cap) chunks = cap;
     if (chunks < 1) chunks = 1;
     return dim3((unsigned)chunks, x->n);
   };
-  constexpr int VH = V / 2 > 0 ? V / 2 : 1;      // half-width vectors: ~60 registers -> 4 blocks per SM
+  constexpr int VH = V;
   if (vec_ok(x, V) && x->c / VH <= 256) {
     int cvn = x->c / VH;
     int rows = 256 / cvn;
@@ -206,7 +188,7 @@ __global__ void scale_shift_act_kernel(View<const TI> x, View<TO> y, const float
 // -------------------------------------------------------------------------------- norm+act backward, pass 1
 // same thread layout as channel_sums; accumulates (sum g, sum g*xhat) per (n,c)
 template <typename T, int VEC>
-__global__ void norm_act_bwd_reduce_kernel(View<const T> x, View<const T> dy, const float* __restrict__ mean,
+__global__ void __launch_bounds__(256, 3) norm_act_bwd_reduce_kernel(View<const T> x, View<const T> dy, const float* __restrict__ mean,
                                            const float* __restrict__ rstd, int groups,
                                            const float* __restrict__ gamma, const float* __restrict__ beta, int act,
                                            double* __restrict__ red, int cv_count, int rows) {
@@ -217,17 +199,18 @@ __global__ void norm_act_bwd_reduce_kernel(View<const T> x, View<const T> dy, co
   const int row = tid / cv_count;
   const int cpg = x.c / groups;
   if (row < rows) {
-    double acc[VEC], acc2[VEC];
-    float mu[VEC], rs[VEC], ga[VEC], be[VEC];
+    // ypre = x*ka + kb with ka = rs*ga, kb = be - mu*rs*ga.  Accumulates (sum g, sum g*x); the finalize kernel turns
+    // the second one into sum g*xhat = rs*sum(g*x) - mu*rs*sum(g), which keeps this loop at two constants per channel.
+    float ka[VEC], kb[VEC], s[VEC], s2[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      acc[i] = acc2[i] = 0.0;
       int c = cv * VEC + i;
       int g = c / cpg;
-      mu[i] = mean[(int64_t)n * groups + g];
-      rs[i] = rstd[(int64_t)n * groups + g];
-      ga[i] = gamma ? gamma[c] : 1.f;
-      be[i] = beta ? beta[c] : 0.f;
+      float mu = mean[(int64_t)n * groups + g], r = rstd[(int64_t)n * groups + g];
+      float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+      ka[i] = r * ga;
+      kb[i] = be - mu * r * ga;
+      s[i] = s2[i] = 0.f;
     }
     const int64_t chunk = (x.spatial + gridDim.x - 1) / gridDim.x;
     const int64_t v0 = (int64_t)blockIdx.x * chunk;
@@ -235,11 +218,7 @@ __global__ void norm_act_bwd_reduce_kernel(View<const T> x, View<const T> dy, co
     if (v1 > x.spatial) v1 = x.spatial;
     const T* xb = x.p + (int64_t)n * x.spatial * x.ld + (int64_t)cv * VEC;
     const T* db = dy.p + (int64_t)n * x.spatial * dy.ld + (int64_t)cv * VEC;
-    float fx[VEC], fd[VEC], s[VEC], s2[VEC];
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) s[i] = s2[i] = 0.f;
-    int cnt = 0;
-    float fx2[VEC], fd2[VEC];
+    float fx[VEC], fd[VEC], fx2[VEC], fd2[VEC];
     for (int64_t v = v0 + row; v < v1; v += 2 * rows) {
       const bool two = v + rows < v1;
       load_vec<T, VEC>(xb + v * x.ld, fx);
@@ -250,32 +229,21 @@ __global__ void norm_act_bwd_reduce_kernel(View<const T> x, View<const T> dy, co
       }
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
-        float xh = (fx[i] - mu[i]) * rs[i];
-        float g = fd[i] * act_grad(act, fmaf(xh, ga[i], be[i]));
+        float g = fd[i] * act_grad(act, fmaf(fx[i], ka[i], kb[i]));
         s[i] += g;
-        s2[i] = fmaf(g, xh, s2[i]);
+        s2[i] = fmaf(g, fx[i], s2[i]);
         if (two) {
-          float xh2 = (fx2[i] - mu[i]) * rs[i];
-          float g2 = fd2[i] * act_grad(act, fmaf(xh2, ga[i], be[i]));
+          float g2 = fd2[i] * act_grad(act, fmaf(fx2[i], ka[i], kb[i]));
           s[i] += g2;
-          s2[i] = fmaf(g2, xh2, s2[i]);
+          s2[i] = fmaf(g2, fx2[i], s2[i]);
         }
-      }
-      if (++cnt == 16) {
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-          acc[i] += (double)s[i];
-          acc2[i] += (double)s2[i];
-          s[i] = s2[i] = 0.f;
-        }
-        cnt = 0;
       }
     }
     double* dst = s_red + ((int64_t)row * cv_count + cv) * VEC * 2;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      dst[2 * i] = acc[i] + (double)s[i];
-      dst[2 * i + 1] = acc2[i] + (double)s2[i];
+      dst[2 * i] = (double)s[i];
+      dst[2 * i + 1] = (double)s2[i];
     }
   }
   __syncthreads();
@@ -293,18 +261,22 @@ __global__ void norm_bwd_finalize_kernel(const double* __restrict__ red, const f
                                          const float* __restrict__ beta, int n, int c, int groups, int64_t spatial,
                                          int batch_stats, float* __restrict__ coef, float* __restrict__ dgamma,
                                          float* __restrict__ dbeta) {
+  // red[n][c] = (S1 = sum g, Sgx = sum g*x);  S2 = sum g*xhat = rstd*Sgx - mean*rstd*S1
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   int cpg = c / groups;
   if (idx < n * groups) {
     int ni = idx / groups, g = idx % groups;
     int n0 = batch_stats ? 0 : ni, n1 = batch_stats ? n : ni + 1;
     double a = 0.0, b = 0.0;
-    for (int nn = n0; nn < n1; ++nn)
+    for (int nn = n0; nn < n1; ++nn) {
+      const double r = (double)rstd[(int64_t)nn * groups + g], mu = (double)mean[(int64_t)nn * groups + g];
       for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) {
         double ga = gamma ? (double)gamma[cc] : 1.0;
-        a += ga * red[((int64_t)nn * c + cc) * 2];
-        b += ga * red[((int64_t)nn * c + cc) * 2 + 1];
+        double s1 = red[((int64_t)nn * c + cc) * 2], sgx = red[((int64_t)nn * c + cc) * 2 + 1];
+        a += ga * s1;
+        b += ga * (r * sgx - mu * r * s1);
       }
+    }
     double m = (double)spatial * cpg * (n1 - n0);
     // with ypre = x*k0 + B and g = dy*act'(ypre):  dx = g*k0 - x*P - Q
     float r = rstd[idx], mu = mean[idx];
@@ -319,10 +291,13 @@ __global__ void norm_bwd_finalize_kernel(const double* __restrict__ red, const f
     }
   }
   if (idx < c) {
+    int g = idx / cpg;
     double sg = 0.0, sb = 0.0;
     for (int nn = 0; nn < n; ++nn) {
-      sb += red[((int64_t)nn * c + idx) * 2];
-      sg += red[((int64_t)nn * c + idx) * 2 + 1];
+      const double r = (double)rstd[(int64_t)nn * groups + g], mu = (double)mean[(int64_t)nn * groups + g];
+      double s1 = red[((int64_t)nn * c + idx) * 2], sgx = red[((int64_t)nn * c + idx) * 2 + 1];
+      sb += s1;
+      sg += r * sgx - mu * r * s1;
     }
     if (dgamma) dgamma[idx] += (float)sg;
     if (dbeta) dbeta[idx] += (float)sb;
@@ -829,15 +804,15 @@ B200_EXPORT int b200_norm_act_bwd_reduce(const b200_tensor* x, const b200_tensor
   cudaStream_t st = (cudaStream_t)stream;
   int64_t spatial = (int64_t)x->d * x->h * x->w;
   auto grid_of = [&](int rows) {
-    int64_t chunks = ceil_div(spatial, (int64_t)rows * 16);
-    int64_t cap = ceil_div((int64_t)sm_count() * 8, x->n);
+    int64_t chunks = ceil_div(spatial, (int64_t)rows * 64);
+    int64_t cap = ceil_div((int64_t)sm_count() * 16, x->n);
     if (chunks > cap) chunks = cap;
     if (chunks < 1) chunks = 1;
     return dim3((unsigned)chunks, x->n);
   };
   B200_DISPATCH_DTYPE(x->dtype, T, {
     constexpr int V = VecOf<T>::n;
-    constexpr int VH = V / 2;
+    constexpr int VH = V;
     View<const T> xv{(const T*)x->data, x->ld, x->c, voxels(x), spatial};
     View<const T> dv{(const T*)dy->data, dy->ld, dy->c, voxels(dy), spatial};
     if (vec_ok(x, V) && vec_ok(dy, V) && x->c / VH <= 256) {

@@ -93,7 +93,8 @@ class Tape:
         self.steps: List[Callable[[], None]] = []
         self.use_xfold = os.environ.get("B200_XFOLD", "1") != "0"
         self.param_grads: Dict[torch.nn.Parameter, torch.Tensor] = {}
-        self._packed: Dict[Tuple[int, bool], torch.Tensor] = {}
+        self._packed: Dict[Tuple, torch.Tensor] = {}
+        self._pad16: Dict[int, torch.Tensor] = {}
 
     # ------------------------------------------------------------------------------------------ helpers
     def new(self, like: torch.Tensor, channels: int, spatial: Optional[Sequence[int]] = None) -> TT:
@@ -108,21 +109,36 @@ class Tape:
             self.param_grads[p] = g
         return g
 
-    def _pack(self, w: torch.nn.Parameter, flip: bool, xfold: bool = False) -> torch.Tensor:
+    def _pack(self, w, flip: bool, xfold: bool = False, wsrc=None) -> torch.Tensor:
+        """Packed copy of a weight for this step; `w` is the cache key, `wsrc` the tensor to pack (defaults to w)."""
         key = (id(w), flip, xfold)
         t = self._packed.get(key)
         if t is None:
-            t = ops.pack_conv_weight_xfold(w, self.dtype, flip) if xfold else ops.pack_conv_weight(w, self.dtype, flip)
+            src = w if wsrc is None else wsrc
+            t = ops.pack_conv_weight_xfold(src, self.dtype, flip) if xfold else ops.pack_conv_weight(src, self.dtype, flip)
             self._packed[key] = t
         return t
 
-    def _conv_launch(self, x: torch.Tensor, w, flip: bool, bias, y: torch.Tensor, k, accumulate: bool):
+    def _dense_for_xfold(self, t: torch.Tensor, other_c: int) -> torch.Tensor:
+        """Gradients that arrive as a channel slice of a concat buffer are copied once into a dense tensor when the
+        layer is small-channel: both the x-folded dgrad and wgrad need contiguous voxel rows, and the streaming copy is
+        much cheaper than running the direct kernels on 32-byte TMA rows."""
+        if (self.dtype == torch.float32 or not self.use_xfold or self.impl != _lib.IMPL_AUTO or t.stride(3) == t.shape[4]
+                or t.shape[4] > 96 or other_c > 96 or t.shape[3] % 4 != 0 or t.shape[3] < 8 or t.shape[1] * t.shape[2] < 128):
+            return t
+        dense = torch.empty(t.shape, dtype=t.dtype, device=t.device)
+        ops.binary(t, None, dense, ops.OP_COPY)
+        return dense
+
+    def _conv_launch(self, x: torch.Tensor, w, flip: bool, bias, y: torch.Tensor, k, accumulate: bool, wkey=None):
         """Pick the kernel family for (x -> y) and launch it with the matching weight packing."""
         impl = self.impl
         if impl == _lib.IMPL_AUTO and self.dtype != torch.float32 and self.use_xfold:
+            x = self._dense_for_xfold(x, y.shape[4])
             if ops.conv_impl_query(x, y, k) == _lib.IMPL_XFOLD:
                 impl = _lib.IMPL_XFOLD
-        ops.conv_fprop(x, self._pack(w, flip, impl == _lib.IMPL_XFOLD), bias, y, k, accumulate=accumulate, impl=impl)
+        wkey = w if wkey is None else wkey
+        ops.conv_fprop(x, self._pack(wkey, flip, impl == _lib.IMPL_XFOLD, wsrc=w), bias, y, k, accumulate=accumulate, impl=impl)
 
     @staticmethod
     def _k3(k) -> Tuple[int, int, int]:
@@ -150,7 +166,7 @@ class Tape:
         self._conv_launch(x.data, w, False, self._f32(b), out.data, k, accumulate)
         if self.training:
             def bwd(x=x, out=out, w=w, b=b, k=k, cout=cout, cin=cin):
-                dy = out.grad()
+                dy = self._dense_for_xfold(out.grad(), cin)
                 assert out.grad_ready, "conv output gradient was never produced"
                 if w.requires_grad:
                     gb = self._pgrad(b) if (b is not None and b.requires_grad) else None
@@ -170,14 +186,12 @@ class Tape:
             buf = torch.zeros(tuple(x.shape[:4]) + (16,), dtype=self.dtype, device=self.device)
             ops.convert(x.data, buf[..., :cin])
             x.padded = buf
-        key = (id(w), "pad16")
-        wp = self._packed.get(key)
-        if wp is None:
+        w16 = self._pad16.get(id(w))
+        if w16 is None:
             w16 = torch.zeros((cout, 16) + tuple(w.shape[2:]), dtype=torch.float32, device=self.device)
             w16[:, :cin] = w.detach()
-            wp = ops.pack_conv_weight(w16, self.dtype, False)
-            self._packed[key] = wp
-        ops.conv_fprop(x.padded, wp, self._f32(b), out.data, k, accumulate=accumulate, impl=self.impl)
+            self._pad16[id(w)] = w16
+        self._conv_launch(x.padded, w16, False, self._f32(b), out.data, k, accumulate)
         if self.training:
             def bwd(x=x, out=out, w=w, b=b, k=k, cout=cout, cin=cin):
                 assert out.grad_ready, "conv output gradient was never produced"

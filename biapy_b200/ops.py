@@ -103,10 +103,10 @@ def pack_conv_weight_xfold(w: torch.Tensor, dtype: torch.dtype, flip_transpose: 
     k = tuple(w.shape[2:])
     if len(k) == 2:
         k = (1,) + k
-    assert k[2] == 3
+    assert k[2] in (1, 3)
     co_l, ci_l = (cin, cout) if flip_transpose else (cout, cin)
-    out = torch.empty(4 * co_l * k[0] * k[1] * 6 * ci_l, dtype=dtype, device=w.device)
-    _launch("b200_pack_conv_weight_xfold", _ptr(w), _ptr(out), _lib.torch_dtype_code(dtype), cout, cin, k[0], k[1],
+    out = torch.empty(4 * co_l * k[0] * k[1] * (3 + k[2]) * ci_l, dtype=dtype, device=w.device)
+    _launch("b200_pack_conv_weight_xfold", _ptr(w), _ptr(out), _lib.torch_dtype_code(dtype), cout, cin, k[0], k[1], k[2],
             1 if flip_transpose else 0, stream_ptr())
     return out
 

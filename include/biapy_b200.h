@@ -109,12 +109,12 @@ int b200_conv_fprop(const b200_tensor* x, const void* w_packed, const float* bia
  * Both outputs must be zero-initialised by the caller (they are accumulated with atomics).                  */
 int b200_conv_wgrad(const b200_tensor* x, const b200_tensor* dy, float* dw_packed, float* dbias,
                     int32_t kd, int32_t kh, int32_t kw, int32_t impl, void* stream);
-/* x-folded tensor-core kernel for small-channel 3x3(x3) layers (see csrc/conv_umma.cu): block-Toeplitz packing
- *   [(j, co)][(dz, dy, xi, ci)], j < 4, xi < 6  -- 8x the plain packing; elements = 4*Cout' * kd*kh*6*Cin'
+/* x-folded tensor-core kernel for small-channel layers with kw in {1, 3} (see csrc/conv_umma.cu): block-Toeplitz packing
+ *   [(j, co)][(dz, dy, xi, ci)], j < 4, xi < 3+kw; elements = 4*Cout' * kd*kh*(3+kw)*Cin'
  * where (Cout', Cin') = (Cout, Cin), or (Cin, Cout) when flip_transpose (dgrad operand).  Used with impl =
  * B200_IMPL_XFOLD in b200_conv_fprop; B200_IMPL_AUTO never selects it (the packing differs). */
 int b200_pack_conv_weight_xfold(const float* w, void* packed, int32_t dtype, int32_t cout, int32_t cin, int32_t kd,
-                                int32_t kh, int32_t flip_transpose, void* stream);
+                                int32_t kh, int32_t kw, int32_t flip_transpose, void* stream);
 /* best kernel family for these operands: B200_IMPL_XFOLD, B200_IMPL_UMMA or B200_IMPL_SIMT
  * (wgrad != 0: for b200_conv_wgrad with y = dy; never XFOLD) */
 int b200_conv_impl_query(const b200_tensor* x, const b200_tensor* y, int32_t kd, int32_t kh, int32_t kw, int32_t wgrad);
@@ -170,7 +170,7 @@ int b200_norm_finalize(const double* sums, int32_t n, int32_t c, int32_t groups,
 int b200_scale_shift_act(const b200_tensor* x, const float* scale, const float* shift, int32_t act,
                          const b200_tensor* y, void* stream);
 /* backward, pass 1: with xhat = (x-mean)*rstd, ypre = xhat*gamma+beta, g = dy*act'(ypre):
- *   red[N][C][2] (double, zero-initialised) += (sum g, sum g*xhat)                                            */
+ *   red[N][C][2] (double, zero-initialised) += (sum g, sum g*x)   [b200_norm_bwd_finalize derives sum g*xhat]  */
 int b200_norm_act_bwd_reduce(const b200_tensor* x, const b200_tensor* dy, const float* mean, const float* rstd,
                              int32_t groups, const float* gamma, const float* beta, int32_t act,
                              double* red, void* stream);

@@ -92,6 +92,9 @@ WGRAD_CASES = [
     (1, 4, 8, 8, 64, 32, (1, 1, 1)),       # pointwise
     (3, 16, 16, 16, 16, 32, (3, 3, 3)),    # many voxel tiles per CTA
     (1, 32, 32, 32, 96, 32, (3, 3, 3)),
+    (1, 8, 16, 16, 48, 16, (1, 1, 1)),     # x-folded wgrad, pointwise
+    (2, 9, 20, 12, 16, 64, (3, 3, 3)),     # x-folded wgrad, N = 256, partial tiles
+    (1, 16, 16, 8, 48, 16, (3, 3, 3)),     # x-folded wgrad, 3 M-groups
 ]
 
 
@@ -156,6 +159,9 @@ XFOLD_CASES = [
     (1, 9, 20, 12, 16, 16, (3, 3, 3)),     # partial tiles in y and z
     (3, 1, 128, 16, 32, 16, (1, 3, 3)),    # 2D (kd = 1)
     (1, 32, 32, 32, 16, 64, (3, 3, 3)),    # N = 256, more tiles than SMs
+    (1, 8, 16, 16, 48, 16, (1, 1, 1)),     # pointwise shortcut: window of 4 voxels, block-diagonal weights
+    (2, 16, 8, 8, 16, 32, (1, 1, 1)),
+    (1, 8, 16, 32, 96, 32, (1, 1, 1)),
 ]
 
 
