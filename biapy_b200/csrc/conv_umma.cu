@@ -84,6 +84,9 @@ struct FpropParams {
   uint32_t tmem_cols;
   int64_t ysw, ysh, ysd, ysn;           // output element strides (x, y, z, batch)
   int accumulate;
+  // transposed-convolution mode: GEMM column c = phase * pcout + co is scattered to the fine voxel
+  // (z*usd + a, y*ush + b, x*usw + c') of phase (a, b, c'); ys* are then the strides of the FINE tensor.  usd == 0: off.
+  int usd, ush, usw, pcout;
 };
 
 constexpr int kMaxStages = 12;
@@ -199,19 +202,33 @@ conv_fprop_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
       tc_fence_after();
       const int gz = z0 + lz, gy = y0 + ly, gx = x0 + lx;
       const bool valid = gz < p.d && gy < p.h && gx < p.w;
-      T* yrow = y + (int64_t)n * p.ysn + (int64_t)gz * p.ysd + (int64_t)gy * p.ysh + (int64_t)gx * p.ysw + n0;
+      const bool up = p.usd != 0;
+      T* ybase = up ? y + (int64_t)n * p.ysn + (int64_t)gz * p.usd * p.ysd + (int64_t)gy * p.ush * p.ysh + (int64_t)gx * p.usw * p.ysw
+                    : y + (int64_t)n * p.ysn + (int64_t)gz * p.ysd + (int64_t)gy * p.ysh + (int64_t)gx * p.ysw + n0;
+      // transposed mode: running (phase, channel) of the current 16-column chunk
+      int ph_t = up ? n0 / p.pcout : 0, ph_co = up ? n0 - ph_t * p.pcout : 0;
       const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.nt);
       for (int j0 = 0; j0 < p.nt; j0 += 16) {
         uint32_t r[16];
         tmem_ld16(taddr + j0, r);
         tmem_ld_wait();
         if (valid && n0 + j0 < p.cout) {
+          T* yrow;
+          const float* brow;
+          if (up) {
+            const int pc = ph_t % p.usw, pb = (ph_t / p.usw) % p.ush, pa = ph_t / (p.usw * p.ush);
+            yrow = ybase + (int64_t)pa * p.ysd + (int64_t)pb * p.ysh + (int64_t)pc * p.ysw + ph_co;
+            brow = bias ? bias + ph_co : nullptr;
+          } else {
+            yrow = ybase + j0;
+            brow = bias ? bias + n0 + j0 : nullptr;
+          }
           float f[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(r[j]) + (bias ? __ldg(bias + n0 + j0 + j) : 0.f);
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(r[j]) + (brow ? __ldg(brow + j) : 0.f);
           if (p.accumulate) {
-            Pack<T, 8> o0 = *reinterpret_cast<const Pack<T, 8>*>(yrow + j0);
-            Pack<T, 8> o1 = *reinterpret_cast<const Pack<T, 8>*>(yrow + j0 + 8);
+            Pack<T, 8> o0 = *reinterpret_cast<const Pack<T, 8>*>(yrow);
+            Pack<T, 8> o1 = *reinterpret_cast<const Pack<T, 8>*>(yrow + 8);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               f[j] += to_f<T>(o0.v[j]);
@@ -224,8 +241,12 @@ conv_fprop_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
             w0.v[j] = from_f<T>(f[j]);
             w1.v[j] = from_f<T>(f[8 + j]);
           }
-          *reinterpret_cast<Pack<T, 8>*>(yrow + j0) = w0;
-          *reinterpret_cast<Pack<T, 8>*>(yrow + j0 + 8) = w1;
+          *reinterpret_cast<Pack<T, 8>*>(yrow) = w0;
+          *reinterpret_cast<Pack<T, 8>*>(yrow + 8) = w1;
+        }
+        if (up) {
+          ph_co += 16;
+          if (ph_co == p.pcout) { ph_co = 0; ++ph_t; }
         }
       }
       tc_fence_before();
@@ -708,8 +729,9 @@ static int loader_mode() {
   return mode;
 }
 
+struct Upscale { int sd = 0, sh = 0, sw = 0, cout = 0; };   // transposed-convolution scatter epilogue (off when sd == 0)
 int conv_fprop_umma_v(const ActView& x, const void* w, const float* bias, const ActView& y, int kd, int kh, int kw,
-                      int accumulate, cudaStream_t st);
+                      int accumulate, cudaStream_t st, Upscale up = Upscale());
 int conv_wgrad_umma_v(const ActView& x, const ActView& dy, float* dw, int kd, int kh, int kw, cudaStream_t st);
 bool conv_wgrad_xfold_ok(const ActView& x, const ActView& dy, int kd, int kh, int kw);
 int conv_wgrad_xfold_v(const ActView& x, const ActView& dy, float* dw, int kd, int kh, int kw, cudaStream_t st);
@@ -779,10 +801,13 @@ static int conv_fprop_umma2_v(const ActView& x, const void* w, const float* bias
   return B200_OK;
 }
 
-int conv_fprop_umma_v(const ActView& xv, const void* w, const float* bias, const ActView& yv, int kd, int kh, int kw,
-                      int accumulate, cudaStream_t st) {
-  if (loader_mode() == 1) return conv_fprop_umma2_v(xv, w, bias, yv, kd, kh, kw, accumulate, st);
+int conv_fprop_umma_v(const ActView& xv, const void* w, const float* bias, const ActView& yv_in, int kd, int kh, int kw,
+                      int accumulate, cudaStream_t st, Upscale up) {
+  if (loader_mode() == 1 && up.sd == 0) return conv_fprop_umma2_v(xv, w, bias, yv_in, kd, kh, kw, accumulate, st);
   const ActView* x = &xv;
+  // in transposed mode the GEMM has taps*Cout columns; `yv` keeps the fine tensor's strides and gets c = taps*Cout
+  ActView yv = yv_in;
+  if (up.sd) yv.c = up.sd * up.sh * up.sw * up.cout;
   const ActView* y = &yv;
   B200_CHECK_ARG(aligned16(w), "conv_fprop(umma): packed weights must be 16-byte aligned");
   FpropParams p{};
@@ -810,6 +835,7 @@ int conv_fprop_umma_v(const ActView& xv, const void* w, const float* bias, const
   p.tmem_cols = cols;
   p.ysw = y->sw; p.ysh = y->sh; p.ysd = y->sd; p.ysn = y->sn;
   p.accumulate = accumulate;
+  p.usd = up.sd; p.ush = up.sh; p.usw = up.sw; p.pcout = up.cout;
 
   CUtensorMap tx, tw;
   int rc = make_act_tmap(&tx, *x, p.ck, p.bw, p.bh, p.bd);
@@ -1744,17 +1770,10 @@ B200_EXPORT int b200_convT_fprop_tc(const b200_tensor* x, const void* w_packed, 
                                     int32_t sd, int32_t sh, int32_t sw, void* stream) {
   B200_CHECK_ARG(check_tensor(x, "convT_fprop_tc.x") && check_tensor(y, "convT_fprop_tc.y") && w_packed, "%s", b200_last_error());
   B200_CHECK_ARG(convT_tc_ok(x, y, sd, sh, sw), "convT_fprop_tc: unsupported operands (query b200_convT_tc_supported first)");
-  const ActView xv = view_of(x);
-  int t = 0;
-  for (int a = 0; a < sd; ++a)
-    for (int b = 0; b < sh; ++b)
-      for (int c = 0; c < sw; ++c, ++t) {
-        const ActView yv = phase_view(y, sd, sh, sw, a, b, c);
-        const char* wt = (const char*)w_packed + (size_t)t * y->c * x->c * 2;
-        int rc = conv_fprop_umma_v(xv, wt, bias, yv, 1, 1, 1, 0, (cudaStream_t)stream);
-        if (rc) return rc;
-      }
-  return B200_OK;
+  // ONE GEMM [voxels][Cin] x [Cin][taps*Cout] whose epilogue scatters column block t to output phase t
+  Upscale up;
+  up.sd = sd; up.sh = sh; up.sw = sw; up.cout = y->c;
+  return conv_fprop_umma_v(view_of(x), w_packed, bias, view_of(y), 1, 1, 1, 0, (cudaStream_t)stream, up);
 }
 
 B200_EXPORT int b200_convT_dgrad_tc(const b200_tensor* dy, const void* w_packed_t, const b200_tensor* dx, int32_t sd,
