@@ -339,18 +339,35 @@ __global__ void norm_act_bwd_apply_rows_kernel(View<const T> x, View<const T> dy
   const T* xb = x.p + (int64_t)n * x.spatial * x.ld + cv * VEC;
   const T* db = dy.p + (int64_t)n * x.spatial * dy.ld + cv * VEC;
   T* ob = dx.p + (int64_t)n * x.spatial * dx.ld + cv * VEC;
-  for (int64_t v = (int64_t)blockIdx.x * rows + row; v < x.spatial; v += (int64_t)gridDim.x * rows) {
-    float fx[VEC], fd[VEC], fo[VEC];
-    load_vec<T, VEC>(xb + v * x.ld, fx);
-    load_vec<T, VEC>(db + v * dy.ld, fd);
-    if (accumulate) load_vec<T, VEC>(ob + v * dx.ld, fo);
+  constexpr int U = 4;                                   // independent 16-byte loads in flight per thread and tensor
+  const int64_t stride = (int64_t)gridDim.x * rows;
+  for (int64_t v0 = (int64_t)blockIdx.x * rows + row; v0 < x.spatial; v0 += U * stride) {
+    Pack<T, VEC> px[U], pd[U], po[U];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      float g = fd[i] * act_grad(act, fmaf(fx[i], k0[i], kb[i]));
-      float r = g * k0[i] - fx[i] * kp[i] - kq[i];
-      fo[i] = accumulate ? fo[i] + r : r;
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = v0 + u * stride;
+      if (v < x.spatial) {
+        px[u] = *reinterpret_cast<const Pack<T, VEC>*>(xb + v * x.ld);
+        pd[u] = *reinterpret_cast<const Pack<T, VEC>*>(db + v * dy.ld);
+        if (accumulate) po[u] = *reinterpret_cast<const Pack<T, VEC>*>(ob + v * dx.ld);
+      }
     }
-    store_vec<T, VEC>(ob + v * dx.ld, fo);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = v0 + u * stride;
+      if (v < x.spatial) {
+        Pack<T, VEC> out;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          const float fx = to_f<T>(px[u].v[i]);
+          const float g = to_f<T>(pd[u].v[i]) * act_grad(act, fmaf(fx, k0[i], kb[i]));
+          float r = g * k0[i] - fx * kp[i] - kq[i];
+          if (accumulate) r += to_f<T>(po[u].v[i]);
+          out.v[i] = from_f<T>(r);
+        }
+        *reinterpret_cast<Pack<T, VEC>*>(ob + v * dx.ld) = out;
+      }
+    }
   }
 }
 
@@ -368,12 +385,25 @@ __global__ void scale_shift_act_rows_kernel(View<const T> x, View<T> y, const fl
   }
   const T* xb = x.p + (int64_t)n * x.spatial * x.ld + cv * VEC;
   T* yb = y.p + (int64_t)n * x.spatial * y.ld + cv * VEC;
-  for (int64_t v = (int64_t)blockIdx.x * rows + row; v < x.spatial; v += (int64_t)gridDim.x * rows) {
-    float f[VEC];
-    load_vec<T, VEC>(xb + v * x.ld, f);
+  constexpr int U = 4;
+  const int64_t stride = (int64_t)gridDim.x * rows;
+  for (int64_t v0 = (int64_t)blockIdx.x * rows + row; v0 < x.spatial; v0 += U * stride) {
+    Pack<T, VEC> px[U];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) f[i] = act_fwd(act, fmaf(f[i], sc[i], sh[i]));
-    store_vec<T, VEC>(yb + v * y.ld, f);
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = v0 + u * stride;
+      if (v < x.spatial) px[u] = *reinterpret_cast<const Pack<T, VEC>*>(xb + v * x.ld);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = v0 + u * stride;
+      if (v < x.spatial) {
+        Pack<T, VEC> out;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) out.v[i] = from_f<T>(act_fwd(act, fmaf(to_f<T>(px[u].v[i]), sc[i], sh[i])));
+        *reinterpret_cast<Pack<T, VEC>*>(yb + v * y.ld) = out;
+      }
+    }
   }
 }
 
@@ -735,7 +765,7 @@ __global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, double* __r
 using namespace b200;
 
 static inline unsigned rows_grid(int64_t spatial, int rows, int n) {
-  int64_t b = ceil_div(spatial, (int64_t)rows * 4);
+  int64_t b = ceil_div(spatial, (int64_t)rows * 8);
   int64_t cap = ceil_div((int64_t)sm_count() * 8, n);
   if (b > cap) b = cap;
   if (b < 1) b = 1;
