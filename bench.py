@@ -34,6 +34,9 @@ CFG2 = dict(image_shape=(128, 128, 128, 2), activation="silu", feature_maps=[16,
             normalization="gn", k_size=3, yx_down=[2] * 4, z_down=[2] * 4, isotropy=[True] * 5, larger_io=False,
             conv_layers=[2] * 5, output_channels=[1])
 BATCH = 4
+METRIC = "3D patches/sec (128^3x2ch bf16 ResU-Net training step)"
+WORKLOAD = ("BASELINE config[1]: 3D Residual U-Net fm[16,32,64,128,256] gn/silu, 128^3x2ch, batch 4 per GPU, "
+            "training step = fwd + BCEWithLogits + bwd + grad all-reduce + AdamW(lr 1e-3, wd 0.02)")
 FWD_GFLOP_PER_PATCH = 305.61      # conv + convT, 2*MAC
 STEP_GFLOP_PER_PATCH = 913.08     # fwd + dgrad + wgrad minus dgrad of the two input-fed layers
 
@@ -180,11 +183,11 @@ def run_reference(args):
     ts = [cpu_step_time(threads) for _ in range(max(1, args.steps))]
     sec = sum(ts) / len(ts)
     v = 1.0 / sec
-    out = {"impl": "reference", "metric": "3D patches/sec (128^3x2ch ResU-Net training step)", "value": v, "unit": "patches/s",
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "patches/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "ResUNet fm[16,32,64,128,256] gn/silu 128^3x2ch training step (fwd+BCE+bwd+AdamW)",
-                      "sample": "batch 1 per step (the B200 arm runs batch 4 per GPU)"},
+           "config": {"workload": WORKLOAD, "sample": "bounded sample: one 128^3x2 patch (batch 1) per step on the host cores, fp32 "
+                                                       "(the reference has no AMP); the B200 arm runs batch 4 per GPU"},
            "cpu_baseline": {"value": v, "unit": "patches/s", "cores": threads, "kind": "port",
                             "sample": "one 128^3x2 patch per step, fwd+bwd+AdamW, torch CPU fp32 via oracle/port_models.py"},
            "e2e": {"value": v, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -271,11 +274,10 @@ def run_train(args):
         cpu = {"value": 1.0 / sec, "unit": "patches/s", "cores": cores, "kind": "port",
                "sample": "one training step on one 128^3x2 patch (batch 1), fp32, torch CPU via oracle/port_models.py"}
     out = {
-        "metric": "3D patches/sec (128^3x2ch bf16 ResU-Net training step)", "value": value, "unit": "patches/s",
+        "metric": METRIC, "value": value, "unit": "patches/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": "BASELINE config[1]: 3D Residual U-Net fm[16,32,64,128,256] gn/silu, 128^3x2ch, batch 4 per GPU, "
-                               "training step = fwd + BCEWithLogits + bwd + grad all-reduce + AdamW(lr 1e-3, wd 0.02)",
+        "config": {"workload": WORKLOAD,
                    "global_batch": patches, "parallelism": f"dp{world}", "cuda_graph": bool(args.graph),
                    "l2": "per-step working set (activations + gradients, several GB) >> 126 MB L2; no explicit flush",
                    "algorithmic_gflop_per_step": STEP_GFLOP_PER_PATCH * BATCH},
@@ -325,7 +327,9 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--detail", action="store_true", help="per-layer-shape kernel table in roofline.all")
-    ap.add_argument("--graph", action="store_true", help="replay forward+backward from a CUDA graph (e2e and value)")
+    ap.add_argument("--graph", dest="graph", action="store_true", default=True,
+                    help="replay forward+backward from a CUDA graph (default)")
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="eager launches (per-kernel events in the timed region)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

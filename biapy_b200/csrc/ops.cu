@@ -325,7 +325,7 @@ __global__ void norm_act_bwd_apply_kernel(View<const T> x, View<const T> dy, Vie
 // vectorised: grid = (chunks, N), block = rows x cvn threads; every thread keeps the coefficients of its 8 (4) channels
 // in registers, so the loop body is 2-3 16-byte loads, the activation derivative and one 16-byte store
 template <typename T, int VEC>
-__global__ void norm_act_bwd_apply_rows_kernel(View<const T> x, View<const T> dy, View<T> dx, int act,
+__global__ void __launch_bounds__(256, 2) norm_act_bwd_apply_rows_kernel(View<const T> x, View<const T> dy, View<T> dx, int act,
                                                const float* __restrict__ coef, int accumulate, int cvn, int rows) {
   const int n = blockIdx.y;
   const int cv = threadIdx.x % cvn, row = threadIdx.x / cvn;
@@ -339,7 +339,7 @@ __global__ void norm_act_bwd_apply_rows_kernel(View<const T> x, View<const T> dy
   const T* xb = x.p + (int64_t)n * x.spatial * x.ld + cv * VEC;
   const T* db = dy.p + (int64_t)n * x.spatial * dy.ld + cv * VEC;
   T* ob = dx.p + (int64_t)n * x.spatial * dx.ld + cv * VEC;
-  constexpr int U = 4;                                   // independent 16-byte loads in flight per thread and tensor
+  constexpr int U = 2;                                   // independent 16-byte loads in flight per thread and tensor
   const int64_t stride = (int64_t)gridDim.x * rows;
   for (int64_t v0 = (int64_t)blockIdx.x * rows + row; v0 < x.spatial; v0 += U * stride) {
     Pack<T, VEC> px[U], pd[U], po[U];
