@@ -454,6 +454,209 @@ conv_fprop_xfold_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid_
   }
 }
 
+// ---------------------------------------------------------------------------------- x-folded fprop, z-slab variant
+// The x-folded kernel above re-reads every input row once per (dz, dy) tap: 9x for a 3x3x3 layer, and it re-reads the
+// Toeplitz weights once per 128-row tile; it runs at the L2->SMEM limit (~8 TB/s, profiles/README.md).  This variant
+// keeps the GEMM but changes what travels: for each dy one SLAB of (8*RT + kd - 1) z-lines x 16 y-rows is loaded once
+// and the kd taps in z are served from it by moving the descriptor start address by whole 16-row lines (always a
+// multiple of the 1 KB / 512 B swizzle atom, so the TMA-written swizzle stays valid); RT = 2 row tiles (16 z-lines)
+// share every weight tile.  A bytes per voxel drop 2.4x, weight bytes 2x.  Separate rings for slabs and weight tiles.
+struct XslabParams {
+  int n, d, h, w, cin, cout;
+  int kd, kh, kw;
+  int rt;                               // row tiles per CTA tile (1 or 2): 8*rt z-lines x 16 y-rows x 4 x-voxels
+  int zl;                               // z-lines per slab = 8*rt + kd - 1
+  int groups_x, tiles_h, tiles_d, num_tiles;
+  int kx, boxes64, has32;
+  int nt, nbuf;                         // 4*cout; TMEM accumulator buffers (1 or 2)
+  int a_stages, b_stages;
+  uint32_t a_bytes, b_bytes, b_off;     // ring slot sizes (max box) and offset of the weight ring
+  uint32_t idesc, tmem_cols;
+  int64_t ysw, ysh, ysd, ysn;
+  int accumulate;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(192, 1)
+conv_fprop_xslab_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid_constant__ CUtensorMap tmx32,
+                        const __grid_constant__ CUtensorMap tmw64, const __grid_constant__ CUtensorMap tmw32,
+                        const float* __restrict__ bias, T* __restrict__ y, const XslabParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t s_bar[4 * kMaxStages + 4];
+  __shared__ uint32_t s_tmem;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_afull = smem_u32(&s_bar[0]);
+  const uint32_t bar_aempty = smem_u32(&s_bar[kMaxStages]);
+  const uint32_t bar_bfull = smem_u32(&s_bar[2 * kMaxStages]);
+  const uint32_t bar_bempty = smem_u32(&s_bar[3 * kMaxStages]);
+  const uint32_t bar_tfull = smem_u32(&s_bar[4 * kMaxStages]);
+  const uint32_t bar_tempty = smem_u32(&s_bar[4 * kMaxStages + 2]);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1); }
+    for (int s = 0; s < p.b_stages; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 128); }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmx64); tma_prefetch_desc(&tmx32); tma_prefetch_desc(&tmw64); tma_prefetch_desc(&tmw32);
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&s_tmem), p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  const int pd = p.kd / 2, ph = p.kh / 2;
+  const int nboxes = p.boxes64 + p.has32;
+  const uint32_t slab_rows = (uint32_t)p.zl * 16u;
+
+  auto decode = [&](int tile, int& n, int& z0, int& y0, int& g) {
+    int t = tile;
+    g = t % p.groups_x; t /= p.groups_x;
+    y0 = (t % p.tiles_h) * 16; t /= p.tiles_h;
+    z0 = (t % p.tiles_d) * 8 * p.rt; t /= p.tiles_d;
+    n = t;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================================================================= TMA producer (slab ring + weight ring)
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int n, z0, y0, g;
+        decode(tile, n, z0, y0, g);
+        const int e0 = (4 * g - p.kw / 2) * p.cin;
+        for (int dy = 0; dy < p.kh; ++dy)
+          for (int b = 0; b < nboxes; ++b) {
+            const bool wide = b < p.boxes64;
+            const uint32_t wbytes = wide ? 128u : 64u;
+            mbar_wait(bar_aempty + 8 * as, aph ^ 1);
+            const uint32_t fa = bar_afull + 8 * as;
+            mbar_expect_tx(fa, slab_rows * wbytes);
+            asm volatile(
+                "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                ::"r"(smem0 + as * p.a_bytes), "l"((uint64_t)(wide ? &tmx64 : &tmx32)), "r"(fa), "r"(e0 + b * 64),
+                  "r"(y0 + dy - ph), "r"(z0 - pd), "r"(n)
+                : "memory");
+            if (++as == p.a_stages) { as = 0; aph ^= 1; }
+            for (int dz = 0; dz < p.kd; ++dz) {
+              mbar_wait(bar_bempty + 8 * bs, bph ^ 1);
+              const uint32_t fb = bar_bfull + 8 * bs;
+              mbar_expect_tx(fb, (uint32_t)p.nt * wbytes);
+              tma_load_2d(smem0 + p.b_off + bs * p.b_bytes, wide ? &tmw64 : &tmw32, fb, (dz * p.kh + dy) * p.kx + b * 64, 0);
+              if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+            }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ================================================================= MMA issuer
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int buf = p.nbuf == 2 ? (it & 1) : 0;
+        const uint32_t par = p.nbuf == 2 ? ((it >> 1) & 1) : (it & 1);
+        mbar_wait(bar_tempty + 8 * buf, par ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem + (uint32_t)(buf * p.rt * p.nt);
+        bool first = true;
+        for (int dy = 0; dy < p.kh; ++dy)
+          for (int b = 0; b < nboxes; ++b) {
+            const bool wide = b < p.boxes64;
+            const uint32_t rowb = wide ? 128u : 64u;
+            const uint32_t layout = wide ? kSwizzle128 : kSwizzle64;
+            const uint32_t sbo = 8u * rowb;
+            const int ksteps = wide ? 4 : 2;
+            mbar_wait(bar_afull + 8 * as, aph);
+            tc_fence_after();
+            const uint32_t a_base = smem0 + as * p.a_bytes;
+            for (int dz = 0; dz < p.kd; ++dz) {
+              mbar_wait(bar_bfull + 8 * bs, bph);
+              tc_fence_after();
+              const uint32_t b_base = smem0 + p.b_off + bs * p.b_bytes;
+              for (int r = 0; r < p.rt; ++r) {
+                const uint32_t a_tile = a_base + (uint32_t)((r * 8 + dz) * 16) * rowb;    // whole 16-row lines: atom aligned
+                for (int k = 0; k < ksteps; ++k) {
+                  const uint64_t ad = make_smem_desc(a_tile + k * 32, 16, sbo, layout);
+                  const uint64_t bd = make_smem_desc(b_base + k * 32, 16, sbo, layout);
+                  umma_f16(d_tmem + (uint32_t)(r * p.nt), ad, bd, p.idesc, (first && k == 0) ? 0u : 1u);
+                }
+              }
+              first = false;
+              umma_commit(bar_bempty + 8 * bs);
+              if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+            }
+            umma_commit(bar_aempty + 8 * as);
+            if (++as == p.a_stages) { as = 0; aph ^= 1; }
+          }
+        umma_commit(bar_tfull + 8 * buf);
+      }
+    }
+  } else {
+    // =================================================================== epilogue
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int ly = row & 15, lzr = row >> 4;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int buf = p.nbuf == 2 ? (it & 1) : 0;
+      const uint32_t par = p.nbuf == 2 ? ((it >> 1) & 1) : (it & 1);
+      int n, z0, y0, g;
+      decode(tile, n, z0, y0, g);
+      mbar_wait(bar_tfull + 8 * buf, par);
+      tc_fence_after();
+      for (int r = 0; r < p.rt; ++r) {
+        const int gz = z0 + r * 8 + lzr, gy = y0 + ly;
+        const bool valid = gz < p.d && gy < p.h;
+        T* ybase = y + (int64_t)n * p.ysn + (int64_t)gz * p.ysd + (int64_t)gy * p.ysh + (int64_t)(4 * g) * p.ysw;
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.rt + r) * p.nt);
+        int j = 0, co = 0;
+        for (int c0 = 0; c0 < p.nt; c0 += 16) {
+          uint32_t rr[16];
+          tmem_ld16(taddr + c0, rr);
+          tmem_ld_wait();
+          if (valid && 4 * g + j < p.w) {
+            T* yrow = ybase + (int64_t)j * p.ysw + co;
+            float f[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(rr[i]) + (bias ? __ldg(bias + co + i) : 0.f);
+            if (p.accumulate) {
+              Pack<T, 8> o0 = *reinterpret_cast<const Pack<T, 8>*>(yrow);
+              Pack<T, 8> o1 = *reinterpret_cast<const Pack<T, 8>*>(yrow + 8);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                f[i] += to_f<T>(o0.v[i]);
+                f[8 + i] += to_f<T>(o1.v[i]);
+              }
+            }
+            Pack<T, 8> w0, w1;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              w0.v[i] = from_f<T>(f[i]);
+              w1.v[i] = from_f<T>(f[8 + i]);
+            }
+            *reinterpret_cast<Pack<T, 8>*>(yrow) = w0;
+            *reinterpret_cast<Pack<T, 8>*>(yrow + 8) = w1;
+          }
+          co += 16;
+          if (co == p.cout) { co = 0; ++j; }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_tempty + 8 * buf);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem, p.tmem_cols);
+  }
+}
+
 // Toeplitz packing: out[(j, co)][(dz, dy, xi, ci)] from w (Cout, Cin, kd, kh, 3) fp32; flip_transpose builds the dgrad
 // operand (roles of Cin/Cout swapped, taps mirrored) directly.
 template <typename T>
@@ -883,9 +1086,83 @@ bool conv_xfold_ok(const ActView& x, const ActView& y, int kd, int kh, int kw) {
   return encode_tiled_fn() != nullptr;
 }
 
+static int xslab_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("B200_XSLAB");
+    mode = (e && strcmp(e, "0") == 0) ? 0 : 1;
+  }
+  return mode;
+}
+
+static int conv_fprop_xslab_v(const ActView& x, const void* w, const float* bias, const ActView& y, int kd, int kh, int kw,
+                              int accumulate, cudaStream_t st) {
+  XslabParams p{};
+  p.n = x.n; p.d = x.d; p.h = x.h; p.w = x.w; p.cin = x.c; p.cout = y.c;
+  p.kd = kd; p.kh = kh; p.kw = kw;
+  p.nt = 4 * y.c;
+  p.rt = (x.d >= 16) ? 2 : 1;
+  p.nbuf = (2 * p.rt * p.nt <= 512) ? 2 : 1;
+  p.zl = 8 * p.rt + kd - 1;
+  p.groups_x = x.w / 4;
+  p.tiles_h = (int)ceil_div(x.h, 16); p.tiles_d = (int)ceil_div(x.d, 8 * p.rt);
+  p.num_tiles = x.n * p.tiles_d * p.tiles_h * p.groups_x;
+  p.kx = (3 + kw) * x.c;
+  p.boxes64 = p.kx / 64; p.has32 = (p.kx % 64) ? 1 : 0;
+  p.a_bytes = (((uint32_t)p.zl * 16u * 128u) + 1023u) & ~1023u;
+  p.b_bytes = (((uint32_t)p.nt * 128u) + 1023u) & ~1023u;
+  // split ~200 KB between the two rings: at least 2 slabs, the rest for weight tiles (3..6)
+  int a_st = 3, b_st;
+  for (;;) {
+    b_st = (int)((200u * 1024u - (uint32_t)a_st * p.a_bytes) / p.b_bytes);
+    if (b_st >= 3 || a_st == 2) break;
+    --a_st;
+  }
+  if (b_st > 6) b_st = 6;
+  B200_CHECK_ARG(b_st >= 2, "conv_fprop(xslab): tiles do not fit in shared memory");
+  p.a_stages = a_st; p.b_stages = b_st;
+  p.b_off = (uint32_t)a_st * p.a_bytes;
+  p.idesc = make_idesc(x.dtype == B200_BF16, p.nt, 0, 0);
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(p.nbuf * p.rt * p.nt)) cols <<= 1;
+  p.tmem_cols = cols;
+  p.ysw = y.sw; p.ysh = y.sh; p.ysd = y.sd; p.ysn = y.sn;
+  p.accumulate = accumulate;
+
+  CUtensorMap tx64, tx32, tw64, tw32;
+  const cuuint64_t xd[4] = {(cuuint64_t)x.w * x.c, (cuuint64_t)x.h, (cuuint64_t)x.d, (cuuint64_t)x.n};
+  const cuuint64_t xs[3] = {(cuuint64_t)x.sh * 2, (cuuint64_t)x.sd * 2, (cuuint64_t)x.sn * 2};
+  const cuuint32_t b64[4] = {64, 16, (cuuint32_t)p.zl, 1};
+  const cuuint32_t b32[4] = {32, 16, (cuuint32_t)p.zl, 1};
+  int rc = make_tmap4(&tx64, x.data, x.dtype, xd, xs, b64);
+  if (rc) return rc;
+  rc = make_tmap4(&tx32, x.data, x.dtype, xd, xs, b32);
+  if (rc) return rc;
+  const int64_t ktot = (int64_t)kd * kh * p.kx;
+  rc = make_matrix_tmap(&tw64, w, x.dtype, p.nt, ktot, p.nt, 64);
+  if (rc) return rc;
+  rc = make_matrix_tmap(&tw32, w, x.dtype, p.nt, ktot, p.nt, 32);
+  if (rc) return rc;
+
+  const size_t smem = (size_t)p.b_off + (size_t)p.b_stages * p.b_bytes + 1024;
+  int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  if (x.dtype == B200_BF16) {
+    auto kern = conv_fprop_xslab_kernel<__nv_bfloat16>;
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 192, smem, st>>>(tx64, tx32, tw64, tw32, bias, (__nv_bfloat16*)y.data, p);
+  } else {
+    auto kern = conv_fprop_xslab_kernel<__half>;
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 192, smem, st>>>(tx64, tx32, tw64, tw32, bias, (__half*)y.data, p);
+  }
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
 int conv_fprop_xfold_v(const ActView& x, const void* w, const float* bias, const ActView& y, int kd, int kh, int kw,
                        int accumulate, cudaStream_t st) {
   B200_CHECK_ARG(conv_xfold_ok(x, y, kd, kh, kw), "conv_fprop(xfold): unsupported operands");
+  if (xslab_mode() && kd == 3 && x.d >= 8 && x.h >= 16) return conv_fprop_xslab_v(x, w, bias, y, kd, kh, kw, accumulate, st);
   XfoldParams p{};
   p.n = x.n; p.d = x.d; p.h = x.h; p.w = x.w; p.cin = x.c; p.cout = y.c;
   p.kd = kd; p.kh = kh; p.kw = kw;

@@ -159,6 +159,9 @@ XFOLD_CASES = [
     (1, 9, 20, 12, 16, 16, (3, 3, 3)),     # partial tiles in y and z
     (3, 1, 128, 16, 32, 16, (1, 3, 3)),    # 2D (kd = 1)
     (1, 32, 32, 32, 16, 64, (3, 3, 3)),    # N = 256, more tiles than SMs
+    (1, 24, 24, 8, 48, 16, (3, 3, 3)),     # z-slab variant: two row tiles per CTA, partial tile in z and y
+    (1, 20, 16, 8, 16, 48, (3, 3, 3)),     # z-slab, N = 192: single TMEM buffer
+    (2, 40, 64, 32, 16, 16, (3, 3, 3)),    # z-slab, several tiles per CTA (ring wrap-around across tiles)
     (1, 8, 16, 16, 48, 16, (1, 1, 1)),     # pointwise shortcut: window of 4 voxels, block-diagonal weights
     (2, 16, 8, 8, 16, 32, (1, 1, 1)),
     (1, 8, 16, 32, 96, 32, (1, 1, 1)),
