@@ -92,7 +92,7 @@ struct FpropParams {
 constexpr int kMaxStages = 12;
 
 template <typename T>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(224, 1)
 conv_fprop_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                        const float* __restrict__ bias, T* __restrict__ y, const FpropParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -107,7 +107,7 @@ conv_fprop_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_full + 8 * s, 2);                    // activation producer + weight producer
       mbar_init(bar_empty + 8 * s, 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -137,33 +137,46 @@ conv_fprop_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     n = t;
   };
 
-  if (warp == 0) {
-    if (lane == 0) {
-      // ================================================================= TMA producer
+  if (warp == 0 || warp == 6) {
+    // =================================================================== TMA producers
+    // warp 0: activation boxes, warp 6: weight boxes.  One thread sustains one bulk-tensor copy per ~450 cycles whatever
+    // its size (tools/pipe_rates.py), so the two streams are issued by different warps; both arrive on the stage's full
+    // barrier (count 2) with their own byte counts.  Nested tap loops: no integer division in the issue loop.
+    if (elect_one()) {
+      const bool a_role = warp == 0;
+      const int kd = p.kd, kh = p.kh, kw = p.kw, chunks = p.chunks, ck = p.ck, stages = p.stages;
+      const uint32_t a_bytes = p.a_bytes, b_bytes = p.b_bytes, stage_bytes = p.stage_bytes;
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         int n, z0, y0, x0, n0;
         decode(tile, n, z0, y0, x0, n0);
-        // nested tap loops: the single producer lane must not spend its issue slots on integer division
         int kcol = 0;
-        for (int dz = 0; dz < p.kd; ++dz)
-          for (int dy = 0; dy < p.kh; ++dy)
-            for (int dx = 0; dx < p.kw; ++dx)
-              for (int ch = 0; ch < p.chunks; ++ch, kcol += p.ck) {
+        for (int dz = 0; dz < kd; ++dz)
+          for (int dy = 0; dy < kh; ++dy)
+            for (int dx = 0; dx < kw; ++dx)
+              for (int ch = 0; ch < chunks; ++ch, kcol += ck) {
                 mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                const uint32_t a_dst = smem0 + stage * p.stage_bytes;
+                const uint32_t a_dst = smem0 + stage * stage_bytes;
                 const uint32_t fb = bar_full + 8 * stage;
-                mbar_expect_tx(fb, p.a_bytes + p.b_bytes);
-                tma_load_5d(a_dst, &tmap_x, fb, ch * p.ck, x0 + dx - pw, y0 + dy - ph, z0 + dz - pd, n);
-                tma_load_2d(a_dst + p.a_bytes, &tmap_w, fb, kcol, n0);
-                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                if (a_role) {
+                  mbar_expect_tx(fb, a_bytes);
+                  tma_load_5d(a_dst, &tmap_x, fb, ch * ck, x0 + dx - pw, y0 + dy - ph, z0 + dz - pd, n);
+                } else {
+                  mbar_expect_tx(fb, b_bytes);
+                  tma_load_2d(a_dst + a_bytes, &tmap_w, fb, kcol, n0);
+                }
+                if (++stage == stages) { stage = 0; phase ^= 1; }
               }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ================================================================= MMA issuer
+      // descriptor template + slot address in 16-byte units: two 64-bit adds per MMA (umma_ksteps)
+      const int stages = p.stages, ksteps = p.ck / 16;
+      const uint32_t idesc = p.idesc, stage16 = p.stage_bytes >> 4, aoff16 = p.a_bytes >> 4, s0 = smem0 >> 4;
+      const uint64_t tmpl = make_smem_desc(0, 16, p.sbo, p.layout);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -172,18 +185,18 @@ conv_fprop_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
         mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem + buf * p.nt;
+        uint32_t acc = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
-          const uint32_t a_base = smem0 + stage * p.stage_bytes;
-          const uint32_t b_base = a_base + p.a_bytes;
-          for (int k = 0; k < p.ck / 16; ++k) {
-            const uint64_t ad = make_smem_desc(a_base + k * 32, 16, p.sbo, p.layout);
-            const uint64_t bd = make_smem_desc(b_base + k * 32, 16, p.sbo, p.layout);
-            umma_f16(d_tmem, ad, bd, p.idesc, (kb | k) != 0 ? 1u : 0u);
-          }
+          const uint32_t a16 = s0 + (uint32_t)stage * stage16;
+          const uint64_t ad = tmpl + a16, bd = tmpl + (a16 + aoff16);
+          if (ksteps == 4) umma_ksteps<4>(d_tmem, ad, bd, idesc, acc);
+          else if (ksteps == 2) umma_ksteps<2>(d_tmem, ad, bd, idesc, acc);
+          else umma_ksteps<1>(d_tmem, ad, bd, idesc, acc);
+          acc = 1;
           umma_commit(bar_empty + 8 * stage);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(bar_tfull + 8 * buf);
       }
@@ -288,7 +301,7 @@ struct XfoldParams {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(224, 1)
 conv_fprop_xfold_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid_constant__ CUtensorMap tmx32,
                         const __grid_constant__ CUtensorMap tmw64, const __grid_constant__ CUtensorMap tmw32,
                         const float* __restrict__ bias, T* __restrict__ y, const XfoldParams p) {
@@ -304,7 +317,7 @@ conv_fprop_xfold_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid_
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_full + 8 * s, 2);                    // activation producer + weight producer
       mbar_init(bar_empty + 8 * s, 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -330,9 +343,12 @@ conv_fprop_xfold_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid_
     n = t;
   };
 
-  if (warp == 0) {
-    if (lane == 0) {
-      // ================================================================= TMA producer
+  if (warp == 0 || warp == 6) {
+    // =================================================================== TMA producers
+    // warp 0 streams the activation boxes, warp 6 the weight boxes (one thread sustains only one bulk-tensor copy per
+    // ~450 cycles, tools/pipe_rates.py); both arrive on the stage's full barrier (count 2) with their own byte counts
+    if (elect_one()) {
+      const bool a_role = warp == 0;
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -348,21 +364,29 @@ conv_fprop_xfold_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid_
               const uint32_t a_dst = smem0 + stage * p.stage_bytes;
               const uint32_t fb = bar_full + 8 * stage;
               const uint32_t wbytes = wide ? 128u : 64u;
-              mbar_expect_tx(fb, 128u * wbytes + (uint32_t)p.nt * wbytes);
-              asm volatile(
-                  "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                  ::"r"(a_dst), "l"((uint64_t)(wide ? &tmx64 : &tmx32)), "r"(fb), "r"(e0 + b * 64), "r"(y0 + dy - ph),
-                    "r"(z0 + dz - pd), "r"(n)
-                  : "memory");
-              tma_load_2d(a_dst + p.a_bytes, wide ? &tmw64 : &tmw32, fb, kcol, 0);
+              if (a_role) {
+                mbar_expect_tx(fb, 128u * wbytes);
+                asm volatile(
+                    "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                    ::"r"(a_dst), "l"((uint64_t)(wide ? &tmx64 : &tmx32)), "r"(fb), "r"(e0 + b * 64), "r"(y0 + dy - ph),
+                      "r"(z0 + dz - pd), "r"(n)
+                    : "memory");
+              } else {
+                mbar_expect_tx(fb, (uint32_t)p.nt * wbytes);
+                tma_load_2d(a_dst + p.a_bytes, wide ? &tmw64 : &tmw32, fb, kcol, 0);
+              }
               kcol += wide ? 64 : 32;
               if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ================================================================= MMA issuer
+      const int stages = p.stages, boxes64 = p.boxes64;
+      const uint32_t idesc = p.idesc, stage16 = p.stage_bytes >> 4, aoff16 = p.a_bytes >> 4;
+      const uint64_t tmpl128 = make_smem_desc(0, 16, 1024, kSwizzle128), tmpl64 = make_smem_desc(0, 16, 512, kSwizzle64);
+      const uint32_t s0 = smem0 >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -373,22 +397,17 @@ conv_fprop_xfold_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid_
         tc_fence_after();
         const uint32_t d_tmem = tmem + buf * p.nt;
         int b = 0;
+        uint32_t acc = 0;
         for (int kb = 0; kb < nkb; ++kb) {
-          const bool wide = b < p.boxes64;
+          const bool wide = b < boxes64;
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
-          const uint32_t a_base = smem0 + stage * p.stage_bytes;
-          const uint32_t b_base = a_base + p.a_bytes;
-          const uint32_t layout = wide ? kSwizzle128 : kSwizzle64;
-          const uint32_t sbo = wide ? 1024u : 512u;
-          const int ksteps = wide ? 4 : 2;
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t ad = make_smem_desc(a_base + k * 32, 16, sbo, layout);
-            const uint64_t bd = make_smem_desc(b_base + k * 32, 16, sbo, layout);
-            umma_f16(d_tmem, ad, bd, p.idesc, (kb | k) != 0 ? 1u : 0u);
-          }
+          const uint32_t a16 = s0 + (uint32_t)stage * stage16;
+          if (wide) umma_ksteps<4>(d_tmem, tmpl128 + a16, tmpl128 + (a16 + aoff16), idesc, acc);
+          else umma_ksteps<2>(d_tmem, tmpl64 + a16, tmpl64 + (a16 + aoff16), idesc, acc);
+          acc = 1;
           umma_commit(bar_empty + 8 * stage);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          if (++stage == stages) { stage = 0; phase ^= 1; }
           if (++b == nboxes) b = 0;
         }
         umma_commit(bar_tfull + 8 * buf);
@@ -476,8 +495,10 @@ struct XslabParams {
   int accumulate;
 };
 
+constexpr int kSlabAWarps = 1, kSlabBWarps = 3;
+
 template <typename T>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(32 * (5 + kSlabAWarps + kSlabBWarps), 1)
 conv_fprop_xslab_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid_constant__ CUtensorMap tmx32,
                         const __grid_constant__ CUtensorMap tmw64, const __grid_constant__ CUtensorMap tmw32,
                         const float* __restrict__ bias, T* __restrict__ y, const XslabParams p) {
@@ -500,12 +521,12 @@ conv_fprop_xslab_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid_
     fence_barrier_init();
     tma_prefetch_desc(&tmx64); tma_prefetch_desc(&tmx32); tma_prefetch_desc(&tmw64); tma_prefetch_desc(&tmw32);
   }
-  if (warp == 1) tmem_alloc(smem_u32(&s_tmem), p.tmem_cols);
+  if (warp == 4) tmem_alloc(smem_u32(&s_tmem), p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s_tmem;
-  const int pd = p.kd / 2, ph = p.kh / 2;
+  const int pd = p.kd / 2, ph_pad = p.kh / 2;
   const int nboxes = p.boxes64 + p.has32;
   const uint32_t slab_rows = (uint32_t)p.zl * 16u;
 
@@ -517,11 +538,16 @@ conv_fprop_xslab_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid_
     n = t;
   };
 
-  if (warp == 0) {
-    if (lane == 0) {
-      // ================================================================= TMA producer (slab ring + weight ring)
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
+  if (warp >= 5) {
+    // =================================================================== TMA producers
+    // One thread sustains only one bulk-tensor copy per ~450 cycles whatever the box size (tools/pipe_rates.py), so the
+    // slab ring is fed by kSlabAWarps warps and the weight ring by kSlabBWarps warps, each taking every k-th item.
+    if (elect_one()) {
+      const bool a_role = warp < 5 + kSlabAWarps;
+      const int rank = a_role ? warp - 5 : warp - 5 - kSlabAWarps;
+      const int nrole = a_role ? kSlabAWarps : kSlabBWarps;
+      int turn = 0, slot = 0;
+      uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         int n, z0, y0, g;
         decode(tile, n, z0, y0, g);
@@ -530,28 +556,42 @@ conv_fprop_xslab_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid_
           for (int b = 0; b < nboxes; ++b) {
             const bool wide = b < p.boxes64;
             const uint32_t wbytes = wide ? 128u : 64u;
-            mbar_wait(bar_aempty + 8 * as, aph ^ 1);
-            const uint32_t fa = bar_afull + 8 * as;
-            mbar_expect_tx(fa, slab_rows * wbytes);
-            asm volatile(
-                "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                ::"r"(smem0 + as * p.a_bytes), "l"((uint64_t)(wide ? &tmx64 : &tmx32)), "r"(fa), "r"(e0 + b * 64),
-                  "r"(y0 + dy - ph), "r"(z0 - pd), "r"(n)
-                : "memory");
-            if (++as == p.a_stages) { as = 0; aph ^= 1; }
-            for (int dz = 0; dz < p.kd; ++dz) {
-              mbar_wait(bar_bempty + 8 * bs, bph ^ 1);
-              const uint32_t fb = bar_bfull + 8 * bs;
-              mbar_expect_tx(fb, (uint32_t)p.nt * wbytes);
-              tma_load_2d(smem0 + p.b_off + bs * p.b_bytes, wide ? &tmw64 : &tmw32, fb, (dz * p.kh + dy) * p.kx + b * 64, 0);
-              if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+            if (a_role) {
+              if (turn == rank) {
+                mbar_wait(bar_aempty + 8 * slot, ph ^ 1);
+                const uint32_t fa = bar_afull + 8 * slot;
+                mbar_expect_tx(fa, slab_rows * wbytes);
+                asm volatile(
+                    "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                    ::"r"(smem0 + slot * p.a_bytes), "l"((uint64_t)(wide ? &tmx64 : &tmx32)), "r"(fa), "r"(e0 + b * 64),
+                      "r"(y0 + dy - ph_pad), "r"(z0 - pd), "r"(n)
+                    : "memory");
+              }
+              if (++turn == nrole) turn = 0;
+              if (++slot == p.a_stages) { slot = 0; ph ^= 1; }
+            } else {
+              for (int dz = 0; dz < p.kd; ++dz) {
+                if (turn == rank) {
+                  mbar_wait(bar_bempty + 8 * slot, ph ^ 1);
+                  const uint32_t fb = bar_bfull + 8 * slot;
+                  mbar_expect_tx(fb, (uint32_t)p.nt * wbytes);
+                  tma_load_2d(smem0 + p.b_off + slot * p.b_bytes, wide ? &tmw64 : &tmw32, fb, (dz * p.kh + dy) * p.kx + b * 64, 0);
+                }
+                if (++turn == nrole) turn = 0;
+                if (++slot == p.b_stages) { slot = 0; ph ^= 1; }
+              }
             }
           }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
+  } else if (warp == 4) {
+    if (elect_one()) {
       // ================================================================= MMA issuer
+      // kernel parameters and descriptor templates live in registers; per MMA the loop does two 64-bit adds
+      const int kh = p.kh, kd = p.kd, rt = p.rt, a_stages = p.a_stages, b_stages = p.b_stages, boxes64 = p.boxes64;
+      const uint32_t nt = (uint32_t)p.nt, idesc = p.idesc, a_bytes = p.a_bytes, b_bytes = p.b_bytes;
+      const uint64_t tmpl128 = make_smem_desc(0, 16, 1024, kSwizzle128), tmpl64 = make_smem_desc(0, 16, 512, kSwizzle64);
+      const uint32_t a0 = smem0 >> 4, b0 = (smem0 + p.b_off) >> 4;
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       int it = 0;
@@ -560,36 +600,36 @@ conv_fprop_xslab_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid_
         const uint32_t par = p.nbuf == 2 ? ((it >> 1) & 1) : (it & 1);
         mbar_wait(bar_tempty + 8 * buf, par ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem + (uint32_t)(buf * p.rt * p.nt);
-        bool first = true;
-        for (int dy = 0; dy < p.kh; ++dy)
+        const uint32_t d0 = tmem + (uint32_t)buf * (uint32_t)rt * nt;
+        const uint32_t d1 = d0 + nt;
+        uint32_t acc = 0;
+        for (int dy = 0; dy < kh; ++dy)
           for (int b = 0; b < nboxes; ++b) {
-            const bool wide = b < p.boxes64;
-            const uint32_t rowb = wide ? 128u : 64u;
-            const uint32_t layout = wide ? kSwizzle128 : kSwizzle64;
-            const uint32_t sbo = 8u * rowb;
-            const int ksteps = wide ? 4 : 2;
+            const bool wide = b < boxes64;
+            // 16-row line of the slab in 16-byte units: 16 x 128 B = 128, 16 x 64 B = 64
+            const uint32_t line = wide ? 128u : 64u;
+            const uint64_t tmpl = wide ? tmpl128 : tmpl64;
             mbar_wait(bar_afull + 8 * as, aph);
             tc_fence_after();
-            const uint32_t a_base = smem0 + as * p.a_bytes;
-            for (int dz = 0; dz < p.kd; ++dz) {
+            const uint64_t a_slab = tmpl + (uint64_t)(a0 + (uint32_t)as * (a_bytes >> 4));
+            for (int dz = 0; dz < kd; ++dz) {
               mbar_wait(bar_bfull + 8 * bs, bph);
               tc_fence_after();
-              const uint32_t b_base = smem0 + p.b_off + bs * p.b_bytes;
-              for (int r = 0; r < p.rt; ++r) {
-                const uint32_t a_tile = a_base + (uint32_t)((r * 8 + dz) * 16) * rowb;    // whole 16-row lines: atom aligned
-                for (int k = 0; k < ksteps; ++k) {
-                  const uint64_t ad = make_smem_desc(a_tile + k * 32, 16, sbo, layout);
-                  const uint64_t bd = make_smem_desc(b_base + k * 32, 16, sbo, layout);
-                  umma_f16(d_tmem + (uint32_t)(r * p.nt), ad, bd, p.idesc, (first && k == 0) ? 0u : 1u);
-                }
+              const uint64_t bd = tmpl + (uint64_t)(b0 + (uint32_t)bs * (b_bytes >> 4));
+              const uint64_t ad = a_slab + (uint64_t)((uint32_t)dz * line);
+              if (wide) {
+                umma_ksteps<4>(d0, ad, bd, idesc, acc);
+                if (rt == 2) umma_ksteps<4>(d1, ad + 8u * 128u, bd, idesc, acc);
+              } else {
+                umma_ksteps<2>(d0, ad, bd, idesc, acc);
+                if (rt == 2) umma_ksteps<2>(d1, ad + 8u * 64u, bd, idesc, acc);
               }
-              first = false;
+              acc = 1;
               umma_commit(bar_bempty + 8 * bs);
-              if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+              if (++bs == b_stages) { bs = 0; bph ^= 1; }
             }
             umma_commit(bar_aempty + 8 * as);
-            if (++as == p.a_stages) { as = 0; aph ^= 1; }
+            if (++as == a_stages) { as = 0; aph ^= 1; }
           }
         umma_commit(bar_tfull + 8 * buf);
       }
@@ -650,7 +690,7 @@ conv_fprop_xslab_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 4) {
     __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem, p.tmem_cols);
@@ -1051,11 +1091,11 @@ int conv_fprop_umma_v(const ActView& xv, const void* w, const float* bias, const
   if (x->dtype == B200_BF16) {
     auto kern = conv_fprop_umma_kernel<__nv_bfloat16>;
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, 192, smem, st>>>(tx, tw, bias, (__nv_bfloat16*)y->data, p);
+    kern<<<grid, 224, smem, st>>>(tx, tw, bias, (__nv_bfloat16*)y->data, p);
   } else {
     auto kern = conv_fprop_umma_kernel<__half>;
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, 192, smem, st>>>(tx, tw, bias, (__half*)y->data, p);
+    kern<<<grid, 224, smem, st>>>(tx, tw, bias, (__half*)y->data, p);
   }
   B200_LAUNCH_CHECK();
   return B200_OK;
@@ -1149,11 +1189,11 @@ static int conv_fprop_xslab_v(const ActView& x, const void* w, const float* bias
   if (x.dtype == B200_BF16) {
     auto kern = conv_fprop_xslab_kernel<__nv_bfloat16>;
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, 192, smem, st>>>(tx64, tx32, tw64, tw32, bias, (__nv_bfloat16*)y.data, p);
+    kern<<<grid, 32 * (5 + kSlabAWarps + kSlabBWarps), smem, st>>>(tx64, tx32, tw64, tw32, bias, (__nv_bfloat16*)y.data, p);
   } else {
     auto kern = conv_fprop_xslab_kernel<__half>;
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, 192, smem, st>>>(tx64, tx32, tw64, tw32, bias, (__half*)y.data, p);
+    kern<<<grid, 32 * (5 + kSlabAWarps + kSlabBWarps), smem, st>>>(tx64, tx32, tw64, tw32, bias, (__half*)y.data, p);
   }
   B200_LAUNCH_CHECK();
   return B200_OK;
@@ -1213,11 +1253,11 @@ int conv_fprop_xfold_v(const ActView& x, const void* w, const float* bias, const
   if (x.dtype == B200_BF16) {
     auto kern = conv_fprop_xfold_kernel<__nv_bfloat16>;
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, 192, smem, st>>>(tx64, tx32, tw64, tw32, bias, (__nv_bfloat16*)y.data, p);
+    kern<<<grid, 224, smem, st>>>(tx64, tx32, tw64, tw32, bias, (__nv_bfloat16*)y.data, p);
   } else {
     auto kern = conv_fprop_xfold_kernel<__half>;
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, 192, smem, st>>>(tx64, tx32, tw64, tw32, bias, (__half*)y.data, p);
+    kern<<<grid, 224, smem, st>>>(tx64, tx32, tw64, tw32, bias, (__half*)y.data, p);
   }
   B200_LAUNCH_CHECK();
   return B200_OK;
@@ -1279,7 +1319,7 @@ constexpr uint32_t kBlockBytes = 8u * kChunkBytes;   // one M-block of A
 constexpr int kMaxAStages = 6, kMaxBStages = 3;
 
 template <typename T>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
                        float* __restrict__ dw, const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -1294,7 +1334,7 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   const uint32_t bar_done = smem_u32(&s_bar[2 * kMaxAStages + 2 * kMaxBStages]);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.a_stages; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1); }
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(bar_afull + 8 * s, 4); mbar_init(bar_aempty + 8 * s, 1); }   // 4 chunk producers
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); }
     mbar_init(bar_done, 1);
     fence_barrier_init();
@@ -1320,10 +1360,10 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   };
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ================================================================= TMA producer
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
+    if (elect_one()) {
+      // ================================================================= TMA producer of the dY tiles (B operand)
+      int bs = 0;
+      uint32_t bph = 0;
       for (int vt = blockIdx.x; vt < p.num_vtiles; vt += gridDim.x) {
         int n, z0, y0, x0;
         decode(vt, n, z0, y0, x0);
@@ -1333,56 +1373,82 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
         for (uint32_t i = 0; i < p.b_boxes; ++i)
           tma_load_5d(b_dst + i * 128u * p.b_box_c * 2u, &tmap_dy, bar_bfull + 8 * bs, (int)(i * p.b_box_c), x0, y0, z0, n);
         if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
-        // first chunk of this CTA's M-group, then advanced incrementally (no division per chunk)
-        int cc, dx, dy, dz;
-        {
-          const int q = mb0 * 8;
-          const int tap = q / p.chunks16;
-          cc = q - tap * p.chunks16;
-          dx = tap % p.kw; dy = (tap / p.kw) % p.kh; dz = tap / (p.kw * p.kh);
-        }
+      }
+    }
+  } else if (warp >= 6) {
+    if (elect_one()) {
+      // ================================================================= TMA producers of the input chunks (A operand)
+      // one thread sustains one bulk-tensor copy per ~450 cycles (tools/pipe_rates.py): warp 6 + j fetches chunks j and
+      // j + 4 of every M-block; all four warps arrive on the block's full barrier
+      const int j = warp - 6;
+      const int chunks16 = p.chunks16, kw = p.kw, kh = p.kh, a_stages = p.a_stages, q_total = p.q_total;
+      struct Pos { int cc, dx, dy, dz; };
+      auto advance = [&](Pos& c, int steps) {
+        c.cc += steps;
+        while (c.cc >= chunks16) { c.cc -= chunks16; if (++c.dx == kw) { c.dx = 0; if (++c.dy == kh) { c.dy = 0; ++c.dz; } } }
+      };
+      Pos start{0, 0, 0, 0};
+      {
+        const int q = mb0 * 8 + j;
+        const int tap = q / chunks16;
+        start.cc = q - tap * chunks16;
+        start.dx = tap % kw; start.dy = (tap / kw) % kh; start.dz = tap / (kw * kh);
+      }
+      int as = 0;
+      uint32_t aph = 0;
+      for (int vt = blockIdx.x; vt < p.num_vtiles; vt += gridDim.x) {
+        int n, z0, y0, x0;
+        decode(vt, n, z0, y0, x0);
+        Pos c0 = start, c1 = start;
+        advance(c1, 4);
         for (int mb = mb0; mb < mb1; ++mb) {
           mbar_wait(bar_aempty + 8 * as, aph ^ 1);
+          const uint32_t fa = bar_afull + 8 * as;
           const uint32_t a_dst = smem0 + p.a_off + as * kBlockBytes;
-          const int nq = min(8, p.q_total - mb * 8);
-          mbar_expect_tx(bar_afull + 8 * as, (uint32_t)nq * kChunkBytes);
-          for (int j = 0; j < nq; ++j) {
-            tma_load_5d(a_dst + j * kChunkBytes, &tmap_x, bar_afull + 8 * as, cc * 16, x0 + dx - pw, y0 + dy - ph,
-                        z0 + dz - pd, n);
-            if (++cc == p.chunks16) { cc = 0; if (++dx == p.kw) { dx = 0; if (++dy == p.kh) { dy = 0; ++dz; } } }
+          const int q = mb * 8 + j;
+          const int mine = (q < q_total ? 1 : 0) + (q + 4 < q_total ? 1 : 0);
+          if (mine) {
+            mbar_expect_tx(fa, (uint32_t)mine * kChunkBytes);
+            tma_load_5d(a_dst + j * kChunkBytes, &tmap_x, fa, c0.cc * 16, x0 + c0.dx - pw, y0 + c0.dy - ph, z0 + c0.dz - pd, n);
+            if (mine == 2)
+              tma_load_5d(a_dst + (j + 4) * kChunkBytes, &tmap_x, fa, c1.cc * 16, x0 + c1.dx - pw, y0 + c1.dy - ph,
+                          z0 + c1.dz - pd, n);
+          } else {
+            mbar_arrive(fa);
           }
-          if (++as == p.a_stages) { as = 0; aph ^= 1; }
+          advance(c0, 8);
+          advance(c1, 8);
+          if (++as == a_stages) { as = 0; aph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ================================================================= MMA issuer
+      // A: M-major, SWIZZLE_32B: 16 voxels (K) per instruction = 512 bytes of every chunk tile
+      const uint64_t tmpl_a = make_smem_desc(0, kChunkBytes, 256u, kSwizzle32);
+      const uint64_t tmpl_b = make_smem_desc(0, p.b_lbo, p.b_sbo, p.b_layout);
+      const uint32_t a0 = (smem0 + p.a_off) >> 4, b0 = smem0 >> 4, b16 = p.b_bytes >> 4, bstep16 = p.b_kstep >> 4;
+      const uint32_t idesc = p.idesc, cout = (uint32_t)p.cout;
+      const int a_stages = p.a_stages, b_stages = p.b_stages;
       int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
-      bool first = true;
+      uint32_t aph = 0, bph = 0, acc = 0;
       for (int vt = blockIdx.x; vt < p.num_vtiles; vt += gridDim.x) {
         mbar_wait(bar_bfull + 8 * bs, bph);
         tc_fence_after();
-        const uint32_t b_base = smem0 + bs * p.b_bytes;
-        for (int mb = mb0; mb < mb1; ++mb) {
+        const uint64_t bd = tmpl_b + (uint64_t)(b0 + (uint32_t)bs * b16);
+        uint32_t d_tmem = tmem;
+        for (int mb = mb0; mb < mb1; ++mb, d_tmem += cout) {
           mbar_wait(bar_afull + 8 * as, aph);
           tc_fence_after();
-          const uint32_t a_base = smem0 + p.a_off + as * kBlockBytes;
-          const uint32_t d_tmem = tmem + (uint32_t)((mb - mb0) * p.cout);
-#pragma unroll 1
-          for (int ks = 0; ks < 8; ++ks) {
-            // A: M-major, SWIZZLE_32B: 16 voxels (K) per instruction = 512 bytes of every chunk tile
-            const uint64_t ad = make_smem_desc(a_base + ks * 512u, kChunkBytes, 256u, kSwizzle32);
-            const uint64_t bd = make_smem_desc(b_base + ks * p.b_kstep, p.b_lbo, p.b_sbo, p.b_layout);
-            umma_f16(d_tmem, ad, bd, p.idesc, (first && ks == 0) ? 0u : 1u);
-          }
+          const uint64_t ad = tmpl_a + (uint64_t)(a0 + (uint32_t)as * (kBlockBytes >> 4));
+          umma_ksteps_strided<8>(d_tmem, ad, bd, 512u >> 4, bstep16, idesc, acc);
           umma_commit(bar_aempty + 8 * as);
-          if (++as == p.a_stages) { as = 0; aph ^= 1; }
+          if (++as == a_stages) { as = 0; aph ^= 1; }
         }
         umma_commit(bar_bempty + 8 * bs);
-        if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
-        first = false;
+        if (++bs == b_stages) { bs = 0; bph ^= 1; }
+        acc = 1;
       }
       umma_commit(bar_done);
     }
@@ -1446,7 +1512,7 @@ constexpr uint32_t kXAtomBytes = 128u * 64u;          // [128 rows][32 el]
 constexpr uint32_t kXBlockBytes = 4u * kXAtomBytes;    // one M-block of A
 
 template <typename T>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 conv_wgrad_xfold_kernel(const __grid_constant__ CUtensorMap tmx32, const __grid_constant__ CUtensorMap tmy64,
                         float* __restrict__ dw, const WgradXParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -1461,7 +1527,7 @@ conv_wgrad_xfold_kernel(const __grid_constant__ CUtensorMap tmx32, const __grid_
   const uint32_t bar_done = smem_u32(&s_bar[2 * kMaxAStages + 2 * kMaxBStages]);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.a_stages; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1); }
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(bar_afull + 8 * s, 4); mbar_init(bar_aempty + 8 * s, 1); }   // 4 atom producers
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); }
     mbar_init(bar_done, 1);
     fence_barrier_init();
@@ -1487,10 +1553,10 @@ conv_wgrad_xfold_kernel(const __grid_constant__ CUtensorMap tmx32, const __grid_
   };
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ================================================================= TMA producer
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
+    if (elect_one()) {
+      // ================================================================= TMA producer of the dY tiles (B operand)
+      int bs = 0;
+      uint32_t bph = 0;
       for (int vt = blockIdx.x; vt < p.num_vtiles; vt += gridDim.x) {
         int n, z0, y0, g;
         decode(vt, n, z0, y0, g);
@@ -1504,60 +1570,74 @@ conv_wgrad_xfold_kernel(const __grid_constant__ CUtensorMap tmx32, const __grid_
                 "r"(y0), "r"(z0), "r"(n)
               : "memory");
         if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
-        // first atom of this CTA's M-group, then advanced incrementally
-        int at, dy, dz;
-        {
-          const int q = mb0 * 4;
-          const int slab = q / p.atoms_per_slab;
-          at = q - slab * p.atoms_per_slab;
-          dy = slab % p.kh; dz = slab / p.kh;
-        }
+      }
+    }
+  } else if (warp >= 6) {
+    if (elect_one()) {
+      // ================================================================= TMA producers of the input atoms (A operand)
+      // one thread sustains one bulk-tensor copy per ~450 cycles (tools/pipe_rates.py): warp 6 + j fetches atom j of every
+      // M-block; all four arrive on the block's full barrier (a producer without an atom in the last block just arrives)
+      const int j = warp - 6;
+      const int aps = p.atoms_per_slab, kh = p.kh, a_stages = p.a_stages, q_total = p.q_total;
+      int at0, dy0, dz0;
+      {
+        const int q = mb0 * 4 + j;
+        const int slab = q / aps;
+        at0 = q - slab * aps;
+        dy0 = slab % kh; dz0 = slab / kh;
+      }
+      int as = 0;
+      uint32_t aph = 0;
+      for (int vt = blockIdx.x; vt < p.num_vtiles; vt += gridDim.x) {
+        int n, z0, y0, g;
+        decode(vt, n, z0, y0, g);
         const int e0 = (4 * g - pw) * p.cin;
+        int at = at0, dy = dy0, dz = dz0;
         for (int mb = mb0; mb < mb1; ++mb) {
           mbar_wait(bar_aempty + 8 * as, aph ^ 1);
-          const uint32_t a_dst = smem0 + p.a_off + as * kXBlockBytes;
-          const int nq = min(4, p.q_total - mb * 4);
-          mbar_expect_tx(bar_afull + 8 * as, (uint32_t)nq * kXAtomBytes);
-          for (int j = 0; j < nq; ++j) {
+          const uint32_t fa = bar_afull + 8 * as;
+          if (mb * 4 + j < q_total) {
+            mbar_expect_tx(fa, kXAtomBytes);
             asm volatile(
                 "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                ::"r"(a_dst + j * kXAtomBytes), "l"((uint64_t)&tmx32), "r"(bar_afull + 8 * as), "r"(e0 + at * 32),
+                ::"r"(smem0 + p.a_off + as * kXBlockBytes + j * kXAtomBytes), "l"((uint64_t)&tmx32), "r"(fa), "r"(e0 + at * 32),
                   "r"(y0 + dy - ph), "r"(z0 + dz - pd), "r"(n)
                 : "memory");
-            if (++at == p.atoms_per_slab) { at = 0; if (++dy == p.kh) { dy = 0; ++dz; } }
+          } else {
+            mbar_arrive(fa);
           }
-          if (++as == p.a_stages) { as = 0; aph ^= 1; }
+          at += 4;
+          while (at >= aps) { at -= aps; if (++dy == kh) { dy = 0; ++dz; } }
+          if (++as == a_stages) { as = 0; aph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ================================================================= MMA issuer
+      // A: M-major SWIZZLE_64B atoms (32 el), 16 K rows = 1024 B; B: N-major SWIZZLE_128B atoms (64 el), 16 rows = 2048 B
+      const uint64_t tmpl_a = make_smem_desc(0, kXAtomBytes, 512u, kSwizzle64);
+      const uint64_t tmpl_b = make_smem_desc(0, 128u * 128u, 1024u, kSwizzle128);
+      const uint32_t a0 = (smem0 + p.a_off) >> 4, b0 = smem0 >> 4, b16 = p.b_bytes >> 4, idesc = p.idesc, nt = (uint32_t)p.nt;
+      const int a_stages = p.a_stages, b_stages = p.b_stages;
       int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
-      bool first = true;
+      uint32_t aph = 0, bph = 0, acc = 0;
       for (int vt = blockIdx.x; vt < p.num_vtiles; vt += gridDim.x) {
         mbar_wait(bar_bfull + 8 * bs, bph);
         tc_fence_after();
-        const uint32_t b_base = smem0 + bs * p.b_bytes;
-        for (int mb = mb0; mb < mb1; ++mb) {
+        const uint64_t bd = tmpl_b + (uint64_t)(b0 + (uint32_t)bs * b16);
+        uint32_t d_tmem = tmem;
+        for (int mb = mb0; mb < mb1; ++mb, d_tmem += nt) {
           mbar_wait(bar_afull + 8 * as, aph);
           tc_fence_after();
-          const uint32_t a_base = smem0 + p.a_off + as * kXBlockBytes;
-          const uint32_t d_tmem = tmem + (uint32_t)((mb - mb0) * p.nt);
-#pragma unroll 1
-          for (int ks = 0; ks < 8; ++ks) {
-            // A: M-major SWIZZLE_64B atoms (32 el), 16 K rows = 1024 B; B: N-major SWIZZLE_128B atoms (64 el), 16 rows = 2048 B
-            const uint64_t ad = make_smem_desc(a_base + ks * 1024u, kXAtomBytes, 512u, kSwizzle64);
-            const uint64_t bd = make_smem_desc(b_base + ks * 2048u, 128u * 128u, 1024u, kSwizzle128);
-            umma_f16(d_tmem, ad, bd, p.idesc, (first && ks == 0) ? 0u : 1u);
-          }
+          const uint64_t ad = tmpl_a + (uint64_t)(a0 + (uint32_t)as * (kXBlockBytes >> 4));
+          umma_ksteps_strided<8>(d_tmem, ad, bd, 1024u >> 4, 2048u >> 4, idesc, acc);
           umma_commit(bar_aempty + 8 * as);
-          if (++as == p.a_stages) { as = 0; aph ^= 1; }
+          if (++as == a_stages) { as = 0; aph ^= 1; }
         }
         umma_commit(bar_bempty + 8 * bs);
-        if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
-        first = false;
+        if (++bs == b_stages) { bs = 0; bph ^= 1; }
+        acc = 1;
       }
       umma_commit(bar_done);
     }
@@ -1840,11 +1920,11 @@ int conv_wgrad_xfold_v(const ActView& x, const ActView& dy, float* dw, int kd, i
   if (x.dtype == B200_BF16) {
     auto kern = conv_wgrad_xfold_kernel<__nv_bfloat16>;
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, 192, smem, st>>>(tx, ty, dw, p);
+    kern<<<grid, 320, smem, st>>>(tx, ty, dw, p);
   } else {
     auto kern = conv_wgrad_xfold_kernel<__half>;
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, 192, smem, st>>>(tx, ty, dw, p);
+    kern<<<grid, 320, smem, st>>>(tx, ty, dw, p);
   }
   B200_LAUNCH_CHECK();
   return B200_OK;
@@ -1946,11 +2026,11 @@ int conv_wgrad_umma_v(const ActView& xv, const ActView& dyv, float* dw, int kd, 
   if (x->dtype == B200_BF16) {
     auto kern = conv_wgrad_umma_kernel<__nv_bfloat16>;
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, 192, smem, st>>>(tx, tdy, dw, p);
+    kern<<<grid, 320, smem, st>>>(tx, tdy, dw, p);
   } else {
     auto kern = conv_wgrad_umma_kernel<__half>;
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, 192, smem, st>>>(tx, tdy, dw, p);
+    kern<<<grid, 320, smem, st>>>(tx, tdy, dw, p);
   }
   B200_LAUNCH_CHECK();
   return B200_OK;
@@ -2089,8 +2169,164 @@ B200_EXPORT int b200_convT_wgrad_tc(const b200_tensor* x, const b200_tensor* dy,
   return B200_OK;
 }
 
+// ------------------------------------------------------------------------------- tensor-pipe microbenchmark (diagnostic)
+// Issues `iters` tcgen05.mma (M = 128, N = n, K = 16, bf16) from one thread per CTA over shared memory tiles and reports
+// cycles per instruction: the ceiling the conv kernels' MMA lane can reach for a given N / swizzle / commit cadence.
+namespace b200 { namespace sm100 {
+template <int CE>
+__global__ void __launch_bounds__(128, 1)
+umma_rate_kernel(int n, int groups, uint32_t idesc, long long* out) {
+  // CE = MMAs per commit (0: one commit at the very end); descriptors are precomputed so the issue loop is MMA + commit only
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t s_bar[9];
+  __shared__ uint32_t s_tmem;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  for (int i = threadIdx.x; i < 96 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 9; ++i) mbar_init(smem_u32(&s_bar[i]), 1);
+    fence_barrier_init();
+  }
+  fence_proxy_async();
+  if (threadIdx.x < 32) tmem_alloc(smem_u32(&s_tmem), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  if (threadIdx.x == 0) {
+    constexpr int G = CE > 0 ? CE : 8;
+    uint64_t ad[4], bd[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      ad[k] = make_smem_desc(smem0 + k * 32, 16, 1024, kSwizzle128);
+      bd[k] = make_smem_desc(smem0 + 48 * 1024 + k * 32, 16, 1024, kSwizzle128);
+    }
+    const long long t0 = clock64();
+    uint32_t ring = smem_u32(&s_bar[0]);
+    for (int g = 0; g < groups; ++g) {
+#pragma unroll
+      for (int j = 0; j < G; ++j) umma_f16(tmem + ((j & 1) ? (uint32_t)n : 0u), ad[j & 3], bd[j & 3], idesc, 1u);
+      if (CE > 0) {
+        umma_commit(ring);
+        ring = (g & 7) == 7 ? smem_u32(&s_bar[0]) : ring + 8;
+      }
+    }
+    umma_commit(smem_u32(&s_bar[8]));
+    const long long t_issue = clock64();
+    mbar_wait(smem_u32(&s_bar[8]), 0);
+    const long long t1 = clock64();
+    out[2 * blockIdx.x] = t1 - t0;
+    out[2 * blockIdx.x + 1] = t_issue - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// TMA rate: each CTA streams `iters` boxes of [box_rows][inner] 16-bit elements of an L2-resident matrix through a ring of
+// `stages` shared-memory slots; reports cycles per box (one elected thread issues and waits, no consumer work).
+__global__ void __launch_bounds__(128, 1)
+tma_rate_kernel(const __grid_constant__ CUtensorMap tm, int iters, int stages, int box_rows, int box_bytes, int total_rows,
+                long long* out) {
+  // every warp's lane 0 drives an independent ring (blockDim.x / 32 concurrent issuers)
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t s_bar[4][8];
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) {
+    for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&s_bar[warp][i]), 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tm);
+    const uint32_t slot = (uint32_t)(box_rows * box_bytes + 1023) & ~1023u;
+    const uint32_t base = smem0 + warp * stages * slot;
+    const int nboxes = total_rows / box_rows;
+    int row_box = ((blockIdx.x * 4 + warp) * 37) % nboxes;
+    const long long t0 = clock64();
+    for (int i = 0; i < iters + stages; ++i) {
+      const int s = i % stages;
+      if (i >= stages) mbar_wait(smem_u32(&s_bar[warp][s]), ((i / stages) - 1) & 1);
+      if (i < iters) {
+        mbar_expect_tx(smem_u32(&s_bar[warp][s]), (uint32_t)(box_rows * box_bytes));
+        tma_load_2d(base + s * slot, &tm, smem_u32(&s_bar[warp][s]), 0, row_box * box_rows);
+        row_box += 1;
+        if (row_box >= nboxes) row_box = 0;
+      }
+    }
+    out[blockIdx.x * 4 + warp] = clock64() - t0;
+  }
+}
+}}  // namespace b200::sm100
+
+static int tma_rate_sweep(int verbose, cudaStream_t st, long long* d_out) {
+  using namespace b200;
+  using namespace b200::sm100;
+  const int total_rows = 256 * 1024;                 // x 128 B = 32 MB: L2 resident after the first pass
+  void* buf = nullptr;
+  B200_CUDA(cudaMalloc(&buf, (size_t)total_rows * 128));
+  B200_CUDA(cudaMemsetAsync(buf, 0, (size_t)total_rows * 128, st));
+  auto kern = tma_rate_kernel;
+  B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  const int iters = 2048;
+  for (int inner : {16, 64})
+    for (int rows : {64, 128, 256})
+      for (int warps : {1, 2, 4})
+        for (int stages : {2, 4}) {
+          if ((size_t)warps * stages * rows * inner * 2 > 190 * 1024) continue;
+          CUtensorMap tm;
+          int rc = make_matrix_tmap(&tm, buf, B200_BF16, total_rows, 64, rows, inner);
+          if (rc) return rc;
+          for (int rep = 0; rep < 2; ++rep)
+            kern<<<148, 32 * warps, 200 * 1024, st>>>(tm, iters, stages, rows, inner * 2, total_rows, d_out);
+          B200_LAUNCH_CHECK();
+          long long h[148 * 4];
+          B200_CUDA(cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, st));
+          B200_CUDA(cudaStreamSynchronize(st));
+          long long worst = 0;
+          for (int b = 0; b < 148; ++b)
+            for (int w = 0; w < warps; ++w) if (h[b * 4 + w] > worst) worst = h[b * 4 + w];
+          const double cyc = (double)worst / (iters * warps);
+          if (verbose)
+            printf("tma_rate box=%dx%dB issuers=%d stages=%d: %.0f cycles/box/SM, %.1f B/clk/SM\n", rows, inner * 2, warps, stages,
+                   cyc, rows * inner * 2 / cyc);
+        }
+  cudaFree(buf);
+  return B200_OK;
+}
+
 B200_EXPORT int b200_umma_selftest(int32_t verbose, void* stream) {
-  (void)verbose; (void)stream;
-  b200::set_error("umma_selftest: use tests/test_gpu_umma.py");
-  return B200_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  long long* d_out = nullptr;
+  const int max_blocks = 148;
+  B200_CUDA(cudaMalloc(&d_out, sizeof(long long) * 4 * max_blocks));
+  {
+    int rc = tma_rate_sweep(verbose, st, d_out);
+    if (rc) return rc;
+  }
+  {
+    typedef void (*RateKern)(int, int, uint32_t, long long*);
+    const RateKern kerns[7] = {umma_rate_kernel<0>, umma_rate_kernel<1>, umma_rate_kernel<2>, umma_rate_kernel<4>,
+                               umma_rate_kernel<8>, umma_rate_kernel<16>, umma_rate_kernel<32>};
+    const int ces[7] = {0, 1, 2, 4, 8, 16, 32};
+    const int ns[4] = {64, 128, 192, 256};
+    for (int ki = 0; ki < 7; ++ki) {
+      B200_CUDA(cudaFuncSetAttribute(kerns[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      for (int ni = 0; ni < 4; ++ni) {
+        const int per_group = ces[ki] > 0 ? ces[ki] : 8;
+        const int groups = 8192 / per_group;
+        const uint32_t idesc = make_idesc(1, ns[ni], 0, 0);
+        kerns[ki]<<<max_blocks, 128, 100 * 1024, st>>>(ns[ni], groups, idesc, d_out);
+        B200_LAUNCH_CHECK();
+        long long h[2 * max_blocks];
+        B200_CUDA(cudaMemcpyAsync(h, d_out, sizeof(long long) * 2 * max_blocks, cudaMemcpyDeviceToHost, st));
+        B200_CUDA(cudaStreamSynchronize(st));
+        long long worst = 0, issue = 0;
+        for (int b = 0; b < max_blocks; ++b) { if (h[2 * b] > worst) worst = h[2 * b]; if (h[2 * b + 1] > issue) issue = h[2 * b + 1]; }
+        if (verbose)
+          printf("umma_rate N=%d mma_per_commit=%d: %.1f cycles/MMA (issue %.1f), ideal %.0f\n", ns[ni], ces[ki],
+                 (double)worst / 8192, (double)issue / 8192, ns[ni] / 2.0);
+      }
+    }
+  }
+  cudaFree(d_out);
+  if (verbose) fflush(stdout);
+  return B200_OK;
 }

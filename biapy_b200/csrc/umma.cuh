@@ -100,6 +100,37 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// One lane of a converged warp (the compiler knows the guarded region is single-threaded, so tcgen05 operands move to
+// uniform registers without a per-lane waterfall loop)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// KS consecutive K = 16 steps of one operand pair.  `adesc` / `bdesc` are complete descriptors of the first step; a step
+// advances the 14-bit start-address field by 32 bytes (>> 4 = 2), which never carries out of the field for shared
+// memory addresses.  ncu on the first kernels showed ~200 cycles of dependent scalar work per MMA when descriptors
+// were rebuilt per step (profiles/README.md); this form is two 64-bit adds per MMA.
+template <int KS>
+__device__ __forceinline__ void umma_ksteps(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc_first) {
+#pragma unroll
+  for (int k = 0; k < KS; ++k) umma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k == 0 ? acc_first : 1u);
+}
+
+// Same with explicit per-step advances (in 16-byte units) for MN-major operands whose K steps are whole swizzle-atom rows.
+template <int KS>
+__device__ __forceinline__ void umma_ksteps_strided(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t astep16,
+                                                    uint32_t bstep16, uint32_t idesc, uint32_t acc_first) {
+#pragma unroll
+  for (int k = 0; k < KS; ++k)
+    umma_f16(tmem_d, adesc + (uint64_t)(astep16 * k), bdesc + (uint64_t)(bstep16 * k), idesc, k == 0 ? acc_first : 1u);
+}
+
 // 32 lanes x 16 consecutive fp32 columns: thread t of the warp receives row (lane base + t)
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(

@@ -21,14 +21,14 @@ ap.add_argument("--op", default="fprop", choices=["fprop", "wgrad"])
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--impl", default="umma")
 a = ap.parse_args()
-impl = {"umma": _lib.IMPL_UMMA, "simt": _lib.IMPL_SIMT}[a.impl]
+impl = {"umma": _lib.IMPL_UMMA, "simt": _lib.IMPL_SIMT, "xfold": _lib.IMPL_XFOLD}[a.impl]
 dt = torch.bfloat16
 x = torch.randn(a.batch, a.size, a.size, a.size, a.cin, device="cuda").to(dt)
 w = torch.randn(a.cout, a.cin, a.k, a.k, a.k, device="cuda") * 0.05
 b = torch.zeros(a.cout, device="cuda")
 y = torch.empty(a.batch, a.size, a.size, a.size, a.cout, device="cuda", dtype=dt)
 k = (a.k,) * 3
-wp = ops.pack_conv_weight(w, dt, False)
+wp = ops.pack_conv_weight_xfold(w, dt, False) if a.impl == "xfold" else ops.pack_conv_weight(w, dt, False)
 flops = 2.0 * a.batch * a.size ** 3 * a.cin * a.cout * a.k ** 3
 
 
@@ -50,5 +50,5 @@ for _ in range(a.iters):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.iters
-print(f"{a.op} {a.cin}->{a.cout} k{a.k} @{a.size}^3 x{a.batch} loader={os.environ.get('B200_CONV_LOADER', 'cpasync')}: "
+print(f"{a.op} {a.cin}->{a.cout} k{a.k} @{a.size}^3 x{a.batch} impl={a.impl}: "
       f"{ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s")
