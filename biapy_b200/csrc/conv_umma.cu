@@ -493,12 +493,14 @@ struct XslabParams {
   uint32_t idesc, tmem_cols;
   int64_t ysw, ysh, ysd, ysn;
   int accumulate;
+  int ablate;                           // diagnostics (B200_ABLATE): 1 = no TMA, 2 = no MMA, 4 = no epilogue stores
+  long long* dbg;                       // diagnostics (B200_DBG): per-CTA cycle counters of the role loops, or nullptr
 };
 
 constexpr int kSlabAWarps = 1, kSlabBWarps = 3;
 
 template <typename T>
-__global__ void __launch_bounds__(32 * (5 + kSlabAWarps + kSlabBWarps), 1)
+__global__ void __launch_bounds__(32 * (6 + kSlabAWarps + kSlabBWarps), 1)
 conv_fprop_xslab_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid_constant__ CUtensorMap tmx32,
                         const __grid_constant__ CUtensorMap tmw64, const __grid_constant__ CUtensorMap tmw32,
                         const float* __restrict__ bias, T* __restrict__ y, const XslabParams p) {
@@ -515,9 +517,10 @@ conv_fprop_xslab_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid_
   const uint32_t bar_tempty = smem_u32(&s_bar[4 * kMaxStages + 2]);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.a_stages; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1); }
-    for (int s = 0; s < p.b_stages; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 128); }
+    // every row tile has its own MMA-issuing warp: slots are released and accumulators published by p.rt commits
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, p.rt); }
+    for (int s = 0; s < p.b_stages; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, p.rt); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, p.rt); mbar_init(bar_tempty + 8 * b, 128); }
     fence_barrier_init();
     tma_prefetch_desc(&tmx64); tma_prefetch_desc(&tmx32); tma_prefetch_desc(&tmw64); tma_prefetch_desc(&tmw32);
   }
@@ -538,13 +541,13 @@ conv_fprop_xslab_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid_
     n = t;
   };
 
-  if (warp >= 5) {
+  if (warp >= 6) {
     // =================================================================== TMA producers
     // One thread sustains only one bulk-tensor copy per ~450 cycles whatever the box size (tools/pipe_rates.py), so the
     // slab ring is fed by kSlabAWarps warps and the weight ring by kSlabBWarps warps, each taking every k-th item.
-    if (elect_one()) {
-      const bool a_role = warp < 5 + kSlabAWarps;
-      const int rank = a_role ? warp - 5 : warp - 5 - kSlabAWarps;
+    if (!(p.ablate & 1) && elect_one()) {
+      const bool a_role = warp < 6 + kSlabAWarps;
+      const int rank = a_role ? warp - 6 : warp - 6 - kSlabAWarps;
       const int nrole = a_role ? kSlabAWarps : kSlabBWarps;
       int turn = 0, slot = 0;
       uint32_t ph = 0;
@@ -584,52 +587,266 @@ conv_fprop_xslab_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid_
           }
       }
     }
-  } else if (warp == 4) {
-    if (elect_one()) {
-      // ================================================================= MMA issuer
-      // kernel parameters and descriptor templates live in registers; per MMA the loop does two 64-bit adds
-      const int kh = p.kh, kd = p.kd, rt = p.rt, a_stages = p.a_stages, b_stages = p.b_stages, boxes64 = p.boxes64;
-      const uint32_t nt = (uint32_t)p.nt, idesc = p.idesc, a_bytes = p.a_bytes, b_bytes = p.b_bytes;
+  } else if (warp >= 4) {
+    const int r = warp - 4;                       // row tile issued by this warp
+    if (r < p.rt && elect_one()) {
+      // ================================================================= MMA issuers (one warp per row tile)
+      // The issuing thread is the critical path of the N = 64 layers (ncu: ~8 cycles per dependent scalar instruction,
+      // tensor pipe 30 % busy), so: loop constants pinned in registers, descriptors = template + slot offset, the
+      // barrier try_wait of the NEXT weight stage is issued before the current stage's MMAs, and the two row tiles
+      // that share every operand stage are issued by two warps.
+      const int kh = in_reg(p.kh), kd = in_reg(p.kd), a_stages = in_reg(p.a_stages), b_stages = in_reg(p.b_stages);
+      const int boxes64 = in_reg(p.boxes64), nb = in_reg(nboxes), nbuf = in_reg(p.nbuf), num_tiles = in_reg(p.num_tiles);
+      const uint32_t nt = in_reg((uint32_t)p.nt), idesc = in_reg(p.idesc);
+      const uint32_t a16 = in_reg(p.a_bytes >> 4), b16 = in_reg(p.b_bytes >> 4);
       const uint64_t tmpl128 = make_smem_desc(0, 16, 1024, kSwizzle128), tmpl64 = make_smem_desc(0, 16, 512, kSwizzle64);
-      const uint32_t a0 = smem0 >> 4, b0 = (smem0 + p.b_off) >> 4;
+      const uint32_t a0 = in_reg(smem0 >> 4), b0 = in_reg((smem0 + p.b_off) >> 4);
+      const uint32_t rt_n = in_reg((uint32_t)p.rt * nt), stride = in_reg((int)gridDim.x);
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        const int buf = p.nbuf == 2 ? (it & 1) : 0;
-        const uint32_t par = p.nbuf == 2 ? ((it >> 1) & 1) : (it & 1);
-        mbar_wait(bar_tempty + 8 * buf, par ^ 1);
+      const bool no_tma = p.ablate & 1, no_mma = p.ablate & 2;
+      bool b_ready = no_tma || mbar_try_wait(bar_bfull, 0);
+      long long c_tempty = 0, c_afull = 0, c_bfull = 0;
+      const bool dbg = p.dbg != nullptr;
+      const long long c_start = clock64();
+      for (int tile = blockIdx.x; tile < num_tiles; tile += stride, ++it) {
+        const int buf = nbuf == 2 ? (it & 1) : 0;
+        const uint32_t par = nbuf == 2 ? ((it >> 1) & 1) : (it & 1);
+        {
+          const long long c0 = dbg ? clock64() : 0;
+          mbar_wait(bar_tempty + 8 * buf, par ^ 1);
+          if (dbg) c_tempty += clock64() - c0;
+        }
         tc_fence_after();
-        const uint32_t d0 = tmem + (uint32_t)buf * (uint32_t)rt * nt;
-        const uint32_t d1 = d0 + nt;
+        const uint32_t d_tmem = tmem + (uint32_t)buf * rt_n + (uint32_t)r * nt;
         uint32_t acc = 0;
         for (int dy = 0; dy < kh; ++dy)
-          for (int b = 0; b < nboxes; ++b) {
+          for (int b = 0; b < nb; ++b) {
             const bool wide = b < boxes64;
-            // 16-row line of the slab in 16-byte units: 16 x 128 B = 128, 16 x 64 B = 64
+            // one 16-row line of the slab in 16-byte units (16 x 128 B or 16 x 64 B); row tile r starts 8 lines in
             const uint32_t line = wide ? 128u : 64u;
             const uint64_t tmpl = wide ? tmpl128 : tmpl64;
-            mbar_wait(bar_afull + 8 * as, aph);
-            tc_fence_after();
-            const uint64_t a_slab = tmpl + (uint64_t)(a0 + (uint32_t)as * (a_bytes >> 4));
-            for (int dz = 0; dz < kd; ++dz) {
-              mbar_wait(bar_bfull + 8 * bs, bph);
-              tc_fence_after();
-              const uint64_t bd = tmpl + (uint64_t)(b0 + (uint32_t)bs * (b_bytes >> 4));
-              const uint64_t ad = a_slab + (uint64_t)((uint32_t)dz * line);
-              if (wide) {
-                umma_ksteps<4>(d0, ad, bd, idesc, acc);
-                if (rt == 2) umma_ksteps<4>(d1, ad + 8u * 128u, bd, idesc, acc);
-              } else {
-                umma_ksteps<2>(d0, ad, bd, idesc, acc);
-                if (rt == 2) umma_ksteps<2>(d1, ad + 8u * 64u, bd, idesc, acc);
+            if (!no_tma) {
+              const long long c0 = dbg ? clock64() : 0;
+              mbar_wait(bar_afull + 8 * as, aph);
+              if (dbg) c_afull += clock64() - c0;
+            }
+            uint64_t ad = tmpl + (uint64_t)(a0 + (uint32_t)as * a16 + (uint32_t)r * 8u * line);
+            for (int dz = 0; dz < kd; ++dz, ad += line) {
+              if (!b_ready) {
+                const long long c0 = dbg ? clock64() : 0;
+                mbar_wait(bar_bfull + 8 * bs, bph);
+                if (dbg) c_bfull += clock64() - c0;
               }
-              acc = 1;
-              umma_commit(bar_bempty + 8 * bs);
+              tc_fence_after();
+              const uint64_t bd = tmpl + (uint64_t)(b0 + (uint32_t)bs * b16);
+              const uint32_t cur = bar_bempty + 8 * bs;
               if (++bs == b_stages) { bs = 0; bph ^= 1; }
+              b_ready = no_tma || mbar_try_wait(bar_bfull + 8 * bs, bph);          // overlaps the issue below
+              if (no_mma) {
+              } else if (wide) umma_ksteps<4>(d_tmem, ad, bd, idesc, acc);
+              else umma_ksteps<2>(d_tmem, ad, bd, idesc, acc);
+              acc = 1;
+              umma_commit(cur);
             }
             umma_commit(bar_aempty + 8 * as);
             if (++as == a_stages) { as = 0; aph ^= 1; }
+          }
+        umma_commit(bar_tfull + 8 * buf);
+      }
+      if (dbg) {
+        long long* o = p.dbg + (blockIdx.x * 2 + r) * 8;
+        o[0] = clock64() - c_start; o[1] = c_tempty; o[2] = c_afull; o[3] = c_bfull;
+      }
+    }
+  } else {
+    // =================================================================== epilogue
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int ly = row & 15, lzr = row >> 4;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int buf = p.nbuf == 2 ? (it & 1) : 0;
+      const uint32_t par = p.nbuf == 2 ? ((it >> 1) & 1) : (it & 1);
+      int n, z0, y0, g;
+      decode(tile, n, z0, y0, g);
+      {
+        const long long c0 = p.dbg ? clock64() : 0;
+        mbar_wait(bar_tfull + 8 * buf, par);
+        if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 16 + 4] += clock64() - c0;
+      }
+      tc_fence_after();
+      for (int r = 0; r < ((p.ablate & 4) ? 0 : p.rt); ++r) {
+        const int gz = z0 + r * 8 + lzr, gy = y0 + ly;
+        const bool valid = gz < p.d && gy < p.h;
+        T* ybase = y + (int64_t)n * p.ysn + (int64_t)gz * p.ysd + (int64_t)gy * p.ysh + (int64_t)(4 * g) * p.ysw;
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.rt + r) * p.nt);
+        int j = 0, co = 0;
+        for (int c0 = 0; c0 < p.nt; c0 += 16) {
+          uint32_t rr[16];
+          tmem_ld16(taddr + c0, rr);
+          tmem_ld_wait();
+          if (valid && 4 * g + j < p.w) {
+            T* yrow = ybase + (int64_t)j * p.ysw + co;
+            float f[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(rr[i]) + (bias ? __ldg(bias + co + i) : 0.f);
+            if (p.accumulate) {
+              Pack<T, 8> o0 = *reinterpret_cast<const Pack<T, 8>*>(yrow);
+              Pack<T, 8> o1 = *reinterpret_cast<const Pack<T, 8>*>(yrow + 8);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                f[i] += to_f<T>(o0.v[i]);
+                f[8 + i] += to_f<T>(o1.v[i]);
+              }
+            }
+            Pack<T, 8> w0, w1;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              w0.v[i] = from_f<T>(f[i]);
+              w1.v[i] = from_f<T>(f[8 + i]);
+            }
+            *reinterpret_cast<Pack<T, 8>*>(yrow) = w0;
+            *reinterpret_cast<Pack<T, 8>*>(yrow + 8) = w1;
+          }
+          co += 16;
+          if (co == p.cout) { co = 0; ++j; }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_tempty + 8 * buf);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem, p.tmem_cols);
+  }
+}
+
+// Unified-stage variant for the narrow layers (kd * N * 128 B of weights per (dy, box) fit next to the slab): one stage =
+// slab box + the kd weight tiles that multiply it, one full/empty barrier pair per stage.  The issuing threads are the
+// critical path of the N = 64 layers -- a stage hand-over costs ~250 cycles of dependent scalar instructions however
+// little it moves (B200_ABLATE / B200_DBG measurements, profiles/README.md) -- so a CTA tile takes kh * boxes (6 for
+// 16 -> 16) hand-overs here instead of kh * boxes * (kd + 1) (24) in conv_fprop_xslab_kernel.
+template <typename T>
+__global__ void __launch_bounds__(320, 1)
+conv_fprop_xslab1_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid_constant__ CUtensorMap tmx32,
+                         const __grid_constant__ CUtensorMap tmw64, const __grid_constant__ CUtensorMap tmw32,
+                         const float* __restrict__ bias, T* __restrict__ y, const XslabParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t s_bar[4 * kMaxStages + 4];
+  __shared__ uint32_t s_tmem;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_afull = smem_u32(&s_bar[0]);
+  const uint32_t bar_aempty = smem_u32(&s_bar[kMaxStages]);
+  const uint32_t bar_tfull = smem_u32(&s_bar[4 * kMaxStages]);
+  const uint32_t bar_tempty = smem_u32(&s_bar[4 * kMaxStages + 2]);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(bar_afull + 8 * s, 1 + p.kd); mbar_init(bar_aempty + 8 * s, p.rt); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, p.rt); mbar_init(bar_tempty + 8 * b, 128); }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmx64); tma_prefetch_desc(&tmx32); tma_prefetch_desc(&tmw64); tma_prefetch_desc(&tmw32);
+  }
+  if (warp == 4) tmem_alloc(smem_u32(&s_tmem), p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  const int pd = p.kd / 2, ph_pad = p.kh / 2;
+  const int nboxes = p.boxes64 + p.has32;
+  const uint32_t slab_rows = (uint32_t)p.zl * 16u;
+  const uint32_t w_off = slab_rows * 128u;                 // weight tiles follow the (max-size) slab box inside a stage
+  const uint32_t w_tile = (uint32_t)p.nt * 128u;
+
+  auto decode = [&](int tile, int& n, int& z0, int& y0, int& g) {
+    int t = tile;
+    g = t % p.groups_x; t /= p.groups_x;
+    y0 = (t % p.tiles_h) * 16; t /= p.tiles_h;
+    z0 = (t % p.tiles_d) * 8 * p.rt; t /= p.tiles_d;
+    n = t;
+  };
+
+  if (warp >= 6) {
+    // =================================================================== TMA producers: warp 6 = slab, warp 7 + dz = weight tile dz
+    const int role = warp - 6;
+    if (role <= p.kd && elect_one()) {
+      const int a_stages = p.a_stages;
+      int slot = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int n, z0, y0, g;
+        decode(tile, n, z0, y0, g);
+        const int e0 = (4 * g - p.kw / 2) * p.cin;
+        for (int dy = 0; dy < p.kh; ++dy)
+          for (int b = 0; b < nboxes; ++b) {
+            const bool wide = b < p.boxes64;
+            const uint32_t wbytes = wide ? 128u : 64u;
+            mbar_wait(bar_aempty + 8 * slot, ph ^ 1);
+            const uint32_t fa = bar_afull + 8 * slot;
+            const uint32_t dst = smem0 + slot * p.a_bytes;
+            if (role == 0) {
+              mbar_expect_tx(fa, slab_rows * wbytes);
+              asm volatile(
+                  "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                  ::"r"(dst), "l"((uint64_t)(wide ? &tmx64 : &tmx32)), "r"(fa), "r"(e0 + b * 64), "r"(y0 + dy - ph_pad),
+                    "r"(z0 - pd), "r"(n)
+                  : "memory");
+            } else {
+              const int dz = role - 1;
+              mbar_expect_tx(fa, (uint32_t)p.nt * wbytes);
+              tma_load_2d(dst + w_off + (uint32_t)dz * w_tile, wide ? &tmw64 : &tmw32, fa, (dz * p.kh + dy) * p.kx + b * 64, 0);
+            }
+            if (++slot == a_stages) { slot = 0; ph ^= 1; }
+          }
+      }
+    }
+  } else if (warp >= 4) {
+    const int r = warp - 4;                       // row tile issued by this warp
+    if (r < p.rt && elect_one()) {
+      // ================================================================= MMA issuers (one warp per row tile)
+      const int kh = in_reg(p.kh), kd = in_reg(p.kd), a_stages = in_reg(p.a_stages);
+      const int boxes64 = in_reg(p.boxes64), nb = in_reg(nboxes), nbuf = in_reg(p.nbuf), num_tiles = in_reg(p.num_tiles);
+      const uint32_t nt = in_reg((uint32_t)p.nt), idesc = in_reg(p.idesc);
+      const uint32_t a16 = in_reg(p.a_bytes >> 4), w16 = in_reg(w_off >> 4), wt16 = in_reg(w_tile >> 4);
+      const uint64_t tmpl128 = make_smem_desc(0, 16, 1024, kSwizzle128), tmpl64 = make_smem_desc(0, 16, 512, kSwizzle64);
+      const uint32_t a0 = in_reg(smem0 >> 4);
+      const uint32_t rt_n = in_reg((uint32_t)p.rt * nt), stride = in_reg((int)gridDim.x);
+      int as = 0;
+      uint32_t aph = 0;
+      int it = 0;
+      bool ready = mbar_try_wait(bar_afull, 0);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += stride, ++it) {
+        const int buf = nbuf == 2 ? (it & 1) : 0;
+        const uint32_t par = nbuf == 2 ? ((it >> 1) & 1) : (it & 1);
+        mbar_wait(bar_tempty + 8 * buf, par ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem + (uint32_t)buf * rt_n + (uint32_t)r * nt;
+        uint32_t acc = 0;
+        for (int dy = 0; dy < kh; ++dy)
+          for (int b = 0; b < nb; ++b) {
+            const bool wide = b < boxes64;
+            const uint32_t line = wide ? 128u : 64u;         // one 16-row slab line in 16-byte units
+            const uint64_t tmpl = wide ? tmpl128 : tmpl64;
+            if (!ready) mbar_wait(bar_afull + 8 * as, aph);
+            tc_fence_after();
+            const uint32_t s16 = a0 + (uint32_t)as * a16;
+            uint64_t ad = tmpl + (uint64_t)(s16 + (uint32_t)r * 8u * line);
+            uint64_t bd = tmpl + (uint64_t)(s16 + w16);
+            const uint32_t cur = bar_aempty + 8 * as;
+            if (++as == a_stages) { as = 0; aph ^= 1; }
+            ready = mbar_try_wait(bar_afull + 8 * as, aph);              // latency overlaps the issue below
+            for (int dz = 0; dz < kd; ++dz, ad += line, bd += wt16) {
+              if (wide) umma_ksteps<4>(d_tmem, ad, bd, idesc, acc);
+              else umma_ksteps<2>(d_tmem, ad, bd, idesc, acc);
+              acc = 1;
+            }
+            umma_commit(cur);
           }
         umma_commit(bar_tfull + 8 * buf);
       }
@@ -1168,6 +1385,16 @@ static int conv_fprop_xslab_v(const ActView& x, const void* w, const float* bias
   p.tmem_cols = cols;
   p.ysw = y.sw; p.ysh = y.sh; p.ysd = y.sd; p.ysn = y.sn;
   p.accumulate = accumulate;
+  {
+    const char* e = getenv("B200_ABLATE");
+    p.ablate = e ? atoi(e) : 0;
+  }
+  static long long* dbg_buf = nullptr;
+  if (getenv("B200_DBG")) {
+    if (!dbg_buf) B200_CUDA(cudaMalloc(&dbg_buf, sizeof(long long) * 16 * 148));
+    B200_CUDA(cudaMemsetAsync(dbg_buf, 0, sizeof(long long) * 16 * 148, st));
+    p.dbg = dbg_buf;
+  }
 
   CUtensorMap tx64, tx32, tw64, tw32;
   const cuuint64_t xd[4] = {(cuuint64_t)x.w * x.c, (cuuint64_t)x.h, (cuuint64_t)x.d, (cuuint64_t)x.n};
@@ -1184,18 +1411,56 @@ static int conv_fprop_xslab_v(const ActView& x, const void* w, const float* bias
   rc = make_matrix_tmap(&tw32, w, x.dtype, p.nt, ktot, p.nt, 32);
   if (rc) return rc;
 
-  const size_t smem = (size_t)p.b_off + (size_t)p.b_stages * p.b_bytes + 1024;
   int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  // narrow layers: slab box + its kd weight tiles in ONE stage (conv_fprop_xslab1_kernel) when >= 3 such stages fit
+  const uint32_t uni_bytes = (uint32_t)p.zl * 16u * 128u + (uint32_t)kd * (uint32_t)p.nt * 128u;
+  static const bool allow_unified = !(getenv("B200_XSLAB_UNIFIED") && strcmp(getenv("B200_XSLAB_UNIFIED"), "0") == 0);
+  if (allow_unified && kd <= 3 && 3u * uni_bytes <= 200u * 1024u && !p.ablate && !p.dbg) {
+    p.a_bytes = uni_bytes;
+    p.a_stages = (int)((200u * 1024u) / uni_bytes);
+    if (p.a_stages > 6) p.a_stages = 6;
+    const size_t smem1 = (size_t)p.a_stages * p.a_bytes + 1024;
+    if (x.dtype == B200_BF16) {
+      auto kern = conv_fprop_xslab1_kernel<__nv_bfloat16>;
+      B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+      kern<<<grid, 320, smem1, st>>>(tx64, tx32, tw64, tw32, bias, (__nv_bfloat16*)y.data, p);
+    } else {
+      auto kern = conv_fprop_xslab1_kernel<__half>;
+      B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+      kern<<<grid, 320, smem1, st>>>(tx64, tx32, tw64, tw32, bias, (__half*)y.data, p);
+    }
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+  }
+  const size_t smem = (size_t)p.b_off + (size_t)p.b_stages * p.b_bytes + 1024;
   if (x.dtype == B200_BF16) {
     auto kern = conv_fprop_xslab_kernel<__nv_bfloat16>;
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, 32 * (5 + kSlabAWarps + kSlabBWarps), smem, st>>>(tx64, tx32, tw64, tw32, bias, (__nv_bfloat16*)y.data, p);
+    kern<<<grid, 32 * (6 + kSlabAWarps + kSlabBWarps), smem, st>>>(tx64, tx32, tw64, tw32, bias, (__nv_bfloat16*)y.data, p);
   } else {
     auto kern = conv_fprop_xslab_kernel<__half>;
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, 32 * (5 + kSlabAWarps + kSlabBWarps), smem, st>>>(tx64, tx32, tw64, tw32, bias, (__half*)y.data, p);
+    kern<<<grid, 32 * (6 + kSlabAWarps + kSlabBWarps), smem, st>>>(tx64, tx32, tw64, tw32, bias, (__half*)y.data, p);
   }
   B200_LAUNCH_CHECK();
+  if (p.dbg) {
+    long long h[16 * 148];
+    B200_CUDA(cudaMemcpyAsync(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    double tot[2] = {0, 0}, te[2] = {0, 0}, af[2] = {0, 0}, bf[2] = {0, 0}, ep = 0;
+    for (int b = 0; b < grid; ++b) {
+      for (int r = 0; r < 2; ++r) {
+        tot[r] += h[b * 16 + r * 8]; te[r] += h[b * 16 + r * 8 + 1]; af[r] += h[b * 16 + r * 8 + 2]; bf[r] += h[b * 16 + r * 8 + 3];
+      }
+      ep += h[b * 16 + 4];
+    }
+    const double tiles = (double)p.num_tiles;
+    printf("xslab dbg: per CTA tile  MMA warp0: loop %.0f  wait tmem-empty %.0f  wait slab %.0f  wait weights %.0f | warp1: loop %.0f "
+           "tmem %.0f slab %.0f weights %.0f | epilogue wait tmem-full %.0f\n",
+           tot[0] / tiles, te[0] / tiles, af[0] / tiles, bf[0] / tiles, tot[1] / tiles, te[1] / tiles, af[1] / tiles, bf[1] / tiles,
+           ep / tiles);
+    fflush(stdout);
+  }
   return B200_OK;
 }
 
@@ -1316,7 +1581,7 @@ struct WgradParams {
 
 constexpr uint32_t kChunkBytes = 128u * 16u * 2u;   // one [128 voxels][16 ch] tile
 constexpr uint32_t kBlockBytes = 8u * kChunkBytes;   // one M-block of A
-constexpr int kMaxAStages = 6, kMaxBStages = 3;
+constexpr int kMaxAStages = 6, kMaxBStages = 6;
 
 template <typename T>
 __global__ void __launch_bounds__(320, 1)
@@ -1618,22 +1883,26 @@ conv_wgrad_xfold_kernel(const __grid_constant__ CUtensorMap tmx32, const __grid_
       // A: M-major SWIZZLE_64B atoms (32 el), 16 K rows = 1024 B; B: N-major SWIZZLE_128B atoms (64 el), 16 rows = 2048 B
       const uint64_t tmpl_a = make_smem_desc(0, kXAtomBytes, 512u, kSwizzle64);
       const uint64_t tmpl_b = make_smem_desc(0, 128u * 128u, 1024u, kSwizzle128);
-      const uint32_t a0 = (smem0 + p.a_off) >> 4, b0 = smem0 >> 4, b16 = p.b_bytes >> 4, idesc = p.idesc, nt = (uint32_t)p.nt;
-      const int a_stages = p.a_stages, b_stages = p.b_stages;
+      const uint32_t a0 = in_reg((smem0 + p.a_off) >> 4), b0 = in_reg(smem0 >> 4), b16 = in_reg(p.b_bytes >> 4);
+      const uint32_t idesc = in_reg(p.idesc), nt = in_reg((uint32_t)p.nt);
+      const int a_stages = in_reg(p.a_stages), b_stages = in_reg(p.b_stages), num_vtiles = in_reg(p.num_vtiles);
+      const int stride = in_reg((int)gridDim.x), nmb = in_reg(mb1 - mb0);
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0, acc = 0;
-      for (int vt = blockIdx.x; vt < p.num_vtiles; vt += gridDim.x) {
+      bool a_ready = mbar_try_wait(bar_afull, 0);
+      for (int vt = blockIdx.x; vt < num_vtiles; vt += stride) {
         mbar_wait(bar_bfull + 8 * bs, bph);
-        tc_fence_after();
         const uint64_t bd = tmpl_b + (uint64_t)(b0 + (uint32_t)bs * b16);
         uint32_t d_tmem = tmem;
-        for (int mb = mb0; mb < mb1; ++mb, d_tmem += nt) {
-          mbar_wait(bar_afull + 8 * as, aph);
+        for (int mb = 0; mb < nmb; ++mb, d_tmem += nt) {
+          if (!a_ready) mbar_wait(bar_afull + 8 * as, aph);
           tc_fence_after();
           const uint64_t ad = tmpl_a + (uint64_t)(a0 + (uint32_t)as * (kXBlockBytes >> 4));
-          umma_ksteps_strided<8>(d_tmem, ad, bd, 1024u >> 4, 2048u >> 4, idesc, acc);
-          umma_commit(bar_aempty + 8 * as);
+          const uint32_t cur = bar_aempty + 8 * as;
           if (++as == a_stages) { as = 0; aph ^= 1; }
+          a_ready = mbar_try_wait(bar_afull + 8 * as, aph);            // latency overlaps the issue below
+          umma_ksteps_strided<8>(d_tmem, ad, bd, 1024u >> 4, 2048u >> 4, idesc, acc);
+          umma_commit(cur);
         }
         umma_commit(bar_bempty + 8 * bs);
         if (++bs == b_stages) { bs = 0; bph ^= 1; }
@@ -1669,6 +1938,214 @@ conv_wgrad_xfold_kernel(const __grid_constant__ CUtensorMap tmx32, const __grid_
         }
         co += 16;
         if (co == p.cout) { co = 0; ++j; }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------ x-folded wgrad, z-slab variant
+// Same GEMM as conv_wgrad_xfold_kernel, but the input window is fetched as SLAB atoms: for one dy and one 32-element atom
+// of the window, (8 + kd - 1) z-lines x 16 y-rows x 64 B.  The kd taps in z read the same slab atom with the descriptor
+// start moved by whole 16-row lines (1 KB = two 64B-swizzle atoms, so the TMA-written swizzle stays valid).  Four slab
+// atoms (consecutive in (dy, atom) order, LBO = slab-atom size) form the M = 128 operand of kd M-blocks, one per dz.
+// A bytes per voxel tile drop ~2.4x; the old kernel ran at ~65 % of L2 bandwidth (profiles/README.md).
+struct WgradSParams {
+  int n, d, h, w, cin, cout;
+  int kd, kh, kw;
+  int zl;                               // z-lines per slab atom = 8 + kd - 1
+  int groups_x, tiles_h, tiles_d, num_vtiles;
+  int aps;                              // 32-element atoms per window row = win * cin / 32
+  int sa_total;                         // slab atoms = kh * aps
+  int grp_total, gpc;                   // groups of 4 slab atoms; groups per CTA (blockIdx.y)
+  int a_stages, b_stages;
+  int nt;                               // 4 * cout
+  uint32_t sa_bytes;                    // one slab atom: zl * 16 rows * 64 B
+  uint32_t b_boxes, b_bytes, a_off;
+  uint32_t idesc, tmem_cols;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(320, 1)
+conv_wgrad_xslab_kernel(const __grid_constant__ CUtensorMap tmx32, const __grid_constant__ CUtensorMap tmy64,
+                        float* __restrict__ dw, const WgradSParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t s_bar[2 * kMaxAStages + 2 * kMaxBStages + 1];
+  __shared__ uint32_t s_tmem;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_afull = smem_u32(&s_bar[0]);
+  const uint32_t bar_aempty = smem_u32(&s_bar[kMaxAStages]);
+  const uint32_t bar_bfull = smem_u32(&s_bar[2 * kMaxAStages]);
+  const uint32_t bar_bempty = smem_u32(&s_bar[2 * kMaxAStages + kMaxBStages]);
+  const uint32_t bar_done = smem_u32(&s_bar[2 * kMaxAStages + 2 * kMaxBStages]);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(bar_afull + 8 * s, 4); mbar_init(bar_aempty + 8 * s, 1); }   // 4 atom producers
+    for (int s = 0; s < p.b_stages; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); }
+    mbar_init(bar_done, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmx32);
+    tma_prefetch_desc(&tmy64);
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&s_tmem), p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+
+  const int pd = p.kd / 2, ph = p.kh / 2, pw = p.kw / 2;
+  const int g0 = blockIdx.y * p.gpc;
+  const int g1 = min(g0 + p.gpc, p.grp_total);
+  const uint32_t grp_bytes = 4u * p.sa_bytes;
+
+  auto decode = [&](int vt, int& n, int& z0, int& y0, int& g) {
+    int t = vt;
+    g = t % p.groups_x; t /= p.groups_x;
+    y0 = (t % p.tiles_h) * 16; t /= p.tiles_h;
+    z0 = (t % p.tiles_d) * 8; t /= p.tiles_d;
+    n = t;
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // ================================================================= TMA producer of the dY tiles (B operand)
+      int bs = 0;
+      uint32_t bph = 0;
+      for (int vt = blockIdx.x; vt < p.num_vtiles; vt += gridDim.x) {
+        int n, z0, y0, g;
+        decode(vt, n, z0, y0, g);
+        mbar_wait(bar_bempty + 8 * bs, bph ^ 1);
+        const uint32_t b_dst = smem0 + bs * p.b_bytes;
+        mbar_expect_tx(bar_bfull + 8 * bs, p.b_bytes);
+        for (uint32_t i = 0; i < p.b_boxes; ++i)
+          asm volatile(
+              "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+              ::"r"(b_dst + i * 128u * 128u), "l"((uint64_t)&tmy64), "r"(bar_bfull + 8 * bs), "r"(4 * g * p.cout + (int)i * 64),
+                "r"(y0), "r"(z0), "r"(n)
+              : "memory");
+        if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+        // dY is streamed from DRAM: pull the tile this CTA needs a few iterations from now into L2
+        const int vt2 = vt + 4 * (int)gridDim.x;
+        if (vt2 < p.num_vtiles) {
+          int n2, z2, y2, g2;
+          decode(vt2, n2, z2, y2, g2);
+          for (uint32_t i = 0; i < p.b_boxes; ++i)
+            asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];"
+                         ::"l"((uint64_t)&tmy64), "r"(4 * g2 * p.cout + (int)i * 64), "r"(y2), "r"(z2), "r"(n2)
+                         : "memory");
+        }
+      }
+    }
+  } else if (warp >= 6) {
+    if (elect_one()) {
+      // ================================================================= TMA producers of the slab atoms (A operand)
+      // warp 6 + j fetches slab atom j of every group (one thread sustains one bulk-tensor copy per ~450 cycles)
+      const int j = warp - 6;
+      const int aps = p.aps, a_stages = p.a_stages, sa_total = p.sa_total;
+      int at0, dy0;
+      {
+        const int s = g0 * 4 + j;
+        dy0 = s / aps;
+        at0 = s - dy0 * aps;
+      }
+      int as = 0;
+      uint32_t aph = 0;
+      for (int vt = blockIdx.x; vt < p.num_vtiles; vt += gridDim.x) {
+        int n, z0, y0, g;
+        decode(vt, n, z0, y0, g);
+        const int e0 = (4 * g - pw) * p.cin;
+        int at = at0, dy = dy0;
+        for (int gi = g0; gi < g1; ++gi) {
+          mbar_wait(bar_aempty + 8 * as, aph ^ 1);
+          const uint32_t fa = bar_afull + 8 * as;
+          if (gi * 4 + j < sa_total) {
+            mbar_expect_tx(fa, p.sa_bytes);
+            asm volatile(
+                "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                ::"r"(smem0 + p.a_off + as * grp_bytes + j * p.sa_bytes), "l"((uint64_t)&tmx32), "r"(fa), "r"(e0 + at * 32),
+                  "r"(y0 + dy - ph), "r"(z0 - pd), "r"(n)
+                : "memory");
+          } else {
+            mbar_arrive(fa);
+          }
+          at += 4;
+          while (at >= aps) { at -= aps; ++dy; }
+          if (++as == a_stages) { as = 0; aph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // ================================================================= MMA issuer
+      // A: M-major SWIZZLE_64B atoms (32 el), LBO = slab atom, one K step = 16 rows = 1 KB; tap dz starts dz lines in.
+      // B: N-major SWIZZLE_128B atoms (64 el), one K step = 16 rows = 2 KB
+      const uint64_t tmpl_a = make_smem_desc(0, p.sa_bytes, 512u, kSwizzle64);
+      const uint64_t tmpl_b = make_smem_desc(0, 128u * 128u, 1024u, kSwizzle128);
+      const uint32_t a0 = in_reg((smem0 + p.a_off) >> 4), b0 = in_reg(smem0 >> 4), b16 = in_reg(p.b_bytes >> 4);
+      const uint32_t grp16 = in_reg(grp_bytes >> 4), idesc = in_reg(p.idesc), nt = in_reg((uint32_t)p.nt);
+      const int a_stages = in_reg(p.a_stages), b_stages = in_reg(p.b_stages), num_vtiles = in_reg(p.num_vtiles);
+      const int stride = in_reg((int)gridDim.x), ngrp = in_reg(g1 - g0), kd = in_reg(p.kd);
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0, acc = 0;
+      bool a_ready = mbar_try_wait(bar_afull, 0);
+      for (int vt = blockIdx.x; vt < num_vtiles; vt += stride) {
+        mbar_wait(bar_bfull + 8 * bs, bph);
+        const uint64_t bd = tmpl_b + (uint64_t)(b0 + (uint32_t)bs * b16);
+        uint32_t d_tmem = tmem;
+        for (int gi = 0; gi < ngrp; ++gi) {
+          if (!a_ready) mbar_wait(bar_afull + 8 * as, aph);
+          tc_fence_after();
+          uint64_t ad = tmpl_a + (uint64_t)(a0 + (uint32_t)as * grp16);
+          const uint32_t cur = bar_aempty + 8 * as;
+          if (++as == a_stages) { as = 0; aph ^= 1; }
+          a_ready = mbar_try_wait(bar_afull + 8 * as, aph);            // latency overlaps the issue below
+          for (int dz = 0; dz < kd; ++dz, ad += 1024u >> 4, d_tmem += nt)
+            umma_ksteps_strided<8>(d_tmem, ad, bd, 1024u >> 4, 2048u >> 4, idesc, acc);
+          umma_commit(cur);
+        }
+        umma_commit(bar_bempty + 8 * bs);
+        if (++bs == b_stages) { bs = 0; bph ^= 1; }
+        acc = 1;
+      }
+      umma_commit(bar_done);
+    }
+  } else {
+    // =================================================================== epilogue: fold Toeplitz diagonals into dw
+    const int q4 = warp & 3;
+    const int row = q4 * 32 + lane;
+    const int taps = p.kd * p.kh * p.kw;
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+    for (int gi = g0; gi < g1; ++gi) {
+      const int s = gi * 4 + row / 32;                  // slab atom of this row
+      const bool valid = s < p.sa_total;
+      const int dyy = valid ? s / p.aps : 0;
+      const int e = valid ? (s - dyy * p.aps) * 32 + (row & 31) : 0;      // element inside the window
+      const int xi = e / p.cin, ci = e - xi * p.cin;
+      for (int dz = 0; dz < p.kd; ++dz) {
+        const uint32_t taddr = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(((gi - g0) * p.kd + dz) * p.nt);
+        int j = 0, co = 0;
+        for (int c0 = 0; c0 < p.nt; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + c0, r);
+          tmem_ld_wait();
+          const int kx = xi - j;
+          if (valid && kx >= 0 && kx < p.kw) {
+            const int tap = (dz * p.kh + dyy) * p.kw + kx;
+            float* dst = dw + ((int64_t)co * taps + tap) * p.cin + ci;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) atomicAdd(dst + (int64_t)i * taps * p.cin, __uint_as_float(r[i]));
+          }
+          co += 16;
+          if (co == p.cout) { co = 0; ++j; }
+        }
       }
     }
   }
@@ -1864,8 +2341,84 @@ bool conv_wgrad_xfold_ok(const ActView& x, const ActView& dy, int kd, int kh, in
   return encode_tiled_fn() != nullptr;
 }
 
+static int conv_wgrad_xslab_v(const ActView& x, const ActView& dy, float* dw, int kd, int kh, int kw, cudaStream_t st) {
+  WgradSParams p{};
+  p.n = x.n; p.d = x.d; p.h = x.h; p.w = x.w; p.cin = x.c; p.cout = dy.c;
+  p.kd = kd; p.kh = kh; p.kw = kw;
+  p.zl = 8 + kd - 1;
+  p.groups_x = x.w / 4;
+  p.tiles_h = (int)ceil_div(x.h, 16); p.tiles_d = (int)ceil_div(x.d, 8);
+  p.num_vtiles = x.n * p.tiles_d * p.tiles_h * p.groups_x;
+  p.aps = (3 + kw) * x.c / 32;
+  p.sa_total = kh * p.aps;
+  p.grp_total = (int)ceil_div(p.sa_total, 4);
+  p.nt = 4 * dy.c;
+  // groups per CTA: TMEM holds gpc * kd accumulators of nt columns; among the feasible values take the one that
+  // minimises (M-blocks per CTA) / (CTAs along the voxel-tile axis)
+  const int gpc_max = 512 / (kd * p.nt);
+  B200_CHECK_ARG(gpc_max >= 1, "conv_wgrad(xslab): accumulators do not fit in TMEM");
+  double best = 1e30;
+  for (int gpc = 1; gpc <= gpc_max && gpc <= p.grp_total; ++gpc) {
+    const int gy = (int)ceil_div(p.grp_total, gpc);
+    int vs = sm_count() / gy;
+    if (vs < 1) vs = 1;
+    const double cost = (double)gpc / vs;
+    if (cost < best - 1e-12) { best = cost; p.gpc = gpc; }
+  }
+  const int gy = (int)ceil_div(p.grp_total, p.gpc);
+  p.sa_bytes = (uint32_t)p.zl * 16u * 64u;
+  p.b_boxes = (uint32_t)p.nt / 64u;
+  p.b_bytes = 128u * (uint32_t)p.nt * 2u;
+  // the dY tiles come from DRAM (each is read once per CTA row): give that ring the depth, keep 3 slab groups in flight
+  int a_st = 3;
+  int b_st = (int)((200u * 1024u - (uint32_t)a_st * 4u * p.sa_bytes) / p.b_bytes);
+  if (b_st < 2) { a_st = 2; b_st = (int)((200u * 1024u - (uint32_t)a_st * 4u * p.sa_bytes) / p.b_bytes); }
+  if (b_st > kMaxBStages) b_st = kMaxBStages;
+  B200_CHECK_ARG(b_st >= 2, "conv_wgrad(xslab): tiles do not fit in shared memory");
+  p.b_stages = b_st;
+  p.a_off = p.b_stages * p.b_bytes;
+  a_st = (int)((200u * 1024u - p.a_off) / (4u * p.sa_bytes));
+  if (a_st > kMaxAStages) a_st = kMaxAStages;
+  p.a_stages = a_st;
+  p.idesc = make_idesc(x.dtype == B200_BF16, p.nt, 1, 1);
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(p.gpc * kd * p.nt)) cols <<= 1;
+  p.tmem_cols = cols;
+
+  CUtensorMap tx, ty;
+  const cuuint64_t xd[4] = {(cuuint64_t)x.w * x.c, (cuuint64_t)x.h, (cuuint64_t)x.d, (cuuint64_t)x.n};
+  const cuuint64_t xs[3] = {(cuuint64_t)x.sh * 2, (cuuint64_t)x.sd * 2, (cuuint64_t)x.sn * 2};
+  const cuuint32_t bx[4] = {32, 16, (cuuint32_t)p.zl, 1};
+  int rc = make_tmap4(&tx, x.data, x.dtype, xd, xs, bx);
+  if (rc) return rc;
+  const cuuint64_t yd[4] = {(cuuint64_t)dy.w * dy.c, (cuuint64_t)dy.h, (cuuint64_t)dy.d, (cuuint64_t)dy.n};
+  const cuuint64_t ys[3] = {(cuuint64_t)dy.sh * 2, (cuuint64_t)dy.sd * 2, (cuuint64_t)dy.sn * 2};
+  const cuuint32_t by[4] = {64, 16, 8, 1};
+  rc = make_tmap4(&ty, dy.data, dy.dtype, yd, ys, by);
+  if (rc) return rc;
+
+  int vsplit = sm_count() / gy;
+  if (vsplit < 1) vsplit = 1;
+  if (vsplit > p.num_vtiles) vsplit = p.num_vtiles;
+  dim3 grid((unsigned)vsplit, (unsigned)gy);
+  const size_t smem = (size_t)p.a_off + (size_t)p.a_stages * 4u * p.sa_bytes + 1024;
+  if (x.dtype == B200_BF16) {
+    auto kern = conv_wgrad_xslab_kernel<__nv_bfloat16>;
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 320, smem, st>>>(tx, ty, dw, p);
+  } else {
+    auto kern = conv_wgrad_xslab_kernel<__half>;
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 320, smem, st>>>(tx, ty, dw, p);
+  }
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
 int conv_wgrad_xfold_v(const ActView& x, const ActView& dy, float* dw, int kd, int kh, int kw, cudaStream_t st) {
   B200_CHECK_ARG(conv_wgrad_xfold_ok(x, dy, kd, kh, kw), "conv_wgrad(xfold): unsupported operands");
+  if (xslab_mode() && kd == 3 && x.d >= 8 && x.h >= 16 && kd * 4 * dy.c <= 512)
+    return conv_wgrad_xslab_v(x, dy, dw, kd, kh, kw, st);
   WgradXParams p{};
   p.n = x.n; p.d = x.d; p.h = x.h; p.w = x.w; p.cin = x.c; p.cout = dy.c;
   p.kd = kd; p.kh = kh; p.kw = kw; p.win = 3 + kw;
@@ -2222,6 +2775,44 @@ umma_rate_kernel(int n, int groups, uint32_t idesc, long long* out) {
   if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
+// Handshake latency: thread 0 of warp 0 signals bar1 (plain arrive, or tcgen05.commit on an idle pipe), `nwait` threads of
+// warps 1.. wait for it and arrive on bar2, thread 0 waits for bar2.  Reports cycles per round trip.
+__global__ void __launch_bounds__(160, 1)
+handshake_kernel(int iters, int use_commit, int use_test_wait, int nwait, long long* out) {
+  __shared__ uint64_t s_bar[2];
+  __shared__ uint32_t s_tmem;
+  const uint32_t b1 = smem_u32(&s_bar[0]), b2 = smem_u32(&s_bar[1]);
+  if (threadIdx.x == 0) {
+    mbar_init(b1, 1);
+    mbar_init(b2, nwait);
+    fence_barrier_init();
+  }
+  if (threadIdx.x < 32) tmem_alloc(smem_u32(&s_tmem), 32);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  auto wait = [&](uint32_t bar, uint32_t par) {
+    if (use_test_wait) { while (!mbar_test_wait(bar, par)) {} }
+    else { while (!mbar_try_wait(bar, par)) {} }
+  };
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+      if (use_commit) umma_commit(b1); else mbar_arrive(b1);
+      wait(b2, i & 1);
+    }
+    out[blockIdx.x] = clock64() - t0;
+  } else if (threadIdx.x >= 32 && (int)threadIdx.x < 32 + nwait) {
+    for (int i = 0; i < iters; ++i) {
+      wait(b1, i & 1);
+      mbar_arrive(b2);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(s_tmem, 32); }
+}
+
 // TMA rate: each CTA streams `iters` boxes of [box_rows][inner] 16-bit elements of an L2-resident matrix through a ring of
 // `stages` shared-memory slots; reports cycles per box (one elected thread issues and waits, no consumer work).
 __global__ void __launch_bounds__(128, 1)
@@ -2297,11 +2888,25 @@ B200_EXPORT int b200_umma_selftest(int32_t verbose, void* stream) {
   long long* d_out = nullptr;
   const int max_blocks = 148;
   B200_CUDA(cudaMalloc(&d_out, sizeof(long long) * 4 * max_blocks));
-  {
+  for (int use_commit = 0; use_commit < 2; ++use_commit)
+    for (int use_test = 0; use_test < 2; ++use_test)
+      for (int nwait : {1, 32, 128}) {
+        handshake_kernel<<<148, 160, 0, st>>>(4096, use_commit, use_test, nwait, d_out);
+        B200_LAUNCH_CHECK();
+        long long h[148];
+        B200_CUDA(cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, st));
+        B200_CUDA(cudaStreamSynchronize(st));
+        long long worst = 0;
+        for (int b = 0; b < 148; ++b) if (h[b] > worst) worst = h[b];
+        if (verbose)
+          printf("handshake signal=%s wait=%s waiters=%d: %.0f cycles per round trip\n", use_commit ? "tcgen05.commit" : "arrive",
+                 use_test ? "test_wait" : "try_wait", nwait, (double)worst / 4096);
+      }
+  if (verbose > 1) {
     int rc = tma_rate_sweep(verbose, st, d_out);
     if (rc) return rc;
   }
-  {
+  if (verbose > 1) {
     typedef void (*RateKern)(int, int, uint32_t, long long*);
     const RateKern kerns[7] = {umma_rate_kernel<0>, umma_rate_kernel<1>, umma_rate_kernel<2>, umma_rate_kernel<4>,
                                umma_rate_kernel<8>, umma_rate_kernel<16>, umma_rate_kernel<32>};

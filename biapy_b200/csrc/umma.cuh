@@ -37,6 +37,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug traps (CUDA error) after ~2 s instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
@@ -110,6 +121,17 @@ __device__ __forceinline__ bool elect_one() {
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(pred));
   return pred != 0;
+}
+
+// Keeps a loop constant in a register: without it the compiler re-loads kernel parameters from the constant bank
+// after every asm volatile("...": "memory"), and the single MMA-issuing thread stalls on each of those loads.
+__device__ __forceinline__ uint32_t in_reg(uint32_t v) {
+  asm volatile("" : "+r"(v));
+  return v;
+}
+__device__ __forceinline__ int in_reg(int v) {
+  asm volatile("" : "+r"(v));
+  return v;
 }
 
 // KS consecutive K = 16 steps of one operand pair.  `adesc` / `bdesc` are complete descriptors of the first step; a step

@@ -95,6 +95,9 @@ WGRAD_CASES = [
     (1, 8, 16, 16, 48, 16, (1, 1, 1)),     # x-folded wgrad, pointwise
     (2, 9, 20, 12, 16, 64, (3, 3, 3)),     # x-folded wgrad, N = 256, partial tiles
     (1, 16, 16, 8, 48, 16, (3, 3, 3)),     # x-folded wgrad, 3 M-groups
+    (1, 9, 20, 12, 16, 16, (3, 3, 3)),     # z-slab wgrad: partial tiles in z and y, 9 slab atoms -> 3 groups
+    (2, 24, 32, 16, 16, 16, (3, 3, 3)),    # z-slab wgrad: several voxel tiles per CTA (ring wrap-around)
+    (1, 16, 16, 16, 96, 16, (3, 3, 3)),    # z-slab wgrad: 54 slab atoms
 ]
 
 
