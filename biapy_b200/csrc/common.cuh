@@ -110,6 +110,20 @@ __device__ __forceinline__ float act_grad(int act, float x) {
   }
 }
 
+// Compile-time activation (ACT >= 0) or the runtime switch (ACT == -1).  The HBM-bound row kernels are instantiated for
+// the activations the U-Net family uses; a per-element jump table costs them more than the memory traffic does.
+template <int ACT> __device__ __forceinline__ float act_fwd_t(int act, float x) { return act_fwd(ACT >= 0 ? ACT : act, x); }
+template <int ACT> __device__ __forceinline__ float act_grad_t(int act, float x) { return act_grad(ACT >= 0 ? ACT : act, x); }
+
+#define B200_DISPATCH_ACT(act, ACT, ...)                                                    \
+  switch (act) {                                                                            \
+    case B200_ACT_NONE: { constexpr int ACT = B200_ACT_NONE; __VA_ARGS__; break; }          \
+    case B200_ACT_RELU: { constexpr int ACT = B200_ACT_RELU; __VA_ARGS__; break; }          \
+    case B200_ACT_ELU: { constexpr int ACT = B200_ACT_ELU; __VA_ARGS__; break; }            \
+    case B200_ACT_SILU: { constexpr int ACT = B200_ACT_SILU; __VA_ARGS__; break; }          \
+    default: { constexpr int ACT = -1; __VA_ARGS__; break; }                                \
+  }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -2,6 +2,7 @@
 // element-wise glue, losses and the optimiser step.  All tensors are channels-last with a voxel pitch `ld`.
 // Reference call sites are listed next to each entry point in include/biapy_b200.h.
 #include "common.cuh"
+#include <stdlib.h>
 
 #include <type_traits>
 
@@ -52,7 +53,7 @@ __device__ __forceinline__ void store_vec(T* p, const float (&f)[VEC]) {
 // vector and strides over the voxels of its chunk.  fp32 partials are flushed into fp64 every 32 voxels, the
 // block result is reduced through shared memory and added to sums[n][c][0..1] with one fp64 atomic each.
 template <typename T, int VEC>
-__global__ void channel_sums_kernel(View<const T> x, double* __restrict__ sums, int cv_count, int rows) {
+__global__ void __launch_bounds__(256, 4) channel_sums_kernel(View<const T> x, double* __restrict__ sums, int cv_count, int rows) {
   extern __shared__ double s_red[];  // rows * cv_count * VEC * 2
   const int n = blockIdx.y;
   const int tid = threadIdx.x;
@@ -68,20 +69,23 @@ __global__ void channel_sums_kernel(View<const T> x, double* __restrict__ sums, 
     int64_t v1 = v0 + chunk;
     if (v1 > x.spatial) v1 = x.spatial;
     const T* base = x.p + (int64_t)n * x.spatial * x.ld + (int64_t)cv * VEC;
-    float f[VEC], f2[VEC];
-    for (int64_t v = v0 + row; v < v1; v += 2 * rows) {
-      const bool two = v + rows < v1;
-      load_vec<T, VEC>(base + v * x.ld, f);
-      if (two) load_vec<T, VEC>(base + (v + rows) * x.ld, f2);
+    // U independent 16-byte loads in flight per thread, kept packed until they are consumed (register budget: 4 blocks/SM)
+    constexpr int U = 4;
+    for (int64_t v = v0 + row; v < v1; v += (int64_t)U * rows) {
+      Pack<T, VEC> pk[U];
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        s[i] += f[i];
-        s2[i] = fmaf(f[i], f[i], s2[i]);
-        if (two) {
-          s[i] += f2[i];
-          s2[i] = fmaf(f2[i], f2[i], s2[i]);
+      for (int u = 0; u < U; ++u)
+        if (v + (int64_t)u * rows < v1) pk[u] = *reinterpret_cast<const Pack<T, VEC>*>(base + (v + (int64_t)u * rows) * x.ld);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (v + (int64_t)u * rows < v1) {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) {
+            const float f = to_f<T>(pk[u].v[i]);
+            s[i] += f;
+            s2[i] = fmaf(f, f, s2[i]);
+          }
         }
-      }
     }
     double* dst = s_red + ((int64_t)row * cv_count + cv) * VEC * 2;
 #pragma unroll
@@ -105,7 +109,7 @@ static int launch_channel_sums(const b200_tensor* x, double* sums, cudaStream_t 
   View<const T> xv{(const T*)x->data, x->ld, x->c, voxels(x), (int64_t)x->d * x->h * x->w};
   auto grid_of = [&](int rows) {
     int64_t chunks = ceil_div(xv.spatial, (int64_t)rows * 64);
-    int64_t cap = ceil_div((int64_t)sm_count() * 16, x->n);
+    int64_t cap = ceil_div((int64_t)sm_count() * 4, x->n);
     if (chunks > cap) chunks = cap;
     if (chunks < 1) chunks = 1;
     return dim3((unsigned)chunks, x->n);
@@ -187,8 +191,8 @@ __global__ void scale_shift_act_kernel(View<const TI> x, View<TO> y, const float
 
 // -------------------------------------------------------------------------------- norm+act backward, pass 1
 // same thread layout as channel_sums; accumulates (sum g, sum g*xhat) per (n,c)
-template <typename T, int VEC>
-__global__ void __launch_bounds__(256, 3) norm_act_bwd_reduce_kernel(View<const T> x, View<const T> dy, const float* __restrict__ mean,
+template <typename T, int VEC, int ACT, int U, int MINB>
+__global__ void __launch_bounds__(256, MINB) norm_act_bwd_reduce_kernel(View<const T> x, View<const T> dy, const float* __restrict__ mean,
                                            const float* __restrict__ rstd, int groups,
                                            const float* __restrict__ gamma, const float* __restrict__ beta, int act,
                                            double* __restrict__ red, int cv_count, int rows) {
@@ -218,26 +222,26 @@ __global__ void __launch_bounds__(256, 3) norm_act_bwd_reduce_kernel(View<const 
     if (v1 > x.spatial) v1 = x.spatial;
     const T* xb = x.p + (int64_t)n * x.spatial * x.ld + (int64_t)cv * VEC;
     const T* db = dy.p + (int64_t)n * x.spatial * dy.ld + (int64_t)cv * VEC;
-    float fx[VEC], fd[VEC], fx2[VEC], fd2[VEC];
-    for (int64_t v = v0 + row; v < v1; v += 2 * rows) {
-      const bool two = v + rows < v1;
-      load_vec<T, VEC>(xb + v * x.ld, fx);
-      load_vec<T, VEC>(db + v * dy.ld, fd);
-      if (two) {
-        load_vec<T, VEC>(xb + (v + rows) * x.ld, fx2);
-        load_vec<T, VEC>(db + (v + rows) * dy.ld, fd2);
-      }
+    // U packed 16-byte loads in flight per thread and tensor
+    for (int64_t v = v0 + row; v < v1; v += (int64_t)U * rows) {
+      Pack<T, VEC> px[U], pd[U];
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        float g = fd[i] * act_grad(act, fmaf(fx[i], ka[i], kb[i]));
-        s[i] += g;
-        s2[i] = fmaf(g, fx[i], s2[i]);
-        if (two) {
-          float g2 = fd2[i] * act_grad(act, fmaf(fx2[i], ka[i], kb[i]));
-          s[i] += g2;
-          s2[i] = fmaf(g2, fx2[i], s2[i]);
+      for (int u = 0; u < U; ++u)
+        if (v + (int64_t)u * rows < v1) {
+          px[u] = *reinterpret_cast<const Pack<T, VEC>*>(xb + (v + (int64_t)u * rows) * x.ld);
+          pd[u] = *reinterpret_cast<const Pack<T, VEC>*>(db + (v + (int64_t)u * rows) * dy.ld);
         }
-      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (v + (int64_t)u * rows < v1) {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) {
+            const float fx = to_f<T>(px[u].v[i]);
+            const float g = to_f<T>(pd[u].v[i]) * act_grad_t<ACT>(act, fmaf(fx, ka[i], kb[i]));
+            s[i] += g;
+            s2[i] = fmaf(g, fx, s2[i]);
+          }
+        }
     }
     double* dst = s_red + ((int64_t)row * cv_count + cv) * VEC * 2;
 #pragma unroll
@@ -324,8 +328,8 @@ __global__ void norm_act_bwd_apply_kernel(View<const T> x, View<const T> dy, Vie
 
 // vectorised: grid = (chunks, N), block = rows x cvn threads; every thread keeps the coefficients of its 8 (4) channels
 // in registers, so the loop body is 2-3 16-byte loads, the activation derivative and one 16-byte store
-template <typename T, int VEC>
-__global__ void __launch_bounds__(256, 2) norm_act_bwd_apply_rows_kernel(View<const T> x, View<const T> dy, View<T> dx, int act,
+template <typename T, int VEC, int ACT, int U, int MINB>
+__global__ void __launch_bounds__(256, MINB) norm_act_bwd_apply_rows_kernel(View<const T> x, View<const T> dy, View<T> dx, int act,
                                                const float* __restrict__ coef, int accumulate, int cvn, int rows) {
   const int n = blockIdx.y;
   const int cv = threadIdx.x % cvn, row = threadIdx.x / cvn;
@@ -339,7 +343,7 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_apply_rows_kernel(View<co
   const T* xb = x.p + (int64_t)n * x.spatial * x.ld + cv * VEC;
   const T* db = dy.p + (int64_t)n * x.spatial * dy.ld + cv * VEC;
   T* ob = dx.p + (int64_t)n * x.spatial * dx.ld + cv * VEC;
-  constexpr int U = 2;                                   // independent 16-byte loads in flight per thread and tensor
+  // U independent 16-byte loads in flight per thread and tensor
   const int64_t stride = (int64_t)gridDim.x * rows;
   for (int64_t v0 = (int64_t)blockIdx.x * rows + row; v0 < x.spatial; v0 += U * stride) {
     Pack<T, VEC> px[U], pd[U], po[U];
@@ -360,7 +364,7 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_apply_rows_kernel(View<co
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
           const float fx = to_f<T>(px[u].v[i]);
-          const float g = to_f<T>(pd[u].v[i]) * act_grad(act, fmaf(fx, k0[i], kb[i]));
+          const float g = to_f<T>(pd[u].v[i]) * act_grad_t<ACT>(act, fmaf(fx, k0[i], kb[i]));
           float r = g * k0[i] - fx * kp[i] - kq[i];
           if (accumulate) r += to_f<T>(po[u].v[i]);
           out.v[i] = from_f<T>(r);
@@ -371,7 +375,7 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_apply_rows_kernel(View<co
   }
 }
 
-template <typename T, int VEC>
+template <typename T, int VEC, int ACT>
 __global__ void scale_shift_act_rows_kernel(View<const T> x, View<T> y, const float* __restrict__ scale,
                                             const float* __restrict__ shift, int act, int cvn, int rows) {
   const int n = blockIdx.y;
@@ -400,7 +404,7 @@ __global__ void scale_shift_act_rows_kernel(View<const T> x, View<T> y, const fl
       if (v < x.spatial) {
         Pack<T, VEC> out;
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) out.v[i] = from_f<T>(act_fwd(act, fmaf(to_f<T>(px[u].v[i]), sc[i], sh[i])));
+        for (int i = 0; i < VEC; ++i) out.v[i] = from_f<T>(act_fwd_t<ACT>(act, fmaf(to_f<T>(px[u].v[i]), sc[i], sh[i])));
         *reinterpret_cast<Pack<T, VEC>*>(yb + v * y.ld) = out;
       }
     }
@@ -808,7 +812,7 @@ B200_EXPORT int b200_scale_shift_act(const b200_tensor* x, const float* scale, c
       int cvn = x->c / VV, rows = 256 / cvn;                                                                      \
       dim3 grid(rows_grid(xv.spatial, rows, x->n), x->n);                                                         \
       View<TI> yv2{(TI*)y->data, y->ld, y->c, voxels(y), (int64_t)y->d * y->h * y->w};                              \
-      scale_shift_act_rows_kernel<TI, VV><<<grid, 256, 0, st>>>(xv, yv2, scale, shift, act, cvn, rows);           \
+      B200_DISPATCH_ACT(act, ACT, (scale_shift_act_rows_kernel<TI, VV, ACT><<<grid, 256, 0, st>>>(xv, yv2, scale, shift, act, cvn, rows))); \
     } else if (vec_ok(x, V) && vec_ok(y, V) && sizeof(TI) == sizeof(TO))                                          \
       scale_shift_act_kernel<TI, TO, V><<<grid_for(xv.vox * (x->c / V), 256), 256, 0, st>>>(xv, yv, scale, shift, act); \
     else                                                                                                         \
@@ -835,7 +839,7 @@ B200_EXPORT int b200_norm_act_bwd_reduce(const b200_tensor* x, const b200_tensor
   int64_t spatial = (int64_t)x->d * x->h * x->w;
   auto grid_of = [&](int rows) {
     int64_t chunks = ceil_div(spatial, (int64_t)rows * 64);
-    int64_t cap = ceil_div((int64_t)sm_count() * 16, x->n);
+    int64_t cap = ceil_div((int64_t)sm_count() * 4, x->n);
     if (chunks > cap) chunks = cap;
     if (chunks < 1) chunks = 1;
     return dim3((unsigned)chunks, x->n);
@@ -848,8 +852,16 @@ B200_EXPORT int b200_norm_act_bwd_reduce(const b200_tensor* x, const b200_tensor
     if (vec_ok(x, V) && vec_ok(dy, V) && x->c / VH <= 256) {
       int cvn = x->c / VH, rows = 256 / cvn;
       int threads = ((rows * cvn + 31) / 32) * 32;
-      norm_act_bwd_reduce_kernel<T, VH><<<grid_of(rows), threads, sizeof(double) * rows * cvn * VH * 2, st>>>(
-          xv, dv, mean, rstd, groups, gamma, beta, act, red, cvn, rows);
+      static const int variant = getenv("B200_ROWS_VARIANT") ? atoi(getenv("B200_ROWS_VARIANT")) : 0;
+      const size_t smem = sizeof(double) * rows * cvn * VH * 2;
+      B200_DISPATCH_ACT(act, ACT, {
+        if (variant == 1)
+          norm_act_bwd_reduce_kernel<T, VH, ACT, 2, 3><<<grid_of(rows), threads, smem, st>>>(xv, dv, mean, rstd, groups, gamma, beta, act, red, cvn, rows);
+        else if (variant == 2)
+          norm_act_bwd_reduce_kernel<T, VH, ACT, 2, 4><<<grid_of(rows), threads, smem, st>>>(xv, dv, mean, rstd, groups, gamma, beta, act, red, cvn, rows);
+        else
+          norm_act_bwd_reduce_kernel<T, VH, ACT, 1, 4><<<grid_of(rows), threads, smem, st>>>(xv, dv, mean, rstd, groups, gamma, beta, act, red, cvn, rows);
+      });
     } else {
       dim3 grid = grid_of(1);
       B200_CHECK_ARG(x->c <= 1024, "bwd_reduce: too many channels");
@@ -857,7 +869,7 @@ B200_EXPORT int b200_norm_act_bwd_reduce(const b200_tensor* x, const b200_tensor
       if (rows < 1) rows = 1;
       if (rows > 32) rows = 32;
       int threads = ((rows * cvn + 31) / 32) * 32;
-      norm_act_bwd_reduce_kernel<T, 1><<<grid, threads, sizeof(double) * rows * cvn * 2, st>>>(
+      norm_act_bwd_reduce_kernel<T, 1, -1, 1, 4><<<grid, threads, sizeof(double) * rows * cvn * 2, st>>>(
           xv, dv, mean, rstd, groups, gamma, beta, act, red, cvn, rows);
     }
   });
@@ -891,7 +903,12 @@ B200_EXPORT int b200_norm_act_bwd_apply(const b200_tensor* x, const b200_tensor*
     if (vec_ok(x, V) && vec_ok(dy, V) && vec_ok(dx, V) && x->c / V <= 256) {
       int cvn = x->c / V, rows = 256 / cvn;
       dim3 grid(rows_grid(xv.spatial, rows, x->n), x->n);
-      norm_act_bwd_apply_rows_kernel<T, V><<<grid, 256, 0, st>>>(xv, dv, ov, act, coef, accumulate, cvn, rows);
+      static const int variant = getenv("B200_ROWS_VARIANT") ? atoi(getenv("B200_ROWS_VARIANT")) : 0;
+      B200_DISPATCH_ACT(act, ACT, {
+        // measured (profiles/rows_micro.py, c48 @128^3 x4): U=2/2 blocks 3.5 TB/s, U=1/3 blocks 4.5, U=1/4 blocks 5.2 -- occupancy wins
+        if (variant == 1) norm_act_bwd_apply_rows_kernel<T, V, ACT, 2, 4><<<grid, 256, 0, st>>>(xv, dv, ov, act, coef, accumulate, cvn, rows);
+        else norm_act_bwd_apply_rows_kernel<T, V, ACT, 1, 4><<<grid, 256, 0, st>>>(xv, dv, ov, act, coef, accumulate, cvn, rows);
+      });
     } else {
       norm_act_bwd_apply_kernel<T><<<grid_for(xv.vox * x->c, 256), 256, 0, st>>>(xv, dv, ov, act, coef, accumulate);
     }
