@@ -219,8 +219,59 @@ __global__ void bias_grad_kernel(const T* __restrict__ dy, int64_t ld, int c, in
   }
 }
 
+// vectorised form for 16-byte aligned channels-last rows: thread = (voxel row, 8-channel vector), four packed loads in flight
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256, 4) bias_grad_vec_kernel(const T* __restrict__ dy, int64_t ld, int c, int64_t nvox,
+                                                              float* __restrict__ dbias, int cvn, int rows) {
+  extern __shared__ float s_part[];   // [rows][c]
+  const int cv = threadIdx.x % cvn, row = threadIdx.x / cvn;
+  float acc[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+  if (row < rows) {
+    const int64_t chunk = (nvox + gridDim.x - 1) / gridDim.x;
+    const int64_t v0 = (int64_t)blockIdx.x * chunk;
+    const int64_t v1 = v0 + chunk < nvox ? v0 + chunk : nvox;
+    const T* base = dy + (int64_t)cv * VEC;
+    constexpr int U = 4;
+    for (int64_t v = v0 + row; v < v1; v += (int64_t)U * rows) {
+      Pack<T, VEC> pk[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (v + (int64_t)u * rows < v1) pk[u] = *reinterpret_cast<const Pack<T, VEC>*>(base + (v + (int64_t)u * rows) * ld);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (v + (int64_t)u * rows < v1) {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) acc[i] += to_f<T>(pk[u].v[i]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) s_part[row * c + cv * VEC + i] = acc[i];
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float t = 0.f;
+    for (int r = 0; r < rows; ++r) t += s_part[r * c + ch];
+    atomicAdd(&dbias[ch], t);
+  }
+}
+
 int conv_bias_grad(const b200_tensor* dy, float* dbias, cudaStream_t st) {
   B200_CHECK_ARG(dy->c <= 1024, "conv_bias_grad: too many channels");
+  if (dy->dtype != B200_F32 && dy->c % 8 == 0 && dy->ld % 8 == 0 && dy->c / 8 <= 256 && ((uintptr_t)dy->data & 15) == 0) {
+    const int cvn = dy->c / 8, rows = 256 / cvn;
+    const int64_t nvox = voxels(dy);
+    int64_t blocks = ceil_div(nvox, (int64_t)rows * 64);
+    if (blocks > (int64_t)sm_count() * 4) blocks = (int64_t)sm_count() * 4;
+    const size_t smem = sizeof(float) * rows * dy->c;
+    if (dy->dtype == B200_BF16)
+      bias_grad_vec_kernel<__nv_bfloat16, 8><<<(unsigned)blocks, 256, smem, st>>>((const __nv_bfloat16*)dy->data, dy->ld, dy->c, nvox, dbias, cvn, rows);
+    else
+      bias_grad_vec_kernel<__half, 8><<<(unsigned)blocks, 256, smem, st>>>((const __half*)dy->data, dy->ld, dy->c, nvox, dbias, cvn, rows);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+  }
   int threads = dy->c <= 256 ? 256 : 1024;
   threads = (threads / dy->c) * dy->c;
   int64_t nvox = voxels(dy);
@@ -335,6 +386,125 @@ __global__ void conv1x1_small_wgrad_kernel(const T* __restrict__ x, int64_t ldx,
   }
 }
 
+// 16-bit, 16-byte-aligned forms: one thread per voxel, the wide side moves as 16-byte vectors (the scalar forms above
+// issue one 2-byte access per channel and are LSU-bound at a fifth of the HBM rate)
+// y[vox][co < cout <= 8] from cin = 8 * CV channels
+template <typename T>
+__global__ void __launch_bounds__(256) conv1x1_cout_vec_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ wp,
+                                                               const float* __restrict__ bias, T* __restrict__ y, int64_t ldy, int cin,
+                                                               int cout, int64_t nvox, int accumulate) {
+  extern __shared__ float s_w[];   // [cout][cin]
+  for (int i = threadIdx.x; i < cin * cout; i += blockDim.x) s_w[i] = to_f<T>(wp[i]);
+  __syncthreads();
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (int64_t)gridDim.x * blockDim.x) {
+    float acc[kSmallMax];
+#pragma unroll
+    for (int j = 0; j < kSmallMax; ++j) acc[j] = (bias && j < cout) ? bias[j] : 0.f;
+    const T* xr = x + v * ldx;
+    for (int c0 = 0; c0 < cin; c0 += 8) {
+      const Pack<T, 8> px = *reinterpret_cast<const Pack<T, 8>*>(xr + c0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float a = to_f<T>(px.v[i]);
+#pragma unroll
+        for (int j = 0; j < kSmallMax; ++j)
+          if (j < cout) acc[j] = fmaf(a, s_w[j * cin + c0 + i], acc[j]);
+      }
+    }
+    T* yr = y + v * ldy;
+#pragma unroll
+    for (int j = 0; j < kSmallMax; ++j)
+      if (j < cout) yr[j] = from_f<T>(accumulate ? to_f<T>(yr[j]) + acc[j] : acc[j]);
+  }
+}
+
+// y[vox][cout = 8 * CV] from cin <= 8 channels
+template <typename T>
+__global__ void __launch_bounds__(256) conv1x1_cin_vec_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ wp,
+                                                              const float* __restrict__ bias, T* __restrict__ y, int64_t ldy, int cin,
+                                                              int cout, int64_t nvox, int accumulate) {
+  extern __shared__ float s_w[];   // [cout][cin]
+  for (int i = threadIdx.x; i < cin * cout; i += blockDim.x) s_w[i] = to_f<T>(wp[i]);
+  __syncthreads();
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (int64_t)gridDim.x * blockDim.x) {
+    float a[kSmallMax];
+#pragma unroll
+    for (int i = 0; i < kSmallMax; ++i) a[i] = i < cin ? to_f<T>(x[v * ldx + i]) : 0.f;
+    T* yr = y + v * ldy;
+    for (int c0 = 0; c0 < cout; c0 += 8) {
+      Pack<T, 8> old;
+      if (accumulate) old = *reinterpret_cast<const Pack<T, 8>*>(yr + c0);
+      Pack<T, 8> out;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float acc = bias ? bias[c0 + j] : 0.f;
+#pragma unroll
+        for (int i = 0; i < kSmallMax; ++i)
+          if (i < cin) acc = fmaf(a[i], s_w[(c0 + j) * cin + i], acc);
+        if (accumulate) acc += to_f<T>(old.v[j]);
+        out.v[j] = from_f<T>(acc);
+      }
+      *reinterpret_cast<Pack<T, 8>*>(yr + c0) = out;
+    }
+  }
+}
+
+// dw[co][ci], dbias[co] for cout <= 2 and cin = 8 * CV <= 32 (segmentation heads): per-thread fp32 partials, block reduce
+template <typename T>
+__global__ void __launch_bounds__(256) conv1x1_wgrad_head_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy,
+                                                                 int64_t lddy, float* __restrict__ dw, float* __restrict__ dbias,
+                                                                 int cin, int cout, int64_t nvox) {
+  constexpr int kMaxCin = 32, kMaxCout = 2;
+  __shared__ float s_red[8][kMaxCout * (kMaxCin + 1)];
+  float acc[kMaxCout][kMaxCin], bacc[kMaxCout];
+#pragma unroll
+  for (int j = 0; j < kMaxCout; ++j) {
+    bacc[j] = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxCin; ++i) acc[j][i] = 0.f;
+  }
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (int64_t)gridDim.x * blockDim.x) {
+    float d[kMaxCout];
+#pragma unroll
+    for (int j = 0; j < kMaxCout; ++j) d[j] = j < cout ? to_f<T>(dy[v * lddy + j]) : 0.f;
+#pragma unroll
+    for (int c0 = 0; c0 < kMaxCin; c0 += 8)
+      if (c0 < cin) {
+        const Pack<T, 8> px = *reinterpret_cast<const Pack<T, 8>*>(x + v * ldx + c0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float a = to_f<T>(px.v[i]);
+#pragma unroll
+          for (int j = 0; j < kMaxCout; ++j) acc[j][c0 + i] = fmaf(d[j], a, acc[j][c0 + i]);
+        }
+      }
+#pragma unroll
+    for (int j = 0; j < kMaxCout; ++j) bacc[j] += d[j];
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < kMaxCout; ++j) {
+#pragma unroll
+    for (int i = 0; i < kMaxCin; ++i) {
+      const float t = warp_sum(acc[j][i]);
+      if (lane == 0) s_red[warp][j * (kMaxCin + 1) + i] = t;
+    }
+    const float tb = warp_sum(bacc[j]);
+    if (lane == 0) s_red[warp][j * (kMaxCin + 1) + kMaxCin] = tb;
+  }
+  __syncthreads();
+  for (int it = threadIdx.x; it < kMaxCout * (kMaxCin + 1); it += blockDim.x) {
+    const int j = it / (kMaxCin + 1), i = it % (kMaxCin + 1);
+    if (j >= cout) continue;
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += s_red[w][it];
+    if (i < cin) atomicAdd(&dw[(int64_t)j * cin + i], t);
+    else if (i == kMaxCin && dbias) atomicAdd(&dbias[j], t);
+  }
+}
+
+static bool vec16(const b200_tensor* t) { return t->dtype != B200_F32 && t->c % 8 == 0 && t->ld % 8 == 0 && ((uintptr_t)t->data & 15) == 0; }
+
 static bool small_pointwise(const b200_tensor* x, const b200_tensor* y, int kd, int kh, int kw) {
   return kd == 1 && kh == 1 && kw == 1 && (x->c <= kSmallMax || y->c <= kSmallMax) && x->c * y->c <= 128;
 }
@@ -348,8 +518,17 @@ int conv_fprop_simt(const b200_tensor* x, const void* w, const float* bias, cons
       if (y->c <= kSmallMax) {
         int64_t blocks = ceil_div(nvox, 256);
         if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
-        conv1x1_small_cout_kernel<T><<<(unsigned)blocks, 256, smem, st>>>((const T*)x->data, x->ld, (const T*)w, bias, (T*)y->data,
+        if (vec16(x))
+          conv1x1_cout_vec_kernel<T><<<(unsigned)blocks, 256, smem, st>>>((const T*)x->data, x->ld, (const T*)w, bias, (T*)y->data,
                                                                         y->ld, x->c, y->c, nvox, accumulate);
+        else
+          conv1x1_small_cout_kernel<T><<<(unsigned)blocks, 256, smem, st>>>((const T*)x->data, x->ld, (const T*)w, bias, (T*)y->data,
+                                                                          y->ld, x->c, y->c, nvox, accumulate);
+      } else if (vec16(y)) {
+        int64_t blocks = ceil_div(nvox, 256);
+        if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
+        conv1x1_cin_vec_kernel<T><<<(unsigned)blocks, 256, smem, st>>>((const T*)x->data, x->ld, (const T*)w, bias, (T*)y->data,
+                                                                     y->ld, x->c, y->c, nvox, accumulate);
       } else {
         int64_t blocks = ceil_div(nvox * y->c, 256);
         if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
@@ -382,6 +561,16 @@ int conv_fprop_simt(const b200_tensor* x, const void* w, const float* bias, cons
 
 int conv_wgrad_simt(const b200_tensor* x, const b200_tensor* dy, float* dw, float* dbias, int kd, int kh, int kw,
                     cudaStream_t st) {
+  if (small_pointwise(x, dy, kd, kh, kw) && dy->c <= 2 && x->c <= 32 && vec16(x)) {
+    const int64_t nvox = voxels(x);
+    int64_t blocks = ceil_div(nvox, 256 * 8);
+    if (blocks > (int64_t)sm_count() * 4) blocks = (int64_t)sm_count() * 4;
+    if (blocks < 1) blocks = 1;
+    B200_DISPATCH_DTYPE(x->dtype, T, (conv1x1_wgrad_head_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(
+                                         (const T*)x->data, x->ld, (const T*)dy->data, dy->ld, dw, dbias, x->c, dy->c, nvox)));
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+  }
   if (small_pointwise(x, dy, kd, kh, kw)) {
     const int64_t nvox = voxels(x);
     const int pairs = x->c * dy->c;

@@ -87,14 +87,23 @@ struct FpropParams {
   // transposed-convolution mode: GEMM column c = phase * pcout + co is scattered to the fine voxel
   // (z*usd + a, y*ush + b, x*usw + c') of phase (a, b, c'); ys* are then the strides of the FINE tensor.  usd == 0: off.
   int usd, ush, usw, pcout;
+  // phase-gather mode (dgrad of a transposed convolution): tap t reads its A box through PhaseMaps::m[t] at unshifted
+  // coordinates and its weights from rows [t * wrows, t * wrows + cout) of the packed matrix; kd = phases, kh = kw = 1
+  int phases, wrows;
 };
 
 constexpr int kMaxStages = 12;
 
+// Tensor maps of the (up to 8) output phases of a stride-s transposed convolution: phase t of the fine tensor is the
+// strided sub-lattice (a, b, c) seen as an ordinary coarse tensor (phase_view).  Lets ONE launch run over all phases:
+// K blocks of the dgrad GEMM / N boxes of the wgrad GEMM pick their map by phase instead of one launch per phase.
+struct alignas(64) PhaseMaps { CUtensorMap m[8]; };
+
 template <typename T>
 __global__ void __launch_bounds__(224, 1)
 conv_fprop_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                       const float* __restrict__ bias, T* __restrict__ y, const FpropParams p) {
+                       const __grid_constant__ PhaseMaps pm, const float* __restrict__ bias, T* __restrict__ y,
+                       const FpropParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t s_bar[2 * kMaxStages + 4];
   __shared__ uint32_t s_tmem;
@@ -126,7 +135,8 @@ conv_fprop_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
 
   const int taps = p.kd * p.kh * p.kw;
   const int num_kb = taps * p.chunks;
-  const int pd = p.kd / 2, ph = p.kh / 2, pw = p.kw / 2;
+  const bool pmode = p.phases > 0;
+  const int pd = pmode ? 0 : p.kd / 2, ph = p.kh / 2, pw = p.kw / 2;
 
   auto decode = [&](int tile, int& n, int& z0, int& y0, int& x0, int& n0) {
     int t = tile;
@@ -161,10 +171,12 @@ conv_fprop_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
                 const uint32_t fb = bar_full + 8 * stage;
                 if (a_role) {
                   mbar_expect_tx(fb, a_bytes);
-                  tma_load_5d(a_dst, &tmap_x, fb, ch * ck, x0 + dx - pw, y0 + dy - ph, z0 + dz - pd, n);
+                  if (pmode) tma_load_5d(a_dst, &pm.m[dz], fb, ch * ck, x0, y0, z0, n);
+                  else tma_load_5d(a_dst, &tmap_x, fb, ch * ck, x0 + dx - pw, y0 + dy - ph, z0 + dz - pd, n);
                 } else {
                   mbar_expect_tx(fb, b_bytes);
-                  tma_load_2d(a_dst + a_bytes, &tmap_w, fb, kcol, n0);
+                  if (pmode) tma_load_2d(a_dst + a_bytes, &tmap_w, fb, ch * ck, dz * p.wrows + n0);
+                  else tma_load_2d(a_dst + a_bytes, &tmap_w, fb, kcol, n0);
                 }
                 if (++stage == stages) { stage = 0; phase ^= 1; }
               }
@@ -1193,6 +1205,8 @@ struct Upscale { int sd = 0, sh = 0, sw = 0, cout = 0; };   // transposed-convol
 int conv_fprop_umma_v(const ActView& x, const void* w, const float* bias, const ActView& y, int kd, int kh, int kw,
                       int accumulate, cudaStream_t st, Upscale up = Upscale());
 int conv_wgrad_umma_v(const ActView& x, const ActView& dy, float* dw, int kd, int kh, int kw, cudaStream_t st);
+int conv_fprop_phases_v(const ActView* phase_views, int nphases, const void* w, const ActView& y, int accumulate, cudaStream_t st);
+int conv_wgrad_phases_v(const ActView& x, const ActView* phase_views, int nphases, float* dw, cudaStream_t st);
 bool conv_wgrad_xfold_ok(const ActView& x, const ActView& dy, int kd, int kh, int kw);
 int conv_wgrad_xfold_v(const ActView& x, const ActView& dy, float* dw, int kd, int kh, int kw, cudaStream_t st);
 
@@ -1261,9 +1275,23 @@ static int conv_fprop_umma2_v(const ActView& x, const void* w, const float* bias
   return B200_OK;
 }
 
+static int conv_fprop_umma_impl(const ActView& xv, const void* w, const float* bias, const ActView& yv_in, int kd, int kh, int kw,
+                                int accumulate, cudaStream_t st, Upscale up, const ActView* phase_views, int nphases);
+
 int conv_fprop_umma_v(const ActView& xv, const void* w, const float* bias, const ActView& yv_in, int kd, int kh, int kw,
                       int accumulate, cudaStream_t st, Upscale up) {
-  if (loader_mode() == 1 && up.sd == 0) return conv_fprop_umma2_v(xv, w, bias, yv_in, kd, kh, kw, accumulate, st);
+  return conv_fprop_umma_impl(xv, w, bias, yv_in, kd, kh, kw, accumulate, st, up, nullptr, 0);
+}
+
+// y[v][:] (+)= sum_t phase_t[v][:] * W_t^T with W packed as [t][y.c][x.c]: all phases in one launch
+int conv_fprop_phases_v(const ActView* phase_views, int nphases, const void* w, const ActView& y, int accumulate, cudaStream_t st) {
+  B200_CHECK_ARG(nphases >= 1 && nphases <= 8, "conv_fprop(phases): 1..8 phases");
+  return conv_fprop_umma_impl(phase_views[0], w, nullptr, y, nphases, 1, 1, accumulate, st, Upscale{}, phase_views, nphases);
+}
+
+static int conv_fprop_umma_impl(const ActView& xv, const void* w, const float* bias, const ActView& yv_in, int kd, int kh, int kw,
+                                int accumulate, cudaStream_t st, Upscale up, const ActView* phase_views, int nphases) {
+  if (loader_mode() == 1 && up.sd == 0 && nphases == 0) return conv_fprop_umma2_v(xv, w, bias, yv_in, kd, kh, kw, accumulate, st);
   const ActView* x = &xv;
   // in transposed mode the GEMM has taps*Cout columns; `yv` keeps the fine tensor's strides and gets c = taps*Cout
   ActView yv = yv_in;
@@ -1296,11 +1324,22 @@ int conv_fprop_umma_v(const ActView& xv, const void* w, const float* bias, const
   p.ysw = y->sw; p.ysh = y->sh; p.ysd = y->sd; p.ysn = y->sn;
   p.accumulate = accumulate;
   p.usd = up.sd; p.ush = up.sh; p.usw = up.sw; p.pcout = up.cout;
+  p.phases = nphases; p.wrows = y->c;
 
   CUtensorMap tx, tw;
+  PhaseMaps pm;
+  memset(&pm, 0, sizeof(pm));
   int rc = make_act_tmap(&tx, *x, p.ck, p.bw, p.bh, p.bd);
   if (rc) return rc;
-  rc = make_matrix_tmap(&tw, w, x->dtype, y->c, (int64_t)kd * kh * kw * x->c, p.nt, p.ck);
+  if (nphases) {
+    for (int t = 0; t < nphases; ++t) {
+      rc = make_act_tmap(&pm.m[t], phase_views[t], p.ck, p.bw, p.bh, p.bd);
+      if (rc) return rc;
+    }
+    rc = make_matrix_tmap(&tw, w, x->dtype, (int64_t)nphases * y->c, x->c, p.nt, p.ck);
+  } else {
+    rc = make_matrix_tmap(&tw, w, x->dtype, y->c, (int64_t)kd * kh * kw * x->c, p.nt, p.ck);
+  }
   if (rc) return rc;
 
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
@@ -1308,11 +1347,11 @@ int conv_fprop_umma_v(const ActView& xv, const void* w, const float* bias, const
   if (x->dtype == B200_BF16) {
     auto kern = conv_fprop_umma_kernel<__nv_bfloat16>;
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, 224, smem, st>>>(tx, tw, bias, (__nv_bfloat16*)y->data, p);
+    kern<<<grid, 224, smem, st>>>(tx, tw, pm, bias, (__nv_bfloat16*)y->data, p);
   } else {
     auto kern = conv_fprop_umma_kernel<__half>;
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, 224, smem, st>>>(tx, tw, bias, (__half*)y->data, p);
+    kern<<<grid, 224, smem, st>>>(tx, tw, pm, bias, (__half*)y->data, p);
   }
   B200_LAUNCH_CHECK();
   return B200_OK;
@@ -1577,6 +1616,7 @@ struct WgradParams {
   uint32_t b_bytes, b_box_c, b_boxes, b_layout, b_sbo, b_lbo, b_kstep;
   uint32_t idesc, tmem_cols;
   uint32_t a_off;          // byte offset of the A ring inside dynamic smem (after the B ring)
+  int bpp;                 // > 0: phase mode -- B box i is channel box (i % bpp) of PhaseMaps::m[i / bpp]
 };
 
 constexpr uint32_t kChunkBytes = 128u * 16u * 2u;   // one [128 voxels][16 ch] tile
@@ -1586,7 +1626,7 @@ constexpr int kMaxAStages = 6, kMaxBStages = 6;
 template <typename T>
 __global__ void __launch_bounds__(320, 1)
 conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
-                       float* __restrict__ dw, const WgradParams p) {
+                       const __grid_constant__ PhaseMaps pm, float* __restrict__ dw, const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t s_bar[2 * kMaxAStages + 2 * kMaxBStages + 1];
   __shared__ uint32_t s_tmem;
@@ -1635,8 +1675,15 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
         mbar_wait(bar_bempty + 8 * bs, bph ^ 1);
         const uint32_t b_dst = smem0 + bs * p.b_bytes;
         mbar_expect_tx(bar_bfull + 8 * bs, p.b_bytes);
-        for (uint32_t i = 0; i < p.b_boxes; ++i)
-          tma_load_5d(b_dst + i * 128u * p.b_box_c * 2u, &tmap_dy, bar_bfull + 8 * bs, (int)(i * p.b_box_c), x0, y0, z0, n);
+        if (p.bpp > 0) {
+          uint32_t i = 0;
+          for (int t = 0; i < p.b_boxes; ++t)
+            for (int c = 0; c < p.bpp; ++c, ++i)
+              tma_load_5d(b_dst + i * 128u * p.b_box_c * 2u, &pm.m[t], bar_bfull + 8 * bs, (int)(c * p.b_box_c), x0, y0, z0, n);
+        } else {
+          for (uint32_t i = 0; i < p.b_boxes; ++i)
+            tma_load_5d(b_dst + i * 128u * p.b_box_c * 2u, &tmap_dy, bar_bfull + 8 * bs, (int)(i * p.b_box_c), x0, y0, z0, n);
+        }
         if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
       }
     }
@@ -2517,11 +2564,33 @@ int conv_wgrad_umma(const b200_tensor* x, const b200_tensor* dy, float* dw, floa
 }
 
 namespace sm100 {
+static int conv_wgrad_umma_impl(const ActView& xv, const ActView& dyv, float* dw, int kd, int kh, int kw, cudaStream_t st,
+                                const ActView* phase_views, int nphases);
+
 int conv_wgrad_umma_v(const ActView& xv, const ActView& dyv, float* dw, int kd, int kh, int kw, cudaStream_t st) {
+  return conv_wgrad_umma_impl(xv, dyv, dw, kd, kh, kw, st, nullptr, 0);
+}
+
+// dw[t][co][ci] = sum_v phase_t[v][co] * x[v][ci] for all phases: the GEMM N dimension is (phase, co), <= 256 columns per launch
+int conv_wgrad_phases_v(const ActView& x, const ActView* phase_views, int nphases, float* dw, cudaStream_t st) {
+  const int co = phase_views[0].c;
+  int per = 256 / co;
+  if (per < 1) per = 1;
+  if (per > 8) per = 8;
+  for (int t0 = 0; t0 < nphases; t0 += per) {
+    const int nt = nphases - t0 < per ? nphases - t0 : per;
+    int rc = conv_wgrad_umma_impl(x, phase_views[t0], dw + (size_t)t0 * co * x.c, 1, 1, 1, st, phase_views + t0, nt);
+    if (rc) return rc;
+  }
+  return B200_OK;
+}
+
+static int conv_wgrad_umma_impl(const ActView& xv, const ActView& dyv, float* dw, int kd, int kh, int kw, cudaStream_t st,
+                                const ActView* phase_views, int nphases) {
   const ActView* x = &xv;
   const ActView* dy = &dyv;
   WgradParams p{};
-  p.n = x->n; p.d = x->d; p.h = x->h; p.w = x->w; p.cin = x->c; p.cout = dy->c;
+  p.n = x->n; p.d = x->d; p.h = x->h; p.w = x->w; p.cin = x->c; p.cout = dy->c * (nphases ? nphases : 1);
   p.kd = kd; p.kh = kh; p.kw = kw;
   pick_tile(x->d, x->h, x->w, &p.bd, &p.bh, &p.bw);
   p.tiles_d = (int)ceil_div(x->d, p.bd); p.tiles_h = (int)ceil_div(x->h, p.bh); p.tiles_w = (int)ceil_div(x->w, p.bw);
@@ -2533,8 +2602,9 @@ int conv_wgrad_umma_v(const ActView& xv, const ActView& dyv, float* dw, int kd, 
   if (p.g > p.mb_total) p.g = p.mb_total;
   const int groups = (int)ceil_div(p.mb_total, p.g);
   // B operand (dy tile): channels per TMA box = min(cout, 64); N-major atoms of that width
-  p.b_box_c = p.cout < 64 ? (uint32_t)p.cout : 64u;
+  p.b_box_c = dy->c < 64 ? (uint32_t)dy->c : 64u;
   p.b_boxes = (uint32_t)p.cout / p.b_box_c;
+  p.bpp = nphases ? dy->c / (int)p.b_box_c : 0;
   const uint32_t rp = p.b_box_c * 2;                  // row pitch in bytes = swizzle width
   p.b_layout = rp == 128 ? kSwizzle128 : (rp == 64 ? kSwizzle64 : kSwizzle32);
   p.b_sbo = 8u * rp;
@@ -2557,7 +2627,7 @@ int conv_wgrad_umma_v(const ActView& xv, const ActView& dyv, float* dw, int kd, 
   if (vsplit > p.num_vtiles) vsplit = p.num_vtiles;
   dim3 grid((unsigned)vsplit, (unsigned)groups);
   const size_t smem = (size_t)p.a_off + (size_t)p.a_stages * kBlockBytes + 1024;
-  if (loader_mode() == 1) {
+  if (loader_mode() == 1 && nphases == 0) {
     WgradParams2 pp{p, x->sw, x->sh, x->sd, x->sn, dy->sw, dy->sh, dy->sd, dy->sn};
     if (x->dtype == B200_BF16) {
       auto kern = conv_wgrad_umma2_kernel<__nv_bfloat16>;
@@ -2576,14 +2646,20 @@ int conv_wgrad_umma_v(const ActView& xv, const ActView& dyv, float* dw, int kd, 
   if (rc) return rc;
   rc = make_act_tmap(&tdy, *dy, (int)p.b_box_c, p.bw, p.bh, p.bd);
   if (rc) return rc;
+  PhaseMaps pm;
+  memset(&pm, 0, sizeof(pm));
+  for (int t = 0; t < nphases; ++t) {
+    rc = make_act_tmap(&pm.m[t], phase_views[t], (int)p.b_box_c, p.bw, p.bh, p.bd);
+    if (rc) return rc;
+  }
   if (x->dtype == B200_BF16) {
     auto kern = conv_wgrad_umma_kernel<__nv_bfloat16>;
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, 320, smem, st>>>(tx, tdy, dw, p);
+    kern<<<grid, 320, smem, st>>>(tx, tdy, pm, dw, p);
   } else {
     auto kern = conv_wgrad_umma_kernel<__half>;
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, 320, smem, st>>>(tx, tdy, dw, p);
+    kern<<<grid, 320, smem, st>>>(tx, tdy, pm, dw, p);
   }
   B200_LAUNCH_CHECK();
   return B200_OK;
@@ -2692,6 +2768,16 @@ B200_EXPORT int b200_convT_dgrad_tc(const b200_tensor* dy, const void* w_packed_
                  b200_last_error());
   B200_CHECK_ARG(convT_tc_ok(dx, dy, sd, sh, sw), "convT_dgrad_tc: unsupported operands");
   const ActView xv = view_of(dx);
+  ActView phases[8];
+  const int T = sd * sh * sw;
+  if (T <= 8) {
+    int t = 0;
+    for (int a = 0; a < sd; ++a)
+      for (int b = 0; b < sh; ++b)
+        for (int c = 0; c < sw; ++c, ++t) phases[t] = phase_view(dy, sd, sh, sw, a, b, c);
+    // one GEMM with K = (phase, Cout): every K block reads its A box through the tensor map of its phase
+    return conv_fprop_phases_v(phases, T, w_packed_t, xv, accumulate ? 1 : 0, (cudaStream_t)stream);
+  }
   int t = 0;
   for (int a = 0; a < sd; ++a)
     for (int b = 0; b < sh; ++b)
@@ -2710,14 +2796,26 @@ B200_EXPORT int b200_convT_wgrad_tc(const b200_tensor* x, const b200_tensor* dy,
                  b200_last_error());
   B200_CHECK_ARG(convT_tc_ok(x, dy, sd, sh, sw), "convT_wgrad_tc: unsupported operands");
   const ActView xv = view_of(x);
-  int t = 0;
-  for (int a = 0; a < sd; ++a)
-    for (int b = 0; b < sh; ++b)
-      for (int c = 0; c < sw; ++c, ++t) {
-        const ActView yv = phase_view(dy, sd, sh, sw, a, b, c);
-        int rc = conv_wgrad_umma_v(xv, yv, dw_packed + (size_t)t * dy->c * x->c, 1, 1, 1, (cudaStream_t)stream);
-        if (rc) return rc;
-      }
+  const int T = sd * sh * sw;
+  if (T <= 8) {
+    ActView phases[8];
+    int t = 0;
+    for (int a = 0; a < sd; ++a)
+      for (int b = 0; b < sh; ++b)
+        for (int c = 0; c < sw; ++c, ++t) phases[t] = phase_view(dy, sd, sh, sw, a, b, c);
+    // GEMM N dimension = (phase, Cout): the dY boxes of up to 256 / Cout phases sit side by side in one B tile
+    int rc = conv_wgrad_phases_v(xv, phases, T, dw_packed, (cudaStream_t)stream);
+    if (rc) return rc;
+  } else {
+    int t = 0;
+    for (int a = 0; a < sd; ++a)
+      for (int b = 0; b < sh; ++b)
+        for (int c = 0; c < sw; ++c, ++t) {
+          const ActView yv = phase_view(dy, sd, sh, sw, a, b, c);
+          int rc = conv_wgrad_umma_v(xv, yv, dw_packed + (size_t)t * dy->c * x->c, 1, 1, 1, (cudaStream_t)stream);
+          if (rc) return rc;
+        }
+  }
   if (dbias) return conv_bias_grad(dy, dbias, (cudaStream_t)stream);
   return B200_OK;
 }
