@@ -108,7 +108,7 @@ static int launch_channel_sums(const b200_tensor* x, double* sums, cudaStream_t 
   constexpr int V = VecOf<T>::n;
   View<const T> xv{(const T*)x->data, x->ld, x->c, voxels(x), (int64_t)x->d * x->h * x->w};
   auto grid_of = [&](int rows) {
-    int64_t chunks = ceil_div(xv.spatial, (int64_t)rows * 64);
+    int64_t chunks = ceil_div(xv.spatial, (int64_t)rows * 8);     // small tensors: many short blocks beat a few long ones
     int64_t cap = ceil_div((int64_t)sm_count() * 4, x->n);
     if (chunks > cap) chunks = cap;
     if (chunks < 1) chunks = 1;
@@ -598,6 +598,48 @@ __global__ void binary_kernel(View<const TA> a, View<const TB> b, View<TY> y, in
   }
 }
 
+// 16-byte form (no channel broadcast): thread = (voxel, 8-channel vector), two vectors in flight
+template <typename T, int VEC, int OP>
+__global__ void __launch_bounds__(256, 4) binary_vec_kernel(View<const T> a, View<const T> b, View<T> y) {
+  const int cvn = a.c / VEC;
+  const int64_t total = a.vox * cvn;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  constexpr int U = 2;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += U * stride) {
+    Pack<T, VEC> pa[U], pb[U];
+    int64_t vox[U];
+    int cv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      vox[u] = i / cvn;
+      cv[u] = (int)(i - vox[u] * cvn) * VEC;
+      if (i < total) {
+        pa[u] = *reinterpret_cast<const Pack<T, VEC>*>(a.p + vox[u] * a.ld + cv[u]);
+        if (OP != 3 && OP != 4) pb[u] = *reinterpret_cast<const Pack<T, VEC>*>(b.p + vox[u] * b.ld + cv[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i0 + u * stride >= total) continue;
+      Pack<T, VEC> out;
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const float va = to_f<T>(pa[u].v[k]);
+        const float vb = (OP != 3 && OP != 4) ? to_f<T>(pb[u].v[k]) : 0.f;
+        float r;
+        if (OP == 0) r = va + vb;
+        else if (OP == 1) r = va * vb;
+        else if (OP == 2) r = fmaxf(va + vb, 0.f);
+        else if (OP == 3) r = va;
+        else r = 1.f / (1.f + expf(-va));
+        out.v[k] = from_f<T>(r);
+      }
+      *reinterpret_cast<Pack<T, VEC>*>(y.p + vox[u] * y.ld + cv[u]) = out;
+    }
+  }
+}
+
 // out = psi * x (psi has 1 channel): dpsi[vox] = sum_c dout*x ; dx (+)= dout*psi
 template <typename T>
 __global__ void gate_bwd_kernel(View<const T> x, View<const T> psi, View<const T> dout, View<T> dpsi, View<T> dx,
@@ -838,7 +880,7 @@ B200_EXPORT int b200_norm_act_bwd_reduce(const b200_tensor* x, const b200_tensor
   cudaStream_t st = (cudaStream_t)stream;
   int64_t spatial = (int64_t)x->d * x->h * x->w;
   auto grid_of = [&](int rows) {
-    int64_t chunks = ceil_div(spatial, (int64_t)rows * 64);
+    int64_t chunks = ceil_div(spatial, (int64_t)rows * 8);
     int64_t cap = ceil_div((int64_t)sm_count() * 4, x->n);
     if (chunks > cap) chunks = cap;
     if (chunks < 1) chunks = 1;
@@ -1001,6 +1043,21 @@ B200_EXPORT int b200_binary(const b200_tensor* a, const b200_tensor* b, const b2
   cudaStream_t st = (cudaStream_t)stream;
   const b200_tensor* bb = needs_b ? b : a;
   int bcast = needs_b && b->c == 1 && a->c != 1;
+  if (a->dtype != B200_F32 && !bcast && vec_ok(a, 8) && vec_ok(bb, 8) && vec_ok(y, 8) && op >= 0 && op <= 4) {
+    int64_t total = voxels(a) * (a->c / 8);
+    int64_t blocks = ceil_div(total, 256 * 2);
+    if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
+    if (blocks < 1) blocks = 1;
+#define B200_BIN(T, OP) binary_vec_kernel<T, 8, OP><<<(unsigned)blocks, 256, 0, st>>>(view<const T>(a), view<const T>(bb), view<T>(y))
+#define B200_BIN_OPS(T)                                                                                            \
+    switch (op) { case 0: B200_BIN(T, 0); break; case 1: B200_BIN(T, 1); break; case 2: B200_BIN(T, 2); break;      \
+                  case 3: B200_BIN(T, 3); break; default: B200_BIN(T, 4); break; }
+    if (a->dtype == B200_BF16) { B200_BIN_OPS(__nv_bfloat16) } else { B200_BIN_OPS(__half) }
+#undef B200_BIN_OPS
+#undef B200_BIN
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+  }
   B200_DISPATCH_DTYPE(a->dtype, T, (binary_kernel<T, T, T><<<grid_for(voxels(a) * a->c, 256), 256, 0, st>>>(
                                        view<const T>(a), view<const T>(bb), view<T>(y), op, bcast)));
   B200_LAUNCH_CHECK();
