@@ -848,14 +848,15 @@ conv_fprop_xslab1_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid
             if (!ready) mbar_wait(bar_afull + 8 * as, aph);
             tc_fence_after();
             const uint32_t s16 = a0 + (uint32_t)as * a16;
-            uint64_t ad = tmpl + (uint64_t)(s16 + (uint32_t)r * 8u * line);
-            uint64_t bd = tmpl + (uint64_t)(s16 + w16);
+            const uint32_t t_lo = (uint32_t)tmpl, t_hi = (uint32_t)(tmpl >> 32);
+            uint32_t ad = t_lo + s16 + (uint32_t)r * 8u * line;
+            uint32_t bd = t_lo + s16 + w16;
             const uint32_t cur = bar_aempty + 8 * as;
             if (++as == a_stages) { as = 0; aph ^= 1; }
             ready = mbar_try_wait(bar_afull + 8 * as, aph);              // latency overlaps the issue below
             for (int dz = 0; dz < kd; ++dz, ad += line, bd += wt16) {
-              if (wide) umma_ksteps<4>(d_tmem, ad, bd, idesc, acc);
-              else umma_ksteps<2>(d_tmem, ad, bd, idesc, acc);
+              if (wide) umma_ksteps_split<4>(d_tmem, ad, t_hi, bd, t_hi, 2u, 2u, idesc, acc);
+              else umma_ksteps_split<2>(d_tmem, ad, t_hi, bd, t_hi, 2u, 2u, idesc, acc);
               acc = 1;
             }
             umma_commit(cur);
@@ -2016,6 +2017,7 @@ struct WgradSParams {
   uint32_t sa_bytes;                    // one slab atom: zl * 16 rows * 64 B
   uint32_t b_boxes, b_bytes, a_off;
   uint32_t idesc, tmem_cols;
+  long long* dbg;                       // diagnostics (B200_DBG): per-CTA cycle counters of the MMA lane, or nullptr
 };
 
 template <typename T>
@@ -2135,6 +2137,8 @@ conv_wgrad_xslab_kernel(const __grid_constant__ CUtensorMap tmx32, const __grid_
       // B: N-major SWIZZLE_128B atoms (64 el), one K step = 16 rows = 2 KB
       const uint64_t tmpl_a = make_smem_desc(0, p.sa_bytes, 512u, kSwizzle64);
       const uint64_t tmpl_b = make_smem_desc(0, 128u * 128u, 1024u, kSwizzle128);
+      const uint32_t ta_lo = in_reg((uint32_t)tmpl_a), ta_hi = in_reg((uint32_t)(tmpl_a >> 32));
+      const uint32_t tb_lo = in_reg((uint32_t)tmpl_b), tb_hi = in_reg((uint32_t)(tmpl_b >> 32));
       const uint32_t a0 = in_reg((smem0 + p.a_off) >> 4), b0 = in_reg(smem0 >> 4), b16 = in_reg(p.b_bytes >> 4);
       const uint32_t grp16 = in_reg(grp_bytes >> 4), idesc = in_reg(p.idesc), nt = in_reg((uint32_t)p.nt);
       const int a_stages = in_reg(p.a_stages), b_stages = in_reg(p.b_stages), num_vtiles = in_reg(p.num_vtiles);
@@ -2142,19 +2146,30 @@ conv_wgrad_xslab_kernel(const __grid_constant__ CUtensorMap tmx32, const __grid_
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0, acc = 0;
       bool a_ready = mbar_try_wait(bar_afull, 0);
+      const bool dbg = p.dbg != nullptr;
+      long long c_a = 0, c_b = 0;
+      const long long c_start = clock64();
       for (int vt = blockIdx.x; vt < num_vtiles; vt += stride) {
-        mbar_wait(bar_bfull + 8 * bs, bph);
-        const uint64_t bd = tmpl_b + (uint64_t)(b0 + (uint32_t)bs * b16);
+        {
+          const long long c0 = dbg ? clock64() : 0;
+          mbar_wait(bar_bfull + 8 * bs, bph);
+          if (dbg) c_b += clock64() - c0;
+        }
+        const uint32_t bd_lo = tb_lo + b0 + (uint32_t)bs * b16;
         uint32_t d_tmem = tmem;
         for (int gi = 0; gi < ngrp; ++gi) {
-          if (!a_ready) mbar_wait(bar_afull + 8 * as, aph);
+          if (!a_ready) {
+            const long long c0 = dbg ? clock64() : 0;
+            mbar_wait(bar_afull + 8 * as, aph);
+            if (dbg) c_a += clock64() - c0;
+          }
           tc_fence_after();
-          uint64_t ad = tmpl_a + (uint64_t)(a0 + (uint32_t)as * grp16);
+          uint32_t ad_lo = ta_lo + a0 + (uint32_t)as * grp16;
           const uint32_t cur = bar_aempty + 8 * as;
           if (++as == a_stages) { as = 0; aph ^= 1; }
           a_ready = mbar_try_wait(bar_afull + 8 * as, aph);            // latency overlaps the issue below
-          for (int dz = 0; dz < kd; ++dz, ad += 1024u >> 4, d_tmem += nt)
-            umma_ksteps_strided<8>(d_tmem, ad, bd, 1024u >> 4, 2048u >> 4, idesc, acc);
+          for (int dz = 0; dz < kd; ++dz, ad_lo += 1024u >> 4, d_tmem += nt)
+            umma_ksteps_split<8>(d_tmem, ad_lo, ta_hi, bd_lo, tb_hi, 1024u >> 4, 2048u >> 4, idesc, acc);
           umma_commit(cur);
         }
         umma_commit(bar_bempty + 8 * bs);
@@ -2162,6 +2177,10 @@ conv_wgrad_xslab_kernel(const __grid_constant__ CUtensorMap tmx32, const __grid_
         acc = 1;
       }
       umma_commit(bar_done);
+      if (dbg) {
+        long long* o = p.dbg + (blockIdx.y * gridDim.x + blockIdx.x) * 4;
+        o[0] = clock64() - c_start; o[1] = c_a; o[2] = c_b;
+      }
     }
   } else {
     // =================================================================== epilogue: fold Toeplitz diagonals into dw
@@ -2448,6 +2467,12 @@ static int conv_wgrad_xslab_v(const ActView& x, const ActView& dy, float* dw, in
   if (vsplit < 1) vsplit = 1;
   if (vsplit > p.num_vtiles) vsplit = p.num_vtiles;
   dim3 grid((unsigned)vsplit, (unsigned)gy);
+  static long long* dbg_buf = nullptr;
+  if (getenv("B200_DBG")) {
+    if (!dbg_buf) B200_CUDA(cudaMalloc(&dbg_buf, sizeof(long long) * 4 * 1024));
+    B200_CUDA(cudaMemsetAsync(dbg_buf, 0, sizeof(long long) * 4 * 1024, st));
+    p.dbg = dbg_buf;
+  }
   const size_t smem = (size_t)p.a_off + (size_t)p.a_stages * 4u * p.sa_bytes + 1024;
   if (x.dtype == B200_BF16) {
     auto kern = conv_wgrad_xslab_kernel<__nv_bfloat16>;
@@ -2459,6 +2484,18 @@ static int conv_wgrad_xslab_v(const ActView& x, const ActView& dy, float* dw, in
     kern<<<grid, 320, smem, st>>>(tx, ty, dw, p);
   }
   B200_LAUNCH_CHECK();
+  if (p.dbg) {
+    long long h[4 * 1024];
+    B200_CUDA(cudaMemcpyAsync(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    double tot = 0, ca = 0, cb = 0;
+    const int nct = vsplit * gy;
+    for (int b = 0; b < nct && b < 1024; ++b) { tot += h[b * 4]; ca += h[b * 4 + 1]; cb += h[b * 4 + 2]; }
+    const double per = (double)p.num_vtiles * gy;      // (voxel tile, CTA row) pairs
+    printf("wgrad xslab dbg: grid %dx%d gpc %d stages a%d b%d | per voxel tile and CTA: MMA-lane loop %.0f cycles, wait slab atoms %.0f, "
+           "wait dY %.0f\n", vsplit, gy, p.gpc, p.a_stages, p.b_stages, tot / per, ca / per, cb / per);
+    fflush(stdout);
+  }
   return B200_OK;
 }
 

@@ -134,6 +134,28 @@ __device__ __forceinline__ int in_reg(int v) {
   return v;
 }
 
+// Descriptor passed as (low word, high word): only the low word (start address, LBO) changes between K steps, slots and
+// taps, so stepping a descriptor is ONE 32-bit add.  The issuing thread runs ~8 cycles per dependent scalar instruction
+// (B200_DBG counters, profiles/README.md): at N = 64 the 64-bit descriptor arithmetic cost more than the MMA itself.
+__device__ __forceinline__ void umma_f16_split(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <int KS>
+__device__ __forceinline__ void umma_ksteps_split(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                  uint32_t astep16, uint32_t bstep16, uint32_t idesc, uint32_t acc_first) {
+#pragma unroll
+  for (int k = 0; k < KS; ++k)
+    umma_f16_split(tmem_d, a_lo + astep16 * k, a_hi, b_lo + bstep16 * k, b_hi, idesc, k == 0 ? acc_first : 1u);
+}
+
 // KS consecutive K = 16 steps of one operand pair.  `adesc` / `bdesc` are complete descriptors of the first step; a step
 // advances the 14-bit start-address field by 32 bytes (>> 4 = 2), which never carries out of the field for shared
 // memory addresses.  ncu on the first kernels showed ~200 cycles of dependent scalar work per MMA when descriptors
