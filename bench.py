@@ -262,8 +262,18 @@ def run_train(args):
         top = max((k for k in agg if agg[k][1] > 0), key=lambda k: agg[k][0])
         t, fl, by, cnt = agg[top]
         ach = fl / (t / 1e3) / 1e12
+        # DRAM traffic of the dominant launch of that family, from the committed `ncu --set full` capture (profiles/)
+        traffic, traffic_note = None, None
+        try:
+            tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic_r1.json")))
+            if top in tj:
+                traffic = tj[top]["dram_bytes_per_launch"]
+                traffic_note = tj[top]
+        except (OSError, ValueError, KeyError):
+            pass
         roof = {"kernel": top, "region": roofline_region, "bound": "tensor", "achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
-                "frac": ach / peaks["tf_sust"], "traffic": None, "launches": cnt, "ms_in_step": t / args.steps,
+                "frac": ach / peaks["tf_sust"], "traffic": traffic, "traffic_note": traffic_note, "launches": cnt,
+                "ms_in_step": t / args.steps,
                 "peak_source": peaks["src"] + ", sustained figure (kernel timed inside a long step)",
                 "all": {k: {"ms_per_step": round(v[0] / args.steps, 3), "TFLOP/s": round(v[1] / (v[0] / 1e3) / 1e12, 1),
                             "launches": v[3] // args.steps} for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}}
