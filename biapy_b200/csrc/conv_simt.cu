@@ -503,6 +503,60 @@ __global__ void __launch_bounds__(256) conv1x1_wgrad_head_kernel(const T* __rest
   }
 }
 
+// dw[co][ci], dbias[co] for cin <= 4 and cout = 8 or 16 (image-fed pointwise shortcut): thread per voxel, dY row as 16-byte
+// vectors, fp32 partials per thread, warp shuffle + shared-memory block reduce, one atomic per (block, entry)
+template <typename T>
+__global__ void __launch_bounds__(256) conv1x1_wgrad_image_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy,
+                                                                  int64_t lddy, float* __restrict__ dw, float* __restrict__ dbias,
+                                                                  int cin, int cout, int64_t nvox) {
+  constexpr int kCi = 4, kCo = 16;
+  __shared__ float s_red[8][kCo * (kCi + 1)];
+  float acc[kCi][kCo], bacc[kCo];
+#pragma unroll
+  for (int j = 0; j < kCo; ++j) {
+    bacc[j] = 0.f;
+#pragma unroll
+    for (int i = 0; i < kCi; ++i) acc[i][j] = 0.f;
+  }
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (int64_t)gridDim.x * blockDim.x) {
+    float a[kCi];
+#pragma unroll
+    for (int i = 0; i < kCi; ++i) a[i] = i < cin ? to_f<T>(x[v * ldx + i]) : 0.f;
+#pragma unroll
+    for (int c0 = 0; c0 < kCo; c0 += 8)
+      if (c0 < cout) {
+        const Pack<T, 8> pd = *reinterpret_cast<const Pack<T, 8>*>(dy + v * lddy + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = to_f<T>(pd.v[j]);
+          bacc[c0 + j] += d;
+#pragma unroll
+          for (int i = 0; i < kCi; ++i) acc[i][c0 + j] = fmaf(d, a[i], acc[i][c0 + j]);
+        }
+      }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < kCo; ++j) {
+#pragma unroll
+    for (int i = 0; i < kCi; ++i) {
+      const float t = warp_sum(acc[i][j]);
+      if (lane == 0) s_red[warp][j * (kCi + 1) + i] = t;
+    }
+    const float tb = warp_sum(bacc[j]);
+    if (lane == 0) s_red[warp][j * (kCi + 1) + kCi] = tb;
+  }
+  __syncthreads();
+  for (int it = threadIdx.x; it < kCo * (kCi + 1); it += blockDim.x) {
+    const int j = it / (kCi + 1), i = it % (kCi + 1);
+    if (j >= cout) continue;
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += s_red[w][it];
+    if (i < cin) atomicAdd(&dw[(int64_t)j * cin + i], t);
+    else if (i == kCi && dbias) atomicAdd(&dbias[j], t);
+  }
+}
+
 static bool vec16(const b200_tensor* t) { return t->dtype != B200_F32 && t->c % 8 == 0 && t->ld % 8 == 0 && ((uintptr_t)t->data & 15) == 0; }
 
 static bool small_pointwise(const b200_tensor* x, const b200_tensor* y, int kd, int kh, int kw) {
@@ -567,6 +621,16 @@ int conv_wgrad_simt(const b200_tensor* x, const b200_tensor* dy, float* dw, floa
     if (blocks > (int64_t)sm_count() * 4) blocks = (int64_t)sm_count() * 4;
     if (blocks < 1) blocks = 1;
     B200_DISPATCH_DTYPE(x->dtype, T, (conv1x1_wgrad_head_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(
+                                         (const T*)x->data, x->ld, (const T*)dy->data, dy->ld, dw, dbias, x->c, dy->c, nvox)));
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+  }
+  if (small_pointwise(x, dy, kd, kh, kw) && x->c <= 4 && (dy->c == 8 || dy->c == 16) && vec16(dy) && x->dtype != B200_F32) {
+    const int64_t nvox = voxels(x);
+    int64_t blocks = ceil_div(nvox, 256 * 8);
+    if (blocks > (int64_t)sm_count() * 4) blocks = (int64_t)sm_count() * 4;
+    if (blocks < 1) blocks = 1;
+    B200_DISPATCH_DTYPE(x->dtype, T, (conv1x1_wgrad_image_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(
                                          (const T*)x->data, x->ld, (const T*)dy->data, dy->ld, dw, dbias, x->c, dy->c, nvox)));
     B200_LAUNCH_CHECK();
     return B200_OK;

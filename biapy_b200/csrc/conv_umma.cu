@@ -498,7 +498,8 @@ struct XslabParams {
   int rt;                               // row tiles per CTA tile (1 or 2): 8*rt z-lines x 16 y-rows x 4 x-voxels
   int zl;                               // z-lines per slab = 8*rt + kd - 1
   int groups_x, tiles_h, tiles_d, num_tiles;
-  int kx, boxes64, has32;
+  int kx, boxes64, has32;               // kx = window elements per (dz, dy) incl. padding (xfold_geom)
+  int xoff;                             // extra voxels at the window start (image-fed layers), 0 for Cin % 16 == 0
   int nt, nbuf;                         // 4*cout; TMEM accumulator buffers (1 or 2)
   int a_stages, b_stages;
   uint32_t a_bytes, b_bytes, b_off;     // ring slot sizes (max box) and offset of the weight ring
@@ -794,7 +795,7 @@ conv_fprop_xslab1_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         int n, z0, y0, g;
         decode(tile, n, z0, y0, g);
-        const int e0 = (4 * g - p.kw / 2) * p.cin;
+        const int e0 = (4 * g - p.kw / 2 - p.xoff) * p.cin;
         for (int dy = 0; dy < p.kh; ++dy)
           for (int b = 0; b < nboxes; ++b) {
             const bool wide = b < p.boxes64;
@@ -929,13 +930,34 @@ conv_fprop_xslab1_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid
 
 // Toeplitz packing: out[(j, co)][(dz, dy, xi, ci)] from w (Cout, Cin, kd, kh, 3) fp32; flip_transpose builds the dgrad
 // operand (roles of Cin/Cout swapped, taps mirrored) directly.
+// Window of the x-folded row for (Cin, kw): it starts `xoff` voxels before the first tap (4g - kw/2 - xoff) and holds kxp
+// elements per (dz, dy).  Cin a multiple of 16: xoff = 0, kxp = (3 + kw) * Cin.  Image-fed layers (Cin = 2, 4, 8) get the
+// smallest xoff that makes the window start 16-byte aligned and a length padded to whole 32-element TMA boxes
+// (Cin = 2, kw = 3: xoff = 3, 9 voxels -> 32 elements, i.e. two K steps per (dz, dy) instead of the six of a 16-padded input).
+__host__ __device__ inline bool xfold_geom(int cin, int kw, int* xoff, int* kxp) {
+  const int pw = kw / 2;
+  if (cin % 16 == 0) {
+    *xoff = 0;
+    *kxp = (3 + kw) * cin;
+    return *kxp % 32 == 0;
+  }
+  if (cin != 2 && cin != 4 && cin != 8) return false;
+  int xo = 0;
+  while (((pw + xo) * cin * 2) % 16 != 0) ++xo;
+  *xoff = xo;
+  *kxp = ((xo + 4 + 2 * pw) * cin + 31) / 32 * 32;
+  return true;
+}
+
 template <typename T>
 __global__ void pack_weight_xfold_kernel(const float* __restrict__ w, T* __restrict__ out, int cout, int cin, int kd, int kh,
                                          int kw, int flip) {
   // logical conv: co_l in [0, CO), ci_l in [0, CI) with CO = flip ? cin : cout, CI = flip ? cout : cin
   const int CO = flip ? cin : cout, CI = flip ? cout : cin;
-  const int win = 3 + kw;
-  const int64_t ktot = (int64_t)kd * kh * win * CI;
+  int xoff = 0, kxp = 0;
+  xfold_geom(CI, kw, &xoff, &kxp);
+  const int win = kxp / CI;                              // voxels per (dz, dy) window, padding included
+  const int64_t ktot = (int64_t)kd * kh * kxp;
   const int64_t total = (int64_t)4 * CO * ktot;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t t = i;
@@ -945,7 +967,7 @@ __global__ void pack_weight_xfold_kernel(const float* __restrict__ w, T* __restr
     const int dz = (int)(t % kd); t /= kd;
     const int co = (int)(t % CO);
     const int j = (int)(t / CO);
-    const int kx = xi - j;
+    const int kx = xi - xoff - j;
     float v = 0.f;
     if (kx >= 0 && kx < kw) {
       if (!flip) v = w[((((int64_t)co * cin + ci) * kd + dz) * kh + dy) * kw + kx];
@@ -1375,7 +1397,13 @@ static int make_tmap4(CUtensorMap* out, const void* base, int dtype, const cuuin
 bool conv_xfold_ok(const ActView& x, const ActView& y, int kd, int kh, int kw) {
   if (x.dtype != B200_BF16 && x.dtype != B200_F16) return false;
   if ((kw != 3 && kw != 1) || kd > 5 || kh > 5) return false;
-  if (x.c % 16 != 0 || y.c % 16 != 0 || y.c > 64 || x.c > 96) return false;
+  if (y.c % 16 != 0 || y.c > 64 || x.c > 96) return false;
+  if (x.c % 16 != 0) {
+    // image-fed layers (Cin = 2, 4, 8): only the unified-stage slab kernel knows the padded window
+    int xoff, kxp;
+    if (!xfold_geom(x.c, kw, &xoff, &kxp)) return false;
+    if (kd != 3 || x.d < 8 || x.h < 16 || y.c > 16) return false;
+  }
   if (x.sw != x.c || x.sh != (int64_t)x.w * x.c) return false;              // dense rows: 6 voxels are contiguous
   if (x.w % 4 != 0 || x.w < 8) return false;
   if (y.sw % 8 != 0 || !aligned16(x.data) || !aligned16(y.data)) return false;
@@ -1404,7 +1432,7 @@ static int conv_fprop_xslab_v(const ActView& x, const void* w, const float* bias
   p.groups_x = x.w / 4;
   p.tiles_h = (int)ceil_div(x.h, 16); p.tiles_d = (int)ceil_div(x.d, 8 * p.rt);
   p.num_tiles = x.n * p.tiles_d * p.tiles_h * p.groups_x;
-  p.kx = (3 + kw) * x.c;
+  B200_CHECK_ARG(xfold_geom(x.c, kw, &p.xoff, &p.kx), "conv_fprop(xslab): unsupported Cin");
   p.boxes64 = p.kx / 64; p.has32 = (p.kx % 64) ? 1 : 0;
   p.a_bytes = (((uint32_t)p.zl * 16u * 128u) + 1023u) & ~1023u;
   p.b_bytes = (((uint32_t)p.nt * 128u) + 1023u) & ~1023u;
@@ -1472,6 +1500,7 @@ static int conv_fprop_xslab_v(const ActView& x, const void* w, const float* bias
     B200_LAUNCH_CHECK();
     return B200_OK;
   }
+  B200_CHECK_ARG(p.xoff == 0, "conv_fprop(xslab): image-fed layers need the unified-stage kernel");
   const size_t smem = (size_t)p.b_off + (size_t)p.b_stages * p.b_bytes + 1024;
   if (x.dtype == B200_BF16) {
     auto kern = conv_fprop_xslab_kernel<__nv_bfloat16>;
@@ -1580,7 +1609,9 @@ int conv_fprop_xfold(const b200_tensor* x, const void* w, const float* bias, con
 int pack_weight_xfold(const float* w, void* packed, int dtype, int cout, int cin, int kd, int kh, int kw, int flip,
                       cudaStream_t st) {
   const int CO = flip ? cin : cout, CI = flip ? cout : cin;
-  int64_t total = (int64_t)4 * CO * kd * kh * (3 + kw) * CI;
+  int xoff = 0, kxp = 0;
+  B200_CHECK_ARG(sm100::xfold_geom(CI, kw, &xoff, &kxp), "pack_weight_xfold: unsupported input channel count %d", CI);
+  int64_t total = (int64_t)4 * CO * kd * kh * kxp;
   unsigned blocks = (unsigned)(ceil_div(total, 256) < 8192 ? ceil_div(total, 256) : 8192);
   if (dtype == B200_BF16)
     sm100::pack_weight_xfold_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w, (__nv_bfloat16*)packed, cout, cin, kd, kh, kw, flip);
@@ -2009,7 +2040,8 @@ struct WgradSParams {
   int kd, kh, kw;
   int zl;                               // z-lines per slab atom = 8 + kd - 1
   int groups_x, tiles_h, tiles_d, num_vtiles;
-  int aps;                              // 32-element atoms per window row = win * cin / 32
+  int aps;                              // 32-element atoms per window row = kxp / 32 (xfold_geom)
+  int xoff;                             // extra voxels at the window start (image-fed layers)
   int sa_total;                         // slab atoms = kh * aps
   int grp_total, gpc;                   // groups of 4 slab atoms; groups per CTA (blockIdx.y)
   int a_stages, b_stages;
@@ -2109,7 +2141,7 @@ conv_wgrad_xslab_kernel(const __grid_constant__ CUtensorMap tmx32, const __grid_
       for (int vt = blockIdx.x; vt < p.num_vtiles; vt += gridDim.x) {
         int n, z0, y0, g;
         decode(vt, n, z0, y0, g);
-        const int e0 = (4 * g - pw) * p.cin;
+        const int e0 = (4 * g - pw - p.xoff) * p.cin;
         int at = at0, dy = dy0;
         for (int gi = g0; gi < g1; ++gi) {
           mbar_wait(bar_aempty + 8 * as, aph ^ 1);
@@ -2202,7 +2234,7 @@ conv_wgrad_xslab_kernel(const __grid_constant__ CUtensorMap tmx32, const __grid_
           uint32_t r[16];
           tmem_ld16(taddr + c0, r);
           tmem_ld_wait();
-          const int kx = xi - j;
+          const int kx = xi - p.xoff - j;
           if (valid && kx >= 0 && kx < p.kw) {
             const int tap = (dz * p.kh + dyy) * p.kw + kx;
             float* dst = dw + ((int64_t)co * taps + tap) * p.cin + ci;
@@ -2397,7 +2429,14 @@ conv_wgrad_umma2_kernel(const T* __restrict__ x, const T* __restrict__ dy, float
 bool conv_wgrad_xfold_ok(const ActView& x, const ActView& dy, int kd, int kh, int kw) {
   if (x.dtype != B200_BF16 && x.dtype != B200_F16) return false;
   if ((kw != 3 && kw != 1) || kd > 5 || kh > 5) return false;
-  if (x.c % 16 != 0 || x.c > 96 || ((3 + kw) * x.c) % 32 != 0) return false;
+  if (x.c > 96) return false;
+  if (x.c % 16 != 0) {
+    int xoff, kxp;
+    if (!xfold_geom(x.c, kw, &xoff, &kxp)) return false;
+    if (kd != 3 || x.d < 8 || x.h < 16 || kd * 4 * dy.c > 512) return false;      // z-slab kernel only
+  } else if (((3 + kw) * x.c) % 32 != 0) {
+    return false;
+  }
   if (!(dy.c == 16 || dy.c == 32 || dy.c == 64)) return false;
   if (x.sw != x.c || x.sh != (int64_t)x.w * x.c) return false;
   if (dy.sw != dy.c || dy.sh != (int64_t)dy.w * dy.c) return false;
@@ -2415,7 +2454,9 @@ static int conv_wgrad_xslab_v(const ActView& x, const ActView& dy, float* dw, in
   p.groups_x = x.w / 4;
   p.tiles_h = (int)ceil_div(x.h, 16); p.tiles_d = (int)ceil_div(x.d, 8);
   p.num_vtiles = x.n * p.tiles_d * p.tiles_h * p.groups_x;
-  p.aps = (3 + kw) * x.c / 32;
+  int kxp = 0;
+  B200_CHECK_ARG(xfold_geom(x.c, kw, &p.xoff, &kxp), "conv_wgrad(xslab): unsupported Cin");
+  p.aps = kxp / 32;
   p.sa_total = kh * p.aps;
   p.grp_total = (int)ceil_div(p.sa_total, 4);
   p.nt = 4 * dy.c;
@@ -2571,6 +2612,8 @@ int conv_wgrad_xfold_v(const ActView& x, const ActView& dy, float* dw, int kd, i
 
 bool conv_wgrad_umma_supported(const b200_tensor* x, const b200_tensor* dy, int kd, int kh, int kw) {
   if (x->dtype != B200_BF16 && x->dtype != B200_F16) return false;
+  if (x->c % 16 != 0 && x->c <= 8 && dy->ld % 8 == 0)
+    return sm100::conv_wgrad_xfold_ok(sm100::view_of(x), sm100::view_of(dy), kd, kh, kw);   // image-fed layer: x-folded slab kernel
   if (x->c % 16 != 0 || x->ld % 8 != 0 || dy->ld % 8 != 0) return false;
   const int co = dy->c;
   if (!(co == 16 || co == 32 || co == 64 || co == 128 || co == 256)) return false;

@@ -174,13 +174,17 @@ class Tape:
         assert x.c == cin, (x.c, cin)
         if out is None:
             out = self.new(x.data, cout)
+        # image-fed layers (Cin = 2, 4, 8): the x-folded slab kernels take the narrow input as it is (3x3x3), the pointwise
+        # shortcut is an HBM stream on the CUDA cores; anything else with Cin < 16 is zero-padded to 16 channels
+        narrow = (cin in (2, 4, 8) and self.dtype != torch.float32 and self.impl == _lib.IMPL_AUTO and self.use_xfold
+                  and (k == (1, 1, 1) or ops.conv_impl_query(x.data, out.data, k) == _lib.IMPL_XFOLD))
         if (cin < 16 and cout % 16 == 0 and not x.requires_grad and self.dtype != torch.float32
-                and self.impl != _lib.IMPL_SIMT):
+                and self.impl != _lib.IMPL_SIMT and not narrow):
             return self._conv_padded_input(x, mod, out, accumulate, k, cout, cin)
         self._conv_launch(x.data, w, False, self._f32(b), out.data, k, accumulate)
         if self.training:
-            def bwd(x=x, out=out, w=w, b=b, k=k, cout=cout, cin=cin):
-                dy = self._dense_for_xfold(out.grad(), cin)
+            def bwd(x=x, out=out, w=w, b=b, k=k, cout=cout, cin=cin, narrow=narrow):
+                dy = out.grad() if (narrow and k == (1, 1, 1)) else self._dense_for_xfold(out.grad(), cin)
                 assert out.grad_ready, "conv output gradient was never produced"
                 if w.requires_grad:
                     gb = self._pgrad(b) if (b is not None and b.requires_grad) else None

@@ -94,6 +94,19 @@ def pack_conv_weight(w: torch.Tensor, dtype: torch.dtype, flip_transpose: bool) 
     return out
 
 
+def xfold_window(cin: int, kw: int) -> Tuple[int, int]:
+    """(xoff, kxp) of the x-folded row window -- mirrors `xfold_geom` in csrc/conv_umma.cu."""
+    pw = kw // 2
+    if cin % 16 == 0:
+        return 0, (3 + kw) * cin
+    if cin not in (2, 4, 8):
+        raise _lib.B200Error(f"x-folded kernels take Cin in (2, 4, 8) or a multiple of 16, got {cin}")
+    xo = 0
+    while ((pw + xo) * cin * 2) % 16:
+        xo += 1
+    return xo, ((xo + 4 + 2 * pw) * cin + 31) // 32 * 32
+
+
 def pack_conv_weight_xfold(w: torch.Tensor, dtype: torch.dtype, flip_transpose: bool) -> torch.Tensor:
     """w: (Cout, Cin, kd, kh, 3) or (Cout, Cin, kh, 3) fp32 -> block-Toeplitz packing of the x-folded kernel."""
     w = w.detach()
@@ -105,7 +118,7 @@ def pack_conv_weight_xfold(w: torch.Tensor, dtype: torch.dtype, flip_transpose: 
         k = (1,) + k
     assert k[2] in (1, 3)
     co_l, ci_l = (cin, cout) if flip_transpose else (cout, cin)
-    out = torch.empty(4 * co_l * k[0] * k[1] * (3 + k[2]) * ci_l, dtype=dtype, device=w.device)
+    out = torch.empty(4 * co_l * k[0] * k[1] * xfold_window(ci_l, k[2])[1], dtype=dtype, device=w.device)
     _launch("b200_pack_conv_weight_xfold", _ptr(w), _ptr(out), _lib.torch_dtype_code(dtype), cout, cin, k[0], k[1], k[2],
             1 if flip_transpose else 0, stream_ptr())
     return out

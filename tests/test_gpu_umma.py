@@ -203,3 +203,54 @@ def test_conv_fprop_xfold(case, dtype):
         wpf = ops.pack_conv_weight_xfold(wt.cuda(), dtype, True)
         ops.conv_fprop(gyd, wpf, None, dx, k, impl=_lib.IMPL_XFOLD)
         assert nerr(ncdhw(dx), x.grad) < 1.5e-2
+
+
+IMAGE_CASES = [
+    # n, d, h, w, cin, cout, k        image-fed layers: narrow x-folded window (3x3x3) / CUDA-core stream (1x1x1)
+    (1, 16, 16, 16, 2, 16, (3, 3, 3)),
+    (2, 9, 20, 12, 2, 16, (3, 3, 3)),      # partial tiles in z and y
+    (1, 8, 32, 16, 4, 16, (3, 3, 3)),
+    (1, 24, 16, 8, 8, 16, (3, 3, 3)),
+    (1, 8, 16, 16, 2, 16, (1, 1, 1)),
+    (2, 4, 8, 8, 1, 16, (1, 1, 1)),
+]
+
+
+@pytest.mark.parametrize("case", IMAGE_CASES)
+def test_conv_image_fed(case):
+    """Cin = 1..8 layers without channel padding: fprop (+ accumulate) and wgrad through the automatic dispatch."""
+    from biapy_b200 import _lib, ops
+    n, d, h, w, cin, cout, k = case
+    dtype = torch.bfloat16
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(n, cin, d, h, w, generator=g).to(dtype).float()
+    wt = (torch.randn(cout, cin, *k, generator=g) * 0.2).to(dtype).float().requires_grad_(True)
+    b = torch.randn(cout, generator=g).requires_grad_(True)
+    gy = torch.randn(n, cout, d, h, w, generator=g).to(dtype).float()
+    yr = F.conv3d(x, wt, b, padding=[kk // 2 for kk in k])
+    yr.backward(gy)
+    xd = cl(x).to(dtype)
+    # output and its gradient live in a channel slice of a wider buffer, as the first encoder block's do
+    ybuf = torch.zeros(n, d, h, w, cout + 32, dtype=dtype, device="cuda")
+    yv = ybuf[..., 16:16 + cout]
+    impl = ops.conv_impl_query(xd, yv, k)
+    if k == (3, 3, 3) and cin in (2, 4, 8):
+        assert impl == _lib.IMPL_XFOLD
+        wp = ops.pack_conv_weight_xfold(wt.detach().cuda(), dtype, False)
+    else:
+        impl = _lib.IMPL_AUTO
+        wp = ops.pack_conv_weight(wt.detach().cuda(), dtype, False)
+    ops.conv_fprop(xd, wp, b.detach().cuda(), yv, k, impl=impl)
+    torch.cuda.synchronize()
+    assert nerr(ncdhw(yv), yr.detach()) < 1.5e-2
+    assert ybuf[..., :16].abs().max().item() == 0 and ybuf[..., 16 + cout:].abs().max().item() == 0
+    before = ncdhw(yv)
+    ops.conv_fprop(xd, wp, b.detach().cuda(), yv, k, accumulate=True, impl=impl)
+    assert nerr(ncdhw(yv), before + yr.detach()) < 3e-2
+    gyd = cl(gy).to(dtype)
+    dw = torch.empty(cout, cin, *k, device="cuda")
+    db = torch.zeros(cout, device="cuda")
+    ops.conv_wgrad(xd, gyd, cout, cin, k, dw, db)
+    torch.cuda.synchronize()
+    assert nerr(dw.cpu(), wt.grad) < 2e-3
+    assert nerr(db.cpu(), b.grad) < 2e-3
