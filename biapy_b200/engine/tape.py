@@ -85,8 +85,13 @@ class TT:
 
 
 class Tape:
-    def __init__(self, dtype: torch.dtype, device, training: bool, conv_impl: int = _lib.IMPL_AUTO):
+    def __init__(self, dtype: torch.dtype, device, training: bool, conv_impl: int = _lib.IMPL_AUTO,
+                 pack_cache: Optional[Dict] = None):
+        """`pack_cache`: a dict owned by the model that keeps packed weights across forward calls while the module is in
+        eval mode (sliding-window inference runs 54 batches on frozen weights); entries are validated against the
+        parameters' autograd version counters and the cache is dropped by `train()` / `load_state_dict()`."""
         self.dtype = dtype
+        self._pack_cache = pack_cache
         self.device = device
         self.training = training
         self.impl = conv_impl
@@ -111,11 +116,23 @@ class Tape:
 
     def _pack(self, w, flip: bool, xfold: bool = False, wsrc=None) -> torch.Tensor:
         """Packed copy of a weight for this step; `w` is the cache key, `wsrc` the tensor to pack (defaults to w)."""
-        key = (id(w), flip, xfold)
+        src = w if wsrc is None else wsrc
+        return self._cached((id(w), flip, xfold), src,
+                            lambda: ops.pack_conv_weight_xfold(src, self.dtype, flip) if xfold
+                            else ops.pack_conv_weight(src, self.dtype, flip))
+
+    def _cached(self, key, src: torch.Tensor, build: Callable[[], torch.Tensor]) -> torch.Tensor:
+        """Packed form of `src` for this step; served from the model's eval-mode cache when the parameter is unchanged."""
         t = self._packed.get(key)
         if t is None:
-            src = w if wsrc is None else wsrc
-            t = ops.pack_conv_weight_xfold(src, self.dtype, flip) if xfold else ops.pack_conv_weight(src, self.dtype, flip)
+            ver = getattr(src, "_version", None)
+            hit = self._pack_cache.get((key, self.dtype)) if self._pack_cache is not None else None
+            if hit is not None and hit[0] == ver and hit[2] == src.data_ptr():
+                t = hit[1]
+            else:
+                t = build()
+                if self._pack_cache is not None:
+                    self._pack_cache[(key, self.dtype)] = (ver, t, src.data_ptr())
             self._packed[key] = t
         return t
 
@@ -144,11 +161,9 @@ class Tape:
                 cuts = [(0, 64), (64, y.shape[4])]
                 if all(ops.conv_impl_query(x, y[..., a:b], k) == _lib.IMPL_XFOLD for a, b in cuts):
                     for a, b in cuts:
-                        key = (id(wkey), flip, "xfold", a, b)
-                        wp = self._packed.get(key)
-                        if wp is None:
-                            ws = (w[:, a:b] if flip else w[a:b]).detach().contiguous()
-                            wp = self._packed[key] = ops.pack_conv_weight_xfold(ws, self.dtype, flip)
+                        wp = self._cached((id(wkey), flip, "xfold", a, b), w,
+                                          lambda a=a, b=b: ops.pack_conv_weight_xfold(
+                                              (w[:, a:b] if flip else w[a:b]).detach().contiguous(), self.dtype, flip))
                         ops.conv_fprop(x, wp, None if bias is None else bias[a:b], y[..., a:b], k, accumulate=accumulate,
                                        impl=_lib.IMPL_XFOLD)
                     return
@@ -234,10 +249,7 @@ class Tape:
         wf = self._f32(w).contiguous()
         tc = self.dtype != torch.float32 and self.impl != _lib.IMPL_SIMT and ops.convT_tc_supported(x.data, out.data, s)
         if tc:
-            key = (id(w), "convT")
-            wp = self._packed.get(key)
-            if wp is None:
-                wp = self._packed[key] = ops.pack_convT_weight(wf, self.dtype, False)
+            wp = self._cached((id(w), "convT"), w, lambda: ops.pack_convT_weight(wf, self.dtype, False))
             ops.convT_fprop_tc(x.data, wp, self._f32(b), out.data, s)
         else:
             ops.convT_fprop(x.data, wf, self._f32(b), out.data, s)

@@ -135,15 +135,47 @@ class Trainer:
         ops.PROFILE = prof
         return self
 
+    def _stage_host_batch(self, xs: torch.Tensor, ts: torch.Tensor):
+        """Host batch -> device staging buffers on a dedicated copy stream (two slots), then a device-to-device copy
+        into the graph's static inputs on the compute stream.  `step()` never blocks the host, so the host-to-device copy
+        of step i+1 runs while step i computes; the compute stream only waits for the copy of its own batch."""
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._stage = [(torch.empty_like(self._x_static, dtype=xs.dtype), torch.empty_like(self._t_static, dtype=ts.dtype))
+                           for _ in range(2)]
+            self._stage_ready = [torch.cuda.Event() for _ in range(2)]
+            self._stage_free = [torch.cuda.Event() for _ in range(2)]
+            self._stage_k = 0
+        k = self._stage_k
+        self._stage_k ^= 1
+        sx, st = self._stage[k]
+        if sx.dtype != xs.dtype or st.dtype != ts.dtype or sx.shape != xs.shape or st.shape != ts.shape:
+            sx = torch.empty(xs.shape, dtype=xs.dtype, device=self.device)
+            st = torch.empty(ts.shape, dtype=ts.dtype, device=self.device)
+            self._stage[k] = (sx, st)
+        main = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._stage_free[k])        # slot k was last read two steps ago
+            sx.copy_(xs, non_blocking=True)
+            st.copy_(ts, non_blocking=True)
+            self._stage_ready[k].record(self._copy_stream)
+        main.wait_event(self._stage_ready[k])
+        self._x_static.copy_(sx, non_blocking=True)
+        self._t_static.copy_(st, non_blocking=True)
+        self._stage_free[k].record(main)
+
     def _step_graphed(self, x, target) -> torch.Tensor:
         xs = x if isinstance(x, torch.Tensor) else torch.from_numpy(x)
         ts = target if isinstance(target, torch.Tensor) else torch.from_numpy(target)
         if self.ndim == 2:
             xs, ts = xs.unsqueeze(1), ts.unsqueeze(1)
-        if xs.data_ptr() != self._x_static.data_ptr():
-            self._x_static.copy_(xs, non_blocking=True)
-        if ts.data_ptr() != self._t_static.data_ptr():
-            self._t_static.copy_(ts, non_blocking=True)
+        if not xs.is_cuda and not ts.is_cuda:
+            self._stage_host_batch(xs, ts)
+        else:
+            if xs.data_ptr() != self._x_static.data_ptr():
+                self._x_static.copy_(xs, non_blocking=True)
+            if ts.data_ptr() != self._t_static.data_ptr():
+                self._t_static.copy_(ts, non_blocking=True)
         self._graph.replay()
         ops.LAUNCHES += self.graph_launches
         self._reduce_and_update()

@@ -197,6 +197,15 @@ class UNetFamily(nn.Module):
             self.conv_impl = conv_impl
         return self
 
+    # packed-weight cache of eval-mode forwards (see Tape): dropped whenever the weights may change outside autograd's view
+    def train(self, mode: bool = True):
+        self.__dict__.pop("_pack_cache", None)
+        return super().train(mode)
+
+    def load_state_dict(self, *args, **kwargs):
+        self.__dict__.pop("_pack_cache", None)
+        return super().load_state_dict(*args, **kwargs)
+
     def _run(self, tape: Tape, x: TT):
         """Encoder / bottleneck / decoder(s) / heads on the tape.  Returns (pred TT, class TT | None)."""
         if self.conv_in is not None:
@@ -257,7 +266,10 @@ class UNetFamily(nn.Module):
             xcl = xcl.contiguous()
         if xcl.dtype not in (torch.float32, torch.bfloat16, torch.float16):
             xcl = xcl.float()
-        tape = Tape(self.engine_dtype, x.device, training=record, conv_impl=self.conv_impl)
+        cache = None
+        if not record and not self.training:
+            cache = self.__dict__.setdefault("_pack_cache", {})
+        tape = Tape(self.engine_dtype, x.device, training=record, conv_impl=self.conv_impl, pack_cache=cache)
         if xcl.dtype == self.engine_dtype:
             x_tt = TT(xcl, requires_grad=x_requires_grad)
         else:
