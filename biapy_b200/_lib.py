@@ -38,6 +38,7 @@ _P = C.c_void_p
 _I = C.c_int32
 _L = C.c_int64
 _F = C.c_float
+_D = C.c_double
 _T = C.POINTER(Tensor)
 
 # name -> (restype, argtypes).  Must list every symbol of include/biapy_b200.h (tests/test_cabi.py checks).
@@ -72,6 +73,11 @@ SIGNATURES = {
     "b200_norm_finalize": (_I, [_P, _I, _I, _I, _L, _I, _P, _P, _F, _P, _P, _P, _P, _P]),
     "b200_scale_shift_act": (_I, [_T, _P, _P, _I, _T, _P]),
     "b200_norm_act_bwd_reduce": (_I, [_T, _T, _P, _P, _I, _P, _P, _I, _P, _P]),
+    "b200_dropout": (_I, [_T, _T, _F, _P, _L, _I, _P]),
+    "b200_upsample_linear_fwd": (_I, [_T, _T, _P]),
+    "b200_upsample_linear_bwd": (_I, [_T, _T, _I, _P]),
+    "b200_bn_update_running": (_I, [_P, _P, _F, _D, _F, _P, _P, _I, _P]),
+    "b200_bn_eval_coeffs": (_I, [_P, _P, _P, _P, _F, _I, _I, _P, _P, _P]),
     "b200_norm_bwd_finalize": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _L, _I, _P, _P, _P, _P]),
     "b200_norm_act_bwd_apply": (_I, [_T, _T, _I, _P, _T, _I, _P]),
     "b200_act_bwd": (_I, [_T, _T, _I, _T, _I, _P]),

@@ -930,6 +930,207 @@ B200_EXPORT int b200_norm_bwd_finalize(const double* red, const float* mean, con
   return B200_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ dropout
+// nn.Dropout(p) in training mode (reference blocks.py:162-163): y = keep ? x / (1 - p) : 0.  The keep decision is a pure
+// function of (seed, layer id, logical element index), so the backward pass re-derives the mask instead of storing it and
+// a replayed CUDA graph gets fresh masks by bumping the device-resident seed.  Counter-based generator: two rounds of
+// the splitmix64 finaliser over (seed, layer, index) -- not torch's Philox stream, so masks differ from the reference's
+// bit for bit (they are random numbers there too); the distribution and the scaling are the same.
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t layer, uint64_t idx, uint32_t thresh) {
+  const uint64_t h = mix64(mix64(seed + 0x9E3779B97F4A7C15ull * (layer + 1)) ^ (idx * 0xD1342543DE82EF95ull + 0x2545F4914F6CDD1Dull));
+  return (uint32_t)(h >> 32) >= thresh;              // P(keep) = 1 - p
+}
+
+template <typename T>
+__global__ void dropout_kernel(View<const T> x, View<T> y, float scale, uint32_t thresh, const int64_t* __restrict__ seed_dev,
+                               uint64_t layer, int accumulate) {
+  const uint64_t seed = (uint64_t)*seed_dev;
+  const int64_t total = x.vox * x.c;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t vox = i / x.c;
+    const int c = (int)(i - vox * x.c);
+    const float v = dropout_keep(seed, layer, (uint64_t)i, thresh) ? to_f<T>(x.p[vox * x.ld + c]) * scale : 0.f;
+    T* o = y.p + vox * y.ld + c;
+    *o = from_f<T>(accumulate ? to_f<T>(*o) + v : v);
+  }
+}
+
+B200_EXPORT int b200_dropout(const b200_tensor* x, const b200_tensor* y, float p, const int64_t* seed_dev, int64_t layer_id,
+                             int32_t accumulate, void* stream) {
+  B200_CHECK_ARG(check_tensor(x, "dropout.x") && check_tensor(y, "dropout.y") && seed_dev, "%s", b200_last_error());
+  B200_CHECK_ARG(same_spatial(x, y) && x->c == y->c && x->dtype == y->dtype, "dropout: shape/dtype mismatch");
+  B200_CHECK_ARG(p >= 0.f && p < 1.f, "dropout: p must be in [0, 1)");
+  const double t = (double)p * 4294967296.0;
+  const uint32_t thresh = t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
+  B200_DISPATCH_DTYPE(x->dtype, T, (dropout_kernel<T><<<grid_for(voxels(x) * x->c, 256), 256, 0, (cudaStream_t)stream>>>(
+                                       view<const T>(x), view<T>(y), 1.f / (1.f - p), thresh, seed_dev, (uint64_t)layer_id, accumulate)));
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+// ------------------------------------------------------------------------------ linear up-sampling (nn.Upsample)
+// mode = 'bilinear' / 'trilinear', align_corners = False, integer scale factors (reference blocks.py:604-606):
+// src = max((dst + 0.5) / s - 0.5, 0), i0 = floor(src), i1 = min(i0 + 1, in - 1), y = (1 - l) * x[i0] + l * x[i1] per axis.
+struct LinAxis { int i0, i1; float l; };
+__device__ __forceinline__ LinAxis lin_axis(int o, int s, int in) {
+  float src = ((float)o + 0.5f) / (float)s - 0.5f;
+  if (src < 0.f) src = 0.f;
+  int i0 = (int)src;
+  if (i0 > in - 1) i0 = in - 1;
+  LinAxis a;
+  a.i0 = i0;
+  a.i1 = i0 < in - 1 ? i0 + 1 : i0;
+  a.l = src - (float)i0;
+  return a;
+}
+// weight of input index i in output index o along one axis
+__device__ __forceinline__ float lin_weight(int o, int i, int s, int in) {
+  const LinAxis a = lin_axis(o, s, in);
+  return (a.i0 == i ? 1.f - a.l : 0.f) + (a.i1 == i ? a.l : 0.f);
+}
+
+template <typename T>
+__global__ void upsample_linear_fwd_kernel(const T* __restrict__ x, int64_t ldx, T* __restrict__ y, int64_t ldy, int n, int d, int h,
+                                           int w, int c, int sd, int sh, int sw) {
+  const int od = d * sd, oh = h * sh, ow = w * sw;
+  const int64_t total = (int64_t)n * od * oh * ow * c;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = i;
+    const int ch = (int)(t % c); t /= c;
+    const int ox = (int)(t % ow); t /= ow;
+    const int oy = (int)(t % oh); t /= oh;
+    const int oz = (int)(t % od);
+    const int nn = (int)(t / od);
+    const LinAxis az = lin_axis(oz, sd, d), ay = lin_axis(oy, sh, h), ax = lin_axis(ox, sw, w);
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int iz = a ? az.i1 : az.i0, iy = b ? ay.i1 : ay.i0, ix = e ? ax.i1 : ax.i0;
+          const float wt = (a ? az.l : 1.f - az.l) * (b ? ay.l : 1.f - ay.l) * (e ? ax.l : 1.f - ax.l);
+          acc = fmaf(wt, to_f<T>(x[((((int64_t)nn * d + iz) * h + iy) * w + ix) * ldx + ch]), acc);
+        }
+    y[((((int64_t)nn * od + oz) * oh + oy) * ow + ox) * ldy + ch] = from_f<T>(acc);
+  }
+}
+
+// gather form of the adjoint: every input element sums the output gradients it contributed to
+template <typename T>
+__global__ void upsample_linear_bwd_kernel(const T* __restrict__ dy, int64_t lddy, T* __restrict__ dx, int64_t lddx, int n, int d,
+                                           int h, int w, int c, int sd, int sh, int sw, int accumulate) {
+  const int od = d * sd, oh = h * sh, ow = w * sw;
+  const int64_t total = (int64_t)n * d * h * w * c;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = i;
+    const int ch = (int)(t % c); t /= c;
+    const int ix = (int)(t % w); t /= w;
+    const int iy = (int)(t % h); t /= h;
+    const int iz = (int)(t % d);
+    const int nn = (int)(t / d);
+    const int z0 = max(0, sd * iz - sd), z1 = min(od, sd * iz + 2 * sd);
+    const int y0 = max(0, sh * iy - sh), y1 = min(oh, sh * iy + 2 * sh);
+    const int x0 = max(0, sw * ix - sw), x1 = min(ow, sw * ix + 2 * sw);
+    float acc = 0.f;
+    for (int oz = z0; oz < z1; ++oz) {
+      const float wz = lin_weight(oz, iz, sd, d);
+      if (wz == 0.f) continue;
+      for (int oy = y0; oy < y1; ++oy) {
+        const float wy = lin_weight(oy, iy, sh, h);
+        if (wy == 0.f) continue;
+        for (int ox = x0; ox < x1; ++ox) {
+          const float wx = lin_weight(ox, ix, sw, w);
+          if (wx == 0.f) continue;
+          acc = fmaf(wz * wy * wx, to_f<T>(dy[((((int64_t)nn * od + oz) * oh + oy) * ow + ox) * lddy + ch]), acc);
+        }
+      }
+    }
+    T* o = dx + ((((int64_t)nn * d + iz) * h + iy) * w + ix) * lddx + ch;
+    *o = from_f<T>(accumulate ? to_f<T>(*o) + acc : acc);
+  }
+}
+
+static int upsample_geom(const b200_tensor* coarse, const b200_tensor* fine, int* sd, int* sh, int* sw) {
+  B200_CHECK_ARG(coarse->n == fine->n && coarse->c == fine->c && coarse->dtype == fine->dtype &&
+                     fine->d % coarse->d == 0 && fine->h % coarse->h == 0 && fine->w % coarse->w == 0,
+                 "upsample_linear: fine dims must be integer multiples of the coarse dims, same N / C / dtype");
+  *sd = fine->d / coarse->d; *sh = fine->h / coarse->h; *sw = fine->w / coarse->w;
+  return B200_OK;
+}
+
+B200_EXPORT int b200_upsample_linear_fwd(const b200_tensor* x, const b200_tensor* y, void* stream) {
+  B200_CHECK_ARG(check_tensor(x, "upsample.x") && check_tensor(y, "upsample.y"), "%s", b200_last_error());
+  int sd, sh, sw;
+  int rc = upsample_geom(x, y, &sd, &sh, &sw);
+  if (rc) return rc;
+  B200_DISPATCH_DTYPE(x->dtype, T, (upsample_linear_fwd_kernel<T><<<grid_for(voxels(y) * y->c, 256), 256, 0, (cudaStream_t)stream>>>(
+                                       (const T*)x->data, x->ld, (T*)y->data, y->ld, x->n, x->d, x->h, x->w, x->c, sd, sh, sw)));
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+B200_EXPORT int b200_upsample_linear_bwd(const b200_tensor* dy, const b200_tensor* dx, int32_t accumulate, void* stream) {
+  B200_CHECK_ARG(check_tensor(dy, "upsample_bwd.dy") && check_tensor(dx, "upsample_bwd.dx"), "%s", b200_last_error());
+  int sd, sh, sw;
+  int rc = upsample_geom(dx, dy, &sd, &sh, &sw);
+  if (rc) return rc;
+  B200_DISPATCH_DTYPE(dx->dtype, T, (upsample_linear_bwd_kernel<T><<<grid_for(voxels(dx) * dx->c, 256), 256, 0, (cudaStream_t)stream>>>(
+                                        (const T*)dy->data, dy->ld, (T*)dx->data, dx->ld, dx->n, dx->d, dx->h, dx->w, dx->c, sd, sh,
+                                        sw, accumulate)));
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+// BatchNorm bookkeeping (tiny): running statistics from the batch statistics of b200_norm_finalize(batch_stats = 1), and
+// the per-(n, c) scale / shift of eval mode from the running statistics
+__global__ void bn_update_running_kernel(const float* __restrict__ mean, const float* __restrict__ rstd, float eps, double count,
+                                         float momentum, float* __restrict__ rm, float* __restrict__ rv, int c) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  const double r = (double)rstd[i];
+  double var = 1.0 / (r * r) - (double)eps;                 // biased batch variance
+  if (var < 0.0) var = 0.0;
+  const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+  rm[i] = (float)((1.0 - (double)momentum) * (double)rm[i] + (double)momentum * (double)mean[i]);
+  rv[i] = (float)((1.0 - (double)momentum) * (double)rv[i] + (double)momentum * unbiased);
+}
+
+__global__ void bn_eval_coeffs_kernel(const float* __restrict__ rm, const float* __restrict__ rv, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, float eps, int n, int c, float* __restrict__ scale,
+                                      float* __restrict__ shift) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * c) return;
+  const int cc = i % c;
+  const float sc = (gamma ? gamma[cc] : 1.f) / sqrtf(rv[cc] + eps);
+  scale[i] = sc;
+  shift[i] = (beta ? beta[cc] : 0.f) - rm[cc] * sc;
+}
+
+B200_EXPORT int b200_bn_update_running(const float* mean, const float* rstd, float eps, double count, float momentum,
+                                       float* running_mean, float* running_var, int32_t c, void* stream) {
+  B200_CHECK_ARG(mean && rstd && running_mean && running_var && c > 0 && count > 0, "bn_update_running: bad args");
+  bn_update_running_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mean, rstd, eps, count, momentum, running_mean,
+                                                                             running_var, c);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+B200_EXPORT int b200_bn_eval_coeffs(const float* running_mean, const float* running_var, const float* gamma, const float* beta,
+                                    float eps, int32_t n, int32_t c, float* scale, float* shift, void* stream) {
+  B200_CHECK_ARG(running_mean && running_var && scale && shift && n > 0 && c > 0, "bn_eval_coeffs: bad args");
+  bn_eval_coeffs_kernel<<<(n * c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(running_mean, running_var, gamma, beta, eps, n, c,
+                                                                              scale, shift);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
 B200_EXPORT int b200_norm_act_bwd_apply(const b200_tensor* x, const b200_tensor* dy, int32_t act, const float* coef,
                                         const b200_tensor* dx, int32_t accumulate, void* stream) {
   B200_CHECK_ARG(check_tensor(x, "bwd_apply.x") && check_tensor(dy, "bwd_apply.dy") && check_tensor(dx, "bwd_apply.dx") && coef,

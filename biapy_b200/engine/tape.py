@@ -92,6 +92,8 @@ class Tape:
         parameters' autograd version counters and the cache is dropped by `train()` / `load_state_dict()`."""
         self.dtype = dtype
         self._pack_cache = pack_cache
+        self.rng_seed: Optional[torch.Tensor] = None        # int64[1] on the device; set by the model / trainer for dropout
+        self._dropout_layers = 0
         self.device = device
         self.training = training
         self.impl = conv_impl
@@ -296,9 +298,31 @@ class Tape:
         groups = norm_groups(norm, x.c)
         gamma, beta = getattr(norm, "weight", None), getattr(norm, "bias", None)
         g32, b32 = self._f32(gamma), self._f32(beta)
-        st = ops.norm_stats(x.data, groups, g32, b32, eps=float(norm.eps))
+        if isinstance(norm, torch.nn.modules.batchnorm._BatchNorm):
+            # BatchNorm / SyncBatchNorm (reference blocks.py:2117-2120): batch statistics + running-statistics update in
+            # train mode, running statistics in eval mode.  Statistics over (N, D, H, W) = the per-channel sums of all samples.
+            use_batch = norm.training or norm.running_mean is None
+            if use_batch:
+                sync = isinstance(norm, torch.nn.SyncBatchNorm) and norm.training
+                pg = getattr(norm, "process_group", None)
+                st = ops.norm_stats(x.data, groups, g32, b32, eps=float(norm.eps), batch_stats=True,
+                                    sync_group=(pg if pg is not None else True) if sync else False)
+                if norm.training and norm.track_running_stats and norm.running_mean is not None:
+                    if norm.momentum is None:
+                        raise NotImplementedError("BatchNorm(momentum=None) (cumulative average) is not implemented by the B200 "
+                                                  "engine; BiaPy always passes a momentum")
+                    count = x.shape[0] * x.shape[1] * x.shape[2] * x.shape[3] * st.world
+                    ops.bn_update_running(st, x.c, count, float(norm.eps), float(norm.momentum), norm.running_mean,
+                                          norm.running_var)
+                    norm.num_batches_tracked.add_(1)
+            else:
+                if self.training and x.requires_grad:
+                    raise NotImplementedError("gradients through eval-mode BatchNorm are not implemented by the B200 engine")
+                st = ops.bn_eval_stats(x.data, norm.running_mean, norm.running_var, g32, b32, float(norm.eps))
+        else:
+            st = ops.norm_stats(x.data, groups, g32, b32, eps=float(norm.eps))
         ops.scale_shift_act(x.data, st.scale, st.shift, act, out.data)
-        if self.training:
+        if self.training and st.mean is not None:
             def bwd(x=x, out=out, st=st, gamma=gamma, beta=beta, g32=g32, b32=b32, act=act):
                 assert out.grad_ready
                 dg = self._pgrad(gamma) if (gamma is not None and gamma.requires_grad) else None
@@ -308,6 +332,40 @@ class Tape:
                     acc = x.prepare_accumulate()
                     dx = x.grad()
                 ops.norm_act_bwd(x.data, out.grad(), st, g32, b32, act, dx, dg, db, accumulate=acc)
+            self.steps.append(bwd)
+        return out
+
+    def dropout(self, x: TT, p: float, out: Optional[TT] = None) -> TT:
+        """nn.Dropout(p) in training mode.  The mask is re-derived in backward from (seed, layer counter), never stored."""
+        if out is None:
+            out = self.new(x.data, x.c)
+        if self.rng_seed is None:
+            raise _lib.B200Error("dropout needs the tape's rng_seed (a 1-element int64 CUDA tensor)")
+        layer = self._dropout_layers
+        self._dropout_layers += 1
+        ops.dropout(x.data, out.data, p, self.rng_seed, layer)
+        if self.training:
+            def bwd(x=x, out=out, p=p, layer=layer):
+                assert out.grad_ready
+                if x.requires_grad:
+                    acc = x.prepare_accumulate()
+                    ops.dropout(out.grad(), x.grad(), p, self.rng_seed, layer, accumulate=acc)
+            self.steps.append(bwd)
+        return out
+
+    def upsample_linear(self, x: TT, scale: Sequence[int], out: Optional[TT] = None) -> TT:
+        """nn.Upsample(mode='bilinear'|'trilinear', align_corners=False) by integer factors (reference blocks.py:605)."""
+        s = self._k3(scale)
+        sp = (x.shape[1] * s[0], x.shape[2] * s[1], x.shape[3] * s[2])
+        if out is None:
+            out = self.new(x.data, x.c, sp)
+        ops.upsample_linear_fwd(x.data, out.data)
+        if self.training:
+            def bwd(x=x, out=out):
+                assert out.grad_ready
+                if x.requires_grad:
+                    acc = x.prepare_accumulate()
+                    ops.upsample_linear_bwd(out.grad(), x.grad(), accumulate=acc)
             self.steps.append(bwd)
         return out
 
@@ -398,5 +456,7 @@ def norm_groups(norm: torch.nn.Module, channels: int) -> int:
         return norm.num_groups
     if isinstance(norm, (torch.nn.InstanceNorm2d, torch.nn.InstanceNorm3d)):
         return channels
+    if isinstance(norm, torch.nn.modules.batchnorm._BatchNorm):
+        return channels                     # per-channel statistics; the batch axis is folded in by batch_stats=True
     raise NotImplementedError(f"normalization layer {type(norm).__name__} is not supported by the B200 engine "
                               "(supported: 'gn', 'in', 'none')")

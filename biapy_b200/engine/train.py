@@ -185,6 +185,8 @@ class Trainer:
         model = self.model
         tape = Tape(model.engine_dtype, self.device, training=True, conv_impl=model.conv_impl)
         tape.param_grads = dict(self.fp.grad_views)           # gradients land directly in the flat buffer
+        if model.training:
+            tape.rng_seed = model.next_rng_seed(self.device)
         self.fp.grad.zero_()
         if xd.dtype == model.engine_dtype and xd.is_contiguous():
             x_tt = TT(xd, requires_grad=False)

@@ -197,6 +197,17 @@ class UNetFamily(nn.Module):
             self.conv_impl = conv_impl
         return self
 
+    def next_rng_seed(self, device) -> torch.Tensor:
+        """Device-resident dropout seed (int64[1]), started from torch.initial_seed() and advanced once per training
+        forward with an in-stream add -- a captured CUDA graph therefore draws new masks on every replay."""
+        s = self.__dict__.get("_rng_seed")
+        if s is None or s.device != torch.device(device):
+            s = torch.tensor([torch.initial_seed() & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device=device)
+            self.__dict__["_rng_seed"] = s
+        else:
+            s.add_(1)
+        return s
+
     # packed-weight cache of eval-mode forwards (see Tape): dropped whenever the weights may change outside autograd's view
     def train(self, mode: bool = True):
         self.__dict__.pop("_pack_cache", None)
@@ -270,6 +281,8 @@ class UNetFamily(nn.Module):
         if not record and not self.training:
             cache = self.__dict__.setdefault("_pack_cache", {})
         tape = Tape(self.engine_dtype, x.device, training=record, conv_impl=self.conv_impl, pack_cache=cache)
+        if self.training:
+            tape.rng_seed = self.next_rng_seed(x.device)
         if xcl.dtype == self.engine_dtype:
             x_tt = TT(xcl, requires_grad=x_requires_grad)
         else:

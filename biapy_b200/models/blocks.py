@@ -50,9 +50,10 @@ def _get_norm(ndim: int, norm: str, channels: int, bn_momentum: float = 0.1) -> 
         return nn.GroupNorm(8 if ndim == 3 else 16, channels)
     if norm == "in":
         return (nn.InstanceNorm3d if ndim == 3 else nn.InstanceNorm2d)(channels, affine=True, momentum=bn_momentum)
-    if norm in ("bn", "sync_bn"):
-        raise NotImplementedError("normalization 'bn'/'sync_bn' is not implemented by the B200 engine yet "
-                                  "(supported: 'gn', 'in', 'none')")
+    if norm == "bn":
+        return (nn.BatchNorm3d if ndim == 3 else nn.BatchNorm2d)(channels, momentum=bn_momentum)
+    if norm == "sync_bn":
+        return nn.SyncBatchNorm(channels, momentum=bn_momentum)
     return nn.Identity()
 
 
@@ -177,7 +178,16 @@ class ConvBlock(nn.Module):
             return x
         conv, norm, act = self._parts()
         if self.dropout_p > 0 and self.training:
-            raise NotImplementedError("dropout > 0 in training mode is not implemented by the B200 engine")
+            # nn.Dropout is the last layer of the block (reference blocks.py:162-163); `into` is never set here because
+            # a block with dropout does not end with a bare convolution
+            assert into is None
+            if self.order == "norm_act_conv":
+                y = tape.conv(tape.norm_act(x, norm, act), conv)
+            elif norm is None and (act in (None, "none")):
+                y = tape.conv(x, conv)
+            else:
+                y = tape.norm_act(tape.conv(x, conv), norm, act)
+            return tape.dropout(y, self.dropout_p, out=out)
         if self.order == "norm_act_conv":
             h = tape.norm_act(x, norm, act)
             if into is not None:
@@ -251,9 +261,15 @@ class UpBlock(nn.Module):
             in_size_bridge = out_size
         self.out_size, self.in_size_bridge = out_size, in_size_bridge
         mpool = (z_down, yx_down, yx_down) if ndim == 3 else (yx_down, yx_down)
-        if up_mode != "convtranspose":
-            raise NotImplementedError("MODEL.UPSAMPLE_LAYER='upsampling' is not implemented by the B200 engine yet")
-        layers: List[nn.Module] = [convtranspose(in_size, out_size, kernel_size=mpool, stride=mpool)]
+        self.up_mode, self.mpool = up_mode, mpool
+        if up_mode == "convtranspose":
+            layers: List[nn.Module] = [convtranspose(in_size, out_size, kernel_size=mpool, stride=mpool)]
+        elif up_mode == "upsampling":
+            # reference blocks.py:604-606: nn.Upsample(bi/trilinear) followed by a 1x1 convolution
+            layers = [nn.Upsample(mode="bilinear" if ndim == 2 else "trilinear", scale_factor=mpool),
+                      conv(in_size, out_size, kernel_size=1)]
+        else:
+            raise ValueError(f"unknown up_mode {up_mode!r}")
         self._norm_idx = self._act_idx = None
         if norm != "none":
             layers.append(_get_norm(ndim, norm, out_size))
@@ -275,10 +291,20 @@ class UpBlock(nn.Module):
         up_slot = cat.slice(0, self.out_size)
         norm = _norm_or_none(self.up[self._norm_idx]) if self._norm_idx is not None else None
         act = _act_name(self.up[self._act_idx]) if self._act_idx is not None else None
-        if norm is None and act in (None, "none"):
-            tape.convT(x, self.up[0], out=up_slot)
+        plain = norm is None and act in (None, "none")
+        if self.up_mode == "convtranspose":
+            if plain:
+                tape.convT(x, self.up[0], out=up_slot)
+            else:
+                tape.norm_act(tape.convT(x, self.up[0]), norm, act, out=up_slot)
         else:
-            tape.norm_act(tape.convT(x, self.up[0]), norm, act, out=up_slot)
+            # Upsample then 1x1 conv == 1x1 conv then Upsample (both linear, interpolation weights sum to one, so the bias
+            # passes through): the convolution runs at the coarse resolution, 1/s^3 of the reference's work
+            t = tape.conv(x, self.up[1])
+            if plain:
+                tape.upsample_linear(t, self.mpool, out=up_slot)
+            else:
+                tape.norm_act(tape.upsample_linear(t, self.mpool), norm, act, out=up_slot)
         if self.attention_gate is not None:
             self.attention_gate.run(tape, up_slot, bridge, out=cat.slice(self.out_size, self.in_size_bridge))
         return self.conv_block.run(tape, cat)
@@ -369,9 +395,13 @@ class ResUpBlock(nn.Module):
         self.ndim = ndim
         self.in_size, self.in_size_bridge = in_size, in_size_bridge
         mpool = (z_down, yx_down, yx_down) if ndim == 3 else (yx_down, yx_down)
-        if up_mode != "convtranspose":
-            raise NotImplementedError("MODEL.UPSAMPLE_LAYER='upsampling' is not implemented by the B200 engine yet")
-        self.up = convtranspose(in_size, in_size, kernel_size=mpool, stride=mpool)
+        self.up_mode, self.mpool = up_mode, mpool
+        if up_mode == "convtranspose":
+            self.up = convtranspose(in_size, in_size, kernel_size=mpool, stride=mpool)
+        elif up_mode == "upsampling":
+            self.up = nn.Upsample(mode="bilinear" if ndim == 2 else "trilinear", scale_factor=mpool)   # reference blocks.py:1608
+        else:
+            raise ValueError(f"unknown up_mode {up_mode!r}")
         self.conv_block = ResConvBlock(conv=conv, in_size=in_size + in_size_bridge, out_size=out_size, k_size=k_size, act=act,
                                        norm=norm, dropout=dropout, skip_k_size=skip_k_size, skip_norm=skip_norm,
                                        se_block=se_block, extra_conv=extra_conv, nconvs=nconvs, order=order)
@@ -380,5 +410,8 @@ class ResUpBlock(nn.Module):
     bridge_in_cat = True
 
     def run(self, tape: Tape, x: TT, bridge: TT, cat: TT) -> TT:
-        tape.convT(x, self.up, out=cat.slice(0, self.in_size))
+        if self.up_mode == "convtranspose":
+            tape.convT(x, self.up, out=cat.slice(0, self.in_size))
+        else:
+            tape.upsample_linear(x, self.mpool, out=cat.slice(0, self.in_size))
         return self.conv_block.run(tape, cat)

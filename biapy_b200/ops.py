@@ -211,6 +211,24 @@ def convT_wgrad_tc(x, dy, dw: torch.Tensor, dbias, s: Sequence[int], accumulate=
     _launch("b200_unpack_convT_wgrad", _ptr(packed), _ptr(dw), cin, cout, taps, 1 if accumulate else 0, stream_ptr())
 
 
+# ------------------------------------------------------------------------------------------------- dropout
+def dropout(x, y, p: float, seed_dev: torch.Tensor, layer_id: int, accumulate=False):
+    """y (+)= mask * x / (1 - p); the mask is a function of (seed_dev[0], layer_id, element index)."""
+    _launch("b200_dropout", _ref(x), _ref(y), float(p), _ptr(seed_dev), int(layer_id), 1 if accumulate else 0, stream_ptr())
+    return y
+
+
+# ------------------------------------------------------------------------------------- linear up-sampling
+def upsample_linear_fwd(x, y):
+    """nn.Upsample(bilinear/trilinear, align_corners=False); integer scale factors = y dims / x dims."""
+    _launch("b200_upsample_linear_fwd", _ref(x), _ref(y), stream_ptr())
+    return y
+
+
+def upsample_linear_bwd(dy, dx, accumulate=False):
+    _launch("b200_upsample_linear_bwd", _ref(dy), _ref(dx), 1 if accumulate else 0, stream_ptr())
+
+
 # ------------------------------------------------------------------------------------------------- pooling
 def maxpool_fwd(x, y, p: Sequence[int]):
     _launch("b200_maxpool_fwd", _ref(x), _ref(y), p[0], p[1], p[2], stream_ptr())
@@ -223,20 +241,56 @@ def maxpool_bwd(x, y, dy, dx, p: Sequence[int], accumulate=False):
 
 # ------------------------------------------------------------------------------------- normalisation / act
 class NormStats:
-    __slots__ = ("mean", "rstd", "scale", "shift", "groups", "batch_stats")
+    __slots__ = ("mean", "rstd", "scale", "shift", "groups", "batch_stats", "world", "sync_group")
 
 
-def norm_stats(x, groups: int, gamma, beta, eps: float = 1e-5, batch_stats: bool = False) -> NormStats:
+def _sync_world(sync_group) -> int:
+    """World size for synchronised batch statistics (1 = no collective)."""
+    if sync_group is False or not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        return 1
+    return torch.distributed.get_world_size(None if sync_group is True else sync_group)
+
+
+def norm_stats(x, groups: int, gamma, beta, eps: float = 1e-5, batch_stats: bool = False, sync_group=False) -> NormStats:
+    """`sync_group`: False, True (default process group) or a process group -- SyncBatchNorm: the per-rank channel sums
+    are all-reduced before the statistics are finalised (equal per-rank batch sizes assumed, as under DDP)."""
     n, d, h, w, c = x.shape
     sums = torch.zeros(n * c * 2, dtype=torch.float64, device=x.device)
     _launch("b200_channel_sums", _ref(x), _ptr(sums), stream_ptr(), shape=x.shape)
+    world = _sync_world(sync_group) if batch_stats else 1
+    if world > 1:
+        # batch statistics only need the sum over samples: reduce the (C, 2) totals, not the per-sample table
+        tot = sums.view(n, c * 2).sum(0)
+        torch.distributed.all_reduce(tot, group=None if sync_group is True else sync_group)
+        sums = torch.zeros_like(sums)
+        sums.view(n, c * 2)[0] = tot
     st = NormStats()
     st.groups, st.batch_stats = groups, batch_stats
+    st.world, st.sync_group = world, sync_group
     buf = torch.empty(2 * n * groups + 2 * n * c, dtype=torch.float32, device=x.device)
     st.mean, st.rstd = buf[: n * groups], buf[n * groups: 2 * n * groups]
     st.scale, st.shift = buf[2 * n * groups: 2 * n * groups + n * c], buf[2 * n * groups + n * c:]
-    _launch("b200_norm_finalize", _ptr(sums), n, c, groups, d * h * w, 1 if batch_stats else 0, _ptr(gamma), _ptr(beta),
+    _launch("b200_norm_finalize", _ptr(sums), n, c, groups, d * h * w * world, 1 if batch_stats else 0, _ptr(gamma), _ptr(beta),
             eps, _ptr(st.mean), _ptr(st.rstd), _ptr(st.scale), _ptr(st.shift), stream_ptr())
+    return st
+
+
+def bn_update_running(st: NormStats, c: int, count: float, eps: float, momentum: float, running_mean, running_var):
+    """running statistics of nn.BatchNorm from the batch statistics in `st` (unbiased variance, PyTorch semantics)."""
+    _launch("b200_bn_update_running", _ptr(st.mean), _ptr(st.rstd), float(eps), float(count), float(momentum), _ptr(running_mean),
+            _ptr(running_var), c, stream_ptr())
+
+
+def bn_eval_stats(x, running_mean, running_var, gamma, beta, eps: float) -> NormStats:
+    """eval-mode BatchNorm: scale/shift from the running statistics (no reduction over x)."""
+    n, c = x.shape[0], x.shape[-1]
+    st = NormStats()
+    st.groups, st.batch_stats, st.world, st.sync_group = c, True, 1, False
+    buf = torch.empty(2 * n * c, dtype=torch.float32, device=x.device)
+    st.mean = st.rstd = None
+    st.scale, st.shift = buf[: n * c], buf[n * c:]
+    _launch("b200_bn_eval_coeffs", _ptr(running_mean), _ptr(running_var), _ptr(gamma), _ptr(beta), float(eps), n, c,
+            _ptr(st.scale), _ptr(st.shift), stream_ptr())
     return st
 
 
@@ -251,8 +305,19 @@ def norm_act_bwd(x, dy, st: NormStats, gamma, beta, act: str, dx, dgamma, dbeta,
     _launch("b200_norm_act_bwd_reduce", _ref(x), _ref(dy), _ptr(st.mean), _ptr(st.rstd), st.groups, _ptr(gamma), _ptr(beta),
             ACT[act], _ptr(red), stream_ptr(), shape=x.shape)
     coef = torch.empty(n * c * 4, dtype=torch.float32, device=x.device)
+    world = getattr(st, "world", 1) or 1
+    if world > 1:
+        # SyncBatchNorm: dgamma/dbeta are this rank's own sums (DDP averages them later); the dx coefficients need the
+        # sums over all ranks (torch.nn.SyncBatchNorm backward does the same all-reduce of sum_dy, sum_dy_xmu)
+        _launch("b200_norm_bwd_finalize", _ptr(red), _ptr(st.mean), _ptr(st.rstd), _ptr(gamma), _ptr(beta), n, c, st.groups,
+                d * h * w, 1, _ptr(coef), _ptr(dgamma), _ptr(dbeta), stream_ptr())
+        tot = red.view(n, c * 2).sum(0)
+        torch.distributed.all_reduce(tot, group=None if st.sync_group is True else st.sync_group)
+        red = torch.zeros_like(red)
+        red.view(n, c * 2)[0] = tot
+        dgamma = dbeta = None
     _launch("b200_norm_bwd_finalize", _ptr(red), _ptr(st.mean), _ptr(st.rstd), _ptr(gamma), _ptr(beta), n, c, st.groups,
-            d * h * w, 1 if st.batch_stats else 0, _ptr(coef), _ptr(dgamma), _ptr(dbeta), stream_ptr())
+            d * h * w * world, 1 if st.batch_stats else 0, _ptr(coef), _ptr(dgamma), _ptr(dbeta), stream_ptr())
     if dx is not None:
         _launch("b200_norm_act_bwd_apply", _ref(x), _ref(dy), ACT[act], _ptr(coef), _ref(dx), 1 if accumulate else 0,
                 stream_ptr(), shape=x.shape)

@@ -166,6 +166,22 @@ int b200_channel_sums(const b200_tensor* x, double* sums, void* stream);
 int b200_norm_finalize(const double* sums, int32_t n, int32_t c, int32_t groups, int64_t spatial, int32_t batch_stats,
                        const float* gamma, const float* beta, float eps,
                        float* mean, float* rstd, float* scale, float* shift, void* stream);
+/* nn.Dropout(p), training mode (reference blocks.py:162-163): y (+)= keep ? x/(1-p) : 0 with a counter-based mask that is
+ * a function of (*seed_dev, layer_id, element index); calling it on dy with the same (seed, layer_id) is the backward.   */
+int b200_dropout(const b200_tensor* x, const b200_tensor* y, float p, const int64_t* seed_dev, int64_t layer_id,
+                 int32_t accumulate, void* stream);
+/* nn.Upsample(mode = 'bilinear' | 'trilinear', align_corners = False) with integer scale factors = y dims / x dims
+ * (reference blocks.py:604-606, the 'upsampling' decoder variant); bwd is its adjoint in gather form.            */
+int b200_upsample_linear_fwd(const b200_tensor* x, const b200_tensor* y, void* stream);
+int b200_upsample_linear_bwd(const b200_tensor* dy, const b200_tensor* dx, int32_t accumulate, void* stream);
+/* BatchNorm bookkeeping (torch.nn.BatchNorm{2,3}d / SyncBatchNorm semantics, reference blocks.py:2117-2120, 2155-2158):
+ * running_mean/var <- (1-momentum)*running + momentum*(batch mean, UNBIASED batch variance); `mean`/`rstd` are the
+ * first C entries written by b200_norm_finalize(groups = C, batch_stats = 1), `count` = N*D*H*W (x world size).   */
+int b200_bn_update_running(const float* mean, const float* rstd, float eps, double count, float momentum,
+                           float* running_mean, float* running_var, int32_t c, void* stream);
+/* eval mode: scale[n,c] = gamma/sqrt(running_var+eps), shift[n,c] = beta - running_mean*scale (for b200_scale_shift_act) */
+int b200_bn_eval_coeffs(const float* running_mean, const float* running_var, const float* gamma, const float* beta,
+                        float eps, int32_t n, int32_t c, float* scale, float* shift, void* stream);
 /* y = act(x * scale[n,c] + shift[n,c]);  scale/shift may be NULL (pure activation)                           */
 int b200_scale_shift_act(const b200_tensor* x, const float* scale, const float* shift, int32_t act,
                          const b200_tensor* y, void* stream);

@@ -49,6 +49,14 @@ MODEL_CASES = [
     ("resunet3d_none_relu", "resunet", dict(image_shape=(8, 8, 8, 1), activation="relu", feature_maps=[8, 16],
                                              drop_values=[0, 0], normalization="none", k_size=3, yx_down=[2], z_down=[2],
                                              isotropy=[True] * 2, larger_io=False, conv_layers=[2, 2], output_channels=[1]), 1),
+    # BatchNorm (BiaPy's default normalisation): train-mode forward/backward with batch statistics, the running
+    # statistics after that step ("sd_after.*") and an eval-mode forward on them ("y_eval")
+    ("unet3d_bn_relu", "unet", dict(image_shape=(8, 16, 16, 1), activation="relu", feature_maps=[8, 16],
+                                     drop_values=[0, 0], normalization="bn", k_size=3, yx_down=[2], z_down=[2],
+                                     isotropy=[True] * 2, larger_io=False, conv_layers=[2] * 2, output_channels=[1]), 3),
+    ("resunet2d_bn_silu", "resunet", dict(image_shape=(32, 32, 2), activation="silu", feature_maps=[16, 32],
+                                           drop_values=[0, 0], normalization="bn", k_size=3, yx_down=[2], z_down=[2],
+                                           isotropy=[True] * 2, larger_io=False, conv_layers=[2] * 2, output_channels=[2]), 2),
 ]
 
 STITCH_3D = [
@@ -89,8 +97,10 @@ def _quiet():
     return contextlib.redirect_stdout(io.StringIO())
 
 
-def make_models(R):
+def make_models(R, only=None):
     for name, arch, kw, batch in MODEL_CASES:
+        if only and name not in only:
+            continue
         cls = {"unet": R.unet.U_Net, "resunet": R.resunet.ResUNet, "attention_unet": R.attention_unet.Attention_U_Net}[arch]
         torch.manual_seed(0)
         with _quiet():
@@ -101,7 +111,8 @@ def make_models(R):
             for k, p in m.named_parameters():
                 if p.ndim == 1:
                     p.add_(0.2 * torch.randn(p.shape, generator=g))
-        m.train()  # exercise the training-mode graph (norm layers here carry no running stats)
+        m.train()  # exercise the training-mode graph
+        sd0 = {k: v.detach().clone() for k, v in m.state_dict().items()}     # before the step (BatchNorm buffers change)
         shape = kw["image_shape"]
         x = torch.randn((batch, shape[-1]) + tuple(shape[:-1]), generator=g)
         x.requires_grad_(True)
@@ -110,10 +121,17 @@ def make_models(R):
         (y * gy).sum().backward()
         out = {"x": x.detach().numpy(), "y": y.detach().numpy(), "gy": gy.numpy(), "gx": x.grad.numpy(),
                "kwargs_json": np.array(json.dumps(kw)), "arch": np.array(arch)}
-        for k, v in m.state_dict().items():
+        for k, v in sd0.items():
             out["sd." + k] = v.numpy()
         for k, p in m.named_parameters():
             out["grad." + k] = p.grad.numpy()
+        if kw["normalization"] in ("bn", "sync_bn"):
+            for k, v in m.state_dict().items():
+                if "running_" in k or "num_batches_tracked" in k:
+                    out["sd_after." + k] = v.numpy()
+            m.eval()
+            with torch.no_grad():
+                out["y_eval"] = m(x.detach()).numpy()
         np.savez_compressed(os.path.join(OUT, f"model_{name}.npz"), **out)
         print("model", name, tuple(y.shape), "params", sum(p.numel() for p in m.parameters()))
 
@@ -179,6 +197,11 @@ def make_grids(R):
 def main():
     os.makedirs(OUT, exist_ok=True)
     R = ref_loader.load()
+    import sys
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]
+    if only:                      # add fixtures without rewriting the committed ones: python -m oracle.make_golden <model name>...
+        make_models(R, only)
+        return
     make_grids(R)
     make_stitch(R)
     make_models(R)

@@ -43,7 +43,7 @@ def l2err(a, b):
     return ((a - b).double().norm() / b.double().norm().clamp_min(1e-30)).item()
 
 
-FIXTURES = [p for p in sorted(glob.glob(os.path.join(GOLDEN, "model_*.npz"))) if "upsampling" not in p]
+FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "model_*.npz")))
 
 
 @pytest.mark.parametrize("path", FIXTURES)
@@ -78,6 +78,27 @@ def test_golden_forward_backward(path, dtype, tol_fwd, tol_bwd):
         assert e_fwd < tol_fwd and e_gx < tol_bwd and e_p < tol_bwd
     else:                               # bf16 storage: stated, looser bound on the relative L2 error
         assert l2_fwd < tol_fwd and l2_gx < tol_bwd and e_p < tol_bwd
+    # BatchNorm fixtures: running statistics after the step (momentum update with the unbiased batch variance,
+    # num_batches_tracked) and the eval-mode forward on them
+    after = [k for k in z.files if k.startswith("sd_after.")]
+    if after:
+        sd_now = m.state_dict()
+        tol = 1e-4 if dtype == torch.float32 else 3e-2
+        for k in after:
+            ref_b = torch.from_numpy(z[k])
+            got = sd_now[k[9:]].cpu()
+            if "num_batches_tracked" in k:
+                assert int(got) == int(ref_b), k
+            else:
+                assert (got - ref_b).abs().max().item() <= tol * max(1.0, ref_b.abs().max().item()), k
+        m.eval()
+        with torch.no_grad():
+            ye = m(x.detach())
+        ref_e = torch.from_numpy(z["y_eval"])
+        if dtype == torch.float32:
+            assert nerr(ye.cpu(), ref_e) < 1e-3
+        else:
+            assert l2err(ye.cpu(), ref_e) < 5e-2
 
 
 def test_eval_mode_no_grad_and_second_call():
@@ -150,3 +171,33 @@ def test_against_cpu_oracle_larger(arch, kw, batch):
     scale = max(v.grad.abs().max().item() for v in sd_r.values() if v.grad is not None)
     for name, p in m.named_parameters():
         assert (p.grad.cpu() - sd_r[name].grad).abs().max().item() / scale < 1e-3, name
+
+
+def test_dropout_training_and_eval():
+    """drop_values > 0: training forwards draw a new mask per call and back-propagate through it; eval is deterministic and
+    equal to the same network without dropout layers (nn.Dropout is the identity in eval mode)."""
+    kw = dict(image_shape=(8, 16, 16, 1), activation="relu", feature_maps=[8, 16], drop_values=[0.2, 0.3], normalization="gn",
+              k_size=3, yx_down=[2], z_down=[2], isotropy=[True] * 2, larger_io=False, conv_layers=[2] * 2, output_channels=[1])
+    torch.manual_seed(3)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = _cls("unet")(**kw)
+        m0 = _cls("unet")(**dict(kw, drop_values=[0, 0]))
+    # the dropout-free twin has the same parameters under different Sequential indices: copy by position
+    with torch.no_grad():
+        for (_, a), (_, b) in zip(m.named_parameters(), m0.named_parameters()):
+            b.copy_(a)
+    m = m.cuda().set_engine(dtype=torch.float32)
+    m0 = m0.cuda().set_engine(dtype=torch.float32)
+    x = torch.randn(2, 1, 8, 16, 16, device="cuda")
+    m.train()
+    xa = x.clone().requires_grad_(True)
+    y1 = m(xa)
+    y1.sum().backward()
+    assert torch.isfinite(xa.grad).all() and all(torch.isfinite(p.grad).all() for p in m.parameters())
+    y2 = m(x)
+    assert not torch.equal(y1.detach(), y2.detach())
+    m.eval(); m0.eval()
+    with torch.no_grad():
+        e1, e2, e0 = m(x), m(x), m0(x)
+    assert torch.equal(e1, e2)
+    assert nerr(e1.cpu(), e0.cpu()) < 1e-5

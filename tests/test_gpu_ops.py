@@ -260,3 +260,57 @@ def test_optimizers_match_torch():
     assert nerr(p.cpu(), pr.detach()) < 1e-6
     ss = ops.sumsq(grads[0].cuda())
     assert abs(ss.item() - float((grads[0].double() ** 2).sum())) < 1e-6 * ss.item()
+
+
+@pytest.mark.parametrize("shape,scale", [((2, 8, 3, 4, 5), (2, 2, 2)), ((1, 3, 4, 6, 6), (1, 2, 2)), ((2, 16, 1, 7, 9), (1, 2, 2)),
+                                         ((1, 4, 3, 3, 3), (3, 2, 1))])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_upsample_linear(shape, scale, dtype):
+    """nn.Upsample(bi/trilinear, align_corners=False) forward and its adjoint vs ATen (reference blocks.py:605)."""
+    from biapy_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(*shape, generator=g).to(dtype).float().requires_grad_(True)          # (N, C, D, H, W)
+    yr = F.interpolate(x, scale_factor=tuple(float(s) for s in scale), mode="trilinear", align_corners=False)
+    gy = torch.randn(yr.shape, generator=g).to(dtype).float()
+    yr.backward(gy)
+    xd = cl(x.detach()).to(dtype)
+    n, c, d, h, w = shape
+    ybuf = torch.zeros(n, d * scale[0], h * scale[1], w * scale[2], c + 8, dtype=dtype, device="cuda")
+    yv = ybuf[..., 8:]                                                                    # a channel slice, as in the decoder
+    ops.upsample_linear_fwd(xd, yv)
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert nerr(ncdhw(yv), yr.detach()) < tol
+    assert ybuf[..., :8].abs().max().item() == 0
+    dx = torch.empty_like(xd)
+    ops.upsample_linear_bwd(cl(gy).to(dtype), dx)
+    assert nerr(ncdhw(dx), x.grad) < (1e-5 if dtype == torch.float32 else 2e-2)
+    before = ncdhw(dx)
+    ops.upsample_linear_bwd(cl(gy).to(dtype), dx, accumulate=True)
+    assert nerr(ncdhw(dx), 2 * before) < 2e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_dropout_mask_statistics_and_backward(dtype):
+    """nn.Dropout training semantics: values are 0 or x/(1-p), keep rate 1-p, the backward reuses the forward mask, masks
+    change with the layer id and with the device-resident seed."""
+    from biapy_b200 import ops
+    p = 0.3
+    x = torch.ones(2, 8, 16, 16, 16, dtype=dtype, device="cuda")
+    seed = torch.tensor([1234], dtype=torch.int64, device="cuda")
+    y = ops.dropout(x, torch.empty_like(x), p, seed, 0).float()
+    kept = y != 0
+    assert torch.allclose(y[kept], torch.full_like(y[kept], 1 / (1 - p)), rtol=1e-2)
+    n = y.numel()
+    frac = kept.float().mean().item()
+    assert abs(frac - (1 - p)) < 5 * (p * (1 - p) / n) ** 0.5
+    y_again = ops.dropout(x, torch.empty_like(x), p, seed, 0).float()
+    assert torch.equal(y, y_again)                                   # same (seed, layer) -> same mask: this is the backward
+    y_other = ops.dropout(x, torch.empty_like(x), p, seed, 1).float()
+    agree = ((y_other != 0) == kept).float().mean().item()
+    assert abs(agree - (p * p + (1 - p) * (1 - p))) < 0.02           # independent masks
+    seed.add_(1)
+    y_next = ops.dropout(x, torch.empty_like(x), p, seed, 0).float()
+    assert not torch.equal(y_next, y)
+    dy = torch.randn_like(x)
+    dx = ops.dropout(dy, torch.empty_like(x), p, seed, 0).float()
+    assert torch.allclose(dx, dy.float() * (y_next != 0) / (1 - p), rtol=2e-2, atol=1e-3)

@@ -29,10 +29,6 @@ def _build(arch, kw):
 def test_state_dict_matches_reference_layout(path):
     z = np.load(path)
     kw = json.loads(str(z["kwargs_json"]))
-    if kw.get("upsample_layer") == "upsampling":
-        with pytest.raises(NotImplementedError):
-            _build(str(z["arch"]), kw)
-        return
     m = _build(str(z["arch"]), kw)
     sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
     m.load_state_dict(sd, strict=True)          # same keys, same shapes as the reference class
@@ -71,7 +67,25 @@ def test_build_model_from_cfg_dict():
                     [1], ["F"], ["ce_sigmoid"], "cpu")
 
 
-def test_unsupported_options_fail_loudly():
-    with pytest.raises(NotImplementedError):
-        _build("unet", dict(image_shape=(16, 16, 1), feature_maps=[8, 16], drop_values=[0, 0], normalization="bn",
+def test_batchnorm_modules_follow_the_reference_factory():
+    """'bn' -> nn.BatchNorm{2,3}d(momentum), 'sync_bn' -> nn.SyncBatchNorm (reference blocks.py:2117-2120, 2155-2158)."""
+    m = _build("unet", dict(image_shape=(16, 16, 1), feature_maps=[8, 16], drop_values=[0, 0], normalization="bn",
                             yx_down=[2], z_down=[2], larger_io=False, conv_layers=[2, 2]))
+    bns = [mod for mod in m.modules() if isinstance(mod, torch.nn.BatchNorm2d)]
+    assert bns and all(b.momentum == 0.1 and b.track_running_stats for b in bns)
+    assert any(k.endswith("running_var") for k in m.state_dict())
+    m = _build("resunet", dict(image_shape=(8, 16, 16, 1), feature_maps=[8, 16], drop_values=[0, 0], normalization="sync_bn",
+                               yx_down=[2], z_down=[2], larger_io=False, conv_layers=[2, 2]))
+    assert any(isinstance(mod, torch.nn.SyncBatchNorm) for mod in m.modules())
+
+
+def test_unsupported_options_fail_loudly():
+    """Options outside the hot path (SURVEY §8 out-of-scope rows) raise instead of silently doing something else."""
+    base = dict(image_shape=(16, 16, 1), feature_maps=[8, 16], drop_values=[0, 0], normalization="gn",
+                yx_down=[2], z_down=[2], larger_io=False, conv_layers=[2, 2])
+    with pytest.raises(NotImplementedError):
+        _build("unet", dict(base, contrast=True))
+    with pytest.raises(NotImplementedError):
+        _build("unet", dict(base, upsampling_factor=(2, 2)))
+    with pytest.raises(ValueError):
+        _build("unet", dict(base, upsample_layer="nearest"))

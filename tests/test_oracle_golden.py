@@ -93,7 +93,8 @@ def test_model_port(path):
     z = np.load(path)
     kw = json.loads(str(z["kwargs_json"]))
     arch = str(z["arch"])
-    sd = {k[3:]: torch.from_numpy(z[k]).requires_grad_(z[k].dtype == np.float32) for k in z.files if k.startswith("sd.")}
+    sd = {k[3:]: torch.from_numpy(z[k].copy()).requires_grad_(z[k].dtype == np.float32 and "running_" not in k)
+          for k in z.files if k.startswith("sd.")}
     x = torch.from_numpy(z["x"]).requires_grad_(True)
     y = port_models.forward(arch, sd, x, training=True, **kw)
     ref = torch.from_numpy(z["y"])
@@ -111,3 +112,12 @@ def test_model_port(path):
             got = sd[k[5:]].grad
             assert got is not None, k
             assert (got - g).abs().max() <= 1e-4 * max(1.0, scale), k
+    # BatchNorm fixtures: running statistics after the training step and the eval-mode forward on them
+    after = [k for k in z.files if k.startswith("sd_after.") and "running_" in k]
+    for k in after:
+        assert (sd[k[9:]].detach() - torch.from_numpy(z[k])).abs().max() <= 1e-5, k
+    if "y_eval" in z.files:
+        with torch.no_grad():
+            ye = port_models.forward(arch, {k: v.detach() for k, v in sd.items()}, x.detach(), training=False, **kw)
+        ref_e = torch.from_numpy(z["y_eval"])
+        assert (ye - ref_e).abs().max() <= 1e-5 * max(1.0, ref_e.abs().max().item())
