@@ -242,7 +242,12 @@ def run_train(args):
     if not args.graph:                      # eager mode: per-kernel CUDA events inside the timed region itself
         ops.PROFILE = {} if rank == 0 else None
         ops.PROFILE_SHAPES = args.detail
+    ncu_range = os.environ.get("BENCH_PROFILER_RANGE") == "1"   # `ncu --profile-from-start off`: only the timed region
+    if ncu_range:
+        torch.cuda.profiler.start()
     ms = timed(dev_step, args.steps, world)
+    if ncu_range:
+        torch.cuda.profiler.stop()
     prof, ops.PROFILE = ops.PROFILE, None
     clocks = sampler.stop()
     launches = (ops.LAUNCHES - n0)

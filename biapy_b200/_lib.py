@@ -27,6 +27,11 @@ class AxisPlan(C.Structure):
     _fields_ = [(k, C.c_int64) for k in ("dim", "patch", "pad", "step", "n", "last", "core", "ov_px")]
 
 
+class ChunkGrid(C.Structure):
+    _fields_ = [("dim", C.c_int64 * 3), ("crop", C.c_int64 * 3), ("pad", C.c_int64 * 3), ("step", C.c_int64 * 3),
+                ("vols", C.c_int64 * 3), ("z_vol_start", C.c_int64), ("z_vol_end", C.c_int64), ("total", C.c_int64)]
+
+
 class B200Error(RuntimeError):
     pass
 
@@ -52,6 +57,10 @@ SIGNATURES = {
     "b200_crop_gather": (_I, [_P, _I, _L, _L, _L, _L, _P, _L, _L, _L, _P, _L, _P, _L, _P, _L, _L, _L, _L, _I, _P]),
     "b200_overlap_add": (_I, [_P, _I, _P, _I, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _P, _L, _P, _L, _P, _L,
                               _P, _P, _P, _P]),
+    "b200_chunk_grid_plan": (_I, [C.POINTER(_L), C.POINTER(_L), C.POINTER(_L), _L, _L, C.POINTER(ChunkGrid)]),
+    "b200_chunk_patch_coords": (_I, [C.POINTER(ChunkGrid), _L, C.POINTER(_L)]),
+    "b200_chunk_extract": (_I, [_P, _I, _L, _L, _L, _L, _P, _L, _L, _L, _L, _P, _P]),
+    "b200_chunk_insert": (_I, [_P, _I, _L, _L, _L, _L, _L, _P, _I, _L, _L, _L, _P, _I, _P]),
     "b200_pack_conv_weight": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "b200_conv_fprop": (_I, [_T, _P, _P, _T, _T, _I, _I, _I, _I, _I, _P]),
     "b200_conv_wgrad": (_I, [_T, _T, _P, _P, _I, _I, _I, _I, _P]),

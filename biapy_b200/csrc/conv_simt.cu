@@ -262,7 +262,7 @@ int conv_bias_grad(const b200_tensor* dy, float* dbias, cudaStream_t st) {
   if (dy->dtype != B200_F32 && dy->c % 8 == 0 && dy->ld % 8 == 0 && dy->c / 8 <= 256 && ((uintptr_t)dy->data & 15) == 0) {
     const int cvn = dy->c / 8, rows = 256 / cvn;
     const int64_t nvox = voxels(dy);
-    int64_t blocks = ceil_div(nvox, (int64_t)rows * 64);
+    int64_t blocks = ceil_div(nvox, (int64_t)rows * 8);   // <= 2 rounds of 4 loads per thread on small tensors (latency-bound otherwise)
     if (blocks > (int64_t)sm_count() * 4) blocks = (int64_t)sm_count() * 4;
     const size_t smem = sizeof(float) * rows * dy->c;
     if (dy->dtype == B200_BF16)
@@ -605,7 +605,7 @@ int conv_fprop_simt(const b200_tensor* x, const void* w, const float* bias, cons
   B200_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "conv_fprop(simt): grid too large");
   B200_DISPATCH_DTYPE(x->dtype, T, {
     auto kern = conv_fprop_simt_kernel<T>;
-    if (smem > 48 * 1024) B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));  // function-level cap: keep it at the maximum (graph nodes replayed alone)
     kern<<<grid, 128, smem, st>>>((const T*)x->data, (const T*)w, bias, res ? (const T*)res->data : nullptr, (T*)y->data, g,
                                   accumulate, CK);
   });
@@ -662,7 +662,7 @@ int conv_wgrad_simt(const b200_tensor* x, const b200_tensor* dy, float* dw, floa
   B200_CHECK_ARG(grid.y <= 65535, "conv_wgrad(simt): too many channel tiles");
   B200_DISPATCH_DTYPE(x->dtype, T, {
     auto kern = conv_wgrad_simt_kernel<T>;
-    if (smem > 48 * 1024) B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));  // function-level cap: keep it at the maximum (graph nodes replayed alone)
     kern<<<grid, 256, smem, st>>>((const T*)x->data, (const T*)dy->data, dw, dbias, g, tpc, units);
   });
   B200_LAUNCH_CHECK();

@@ -19,6 +19,11 @@
 namespace b200 {
 int conv_bias_grad(const b200_tensor* dy, float* dbias, cudaStream_t st);   // conv_simt.cu
 
+// The opt-in cap is a property of the FUNCTION, not of a launch: a CUDA-graph kernel node replayed on its own (ncu's per-node
+// profiling) sees whatever value the last eager launch of the same kernel left behind.  Always raise it to the hardware
+// maximum (227 KB) so every recorded launch stays valid.
+static constexpr int kMaxDynSmem = 227 * 1024;
+
 namespace sm100 {
 
 // ---------------------------------------------------------------------------------------- tensor-map helpers
@@ -1287,11 +1292,11 @@ static int conv_fprop_umma2_v(const ActView& x, const void* w, const float* bias
   int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
   if (x.dtype == B200_BF16) {
     auto kern = conv_fprop_umma2_kernel<__nv_bfloat16>;
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     kern<<<grid, 288, smem, st>>>((const __nv_bfloat16*)x.data, (const __nv_bfloat16*)w, bias, (__nv_bfloat16*)y.data, p);
   } else {
     auto kern = conv_fprop_umma2_kernel<__half>;
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     kern<<<grid, 288, smem, st>>>((const __half*)x.data, (const __half*)w, bias, (__half*)y.data, p);
   }
   B200_LAUNCH_CHECK();
@@ -1369,11 +1374,11 @@ static int conv_fprop_umma_impl(const ActView& xv, const void* w, const float* b
   int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
   if (x->dtype == B200_BF16) {
     auto kern = conv_fprop_umma_kernel<__nv_bfloat16>;
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     kern<<<grid, 224, smem, st>>>(tx, tw, pm, bias, (__nv_bfloat16*)y->data, p);
   } else {
     auto kern = conv_fprop_umma_kernel<__half>;
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     kern<<<grid, 224, smem, st>>>(tx, tw, pm, bias, (__half*)y->data, p);
   }
   B200_LAUNCH_CHECK();
@@ -1490,11 +1495,11 @@ static int conv_fprop_xslab_v(const ActView& x, const void* w, const float* bias
     const size_t smem1 = (size_t)p.a_stages * p.a_bytes + 1024;
     if (x.dtype == B200_BF16) {
       auto kern = conv_fprop_xslab1_kernel<__nv_bfloat16>;
-      B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+      B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
       kern<<<grid, 320, smem1, st>>>(tx64, tx32, tw64, tw32, bias, (__nv_bfloat16*)y.data, p);
     } else {
       auto kern = conv_fprop_xslab1_kernel<__half>;
-      B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+      B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
       kern<<<grid, 320, smem1, st>>>(tx64, tx32, tw64, tw32, bias, (__half*)y.data, p);
     }
     B200_LAUNCH_CHECK();
@@ -1504,11 +1509,11 @@ static int conv_fprop_xslab_v(const ActView& x, const void* w, const float* bias
   const size_t smem = (size_t)p.b_off + (size_t)p.b_stages * p.b_bytes + 1024;
   if (x.dtype == B200_BF16) {
     auto kern = conv_fprop_xslab_kernel<__nv_bfloat16>;
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     kern<<<grid, 32 * (6 + kSlabAWarps + kSlabBWarps), smem, st>>>(tx64, tx32, tw64, tw32, bias, (__nv_bfloat16*)y.data, p);
   } else {
     auto kern = conv_fprop_xslab_kernel<__half>;
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     kern<<<grid, 32 * (6 + kSlabAWarps + kSlabBWarps), smem, st>>>(tx64, tx32, tw64, tw32, bias, (__half*)y.data, p);
   }
   B200_LAUNCH_CHECK();
@@ -1586,11 +1591,11 @@ int conv_fprop_xfold_v(const ActView& x, const void* w, const float* bias, const
   int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
   if (x.dtype == B200_BF16) {
     auto kern = conv_fprop_xfold_kernel<__nv_bfloat16>;
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     kern<<<grid, 224, smem, st>>>(tx64, tx32, tw64, tw32, bias, (__nv_bfloat16*)y.data, p);
   } else {
     auto kern = conv_fprop_xfold_kernel<__half>;
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     kern<<<grid, 224, smem, st>>>(tx64, tx32, tw64, tw32, bias, (__half*)y.data, p);
   }
   B200_LAUNCH_CHECK();
@@ -2517,11 +2522,11 @@ static int conv_wgrad_xslab_v(const ActView& x, const ActView& dy, float* dw, in
   const size_t smem = (size_t)p.a_off + (size_t)p.a_stages * 4u * p.sa_bytes + 1024;
   if (x.dtype == B200_BF16) {
     auto kern = conv_wgrad_xslab_kernel<__nv_bfloat16>;
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     kern<<<grid, 320, smem, st>>>(tx, ty, dw, p);
   } else {
     auto kern = conv_wgrad_xslab_kernel<__half>;
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     kern<<<grid, 320, smem, st>>>(tx, ty, dw, p);
   }
   B200_LAUNCH_CHECK();
@@ -2597,11 +2602,11 @@ int conv_wgrad_xfold_v(const ActView& x, const ActView& dy, float* dw, int kd, i
   const size_t smem = (size_t)p.a_off + (size_t)p.a_stages * kXBlockBytes + 1024;
   if (x.dtype == B200_BF16) {
     auto kern = conv_wgrad_xfold_kernel<__nv_bfloat16>;
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     kern<<<grid, 320, smem, st>>>(tx, ty, dw, p);
   } else {
     auto kern = conv_wgrad_xfold_kernel<__half>;
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     kern<<<grid, 320, smem, st>>>(tx, ty, dw, p);
   }
   B200_LAUNCH_CHECK();
@@ -2711,11 +2716,11 @@ static int conv_wgrad_umma_impl(const ActView& xv, const ActView& dyv, float* dw
     WgradParams2 pp{p, x->sw, x->sh, x->sd, x->sn, dy->sw, dy->sh, dy->sd, dy->sn};
     if (x->dtype == B200_BF16) {
       auto kern = conv_wgrad_umma2_kernel<__nv_bfloat16>;
-      B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
       kern<<<grid, 288, smem, st>>>((const __nv_bfloat16*)x->data, (const __nv_bfloat16*)dy->data, dw, pp);
     } else {
       auto kern = conv_wgrad_umma2_kernel<__half>;
-      B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
       kern<<<grid, 288, smem, st>>>((const __half*)x->data, (const __half*)dy->data, dw, pp);
     }
     B200_LAUNCH_CHECK();
@@ -2734,11 +2739,11 @@ static int conv_wgrad_umma_impl(const ActView& xv, const ActView& dyv, float* dw
   }
   if (x->dtype == B200_BF16) {
     auto kern = conv_wgrad_umma_kernel<__nv_bfloat16>;
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     kern<<<grid, 320, smem, st>>>(tx, tdy, pm, dw, p);
   } else {
     auto kern = conv_wgrad_umma_kernel<__half>;
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     kern<<<grid, 320, smem, st>>>(tx, tdy, pm, dw, p);
   }
   B200_LAUNCH_CHECK();

@@ -294,3 +294,168 @@ B200_EXPORT int b200_overlap_add(const void* patches, int32_t dtype_in, void* ou
   set_error("overlap_add: unsupported dtype pair %d -> %d", dtype_in, dtype_out);
   return B200_ERR_UNSUPPORTED;
 }
+
+// ---------------------------------------------------------------------------------------- by-chunks tile grid
+// chunked_test_pair_data_generator.py:276-295 (plain integer arithmetic: math.ceil(a / b) on Python ints is evaluated
+// through a double division there; every value on this path is far below 2^53, so the integer ceil is identical).
+static inline int64_t ceil_div_i(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+B200_EXPORT int b200_chunk_grid_plan(const int64_t dim[3], const int64_t crop[3], const int64_t pad[3], int64_t z_start,
+                                     int64_t z_end, b200_chunk_grid* g) {
+  B200_CHECK_ARG(dim && crop && pad && g, "chunk_grid_plan: null pointer");
+  static const char* ax = "ZYX";
+  for (int a = 0; a < 3; ++a) {
+    B200_CHECK_ARG(dim[a] > 0 && crop[a] > 0 && pad[a] >= 0, "chunk_grid_plan: bad sizes on axis %c", ax[a]);
+    B200_CHECK_ARG(crop[a] <= dim[a], "%c Axis problem: %lld greater than %lld (you can reduce 'DATA.PATCH_SIZE' in that axis)",
+                   ax[a], (long long)crop[a], (long long)dim[a]);
+  }
+  for (int a = 0; a < 3; ++a)
+    B200_CHECK_ARG(pad[a] < crop[a] / 2, "'Padding' can not be greater than half of 'crop_shape'. Max value for the given input "
+                   "shape is (%lld, %lld, %lld)", (long long)(crop[0] / 2 - 1), (long long)(crop[1] / 2 - 1), (long long)(crop[2] / 2 - 1));
+  for (int a = 0; a < 3; ++a) {
+    g->dim[a] = dim[a]; g->crop[a] = crop[a]; g->pad[a] = pad[a];
+    g->step[a] = crop[a] - 2 * pad[a];
+    g->vols[a] = ceil_div_i(dim[a], g->step[a]);
+  }
+  const int64_t ez0 = (z_start == -1) ? 0 : z_start, ez1 = (z_end == -1) ? dim[0] : z_end;
+  B200_CHECK_ARG(ez0 >= 0 && ez1 >= 0, "chunk_grid_plan: negative Z range");
+  g->z_vol_start = ceil_div_i(ez0, g->step[0]);
+  const int64_t zend = ceil_div_i(ez1, g->step[0]);
+  g->z_vol_end = zend < g->vols[0] ? zend : g->vols[0];
+  g->total = (g->z_vol_end - g->z_vol_start) * g->vols[1] * g->vols[2];
+  return B200_OK;
+}
+
+B200_EXPORT int b200_chunk_patch_coords(const b200_chunk_grid* g, int64_t vol_id, int64_t out[27]) {
+  B200_CHECK_ARG(g && out, "chunk_patch_coords: null pointer");
+  B200_CHECK_ARG(vol_id >= 0 && vol_id < g->total, "chunk_patch_coords: tile %lld outside the grid of %lld", (long long)vol_id,
+                 (long long)g->total);
+  int64_t pos[3];
+  pos[2] = vol_id % g->vols[2];
+  pos[1] = (vol_id / g->vols[2]) % g->vols[1];
+  pos[0] = vol_id / (g->vols[2] * g->vols[1]) + g->z_vol_start;
+  for (int a = 0; a < 3; ++a) {
+    out[a] = pos[a];
+    const int64_t lo = pos[a] * g->step[a] - g->pad[a], hi = (pos[a] + 1) * g->step[a] + g->pad[a];
+    const int64_t es = lo > 0 ? lo : 0, ee = hi < g->dim[a] ? hi : g->dim[a];                      // :463-470
+    out[3 + 2 * a] = es; out[4 + 2 * a] = ee;
+    out[9 + 2 * a] = pos[a] * g->step[a];                                                          // :474-481
+    out[10 + 2 * a] = (pos[a] + 1) * g->step[a] < g->dim[a] ? (pos[a] + 1) * g->step[a] : g->dim[a];
+    const int64_t left = lo < 0 ? -lo : 0, right = g->crop[a] - (ee - es) - left;                    // :536-541
+    out[15 + 2 * a] = left; out[16 + 2 * a] = right;
+    out[21 + 2 * a] = left > g->pad[a] ? left : g->pad[a];                                          // :555-560
+    out[22 + 2 * a] = right > g->pad[a] ? right : g->pad[a];
+  }
+  return B200_OK;
+}
+
+namespace b200 {
+
+__device__ __forceinline__ int reflect_in(int j, int len) {      // numpy 'reflect' (edge not repeated), any reach
+  if (len == 1) return 0;
+  const int period = 2 * (len - 1);
+  int m = j % period;
+  if (m < 0) m += period;
+  return m < len ? m : period - m;
+}
+
+// grid = (chunks of a (ph, pw, C) plane, pd, n tiles).  Rows of `pw * C` elements are contiguous on both sides wherever the
+// x window is not reflected, so consecutive threads read / write consecutive addresses.
+template <typename U>
+__global__ void chunk_extract_kernel(const U* __restrict__ src, U* __restrict__ dst, const int64_t* __restrict__ desc, int H, int W,
+                                     int C, int pd, int ph, int pw) {
+  const int t = blockIdx.z, lz = blockIdx.y;
+  const int64_t* d = desc + (int64_t)t * 9;
+  const int z0 = (int)d[0], zl = (int)d[1], zp = (int)d[2], y0 = (int)d[3], yl = (int)d[4], yp = (int)d[5];
+  const int x0 = (int)d[6], xl = (int)d[7], xp = (int)d[8];
+  const int64_t z = z0 + reflect_in(lz - zp, zl);
+  const int plane = ph * pw * C;
+  U* out = dst + ((int64_t)t * pd + lz) * plane;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += gridDim.x * blockDim.x) {
+    const int ch = i % C, q = i / C;
+    const int lx = q % pw, ly = q / pw;
+    const int64_t y = y0 + reflect_in(ly - yp, yl), x = x0 + reflect_in(lx - xp, xl);
+    out[i] = src[((z * H + y) * W + x) * C + ch];
+  }
+}
+
+template <typename TI, typename TO>
+__global__ void chunk_insert_kernel(const TI* __restrict__ patches, TO* __restrict__ out, const int64_t* __restrict__ desc, int H, int W,
+                                    int C, int pd, int ph, int pw, int mode) {
+  const int t = blockIdx.z;
+  const int64_t* d = desc + (int64_t)t * 9;
+  const int oz = (int)d[0], sz = (int)d[1], cz = (int)d[2], oy = (int)d[3], sy = (int)d[4], cy = (int)d[5];
+  const int ox = (int)d[6], sx = (int)d[7], cx = (int)d[8];
+  const int row = sx * C;                       // contiguous in the patch (from cx) and in the volume (from ox)
+  const int plane = sy * row;
+  for (int lz = blockIdx.y; lz < sz; lz += gridDim.y) {
+    const TI* pz = patches + (((int64_t)t * pd + cz + lz) * ph + cy) * (int64_t)pw * C + (int64_t)cx * C;
+    TO* vz = out + (((int64_t)(oz + lz) * H + oy) * W + ox) * (int64_t)C;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += gridDim.x * blockDim.x) {
+      const int ly = i / row, r = i - ly * row;
+      const float v = to_f<TI>(pz[(int64_t)ly * pw * C + r]);
+      TO* o = vz + (int64_t)ly * W * C + r;
+      *o = mode ? from_f<TO>(__fadd_rn(to_f<TO>(*o), v)) : from_f<TO>(v);
+    }
+  }
+}
+
+template <typename TI, typename TO>
+static int launch_chunk_insert(const void* patches, void* out, const int64_t* desc, int64_t n, int H, int W, int C, int pd, int ph,
+                               int pw, int mode, cudaStream_t st) {
+  int64_t bx = ceil_div((int64_t)ph * pw * C, 256);
+  if (bx > 32) bx = 32;
+  dim3 blocks((unsigned)bx, (unsigned)pd, (unsigned)n);
+  chunk_insert_kernel<TI, TO><<<blocks, 256, 0, st>>>((const TI*)patches, (TO*)out, desc, H, W, C, pd, ph, pw, mode);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+}  // namespace b200
+
+B200_EXPORT int b200_chunk_extract(const void* src, int32_t dtype, int64_t D, int64_t H, int64_t W, int64_t C, void* dst, int64_t n,
+                                   int64_t pd, int64_t ph, int64_t pw, const int64_t* desc, void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(src && dst && desc, "chunk_extract: null pointer");
+  B200_CHECK_ARG(valid_dtype(dtype) || dtype == 3, "chunk_extract: bad dtype");
+  B200_CHECK_ARG(n > 0 && n <= 65535 && pd > 0 && pd <= 65535 && ph * pw * C < (1LL << 30), "chunk_extract: bad tile batch");
+  B200_CHECK_ARG(D < (1LL << 31) && H < (1LL << 31) && W < (1LL << 31), "chunk_extract: volume axis too long");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t bx = ceil_div(ph * pw * C, 256);
+  if (bx > 32) bx = 32;
+  dim3 blocks((unsigned)bx, (unsigned)pd, (unsigned)n);
+  if (dtype == 3)
+    chunk_extract_kernel<uint8_t><<<blocks, 256, 0, st>>>((const uint8_t*)src, (uint8_t*)dst, desc, (int)H, (int)W, (int)C, (int)pd,
+                                                          (int)ph, (int)pw);
+  else if (dtype == B200_F32)
+    chunk_extract_kernel<uint32_t><<<blocks, 256, 0, st>>>((const uint32_t*)src, (uint32_t*)dst, desc, (int)H, (int)W, (int)C, (int)pd,
+                                                           (int)ph, (int)pw);
+  else
+    chunk_extract_kernel<uint16_t><<<blocks, 256, 0, st>>>((const uint16_t*)src, (uint16_t*)dst, desc, (int)H, (int)W, (int)C, (int)pd,
+                                                           (int)ph, (int)pw);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+B200_EXPORT int b200_chunk_insert(const void* patches, int32_t dtype_in, int64_t n, int64_t pd, int64_t ph, int64_t pw, int64_t C,
+                                  void* out, int32_t dtype_out, int64_t D, int64_t H, int64_t W, const int64_t* desc, int32_t mode,
+                                  void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(patches && out && desc, "chunk_insert: null pointer");
+  B200_CHECK_ARG(valid_dtype(dtype_in) && valid_dtype(dtype_out), "chunk_insert: bad dtype");
+  B200_CHECK_ARG(mode == 0 || mode == 1, "chunk_insert: mode must be 0 (replace) or 1 (add)");
+  B200_CHECK_ARG(n > 0 && n <= 65535 && pd > 0 && pd <= 65535 && ph * pw * C < (1LL << 30), "chunk_insert: bad tile batch");
+  B200_CHECK_ARG(D < (1LL << 31) && H < (1LL << 31) && W < (1LL << 31), "chunk_insert: volume axis too long");
+  cudaStream_t st = (cudaStream_t)stream;
+#define CI(TI, TO) return launch_chunk_insert<TI, TO>(patches, out, desc, n, (int)H, (int)W, (int)C, (int)pd, (int)ph, (int)pw, mode, st)
+  if (dtype_in == B200_F32 && dtype_out == B200_F32) CI(float, float);
+  if (dtype_in == B200_F16 && dtype_out == B200_F16) CI(__half, __half);
+  if (dtype_in == B200_F16 && dtype_out == B200_F32) CI(__half, float);
+  if (dtype_in == B200_BF16 && dtype_out == B200_BF16) CI(__nv_bfloat16, __nv_bfloat16);
+  if (dtype_in == B200_BF16 && dtype_out == B200_F32) CI(__nv_bfloat16, float);
+  if (dtype_in == B200_F32 && dtype_out == B200_F16) CI(float, __half);
+  if (dtype_in == B200_F32 && dtype_out == B200_BF16) CI(float, __nv_bfloat16);
+#undef CI
+  set_error("chunk_insert: unsupported dtype pair %d -> %d", dtype_in, dtype_out);
+  return B200_ERR_UNSUPPORTED;
+}

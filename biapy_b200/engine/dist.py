@@ -33,6 +33,26 @@ def deal_patches(n_patches: int, rank: int, world: int) -> List[int]:
     return list(range(rank, n_patches, world))
 
 
+def deal_tiles(n_tiles: int, rank: int, world: int, num_workers: int = 1, worker_id: int = 0, drop_repeats: bool = False) -> List[int]:
+    """Indices (into the sorted tile-id list) that one (rank, worker) visits in the reference's by-chunks ``__iter__``
+    (``chunked_test_pair_data_generator.py:612-618``): ``DistributedSampler(tile_ids, num_replicas=workers*world,
+    rank=rank*workers+worker, shuffle=False)`` -- the index list is padded by wrapping around so every replica gets
+    ``ceil(n / replicas)`` tiles, then strided.  Repeated tiles are predicted but used once (``base_workflow.py:2582-2590``);
+    `drop_repeats` leaves them out (every tile then has exactly one owner across the replicas)."""
+    import math
+    replicas = max(1, num_workers) * max(1, world)
+    r = rank * max(1, num_workers) + worker_id
+    if n_tiles == 0:
+        return []
+    total = math.ceil(n_tiles / replicas) * replicas
+    idx = list(range(n_tiles))
+    pad = total - n_tiles
+    idx += idx[:pad] if pad <= n_tiles else (idx * math.ceil(pad / n_tiles))[:pad]
+    if drop_repeats:      # the wrapped-around tail only evens out the replicas; its tiles already belong to an earlier position
+        return [idx[p] for p in range(r, n_tiles, replicas)]
+    return idx[r:total:replicas]
+
+
 def gather_patch_predictions(pred: torch.Tensor, n_patches: int, group=None) -> torch.Tensor:
     """`pred` (n_patches, ...) holds valid rows only for this rank's dealt patches; after the call every rank holds
     all rows.  One all_gather of ceil(n/world) rows per rank."""

@@ -83,3 +83,39 @@ def predict_volume(model, vol, patch_shape: Sequence[int], overlap=(0, 0, 0), pa
     axes_m = [_stitch.Axis(dev_vol.shape[i], patch_shape[i], padding[i], overlap[i]) for i in range(3)]
     merged = _stitch.merge_device(pred, (Z, Y, X), [a.starts(1) for a in axes_m], [a.window() for a in axes_m], padding)
     return merged.cpu().numpy() if is_np else merged
+
+
+@torch.no_grad()
+def predict_by_chunks(model, vol, patch_shape: Sequence[int], padding=(0, 0, 0), batch_size: int = 4,
+                      head_activations: Optional[List[str]] = None, out_dtype=torch.float32, rank: int = 0, world: int = 1,
+                      z_start: int = -1, z_end: int = -1, patches_per_tile=(1, 1, 1), out: Optional[torch.Tensor] = None,
+                      reduce: bool = True):
+    """The reference's multi-GPU inference semantics (``TEST.BY_CHUNKS``, ``base_workflow.py:2559-2614``): non-blended tiles
+    of ``patch - 2 * padding`` read with a halo, reflect-padded at the volume border, predicted in batches and written back
+    without the halo.  Tiles are dealt to ranks exactly as the reference's ``DistributedSampler`` deals them; every rank
+    writes only its own tiles (disjoint regions), so with ``reduce=True`` one NCCL all-reduce (sum of disjoint supports)
+    leaves the full prediction on every rank -- the reference gets the same effect by writing into a shared Zarr file.
+    vol: (Z, Y, X, C) numpy array or CUDA tensor; returns (Z, Y, X, C_out) in the same container type."""
+    from ..data.generators.chunked_test_pair_data_generator import chunked_test_pair_data_generator
+    is_np = isinstance(vol, np.ndarray)
+    gen = chunked_test_pair_data_generator(dict(X=_stitch.to_device(vol), Y=None, X_filename="", X_dir=""), None, "ZYXC", "ZYXC",
+                                           tuple(patch_shape), tuple(padding), z_start=z_start, z_end=z_end,
+                                           patches_per_tile=patches_per_tile)
+    c_out = sum(model.output_channels)
+    acts = head_activations or ["linear"] * c_out
+    dev = gen.X_parallel_data.device
+    if out is None:
+        out = torch.zeros((gen.z_dim, gen.y_dim, gen.x_dim, c_out), dtype=out_dtype, device=dev)
+    # tiles the sampler repeats to even out the ranks are "predicted but not used" in the reference (:2582-2590): skip them,
+    # so that every tile has one owner and the final all-reduce adds disjoint supports
+    todo = gen.rank_patches(world, rank, drop_repeats=True)
+    for k in range(0, len(todo), batch_size):
+        xb, pads, coords = gen.extract_batch(todo[k:k + batch_size])
+        y = model(xb.permute(0, 4, 1, 2, 3))
+        ycl = y.permute(0, 2, 3, 4, 1)
+        act = torch.empty(ycl.shape, dtype=out_dtype, device=dev)
+        apply_head_activations(ycl, acts, act)
+        gen.insert_batch(act, pads, coords, out=out)
+    if world > 1 and reduce:
+        torch.distributed.all_reduce(out)
+    return out.cpu().numpy() if is_np else out

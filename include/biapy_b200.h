@@ -94,6 +94,41 @@ int b200_overlap_add(const void* patches, int32_t dtype_in, void* out, int32_t d
                      const int64_t* starts_x, int64_t nx,
                      const float* win_z, const float* win_y, const float* win_x, void* stream);
 
+/* ------------------------------------------------------------------------------ by-chunks tile grid (host)
+ * The reference's multi-GPU inference path (TEST.BY_CHUNKS): non-blended tiles of (crop - 2*pad), read with a halo,
+ * reflect-padded to the crop shape, written back without the halo.  Integer bookkeeping, bit-exact with
+ *   chunked_test_pair_data_generator.__init__   biapy/data/generators/chunked_test_pair_data_generator.py:276-295
+ *   chunked_test_pair_data_generator._patch_coords                                            ...:440-486
+ *   extract_and_prepare_sample (pad_to_add and the "real padding info")                       ...:536-560
+ * Host-only, no CUDA.                                                                                        */
+typedef struct b200_chunk_grid {
+  int64_t dim[3], crop[3], pad[3];           /* inputs (z, y, x) */
+  int64_t step[3], vols[3];                  /* crop - 2*pad; ceil(dim / step) */
+  int64_t z_vol_start, z_vol_end, total;     /* tile range of the requested Z slab; tiles to process */
+} b200_chunk_grid;
+/* z_start / z_end = -1: whole volume.  Errors (B200_ERR_ARG) mirror the reference's ValueErrors (:247-274). */
+int b200_chunk_grid_plan(const int64_t dim[3], const int64_t crop[3], const int64_t pad[3], int64_t z_start, int64_t z_end,
+                         b200_chunk_grid* out);
+/* out[27] for tile `vol_id`: grid position z,y,x | region to read [zs,ze,ys,ye,xs,xe] (halo included, clipped) |
+ * region to write back [zs,ze,ys,ye,xs,xe] | np.pad amounts [zl,zr,yl,yr,xl,xr] | real padding info (max(pad, amount)) */
+int b200_chunk_patch_coords(const b200_chunk_grid* grid, int64_t vol_id, int64_t out[27]);
+
+/* -------------------------------------------------------------------------- by-chunks extract / insert (device)
+ * b200_chunk_extract replaces extract_patch_within_image + np.pad(..., "reflect") (chunked_test_pair_data_generator.py
+ * :505-551): tile t of `n` is the window [start, start+len) per axis of the resident volume (D,H,W,C), reflected about the
+ * WINDOW's own ends (numpy pads the extracted array, not the volume) and shifted by `left`.
+ *   desc (DEVICE int64 [n][9]) = start_z, len_z, left_z, start_y, len_y, left_y, start_x, len_x, left_x
+ * dst: (n, pd, ph, pw, C) dense, same dtype as src (f32 / bf16 / f16 / u8).
+ * b200_chunk_insert replaces the strip (base_workflow.py:2606-2612) + insert_patch_in_efficient_file
+ * (data_3D_manipulation.py:286-351; mode 0 = "replace", 1 = "add"): the region [strip, strip+size) of tile t goes to
+ * out[o : o+size).   desc (DEVICE int64 [n][9]) = out_z, size_z, strip_z, out_y, size_y, strip_y, out_x, size_x, strip_x
+ * patches: (n, pd, ph, pw, C) dense; out: (D,H,W,C) dense; dtype pairs as in b200_overlap_add.               */
+int b200_chunk_extract(const void* src, int32_t dtype, int64_t D, int64_t H, int64_t W, int64_t C, void* dst, int64_t n,
+                       int64_t pd, int64_t ph, int64_t pw, const int64_t* desc, void* stream);
+int b200_chunk_insert(const void* patches, int32_t dtype_in, int64_t n, int64_t pd, int64_t ph, int64_t pw, int64_t C,
+                      void* out, int32_t dtype_out, int64_t D, int64_t H, int64_t W, const int64_t* desc, int32_t mode,
+                      void* stream);
+
 /* ---------------------------------------------------------------------------------------------- convolution
  * nn.Conv3d / nn.Conv2d, stride 1, padding='same', bias (biapy/models/blocks.py:154,157,1372; unet.py:347).
  * Weights are packed once per step from the PyTorch layout (Cout,Cin,kd,kh,kw) fp32:

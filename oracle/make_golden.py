@@ -194,17 +194,104 @@ def make_grids(R):
         json.dump(grids, f, indent=0)
 
 
+# by-chunks tile grid: (name, volume shape ZYXC, crop ZYXC, padding, z_start, z_end, patches_per_tile, keep arrays)
+CHUNK_CASES = [
+    ("c_a", (50, 70, 60, 2), (32, 32, 32, 2), (4, 6, 8), -1, -1, (1, 1, 1), True),
+    ("c_b", (40, 33, 47, 1), (16, 24, 16, 1), (0, 0, 0), -1, -1, (2, 1, 3), True),     # no padding, ragged last tiles, grouped tiles
+    ("c_c", (37, 41, 35, 1), (16, 16, 16, 1), (7, 7, 7), -1, -1, (1, 1, 1), True),      # step 2: last window shorter than the reflect reach
+    ("c_d", (96, 64, 64, 1), (32, 32, 32, 1), (8, 8, 8), 20, 70, (1, 2, 2), False),      # Z range
+    ("c_e", (512, 512, 512, 1), (128, 128, 128, 1), (16, 16, 16), -1, -1, (1, 1, 1), False),   # cfg-3 volume, by-chunks semantics
+]
+
+
+def make_chunks():
+    """Fixtures from the reference's own `chunked_test_pair_data_generator` (grid, coordinates, extracted + reflect-padded
+    samples, strip + insert with an identity model, DistributedSampler dealing)."""
+    import zlib
+    from torch.utils.data import DistributedSampler
+    C = ref_loader.load_chunked()
+    meta = []
+    for name, shape, crop, pad, z0, z1, ppt, keep in CHUNK_CASES:
+        rng = np.random.default_rng(zlib.crc32(name.encode()))
+        small = keep or int(np.prod(shape)) <= 1 << 22
+        vol = rng.standard_normal(shape).astype(np.float32) if small else np.zeros((1, 1, 1, 1), np.float32)
+        X = vol if small else np.lib.stride_tricks.as_strided(vol, shape=shape, strides=(0, 0, 0, 0))
+        with _quiet():
+            g = C.cls(dict(X=X, Y=None, X_filename=name + ".zarr", X_dir="."), {}, "ZYXC", "ZYXC", crop, pad, out_dir="/tmp/_b200_golden",
+                      z_start=z0, z_end=z1, patches_per_tile=ppt)
+        coords = np.zeros((g.total_vols, 3 + 6 + 6 + 6), dtype=np.int64)
+        out = np.zeros(shape, np.float32) if small else None
+        samples = []
+        for vid in range(g.total_vols):
+            z, y, x, pe, pr = g._patch_coords(vid)
+            if small:
+                data, padinfo = g.extract_and_prepare_sample(z, y, x, pe)
+            else:                       # coordinates + padding bookkeeping only (same arithmetic, no 512^3 copies)
+                data, padinfo = None, None
+                px = []
+                for a, (s, e) in enumerate([(pe.z_start, pe.z_end), (pe.y_start, pe.y_end), (pe.x_start, pe.x_end)]):
+                    pos = (z, y, x)[a]
+                    step = (g.step_z, g.step_y, g.step_x)[a]
+                    left = abs(pos * step - pad[a]) if pos * step - pad[a] < 0 else 0
+                    right = crop[a] - (e - s) - left
+                    px.append([max(left, pad[a]), max(right, pad[a])])
+                padinfo = px
+            coords[vid] = [z, y, x, pe.z_start, pe.z_end, pe.y_start, pe.y_end, pe.x_start, pe.x_end,
+                           pr.z_start, pr.z_end, pr.y_start, pr.y_end, pr.x_start, pr.x_end,
+                           padinfo[0][0], padinfo[0][1], padinfo[1][0], padinfo[1][1], padinfo[2][0], padinfo[2][1]]
+            if small:
+                samples.append(data)
+                # base_workflow.py:2606-2614 (strip) + insert_patch_in_efficient_file (replace), identity "model"
+                raw = data[padinfo[0][0]: data.shape[0] - padinfo[0][1], padinfo[1][0]: data.shape[1] - padinfo[1][1],
+                           padinfo[2][0]: data.shape[2] - padinfo[2][1]]
+                C.d3.insert_patch_in_efficient_file(out, raw, pr, data_axes_order="ZYXC", patch_axes_order="ZYXC", mode="replace")
+        deal = {}
+        for world in (1, 2, 3, 8):
+            for rank in range(world):
+                smp = DistributedSampler(g.tile_ids, num_replicas=world, rank=rank, shuffle=False)
+                vids = [v for i in smp for v in g.patches_of_tile[g.tile_ids[int(i)]]]
+                deal[f"{world}:{rank}"] = dict(crc=zlib.crc32(np.asarray(vids, np.int64).tobytes()), n=len(vids), head=vids[:6],
+                                               workload=list(g.rank_workload(1, world, rank)))
+        m = dict(name=name, shape=list(shape), crop=list(crop), padding=list(pad), z_start=z0, z_end=z1, patches_per_tile=list(ppt),
+                 steps=[g.step_z, g.step_y, g.step_x], vols=[g.vols_per_z, g.vols_per_y, g.vols_per_x],
+                 z_vol=[g.z_vol_start, g.z_vol_end], total_vols=g.total_vols, n_tiles=len(g.tile_ids),
+                 tiles=[g.tiles_per_z, g.tiles_per_y, g.tiles_per_x], tile_ids_crc=zlib.crc32(np.asarray(g.tile_ids, np.int64).tobytes()),
+                 tile0=[getattr(g.tile_coords(g.tile_ids[-1]), k) for k in ("z_start", "z_end", "y_start", "y_end", "x_start", "x_end")],
+                 coords_crc=zlib.crc32(coords.tobytes()), deal=deal, arrays=bool(keep))
+        if small:
+            m["roundtrip_equal"] = bool(np.array_equal(out[g.z_vol_start * g.step_z: min(g.z_vol_end * g.step_z, shape[0])],
+                                                       vol[g.z_vol_start * g.step_z: min(g.z_vol_end * g.step_z, shape[0])]))
+            m["samples_crc"] = zlib.crc32(np.stack(samples).tobytes())
+        if keep:
+            pick = sorted({0, g.total_vols // 2, g.total_vols - 1, min(g.total_vols - 1, g.vols_per_x * g.vols_per_y - 1)})
+            # the volume is NOT stored: tests regenerate it from the same seeded generator (vol_crc pins it)
+            m["vol_crc"] = zlib.crc32(vol.tobytes())
+            m["out_crc"] = zlib.crc32(out.tobytes())
+            np.savez_compressed(os.path.join(OUT, f"chunks_{name}.npz"), coords=coords, pick=np.asarray(pick),
+                                samples=np.stack([samples[i] for i in pick]))
+        else:
+            np.savez_compressed(os.path.join(OUT, f"chunks_{name}.npz"), coords=coords)
+        meta.append(m)
+        print("chunks", name, shape, crop, pad, "->", g.total_vols, "patches,", len(g.tile_ids), "tiles", m.get("roundtrip_equal"))
+    with open(os.path.join(OUT, "chunks.json"), "w") as f:
+        json.dump(meta, f, indent=0)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     R = ref_loader.load()
     import sys
     only = [a for a in sys.argv[1:] if not a.startswith("-")]
+    if only == ["chunks"]:        # python -m oracle.make_golden chunks
+        make_chunks()
+        return
     if only:                      # add fixtures without rewriting the committed ones: python -m oracle.make_golden <model name>...
         make_models(R, only)
         return
     make_grids(R)
     make_stitch(R)
     make_models(R)
+    make_chunks()
     with open(os.path.join(OUT, "PROVENANCE.txt"), "w") as f:
         f.write("generated by oracle/make_golden.py from /root/reference (BiaPy 3.7.0 @ 29539acd), "
                 f"torch {torch.__version__}, numpy {np.__version__}; GN call patched as documented in oracle/ref_loader.py\n")

@@ -107,3 +107,62 @@ def load():
                 sys.modules[k] = v
     _loaded = ns
     return ns
+
+
+_chunked = None
+
+
+def _functions_from_source(relpath: str, names, env: dict) -> dict:
+    """Execute only the named top-level functions of a reference file (the file itself imports packages that are not
+    installed here: tifffile, imageio, ...).  The code that runs is the reference's own source, read where it lies."""
+    import ast
+    path = os.path.join(REFERENCE_ROOT, relpath)
+    with open(path) as f:
+        tree = ast.parse(f.read(), filename=path)
+    body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    missing = set(names) - {n.name for n in body}
+    if missing:
+        raise RuntimeError(f"{relpath}: functions not found: {sorted(missing)}")
+    mod = ast.Module(body=body, type_ignores=[])
+    glb = dict(env)
+    exec(compile(mod, path, "exec"), glb)
+    return {n: glb[n] for n in names}
+
+
+def load_chunked():
+    """The reference's by-chunks generator class (`chunked_test_pair_data_generator`), importable here
+    because its grid / extract / insert methods only need numpy: `biapy.data.data_manipulation` is replaced by a stub module
+    holding the reference's own `extract_patch_within_image` (AST-extracted), `norm` / `roi_mask` by inert stubs."""
+    global _chunked
+    if _chunked is not None:
+        return _chunked
+    ns = load()
+    import numpy as np
+    from numpy.typing import NDArray
+    saved = {k: sys.modules.get(k) for k in list(sys.modules) if k == "biapy" or k.startswith("biapy.")}
+    for k in saved:
+        del sys.modules[k]
+    try:
+        _stub("biapy")
+        _stub("biapy.data")
+        _stub("biapy.utils")
+        _stub("biapy.utils.misc", is_main_process=lambda: False, get_world_size=lambda: 1, get_rank=lambda: 0)
+        sys.modules["biapy.data.dataset"] = ns.dataset
+        sys.modules["biapy.data.data_3D_manipulation"] = ns.d3
+        fns = _functions_from_source("biapy/data/data_manipulation.py", ["extract_patch_within_image"],
+                                     dict(np=np, NDArray=NDArray, PatchCoords=ns.dataset.PatchCoords))
+        _stub("biapy.data.data_manipulation", sample_satisfy_conds=None, save_tif=None, **fns)
+        _stub("biapy.data.norm", normalize_image=None, normalize_mask=None)
+        _stub("biapy.data.roi_mask", load_roi_mask=None)
+        _stub("biapy.data.generators")
+        gen = _load("biapy.data.generators.chunked_test_pair_data_generator",
+                    "biapy/data/generators/chunked_test_pair_data_generator.py")
+    finally:
+        for k in [k for k in sys.modules if k == "biapy" or k.startswith("biapy.")]:
+            del sys.modules[k]
+        for k, v in saved.items():
+            if v is not None:
+                sys.modules[k] = v
+    _chunked = types.SimpleNamespace(gen=gen, cls=gen.chunked_test_pair_data_generator, d3=ns.d3,
+                                     PatchCoords=ns.dataset.PatchCoords)
+    return _chunked

@@ -110,3 +110,42 @@ def test_reference_error_messages():
         crop_3D_data_with_overlap(np.zeros((8, 8, 8, 1)), (4, 4, 4, 1), overlap=(1, 0, 0), verbose=False)
     with pytest.raises(AssertionError):
         merge_3D_data_with_overlap(np.zeros((4, 4, 4, 1)), (4, 4, 4, 1), verbose=False)
+
+
+def test_chunk_planner_matches_golden_and_oracle():
+    """Host-side by-chunks bookkeeping (b200_chunk_grid_plan / b200_chunk_patch_coords) vs the reference fixtures."""
+    import zlib
+    from oracle import port_chunks
+    cases = json.load(open(os.path.join(GOLDEN, "chunks.json")))
+    L3 = C.c_int64 * 3
+    for case in cases:
+        g = _lib.ChunkGrid()
+        st = _lib.lib().b200_chunk_grid_plan(L3(*case["shape"][:3]), L3(*case["crop"][:3]), L3(*case["padding"]), case["z_start"],
+                                             case["z_end"], C.byref(g))
+        assert st == 0
+        assert list(g.step) == case["steps"] and list(g.vols) == case["vols"]
+        assert [g.z_vol_start, g.z_vol_end] == case["z_vol"] and g.total == case["total_vols"]
+        rows = np.zeros((g.total, 21), dtype=np.int64)
+        buf = (C.c_int64 * 27)()
+        for vid in range(g.total):
+            assert _lib.lib().b200_chunk_patch_coords(C.byref(g), vid, buf) == 0
+            r = list(buf)
+            rows[vid] = r[:15] + r[21:27]
+        assert zlib.crc32(rows.tobytes()) == case["coords_crc"]
+        assert _lib.lib().b200_chunk_patch_coords(C.byref(g), g.total, buf) != 0
+    # randomised against the oracle (raw np.pad amounts included)
+    rng = np.random.default_rng(1)
+    for _ in range(300):
+        crop = [int(rng.integers(4, 40)) for _ in range(3)]
+        pad = [int(rng.integers(0, c // 2)) for c in crop]
+        dim = [int(rng.integers(c, 4 * c + 5)) for c in crop]
+        og = port_chunks.ChunkGrid(dim, crop, pad)
+        g = _lib.ChunkGrid()
+        assert _lib.lib().b200_chunk_grid_plan(L3(*dim), L3(*crop), L3(*pad), -1, -1, C.byref(g)) == 0
+        assert g.total == og.total_vols
+        buf = (C.c_int64 * 27)()
+        for vid in rng.integers(0, g.total, size=min(8, g.total)).tolist():
+            _lib.lib().b200_chunk_patch_coords(C.byref(g), vid, buf)
+            z, y, x, ext, real = og.patch_coords(vid)
+            raw, info = og.pad_to_add((z, y, x), ext)
+            assert list(buf) == [z, y, x] + ext + real + [v for ax in raw for v in ax] + [v for ax in info for v in ax]

@@ -41,6 +41,15 @@ def _worker(rank, world, port, q):
         out = bd.gather_patch_predictions(pred, n)
         expect = torch.arange(1, n + 1, dtype=torch.float32).view(n, 1, 1).expand(n, 2, 3)
         assert torch.equal(out, expect)
+        # 4. by-chunks tile dealing == torch's DistributedSampler(shuffle=False); disjoint writes + one all-reduce = full volume
+        from torch.utils.data import DistributedSampler
+        for n_tiles in (1, 2, 7, 48):
+            mine_t = bd.deal_tiles(n_tiles, rank, world)
+            assert mine_t == list(DistributedSampler(list(range(n_tiles)), num_replicas=world, rank=rank, shuffle=False))
+            own = torch.zeros(n_tiles)
+            own[bd.deal_tiles(n_tiles, rank, world, drop_repeats=True)] = 1
+            dist.all_reduce(own)
+            assert torch.equal(own, torch.ones(n_tiles))      # without the repeats: exactly one owner per tile
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))

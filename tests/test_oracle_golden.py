@@ -121,3 +121,65 @@ def test_model_port(path):
             ye = port_models.forward(arch, {k: v.detach() for k, v in sd.items()}, x.detach(), training=False, **kw)
         ref_e = torch.from_numpy(z["y_eval"])
         assert (ye - ref_e).abs().max() <= 1e-5 * max(1.0, ref_e.abs().max().item())
+
+
+# ------------------------------------------------------------------------------------- by-chunks tile grid (row a18)
+def _chunk_cases():
+    with open(os.path.join(GOLDEN, "chunks.json")) as f:
+        return json.load(f)
+
+
+def chunk_volume(case):
+    """The seeded volume oracle/make_golden.py fed to the reference (not stored in the fixture)."""
+    rng = np.random.default_rng(zlib.crc32(case["name"].encode()))
+    return rng.standard_normal(tuple(case["shape"])).astype(np.float32)
+
+
+def oracle_chunk_coords(g):
+    from oracle import port_chunks  # noqa: F401
+    rows = np.zeros((g.total_vols, 21), dtype=np.int64)
+    for vid in range(g.total_vols):
+        z, y, x, ext, real = g.patch_coords(vid)
+        _, info = g.pad_to_add((z, y, x), ext)
+        rows[vid] = [z, y, x] + ext + real + [v for ax in info for v in ax]
+    return rows
+
+
+@pytest.mark.parametrize("case", _chunk_cases(), ids=lambda c: c["name"])
+def test_chunk_grid_oracle_matches_reference(case):
+    from oracle import port_chunks
+    g = port_chunks.ChunkGrid(case["shape"], case["crop"], case["padding"], case["z_start"], case["z_end"], case["patches_per_tile"])
+    assert [g.step_z, g.step_y, g.step_x] == case["steps"]
+    assert [g.vols_per_z, g.vols_per_y, g.vols_per_x] == case["vols"]
+    assert [g.z_vol_start, g.z_vol_end] == case["z_vol"] and g.total_vols == case["total_vols"]
+    assert len(g.tile_ids) == case["n_tiles"] and [g.tiles_per_z, g.tiles_per_y, g.tiles_per_x] == case["tiles"]
+    assert zlib.crc32(np.asarray(g.tile_ids, np.int64).tobytes()) == case["tile_ids_crc"]
+    assert g.tile_coords(g.tile_ids[-1]) == case["tile0"]
+    rows = oracle_chunk_coords(g)
+    fx = np.load(os.path.join(GOLDEN, f"chunks_{case['name']}.npz"))
+    assert np.array_equal(rows, fx["coords"]) and zlib.crc32(rows.tobytes()) == case["coords_crc"]
+    for key, d in case["deal"].items():
+        world, rank = (int(v) for v in key.split(":"))
+        vids = g.rank_patches(world, rank)
+        assert len(vids) == d["n"] and vids[:6] == d["head"]
+        assert zlib.crc32(np.asarray(vids, np.int64).tobytes()) == d["crc"]
+        assert list(g.rank_workload(1, world, rank)) == d["workload"]
+
+
+@pytest.mark.parametrize("case", [c for c in _chunk_cases() if c["arrays"]], ids=lambda c: c["name"])
+def test_chunk_extract_insert_oracle_matches_reference(case):
+    from oracle import port_chunks
+    vol = chunk_volume(case)
+    assert zlib.crc32(vol.tobytes()) == case["vol_crc"]
+    g = port_chunks.ChunkGrid(case["shape"], case["crop"], case["padding"], case["z_start"], case["z_end"], case["patches_per_tile"])
+    fx = np.load(os.path.join(GOLDEN, f"chunks_{case['name']}.npz"))
+    for i, vid in enumerate(fx["pick"].tolist()):
+        assert np.array_equal(g.extract(vol, vid)[0], fx["samples"][i])
+    allp = np.stack([g.extract(vol, v)[0] for v in range(g.total_vols)])
+    assert zlib.crc32(allp.tobytes()) == case["samples_crc"]
+    # identity model: extract -> strip -> insert reproduces the volume, on any number of ranks
+    for world in (1, 3):
+        out = np.zeros(vol.shape, np.float32)
+        for rank in range(world):
+            port_chunks.predict_by_chunks(vol, g, lambda b: b, vol.shape[-1], world, rank, out=out)
+        assert zlib.crc32(out.tobytes()) == case["out_crc"] and np.array_equal(out, vol)
