@@ -61,9 +61,12 @@ SIGNATURES = {
     "b200_chunk_patch_coords": (_I, [C.POINTER(ChunkGrid), _L, C.POINTER(_L)]),
     "b200_chunk_extract": (_I, [_P, _I, _L, _L, _L, _L, _P, _L, _L, _L, _L, _P, _P]),
     "b200_chunk_insert": (_I, [_P, _I, _L, _L, _L, _L, _L, _P, _I, _L, _L, _L, _P, _I, _P]),
+    "b200_orient_apply": (_I, [_T, _T, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), _I, _P]),
+    "b200_orient_reduce": (_I, [_T, C.POINTER(_I), C.POINTER(_I), _I, C.POINTER(_I), _T, _P]),
     "b200_pack_conv_weight": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "b200_conv_fprop": (_I, [_T, _P, _P, _T, _T, _I, _I, _I, _I, _I, _P]),
     "b200_conv_wgrad": (_I, [_T, _T, _P, _P, _I, _I, _I, _I, _P]),
+    "b200_conv_fprop_stats": (_I, [_T, _P, _P, _T, _I, _I, _I, _I, _P, C.POINTER(_I), _P]),
     "b200_pack_conv_weight_xfold": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "b200_conv_impl_query": (_I, [_T, _T, _I, _I, _I, _I]),
     "b200_unpack_conv_wgrad": (_I, [_P, _P, _I, _I, _I, _I, _P]),

@@ -10,6 +10,8 @@
 #include <math.h>
 
 #include "../../include/biapy_b200.h"
+#include <mutex>
+#include <vector>
 
 #define B200_EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -133,6 +135,28 @@ __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// Opt-in dynamic shared memory cap of a kernel, raised ONCE to the hardware maximum (227 KB per block minus the kernel's
+// static shared memory).  The cap is a property of the function, not of a launch: a CUDA-graph kernel node replayed on its
+// own (ncu's per-node profiling) sees whatever value the last eager launch left behind, so it must never be lowered.
+template <typename K>
+inline cudaError_t raise_dyn_smem_cap(K kern) {
+  static std::mutex mu;
+  static std::vector<const void*> done;
+  std::lock_guard<std::mutex> lock(mu);
+  for (const void* k : done)
+    if (k == (const void*)kern) return cudaSuccess;
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+  if (e != cudaSuccess) return e;
+  int dev = 0, optin = 0;
+  cudaGetDevice(&dev);
+  e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+  if (e == cudaSuccess) done.push_back((const void*)kern);
+  return e;
 }
 
 inline bool valid_dtype(int dt) { return dt == B200_F32 || dt == B200_BF16 || dt == B200_F16; }

@@ -605,7 +605,7 @@ int conv_fprop_simt(const b200_tensor* x, const void* w, const float* bias, cons
   B200_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "conv_fprop(simt): grid too large");
   B200_DISPATCH_DTYPE(x->dtype, T, {
     auto kern = conv_fprop_simt_kernel<T>;
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));  // function-level cap: keep it at the maximum (graph nodes replayed alone)
+    B200_CUDA(raise_dyn_smem_cap(kern));  // function-level cap: keep it at the maximum (graph nodes replayed alone)
     kern<<<grid, 128, smem, st>>>((const T*)x->data, (const T*)w, bias, res ? (const T*)res->data : nullptr, (T*)y->data, g,
                                   accumulate, CK);
   });
@@ -662,7 +662,7 @@ int conv_wgrad_simt(const b200_tensor* x, const b200_tensor* dy, float* dw, floa
   B200_CHECK_ARG(grid.y <= 65535, "conv_wgrad(simt): too many channel tiles");
   B200_DISPATCH_DTYPE(x->dtype, T, {
     auto kern = conv_wgrad_simt_kernel<T>;
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));  // function-level cap: keep it at the maximum (graph nodes replayed alone)
+    B200_CUDA(raise_dyn_smem_cap(kern));  // function-level cap: keep it at the maximum (graph nodes replayed alone)
     kern<<<grid, 256, smem, st>>>((const T*)x->data, (const T*)dy->data, dw, dbias, g, tpc, units);
   });
   B200_LAUNCH_CHECK();

@@ -19,11 +19,6 @@
 namespace b200 {
 int conv_bias_grad(const b200_tensor* dy, float* dbias, cudaStream_t st);   // conv_simt.cu
 
-// The opt-in cap is a property of the FUNCTION, not of a launch: a CUDA-graph kernel node replayed on its own (ncu's per-node
-// profiling) sees whatever value the last eager launch of the same kernel left behind.  Always raise it to the hardware
-// maximum (227 KB) so every recorded launch stays valid.
-static constexpr int kMaxDynSmem = 227 * 1024;
-
 namespace sm100 {
 
 // ---------------------------------------------------------------------------------------- tensor-map helpers
@@ -497,6 +492,13 @@ conv_fprop_xfold_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid_
 // and the kd taps in z are served from it by moving the descriptor start address by whole 16-row lines (always a
 // multiple of the 1 KB / 512 B swizzle atom, so the TMA-written swizzle stays valid); RT = 2 row tiles (16 z-lines)
 // share every weight tile.  A bytes per voxel drop 2.4x, weight bytes 2x.  Separate rings for slabs and weight tiles.
+// Optional per-(sample, channel) statistics fused into the x-slab epilogues (conv -> GroupNorm / InstanceNorm / BatchNorm,
+// reference blocks.py:154-160): the epilogue holds every output element in registers, so
+//   sums[n][c] += (sum v, sum v*v) of the stored (rounded) value v        (== b200_channel_sums of the output)
+// comes out of the convolution and the normalisation's own read of the tensor for its statistics disappears.
+// (The backward counterpart -- the (g, g*x) sums of the norm + activation backward inside the dgrad epilogue -- was built
+// and measured: 0.69 ms against 0.28 + 0.29 ms for dgrad + stand-alone reduction on 16 -> 16 @128^3; it needs the norm input
+// in the epilogue, i.e. a second operand stream, and was dropped.)
 struct XslabParams {
   int n, d, h, w, cin, cout;
   int kd, kh, kw;
@@ -513,15 +515,239 @@ struct XslabParams {
   int accumulate;
   int ablate;                           // diagnostics (B200_ABLATE): 1 = no TMA, 2 = no MMA, 4 = no epilogue stores
   long long* dbg;                       // diagnostics (B200_DBG): per-CTA cycle counters of the role loops, or nullptr
+  double* stats;                        // fused channel sums [n][cout][2] (kernels instantiated with CB = cout / 16 > 0) or nullptr
+  // TMA-store epilogue (xslab_epilogue_tma): byte offset of the 2 x 16 KB staging ring behind the operand rings, and the
+  // XOR mask of the output map's shared-memory swizzle on the 16-byte chunk index (7 / 3 / 1 / 0 = 128B / 64B / 32B / none)
+  int epi_tma;
+  uint32_t epi_off, epi_swz;
 };
 
 constexpr int kSlabAWarps = 1, kSlabBWarps = 3;
 
-template <typename T>
+__device__ __forceinline__ void xslab_decode(const XslabParams& p, int tile, int& n, int& z0, int& y0, int& g) {
+  int t = tile;
+  g = t % p.groups_x; t /= p.groups_x;
+  y0 = (t % p.tiles_h) * 16; t /= p.tiles_h;
+  z0 = (t % p.tiles_d) * 8 * p.rt; t /= p.tiles_d;
+  n = t;
+}
+
+// Per-thread partial channel sums of the fused statistics (CB = Cout / 16 column blocks held in registers); folded with warp
+// shuffles and added to `stats` with one fp64 atomic per (warp, channel, quantity) whenever the sample changes.
+template <int CB>
+struct EpiStats {
+  static constexpr int NC = CB > 0 ? CB * 16 : 1;
+  float s1[NC], s2[NC];
+  int cur_n;
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) s1[i] = s2[i] = 0.f;
+    cur_n = -1;
+  }
+  __device__ __forceinline__ void flush(double* stats, int cout) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      const float a = warp_sum(s1[i]), b = warp_sum(s2[i]);
+      if (lane == 0) {
+        atomicAdd(stats + ((int64_t)cur_n * cout + i) * 2, (double)a);
+        atomicAdd(stats + ((int64_t)cur_n * cout + i) * 2 + 1, (double)b);
+      }
+      s1[i] = s2[i] = 0.f;
+    }
+  }
+  __device__ __forceinline__ void sample(double* stats, int cout, int n) {
+    if (n != cur_n) {
+      if (cur_n >= 0) flush(stats, cout);
+      cur_n = n;
+    }
+  }
+  template <typename T>
+  __device__ __forceinline__ void add16(int co, const Pack<T, 8>& w0, const Pack<T, 8>& w1) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float v = to_f<T>(i < 8 ? w0.v[i] : w1.v[i - 8]);
+      s1[co + i] += v;
+      s2[co + i] = fmaf(v, v, s2[co + i]);
+    }
+  }
+};
+
+// Direct-store epilogue of both x-slab kernels (warps 0-3, thread = one GEMM row = 4 x-voxels of one (y, z) line): TMEM ->
+// +bias (-> +old value) -> T -> two 16-byte stores per 16 channels.  CB = 0: any Cout, no statistics.  CB = Cout / 16 in 1..3:
+// the (j, channel-block) loop is unrolled so that the partial sums of EpiStats stay in registers.  Used when the output does
+// not meet the alignment rules of the TMA-store epilogue below (or with B200_EPI_TMA=0).
+template <typename T, int CB>
+__device__ __forceinline__ void xslab_epilogue(const XslabParams& p, const float* __restrict__ bias, T* __restrict__ y, uint32_t tmem,
+                                               uint32_t bar_tfull, uint32_t bar_tempty) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = warp & 3;
+  const int row = q * 32 + lane;
+  const int ly = row & 15, lzr = row >> 4;
+  EpiStats<CB> es;
+  es.init();
+  const bool stats = CB > 0 && p.stats != nullptr;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    const int buf = p.nbuf == 2 ? (it & 1) : 0;
+    const uint32_t par = p.nbuf == 2 ? ((it >> 1) & 1) : (it & 1);
+    int n, z0, y0, g;
+    xslab_decode(p, tile, n, z0, y0, g);
+    if (stats) es.sample(p.stats, p.cout, n);
+    {
+      const long long c0 = p.dbg ? clock64() : 0;
+      mbar_wait(bar_tfull + 8 * buf, par);
+      if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 16 + 4] += clock64() - c0;
+    }
+    tc_fence_after();
+    for (int r = 0; r < ((p.ablate & 4) ? 0 : p.rt); ++r) {
+      const int gz = z0 + r * 8 + lzr, gy = y0 + ly;
+      const bool valid = gz < p.d && gy < p.h;
+      T* ybase = y + (int64_t)n * p.ysn + (int64_t)gz * p.ysd + (int64_t)gy * p.ysh + (int64_t)(4 * g) * p.ysw;
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.rt + r) * p.nt);
+      auto chunk = [&](int c0, int j, int co) {
+        uint32_t rr[16];
+        tmem_ld16(taddr + c0, rr);
+        tmem_ld_wait();
+        if (valid && 4 * g + j < p.w) {
+          T* yrow = ybase + (int64_t)j * p.ysw + co;
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(rr[i]) + (bias ? __ldg(bias + co + i) : 0.f);
+          if (p.accumulate) {
+            Pack<T, 8> o0 = *reinterpret_cast<const Pack<T, 8>*>(yrow);
+            Pack<T, 8> o1 = *reinterpret_cast<const Pack<T, 8>*>(yrow + 8);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              f[i] += to_f<T>(o0.v[i]);
+              f[8 + i] += to_f<T>(o1.v[i]);
+            }
+          }
+          Pack<T, 8> w0, w1;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            w0.v[i] = from_f<T>(f[i]);
+            w1.v[i] = from_f<T>(f[8 + i]);
+          }
+          *reinterpret_cast<Pack<T, 8>*>(yrow) = w0;
+          *reinterpret_cast<Pack<T, 8>*>(yrow + 8) = w1;
+          if (CB > 0 && stats) es.template add16<T>(CB > 0 ? co : 0, w0, w1);
+        }
+      };
+      if (CB > 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int cb = 0; cb < (CB > 0 ? CB : 1); ++cb) chunk((j * CB + cb) * 16, j, cb * 16);
+      } else {
+        int j = 0, co = 0;
+        for (int c0 = 0; c0 < p.nt; c0 += 16) {
+          chunk(c0, j, co);
+          co += 16;
+          if (co == p.cout) { co = 0; ++j; }
+        }
+      }
+    }
+    tc_fence_before();
+    mbar_arrive(bar_tempty + 8 * buf);
+  }
+  if (stats && es.cur_n >= 0) es.flush(p.stats, p.cout);
+}
+
+// TMA-store epilogue of the x-slab kernels.  The direct epilogue above has every thread store 16-byte pieces of its own
+// (y, z) line: 32 lines per warp instruction, i.e. 32 LSU wavefronts and 32 half-written sectors per store, and the
+// accumulate variant waits on a dependent global load per piece (B200: 16 -> 16 @128^3 0.280 ms plain, 0.435 ms
+// accumulating; 16 -> 48: 0.90 / 1.59 ms).  Here a (row tile, 16-channel block) box -- 128 lines x 4 voxels x 16 channels =
+// 16 KB -- is staged in shared memory in the layout of a rank-5 output map (C, W, H, D, N), box (16, 4, 16, 8, 1), and leaves
+// with ONE bulk tensor store; `accumulate` becomes the element-wise add of the TMA unit (cp.reduce.async.bulk.tensor .add:
+// the sum is formed in L2 on the rounded value, no read-back through the SM).  Two staging buffers alternate; TMEM is
+// released as soon as the last column block of a tile sits in registers.  Same shapes: 0.248 / 0.268 ms and 0.73 / 0.78 ms.
+template <typename T, int CB>
+__device__ __forceinline__ void xslab_epilogue_tma(const XslabParams& p, const CUtensorMap* tmy, const float* __restrict__ bias,
+                                                   uint32_t tmem, uint32_t bar_tfull, uint32_t bar_tempty, uint32_t stage) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = warp & 3;
+  const int row = q * 32 + lane;
+  const int ly = row & 15, lzr = row >> 4;
+  const int ncb = CB > 0 ? CB : p.cout / 16;
+  EpiStats<CB> es;
+  es.init();
+  const bool stats = CB > 0 && p.stats != nullptr;
+  const uint32_t swz = (uint32_t)row & p.epi_swz;
+  const uint32_t srow = stage + (uint32_t)row * 128u;
+  const bool issuer = threadIdx.x == 0;
+  uint32_t nbox = 0;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    const int buf = p.nbuf == 2 ? (it & 1) : 0;
+    const uint32_t par = p.nbuf == 2 ? ((it >> 1) & 1) : (it & 1);
+    int n, z0, y0, g;
+    xslab_decode(p, tile, n, z0, y0, g);
+    if (stats) es.sample(p.stats, p.cout, n);
+    mbar_wait(bar_tfull + 8 * buf, par);
+    tc_fence_after();
+    for (int r = 0; r < p.rt; ++r) {
+      const int gz = z0 + r * 8 + lzr, gy = y0 + ly;
+      const bool valid = gz < p.d && gy < p.h;
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.rt + r) * p.nt);
+      auto box = [&](int cb) {
+        const int co = cb * 16;
+        const uint32_t sbuf = srow + (nbox & 1u) * 16384u;
+#pragma unroll
+        for (int jp = 0; jp < 2; ++jp) {
+          uint32_t rr[2][16];
+          tmem_ld16(taddr + (uint32_t)(((2 * jp) * ncb + cb) * 16), rr[0]);
+          tmem_ld16(taddr + (uint32_t)(((2 * jp + 1) * ncb + cb) * 16), rr[1]);
+          tmem_ld_wait();
+          if (jp == 0) {
+            // staging buffer (nbox & 1) was last read by the store issued two boxes ago
+            if (issuer) bulk_wait_group_read<1>();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+          } else if (r == p.rt - 1 && cb == ncb - 1) {
+            tc_fence_before();
+            mbar_arrive(bar_tempty + 8 * buf);     // the whole accumulator of this tile has been read
+          }
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            const int j = 2 * jp + jj;
+            Pack<T, 8> w0, w1;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              w0.v[i] = from_f<T>(__uint_as_float(rr[jj][i]) + (bias ? __ldg(bias + co + i) : 0.f));
+              w1.v[i] = from_f<T>(__uint_as_float(rr[jj][8 + i]) + (bias ? __ldg(bias + co + 8 + i) : 0.f));
+            }
+            st_shared_v4(sbuf + (((uint32_t)(2 * j)) ^ swz) * 16u, *reinterpret_cast<const uint4*>(&w0));
+            st_shared_v4(sbuf + (((uint32_t)(2 * j + 1)) ^ swz) * 16u, *reinterpret_cast<const uint4*>(&w1));
+            if (CB > 0 && stats && valid && 4 * g + j < p.w) es.template add16<T>(CB > 0 ? co : 0, w0, w1);
+          }
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (issuer) {
+          if (p.accumulate) tma_reduce_add_5d(tmy, stage + (nbox & 1u) * 16384u, co, 4 * g, y0, z0 + r * 8, n);
+          else tma_store_5d(tmy, stage + (nbox & 1u) * 16384u, co, 4 * g, y0, z0 + r * 8, n);
+          bulk_commit_group();
+        }
+        ++nbox;
+      };
+      if (CB > 0) {
+#pragma unroll
+        for (int cb = 0; cb < (CB > 0 ? CB : 1); ++cb) box(cb);
+      } else {
+        for (int cb = 0; cb < ncb; ++cb) box(cb);
+      }
+    }
+  }
+  if (stats && es.cur_n >= 0) es.flush(p.stats, p.cout);
+  if (issuer) bulk_wait_group_read<0>();
+}
+
+template <typename T, int CB>
 __global__ void __launch_bounds__(32 * (6 + kSlabAWarps + kSlabBWarps), 1)
 conv_fprop_xslab_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid_constant__ CUtensorMap tmx32,
                         const __grid_constant__ CUtensorMap tmw64, const __grid_constant__ CUtensorMap tmw32,
-                        const float* __restrict__ bias, T* __restrict__ y, const XslabParams p) {
+                        const __grid_constant__ CUtensorMap tmy, const float* __restrict__ bias, T* __restrict__ y,
+                        const XslabParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t s_bar[4 * kMaxStages + 4];
   __shared__ uint32_t s_tmem;
@@ -541,6 +767,7 @@ conv_fprop_xslab_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid_
     for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, p.rt); mbar_init(bar_tempty + 8 * b, 128); }
     fence_barrier_init();
     tma_prefetch_desc(&tmx64); tma_prefetch_desc(&tmx32); tma_prefetch_desc(&tmw64); tma_prefetch_desc(&tmw32);
+    if (p.epi_tma) tma_prefetch_desc(&tmy);
   }
   if (warp == 4) tmem_alloc(smem_u32(&s_tmem), p.tmem_cols);
   tc_fence_before();
@@ -680,61 +907,8 @@ conv_fprop_xslab_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid_
     }
   } else {
     // =================================================================== epilogue
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int ly = row & 15, lzr = row >> 4;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const int buf = p.nbuf == 2 ? (it & 1) : 0;
-      const uint32_t par = p.nbuf == 2 ? ((it >> 1) & 1) : (it & 1);
-      int n, z0, y0, g;
-      decode(tile, n, z0, y0, g);
-      {
-        const long long c0 = p.dbg ? clock64() : 0;
-        mbar_wait(bar_tfull + 8 * buf, par);
-        if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 16 + 4] += clock64() - c0;
-      }
-      tc_fence_after();
-      for (int r = 0; r < ((p.ablate & 4) ? 0 : p.rt); ++r) {
-        const int gz = z0 + r * 8 + lzr, gy = y0 + ly;
-        const bool valid = gz < p.d && gy < p.h;
-        T* ybase = y + (int64_t)n * p.ysn + (int64_t)gz * p.ysd + (int64_t)gy * p.ysh + (int64_t)(4 * g) * p.ysw;
-        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.rt + r) * p.nt);
-        int j = 0, co = 0;
-        for (int c0 = 0; c0 < p.nt; c0 += 16) {
-          uint32_t rr[16];
-          tmem_ld16(taddr + c0, rr);
-          tmem_ld_wait();
-          if (valid && 4 * g + j < p.w) {
-            T* yrow = ybase + (int64_t)j * p.ysw + co;
-            float f[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(rr[i]) + (bias ? __ldg(bias + co + i) : 0.f);
-            if (p.accumulate) {
-              Pack<T, 8> o0 = *reinterpret_cast<const Pack<T, 8>*>(yrow);
-              Pack<T, 8> o1 = *reinterpret_cast<const Pack<T, 8>*>(yrow + 8);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                f[i] += to_f<T>(o0.v[i]);
-                f[8 + i] += to_f<T>(o1.v[i]);
-              }
-            }
-            Pack<T, 8> w0, w1;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              w0.v[i] = from_f<T>(f[i]);
-              w1.v[i] = from_f<T>(f[8 + i]);
-            }
-            *reinterpret_cast<Pack<T, 8>*>(yrow) = w0;
-            *reinterpret_cast<Pack<T, 8>*>(yrow + 8) = w1;
-          }
-          co += 16;
-          if (co == p.cout) { co = 0; ++j; }
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(bar_tempty + 8 * buf);
-    }
+    if (p.epi_tma) xslab_epilogue_tma<T, CB>(p, &tmy, bias, tmem, bar_tfull, bar_tempty, smem0 + p.epi_off);
+    else xslab_epilogue<T, CB>(p, bias, y, tmem, bar_tfull, bar_tempty);
   }
   tc_fence_before();
   __syncthreads();
@@ -750,11 +924,12 @@ conv_fprop_xslab_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid_
 // critical path of the N = 64 layers -- a stage hand-over costs ~250 cycles of dependent scalar instructions however
 // little it moves (B200_ABLATE / B200_DBG measurements, profiles/README.md) -- so a CTA tile takes kh * boxes (6 for
 // 16 -> 16) hand-overs here instead of kh * boxes * (kd + 1) (24) in conv_fprop_xslab_kernel.
-template <typename T>
+template <typename T, int CB>
 __global__ void __launch_bounds__(320, 1)
 conv_fprop_xslab1_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid_constant__ CUtensorMap tmx32,
                          const __grid_constant__ CUtensorMap tmw64, const __grid_constant__ CUtensorMap tmw32,
-                         const float* __restrict__ bias, T* __restrict__ y, const XslabParams p) {
+                         const __grid_constant__ CUtensorMap tmy, const float* __restrict__ bias, T* __restrict__ y,
+                         const XslabParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t s_bar[4 * kMaxStages + 4];
   __shared__ uint32_t s_tmem;
@@ -770,6 +945,7 @@ conv_fprop_xslab1_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid
     for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, p.rt); mbar_init(bar_tempty + 8 * b, 128); }
     fence_barrier_init();
     tma_prefetch_desc(&tmx64); tma_prefetch_desc(&tmx32); tma_prefetch_desc(&tmw64); tma_prefetch_desc(&tmw32);
+    if (p.epi_tma) tma_prefetch_desc(&tmy);
   }
   if (warp == 4) tmem_alloc(smem_u32(&s_tmem), p.tmem_cols);
   tc_fence_before();
@@ -872,57 +1048,8 @@ conv_fprop_xslab1_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid
     }
   } else {
     // =================================================================== epilogue
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int ly = row & 15, lzr = row >> 4;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const int buf = p.nbuf == 2 ? (it & 1) : 0;
-      const uint32_t par = p.nbuf == 2 ? ((it >> 1) & 1) : (it & 1);
-      int n, z0, y0, g;
-      decode(tile, n, z0, y0, g);
-      mbar_wait(bar_tfull + 8 * buf, par);
-      tc_fence_after();
-      for (int r = 0; r < p.rt; ++r) {
-        const int gz = z0 + r * 8 + lzr, gy = y0 + ly;
-        const bool valid = gz < p.d && gy < p.h;
-        T* ybase = y + (int64_t)n * p.ysn + (int64_t)gz * p.ysd + (int64_t)gy * p.ysh + (int64_t)(4 * g) * p.ysw;
-        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.rt + r) * p.nt);
-        int j = 0, co = 0;
-        for (int c0 = 0; c0 < p.nt; c0 += 16) {
-          uint32_t rr[16];
-          tmem_ld16(taddr + c0, rr);
-          tmem_ld_wait();
-          if (valid && 4 * g + j < p.w) {
-            T* yrow = ybase + (int64_t)j * p.ysw + co;
-            float f[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(rr[i]) + (bias ? __ldg(bias + co + i) : 0.f);
-            if (p.accumulate) {
-              Pack<T, 8> o0 = *reinterpret_cast<const Pack<T, 8>*>(yrow);
-              Pack<T, 8> o1 = *reinterpret_cast<const Pack<T, 8>*>(yrow + 8);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                f[i] += to_f<T>(o0.v[i]);
-                f[8 + i] += to_f<T>(o1.v[i]);
-              }
-            }
-            Pack<T, 8> w0, w1;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              w0.v[i] = from_f<T>(f[i]);
-              w1.v[i] = from_f<T>(f[8 + i]);
-            }
-            *reinterpret_cast<Pack<T, 8>*>(yrow) = w0;
-            *reinterpret_cast<Pack<T, 8>*>(yrow + 8) = w1;
-          }
-          co += 16;
-          if (co == p.cout) { co = 0; ++j; }
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(bar_tempty + 8 * buf);
-    }
+    if (p.epi_tma) xslab_epilogue_tma<T, CB>(p, &tmy, bias, tmem, bar_tfull, bar_tempty, smem0 + p.epi_off);
+    else xslab_epilogue<T, CB>(p, bias, y, tmem, bar_tfull, bar_tempty);
   }
   tc_fence_before();
   __syncthreads();
@@ -1292,11 +1419,11 @@ static int conv_fprop_umma2_v(const ActView& x, const void* w, const float* bias
   int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
   if (x.dtype == B200_BF16) {
     auto kern = conv_fprop_umma2_kernel<__nv_bfloat16>;
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    B200_CUDA(raise_dyn_smem_cap(kern));
     kern<<<grid, 288, smem, st>>>((const __nv_bfloat16*)x.data, (const __nv_bfloat16*)w, bias, (__nv_bfloat16*)y.data, p);
   } else {
     auto kern = conv_fprop_umma2_kernel<__half>;
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    B200_CUDA(raise_dyn_smem_cap(kern));
     kern<<<grid, 288, smem, st>>>((const __half*)x.data, (const __half*)w, bias, (__half*)y.data, p);
   }
   B200_LAUNCH_CHECK();
@@ -1374,11 +1501,11 @@ static int conv_fprop_umma_impl(const ActView& xv, const void* w, const float* b
   int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
   if (x->dtype == B200_BF16) {
     auto kern = conv_fprop_umma_kernel<__nv_bfloat16>;
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    B200_CUDA(raise_dyn_smem_cap(kern));
     kern<<<grid, 224, smem, st>>>(tx, tw, pm, bias, (__nv_bfloat16*)y->data, p);
   } else {
     auto kern = conv_fprop_umma_kernel<__half>;
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    B200_CUDA(raise_dyn_smem_cap(kern));
     kern<<<grid, 224, smem, st>>>(tx, tw, pm, bias, (__half*)y->data, p);
   }
   B200_LAUNCH_CHECK();
@@ -1425,9 +1552,30 @@ static int xslab_mode() {
   return mode;
 }
 
+// The fused channel statistics are offered for Cout = 16 only.  Measured on the B200 (tools/epi_micro.py, @128^3 / @64^3 x4):
+// +0.027 ms on 16 -> 16 against 0.061 ms for b200_channel_sums, but +0.032 ms on 32 -> 32 @64^3 (stand-alone: 0.022 ms) and
+// +0.27 ms on 16 -> 48 -- 64 / 96 running sums per thread push the epilogue warps past the 168-register budget.
+static bool xslab_stats_ok(const ActView& y, const double* stats) {
+  if (!stats) return false;
+  if (y.c != 16) return false;
+  return getenv("B200_NO_EPI_STATS") == nullptr;
+}
+
 static int conv_fprop_xslab_v(const ActView& x, const void* w, const float* bias, const ActView& y, int kd, int kh, int kw,
-                              int accumulate, cudaStream_t st) {
+                              int accumulate, cudaStream_t st, double* stats = nullptr, int* stats_applied = nullptr) {
   XslabParams p{};
+  // TMA-store epilogue (default): needs a 16-byte aligned output whose voxel pitch is a multiple of 16 bytes.  B200_EPI_TMA=0
+  // selects the direct-store epilogue, B200_EPI_SWZ = 128 (default) / 64 / 32 / 0 the swizzle of the staging buffers.
+  static const int epi_env = getenv("B200_EPI_TMA") ? atoi(getenv("B200_EPI_TMA")) : 1;
+  // (SWIZZLE_128B with the 32-byte inner box faults on the B200 -- illegal memory access; 32B is the box's own span)
+  static const int epi_swz_env = getenv("B200_EPI_SWZ") ? atoi(getenv("B200_EPI_SWZ")) : 32;
+  p.epi_tma = (epi_env != 0 && y.c % 16 == 0 && y.sw % 8 == 0 && y.sh % 8 == 0 && y.sd % 8 == 0 && y.sn % 8 == 0 && aligned16(y.data)) ? 1 : 0;
+  p.epi_swz = epi_swz_env == 128 ? 7u : (epi_swz_env == 64 ? 3u : (epi_swz_env == 32 ? 1u : 0u));
+  // the element-wise add of the TMA unit never shows the final value to the SM: no fused reduction on accumulating launches
+  const int cb = (xslab_stats_ok(y, stats) && !(p.epi_tma && accumulate)) ? y.c / 16 : 0;
+  p.stats = cb ? stats : nullptr;
+  if (stats_applied) *stats_applied = cb ? 1 : 0;
+  const uint32_t ring_budget = p.epi_tma ? 188u * 1024u : 200u * 1024u;
   p.n = x.n; p.d = x.d; p.h = x.h; p.w = x.w; p.cin = x.c; p.cout = y.c;
   p.kd = kd; p.kh = kh; p.kw = kw;
   p.nt = 4 * y.c;
@@ -1444,7 +1592,7 @@ static int conv_fprop_xslab_v(const ActView& x, const void* w, const float* bias
   // split ~200 KB between the two rings: at least 2 slabs, the rest for weight tiles (3..6)
   int a_st = 3, b_st;
   for (;;) {
-    b_st = (int)((200u * 1024u - (uint32_t)a_st * p.a_bytes) / p.b_bytes);
+    b_st = (int)((ring_budget - (uint32_t)a_st * p.a_bytes) / p.b_bytes);
     if (b_st >= 3 || a_st == 2) break;
     --a_st;
   }
@@ -1484,38 +1632,66 @@ static int conv_fprop_xslab_v(const ActView& x, const void* w, const float* bias
   rc = make_matrix_tmap(&tw32, w, x.dtype, p.nt, ktot, p.nt, 32);
   if (rc) return rc;
 
+  // output map of the TMA-store epilogue: (C, W, H, D, N), box = 16 channels x 4 voxels x 16 rows x 8 lines
+  CUtensorMap ty = tx64;
+  if (p.epi_tma) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    const cuuint64_t yd[5] = {(cuuint64_t)y.c, (cuuint64_t)y.w, (cuuint64_t)y.h, (cuuint64_t)y.d, (cuuint64_t)y.n};
+    const cuuint64_t ys[4] = {(cuuint64_t)y.sw * 2, (cuuint64_t)y.sh * 2, (cuuint64_t)y.sd * 2, (cuuint64_t)y.sn * 2};
+    const cuuint32_t yb[5] = {16, 4, 16, 8, 1};
+    const cuuint32_t ye[5] = {1, 1, 1, 1, 1};
+    const CUtensorMapSwizzle sw = p.epi_swz == 7u ? CU_TENSOR_MAP_SWIZZLE_128B : (p.epi_swz == 3u ? CU_TENSOR_MAP_SWIZZLE_64B
+                                  : (p.epi_swz == 1u ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE));
+    CUresult r = fn(&ty, tm_dtype(y.dtype), 5, y.data, yd, ys, yb, ye, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(xslab output) failed with %d (c=%d sw=%lld)", (int)r, y.c, (long long)y.sw);
+  }
+
   int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
   // narrow layers: slab box + its kd weight tiles in ONE stage (conv_fprop_xslab1_kernel) when >= 3 such stages fit
   const uint32_t uni_bytes = (uint32_t)p.zl * 16u * 128u + (uint32_t)kd * (uint32_t)p.nt * 128u;
   static const bool allow_unified = !(getenv("B200_XSLAB_UNIFIED") && strcmp(getenv("B200_XSLAB_UNIFIED"), "0") == 0);
-  if (allow_unified && kd <= 3 && 3u * uni_bytes <= 200u * 1024u && !p.ablate && !p.dbg) {
+  if (allow_unified && kd <= 3 && 3u * uni_bytes <= ring_budget && !p.ablate && !p.dbg) {
     p.a_bytes = uni_bytes;
-    p.a_stages = (int)((200u * 1024u) / uni_bytes);
+    p.a_stages = (int)(ring_budget / uni_bytes);
     if (p.a_stages > 6) p.a_stages = 6;
-    const size_t smem1 = (size_t)p.a_stages * p.a_bytes + 1024;
-    if (x.dtype == B200_BF16) {
-      auto kern = conv_fprop_xslab1_kernel<__nv_bfloat16>;
-      B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-      kern<<<grid, 320, smem1, st>>>(tx64, tx32, tw64, tw32, bias, (__nv_bfloat16*)y.data, p);
-    } else {
-      auto kern = conv_fprop_xslab1_kernel<__half>;
-      B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-      kern<<<grid, 320, smem1, st>>>(tx64, tx32, tw64, tw32, bias, (__half*)y.data, p);
-    }
+    p.epi_off = ((uint32_t)p.a_stages * p.a_bytes + 1023u) & ~1023u;
+    const size_t smem1 = (size_t)p.epi_off + (p.epi_tma ? 32768u : 0u) + 1024;
+#define XSLAB1_LAUNCH(TT, CBV)                                                                            \
+  {                                                                                                      \
+    auto kern = conv_fprop_xslab1_kernel<TT, CBV>;                                                       \
+    B200_CUDA(raise_dyn_smem_cap(kern));                                                                 \
+    kern<<<grid, 320, smem1, st>>>(tx64, tx32, tw64, tw32, ty, bias, (TT*)y.data, p);                        \
+  }
+#define XSLAB1_BY_CB(TT)                                                                                 \
+  switch (cb) {                                                                                          \
+    case 1: XSLAB1_LAUNCH(TT, 1) break;                                                                  \
+    default: XSLAB1_LAUNCH(TT, 0) break;                                                                 \
+  }
+    if (x.dtype == B200_BF16) XSLAB1_BY_CB(__nv_bfloat16) else XSLAB1_BY_CB(__half)
+#undef XSLAB1_BY_CB
+#undef XSLAB1_LAUNCH
     B200_LAUNCH_CHECK();
     return B200_OK;
   }
   B200_CHECK_ARG(p.xoff == 0, "conv_fprop(xslab): image-fed layers need the unified-stage kernel");
-  const size_t smem = (size_t)p.b_off + (size_t)p.b_stages * p.b_bytes + 1024;
-  if (x.dtype == B200_BF16) {
-    auto kern = conv_fprop_xslab_kernel<__nv_bfloat16>;
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    kern<<<grid, 32 * (6 + kSlabAWarps + kSlabBWarps), smem, st>>>(tx64, tx32, tw64, tw32, bias, (__nv_bfloat16*)y.data, p);
-  } else {
-    auto kern = conv_fprop_xslab_kernel<__half>;
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    kern<<<grid, 32 * (6 + kSlabAWarps + kSlabBWarps), smem, st>>>(tx64, tx32, tw64, tw32, bias, (__half*)y.data, p);
+  p.epi_off = (p.b_off + (uint32_t)p.b_stages * p.b_bytes + 1023u) & ~1023u;
+  const size_t smem = (size_t)p.epi_off + (p.epi_tma ? 32768u : 0u) + 1024;
+  const int threads = 32 * (6 + kSlabAWarps + kSlabBWarps);
+#define XSLAB_LAUNCH(TT, CBV)                                                                             \
+  {                                                                                                      \
+    auto kern = conv_fprop_xslab_kernel<TT, CBV>;                                                        \
+    B200_CUDA(raise_dyn_smem_cap(kern));                                                                 \
+    kern<<<grid, threads, smem, st>>>(tx64, tx32, tw64, tw32, ty, bias, (TT*)y.data, p);                     \
   }
+#define XSLAB_BY_CB(TT)                                                                                  \
+  switch (cb) {                                                                                          \
+    case 1: XSLAB_LAUNCH(TT, 1) break;                                                                   \
+    default: XSLAB_LAUNCH(TT, 0) break;                                                                  \
+  }
+  if (x.dtype == B200_BF16) XSLAB_BY_CB(__nv_bfloat16) else XSLAB_BY_CB(__half)
+#undef XSLAB_BY_CB
+#undef XSLAB_LAUNCH
   B200_LAUNCH_CHECK();
   if (p.dbg) {
     long long h[16 * 148];
@@ -1539,9 +1715,11 @@ static int conv_fprop_xslab_v(const ActView& x, const void* w, const float* bias
 }
 
 int conv_fprop_xfold_v(const ActView& x, const void* w, const float* bias, const ActView& y, int kd, int kh, int kw,
-                       int accumulate, cudaStream_t st) {
+                       int accumulate, cudaStream_t st, double* stats = nullptr, int* stats_applied = nullptr) {
   B200_CHECK_ARG(conv_xfold_ok(x, y, kd, kh, kw), "conv_fprop(xfold): unsupported operands");
-  if (xslab_mode() && kd == 3 && x.d >= 8 && x.h >= 16) return conv_fprop_xslab_v(x, w, bias, y, kd, kh, kw, accumulate, st);
+  if (stats_applied) *stats_applied = 0;
+  if (xslab_mode() && kd == 3 && x.d >= 8 && x.h >= 16)
+    return conv_fprop_xslab_v(x, w, bias, y, kd, kh, kw, accumulate, st, stats, stats_applied);
   XfoldParams p{};
   p.n = x.n; p.d = x.d; p.h = x.h; p.w = x.w; p.cin = x.c; p.cout = y.c;
   p.kd = kd; p.kh = kh; p.kw = kw;
@@ -1591,11 +1769,11 @@ int conv_fprop_xfold_v(const ActView& x, const void* w, const float* bias, const
   int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
   if (x.dtype == B200_BF16) {
     auto kern = conv_fprop_xfold_kernel<__nv_bfloat16>;
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    B200_CUDA(raise_dyn_smem_cap(kern));
     kern<<<grid, 224, smem, st>>>(tx64, tx32, tw64, tw32, bias, (__nv_bfloat16*)y.data, p);
   } else {
     auto kern = conv_fprop_xfold_kernel<__half>;
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    B200_CUDA(raise_dyn_smem_cap(kern));
     kern<<<grid, 224, smem, st>>>(tx64, tx32, tw64, tw32, bias, (__half*)y.data, p);
   }
   B200_LAUNCH_CHECK();
@@ -1611,6 +1789,24 @@ int conv_fprop_xfold(const b200_tensor* x, const void* w, const float* bias, con
                      int accumulate, cudaStream_t st) {
   return sm100::conv_fprop_xfold_v(sm100::view_of(x), w, bias, sm100::view_of(y), kd, kh, kw, accumulate, st);
 }
+}  // namespace b200
+
+B200_EXPORT int b200_conv_fprop_stats(const b200_tensor* x, const void* w_packed, const float* bias, const b200_tensor* y,
+                                      int32_t kd, int32_t kh, int32_t kw, int32_t accumulate, double* sums, int32_t* applied,
+                                      void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(x && y && w_packed && sums && applied, "conv_fprop_stats: null pointer");
+  B200_CHECK_ARG(check_tensor(x, "conv_fprop_stats.x") && check_tensor(y, "conv_fprop_stats.y"), "%s", b200_last_error());
+  B200_CHECK_ARG(conv_fprop_xfold_supported(x, y, kd, kh, kw),
+                 "conv_fprop_stats: operands not supported by the x-folded kernel (query b200_conv_impl_query)");
+  int ok = 0;
+  int rc = sm100::conv_fprop_xfold_v(sm100::view_of(x), w_packed, bias, sm100::view_of(y), kd, kh, kw, accumulate, (cudaStream_t)stream,
+                                     sums, &ok);
+  *applied = ok;
+  return rc;
+}
+
+namespace b200 {
 int pack_weight_xfold(const float* w, void* packed, int dtype, int cout, int cin, int kd, int kh, int kw, int flip,
                       cudaStream_t st) {
   const int CO = flip ? cin : cout, CI = flip ? cout : cin;
@@ -2522,11 +2718,11 @@ static int conv_wgrad_xslab_v(const ActView& x, const ActView& dy, float* dw, in
   const size_t smem = (size_t)p.a_off + (size_t)p.a_stages * 4u * p.sa_bytes + 1024;
   if (x.dtype == B200_BF16) {
     auto kern = conv_wgrad_xslab_kernel<__nv_bfloat16>;
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    B200_CUDA(raise_dyn_smem_cap(kern));
     kern<<<grid, 320, smem, st>>>(tx, ty, dw, p);
   } else {
     auto kern = conv_wgrad_xslab_kernel<__half>;
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    B200_CUDA(raise_dyn_smem_cap(kern));
     kern<<<grid, 320, smem, st>>>(tx, ty, dw, p);
   }
   B200_LAUNCH_CHECK();
@@ -2602,11 +2798,11 @@ int conv_wgrad_xfold_v(const ActView& x, const ActView& dy, float* dw, int kd, i
   const size_t smem = (size_t)p.a_off + (size_t)p.a_stages * kXBlockBytes + 1024;
   if (x.dtype == B200_BF16) {
     auto kern = conv_wgrad_xfold_kernel<__nv_bfloat16>;
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    B200_CUDA(raise_dyn_smem_cap(kern));
     kern<<<grid, 320, smem, st>>>(tx, ty, dw, p);
   } else {
     auto kern = conv_wgrad_xfold_kernel<__half>;
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    B200_CUDA(raise_dyn_smem_cap(kern));
     kern<<<grid, 320, smem, st>>>(tx, ty, dw, p);
   }
   B200_LAUNCH_CHECK();
@@ -2716,11 +2912,11 @@ static int conv_wgrad_umma_impl(const ActView& xv, const ActView& dyv, float* dw
     WgradParams2 pp{p, x->sw, x->sh, x->sd, x->sn, dy->sw, dy->sh, dy->sd, dy->sn};
     if (x->dtype == B200_BF16) {
       auto kern = conv_wgrad_umma2_kernel<__nv_bfloat16>;
-      B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+      B200_CUDA(raise_dyn_smem_cap(kern));
       kern<<<grid, 288, smem, st>>>((const __nv_bfloat16*)x->data, (const __nv_bfloat16*)dy->data, dw, pp);
     } else {
       auto kern = conv_wgrad_umma2_kernel<__half>;
-      B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+      B200_CUDA(raise_dyn_smem_cap(kern));
       kern<<<grid, 288, smem, st>>>((const __half*)x->data, (const __half*)dy->data, dw, pp);
     }
     B200_LAUNCH_CHECK();
@@ -2739,11 +2935,11 @@ static int conv_wgrad_umma_impl(const ActView& xv, const ActView& dyv, float* dw
   }
   if (x->dtype == B200_BF16) {
     auto kern = conv_wgrad_umma_kernel<__nv_bfloat16>;
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    B200_CUDA(raise_dyn_smem_cap(kern));
     kern<<<grid, 320, smem, st>>>(tx, tdy, pm, dw, p);
   } else {
     auto kern = conv_wgrad_umma_kernel<__half>;
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    B200_CUDA(raise_dyn_smem_cap(kern));
     kern<<<grid, 320, smem, st>>>(tx, tdy, pm, dw, p);
   }
   B200_LAUNCH_CHECK();

@@ -26,7 +26,7 @@ from .. import _lib, ops
 class TT:
     """A tensor on the tape: data + lazily allocated gradient; may be a channel slice of a parent buffer."""
 
-    __slots__ = ("data", "_grad", "_ready", "parent", "off", "requires_grad", "padded")
+    __slots__ = ("data", "_grad", "_ready", "parent", "off", "requires_grad", "padded", "sums")
 
     def __init__(self, data: torch.Tensor, requires_grad: bool = True, parent: "Optional[TT]" = None, off: int = 0):
         self.data = data
@@ -36,6 +36,7 @@ class TT:
         self.off = off
         self.requires_grad = requires_grad
         self.padded = None          # zero-padded 16-channel copy (network inputs with < 16 channels, see Tape.conv)
+        self.sums = None            # (N, C, 2) float64 channel sums left by the producing convolution's epilogue (Tape.conv)
 
     @property
     def shape(self):
@@ -99,6 +100,8 @@ class Tape:
         self.impl = conv_impl
         self.steps: List[Callable[[], None]] = []
         self.use_xfold = os.environ.get("B200_XFOLD", "1") != "0"
+        # conv -> norm: channel sums of the normalisation produced by the convolution epilogue (x-slab kernels)
+        self.fuse_stats = os.environ.get("B200_FUSE_STATS", "1") != "0"
         self.param_grads: Dict[torch.nn.Parameter, torch.Tensor] = {}
         self._packed: Dict[Tuple, torch.Tensor] = {}
         self._pad16: Dict[int, torch.Tensor] = {}
@@ -149,8 +152,11 @@ class Tape:
         ops.binary(t, None, dense, ops.OP_COPY)
         return dense
 
-    def _conv_launch(self, x: torch.Tensor, w, flip: bool, bias, y: torch.Tensor, k, accumulate: bool, wkey=None):
-        """Pick the kernel family for (x -> y) and launch it with the matching weight packing."""
+    def _conv_launch(self, x: torch.Tensor, w, flip: bool, bias, y: torch.Tensor, k, accumulate: bool, wkey=None,
+                     stats: bool = False) -> Optional[torch.Tensor]:
+        """Pick the kernel family for (x -> y) and launch it with the matching weight packing.  `stats` asks for the channel
+        sums of y from the epilogue; returns the (N, C, 2) float64 sums when the kernel produced them, else None (the
+        normalisation then runs the stand-alone reduction)."""
         impl = self.impl
         wkey = w if wkey is None else wkey
         if impl == _lib.IMPL_AUTO and self.dtype != torch.float32 and self.use_xfold:
@@ -169,7 +175,12 @@ class Tape:
                         ops.conv_fprop(x, wp, None if bias is None else bias[a:b], y[..., a:b], k, accumulate=accumulate,
                                        impl=_lib.IMPL_XFOLD)
                     return
-        ops.conv_fprop(x, self._pack(wkey, flip, impl == _lib.IMPL_XFOLD, wsrc=w), bias, y, k, accumulate=accumulate, impl=impl)
+        wp = self._pack(wkey, flip, impl == _lib.IMPL_XFOLD, wsrc=w)
+        if stats and impl == _lib.IMPL_XFOLD and self.fuse_stats and not accumulate and y.shape[4] == 16:
+            sums = torch.zeros(y.shape[0] * y.shape[4] * 2, dtype=torch.float64, device=y.device)
+            return sums if ops.conv_fprop_stats(x, wp, bias, y, k, sums, accumulate=accumulate) else None
+        ops.conv_fprop(x, wp, bias, y, k, accumulate=accumulate, impl=impl)
+        return None
 
     @staticmethod
     def _k3(k) -> Tuple[int, int, int]:
@@ -183,8 +194,9 @@ class Tape:
         return t if t.dtype == torch.float32 else t.float()
 
     # --------------------------------------------------------------------------------------------- ops
-    def conv(self, x: TT, mod: torch.nn.Module, out: Optional[TT] = None, accumulate: bool = False) -> TT:
-        """y = conv(x) + bias, stride 1, 'same' padding.  `accumulate` adds into `out` (residual epilogue)."""
+    def conv(self, x: TT, mod: torch.nn.Module, out: Optional[TT] = None, accumulate: bool = False, stats: bool = False) -> TT:
+        """y = conv(x) + bias, stride 1, 'same' padding.  `accumulate` adds into `out` (residual epilogue).  `stats`: the
+        result goes straight into a normalisation -- leave its channel sums in `out.sums` when the kernel can."""
         w, b = mod.weight, mod.bias
         k = self._k3(w.shape[2:])
         cout, cin = w.shape[0], w.shape[1]
@@ -198,7 +210,7 @@ class Tape:
         if (cin < 16 and cout % 16 == 0 and not x.requires_grad and self.dtype != torch.float32
                 and self.impl != _lib.IMPL_SIMT and not narrow):
             return self._conv_padded_input(x, mod, out, accumulate, k, cout, cin)
-        self._conv_launch(x.data, w, False, self._f32(b), out.data, k, accumulate)
+        out.sums = self._conv_launch(x.data, w, False, self._f32(b), out.data, k, accumulate, stats=stats and not accumulate)
         if self.training:
             def bwd(x=x, out=out, w=w, b=b, k=k, cout=cout, cin=cin, narrow=narrow):
                 dy = out.grad() if (narrow and k == (1, 1, 1)) else self._dense_for_xfold(out.grad(), cin)
@@ -283,6 +295,7 @@ class Tape:
         act = (act or "none").lower()
         if norm is None and act in ("none", "linear"):
             return x
+        sums, x.sums = x.sums, None
         if out is None:
             out = self.new(x.data, x.c)
         if norm is None:
@@ -306,7 +319,7 @@ class Tape:
                 sync = isinstance(norm, torch.nn.SyncBatchNorm) and norm.training
                 pg = getattr(norm, "process_group", None)
                 st = ops.norm_stats(x.data, groups, g32, b32, eps=float(norm.eps), batch_stats=True,
-                                    sync_group=(pg if pg is not None else True) if sync else False)
+                                    sync_group=(pg if pg is not None else True) if sync else False, sums=sums)
                 if norm.training and norm.track_running_stats and norm.running_mean is not None:
                     if norm.momentum is None:
                         raise NotImplementedError("BatchNorm(momentum=None) (cumulative average) is not implemented by the B200 "
@@ -320,7 +333,7 @@ class Tape:
                     raise NotImplementedError("gradients through eval-mode BatchNorm are not implemented by the B200 engine")
                 st = ops.bn_eval_stats(x.data, norm.running_mean, norm.running_var, g32, b32, float(norm.eps))
         else:
-            st = ops.norm_stats(x.data, groups, g32, b32, eps=float(norm.eps))
+            st = ops.norm_stats(x.data, groups, g32, b32, eps=float(norm.eps), sums=sums)
         ops.scale_shift_act(x.data, st.scale, st.shift, act, out.data)
         if self.training and st.mean is not None:
             def bwd(x=x, out=out, st=st, gamma=gamma, beta=beta, g32=g32, b32=b32, act=act):

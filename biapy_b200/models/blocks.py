@@ -186,7 +186,7 @@ class ConvBlock(nn.Module):
             elif norm is None and (act in (None, "none")):
                 y = tape.conv(x, conv)
             else:
-                y = tape.norm_act(tape.conv(x, conv), norm, act)
+                y = tape.norm_act(tape.conv(x, conv, stats=norm is not None), norm, act)
             return tape.dropout(y, self.dropout_p, out=out)
         if self.order == "norm_act_conv":
             h = tape.norm_act(x, norm, act)
@@ -198,7 +198,8 @@ class ConvBlock(nn.Module):
                 return tape.conv(x, conv, out=into, accumulate=True)
             return tape.conv(x, conv, out=out)
         assert into is None, "only a bare convolution can be accumulated into a residual"
-        return tape.norm_act(tape.conv(x, conv), norm, act, out=out)
+        # conv -> norm: the channel sums of the normalisation come out of the convolution's epilogue when the kernel has one
+        return tape.norm_act(tape.conv(x, conv, stats=norm is not None), norm, act, out=out)
 
     @property
     def ends_with_bare_conv(self) -> bool:
@@ -236,7 +237,7 @@ class AttentionBlock(nn.Module):
         self._has_norm = norm != "none"
 
     def run(self, tape: Tape, g: TT, x: TT, out: Optional[TT] = None) -> TT:
-        g1 = tape.conv(g, self.w_g[0])
+        g1 = tape.conv(g, self.w_g[0], stats=self._has_norm)
         if self._has_norm:
             g1 = tape.norm_act(g1, self.w_g[1], None)
         x1 = tape.conv(x, self.w_x[0])

@@ -138,6 +138,24 @@ def conv_fprop(x, w_packed, bias, y, k: Sequence[int], residual=None, accumulate
     return y
 
 
+def conv_fprop_stats(x, w_packed_xfold, bias, y, k: Sequence[int], sums: torch.Tensor, accumulate=False) -> bool:
+    """x-folded convolution with the channel statistics of its output fused into the epilogue (`b200_conv_fprop_stats`):
+    ``sums[n][c] += (sum y, sum y^2)`` -- what `b200_channel_sums` would compute from y.  Returns True when the kernel
+    produced them; on False `sums` is untouched (the convolution still ran)."""
+    label = flops = nbytes = None
+    if PROFILE is not None:
+        vox = x.shape[0] * x.shape[1] * x.shape[2] * x.shape[3]
+        flops = 2.0 * vox * x.shape[-1] * y.shape[-1] * k[0] * k[1] * k[2]
+        nbytes = vox * (x.shape[-1] + y.shape[-1] * (2 if accumulate else 1)) * x.element_size()
+        label = "conv_fprop_xfold"
+        if PROFILE_SHAPES:
+            label += f" {x.shape[-1]}->{y.shape[-1]} k{k[0]}{k[1]}{k[2]} @{x.shape[1]}x{x.shape[2]}x{x.shape[3]} +stats"
+    applied = C.c_int32(0)
+    _launch_timed(label, flops, nbytes, "b200_conv_fprop_stats", _ref(x), _ptr(w_packed_xfold), _ptr(bias), _ref(y), k[0], k[1], k[2],
+                  1 if accumulate else 0, _ptr(sums), C.byref(applied), stream_ptr())
+    return bool(applied.value)
+
+
 def conv_wgrad(x, dy, cout: int, cin: int, k: Sequence[int], dw_out: torch.Tensor, dbias_out: Optional[torch.Tensor],
                accumulate=False, impl=_lib.IMPL_AUTO):
     """dw_out: (Cout, Cin, *k) fp32; dbias_out: (Cout,) fp32, must be zero-initialised unless accumulate."""
@@ -251,12 +269,15 @@ def _sync_world(sync_group) -> int:
     return torch.distributed.get_world_size(None if sync_group is True else sync_group)
 
 
-def norm_stats(x, groups: int, gamma, beta, eps: float = 1e-5, batch_stats: bool = False, sync_group=False) -> NormStats:
+def norm_stats(x, groups: int, gamma, beta, eps: float = 1e-5, batch_stats: bool = False, sync_group=False,
+               sums: Optional[torch.Tensor] = None) -> NormStats:
     """`sync_group`: False, True (default process group) or a process group -- SyncBatchNorm: the per-rank channel sums
-    are all-reduced before the statistics are finalised (equal per-rank batch sizes assumed, as under DDP)."""
+    are all-reduced before the statistics are finalised (equal per-rank batch sizes assumed, as under DDP).
+    `sums`: the (N, C, 2) float64 channel sums of x when the producing convolution already reduced them in its epilogue."""
     n, d, h, w, c = x.shape
-    sums = torch.zeros(n * c * 2, dtype=torch.float64, device=x.device)
-    _launch("b200_channel_sums", _ref(x), _ptr(sums), stream_ptr(), shape=x.shape)
+    if sums is None:
+        sums = torch.zeros(n * c * 2, dtype=torch.float64, device=x.device)
+        _launch("b200_channel_sums", _ref(x), _ptr(sums), stream_ptr(), shape=x.shape)
     world = _sync_world(sync_group) if batch_stats else 1
     if world > 1:
         # batch statistics only need the sum over samples: reduce the (C, 2) totals, not the per-sample table

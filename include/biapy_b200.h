@@ -129,6 +129,22 @@ int b200_chunk_insert(const void* patches, int32_t dtype_in, int64_t n, int64_t 
                       void* out, int32_t dtype_out, int64_t D, int64_t H, int64_t W, const int64_t* desc, int32_t mode,
                       void* stream);
 
+/* ---------------------------------------------------------------------------------- test-time augmentation
+ * Signed axis permutations of biapy/data/post_processing/tta.py:65-260 (AxisTransform: output axis a comes from input axis
+ * perm[a], reversed when sign[a] == -1; axes are (z, y, x), 2D uses D = 1 with perm[0] = 0) as used by
+ * ensemble_predictions (biapy/data/post_processing/post_processing.py:1386-1555) for scalar predictions (tta_spec = None).
+ * b200_orient_apply  = AxisTransform.apply (tta.py:158-166) on every batch element of src, fused with the front padding of
+ *   _pad_for_orientations (post_processing.py:1285-1339): dst dims = (src dims + pad_before) permuted; pad_mode as in
+ *   b200_crop_gather (0 constant, 1 reflect, 3 edge).  src, dst: same dtype.
+ * b200_orient_reduce = steps 4-5 of ensemble_predictions: pred holds one prediction per orientation (batch axis = orientation,
+ *   perms / signs: [N][3], the FORWARD transforms), each is read through its inverse, reduced with mode 0 mean / 1 min / 2 max
+ *   (_reduce_orientations :1349-1383; the mean adds the orientations in order in float32 and divides once, like np.mean)
+ *   and the front padding is cropped (_crop_padding :1342-1346).  out: float32, batch 1, dims = pred dims - pad_before.    */
+int b200_orient_apply(const b200_tensor* src, const b200_tensor* dst, const int32_t* perm, const int32_t* sign,
+                      const int32_t* pad_before, int32_t pad_mode, void* stream);
+int b200_orient_reduce(const b200_tensor* pred, const int32_t* perms, const int32_t* signs, int32_t mode,
+                       const int32_t* pad_before, const b200_tensor* out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------- convolution
  * nn.Conv3d / nn.Conv2d, stride 1, padding='same', bias (biapy/models/blocks.py:154,157,1372; unet.py:347).
  * Weights are packed once per step from the PyTorch layout (Cout,Cin,kd,kh,kw) fp32:
@@ -144,6 +160,15 @@ int b200_conv_fprop(const b200_tensor* x, const void* w_packed, const float* bia
  * Both outputs must be zero-initialised by the caller (they are accumulated with atomics).                  */
 int b200_conv_wgrad(const b200_tensor* x, const b200_tensor* dy, float* dw_packed, float* dbias,
                     int32_t kd, int32_t kh, int32_t kw, int32_t impl, void* stream);
+/* Convolution (x-folded kernel family, weights from b200_pack_conv_weight_xfold) with the channel statistics of the
+ * following normalisation fused into the epilogue -- the "GroupNorm statistics in the producer epilogue" half of the
+ * Conv3D -> GN -> SiLU fusion (reference order blocks.py:154-160):
+ *   sums[n][c] += (sum y, sum y*y) over the stored (rounded) output            == b200_channel_sums(y)
+ * sums: double [N][C][2], zero-initialised by the caller.  *applied = 1 if the statistics were produced inside the
+ * convolution, 0 if this shape has no fused epilogue (Cout != 16) or the call accumulates (the convolution still ran; call
+ * b200_channel_sums).                                                                                                   */
+int b200_conv_fprop_stats(const b200_tensor* x, const void* w_packed_xfold, const float* bias, const b200_tensor* y,
+                          int32_t kd, int32_t kh, int32_t kw, int32_t accumulate, double* sums, int32_t* applied, void* stream);
 /* x-folded tensor-core kernel for small-channel layers with kw in {1, 3} (see csrc/conv_umma.cu): block-Toeplitz packing
  *   [(j, co)][(dz, dy, xi, ci)], j < 4, xi < 3+kw; elements = 4*Cout' * kd*kh*(3+kw)*Cin'
  * where (Cout', Cin') = (Cout, Cin), or (Cin, Cout) when flip_transpose (dgrad operand).  Used with impl =

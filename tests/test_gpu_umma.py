@@ -254,3 +254,97 @@ def test_conv_image_fed(case):
     torch.cuda.synchronize()
     assert nerr(dw.cpu(), wt.grad) < 2e-3
     assert nerr(db.cpu(), b.grad) < 2e-3
+
+
+STATS_CASES = [
+    # n, d, h, w, cin, cout      x-slab shapes with fused channel statistics (Cout = 16)
+    (2, 16, 16, 16, 16, 16),
+    (1, 20, 24, 12, 48, 16),       # partial tiles in z and y
+    (2, 16, 32, 8, 32, 16),
+    (1, 9, 20, 12, 16, 16),        # thin volume: one row tile per CTA tile
+    (3, 40, 32, 16, 2, 16),        # image-fed layer, several tiles and several samples per CTA
+]
+
+
+@pytest.mark.parametrize("case", STATS_CASES)
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_conv_epilogue_statistics(case, dtype):
+    """b200_conv_fprop_stats: the channel sums that leave the convolution epilogue equal b200_channel_sums run on the stored
+    output, and the output itself is bit-identical to the plain launch."""
+    from biapy_b200 import _lib, ops
+    n, d, h, w, cin, cout = case
+    k = (3, 3, 3)
+    g = torch.Generator().manual_seed(11)
+    x = cl(torch.randn(n, cin, d, h, w, generator=g)).to(dtype)
+    wt = (torch.randn(cout, cin, *k, generator=g) * 0.1).cuda()
+    b = torch.randn(cout, generator=g).cuda()
+    wp = ops.pack_conv_weight_xfold(wt, dtype, False)
+    y_ref = torch.empty(n, d, h, w, cout, dtype=dtype, device="cuda")
+    assert ops.conv_impl_query(x, y_ref, k) == _lib.IMPL_XFOLD
+    ops.conv_fprop(x, wp, b, y_ref, k, impl=_lib.IMPL_XFOLD)
+    y = torch.empty_like(y_ref)
+    sums = torch.zeros(n * cout * 2, dtype=torch.float64, device="cuda")
+    assert ops.conv_fprop_stats(x, wp, b, y, k, sums)
+    torch.cuda.synchronize()
+    assert torch.equal(y, y_ref)
+    ref = torch.zeros_like(sums)
+    _lib.call("b200_channel_sums", ops._ref(y_ref), ops._ptr(ref), _lib.stream_ptr())
+    yf = y_ref.double()
+    exact = torch.stack([yf.sum((1, 2, 3)), (yf * yf).sum((1, 2, 3))], -1).reshape(-1)
+    scale = exact.abs().max().item()
+    assert (ref - exact).abs().max().item() < 1e-4 * scale
+    assert (sums - exact).abs().max().item() < 1e-4 * scale         # fp32 partials per thread, fp64 across threads
+    # an accumulating launch cannot see the final value in the TMA-store epilogue: it reports "not applied" and leaves sums alone
+    before = sums.clone()
+    applied = ops.conv_fprop_stats(x, wp, b, y, k, sums, accumulate=True)
+    torch.cuda.synchronize()
+    if not applied:
+        assert torch.equal(sums, before)
+
+
+@pytest.mark.parametrize("swz", ["32", "0"])
+def test_xslab_tma_store_epilogue_matches_direct_stores(swz):
+    """The TMA-store epilogue (staged boxes, bulk tensor store / element-wise add) against the direct-store epilogue of the same
+    kernel, run in a subprocess per staging-buffer swizzle because the mode is latched from the environment."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import torch
+from biapy_b200 import _lib, ops
+torch.manual_seed(0)
+for (n, d, h, w, cin, cout) in [(2, 16, 16, 16, 16, 16), (1, 20, 24, 12, 48, 16), (1, 24, 16, 8, 16, 48), (1, 16, 32, 16, 32, 32),
+                                (1, 32, 32, 32, 16, 64), (2, 9, 20, 12, 2, 16)]:
+    for dtype in (torch.bfloat16, torch.float16):
+        x = torch.randn(n, d, h, w, cin, device="cuda").to(dtype)
+        wt = torch.randn(cout, cin, 3, 3, 3, device="cuda") * 0.1
+        b = torch.randn(cout, device="cuda")
+        wp = ops.pack_conv_weight_xfold(wt, dtype, False)
+        ybuf = torch.zeros(n, d, h, w, cout + 16, dtype=dtype, device="cuda")
+        y = ybuf[..., 8:8 + cout]
+        ops.conv_fprop(x, wp, b, y, (3, 3, 3), impl=_lib.IMPL_XFOLD)
+        y1 = y.float().clone()
+        ops.conv_fprop(x, wp, b, y, (3, 3, 3), accumulate=True, impl=_lib.IMPL_XFOLD)
+        torch.cuda.synchronize()
+        print("RES", n, d, h, w, cin, cout, str(dtype), y1.double().sum().item(), y1.abs().max().item(),
+              (y.float() - 2 * y1).abs().max().item(), ybuf[..., :8].abs().max().item() + ybuf[..., 8 + cout:].abs().max().item())
+        torch.save(y1.cpu(), f"{OUT}/y_{n}_{d}_{h}_{w}_{cin}_{cout}_{dtype}.pt")
+'''
+    import tempfile
+    outs = {}
+    for tma in ("0", "1"):
+        tmp = tempfile.mkdtemp()
+        env = dict(os.environ, B200_EPI_TMA=tma, B200_EPI_SWZ=swz)
+        r = subprocess.run([sys.executable, "-c", f"OUT={tmp!r}\n" + code], env=env, capture_output=True, text=True, timeout=600,
+                           cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[tma] = (tmp, [ln.split()[1:] for ln in r.stdout.splitlines() if ln.startswith("RES")])
+    assert len(outs["0"][1]) == len(outs["1"][1]) == 12
+    for a, b in zip(outs["0"][1], outs["1"][1]):
+        assert a[:7] == b[:7]
+        ya = torch.load(f"{outs['0'][0]}/y_{'_'.join(a[:6])}_{a[6]}.pt")
+        yb = torch.load(f"{outs['1'][0]}/y_{'_'.join(b[:6])}_{b[6]}.pt")
+        assert torch.equal(ya, yb), a[:7]                      # plain stores: bit-identical
+        assert float(b[10]) == 0.0                             # neighbouring channels of the slice untouched
+        # accumulate: y + y, rounded once more by the element-wise add of the TMA unit
+        assert float(b[9]) <= 2 ** -7 * 2 * float(b[8]) + 1e-6, b
