@@ -45,11 +45,14 @@ def apply_head_activations(pred_cl: torch.Tensor, head_activations: Sequence[str
 @torch.no_grad()
 def predict_volume(model, vol, patch_shape: Sequence[int], overlap=(0, 0, 0), padding=(0, 0, 0), batch_size: int = 4,
                    head_activations: Optional[List[str]] = None, pad_type: str = "reflect", out_dtype=torch.float32,
-                   rank: int = 0, world: int = 1):
+                   rank: int = 0, world: int = 1, tta: bool = False, tta_mode: str = "mean", tta_group: str = "auto"):
     """vol: (Z, Y, X, C) numpy array or CUDA tensor.  Returns the merged prediction (Z, Y, X, C_out) with the same
     container type.  With world > 1 every rank predicts the patches ``rank::world`` (embarrassingly parallel, the
     reference's by-chunks dealing, ``chunked_test_pair_data_generator.py:613-618``) and the patch predictions are
-    all-gathered over NCCL before each rank merges (every rank ends with the full volume)."""
+    all-gathered over NCCL before each rank merges (every rank ends with the full volume).
+    ``tta`` = ``TEST.AUGMENTATION``: every patch is predicted in the 16 orientations of ``ensemble_predictions`` (activated
+    outputs are ensembled, as ``predict_batches_in_test`` does, ``base_workflow.py:1659-1672``); mode / group =
+    ``TEST.AUGMENTATION_MODE`` / ``TEST.AUGMENTATION_GROUP``."""
     is_np = isinstance(vol, np.ndarray)
     dev_vol = _stitch.to_device(vol)
     Z, Y, X, Cin = dev_vol.shape
@@ -70,9 +73,23 @@ def predict_volume(model, vol, patch_shape: Sequence[int], overlap=(0, 0, 0), pa
             ids = torch.tensor(mine[k:k + batch_size], device=patches.device)
             xb = patches.index_select(0, ids)
             sel = ids
-        y = model(xb.permute(0, 4, 1, 2, 3))                                  # (b, C_out, z, y, x) fp32 view of NDHWC
-        ycl = y.permute(0, 2, 3, 4, 1)
-        if world == 1:
+        if tta:
+            from ..data.post_processing.post_processing import ensemble_predictions
+
+            def call(b):
+                yb = model(b.permute(0, 4, 1, 2, 3)).permute(0, 2, 3, 4, 1)
+                return apply_head_activations(yb, acts, torch.empty(yb.shape, dtype=torch.float32, device=yb.device)).permute(0, 4, 1, 2, 3)
+            ycl = torch.cat([ensemble_predictions(xb[j], call, (0, 2, 3, 4, 1), (0, 4, 1, 2, 3), xb.device, 3, batch_size_value=batch_size,
+                                                  mode=tta_mode, group=tta_group).permute(0, 2, 3, 4, 1) for j in range(xb.shape[0])], 0)
+        else:
+            y = model(xb.permute(0, 4, 1, 2, 3))                              # (b, C_out, z, y, x) fp32 view of NDHWC
+            ycl = y.permute(0, 2, 3, 4, 1)
+        if tta:
+            if world == 1:
+                pred[sel] = ycl.to(out_dtype)
+            else:
+                pred.index_copy_(0, sel, ycl.to(out_dtype))
+        elif world == 1:
             apply_head_activations(ycl, acts, pred[sel])
         else:
             tmp = torch.empty(ycl.shape, dtype=out_dtype, device=ycl.device)

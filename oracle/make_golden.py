@@ -277,6 +277,40 @@ def make_chunks():
         json.dump(meta, f, indent=0)
 
 
+TTA_CASES = [
+    # name, image shape (spatial..., C), ndim, mode, group, batch
+    ("a", (6, 9, 7, 2), 3, "mean", "auto", 3),        # y != x: front padding (reflect) before the swaps
+    ("b", (12, 9, 1), 2, "mean", "auto", 5),
+    ("c", (5, 8, 8, 3), 3, "max", "full", 16),        # square in-plane: no padding
+    ("d", (4, 3, 9, 1), 3, "min", "auto", 1),         # pad 6 >= dim 3: reflect degrades to edge (np.pad rule)
+    ("e", (10, 7, 2), 2, "mean", "flips", 2),
+    ("f", (3, 5, 6, 1), 3, "mean", "none", 4),
+]
+
+
+def tta_image(shape, name):
+    return np.random.default_rng(sum(map(ord, "tta" + name))).standard_normal(shape).astype(np.float32)
+
+
+def make_tta():
+    """Scalar test-time augmentation: the reference's own `ensemble_predictions` driven by the fixed toy
+    network of oracle/port_tta.py.  Stores the ensemble and the orientation list the reference enumerated."""
+    from . import port_tta
+    R = ref_loader.load_tta()
+    for name, shape, nd, mode, group, bs in TTA_CASES:
+        img = tta_image(shape, name)
+        ao = {2: (0, 3, 1, 2), 3: (0, 4, 1, 2, 3)}[nd]
+        aob = {2: (0, 2, 3, 1), 3: (0, 2, 3, 4, 1)}[nd]
+        out = R.ensemble_predictions(img, lambda b: torch.from_numpy(port_tta.toy_pred_func(b)).permute(ao), aob, ao,
+                                     torch.device("cpu"), nd, batch_size_value=bs, mode=mode, group=group)
+        out = out.permute(aob)[0].numpy()
+        grp = R.tta.build_axis_transform_group(nd, level=("full" if group == "auto" else group))
+        np.savez_compressed(os.path.join(OUT, f"tta_{name}.npz"), out=out,
+                            perms=np.array([t.perm for t in grp], np.int32), signs=np.array([t.sign for t in grp], np.int32),
+                            meta=np.array(json.dumps(dict(shape=shape, ndim=nd, mode=mode, group=group, batch=bs))))
+        print("tta", name, shape, mode, group, "->", out.shape, len(grp), "orientations")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     R = ref_loader.load()
@@ -285,6 +319,9 @@ def main():
     if only == ["chunks"]:        # python -m oracle.make_golden chunks
         make_chunks()
         return
+    if only == ["tta"]:           # python -m oracle.make_golden tta
+        make_tta()
+        return
     if only:                      # add fixtures without rewriting the committed ones: python -m oracle.make_golden <model name>...
         make_models(R, only)
         return
@@ -292,6 +329,7 @@ def main():
     make_stitch(R)
     make_models(R)
     make_chunks()
+    make_tta()
     with open(os.path.join(OUT, "PROVENANCE.txt"), "w") as f:
         f.write("generated by oracle/make_golden.py from /root/reference (BiaPy 3.7.0 @ 29539acd), "
                 f"torch {torch.__version__}, numpy {np.__version__}; GN call patched as documented in oracle/ref_loader.py\n")

@@ -166,3 +166,33 @@ def load_chunked():
     _chunked = types.SimpleNamespace(gen=gen, cls=gen.chunked_test_pair_data_generator, d3=ns.d3,
                                      PatchCoords=ns.dataset.PatchCoords)
     return _chunked
+
+
+_tta = None
+
+
+def load_tta():
+    """The reference's scalar TTA: `tta.py` is numpy-only and loads as it is; `ensemble_predictions` and its
+    three helpers are AST-extracted from `post_processing.py` (whose module imports cv2 / skimage / fill_voids ...), together
+    with `to_numpy_format` / `to_pytorch_format` from `biapy/utils/misc.py`."""
+    global _tta
+    if _tta is not None:
+        return _tta
+    if not available():
+        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+    import math
+    import numpy as np
+    import torch
+    from typing import Callable, Dict, List, Optional, Tuple
+    from numpy.typing import NDArray
+    tta = _load("_ref_biapy_tta", "biapy/data/post_processing/tta.py")
+    sys.modules.pop("_ref_biapy_tta", None)
+    misc = _functions_from_source("biapy/utils/misc.py", ["to_numpy_format", "to_pytorch_format"],
+                                  dict(torch=torch, np=np, NDArray=NDArray, Tuple=Tuple))
+    env = dict(np=np, torch=torch, math=math, NDArray=NDArray, Callable=Callable, Dict=Dict, List=List, Optional=Optional, Tuple=Tuple,
+               AxisTransform=tta.AxisTransform, TTASpec=tta.TTASpec, TTA_GROUPS=tta.TTA_GROUPS,
+               build_axis_transform_group=tta.build_axis_transform_group, **misc)
+    fns = _functions_from_source("biapy/data/post_processing/post_processing.py",
+                                 ["_pad_for_orientations", "_crop_padding", "_reduce_orientations", "ensemble_predictions"], env)
+    _tta = types.SimpleNamespace(tta=tta, **fns)
+    return _tta

@@ -183,3 +183,43 @@ def test_chunk_extract_insert_oracle_matches_reference(case):
         for rank in range(world):
             port_chunks.predict_by_chunks(vol, g, lambda b: b, vol.shape[-1], world, rank, out=out)
         assert zlib.crc32(out.tobytes()) == case["out_crc"] and np.array_equal(out, vol)
+
+
+# ------------------------------------------------------------------------------- test-time augmentation
+def tta_image(shape, name):
+    """The seeded image oracle/make_golden.py fed to the reference (not stored in the fixture)."""
+    return np.random.default_rng(sum(map(ord, "tta" + name))).standard_normal(shape).astype(np.float32)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "tta_*.npz"))))
+def test_tta_oracle_matches_reference(path):
+    """oracle/port_tta.py against the reference's ensemble_predictions: orientation order and the ensemble, bit-exact."""
+    from oracle import port_tta
+    z = np.load(path)
+    meta = json.loads(str(z["meta"]))
+    name = os.path.basename(path)[4:-4]
+    orients = port_tta.orientations(meta["ndim"], "full" if meta["group"] == "auto" else meta["group"])
+    assert [list(p) for p, _ in orients] == z["perms"].tolist()
+    assert [list(s) for _, s in orients] == z["signs"].tolist()
+    out = port_tta.ensemble_predictions(tta_image(tuple(meta["shape"]), name), port_tta.toy_pred_func, meta["ndim"],
+                                        meta["batch"], meta["mode"], meta["group"])
+    assert out.dtype == np.float32 and np.array_equal(out, z["out"])
+
+
+def test_tta_orientation_group_host_mirror():
+    """biapy_b200's AxisTransform / build_axis_transform_group (host bookkeeping, no GPU) against the oracle enumeration."""
+    from biapy_b200.data.post_processing.tta import AxisTransform, build_axis_transform_group
+    from oracle import port_tta
+    for nd in (2, 3):
+        for level in ("full", "flips", "none"):
+            got = build_axis_transform_group(nd, level)
+            assert [(t.perm, t.sign) for t in got] == port_tta.orientations(nd, level)
+            assert got[0].is_identity
+            for t in got:
+                assert (t.inverse.perm, t.inverse.sign) == port_tta.inverse(t.perm, t.sign)
+                assert t.inverse.inverse == t
+    assert len(build_axis_transform_group(2)) == 8 and len(build_axis_transform_group(3)) == 16
+    with pytest.raises(ValueError):
+        AxisTransform((0, 0), (1, 1))
+    with pytest.raises(ValueError):
+        build_axis_transform_group(4)
