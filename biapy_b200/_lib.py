@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libbiapy_b200.so")
 
-F32, BF16, F16, U8 = 0, 1, 2, 3
+F32, BF16, F16, U8, U16 = 0, 1, 2, 3, 4
 ACT = {None: 0, "none": 0, "linear": 0, "relu": 1, "elu": 2, "silu": 3, "leaky_relu": 4, "gelu": 5, "tanh": 6,
        "sigmoid": 7, "softplus": 8}
 PAD_MODE = {"zeros": 0, "constant": 0, "reflect": 1, "symmetric": 2, "edge": 3, "wrap": 4}
@@ -61,6 +61,11 @@ SIGNATURES = {
     "b200_chunk_patch_coords": (_I, [C.POINTER(ChunkGrid), _L, C.POINTER(_L)]),
     "b200_chunk_extract": (_I, [_P, _I, _L, _L, _L, _L, _P, _L, _L, _L, _L, _P, _P]),
     "b200_chunk_insert": (_I, [_P, _I, _L, _L, _L, _L, _L, _P, _I, _L, _L, _L, _P, _I, _P]),
+    "b200_image_stats": (_I, [_P, _I, _L, _I, C.POINTER(_F), _P, _P]),
+    "b200_image_norm_apply": (_I, [_P, _I, _L, _I, C.POINTER(_F), _P, _P]),
+    "b200_image_denorm_apply": (_I, [_P, _L, _I, C.POINTER(_D), _P, _I, _P]),
+    "b200_binarize": (_I, [_P, _L, _F, _P, _P]),
+    "b200_argmax_channels": (_I, [_P, _L, _I, _P, _I, _P]),
     "b200_orient_apply": (_I, [_T, _T, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), _I, _P]),
     "b200_orient_reduce": (_I, [_T, C.POINTER(_I), C.POINTER(_I), _I, C.POINTER(_I), _T, _P]),
     "b200_pack_conv_weight": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
@@ -151,6 +156,8 @@ def torch_dtype_code(dt) -> int:
         return F16
     if dt == torch.uint8:
         return U8
+    if dt == torch.uint16:
+        return U16
     raise B200Error(f"unsupported dtype {dt}")
 
 

@@ -29,7 +29,7 @@ extern "C" {
 #define B200_ERR_CUDA -2
 #define B200_ERR_UNSUPPORTED -3
 
-enum b200_dtype { B200_F32 = 0, B200_BF16 = 1, B200_F16 = 2, B200_U8 = 3 /* crop only */ };
+enum b200_dtype { B200_F32 = 0, B200_BF16 = 1, B200_F16 = 2, B200_U8 = 3 /* crop, image ends */, B200_U16 = 4 /* image ends only */ };
 enum b200_act {
   B200_ACT_NONE = 0, B200_ACT_RELU = 1, B200_ACT_ELU = 2, B200_ACT_SILU = 3, B200_ACT_LEAKY_RELU = 4,
   B200_ACT_GELU = 5, B200_ACT_TANH = 6, B200_ACT_SIGMOID = 7, B200_ACT_SOFTPLUS = 8
@@ -128,6 +128,32 @@ int b200_chunk_extract(const void* src, int32_t dtype, int64_t D, int64_t H, int
 int b200_chunk_insert(const void* patches, int32_t dtype_in, int64_t n, int64_t pd, int64_t ph, int64_t pw, int64_t C,
                       void* out, int32_t dtype_out, int64_t D, int64_t H, int64_t W, const int64_t* desc, int32_t mode,
                       void* stream);
+
+/* ------------------------------------------------------------------------------------- the ends of the path
+ * Image normalisation in front of the first convolution and its inverse / the binarisation behind the merge.
+ * Images are dense (voxels, C) arrays of dtype u8 / u16 / f32.
+ * b200_image_stats: one pass, per channel c: out[c] = (min, max, sum, sum of squares, is_binary) as doubles (is_binary = 1 when
+ *   every value is 0 or 1: biapy/data/norm.py:38-42 -- binary channels are never normalised).  clip (host, [c][3] = on, lo, hi,
+ *   or NULL): statistics of min(max(x, lo), hi), what the reference sees after its in-place percentile clip.
+ * b200_image_norm_apply = the per-channel body of normalize_image (norm.py:188-218) in float32, same operation order:
+ *   params[c] = (clip, lo, hi, kind, a, b):  clip != 0 -> x = min(max(x, lo), hi)              (percentile_clip :468-472)
+ *     kind 1 -> x = (x - a) / b   a = min_val_to_div, b = max(max_val_to_div - min_val_to_div, eps)      (norm_range01 :575-578)
+ *     kind 2 -> x = (x - a) / b   a = mean,           b = max(std, eps)       (zero_mean_unit_variance_normalization :632-633)
+ *     kind 0 -> x unchanged (binary channel).   dst: float32.
+ * b200_image_denorm_apply = undo_image_norm (norm.py:641-780) in float64 like numpy (float32 data * Python-list factors):
+ *   kind 1: clip(x, 0, 1) * a + b  (a = max_val_to_div, b = min_val_to_div, :703-713);  kind 2: x * a + b (a = std, b = mean),
+ *   rounded and clamped to the integer range when dst is u8 / u16 (:767-778); conversion to dst dtype as numpy's astype
+ *   (truncation for integers).  src: float32; dst: u8 / u16 / f32.
+ * b200_binarize: dst u8 = src > threshold (semantic_seg.py:420-421, by-chunks fixed 0.5 :524-529);
+ * b200_argmax_channels: dst (u8 / u16, 1 channel) = first index of the channel maximum (np.argmax, :423-424, :531).      */
+int b200_image_stats(const void* src, int32_t dtype, int64_t voxels, int32_t c, const float* clip, double* out /* [c][5], device */,
+                     void* stream);
+int b200_image_norm_apply(const void* src, int32_t dtype, int64_t voxels, int32_t c, const float* params /* [c][6], host */,
+                          float* dst, void* stream);
+int b200_image_denorm_apply(const float* src, int64_t voxels, int32_t c, const double* params /* [c][3] kind,a,b, host */,
+                            void* dst, int32_t dst_dtype, void* stream);
+int b200_binarize(const float* src, int64_t n, float threshold, uint8_t* dst, void* stream);
+int b200_argmax_channels(const float* src, int64_t voxels, int32_t c, void* dst, int32_t dst_dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------- test-time augmentation
  * Signed axis permutations of biapy/data/post_processing/tta.py:65-260 (AxisTransform: output axis a comes from input axis

@@ -311,6 +311,43 @@ def make_tta():
         print("tta", name, shape, mode, group, "->", out.shape, len(grp), "orientations")
 
 
+NORM_MODULES = [
+    dict(type="div", percentile_clip=False, out_dtype="float32"),
+    dict(type="scale_range", percentile_clip=False, out_dtype="float32"),
+    dict(type="zero_mean_unit_variance", percentile_clip=False, out_dtype="float32"),
+    dict(type="zero_mean_unit_variance", percentile_clip=False, out_dtype="float32", mean=[0.5], std=[2.0]),
+    dict(type="scale_range", percentile_clip=True, out_dtype="float32", lower_bound_val=[10.0], upper_bound_val=[200.0],
+         per_lower_bound=-1, per_upper_bound=-1),
+    dict(type="zero_mean_unit_variance", percentile_clip=True, out_dtype="float32", lower_bound_val=[-1.5], upper_bound_val=[2.5],
+         per_lower_bound=-1, per_upper_bound=-1),
+]
+
+
+def norm_images():
+    rng = np.random.default_rng(2026)
+    a = rng.integers(0, 256, (5, 9, 7, 2)).astype(np.uint8)
+    b = rng.integers(0, 4000, (6, 8, 3)).astype(np.uint16)
+    c = (rng.standard_normal((4, 6, 6, 2)) * 3 + 1).astype(np.float32)
+    d = np.concatenate([rng.integers(0, 2, (4, 6, 6, 1)).astype(np.float32), c[..., :1]], -1)      # one binary channel
+    return dict(a=a, b=b, c=c, d=d)
+
+
+def make_norm():
+    """Image normalisation at the ends: the reference's normalize_image / undo_image_norm on seeded images."""
+    import copy
+    R = ref_loader.load_norm()
+    out = {}
+    meta = []
+    for name, img in norm_images().items():
+        for i, m in enumerate(NORM_MODULES):
+            y, info = R.normalize_image(img.copy(), copy.deepcopy(m))
+            u = R.undo_image_norm(y.copy(), info)
+            out[f"{name}{i}_y"], out[f"{name}{i}_u"] = y, u
+            meta.append(dict(image=name, module=i, info=info))
+    np.savez_compressed(os.path.join(OUT, "norm_cases.npz"), meta=np.array(json.dumps(meta)), **out)
+    print("norm:", len(meta), "cases")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     R = ref_loader.load()
@@ -322,6 +359,9 @@ def main():
     if only == ["tta"]:           # python -m oracle.make_golden tta
         make_tta()
         return
+    if only == ["norm"]:          # python -m oracle.make_golden norm
+        make_norm()
+        return
     if only:                      # add fixtures without rewriting the committed ones: python -m oracle.make_golden <model name>...
         make_models(R, only)
         return
@@ -330,6 +370,7 @@ def main():
     make_models(R)
     make_chunks()
     make_tta()
+    make_norm()
     with open(os.path.join(OUT, "PROVENANCE.txt"), "w") as f:
         f.write("generated by oracle/make_golden.py from /root/reference (BiaPy 3.7.0 @ 29539acd), "
                 f"torch {torch.__version__}, numpy {np.__version__}; GN call patched as documented in oracle/ref_loader.py\n")

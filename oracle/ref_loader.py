@@ -196,3 +196,28 @@ def load_tta():
                                  ["_pad_for_orientations", "_crop_padding", "_reduce_orientations", "ensemble_predictions"], env)
     _tta = types.SimpleNamespace(tta=tta, **fns)
     return _tta
+
+
+_norm = None
+
+
+def load_norm():
+    """The reference's image normalisation functions, AST-extracted from `biapy/data/norm.py` (the module
+    imports the dataset machinery); `torch_numpy_dtype_dict` is rebuilt for the dtypes the fixtures use."""
+    global _norm
+    if _norm is not None:
+        return _norm
+    if not available():
+        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+    import numpy as np
+    import torch
+    from typing import Dict, Optional, Tuple
+    from numpy.typing import NDArray
+    names = ["_is_binary_channel", "normalize_image", "percentile_clip", "torch_percentile", "norm_range01",
+             "zero_mean_unit_variance_normalization", "undo_image_norm", "undo_norm_range01",
+             "undo_zero_mean_unit_variance_normalization"]
+    env = dict(np=np, torch=torch, NDArray=NDArray, Dict=Dict, Optional=Optional, Tuple=Tuple,
+               torch_numpy_dtype_dict={"uint8": [torch.uint8, np.uint8], "uint16": [torch.uint16, np.uint16],
+                                       "float32": [torch.float32, np.float32]})
+    _norm = types.SimpleNamespace(**_functions_from_source("biapy/data/norm.py", names, env))
+    return _norm

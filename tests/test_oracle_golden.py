@@ -223,3 +223,18 @@ def test_tta_orientation_group_host_mirror():
         AxisTransform((0, 0), (1, 1))
     with pytest.raises(ValueError):
         build_axis_transform_group(4)
+
+
+# --------------------------------------------------------------------------- image normalisation at the ends
+def test_norm_oracle_matches_reference():
+    import copy
+    from oracle import port_norm
+    n = 0
+    for img, mod, y_ref, u_ref, info_ref, key in port_norm.golden_cases(GOLDEN):
+        y, info = port_norm.normalize_image(img.copy(), copy.deepcopy(mod))
+        assert y.dtype == y_ref.dtype and np.array_equal(y, y_ref), key
+        assert json.loads(json.dumps(info)) == info_ref, key
+        u = port_norm.undo_image_norm(y.copy(), info)
+        assert u.dtype == u_ref.dtype and np.array_equal(u, u_ref), key
+        n += 1
+    assert n == 24
