@@ -285,9 +285,10 @@ def run_train(args):
         traffic, traffic_note = None, None
         try:
             tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic_r1.json")))
-            if top in tj:
-                traffic = tj[top]["dram_bytes_per_launch"]
-                traffic_note = tj[top]
+            fam = top.split(" ")[0]               # --detail labels carry the layer shape after the family name
+            if fam in tj:
+                traffic = tj[fam]["dram_bytes_per_launch"]
+                traffic_note = tj[fam]
         except (OSError, ValueError, KeyError):
             pass
         roof = {"kernel": top, "region": roofline_region, "bound": "tensor", "achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
