@@ -520,6 +520,10 @@ struct XslabParams {
   // XOR mask of the output map's shared-memory swizzle on the 16-byte chunk index (7 / 3 / 1 / 0 = 128B / 64B / 32B / none)
   int epi_tma;
   uint32_t epi_off, epi_swz;
+  // resident-weight mode of conv_fprop_xslab1_kernel: the whole Toeplitz matrix (nt x kd*kh*kx) stays in shared memory for the
+  // life of the CTA at byte offset wres_off; the ring then carries slab boxes only
+  int wres;
+  uint32_t wres_off;
 };
 
 constexpr int kSlabAWarps = 1, kSlabBWarps = 3;
@@ -937,11 +941,14 @@ conv_fprop_xslab1_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar_afull = smem_u32(&s_bar[0]);
   const uint32_t bar_aempty = smem_u32(&s_bar[kMaxStages]);
+  const uint32_t bar_wres = smem_u32(&s_bar[2 * kMaxStages]);
   const uint32_t bar_tfull = smem_u32(&s_bar[4 * kMaxStages]);
   const uint32_t bar_tempty = smem_u32(&s_bar[4 * kMaxStages + 2]);
+  const bool wres = p.wres != 0;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.a_stages; ++s) { mbar_init(bar_afull + 8 * s, 1 + p.kd); mbar_init(bar_aempty + 8 * s, p.rt); }
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(bar_afull + 8 * s, wres ? 1 : 1 + p.kd); mbar_init(bar_aempty + 8 * s, p.rt); }
+    if (wres) mbar_init(bar_wres, p.kd);
     for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, p.rt); mbar_init(bar_tempty + 8 * b, 128); }
     fence_barrier_init();
     tma_prefetch_desc(&tmx64); tma_prefetch_desc(&tmx32); tma_prefetch_desc(&tmw64); tma_prefetch_desc(&tmw32);
@@ -957,6 +964,9 @@ conv_fprop_xslab1_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid
   const uint32_t slab_rows = (uint32_t)p.zl * 16u;
   const uint32_t w_off = slab_rows * 128u;                 // weight tiles follow the (max-size) slab box inside a stage
   const uint32_t w_tile = (uint32_t)p.nt * 128u;
+  // resident weights: tile (dy, b, dz) at wres_off + dy * wres_dy + (b < boxes64 ? b * kd * t64 : boxes64 * kd * t64) + dz * (t64 | t32)
+  const uint32_t t64 = (uint32_t)p.nt * 128u, t32 = (uint32_t)p.nt * 64u;
+  const uint32_t wres_dy = (uint32_t)p.kd * ((uint32_t)p.boxes64 * t64 + (uint32_t)p.has32 * t32);
 
   auto decode = [&](int tile, int& n, int& z0, int& y0, int& g) {
     int t = tile;
@@ -969,7 +979,18 @@ conv_fprop_xslab1_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid
   if (warp >= 6) {
     // =================================================================== TMA producers: warp 6 = slab, warp 7 + dz = weight tile dz
     const int role = warp - 6;
-    if (role <= p.kd && elect_one()) {
+    if (wres && role >= 1 && role <= p.kd && elect_one()) {
+      // resident weights: warp 7 + dz fetches every (dy, box) tile of its dz once; all kd warps signal one barrier
+      const int dz = role - 1;
+      mbar_expect_tx(bar_wres, (uint32_t)p.kh * ((uint32_t)p.boxes64 * t64 + (uint32_t)p.has32 * t32));
+      for (int dy = 0; dy < p.kh; ++dy)
+        for (int b = 0; b < nboxes; ++b) {
+          const bool wide = b < p.boxes64;
+          const uint32_t dst = smem0 + p.wres_off + (uint32_t)dy * wres_dy +
+                               (wide ? (uint32_t)b * p.kd * t64 : (uint32_t)p.boxes64 * p.kd * t64) + (uint32_t)dz * (wide ? t64 : t32);
+          tma_load_2d(dst, wide ? &tmw64 : &tmw32, bar_wres, (dz * p.kh + dy) * p.kx + b * 64, 0);
+        }
+    } else if (role <= (wres ? 0 : p.kd) && elect_one()) {
       const int a_stages = p.a_stages;
       int slot = 0;
       uint32_t ph = 0;
@@ -1011,9 +1032,15 @@ conv_fprop_xslab1_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid
       const uint64_t tmpl128 = make_smem_desc(0, 16, 1024, kSwizzle128), tmpl64 = make_smem_desc(0, 16, 512, kSwizzle64);
       const uint32_t a0 = in_reg(smem0 >> 4);
       const uint32_t rt_n = in_reg((uint32_t)p.rt * nt), stride = in_reg((int)gridDim.x);
+      const uint32_t wres16 = in_reg((smem0 + p.wres_off) >> 4), wres_dy16 = in_reg(wres_dy >> 4), t64_16 = in_reg(t64 >> 4),
+                     t32_16 = in_reg(t32 >> 4);
       int as = 0;
       uint32_t aph = 0;
       int it = 0;
+      if (wres) {
+        mbar_wait(bar_wres, 0);
+        tc_fence_after();
+      }
       bool ready = mbar_try_wait(bar_afull, 0);
       for (int tile = blockIdx.x; tile < num_tiles; tile += stride, ++it) {
         const int buf = nbuf == 2 ? (it & 1) : 0;
@@ -1033,10 +1060,15 @@ conv_fprop_xslab1_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid
             const uint32_t t_lo = (uint32_t)tmpl, t_hi = (uint32_t)(tmpl >> 32);
             uint32_t ad = t_lo + s16 + (uint32_t)r * 8u * line;
             uint32_t bd = t_lo + s16 + w16;
+            uint32_t bstep = wt16;
+            if (wres) {
+              bd = t_lo + wres16 + (uint32_t)dy * wres_dy16 + (wide ? (uint32_t)b * (uint32_t)kd * t64_16 : (uint32_t)boxes64 * (uint32_t)kd * t64_16);
+              bstep = wide ? t64_16 : t32_16;
+            }
             const uint32_t cur = bar_aempty + 8 * as;
             if (++as == a_stages) { as = 0; aph ^= 1; }
             ready = mbar_try_wait(bar_afull + 8 * as, aph);              // latency overlaps the issue below
-            for (int dz = 0; dz < kd; ++dz, ad += line, bd += wt16) {
+            for (int dz = 0; dz < kd; ++dz, ad += line, bd += bstep) {
               if (wide) umma_ksteps_split<4>(d_tmem, ad, t_hi, bd, t_hi, 2u, 2u, idesc, acc);
               else umma_ksteps_split<2>(d_tmem, ad, t_hi, bd, t_hi, 2u, 2u, idesc, acc);
               acc = 1;
@@ -1580,6 +1612,37 @@ static int conv_fprop_xslab_v(const ActView& x, const void* w, const float* bias
   p.kd = kd; p.kh = kh; p.kw = kw;
   p.nt = 4 * y.c;
   p.rt = (x.d >= 16) ? 2 : 1;
+  // Resident weights (conv_fprop_xslab1_kernel, p.wres): when the Toeplitz matrix of the layer (nt x kd*kh*kx elements: 108 KB
+  // for 16 -> 16, 36 KB for 2 -> 16) fits next to the slab ring it is fetched ONCE per CTA instead of once per tile.  The x-slab
+  // kernels run at the L2 -> shared-memory rate of the TMA unit (~70 B/clk/SM, tools/pipe_rates.py): 16 -> 16 moves 270 KB per
+  // 512 voxels, 108 KB of it weights.  Row tiles per CTA tile drop to 1 when only two 2-row-tile slabs would fit.
+  // (Also measured and dropped: an extra warp issuing cp.async.bulk.prefetch.tensor 1 / 2 / 4 tiles ahead of the slab producer.
+  // Every x-slab layer got slower -- 16 -> 16 0.252 -> 0.35 ms, 48 -> 16 0.60 -> 0.71 ms, step 15.7 -> 16.3 ms: the prefetches
+  // go through the same TMA unit and take request slots from the loads.  profiles/xslab_negative_results_r1.log)
+  static const int wres_env = getenv("B200_WRES") ? atoi(getenv("B200_WRES")) : 1;
+  static const int wres_rt_env = getenv("B200_WRES_RT") ? atoi(getenv("B200_WRES_RT")) : 0;
+  uint32_t wres_bytes = 0;
+  {
+    int xo = 0, kxp = 0;
+    if (wres_env && kd <= 3 && xfold_geom(x.c, kw, &xo, &kxp)) {
+      const uint32_t wb = (uint32_t)(4 * y.c) * (uint32_t)(kd * kh * kxp) * 2u;
+      const uint32_t avail = 232448u - 1024u - 1024u - (p.epi_tma ? 32768u : 0u);     // 227 KB - static - alignment - staging
+      if (wb <= 112u * 1024u) {
+        const uint32_t slab2 = (uint32_t)(16 + kd - 1) * 16u * 128u, slab1 = (uint32_t)(8 + kd - 1) * 16u * 128u;
+        int rt = p.rt;
+        if (wres_rt_env == 1 || wres_rt_env == 2) rt = (wres_rt_env == 2 && x.d >= 16) ? 2 : 1;
+        else if (rt == 2 && (avail - wb) / slab2 < 3) rt = 1;
+        // Default (B200_WRES=1): only when the ring keeps >= 4 slabs in flight -- the kernels run at bytes-in-flight / latency,
+        // and 16 -> 16 lost with 2 x 36 KB or 4 x 20 KB slabs (0.251 -> 0.30 ms) while 2 -> 16 won (0.191 -> 0.131 ms).
+        // B200_WRES=2 takes every layer whose matrix fits.
+        const uint32_t slabs = (avail - wb) / (rt == 2 ? slab2 : slab1);
+        if (slabs >= (wres_env >= 2 ? 2u : 4u) && (wres_env >= 2 || rt == p.rt)) {
+          wres_bytes = wb;
+          p.rt = rt;
+        }
+      }
+    }
+  }
   p.nbuf = (2 * p.rt * p.nt <= 512) ? 2 : 1;
   p.zl = 8 * p.rt + kd - 1;
   p.groups_x = x.w / 4;
@@ -1651,11 +1714,22 @@ static int conv_fprop_xslab_v(const ActView& x, const void* w, const float* bias
   // narrow layers: slab box + its kd weight tiles in ONE stage (conv_fprop_xslab1_kernel) when >= 3 such stages fit
   const uint32_t uni_bytes = (uint32_t)p.zl * 16u * 128u + (uint32_t)kd * (uint32_t)p.nt * 128u;
   static const bool allow_unified = !(getenv("B200_XSLAB_UNIFIED") && strcmp(getenv("B200_XSLAB_UNIFIED"), "0") == 0);
-  if (allow_unified && kd <= 3 && 3u * uni_bytes <= ring_budget && !p.ablate && !p.dbg) {
-    p.a_bytes = uni_bytes;
-    p.a_stages = (int)(ring_budget / uni_bytes);
+  if (wres_bytes && !p.ablate && !p.dbg) {
+    const uint32_t avail = 232448u - 1024u - 1024u - (p.epi_tma ? 32768u : 0u);
+    p.wres = 1;
+    p.a_bytes = (uint32_t)p.zl * 16u * 128u;                       // slab box only (a multiple of 2 KB)
+    p.a_stages = (int)((avail - wres_bytes) / p.a_bytes);
     if (p.a_stages > 6) p.a_stages = 6;
-    p.epi_off = ((uint32_t)p.a_stages * p.a_bytes + 1023u) & ~1023u;
+    p.wres_off = (uint32_t)p.a_stages * p.a_bytes;
+    p.epi_off = (p.wres_off + wres_bytes + 1023u) & ~1023u;
+  }
+  if (p.wres || (allow_unified && kd <= 3 && 3u * uni_bytes <= ring_budget && !p.ablate && !p.dbg)) {
+    if (!p.wres) {
+      p.a_bytes = uni_bytes;
+      p.a_stages = (int)(ring_budget / uni_bytes);
+      if (p.a_stages > 6) p.a_stages = 6;
+      p.epi_off = ((uint32_t)p.a_stages * p.a_bytes + 1023u) & ~1023u;
+    }
     const size_t smem1 = (size_t)p.epi_off + (p.epi_tma ? 32768u : 0u) + 1024;
 #define XSLAB1_LAUNCH(TT, CBV)                                                                            \
   {                                                                                                      \

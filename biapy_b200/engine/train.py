@@ -83,6 +83,55 @@ class Trainer:
         self._graph = None
         self.graph_launches = 0
 
+    # ------------------------------------------------------------------------------------- optimiser state
+    def state_dict(self) -> Dict:
+        """Optimiser state in ``torch.optim.AdamW`` / ``SGD`` ``state_dict()`` layout (per-parameter ``step`` / ``exp_avg`` /
+        ``exp_avg_sq`` or ``momentum_buffer``, one param group), so BiaPy checkpoints (``misc.py:328-386``) carry it and a
+        torch optimiser can resume from it."""
+        state = {}
+        for i, (p, o) in enumerate(zip(self.fp.params, self.fp.offsets)):
+            sl = slice(o, o + p.numel())
+            if self.opt_kind == "adamw":
+                if self.t > 0:
+                    state[i] = {"step": torch.tensor(float(self.t)), "exp_avg": self.m[sl].view(p.shape).detach().cpu().clone(),
+                                "exp_avg_sq": self.v[sl].view(p.shape).detach().cpu().clone()}
+            elif self.t > 0 and self.momentum:
+                state[i] = {"momentum_buffer": self.m[sl].view(p.shape).detach().cpu().clone()}
+        group = {"lr": self.lr, "weight_decay": self.wd, "params": list(range(len(self.fp.params)))}
+        if self.opt_kind == "adamw":
+            group.update(betas=tuple(self.betas), eps=self.eps, amsgrad=False)
+        else:
+            group.update(momentum=self.momentum)
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd: Dict, strict: bool = False):
+        """Inverse of :meth:`state_dict`; also accepts the ``state_dict()`` of a torch AdamW / SGD over the same parameters."""
+        st = sd.get("state", {})
+        steps = []
+        for i, (p, o) in enumerate(zip(self.fp.params, self.fp.offsets)):
+            e = st.get(i, st.get(str(i)))
+            if e is None:
+                continue
+            sl = slice(o, o + p.numel())
+            if self.opt_kind == "adamw":
+                self.m[sl].view(p.shape).copy_(e["exp_avg"])
+                self.v[sl].view(p.shape).copy_(e["exp_avg_sq"])
+                steps.append(int(float(e["step"])))
+            elif "momentum_buffer" in e and e["momentum_buffer"] is not None:
+                self.m[sl].view(p.shape).copy_(e["momentum_buffer"])
+                steps.append(1)
+        if steps:
+            self.t = max(steps)
+        groups = sd.get("param_groups") or [{}]
+        g = groups[0]
+        self.lr = g.get("lr", self.lr)
+        self.wd = g.get("weight_decay", self.wd)
+        if "betas" in g:
+            self.betas = tuple(g["betas"])
+        self.eps = g.get("eps", self.eps)
+        self.momentum = g.get("momentum", self.momentum)
+        self._graph = None                       # hyper-parameters are baked into a captured step
+
     # ------------------------------------------------------------------------------------------------- data
     def _to_device_cl(self, a, dtype=None) -> torch.Tensor:
         """host/device array in BiaPy layout -> (N, D, H, W, C) CUDA tensor (async copy from pinned memory)."""

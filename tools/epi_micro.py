@@ -11,8 +11,11 @@ import torch
 from biapy_b200 import _lib, ops
 
 dt = torch.bfloat16
-tag = f"EPI_TMA={os.environ.get('B200_EPI_TMA', '1')} SWZ={os.environ.get('B200_EPI_SWZ', '32')}"
-for (cin, cout, size, batch) in [(16, 16, 128, 4), (48, 16, 128, 4), (16, 48, 128, 4), (32, 32, 64, 4), (96, 32, 64, 4), (16, 64, 64, 4)]:
+tag = f"EPI_TMA={os.environ.get('B200_EPI_TMA', '1')} WRES={os.environ.get('B200_WRES', '1')} RT={os.environ.get('B200_WRES_RT', '0')}"
+SHAPES = [(16, 16, 128, 4), (2, 16, 128, 4), (48, 16, 128, 4), (16, 48, 128, 4), (32, 32, 64, 4), (96, 32, 64, 4), (16, 64, 64, 4)]
+if os.environ.get('EPI_MICRO_SHAPES') == 'wres':
+    SHAPES = SHAPES[:2]
+for (cin, cout, size, batch) in SHAPES:
     x = torch.randn(batch, size, size, size, cin, device="cuda").to(dt)
     w = torch.randn(cout, cin, 3, 3, 3, device="cuda") * 0.05
     b = torch.zeros(cout, device="cuda")
