@@ -96,3 +96,46 @@ def test_sliding_window_inference_matches_oracle_pipeline():
     ref = port_stitch.merge_3d(np.ascontiguousarray(p), (72, 64, 80, 1), ov, pad)
     assert got.shape == ref.shape and got.dtype == np.float32
     assert np.abs(got - ref).max() < 1e-4
+
+
+def test_trainer_optimizer_state_interoperates_with_torch_adamw(tmp_path):
+    """Trainer.state_dict() is a torch.optim.AdamW state: after 2 fused steps, a torch AdamW resumed from it takes the same
+    third step as the Trainer (same gradients fed to both), and the checkpoint round trip restores the Trainer."""
+    from biapy_b200.engine.train import Trainer
+    from biapy_b200.utils.misc import load_model_checkpoint, save_model
+    m, _ = _model(torch.float32)
+    m = m.cuda().set_engine(dtype=torch.float32)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(1, 32, 32, 32, 2, generator=g)
+    t = (torch.rand(1, 32, 32, 32, 1, generator=g) < 0.3).float()
+    tr = Trainer(m, loss="bce", optimizer="adamw", lr=1e-3, weight_decay=0.02)
+    for _ in range(2):
+        tr.step(x.numpy(), t.numpy())
+    sd = tr.state_dict()
+    assert set(sd) == {"state", "param_groups"} and len(sd["state"]) == len(tr.fp.params)
+    assert float(sd["state"][0]["step"]) == 2.0
+    # torch AdamW over copies of the parameters, resumed from the exported state
+    params = [torch.nn.Parameter(p.detach().cpu().clone()) for p in tr.fp.params]
+    opt = torch.optim.AdamW(params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.02)
+    opt.load_state_dict(sd)
+    cfg = {"PATHS": {"CHECKPOINT": str(tmp_path), "CHECKPOINT_FILE": ""},
+           "MODEL": {"LOAD_CHECKPOINT_EPOCH": "last_on_train", "ITEMS_TO_LOAD_FROM_CHECKPOINT": ["model", "optimizer", "epoch"]}}
+    save_model(tmp_path, cfg, "3.7.0", "job", 2, m, [tr])
+    tr.step(x.numpy(), t.numpy())                                  # third step: fills tr.fp.grad, updates the weights
+    torch.cuda.synchronize()
+    for p, gv in zip(params, (tr.fp.grad_views[q] for q in tr.fp.params)):
+        p.grad = gv.detach().cpu().clone()
+    opt.step()
+    num = sum(((p.detach() - q.detach().cpu()).double() ** 2).sum().item() for p, q in zip(params, tr.fp.params))
+    den = sum((p.detach().double() ** 2).sum().item() for p in params)
+    assert (num / den) ** 0.5 < 1e-5
+    # a fresh Trainer restored from the checkpoint repeats that third step
+    m2, _ = _model(torch.float32)
+    m2 = m2.cuda().set_engine(dtype=torch.float32)
+    tr2 = Trainer(m2, loss="bce", optimizer="adamw", lr=5e-2, weight_decay=0.0)
+    epoch, _ = load_model_checkpoint(cfg, "job", m2, "cuda", optimizer=[tr2])
+    assert epoch == 2 and tr2.t == 2 and tr2.lr == 1e-3 and tr2.wd == 0.02
+    tr2.step(x.numpy(), t.numpy())
+    torch.cuda.synchronize()
+    for a, b in zip(tr.fp.params, tr2.fp.params):
+        assert (a - b).abs().max().item() <= 1e-6 * max(1.0, a.abs().max().item())
