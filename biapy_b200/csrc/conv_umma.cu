@@ -524,6 +524,9 @@ struct XslabParams {
   // life of the CTA at byte offset wres_off; the ring then carries slab boxes only
   int wres;
   uint32_t wres_off;
+  // variable-slot ring of conv_fprop_xslab1_kernel (one 64-box + one 32-box per dy): slots alternate big (128-byte rows) and
+  // small (64-byte rows, packed) instead of all being big -- 4 stages in the space of 3
+  int varslot;
 };
 
 constexpr int kSlabAWarps = 1, kSlabBWarps = 3;
@@ -962,8 +965,15 @@ conv_fprop_xslab1_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid
   const int pd = p.kd / 2, ph_pad = p.kh / 2;
   const int nboxes = p.boxes64 + p.has32;
   const uint32_t slab_rows = (uint32_t)p.zl * 16u;
-  const uint32_t w_off = slab_rows * 128u;                 // weight tiles follow the (max-size) slab box inside a stage
-  const uint32_t w_tile = (uint32_t)p.nt * 128u;
+  // weight tiles follow the (max-size) slab box inside a stage; rowb = bytes per row of the widest box (128, or 64 when the
+  // window is cut into 32-element boxes only)
+  const uint32_t rowb = p.boxes64 > 0 ? 128u : 64u;
+  const uint32_t w_off = slab_rows * rowb;
+  const uint32_t w_tile = (uint32_t)p.nt * rowb;
+  // variable slots: even slots hold a 64-box stage (slab + kd tiles, 128-byte rows), odd slots a 32-box stage packed at 64-byte
+  // rows; slot s starts at (s / 2) * (big + small) + (s & 1) * big
+  const bool varslot = p.varslot != 0;
+  const uint32_t vs_big = slab_rows * 128u + (uint32_t)p.kd * (uint32_t)p.nt * 128u, vs_small = vs_big >> 1;
   // resident weights: tile (dy, b, dz) at wres_off + dy * wres_dy + (b < boxes64 ? b * kd * t64 : boxes64 * kd * t64) + dz * (t64 | t32)
   const uint32_t t64 = (uint32_t)p.nt * 128u, t32 = (uint32_t)p.nt * 64u;
   const uint32_t wres_dy = (uint32_t)p.kd * ((uint32_t)p.boxes64 * t64 + (uint32_t)p.has32 * t32);
@@ -987,8 +997,9 @@ conv_fprop_xslab1_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid
         for (int b = 0; b < nboxes; ++b) {
           const bool wide = b < p.boxes64;
           const uint32_t dst = smem0 + p.wres_off + (uint32_t)dy * wres_dy +
-                               (wide ? (uint32_t)b * p.kd * t64 : (uint32_t)p.boxes64 * p.kd * t64) + (uint32_t)dz * (wide ? t64 : t32);
-          tma_load_2d(dst, wide ? &tmw64 : &tmw32, bar_wres, (dz * p.kh + dy) * p.kx + b * 64, 0);
+                               (wide ? (uint32_t)b * p.kd * t64 : (uint32_t)p.boxes64 * p.kd * t64 + (uint32_t)(b - p.boxes64) * p.kd * t32) +
+                               (uint32_t)dz * (wide ? t64 : t32);
+          tma_load_2d(dst, wide ? &tmw64 : &tmw32, bar_wres, (dz * p.kh + dy) * p.kx + (wide ? b * 64 : p.boxes64 * 64 + (b - p.boxes64) * 32), 0);
         }
     } else if (role <= (wres ? 0 : p.kd) && elect_one()) {
       const int a_stages = p.a_stages;
@@ -1002,20 +1013,24 @@ conv_fprop_xslab1_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid
           for (int b = 0; b < nboxes; ++b) {
             const bool wide = b < p.boxes64;
             const uint32_t wbytes = wide ? 128u : 64u;
+            const int koff = wide ? b * 64 : p.boxes64 * 64 + (b - p.boxes64) * 32;      // element offset of box b in the window
             mbar_wait(bar_aempty + 8 * slot, ph ^ 1);
             const uint32_t fa = bar_afull + 8 * slot;
-            const uint32_t dst = smem0 + slot * p.a_bytes;
+            const uint32_t dst = smem0 + (varslot ? (uint32_t)(slot >> 1) * (vs_big + vs_small) + (uint32_t)(slot & 1) * vs_big
+                                                  : (uint32_t)slot * p.a_bytes);
+            const uint32_t w_off_b = (varslot && !wide) ? slab_rows * 64u : w_off;
+            const uint32_t w_tile_b = (varslot && !wide) ? (uint32_t)p.nt * 64u : w_tile;
             if (role == 0) {
               mbar_expect_tx(fa, slab_rows * wbytes);
               asm volatile(
                   "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                  ::"r"(dst), "l"((uint64_t)(wide ? &tmx64 : &tmx32)), "r"(fa), "r"(e0 + b * 64), "r"(y0 + dy - ph_pad),
+                  ::"r"(dst), "l"((uint64_t)(wide ? &tmx64 : &tmx32)), "r"(fa), "r"(e0 + koff), "r"(y0 + dy - ph_pad),
                     "r"(z0 - pd), "r"(n)
                   : "memory");
             } else {
               const int dz = role - 1;
               mbar_expect_tx(fa, (uint32_t)p.nt * wbytes);
-              tma_load_2d(dst + w_off + (uint32_t)dz * w_tile, wide ? &tmw64 : &tmw32, fa, (dz * p.kh + dy) * p.kx + b * 64, 0);
+              tma_load_2d(dst + w_off_b + (uint32_t)dz * w_tile_b, wide ? &tmw64 : &tmw32, fa, (dz * p.kh + dy) * p.kx + koff, 0);
             }
             if (++slot == a_stages) { slot = 0; ph ^= 1; }
           }
@@ -1034,6 +1049,8 @@ conv_fprop_xslab1_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid
       const uint32_t rt_n = in_reg((uint32_t)p.rt * nt), stride = in_reg((int)gridDim.x);
       const uint32_t wres16 = in_reg((smem0 + p.wres_off) >> 4), wres_dy16 = in_reg(wres_dy >> 4), t64_16 = in_reg(t64 >> 4),
                      t32_16 = in_reg(t32 >> 4);
+      const uint32_t vs_big16 = in_reg(vs_big >> 4), vs_small16 = in_reg(vs_small >> 4);
+      const uint32_t w16s = in_reg((slab_rows * 64u) >> 4), wt16s = in_reg(((uint32_t)p.nt * 64u) >> 4);
       int as = 0;
       uint32_t aph = 0;
       int it = 0;
@@ -1056,13 +1073,15 @@ conv_fprop_xslab1_kernel(const __grid_constant__ CUtensorMap tmx64, const __grid
             const uint64_t tmpl = wide ? tmpl128 : tmpl64;
             if (!ready) mbar_wait(bar_afull + 8 * as, aph);
             tc_fence_after();
-            const uint32_t s16 = a0 + (uint32_t)as * a16;
+            const uint32_t s16 = varslot ? a0 + (uint32_t)(as >> 1) * (vs_big16 + vs_small16) + (uint32_t)(as & 1) * vs_big16
+                                         : a0 + (uint32_t)as * a16;
             const uint32_t t_lo = (uint32_t)tmpl, t_hi = (uint32_t)(tmpl >> 32);
             uint32_t ad = t_lo + s16 + (uint32_t)r * 8u * line;
-            uint32_t bd = t_lo + s16 + w16;
-            uint32_t bstep = wt16;
+            uint32_t bd = t_lo + s16 + ((varslot && !wide) ? w16s : w16);
+            uint32_t bstep = (varslot && !wide) ? wt16s : wt16;
             if (wres) {
-              bd = t_lo + wres16 + (uint32_t)dy * wres_dy16 + (wide ? (uint32_t)b * (uint32_t)kd * t64_16 : (uint32_t)boxes64 * (uint32_t)kd * t64_16);
+              bd = t_lo + wres16 + (uint32_t)dy * wres_dy16 +
+                   (wide ? (uint32_t)b * (uint32_t)kd * t64_16 : (uint32_t)boxes64 * (uint32_t)kd * t64_16 + (uint32_t)(b - boxes64) * (uint32_t)kd * t32_16);
               bstep = wide ? t64_16 : t32_16;
             }
             const uint32_t cur = bar_aempty + 8 * as;
@@ -1649,7 +1668,7 @@ static int conv_fprop_xslab_v(const ActView& x, const void* w, const float* bias
   p.tiles_h = (int)ceil_div(x.h, 16); p.tiles_d = (int)ceil_div(x.d, 8 * p.rt);
   p.num_tiles = x.n * p.tiles_d * p.tiles_h * p.groups_x;
   B200_CHECK_ARG(xfold_geom(x.c, kw, &p.xoff, &p.kx), "conv_fprop(xslab): unsupported Cin");
-  p.boxes64 = p.kx / 64; p.has32 = (p.kx % 64) ? 1 : 0;
+  p.boxes64 = p.kx / 64; p.has32 = (p.kx % 64) ? 1 : 0;           // has32 = number of 32-element boxes behind the 64-element ones
   p.a_bytes = (((uint32_t)p.zl * 16u * 128u) + 1023u) & ~1023u;
   p.b_bytes = (((uint32_t)p.nt * 128u) + 1023u) & ~1023u;
   // split ~200 KB between the two rings: at least 2 slabs, the rest for weight tiles (3..6)
@@ -1712,8 +1731,19 @@ static int conv_fprop_xslab_v(const ActView& x, const void* w, const float* bias
 
   int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
   // narrow layers: slab box + its kd weight tiles in ONE stage (conv_fprop_xslab1_kernel) when >= 3 such stages fit
-  const uint32_t uni_bytes = (uint32_t)p.zl * 16u * 128u + (uint32_t)kd * (uint32_t)p.nt * 128u;
+  // A 96-element window (Cin = 16, kw = 3) is one 64-box + one 32-box.  Cut into three 32-boxes a unified stage halves, so the
+  // N = 128 / 192 layers (16 -> 32, 16 -> 48) fit the unified-stage kernel, which they do not with 128-byte rows: 16 -> 48 @128^3
+  // 0.729 -> 0.621 ms (9 stage hand-overs per tile instead of 24).  Where the 128-byte stages fit anyway (16 -> 16) the cut only
+  // adds hand-overs (6 -> 9 per tile): 0.251 -> 0.273 ms, so it is not applied there (B200_XSLAB_ALL32: 0 never, 1 always,
+  // 2 = default, only when needed).
+  static const int all32_env = getenv("B200_XSLAB_ALL32") ? atoi(getenv("B200_XSLAB_ALL32")) : 2;
   static const bool allow_unified = !(getenv("B200_XSLAB_UNIFIED") && strcmp(getenv("B200_XSLAB_UNIFIED"), "0") == 0);
+  uint32_t uni_bytes = (uint32_t)p.zl * 16u * 128u + (uint32_t)kd * (uint32_t)p.nt * 128u;
+  if (all32_env && p.kx == 96 && kd <= 3 && !wres_bytes && allow_unified && !p.ablate && !p.dbg &&
+      (all32_env == 1 || 3u * uni_bytes > ring_budget)) {
+    const uint32_t u32 = (uint32_t)p.zl * 16u * 64u + (uint32_t)kd * (uint32_t)p.nt * 64u;
+    if (3u * u32 <= ring_budget) { p.boxes64 = 0; p.has32 = 3; uni_bytes = u32; }
+  }
   if (wres_bytes && !p.ablate && !p.dbg) {
     const uint32_t avail = 232448u - 1024u - 1024u - (p.epi_tma ? 32768u : 0u);
     p.wres = 1;
@@ -1729,6 +1759,15 @@ static int conv_fprop_xslab_v(const ActView& x, const void* w, const float* bias
       p.a_stages = (int)(ring_budget / uni_bytes);
       if (p.a_stages > 6) p.a_stages = 6;
       p.epi_off = ((uint32_t)p.a_stages * p.a_bytes + 1023u) & ~1023u;
+      // 64-box + 32-box windows (Cin = 16): the 32-box stage needs half a slot.  Alternating big / small slots puts 4 stages
+      // where 3 uniform ones fit -- same hand-overs per tile, one more stage of TMA latency covered.
+      static const int vs_env = getenv("B200_XSLAB_VARSLOT") ? atoi(getenv("B200_XSLAB_VARSLOT")) : 1;
+      const uint32_t pair = uni_bytes + uni_bytes / 2;
+      if (vs_env && p.boxes64 == 1 && p.has32 == 1 && p.a_stages < 4 && 2u * pair <= ring_budget && (uni_bytes / 2) % 1024u == 0) {
+        p.varslot = 1;
+        p.a_stages = 4;
+        p.epi_off = (2u * pair + 1023u) & ~1023u;
+      }
     }
     const size_t smem1 = (size_t)p.epi_off + (p.epi_tma ? 32768u : 0u) + 1024;
 #define XSLAB1_LAUNCH(TT, CBV)                                                                            \

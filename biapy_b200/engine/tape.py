@@ -177,7 +177,7 @@ class Tape:
                     return
         wp = self._pack(wkey, flip, impl == _lib.IMPL_XFOLD, wsrc=w)
         if stats and impl == _lib.IMPL_XFOLD and self.fuse_stats and not accumulate and y.shape[4] == 16:
-            sums = torch.zeros(y.shape[0] * y.shape[4] * 2, dtype=torch.float64, device=y.device)
+            sums = ops.zeros(y.shape[0] * y.shape[4] * 2, torch.float64, y.device)
             return sums if ops.conv_fprop_stats(x, wp, bias, y, k, sums, accumulate=accumulate) else None
         ops.conv_fprop(x, wp, bias, y, k, accumulate=accumulate, impl=impl)
         return None

@@ -82,6 +82,7 @@ class Trainer:
         self.ndim = model.ndim
         self._graph = None
         self.graph_launches = 0
+        self._arena = ops.ZeroArena()
 
     # ------------------------------------------------------------------------------------- optimiser state
     def state_dict(self) -> Dict:
@@ -237,6 +238,13 @@ class Trainer:
         if model.training:
             tape.rng_seed = model.next_rng_seed(self.device)
         self.fp.grad.zero_()
+        self._arena.begin(self.device)            # one fill for all the accumulators of this pass
+        try:
+            return self._run_pass(model, tape, xd, td)
+        finally:
+            self._arena.end()
+
+    def _run_pass(self, model, tape, xd: torch.Tensor, td: torch.Tensor) -> torch.Tensor:
         if xd.dtype == model.engine_dtype and xd.is_contiguous():
             x_tt = TT(xd, requires_grad=False)
         else:

@@ -23,6 +23,56 @@ PROFILE = None
 PROFILE_SHAPES = False     # append the layer shape to the conv labels (bench.py --detail)
 
 
+class ZeroArena:
+    """Zero-initialised scratch for one training pass.  The accumulators of a step (channel sums, backward sums, packed
+    weight-gradient buffers: ~70 small tensors) each cost a fill kernel when allocated with ``torch.zeros``; between
+    :meth:`begin` and :meth:`end` they are carved out of ONE buffer that is cleared by a single fill.  The buffer grows to the
+    high-water mark of the previous pass (the first pass falls back to ``torch.zeros``)."""
+
+    def __init__(self):
+        self.buf = None
+        self._retired = []          # outgrown buffers stay alive: a captured CUDA graph may still point into them
+        self.off = self.need = 0
+
+    def begin(self, device):
+        """Make this the active arena (module-level `ARENA`) and clear it."""
+        global ARENA
+        size = (self.need + 4095) // 4096 * 4096
+        if size and (self.buf is None or self.buf.numel() < size or self.buf.device != torch.device(device)):
+            if self.buf is not None:
+                self._retired.append(self.buf)
+            self.buf = torch.empty(size, dtype=torch.uint8, device=device)
+        if self.buf is not None:
+            self.buf.zero_()
+        self.off = self.need = 0
+        ARENA = self
+
+    def end(self):
+        global ARENA
+        ARENA = None
+
+    def take(self, numel: int, dtype: torch.dtype, device) -> Optional[torch.Tensor]:
+        nbytes = (numel * dtype.itemsize + 255) // 256 * 256
+        self.need += nbytes
+        if self.buf is None or self.off + nbytes > self.buf.numel() or self.buf.device != torch.device(device):
+            return None
+        t = self.buf[self.off:self.off + nbytes].view(dtype)[:numel]
+        self.off += nbytes
+        return t
+
+
+ARENA: Optional[ZeroArena] = None      # the arena of the training pass in flight (set by ZeroArena.begin / end)
+
+
+def zeros(numel: int, dtype: torch.dtype, device) -> torch.Tensor:
+    """Zero-filled 1-D scratch tensor: a slice of the step's arena when one is active, else ``torch.zeros``."""
+    if ARENA is not None:
+        t = ARENA.take(numel, dtype, device)
+        if t is not None:
+            return t
+    return torch.zeros(numel, dtype=dtype, device=device)
+
+
 def _timed_call(label, flops, nbytes, name, *args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -160,7 +210,7 @@ def conv_wgrad(x, dy, cout: int, cin: int, k: Sequence[int], dw_out: torch.Tenso
                accumulate=False, impl=_lib.IMPL_AUTO):
     """dw_out: (Cout, Cin, *k) fp32; dbias_out: (Cout,) fp32, must be zero-initialised unless accumulate."""
     taps = k[0] * k[1] * k[2]
-    packed = torch.zeros(cout * taps * cin, dtype=torch.float32, device=x.device)
+    packed = zeros(cout * taps * cin, torch.float32, x.device)
     label = flops = nbytes = None
     if PROFILE is not None:
         vox = x.shape[0] * x.shape[1] * x.shape[2] * x.shape[3]
@@ -223,7 +273,7 @@ def convT_wgrad_tc(x, dy, dw: torch.Tensor, dbias, s: Sequence[int], accumulate=
     """dw: (Cin, Cout, *s) fp32 parameter-layout gradient."""
     cin, cout = x.shape[-1], dy.shape[-1]
     taps = s[0] * s[1] * s[2]
-    packed = torch.zeros(taps * cout * cin, dtype=torch.float32, device=x.device)
+    packed = zeros(taps * cout * cin, torch.float32, x.device)
     _launch_timed("convT_wgrad_tc", _convT_work(x, cout, s) if PROFILE is not None else 0, 0,
                   "b200_convT_wgrad_tc", _ref(x), _ref(dy), _ptr(packed), _ptr(dbias), s[0], s[1], s[2], stream_ptr())
     _launch("b200_unpack_convT_wgrad", _ptr(packed), _ptr(dw), cin, cout, taps, 1 if accumulate else 0, stream_ptr())
@@ -276,7 +326,7 @@ def norm_stats(x, groups: int, gamma, beta, eps: float = 1e-5, batch_stats: bool
     `sums`: the (N, C, 2) float64 channel sums of x when the producing convolution already reduced them in its epilogue."""
     n, d, h, w, c = x.shape
     if sums is None:
-        sums = torch.zeros(n * c * 2, dtype=torch.float64, device=x.device)
+        sums = zeros(n * c * 2, torch.float64, x.device)
         _launch("b200_channel_sums", _ref(x), _ptr(sums), stream_ptr(), shape=x.shape)
     world = _sync_world(sync_group) if batch_stats else 1
     if world > 1:
@@ -322,7 +372,7 @@ def scale_shift_act(x, scale, shift, act: str, y):
 
 def norm_act_bwd(x, dy, st: NormStats, gamma, beta, act: str, dx, dgamma, dbeta, accumulate=False):
     n, d, h, w, c = x.shape
-    red = torch.zeros(n * c * 2, dtype=torch.float64, device=x.device)
+    red = zeros(n * c * 2, torch.float64, x.device)
     _launch("b200_norm_act_bwd_reduce", _ref(x), _ref(dy), _ptr(st.mean), _ptr(st.rstd), st.groups, _ptr(gamma), _ptr(beta),
             ACT[act], _ptr(red), stream_ptr(), shape=x.shape)
     coef = torch.empty(n * c * 4, dtype=torch.float32, device=x.device)

@@ -334,7 +334,9 @@ for (n, d, h, w, cin, cout) in [(2, 16, 16, 16, 16, 16), (1, 20, 24, 12, 48, 16)
     outs = {}
     for tma in ("0", "1"):
         tmp = tempfile.mkdtemp()
-        env = dict(os.environ, B200_EPI_TMA=tma, B200_EPI_SWZ=swz)
+        # the main loop is pinned: the operand-ring budget, hence the box cut / slot layout, depends on the epilogue's staging
+        # buffers, and a different K order changes the fp32 rounding (1 ulp on ~3e-5 of the outputs), not the epilogue under test
+        env = dict(os.environ, B200_EPI_TMA=tma, B200_EPI_SWZ=swz, B200_XSLAB_ALL32="0", B200_XSLAB_VARSLOT="0")
         r = subprocess.run([sys.executable, "-c", f"OUT={tmp!r}\n" + code], env=env, capture_output=True, text=True, timeout=600,
                            cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
         assert r.returncode == 0, r.stderr[-2000:]
@@ -344,7 +346,7 @@ for (n, d, h, w, cin, cout) in [(2, 16, 16, 16, 16, 16), (1, 20, 24, 12, 48, 16)
         assert a[:7] == b[:7]
         ya = torch.load(f"{outs['0'][0]}/y_{'_'.join(a[:6])}_{a[6]}.pt")
         yb = torch.load(f"{outs['1'][0]}/y_{'_'.join(b[:6])}_{b[6]}.pt")
-        assert torch.equal(ya, yb), a[:7]                      # plain stores: bit-identical
+        assert torch.equal(ya, yb), (a[:7], (ya - yb).abs().max().item(), int((ya != yb).sum()), ya.abs().max().item())   # plain stores: bit-identical
         assert float(b[10]) == 0.0                             # neighbouring channels of the slice untouched
         # accumulate: y + y, rounded once more by the element-wise add of the TMA unit
         assert float(b[9]) <= 2 ** -7 * 2 * float(b[8]) + 1e-6, b

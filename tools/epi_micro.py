@@ -11,7 +11,7 @@ import torch
 from biapy_b200 import _lib, ops
 
 dt = torch.bfloat16
-tag = f"EPI_TMA={os.environ.get('B200_EPI_TMA', '1')} WRES={os.environ.get('B200_WRES', '1')} RT={os.environ.get('B200_WRES_RT', '0')}"
+tag = f"VARSLOT={os.environ.get('B200_XSLAB_VARSLOT', '1')}"
 SHAPES = [(16, 16, 128, 4), (2, 16, 128, 4), (48, 16, 128, 4), (16, 48, 128, 4), (32, 32, 64, 4), (96, 32, 64, 4), (16, 64, 64, 4)]
 if os.environ.get('EPI_MICRO_SHAPES') == 'wres':
     SHAPES = SHAPES[:2]
