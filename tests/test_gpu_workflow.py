@@ -1,0 +1,85 @@
+"""GPU test of the workflow surface: a YAML-configured `BiaPy` object trains and predicts through the B200 engine and agrees
+with the CPU oracle pipeline (normalise -> crop -> forward -> sigmoid -> merge -> binarise) and with the bare Trainer."""
+import contextlib
+import copy
+import io
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import port_models, port_norm, port_stitch
+
+pytestmark = pytest.mark.gpu
+
+YAML = """
+PROBLEM: {TYPE: SEMANTIC_SEG, NDIM: 3D}
+DATA:
+    PATCH_SIZE: (32, 32, 32, 1)
+    NORMALIZATION: {TYPE: scale_range}
+    TEST: {OVERLAP: "(0.25, 0.25, 0)", PADDING: "(4, 0, 2)"}
+MODEL:
+    ARCHITECTURE: resunet
+    FEATURE_MAPS: [16, 32, 64]
+    DROPOUT_VALUES: [0, 0, 0]
+    ISOTROPY: [True, True, True]
+    CONV_LAYERS: [2, 2, 2]
+    Z_DOWN: [0, 0]
+    YX_DOWN: [0, 0]
+    NORMALIZATION: gn
+    ACTIVATION: silu
+TRAIN: {OPTIMIZER: ADAMW, LR: 1.E-3, BATCH_SIZE: 2, W_DECAY: 0.02}
+"""
+KW = dict(image_shape=(32, 32, 32, 1), activation="silu", feature_maps=[16, 32, 64], drop_values=[0, 0, 0], normalization="gn", k_size=3,
+          yx_down=[2, 2], z_down=[2, 2], isotropy=[True] * 3, larger_io=False, conv_layers=[2] * 3, output_channels=[1])
+
+
+def _biapy(dtype):
+    from biapy_b200._biapy import BiaPy
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        return BiaPy(YAML, name="job", run_id=1, engine_dtype=dtype)
+
+
+def test_yaml_configured_prediction_matches_oracle_pipeline():
+    b = _biapy(torch.float32)
+    assert type(b.workflow).__name__ == "Semantic_Segmentation_Workflow" and b.job_identifier == "job_1"
+    sd = {k: v.detach().cpu().clone() for k, v in b.workflow.model.state_dict().items()}
+    img = np.random.default_rng(3).integers(0, 256, (48, 40, 70, 1)).astype(np.uint8)
+    pred, mask = b.workflow.process_test_sample(img)
+    # oracle: the reference's numpy / ATen path
+    x, info = port_norm.normalize_image(img.copy(), dict(b.workflow.test_norm_module))
+    patch, ov, pad = (32, 32, 32, 1), (0.25, 0.25, 0.0), (4, 0, 2)
+    patches, _ = port_stitch.crop_3d(x, patch, ov, pad, "reflect")
+    with torch.no_grad():
+        y = port_models.forward("resunet", sd, torch.from_numpy(patches).permute(0, 4, 1, 2, 3), training=False, **KW)
+        p = port_models.apply_head_activations(y, ["ce_sigmoid"], training=False).permute(0, 2, 3, 4, 1).numpy()
+    ref = port_stitch.merge_3d(np.ascontiguousarray(p), (48, 40, 70, 1), ov, pad)
+    assert pred.shape == ref.shape and np.abs(pred - ref).max() < 1e-4
+    assert b.workflow.current_sample["norm_info"]["per_channel_info"] == info["per_channel_info"]
+    away = np.abs(ref - 0.5) > 1e-3                                 # voxels whose side of the threshold does not hinge on 1e-4
+    assert mask.dtype == np.uint8 and np.array_equal(mask[away], port_norm.binarize(ref, 2)[away])
+    assert np.array_equal(b.predict(img), pred)
+    # patches through predict_batches_in_test (the reference's per-batch entry point)
+    pb = b.workflow.predict_batches_in_test(patches[:3])
+    assert np.abs(pb - p[:3]).max() < 1e-4
+
+
+def test_yaml_configured_training_equals_the_trainer():
+    from biapy_b200.engine.train import Trainer
+    from biapy_b200.models.resunet import ResUNet
+    g = torch.Generator().manual_seed(1)
+    X = torch.randn(4, 32, 32, 32, 1, generator=g).numpy()
+    Y = (torch.rand(4, 32, 32, 32, 1, generator=g) < 0.3).float().numpy()
+    b = _biapy(torch.float32)
+    losses = b.train(X, Y, steps=3)
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = ResUNet(**dict(KW, output_channel_info=["pred0"], head_activations=["ce_sigmoid"]))
+    m = m.cuda().set_engine(dtype=torch.float32)
+    tr = Trainer(m, loss="bce", optimizer="adamw", lr=1e-3, betas=(0.9, 0.999), weight_decay=0.02)
+    ref = []
+    for s in range(3):
+        lo = (s * 2) % 3
+        ref.append(float(tr.step(X[lo:lo + 2], Y[lo:lo + 2]).item()))
+    assert losses == ref and losses[-1] < losses[0]
