@@ -82,4 +82,5 @@ def test_yaml_configured_training_equals_the_trainer():
     for s in range(3):
         lo = (s * 2) % 3
         ref.append(float(tr.step(X[lo:lo + 2], Y[lo:lo + 2]).item()))
-    assert losses == ref and losses[-1] < losses[0]
+    # same kernels on the same data; fp32 atomics (weight gradients) make the trajectories agree to rounding, not bit for bit
+    assert all(abs(a - r) <= 1e-6 * max(1.0, abs(r)) for a, r in zip(losses, ref)) and losses[-1] < losses[0]
