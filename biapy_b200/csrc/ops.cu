@@ -190,7 +190,7 @@ __global__ void scale_shift_act_kernel(View<const TI> x, View<TO> y, const float
 }
 
 // -------------------------------------------------------------------------------- norm+act backward, pass 1
-// same thread layout as channel_sums; accumulates (sum g, sum g*xhat) per (n,c)
+// same thread layout as channel_sums; accumulates (sum g, sum g*(x - mean)) per (n,c)
 template <typename T, int VEC, int ACT, int U, int MINB>
 __global__ void __launch_bounds__(256, MINB) norm_act_bwd_reduce_kernel(View<const T> x, View<const T> dy, const float* __restrict__ mean,
                                            const float* __restrict__ rstd, int groups,
@@ -203,9 +203,11 @@ __global__ void __launch_bounds__(256, MINB) norm_act_bwd_reduce_kernel(View<con
   const int row = tid / cv_count;
   const int cpg = x.c / groups;
   if (row < rows) {
-    // ypre = x*ka + kb with ka = rs*ga, kb = be - mu*rs*ga.  Accumulates (sum g, sum g*x); the finalize kernel turns
-    // the second one into sum g*xhat = rs*sum(g*x) - mu*rs*sum(g), which keeps this loop at two constants per channel.
-    float ka[VEC], kb[VEC], s[VEC], s2[VEC];
+    // ypre = x*ka + kb with ka = rs*ga, kb = be - mu*rs*ga.  Accumulates (sum g, sum g*(x - mu)): the CENTRED second moment,
+    // so that sum g*xhat = rs * it without the cancellation of rs*sum(g*x) - mu*rs*sum(g) (fp32 partials over thousands of
+    // voxels per thread: with |mu| of a few sigma that difference lost 3-4 digits -- input gradients of the 64^3 Attention
+    // U-Net were 3e-2 off the CPU reference, 1e-3 after centring).
+    float ka[VEC], kb[VEC], mu_c[VEC], s[VEC], s2[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       int c = cv * VEC + i;
@@ -214,6 +216,7 @@ __global__ void __launch_bounds__(256, MINB) norm_act_bwd_reduce_kernel(View<con
       float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
       ka[i] = r * ga;
       kb[i] = be - mu * r * ga;
+      mu_c[i] = mu;
       s[i] = s2[i] = 0.f;
     }
     const int64_t chunk = (x.spatial + gridDim.x - 1) / gridDim.x;
@@ -239,7 +242,7 @@ __global__ void __launch_bounds__(256, MINB) norm_act_bwd_reduce_kernel(View<con
             const float fx = to_f<T>(px[u].v[i]);
             const float g = to_f<T>(pd[u].v[i]) * act_grad_t<ACT>(act, fmaf(fx, ka[i], kb[i]));
             s[i] += g;
-            s2[i] = fmaf(g, fx, s2[i]);
+            s2[i] = fmaf(g, fx - mu_c[i], s2[i]);
           }
         }
     }
@@ -265,7 +268,7 @@ __global__ void norm_bwd_finalize_kernel(const double* __restrict__ red, const f
                                          const float* __restrict__ beta, int n, int c, int groups, int64_t spatial,
                                          int batch_stats, float* __restrict__ coef, float* __restrict__ dgamma,
                                          float* __restrict__ dbeta) {
-  // red[n][c] = (S1 = sum g, Sgx = sum g*x);  S2 = sum g*xhat = rstd*Sgx - mean*rstd*S1
+  // red[n][c] = (S1 = sum g, Sgc = sum g*(x - mean));  S2 = sum g*xhat = rstd*Sgc
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   int cpg = c / groups;
   if (idx < n * groups) {
@@ -273,12 +276,12 @@ __global__ void norm_bwd_finalize_kernel(const double* __restrict__ red, const f
     int n0 = batch_stats ? 0 : ni, n1 = batch_stats ? n : ni + 1;
     double a = 0.0, b = 0.0;
     for (int nn = n0; nn < n1; ++nn) {
-      const double r = (double)rstd[(int64_t)nn * groups + g], mu = (double)mean[(int64_t)nn * groups + g];
+      const double r = (double)rstd[(int64_t)nn * groups + g];
       for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) {
         double ga = gamma ? (double)gamma[cc] : 1.0;
-        double s1 = red[((int64_t)nn * c + cc) * 2], sgx = red[((int64_t)nn * c + cc) * 2 + 1];
+        double s1 = red[((int64_t)nn * c + cc) * 2], sgc = red[((int64_t)nn * c + cc) * 2 + 1];
         a += ga * s1;
-        b += ga * (r * sgx - mu * r * s1);
+        b += ga * (r * sgc);
       }
     }
     double m = (double)spatial * cpg * (n1 - n0);
@@ -298,10 +301,10 @@ __global__ void norm_bwd_finalize_kernel(const double* __restrict__ red, const f
     int g = idx / cpg;
     double sg = 0.0, sb = 0.0;
     for (int nn = 0; nn < n; ++nn) {
-      const double r = (double)rstd[(int64_t)nn * groups + g], mu = (double)mean[(int64_t)nn * groups + g];
-      double s1 = red[((int64_t)nn * c + idx) * 2], sgx = red[((int64_t)nn * c + idx) * 2 + 1];
+      const double r = (double)rstd[(int64_t)nn * groups + g];
+      double s1 = red[((int64_t)nn * c + idx) * 2], sgc = red[((int64_t)nn * c + idx) * 2 + 1];
       sb += s1;
-      sg += r * sgx - mu * r * s1;
+      sg += r * sgc;
     }
     if (dgamma) dgamma[idx] += (float)sg;
     if (dbeta) dbeta[idx] += (float)sb;

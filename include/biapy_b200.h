@@ -272,7 +272,7 @@ int b200_bn_eval_coeffs(const float* running_mean, const float* running_var, con
 int b200_scale_shift_act(const b200_tensor* x, const float* scale, const float* shift, int32_t act,
                          const b200_tensor* y, void* stream);
 /* backward, pass 1: with xhat = (x-mean)*rstd, ypre = xhat*gamma+beta, g = dy*act'(ypre):
- *   red[N][C][2] (double, zero-initialised) += (sum g, sum g*x)   [b200_norm_bwd_finalize derives sum g*xhat]  */
+ *   red[N][C][2] (double, zero-initialised) += (sum g, sum g*(x - mean))   [centred: sum g*xhat = rstd * it]     */
 int b200_norm_act_bwd_reduce(const b200_tensor* x, const b200_tensor* dy, const float* mean, const float* rstd,
                              int32_t groups, const float* gamma, const float* beta, int32_t act,
                              double* red, void* stream);
