@@ -320,31 +320,93 @@ def run_train(args):
     print(json.dumps(out), flush=True)
 
 
+def cpu_infer_patch_time(threads):
+    """Reference CPU path of the sliding-window pipeline per patch, on a bounded sample: eval forward + sigmoid of ONE 128^3 x 2
+    patch (fp32, oracle port) plus numpy crop + spline merge of a 256^3 volume (27 patches) scaled to one patch."""
+    from oracle import port_models, port_stitch
+    from biapy_b200.models.resunet import ResUNet
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = ResUNet(**CFG2)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    x = torch.randn(1, 2, 128, 128, 128, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        port_models.forward("resunet", sd, x[:, :, :64, :64, :64], training=False, **dict(CFG2, image_shape=(64, 64, 64, 2)))   # warm-up
+        t0 = time.perf_counter()
+        y = port_models.forward("resunet", sd, x, training=False, **CFG2)
+        torch.sigmoid(y)
+        t_fwd = time.perf_counter() - t0
+    vol = np.random.default_rng(0).standard_normal((256, 256, 256, 2)).astype(np.float32)
+    t0 = time.perf_counter()
+    patches, _ = port_stitch.crop_3d(vol, (128, 128, 128, 2), (0.25,) * 3, (0, 0, 0), "reflect")
+    port_stitch.merge_3d(np.ascontiguousarray(patches[..., :1]), (256, 256, 256, 1), (0.25,) * 3, (0, 0, 0))
+    t_stitch = (time.perf_counter() - t0) / patches.shape[0]
+    return t_fwd + t_stitch, t_fwd, t_stitch
+
+
 def run_infer(args):
     """BASELINE config[2]: 512^3 volume, 128^3 patches, 25% overlap -> 216 patches, sigmoid head, device-resident."""
     from biapy_b200 import ops
+    from biapy_b200.data import _stitch
     from biapy_b200.engine.inference import predict_volume
     rank, world, local = dist_setup(args.gpus)
+    peaks = load_peaks()
     model = build_model(torch.bfloat16).eval()
     g = torch.Generator().manual_seed(1)
     vol_h = torch.randn(512, 512, 512, 2, generator=g).to(torch.float16).pin_memory()
     vol_d = vol_h.cuda()
+    kw = dict(overlap=(0.25,) * 3, padding=(0, 0, 0), batch_size=4, head_activations=["ce_sigmoid"])
 
     def step(i):
-        predict_volume(model, vol_d, (128, 128, 128, 2), overlap=(0.25,) * 3, padding=(0, 0, 0), batch_size=4,
-                       head_activations=["ce_sigmoid"])
+        predict_volume(model, vol_d, (128, 128, 128, 2), **kw)
+
+    out_h = torch.empty(512, 512, 512, 1, dtype=torch.float32).pin_memory()
+
+    def e2e_step(i):                                          # host volume in, host prediction out
+        out_h.copy_(predict_volume(model, vol_h.cuda(non_blocking=True), (128, 128, 128, 2), **kw), non_blocking=True)
 
     for i in range(max(1, args.warmup // 2)):
         step(i)
+    sampler = ClockSampler(local)
+    sampler.start()
     n0 = ops.LAUNCHES
     ms = timed(step, args.steps, world)
-    if rank == 0:
-        print(json.dumps({"metric": "3D patches/sec (sliding-window inference, 512^3 volume)", "value": 216 * world / (ms / 1e3),
-                          "unit": "patches/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                          "config": {"workload": "BASELINE config[2]: crop 512^3 -> 216x128^3 (25% overlap) -> ResUNet fwd -> "
-                                                 "sigmoid -> spline overlap-add, one volume per GPU"},
-                          "gpu_launches": ops.LAUNCHES - n0}), flush=True)
+    launches = ops.LAUNCHES - n0
+    clocks = sampler.stop()
+    e2e_step(0)
+    ms_e2e = timed(e2e_step, max(2, args.steps // 3), world)
+    if rank != 0:
+        return
+    # roofline of the HBM-bound stitch kernels (SURVEY 8d): spline overlap-add of 216 fp32 patch predictions into the volume
+    axes = [_stitch.Axis(512, 128, 0, 0.25) for _ in range(3)]
+    pred = torch.rand(216, 128, 128, 128, 1, device="cuda")
+    starts, wins = [a.starts(1) for a in axes], [a.window() for a in axes]
+    merge = lambda i: _stitch.merge_device(pred, (512, 512, 512), starts, wins, (0, 0, 0))
+    merge(0)
+    ms_merge = timed(merge, 10, 1)
+    alg = 216 * 128 ** 3 * 4 + 512 ** 3 * 4                  # every patch element read once + every output element written once
+    roof = {"kernel": "overlap_add (spline-weighted merge of 216 x 128^3 fp32 patches into 512^3)", "bound": "hbm",
+            "achieved": alg / (ms_merge / 1e3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s", "frac": alg / (ms_merge / 1e3) / 1e9 / peaks["hbm"],
+            "traffic": None, "ms_per_launch": ms_merge, "algorithmic_bytes": alg, "peak_source": peaks["src"],
+            "share_of_step": ms_merge / ms}
+    cpu = None
+    if args.cpu_baseline and world == 1:
+        cores = pick_cpu_threads()
+        sec, t_fwd, t_st = cpu_infer_patch_time(cores)
+        cpu = {"value": 1.0 / sec, "unit": "patches/s", "cores": cores, "kind": "port",
+               "sample": f"eval forward + sigmoid of one 128^3x2 patch ({t_fwd:.2f} s) + numpy crop / spline merge of a 256^3 volume "
+                         f"(27 patches, {t_st:.2f} s per patch), fp32, oracle port"}
+    print(json.dumps({"metric": "3D patches/sec (sliding-window inference, 512^3 volume)", "value": 216 * world / (ms / 1e3),
+                      "unit": "patches/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                      "config": {"workload": "BASELINE config[2]: crop 512^3 -> 216x128^3 (25% overlap) -> ResUNet fwd -> "
+                                             "sigmoid -> spline overlap-add, one volume per GPU",
+                                 "l2": "2 GB volume + 3.6 GB of patches + 1.8 GB of predictions per step >> 126 MB L2; no explicit flush"},
+                      "e2e": {"value": 216 * world / (ms_e2e / 1e3), "unit": "patches/s", "ms_per_step": ms_e2e,
+                              "h2d_bytes_per_step": vol_h.numel() * 2, "d2h_bytes_per_step": out_h.numel() * 4,
+                              "api": "biapy_b200.engine.inference.predict_volume(host fp16 volume) -> host fp32 prediction"},
+                      "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}), flush=True)
 
 
 def main():

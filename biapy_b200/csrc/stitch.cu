@@ -249,6 +249,79 @@ __global__ void overlap_add_kernel(const TI* __restrict__ patches, TO* __restric
   }
 }
 
+// Cover-table variant (the default): every block first tabulates, for all x and all y of the plane, WHICH patches of that
+// axis cover the coordinate -- a 64-bit mask per coordinate in shared memory (W*nx + H*ny compares spread over the block; the
+// covering set is not always an index range: with padding and overlap the reference's merge starts are not monotone, e.g.
+// [0, 3, 6, 9, 12, 10, 13]) -- and each output element then visits exactly its covering patches in increasing index order
+// with 32-bit arithmetic, instead of walking the nz x ny x nx loop nest of the kernel above with 64-bit range checks at every
+// level.  Same operation order, bit-identical results; used when no axis has more than 64 patches.
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) overlap_add_cover_kernel(const TI* __restrict__ patches, TO* __restrict__ out, MergeParams p,
+                                         const int64_t* __restrict__ sz, const int64_t* __restrict__ sy,
+                                         const int64_t* __restrict__ sx, const float* __restrict__ wz,
+                                         const float* __restrict__ wy, const float* __restrict__ wx) {
+  extern __shared__ unsigned long long s_mask[];             // x masks [W], y masks [H], then the starts as int
+  const int nz = (int)p.nz, ny = (int)p.ny, nx = (int)p.nx, H = (int)p.H, W = (int)p.W, C = (int)p.C;
+  const int cz = (int)p.cz, cy = (int)p.cy, cx = (int)p.cx;
+  unsigned long long* x_mask = s_mask;
+  unsigned long long* y_mask = x_mask + W;
+  int* s_z = reinterpret_cast<int*>(y_mask + H);
+  int* s_y = s_z + nz;
+  int* s_x = s_y + ny;
+  for (int i = threadIdx.x; i < nz; i += blockDim.x) s_z[i] = (int)sz[i];
+  for (int i = threadIdx.x; i < ny; i += blockDim.x) s_y[i] = (int)sy[i];
+  for (int i = threadIdx.x; i < nx; i += blockDim.x) s_x[i] = (int)sx[i];
+  __syncthreads();
+  for (int c = threadIdx.x; c < W + H; c += blockDim.x) {
+    const bool isx = c < W;
+    const int coord = isx ? c : c - W, n = isx ? nx : ny, core = isx ? cx : cy;
+    const int* st = isx ? s_x : s_y;
+    unsigned long long m = 0;
+    for (int i = 0; i < n; ++i) {
+      const int l = coord - st[i];
+      if (l >= 0 && l < core) m |= 1ull << i;
+    }
+    (isx ? x_mask : y_mask)[coord] = m;
+  }
+  __syncthreads();
+  const int plane = H * W * C;
+  const int64_t pvol = p.pz * p.py * p.px * p.C;           // elements per patch
+  const int row_el = (int)(p.px * p.C);
+  for (int z = blockIdx.y; z < (int)p.D; z += gridDim.y) {
+    unsigned long long zm = 0;
+    for (int i = 0; i < nz; ++i) {
+      const int l = z - s_z[i];
+      if (l >= 0 && l < cz) zm |= 1ull << i;
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += gridDim.x * blockDim.x) {
+      const int ch = i % C;
+      const int tq = i / C;
+      const int x = tq % W, y = tq / W;
+      const unsigned long long xm = x_mask[x], ym = y_mask[y];
+      float acc = 0.f, wsum = 0.f;
+      for (unsigned long long a = zm; a; a &= a - 1) {
+        const int iz = __ffsll((long long)a) - 1, lz = z - s_z[iz];
+        const float fz = __ldg(wz + lz);
+        for (unsigned long long b = ym; b; b &= b - 1) {
+          const int iy = __ffsll((long long)b) - 1, ly = y - s_y[iy];
+          const float fzy = __fmul_rn(fz, __ldg(wy + ly));
+          // element offset of (patch (iz, iy, 0), row lz, ly) -- 64-bit once per (z, y) pair
+          const TI* rowp = patches + ((int64_t)(iz * ny + iy) * nx) * pvol +
+                           ((int64_t)(lz + (int)p.pad_z) * p.py + (ly + (int)p.pad_y)) * row_el + ch;
+          for (unsigned long long c = xm; c; c &= c - 1) {
+            const int ix = __ffsll((long long)c) - 1, lx = x - s_x[ix];
+            const float w = __fmul_rn(fzy, __ldg(wx + lx));
+            const float v = to_f<TI>(rowp[(int64_t)ix * pvol + (lx + (int)p.pad_x) * C]);
+            acc = __fadd_rn(acc, __fmul_rn(v, w));
+            wsum = __fadd_rn(wsum, w);
+          }
+        }
+      }
+      out[(int64_t)z * plane + i] = from_f<TO>(__fdiv_rn(acc, __fadd_rn(wsum, 1e-18f)));
+    }
+  }
+}
+
 template <typename TI, typename TO>
 static int launch_overlap_add(const void* patches, void* out, const MergeParams& p, const int64_t* sz,
                               const int64_t* sy, const int64_t* sx, const float* wz, const float* wy,
@@ -258,6 +331,19 @@ static int launch_overlap_add(const void* patches, void* out, const MergeParams&
   int64_t bx = ceil_div(p.H * p.W * p.C, threads);
   if (bx > 1024) bx = 1024;
   dim3 blocks((unsigned)bx, (unsigned)(p.D < 65535 ? p.D : 65535));
+  // cover masks in shared memory (64 patches per axis at most), 32-bit coordinates, <= 48 KB
+  const size_t tab = sizeof(unsigned long long) * (size_t)(p.W + p.H) + sizeof(int) * (size_t)(p.nz + p.ny + p.nx);
+  static const bool use_cover = !(getenv("B200_MERGE_COVER") && strcmp(getenv("B200_MERGE_COVER"), "0") == 0);
+  if (use_cover && tab <= 48 * 1024 && p.nz <= 64 && p.ny <= 64 && p.nx <= 64 && p.D < (1LL << 30) && p.px * p.C < (1LL << 30)) {
+    // few, fat blocks per plane: the table build is per block
+    int64_t bxc = ceil_div(p.H * p.W * p.C, (int64_t)threads * 8);
+    if (bxc > 64) bxc = 64;
+    if (bxc < 1) bxc = 1;
+    dim3 bc((unsigned)bxc, (unsigned)(p.D < 65535 ? p.D : 65535));
+    overlap_add_cover_kernel<TI, TO><<<bc, threads, tab, st>>>((const TI*)patches, (TO*)out, p, sz, sy, sx, wz, wy, wx);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+  }
   size_t smem = sizeof(int64_t) * (p.nz + p.ny + p.nx);
   overlap_add_kernel<TI, TO><<<blocks, threads, smem, st>>>((const TI*)patches, (TO*)out, p, sz, sy, sx,
                                                                      wz, wy, wx);
