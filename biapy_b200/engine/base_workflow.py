@@ -141,14 +141,20 @@ class Base_Workflow:
         ``after_merge_patches`` (reference ``:1874-2013``).  Returns ``(prediction, what after_merge_patches returned)``."""
         assert self.model is not None, "call prepare_model() first"
         cfg = self.cfg
-        if self.ndim == 2:
-            raise NotImplementedError("process_test_sample drives the 3D sliding window; 2D images go through "
-                                      "biapy_b200.data.data_2D_manipulation + predict_batches_in_test")
         self.model.eval()
         if norm:
             X, self.current_sample["norm_info"] = _norm.normalize_image(X, dict(self.test_norm_module))
         vol, patch = X, tuple(cfg.DATA.PATCH_SIZE)
         ov, pad = tuple(cfg.DATA.TEST.OVERLAP), tuple(cfg.DATA.TEST.PADDING)
+        if self.ndim == 2:
+            # one (y, x, C) image: the 2D crop / merge mirrors around predict_batches_in_test (reference :1944-1997 with
+            # crop_data_with_overlap / merge_data_with_overlap)
+            from ..data.data_2D_manipulation import crop_data_with_overlap, merge_data_with_overlap
+            img = vol[None]
+            patches, _ = crop_data_with_overlap(img, patch, overlap=ov, padding=pad, verbose=False)
+            pp = self.predict_batches_in_test(patches)
+            pred = merge_data_with_overlap(pp, tuple(img.shape[:-1]) + (pp.shape[-1],), overlap=ov, padding=pad, verbose=False)[0]
+            return pred, self.after_merge_patches(pred)
         if cfg.TEST.BY_CHUNKS.ENABLE:
             pred = predict_by_chunks(self.model, vol, patch, padding=pad, batch_size=int(cfg.TRAIN.BATCH_SIZE),
                                      head_activations=self.head_activations)

@@ -84,3 +84,47 @@ def test_yaml_configured_training_equals_the_trainer():
         ref.append(float(tr.step(X[lo:lo + 2], Y[lo:lo + 2]).item()))
     # same kernels on the same data; fp32 atomics (weight gradients) make the trajectories agree to rounding, not bit for bit
     assert all(abs(a - r) <= 1e-6 * max(1.0, abs(r)) for a, r in zip(losses, ref)) and losses[-1] < losses[0]
+
+
+YAML_2D = """
+PROBLEM: {TYPE: DENOISING, NDIM: 2D}
+DATA:
+    PATCH_SIZE: (64, 64, 1)
+    NORMALIZATION: {TYPE: zero_mean_unit_variance, ZERO_MEAN_UNIT_VAR: {MEAN_VAL: [100.0], STD_VAL: [40.0]}}
+    TEST: {OVERLAP: "(0.25, 0.5)", PADDING: "(8, 4)"}
+MODEL:
+    ARCHITECTURE: unet
+    FEATURE_MAPS: [16, 32, 64]
+    DROPOUT_VALUES: [0, 0, 0]
+    ISOTROPY: [True, True, True]
+    CONV_LAYERS: [2, 2, 2]
+    Z_DOWN: [0, 0]
+    YX_DOWN: [0, 0]
+TRAIN: {BATCH_SIZE: 3}
+"""
+KW2D = dict(image_shape=(64, 64, 1), activation="elu", feature_maps=[16, 32, 64], drop_values=[0, 0, 0], normalization="in", k_size=3,
+            yx_down=[2, 2], z_down=[2, 2], isotropy=[True] * 3, larger_io=False, conv_layers=[2] * 3, output_channels=[1])
+
+
+def test_2d_denoising_workflow_matches_oracle_pipeline():
+    """2D image through the denoising workflow: normalise (given mean / std) -> 2D crop -> U-Net -> linear head -> 2D merge ->
+    undo the normalisation back to uint8, against the same chain on the CPU oracle."""
+    from biapy_b200._biapy import BiaPy
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        b = BiaPy(YAML_2D, engine_dtype=torch.float32)
+    assert type(b.workflow).__name__ == "Denoising_Workflow" and b.workflow.head_activations == ["linear"]
+    sd = {k: v.detach().cpu().clone() for k, v in b.workflow.model.state_dict().items()}
+    img = np.random.default_rng(5).integers(0, 256, (150, 170, 1)).astype(np.uint8)
+    pred, restored = b.workflow.process_test_sample(img)
+    x, info = port_norm.normalize_image(img.copy(), dict(b.workflow.test_norm_module))
+    patch, ov, pad = (64, 64, 1), (0.25, 0.5), (8, 4)
+    patches, _ = port_stitch.crop_2d(x[None], patch, ov, pad, "reflect")
+    with torch.no_grad():
+        y = port_models.forward("unet", sd, torch.from_numpy(patches).permute(0, 3, 1, 2), training=False, **KW2D)
+    ref = port_stitch.merge_2d(np.ascontiguousarray(y.permute(0, 2, 3, 1).numpy()), (1, 150, 170, 1), ov, pad)[0]
+    assert pred.shape == ref.shape and np.abs(pred - ref).max() < 1e-4 * max(1.0, np.abs(ref).max())
+    back = port_norm.undo_image_norm(ref, info)
+    assert restored.dtype == np.uint8 and restored.shape == back.shape
+    # rounding to uint8 can flip where the two float predictions straddle x.5
+    assert np.abs(restored.astype(np.int32) - back.astype(np.int32)).max() <= 1 and (restored != back).mean() < 1e-3
