@@ -89,3 +89,34 @@ def test_unsupported_options_fail_loudly():
         _build("unet", dict(base, upsampling_factor=(2, 2)))
     with pytest.raises(ValueError):
         _build("unet", dict(base, upsample_layer="nearest"))
+
+
+def test_zero_arena_carves_one_cleared_buffer():
+    """ops.ZeroArena (host logic, CPU tensors): first pass measures, later passes hand out aligned zeroed slices of one buffer;
+    an outgrown buffer is retired, not freed (a captured CUDA graph may still point into it)."""
+    import torch
+    from biapy_b200 import ops
+    a = ops.ZeroArena()
+    a.begin("cpu")
+    t = ops.zeros(10, torch.float64, "cpu")                  # no buffer yet: falls back to torch.zeros, records the need
+    assert t.shape == (10,) and a.buf is None and a.need == 256
+    ops.zeros(3, torch.float32, "cpu")
+    a.end()
+    assert ops.ARENA is None and a.need == 512
+    a.begin("cpu")
+    assert a.buf is not None and a.buf.numel() == 4096
+    x = ops.zeros(10, torch.float64, "cpu")
+    y = ops.zeros(3, torch.float32, "cpu")
+    assert x.data_ptr() == a.buf.data_ptr() and y.data_ptr() - x.data_ptr() == 256 and x.dtype == torch.float64
+    x.fill_(7.0)
+    y.fill_(1.0)
+    big = ops.zeros(4096, torch.float32, "cpu")              # does not fit: falls back, raises the high-water mark
+    assert big.data_ptr() != a.buf.data_ptr() and a.need > 4096
+    a.end()
+    old = a.buf
+    a.begin("cpu")
+    assert a.buf is not old and a._retired == [old]
+    x2 = ops.zeros(10, torch.float64, "cpu")
+    assert float(x2.abs().sum()) == 0.0                      # cleared by the single fill of begin()
+    a.end()
+    assert ops.zeros(4, torch.float32, "cpu").sum().item() == 0.0     # no arena active: plain torch.zeros
