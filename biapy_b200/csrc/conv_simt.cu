@@ -5,6 +5,7 @@
 //   dgrad : the same kernel with the flipped/transposed packing of the weights
 //   wgrad : dw[co][tap][ci] += sum_vox dy[vox][co] * x[vox+tap][ci]
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace b200 {
 
@@ -557,6 +558,317 @@ __global__ void __launch_bounds__(256) conv1x1_wgrad_image_kernel(const T* __res
   }
 }
 
+// ---- coalesced forms (B200_PW_COALESCED=0 falls back to the thread-per-voxel kernels above) ---------------------------------
+// thread = (voxel, 16-byte channel vector) of the WIDE tensor, so a warp instruction moves 512 contiguous bytes; the
+// thread-per-voxel forms touch every 32-byte sector with two half-filled requests (stores) or two instructions (loads)
+// and ran at 1.6-2.2 TB/s (0.13-0.18 ms per launch at 128^3 x 16 ch x batch 4 against a 0.045 ms HBM floor).
+// CVN = vectors per voxel row, a power of two (the grid stride is a multiple of it, so a thread keeps its channel vector).
+
+// y[vox][co < cout <= JMAX] from cin = 8 * CVN channels; the CVN partial dot products of a voxel meet by shuffle
+template <typename T, int CVN, int JMAX>
+__global__ void __launch_bounds__(256) conv1x1_cout_cv_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ wp,
+                                                              const float* __restrict__ bias, T* __restrict__ y, int64_t ldy,
+                                                              int cout, int64_t nvox, int accumulate) {
+  constexpr int cin = 8 * CVN;
+  const int cv = threadIdx.x & (CVN - 1);
+  float w[JMAX][8];
+#pragma unroll
+  for (int j = 0; j < JMAX; ++j)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[j][i] = j < cout ? to_f<T>(wp[j * cin + cv * 8 + i]) : 0.f;
+  const int64_t total = nvox * CVN, stride = (int64_t)gridDim.x * blockDim.x;
+  constexpr int U = 2;   // two voxel vectors in flight per thread
+  // warp-uniform trip count: the shuffles below need every lane
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < total; i0 += U * stride) {
+    int64_t v[U];
+    bool live[U];
+    Pack<T, 8> px[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride + (threadIdx.x & 31);
+      live[u] = i < total;
+      v[u] = i / CVN;
+      if (live[u]) px[u] = *reinterpret_cast<const Pack<T, 8>*>(x + v[u] * ldx + cv * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float acc[JMAX];
+#pragma unroll
+      for (int j = 0; j < JMAX; ++j) acc[j] = 0.f;
+      if (live[u]) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float a = to_f<T>(px[u].v[k]);
+#pragma unroll
+          for (int j = 0; j < JMAX; ++j) acc[j] = fmaf(a, w[j][k], acc[j]);
+        }
+      }
+#pragma unroll
+      for (int o = CVN / 2; o > 0; o >>= 1)
+#pragma unroll
+        for (int j = 0; j < JMAX; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+      if (live[u] && cv == 0) {
+        T* yr = y + v[u] * ldy;
+#pragma unroll
+        for (int j = 0; j < JMAX; ++j)
+          if (j < cout) {
+            const float r = acc[j] + (bias ? bias[j] : 0.f);
+            yr[j] = from_f<T>(accumulate ? to_f<T>(yr[j]) + r : r);
+          }
+      }
+    }
+  }
+}
+
+// y[vox][cout = 8 * cvn] from cin <= CMAX channels; cvn (a power of two) vectors per voxel, weights of the thread's vector
+// in registers
+template <typename T, int CMAX>
+__global__ void __launch_bounds__(256) conv1x1_cin_cv_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ wp,
+                                                             const float* __restrict__ bias, T* __restrict__ y, int64_t ldy, int cin,
+                                                             int cvn_log2, int64_t nvox, int accumulate) {
+  const int cvn = 1 << cvn_log2;
+  const int cv = threadIdx.x & (cvn - 1);
+  float w[8][CMAX], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    b[j] = bias ? bias[cv * 8 + j] : 0.f;
+#pragma unroll
+    for (int i = 0; i < CMAX; ++i) w[j][i] = i < cin ? to_f<T>(wp[(cv * 8 + j) * cin + i]) : 0.f;
+  }
+  const int64_t total = nvox << cvn_log2, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t v = i >> cvn_log2;
+    float a[CMAX];
+#pragma unroll
+    for (int k = 0; k < CMAX; ++k) a[k] = k < cin ? to_f<T>(x[v * ldx + k]) : 0.f;
+    T* yr = y + v * ldy + cv * 8;
+    Pack<T, 8> old;
+    if (accumulate) old = *reinterpret_cast<const Pack<T, 8>*>(yr);
+    Pack<T, 8> out;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float acc = b[j];
+#pragma unroll
+      for (int k = 0; k < CMAX; ++k) acc = fmaf(a[k], w[j][k], acc);
+      if (accumulate) acc += to_f<T>(old.v[j]);
+      out.v[j] = from_f<T>(acc);
+    }
+    *reinterpret_cast<Pack<T, 8>*>(yr) = out;
+  }
+}
+
+// dw[co][ci], dbias[co] for cout <= 2 and cin = 8 * CVN <= 32 (segmentation heads)
+template <typename T, int CVN>
+__global__ void __launch_bounds__(256) conv1x1_wgrad_head_cv_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy,
+                                                                    int64_t lddy, float* __restrict__ dw, float* __restrict__ dbias,
+                                                                    int cout, int64_t nvox) {
+  constexpr int kMaxCin = 32, kMaxCout = 2, cin = 8 * CVN;
+  __shared__ float s_red[8][kMaxCout * (kMaxCin + 1)];
+  const int cv = threadIdx.x & (CVN - 1);
+  float acc[kMaxCout][8], bacc[kMaxCout];
+#pragma unroll
+  for (int j = 0; j < kMaxCout; ++j) {
+    bacc[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[j][k] = 0.f;
+  }
+  const int64_t total = nvox * CVN, stride = (int64_t)gridDim.x * blockDim.x;
+  constexpr int U = 4;   // four voxel vectors in flight per thread (loads first, then the FMAs)
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += U * stride) {
+    Pack<T, 8> px[U];
+    float d[U][kMaxCout];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      const bool live = i < total;
+      const int64_t v = live ? i / CVN : 0;
+      px[u] = *reinterpret_cast<const Pack<T, 8>*>(x + v * ldx + cv * 8);
+#pragma unroll
+      for (int j = 0; j < kMaxCout; ++j) d[u][j] = (live && j < cout) ? to_f<T>(dy[v * lddy + j]) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float a = to_f<T>(px[u].v[k]);
+#pragma unroll
+        for (int j = 0; j < kMaxCout; ++j) acc[j][k] = fmaf(d[u][j], a, acc[j][k]);
+      }
+      if (cv == 0) {
+#pragma unroll
+        for (int j = 0; j < kMaxCout; ++j) bacc[j] += d[u][j];
+      }
+    }
+  }
+  // lanes with the same channel vector (lane % CVN) meet: xor offsets 16 .. CVN
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int it = threadIdx.x; it < 8 * kMaxCout * (kMaxCin + 1); it += blockDim.x) (&s_red[0][0])[it] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kMaxCout; ++j) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float t = acc[j][k];
+#pragma unroll
+      for (int o = 16; o >= CVN; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane < CVN) s_red[warp][j * (kMaxCin + 1) + lane * 8 + k] = t;
+    }
+    float tb = bacc[j];
+#pragma unroll
+    for (int o = 16; o >= CVN; o >>= 1) tb += __shfl_xor_sync(0xffffffffu, tb, o);
+    if (lane == 0) s_red[warp][j * (kMaxCin + 1) + kMaxCin] = tb;
+  }
+  __syncthreads();
+  for (int it = threadIdx.x; it < kMaxCout * (kMaxCin + 1); it += blockDim.x) {
+    const int j = it / (kMaxCin + 1), k = it % (kMaxCin + 1);
+    if (j >= cout) continue;
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += s_red[w][it];
+    if (k < cin) atomicAdd(&dw[(int64_t)j * cin + k], t);
+    else if (k == kMaxCin && dbias) atomicAdd(&dbias[j], t);
+  }
+}
+
+// dw[co][ci], dbias[co] for cin <= 4 and cout = 8 * CVN in {8, 16} (image-fed pointwise shortcut)
+template <typename T, int CVN>
+__global__ void __launch_bounds__(256) conv1x1_wgrad_image_cv_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy,
+                                                                     int64_t lddy, float* __restrict__ dw, float* __restrict__ dbias,
+                                                                     int cin, int64_t nvox) {
+  constexpr int kCi = 4, kCo = 16, cout = 8 * CVN;
+  __shared__ float s_red[8][kCo * (kCi + 1)];
+  const int cv = threadIdx.x & (CVN - 1);
+  float acc[kCi][8], bacc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    bacc[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < kCi; ++k) acc[k][j] = 0.f;
+  }
+  const int64_t total = nvox * CVN, stride = (int64_t)gridDim.x * blockDim.x;
+  constexpr int U = 4;   // four voxel vectors in flight per thread
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += U * stride) {
+    Pack<T, 8> pd[U];
+    float a[U][kCi];
+    bool live[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      live[u] = i < total;
+      const int64_t v = live[u] ? i / CVN : 0;
+      pd[u] = *reinterpret_cast<const Pack<T, 8>*>(dy + v * lddy + cv * 8);
+#pragma unroll
+      for (int k = 0; k < kCi; ++k) a[u][k] = k < cin ? to_f<T>(x[v * ldx + k]) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = live[u] ? to_f<T>(pd[u].v[j]) : 0.f;
+        bacc[j] += d;
+#pragma unroll
+        for (int k = 0; k < kCi; ++k) acc[k][j] = fmaf(d, a[u][k], acc[k][j]);
+      }
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+#pragma unroll
+    for (int k = 0; k < kCi; ++k) {
+      float t = acc[k][j];
+#pragma unroll
+      for (int o = 16; o >= CVN; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane < CVN) s_red[warp][(lane * 8 + j) * (kCi + 1) + k] = t;
+    }
+    float tb = bacc[j];
+#pragma unroll
+    for (int o = 16; o >= CVN; o >>= 1) tb += __shfl_xor_sync(0xffffffffu, tb, o);
+    if (lane < CVN) s_red[warp][(lane * 8 + j) * (kCi + 1) + kCi] = tb;
+  }
+  __syncthreads();
+  for (int it = threadIdx.x; it < cout * (kCi + 1); it += blockDim.x) {
+    const int j = it / (kCi + 1), k = it % (kCi + 1);
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += s_red[w][it];
+    if (k < cin) atomicAdd(&dw[(int64_t)j * cin + k], t);
+    else if (k == kCi && dbias) atomicAdd(&dbias[j], t);
+  }
+}
+
+static inline bool pw_coalesced_enabled() {
+  static const bool on = !(getenv("B200_PW_COALESCED") && atoi(getenv("B200_PW_COALESCED")) == 0);
+  return on;
+}
+static inline unsigned pw_blocks(int64_t threads) {
+  int64_t blocks = ceil_div(threads, 256);
+  if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
+  return (unsigned)(blocks < 1 ? 1 : blocks);
+}
+
+template <typename T>
+static void launch_cout_cv(const b200_tensor* x, const void* w, const float* bias, const b200_tensor* y, int64_t nvox, int accumulate,
+                           cudaStream_t st) {
+  const unsigned nb = pw_blocks(nvox * (x->c / 8));
+  const T* xp = (const T*)x->data;
+  const T* wp = (const T*)w;
+  T* yp = (T*)y->data;
+  const bool narrow = y->c <= 2;
+  switch (x->c / 8) {
+    case 1:
+      if (narrow) conv1x1_cout_cv_kernel<T, 1, 2><<<nb, 256, 0, st>>>(xp, x->ld, wp, bias, yp, y->ld, y->c, nvox, accumulate);
+      else conv1x1_cout_cv_kernel<T, 1, kSmallMax><<<nb, 256, 0, st>>>(xp, x->ld, wp, bias, yp, y->ld, y->c, nvox, accumulate);
+      break;
+    case 2:
+      if (narrow) conv1x1_cout_cv_kernel<T, 2, 2><<<nb, 256, 0, st>>>(xp, x->ld, wp, bias, yp, y->ld, y->c, nvox, accumulate);
+      else conv1x1_cout_cv_kernel<T, 2, kSmallMax><<<nb, 256, 0, st>>>(xp, x->ld, wp, bias, yp, y->ld, y->c, nvox, accumulate);
+      break;
+    default:
+      if (narrow) conv1x1_cout_cv_kernel<T, 4, 2><<<nb, 256, 0, st>>>(xp, x->ld, wp, bias, yp, y->ld, y->c, nvox, accumulate);
+      else conv1x1_cout_cv_kernel<T, 4, kSmallMax><<<nb, 256, 0, st>>>(xp, x->ld, wp, bias, yp, y->ld, y->c, nvox, accumulate);
+      break;
+  }
+}
+
+template <typename T>
+static void launch_cin_cv(const b200_tensor* x, const void* w, const float* bias, const b200_tensor* y, int64_t nvox, int accumulate,
+                          cudaStream_t st) {
+  const int cvn = y->c / 8;
+  int lg = 0;
+  while ((1 << lg) < cvn) ++lg;
+  const unsigned nb = pw_blocks(nvox * cvn);
+  const T* xp = (const T*)x->data;
+  const T* wp = (const T*)w;
+  T* yp = (T*)y->data;
+  if (x->c <= 2) conv1x1_cin_cv_kernel<T, 2><<<nb, 256, 0, st>>>(xp, x->ld, wp, bias, yp, y->ld, x->c, lg, nvox, accumulate);
+  else if (x->c <= 4) conv1x1_cin_cv_kernel<T, 4><<<nb, 256, 0, st>>>(xp, x->ld, wp, bias, yp, y->ld, x->c, lg, nvox, accumulate);
+  else conv1x1_cin_cv_kernel<T, 8><<<nb, 256, 0, st>>>(xp, x->ld, wp, bias, yp, y->ld, x->c, lg, nvox, accumulate);
+}
+
+template <typename T>
+static void launch_wgrad_head_cv(const b200_tensor* x, const b200_tensor* dy, float* dw, float* dbias, int64_t nvox, cudaStream_t st) {
+  const int cvn = x->c / 8;
+  int64_t blocks = ceil_div(nvox * cvn, 256 * 8);
+  if (blocks > (int64_t)sm_count() * 6) blocks = (int64_t)sm_count() * 6;
+  if (blocks < 1) blocks = 1;
+  const T* xp = (const T*)x->data;
+  const T* gp = (const T*)dy->data;
+  if (cvn == 1) conv1x1_wgrad_head_cv_kernel<T, 1><<<(unsigned)blocks, 256, 0, st>>>(xp, x->ld, gp, dy->ld, dw, dbias, dy->c, nvox);
+  else if (cvn == 2) conv1x1_wgrad_head_cv_kernel<T, 2><<<(unsigned)blocks, 256, 0, st>>>(xp, x->ld, gp, dy->ld, dw, dbias, dy->c, nvox);
+  else conv1x1_wgrad_head_cv_kernel<T, 4><<<(unsigned)blocks, 256, 0, st>>>(xp, x->ld, gp, dy->ld, dw, dbias, dy->c, nvox);
+}
+
+template <typename T>
+static void launch_wgrad_image_cv(const b200_tensor* x, const b200_tensor* dy, float* dw, float* dbias, int64_t nvox, cudaStream_t st) {
+  const int cvn = dy->c / 8;
+  int64_t blocks = ceil_div(nvox * cvn, 256 * 8);
+  if (blocks > (int64_t)sm_count() * 6) blocks = (int64_t)sm_count() * 6;
+  if (blocks < 1) blocks = 1;
+  const T* xp = (const T*)x->data;
+  const T* gp = (const T*)dy->data;
+  if (cvn == 1) conv1x1_wgrad_image_cv_kernel<T, 1><<<(unsigned)blocks, 256, 0, st>>>(xp, x->ld, gp, dy->ld, dw, dbias, x->c, nvox);
+  else conv1x1_wgrad_image_cv_kernel<T, 2><<<(unsigned)blocks, 256, 0, st>>>(xp, x->ld, gp, dy->ld, dw, dbias, x->c, nvox);
+}
+
 static bool vec16(const b200_tensor* t) { return t->dtype != B200_F32 && t->c % 8 == 0 && t->ld % 8 == 0 && ((uintptr_t)t->data & 15) == 0; }
 
 static bool small_pointwise(const b200_tensor* x, const b200_tensor* y, int kd, int kh, int kw) {
@@ -572,12 +884,16 @@ int conv_fprop_simt(const b200_tensor* x, const void* w, const float* bias, cons
       if (y->c <= kSmallMax) {
         int64_t blocks = ceil_div(nvox, 256);
         if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
-        if (vec16(x))
+        if (pw_coalesced_enabled() && vec16(x) && (x->c == 8 || x->c == 16 || x->c == 32))
+          launch_cout_cv<T>(x, w, bias, y, nvox, accumulate, st);
+        else if (vec16(x))
           conv1x1_cout_vec_kernel<T><<<(unsigned)blocks, 256, smem, st>>>((const T*)x->data, x->ld, (const T*)w, bias, (T*)y->data,
                                                                         y->ld, x->c, y->c, nvox, accumulate);
         else
           conv1x1_small_cout_kernel<T><<<(unsigned)blocks, 256, smem, st>>>((const T*)x->data, x->ld, (const T*)w, bias, (T*)y->data,
                                                                           y->ld, x->c, y->c, nvox, accumulate);
+      } else if (pw_coalesced_enabled() && vec16(y) && x->c <= 8 && ((y->c / 8) & (y->c / 8 - 1)) == 0) {
+        launch_cin_cv<T>(x, w, bias, y, nvox, accumulate, st);
       } else if (vec16(y)) {
         int64_t blocks = ceil_div(nvox, 256);
         if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
@@ -620,8 +936,12 @@ int conv_wgrad_simt(const b200_tensor* x, const b200_tensor* dy, float* dw, floa
     int64_t blocks = ceil_div(nvox, 256 * 8);
     if (blocks > (int64_t)sm_count() * 4) blocks = (int64_t)sm_count() * 4;
     if (blocks < 1) blocks = 1;
-    B200_DISPATCH_DTYPE(x->dtype, T, (conv1x1_wgrad_head_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(
-                                         (const T*)x->data, x->ld, (const T*)dy->data, dy->ld, dw, dbias, x->c, dy->c, nvox)));
+    if (pw_coalesced_enabled() && (x->c == 8 || x->c == 16 || x->c == 32)) {
+      B200_DISPATCH_DTYPE(x->dtype, T, (launch_wgrad_head_cv<T>(x, dy, dw, dbias, nvox, st)));
+    } else {
+      B200_DISPATCH_DTYPE(x->dtype, T, (conv1x1_wgrad_head_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(
+                                           (const T*)x->data, x->ld, (const T*)dy->data, dy->ld, dw, dbias, x->c, dy->c, nvox)));
+    }
     B200_LAUNCH_CHECK();
     return B200_OK;
   }
@@ -630,8 +950,12 @@ int conv_wgrad_simt(const b200_tensor* x, const b200_tensor* dy, float* dw, floa
     int64_t blocks = ceil_div(nvox, 256 * 8);
     if (blocks > (int64_t)sm_count() * 4) blocks = (int64_t)sm_count() * 4;
     if (blocks < 1) blocks = 1;
-    B200_DISPATCH_DTYPE(x->dtype, T, (conv1x1_wgrad_image_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(
-                                         (const T*)x->data, x->ld, (const T*)dy->data, dy->ld, dw, dbias, x->c, dy->c, nvox)));
+    if (pw_coalesced_enabled()) {
+      B200_DISPATCH_DTYPE(x->dtype, T, (launch_wgrad_image_cv<T>(x, dy, dw, dbias, nvox, st)));
+    } else {
+      B200_DISPATCH_DTYPE(x->dtype, T, (conv1x1_wgrad_image_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(
+                                           (const T*)x->data, x->ld, (const T*)dy->data, dy->ld, dw, dbias, x->c, dy->c, nvox)));
+    }
     B200_LAUNCH_CHECK();
     return B200_OK;
   }

@@ -1,0 +1,75 @@
+"""CPU check of the plain SIMT kernels' index arithmetic (no GPU in the build container).
+
+The kernel *source text* is cut out of ``biapy_b200/csrc/*.cu``, compiled with g++ behind ``tests/simt_emu/emu.h`` (one
+std::thread per CUDA thread, barriers for ``__syncthreads`` / ``__shfl_xor_sync``) and run against straightforward loops:
+the coalesced pointwise convolutions (fprop / dgrad / wgrad of the 1-2 channel layers) and the compile-time-window max-pool
+kernels.  This is test infrastructure: it proves the indexing, the shuffle patterns and the reduction layouts, not speed;
+the device run of the same kernels is covered by the ``-m gpu`` parity tests.
+"""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "biapy_b200", "csrc")
+EMU = os.path.join(ROOT, "tests", "simt_emu")
+
+KERNELS = {
+    "conv_simt.cu": ["conv1x1_cout_cv_kernel", "conv1x1_cin_cv_kernel", "conv1x1_wgrad_head_cv_kernel",
+                     "conv1x1_wgrad_image_cv_kernel"],
+    "ops.cu": ["maxpool_fwd_win_kernel", "maxpool_bwd_win_kernel"],
+}
+
+
+def cut_kernel(src: str, name: str) -> str:
+    """`template <...> __global__ void ... name(...) { ... }` as it stands in the source."""
+    m = re.search(r"__global__[^;{]*?\b" + re.escape(name) + r"\(", src)
+    assert m, f"kernel {name} not found"
+    start = src.rfind("\ntemplate <", 0, m.start()) + 1
+    assert start > 0
+    i = src.index("{", src.index(")", m.end()))
+    # the signature may hold several ')' -- find the brace that opens the body: first '{' after the parameter list closes
+    depth, j = 0, m.end() - 1
+    while True:
+        ch = src[j]
+        if ch == "(":
+            depth += 1
+        elif ch == ")":
+            depth -= 1
+            if depth == 0:
+                break
+        j += 1
+    i = src.index("{", j)
+    depth, k = 0, i
+    while True:
+        ch = src[k]
+        if ch == "{":
+            depth += 1
+        elif ch == "}":
+            depth -= 1
+            if depth == 0:
+                break
+        k += 1
+    return src[start:k + 1]
+
+
+def test_simt_kernels_on_the_host_emulator(tmp_path):
+    parts = []
+    for fname, names in KERNELS.items():
+        with open(os.path.join(CSRC, fname)) as f:
+            src = f.read()
+        for n in names:
+            parts.append(f"// ---- {fname}: {n}\n" + cut_kernel(src, n))
+    (tmp_path / "kernels.inc").write_text("\n\n".join(parts) + "\n")
+    exe = tmp_path / "simt_emu"
+    cmd = ["g++", "-std=c++20", "-O1", "-pthread", "-Wno-unknown-pragmas", "-I", str(tmp_path), "-I", EMU,
+           os.path.join(EMU, "driver.cpp"), "-o", str(exe)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-4000:]
+    try:
+        r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    except subprocess.TimeoutExpired:
+        pytest.fail("emulated kernels dead-locked (a shuffle or barrier not reached by every thread)")
+    assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout[-4000:] + r.stderr[-2000:]
