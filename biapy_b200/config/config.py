@@ -28,11 +28,13 @@ DEFAULTS: Dict[str, Any] = {
         "NORMALIZATION": "in", "KERNEL_SIZE": 3, "UPSAMPLE_LAYER": "convtranspose", "ACTIVATION": "elu", "Z_DOWN": [0, 0, 0, 0],
         "YX_DOWN": [0, 0, 0, 0], "ISOTROPY": [True] * 5, "LARGER_IO": False, "CONV_LAYERS": [2] * 5,
         "CONV_BLOCK_ORDER": "conv_norm_act", "LOAD_CHECKPOINT": False, "LOAD_CHECKPOINT_EPOCH": "best_on_val",
-        "ITEMS_TO_LOAD_FROM_CHECKPOINT": ["model"],
+        "ITEMS_TO_LOAD_FROM_CHECKPOINT": ["model"], "SAVE_CKPT_FREQ": -1,
     },
     "LOSS": {"TYPE": "", "CONTRAST": {"ENABLE": False, "PROJ_DIM": 256}},                    # :1916
     "TRAIN": {"ENABLE": False, "OPTIMIZER": ["SGD"], "LR": [1.0e-4], "W_DECAY": 0.02, "OPT_BETAS": [[0.9, 0.999]],   # :1964-1990
-              "BATCH_SIZE": 2, "GRADIENT_CLIP_NORM": 0.0, "EPOCHS": 360},
+              "BATCH_SIZE": 2, "GRADIENT_CLIP_NORM": 0.0, "EPOCHS": 360, "PATIENCE": -1, "VERBOSE": False,
+              "LR_SCHEDULER": {"NAME": "", "MIN_LR": [-1.0], "REDUCEONPLATEAU_FACTOR": 0.5,                           # :2005-2031
+                               "REDUCEONPLATEAU_PATIENCE": -1, "WARMUP_COSINE_DECAY_EPOCHS": -1}},
     "TEST": {"ENABLE": False, "AUGMENTATION": False, "AUGMENTATION_MODE": "mean", "AUGMENTATION_GROUP": "auto",     # :2049-2138
              "REDUCE_MEMORY": False, "BY_CHUNKS": {"ENABLE": False}},
     "PATHS": {"CHECKPOINT": "checkpoints", "CHECKPOINT_FILE": ""},

@@ -1,0 +1,56 @@
+"""Engine entry points of the hot path (``biapy/engine/__init__.py``): ``prepare_optimizer`` and ``build_callbacks`` with the
+reference's signatures.  The "optimizer" returned is the :class:`~biapy_b200.engine.train.Trainer` of the model -- the object
+that owns the flat parameter / gradient / moment buffers and launches the fused optimiser kernel -- which exposes the
+``param_groups`` / ``state_dict`` / ``zero_grad`` surface the training loop and ``save_model`` use."""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+
+def _scalar(v, i: int = 0):
+    """``TRAIN.LR`` / ``MIN_LR`` / ``OPTIMIZER`` are per-optimiser lists since BiaPy 3.6, scalars in older YAMLs."""
+    return v[i] if isinstance(v, (list, tuple)) else v
+
+
+def prepare_optimizer(cfg, model_without_ddp, steps_per_epoch: int, loss: Optional[str] = None) -> Tuple[List, List]:
+    """Optimiser + LR scheduler per ``TRAIN.OPTIMIZER`` entry (reference ``biapy/engine/__init__.py:21-107``; one entry on the
+    hot path).  ``warmupcosine`` starts from ``MIN_LR`` (``:58``); ``timm.create_optimizer_v2`` given a parameter *list* applies
+    the weight decay to every parameter, which is what the fused kernel does.  `loss`: the workflow's loss kind
+    (``bce`` / ``ce`` / ``n2v_mse``), default from the model's attached workflow or ``bce``."""
+    from .schedulers import OneCycleLR, ReduceLROnPlateau, WarmUpCosineDecayScheduler, WarmUpReduceOnPlateauScheduler
+    from .train import Trainer
+
+    name = str(cfg.TRAIN.LR_SCHEDULER.NAME)
+    opts = cfg.TRAIN.OPTIMIZER if isinstance(cfg.TRAIN.OPTIMIZER, (list, tuple)) else [cfg.TRAIN.OPTIMIZER]
+    if len(opts) != 1:
+        raise NotImplementedError("one optimiser per model on the B200 hot path (TRAIN.OPTIMIZER has several entries)")
+    opt = str(opts[0]).lower()
+    if opt not in ("adamw", "sgd"):
+        raise NotImplementedError(f"TRAIN.OPTIMIZER={opts[0]!r}: the fused optimiser kernels cover ADAMW and SGD")
+    lr = float(_scalar(cfg.TRAIN.LR_SCHEDULER.MIN_LR if name == "warmupcosine" else cfg.TRAIN.LR))
+    betas = cfg.TRAIN.OPT_BETAS
+    betas = tuple(betas[0]) if isinstance(betas[0], (list, tuple)) else tuple(betas)
+    trainer = Trainer(model_without_ddp, loss=loss or getattr(model_without_ddp, "loss_kind", "bce"), optimizer=opt, lr=lr,
+                      betas=betas, weight_decay=float(cfg.TRAIN.W_DECAY), clip_norm=float(cfg.TRAIN.GRADIENT_CLIP_NORM))
+    sched = None
+    if name == "reduceonplateau":
+        sched = ReduceLROnPlateau(trainer, patience=int(cfg.TRAIN.LR_SCHEDULER.REDUCEONPLATEAU_PATIENCE),
+                                  factor=float(cfg.TRAIN.LR_SCHEDULER.REDUCEONPLATEAU_FACTOR),
+                                  min_lr=float(_scalar(cfg.TRAIN.LR_SCHEDULER.MIN_LR)))
+    elif name == "warmupcosine":
+        sched = WarmUpCosineDecayScheduler(lr=float(_scalar(cfg.TRAIN.LR)), min_lr=float(_scalar(cfg.TRAIN.LR_SCHEDULER.MIN_LR)),
+                                           warmup_epochs=cfg.TRAIN.LR_SCHEDULER.WARMUP_COSINE_DECAY_EPOCHS,
+                                           epochs=int(cfg.TRAIN.EPOCHS))
+    elif name == "onecycle":
+        sched = OneCycleLR(trainer, float(_scalar(cfg.TRAIN.LR)), epochs=int(cfg.TRAIN.EPOCHS), steps_per_epoch=steps_per_epoch)
+    elif name == "warmupreduceonplateau":
+        sched = WarmUpReduceOnPlateauScheduler(lr=float(_scalar(cfg.TRAIN.LR)), epochs=int(cfg.TRAIN.EPOCHS))
+    elif name != "":
+        raise ValueError(f"unknown TRAIN.LR_SCHEDULER.NAME {name!r}")
+    return [trainer], [sched]
+
+
+def build_callbacks(cfg):
+    """``EarlyStopping(patience=TRAIN.PATIENCE)`` or None for ``-1`` (reference ``:110-132``)."""
+    from ..utils.callbacks import EarlyStopping
+    return EarlyStopping(patience=int(cfg.TRAIN.PATIENCE)) if int(cfg.TRAIN.PATIENCE) != -1 else None

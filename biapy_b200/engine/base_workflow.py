@@ -176,6 +176,56 @@ class Base_Workflow:
                                clip_norm=float(cfg.TRAIN.GRADIENT_CLIP_NORM))
         return self.trainer
 
+    def train(self, train_generator, val_generator=None, cuda_graph: bool = False):
+        """The epoch loop of ``Base_Workflow.train`` (reference ``:1017-1290``) on in-memory generators: iterables of
+        ``(batch, targets)`` in ``(N, [Z,] Y, X, C)`` layout with a ``len()`` (a list, a ``DataLoader`` ...).  Per epoch:
+        ``train_one_epoch`` -> optional ``evaluate`` (+ ``reduceonplateau``) -> best-on-validation bookkeeping -> early stopping.
+        File outputs of the reference (checkpoints, tensorboard, charts, log file) are left to the caller: ``self.optimizer[0]``
+        is the Trainer (``state_dict()`` in ``torch.optim`` layout for ``save_model``).  Returns the per-epoch statistics."""
+        from . import build_callbacks, prepare_optimizer
+        from .train_engine import evaluate, train_one_epoch
+        cfg = self.cfg
+        if self.model is None:
+            self.prepare_model()
+        self.optimizer, self.lr_scheduler = prepare_optimizer(cfg, self.model, len(train_generator), loss=self.loss_kind)
+        self.trainer = self.optimizer[0]
+        self.early_stopping = build_callbacks(cfg)
+        self.loss_names = ["loss"]
+        if cuda_graph:
+            b0, t0 = next(iter(train_generator))
+            self.trainer.enable_cuda_graph(b0, self.prepare_targets(t0, b0))
+        self.val_best_loss = float("inf")
+        start = int(getattr(self, "start_epoch", 0) or 0)
+        history = []
+        for epoch in range(start, int(cfg.TRAIN.EPOCHS)):
+            print("~~~ Epoch {}/{} ~~~\n".format(epoch + 1, cfg.TRAIN.EPOCHS))
+            sampler = getattr(train_generator, "sampler", None)
+            if sampler is not None and hasattr(sampler, "set_epoch"):
+                sampler.set_epoch(epoch)
+            train_stats, _ = train_one_epoch(cfg, model=self.model, model_call_func=self.model_call_func, loss_function=None,
+                                             metric_function=None, prepare_targets=self.prepare_targets,
+                                             data_loader=train_generator, optimizer=self.optimizer, device=self.device, epoch=epoch,
+                                             lr_scheduler=self.lr_scheduler, verbose=bool(cfg.TRAIN.VERBOSE),
+                                             loss_names=self.loss_names)
+            log_stats = {**{f"train_{k}": v for k, v in train_stats.items()}, "epoch": epoch}
+            if val_generator is not None:
+                test_stats = evaluate(cfg, model=self.model, model_call_func=self.model_call_func, loss_function=None,
+                                      metric_function=None, prepare_targets=self.prepare_targets, epoch=epoch,
+                                      data_loader=val_generator, lr_scheduler=self.lr_scheduler, loss_names=self.loss_names,
+                                      optimizer=self.optimizer)
+                if test_stats["loss"] < self.val_best_loss:
+                    print("Val loss improved from {} to {}".format(self.val_best_loss, test_stats["loss"]))
+                    self.val_best_loss = test_stats["loss"]
+                log_stats.update({f"test_{k}": v for k, v in test_stats.items()})
+            history.append(log_stats)
+            if val_generator is not None and self.early_stopping is not None:
+                self.early_stopping(test_stats["loss"])
+                if self.early_stopping.early_stop:
+                    print("Early stopping")
+                    break
+        print("Finished Training")
+        return history
+
     def train_step(self, batch, targets) -> torch.Tensor:
         """One iteration of ``train_one_epoch`` (``train_engine.py:106-203``) on a ``(N, [Z,] Y, X, C)`` batch; returns the loss
         as a device tensor (no host synchronisation)."""

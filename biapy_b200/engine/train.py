@@ -68,7 +68,12 @@ class Trainer:
         assert self.loss_kind in ("bce", "ce", "n2v_mse"), loss
         self.opt_kind = optimizer.lower()
         assert self.opt_kind in ("adamw", "sgd"), optimizer
-        self.lr, self.betas, self.eps, self.wd, self.momentum = lr, betas, eps, weight_decay, momentum
+        # one parameter group in torch.optim layout: the LR schedulers (engine/schedulers) and BiaPy's per-iteration
+        # `adjust_learning_rate` write `param_groups[i]["lr"]` (and 1cycle the first beta); the optimiser launch reads it back
+        self.param_groups = [{"lr": lr, "betas": tuple(betas), "eps": eps, "weight_decay": weight_decay, "momentum": momentum}]
+        if self.opt_kind != "adamw":
+            del self.param_groups[0]["betas"]
+            self._betas = tuple(betas)
         self.clip_norm = clip_norm
         self.fp = FlatParams(model)
         self.m = torch.zeros_like(self.fp.flat)
@@ -83,6 +88,30 @@ class Trainer:
         self._graph = None
         self.graph_launches = 0
         self._arena = ops.ZeroArena()
+
+    # hyper-parameters live in `param_groups[0]` (see __init__); attribute access stays for callers and checkpoints
+    lr = property(lambda self: self.param_groups[0]["lr"], lambda self, v: self.param_groups[0].__setitem__("lr", v))
+    wd = property(lambda self: self.param_groups[0]["weight_decay"],
+                  lambda self, v: self.param_groups[0].__setitem__("weight_decay", v))
+    eps = property(lambda self: self.param_groups[0]["eps"], lambda self, v: self.param_groups[0].__setitem__("eps", v))
+    momentum = property(lambda self: self.param_groups[0]["momentum"],
+                        lambda self, v: self.param_groups[0].__setitem__("momentum", v))
+
+    @property
+    def betas(self):
+        g = self.param_groups[0]
+        return tuple(g["betas"]) if "betas" in g else self._betas
+
+    @betas.setter
+    def betas(self, v):
+        if "betas" in self.param_groups[0]:
+            self.param_groups[0]["betas"] = tuple(v)
+        else:
+            self._betas = tuple(v)
+
+    def zero_grad(self, set_to_none: bool = False):
+        """torch.optim API used by ``train_one_epoch``; the gradient buffer is cleared at the start of every pass anyway."""
+        self.fp.grad.zero_()
 
     # ------------------------------------------------------------------------------------- optimiser state
     def state_dict(self) -> Dict:
@@ -258,6 +287,34 @@ class Trainer:
         pred.mark_written()
         tape.backward()
         return loss
+
+    def evaluate(self, x, target) -> torch.Tensor:
+        """Mean loss of one batch, forward only (the validation loop, ``train_engine.py:266-317``): no tape closures, no
+        gradient buffers, no update.  The caller puts the model in eval mode (``model.eval()``), as the reference does."""
+        xd = self._to_device_cl(x)
+        td = self._to_device_cl(target)
+        model = self.model
+        tape = Tape(model.engine_dtype, self.device, training=False, conv_impl=model.conv_impl)
+        if model.training:
+            tape.rng_seed = model.next_rng_seed(self.device)
+        if xd.dtype == model.engine_dtype and xd.is_contiguous():
+            x_tt = TT(xd, requires_grad=False)
+        else:
+            if xd.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+                xd = xd.float()
+            x_tt = TT(torch.empty(xd.shape, dtype=model.engine_dtype, device=self.device), requires_grad=False)
+            ops.convert(xd.contiguous(), x_tt.data)
+        pred, _ = model._run(tape, x_tt)
+        numel = pred.data.numel()
+        if self.loss_kind == "bce":
+            t32 = td if td.dtype == torch.float32 and td.is_contiguous() else self._as_f32(td)
+            return ops.bce_logits(pred.data, t32, None) / numel
+        if self.loss_kind == "ce":
+            cls = td[..., 0].long().contiguous()
+            return ops.softmax_ce(pred.data, cls, None) / cls.numel()
+        t32 = td if td.dtype == torch.float32 and td.is_contiguous() else self._as_f32(td)
+        sums = ops.n2v_mse_sums(pred.data, t32)
+        return sums[0:1] / sums[1:2]
 
     def _loss_and_grad(self, pred: TT, td: torch.Tensor) -> torch.Tensor:
         numel = pred.data.numel()

@@ -128,3 +128,55 @@ def test_2d_denoising_workflow_matches_oracle_pipeline():
     assert restored.dtype == np.uint8 and restored.shape == back.shape
     # rounding to uint8 can flip where the two float predictions straddle x.5
     assert np.abs(restored.astype(np.int32) - back.astype(np.int32)).max() <= 1 and (restored != back).mean() < 1e-3
+
+
+YAML_TRAIN = YAML.replace("TRAIN: {OPTIMIZER: ADAMW, LR: 1.E-3, BATCH_SIZE: 2, W_DECAY: 0.02}",
+                          "TRAIN: {OPTIMIZER: ADAMW, LR: 2.E-3, BATCH_SIZE: 2, W_DECAY: 0.02, EPOCHS: 2, PATIENCE: 1,\n"
+                          "        LR_SCHEDULER: {NAME: onecycle}}")
+
+
+def test_epoch_loop_with_onecycle_follows_torch_cpu():
+    """``Base_Workflow.train`` (prepare_optimizer -> train_one_epoch -> evaluate -> early stopping) on in-memory generators: the
+    loss of every update follows torch CPU running the reference's recipe -- AdamW + ``OneCycleLR`` stepped after every update
+    (``train_engine.py:166-174``), which also cycles beta1 -- and the validation loss is the eval-mode forward loss."""
+    from biapy_b200._biapy import BiaPy
+    assert "onecycle" in YAML_TRAIN
+    g = torch.Generator().manual_seed(5)
+    X = torch.randn(6, 32, 32, 32, 1, generator=g)
+    Y = (torch.rand(6, 32, 32, 32, 1, generator=g) < 0.3).float()
+    train_gen = [(X[i:i + 2].numpy(), Y[i:i + 2].numpy()) for i in (0, 2)]
+    val_gen = [(X[4:6].numpy(), Y[4:6].numpy())]
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        b = BiaPy(YAML_TRAIN, name="job", run_id=2, engine_dtype=torch.float32)
+    wf = b.workflow
+    sd = {k: v.detach().cpu().clone() for k, v in wf.model.state_dict().items()}
+    with contextlib.redirect_stdout(io.StringIO()):
+        hist = wf.train(train_gen, val_gen)
+    # torch CPU: the reference's loop
+    sd_r = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    opt = torch.optim.AdamW(list(sd_r.values()), lr=2e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.02)
+    sched = torch.optim.lr_scheduler.OneCycleLR(opt, 2e-3, epochs=2, steps_per_epoch=2)
+    ref = []
+    for epoch in range(2):
+        tl, lr = [], None
+        for xb, yb in train_gen:
+            y = port_models.forward("resunet", sd_r, torch.from_numpy(xb).permute(0, 4, 1, 2, 3), training=True, **KW)
+            loss = port_models.bce_with_logits_loss(y, torch.from_numpy(yb).permute(0, 4, 1, 2, 3))
+            opt.zero_grad()
+            loss.backward()
+            lr = opt.param_groups[0]["lr"]
+            opt.step()
+            sched.step()
+            tl.append(loss.item())
+        with torch.no_grad():
+            yv = port_models.forward("resunet", sd_r, torch.from_numpy(val_gen[0][0]).permute(0, 4, 1, 2, 3), training=False, **KW)
+            vl = port_models.bce_with_logits_loss(yv, torch.from_numpy(val_gen[0][1]).permute(0, 4, 1, 2, 3)).item()
+        ref.append((sum(tl) / len(tl), lr, vl))
+    assert len(hist) == 2 and [h["epoch"] for h in hist] == [0, 1]
+    for h, (tl, lr, vl) in zip(hist, ref):
+        assert abs(h["train_loss"] - tl) < 1e-3 * max(1.0, abs(tl)), (h, tl)
+        assert h["train_lr"] == pytest.approx(lr, rel=1e-9)
+        assert abs(h["test_loss"] - vl) < 1e-3 * max(1.0, abs(vl)), (h, vl)
+    assert wf.trainer.param_groups[0]["betas"][0] == pytest.approx(opt.param_groups[0]["betas"][0], rel=1e-9)
+    assert wf.val_best_loss == pytest.approx(min(h["test_loss"] for h in hist))
