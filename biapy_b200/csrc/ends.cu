@@ -132,6 +132,33 @@ __global__ void __launch_bounds__(256) argmax_kernel(const float* __restrict__ s
   }
 }
 
+// ------------------------------------------------------------------------------------------- order statistics
+// np.percentile / kthvalue need the k-th smallest value of a channel exactly.  Radix select: the values map to 32-bit keys
+// that sort like the values (unsigned integers as they are; floats with the sign bit flipped, negative floats inverted), and
+// each pass histograms one digit of the keys that share the digits found so far.  One pass = one read of the channel.
+template <typename S> __device__ __forceinline__ uint32_t select_key(S v) { return (uint32_t)v; }
+template <> __device__ __forceinline__ uint32_t select_key<float>(float v) {
+  const uint32_t b = __float_as_uint(v);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+template <typename S>
+__global__ void __launch_bounds__(256) select_hist_kernel(const S* __restrict__ x, int64_t nvox, int c, int ch, int shift, int bits,
+                                                          uint32_t prefix, int has_prefix, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t s_h[2048];
+  const int nb = 1 << bits;
+  for (int b = threadIdx.x; b < nb; b += blockDim.x) s_h[b] = 0u;
+  __syncthreads();
+  const uint32_t mask = (uint32_t)nb - 1u;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvox; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t key = select_key<S>(x[i * c + ch]);
+    if (!has_prefix || (key >> (shift + bits)) == prefix) atomicAdd(&s_h[(key >> shift) & mask], 1u);
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < nb; b += blockDim.x)
+    if (s_h[b]) atomicAdd(&hist[b], s_h[b]);
+}
+
 static int stream_grid(int64_t total) {
   int64_t b = ceil_div(total, 256);
   const int64_t cap = (int64_t)sm_count() * 16;
@@ -220,6 +247,25 @@ B200_EXPORT int b200_argmax_channels(const float* src, int64_t voxels, int32_t c
   if (dst_dtype == B200_U8) argmax_kernel<uint8_t><<<stream_grid(voxels), 256, 0, st>>>(src, (uint8_t*)dst, voxels, c);
   else if (dst_dtype == B200_U16) argmax_kernel<uint16_t><<<stream_grid(voxels), 256, 0, st>>>(src, (uint16_t*)dst, voxels, c);
   else B200_CHECK_ARG(false, "argmax_channels: dst dtype must be u8 or u16");
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+B200_EXPORT int b200_select_hist(const void* src, int32_t dtype, int64_t voxels, int32_t c, int32_t ch, int32_t shift, int32_t bits,
+                                 uint32_t prefix, int32_t has_prefix, uint32_t* hist, void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(src && hist && voxels > 0 && c > 0 && ch >= 0 && ch < c, "select_hist: bad arguments");
+  B200_CHECK_ARG(bits >= 1 && bits <= 11 && shift >= 0 && shift + bits <= 32 && (has_prefix == 0 || shift + bits < 32),
+                 "select_hist: digit (shift %d, bits %d) out of range", shift, bits);
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint32_t) << bits, st));
+  int64_t bx = ceil_div(voxels, 256 * 8);
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  B200_DISPATCH_IMG(dtype, S, {
+    select_hist_kernel<S><<<(unsigned)bx, 256, 0, st>>>((const S*)src, voxels, c, ch, shift, bits, prefix, has_prefix, hist);
+  });
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

@@ -5,14 +5,16 @@ The statistics (min / max / mean / std / "is this channel binary") come from one
 normalisation itself is one float32 stream (``b200_image_norm_apply``: clip -> subtract -> divide in the reference's operation
 order, so given the same statistics the result is bit-identical to numpy's).  Differences kept deliberately small and loud:
 
-* percentile bounds must be given as values (``lower_bound_val`` / ``upper_bound_val`` or a ``per_channel_info`` from a
-  previous call); computing percentiles from the data (a global selection) raises ``NotImplementedError``;
+* percentile bounds computed from the data (``per_lower_bound`` / ``per_upper_bound``) are exact order statistics from a radix
+  select on the device (``b200_select_hist``) combined on the host the way numpy (numpy input: ``np.percentile``, linear,
+  float32) or the reference's ``torch_percentile`` (tensor input: ``kthvalue``) combine them; NaN-holding channels are not
+  special-cased (numpy would answer NaN);
 * ``out_dtype`` must be ``float32`` (what the engine consumes).
 """
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, List, Optional, Tuple
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -35,6 +37,103 @@ def image_stats(img: torch.Tensor, clip: Optional[np.ndarray] = None) -> np.ndar
     ops._launch("b200_image_stats", ops._ptr(img), _lib.torch_dtype_code(img.dtype), img.numel() // c, c, cp, ops._ptr(out),
                 _lib.stream_ptr())
     return out.cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------ percentiles from the data
+# percentile_clip (norm.py:445-466) asks numpy for `np.percentile(channel, q)` (numpy input) or takes one order statistic with
+# `kthvalue` (torch input, `torch_percentile` :475-497).  Both need exact order statistics of a whole channel: a radix select on
+# the device (b200_select_hist: one histogram pass per 11-bit digit of an order-preserving key), then the same scalar
+# arithmetic on the host that numpy / the reference do with the two neighbouring values.
+_SELECT_PLAN = {torch.uint8: ((0, 11),), torch.uint16: ((11, 11), (0, 11)), torch.float32: ((21, 11), (10, 11), (0, 10))}
+
+
+def _key_to_value(key: int, dtype: torch.dtype) -> np.float32:
+    """Inverse of the device key mapping, as the float32 value the reference sees (it casts integer images to float32 first)."""
+    if dtype != torch.float32:
+        return np.float32(key)
+    bits = (key ^ 0x80000000) if (key & 0x80000000) else (~key & 0xFFFFFFFF)
+    return np.array([bits], dtype=np.uint32).view(np.float32)[0]
+
+
+def select_keys(hist_fn: Callable[[int, int, int, int], np.ndarray], plan, ranks: Sequence[int]) -> Dict[int, int]:
+    """Keys of the elements at the (0-based, ascending-order) `ranks`.  `hist_fn(shift, bits, prefix, has_prefix)` returns the
+    digit histogram of the keys below `prefix`; ranks that share their leading digits share the passes."""
+    out: Dict[int, int] = {}
+
+    def solve(level: int, prefix: int, has: int, rel: List[Tuple[int, int]]):
+        shift, bits = plan[level]
+        hist = np.asarray(hist_fn(shift, bits, prefix, has), dtype=np.int64)
+        cum = np.cumsum(hist)
+        groups: Dict[int, List[Tuple[int, int]]] = {}
+        for rank, r in rel:
+            d = int(np.searchsorted(cum, r, side="right"))
+            assert d < len(hist), "rank beyond the number of elements"
+            groups.setdefault(d, []).append((rank, r - (int(cum[d - 1]) if d else 0)))
+        for d, sub in groups.items():
+            key = ((prefix << bits) | d) if has else d
+            if level + 1 == len(plan):
+                for rank, _ in sub:
+                    out[rank] = key
+            else:
+                solve(level + 1, key, 1, sub)
+
+    uniq = sorted(set(int(r) for r in ranks))
+    solve(0, 0, 0, [(r, r) for r in uniq])
+    return out
+
+
+def _numpy_percentile_ranks(n: int, q: float):
+    """The two neighbouring ranks and the weight of ``np.percentile(float32 array of n values, q)`` (method 'linear'): numpy
+    divides q by float32(100) and keeps the virtual index (n - 1) * q in the array's dtype, float32 (numpy
+    ``_function_base_impl.percentile`` / ``_quantile``)."""
+    quant = np.true_divide(q, np.float32(100))
+    vi = np.float32((n - 1) * quant)
+    prev = int(np.floor(vi))
+    gamma = np.float32(vi - np.floor(vi))
+    if vi >= n - 1:
+        return n - 1, n - 1, gamma
+    if vi < 0:
+        return 0, 0, gamma
+    return prev, prev + 1, gamma
+
+
+def _numpy_lerp(a: np.float32, b: np.float32, t: np.float32) -> float:
+    """numpy's ``_lerp`` on float32 scalars: a + (b - a) * t, or b - (b - a) * (1 - t) from the midpoint on."""
+    diff = np.float32(b - a)
+    if t >= 0.5:
+        return float(np.float32(b - np.float32(diff * np.float32(1 - t))))
+    return float(np.float32(a + np.float32(diff * t)))
+
+
+def channel_percentiles(hist_fn, plan, dtype: torch.dtype, n: int, qs: Sequence[float], torch_rule: bool) -> List[float]:
+    """``[percentile(channel, q) for q in qs]`` with the reference's rule for the input type: ``np.percentile`` (linear
+    interpolation in float32) for numpy images, ``kthvalue(1 + round(0.01 * q * (n - 1)))`` for tensors."""
+    need, plans = [], []
+    for q in qs:
+        if torch_rule:
+            k = 1 + round(0.01 * float(q) * (n - 1))
+            plans.append((k - 1, k - 1, np.float32(0)))
+        else:
+            plans.append(_numpy_percentile_ranks(n, q))
+        need += [plans[-1][0], plans[-1][1]]
+    keys = select_keys(hist_fn, plan, need)
+    res = []
+    for lo, hi, gamma in plans:
+        a, b = _key_to_value(keys[lo], dtype), _key_to_value(keys[hi], dtype)
+        res.append(float(a) if lo == hi else _numpy_lerp(a, b, gamma))
+    return res
+
+
+def _device_hist_fn(img: torch.Tensor, ch: int):
+    c = img.shape[-1]
+    nvox = img.numel() // c
+    buf = torch.empty(2048, dtype=torch.int32, device=img.device)
+
+    def hist_fn(shift: int, bits: int, prefix: int, has_prefix: int) -> np.ndarray:
+        ops._launch("b200_select_hist", ops._ptr(img), _lib.torch_dtype_code(img.dtype), nvox, c, ch, shift, bits, prefix, has_prefix,
+                    ops._ptr(buf), _lib.stream_ptr())
+        return buf[:1 << bits].cpu().numpy().view(np.uint32)
+    return hist_fn
 
 
 def _per_channel(norm_module: Dict, key: str, c: int) -> Optional[List[float]]:
@@ -79,9 +178,28 @@ def normalize_image(img, norm_module: Dict, apply_norm: bool = True) -> Tuple[ob
             hi = [pci[str(k)].get("upper_bound_val") for k in range(c)]
         else:
             lo, hi = _per_channel(norm_module, "lower_bound_val", c), _per_channel(norm_module, "upper_bound_val", c)
+        if pci is None:
+            # bounds from the data (norm.py:445-466): a percentile of -1 / None means "use the value given"
+            pl, pu = norm_module.get("per_lower_bound"), norm_module.get("per_upper_bound")
+            use_l, use_u = pl is not None and pl != -1, pu is not None and pu != -1
+            if use_l:
+                assert pl > 0, "Value in 'per_lower_bound' should be less than 100"
+            if use_u:
+                assert pu < 100, "Value in 'per_upper_bound' should be less than 100"
+            if use_l or use_u:
+                lo, hi = list(lo) if lo is not None else [None] * c, list(hi) if hi is not None else [None] * c
+                plan, cont = _SELECT_PLAN[dev.dtype], dev.contiguous()
+                for k in range(c):
+                    qs = ([pl] if use_l else []) + ([pu] if use_u else [])
+                    vals = channel_percentiles(_device_hist_fn(cont, k), plan, dev.dtype, cont.numel() // c, qs,
+                                               torch_rule=isinstance(img, torch.Tensor))
+                    if use_l:
+                        lo[k] = vals[0]
+                    if use_u:
+                        hi[k] = vals[-1]
         if lo is None or hi is None or any(v is None for v in lo + hi):
-            raise NotImplementedError("percentile bounds computed from the data (per_lower_bound / per_upper_bound) are not implemented "
-                                      "on the device; pass lower_bound_val / upper_bound_val or a per_channel_info")
+            raise AssertionError("If 'per_lower_bound' / 'per_upper_bound' is not provided, 'lower_bound_val' / 'upper_bound_val' "
+                                 "should be provided")
     raw = image_stats(dev)
     nvox = dev.numel() // c
     params = np.zeros((c, 6), np.float32)

@@ -129,6 +129,13 @@ int b200_chunk_insert(const void* patches, int32_t dtype_in, int64_t n, int64_t 
                       void* out, int32_t dtype_out, int64_t D, int64_t H, int64_t W, const int64_t* desc, int32_t mode,
                       void* stream);
 
+/* b200_select_hist: one pass of a radix select over channel `ch` of an interleaved image (percentile clipping, norm.py:445-466:
+ * np.percentile / torch kthvalue need exact order statistics).  Values map to 32-bit keys that sort like the values (unsigned
+ * integers unchanged; float32 with the sign bit flipped / negatives inverted); hist[d] (device, 1 << bits counters, cleared by the
+ * call) = number of elements whose key has digit d = (key >> shift) & (2^bits - 1) and, when has_prefix, whose higher bits
+ * key >> (shift + bits) equal `prefix`.  bits <= 11. */
+int b200_select_hist(const void* src, int32_t dtype, int64_t voxels, int32_t c, int32_t ch, int32_t shift, int32_t bits,
+                     uint32_t prefix, int32_t has_prefix, uint32_t* hist /* device */, void* stream);
 /* ------------------------------------------------------------------------------------- the ends of the path
  * Image normalisation in front of the first convolution and its inverse / the binarisation behind the merge.
  * Images are dense (voxels, C) arrays of dtype u8 / u16 / f32.

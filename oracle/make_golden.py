@@ -320,6 +320,10 @@ NORM_MODULES = [
          per_lower_bound=-1, per_upper_bound=-1),
     dict(type="zero_mean_unit_variance", percentile_clip=True, out_dtype="float32", lower_bound_val=[-1.5], upper_bound_val=[2.5],
          per_lower_bound=-1, per_upper_bound=-1),
+    # bounds from the data: np.percentile of each channel (norm.py:445-466)
+    dict(type="scale_range", percentile_clip=True, out_dtype="float32", per_lower_bound=2.0, per_upper_bound=97.5),
+    dict(type="zero_mean_unit_variance", percentile_clip=True, out_dtype="float32", per_lower_bound=0.7, per_upper_bound=-1,
+         upper_bound_val=[150.0]),
 ]
 
 

@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- numpy restatement of the image normalisation at the ends of the path.
 
 Follows ``biapy/data/norm.py``: normalize_image :44-220 (per-channel loop :188-218), percentile_clip :408-473 (value bounds
-only), norm_range01 :496-580, zero_mean_unit_variance_normalization :582-639, undo_image_norm :641-683, undo_norm_range01
+and np.percentile of the channel), norm_range01 :496-580, zero_mean_unit_variance_normalization :582-639, undo_image_norm :641-683, undo_norm_range01
 :685-713, undo_zero_mean_unit_variance_normalization :715-780; and the binarisation of ``biapy/engine/semantic_seg.py:418-425,
 524-531``.  Pinned against the reference's own functions by ``tests/test_oracle_golden.py`` / ``tests/golden/norm_*.npz``.
 """
@@ -40,7 +40,12 @@ def normalize_image(img: np.ndarray, norm_module: Dict, apply_norm: bool = True)
             if pci is not None:
                 lo, hi = pci[str(k)]["lower_bound_val"], pci[str(k)]["upper_bound_val"]
             else:
-                lo, hi = _bounds(norm_module, "lower_bound_val", c)[k], _bounds(norm_module, "upper_bound_val", c)[k]
+                # norm.py:445-466: a percentile of the (float32) channel unless it is None / -1, else the value given
+                pl, pu = norm_module.get("per_lower_bound"), norm_module.get("per_upper_bound")
+                lo = (float(np.percentile(d, pl)) if pl is not None and pl != -1
+                      else _bounds(norm_module, "lower_bound_val", c)[k])
+                hi = (float(np.percentile(d, pu)) if pu is not None and pu != -1
+                      else _bounds(norm_module, "upper_bound_val", c)[k])
             if is_binary(d):
                 lo, hi = 0.0, 1.0
             elif apply_norm:

@@ -71,6 +71,18 @@ static inline float atomicAdd(float* p, float v) {
   return old;
 }
 
+static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) {
+  std::lock_guard<std::mutex> l(g_atomic_mu);
+  const uint32_t old = *p;
+  *p = old + v;
+  return old;
+}
+static inline uint32_t __float_as_uint(float f) {
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  return u;
+}
+
 // launch(grid, block, [&]{ kernel(args...); })
 static inline void emu_launch(unsigned grid, unsigned block, const std::function<void()>& body) {
   for (unsigned b = 0; b < grid; ++b) {

@@ -40,8 +40,8 @@ def test_normalize_image_matches_reference_golden():
 def test_normalize_image_errors_and_apply_norm_false():
     from biapy_b200.data.norm import normalize_image
     img = np.random.default_rng(0).integers(0, 255, (4, 8, 8, 1)).astype(np.uint8)
-    with pytest.raises(NotImplementedError):
-        normalize_image(img, dict(type="div", percentile_clip=True, out_dtype="float32", per_lower_bound=1.0, per_upper_bound=99.0))
+    with pytest.raises(AssertionError):                  # neither a percentile nor a value for the bounds (norm.py:446, 457)
+        normalize_image(img, dict(type="div", percentile_clip=True, out_dtype="float32", per_lower_bound=-1, per_upper_bound=-1))
     with pytest.raises(NotImplementedError):
         normalize_image(img, dict(type="div", percentile_clip=False, out_dtype="uint8"))
     with pytest.raises(AssertionError):
@@ -50,6 +50,38 @@ def test_normalize_image_errors_and_apply_norm_false():
     y, info = normalize_image(img, mod, apply_norm=False)
     yr, ir = port_norm.normalize_image(img.copy(), mod, apply_norm=False)
     assert np.array_equal(y, yr) and json.loads(json.dumps(info)) == json.loads(json.dumps(ir))
+
+
+@pytest.mark.parametrize("kind", ["float32", "uint16", "uint8"])
+def test_percentile_bounds_from_the_data(kind):
+    """``per_lower_bound`` / ``per_upper_bound``: exact order statistics from the device radix select, combined like
+    ``np.percentile`` for numpy images (the oracle, pinned to the reference by the golden cases) and like the reference's
+    ``torch_percentile`` (``kthvalue``, norm.py:475-497) for tensors -- bit-exact bounds either way."""
+    from biapy_b200.data.norm import normalize_image
+    rng = np.random.default_rng(11)
+    if kind == "float32":
+        img = (rng.standard_normal((6, 21, 24, 2)) * 40 - 5).astype(np.float32)
+        img[0, 0, :5, 0] = img[1, 1, :5, 0]                               # ties
+    elif kind == "uint16":
+        img = rng.integers(0, 50000, (5, 17, 19, 3)).astype(np.uint16)
+    else:
+        img = rng.integers(0, 256, (40, 33, 2)).astype(np.uint8)
+    mod = dict(type="scale_range", percentile_clip=True, out_dtype="float32", per_lower_bound=1.5, per_upper_bound=99.2)
+    y, info = normalize_image(img.copy(), copy.deepcopy(mod))
+    yr, ir = port_norm.normalize_image(img.copy(), copy.deepcopy(mod))
+    assert json.loads(json.dumps(info)) == json.loads(json.dumps(ir))
+    assert np.array_equal(y, yr)
+    y2, info2 = normalize_image(torch.from_numpy(img).cuda(), copy.deepcopy(mod))
+    for k in range(img.shape[-1]):
+        ch = torch.from_numpy(img[..., k].astype(np.float32)).reshape(-1)
+        n = ch.numel()
+        lo = ch.kthvalue(1 + round(0.01 * 1.5 * (n - 1))).values.item()
+        hi = ch.kthvalue(1 + round(0.01 * 99.2 * (n - 1))).values.item()
+        got = info2["per_channel_info"][str(k)]
+        assert (got["lower_bound_val"], got["upper_bound_val"]) == (lo, hi), k
+        d = np.clip(img[..., k].astype(np.float32), lo, hi)
+        want = (d - d.min()) / max(float(d.max()) - float(d.min()), 1e-6)
+        assert np.abs(y2[..., k].cpu().numpy() - want).max() <= 1e-6, k
 
 
 @pytest.mark.parametrize("shape", [(9, 33, 17, 1), (5, 12, 12, 2), (7, 9, 11, 5)])

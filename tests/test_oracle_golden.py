@@ -237,4 +237,4 @@ def test_norm_oracle_matches_reference():
         u = port_norm.undo_image_norm(y.copy(), info)
         assert u.dtype == u_ref.dtype and np.array_equal(u, u_ref), key
         n += 1
-    assert n == 24
+    assert n == 32

@@ -20,6 +20,7 @@ KERNELS = {
     "conv_simt.cu": ["conv1x1_cout_cv_kernel", "conv1x1_cin_cv_kernel", "conv1x1_wgrad_head_cv_kernel",
                      "conv1x1_wgrad_image_cv_kernel"],
     "ops.cu": ["maxpool_fwd_win_kernel", "maxpool_bwd_win_kernel"],
+    "ends.cu": ["select_hist_kernel"],
 }
 
 
@@ -61,7 +62,11 @@ def test_simt_kernels_on_the_host_emulator(tmp_path):
         with open(os.path.join(CSRC, fname)) as f:
             src = f.read()
         for n in names:
-            parts.append(f"// ---- {fname}: {n}\n" + cut_kernel(src, n))
+            body = cut_kernel(src, n)
+            if n == "select_hist_kernel":          # plus its key mapping: the two select_key definitions right above it
+                a = src.index("template <typename S> __device__ __forceinline__ uint32_t select_key")
+                body = src[a:src.index(body)] + body
+            parts.append(f"// ---- {fname}: {n}\n" + body)
     (tmp_path / "kernels.inc").write_text("\n\n".join(parts) + "\n")
     exe = tmp_path / "simt_emu"
     cmd = ["g++", "-std=c++20", "-O1", "-pthread", "-Wno-unknown-pragmas", "-I", str(tmp_path), "-I", EMU,
