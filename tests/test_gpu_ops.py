@@ -80,6 +80,90 @@ def test_conv_fprop_dgrad_wgrad_simt(case, dtype):
     assert nerr(db.cpu(), br.grad) < tol
 
 
+@pytest.mark.parametrize("cin,cout", [(16, 1), (16, 2), (32, 2), (8, 1), (8, 8), (32, 4), (1, 16), (2, 16), (2, 8), (4, 32), (3, 16),
+                                      (8, 16), (1, 128)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_pointwise_narrow_layers_coalesced(cin, cout, dtype):
+    """The 1-2 channel layers of the step (segmentation head 16->1 and its dgrad 1->16 / wgrad, the image-fed shortcut 2->16 and
+    its wgrad) run on the coalesced CUDA-core kernels (thread = voxel x 16-byte vector): dense tensors and 16-byte-aligned
+    channel slices, ragged voxel counts, plain and accumulate epilogues, against ATen on the same 16-bit-rounded operands."""
+    from biapy_b200 import _lib, ops
+    n, d, h, w, k = 2, 3, 7, 11, (1, 1, 1)
+    g = torch.Generator().manual_seed(cin * 131 + cout)
+    x = torch.randn(n, cin, d, h, w, generator=g).to(dtype).float()
+    wt = (torch.randn(cout, cin, 1, 1, 1, generator=g) * 0.3).to(dtype).float()
+    b = torch.randn(cout, generator=g)
+    gy = torch.randn(n, cout, d, h, w, generator=g).to(dtype).float()
+    xr, wr, br = x.clone().requires_grad_(True), wt.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = F.conv3d(xr, wr, br)
+    (yr * gy).sum().backward()
+    tol = 1.5e-2 if dtype == torch.bfloat16 else 3e-3
+    padx, pady = (8 if cin % 8 == 0 else 0), (8 if cout % 8 == 0 else 0)      # aligned slices of wider (concat) buffers
+    xbuf = torch.zeros(n, d, h, w, cin + 2 * padx, dtype=dtype, device="cuda")
+    xv = xbuf[..., padx:padx + cin]
+    xv.copy_(cl(x).to(dtype))
+    ybuf = torch.zeros(n, d, h, w, cout + 2 * pady, dtype=dtype, device="cuda")
+    yv = ybuf[..., pady:pady + cout]
+    wp = ops.pack_conv_weight(wt.cuda(), dtype, False)
+    ops.conv_fprop(xv, wp, b.cuda(), yv, k, impl=_lib.IMPL_SIMT)
+    assert nerr(ncdhw(yv), yr.detach()) < tol
+    if pady:
+        assert ybuf[..., :pady].abs().max().item() == 0 and ybuf[..., pady + cout:].abs().max().item() == 0
+    before = ncdhw(yv)
+    ops.conv_fprop(xv, wp, b.cuda(), yv, k, accumulate=True, impl=_lib.IMPL_SIMT)
+    assert nerr(ncdhw(yv), before + yr.detach()) < 2 * tol
+    # dgrad: the same kernels with the roles of the channel counts swapped
+    gbuf = torch.zeros(n, d, h, w, cout + 2 * pady, dtype=dtype, device="cuda")
+    gv = gbuf[..., pady:pady + cout]
+    gv.copy_(cl(gy).to(dtype))
+    wpf = ops.pack_conv_weight(wt.cuda(), dtype, True)
+    dx = torch.empty(n, d, h, w, cin, dtype=dtype, device="cuda")
+    ops.conv_fprop(gv, wpf, None, dx, k, impl=_lib.IMPL_SIMT)
+    assert nerr(ncdhw(dx), xr.grad) < tol
+    dw = torch.empty_like(wt).cuda()
+    db = torch.zeros(cout, device="cuda")
+    ops.conv_wgrad(xv, gv, cout, cin, k, dw, db, impl=_lib.IMPL_SIMT)
+    assert nerr(dw.cpu(), wr.grad) < tol and nerr(db.cpu(), br.grad) < tol
+
+
+@pytest.mark.parametrize("window", [(2, 2, 2), (1, 2, 2)])
+@pytest.mark.parametrize("dtype,c", [(torch.float32, 8), (torch.bfloat16, 16), (torch.float16, 24)])
+def test_maxpool_vector_kernels(window, dtype, c):
+    """The compile-time-window kernels (16-byte channel vectors, 2x2x2 / 1x2x2): ties go to the first maximum in scan order,
+    plain and accumulate gradient epilogues, tensors that are channel slices of wider buffers, a NaN in one window."""
+    from biapy_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    n, d, h, w = 2, 4, 6, 10
+    x = torch.randint(-2, 3, (n, c, d, h, w), generator=g).float()           # exactly representable, many ties
+    xr = x.clone().requires_grad_(True)
+    yr = F.max_pool3d(xr, window)
+    gy = torch.randint(-4, 5, yr.shape, generator=g).float()
+    (yr * gy).sum().backward()
+    xbuf = torch.zeros(n, d, h, w, c + 16, dtype=dtype, device="cuda")
+    xv = xbuf[..., 8:8 + c]
+    xv.copy_(cl(x).to(dtype))
+    od, oh, ow = d // window[0], h // window[1], w // window[2]
+    ybuf = torch.zeros(n, od, oh, ow, c + 8, dtype=dtype, device="cuda")
+    yv = ybuf[..., :c]
+    ops.maxpool_fwd(xv, yv, window)
+    assert torch.equal(ncdhw(yv), yr.detach()) and ybuf[..., c:].abs().max().item() == 0
+    dxbuf = torch.full((n, d, h, w, c + 8), 3.0, dtype=dtype, device="cuda")
+    dxv = dxbuf[..., 8:8 + c]
+    ops.maxpool_bwd(xv, yv, cl(gy).to(dtype), dxv, window)
+    assert torch.equal(ncdhw(dxv), xr.grad) and (dxbuf[..., :8] == 3.0).all()
+    ops.maxpool_bwd(xv, yv, cl(gy).to(dtype), dxv, window, accumulate=True)
+    assert torch.equal(ncdhw(dxv), 2 * xr.grad)
+    # a NaN wins its window (ATen's rule)
+    x2 = x.clone()
+    x2[0, 1, 1, 2, 3] = float("nan")
+    y2r = F.max_pool3d(x2, window)
+    xd2 = cl(x2).to(dtype)
+    y2 = torch.empty(n, od, oh, ow, c, dtype=dtype, device="cuda")
+    ops.maxpool_fwd(xd2, y2, window)
+    got, want = ncdhw(y2), y2r
+    assert torch.equal(torch.isnan(got), torch.isnan(want)) and torch.equal(torch.nan_to_num(got), torch.nan_to_num(want))
+
+
 @pytest.mark.parametrize("stride", [(2, 2, 2), (1, 2, 2), (2, 1, 1)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_convT(stride, dtype):
