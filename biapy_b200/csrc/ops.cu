@@ -583,18 +583,21 @@ __global__ void maxpool_bwd_vec_kernel(const T* __restrict__ x, int64_t ldx, con
 // the pooled gradient and, when accumulating, the old gradient vectors -- is issued before the first compare, so a thread
 // keeps 8-17 independent 16-byte requests in flight instead of one (the runtime-window loops above cannot be unrolled:
 // 0.44 + 0.19 ms per cfg-2 step against a 0.15 + 0.05 ms HBM floor).  Same scan order and NaN rule as the kernels above.
-template <typename T, int VEC, int PD, int PH, int PW>
+// IDX = uint32_t when the thread count fits 31 bits: the five div / mod pairs of the index decode cost ~100 instructions
+// each in 64-bit arithmetic, more than the memory instructions of the thread.
+template <typename T, int VEC, int PD, int PH, int PW, typename IDX>
 __global__ void __launch_bounds__(256) maxpool_fwd_win_kernel(const T* __restrict__ x, int64_t ldx, T* __restrict__ y, int64_t ldy,
                                                               PoolGeom g) {
   constexpr int NW = PD * PH * PW;
-  const int cvn = g.c / VEC;
-  const int64_t total = (int64_t)g.n * g.od * g.oh * g.ow * cvn;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t t = i;
+  const IDX cvn = (IDX)(g.c / VEC);
+  const IDX total = (IDX)((int64_t)g.n * g.od * g.oh * g.ow * (g.c / VEC));
+  const IDX stride = (IDX)gridDim.x * (IDX)blockDim.x;
+  for (IDX i = (IDX)blockIdx.x * (IDX)blockDim.x + threadIdx.x; i < total; i += stride) {
+    IDX t = i;
     const int cv = (int)(t % cvn); t /= cvn;
-    const int ox = (int)(t % g.ow); t /= g.ow;
-    const int oy = (int)(t % g.oh); t /= g.oh;
-    const int oz = (int)(t % g.od); t /= g.od;
+    const int ox = (int)(t % (IDX)g.ow); t /= (IDX)g.ow;
+    const int oy = (int)(t % (IDX)g.oh); t /= (IDX)g.oh;
+    const int oz = (int)(t % (IDX)g.od); t /= (IDX)g.od;
     const int n = (int)t;
     const T* base = x + ((((int64_t)n * g.d + oz * PD) * g.h + oy * PH) * g.w + ox * PW) * ldx + cv * VEC;
     Pack<T, VEC> p[NW];
@@ -620,18 +623,19 @@ __global__ void __launch_bounds__(256) maxpool_fwd_win_kernel(const T* __restric
   }
 }
 
-template <typename T, int VEC, int PD, int PH, int PW, bool ACC>
+template <typename T, int VEC, int PD, int PH, int PW, bool ACC, typename IDX>
 __global__ void __launch_bounds__(256) maxpool_bwd_win_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy,
                                                               int64_t lddy, T* __restrict__ dx, int64_t lddx, PoolGeom g) {
   constexpr int NW = PD * PH * PW;
-  const int cvn = g.c / VEC;
-  const int64_t total = (int64_t)g.n * g.od * g.oh * g.ow * cvn;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t t = i;
+  const IDX cvn = (IDX)(g.c / VEC);
+  const IDX total = (IDX)((int64_t)g.n * g.od * g.oh * g.ow * (g.c / VEC));
+  const IDX stride = (IDX)gridDim.x * (IDX)blockDim.x;
+  for (IDX i = (IDX)blockIdx.x * (IDX)blockDim.x + threadIdx.x; i < total; i += stride) {
+    IDX t = i;
     const int cv = (int)(t % cvn); t /= cvn;
-    const int ox = (int)(t % g.ow); t /= g.ow;
-    const int oy = (int)(t % g.oh); t /= g.oh;
-    const int oz = (int)(t % g.od); t /= g.od;
+    const int ox = (int)(t % (IDX)g.ow); t /= (IDX)g.ow;
+    const int oy = (int)(t % (IDX)g.oh); t /= (IDX)g.oh;
+    const int oz = (int)(t % (IDX)g.od); t /= (IDX)g.od;
     const int n = (int)t;
     const int64_t vox0 = (((int64_t)n * g.d + oz * PD) * g.h + oy * PH) * g.w + ox * PW;
     const T* xb = x + vox0 * ldx + cv * VEC;
@@ -684,19 +688,45 @@ static inline bool pool_win_enabled() {
   return on;
 }
 
-template <typename T, int V>
-static void launch_pool_bwd_win(const b200_tensor* x, const b200_tensor* dy, const b200_tensor* dx, const PoolGeom& g, int pd,
-                                int accumulate, cudaStream_t st) {
+template <typename T, int V, int PD, typename IDX>
+static void launch_pool_bwd_win2(const b200_tensor* x, const b200_tensor* dy, const b200_tensor* dx, const PoolGeom& g, int accumulate,
+                                 cudaStream_t st) {
   const unsigned grid = grid_for(voxels(dy) * (x->c / V), 256);
   const T* xp = (const T*)x->data;
   const T* gp = (const T*)dy->data;
   T* dp = (T*)dx->data;
+  if (accumulate) maxpool_bwd_win_kernel<T, V, PD, 2, 2, true, IDX><<<grid, 256, 0, st>>>(xp, x->ld, gp, dy->ld, dp, dx->ld, g);
+  else maxpool_bwd_win_kernel<T, V, PD, 2, 2, false, IDX><<<grid, 256, 0, st>>>(xp, x->ld, gp, dy->ld, dp, dx->ld, g);
+}
+
+// 32-bit index decode whenever the (thread count + one grid stride) stays below 2^31
+static inline bool pool_idx32(int64_t threads) { return threads + (int64_t)sm_count() * 8 * 256 < ((int64_t)1 << 31); }
+
+template <typename T, int V>
+static void launch_pool_bwd_win(const b200_tensor* x, const b200_tensor* dy, const b200_tensor* dx, const PoolGeom& g, int pd,
+                                int accumulate, cudaStream_t st) {
+  const bool small = pool_idx32(voxels(dy) * (x->c / V));
   if (pd == 2) {
-    if (accumulate) maxpool_bwd_win_kernel<T, V, 2, 2, 2, true><<<grid, 256, 0, st>>>(xp, x->ld, gp, dy->ld, dp, dx->ld, g);
-    else maxpool_bwd_win_kernel<T, V, 2, 2, 2, false><<<grid, 256, 0, st>>>(xp, x->ld, gp, dy->ld, dp, dx->ld, g);
+    if (small) launch_pool_bwd_win2<T, V, 2, uint32_t>(x, dy, dx, g, accumulate, st);
+    else launch_pool_bwd_win2<T, V, 2, int64_t>(x, dy, dx, g, accumulate, st);
   } else {
-    if (accumulate) maxpool_bwd_win_kernel<T, V, 1, 2, 2, true><<<grid, 256, 0, st>>>(xp, x->ld, gp, dy->ld, dp, dx->ld, g);
-    else maxpool_bwd_win_kernel<T, V, 1, 2, 2, false><<<grid, 256, 0, st>>>(xp, x->ld, gp, dy->ld, dp, dx->ld, g);
+    if (small) launch_pool_bwd_win2<T, V, 1, uint32_t>(x, dy, dx, g, accumulate, st);
+    else launch_pool_bwd_win2<T, V, 1, int64_t>(x, dy, dx, g, accumulate, st);
+  }
+}
+
+template <typename T, int V>
+static void launch_pool_fwd_win(const b200_tensor* x, const b200_tensor* y, const PoolGeom& g, int pd, cudaStream_t st) {
+  const int64_t threads = voxels(y) * (y->c / V);
+  const unsigned grid = grid_for(threads, 256);
+  const T* xp = (const T*)x->data;
+  T* yp = (T*)y->data;
+  if (pool_idx32(threads)) {
+    if (pd == 2) maxpool_fwd_win_kernel<T, V, 2, 2, 2, uint32_t><<<grid, 256, 0, st>>>(xp, x->ld, yp, y->ld, g);
+    else maxpool_fwd_win_kernel<T, V, 1, 2, 2, uint32_t><<<grid, 256, 0, st>>>(xp, x->ld, yp, y->ld, g);
+  } else {
+    if (pd == 2) maxpool_fwd_win_kernel<T, V, 2, 2, 2, int64_t><<<grid, 256, 0, st>>>(xp, x->ld, yp, y->ld, g);
+    else maxpool_fwd_win_kernel<T, V, 1, 2, 2, int64_t><<<grid, 256, 0, st>>>(xp, x->ld, yp, y->ld, g);
   }
 }
 
@@ -1324,12 +1354,7 @@ B200_EXPORT int b200_maxpool_fwd(const b200_tensor* x, const b200_tensor* y, int
   B200_DISPATCH_DTYPE(x->dtype, T, {
     constexpr int V = VecOf<T>::n;
     if (vec_ok(x, V) && vec_ok(y, V) && pool_win_enabled() && ph == 2 && pw == 2 && (pd == 1 || pd == 2)) {
-      if (pd == 2)
-        maxpool_fwd_win_kernel<T, V, 2, 2, 2><<<grid_for(total / V, 256), 256, 0, (cudaStream_t)stream>>>(
-            (const T*)x->data, x->ld, (T*)y->data, y->ld, g);
-      else
-        maxpool_fwd_win_kernel<T, V, 1, 2, 2><<<grid_for(total / V, 256), 256, 0, (cudaStream_t)stream>>>(
-            (const T*)x->data, x->ld, (T*)y->data, y->ld, g);
+      launch_pool_fwd_win<T, V>(x, y, g, pd, (cudaStream_t)stream);
     } else if (vec_ok(x, V) && vec_ok(y, V))
       maxpool_fwd_vec_kernel<T, V><<<grid_for(total / V, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x->data, x->ld, (T*)y->data,
                                                                                              y->ld, g);
