@@ -5,6 +5,7 @@ runs here against ``biapy_b200.engine``.  File discovery, data generators, loggi
 and `test` take arrays instead of reading ``DATA.*.PATH``."""
 from __future__ import annotations
 
+import copy
 import importlib
 from typing import Optional
 
@@ -53,3 +54,60 @@ class BiaPy:
     def test(self, images):
         """Predict a list of images; returns ``[(prediction, post-processed)]``."""
         return [self.workflow.process_test_sample(im) for im in images]
+
+    def run_job(self, train_data=None, test_images=None):
+        """``TRAIN.ENABLE`` -> :meth:`train`, ``TEST.ENABLE`` -> :meth:`test` (``_biapy.py:998-1013``), on in-memory data:
+        `train_data` = ``(X, Y)``, `test_images` = list of ``([z,] y, x, C)`` arrays.  Returns ``(losses, predictions)``."""
+        losses = preds = None
+        if self.cfg.TRAIN.ENABLE:
+            if train_data is None:
+                raise ValueError("TRAIN.ENABLE is set: pass train_data=(X, Y)")
+            losses = self.train(*train_data)
+        if self.cfg.TEST.ENABLE:
+            if test_images is None:
+                raise ValueError("TEST.ENABLE is set: pass test_images=[...]")
+            preds = self.test(test_images)
+        return losses, preds
+
+
+VALID_WORKFLOWS = ["SEMANTIC_SEG", "INSTANCE_SEG", "CLASSIFICATION", "DETECTION", "DENOISING", "SUPER_RESOLUTION", "SELF_SUPERVISED",
+                   "IMAGE_TO_IMAGE"]
+
+
+def _deep_merge(base: dict, over: dict) -> dict:
+    for k, v in over.items():
+        if isinstance(v, dict) and isinstance(base.get(k), dict):
+            _deep_merge(base[k], v)
+        else:
+            base[k] = v
+    return base
+
+
+def build_config(workflow: str, dims: str, phase: str = "both", patch_size: Optional[tuple] = None, model: Optional[dict] = None,
+                 train_data: Optional[dict] = None, val_data: Optional[dict] = None, test_data: Optional[dict] = None,
+                 extra_config: Optional[dict] = None) -> dict:
+    """Configuration overrides from high-level arguments, ready for :class:`BiaPy` (reference ``_biapy.py:1995-2085``): same
+    arguments, validation messages and resulting dict.  All eight workflow names are accepted here as in the reference; the
+    :class:`BiaPy` constructor is what restricts them to the two workflows of the hot path."""
+    workflow = str(workflow).upper()
+    if workflow not in VALID_WORKFLOWS:
+        raise ValueError("'workflow' must be one of {}. Provided: {}".format(VALID_WORKFLOWS, workflow))
+    dims = str(dims).upper()
+    if dims not in ["2D", "3D"]:
+        raise ValueError("'dims' must be either '2D' or '3D'. Provided: {}".format(dims))
+    phase = str(phase).lower()
+    if phase not in ["train", "test", "both"]:
+        raise ValueError("'phase' must be one of ['train', 'test', 'both']. Provided: {}".format(phase))
+    upper = lambda d: {str(k).upper(): v for k, v in d.items()}        # noqa: E731
+    cfg: dict = {"PROBLEM": {"TYPE": workflow, "NDIM": dims}, "TRAIN": {"ENABLE": phase in ("train", "both")},
+                 "TEST": {"ENABLE": phase in ("test", "both")}}
+    if patch_size is not None:
+        cfg.setdefault("DATA", {})["PATCH_SIZE"] = tuple(patch_size)
+    if model:
+        cfg["MODEL"] = upper(model)
+    for key, part in (("TRAIN", train_data), ("VAL", val_data), ("TEST", test_data)):
+        if part:
+            cfg.setdefault("DATA", {})[key] = upper(part)
+    if extra_config:
+        _deep_merge(cfg, copy.deepcopy(extra_config))
+    return cfg

@@ -78,3 +78,34 @@ def test_workflow_hooks_and_model_kwargs():
             super(Semantic_Segmentation_Workflow, self).define_activations_and_channels()
     with pytest.raises(ValueError):
         Broken(c, "j", "cpu")
+
+
+def test_build_config_like_the_reference_api_check():
+    """``build_config`` as ``tests/check_api.py:89-103`` of the reference calls it: high-level arguments -> override dict that
+    loads as a configuration; same validation messages (``_biapy.py:2043-2053``)."""
+    from biapy_b200._biapy import VALID_WORKFLOWS, build_config
+    from biapy_b200.config.config import load_config
+    cfg = build_config(workflow="semantic_seg", dims="3d", phase="both", patch_size=[32, 32, 32, 1], model={"architecture": "resunet"},
+                       train_data={"path": "x", "gt_path": "y", "in_memory": True}, val_data={"split_train": 0.1},
+                       test_data={"path": "tx", "in_memory": False, "overlap": (0.25, 0.25, 0.25)},
+                       extra_config={"TRAIN": {"EPOCHS": 10, "PATIENCE": -1}, "MODEL": {"FEATURE_MAPS": [16, 32]}})
+    assert cfg == {
+        "PROBLEM": {"TYPE": "SEMANTIC_SEG", "NDIM": "3D"},
+        "TRAIN": {"ENABLE": True, "EPOCHS": 10, "PATIENCE": -1},
+        "TEST": {"ENABLE": True},
+        "DATA": {"PATCH_SIZE": (32, 32, 32, 1), "TRAIN": {"PATH": "x", "GT_PATH": "y", "IN_MEMORY": True}, "VAL": {"SPLIT_TRAIN": 0.1},
+                 "TEST": {"PATH": "tx", "IN_MEMORY": False, "OVERLAP": (0.25, 0.25, 0.25)}},
+        "MODEL": {"ARCHITECTURE": "resunet", "FEATURE_MAPS": [16, 32]},
+    }
+    c = load_config(cfg)
+    assert c.PROBLEM.NDIM == "3D" and c.DATA.TEST.OVERLAP == (0.25, 0.25, 0.25) and c.DATA.TEST.PADDING == (0, 0, 0)
+    assert c.TRAIN.EPOCHS == 10 and c.MODEL.ARCHITECTURE == "resunet" and c.MODEL.KERNEL_SIZE == 3
+    only_test = build_config("DENOISING", "2D", phase="test")
+    assert only_test == {"PROBLEM": {"TYPE": "DENOISING", "NDIM": "2D"}, "TRAIN": {"ENABLE": False}, "TEST": {"ENABLE": True}}
+    with pytest.raises(ValueError, match="'workflow' must be one of"):
+        build_config("SEGMENT_ANYTHING", "2D")
+    with pytest.raises(ValueError, match="'dims' must be either '2D' or '3D'. Provided: 4D"):
+        build_config("SEMANTIC_SEG", "4d")
+    with pytest.raises(ValueError, match="'phase' must be one of"):
+        build_config("SEMANTIC_SEG", "2D", phase="validate")
+    assert len(VALID_WORKFLOWS) == 8
