@@ -18,20 +18,27 @@ EMU = os.path.join(ROOT, "tests", "simt_emu")
 
 KERNELS = {
     "conv_simt.cu": ["conv1x1_cout_cv_kernel", "conv1x1_cin_cv_kernel", "conv1x1_wgrad_head_cv_kernel",
-                     "conv1x1_wgrad_image_cv_kernel"],
+                     "conv1x1_wgrad_image_cv_kernel", "pack_weight_kernel", "unpack_wgrad_kernel"],
     "ops.cu": ["maxpool_fwd_win_kernel", "maxpool_bwd_win_kernel"],
     "ends.cu": ["select_hist_kernel"],
+    "conv_umma.cu": ["pack_weight_xfold_kernel", "pack_convT_weight_kernel", "unpack_convT_wgrad_kernel"],
+}
+# helper definitions that sit right above a kernel and are cut out together with it
+PREAMBLE = {
+    "select_hist_kernel": "template <typename S> __device__ __forceinline__ uint32_t select_key",
+    "pack_weight_xfold_kernel": "__host__ __device__ inline bool xfold_geom",
 }
 
 
 def cut_kernel(src: str, name: str) -> str:
-    """`template <...> __global__ void ... name(...) { ... }` as it stands in the source."""
+    """`[template <...>] __global__ void ... name(...) { ... }` as it stands in the source."""
     m = re.search(r"__global__[^;{]*?\b" + re.escape(name) + r"\(", src)
     assert m, f"kernel {name} not found"
-    start = src.rfind("\ntemplate <", 0, m.start()) + 1
-    assert start > 0
-    i = src.index("{", src.index(")", m.end()))
-    # the signature may hold several ')' -- find the brace that opens the body: first '{' after the parameter list closes
+    start = src.rfind("\n", 0, m.start()) + 1
+    prev = src.rfind("\n", 0, start - 1) + 1
+    if src[prev:start].startswith("template <"):
+        start = prev
+    # the brace that opens the body: first '{' after the parameter list closes
     depth, j = 0, m.end() - 1
     while True:
         ch = src[j]
@@ -63,10 +70,14 @@ def test_simt_kernels_on_the_host_emulator(tmp_path):
             src = f.read()
         for n in names:
             body = cut_kernel(src, n)
-            if n == "select_hist_kernel":          # plus its key mapping: the two select_key definitions right above it
-                a = src.index("template <typename S> __device__ __forceinline__ uint32_t select_key")
+            if n in PREAMBLE:
+                a = src.index(PREAMBLE[n])
                 body = src[a:src.index(body)] + body
             parts.append(f"// ---- {fname}: {n}\n" + body)
+    # the staged batched pack kernel (experiments/, not in the library) is held to the product kernels it would replace
+    with open(os.path.join(ROOT, "experiments", "pack_batch.cuh")) as f:
+        staged = f.read()
+    parts.append("// ---- experiments/pack_batch.cuh\n" + staged[staged.index("enum PackKind"):])
     (tmp_path / "kernels.inc").write_text("\n\n".join(parts) + "\n")
     exe = tmp_path / "simt_emu"
     cmd = ["g++", "-std=c++20", "-O1", "-pthread", "-Wno-unknown-pragmas", "-I", str(tmp_path), "-I", EMU,
