@@ -36,7 +36,7 @@ DEFAULTS: Dict[str, Any] = {
               "LR_SCHEDULER": {"NAME": "", "MIN_LR": [-1.0], "REDUCEONPLATEAU_FACTOR": 0.5,                           # :2005-2031
                                "REDUCEONPLATEAU_PATIENCE": -1, "WARMUP_COSINE_DECAY_EPOCHS": -1}},
     "TEST": {"ENABLE": False, "AUGMENTATION": False, "AUGMENTATION_MODE": "mean", "AUGMENTATION_GROUP": "auto",     # :2049-2138
-             "REDUCE_MEMORY": False, "BY_CHUNKS": {"ENABLE": False}},
+             "REDUCE_MEMORY": False, "BY_CHUNKS": {"ENABLE": False}, "FULL_IMG": False},
     "PATHS": {"CHECKPOINT": "checkpoints", "CHECKPOINT_FILE": ""},
 }
 

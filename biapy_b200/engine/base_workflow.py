@@ -146,6 +146,8 @@ class Base_Workflow:
             X, self.current_sample["norm_info"] = _norm.normalize_image(X, dict(self.test_norm_module))
         vol, patch = X, tuple(cfg.DATA.PATCH_SIZE)
         ov, pad = tuple(cfg.DATA.TEST.OVERLAP), tuple(cfg.DATA.TEST.PADDING)
+        if self.ndim == 2 and cfg.TEST.get("FULL_IMG", False):
+            return self._process_full_image(vol)
         if self.ndim == 2:
             # one (y, x, C) image: the 2D crop / merge mirrors around predict_batches_in_test (reference :1944-1997 with
             # crop_data_with_overlap / merge_data_with_overlap)
@@ -163,6 +165,32 @@ class Base_Workflow:
                                   head_activations=self.head_activations, tta=bool(cfg.TEST.AUGMENTATION),
                                   tta_mode=cfg.TEST.AUGMENTATION_MODE, tta_group=cfg.TEST.AUGMENTATION_GROUP)
         return pred, self.after_merge_patches(pred)
+
+    def _process_full_image(self, X):
+        """``TEST.FULL_IMG`` (2D only, reference ``:2224-2290``): the whole ``(y, x, C)`` image goes through the model in one
+        call -- zero-padded at the bottom / right to a multiple of ``2 ** levels`` (``check_downsample_division``), through the TTA
+        ensemble when ``TEST.AUGMENTATION``, cropped back -- and then to ``after_full_image``."""
+        from ..utils.util import check_downsample_division
+        cfg = self.cfg
+        is_np = isinstance(X, np.ndarray)
+        Xp, o_shape = check_downsample_division(X[None], len(cfg.MODEL.FEATURE_MAPS) - 1)
+        with torch.no_grad():
+            if cfg.TEST.AUGMENTATION:
+                from ..data.post_processing.post_processing import ensemble_predictions
+                xin = torch.from_numpy(np.ascontiguousarray(Xp)).to(self.device) if is_np else Xp
+                pred = ensemble_predictions(xin[0], self.model_call_func, self.axes_order_back, self.axes_order, self.device, self.ndim,
+                                            batch_size_value=int(cfg.TRAIN.BATCH_SIZE), mode=cfg.TEST.AUGMENTATION_MODE,
+                                            group=cfg.TEST.AUGMENTATION_GROUP)
+            else:
+                pred = self.model_call_func(Xp)
+        pred = pred.permute(self.axes_order_back).float()[:, :o_shape[1], :o_shape[2]][0]
+        pred = pred.cpu().numpy() if is_np else pred.contiguous()
+        return pred, self.after_full_image(pred)
+
+    def after_full_image(self, pred):
+        """Called with the full-image prediction of one sample (reference hook ``after_full_image``); the two workflows of
+        the hot path post-process it like a merged prediction."""
+        return self.after_merge_patches(pred)
 
     # ------------------------------------------------------------------------------------------- training
     def prepare_trainer(self) -> Trainer:

@@ -109,3 +109,46 @@ def test_build_config_like_the_reference_api_check():
     with pytest.raises(ValueError, match="'phase' must be one of"):
         build_config("SEMANTIC_SEG", "2D", phase="validate")
     assert len(VALID_WORKFLOWS) == 8
+
+
+def test_full_image_inference_pads_calls_the_model_once_and_crops():
+    """``TEST.FULL_IMG`` (2D, reference ``base_workflow.py:2224-2290``): zero padding to a multiple of 2**levels at the bottom /
+    right (``check_downsample_division``, ``util.py:637-674``), ONE model call on the whole image, crop back, ``after_full_image``.
+    The model call is a stand-in here (the real one is the same ``model_call_func`` the patch path uses, covered on the GPU)."""
+    import numpy as np
+    import torch
+    from biapy_b200.config import load_config
+    from biapy_b200.engine.denoising import Denoising_Workflow
+    from biapy_b200.utils.util import check_downsample_division
+    x = np.arange(2 * 5 * 9 * 1, dtype=np.float32).reshape(2, 5, 9, 1)
+    xp, o = check_downsample_division(x, 3)
+    ref = np.pad(x, ((0, 0), (0, 3), (0, 7), (0, 0)))
+    assert o == (2, 5, 9, 1) and xp.shape == (2, 8, 16, 1) and np.array_equal(xp, ref)
+    xt, ot = check_downsample_division(torch.from_numpy(x), 3)
+    assert ot == o and torch.equal(xt, torch.from_numpy(ref))
+    same, _ = check_downsample_division(ref, 3)
+    assert same is ref                                                   # already divisible: untouched
+
+    cfg = load_config({"PROBLEM": {"TYPE": "DENOISING", "NDIM": "2D"}, "DATA": {"PATCH_SIZE": (16, 16, 2)}, "TEST": {"FULL_IMG": True},
+                       "MODEL": {"FEATURE_MAPS": [8, 16, 32]}})
+    w = Denoising_Workflow(cfg, "j", "cpu")
+    calls = []
+
+    class Model:
+        def eval(self):
+            calls.append("eval")
+    w.model = Model()
+
+    def fake_model_call(in_img, is_train=False, apply_act=True):
+        calls.append(tuple(in_img.shape))
+        t = torch.from_numpy(in_img) if isinstance(in_img, np.ndarray) else in_img
+        return (t * 2 + 1).permute(0, 3, 1, 2)                            # (N, C, Y, X) like the engine
+    w.model_call_func = fake_model_call
+    img = np.random.default_rng(0).standard_normal((13, 22, 2)).astype(np.float32)
+    pred, post = w.process_test_sample(img, norm=False)
+    assert calls == ["eval", (1, 16, 24, 2)]                              # padded to multiples of 2**2, one call
+    assert isinstance(pred, np.ndarray) and pred.shape == (13, 22, 2) and np.array_equal(pred, img * 2 + 1)
+    assert np.array_equal(post, pred)                                      # no norm_info recorded: nothing to undo
+    pred_t, _ = w.process_test_sample(torch.from_numpy(img), norm=False)
+    assert isinstance(pred_t, torch.Tensor) and torch.equal(pred_t, torch.from_numpy(img * 2 + 1))
+    assert load_config(None).TEST.FULL_IMG is False                         # reference default (config.py:2071)
