@@ -49,6 +49,8 @@ struct BlockCtx {
   std::unique_ptr<std::barrier<>> block_bar;
   std::vector<std::unique_ptr<std::barrier<>>> warp_bar;
   std::vector<float> xchg;   // [warps][32]
+  std::vector<double> dyn_smem_store;   // dynamic shared memory of the block (8-byte aligned)
+  char* dyn_smem = nullptr;
 };
 static BlockCtx* g_ctx = nullptr;
 static std::mutex g_atomic_mu;
@@ -77,16 +79,31 @@ static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) {
   *p = old + v;
   return old;
 }
+static inline double atomicAdd(double* p, double v) {
+  std::lock_guard<std::mutex> l(g_atomic_mu);
+  const double old = *p;
+  *p = old + v;
+  return old;
+}
+static inline float emu_expf(float x) { return std::exp(x); }
+static inline float emu_fdividef(float a, float b) { return a / b; }
+#define __expf(x) emu_expf(x)          // glibc declares a __expf of its own
+#define __fdividef(a, b) emu_fdividef(a, b)
 static inline uint32_t __float_as_uint(float f) {
   uint32_t u;
   std::memcpy(&u, &f, 4);
   return u;
 }
 
-// launch(grid, block, [&]{ kernel(args...); })
-static inline void emu_launch(unsigned grid, unsigned block, const std::function<void()>& body) {
+// launch(grid, block, [&]{ kernel(args...); }); emu_launch2 adds gridDim.y and dynamic shared memory
+static inline void emu_launch2(unsigned grid_x, unsigned grid_y, unsigned block, size_t dyn_smem_bytes, const std::function<void()>& body);
+static inline void emu_launch(unsigned grid, unsigned block, const std::function<void()>& body) { emu_launch2(grid, 1, block, 0, body); }
+static inline void emu_launch2(unsigned grid, unsigned grid_y, unsigned block, size_t dyn_smem_bytes, const std::function<void()>& body) {
+ for (unsigned by = 0; by < grid_y; ++by)
   for (unsigned b = 0; b < grid; ++b) {
     BlockCtx ctx;
+    ctx.dyn_smem_store.assign(dyn_smem_bytes / 8 + 1, 0.0);
+    ctx.dyn_smem = reinterpret_cast<char*>(ctx.dyn_smem_store.data());
     ctx.block_bar = std::make_unique<std::barrier<>>(block);
     const unsigned warps = (block + 31) / 32;
     for (unsigned w = 0; w < warps; ++w) {
@@ -101,8 +118,10 @@ static inline void emu_launch(unsigned grid, unsigned block, const std::function
       ts.emplace_back([&, t] {
         threadIdx.x = t;
         blockIdx.x = b;
+        blockIdx.y = by;
         blockDim.x = block;
         gridDim.x = grid;
+        gridDim.y = grid_y;
         body();
       });
     for (auto& th : ts) th.join();
@@ -111,6 +130,11 @@ static inline void emu_launch(unsigned grid, unsigned block, const std::function
 }
 
 // ---- the element helpers of common.cuh / ops.cu (same definitions) ---------------------------------------------------
+static inline float warp_sum(float v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 template <typename T> inline float to_f(T v);
 template <> inline float to_f<float>(float v) { return v; }
 template <> inline float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }

@@ -1,10 +1,18 @@
-"""CPU check of the plain SIMT kernels' index arithmetic (no GPU in the build container).
+"""CPU check of the plain SIMT kernels (no GPU in the build container).
 
 The kernel *source text* is cut out of ``biapy_b200/csrc/*.cu``, compiled with g++ behind ``tests/simt_emu/emu.h`` (one
-std::thread per CUDA thread, barriers for ``__syncthreads`` / ``__shfl_xor_sync``) and run against straightforward loops:
-the coalesced pointwise convolutions (fprop / dgrad / wgrad of the 1-2 channel layers) and the compile-time-window max-pool
-kernels.  This is test infrastructure: it proves the indexing, the shuffle patterns and the reduction layouts, not speed;
-the device run of the same kernels is covered by the ``-m gpu`` parity tests.
+std::thread per CUDA thread, barriers for ``__syncthreads`` / ``__shfl_xor_sync``, 2-D grids, dynamic shared memory) and run
+against straightforward loops / textbook formulas in double precision:
+
+* the coalesced pointwise convolutions (fprop / dgrad / wgrad of the 1-2 channel layers) and the compile-time-window max-pool;
+* the radix-select histogram of the percentile clipping;
+* the weight pack / unpack kernels against independent statements of their layouts, and the staged one-launch pack kernel of
+  ``experiments/`` against them;
+* the whole GroupNorm / InstanceNorm + activation chain: ``channel_sums`` -> ``norm_finalize`` -> ``scale_shift_act_rows`` and
+  ``norm_act_bwd_reduce`` -> ``norm_bwd_finalize`` -> ``norm_act_bwd_apply_rows`` (dx, dgamma, dbeta) on channel slices.
+
+This is test infrastructure: it proves indexing, shuffle patterns, reduction layouts and formulas, not speed; the device run of
+the same kernels is covered by the ``-m gpu`` parity tests.  It is what lets a kernel be changed with no GPU at hand.
 """
 import os
 import re
@@ -19,7 +27,9 @@ EMU = os.path.join(ROOT, "tests", "simt_emu")
 KERNELS = {
     "conv_simt.cu": ["conv1x1_cout_cv_kernel", "conv1x1_cin_cv_kernel", "conv1x1_wgrad_head_cv_kernel",
                      "conv1x1_wgrad_image_cv_kernel", "pack_weight_kernel", "unpack_wgrad_kernel"],
-    "ops.cu": ["maxpool_fwd_win_kernel", "maxpool_bwd_win_kernel"],
+    "ops.cu": ["maxpool_fwd_win_kernel", "maxpool_bwd_win_kernel", "channel_sums_kernel", "norm_finalize_kernel",
+               "scale_shift_act_rows_kernel", "norm_act_bwd_reduce_kernel", "norm_bwd_finalize_kernel",
+               "norm_act_bwd_apply_rows_kernel"],
     "ends.cu": ["select_hist_kernel"],
     "conv_umma.cu": ["pack_weight_xfold_kernel", "pack_convT_weight_kernel", "unpack_convT_wgrad_kernel"],
 }
@@ -65,6 +75,15 @@ def cut_kernel(src: str, name: str) -> str:
 
 def test_simt_kernels_on_the_host_emulator(tmp_path):
     parts = []
+    # activation helpers of common.cuh and the kernel-side tensor view of ops.cu, as they stand
+    with open(os.path.join(CSRC, "common.cuh")) as f:
+        common = f.read()
+    parts.append("// ---- common.cuh: activations\n" + common[common.index("__device__ __forceinline__ float act_fwd(int act, float x)"):
+                                                                  common.index("#define B200_DISPATCH_ACT")])
+    with open(os.path.join(CSRC, "ops.cu")) as f:
+        ops_src = f.read()
+    a = ops_src.index("template <typename T>\nstruct View {")
+    parts.append("// ---- ops.cu: View\n" + ops_src[a:ops_src.index("};", a) + 2])
     for fname, names in KERNELS.items():
         with open(os.path.join(CSRC, fname)) as f:
             src = f.read()
@@ -73,6 +92,8 @@ def test_simt_kernels_on_the_host_emulator(tmp_path):
             if n in PREAMBLE:
                 a = src.index(PREAMBLE[n])
                 body = src[a:src.index(body)] + body
+            # dynamic shared memory: `extern __shared__ T name[];` -> the emulator's per-block buffer
+            body = re.sub(r"extern __shared__ (\w+) (\w+)\[\];", r"\1* \2 = reinterpret_cast<\1*>(g_ctx->dyn_smem);", body)
             parts.append(f"// ---- {fname}: {n}\n" + body)
     # the staged batched pack kernel (experiments/, not in the library) is held to the product kernels it would replace
     with open(os.path.join(ROOT, "experiments", "pack_batch.cuh")) as f:
@@ -80,7 +101,7 @@ def test_simt_kernels_on_the_host_emulator(tmp_path):
     parts.append("// ---- experiments/pack_batch.cuh\n" + staged[staged.index("enum PackKind"):])
     (tmp_path / "kernels.inc").write_text("\n\n".join(parts) + "\n")
     exe = tmp_path / "simt_emu"
-    cmd = ["g++", "-std=c++20", "-O1", "-pthread", "-Wno-unknown-pragmas", "-I", str(tmp_path), "-I", EMU,
+    cmd = ["g++", "-std=c++20", "-O1", "-pthread", "-Wno-unknown-pragmas", "-I", str(tmp_path), "-I", EMU, "-I", os.path.join(ROOT, "include"),
            os.path.join(EMU, "driver.cpp"), "-o", str(exe)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-4000:]
