@@ -99,6 +99,10 @@ def test_simt_kernels_on_the_host_emulator(tmp_path):
     with open(os.path.join(ROOT, "experiments", "pack_batch.cuh")) as f:
         staged = f.read()
     parts.append("// ---- experiments/pack_batch.cuh\n" + staged[staged.index("enum PackKind"):])
+    with open(os.path.join(ROOT, "experiments", "norm_fast.cuh")) as f:
+        staged = f.read()
+    staged = re.sub(r"extern __shared__ (\w+) (\w+)\[\];", r"\1* \2 = reinterpret_cast<\1*>(g_ctx->dyn_smem);", staged)
+    parts.append("// ---- experiments/norm_fast.cuh\n" + staged[staged.index("__device__ __forceinline__ float tanh_approx"):])
     (tmp_path / "kernels.inc").write_text("\n\n".join(parts) + "\n")
     exe = tmp_path / "simt_emu"
     cmd = ["g++", "-std=c++20", "-O1", "-pthread", "-Wno-unknown-pragmas", "-I", str(tmp_path), "-I", EMU, "-I", os.path.join(ROOT, "include"),
