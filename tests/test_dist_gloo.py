@@ -1,5 +1,5 @@
 """world_size-2 gloo tests (CPU) of the multi-GPU host logic: gradient all-reduce factor, patch dealing and the
-prediction all-gather used by sliding-window inference."""
+prediction all-gather used by sliding-window inference, cross-rank loss statistics of the epoch loop."""
 import os
 import socket
 
@@ -50,6 +50,34 @@ def _worker(rank, world, port, q):
             own[bd.deal_tiles(n_tiles, rank, world, drop_repeats=True)] = 1
             dist.all_reduce(own)
             assert torch.equal(own, torch.ones(n_tiles))      # without the repeats: exactly one owner per tile
+        # 5. the epoch loop averages the loss over the ranks like MetricLogger.synchronize_between_processes
+        #    (train_engine.py:204-206): sum of values and counts, not a mean of per-rank means
+        import contextlib
+        import io
+        from biapy_b200.config.config import load_config
+        from biapy_b200.engine.train_engine import train_one_epoch
+
+        class FakeTrainer:
+            def __init__(self, losses):
+                self.param_groups, self.losses, self.k = [{"lr": 1e-3}], losses, 0
+
+            def zero_grad(self):
+                pass
+
+            def step(self, batch, targets):
+                self.k += 1
+                return torch.tensor([self.losses[self.k - 1]], dtype=torch.float64)
+
+        class FakeModel:
+            def train(self, flag=True):
+                pass
+
+        cfg = load_config({"PROBLEM": {"NDIM": "2D"}, "DATA": {"PATCH_SIZE": (8, 8, 1)}})
+        losses = [1.0, 2.0, 3.0] if rank == 0 else [10.0]                # ragged: 3 batches on rank 0, 1 on rank 1
+        loader = [(torch.zeros(2, 8, 8, 1), torch.zeros(2, 8, 8, 1)) for _ in losses]
+        with contextlib.redirect_stdout(io.StringIO()):
+            stats, _ = train_one_epoch(cfg, FakeModel(), None, None, None, lambda t, b: t, loader, [FakeTrainer(losses)], "cpu", 0)
+        assert abs(stats["loss"] - 16.0 / 4) < 1e-12, stats
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))
