@@ -108,6 +108,8 @@ def _numpy_lerp(a: np.float32, b: np.float32, t: np.float32) -> float:
 def channel_percentiles(hist_fn, plan, dtype: torch.dtype, n: int, qs: Sequence[float], torch_rule: bool) -> List[float]:
     """``[percentile(channel, q) for q in qs]`` with the reference's rule for the input type: ``np.percentile`` (linear
     interpolation in float32) for numpy images, ``kthvalue(1 + round(0.01 * q * (n - 1)))`` for tensors."""
+    if n >= 2 ** 32:
+        raise NotImplementedError("percentiles of a channel with 2^32 or more voxels: the select histogram counts in 32 bits")
     need, plans = [], []
     for q in qs:
         if torch_rule:

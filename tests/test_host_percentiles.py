@@ -68,3 +68,6 @@ def test_select_shares_passes_between_neighbouring_ranks_and_handles_specials():
     assert len(h2.calls) == 3
     with pytest.raises(AssertionError):
         N.select_keys(numpy_hist_fn(vals), N._SELECT_PLAN[torch.float32], [len(vals)])
+    with pytest.raises(NotImplementedError):
+        N.channel_percentiles(numpy_hist_fn(vals), N._SELECT_PLAN[torch.float32], torch.float32, 2 ** 32, [50.0], torch_rule=False)
+
