@@ -225,6 +225,43 @@ def test_tta_orientation_group_host_mirror():
         build_axis_transform_group(4)
 
 
+def test_tta_oracle_passes_the_reference_unit_tests():
+    """The scalar-path unit tests the reference ships for its TTA (``tests/test_tta_equivariance.py``), held against the oracle
+    and the host mirror of the transforms: inverse round trips (``:198-206``), group sizes and "Z never moves" (``:209-219``),
+    rot90 == numpy (``:222-225``), an identity model comes back unchanged (``:529-546``), non-square inputs keep their shape
+    (``:522-526``), ``TEST.AUGMENTATION_GROUP`` sets the number of forward passes (``:572-590``)."""
+    from biapy_b200.data.post_processing.tta import AxisTransform, build_axis_transform_group
+    from oracle import port_tta
+    rng = np.random.default_rng(0)
+    for ndim in (2, 3):
+        arr = rng.normal(size=(5, 6, 7)[:ndim] + (3,))
+        for perm, sign in port_tta.orientations(ndim, "full"):
+            back = port_tta.apply(port_tta.apply(arr, perm, sign), *port_tta.inverse(perm, sign))
+            assert np.array_equal(back, arr), (perm, sign)
+    assert [len(port_tta.orientations(*a)) for a in ((2, "full"), (2, "flips"), (3, "full"), (3, "flips"), (3, "none"))] == [8, 4, 16, 8, 1]
+    assert all(perm[0] == 0 for perm, _ in port_tta.orientations(3, "full"))
+    assert port_tta.orientations(3, "full")[0] == ((0, 1, 2), (1, 1, 1))
+    arr = rng.normal(size=(8, 8, 2))
+    assert np.array_equal(port_tta.apply(arr, (1, 0), (-1, 1)), np.rot90(arr, 1, axes=(0, 1)))
+    assert AxisTransform((1, 0), (-1, 1)) in build_axis_transform_group(2, "full")
+    # identity model over the full group: the input comes back unchanged
+    img = np.random.default_rng(1).normal(size=(32, 32, 1)).astype(np.float32)
+    out = port_tta.ensemble_predictions(img, lambda b: b.astype(np.float32), 2, 8)
+    assert out.shape == img.shape and np.allclose(out, img, atol=1e-5)
+    # non-square input: padded for the rotations, cropped back
+    img = np.random.default_rng(2).normal(size=(48, 64, 3)).astype(np.float32)
+    out = port_tta.ensemble_predictions(img, lambda b: b.astype(np.float32), 2, 4)
+    assert out.shape == (48, 64, 3) and np.allclose(out, img, atol=1e-5)
+    for group, expected in (("none", 1), ("flips", 4), ("full", 8)):
+        calls = []
+
+        def pred_func(batch):
+            calls.append(batch.shape[0])
+            return batch.astype(np.float32)
+        port_tta.ensemble_predictions(np.random.default_rng(2).normal(size=(16, 16, 1)).astype(np.float32), pred_func, 2, 1, "mean", group)
+        assert sum(calls) == expected
+
+
 # --------------------------------------------------------------------------- image normalisation at the ends (SURVEY 8f row 2)
 def test_norm_oracle_matches_reference():
     import copy
