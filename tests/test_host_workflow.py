@@ -152,3 +152,42 @@ def test_full_image_inference_pads_calls_the_model_once_and_crops():
     pred_t, _ = w.process_test_sample(torch.from_numpy(img), norm=False)
     assert isinstance(pred_t, torch.Tensor) and torch.equal(pred_t, torch.from_numpy(img * 2 + 1))
     assert load_config(None).TEST.FULL_IMG is False                         # reference default (config.py:2071)
+
+
+@pytest.mark.reference
+def test_reference_templates_build_the_same_networks():
+    """The reference's own YAML templates for the two workflows of the hot path (``templates/semantic_segmentation``,
+    ``templates/denoising``) load through ``load_config``, resolve to the workflow classes, and ``prepare_model`` builds a network
+    with the same ``state_dict`` keys and shapes as the reference class constructed from the same keyword arguments (container
+    only: needs /root/reference).  Templates of architectures outside the path (hrnet48) must say so."""
+    import contextlib
+    import glob
+    import io
+    from biapy_b200.config import load_config
+    from biapy_b200.engine.denoising import Denoising_Workflow
+    from biapy_b200.engine.semantic_seg import Semantic_Segmentation_Workflow
+    from oracle import ref_loader
+    R = ref_loader.load()
+    ref_cls = {"U_Net": R.unet.U_Net, "ResUNet": R.resunet.ResUNet, "Attention_U_Net": R.attention_unet.Attention_U_Net}
+    root = "/root/reference/templates"
+    files = sorted(glob.glob(f"{root}/semantic_segmentation/*.yaml") + glob.glob(f"{root}/semantic_segmentation/*/*.yaml")
+                   + glob.glob(f"{root}/denoising/*.yaml"))
+    assert len(files) >= 7
+    built = 0
+    for f in files:
+        c = load_config(f)
+        cls = Denoising_Workflow if c.PROBLEM.TYPE == "DENOISING" else Semantic_Segmentation_Workflow
+        w = cls(c, "job_1", "cpu")
+        if str(c.MODEL.ARCHITECTURE).lower() not in ("unet", "resunet", "attention_unet"):
+            with pytest.raises(NotImplementedError, match="outside the B200 hot path"):
+                w.prepare_model()
+            continue
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = w.prepare_model()
+            ref = ref_cls[type(m).__name__](**w.model_build_kwargs)
+        ours = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        theirs = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+        assert ours == theirs, f
+        assert c.TRAIN.LR_SCHEDULER.NAME in ("", "onecycle", "warmupcosine", "reduceonplateau", "warmupreduceonplateau")
+        built += 1
+    assert built >= 5
