@@ -1,5 +1,6 @@
-"""``OneCycleLR`` and ``ReduceLROnPlateau`` with the arguments ``prepare_optimizer`` passes (reference
-``biapy/engine/__init__.py:74-96``) and torch's defaults for the rest, working on anything that has ``param_groups``.
+"""The four learning-rate schedules ``prepare_optimizer`` can build (reference ``biapy/engine/__init__.py:74-104``), working on
+anything that has ``param_groups``: BiaPy's two per-iteration warm-up rules (``biapy/engine/schedulers/``) and ``OneCycleLR`` /
+``ReduceLROnPlateau`` with the arguments the reference passes and torch's defaults for the rest.
 
 torch's own classes insist on a ``torch.optim.Optimizer`` instance; the engine's optimiser is the fused kernel driven by
 :class:`~biapy_b200.engine.train.Trainer`, so the two schedules are restated here (the formulas are the published 1cycle /
@@ -8,6 +9,62 @@ from __future__ import annotations
 
 import math
 from typing import List, Sequence, Union
+
+import numpy as np
+
+
+def _write_lr(optimizer, lr: float) -> None:
+    """`lr` into every parameter group, scaled by the group's optional ``lr_scale``."""
+    for group in optimizer.param_groups:
+        group["lr"] = lr * group.get("lr_scale", 1.0) if "lr_scale" in group else lr
+
+
+class WarmUpCosineDecayScheduler:
+    """Linear warm-up from 0 to `lr` over `warmup_epochs`, then half a cosine down to `min_lr` at `epochs` (reference
+    ``schedulers/warmup_cosine_decay.py:13-79``).  Driven per iteration with a fractional epoch,
+    ``step / len(data_loader) + epoch`` (``train_engine.py:113-116``)."""
+
+    def __init__(self, lr: float, min_lr: float, warmup_epochs: int, epochs: int):
+        self.lr, self.min_lr, self.warmup_epochs, self.epochs = lr, min_lr, warmup_epochs, epochs
+
+    def lr_at(self, epoch: float) -> float:
+        if epoch < self.warmup_epochs:
+            return self.lr * epoch / self.warmup_epochs
+        # same operation order as the reference (pi * elapsed / span): the doubles agree bit for bit
+        angle = math.pi * (epoch - self.warmup_epochs) / (self.epochs - self.warmup_epochs)
+        return self.min_lr + (self.lr - self.min_lr) * 0.5 * (1.0 + math.cos(angle))
+
+    def adjust_learning_rate(self, optimizer, epoch: float | int) -> float:
+        lr = self.lr_at(epoch)
+        _write_lr(optimizer, lr)
+        return lr
+
+
+def plateau_table(lr: float, n_epochs: int) -> np.ndarray:
+    """One rate per epoch: ten points of a linear ramp 0 -> lr, then lr; runs longer than 100 (300) epochs trade their last
+    50 (100) plateau epochs for ten halvings lasting 5 (10) epochs each (reference
+    ``schedulers/warmup_reduce_on_plateau.py:17-32``)."""
+    table = list(np.linspace(0, lr, 10)) + [lr] * max(0, n_epochs - 10)
+    halving_run = 10 if n_epochs > 300 else 5 if n_epochs > 100 else 0
+    if halving_run:
+        del table[len(table) - 10 * halving_run:]
+        for _ in range(10):
+            table += [table[-1] / 2] * halving_run
+    return np.asarray(table, dtype=np.float64)
+
+
+class WarmUpReduceOnPlateauScheduler:
+    """The tabulated schedule of :func:`plateau_table`, looked up with the integer part of the (fractional) epoch and clamped
+    to its last entry (reference ``schedulers/warmup_reduce_on_plateau.py:6-46``)."""
+
+    def __init__(self, lr: float, epochs: int):
+        self.lr, self.epochs = lr, epochs
+        self.LR = plateau_table(lr, epochs)
+
+    def adjust_learning_rate(self, optimizer, epoch: float | int) -> float:
+        lr = float(self.LR[min(int(epoch), len(self.LR) - 1)])
+        _write_lr(optimizer, lr)
+        return lr
 
 
 def _cos_anneal(start: float, end: float, pct: float) -> float:
