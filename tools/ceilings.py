@@ -18,6 +18,38 @@ BATCH = 4
 ELT = 2          # bf16
 
 
+# launch groups of the cfg-2 model that the detail file labels without shapes: transposed convolutions 256->256 @8^3->16^3,
+# 128->128 @16^3, 64->64 @32^3, 32->32 @64^3->128^3 (k = s = 2) and the four max-pools behind the encoder levels
+_CONVT = [(256, 8), (128, 16), (64, 32), (32, 64)]          # (channels, input edge)
+_POOL = [(16, 128), (32, 64), (64, 32), (128, 16)]          # (channels, input edge)
+
+
+def _convt(reads_in, reads_out, writes_in, writes_out):
+    def f(hbm, tf):
+        flop = sum(2.0 * BATCH * e ** 3 * c * c * 8 for c, e in _CONVT)
+        byts = sum(BATCH * e ** 3 * c * ELT * (reads_in + writes_in) + BATCH * (2 * e) ** 3 * c * ELT * (reads_out + writes_out)
+                   for c, e in _CONVT)
+        t = max(flop / tf, byts / hbm)
+        return f"{flop / 1e9:.1f} GF, {byts / 1e6:.0f} MB", "hbm" if byts / hbm > flop / tf else "tensor", t * 1e3
+    return f
+
+
+def _pool(passes_fine, passes_coarse):
+    def f(hbm, tf):
+        byts = sum(BATCH * e ** 3 * c * ELT * passes_fine + BATCH * (e // 2) ** 3 * c * ELT * passes_coarse for c, e in _POOL)
+        return f"{byts / 1e6:.0f} MB", "hbm", byts / hbm * 1e3
+    return f
+
+
+FIXED = {
+    "convT_fprop_tc": _convt(1, 0, 0, 1),            # read x, write the fine tensor
+    "convT_dgrad_tc": _convt(0, 1, 1, 0),            # read the fine gradient, write dx
+    "convT_wgrad_tc": _convt(1, 1, 0, 0),            # read both
+    "maxpool_fwd": _pool(1, 1),                      # read x, write y
+    "maxpool_bwd": _pool(3, 1),                      # read x, read + write dx (accumulate into the skip gradient), read dy
+}
+
+
 def main(path):
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     hbm = peaks["hbm_gbs"] * 1e9
@@ -57,6 +89,8 @@ def main(path):
                 if per:
                     byts = el * per * ELT
                     bound, ceil_ms, work = "hbm", byts / hbm * 1e3, f"{byts / 1e6:.0f} MB"
+        if bound is None and label in FIXED:
+            work, bound, ceil_ms = FIXED[label](hbm, tf)
         rows.append((ms, label, n, work, bound, ceil_ms))
     rows.sort(reverse=True)
     total = sum(r[0] for r in rows)
@@ -75,8 +109,8 @@ def main(path):
             print(f"| {label} | {n} | {ms:.3f} | {work} | {bound} | {ceil_ms:.3f} | {ms / ceil_ms:.1f}x |")
     km, kc = sum(r[0] for r in known), sum(r[5] for r in known)
     print(f"\nGroups with a modelled ceiling: {km:.2f} ms measured against {kc:.2f} ms of ceilings ({km / kc:.1f}x); "
-          f"the other {total - km:.2f} ms are transposed convolutions, pooling, weight packing, losses and the optimiser "
-          f"(see DESIGN.md 8 for their floors).")
+          f"the other {total - km:.2f} ms are weight packing / unpacking and coefficient kernels (5-10 us launches), strided copies, "
+          f"the loss and the optimiser.")
 
 
 if __name__ == "__main__":
