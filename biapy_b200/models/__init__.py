@@ -39,12 +39,36 @@ def model_kwargs_from_cfg(cfg, output_channels, output_channel_info, head_activa
         z_down = [2] * depth
     if all(v == 0 for v in yx_down):
         yx_down = [2] * depth
+    for key, v in (("MODEL.Z_DOWN", z_down), ("MODEL.YX_DOWN", yx_down)):
+        if len(v) != depth:                                                   # check_configuration.py:2706-2707, 2758-2759
+            raise ValueError(f"'MODEL.FEATURE_MAPS' length minus one and '{key}' length must be equal")
     iso = _get(cfg, "MODEL.ISOTROPY", [True] * len(fm))
+    if not isinstance(iso, bool) and all(x is True or x == 1 for x in iso):
+        iso = [True] * len(fm)                                                # :2761-2763: all-True follows the feature maps
+    # MODEL.DROPOUT_VALUES (:2677-2683): an all-zero list follows the feature maps, anything else must match them
+    drop = list(_get(cfg, "MODEL.DROPOUT_VALUES", [0.0] * len(fm)))
+    if len(drop) != len(fm):
+        if all(x == 0 for x in drop):
+            drop = [0.0] * len(fm)
+        elif any(not (0 <= x <= 1) for x in drop):
+            raise ValueError("'MODEL.DROPOUT_VALUES' not in [0, 1] range")
+        else:
+            raise ValueError("'MODEL.FEATURE_MAPS' and 'MODEL.DROPOUT_VALUES' lengths must be equal")
+    # MODEL.CONV_LAYERS (:2776-2790): empty -> 2 per level, one value or a uniform list -> broadcast to the levels
+    conv_layers = list(_get(cfg, "MODEL.CONV_LAYERS", [2] * len(fm)))
+    if len(conv_layers) == 0:
+        conv_layers = [2] * len(fm)
+    elif len(conv_layers) != len(fm):
+        if len(set(conv_layers)) != 1:
+            raise ValueError("'MODEL.FEATURE_MAPS' and 'MODEL.CONV_LAYERS' lengths must be equal")
+        conv_layers = [conv_layers[0]] * len(fm)
+    if any(x < 1 for x in conv_layers):
+        raise ValueError("'MODEL.CONV_LAYERS' values must be greater than or equal to 1")
     return dict(
         image_shape=tuple(_get(cfg, "DATA.PATCH_SIZE")),
         activation=str(_get(cfg, "MODEL.ACTIVATION", "elu")).lower(),
         feature_maps=fm,
-        drop_values=list(_get(cfg, "MODEL.DROPOUT_VALUES", [0.0] * len(fm))),
+        drop_values=drop,
         normalization=_get(cfg, "MODEL.NORMALIZATION", "in"),
         k_size=_get(cfg, "MODEL.KERNEL_SIZE", 3),
         upsample_layer=_get(cfg, "MODEL.UPSAMPLE_LAYER", "convtranspose"),
@@ -60,7 +84,7 @@ def model_kwargs_from_cfg(cfg, output_channels, output_channel_info, head_activa
         divide_decoder_feature_maps=bool(_get(cfg, "MODEL.DIVIDE_DECODER_FEATURE_MAPS", False)),
         isotropy=list(iso) if not isinstance(iso, bool) else iso,
         larger_io=bool(_get(cfg, "MODEL.LARGER_IO", False)),
-        conv_layers=list(_get(cfg, "MODEL.CONV_LAYERS", [2] * len(fm))),
+        conv_layers=conv_layers,
         conv_block_order=_get(cfg, "MODEL.CONV_BLOCK_ORDER", "conv_norm_act"),
     )
 

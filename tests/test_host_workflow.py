@@ -191,3 +191,36 @@ def test_reference_templates_build_the_same_networks():
         assert c.TRAIN.LR_SCHEDULER.NAME in ("", "onecycle", "warmupcosine", "reduceonplateau", "warmupreduceonplateau")
         built += 1
     assert built >= 5
+
+
+def test_model_lists_follow_the_feature_maps_like_check_configuration():
+    """``MODEL.DROPOUT_VALUES`` / ``ISOTROPY`` / ``CONV_LAYERS`` / ``Z_DOWN`` / ``YX_DOWN`` are fitted to ``MODEL.FEATURE_MAPS`` with
+    the rules of ``check_configuration.py:2677-2790``: defaults written for five levels also serve three or six levels, uniform
+    lists are broadcast, anything else must match (same error messages)."""
+    import contextlib
+    import io
+    from biapy_b200.config import load_config
+    from biapy_b200.models import build_model, model_kwargs_from_cfg
+
+    def kwargs(model):
+        c = load_config({"PROBLEM": {"NDIM": "3D"}, "DATA": {"PATCH_SIZE": (32, 32, 32, 1)}, "MODEL": model})
+        return model_kwargs_from_cfg(c, [1], ["pred0"], ["ce_sigmoid"]), c
+    k, c = kwargs({"FEATURE_MAPS": [4, 8, 16, 32, 64, 128]})                     # six levels on five-level defaults
+    assert k["drop_values"] == [0.0] * 6 and k["isotropy"] == [True] * 6 and k["conv_layers"] == [2] * 6
+    assert k["z_down"] == [2] * 5 and k["yx_down"] == [2] * 5
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = build_model(c, [1], ["pred0"], ["ce_sigmoid"], "cpu")[0]
+    assert len(m.down_path) == 5 and len(m.up_paths[0]) == 5
+    k, _ = kwargs({"FEATURE_MAPS": [8, 16, 32], "CONV_LAYERS": [3]})
+    assert k["conv_layers"] == [3, 3, 3] and k["drop_values"] == [0.0] * 3 and k["isotropy"] == [True] * 3
+    k, _ = kwargs({"FEATURE_MAPS": [8, 16, 32], "CONV_LAYERS": [], "ISOTROPY": [False, True, True], "DROPOUT_VALUES": [0.1, 0.2, 0.3],
+                   "Z_DOWN": [1, 2], "YX_DOWN": [2, 2]})
+    assert k["conv_layers"] == [2, 2, 2] and k["isotropy"] == [False, True, True] and k["drop_values"] == [0.1, 0.2, 0.3]
+    assert k["z_down"] == [1, 2]
+    for model, msg in (({"FEATURE_MAPS": [8, 16, 32], "CONV_LAYERS": [2, 3]}, "'MODEL.FEATURE_MAPS' and 'MODEL.CONV_LAYERS' lengths must be equal"),
+                       ({"FEATURE_MAPS": [8, 16, 32], "CONV_LAYERS": [0]}, "'MODEL.CONV_LAYERS' values must be greater than or equal to 1"),
+                       ({"FEATURE_MAPS": [8, 16, 32], "DROPOUT_VALUES": [0.1, 0.2]}, "'MODEL.FEATURE_MAPS' and 'MODEL.DROPOUT_VALUES' lengths must be equal"),
+                       ({"FEATURE_MAPS": [8, 16, 32], "DROPOUT_VALUES": [0.1, 1.2]}, "'MODEL.DROPOUT_VALUES' not in \\[0, 1\\] range"),
+                       ({"FEATURE_MAPS": [8, 16, 32], "Z_DOWN": [2, 2, 2]}, "'MODEL.FEATURE_MAPS' length minus one and 'MODEL.Z_DOWN' length must be equal")):
+        with pytest.raises(ValueError, match=msg):
+            kwargs(model)
