@@ -42,6 +42,23 @@ def model_kwargs_from_cfg(cfg, output_channels, output_channel_info, head_activa
     for key, v in (("MODEL.Z_DOWN", z_down), ("MODEL.YX_DOWN", yx_down)):
         if len(v) != depth:                                                   # check_configuration.py:2706-2707, 2758-2759
             raise ValueError(f"'MODEL.FEATURE_MAPS' length minus one and '{key}' length must be equal")
+    # every level must divide the patch evenly and leave more than two voxels (check_configuration.py:3140-3205)
+    patch = tuple(_get(cfg, "DATA.PATCH_SIZE"))
+    arch = str(_get(cfg, "MODEL.ARCHITECTURE", "unet")).lower()
+    cur_z = patch[0] if ndim == 3 else 1
+    cur_yx = list(patch[1:-1]) if ndim == 3 else list(patch[:-1])
+    for i in range(depth):
+        yf, zf = yx_down[i], (z_down[i] if ndim == 3 else 1)
+        if any(d % yf != 0 or d <= 2 for d in cur_yx) or (ndim == 3 and (cur_z % zf != 0 or cur_z <= 2)):
+            m = (f"The 'DATA.PATCH_SIZE' provided is not divisible by the downsampling factor at level {i} of the {arch}. "
+                 "You can:\n 1) Reduce the number of levels (by reducing 'cfg.MODEL.FEATURE_MAPS' array length)\n"
+                 " 2) Increase 'DATA.PATCH_SIZE'")
+            if ndim == 3:
+                m += ("\n 3) If the Z axis is the problem (often smaller due to resolution), you can tune 'MODEL.Z_DOWN' to not "
+                      "downsample the Z axis in all levels.")
+            raise ValueError(m)
+        cur_yx = [d // yf for d in cur_yx]
+        cur_z //= zf
     iso = _get(cfg, "MODEL.ISOTROPY", [True] * len(fm))
     if not isinstance(iso, bool) and all(x is True or x == 1 for x in iso):
         iso = [True] * len(fm)                                                # :2761-2763: all-True follows the feature maps

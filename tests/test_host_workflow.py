@@ -202,8 +202,8 @@ def test_model_lists_follow_the_feature_maps_like_check_configuration():
     from biapy_b200.config import load_config
     from biapy_b200.models import build_model, model_kwargs_from_cfg
 
-    def kwargs(model):
-        c = load_config({"PROBLEM": {"NDIM": "3D"}, "DATA": {"PATCH_SIZE": (32, 32, 32, 1)}, "MODEL": model})
+    def kwargs(model, patch=(128, 128, 128, 1)):
+        c = load_config({"PROBLEM": {"NDIM": "3D"}, "DATA": {"PATCH_SIZE": patch}, "MODEL": model})
         return model_kwargs_from_cfg(c, [1], ["pred0"], ["ce_sigmoid"]), c
     k, c = kwargs({"FEATURE_MAPS": [4, 8, 16, 32, 64, 128]})                     # six levels on five-level defaults
     assert k["drop_values"] == [0.0] * 6 and k["isotropy"] == [True] * 6 and k["conv_layers"] == [2] * 6
@@ -224,3 +224,11 @@ def test_model_lists_follow_the_feature_maps_like_check_configuration():
                        ({"FEATURE_MAPS": [8, 16, 32], "Z_DOWN": [2, 2, 2]}, "'MODEL.FEATURE_MAPS' length minus one and 'MODEL.Z_DOWN' length must be equal")):
         with pytest.raises(ValueError, match=msg):
             kwargs(model)
+    # the patch must halve evenly at every level and keep more than two voxels (check_configuration.py:3183-3201)
+    with pytest.raises(ValueError, match="not divisible by the downsampling factor at level 4 of the unet"):
+        kwargs({"FEATURE_MAPS": [4, 8, 16, 32, 64, 128]}, patch=(32, 32, 32, 1))
+    with pytest.raises(ValueError, match="not divisible by the downsampling factor at level 2 of the resunet"):
+        kwargs({"ARCHITECTURE": "resunet", "FEATURE_MAPS": [8, 16, 32, 64]}, patch=(20, 36, 36, 1))      # 20 -> 10 -> 5: odd
+    k, _ = kwargs({"FEATURE_MAPS": [8, 16, 32], "Z_DOWN": [1, 1]}, patch=(5, 36, 36, 1))       # Z not down-sampled: any depth in z
+    assert k["z_down"] == [1, 1]
+
