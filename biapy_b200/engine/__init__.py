@@ -12,6 +12,35 @@ def _scalar(v, i: int = 0):
     return v[i] if isinstance(v, (list, tuple)) else v
 
 
+_SCHEDULERS = ["reduceonplateau", "warmupcosine", "onecycle", "warmupreduceonplateau"]
+
+
+def check_lr_scheduler(cfg) -> None:
+    """The scheduler rules of ``check_configuration.py:3304-3351`` (same messages), applied before anything is built."""
+    s = cfg.TRAIN.LR_SCHEDULER
+    name = str(s.NAME)
+    if name == "":
+        return
+    if name not in _SCHEDULERS:
+        raise ValueError(f"'TRAIN.LR_SCHEDULER.NAME' must be in {_SCHEDULERS}")
+    min_lr = list(s.MIN_LR) if isinstance(s.MIN_LR, (list, tuple)) else [s.MIN_LR]      # a bare float in older YAMLs (:3664-3666)
+    if name in ("reduceonplateau", "warmupcosine") and all(x == -1.0 for x in min_lr):
+        raise ValueError("'TRAIN.LR_SCHEDULER.MIN_LR' needs to be set when 'TRAIN.LR_SCHEDULER.NAME' is between "
+                         "['reduceonplateau', 'warmupcosine']")
+    if name == "reduceonplateau":
+        if s.REDUCEONPLATEAU_PATIENCE == -1:
+            raise ValueError("'TRAIN.LR_SCHEDULER.REDUCEONPLATEAU_PATIENCE' needs to be set when 'TRAIN.LR_SCHEDULER.NAME' is "
+                             "'reduceonplateau'")
+        if cfg.TRAIN.PATIENCE != -1 and s.REDUCEONPLATEAU_PATIENCE >= cfg.TRAIN.PATIENCE:
+            raise ValueError("'TRAIN.LR_SCHEDULER.REDUCEONPLATEAU_PATIENCE' needs to be less than 'TRAIN.PATIENCE' ")
+    if name == "warmupcosine":
+        if s.WARMUP_COSINE_DECAY_EPOCHS == -1:
+            raise ValueError("'TRAIN.LR_SCHEDULER.WARMUP_COSINE_DECAY_EPOCHS' needs to be set when 'TRAIN.LR_SCHEDULER.NAME' is "
+                             "'warmupcosine'")
+        if s.WARMUP_COSINE_DECAY_EPOCHS > cfg.TRAIN.EPOCHS:
+            raise ValueError("'TRAIN.LR_SCHEDULER.WARMUP_COSINE_DECAY_EPOCHS' needs to be less than 'TRAIN.EPOCHS'")
+
+
 def prepare_optimizer(cfg, model_without_ddp, steps_per_epoch: int, loss: Optional[str] = None) -> Tuple[List, List]:
     """Optimiser + LR scheduler per ``TRAIN.OPTIMIZER`` entry (reference ``biapy/engine/__init__.py:21-107``; one entry on the
     hot path).  ``warmupcosine`` starts from ``MIN_LR`` (``:58``); ``timm.create_optimizer_v2`` given a parameter *list* applies
@@ -20,6 +49,7 @@ def prepare_optimizer(cfg, model_without_ddp, steps_per_epoch: int, loss: Option
     from .schedulers import OneCycleLR, ReduceLROnPlateau, WarmUpCosineDecayScheduler, WarmUpReduceOnPlateauScheduler
     from .train import Trainer
 
+    check_lr_scheduler(cfg)
     name = str(cfg.TRAIN.LR_SCHEDULER.NAME)
     opts = cfg.TRAIN.OPTIMIZER if isinstance(cfg.TRAIN.OPTIMIZER, (list, tuple)) else [cfg.TRAIN.OPTIMIZER]
     if len(opts) != 1:

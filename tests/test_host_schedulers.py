@@ -217,3 +217,27 @@ def test_config_carries_the_scheduler_keys_with_reference_defaults():
     assert c.TRAIN.PATIENCE == -1 and c.TRAIN.EPOCHS == 360 and c.MODEL.SAVE_CKPT_FREQ == -1
     c = load_config("TRAIN:\n  LR_SCHEDULER:\n    NAME: onecycle\n")
     assert c.TRAIN.LR_SCHEDULER.NAME == "onecycle" and c.TRAIN.LR_SCHEDULER.REDUCEONPLATEAU_FACTOR == 0.5
+
+
+def test_scheduler_configuration_rules_of_check_configuration():
+    """``prepare_optimizer`` refuses what ``check_configuration.py:3304-3351`` refuses, with its messages, before it touches the
+    model (so this runs without a GPU)."""
+    from biapy_b200.engine import check_lr_scheduler, prepare_optimizer
+
+    def cfg(**sched):
+        patience = sched.pop("PATIENCE", -1)
+        return load_config({"TRAIN": {"EPOCHS": 10, "PATIENCE": patience, "LR_SCHEDULER": sched}})
+    for c in (cfg(NAME=""), cfg(NAME="onecycle"), cfg(NAME="warmupreduceonplateau"),
+              cfg(NAME="warmupcosine", MIN_LR=[1e-5], WARMUP_COSINE_DECAY_EPOCHS=2),
+              cfg(NAME="reduceonplateau", MIN_LR=1e-6, REDUCEONPLATEAU_PATIENCE=2, PATIENCE=5)):
+        check_lr_scheduler(c)
+    bad = [(cfg(NAME="cosine"), "'TRAIN.LR_SCHEDULER.NAME' must be in"),
+           (cfg(NAME="warmupcosine", WARMUP_COSINE_DECAY_EPOCHS=2), "'TRAIN.LR_SCHEDULER.MIN_LR' needs to be set"),
+           (cfg(NAME="reduceonplateau", MIN_LR=[1e-6]), "'TRAIN.LR_SCHEDULER.REDUCEONPLATEAU_PATIENCE' needs to be set"),
+           (cfg(NAME="reduceonplateau", MIN_LR=[1e-6], REDUCEONPLATEAU_PATIENCE=5, PATIENCE=5), "needs to be less than 'TRAIN.PATIENCE'"),
+           (cfg(NAME="warmupcosine", MIN_LR=[1e-5]), "'TRAIN.LR_SCHEDULER.WARMUP_COSINE_DECAY_EPOCHS' needs to be set"),
+           (cfg(NAME="warmupcosine", MIN_LR=[1e-5], WARMUP_COSINE_DECAY_EPOCHS=11), "needs to be less than 'TRAIN.EPOCHS'")]
+    for c, msg in bad:
+        with pytest.raises(ValueError, match=msg):
+            prepare_optimizer(c, model_without_ddp=None, steps_per_epoch=3)
+
