@@ -8,6 +8,7 @@ against straightforward loops / textbook formulas in double precision:
 * the radix-select histogram of the percentile clipping;
 * the weight pack / unpack kernels against independent statements of their layouts, and the staged one-launch pack kernel of
   ``experiments/`` against them;
+* the fused AdamW / SGD kernels (and the staged Adam-with-L2 kernel) against the torch.optim update rules in double precision;
 * the whole GroupNorm / InstanceNorm + activation chain: ``channel_sums`` -> ``norm_finalize`` -> ``scale_shift_act_rows`` and
   ``norm_act_bwd_reduce`` -> ``norm_bwd_finalize`` -> ``norm_act_bwd_apply_rows`` (dx, dgamma, dbeta) on channel slices.
 
@@ -29,7 +30,7 @@ KERNELS = {
                      "conv1x1_wgrad_image_cv_kernel", "pack_weight_kernel", "unpack_wgrad_kernel"],
     "ops.cu": ["maxpool_fwd_win_kernel", "maxpool_bwd_win_kernel", "channel_sums_kernel", "norm_finalize_kernel",
                "scale_shift_act_rows_kernel", "norm_act_bwd_reduce_kernel", "norm_bwd_finalize_kernel",
-               "norm_act_bwd_apply_rows_kernel"],
+               "norm_act_bwd_apply_rows_kernel", "adamw_kernel", "sgd_kernel"],
     "ends.cu": ["select_hist_kernel"],
     "conv_umma.cu": ["pack_weight_xfold_kernel", "pack_convT_weight_kernel", "unpack_convT_wgrad_kernel"],
 }
@@ -103,6 +104,9 @@ def test_simt_kernels_on_the_host_emulator(tmp_path):
         staged = f.read()
     staged = re.sub(r"extern __shared__ (\w+) (\w+)\[\];", r"\1* \2 = reinterpret_cast<\1*>(g_ctx->dyn_smem);", staged)
     parts.append("// ---- experiments/norm_fast.cuh\n" + staged[staged.index("__device__ __forceinline__ float tanh_approx"):])
+    with open(os.path.join(ROOT, "experiments", "optim_adam.cuh")) as f:
+        staged = f.read()
+    parts.append("// ---- experiments/optim_adam.cuh\n" + staged[staged.index("__global__ void adam_kernel"):])
     (tmp_path / "kernels.inc").write_text("\n\n".join(parts) + "\n")
     exe = tmp_path / "simt_emu"
     cmd = ["g++", "-std=c++20", "-O1", "-pthread", "-Wno-unknown-pragmas", "-I", str(tmp_path), "-I", EMU, "-I", os.path.join(ROOT, "include"),
