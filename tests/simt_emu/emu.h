@@ -66,6 +66,17 @@ static inline float __shfl_xor_sync(unsigned, float v, int o) {
   return r;
 }
 
+static inline double __shfl_xor_sync(unsigned, double v, int o) {
+  // two float-sized halves through the same exchange buffer would need care; use a second, double-typed buffer instead
+  static std::vector<double> xd(64 * 32);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  xd[warp * 32 + lane] = v;
+  g_ctx->warp_bar[warp]->arrive_and_wait();
+  const double r = xd[warp * 32 + (lane ^ o)];
+  g_ctx->warp_bar[warp]->arrive_and_wait();
+  return r;
+}
+
 static inline float atomicAdd(float* p, float v) {
   std::lock_guard<std::mutex> l(g_atomic_mu);
   const float old = *p;
@@ -131,6 +142,10 @@ static inline void emu_launch2(unsigned grid, unsigned grid_y, unsigned block, s
 
 // ---- the element helpers of common.cuh / ops.cu (same definitions) ---------------------------------------------------
 static inline float warp_sum(float v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+static inline double warp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }

@@ -8,7 +8,7 @@ against straightforward loops / textbook formulas in double precision:
 * the radix-select histogram of the percentile clipping;
 * the weight pack / unpack kernels against independent statements of their layouts, and the staged one-launch pack kernel of
   ``experiments/`` against them;
-* the fused AdamW / SGD kernels (and the staged Adam-with-L2 kernel) against the torch.optim update rules in double precision;
+* the loss kernels (BCE with logits, soft-max cross-entropy, Noise2Void masked MSE: sums and gradients) and the fused AdamW / SGD kernels (and the staged Adam-with-L2 kernel) against the torch.optim update rules in double precision;
 * the whole GroupNorm / InstanceNorm + activation chain: ``channel_sums`` -> ``norm_finalize`` -> ``scale_shift_act_rows`` and
   ``norm_act_bwd_reduce`` -> ``norm_bwd_finalize`` -> ``norm_act_bwd_apply_rows`` (dx, dgamma, dbeta) on channel slices.
 
@@ -30,7 +30,8 @@ KERNELS = {
                      "conv1x1_wgrad_image_cv_kernel", "pack_weight_kernel", "unpack_wgrad_kernel"],
     "ops.cu": ["maxpool_fwd_win_kernel", "maxpool_bwd_win_kernel", "channel_sums_kernel", "norm_finalize_kernel",
                "scale_shift_act_rows_kernel", "norm_act_bwd_reduce_kernel", "norm_bwd_finalize_kernel",
-               "norm_act_bwd_apply_rows_kernel", "adamw_kernel", "sgd_kernel"],
+               "norm_act_bwd_apply_rows_kernel", "adamw_kernel", "sgd_kernel", "bce_logits_kernel",
+               "n2v_mse_kernel", "softmax_ce_kernel"],
     "ends.cu": ["select_hist_kernel"],
     "conv_umma.cu": ["pack_weight_xfold_kernel", "pack_convT_weight_kernel", "unpack_convT_wgrad_kernel"],
 }
@@ -38,6 +39,7 @@ KERNELS = {
 PREAMBLE = {
     "select_hist_kernel": "template <typename S> __device__ __forceinline__ uint32_t select_key",
     "pack_weight_xfold_kernel": "__host__ __device__ inline bool xfold_geom",
+    "bce_logits_kernel": "__device__ __forceinline__ void block_atomic_add",
 }
 
 
