@@ -98,6 +98,10 @@ SIGNATURES = {
     "b200_bn_eval_coeffs": (_I, [_P, _P, _P, _P, _F, _I, _I, _P, _P, _P]),
     "b200_norm_bwd_finalize": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _L, _I, _P, _P, _P, _P]),
     "b200_norm_act_bwd_apply": (_I, [_T, _T, _I, _P, _T, _I, _P]),
+    "b200_norm_silu_fast_ok": (_I, [_T, _T, _T]),
+    "b200_scale_shift_silu_fast": (_I, [_T, _P, _P, _T, _P]),
+    "b200_norm_silu_bwd_reduce_g": (_I, [_T, _T, _P, _P, _I, _P, _P, _P, _P]),
+    "b200_norm_bwd_apply_g": (_I, [_T, _T, _P, _T, _I, _P]),
     "b200_act_bwd": (_I, [_T, _T, _I, _T, _I, _P]),
     "b200_binary": (_I, [_T, _T, _T, _I, _P]),
     "b200_gate_bwd": (_I, [_T, _T, _T, _T, _T, _I, _P]),
@@ -105,11 +109,15 @@ SIGNATURES = {
     "b200_convert": (_I, [_T, _T, _P]),
     "b200_bce_logits": (_I, [_T, _P, _P, _T, _F, _P]),
     "b200_n2v_mse": (_I, [_T, _P, _P, _T, _F, _I, _P]),
-    "b200_softmax_ce": (_I, [_T, _P, _P, _T, _F, _P]),
+    "b200_softmax_ce": (_I, [_T, _P, _P, _T, _F, _L, _P]),
     "b200_softmax_channels": (_I, [_T, _T, _I, _I, _P]),
     "b200_adamw_step": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _L, _F, _P]),
-    "b200_sgd_step": (_I, [_P, _P, _P, _L, _F, _F, _F, _I, _F, _P]),
+    "b200_adam_step": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _L, _F, _P]),
+    "b200_sgd_step": (_I, [_P, _P, _P, _L, _F, _F, _F, _I, _F, _I, _P]),
+    "b200_optim_step_dev": (_I, [_I, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P, _P]),
     "b200_sumsq": (_I, [_P, _L, _P, _P]),
+    "b200_write_floats": (_I, [_P, C.POINTER(_F), _I, _P]),
+    "b200_scale_by_dev": (_I, [_P, _L, _P, _F, _P]),
     "b200_umma_selftest": (_I, [_I, _P]),
 }
 

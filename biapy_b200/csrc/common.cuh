@@ -185,4 +185,11 @@ inline int64_t voxels(const b200_tensor* t) { return (int64_t)t->n * t->d * t->h
     default: b200::set_error("bad dtype %d", (int)(dt)); return B200_ERR_ARG;   \
   }
 
+#define B200_DISPATCH_DTYPE16(dt, T, ...)                                       \
+  switch (dt) {                                                                 \
+    case B200_BF16: { using T = __nv_bfloat16; __VA_ARGS__; break; }            \
+    case B200_F16: { using T = __half; __VA_ARGS__; break; }                    \
+    default: b200::set_error("16-bit dtype expected, got %d", (int)(dt)); return B200_ERR_ARG; \
+  }
+
 }  // namespace b200

@@ -1,5 +1,3 @@
-// STAGED EXPERIMENT -- not compiled into the library (see experiments/README.md).
-//
 // Cheaper arithmetic for the normalisation + activation kernels of the 16-bit engine.  Measured starting point (ncu, round 1):
 // the c16 @128^3 launches execute ~11 (backward reduce / apply) and ~15 (forward apply) warp instructions per element slot with
 // 57-63 % issue utilisation at 60-73 % of the copy bandwidth, and SiLU needs two MUFU operations per element (ex2 + rcp).

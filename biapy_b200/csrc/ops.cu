@@ -48,6 +48,8 @@ __device__ __forceinline__ void store_vec(T* p, const float (&f)[VEC]) {
   *reinterpret_cast<Pack<T, VEC>*>(p) = v;
 }
 
+#include "norm_fast.cuh"
+
 // ------------------------------------------------------------------------------------------ channel sums
 // grid = (chunks, N).  Block = rows x CV threads (CV = C/VEC channel vectors); every thread owns one channel
 // vector and strides over the voxels of its chunk.  fp32 partials are flushed into fp64 every 32 voxels, the
@@ -873,42 +875,56 @@ __global__ void n2v_mse_kernel(View<const T> y, const float* __restrict__ target
     float t = target[vox * 2 * y.c + c];
     float m = target[vox * 2 * y.c + y.c + c];
     float e = t - v * m;
-    if (mode == 0) {
+    if (mode != 1) {
       a += (double)e * e;
       b += (double)m;
-    } else {
-      dy.p[vox * dy.ld + c] = from_f<T>(-2.f * e * m * grad_scale);
     }
+    if (mode != 0) dy.p[vox * dy.ld + c] = from_f<T>(-2.f * e * m * grad_scale);
   }
-  if (mode == 0) {
+  if (mode != 1) {
     block_atomic_add(a, sums);
     block_atomic_add(b, sums + 1);
   }
 }
 
-// softmax CE over channels; one thread per voxel
+// softmax CE over channels; one thread per voxel.  torch.nn.CrossEntropyLoss(ignore_index) semantics (reference metrics.py:546):
+// voxels labelled `ignore_index` contribute neither loss nor gradient and the mean runs over the others -- sums[0] += loss,
+// sums[1] += number of counted voxels.  A label outside [0, C) that is not the ignore value would be a device-side assert in
+// torch; here the voxel is skipped the same way and counted in sums[2] so the host can raise.
 template <typename T>
 __global__ void softmax_ce_kernel(View<const T> z, const int64_t* __restrict__ target, double* __restrict__ sums,
-                                  View<T> dz, float grad_scale) {
-  double acc = 0.0;
+                                  View<T> dz, float grad_scale, int64_t ignore_index) {
+  double acc = 0.0, cnt = 0.0, bad = 0.0;
   for (int64_t vox = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; vox < z.vox; vox += (int64_t)gridDim.x * blockDim.x) {
     const T* p = z.p + vox * z.ld;
+    const int64_t t = target[vox];
+    const bool valid = t >= 0 && t < z.c;
+    if (!valid) {
+      if (t != ignore_index) bad += 1.0;
+      if (dz.p) {
+        T* o = dz.p + vox * dz.ld;
+        for (int c = 0; c < z.c; ++c) o[c] = from_f<T>(0.f);
+      }
+      continue;
+    }
     float mx = -INFINITY;
     for (int c = 0; c < z.c; ++c) mx = fmaxf(mx, to_f<T>(p[c]));
     float se = 0.f;
     for (int c = 0; c < z.c; ++c) se += expf(to_f<T>(p[c]) - mx);
     float lse = mx + logf(se);
-    int t = (int)target[vox];
     acc += (double)(lse - to_f<T>(p[t]));
+    cnt += 1.0;
     if (dz.p) {
       T* o = dz.p + vox * dz.ld;
       for (int c = 0; c < z.c; ++c) {
         float sm = expf(to_f<T>(p[c]) - lse);
-        o[c] = from_f<T>((sm - (c == t ? 1.f : 0.f)) * grad_scale);
+        o[c] = from_f<T>((sm - (c == (int)t ? 1.f : 0.f)) * grad_scale);
       }
     }
   }
   block_atomic_add(acc, sums);
+  block_atomic_add(cnt, sums + 1);
+  block_atomic_add(bad, sums + 2);
 }
 
 template <typename TI, typename TO>
@@ -926,6 +942,9 @@ __global__ void softmax_channels_kernel(View<const TI> x, View<TO> y, int c0, in
 }
 
 // ------------------------------------------------------------------------------------------------ optimiser
+// adamw_kernel / adam_kernel / sgd_kernel take their hyper-parameters by value (one launch per host-side step);
+// optim_prepare_kernel + optim_dev_kernel read them from device memory so that a captured CUDA graph can replay the update
+// while the LR scheduler rewrites the block between replays (engine/train.py).
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps, float wd,
                              float bc1, float bc2_sqrt, float grad_scale) {
@@ -940,17 +959,105 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
   }
 }
 
+// torch.optim.Adam (timm create_optimizer_v2('adam', weight_decay=wd), reference engine/__init__.py:58-70): the decay is an L2
+// term added to the gradient before the moments; `decoupled` = 1 is AdamW's shrink of the parameter instead.
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+                            float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float grad_scale,
+                            int decoupled) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float pi = p[i];
+    float gi = g[i] * grad_scale;
+    if (decoupled) pi *= (1.f - lr * wd);
+    else gi = fmaf(wd, pi, gi);
+    const float mi = m[i] + (1.f - b1) * (gi - m[i]);
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi -= (lr / bc1) * (mi / denom);
+    p[i] = pi; m[i] = mi; v[i] = vi;
+  }
+}
+
+// torch.optim.SGD: g += wd p; buf = first ? g : momentum buf + g; g = nesterov ? g + momentum buf : buf; p -= lr g
+// (timm's 'sgd' is SGD(momentum=0.9, nesterov=True)).
 __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mom, int64_t n,
-                           float lr, float momentum, float wd, int first, float grad_scale) {
+                           float lr, float momentum, float wd, int first, float grad_scale, int nesterov) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float gi = g[i] * grad_scale + wd * p[i];
     if (momentum != 0.f) {
       float b = first ? gi : momentum * mom[i] + gi;
       mom[i] = b;
-      gi = b;
+      gi = nesterov ? fmaf(momentum, b, gi) : b;
     }
     p[i] -= lr * gi;
   }
+}
+
+// Device-resident hyper-parameters.  hp[B200_HP_*] (float): lr, beta1, beta2, eps, weight_decay, momentum, nesterov, grad_scale,
+// clip_norm.  state (int64): [0] optimiser steps taken, [1] steps skipped because the gradient was not finite (fp16 overflow).
+// derived (float): [0] 1 - beta1^t, [1] sqrt(1 - beta2^t), [2] grad_scale incl. clipping and 1 / *denom, [3] skip, [4] first step.
+// gsq: sum of squares of the raw gradient (clip_grad_norm_, train_engine.py:174-176, and the fp16 overflow test) or null;
+// denom: divisor of the gradient known only on the device (Noise2Void mask count) or null.
+__global__ void optim_prepare_kernel(const float* __restrict__ hp, const double* __restrict__ gsq, const double* __restrict__ denom,
+                                     int64_t* __restrict__ state, float* __restrict__ derived) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  double scale = (double)hp[7];
+  if (denom) scale /= *denom;
+  int skip = !(scale == scale) || scale > 3.0e38 || scale < -3.0e38;
+  if (gsq) {
+    const double total = sqrt(*gsq) * fabs(scale);
+    if (!(total == total) || total > 1.0e300) skip = 1;
+    else if (hp[8] > 0.f) {
+      const double coef = (double)hp[8] / (total + 1e-6);
+      if (coef < 1.0) scale *= coef;
+    }
+  }
+  if (skip) { state[1] += 1; derived[3] = 1.f; return; }
+  const int64_t t = ++state[0];
+  derived[0] = (float)(1.0 - pow((double)hp[1], (double)t));
+  derived[1] = (float)sqrt(1.0 - pow((double)hp[2], (double)t));
+  derived[2] = (float)scale;
+  derived[3] = 0.f;
+  derived[4] = t == 1 ? 1.f : 0.f;
+}
+
+template <int KIND>   // 0 AdamW, 1 Adam (L2), 2 SGD
+__global__ void optim_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                 int64_t n, const float* __restrict__ hp, const float* __restrict__ derived) {
+  if (derived[3] != 0.f) return;
+  const float lr = hp[0], b1 = hp[1], b2 = hp[2], eps = hp[3], wd = hp[4], momentum = hp[5];
+  const int nesterov = hp[6] != 0.f, first = derived[4] != 0.f;
+  const float bc1 = derived[0], bc2_sqrt = derived[1], grad_scale = derived[2];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float pi = p[i];
+    float gi = g[i] * grad_scale;
+    if (KIND == 2) {
+      gi = fmaf(wd, pi, gi);
+      if (momentum != 0.f) {
+        const float b = first ? gi : momentum * m[i] + gi;
+        m[i] = b;
+        gi = nesterov ? fmaf(momentum, b, gi) : b;
+      }
+      p[i] = pi - lr * gi;
+    } else {
+      if (KIND == 0) pi *= (1.f - lr * wd);
+      else gi = fmaf(wd, pi, gi);
+      const float mi = m[i] + (1.f - b1) * (gi - m[i]);
+      const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+      const float denom = sqrtf(vi) / bc2_sqrt + eps;
+      pi -= (lr / bc1) * (mi / denom);
+      p[i] = pi; m[i] = mi; v[i] = vi;
+    }
+  }
+}
+
+struct FloatBlock { float v[16]; };
+__global__ void write_floats_kernel(float* __restrict__ dst, FloatBlock b, int n) {
+  if (threadIdx.x < n) dst[threadIdx.x] = b.v[threadIdx.x];
+}
+
+__global__ void scale_by_dev_kernel(float* __restrict__ g, int64_t n, const double* __restrict__ denom, float mul) {
+  const float f = (float)((double)mul / *denom);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) g[i] *= f;
 }
 
 __global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ out) {
@@ -1314,6 +1421,84 @@ B200_EXPORT int b200_norm_act_bwd_apply(const b200_tensor* x, const b200_tensor*
   return B200_OK;
 }
 
+// ------------------------------------------------------------------------------------- fast SiLU norm chain (16-bit dtypes)
+// One-MUFU sigmoid and a backward that evaluates the activation derivative once (norm_fast.cuh).  Explicit entry points because
+// the contract differs from b200_norm_act_bwd_*: the reduce pass OVERWRITES dy with g = dy * silu'(norm(x)) and the apply pass
+// must be the matching one.  b200_norm_silu_fast_ok tells the caller whether the three tensors qualify.
+static bool norm_fast_ok(const b200_tensor* x, const b200_tensor* dy, const b200_tensor* dx) {
+  if (!x || x->dtype == B200_F32) return false;
+  const int V = 8;
+  if (!vec_ok(x, V) || x->c / V > 256) return false;
+  if (dy && !(vec_ok(dy, V) && dy->dtype == x->dtype && dy->c == x->c && same_spatial(x, dy))) return false;
+  if (dx && !(vec_ok(dx, V) && dx->dtype == x->dtype && dx->c == x->c && same_spatial(x, dx))) return false;
+  return true;
+}
+
+B200_EXPORT int b200_norm_silu_fast_ok(const b200_tensor* x, const b200_tensor* dy, const b200_tensor* dx) {
+  return norm_fast_ok(x, dy, dx) ? 1 : 0;
+}
+
+B200_EXPORT int b200_scale_shift_silu_fast(const b200_tensor* x, const float* scale, const float* shift, const b200_tensor* y,
+                                           void* stream) {
+  B200_CHECK_ARG(check_tensor(x, "silu_fast.x") && check_tensor(y, "silu_fast.y") && scale && shift, "%s", b200_last_error());
+  B200_CHECK_ARG(norm_fast_ok(x, y, nullptr), "scale_shift_silu_fast: tensors do not qualify (16-bit, 8-channel vectors)");
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_DISPATCH_DTYPE16(x->dtype, T, {
+    constexpr int V = 8;
+    View<const T> xv = view<const T>(x);
+    View<T> yv = view<T>(y);
+    int cvn = x->c / V, rows = 256 / cvn;
+    dim3 grid(rows_grid(xv.spatial, rows, x->n), x->n);
+    scale_shift_silu_rows_fast_kernel<T, V><<<grid, 256, 0, st>>>(xv, yv, scale, shift, cvn, rows);
+  });
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+B200_EXPORT int b200_norm_silu_bwd_reduce_g(const b200_tensor* x, const b200_tensor* dy_g, const float* mean, const float* rstd,
+                                            int32_t groups, const float* gamma, const float* beta, double* red, void* stream) {
+  B200_CHECK_ARG(check_tensor(x, "reduce_g.x") && check_tensor(dy_g, "reduce_g.dy") && mean && rstd && red, "%s", b200_last_error());
+  B200_CHECK_ARG(norm_fast_ok(x, dy_g, nullptr), "norm_silu_bwd_reduce_g: tensors do not qualify");
+  B200_CHECK_ARG(groups > 0 && x->c % groups == 0, "norm_silu_bwd_reduce_g: bad groups");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t spatial = (int64_t)x->d * x->h * x->w;
+  B200_DISPATCH_DTYPE16(x->dtype, T, {
+    constexpr int V = 8;
+    View<const T> xv{(const T*)x->data, x->ld, x->c, voxels(x), spatial};
+    View<T> gv{(T*)dy_g->data, dy_g->ld, dy_g->c, voxels(dy_g), spatial};
+    int cvn = x->c / V, rows = 256 / cvn;
+    int threads = ((rows * cvn + 31) / 32) * 32;
+    int64_t chunks = ceil_div(spatial, (int64_t)rows * 8);
+    int64_t cap = ceil_div((int64_t)sm_count() * 4, x->n);
+    if (chunks > cap) chunks = cap;
+    if (chunks < 1) chunks = 1;
+    const size_t smem = sizeof(double) * rows * cvn * V * 2;
+    norm_silu_bwd_reduce_g_kernel<T, V, 1, 4><<<dim3((unsigned)chunks, x->n), threads, smem, st>>>(xv, gv, mean, rstd, groups, gamma,
+                                                                                               beta, red, cvn, rows);
+  });
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+B200_EXPORT int b200_norm_bwd_apply_g(const b200_tensor* x, const b200_tensor* g, const float* coef, const b200_tensor* dx,
+                                      int32_t accumulate, void* stream) {
+  B200_CHECK_ARG(check_tensor(x, "apply_g.x") && check_tensor(g, "apply_g.g") && check_tensor(dx, "apply_g.dx") && coef, "%s",
+                 b200_last_error());
+  B200_CHECK_ARG(norm_fast_ok(x, g, dx), "norm_bwd_apply_g: tensors do not qualify");
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_DISPATCH_DTYPE16(x->dtype, T, {
+    constexpr int V = 8;
+    View<const T> xv = view<const T>(x);
+    View<const T> gv = view<const T>(g);
+    View<T> ov = view<T>(dx);
+    int cvn = x->c / V, rows = 256 / cvn;
+    dim3 grid(rows_grid(xv.spatial, rows, x->n), x->n);
+    norm_bwd_apply_g_rows_kernel<T, V, 1, 4><<<grid, 256, 0, st>>>(xv, gv, ov, coef, accumulate, cvn, rows);
+  });
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
 B200_EXPORT int b200_act_bwd(const b200_tensor* x, const b200_tensor* dy, int32_t act, const b200_tensor* dx,
                              int32_t accumulate, void* stream) {
   B200_CHECK_ARG(check_tensor(x, "act_bwd.x") && check_tensor(dy, "act_bwd.dy") && check_tensor(dx, "act_bwd.dx"), "%s",
@@ -1464,7 +1649,8 @@ B200_EXPORT int b200_bce_logits(const b200_tensor* logits, const float* target, 
 B200_EXPORT int b200_n2v_mse(const b200_tensor* pred, const float* target, double* sums, const b200_tensor* dpred,
                              float grad_scale, int32_t mode, void* stream) {
   B200_CHECK_ARG(check_tensor(pred, "n2v.pred") && target, "%s", b200_last_error());
-  B200_CHECK_ARG(mode == 0 ? sums != nullptr : (dpred && check_tensor(dpred, "n2v.dpred")), "n2v: missing output");
+  B200_CHECK_ARG(mode >= 0 && mode <= 2, "n2v: mode %d (0 sums, 1 gradient, 2 both)", mode);
+  B200_CHECK_ARG((mode == 1 || sums) && (mode == 0 || (dpred && check_tensor(dpred, "n2v.dpred"))), "n2v: missing output");
   B200_DISPATCH_DTYPE(pred->dtype, T, {
     View<T> dv{dpred ? (T*)dpred->data : nullptr, dpred ? dpred->ld : 0, pred->c, voxels(pred), 0};
     n2v_mse_kernel<T><<<grid_for(voxels(pred) * pred->c, 256, 4), 256, 0, (cudaStream_t)stream>>>(
@@ -1475,12 +1661,14 @@ B200_EXPORT int b200_n2v_mse(const b200_tensor* pred, const float* target, doubl
 }
 
 B200_EXPORT int b200_softmax_ce(const b200_tensor* logits, const int64_t* target, double* sums,
-                                const b200_tensor* dlogits, float grad_scale, void* stream) {
+                                const b200_tensor* dlogits, float grad_scale, int64_t ignore_index, void* stream) {
   B200_CHECK_ARG(check_tensor(logits, "ce.logits") && target && sums, "%s", b200_last_error());
+  if (dlogits) B200_CHECK_ARG(check_tensor(dlogits, "ce.dlogits") && same_spatial(logits, dlogits) &&
+                                  logits->c == dlogits->c && logits->dtype == dlogits->dtype, "ce: dlogits mismatch");
   B200_DISPATCH_DTYPE(logits->dtype, T, {
     View<T> dv{dlogits ? (T*)dlogits->data : nullptr, dlogits ? dlogits->ld : 0, logits->c, voxels(logits), 0};
     softmax_ce_kernel<T><<<grid_for(voxels(logits), 128, 4), 128, 0, (cudaStream_t)stream>>>(view<const T>(logits), target,
-                                                                                          sums, dv, grad_scale);
+                                                                                          sums, dv, grad_scale, ignore_index);
   });
   B200_LAUNCH_CHECK();
   return B200_OK;
@@ -1507,11 +1695,53 @@ B200_EXPORT int b200_adamw_step(float* p, const float* g, float* m, float* v, in
   return B200_OK;
 }
 
+B200_EXPORT int b200_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                               float eps, float weight_decay, int64_t step, float grad_scale, void* stream) {
+  B200_CHECK_ARG(p && g && m && v && n > 0 && step > 0, "adam: bad args");
+  float bc1 = 1.f - powf(beta1, (float)step);
+  float bc2 = sqrtf(1.f - powf(beta2, (float)step));
+  adam_kernel<<<grid_for(n, 256, 4), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2,
+                                                                    grad_scale, 0);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
 B200_EXPORT int b200_sgd_step(float* p, const float* g, float* mom, int64_t n, float lr, float momentum,
-                              float weight_decay, int32_t first_step, float grad_scale, void* stream) {
+                              float weight_decay, int32_t first_step, float grad_scale, int32_t nesterov, void* stream) {
   B200_CHECK_ARG(p && g && n > 0 && (momentum == 0.f || mom), "sgd: bad args");
+  B200_CHECK_ARG(!nesterov || momentum > 0.f, "sgd: nesterov needs a momentum");
   sgd_kernel<<<grid_for(n, 256, 4), 256, 0, (cudaStream_t)stream>>>(p, g, mom, n, lr, momentum, weight_decay, first_step,
-                                                                   grad_scale);
+                                                                   grad_scale, nesterov);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+B200_EXPORT int b200_optim_step_dev(int32_t kind, float* p, const float* g, float* m, float* v, int64_t n, const float* hp,
+                                    const double* gsq, const double* denom, int64_t* state, float* derived, void* stream) {
+  B200_CHECK_ARG(p && g && hp && state && derived && n > 0, "optim_step_dev: null pointer");
+  B200_CHECK_ARG(kind >= 0 && kind <= 2, "optim_step_dev: kind %d (0 AdamW, 1 Adam, 2 SGD)", kind);
+  B200_CHECK_ARG(kind == 2 || (m && v), "optim_step_dev: Adam needs both moment buffers");
+  cudaStream_t st = (cudaStream_t)stream;
+  optim_prepare_kernel<<<1, 32, 0, st>>>(hp, gsq, denom, state, derived);
+  if (kind == 0) optim_dev_kernel<0><<<grid_for(n, 256, 4), 256, 0, st>>>(p, g, m, v, n, hp, derived);
+  else if (kind == 1) optim_dev_kernel<1><<<grid_for(n, 256, 4), 256, 0, st>>>(p, g, m, v, n, hp, derived);
+  else optim_dev_kernel<2><<<grid_for(n, 256, 4), 256, 0, st>>>(p, g, m, v, n, hp, derived);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+B200_EXPORT int b200_write_floats(float* dst, const float* values, int32_t n, void* stream) {
+  B200_CHECK_ARG(dst && values && n > 0 && n <= 16, "write_floats: 1..16 values");
+  FloatBlock b;
+  for (int i = 0; i < 16; ++i) b.v[i] = i < n ? values[i] : 0.f;
+  write_floats_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(dst, b, n);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+B200_EXPORT int b200_scale_by_dev(float* g, int64_t n, const double* denom, float mul, void* stream) {
+  B200_CHECK_ARG(g && denom && n > 0, "scale_by_dev: bad args");
+  scale_by_dev_kernel<<<grid_for(n, 256, 4), 256, 0, (cudaStream_t)stream>>>(g, n, denom, mul);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

@@ -1,5 +1,3 @@
-// STAGED EXPERIMENT -- not compiled into the library (see experiments/README.md).
-//
 // One launch for every weight pack / weight-gradient unpack of a training pass.  Each job is one of the element-wise
 // permutations the product launches separately today (biapy_b200/csrc/conv_simt.cu: pack_weight_kernel, unpack_wgrad_kernel;
 // conv_umma.cu: pack_weight_xfold_kernel, pack_convT_weight_kernel, unpack_convT_wgrad_kernel); a block looks up its job in a

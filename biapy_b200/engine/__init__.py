@@ -55,13 +55,16 @@ def prepare_optimizer(cfg, model_without_ddp, steps_per_epoch: int, loss: Option
     if len(opts) != 1:
         raise NotImplementedError("one optimiser per model on the B200 hot path (TRAIN.OPTIMIZER has several entries)")
     opt = str(opts[0]).lower()
-    if opt not in ("adamw", "sgd"):
-        raise NotImplementedError(f"TRAIN.OPTIMIZER={opts[0]!r}: the fused optimiser kernels cover ADAMW and SGD")
+    if opt not in ("adamw", "adam", "sgd"):
+        raise NotImplementedError(f"TRAIN.OPTIMIZER={opts[0]!r}: the fused optimiser kernels cover ADAMW, ADAM and SGD")
     lr = float(_scalar(cfg.TRAIN.LR_SCHEDULER.MIN_LR if name == "warmupcosine" else cfg.TRAIN.LR))
     betas = cfg.TRAIN.OPT_BETAS
     betas = tuple(betas[0]) if isinstance(betas[0], (list, tuple)) else tuple(betas)
+    # timm.optim.create_optimizer_v2(opt='SGD') is torch.optim.SGD(momentum=0.9, nesterov=True) (timm's `momentum` default and its
+    # 'sgd' alias of 'nesterov'); 'ADAM' is torch.optim.Adam (L2 weight decay), 'ADAMW' the decoupled form
+    sgd = dict(momentum=0.9, nesterov=True) if opt == "sgd" else {}
     trainer = Trainer(model_without_ddp, loss=loss or getattr(model_without_ddp, "loss_kind", "bce"), optimizer=opt, lr=lr,
-                      betas=betas, weight_decay=float(cfg.TRAIN.W_DECAY), clip_norm=float(cfg.TRAIN.GRADIENT_CLIP_NORM))
+                      betas=betas, weight_decay=float(cfg.TRAIN.W_DECAY), clip_norm=float(cfg.TRAIN.GRADIENT_CLIP_NORM), **sgd)
     sched = None
     if name == "reduceonplateau":
         sched = ReduceLROnPlateau(trainer, patience=int(cfg.TRAIN.LR_SCHEDULER.REDUCEONPLATEAU_PATIENCE),

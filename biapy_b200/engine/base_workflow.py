@@ -197,11 +197,12 @@ class Base_Workflow:
         cfg = self.cfg
         assert self.model is not None, "call prepare_model() first"
         opt = str(first(cfg.TRAIN.OPTIMIZER)).lower()
-        if opt not in ("adamw", "sgd"):
-            raise NotImplementedError(f"TRAIN.OPTIMIZER={opt!r}: the fused optimiser kernels cover ADAMW and SGD")
+        if opt not in ("adamw", "adam", "sgd"):
+            raise NotImplementedError(f"TRAIN.OPTIMIZER={opt!r}: the fused optimiser kernels cover ADAMW, ADAM and SGD")
+        sgd = dict(momentum=0.9, nesterov=True) if opt == "sgd" else {}      # timm's 'sgd' (see engine/__init__.py)
         self.trainer = Trainer(self.model, loss=self.loss_kind, optimizer=opt, lr=float(first(cfg.TRAIN.LR)),
                                betas=tuple(first(cfg.TRAIN.OPT_BETAS)), weight_decay=float(cfg.TRAIN.W_DECAY),
-                               clip_norm=float(cfg.TRAIN.GRADIENT_CLIP_NORM))
+                               clip_norm=float(cfg.TRAIN.GRADIENT_CLIP_NORM), **sgd)
         return self.trainer
 
     def train(self, train_generator, val_generator=None, cuda_graph: bool = False):

@@ -344,7 +344,7 @@ class Tape:
                 if x.requires_grad:
                     acc = x.prepare_accumulate()
                     dx = x.grad()
-                ops.norm_act_bwd(x.data, out.grad(), st, g32, b32, act, dx, dg, db, accumulate=acc)
+                ops.norm_act_bwd(x.data, out.grad(), st, g32, b32, act, dx, dg, db, accumulate=acc, dy_dead=True)
             self.steps.append(bwd)
         return out
 

@@ -16,7 +16,6 @@ calls ``.item()`` twice and ``synchronize()`` once per step, ``train_engine.py:1
 """
 from __future__ import annotations
 
-import math
 from typing import Dict, Optional, Sequence
 
 import torch
@@ -24,6 +23,10 @@ import torch
 from .. import _lib, ops
 from .dist import allreduce_mean_
 from .tape import TT, Tape
+
+
+def _pow2_floor(n: int) -> int:
+    return 1 << (max(1, int(n)).bit_length() - 1)
 
 
 class FlatParams:
@@ -62,22 +65,34 @@ class Trainer:
 
     def __init__(self, model, loss: str = "bce", optimizer: str = "adamw", lr: float = 1e-3, betas=(0.9, 0.999),
                  eps: float = 1e-8, weight_decay: float = 0.0, momentum: float = 0.0, clip_norm: float = 0.0,
-                 process_group=None):
+                 process_group=None, nesterov: bool = False, loss_scale: Optional[float] = None, ignore_index: int = -100):
+        """`optimizer`: 'adamw' | 'adam' | 'sgd' -- BiaPy's three ``TRAIN.OPTIMIZER`` values (``engine/__init__.py:58-70``).
+        `loss_scale`: factor on the loss gradient that is divided out again inside the optimiser kernel; None = automatic
+        (fp16 engine: the gradient of the *summed* loss is propagated so that it stays inside fp16's range, and a step whose
+        gradient overflowed is skipped like ``torch.amp.GradScaler`` does; other dtypes: 1).  `ignore_index`: the
+        ``CrossEntropyLoss(ignore_index=...)`` label of the reference's wrapper (``metrics.py:534-546``)."""
         self.model = model
         self.loss_kind = loss.lower()
         assert self.loss_kind in ("bce", "ce", "n2v_mse"), loss
         self.opt_kind = optimizer.lower()
-        assert self.opt_kind in ("adamw", "sgd"), optimizer
+        assert self.opt_kind in ("adamw", "adam", "sgd"), optimizer
+        if nesterov and not momentum > 0:
+            raise ValueError("Nesterov momentum requires a momentum")
         # one parameter group in torch.optim layout: the LR schedulers (engine/schedulers) and BiaPy's per-iteration
         # `adjust_learning_rate` write `param_groups[i]["lr"]` (and 1cycle the first beta); the optimiser launch reads it back
-        self.param_groups = [{"lr": lr, "betas": tuple(betas), "eps": eps, "weight_decay": weight_decay, "momentum": momentum}]
-        if self.opt_kind != "adamw":
+        self.param_groups = [{"lr": lr, "betas": tuple(betas), "eps": eps, "weight_decay": weight_decay, "momentum": momentum,
+                              "nesterov": bool(nesterov)}]
+        if self.opt_kind not in ("adamw", "adam"):
             del self.param_groups[0]["betas"]
             self._betas = tuple(betas)
+        else:
+            del self.param_groups[0]["nesterov"]
         self.clip_norm = clip_norm
+        self.loss_scale = loss_scale
+        self.ignore_index = int(ignore_index)
         self.fp = FlatParams(model)
         self.m = torch.zeros_like(self.fp.flat)
-        self.v = torch.zeros_like(self.fp.flat) if self.opt_kind == "adamw" else None
+        self.v = torch.zeros_like(self.fp.flat) if self.opt_kind in ("adamw", "adam") else None
         self.t = 0
         self.pg = process_group
         self.world = 1
@@ -88,6 +103,31 @@ class Trainer:
         self._graph = None
         self.graph_launches = 0
         self._arena = ops.ZeroArena()
+        # device-resident optimiser inputs (ops.optim_step_dev): hyper-parameters, step counters, scratch, gradient norm
+        self._hp_dev = torch.zeros(ops.HP_SIZE, dtype=torch.float32, device=self.device)
+        self._hp_last = None
+        self._opt_state = torch.zeros(2, dtype=torch.int64, device=self.device)
+        self._derived = torch.zeros(8, dtype=torch.float32, device=self.device)
+        self._gsq = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self._bad_labels = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self._unscale = 1.0            # set by _loss_and_grad: what the optimiser multiplies the raw gradient with
+        self._denom = None             # device divisor of the gradient (mask / counted-voxel count), or None
+        self.sync_parameters()
+
+    def sync_parameters(self):
+        """What ``DistributedDataParallel`` does at construction (reference ``base_workflow.py:951-958``): rank 0's parameters
+        and buffers (BatchNorm running statistics) replace every other rank's -- the reference seeds each process with
+        SEED + rank (``misc.py:285``), so the replicas are NOT initialised identically.  Call again after loading a checkpoint
+        on one rank only."""
+        if self.world <= 1:
+            return
+        import torch.distributed as dist
+        src = dist.get_global_rank(self.pg, 0) if self.pg is not None else 0
+        dist.broadcast(self.fp.flat, src=src, group=self.pg)
+        for b in self.model.buffers():
+            if b.numel():
+                dist.broadcast(b.data, src=src, group=self.pg)
+        self.model.__dict__.pop("_pack_cache", None)
 
     # hyper-parameters live in `param_groups[0]` (see __init__); attribute access stays for callers and checkpoints
     lr = property(lambda self: self.param_groups[0]["lr"], lambda self, v: self.param_groups[0].__setitem__("lr", v))
@@ -96,6 +136,7 @@ class Trainer:
     eps = property(lambda self: self.param_groups[0]["eps"], lambda self, v: self.param_groups[0].__setitem__("eps", v))
     momentum = property(lambda self: self.param_groups[0]["momentum"],
                         lambda self, v: self.param_groups[0].__setitem__("momentum", v))
+    nesterov = property(lambda self: bool(self.param_groups[0].get("nesterov", False)))
 
     @property
     def betas(self):
@@ -119,19 +160,20 @@ class Trainer:
         ``exp_avg_sq`` or ``momentum_buffer``, one param group), so BiaPy checkpoints (``misc.py:328-386``) carry it and a
         torch optimiser can resume from it."""
         state = {}
+        self.t = int(self._opt_state[0].item())          # the device counter is the truth (fp16 steps may have been skipped)
         for i, (p, o) in enumerate(zip(self.fp.params, self.fp.offsets)):
             sl = slice(o, o + p.numel())
-            if self.opt_kind == "adamw":
+            if self.opt_kind in ("adamw", "adam"):
                 if self.t > 0:
                     state[i] = {"step": torch.tensor(float(self.t)), "exp_avg": self.m[sl].view(p.shape).detach().cpu().clone(),
                                 "exp_avg_sq": self.v[sl].view(p.shape).detach().cpu().clone()}
             elif self.t > 0 and self.momentum:
                 state[i] = {"momentum_buffer": self.m[sl].view(p.shape).detach().cpu().clone()}
         group = {"lr": self.lr, "weight_decay": self.wd, "params": list(range(len(self.fp.params)))}
-        if self.opt_kind == "adamw":
+        if self.opt_kind in ("adamw", "adam"):
             group.update(betas=tuple(self.betas), eps=self.eps, amsgrad=False)
         else:
-            group.update(momentum=self.momentum)
+            group.update(momentum=self.momentum, nesterov=self.nesterov)
         return {"state": state, "param_groups": [group]}
 
     def load_state_dict(self, sd: Dict, strict: bool = False):
@@ -143,7 +185,7 @@ class Trainer:
             if e is None:
                 continue
             sl = slice(o, o + p.numel())
-            if self.opt_kind == "adamw":
+            if self.opt_kind in ("adamw", "adam"):
                 self.m[sl].view(p.shape).copy_(e["exp_avg"])
                 self.v[sl].view(p.shape).copy_(e["exp_avg_sq"])
                 steps.append(int(float(e["step"])))
@@ -152,6 +194,7 @@ class Trainer:
                 steps.append(1)
         if steps:
             self.t = max(steps)
+            self._opt_state[0] = self.t
         groups = sd.get("param_groups") or [{}]
         g = groups[0]
         self.lr = g.get("lr", self.lr)
@@ -160,7 +203,8 @@ class Trainer:
             self.betas = tuple(g["betas"])
         self.eps = g.get("eps", self.eps)
         self.momentum = g.get("momentum", self.momentum)
-        self._graph = None                       # hyper-parameters are baked into a captured step
+        if "nesterov" in g and "nesterov" in self.param_groups[0]:
+            self.param_groups[0]["nesterov"] = bool(g["nesterov"])
 
     # ------------------------------------------------------------------------------------------------- data
     def _to_device_cl(self, a, dtype=None) -> torch.Tensor:
@@ -189,8 +233,6 @@ class Trainer:
         """Capture forward + loss + backward (~900 kernel launches of fixed shape) into one CUDA graph; the gradient
         all-reduce and the optimiser kernel stay eager (NCCL call, step-dependent bias correction).  Inputs are staged
         through static device buffers; H2D copies stay outside the graph on the same stream."""
-        if self.loss_kind == "n2v_mse":
-            raise NotImplementedError("n2v_mse reads a scalar on the host and cannot be captured")
         xs = self._to_device_cl(x_example)
         ts = self._to_device_cl(t_example)
         self._x_static = torch.empty_like(xs)
@@ -248,6 +290,11 @@ class Trainer:
         ts = target if isinstance(target, torch.Tensor) else torch.from_numpy(target)
         if self.ndim == 2:
             xs, ts = xs.unsqueeze(1), ts.unsqueeze(1)
+        if tuple(xs.shape) != tuple(self._x_static.shape) or tuple(ts.shape) != tuple(self._t_static.shape):
+            # a trailing batch of another size (drop_last=False): the captured step has fixed shapes, run this one eagerly
+            loss = self._forward_backward(xs.to(self.device, non_blocking=True), ts.to(self.device, non_blocking=True))
+            self._reduce_and_update()
+            return loss
         if not xs.is_cuda and not ts.is_cuda:
             self._stage_host_batch(xs, ts)
         else:
@@ -311,26 +358,47 @@ class Trainer:
             return ops.bce_logits(pred.data, t32, None) / numel
         if self.loss_kind == "ce":
             cls = td[..., 0].long().contiguous()
-            return ops.softmax_ce(pred.data, cls, None) / cls.numel()
+            sums = ops.softmax_ce(pred.data, cls, None, ignore_index=self.ignore_index)
+            self._bad_labels += sums[2:3]
+            return sums[0:1] / sums[1:2]
         t32 = td if td.dtype == torch.float32 and td.is_contiguous() else self._as_f32(td)
         sums = ops.n2v_mse_sums(pred.data, t32)
         return sums[0:1] / sums[1:2]
 
+    def check_labels(self):
+        """Raise if a cross-entropy target held a label that is neither a class nor `ignore_index` (torch asserts on the device
+        for those; the kernel skips and counts them).  Reads one scalar: call it where the host synchronises anyway."""
+        bad = int(self._bad_labels.item())
+        if bad:
+            self._bad_labels.zero_()
+            raise ValueError(f"cross-entropy target: {bad} voxels carry a label outside [0, n_classes) that is not "
+                             f"ignore_index={self.ignore_index}")
+
     def _loss_and_grad(self, pred: TT, td: torch.Tensor) -> torch.Tensor:
+        """Loss value (mean) and the gradient of the prediction.  The gradient is written as `S / P * dloss` with P a power of
+        two near the loss's divisor and S the loss scale; `_reduce_and_update` hands `P / S` (and the exact divisor when it
+        only exists on the device) to the optimiser kernel, so fp16 gradients stay in range and nothing is read on the host."""
         numel = pred.data.numel()
+        fp16 = self.model.engine_dtype == torch.float16
+        self._denom = None
         if self.loss_kind == "bce":
+            S = float(self.loss_scale) if self.loss_scale else (float(_pow2_floor(numel)) if fp16 else 1.0)
             t32 = td if td.dtype == torch.float32 and td.is_contiguous() else self._as_f32(td)
-            s = ops.bce_logits(pred.data, t32, pred.grad(), grad_scale=1.0 / numel)
+            s = ops.bce_logits(pred.data, t32, pred.grad(), grad_scale=S / numel)
+            self._unscale = 1.0 / S
             return s / numel
+        S = float(self.loss_scale) if self.loss_scale else 1.0
         if self.loss_kind == "ce":
             cls = td[..., 0].long().contiguous()
-            nvox = cls.numel()
-            s = ops.softmax_ce(pred.data, cls, pred.grad(), grad_scale=1.0 / nvox)
-            return s / nvox
-        t32 = td if td.dtype == torch.float32 and td.is_contiguous() else self._as_f32(td)
-        sums = ops.n2v_mse_sums(pred.data, t32)
-        # grad_scale = 1 / sum(mask): one host read of a scalar (the reference reads the loss here anyway)
-        ops.n2v_mse_bwd(pred.data, t32, pred.grad(), 1.0 / float(sums[1].item()))
+            P = float(_pow2_floor(cls.numel()))
+            sums = ops.softmax_ce(pred.data, cls, pred.grad(), grad_scale=S / P, ignore_index=self.ignore_index)
+            self._bad_labels += sums[2:3]
+        else:
+            P = float(_pow2_floor(max(1, numel // 512)))          # Noise2Void masks ~0.2 % of the voxels (3d_denoising.yaml:11)
+            t32 = td if td.dtype == torch.float32 and td.is_contiguous() else self._as_f32(td)
+            sums = ops.n2v_mse_fused(pred.data, t32, pred.grad(), S / P)
+        self._unscale = P / S
+        self._denom = sums[1:2]
         return sums[0:1] / sums[1:2]
 
     def _as_f32(self, t: torch.Tensor) -> torch.Tensor:
@@ -341,14 +409,28 @@ class Trainer:
         return t.float().contiguous()
 
     def _reduce_and_update(self):
+        """Gradient all-reduce + optimiser, no host synchronisation: the hyper-parameters go to the device as kernel arguments of
+        a tiny write kernel (only when they changed), the clip factor, the fp16 overflow test, the bias corrections and the
+        step counter are evaluated on the device (`b200_optim_step_dev`)."""
         g = self.fp.grad
+        unscale, denom = self._unscale, self._denom
+        if denom is not None and self.world > 1:
+            # DDP averages the gradients of the per-rank *mean* losses: divide by this rank's own count before the reduction
+            ops.scale_by_dev(g, denom, unscale)
+            unscale, denom = 1.0, None
         scale = allreduce_mean_(g, self.pg)                      # one NCCL all-reduce over NVLink (no-op for 1 rank)
-        if self.clip_norm and self.clip_norm > 0:
-            total = math.sqrt(float(ops.sumsq(g).item())) * scale
-            scale *= min(1.0, self.clip_norm / (total + 1e-6))
+        clip = float(self.clip_norm) if self.clip_norm and self.clip_norm > 0 else 0.0
+        need_gsq = clip > 0 or self.model.engine_dtype == torch.float16
+        if need_gsq:
+            self._gsq.zero_()
+            ops.sumsq(g, out=self._gsq)
+        b1, b2 = self.betas
+        hp = (float(self.lr), float(b1), float(b2), float(self.eps), float(self.wd), float(self.momentum),
+              1.0 if self.nesterov else 0.0, float(scale * unscale), clip)
+        if hp != self._hp_last:
+            ops.write_floats(self._hp_dev, hp)
+            self._hp_last = hp
+        ops.optim_step_dev(self.opt_kind, self.fp.flat, g, self.m, self.v, self._hp_dev, self._opt_state, self._derived,
+                           gsq=self._gsq if need_gsq else None, denom=denom)
         self.t += 1
-        if self.opt_kind == "adamw":
-            ops.adamw_step(self.fp.flat, g, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.t,
-                           grad_scale=scale)
-        else:
-            ops.sgd_step(self.fp.flat, g, self.m, self.lr, self.momentum, self.wd, self.t == 1, grad_scale=scale)
+        self.model.__dict__.pop("_pack_cache", None)            # eval-mode packed weights are stale now

@@ -52,6 +52,17 @@ class _LaggedLoss:
             self.values.append(v)
 
 
+def _global_avg(values: List[float], device) -> float:
+    """MetricLogger.synchronize_between_processes + global_avg (reference misc.py): sum of values / sum of counts over the ranks."""
+    tot, cnt = float(sum(values)), float(len(values))
+    if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+        t = torch.tensor([tot, cnt], dtype=torch.float64,
+                         device=device if (device is not None and torch.distributed.get_backend() == "nccl") else "cpu")
+        torch.distributed.all_reduce(t)
+        tot, cnt = float(t[0]), float(t[1])
+    return tot / cnt if cnt else float("nan")
+
+
 def _max_lr(opt) -> float:
     return max(float(g["lr"]) for g in opt.param_groups)
 
@@ -99,13 +110,9 @@ def train_one_epoch(cfg, model, model_call_func: Optional[Callable], loss_functi
             print("Epoch: [{}]  [{}/{}]  {}: {:.4f}  {}: {:.6f}".format(epoch + 1, step, n_batches, loss_names[0], lag.values[-1],
                                                                        lr_names[0], last_lr))
     lag.drain(keep=0)
-    avg = sum(lag.values) / len(lag.values) if lag.values else float("nan")
-    if torch.distributed.is_available() and torch.distributed.is_initialized() and lag.values:
-        # MetricLogger.synchronize_between_processes (misc.py): sum of values and counts over the ranks
-        t = torch.tensor([sum(lag.values), float(len(lag.values))], dtype=torch.float64,
-                         device=device if torch.distributed.get_backend() == "nccl" else "cpu")
-        torch.distributed.all_reduce(t)
-        avg = float(t[0] / t[1])
+    if getattr(trainer, "loss_kind", None) == "ce":
+        trainer.check_labels()                          # the host is synchronised here anyway
+    avg = _global_avg(lag.values, device)
     stats = {loss_names[0]: avg, lr_names[0]: last_lr}
     print("[Train] averaged stats:", "  ".join(f"{k}: {v:.6f}" for k, v in stats.items()))
     return stats, step
@@ -132,7 +139,9 @@ def evaluate(cfg, model, model_call_func: Optional[Callable], loss_function: Opt
         lag.push(trainer.evaluate(images, targets))
         lag.drain(keep=2)
     lag.drain(keep=0)
-    avg = sum(lag.values) / len(lag.values) if lag.values else float("nan")
+    # metric_logger.synchronize_between_processes() + global_avg (reference :318-321): every rank must feed the SAME validation
+    # loss to ReduceLROnPlateau / EarlyStopping / the best-checkpoint test, or learning rates and stop epochs diverge
+    avg = _global_avg(lag.values, getattr(trainer, "device", None))
     stats = {loss_names[0]: avg}
     print("[Val] averaged stats:", "  ".join(f"{k}: {v:.6f}" for k, v in stats.items()))
     if lr_scheduler and str(cfg.TRAIN.LR_SCHEDULER.NAME) == "reduceonplateau":

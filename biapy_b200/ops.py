@@ -6,6 +6,7 @@ and launches hand-written CUDA on the current torch stream.  PyTorch is used for
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -365,16 +366,38 @@ def bn_eval_stats(x, running_mean, running_var, gamma, beta, eps: float) -> Norm
     return st
 
 
+# B200_NORM_FAST: 'auto' (default) = the one-MUFU SiLU chain for bf16 tensors, '1' = also fp16, '0' = off.  tanh.approx has a
+# relative error of 2^-11: below bf16's rounding step, comparable to fp16's -- the fp16 engine is the 1e-3 parity path and keeps
+# the exact exponential unless asked.
+NORM_FAST = os.environ.get("B200_NORM_FAST", "auto").lower()
+
+
+def norm_fast_ok(x, dy=None, dx=None) -> bool:
+    if NORM_FAST in ("0", "off") or x.dtype == torch.float32 or (x.dtype == torch.float16 and NORM_FAST != "1"):
+        return False
+    return bool(_lib.lib().b200_norm_silu_fast_ok(_ref(x), _ref(dy), _ref(dx)))
+
+
 def scale_shift_act(x, scale, shift, act: str, y):
+    if act == "silu" and scale is not None and x.dtype == y.dtype and norm_fast_ok(x, y):
+        _launch("b200_scale_shift_silu_fast", _ref(x), _ptr(scale), _ptr(shift), _ref(y), stream_ptr(), shape=x.shape)
+        return y
     _launch("b200_scale_shift_act", _ref(x), _ptr(scale), _ptr(shift), ACT[act], _ref(y), stream_ptr(), shape=x.shape)
     return y
 
 
-def norm_act_bwd(x, dy, st: NormStats, gamma, beta, act: str, dx, dgamma, dbeta, accumulate=False):
+def norm_act_bwd(x, dy, st: NormStats, gamma, beta, act: str, dx, dgamma, dbeta, accumulate=False, dy_dead: bool = False):
+    """`dy_dead`: nothing reads dy after this call (true for the tape's activation gradients) -- allows the fast SiLU chain,
+    whose reduce pass leaves g = dy * act'(z) in dy's place for the apply pass."""
     n, d, h, w, c = x.shape
     red = zeros(n * c * 2, torch.float64, x.device)
-    _launch("b200_norm_act_bwd_reduce", _ref(x), _ref(dy), _ptr(st.mean), _ptr(st.rstd), st.groups, _ptr(gamma), _ptr(beta),
-            ACT[act], _ptr(red), stream_ptr(), shape=x.shape)
+    fast = dy_dead and act == "silu" and norm_fast_ok(x, dy, dx)
+    if fast:
+        _launch("b200_norm_silu_bwd_reduce_g", _ref(x), _ref(dy), _ptr(st.mean), _ptr(st.rstd), st.groups, _ptr(gamma), _ptr(beta),
+                _ptr(red), stream_ptr(), shape=x.shape)
+    else:
+        _launch("b200_norm_act_bwd_reduce", _ref(x), _ref(dy), _ptr(st.mean), _ptr(st.rstd), st.groups, _ptr(gamma), _ptr(beta),
+                ACT[act], _ptr(red), stream_ptr(), shape=x.shape)
     coef = torch.empty(n * c * 4, dtype=torch.float32, device=x.device)
     world = getattr(st, "world", 1) or 1
     if world > 1:
@@ -390,8 +413,12 @@ def norm_act_bwd(x, dy, st: NormStats, gamma, beta, act: str, dx, dgamma, dbeta,
     _launch("b200_norm_bwd_finalize", _ptr(red), _ptr(st.mean), _ptr(st.rstd), _ptr(gamma), _ptr(beta), n, c, st.groups,
             d * h * w * world, 1 if st.batch_stats else 0, _ptr(coef), _ptr(dgamma), _ptr(dbeta), stream_ptr())
     if dx is not None:
-        _launch("b200_norm_act_bwd_apply", _ref(x), _ref(dy), ACT[act], _ptr(coef), _ref(dx), 1 if accumulate else 0,
-                stream_ptr(), shape=x.shape)
+        if fast:
+            _launch("b200_norm_bwd_apply_g", _ref(x), _ref(dy), _ptr(coef), _ref(dx), 1 if accumulate else 0, stream_ptr(),
+                    shape=x.shape)
+        else:
+            _launch("b200_norm_act_bwd_apply", _ref(x), _ref(dy), ACT[act], _ptr(coef), _ref(dx), 1 if accumulate else 0,
+                    stream_ptr(), shape=x.shape)
 
 
 def act_bwd(x, dy, act: str, dx, accumulate=False):
@@ -425,26 +452,51 @@ def softmax_channels(x, y, c0: int, c1: int):
 
 
 # --------------------------------------------------------------------------------------------------- losses
+def _check_target(pred, target, per_voxel: int, what: str):
+    """The loss kernels index the dense target by the prediction's voxel count: a short buffer would be read out of bounds."""
+    vox = pred.shape[0] * pred.shape[1] * pred.shape[2] * pred.shape[3]
+    if target.numel() != vox * per_voxel or not target.is_contiguous():
+        raise _lib.B200Error(f"{what}: target has {target.numel()} elements (contiguous={target.is_contiguous()}), the prediction "
+                             f"{tuple(pred.shape)} needs {vox * per_voxel}")
+
+
 def bce_logits(logits, target_f32, dlogits=None, grad_scale: float = 1.0) -> torch.Tensor:
     """Returns the SUM of the per-element losses as a 1-element float64 tensor (device)."""
-    out = torch.zeros(1, dtype=torch.float64, device=logits.device)
+    _check_target(logits, target_f32, logits.shape[-1], "bce_logits")
+    out = zeros(1, torch.float64, logits.device)
     _launch("b200_bce_logits", _ref(logits), _ptr(target_f32), _ptr(out), _ref(dlogits), float(grad_scale), stream_ptr())
     return out
 
 
 def n2v_mse_sums(pred, target_f32) -> torch.Tensor:
-    out = torch.zeros(2, dtype=torch.float64, device=pred.device)
+    _check_target(pred, target_f32, 2 * pred.shape[-1], "n2v_mse")
+    out = zeros(2, torch.float64, pred.device)
     _launch("b200_n2v_mse", _ref(pred), _ptr(target_f32), _ptr(out), None, 1.0, 0, stream_ptr())
     return out
 
 
 def n2v_mse_bwd(pred, target_f32, dpred, grad_scale: float):
+    _check_target(pred, target_f32, 2 * pred.shape[-1], "n2v_mse")
     _launch("b200_n2v_mse", _ref(pred), _ptr(target_f32), None, _ref(dpred), float(grad_scale), 1, stream_ptr())
 
 
-def softmax_ce(logits, target_i64, dlogits=None, grad_scale: float = 1.0) -> torch.Tensor:
-    out = torch.zeros(1, dtype=torch.float64, device=logits.device)
-    _launch("b200_softmax_ce", _ref(logits), _ptr(target_i64), _ptr(out), _ref(dlogits), float(grad_scale), stream_ptr())
+def n2v_mse_fused(pred, target_f32, dpred, grad_scale: float) -> torch.Tensor:
+    """One pass: (sum of squared masked errors, sum of the mask) and dpred = -2 (t - y m) m * grad_scale; the division by the
+    mask count is done on the device by the optimiser (`optim_step_dev(denom=sums[1:2])`): no host read of a scalar."""
+    _check_target(pred, target_f32, 2 * pred.shape[-1], "n2v_mse")
+    out = zeros(2, torch.float64, pred.device)
+    _launch("b200_n2v_mse", _ref(pred), _ptr(target_f32), _ptr(out), _ref(dpred), float(grad_scale), 2, stream_ptr())
+    return out
+
+
+def softmax_ce(logits, target_i64, dlogits=None, grad_scale: float = 1.0, ignore_index: int = -100) -> torch.Tensor:
+    """float64[3] on the device: (loss sum over the counted voxels, counted voxels, voxels with an illegal label)."""
+    _check_target(logits, target_i64, 1, "softmax_ce")
+    if target_i64.dtype != torch.int64:
+        raise _lib.B200Error(f"softmax_ce: target must be int64 class indices, got {target_i64.dtype}")
+    out = zeros(3, torch.float64, logits.device)
+    _launch("b200_softmax_ce", _ref(logits), _ptr(target_i64), _ptr(out), _ref(dlogits), float(grad_scale), int(ignore_index),
+            stream_ptr())
     return out
 
 
@@ -454,12 +506,42 @@ def adamw_step(p, g, m, v, lr, beta1, beta2, eps, wd, step: int, grad_scale: flo
             stream_ptr())
 
 
-def sgd_step(p, g, mom, lr, momentum, wd, first: bool, grad_scale: float = 1.0):
-    _launch("b200_sgd_step", _ptr(p), _ptr(g), _ptr(mom), p.numel(), lr, momentum, wd, 1 if first else 0, grad_scale,
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, wd, step: int, grad_scale: float = 1.0):
+    """torch.optim.Adam: the weight decay is an L2 term of the gradient (TRAIN.OPTIMIZER = 'ADAM')."""
+    _launch("b200_adam_step", _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), lr, beta1, beta2, eps, wd, step, grad_scale,
             stream_ptr())
 
 
-def sumsq(g) -> torch.Tensor:
-    out = torch.zeros(1, dtype=torch.float64, device=g.device)
+def sgd_step(p, g, mom, lr, momentum, wd, first: bool, grad_scale: float = 1.0, nesterov: bool = False):
+    _launch("b200_sgd_step", _ptr(p), _ptr(g), _ptr(mom), p.numel(), lr, momentum, wd, 1 if first else 0, grad_scale,
+            1 if nesterov else 0, stream_ptr())
+
+
+OPT_KIND = {"adamw": 0, "adam": 1, "sgd": 2}
+HP_LR, HP_BETA1, HP_BETA2, HP_EPS, HP_WD, HP_MOMENTUM, HP_NESTEROV, HP_GRAD_SCALE, HP_CLIP, HP_SIZE = 0, 1, 2, 3, 4, 5, 6, 7, 8, 16
+
+
+def optim_step_dev(kind: str, p, g, m, v, hp_dev, state_dev, derived_dev, gsq=None, denom=None):
+    """Optimiser update with device-resident hyper-parameters (two launches: a one-thread prepare + the element kernel);
+    capturable in a CUDA graph.  See `b200_optim_step_dev` in include/biapy_b200.h for the layouts."""
+    global LAUNCHES
+    LAUNCHES += 1
+    _launch("b200_optim_step_dev", OPT_KIND[kind], _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), _ptr(hp_dev), _ptr(gsq),
+            _ptr(denom), _ptr(state_dev), _ptr(derived_dev), stream_ptr())
+
+
+def write_floats(dst: torch.Tensor, values):
+    """dst[:len(values)] = values in stream order (values are kernel arguments: no staging buffer, no host race)."""
+    arr = (C.c_float * len(values))(*values)
+    _launch("b200_write_floats", _ptr(dst), arr, len(values), stream_ptr())
+
+
+def scale_by_dev(g: torch.Tensor, denom: torch.Tensor, mul: float = 1.0):
+    _launch("b200_scale_by_dev", _ptr(g), g.numel(), _ptr(denom), float(mul), stream_ptr())
+
+
+def sumsq(g, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if out is None:
+        out = zeros(1, torch.float64, g.device)
     _launch("b200_sumsq", _ptr(g), g.numel(), _ptr(out), stream_ptr())
     return out

@@ -291,6 +291,17 @@ int b200_norm_bwd_finalize(const double* red, const float* mean, const float* rs
 /* pass 2: dx (+)= g*k0 - x*P - Q                                                                               */
 int b200_norm_act_bwd_apply(const b200_tensor* x, const b200_tensor* dy, int32_t act, const float* coef,
                             const b200_tensor* dx, int32_t accumulate, void* stream);
+/* GroupNorm / InstanceNorm + SiLU chain of the 16-bit engine with cheaper arithmetic (one MUFU.TANH per sigmoid, activation
+ * derivative evaluated once).  Same mathematics as scale_shift_act / norm_act_bwd_reduce / norm_act_bwd_apply for act = SiLU
+ * (reference blocks.py:148-160 norm -> act), different contract: b200_norm_silu_bwd_reduce_g OVERWRITES dy with
+ * g = dy * silu'(norm(x)) and b200_norm_bwd_apply_g consumes that g.  b200_norm_silu_fast_ok: 1 when (x, dy, dx) qualify
+ * (bf16 / fp16, 8-channel vectors, <= 2048 channels); dy / dx may be null for the forward-only question. */
+int b200_norm_silu_fast_ok(const b200_tensor* x, const b200_tensor* dy, const b200_tensor* dx);
+int b200_scale_shift_silu_fast(const b200_tensor* x, const float* scale, const float* shift, const b200_tensor* y, void* stream);
+int b200_norm_silu_bwd_reduce_g(const b200_tensor* x, const b200_tensor* dy_g, const float* mean, const float* rstd,
+                                int32_t groups, const float* gamma, const float* beta, double* red, void* stream);
+int b200_norm_bwd_apply_g(const b200_tensor* x, const b200_tensor* g, const float* coef, const b200_tensor* dx,
+                          int32_t accumulate, void* stream);
 /* activation only (norm == 'none'): dx (+)= dy * act'(x) */
 int b200_act_bwd(const b200_tensor* x, const b200_tensor* dy, int32_t act, const b200_tensor* dx,
                  int32_t accumulate, void* stream);
@@ -312,13 +323,16 @@ int b200_convert(const b200_tensor* src, const b200_tensor* dst, void* stream);
  * sum of per-element losses; dlogits = (sigmoid(z) - t) * grad_scale.  target is float32 dense.                */
 int b200_bce_logits(const b200_tensor* logits, const float* target, double* loss_sum, const b200_tensor* dlogits,
                     float grad_scale, void* stream);
-/* N2V masked MSE (metrics.py:2265-2286): sums[0] += sum((t - y*m)^2), sums[1] += sum(m); second call computes
- * dlogits = -2*(t - y*m)*m * grad_scale (grad_scale = upstream / sum(m)).  target dense (N,...,2C) float32.     */
+/* N2V masked MSE (metrics.py:2265-2286).  mode 0: sums[0] += sum((t - y*m)^2), sums[1] += sum(m); mode 1:
+ * dpred = -2*(t - y*m)*m * grad_scale (grad_scale = upstream / sum(m)); mode 2: both in one pass (the division by sum(m)
+ * is then left to b200_optim_step_dev's `denom`).  target dense (N,...,2C) float32.                                */
 int b200_n2v_mse(const b200_tensor* pred, const float* target, double* sums, const b200_tensor* dpred,
                  float grad_scale, int32_t mode, void* stream);
-/* softmax cross-entropy over channels (metrics.py:581-586): target int64 class per voxel; ignore_index < 0 = none */
+/* softmax cross-entropy over channels (metrics.py:546, 581-586): target int64 class per voxel.  sums (double[3], zeroed by the
+ * caller): [0] += loss over the counted voxels, [1] += counted voxels (label != ignore_index), [2] += voxels whose label is
+ * neither a class nor ignore_index (torch asserts on those; they are skipped here and reported). */
 int b200_softmax_ce(const b200_tensor* logits, const int64_t* target, double* sums, const b200_tensor* dlogits,
-                    float grad_scale, void* stream);
+                    float grad_scale, int64_t ignore_index, void* stream);
 /* head activations (biapy/engine/base_workflow.py:1367-1470): sigmoid per channel or softmax over [c0, c1) */
 int b200_softmax_channels(const b200_tensor* x, const b200_tensor* y, int32_t c0, int32_t c1, void* stream);
 
@@ -326,8 +340,26 @@ int b200_softmax_channels(const b200_tensor* x, const b200_tensor* y, int32_t c0
  * AdamW / SGD on a flat fp32 buffer (replaces timm create_optimizer_v2 -> torch.optim, engine/__init__.py:62-68). */
 int b200_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                     float eps, float weight_decay, int64_t step, float grad_scale, void* stream);
+/* torch.optim.Adam (timm create_optimizer_v2('adam')): the weight decay is an L2 term added to the gradient. */
+int b200_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, int64_t step, float grad_scale, void* stream);
+/* torch.optim.SGD incl. Nesterov momentum (timm's 'sgd' = SGD(momentum=0.9, nesterov=True), engine/__init__.py:58-70). */
 int b200_sgd_step(float* p, const float* g, float* mom, int64_t n, float lr, float momentum, float weight_decay,
-                  int32_t first_step, float grad_scale, void* stream);
+                  int32_t first_step, float grad_scale, int32_t nesterov, void* stream);
+/* The same three optimisers with every hyper-parameter read from device memory, so that the update can sit inside a captured
+ * CUDA graph while BiaPy's per-iteration LR schedule (train_engine.py:117-123) rewrites `hp` between replays.
+ * kind: 0 AdamW, 1 Adam, 2 SGD.  hp (float[16]): lr, beta1, beta2, eps, weight_decay, momentum, nesterov, grad_scale, clip_norm.
+ * gsq (nullable): sum of squares of g from b200_sumsq -- clip_grad_norm_ (train_engine.py:174-176) and the overflow test of
+ * the fp16 engine (a non-finite gradient skips the update, as torch's GradScaler does).  denom (nullable): a divisor of the
+ * gradient that only exists on the device (Noise2Void mask count, counted cross-entropy voxels).  state (int64[2]): steps taken,
+ * steps skipped.  derived (float[8]): scratch written by the launch. */
+int b200_optim_step_dev(int32_t kind, float* p, const float* g, float* m, float* v, int64_t n, const float* hp,
+                        const double* gsq, const double* denom, int64_t* state, float* derived, void* stream);
+/* dst[0..n) = values[0..n) (n <= 16) in stream order: the values travel as kernel arguments, so the host array may be reused
+ * at once (how per-iteration hyper-parameters reach b200_optim_step_dev without a pinned staging buffer). */
+int b200_write_floats(float* dst, const float* values, int32_t n, void* stream);
+/* g *= mul / *denom with the divisor read on the device (per-rank mean of a masked loss before the gradient all-reduce). */
+int b200_scale_by_dev(float* g, int64_t n, const double* denom, float mul, void* stream);
 /* sum of squares of a flat fp32 buffer (for clip_grad_norm_, train_engine.py:174-176): out[0] (double) += ...   */
 int b200_sumsq(const float* g, int64_t n, double* out, void* stream);
 

@@ -244,6 +244,45 @@ def test_norm_act_fwd_bwd(kind, c, groups, act, dtype):
     assert nerr(dg.cpu(), gr.grad) < tol and nerr(db.cpu(), br.grad) < tol
 
 
+@pytest.mark.parametrize("c,groups,pad", [(16, 8, 0), (48, 8, 16), (96, 8, 0)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_norm_silu_fast_chain(c, groups, pad, dtype, monkeypatch):
+    """The one-MUFU SiLU chain (norm_fast.cuh) against ATen in fp32 on operands rounded to the engine dtype: forward, dx (plain and
+    accumulated into a channel slice), dgamma / dbeta; dy is overwritten by g = dy * silu'(z) as documented."""
+    from biapy_b200 import ops
+    monkeypatch.setattr(ops, "NORM_FAST", "1")
+    n, d, h, w = 2, 6, 6, 10
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(n, c, d, h, w, generator=g) * 1.7 + 0.4).to(dtype).float()
+    gamma, beta = torch.randn(c, generator=g), torch.randn(c, generator=g)
+    gy = torch.randn(n, c, d, h, w, generator=g).to(dtype).float()
+    xr, gr, br = x.clone().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yr = F.silu(F.group_norm(xr, groups, gr, br, 1e-5))
+    (yr * gy).sum().backward()
+    xbuf = torch.zeros(n, d, h, w, c + pad, dtype=dtype, device="cuda")
+    xd = xbuf[..., pad:]
+    xd.copy_(cl(x).to(dtype))
+    assert ops.norm_fast_ok(xd)
+    st = ops.norm_stats(xd, groups, gamma.cuda(), beta.cuda())
+    y = torch.empty(n, d, h, w, c, dtype=dtype, device="cuda")
+    ops.scale_shift_act(xd, st.scale, st.shift, "silu", y)
+    tol = 2e-2 if dtype == torch.bfloat16 else 3e-3
+    assert nerr(ncdhw(y), yr.detach()) < tol
+    for accumulate in (False, True):
+        dy = cl(gy).to(dtype)
+        dy0 = dy.clone()
+        dxbuf = torch.ones(n, d, h, w, c + pad, dtype=dtype, device="cuda")
+        dx = dxbuf[..., pad:]
+        dg, db = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
+        ops.norm_act_bwd(xd, dy, st, gamma.cuda(), beta.cuda(), "silu", dx, dg, db, accumulate=accumulate, dy_dead=True)
+        assert not torch.equal(dy, dy0)                                   # g left in place of dy
+        want = xr.grad + (1.0 if accumulate else 0.0)
+        assert nerr(ncdhw(dx), want) < tol
+        assert nerr(dg.cpu(), gr.grad) < tol and nerr(db.cpu(), br.grad) < tol
+        if pad:
+            assert torch.equal(dxbuf[..., :pad], torch.ones_like(dxbuf[..., :pad]))
+
+
 def test_act_only_and_elementwise():
     from biapy_b200 import ops
     g = torch.Generator().manual_seed(4)
@@ -312,8 +351,28 @@ def test_losses():
     zcd = cl(zc)
     dzc = torch.empty_like(zcd)
     sc = ops.softmax_ce(zcd, cls.cuda().contiguous(), dzc, grad_scale=1.0 / cls.numel())
-    assert abs(sc.item() / cls.numel() - lc.item()) < 1e-5
+    assert abs(sc[0].item() / cls.numel() - lc.item()) < 1e-5 and sc[1].item() == cls.numel() and sc[2].item() == 0
     assert nerr(ncdhw(dzc), zcr.grad) < 1e-5
+    # CrossEntropyLoss(ignore_index) of the reference's wrapper (metrics.py:534-546): mean over the counted voxels only
+    cls_i = cls.clone()
+    cls_i[:, 0] = -100
+    zcr = zc.clone().requires_grad_(True)
+    li = F.cross_entropy(zcr, cls_i, ignore_index=-100)
+    li.backward()
+    si = ops.softmax_ce(zcd, cls_i.cuda().contiguous(), dzc, grad_scale=1.0, ignore_index=-100)
+    cnt = si[1].item()
+    assert cnt == (cls_i != -100).sum().item() and si[2].item() == 0 and abs(si[0].item() / cnt - li.item()) < 1e-5
+    assert nerr(ncdhw(dzc) / cnt, zcr.grad) < 1e-5
+    cls_b = cls.clone()
+    cls_b[0, 0, 0, 0], cls_b[1, 2, 3, 4] = 255, -7                 # illegal labels: skipped and reported, never dereferenced
+    sb = ops.softmax_ce(zcd, cls_b.cuda().contiguous(), dzc, grad_scale=1.0)
+    assert sb[2].item() == 2 and sb[1].item() == cls.numel() - 2
+    with pytest.raises(Exception):
+        ops.softmax_ce(zcd, cls.cuda()[:1].contiguous(), dzc)      # short target buffer
+    # one-pass Noise2Void form used by the Trainer
+    dy2 = torch.empty_like(yd)
+    s2 = ops.n2v_mse_fused(yd, td, dy2, 0.25)
+    assert torch.equal(s2.cpu(), sums.cpu()) and nerr(ncdhw(dy2) / (0.25 * sums[1].item()), yr.grad) < 1e-5
     out = torch.empty_like(zcd)
     ops.softmax_channels(zcd, out, 0, 4)
     assert nerr(ncdhw(out), torch.softmax(zc, 1)) < 1e-6
@@ -342,6 +401,56 @@ def test_optimizers_match_torch():
         opt.step()
         ops.sgd_step(p, gr.cuda(), mom, 1e-2, 0.9, 1e-4, i == 0)
     assert nerr(p.cpu(), pr.detach()) < 1e-6
+    # TRAIN.OPTIMIZER = 'SGD' is timm's SGD(momentum=0.9, nesterov=True); 'ADAM' is torch.optim.Adam (L2 decay)
+    pr = p0.clone().requires_grad_(True)
+    opt = torch.optim.SGD([pr], lr=1e-2, momentum=0.9, weight_decay=1e-4, nesterov=True)
+    p = p0.clone().cuda()
+    mom = torch.zeros_like(p)
+    for i, gr in enumerate(grads):
+        pr.grad = gr.clone()
+        opt.step()
+        ops.sgd_step(p, gr.cuda(), mom, 1e-2, 0.9, 1e-4, i == 0, nesterov=True)
+    assert nerr(p.cpu(), pr.detach()) < 1e-6
+    pr = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pr], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.02)
+    p = p0.clone().cuda()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for i, gr in enumerate(grads):
+        pr.grad = gr.clone()
+        opt.step()
+        ops.adam_step(p, gr.cuda(), m, v, 1e-3, 0.9, 0.999, 1e-8, 0.02, i + 1)
+    assert nerr(p.cpu(), pr.detach()) < 1e-6
+    # device-hyper-parameter form (what the Trainer launches): clipping, an overflowed step skipped, step counter on the device
+    for kind, mk in (("adamw", lambda q: torch.optim.AdamW([q], lr=1e-3, weight_decay=0.02)),
+                     ("adam", lambda q: torch.optim.Adam([q], lr=1e-3, weight_decay=0.02)),
+                     ("sgd", lambda q: torch.optim.SGD([q], lr=1e-3, momentum=0.9, weight_decay=0.02, nesterov=True))):
+        pr = p0.clone().requires_grad_(True)
+        opt = mk(pr)
+        p = p0.clone().cuda()
+        m, v = torch.zeros_like(p), torch.zeros_like(p)
+        hp = torch.zeros(ops.HP_SIZE, device="cuda")
+        state = torch.zeros(2, dtype=torch.int64, device="cuda")
+        derived = torch.zeros(8, device="cuda")
+        gsq = torch.zeros(1, dtype=torch.float64, device="cuda")
+        ops.write_floats(hp, (1e-3, 0.9, 0.999, 1e-8, 0.02, 0.9 if kind == "sgd" else 0.0, 1.0 if kind == "sgd" else 0.0, 0.5, 2.0))
+        for i, gr in enumerate(grads):
+            pr.grad = 0.5 * gr.clone()
+            torch.nn.utils.clip_grad_norm_([pr], 2.0)
+            opt.step()
+            gd = gr.cuda()
+            if i == 2:                                        # a non-finite gradient is skipped (GradScaler semantics)
+                bad = gd.clone()
+                bad[5] = float("inf")
+                before = p.clone()
+                gsq.zero_()
+                ops.sumsq(bad, out=gsq)
+                ops.optim_step_dev(kind, p, bad, m, v, hp, state, derived, gsq=gsq)
+                assert torch.equal(p, before) and state.tolist() == [2, 1]
+            gsq.zero_()
+            ops.sumsq(gd, out=gsq)
+            ops.optim_step_dev(kind, p, gd, m, v, hp, state, derived, gsq=gsq)
+        assert state.tolist() == [5, 1]
+        assert nerr(p.cpu(), pr.detach()) < 1e-6, kind
     ss = ops.sumsq(grads[0].cuda())
     assert abs(ss.item() - float((grads[0].double() ** 2).sum())) < 1e-6 * ss.item()
 

@@ -6,9 +6,9 @@ against straightforward loops / textbook formulas in double precision:
 
 * the coalesced pointwise convolutions (fprop / dgrad / wgrad of the 1-2 channel layers) and the compile-time-window max-pool;
 * the radix-select histogram of the percentile clipping;
-* the weight pack / unpack kernels against independent statements of their layouts, and the staged one-launch pack kernel of
-  ``experiments/`` against them;
-* the loss kernels (BCE with logits, soft-max cross-entropy, Noise2Void masked MSE: sums and gradients) and the fused AdamW / SGD kernels (and the staged Adam-with-L2 kernel) against the torch.optim update rules in double precision;
+* the weight pack / unpack kernels against independent statements of their layouts, and the one-launch batched pack kernel
+  (``pack_batch.cuh``) against them;
+* the loss kernels (BCE with logits, soft-max cross-entropy, Noise2Void masked MSE: sums and gradients) and the fused AdamW / Adam / SGD (+ Nesterov) kernels, by-value and device-hyper-parameter forms, against the torch.optim update rules in double precision;
 * the whole GroupNorm / InstanceNorm + activation chain: ``channel_sums`` -> ``norm_finalize`` -> ``scale_shift_act_rows`` and
   ``norm_act_bwd_reduce`` -> ``norm_bwd_finalize`` -> ``norm_act_bwd_apply_rows`` (dx, dgamma, dbeta) on channel slices.
 
@@ -30,8 +30,8 @@ KERNELS = {
                      "conv1x1_wgrad_image_cv_kernel", "pack_weight_kernel", "unpack_wgrad_kernel"],
     "ops.cu": ["maxpool_fwd_win_kernel", "maxpool_bwd_win_kernel", "channel_sums_kernel", "norm_finalize_kernel",
                "scale_shift_act_rows_kernel", "norm_act_bwd_reduce_kernel", "norm_bwd_finalize_kernel",
-               "norm_act_bwd_apply_rows_kernel", "adamw_kernel", "sgd_kernel", "bce_logits_kernel",
-               "n2v_mse_kernel", "softmax_ce_kernel"],
+               "norm_act_bwd_apply_rows_kernel", "adamw_kernel", "adam_kernel", "sgd_kernel", "optim_prepare_kernel",
+               "optim_dev_kernel", "bce_logits_kernel", "n2v_mse_kernel", "softmax_ce_kernel"],
     "ends.cu": ["select_hist_kernel"],
     "conv_umma.cu": ["pack_weight_xfold_kernel", "pack_convT_weight_kernel", "unpack_convT_wgrad_kernel"],
 }
@@ -98,17 +98,14 @@ def test_simt_kernels_on_the_host_emulator(tmp_path):
             # dynamic shared memory: `extern __shared__ T name[];` -> the emulator's per-block buffer
             body = re.sub(r"extern __shared__ (\w+) (\w+)\[\];", r"\1* \2 = reinterpret_cast<\1*>(g_ctx->dyn_smem);", body)
             parts.append(f"// ---- {fname}: {n}\n" + body)
-    # the staged batched pack kernel (experiments/, not in the library) is held to the product kernels it would replace
-    with open(os.path.join(ROOT, "experiments", "pack_batch.cuh")) as f:
+    # the batched pack kernel is held to the single-job kernels it replaces inside a training pass
+    with open(os.path.join(CSRC, "pack_batch.cuh")) as f:
         staged = f.read()
-    parts.append("// ---- experiments/pack_batch.cuh\n" + staged[staged.index("enum PackKind"):])
-    with open(os.path.join(ROOT, "experiments", "norm_fast.cuh")) as f:
+    parts.append("// ---- pack_batch.cuh\n" + staged[staged.index("enum PackKind"):])
+    with open(os.path.join(CSRC, "norm_fast.cuh")) as f:
         staged = f.read()
     staged = re.sub(r"extern __shared__ (\w+) (\w+)\[\];", r"\1* \2 = reinterpret_cast<\1*>(g_ctx->dyn_smem);", staged)
-    parts.append("// ---- experiments/norm_fast.cuh\n" + staged[staged.index("__device__ __forceinline__ float tanh_approx"):])
-    with open(os.path.join(ROOT, "experiments", "optim_adam.cuh")) as f:
-        staged = f.read()
-    parts.append("// ---- experiments/optim_adam.cuh\n" + staged[staged.index("__global__ void adam_kernel"):])
+    parts.append("// ---- norm_fast.cuh\n" + staged[staged.index("__device__ __forceinline__ float tanh_approx"):])
     (tmp_path / "kernels.inc").write_text("\n\n".join(parts) + "\n")
     exe = tmp_path / "simt_emu"
     cmd = ["g++", "-std=c++20", "-O1", "-pthread", "-Wno-unknown-pragmas", "-I", str(tmp_path), "-I", EMU, "-I", os.path.join(ROOT, "include"),
