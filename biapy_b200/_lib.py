@@ -57,6 +57,8 @@ SIGNATURES = {
     "b200_crop_gather": (_I, [_P, _I, _L, _L, _L, _L, _P, _L, _L, _L, _P, _L, _P, _L, _P, _L, _L, _L, _L, _I, _P]),
     "b200_overlap_add": (_I, [_P, _I, _P, _I, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _P, _L, _P, _L, _P, _L,
                               _P, _P, _P, _P]),
+    "b200_overlap_add_slab": (_I, [_P, _I, _P, _I, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _P, _L, _P, _L, _P, _L,
+                                   _P, _P, _P, _L, _L, _P]),
     "b200_chunk_grid_plan": (_I, [C.POINTER(_L), C.POINTER(_L), C.POINTER(_L), _L, _L, C.POINTER(ChunkGrid)]),
     "b200_chunk_patch_coords": (_I, [C.POINTER(ChunkGrid), _L, C.POINTER(_L)]),
     "b200_chunk_extract": (_I, [_P, _I, _L, _L, _L, _L, _P, _L, _L, _L, _L, _P, _P]),

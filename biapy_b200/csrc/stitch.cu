@@ -204,7 +204,7 @@ struct MergeParams {
 // and finally out = acc / (wsum + 1e-18f) cast to the output dtype (:849).  The explicit _rn intrinsics
 // forbid FMA contraction, so float32 results are bit-identical to numpy's.
 template <typename TI, typename TO>
-__global__ void overlap_add_kernel(const TI* __restrict__ patches, TO* __restrict__ out, MergeParams p,
+__global__ void overlap_add_kernel(const TI* __restrict__ patches, TO* __restrict__ out, MergeParams p, int z0, int nz_out,
                                    const int64_t* __restrict__ sz, const int64_t* __restrict__ sy,
                                    const int64_t* __restrict__ sx, const float* __restrict__ wz,
                                    const float* __restrict__ wy, const float* __restrict__ wx) {
@@ -218,12 +218,13 @@ __global__ void overlap_add_kernel(const TI* __restrict__ patches, TO* __restric
   __syncthreads();
   const int plane = (int)(p.H * p.W * p.C);
   const int C = (int)p.C, Wd = (int)p.W;
-  for (int64_t z = blockIdx.y; z < p.D; z += gridDim.y)
+  for (int64_t zl = blockIdx.y; zl < nz_out; zl += gridDim.y)
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += gridDim.x * blockDim.x) {
+    const int64_t z = z0 + zl;
     const int ch = i % C;
     const int tq = i / C;
     const int64_t x = tq % Wd, y = tq / Wd;
-    const int64_t idx = z * plane + i;
+    const int64_t idx = zl * plane + i;
     float acc = 0.f, wsum = 0.f;
     for (int64_t iz = 0; iz < p.nz; ++iz) {
       int64_t lz = z - s_z[iz];
@@ -257,7 +258,7 @@ __global__ void overlap_add_kernel(const TI* __restrict__ patches, TO* __restric
 // level.  Same operation order, bit-identical results; used when no axis has more than 64 patches.
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) overlap_add_cover_kernel(const TI* __restrict__ patches, TO* __restrict__ out, MergeParams p,
-                                         const int64_t* __restrict__ sz, const int64_t* __restrict__ sy,
+                                         int z0, int nz_out, const int64_t* __restrict__ sz, const int64_t* __restrict__ sy,
                                          const int64_t* __restrict__ sx, const float* __restrict__ wz,
                                          const float* __restrict__ wy, const float* __restrict__ wx) {
   extern __shared__ unsigned long long s_mask[];             // x masks [W], y masks [H], then the starts as int
@@ -287,7 +288,8 @@ __global__ void __launch_bounds__(256) overlap_add_cover_kernel(const TI* __rest
   const int plane = H * W * C;
   const int64_t pvol = p.pz * p.py * p.px * p.C;           // elements per patch
   const int row_el = (int)(p.px * p.C);
-  for (int z = blockIdx.y; z < (int)p.D; z += gridDim.y) {
+  for (int zl = blockIdx.y; zl < nz_out; zl += gridDim.y) {
+    const int z = z0 + zl;
     unsigned long long zm = 0;
     for (int i = 0; i < nz; ++i) {
       const int l = z - s_z[i];
@@ -317,35 +319,211 @@ __global__ void __launch_bounds__(256) overlap_add_cover_kernel(const TI* __rest
           }
         }
       }
-      out[(int64_t)z * plane + i] = from_f<TO>(__fdiv_rn(acc, __fadd_rn(wsum, 1e-18f)));
+      out[(int64_t)zl * plane + i] = from_f<TO>(__fdiv_rn(acc, __fadd_rn(wsum, 1e-18f)));
+    }
+  }
+}
+
+// Slot variant (default for the usual grids, overlap < 50 %): with at most TWO covering patches per axis the covering set of an
+// output element is a 2 x 2 x 2 box of slots (z slots and y slots are the same for a whole x row, x slots are per thread), so the
+// walk over the covering patches becomes eight predicated, fully unrolled steps whose loads are independent of each other --
+// the cover kernel above chases mask bits one patch at a time and exposes one load latency per patch.  The operation order
+// (z-major, then y, then x: increasing patch index) and every float32 operation are those of overlap_add_kernel: bit-identical.
+// Elements with three or more covering patches on some axis take the mask walk.  `z0`: first output plane of the slab this
+// launch produces (out holds planes [z0, z0 + p.D_slab) of the volume; sharded inference merges one slab per rank).
+template <typename TI, typename TO, int ROWS>
+__global__ void __launch_bounds__(256) overlap_add_slot_kernel(const TI* __restrict__ patches, TO* __restrict__ out, MergeParams p,
+                                         int z0, int nz_out,
+                                         const int64_t* __restrict__ sz, const int64_t* __restrict__ sy,
+                                         const int64_t* __restrict__ sx, const float* __restrict__ wz,
+                                         const float* __restrict__ wy, const float* __restrict__ wx) {
+  extern __shared__ unsigned long long s_mask[];             // x masks [W], y masks [H], then the starts as int
+  const int nz = (int)p.nz, ny = (int)p.ny, nx = (int)p.nx, H = (int)p.H, W = (int)p.W, C = (int)p.C;
+  const int cz = (int)p.cz, cy = (int)p.cy, cx = (int)p.cx;
+  unsigned long long* x_mask = s_mask;
+  unsigned long long* y_mask = x_mask + W;
+  int* s_z = reinterpret_cast<int*>(y_mask + H);
+  int* s_y = s_z + nz;
+  int* s_x = s_y + ny;
+  for (int i = threadIdx.x; i < nz; i += blockDim.x) s_z[i] = (int)sz[i];
+  for (int i = threadIdx.x; i < ny; i += blockDim.x) s_y[i] = (int)sy[i];
+  for (int i = threadIdx.x; i < nx; i += blockDim.x) s_x[i] = (int)sx[i];
+  __syncthreads();
+  for (int c = threadIdx.x; c < W + H; c += blockDim.x) {
+    const bool isx = c < W;
+    const int coord = isx ? c : c - W, n = isx ? nx : ny, core = isx ? cx : cy;
+    const int* st = isx ? s_x : s_y;
+    unsigned long long m = 0;
+    for (int i = 0; i < n; ++i) {
+      const int l = coord - st[i];
+      if (l >= 0 && l < core) m |= 1ull << i;
+    }
+    (isx ? x_mask : y_mask)[coord] = m;
+  }
+  __syncthreads();
+  const int row_el = W * C;                                  // elements of one output x row
+  const int64_t pvol = p.pz * p.py * p.px * p.C;             // elements per patch
+  const int prow = (int)(p.px * p.C);                        // elements of one patch x row
+  const int padz = (int)p.pad_z, pady = (int)p.pad_y, padx = (int)p.pad_x;
+  for (int zl = blockIdx.y; zl < nz_out; zl += gridDim.y) {
+    const int z = z0 + zl;
+    unsigned long long zm = 0;
+    for (int i = 0; i < nz; ++i) {
+      const int l = z - s_z[i];
+      if (l >= 0 && l < cz) zm |= 1ull << i;
+    }
+    const int nzc = __popcll(zm);
+    int a[2] = {0, 0};
+    float fz[2] = {0.f, 0.f};
+    int64_t zoff[2] = {0, 0};
+    if (nzc >= 1 && nzc <= 2) {
+      a[0] = __ffsll((long long)zm) - 1;
+      a[1] = nzc == 2 ? 63 - __clzll((long long)zm) : a[0];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int lz = z - s_z[a[k]];
+        fz[k] = __ldg(wz + lz);
+        zoff[k] = (int64_t)a[k] * ny * nx * pvol + (int64_t)(lz + padz) * p.py * prow;
+      }
+    }
+    // a block walks groups of ROWS x rows; thread t owns elements t, t + 256, ... of each row of the group
+    for (int y0 = blockIdx.x * ROWS; y0 < H; y0 += gridDim.x * ROWS) {
+      for (int e0 = threadIdx.x; e0 < row_el; e0 += blockDim.x) {
+        const int x = e0 / C, ch = e0 - x * C;
+        const unsigned long long xm = x_mask[x];
+        const int nxc = __popcll(xm);
+        const int c0 = __ffsll((long long)xm) - 1, c1 = 63 - __clzll((long long)xm);
+        const int lx0 = nxc ? x - s_x[c0] : 0, lx1 = nxc ? x - s_x[c1] : 0;
+        const float fx0 = nxc ? __ldg(wx + lx0) : 0.f, fx1 = nxc ? __ldg(wx + lx1) : 0.f;
+        const int64_t xoff0 = (int64_t)c0 * pvol + (lx0 + padx) * C + ch, xoff1 = (int64_t)c1 * pvol + (lx1 + padx) * C + ch;
+        float v[ROWS][8];
+        float fzy[ROWS][4];
+        bool fast[ROWS];
+        int nyc_r[ROWS];
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+          const int y = y0 + r;
+          fast[r] = false;
+          nyc_r[r] = 0;
+          if (y >= H) continue;
+          const unsigned long long ym = y_mask[y];
+          const int nyc = __popcll(ym);
+          nyc_r[r] = nyc;
+          fast[r] = nzc <= 2 && nyc <= 2 && nxc <= 2;
+          if (!fast[r] || nzc == 0 || nyc == 0 || nxc == 0) continue;
+          const int b0 = __ffsll((long long)ym) - 1, b1 = 63 - __clzll((long long)ym);
+          const int ly0 = y - s_y[b0], ly1 = y - s_y[b1];
+          const float fy0 = __ldg(wy + ly0), fy1 = __ldg(wy + ly1);
+          const int64_t yoff0 = (int64_t)b0 * nx * pvol + (int64_t)(ly0 + pady) * prow;
+          const int64_t yoff1 = (int64_t)b1 * nx * pvol + (int64_t)(ly1 + pady) * prow;
+#pragma unroll
+          for (int kz = 0; kz < 2; ++kz) {
+            fzy[r][kz * 2 + 0] = __fmul_rn(fz[kz], fy0);
+            fzy[r][kz * 2 + 1] = __fmul_rn(fz[kz], fy1);
+            const bool pz_on = kz < nzc;
+            const TI* b00 = patches + zoff[kz] + yoff0;
+            const TI* b01 = patches + zoff[kz] + yoff1;
+            v[r][kz * 4 + 0] = pz_on ? to_f<TI>(b00[xoff0]) : 0.f;
+            v[r][kz * 4 + 1] = (pz_on && nxc == 2) ? to_f<TI>(b00[xoff1]) : 0.f;
+            v[r][kz * 4 + 2] = (pz_on && nyc == 2) ? to_f<TI>(b01[xoff0]) : 0.f;
+            v[r][kz * 4 + 3] = (pz_on && nyc == 2 && nxc == 2) ? to_f<TI>(b01[xoff1]) : 0.f;
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+          const int y = y0 + r;
+          if (y >= H) continue;
+          float acc = 0.f, wsum = 0.f;
+          if (fast[r]) {
+            if (nzc && nyc_r[r] && nxc) {
+#pragma unroll
+              for (int kz = 0; kz < 2; ++kz)
+#pragma unroll
+                for (int ky = 0; ky < 2; ++ky)
+#pragma unroll
+                  for (int kx = 0; kx < 2; ++kx) {
+                    if (kz < nzc && ky < nyc_r[r] && kx < nxc) {
+                      const float w = __fmul_rn(fzy[r][kz * 2 + ky], kx ? fx1 : fx0);
+                      acc = __fadd_rn(acc, __fmul_rn(v[r][kz * 4 + ky * 2 + kx], w));
+                      wsum = __fadd_rn(wsum, w);
+                    }
+                  }
+            }
+          } else {
+            const unsigned long long ym = y_mask[y];
+            for (unsigned long long am = zm; am; am &= am - 1) {
+              const int iz = __ffsll((long long)am) - 1, lz = z - s_z[iz];
+              const float gz = __ldg(wz + lz);
+              for (unsigned long long bm = ym; bm; bm &= bm - 1) {
+                const int iy = __ffsll((long long)bm) - 1, ly = y - s_y[iy];
+                const float gzy = __fmul_rn(gz, __ldg(wy + ly));
+                const TI* rowp = patches + ((int64_t)(iz * ny + iy) * nx) * pvol + ((int64_t)(lz + padz) * p.py + (ly + pady)) * prow + ch;
+                for (unsigned long long cm = xm; cm; cm &= cm - 1) {
+                  const int ix = __ffsll((long long)cm) - 1, lx = x - s_x[ix];
+                  const float w = __fmul_rn(gzy, __ldg(wx + lx));
+                  const float val = to_f<TI>(rowp[(int64_t)ix * pvol + (lx + padx) * C]);
+                  acc = __fadd_rn(acc, __fmul_rn(val, w));
+                  wsum = __fadd_rn(wsum, w);
+                }
+              }
+            }
+          }
+          out[((int64_t)zl * H + y) * row_el + e0] = from_f<TO>(__fdiv_rn(acc, __fadd_rn(wsum, 1e-18f)));
+        }
+      }
     }
   }
 }
 
 template <typename TI, typename TO>
-static int launch_overlap_add(const void* patches, void* out, const MergeParams& p, const int64_t* sz,
+static int launch_overlap_add(const void* patches, void* out, const MergeParams& p, int64_t z0, int64_t nz_out, const int64_t* sz,
                               const int64_t* sy, const int64_t* sx, const float* wz, const float* wy,
                               const float* wx, cudaStream_t st) {
   int threads = 256;
   B200_CHECK_ARG(p.H * p.W * p.C < (1LL << 31), "overlap_add: plane too large");
+  B200_CHECK_ARG(z0 >= 0 && nz_out > 0 && z0 + nz_out <= p.D, "overlap_add: slab [%lld, %lld) outside the volume (%lld planes)",
+                 (long long)z0, (long long)(z0 + nz_out), (long long)p.D);
   int64_t bx = ceil_div(p.H * p.W * p.C, threads);
   if (bx > 1024) bx = 1024;
-  dim3 blocks((unsigned)bx, (unsigned)(p.D < 65535 ? p.D : 65535));
+  const unsigned gy = (unsigned)(nz_out < 65535 ? nz_out : 65535);
+  dim3 blocks((unsigned)bx, gy);
   // cover masks in shared memory (64 patches per axis at most), 32-bit coordinates, <= 48 KB
   const size_t tab = sizeof(unsigned long long) * (size_t)(p.W + p.H) + sizeof(int) * (size_t)(p.nz + p.ny + p.nx);
-  static const bool use_cover = !(getenv("B200_MERGE_COVER") && strcmp(getenv("B200_MERGE_COVER"), "0") == 0);
-  if (use_cover && tab <= 48 * 1024 && p.nz <= 64 && p.ny <= 64 && p.nx <= 64 && p.D < (1LL << 30) && p.px * p.C < (1LL << 30)) {
+  // B200_MERGE_KERNEL: slot (default) | cover | plain
+  static const int variant = [] {
+    const char* e = getenv("B200_MERGE_KERNEL");
+    if (getenv("B200_MERGE_COVER") && strcmp(getenv("B200_MERGE_COVER"), "0") == 0) return 2;
+    return !e ? 0 : !strcmp(e, "cover") ? 1 : !strcmp(e, "plain") ? 2 : 0;
+  }();
+  if (variant != 2 && tab <= 48 * 1024 && p.nz <= 64 && p.ny <= 64 && p.nx <= 64 && p.D < (1LL << 30) && p.px * p.C < (1LL << 30)) {
+    if (variant == 0) {
+      static const int rows = getenv("B200_MERGE_ROWS") ? atoi(getenv("B200_MERGE_ROWS")) : 2;     // x rows per thread (1, 2, 4)
+      const int R = rows == 1 || rows == 4 ? rows : 2;
+      int64_t groups = ceil_div(p.H, (int64_t)R);
+      // about 16 blocks per SM over the whole launch, every block builds the cover tables once
+      int64_t want = ceil_div((int64_t)sm_count() * 16, (int64_t)gy);
+      int64_t bxs = groups < want ? groups : want;
+      if (bxs < 1) bxs = 1;
+      const dim3 g((unsigned)bxs, gy);
+#define B200_SLOT(ROWS) overlap_add_slot_kernel<TI, TO, ROWS><<<g, threads, tab, st>>>((const TI*)patches, (TO*)out, p, (int)z0, \
+                                                                                 (int)nz_out, sz, sy, sx, wz, wy, wx)
+      if (R == 1) B200_SLOT(1); else if (R == 4) B200_SLOT(4); else B200_SLOT(2);
+#undef B200_SLOT
+      B200_LAUNCH_CHECK();
+      return B200_OK;
+    }
     // few, fat blocks per plane: the table build is per block
     int64_t bxc = ceil_div(p.H * p.W * p.C, (int64_t)threads * 8);
     if (bxc > 64) bxc = 64;
     if (bxc < 1) bxc = 1;
-    dim3 bc((unsigned)bxc, (unsigned)(p.D < 65535 ? p.D : 65535));
-    overlap_add_cover_kernel<TI, TO><<<bc, threads, tab, st>>>((const TI*)patches, (TO*)out, p, sz, sy, sx, wz, wy, wx);
+    dim3 bc((unsigned)bxc, gy);
+    overlap_add_cover_kernel<TI, TO><<<bc, threads, tab, st>>>((const TI*)patches, (TO*)out, p, (int)z0, (int)nz_out, sz, sy, sx, wz,
+                                                              wy, wx);
     B200_LAUNCH_CHECK();
     return B200_OK;
   }
   size_t smem = sizeof(int64_t) * (p.nz + p.ny + p.nx);
-  overlap_add_kernel<TI, TO><<<blocks, threads, smem, st>>>((const TI*)patches, (TO*)out, p, sz, sy, sx,
+  overlap_add_kernel<TI, TO><<<blocks, threads, smem, st>>>((const TI*)patches, (TO*)out, p, (int)z0, (int)nz_out, sz, sy, sx,
                                                                      wz, wy, wx);
   B200_LAUNCH_CHECK();
   return B200_OK;
@@ -353,12 +531,12 @@ static int launch_overlap_add(const void* patches, void* out, const MergeParams&
 
 }  // namespace b200
 
-B200_EXPORT int b200_overlap_add(const void* patches, int32_t dtype_in, void* out, int32_t dtype_out,
-                                 int64_t D, int64_t H, int64_t W, int64_t C,
-                                 int64_t pz, int64_t py, int64_t px, int64_t pad_z, int64_t pad_y, int64_t pad_x,
-                                 const int64_t* starts_z, int64_t nz, const int64_t* starts_y, int64_t ny,
-                                 const int64_t* starts_x, int64_t nx,
-                                 const float* win_z, const float* win_y, const float* win_x, void* stream) {
+static int overlap_add_impl(const void* patches, int32_t dtype_in, void* out, int32_t dtype_out,
+                            int64_t D, int64_t H, int64_t W, int64_t C,
+                            int64_t pz, int64_t py, int64_t px, int64_t pad_z, int64_t pad_y, int64_t pad_x,
+                            const int64_t* starts_z, int64_t nz, const int64_t* starts_y, int64_t ny,
+                            const int64_t* starts_x, int64_t nx,
+                            const float* win_z, const float* win_y, const float* win_x, int64_t z0, int64_t nz_out, void* stream) {
   using namespace b200;
   B200_CHECK_ARG(patches && out && starts_z && starts_y && starts_x && win_z && win_y && win_x,
                  "overlap_add: null pointer");
@@ -368,7 +546,7 @@ B200_EXPORT int b200_overlap_add(const void* patches, int32_t dtype_in, void* ou
   MergeParams p{D, H, W, C, pz, py, px, pad_z, pad_y, pad_x, pz - 2 * pad_z, py - 2 * pad_y, px - 2 * pad_x,
                 nz, ny, nx, D * H * W * C};
   cudaStream_t st = (cudaStream_t)stream;
-#define OA(TI, TO) return launch_overlap_add<TI, TO>(patches, out, p, starts_z, starts_y, starts_x, win_z, win_y, win_x, st)
+#define OA(TI, TO) return launch_overlap_add<TI, TO>(patches, out, p, z0, nz_out, starts_z, starts_y, starts_x, win_z, win_y, win_x, st)
   if (dtype_in == B200_F32 && dtype_out == B200_F32) OA(float, float);
   if (dtype_in == B200_F16 && dtype_out == B200_F16) OA(__half, __half);
   if (dtype_in == B200_F16 && dtype_out == B200_F32) OA(__half, float);
@@ -379,6 +557,27 @@ B200_EXPORT int b200_overlap_add(const void* patches, int32_t dtype_in, void* ou
 #undef OA
   set_error("overlap_add: unsupported dtype pair %d -> %d", dtype_in, dtype_out);
   return B200_ERR_UNSUPPORTED;
+}
+
+B200_EXPORT int b200_overlap_add(const void* patches, int32_t dtype_in, void* out, int32_t dtype_out,
+                                 int64_t D, int64_t H, int64_t W, int64_t C,
+                                 int64_t pz, int64_t py, int64_t px, int64_t pad_z, int64_t pad_y, int64_t pad_x,
+                                 const int64_t* starts_z, int64_t nz, const int64_t* starts_y, int64_t ny,
+                                 const int64_t* starts_x, int64_t nx,
+                                 const float* win_z, const float* win_y, const float* win_x, void* stream) {
+  return overlap_add_impl(patches, dtype_in, out, dtype_out, D, H, W, C, pz, py, px, pad_z, pad_y, pad_x, starts_z, nz, starts_y, ny,
+                          starts_x, nx, win_z, win_y, win_x, 0, D, stream);
+}
+
+B200_EXPORT int b200_overlap_add_slab(const void* patches, int32_t dtype_in, void* out, int32_t dtype_out,
+                                      int64_t D, int64_t H, int64_t W, int64_t C,
+                                      int64_t pz, int64_t py, int64_t px, int64_t pad_z, int64_t pad_y, int64_t pad_x,
+                                      const int64_t* starts_z, int64_t nz, const int64_t* starts_y, int64_t ny,
+                                      const int64_t* starts_x, int64_t nx,
+                                      const float* win_z, const float* win_y, const float* win_x, int64_t z0, int64_t nz_out,
+                                      void* stream) {
+  return overlap_add_impl(patches, dtype_in, out, dtype_out, D, H, W, C, pz, py, px, pad_z, pad_y, pad_x, starts_z, nz, starts_y, ny,
+                          starts_x, nx, win_z, win_y, win_x, z0, nz_out, stream);
 }
 
 // ---------------------------------------------------------------------------------------- by-chunks tile grid

@@ -76,8 +76,9 @@ def crop_device(vol, patch: Sequence[int], starts: Sequence[np.ndarray], pads: S
 
 
 def merge_device(patches, out_shape: Sequence[int], starts: Sequence[np.ndarray], windows: Sequence[np.ndarray],
-                 pads: Sequence[int], out_dtype=None):
-    """patches: CUDA tensor (n, pz, py, px, C) dense incl. padding border.  Returns (D,H,W,C)."""
+                 pads: Sequence[int], out_dtype=None, z_range=None, out=None):
+    """patches: CUDA tensor (n, pz, py, px, C) dense incl. padding border.  Returns (D,H,W,C), or only the output planes
+    `z_range = (z0, z1)` as (z1 - z0, H, W, C) -- then only the patch elements covering that slab are read."""
     import torch
     _lib.require_cuda(patches, "merge input")
     patches = patches.contiguous()
@@ -85,13 +86,16 @@ def merge_device(patches, out_shape: Sequence[int], starts: Sequence[np.ndarray]
     D, H, W = (int(v) for v in out_shape[:3])
     assert n == len(starts[0]) * len(starts[1]) * len(starts[2]), (n, [len(s) for s in starts])
     out_dtype = out_dtype or patches.dtype
-    out = torch.empty((D, H, W, Cc), dtype=out_dtype, device=patches.device)
+    z0, z1 = (0, D) if z_range is None else (int(z_range[0]), int(z_range[1]))
+    if out is None:
+        out = torch.empty((z1 - z0, H, W, Cc), dtype=out_dtype, device=patches.device)
+    assert tuple(out.shape) == (z1 - z0, H, W, Cc) and out.is_contiguous() and out.dtype == out_dtype
     tabs = [_dev(s, patches.device) for s in starts]
     wins = [_dev(w, patches.device) for w in windows]
-    _lib.call("b200_overlap_add", patches.data_ptr(), _lib.torch_dtype_code(patches.dtype), out.data_ptr(),
+    _lib.call("b200_overlap_add_slab", patches.data_ptr(), _lib.torch_dtype_code(patches.dtype), out.data_ptr(),
               _lib.torch_dtype_code(out_dtype), D, H, W, Cc, pz, py, px, int(pads[0]), int(pads[1]), int(pads[2]),
               tabs[0].data_ptr(), len(starts[0]), tabs[1].data_ptr(), len(starts[1]), tabs[2].data_ptr(),
-              len(starts[2]), wins[0].data_ptr(), wins[1].data_ptr(), wins[2].data_ptr(), _lib.stream_ptr())
+              len(starts[2]), wins[0].data_ptr(), wins[1].data_ptr(), wins[2].data_ptr(), z0, z1 - z0, _lib.stream_ptr())
     return out
 
 

@@ -94,6 +94,16 @@ int b200_overlap_add(const void* patches, int32_t dtype_in, void* out, int32_t d
                      const int64_t* starts_x, int64_t nx,
                      const float* win_z, const float* win_y, const float* win_x, void* stream);
 
+/* The same merge restricted to the output planes [z0, z0 + nz_out): `out` is (nz_out, H, W, C) dense.  `patches` is still the
+ * full (n_patches, ...) array, of which only the elements covering the slab are read -- sharded sliding-window inference lets
+ * every rank own one z slab of the volume and receive just those pieces of its neighbours' patch predictions. */
+int b200_overlap_add_slab(const void* patches, int32_t dtype_in, void* out, int32_t dtype_out,
+                          int64_t D, int64_t H, int64_t W, int64_t C,
+                          int64_t pz, int64_t py, int64_t px, int64_t pad_z, int64_t pad_y, int64_t pad_x,
+                          const int64_t* starts_z, int64_t nz, const int64_t* starts_y, int64_t ny,
+                          const int64_t* starts_x, int64_t nx,
+                          const float* win_z, const float* win_y, const float* win_x, int64_t z0, int64_t nz_out, void* stream);
+
 /* ------------------------------------------------------------------------------ by-chunks tile grid (host)
  * The reference's multi-GPU inference path (TEST.BY_CHUNKS): non-blended tiles of (crop - 2*pad), read with a halo,
  * reflect-padded to the crop shape, written back without the halo.  Integer bookkeeping, bit-exact with

@@ -106,6 +106,15 @@ static inline uint32_t __float_as_uint(float f) {
   return u;
 }
 
+// rounding-mode intrinsics of the stitch kernels: plain IEEE single operations (this file is compiled without FMA contraction)
+static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+template <typename T> static inline T __ldg(const T* p) { return *p; }
+static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
+static inline int __ffsll(long long v) { return __builtin_ffsll(v); }
+static inline int __clzll(long long v) { return v ? __builtin_clzll((unsigned long long)v) : 64; }
+
 // launch(grid, block, [&]{ kernel(args...); }); emu_launch2 adds gridDim.y and dynamic shared memory
 static inline void emu_launch2(unsigned grid_x, unsigned grid_y, unsigned block, size_t dyn_smem_bytes, const std::function<void()>& body);
 static inline void emu_launch(unsigned grid, unsigned block, const std::function<void()>& body) { emu_launch2(grid, 1, block, 0, body); }

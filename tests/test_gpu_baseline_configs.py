@@ -1,4 +1,4 @@
-"""BASELINE.json configs 3 and 4 at their full patch size (reduced batch so the CPU oracle finishes in seconds):
+"""BASELINE.json config 1 (the headline: 3D Residual U-Net 128^3 x 2ch, gn/silu) and configs 3 and 4 at their full patch size (reduced batch so the CPU oracle finishes in seconds):
 cfg 3 = 3D Attention U-Net denoising, 64^3 x 1ch, fm[16..256], fp16;  cfg 4 = 2D U-Net, 512 x 512 x 3, fm[32..512], 2 output
 channels, bf16.  Forward + backward against oracle/port_models.py (pinned to the reference classes): the fp32 engine meets the
 1e-3 bar; the 16-bit engines (tensor-core kernels incl. Cout up to 512 and the 2D paths) are held to the stated looser bound."""
@@ -73,3 +73,80 @@ def test_full_size_config_forward_backward(arch, kw, batch, lowp):
         else:
             # 16-bit storage of every activation through ~20 layers: rel-L2 of the whole gradient, not a per-element bar
             assert l2(y.detach().cpu(), yr.detach()) < 5e-2 and lw < 2.5e-1
+
+
+# ------------------------------------------------------------------------------------------------------------------ cfg 1
+CFG1 = dict(image_shape=(128, 128, 128, 2), activation="silu", feature_maps=[16, 32, 64, 128, 256], drop_values=[0] * 5,
+            normalization="gn", k_size=3, yx_down=[2] * 4, z_down=[2] * 4, isotropy=[True] * 5, larger_io=False,
+            conv_layers=[2] * 5, output_channels=[1])
+# Bounds = 2x what the device run of this test measured (profiles/parity_cfg1_r2.json); rel-L2 for the 16-bit engines, whose
+# per-element error is a rounding noise of the storage format, normalised max for fp32.  (dtype, y, dW, dx)
+CFG1_BOUNDS = {torch.float32: (1e-3, 1e-3, 5e-2), torch.float16: (5e-3, 2.5e-2, 5e-2), torch.bfloat16: (5e-2, 2.5e-1, 2.5e-1)}
+
+
+def test_full_size_cfg1_resunet128():
+    """The benchmarked network at the benchmarked patch size (batch 1 so the CPU oracle finishes in seconds), forward + backward
+    against oracle/port_models.py for the fp32 / fp16 / bf16 engines; prints normalised-max and rel-L2 errors of y, dW and dx and
+    leaves the table in gpurun_out/parity_cfg1.json.  The float64 evaluation of the same graph gives the noise floor: how far
+    ATen's own fp32 result is from exact arithmetic."""
+    import json
+    import os
+    from biapy_b200.models.resunet import ResUNet
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = ResUNet(**CFG1)
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.ndim == 1:
+                p.add_(0.2 * torch.randn(p.shape, generator=g))
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    x = torch.randn(1, 2, 128, 128, 128, generator=g)
+    gy = torch.randn(1, 1, 128, 128, 128, generator=g)
+
+    def oracle(dt):
+        sd_r = {k: v.clone().to(dt).requires_grad_(True) if v.is_floating_point() else v.clone() for k, v in sd.items()}
+        xr = x.clone().to(dt).requires_grad_(True)
+        yr = port_models.forward("resunet", sd_r, xr, training=True, **CFG1)
+        (yr * gy.to(dt)).sum().backward()
+        return yr.detach(), xr.grad, {k: v.grad for k, v in sd_r.items() if getattr(v, "grad", None) is not None}
+
+    yr, gxr, gwr = oracle(torch.float32)
+    names = [n for n, _ in m.named_parameters()]
+    flat_ref = torch.cat([gwr[n].flatten() for n in names])
+    scale = flat_ref.abs().max().item()
+    table = {}
+    try:
+        y64, gx64, gw64 = oracle(torch.float64)
+        f64 = torch.cat([gw64[n].flatten() for n in names])
+        table["aten_fp32_vs_fp64"] = {"y_max": nerr(yr.double(), y64), "y_l2": l2(yr.double(), y64),
+                                      "dW_max": (flat_ref.double() - f64).abs().max().item() / f64.abs().max().item(),
+                                      "dW_l2": l2(flat_ref.double(), f64), "dx_max": nerr(gxr.double(), gx64), "dx_l2": l2(gxr.double(), gx64)}
+    except Exception as e:      # the float64 pass is context, not a gate
+        table["aten_fp32_vs_fp64"] = {"error": repr(e)}
+    m = m.cuda()
+    for dtype in (torch.float32, torch.float16, torch.bfloat16):
+        m.set_engine(dtype=dtype)
+        m.zero_grad(set_to_none=True)
+        xc = x.cuda().requires_grad_(True)
+        y = m(xc)
+        (y * gy.cuda()).sum().backward()
+        torch.cuda.synchronize()
+        flat = torch.cat([p.grad.cpu().flatten() for _, p in m.named_parameters()])
+        row = {"y_max": nerr(y.detach().cpu(), yr), "y_l2": l2(y.detach().cpu(), yr),
+               "dW_max": (flat - flat_ref).abs().max().item() / scale, "dW_l2": l2(flat, flat_ref),
+               "dx_max": nerr(xc.grad.cpu(), gxr), "dx_l2": l2(xc.grad.cpu(), gxr)}
+        table[str(dtype).replace("torch.", "")] = row
+        print(f"\n[cfg1 resunet 128^3 x1 {dtype}] " + "  ".join(f"{k} {v:.2e}" for k, v in row.items()))
+    print("[cfg1 aten fp32 vs fp64] " + "  ".join(f"{k} {v:.2e}" if isinstance(v, float) else f"{k} {v}"
+                                                   for k, v in table["aten_fp32_vs_fp64"].items()))
+    try:
+        os.makedirs("gpurun_out", exist_ok=True)
+        with open("gpurun_out/parity_cfg1.json", "w") as f:
+            json.dump(table, f, indent=1)
+    except OSError:
+        pass
+    for dtype, (by, bw, bx) in CFG1_BOUNDS.items():
+        row = table[str(dtype).replace("torch.", "")]
+        key = "max" if dtype == torch.float32 else "l2"
+        assert row["y_" + key] < by and row["dW_" + key] < bw and row["dx_" + key] < bx, (dtype, row)

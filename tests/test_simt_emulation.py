@@ -6,6 +6,8 @@ against straightforward loops / textbook formulas in double precision:
 
 * the coalesced pointwise convolutions (fprop / dgrad / wgrad of the 1-2 channel layers) and the compile-time-window max-pool;
 * the radix-select histogram of the percentile clipping;
+* the three spline overlap-add kernels (plain, cover-mask, slot) against the reference's scatter loop written out in C++, bit for
+  bit, on grids with padding, non-monotone starts, triple overlaps, two channels and z slabs;
 * the weight pack / unpack kernels against independent statements of their layouts, and the one-launch batched pack kernel
   (``pack_batch.cuh``) against them;
 * the loss kernels (BCE with logits, soft-max cross-entropy, Noise2Void masked MSE: sums and gradients) and the fused AdamW / Adam / SGD (+ Nesterov) kernels, by-value and device-hyper-parameter forms, against the torch.optim update rules in double precision;
@@ -33,6 +35,7 @@ KERNELS = {
                "norm_act_bwd_apply_rows_kernel", "adamw_kernel", "adam_kernel", "sgd_kernel", "optim_prepare_kernel",
                "optim_dev_kernel", "bce_logits_kernel", "n2v_mse_kernel", "softmax_ce_kernel"],
     "ends.cu": ["select_hist_kernel"],
+    "stitch.cu": ["overlap_add_kernel", "overlap_add_cover_kernel", "overlap_add_slot_kernel"],
     "conv_umma.cu": ["pack_weight_xfold_kernel", "pack_convT_weight_kernel", "unpack_convT_wgrad_kernel"],
 }
 # helper definitions that sit right above a kernel and are cut out together with it
@@ -40,6 +43,7 @@ PREAMBLE = {
     "select_hist_kernel": "template <typename S> __device__ __forceinline__ uint32_t select_key",
     "pack_weight_xfold_kernel": "__host__ __device__ inline bool xfold_geom",
     "bce_logits_kernel": "__device__ __forceinline__ void block_atomic_add",
+    "overlap_add_kernel": "struct MergeParams {",
 }
 
 
@@ -96,7 +100,7 @@ def test_simt_kernels_on_the_host_emulator(tmp_path):
                 a = src.index(PREAMBLE[n])
                 body = src[a:src.index(body)] + body
             # dynamic shared memory: `extern __shared__ T name[];` -> the emulator's per-block buffer
-            body = re.sub(r"extern __shared__ (\w+) (\w+)\[\];", r"\1* \2 = reinterpret_cast<\1*>(g_ctx->dyn_smem);", body)
+            body = re.sub(r"extern __shared__ ([\w ]+?) (\w+)\[\];", r"\1* \2 = reinterpret_cast<\1*>(g_ctx->dyn_smem);", body)
             parts.append(f"// ---- {fname}: {n}\n" + body)
     # the batched pack kernel is held to the single-job kernels it replaces inside a training pass
     with open(os.path.join(CSRC, "pack_batch.cuh")) as f:
@@ -104,7 +108,7 @@ def test_simt_kernels_on_the_host_emulator(tmp_path):
     parts.append("// ---- pack_batch.cuh\n" + staged[staged.index("enum PackKind"):])
     with open(os.path.join(CSRC, "norm_fast.cuh")) as f:
         staged = f.read()
-    staged = re.sub(r"extern __shared__ (\w+) (\w+)\[\];", r"\1* \2 = reinterpret_cast<\1*>(g_ctx->dyn_smem);", staged)
+    staged = re.sub(r"extern __shared__ ([\w ]+?) (\w+)\[\];", r"\1* \2 = reinterpret_cast<\1*>(g_ctx->dyn_smem);", staged)
     parts.append("// ---- norm_fast.cuh\n" + staged[staged.index("__device__ __forceinline__ float tanh_approx"):])
     (tmp_path / "kernels.inc").write_text("\n\n".join(parts) + "\n")
     exe = tmp_path / "simt_emu"
