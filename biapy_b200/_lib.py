@@ -55,6 +55,8 @@ SIGNATURES = {
     "b200_axis_start": (_L, [C.POINTER(AxisPlan), _L, _I]),
     "b200_spline_window_1d": (_I, [_L, _L, C.POINTER(_F)]),
     "b200_crop_gather": (_I, [_P, _I, _L, _L, _L, _L, _P, _L, _L, _L, _P, _L, _P, _L, _P, _L, _L, _L, _L, _I, _P]),
+    "b200_crop_gather_range": (_I, [_P, _I, _L, _L, _L, _L, _P, _L, _L, _L, _P, _L, _P, _L, _P, _L, _L, _L, _L, _I, _L, _L, _L, _L,
+                                    _P]),
     "b200_overlap_add": (_I, [_P, _I, _P, _I, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _P, _L, _P, _L, _P, _L,
                               _P, _P, _P, _P]),
     "b200_overlap_add_slab": (_I, [_P, _I, _P, _I, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _P, _L, _P, _L, _P, _L,

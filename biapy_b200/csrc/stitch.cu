@@ -125,6 +125,7 @@ __device__ __forceinline__ int64_t pad_src(int64_t j, int64_t dim, int mode) {
 struct CropParams {
   int64_t D, H, W, C, pd, ph, pw, nz, ny, nx, pad_z, pad_y, pad_x, total;
   int mode;
+  int64_t src_z0, src_nz;      // src holds the planes [src_z0, src_z0 + src_nz) of the D-plane volume
 };
 
 constexpr int kMaxAxisPatches = 1024;
@@ -133,16 +134,20 @@ constexpr int kMaxAxisPatches = 1024;
 template <typename U>
 __global__ void crop_gather_kernel(const U* __restrict__ src, U* __restrict__ dst, CropParams p,
                                    const int64_t* __restrict__ sz, const int64_t* __restrict__ sy,
-                                   const int64_t* __restrict__ sx) {
-  const int patch = blockIdx.z;
+                                   const int64_t* __restrict__ sx, int first) {
+  const int patch = first + blockIdx.z;               // grid index of the patch; dst holds patches [first, first + gridDim.z)
   const int lz = blockIdx.y;
   const int ix = patch % (int)p.nx;
   const int iy = (patch / (int)p.nx) % (int)p.ny;
   const int iz = patch / (int)(p.nx * p.ny);
-  const int64_t z = pad_src(sz[iz] + lz - p.pad_z, p.D, p.mode);
+  int64_t z = pad_src(sz[iz] + lz - p.pad_z, p.D, p.mode);
+  if (z >= 0) {
+    z -= p.src_z0;
+    if (z < 0 || z >= p.src_nz) z = -1;               // outside the shard the caller uploaded: never for planes_needed()
+  }
   const int64_t y0 = sy[iy] - p.pad_y, x0 = sx[ix] - p.pad_x;
   const int plane = (int)(p.ph * p.pw * p.C);
-  U* out = dst + ((int64_t)patch * p.pd + lz) * plane;
+  U* out = dst + ((int64_t)blockIdx.z * p.pd + lz) * plane;
   const int C = (int)p.C, pw = (int)p.pw;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += gridDim.x * blockDim.x) {
     const int ch = i % C;
@@ -158,36 +163,60 @@ __global__ void crop_gather_kernel(const U* __restrict__ src, U* __restrict__ ds
 
 }  // namespace b200
 
+static int crop_gather_impl(const void* src, int32_t dtype, int64_t D, int64_t H, int64_t W, int64_t C,
+                            void* dst, int64_t pd, int64_t ph, int64_t pw,
+                            const int64_t* starts_z, int64_t nz, const int64_t* starts_y, int64_t ny,
+                            const int64_t* starts_x, int64_t nx,
+                            int64_t pad_z, int64_t pad_y, int64_t pad_x, int32_t pad_mode, int64_t first, int64_t count,
+                            int64_t src_z0, int64_t src_nz, void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(src && dst && starts_z && starts_y && starts_x, "crop_gather: null pointer");
+  B200_CHECK_ARG(src_z0 >= 0 && src_nz > 0 && src_z0 + src_nz <= D, "crop_gather: source planes [%lld, %lld) outside the volume",
+                 (long long)src_z0, (long long)(src_z0 + src_nz));
+  B200_CHECK_ARG(valid_dtype(dtype) || dtype == 3, "crop_gather: bad dtype");
+  B200_CHECK_ARG(nz > 0 && ny > 0 && nx > 0 && nz <= kMaxAxisPatches && ny <= kMaxAxisPatches && nx <= kMaxAxisPatches,
+                 "crop_gather: patches per axis must be in [1, %d]", kMaxAxisPatches);
+  B200_CHECK_ARG(pad_mode >= 0 && pad_mode <= 4, "crop_gather: bad pad mode");
+  B200_CHECK_ARG(first >= 0 && count > 0 && first + count <= nz * ny * nx, "crop_gather: patch range [%lld, %lld) outside the grid of %lld",
+                 (long long)first, (long long)(first + count), (long long)(nz * ny * nx));
+  cudaStream_t st = (cudaStream_t)stream;
+  CropParams p{D, H, W, C, pd, ph, pw, nz, ny, nx, pad_z, pad_y, pad_x, count * pd * ph * pw * C, pad_mode, src_z0, src_nz};
+  int threads = 256;
+  B200_CHECK_ARG(ph * pw * C < (1LL << 30) && nz * ny * nx <= 65535 * 32 && pd <= 65535, "crop_gather: patch too large");
+  int64_t bx = ceil_div(ph * pw * C, threads);
+  if (bx > 64) bx = 64;
+  B200_CHECK_ARG(count <= 65535, "crop_gather: more than 65535 patches per call");
+  dim3 blocks((unsigned)bx, (unsigned)pd, (unsigned)count);
+  if (dtype == 3)
+    crop_gather_kernel<uint8_t><<<blocks, threads, 0, st>>>((const uint8_t*)src, (uint8_t*)dst, p,
+                                                                     starts_z, starts_y, starts_x, (int)first);
+  else if (dtype == B200_F32)
+    crop_gather_kernel<uint32_t><<<blocks, threads, 0, st>>>((const uint32_t*)src, (uint32_t*)dst, p,
+                                                                      starts_z, starts_y, starts_x, (int)first);
+  else
+    crop_gather_kernel<uint16_t><<<blocks, threads, 0, st>>>((const uint16_t*)src, (uint16_t*)dst, p,
+                                                                      starts_z, starts_y, starts_x, (int)first);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
 B200_EXPORT int b200_crop_gather(const void* src, int32_t dtype, int64_t D, int64_t H, int64_t W, int64_t C,
                                  void* dst, int64_t pd, int64_t ph, int64_t pw,
                                  const int64_t* starts_z, int64_t nz, const int64_t* starts_y, int64_t ny,
                                  const int64_t* starts_x, int64_t nx,
                                  int64_t pad_z, int64_t pad_y, int64_t pad_x, int32_t pad_mode, void* stream) {
-  using namespace b200;
-  B200_CHECK_ARG(src && dst && starts_z && starts_y && starts_x, "crop_gather: null pointer");
-  B200_CHECK_ARG(valid_dtype(dtype) || dtype == 3, "crop_gather: bad dtype");
-  B200_CHECK_ARG(nz > 0 && ny > 0 && nx > 0 && nz <= kMaxAxisPatches && ny <= kMaxAxisPatches && nx <= kMaxAxisPatches,
-                 "crop_gather: patches per axis must be in [1, %d]", kMaxAxisPatches);
-  B200_CHECK_ARG(pad_mode >= 0 && pad_mode <= 4, "crop_gather: bad pad mode");
-  cudaStream_t st = (cudaStream_t)stream;
-  CropParams p{D, H, W, C, pd, ph, pw, nz, ny, nx, pad_z, pad_y, pad_x, nz * ny * nx * pd * ph * pw * C, pad_mode};
-  int threads = 256;
-  B200_CHECK_ARG(ph * pw * C < (1LL << 30) && nz * ny * nx <= 65535 * 32 && pd <= 65535, "crop_gather: patch too large");
-  int64_t bx = ceil_div(ph * pw * C, threads);
-  if (bx > 64) bx = 64;
-  B200_CHECK_ARG(nz * ny * nx <= 65535, "crop_gather: more than 65535 patches per call");
-  dim3 blocks((unsigned)bx, (unsigned)pd, (unsigned)(nz * ny * nx));
-  if (dtype == 3)
-    crop_gather_kernel<uint8_t><<<blocks, threads, 0, st>>>((const uint8_t*)src, (uint8_t*)dst, p,
-                                                                     starts_z, starts_y, starts_x);
-  else if (dtype == B200_F32)
-    crop_gather_kernel<uint32_t><<<blocks, threads, 0, st>>>((const uint32_t*)src, (uint32_t*)dst, p,
-                                                                      starts_z, starts_y, starts_x);
-  else
-    crop_gather_kernel<uint16_t><<<blocks, threads, 0, st>>>((const uint16_t*)src, (uint16_t*)dst, p,
-                                                                      starts_z, starts_y, starts_x);
-  B200_LAUNCH_CHECK();
-  return B200_OK;
+  return crop_gather_impl(src, dtype, D, H, W, C, dst, pd, ph, pw, starts_z, nz, starts_y, ny, starts_x, nx, pad_z, pad_y, pad_x,
+                          pad_mode, 0, nz * ny * nx, 0, D, stream);
+}
+
+B200_EXPORT int b200_crop_gather_range(const void* src, int32_t dtype, int64_t D, int64_t H, int64_t W, int64_t C,
+                                       void* dst, int64_t pd, int64_t ph, int64_t pw,
+                                       const int64_t* starts_z, int64_t nz, const int64_t* starts_y, int64_t ny,
+                                       const int64_t* starts_x, int64_t nx,
+                                       int64_t pad_z, int64_t pad_y, int64_t pad_x, int32_t pad_mode, int64_t first, int64_t count,
+                                       int64_t src_z0, int64_t src_nz, void* stream) {
+  return crop_gather_impl(src, dtype, D, H, W, C, dst, pd, ph, pw, starts_z, nz, starts_y, ny, starts_x, nx, pad_z, pad_y, pad_x,
+                          pad_mode, first, count, src_z0, src_nz, stream);
 }
 
 // ------------------------------------------------------------------------------------------ overlap-add

@@ -56,22 +56,75 @@ def _dev(a: np.ndarray, device):
     return torch.from_numpy(np.ascontiguousarray(a)).to(device)
 
 
-def crop_device(vol, patch: Sequence[int], starts: Sequence[np.ndarray], pads: Sequence[int], pad_mode: str):
-    """vol: CUDA tensor (D,H,W,C) dense.  Returns (n_patches, pd, ph, pw, C) on the same device."""
+class VolumeShard:
+    """The planes ``[z0, z0 + data.shape[0])`` of a ``depth``-plane volume ``(Z, Y, X, C)``: what one rank of the sharded
+    sliding-window inference reads from disk / uploads (``planes_needed`` tells which)."""
+
+    def __init__(self, data, z0: int, depth: int):
+        self.data, self.z0, self.depth = data, int(z0), int(depth)
+        if not (0 <= self.z0 and self.z0 + data.shape[0] <= self.depth):
+            raise ValueError(f"shard planes [{self.z0}, {self.z0 + data.shape[0]}) outside a volume of {self.depth} planes")
+
+    @property
+    def shape(self):
+        return (self.depth,) + tuple(self.data.shape[1:])
+
+
+def _pad_src(j: np.ndarray, dim: int, mode: str) -> np.ndarray:
+    """numpy.pad source coordinate for (possibly out-of-range) coordinates j; -1 = constant fill.  Host twin of `pad_src`."""
+    j = np.asarray(j, dtype=np.int64)
+    inside = (j >= 0) & (j < dim)
+    if mode in ("zeros", "constant"):
+        return np.where(inside, j, -1)
+    if mode == "edge":
+        return np.clip(j, 0, dim - 1)
+    if mode == "reflect":
+        if dim == 1:
+            return np.zeros_like(j)
+        m = np.mod(j, 2 * (dim - 1))
+        return np.where(inside, j, np.where(m < dim, m, 2 * (dim - 1) - m))
+    if mode == "symmetric":
+        m = np.mod(j, 2 * dim)
+        return np.where(inside, j, np.where(m < dim, m, 2 * dim - 1 - m))
+    return np.where(inside, j, np.mod(j, dim))          # wrap
+
+
+def planes_needed(depth: int, patch_z: int, pad_z: int, starts_z_crop: np.ndarray, n_yx: int, patch_range, pad_mode: str):
+    """[z0, z1) of the volume planes the patches `patch_range` = (first, end) read, padding mode included."""
+    first, end = patch_range
+    if end <= first:
+        return 0, 1
+    rows = range(first // n_yx, (end - 1) // n_yx + 1)
+    z = np.concatenate([_pad_src(int(starts_z_crop[iz]) - pad_z + np.arange(patch_z), depth, pad_mode) for iz in rows])
+    z = z[z >= 0]
+    return (int(z.min()), int(z.max()) + 1) if z.size else (0, 1)
+
+
+def crop_device(vol, patch: Sequence[int], starts: Sequence[np.ndarray], pads: Sequence[int], pad_mode: str, patch_range=None):
+    """vol: CUDA tensor (D,H,W,C) dense, or a :class:`VolumeShard` of one.  Returns (n_patches, pd, ph, pw, C) on the same
+    device; with `patch_range = (first, end)` only those patches of the grid (C order over (z,y,x)), as (end - first, ...)."""
     import torch
+    src_z0 = 0
+    depth = None
+    if isinstance(vol, VolumeShard):
+        src_z0, depth, vol = vol.z0, vol.depth, vol.data
     _lib.require_cuda(vol, "crop input")
     vol = vol.contiguous()
-    D, H, W, Cc = vol.shape
+    src_nz, H, W, Cc = vol.shape
+    D = src_nz if depth is None else depth
     pd, ph, pw = (int(p) for p in patch)
     if pad_mode not in _lib.PAD_MODE:
         raise ValueError(f"unsupported pad_type {pad_mode!r}")
     n = len(starts[0]) * len(starts[1]) * len(starts[2])
-    out = torch.empty((n, pd, ph, pw, Cc), dtype=vol.dtype, device=vol.device)
+    first, end = (0, n) if patch_range is None else (int(patch_range[0]), int(patch_range[1]))
+    out = torch.empty((end - first, pd, ph, pw, Cc), dtype=vol.dtype, device=vol.device)
+    if end == first:
+        return out
     tabs = [_dev(s, vol.device) for s in starts]
-    _lib.call("b200_crop_gather", vol.data_ptr(), _lib.torch_dtype_code(vol.dtype), D, H, W, Cc, out.data_ptr(),
+    _lib.call("b200_crop_gather_range", vol.data_ptr(), _lib.torch_dtype_code(vol.dtype), D, H, W, Cc, out.data_ptr(),
               pd, ph, pw, tabs[0].data_ptr(), len(starts[0]), tabs[1].data_ptr(), len(starts[1]),
               tabs[2].data_ptr(), len(starts[2]), int(pads[0]), int(pads[1]), int(pads[2]),
-              _lib.PAD_MODE[pad_mode], _lib.stream_ptr())
+              _lib.PAD_MODE[pad_mode], first, end - first, src_z0, src_nz, _lib.stream_ptr())
     return out
 
 

@@ -2,9 +2,11 @@
 
 * training: ONE all-reduce of the flat fp32 gradient buffer per step (NCCL over NVLink on the GPU box; the same code
   runs on ``gloo`` for the CPU tests) -- replaces DDP's bucketed hooks (``biapy/engine/base_workflow.py:951-958``);
-* inference: patches are dealt round-robin to ranks, as the reference's by-chunks generator deals tiles
-  (``biapy/data/generators/chunked_test_pair_data_generator.py:613-618``), and the per-rank predictions are
-  all-gathered once before the merge.
+* blended sliding-window inference: every rank predicts a contiguous range of the patch grid and OWNS one z slab of
+  the output volume; the only traffic is the z-pieces of patch predictions that reach into another rank's slab (point-to-point
+  over NVLink, contiguous chunks, no packing), after which each rank runs the bit-exact overlap-add on its slab alone;
+* by-chunks inference: tiles are dealt round-robin to ranks exactly as the reference's generator deals them
+  (``biapy/data/generators/chunked_test_pair_data_generator.py:613-618``).
 """
 from __future__ import annotations
 
@@ -28,9 +30,56 @@ def allreduce_mean_(flat: torch.Tensor, group=None) -> float:
     return 1.0 / world
 
 
-def deal_patches(n_patches: int, rank: int, world: int) -> List[int]:
-    """Indices of the patches rank `rank` predicts (round-robin, every patch exactly once across ranks)."""
-    return list(range(rank, n_patches, world))
+def deal_patch_range(n_patches: int, rank: int, world: int):
+    """[first, end) of the patches rank `rank` predicts: contiguous in the grid's C order over (z, y, x), so a rank's patches sit
+    in one or two z rows -- next to the output slab it owns."""
+    return (n_patches * rank) // world, (n_patches * (rank + 1)) // world
+
+
+def slab_range(depth: int, rank: int, world: int):
+    """[z0, z1) of the output planes rank `rank` owns."""
+    return (depth * rank) // world, (depth * (rank + 1)) // world
+
+
+def plan_slab_exchange(starts_z, n_yx: int, core_z: int, pad_z: int, depth: int, world: int):
+    """Who sends which z-piece of which patch prediction to whom.  `starts_z`: merge-frame z start of every z row of the grid
+    (``Axis.starts(1)``), `n_yx`: patches per z row, `core_z` = patch depth - 2 * pad.  Returns a list of
+    ``(patch, src_rank, dst_rank, a0, a1)``: planes ``[a0, a1)`` of the patch ARRAY (pad border included) cover output planes of
+    `dst_rank`'s slab.  Deterministic and identical on every rank; pieces whose src == dst are left out (already in place)."""
+    n = len(starts_z) * n_yx
+    ops = []
+    owners = [0] * n
+    for r in range(world):
+        lo, hi = deal_patch_range(n, r, world)
+        for c in range(lo, hi):
+            owners[c] = r
+    for iz, s in enumerate(starts_z):
+        s = int(s)
+        for d in range(world):
+            z0, z1 = slab_range(depth, d, world)
+            l0, l1 = max(0, z0 - s), min(core_z, z1 - s)
+            if l1 <= l0:
+                continue
+            for c in range(iz * n_yx, (iz + 1) * n_yx):
+                if owners[c] != d:
+                    ops.append((c, owners[c], d, l0 + pad_z, l1 + pad_z))
+    return ops
+
+
+def exchange_patch_slabs(pred_all: torch.Tensor, plan, rank: int, group=None) -> int:
+    """Run the point-to-point plan on `pred_all` (n_patches, pz, py, px, C): a piece is a contiguous chunk on both sides, sent from
+    the predicting rank's array straight into the same place of the slab owner's array.  Returns the bytes this rank received."""
+    p2p, got = [], 0
+    for c, src, dst, a0, a1 in plan:
+        if src == rank:
+            p2p.append(dist.P2POp(dist.isend, pred_all[c, a0:a1], dst if group is None else dist.get_global_rank(group, dst), group))
+        elif dst == rank:
+            p2p.append(dist.P2POp(dist.irecv, pred_all[c, a0:a1], src if group is None else dist.get_global_rank(group, src), group))
+            got += pred_all[c, a0:a1].numel() * pred_all.element_size()
+    if p2p:
+        for w in dist.batch_isend_irecv(p2p):
+            w.wait()
+    return got
 
 
 def deal_tiles(n_tiles: int, rank: int, world: int, num_workers: int = 1, worker_id: int = 0, drop_repeats: bool = False) -> List[int]:
@@ -51,23 +100,3 @@ def deal_tiles(n_tiles: int, rank: int, world: int, num_workers: int = 1, worker
     if drop_repeats:      # the wrapped-around tail only evens out the replicas; its tiles already belong to an earlier position
         return [idx[p] for p in range(r, n_tiles, replicas)]
     return idx[r:total:replicas]
-
-
-def gather_patch_predictions(pred: torch.Tensor, n_patches: int, group=None) -> torch.Tensor:
-    """`pred` (n_patches, ...) holds valid rows only for this rank's dealt patches; after the call every rank holds
-    all rows.  One all_gather of ceil(n/world) rows per rank."""
-    rank, world = world_info(group)
-    if world == 1:
-        return pred
-    per = (n_patches + world - 1) // world
-    mine = deal_patches(n_patches, rank, world)
-    send = torch.zeros((per,) + tuple(pred.shape[1:]), dtype=pred.dtype, device=pred.device)
-    if mine:
-        send[: len(mine)] = pred[mine]
-    gathered = [torch.empty_like(send) for _ in range(world)]
-    dist.all_gather(gathered, send, group=group)
-    for r in range(world):
-        ids = deal_patches(n_patches, r, world)
-        if ids:
-            pred[ids] = gathered[r][: len(ids)]
-    return pred

@@ -79,6 +79,16 @@ int b200_crop_gather(const void* src, int32_t dtype, int64_t D, int64_t H, int64
                      const int64_t* starts_x, int64_t nx,
                      int64_t pad_z, int64_t pad_y, int64_t pad_x, int32_t pad_mode, void* stream);
 
+/* Only the patches [first, first + count) of the grid (C order over (z,y,x)); dst: (count, pd, ph, pw, C).  A rank of the
+ * sharded sliding-window inference crops just the patches it predicts, and `src` may hold just the planes
+ * [src_z0, src_z0 + src_nz) of the D-plane volume (what that rank read / uploaded). */
+int b200_crop_gather_range(const void* src, int32_t dtype, int64_t D, int64_t H, int64_t W, int64_t C,
+                           void* dst, int64_t pd, int64_t ph, int64_t pw,
+                           const int64_t* starts_z, int64_t nz, const int64_t* starts_y, int64_t ny,
+                           const int64_t* starts_x, int64_t nx,
+                           int64_t pad_z, int64_t pad_y, int64_t pad_x, int32_t pad_mode, int64_t first, int64_t count,
+                           int64_t src_z0, int64_t src_nz, void* stream);
+
 /* ------------------------------------------------------------------------ overlap-add merge (device gather)
  * Replaces the accumulate + normalise loop of merge_3D_data_with_overlap (data_3D_manipulation.py:822-849).
  * Gather formulation: one thread per output element walks the covering patches in increasing patch index

@@ -1,5 +1,6 @@
-"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: gradient all-reduce factor, patch dealing and the
-prediction all-gather used by sliding-window inference, cross-rank loss statistics of the epoch loop."""
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: gradient all-reduce factor, patch-range dealing and the slab
+exchange of the sharded sliding-window inference (every rank ends with exactly the pieces its output slab needs), by-chunks tile
+dealing, cross-rank loss statistics of the epoch loop and of the validation pass."""
 import os
 import socket
 
@@ -27,20 +28,36 @@ def _worker(rank, world, port, q):
         g = torch.full((1000,), float(rank + 1))
         f = bd.allreduce_mean_(g)
         assert f == 1.0 / world and torch.allclose(g * f, torch.full((1000,), (1 + world) / 2.0))
-        # 2. patch dealing covers every patch exactly once
-        n = 27
-        mine = bd.deal_patches(n, rank, world)
-        counts = torch.zeros(n)
-        counts[mine] = 1
-        dist.all_reduce(counts)
-        assert torch.equal(counts, torch.ones(n))
-        # 3. prediction gather: every rank ends with all rows
-        pred = torch.zeros(n, 2, 3)
-        for i in mine:
-            pred[i] = float(i + 1)
-        out = bd.gather_patch_predictions(pred, n)
-        expect = torch.arange(1, n + 1, dtype=torch.float32).view(n, 1, 1).expand(n, 2, 3)
-        assert torch.equal(out, expect)
+        # 2. contiguous patch ranges cover every patch exactly once, for any world size
+        for w in (1, 2, 3, 8):
+            seen = []
+            for r in range(w):
+                a, b = bd.deal_patch_range(27, r, w)
+                seen += list(range(a, b))
+            assert seen == list(range(27))
+        # 3. sharded sliding-window merge: after the slab exchange the output slab a rank owns, merged from ITS array alone,
+        #    equals the same planes of the single-process merge bit for bit (patch pieces it never received stay NaN and
+        #    would poison the slab if the plan missed one).  Grid: 40 x 20 x 24 volume, 16^3 patches, 25 % overlap, padding 2.
+        import numpy as np
+        from biapy_b200.data import _stitch
+        from oracle import port_stitch
+        vshape, patch, ov, pad = (40, 20, 24, 1), (16, 16, 16), (0.25, 0.25, 0.25), (2, 0, 0)
+        axes = [_stitch.Axis(vshape[i], patch[i], pad[i], ov[i]) for i in range(3)]
+        starts_m = [a.starts(1) for a in axes]
+        n = len(starts_m[0]) * len(starts_m[1]) * len(starts_m[2])
+        truth = torch.from_numpy(np.random.default_rng(0).standard_normal((n,) + patch + (1,)).astype(np.float32))
+        ref = port_stitch.merge_3d(truth.numpy(), vshape, ov, pad)
+        first, end = bd.deal_patch_range(n, rank, world)
+        mine = torch.full_like(truth, float("nan"))
+        mine[first:end] = truth[first:end]
+        plan = bd.plan_slab_exchange(starts_m[0], len(starts_m[1]) * len(starts_m[2]), axes[0].core, pad[0], vshape[0], world)
+        got = bd.exchange_patch_slabs(mine, plan, rank)
+        assert got == sum((a1 - a0) * 16 * 16 * 4 for c, src, dst, a0, a1 in plan if dst == rank)
+        assert got < (n - (end - first)) * 16 ** 3 * 4                      # less than an all-gather would deliver
+        z0, z1 = bd.slab_range(vshape[0], rank, world)
+        with np.errstate(invalid="ignore"):
+            merged = port_stitch.merge_3d(mine.numpy(), vshape, ov, pad)
+        assert np.array_equal(merged[z0:z1], ref[z0:z1]) and not np.isnan(merged[z0:z1]).any()
         # 4. by-chunks tile dealing == torch's DistributedSampler(shuffle=False); disjoint writes + one all-reduce = full volume
         from torch.utils.data import DistributedSampler
         for n_tiles in (1, 2, 7, 48):
@@ -72,12 +89,28 @@ def _worker(rank, world, port, q):
             def train(self, flag=True):
                 pass
 
+            def eval(self):
+                pass
+
         cfg = load_config({"PROBLEM": {"NDIM": "2D"}, "DATA": {"PATCH_SIZE": (8, 8, 1)}})
         losses = [1.0, 2.0, 3.0] if rank == 0 else [10.0]                # ragged: 3 batches on rank 0, 1 on rank 1
         loader = [(torch.zeros(2, 8, 8, 1), torch.zeros(2, 8, 8, 1)) for _ in losses]
         with contextlib.redirect_stdout(io.StringIO()):
             stats, _ = train_one_epoch(cfg, FakeModel(), None, None, None, lambda t, b: t, loader, [FakeTrainer(losses)], "cpu", 0)
         assert abs(stats["loss"] - 16.0 / 4) < 1e-12, stats
+        # 6. ... and so does the validation pass (reference train_engine.py:318-321): every rank must hand the SAME loss to
+        #    ReduceLROnPlateau / EarlyStopping / the best-checkpoint test
+        from biapy_b200.engine.train_engine import evaluate
+
+        class FakeEval(FakeTrainer):
+            device = None
+
+            def evaluate(self, images, targets):
+                return self.step(images, targets)
+
+        with contextlib.redirect_stdout(io.StringIO()):
+            vstats = evaluate(cfg, FakeModel(), None, None, None, lambda t, b: t, 0, loader, optimizer=[FakeEval(losses)])
+        assert abs(vstats["loss"] - 16.0 / 4) < 1e-12, vstats
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))

@@ -100,3 +100,57 @@ def test_full_size_cfg3_properties():
     del ones
     a = merge_3D_data_with_overlap(patches * 2.0, (512, 512, 512, 1), overlap=(0.25,) * 3, verbose=False)
     assert (a - 2 * rt).abs().max().item() < 4e-6
+
+
+def test_patch_range_crop_shard_and_slab_merge_equal_the_full_calls():
+    """Building blocks of the sharded sliding-window inference: cropping a patch range (from the whole volume or from just the
+    planes `planes_needed` names) gives the same bytes as the rows of the full crop; merging z slabs of the output gives the same
+    bytes as the planes of the full merge, for every merge kernel variant the library holds."""
+    import torch
+    from biapy_b200.data import _stitch
+    g = torch.Generator().manual_seed(3)
+    vshape, patch, ov, pad = (45, 30, 34, 2), (16, 12, 16), (0.25, 0.5, 0.25), (2, 0, 3)
+    vol = torch.randn(vshape, generator=g).cuda()
+    axes = [_stitch.Axis(vshape[i], patch[i], pad[i], ov[i]) for i in range(3)]
+    starts_c, starts_m, wins = [a.starts(0) for a in axes], [a.starts(1) for a in axes], [a.window() for a in axes]
+    full = _stitch.crop_device(vol, patch, starts_c, pad, "reflect")
+    n, n_yx = full.shape[0], axes[1].n * axes[2].n
+    for first, end in ((0, n), (3, 11), (n - 5, n), (7, 8)):
+        part = _stitch.crop_device(vol, patch, starts_c, pad, "reflect", patch_range=(first, end))
+        assert torch.equal(part, full[first:end])
+        z0, z1 = _stitch.planes_needed(vshape[0], patch[0], pad[0], starts_c[0], n_yx, (first, end), "reflect")
+        shard = _stitch.VolumeShard(vol[z0:z1].contiguous(), z0, vshape[0])
+        assert torch.equal(_stitch.crop_device(shard, patch, starts_c, pad, "reflect", patch_range=(first, end)), full[first:end])
+    pred = torch.randn(full.shape[:4] + (1,), generator=g).cuda()
+    ref = _stitch.merge_device(pred, vshape[:3], starts_m, wins, pad)
+    for z0, z1 in ((0, 45), (0, 7), (7, 29), (44, 45)):
+        slab = _stitch.merge_device(pred, vshape[:3], starts_m, wins, pad, z_range=(z0, z1))
+        assert torch.equal(slab, ref[z0:z1])
+    # fp16 predictions -> fp32 volume, the cheaper exchange format of the sharded path
+    ref16 = _stitch.merge_device(pred.half(), vshape[:3], starts_m, wins, pad, out_dtype=torch.float32)
+    assert torch.equal(_stitch.merge_device(pred.half(), vshape[:3], starts_m, wins, pad, out_dtype=torch.float32, z_range=(5, 20)), ref16[5:20])
+
+
+@pytest.mark.parametrize("variant", ["slot", "cover", "plain"])
+def test_merge_kernel_variants_bit_identical(variant):
+    """The three overlap-add kernels (B200_MERGE_KERNEL) against the numpy oracle on a grid with padding and a 50 % overlap axis
+    (three covering patches: the slot kernel's mask-walk branch).  The variant is read once per process, so each runs in a child."""
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, torch, sys\n"
+        "sys.path.insert(0, '.')\n"
+        "from biapy_b200.data.data_3D_manipulation import merge_3D_data_with_overlap\n"
+        "from oracle import port_stitch\n"
+        "rng = np.random.default_rng(5)\n"
+        "for shape, patch, ov, pad in (((40, 36, 44, 1), (16, 16, 16), (0.25, 0.25, 0.25), (0, 0, 0)),\n"
+        "                              ((33, 20, 50, 2), (12, 8, 16), (0.5, 0.25, 0.6), (1, 0, 2))):\n"
+        "    n = port_stitch.crop_3d(np.zeros(shape, np.float32), patch + (shape[-1],), ov, pad)[0].shape[0]\n"
+        "    pred = rng.standard_normal((n,) + patch + (shape[-1],)).astype(np.float32)\n"
+        "    got = merge_3D_data_with_overlap(pred, shape, overlap=ov, padding=pad, verbose=False)\n"
+        "    assert np.array_equal(got, port_stitch.merge_3d(pred, shape, ov, pad)), shape\n"
+        "print('OK')\n")
+    env = dict(os.environ, B200_MERGE_KERNEL=variant)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

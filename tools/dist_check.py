@@ -65,7 +65,9 @@ torch.cuda.synchronize()
 err = ((grad_dp - tr1.fp.grad).norm() / tr1.fp.grad.norm()).item()
 say(f"training: data-parallel gradient vs single process on the concatenated batch: rel-L2 {err:.2e}")
 ok &= err < 1e-5
-m2 = build(ResUNet, 0, **KW).cuda().set_engine(dtype=torch.bfloat16)
+# per-rank seeds, as the reference initialises its replicas (misc.set_seed: SEED + rank): the Trainer must start every rank from
+# rank 0's parameters the way DistributedDataParallel does at construction
+m2 = build(ResUNet, 10 + rank, **KW).cuda().set_engine(dtype=torch.bfloat16)
 tr2 = Trainer(m2, loss="bce", optimizer="adamw", lr=1e-3, weight_decay=0.02)
 for _ in range(3):
     loss = tr2.step(xs[rank].numpy(), ts[rank].numpy())
@@ -74,7 +76,7 @@ lo, hi = flat.clone(), flat.clone()
 dist.all_reduce(lo, op=dist.ReduceOp.MIN)
 dist.all_reduce(hi, op=dist.ReduceOp.MAX)
 same = bool(torch.equal(lo, hi))
-say(f"training: 3 AdamW steps (bf16 engine), parameters identical on all {world} ranks: {same}; loss {loss.item():.4f}")
+say(f"training: replicas built from seeds 10 + rank, 3 AdamW steps (bf16 engine), parameters identical on all {world} ranks: {same}; loss {loss.item():.4f}")
 ok &= same
 
 # ---- 2. SyncBatchNorm --------------------------------------------------------------------------------------------
@@ -104,6 +106,24 @@ many = predict_volume(mi, vol, patch, overlap=ov, padding=pad, batch_size=3, hea
 eq = torch.tensor([float(np.array_equal(one, many))], device="cuda")
 dist.all_reduce(eq, op=dist.ReduceOp.MIN)
 say(f"predict_volume: world={world} result bit-identical to world=1 on every rank: {bool(eq.item())}")
+ok &= bool(eq.item())
+# the volume left sharded, every rank fed only the planes its patches read (what a by-chunks reader would load)
+from biapy_b200.data import _stitch
+from biapy_b200.engine.inference import shard_planes
+a, b = shard_planes(vol.shape, patch, ov, pad, "reflect", rank, world)
+st = {}
+slab, (z0, z1) = predict_volume(mi, _stitch.VolumeShard(vol[a:b], a, vol.shape[0]), patch, overlap=ov, padding=pad, batch_size=3,
+                                head_activations=["ce_sigmoid"], rank=rank, world=world, gather="none", stats=st)
+eq = torch.tensor([float(np.array_equal(one[z0:z1], slab))], device="cuda")
+dist.all_reduce(eq, op=dist.ReduceOp.MIN)
+say(f"predict_volume(gather='none') from volume shards [{a},{b}) of {vol.shape[0]} planes: slab [{z0},{z1}) bit-identical: "
+    f"{bool(eq.item())}; rank 0 received {st.get('exchange_bytes_received')} bytes of patch pieces")
+ok &= bool(eq.item())
+r0 = predict_volume(mi, vol, patch, overlap=ov, padding=pad, batch_size=3, head_activations=["ce_sigmoid"], rank=rank, world=world,
+                    gather="rank0")
+eq = torch.tensor([float((r0 is None) if rank else np.array_equal(one, r0))], device="cuda")
+dist.all_reduce(eq, op=dist.ReduceOp.MIN)
+say(f"predict_volume(gather='rank0'): full volume on rank 0 only, bit-identical: {bool(eq.item())}")
 ok &= bool(eq.item())
 one = predict_by_chunks(mi, vol, patch, padding=(4, 4, 4), batch_size=3, head_activations=["ce_sigmoid"])
 many = predict_by_chunks(mi, vol, patch, padding=(4, 4, 4), batch_size=3, head_activations=["ce_sigmoid"], rank=rank, world=world)
