@@ -25,15 +25,16 @@ class _LaggedLoss:
     """Device loss -> host float without a stream synchronisation: copy into pinned memory, record an event, read it when the
     next iteration has been queued."""
 
+    _POOL: List = []           # pinned one-element buffers, reused across epochs (cudaHostAlloc per step would cost ~0.1 ms)
+
     def __init__(self):
         self.pending = []      # [(pinned tensor, event | None)]
         self.values: List[float] = []
 
     def push(self, loss) -> None:
         if isinstance(loss, torch.Tensor) and loss.is_cuda:
-            host = torch.empty(loss.numel(), dtype=loss.dtype, pin_memory=True)
-            host.copy_(loss.detach().reshape(-1), non_blocking=True)
-            ev = torch.cuda.Event()
+            host, ev = self._POOL.pop() if self._POOL else (torch.empty(1, dtype=torch.float64, pin_memory=True), torch.cuda.Event())
+            host.copy_(loss.detach().reshape(-1)[:1], non_blocking=True)
             ev.record(torch.cuda.current_stream(loss.device))
             self.pending.append((host, ev))
         else:
@@ -46,6 +47,8 @@ class _LaggedLoss:
             if ev is not None:
                 ev.synchronize()
             v = float(host[0])
+            if ev is not None:
+                self._POOL.append((host, ev))
             if not math.isfinite(v):
                 print("Loss is {}, stopping training".format(v))
                 sys.exit(1)

@@ -41,6 +41,16 @@ class _NetFn(torch.autograd.Function):
         tape: Tape = ctx.tape
         if tape is None:
             raise RuntimeError("biapy_b200: backward called twice on the same forward (activations were freed)")
+        # fp16 engine: the gradient of a mean-reduced loss is ~1/numel per element, below fp16's normal range at patch sizes.  It is
+        # propagated times the power of two that brings its largest element to ~1 and divided out of the (fp32) results -- what
+        # torch.amp.GradScaler does for autocast models, chosen from the data because this autograd-compatibility path cannot know
+        # the loss (one scalar read; the Trainer scales inside its loss kernel instead and never synchronises).
+        scale = 1.0
+        if tape.dtype == torch.float16:
+            amax = max((float(g.abs().max()) for g in grads if g is not None), default=0.0)
+            if amax > 0.0 and amax == amax and amax != float("inf"):
+                import math
+                scale = 2.0 ** (-math.ceil(math.log2(amax)))
         for tt, g in zip(ctx.out_tts, grads):
             if g is None:
                 tt.grad().zero_()
@@ -50,6 +60,8 @@ class _NetFn(torch.autograd.Function):
                 gcl = g.permute(0, 2, 3, 4, 1)
                 if gcl.dtype != torch.float32 or not gcl.is_contiguous():
                     gcl = gcl.float().contiguous()
+                if scale != 1.0:
+                    gcl = gcl * scale
                 ops.convert(gcl, tt.grad())
             tt.mark_written()
         tape.backward()
@@ -57,10 +69,14 @@ class _NetFn(torch.autograd.Function):
         if ctx.x_tt.requires_grad:
             gx32 = torch.empty(ctx.x_tt.shape, dtype=torch.float32, device=ctx.x_tt.data.device)
             ops.convert(ctx.x_tt.grad(), gx32)
+            if scale != 1.0:
+                gx32.mul_(1.0 / scale)
             gx = gx32.permute(0, 4, 1, 2, 3)
             if ctx.ndim == 2:
                 gx = gx.squeeze(2)
         pg = tuple(tape.param_grads.get(p) if p.requires_grad else None for p in ctx.params)
+        if scale != 1.0:
+            torch._foreach_mul_([g for g in pg if g is not None], 1.0 / scale)
         ctx.tape = None
         return (None, gx) + pg
 
