@@ -66,6 +66,7 @@ SIGNATURES = {
     "b200_chunk_extract": (_I, [_P, _I, _L, _L, _L, _L, _P, _L, _L, _L, _L, _P, _P]),
     "b200_chunk_insert": (_I, [_P, _I, _L, _L, _L, _L, _L, _P, _I, _L, _L, _L, _P, _I, _P]),
     "b200_image_stats": (_I, [_P, _I, _L, _I, C.POINTER(_F), _P, _P]),
+    "b200_edge_hist": (_I, [_P, _L, _P, _I, _P, _P]),
     "b200_select_hist": (_I, [_P, _I, _L, _I, _I, _I, _I, C.c_uint32, _I, _P, _P]),
     "b200_image_norm_apply": (_I, [_P, _I, _L, _I, C.POINTER(_F), _P, _P]),
     "b200_image_denorm_apply": (_I, [_P, _L, _I, C.POINTER(_D), _P, _I, _P]),

@@ -159,6 +159,38 @@ __global__ void __launch_bounds__(256) select_hist_kernel(const S* __restrict__ 
     if (s_h[b]) atomicAdd(&hist[b], s_h[b]);
 }
 
+// np.histogram(x, bins=nbins) of a float32 array over its own [min, max] -- the equal-bin fast path of numpy
+// (numpy/lib/_histograms_impl.py, "Fast algorithm for equal bins"): tentative index trunc(((x - first) / (last - first)) * nbins) in
+// float32, nbins -> nbins - 1, then one step down if x < edges[i] and one step up if x >= edges[i + 1] (not from the last bin).
+// `edges` (nbins + 1 float32) come from the host's own np.linspace, so the bins are the ones the caller's numpy would use.
+// Every warp counts into a private copy of the histogram in shared memory.
+__global__ void __launch_bounds__(256) edge_hist_kernel(const float* __restrict__ x, int64_t n, const float* __restrict__ edges, int nbins,
+                                                        unsigned long long* __restrict__ counts) {
+  extern __shared__ uint32_t s_eh[];               // [8 warps][nbins] counters, then nbins + 1 edges
+  float* s_e = reinterpret_cast<float*>(s_eh + 8 * nbins);
+  for (int b = threadIdx.x; b < 8 * nbins; b += blockDim.x) s_eh[b] = 0u;
+  for (int b = threadIdx.x; b <= nbins; b += blockDim.x) s_e[b] = edges[b];
+  __syncthreads();
+  const float first = s_e[0], last = s_e[nbins];
+  const float denom = __fsub_rn(last, first);
+  uint32_t* mine = s_eh + (threadIdx.x >> 5) * nbins;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    if (!(v >= first && v <= last)) continue;      // numpy keeps first <= v <= last only (drops NaN)
+    int idx = (int)__fmul_rn(__fdiv_rn(__fsub_rn(v, first), denom), (float)nbins);
+    if (idx == nbins) idx -= 1;
+    if (v < s_e[idx]) idx -= 1;
+    if (v >= s_e[idx + 1] && idx != nbins - 1) idx += 1;
+    atomicAdd(&mine[idx], 1u);
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < nbins; b += blockDim.x) {
+    uint32_t t = 0;
+    for (int w = 0; w < 8; ++w) t += s_eh[w * nbins + b];
+    if (t) atomicAdd(&counts[b], (unsigned long long)t);
+  }
+}
+
 static int stream_grid(int64_t total) {
   int64_t b = ceil_div(total, 256);
   const int64_t cap = (int64_t)sm_count() * 16;
@@ -247,6 +279,23 @@ B200_EXPORT int b200_argmax_channels(const float* src, int64_t voxels, int32_t c
   if (dst_dtype == B200_U8) argmax_kernel<uint8_t><<<stream_grid(voxels), 256, 0, st>>>(src, (uint8_t*)dst, voxels, c);
   else if (dst_dtype == B200_U16) argmax_kernel<uint16_t><<<stream_grid(voxels), 256, 0, st>>>(src, (uint16_t*)dst, voxels, c);
   else B200_CHECK_ARG(false, "argmax_channels: dst dtype must be u8 or u16");
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+B200_EXPORT int b200_edge_hist(const float* src, int64_t n, const float* edges, int32_t nbins, uint64_t* counts, void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(src && edges && counts && n > 0, "edge_hist: null pointer / empty input");
+  B200_CHECK_ARG(nbins >= 1 && nbins <= 1024, "edge_hist: 1..1024 bins, got %d", nbins);
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_CUDA(cudaMemsetAsync(counts, 0, sizeof(uint64_t) * nbins, st));
+  int64_t bx = ceil_div(n, 256 * 16);
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  // a block never sees more than 2^32 elements of one bin: n / blocks < 2^32 for any tensor that fits the device
+  const size_t smem = sizeof(uint32_t) * 8 * nbins + sizeof(float) * (nbins + 1);
+  edge_hist_kernel<<<(unsigned)bx, 256, smem, st>>>(src, n, edges, nbins, (unsigned long long*)counts);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

@@ -354,151 +354,130 @@ __global__ void __launch_bounds__(256) overlap_add_cover_kernel(const TI* __rest
 }
 
 // Slot variant (default for the usual grids, overlap < 50 %): with at most TWO covering patches per axis the covering set of an
-// output element is a 2 x 2 x 2 box of slots (z slots and y slots are the same for a whole x row, x slots are per thread), so the
-// walk over the covering patches becomes eight predicated, fully unrolled steps whose loads are independent of each other --
-// the cover kernel above chases mask bits one patch at a time and exposes one load latency per patch.  The operation order
-// (z-major, then y, then x: increasing patch index) and every float32 operation are those of overlap_add_kernel: bit-identical.
-// Elements with three or more covering patches on some axis take the mask walk.  `z0`: first output plane of the slab this
-// launch produces (out holds planes [z0, z0 + p.D_slab) of the volume; sharded inference merges one slab per rank).
-template <typename TI, typename TO, int ROWS>
+// output element is a 2 x 2 x 2 box of slots, so the walk over the covering patches becomes eight predicated, fully unrolled steps
+// whose loads are independent of each other -- the cover kernel above chases mask bits one patch at a time, exposes one load
+// latency per patch and spends ~280 instructions per element on bookkeeping.  Here the bookkeeping is hoisted: a block owns one
+// output plane z (slots and weights of z are block constants), a band of y rows (their slots, weights and patch-row offsets sit
+// in a shared table built once per block) and every thread keeps the slots of ITS x column in registers while it walks down the
+// band.  The operation order (z-major, then y, then x: increasing patch index) and every float32 operation are those of
+// overlap_add_kernel: bit-identical.  Elements with three or more covering patches on some axis take a plain range walk.
+// `z0`: first output plane of the slab this launch produces (sharded inference merges one z slab per rank).
+// 32-bit element offsets: the launcher checks n_patches * patch volume < 2^31.
+struct SlotRow { int n, off0, off1; float f0, f1; };      // covering patches of one coordinate (n > 2: walk), row offsets, weights
+
+template <typename TI, typename TO, int UNROLL>
 __global__ void __launch_bounds__(256) overlap_add_slot_kernel(const TI* __restrict__ patches, TO* __restrict__ out, MergeParams p,
-                                         int z0, int nz_out,
+                                         int z0, int nz_out, int rows_per_block,
                                          const int64_t* __restrict__ sz, const int64_t* __restrict__ sy,
                                          const int64_t* __restrict__ sx, const float* __restrict__ wz,
                                          const float* __restrict__ wy, const float* __restrict__ wx) {
-  extern __shared__ unsigned long long s_mask[];             // x masks [W], y masks [H], then the starts as int
+  extern __shared__ unsigned long long s_raw[];
   const int nz = (int)p.nz, ny = (int)p.ny, nx = (int)p.nx, H = (int)p.H, W = (int)p.W, C = (int)p.C;
   const int cz = (int)p.cz, cy = (int)p.cy, cx = (int)p.cx;
-  unsigned long long* x_mask = s_mask;
-  unsigned long long* y_mask = x_mask + W;
-  int* s_z = reinterpret_cast<int*>(y_mask + H);
+  SlotRow* s_row = reinterpret_cast<SlotRow*>(s_raw);                 // [rows_per_block]
+  int* s_z = reinterpret_cast<int*>(s_row + rows_per_block);
   int* s_y = s_z + nz;
   int* s_x = s_y + ny;
+  const int pvol = (int)(p.pz * p.py * p.px * p.C);          // elements per patch
+  const int prow = (int)(p.px * p.C);                        // elements of one patch x row
+  const int padz = (int)p.pad_z, pady = (int)p.pad_y, padx = (int)p.pad_x;
+  const int row_el = W * C;
   for (int i = threadIdx.x; i < nz; i += blockDim.x) s_z[i] = (int)sz[i];
   for (int i = threadIdx.x; i < ny; i += blockDim.x) s_y[i] = (int)sy[i];
   for (int i = threadIdx.x; i < nx; i += blockDim.x) s_x[i] = (int)sx[i];
   __syncthreads();
-  for (int c = threadIdx.x; c < W + H; c += blockDim.x) {
-    const bool isx = c < W;
-    const int coord = isx ? c : c - W, n = isx ? nx : ny, core = isx ? cx : cy;
-    const int* st = isx ? s_x : s_y;
-    unsigned long long m = 0;
-    for (int i = 0; i < n; ++i) {
-      const int l = coord - st[i];
-      if (l >= 0 && l < core) m |= 1ull << i;
-    }
-    (isx ? x_mask : y_mask)[coord] = m;
-  }
-  __syncthreads();
-  const int row_el = W * C;                                  // elements of one output x row
-  const int64_t pvol = p.pz * p.py * p.px * p.C;             // elements per patch
-  const int prow = (int)(p.px * p.C);                        // elements of one patch x row
-  const int padz = (int)p.pad_z, pady = (int)p.pad_y, padx = (int)p.pad_x;
-  for (int zl = blockIdx.y; zl < nz_out; zl += gridDim.y) {
-    const int z = z0 + zl;
-    unsigned long long zm = 0;
-    for (int i = 0; i < nz; ++i) {
-      const int l = z - s_z[i];
-      if (l >= 0 && l < cz) zm |= 1ull << i;
-    }
-    const int nzc = __popcll(zm);
-    int a[2] = {0, 0};
-    float fz[2] = {0.f, 0.f};
-    int64_t zoff[2] = {0, 0};
-    if (nzc >= 1 && nzc <= 2) {
-      a[0] = __ffsll((long long)zm) - 1;
-      a[1] = nzc == 2 ? 63 - __clzll((long long)zm) : a[0];
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int lz = z - s_z[a[k]];
-        fz[k] = __ldg(wz + lz);
-        zoff[k] = (int64_t)a[k] * ny * nx * pvol + (int64_t)(lz + padz) * p.py * prow;
+  const int y_begin = blockIdx.x * rows_per_block;
+  const int y_end = H < y_begin + rows_per_block ? H : y_begin + rows_per_block;
+  for (int r = threadIdx.x; r < y_end - y_begin; r += blockDim.x) {
+    const int y = y_begin + r;
+    SlotRow t{0, 0, 0, 0.f, 0.f};
+    for (int i = 0; i < ny; ++i) {
+      const int l = y - s_y[i];
+      if (l >= 0 && l < cy) {
+        const int off = i * nx * pvol + (l + pady) * prow;
+        if (t.n == 0) { t.off0 = off; t.f0 = wy[l]; }
+        else if (t.n == 1) { t.off1 = off; t.f1 = wy[l]; }
+        ++t.n;
       }
     }
-    // a block walks groups of ROWS x rows; thread t owns elements t, t + 256, ... of each row of the group
-    for (int y0 = blockIdx.x * ROWS; y0 < H; y0 += gridDim.x * ROWS) {
-      for (int e0 = threadIdx.x; e0 < row_el; e0 += blockDim.x) {
-        const int x = e0 / C, ch = e0 - x * C;
-        const unsigned long long xm = x_mask[x];
-        const int nxc = __popcll(xm);
-        const int c0 = __ffsll((long long)xm) - 1, c1 = 63 - __clzll((long long)xm);
-        const int lx0 = nxc ? x - s_x[c0] : 0, lx1 = nxc ? x - s_x[c1] : 0;
-        const float fx0 = nxc ? __ldg(wx + lx0) : 0.f, fx1 = nxc ? __ldg(wx + lx1) : 0.f;
-        const int64_t xoff0 = (int64_t)c0 * pvol + (lx0 + padx) * C + ch, xoff1 = (int64_t)c1 * pvol + (lx1 + padx) * C + ch;
-        float v[ROWS][8];
-        float fzy[ROWS][4];
-        bool fast[ROWS];
-        int nyc_r[ROWS];
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r) {
-          const int y = y0 + r;
-          fast[r] = false;
-          nyc_r[r] = 0;
-          if (y >= H) continue;
-          const unsigned long long ym = y_mask[y];
-          const int nyc = __popcll(ym);
-          nyc_r[r] = nyc;
-          fast[r] = nzc <= 2 && nyc <= 2 && nxc <= 2;
-          if (!fast[r] || nzc == 0 || nyc == 0 || nxc == 0) continue;
-          const int b0 = __ffsll((long long)ym) - 1, b1 = 63 - __clzll((long long)ym);
-          const int ly0 = y - s_y[b0], ly1 = y - s_y[b1];
-          const float fy0 = __ldg(wy + ly0), fy1 = __ldg(wy + ly1);
-          const int64_t yoff0 = (int64_t)b0 * nx * pvol + (int64_t)(ly0 + pady) * prow;
-          const int64_t yoff1 = (int64_t)b1 * nx * pvol + (int64_t)(ly1 + pady) * prow;
-#pragma unroll
-          for (int kz = 0; kz < 2; ++kz) {
-            fzy[r][kz * 2 + 0] = __fmul_rn(fz[kz], fy0);
-            fzy[r][kz * 2 + 1] = __fmul_rn(fz[kz], fy1);
-            const bool pz_on = kz < nzc;
-            const TI* b00 = patches + zoff[kz] + yoff0;
-            const TI* b01 = patches + zoff[kz] + yoff1;
-            v[r][kz * 4 + 0] = pz_on ? to_f<TI>(b00[xoff0]) : 0.f;
-            v[r][kz * 4 + 1] = (pz_on && nxc == 2) ? to_f<TI>(b00[xoff1]) : 0.f;
-            v[r][kz * 4 + 2] = (pz_on && nyc == 2) ? to_f<TI>(b01[xoff0]) : 0.f;
-            v[r][kz * 4 + 3] = (pz_on && nyc == 2 && nxc == 2) ? to_f<TI>(b01[xoff1]) : 0.f;
-          }
+    s_row[r] = t;
+  }
+  __syncthreads();
+  for (int zl = blockIdx.y; zl < nz_out; zl += gridDim.y) {
+    const int z = z0 + zl;
+    int nzc = 0, zoff[2] = {0, 0};
+    float fz[2] = {0.f, 0.f};
+    for (int i = 0; i < nz; ++i) {
+      const int l = z - s_z[i];
+      if (l >= 0 && l < cz) {
+        if (nzc < 2) { zoff[nzc] = i * ny * nx * pvol + (l + padz) * (int)p.py * prow; fz[nzc] = __ldg(wz + l); }
+        ++nzc;
+      }
+    }
+    for (int e0 = threadIdx.x; e0 < row_el; e0 += blockDim.x) {
+      const int x = e0 / C, ch = e0 - x * C;
+      int nxc = 0, xoff[2] = {0, 0};
+      float fx[2] = {0.f, 0.f};
+      for (int i = 0; i < nx; ++i) {
+        const int l = x - s_x[i];
+        if (l >= 0 && l < cx) {
+          if (nxc < 2) { xoff[nxc] = i * pvol + (l + padx) * C + ch; fx[nxc] = __ldg(wx + l); }
+          ++nxc;
         }
+      }
+      const bool zx_fast = nzc <= 2 && nxc <= 2;
+      TO* op = out + ((int64_t)zl * H + y_begin) * row_el + e0;
+#pragma unroll UNROLL
+      for (int r = 0; r < y_end - y_begin; ++r) {
+        const SlotRow t = s_row[r];
+        float acc = 0.f, wsum = 0.f;
+        if (zx_fast && t.n <= 2) {
+          float v[8];
 #pragma unroll
-        for (int r = 0; r < ROWS; ++r) {
-          const int y = y0 + r;
-          if (y >= H) continue;
-          float acc = 0.f, wsum = 0.f;
-          if (fast[r]) {
-            if (nzc && nyc_r[r] && nxc) {
+          for (int kz = 0; kz < 2; ++kz)
 #pragma unroll
-              for (int kz = 0; kz < 2; ++kz)
+            for (int ky = 0; ky < 2; ++ky)
 #pragma unroll
-                for (int ky = 0; ky < 2; ++ky)
+              for (int kx = 0; kx < 2; ++kx) {
+                const bool on = kz < nzc && ky < t.n && kx < nxc;
+                v[kz * 4 + ky * 2 + kx] = on ? to_f<TI>(patches[zoff[kz] + (ky ? t.off1 : t.off0) + xoff[kx]]) : 0.f;
+              }
 #pragma unroll
-                  for (int kx = 0; kx < 2; ++kx) {
-                    if (kz < nzc && ky < nyc_r[r] && kx < nxc) {
-                      const float w = __fmul_rn(fzy[r][kz * 2 + ky], kx ? fx1 : fx0);
-                      acc = __fadd_rn(acc, __fmul_rn(v[r][kz * 4 + ky * 2 + kx], w));
-                      wsum = __fadd_rn(wsum, w);
-                    }
-                  }
-            }
-          } else {
-            const unsigned long long ym = y_mask[y];
-            for (unsigned long long am = zm; am; am &= am - 1) {
-              const int iz = __ffsll((long long)am) - 1, lz = z - s_z[iz];
-              const float gz = __ldg(wz + lz);
-              for (unsigned long long bm = ym; bm; bm &= bm - 1) {
-                const int iy = __ffsll((long long)bm) - 1, ly = y - s_y[iy];
-                const float gzy = __fmul_rn(gz, __ldg(wy + ly));
-                const TI* rowp = patches + ((int64_t)(iz * ny + iy) * nx) * pvol + ((int64_t)(lz + padz) * p.py + (ly + pady)) * prow + ch;
-                for (unsigned long long cm = xm; cm; cm &= cm - 1) {
-                  const int ix = __ffsll((long long)cm) - 1, lx = x - s_x[ix];
-                  const float w = __fmul_rn(gzy, __ldg(wx + lx));
-                  const float val = to_f<TI>(rowp[(int64_t)ix * pvol + (lx + padx) * C]);
-                  acc = __fadd_rn(acc, __fmul_rn(val, w));
+          for (int kz = 0; kz < 2; ++kz)
+#pragma unroll
+            for (int ky = 0; ky < 2; ++ky) {
+              const float fzy = __fmul_rn(fz[kz], ky ? t.f1 : t.f0);
+#pragma unroll
+              for (int kx = 0; kx < 2; ++kx)
+                if (kz < nzc && ky < t.n && kx < nxc) {
+                  const float w = __fmul_rn(fzy, fx[kx]);
+                  acc = __fadd_rn(acc, __fmul_rn(v[kz * 4 + ky * 2 + kx], w));
                   wsum = __fadd_rn(wsum, w);
                 }
+            }
+        } else {
+          const int y = y_begin + r;
+          for (int iz = 0; iz < nz; ++iz) {
+            const int lz = z - s_z[iz];
+            if (lz < 0 || lz >= cz) continue;
+            const float gz = __ldg(wz + lz);
+            for (int iy = 0; iy < ny; ++iy) {
+              const int ly = y - s_y[iy];
+              if (ly < 0 || ly >= cy) continue;
+              const float gzy = __fmul_rn(gz, __ldg(wy + ly));
+              for (int ix = 0; ix < nx; ++ix) {
+                const int lx = x - s_x[ix];
+                if (lx < 0 || lx >= cx) continue;
+                const float w = __fmul_rn(gzy, __ldg(wx + lx));
+                const int64_t c = ((int64_t)iz * ny + iy) * nx + ix;
+                const float val = to_f<TI>(patches[c * pvol + ((int64_t)(lz + padz) * p.py + (ly + pady)) * prow + (lx + padx) * C + ch]);
+                acc = __fadd_rn(acc, __fmul_rn(val, w));
+                wsum = __fadd_rn(wsum, w);
               }
             }
           }
-          out[((int64_t)zl * H + y) * row_el + e0] = from_f<TO>(__fdiv_rn(acc, __fadd_rn(wsum, 1e-18f)));
         }
+        op[(int64_t)r * row_el] = from_f<TO>(__fdiv_rn(acc, __fadd_rn(wsum, 1e-18f)));
       }
     }
   }
@@ -525,18 +504,19 @@ static int launch_overlap_add(const void* patches, void* out, const MergeParams&
     return !e ? 0 : !strcmp(e, "cover") ? 1 : !strcmp(e, "plain") ? 2 : 0;
   }();
   if (variant != 2 && tab <= 48 * 1024 && p.nz <= 64 && p.ny <= 64 && p.nx <= 64 && p.D < (1LL << 30) && p.px * p.C < (1LL << 30)) {
-    if (variant == 0) {
-      static const int rows = getenv("B200_MERGE_ROWS") ? atoi(getenv("B200_MERGE_ROWS")) : 2;     // x rows per thread (1, 2, 4)
-      const int R = rows == 1 || rows == 4 ? rows : 2;
-      int64_t groups = ceil_div(p.H, (int64_t)R);
-      // about 16 blocks per SM over the whole launch, every block builds the cover tables once
-      int64_t want = ceil_div((int64_t)sm_count() * 16, (int64_t)gy);
-      int64_t bxs = groups < want ? groups : want;
-      if (bxs < 1) bxs = 1;
-      const dim3 g((unsigned)bxs, gy);
-#define B200_SLOT(ROWS) overlap_add_slot_kernel<TI, TO, ROWS><<<g, threads, tab, st>>>((const TI*)patches, (TO*)out, p, (int)z0, \
-                                                                                 (int)nz_out, sz, sy, sx, wz, wy, wx)
-      if (R == 1) B200_SLOT(1); else if (R == 4) B200_SLOT(4); else B200_SLOT(2);
+    if (variant == 0 && (p.nz * p.ny * p.nx) * (p.pz * p.py * p.px * p.C) < (1LL << 31)) {
+      static const int rows_env = getenv("B200_MERGE_ROWS") ? atoi(getenv("B200_MERGE_ROWS")) : 0;     // y rows per block
+      static const int unroll2 = getenv("B200_MERGE_UNROLL") ? atoi(getenv("B200_MERGE_UNROLL")) : 2;
+      // a block = one z plane x a band of y rows; about 8 blocks per SM over the whole launch, bands of 16..128 rows
+      int64_t bands = ceil_div((int64_t)sm_count() * 8, (int64_t)gy);
+      int64_t rpb = rows_env > 0 ? rows_env : ceil_div(p.H, bands < 1 ? 1 : bands);
+      if (rows_env <= 0) { if (rpb < 16) rpb = 16; if (rpb > 128) rpb = 128; }
+      if (rpb > p.H) rpb = p.H;
+      const dim3 g((unsigned)ceil_div(p.H, rpb), gy);
+      const size_t smem = sizeof(SlotRow) * (size_t)rpb + sizeof(int) * (size_t)(p.nz + p.ny + p.nx) + 16;
+#define B200_SLOT(U) overlap_add_slot_kernel<TI, TO, U><<<g, threads, smem, st>>>((const TI*)patches, (TO*)out, p, (int)z0, (int)nz_out, \
+                                                                              (int)rpb, sz, sy, sx, wz, wy, wx)
+      if (unroll2 == 1) B200_SLOT(1); else if (unroll2 == 4) B200_SLOT(4); else B200_SLOT(2);
 #undef B200_SLOT
       B200_LAUNCH_CHECK();
       return B200_OK;

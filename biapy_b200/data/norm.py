@@ -293,14 +293,51 @@ def undo_image_norm(data, norm_info: Dict):
     return _stitch.like_input(out, data)
 
 
-def binarize_prediction(pred, n_classes: int, threshold: float = 0.5):
+def otsu_from_counts(counts: np.ndarray, bin_edges: np.ndarray) -> np.floating:
+    """The arithmetic of ``skimage.filters.threshold_otsu`` (scikit-image >= 0.21: ``filters/thresholding.py``) on a histogram:
+    counts as float32 (``_validate_image_histogram``), bin centres = means of neighbouring edges (``exposure.histogram``), class
+    weights / means by cumulative sums from both ends, threshold = centre of the bin that maximises the between-class variance."""
+    counts = np.asarray(counts).astype("float32", copy=False)
+    bin_centers = (bin_edges[:-1] + bin_edges[1:]) / 2.0
+    weight1 = np.cumsum(counts)
+    weight2 = np.cumsum(counts[::-1])[::-1]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        mean1 = np.cumsum(counts * bin_centers) / weight1
+        mean2 = (np.cumsum((counts * bin_centers)[::-1]) / weight2[::-1])[::-1]
+    variance12 = weight1[:-1] * weight2[1:] * (mean1[:-1] - mean2[1:]) ** 2
+    return bin_centers[np.argmax(variance12)]
+
+
+def threshold_otsu(pred, nbins: int = 256) -> np.floating:
+    """``skimage.filters.threshold_otsu(pred)`` for the float32 prediction of the engine (``semantic_seg.py:429, 455``).  The two
+    passes over the volume run on the device -- min / max (``b200_image_stats``) and numpy's equal-bin histogram over
+    ``np.linspace(min, max, nbins + 1)`` (``b200_edge_hist``) --, the 256-element arithmetic is skimage's own sequence of numpy
+    calls on the host, so the threshold is the one skimage returns for the same array."""
+    dev = _stitch.to_device(pred)
+    if dev.dtype != torch.float32:
+        raise NotImplementedError("threshold_otsu takes the float32 prediction of the engine")
+    flat = dev.contiguous().reshape(-1, 1)
+    st = image_stats(flat)
+    mn, mx = np.float32(st[0, 0]), np.float32(st[0, 1])
+    if mn == mx:                                   # one intensity value: skimage returns it (first_pixel)
+        return mn
+    edges = np.linspace(mn, mx, nbins + 1, endpoint=True, dtype=np.result_type(mn, mx, np.float32))
+    edges_d = torch.from_numpy(edges).to(flat.device)
+    counts = torch.empty(nbins, dtype=torch.int64, device=flat.device)
+    ops._launch("b200_edge_hist", ops._ptr(flat), flat.numel(), ops._ptr(edges_d), int(nbins), ops._ptr(counts), _lib.stream_ptr())
+    return otsu_from_counts(counts.cpu().numpy(), edges)
+
+
+def binarize_prediction(pred, n_classes: int, threshold: Optional[float] = 0.5):
     """Binarisation behind the merge (``semantic_seg.py:418-425, 524-531``): ``pred > threshold`` as uint8 for binary problems
-    (the by-chunks path's fixed 0.5; pass the Otsu threshold of the whole-image path explicitly), else the channel arg-max as
-    uint8 (uint16 from 255 classes) with a trailing unit channel."""
+    (`threshold` = None: the Otsu threshold of the whole prediction, as ``after_merge_patches`` / ``after_full_image`` do; 0.5: the
+    by-chunks path), else the channel arg-max as uint8 (uint16 from 255 classes) with a trailing unit channel."""
     dev = _stitch.to_device(pred)
     if dev.dtype != torch.float32:
         raise NotImplementedError("binarize_prediction takes the float32 prediction of the engine")
     dev = dev.contiguous()
+    if n_classes <= 2 and threshold is None:
+        threshold = float(threshold_otsu(dev))
     if n_classes <= 2:
         out = torch.empty(dev.shape, dtype=torch.uint8, device=dev.device)
         ops._launch("b200_binarize", ops._ptr(dev), dev.numel(), float(threshold), ops._ptr(out), _lib.stream_ptr())

@@ -72,6 +72,10 @@ class Base_Workflow:
         """Called with the merged prediction of one sample; returns what the workflow keeps of it."""
         return pred
 
+    def after_one_chunk_workflow_process(self, chunks, patch_in_data=None, added_pad=None):
+        """By-chunks twin of ``after_merge_patches`` (reference ``base_workflow.py`` hook of the same name)."""
+        return [self.after_merge_patches(c) for c in chunks]
+
     def prepare_targets(self, targets, batch=None):
         return targets
 
@@ -160,6 +164,9 @@ class Base_Workflow:
         if cfg.TEST.BY_CHUNKS.ENABLE:
             pred = predict_by_chunks(self.model, vol, patch, padding=pad, batch_size=int(cfg.TRAIN.BATCH_SIZE),
                                      head_activations=self.head_activations)
+            # the by-chunks path post-processes chunk by chunk (semantic seg: fixed 0.5 threshold, semantic_seg.py:502-535);
+            # voxel-wise hooks give the same result on the assembled volume
+            return pred, self.after_one_chunk_workflow_process([pred])[0]
         else:
             pred = predict_volume(self.model, vol, patch, overlap=ov, padding=pad, batch_size=int(cfg.TRAIN.BATCH_SIZE),
                                   head_activations=self.head_activations, tta=bool(cfg.TEST.AUGMENTATION),

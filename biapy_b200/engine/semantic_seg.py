@@ -17,7 +17,12 @@ class Semantic_Segmentation_Workflow(Base_Workflow):
         self.loss_kind = "ce" if n > 2 else "bce"
         super().define_activations_and_channels()
 
-    def after_merge_patches(self, pred, threshold: float = 0.5):
-        """Binarised prediction (reference ``:409-425``: Otsu threshold for the whole image; the by-chunks path and this
-        engine use the fixed 0.5 of ``:524-531`` unless a threshold is passed) -- uint8 mask or arg-max class map."""
+    def after_merge_patches(self, pred, threshold=None):
+        """Binarised prediction (reference ``:418-425``, ``after_full_image`` ``:444-459``): ``pred > threshold_otsu(pred)`` for
+        binary problems -- the Otsu threshold of the whole merged prediction, histogram on the device -- or the arg-max class map;
+        a number as `threshold` replaces Otsu."""
         return binarize_prediction(pred, int(self.cfg.DATA.N_CLASSES), threshold=threshold)
+
+    def after_one_chunk_workflow_process(self, chunks, patch_in_data=None, added_pad=None):
+        """By-chunks binarisation (reference ``:502-535``): fixed 0.5, NOT Otsu -- a chunk may hold no foreground at all."""
+        return [binarize_prediction(c, int(self.cfg.DATA.N_CLASSES), threshold=0.5) for c in chunks]

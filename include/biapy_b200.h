@@ -156,6 +156,11 @@ int b200_chunk_insert(const void* patches, int32_t dtype_in, int64_t n, int64_t 
  * key >> (shift + bits) equal `prefix`.  bits <= 11. */
 int b200_select_hist(const void* src, int32_t dtype, int64_t voxels, int32_t c, int32_t ch, int32_t shift, int32_t bits,
                      uint32_t prefix, int32_t has_prefix, uint32_t* hist /* device */, void* stream);
+/* b200_edge_hist: counts (device uint64[nbins], cleared by the call) = np.histogram(src, bins=nbins)[0] for a float32 array and the
+ * bin edges numpy derives from its [min, max] (device float32[nbins + 1], computed by the caller with np.linspace): numpy's
+ * equal-bin index rule incl. its edge corrections.  The heavy half of skimage.filters.threshold_otsu (scikit-image >= 0.21,
+ * pyproject.toml:26), which after_merge_patches / after_full_image call on the merged prediction (semantic_seg.py:429, 455). */
+int b200_edge_hist(const float* src, int64_t n, const float* edges, int32_t nbins, uint64_t* counts, void* stream);
 /* ------------------------------------------------------------------------------------- the ends of the path
  * Image normalisation in front of the first convolution and its inverse / the binarisation behind the merge.
  * Images are dense (voxels, C) arrays of dtype u8 / u16 / f32.

@@ -101,9 +101,52 @@ def undo_image_norm(data: np.ndarray, info: Dict) -> np.ndarray:
     return data.astype(_NP[info["orig_dtype"]])
 
 
-def binarize(pred: np.ndarray, n_classes: int, threshold: float = 0.5) -> np.ndarray:
-    """semantic_seg.py:420-424 (with the threshold given) / :524-531."""
+def threshold_otsu(image: np.ndarray, nbins: int = 256):
+    """``skimage.filters.threshold_otsu(image)`` as ``after_merge_patches`` / ``after_full_image`` call it
+    (``biapy/engine/semantic_seg.py:429, 455``) on the float32 merged prediction.
+
+    PARITY UNPINNED against scikit-image itself: the package (``scikit-image>=0.21.0``, reference ``pyproject.toml:26``) is neither
+    vendored in /root/reference nor installed in this image, so this restates its published algorithm
+    (``skimage/filters/thresholding.py``: ``threshold_otsu`` -> ``_validate_image_histogram`` -> ``skimage.exposure.histogram``):
+      1. one intensity value in the image -> return it;
+      2. ``counts, edges = np.histogram(image.reshape(-1), bins=nbins)`` over the image's own [min, max] (float images);
+         ``bin_centers = (edges[:-1] + edges[1:]) / 2``; counts cast to float32;
+      3. class weights / means by cumulative sums from both ends, between-class variance
+         ``w1[:-1] * w2[1:] * (m1[:-1] - m2[1:]) ** 2``, threshold = centre of its arg-max bin.
+    Step 2 is numpy's own ``np.histogram`` (installed, exact); tests/golden/otsu_cases.npz holds what this function returns so a
+    change of behaviour in a later numpy shows up."""
+    first = image.reshape(-1)[0]
+    if np.all(image == first):
+        return first
+    counts, edges = np.histogram(image.reshape(-1), bins=nbins)
+    centers = (edges[:-1] + edges[1:]) / 2.0
+    counts = counts.astype("float32", copy=False)
+    weight1 = np.cumsum(counts)
+    weight2 = np.cumsum(counts[::-1])[::-1]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        mean1 = np.cumsum(counts * centers) / weight1
+        mean2 = (np.cumsum((counts * centers)[::-1]) / weight2[::-1])[::-1]
+    variance12 = weight1[:-1] * weight2[1:] * (mean1[:-1] - mean2[1:]) ** 2
+    return centers[np.argmax(variance12)]
+
+
+def otsu_cases():
+    """Seeded float32 predictions for the Otsu tests: sigmoid-like bimodal volume, flat noise, heavy ties, a constant image."""
+    rng = np.random.default_rng(11)
+    a = 1.0 / (1.0 + np.exp(-(rng.standard_normal((24, 40, 36, 1)) * 3.0 + np.where(rng.random((24, 40, 36, 1)) < 0.3, 4.0, -4.0))))
+    b = rng.random((50, 70, 1))
+    c = np.round(rng.random((16, 16, 16, 1)) * 7.0) / 7.0
+    d = np.full((8, 8, 8, 1), 0.25)
+    e = rng.standard_normal((33, 65, 1)) * 100.0 - 40.0
+    return {k: v.astype(np.float32) for k, v in dict(bimodal=a, flat=b, ties=c, constant=d, wide=e).items()}
+
+
+def binarize(pred: np.ndarray, n_classes: int, threshold: Optional[float] = 0.5) -> np.ndarray:
+    """semantic_seg.py:418-425 (`threshold` None: Otsu of the whole prediction, as the reference; a number: that threshold) /
+    :524-531 (by chunks: 0.5)."""
     if n_classes <= 2:
+        if threshold is None:
+            threshold = threshold_otsu(pred)
         return (pred > threshold).astype(np.uint8)
     return np.expand_dims(np.argmax(pred, -1), -1).astype(np.uint8 if n_classes < 255 else np.uint16)
 

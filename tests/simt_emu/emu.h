@@ -90,6 +90,13 @@ static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) {
   *p = old + v;
   return old;
 }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) {
+  std::lock_guard<std::mutex> l(g_atomic_mu);
+  const unsigned long long old = *p;
+  *p = old + v;
+  return old;
+}
+static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 static inline double atomicAdd(double* p, double v) {
   std::lock_guard<std::mutex> l(g_atomic_mu);
   const double old = *p;

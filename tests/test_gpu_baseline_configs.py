@@ -124,6 +124,33 @@ def test_full_size_cfg1_resunet128():
                                       "dW_l2": l2(flat_ref.double(), f64), "dx_max": nerr(gxr.double(), gx64), "dx_l2": l2(gxr.double(), gx64)}
     except Exception as e:      # the float64 pass is context, not a gate
         table["aten_fp32_vs_fp64"] = {"error": repr(e)}
+    # context, not a gate: PyTorch's own CUDA kernels on the same graph (the oracle's torch ops moved to the GPU) in fp32 and under
+    # autocast -- what a user of the reference gets from `torch.autocast` at the same storage precision.  The max-pool routing is
+    # discontinuous: a 16-bit rounding that flips an arg-max moves a whole gradient entry, so 16-bit parameter gradients carry an
+    # error ~ sqrt(rounding step), far above the forward's, in ANY implementation.
+    def torch_cuda(autocast_dtype):
+        sd_c = {k: v.clone().cuda().requires_grad_(True) if v.is_floating_point() else v.clone().cuda() for k, v in sd.items()}
+        xc = x.clone().cuda().requires_grad_(True)
+        old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+        torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+        try:
+            with torch.autocast("cuda", dtype=autocast_dtype, enabled=autocast_dtype is not None):
+                yc = port_models.forward("resunet", sd_c, xc, training=True, **CFG1)
+            (yc.float() * gy.cuda()).sum().backward()
+        finally:
+            torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+        flat = torch.cat([sd_c[n].grad.float().cpu().flatten() for n in names])
+        return {"y_max": nerr(yc.detach().float().cpu(), yr), "y_l2": l2(yc.detach().float().cpu(), yr),
+                "dW_max": (flat - flat_ref).abs().max().item() / scale, "dW_l2": l2(flat, flat_ref),
+                "dx_max": nerr(xc.grad.cpu(), gxr), "dx_l2": l2(xc.grad.cpu(), gxr)}
+
+    for key, adt in (("torch_cuda_fp32", None), ("torch_cuda_autocast_fp16", torch.float16), ("torch_cuda_autocast_bf16", torch.bfloat16)):
+        try:
+            table[key] = torch_cuda(adt)
+        except Exception as e:
+            table[key] = {"error": repr(e)[:200]}
+        print(f"\n[cfg1 {key}] " + "  ".join(f"{k} {v:.2e}" if isinstance(v, float) else f"{k} {v}" for k, v in table[key].items()))
+    torch.cuda.empty_cache()
     m = m.cuda()
     for dtype in (torch.float32, torch.float16, torch.bfloat16):
         m.set_engine(dtype=dtype)
@@ -133,9 +160,12 @@ def test_full_size_cfg1_resunet128():
         (y * gy.cuda()).sum().backward()
         torch.cuda.synchronize()
         flat = torch.cat([p.grad.cpu().flatten() for _, p in m.named_parameters()])
+        per = sorted(((l2(p.grad.cpu(), gwr[n]), n) for n, p in m.named_parameters() if gwr[n].norm() > 0), reverse=True)
         row = {"y_max": nerr(y.detach().cpu(), yr), "y_l2": l2(y.detach().cpu(), yr),
                "dW_max": (flat - flat_ref).abs().max().item() / scale, "dW_l2": l2(flat, flat_ref),
                "dx_max": nerr(xc.grad.cpu(), gxr), "dx_l2": l2(xc.grad.cpu(), gxr)}
+        table[str(dtype).replace("torch.", "") + "_worst_parameters"] = [(n, e) for e, n in per[:6]]
+        table[str(dtype).replace("torch.", "") + "_median_parameter_l2"] = per[len(per) // 2][0]
         table[str(dtype).replace("torch.", "")] = row
         print(f"\n[cfg1 resunet 128^3 x1 {dtype}] " + "  ".join(f"{k} {v:.2e}" for k, v in row.items()))
     print("[cfg1 aten fp32 vs fp64] " + "  ".join(f"{k} {v:.2e}" if isinstance(v, float) else f"{k} {v}"

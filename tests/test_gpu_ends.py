@@ -114,3 +114,24 @@ def test_image_stats_kernel():
         clip = np.array([[1, 20, 100], [0, 0, 0], [0, 0, 0]], np.float32)
         st2 = image_stats(torch.from_numpy(img).cuda(), clip)
         assert st2[0, 0] == max(f[..., 0].min(), 20) and st2[0, 1] == min(f[..., 0].max(), 100) and st2[1, 0] == st[1, 0]
+
+
+def test_otsu_threshold_matches_the_oracle_bit_for_bit():
+    """after_merge_patches' Otsu threshold (semantic_seg.py:429): device min / max + numpy-rule histogram, skimage's arithmetic on
+    the host -- the same float32 threshold and the same 256 counts as the CPU oracle / the committed fixture, hence the same mask."""
+    from biapy_b200 import _lib, ops
+    from biapy_b200.data.norm import binarize_prediction, threshold_otsu
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "otsu_cases.npz"))
+    for name, img in port_norm.otsu_cases().items():
+        th = threshold_otsu(img)
+        assert np.float32(th) == z["th." + name], (name, th, z["th." + name])
+        assert np.array_equal(binarize_prediction(img, 2, threshold=None), port_norm.binarize(img, 2, None)), name
+        if "counts." + name in z.files:
+            dev = torch.from_numpy(img).cuda().reshape(-1)
+            edges = torch.from_numpy(np.linspace(img.min(), img.max(), 257, dtype=np.float32)).cuda()
+            counts = torch.empty(256, dtype=torch.int64, device="cuda")
+            ops._launch("b200_edge_hist", ops._ptr(dev), dev.numel(), ops._ptr(edges), 256, ops._ptr(counts), _lib.stream_ptr())
+            assert np.array_equal(counts.cpu().numpy(), z["counts." + name]), name
+    # a sigmoid volume of the size the workflow produces
+    big = torch.sigmoid(torch.randn(96, 160, 160, 1, generator=torch.Generator().manual_seed(0)) * 4).numpy()
+    assert np.float32(threshold_otsu(big)) == port_norm.threshold_otsu(big)

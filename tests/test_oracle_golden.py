@@ -275,3 +275,25 @@ def test_norm_oracle_matches_reference():
         assert u.dtype == u_ref.dtype and np.array_equal(u, u_ref), key
         n += 1
     assert n == 32
+
+
+def test_otsu_threshold_oracle_and_host_arithmetic():
+    """oracle/port_norm.threshold_otsu (skimage's algorithm restated on np.histogram -- scikit-image itself is not installed, see
+    its docstring) against the committed fixture, and the product's host half (`otsu_from_counts`: skimage's arithmetic on the
+    counts the device histogram returns) against the oracle for the same histograms."""
+    import numpy as np
+    from biapy_b200.data.norm import otsu_from_counts
+    from oracle import port_norm
+    z = np.load(os.path.join(GOLDEN, "otsu_cases.npz"))
+    for name, img in port_norm.otsu_cases().items():
+        th = port_norm.threshold_otsu(img)
+        assert th.dtype == np.float32 and th == z["th." + name], name
+        if "counts." + name in z.files:
+            counts, edges = np.histogram(img.reshape(-1), bins=256)
+            assert np.array_equal(counts, z["counts." + name])
+            got = otsu_from_counts(counts.astype(np.int64), np.linspace(img.min(), img.max(), 257, dtype=np.float32))
+            assert got.dtype == np.float32 and got == th, name
+    # hand-checkable case: two well separated clusters -> the threshold falls between them
+    img = np.concatenate([np.full(100, 0.1, np.float32), np.full(50, 0.9, np.float32)])
+    th = port_norm.threshold_otsu(img)
+    assert 0.1 <= th < 0.9 and np.array_equal(port_norm.binarize(img, 2, None), (img > th).astype(np.uint8))

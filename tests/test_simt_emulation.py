@@ -5,7 +5,8 @@ std::thread per CUDA thread, barriers for ``__syncthreads`` / ``__shfl_xor_sync`
 against straightforward loops / textbook formulas in double precision:
 
 * the coalesced pointwise convolutions (fprop / dgrad / wgrad of the 1-2 channel layers) and the compile-time-window max-pool;
-* the radix-select histogram of the percentile clipping;
+* the radix-select histogram of the percentile clipping, and the equal-bin histogram behind the Otsu threshold against
+  ``np.histogram`` itself (data, edges and counts handed over in a file);
 * the three spline overlap-add kernels (plain, cover-mask, slot) against the reference's scatter loop written out in C++, bit for
   bit, on grids with padding, non-monotone starts, triple overlaps, two channels and z slabs;
 * the weight pack / unpack kernels against independent statements of their layouts, and the one-launch batched pack kernel
@@ -34,7 +35,7 @@ KERNELS = {
                "scale_shift_act_rows_kernel", "norm_act_bwd_reduce_kernel", "norm_bwd_finalize_kernel",
                "norm_act_bwd_apply_rows_kernel", "adamw_kernel", "adam_kernel", "sgd_kernel", "optim_prepare_kernel",
                "optim_dev_kernel", "bce_logits_kernel", "n2v_mse_kernel", "softmax_ce_kernel"],
-    "ends.cu": ["select_hist_kernel"],
+    "ends.cu": ["select_hist_kernel", "edge_hist_kernel"],
     "stitch.cu": ["overlap_add_kernel", "overlap_add_cover_kernel", "overlap_add_slot_kernel"],
     "conv_umma.cu": ["pack_weight_xfold_kernel", "pack_convT_weight_kernel", "unpack_convT_wgrad_kernel"],
 }
@@ -44,6 +45,7 @@ PREAMBLE = {
     "pack_weight_xfold_kernel": "__host__ __device__ inline bool xfold_geom",
     "bce_logits_kernel": "__device__ __forceinline__ void block_atomic_add",
     "overlap_add_kernel": "struct MergeParams {",
+    "overlap_add_slot_kernel": "struct SlotRow {",
 }
 
 
@@ -111,13 +113,25 @@ def test_simt_kernels_on_the_host_emulator(tmp_path):
     staged = re.sub(r"extern __shared__ ([\w ]+?) (\w+)\[\];", r"\1* \2 = reinterpret_cast<\1*>(g_ctx->dyn_smem);", staged)
     parts.append("// ---- norm_fast.cuh\n" + staged[staged.index("__device__ __forceinline__ float tanh_approx"):])
     (tmp_path / "kernels.inc").write_text("\n\n".join(parts) + "\n")
+    # np.histogram's answer for the Otsu histogram kernel (numpy is the reference there): data, edges, counts in one binary file
+    import numpy as np
+    from oracle import port_norm
+    blobs = []
+    for name, img in port_norm.otsu_cases().items():
+        flat = img.reshape(-1)
+        if np.all(flat == flat[0]):
+            continue
+        counts, edges = np.histogram(flat, bins=256)
+        assert edges.dtype == np.float32
+        blobs.append(np.int64(flat.size).tobytes() + flat.tobytes() + edges.tobytes() + counts.astype(np.int64).tobytes())
+    (tmp_path / "hist_cases.bin").write_bytes(np.int64(len(blobs)).tobytes() + b"".join(blobs))
     exe = tmp_path / "simt_emu"
     cmd = ["g++", "-std=c++20", "-O1", "-pthread", "-Wno-unknown-pragmas", "-I", str(tmp_path), "-I", EMU, "-I", os.path.join(ROOT, "include"),
            os.path.join(EMU, "driver.cpp"), "-o", str(exe)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-4000:]
     try:
-        r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+        r = subprocess.run([str(exe), str(tmp_path / "hist_cases.bin")], capture_output=True, text=True, timeout=600)
     except subprocess.TimeoutExpired:
         pytest.fail("emulated kernels dead-locked (a shuffle or barrier not reached by every thread)")
     assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout[-4000:] + r.stderr[-2000:]
