@@ -363,7 +363,9 @@ def roofline_from_profile(prof, steps, peaks, timed_region_s, region):
     for name, recs in prof.items():
         t = sum(a.elapsed_time(b) for a, b, _, _ in recs)
         agg[name] = (t, sum(r[2] for r in recs), sum(r[3] for r in recs), len(recs))
-    top = max((k for k in agg if agg[k][1] > 0), key=lambda k: agg[k][0])
+    # dominant family among the tensor-bound ones (conv1x1_* / conv_image_* are HBM streams: see ops._family)
+    tensor_fams = [k for k in agg if agg[k][1] > 0 and not k.startswith(("conv1x1_", "conv_image_"))]
+    top = max(tensor_fams or [k for k in agg if agg[k][1] > 0], key=lambda k: agg[k][0])
     t, fl, by, cnt = agg[top]
     ach = fl / (t / 1e3) / 1e12
     # a short timed region runs at boost clocks: the burst figure is the like-for-like denominator; long runs settle at the sustained one

@@ -3101,7 +3101,7 @@ static bool convT_tc_ok(const b200_tensor* x, const b200_tensor* y, int sd, int 
   if (x->c % 16 != 0 || y->c % 16 != 0 || x->ld % 8 != 0 || y->ld % 8 != 0) return false;
   const int co = y->c;
   if (!(co == 16 || co == 32 || co == 64 || co == 128 || co == 256)) return false;   // wgrad N tile
-  if (x->c > 256) return false;                                                      // dgrad N tile
+  if (x->c > 256 && x->c % 128 != 0) return false;                                   // dgrad N tiles: Cin itself or 128 wide
   if (!aligned16(x->data) || !aligned16(y->data)) return false;
   if (y->d != x->d * sd || y->h != x->h * sh || y->w != x->w * sw) return false;
   if ((int64_t)x->n * x->d * x->h * x->w < 128) return false;

@@ -49,6 +49,16 @@ __device__ __forceinline__ void store_vec(T* p, const float (&f)[VEC]) {
 }
 
 #include "norm_fast.cuh"
+#include "pack_batch.cuh"
+
+// The job table travels as a kernel argument (by value, __grid_constant__): no device-side table to keep alive, nothing to upload,
+// and a captured CUDA graph replays the launch as it is.  3.4 KB of the 4 KB argument space.
+constexpr int kPackBatchMax = 48;
+struct PackJobTable { PackJob j[kPackBatchMax]; };
+template <typename T>
+__global__ void __launch_bounds__(256) pack_batch_table_kernel(const __grid_constant__ PackJobTable tab, int n_jobs) {
+  pack_batch_body<T>(tab.j, n_jobs);
+}
 
 // ------------------------------------------------------------------------------------------ channel sums
 // grid = (chunks, N).  Block = rows x CV threads (CV = C/VEC channel vectors); every thread owns one channel
@@ -1727,6 +1737,44 @@ B200_EXPORT int b200_optim_step_dev(int32_t kind, float* p, const float* g, floa
   else if (kind == 1) optim_dev_kernel<1><<<grid_for(n, 256, 4), 256, 0, st>>>(p, g, m, v, n, hp, derived);
   else optim_dev_kernel<2><<<grid_for(n, 256, 4), 256, 0, st>>>(p, g, m, v, n, hp, derived);
   B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+B200_EXPORT int b200_pack_batch(const b200_pack_job* jobs, int32_t n_jobs, int32_t dtype, void* stream) {
+  B200_CHECK_ARG(jobs && n_jobs > 0, "pack_batch: no jobs");
+  B200_CHECK_ARG(dtype == B200_BF16 || dtype == B200_F16, "pack_batch: 16-bit engine dtypes only");
+  static_assert(sizeof(b200_pack_job) == sizeof(PackJob), "b200_pack_job must mirror PackJob");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int j0 = 0; j0 < n_jobs; j0 += kPackBatchMax) {
+    const int n = n_jobs - j0 < kPackBatchMax ? n_jobs - j0 : kPackBatchMax;
+    PackJobTable tab;
+    int block = 0;
+    for (int k = 0; k < n; ++k) {
+      const b200_pack_job& s = jobs[j0 + k];
+      B200_CHECK_ARG(s.src && s.dst && s.kind >= 0 && s.kind <= 4 && s.cout > 0 && s.cin > 0 && s.kd > 0 && s.kh > 0 && s.kw > 0,
+                     "pack_batch: bad job %d", j0 + k);
+      PackJob& d = tab.j[k];
+      d.src = s.src; d.dst = s.dst; d.kind = s.kind; d.cout = s.cout; d.cin = s.cin; d.kd = s.kd; d.kh = s.kh; d.kw = s.kw;
+      d.flip = s.flip;
+      int64_t total = (int64_t)s.cout * s.cin * s.kd * s.kh * s.kw;
+      if (s.kind == PACK_XFOLD) {
+        const int CO = s.flip ? s.cin : s.cout, CI = s.flip ? s.cout : s.cin;
+        int xoff = 0, kxp = 0;
+        B200_CHECK_ARG(pack_xfold_geom(CI, s.kw, &xoff, &kxp), "pack_batch: job %d: x-folded packing needs Cin in (2, 4, 8) or a multiple of 16", j0 + k);
+        total = (int64_t)4 * CO * s.kd * s.kh * kxp;
+      }
+      d.total = total;
+      int64_t nb = ceil_div(total, 256 * 4);
+      if (nb > 64) nb = 64;
+      if (nb < 1) nb = 1;
+      d.block_begin = block;
+      d.n_blocks = (int)nb;
+      block += (int)nb;
+    }
+    if (dtype == B200_BF16) pack_batch_table_kernel<__nv_bfloat16><<<block, 256, 0, st>>>(tab, n);
+    else pack_batch_table_kernel<__half><<<block, 256, 0, st>>>(tab, n);
+    B200_LAUNCH_CHECK();
+  }
   return B200_OK;
 }
 

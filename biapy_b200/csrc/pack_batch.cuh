@@ -42,7 +42,16 @@ __host__ __device__ inline bool pack_xfold_geom(int cin, int kw, int* xoff, int*
 }
 
 template <typename T>
+__device__ __forceinline__ void pack_batch_body(const PackJob* __restrict__ jobs, int n_jobs);
+
+// job table in device memory (the emulator test drives this form)
+template <typename T>
 __global__ void __launch_bounds__(256) pack_batch_kernel(const PackJob* __restrict__ jobs, int n_jobs) {
+  pack_batch_body<T>(jobs, n_jobs);
+}
+
+template <typename T>
+__device__ __forceinline__ void pack_batch_body(const PackJob* __restrict__ jobs, int n_jobs) {
   __shared__ int s_job;
   if (threadIdx.x == 0) {
     int j = 0;

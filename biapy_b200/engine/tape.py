@@ -103,6 +103,8 @@ class Tape:
         # conv -> norm: channel sums of the normalisation produced by the convolution epilogue (x-slab kernels)
         self.fuse_stats = os.environ.get("B200_FUSE_STATS", "1") != "0"
         self.param_grads: Dict[torch.nn.Parameter, torch.Tensor] = {}
+        # key -> (pack job, packed tensor) of every weight pack this pass launched on its own (Trainer: replayed as one launch)
+        self.pack_record: Optional[Dict] = None
         self._packed: Dict[Tuple, torch.Tensor] = {}
         self._pad16: Dict[int, torch.Tensor] = {}
 
@@ -135,9 +137,13 @@ class Tape:
             if hit is not None and hit[0] == ver and hit[2] == src.data_ptr():
                 t = hit[1]
             else:
+                ops.LAST_PACK = None
                 t = build()
                 if self._pack_cache is not None:
                     self._pack_cache[(key, self.dtype)] = (ver, t, src.data_ptr())
+                job = ops.LAST_PACK
+                if self.pack_record is not None and job is not None and job[2] is t:
+                    self.pack_record[key] = job
             self._packed[key] = t
         return t
 
@@ -247,7 +253,7 @@ class Tape:
                     dw16 = torch.empty((cout, 16) + tuple(w.shape[2:]), dtype=torch.float32, device=self.device)
                     # the block output may live in a channel slice of a concat buffer: dense copy -> x-folded wgrad
                     dy = self._dense_for_xfold(out.grad(), 16)
-                    ops.conv_wgrad(x.padded, dy, cout, 16, k, dw16, gb, accumulate=False, impl=self.impl)
+                    ops.conv_wgrad(x.padded, dy, cout, 16, k, dw16, gb, accumulate=False, impl=self.impl, defer_unpack=False)
                     self._pgrad(w).add_(dw16[:, :cin])
             self.steps.append(bwd)
         return out
@@ -280,10 +286,7 @@ class Tape:
                 if x.requires_grad:
                     acc = x.prepare_accumulate()
                     if tc:
-                        key = (id(w), "convT_d")
-                        wpt = self._packed.get(key)
-                        if wpt is None:
-                            wpt = self._packed[key] = ops.pack_convT_weight(wf, self.dtype, True)
+                        wpt = self._cached((id(w), "convT_d"), w, lambda: ops.pack_convT_weight(wf, self.dtype, True))
                         ops.convT_dgrad_tc(dy, wpt, x.grad(), s, accumulate=acc)
                     else:
                         ops.convT_dgrad(dy, wf, x.grad(), s, accumulate=acc)

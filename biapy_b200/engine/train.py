@@ -110,6 +110,7 @@ class Trainer:
         self._derived = torch.zeros(8, dtype=torch.float32, device=self.device)
         self._gsq = torch.zeros(1, dtype=torch.float64, device=self.device)
         self._bad_labels = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self._pack_plan = None         # (engine dtype, {tape key: pack job}) recorded by the first pass, replayed as one launch
         self._unscale = 1.0            # set by _loss_and_grad: what the optimiser multiplies the raw gradient with
         self._denom = None             # device divisor of the gradient (mask / counted-voxel count), or None
         self.sync_parameters()
@@ -315,9 +316,28 @@ class Trainer:
             tape.rng_seed = model.next_rng_seed(self.device)
         self.fp.grad.zero_()
         self._arena.begin(self.device)            # one fill for all the accumulators of this pass
+        # Weight packs: the first pass launches them one by one and records the jobs whose source is a view of the flat
+        # parameter buffer (stable address, contents rewritten by the optimiser); every later pass replays them as ONE batched
+        # launch into the same packed tensors and hands those to the tape.  Weight-gradient un-packs are queued during backward
+        # and leave as one launch, too (~95 of the ~310 launches of a config-[1] step were these 5-10 us permutation kernels).
+        plan = self._pack_plan if (self._pack_plan is not None and self._pack_plan[0] == model.engine_dtype) else None
+        if plan is not None and model.engine_dtype != torch.float32:
+            ops.pack_batch([j for j in plan[1].values()], model.engine_dtype)
+            tape._packed.update({k: j[2] for k, j in plan[1].items()})
+        else:
+            tape.pack_record = {}
+        ops.UNPACK_QUEUE = [] if model.engine_dtype != torch.float32 else None
         try:
-            return self._run_pass(model, tape, xd, td)
+            loss = self._run_pass(model, tape, xd, td)
+            ops.flush_unpacks()
+            if tape.pack_record is not None:
+                lo = self.fp.flat.data_ptr()
+                hi = lo + self.fp.flat.numel() * 4
+                keep = {k: j for k, j in tape.pack_record.items() if lo <= j[1].data_ptr() < hi and j[1].is_contiguous()}
+                self._pack_plan = (model.engine_dtype, keep)
+            return loss
         finally:
+            ops.UNPACK_QUEUE = None
             self._arena.end()
 
     def _run_pass(self, model, tape, xd: torch.Tensor, td: torch.Tensor) -> torch.Tensor:

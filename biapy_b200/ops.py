@@ -101,9 +101,58 @@ def _launch_timed(label, flops, nbytes, name, *args):
     _timed_call(label, flops, nbytes, name, *args)
 
 
+# ------------------------------------------------------------------------------------------ batched re-packing
+class PackJob(C.Structure):
+    """Mirror of ``b200_pack_job`` (include/biapy_b200.h)."""
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("kind", C.c_int32), ("cout", C.c_int32), ("cin", C.c_int32),
+                ("kd", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32), ("flip", C.c_int32), ("block_begin", C.c_int32),
+                ("n_blocks", C.c_int32), ("total", C.c_int64)]
+
+
+PACK_PLAIN, PACK_XFOLD, PACK_CONVT, UNPACK_WGRAD, UNPACK_CONVT_WGRAD = 0, 1, 2, 3, 4
+# set by the single-job pack functions: (kind, src tensor, dst tensor, cout, cin, kd, kh, kw, flip) of the launch just made --
+# the Tape copies it into the Trainer's pack plan so that later passes replay all packs as one launch
+LAST_PACK = None
+# list while a Trainer pass is in flight: weight-gradient un-packs are queued here and flushed as one launch after backward
+UNPACK_QUEUE = None
+
+
+def pack_batch(jobs, dtype: torch.dtype):
+    """jobs: [(kind, src, dst, cout, cin, kd, kh, kw, flip)] with CUDA tensors src / dst; one launch per 48 jobs."""
+    if not jobs:
+        return
+    arr = (PackJob * len(jobs))()
+    for a, (kind, src, dst, cout, cin, kd, kh, kw, flip) in zip(arr, jobs):
+        a.src, a.dst, a.kind, a.cout, a.cin, a.kd, a.kh, a.kw, a.flip = src.data_ptr(), dst.data_ptr(), kind, cout, cin, kd, kh, kw, flip
+    global LAUNCHES
+    LAUNCHES += (len(jobs) - 1) // 48
+    _launch("b200_pack_batch", arr, len(jobs), _lib.torch_dtype_code(dtype), stream_ptr())
+
+
+def flush_unpacks():
+    """Launch the queued weight-gradient un-packs (see UNPACK_QUEUE) and empty the queue."""
+    global UNPACK_QUEUE
+    q = UNPACK_QUEUE
+    if q:
+        UNPACK_QUEUE = []
+        pack_batch([j[:9] for j in q], torch.bfloat16)      # fp32 -> fp32 jobs: the dtype only selects the (unused) pack type
+
+
 def conv_impl_query(x, y, k, wgrad=False) -> int:
     """Best kernel family for these operands: IMPL_XFOLD / IMPL_UMMA / IMPL_SIMT."""
     return _lib.lib().b200_conv_impl_query(_ref(x), _ref(y), k[0], k[1], k[2], 1 if wgrad else 0)
+
+
+def _family(kind: str, x, y, k, wgrad, impl) -> str:
+    """Profile label of a convolution launch.  Families follow the roofline that bounds them: 3x3(x3) layers with
+    >= 16 input channels are tensor-bound `conv_<kind>_<impl>`; pointwise layers (k = 1: 12 FLOP per byte at 16 <-> 48 channels)
+    and image-fed layers (Cin < 16) are HBM streams and get their own families so that they do not dilute the tensor figure."""
+    name = _impl_name(x, y, k, wgrad, impl)
+    if tuple(k) == (1, 1, 1):
+        return f"conv1x1_{kind}_{name}"
+    if x.shape[-1] < 16:
+        return f"conv_image_{kind}_{name}"
+    return f"conv_{kind}_{name}"
 
 
 def _impl_name(x, y, k, wgrad, impl):
@@ -142,6 +191,8 @@ def pack_conv_weight(w: torch.Tensor, dtype: torch.dtype, flip_transpose: bool) 
     out = torch.empty(w.numel(), dtype=dtype, device=w.device)
     _launch("b200_pack_conv_weight", _ptr(w), _ptr(out), _lib.torch_dtype_code(dtype), cout, cin, k[0], k[1], k[2],
             1 if flip_transpose else 0, stream_ptr())
+    global LAST_PACK
+    LAST_PACK = (PACK_PLAIN, w, out, cout, cin, k[0], k[1], k[2], 1 if flip_transpose else 0)
     return out
 
 
@@ -172,6 +223,8 @@ def pack_conv_weight_xfold(w: torch.Tensor, dtype: torch.dtype, flip_transpose: 
     out = torch.empty(4 * co_l * k[0] * k[1] * xfold_window(ci_l, k[2])[1], dtype=dtype, device=w.device)
     _launch("b200_pack_conv_weight_xfold", _ptr(w), _ptr(out), _lib.torch_dtype_code(dtype), cout, cin, k[0], k[1], k[2],
             1 if flip_transpose else 0, stream_ptr())
+    global LAST_PACK
+    LAST_PACK = (PACK_XFOLD, w, out, cout, cin, k[0], k[1], k[2], 1 if flip_transpose else 0)
     return out
 
 
@@ -181,7 +234,7 @@ def conv_fprop(x, w_packed, bias, y, k: Sequence[int], residual=None, accumulate
         vox = x.shape[0] * x.shape[1] * x.shape[2] * x.shape[3]
         flops = 2.0 * vox * x.shape[-1] * y.shape[-1] * k[0] * k[1] * k[2]
         nbytes = vox * (x.shape[-1] + y.shape[-1] * (2 if accumulate else 1)) * x.element_size()
-        label = "conv_fprop_" + _impl_name(x, y, k, False, impl)
+        label = _family("fprop", x, y, k, False, impl)
         if PROFILE_SHAPES:
             label += f" {x.shape[-1]}->{y.shape[-1]} k{k[0]}{k[1]}{k[2]} @{x.shape[1]}x{x.shape[2]}x{x.shape[3]}"
     _launch_timed(label, flops, nbytes, "b200_conv_fprop", _ref(x), _ptr(w_packed), _ptr(bias), _ref(residual), _ref(y), k[0], k[1], k[2],
@@ -198,7 +251,7 @@ def conv_fprop_stats(x, w_packed_xfold, bias, y, k: Sequence[int], sums: torch.T
         vox = x.shape[0] * x.shape[1] * x.shape[2] * x.shape[3]
         flops = 2.0 * vox * x.shape[-1] * y.shape[-1] * k[0] * k[1] * k[2]
         nbytes = vox * (x.shape[-1] + y.shape[-1] * (2 if accumulate else 1)) * x.element_size()
-        label = "conv_fprop_xfold"
+        label = _family("fprop", x, y, k, False, _lib.IMPL_XFOLD)
         if PROFILE_SHAPES:
             label += f" {x.shape[-1]}->{y.shape[-1]} k{k[0]}{k[1]}{k[2]} @{x.shape[1]}x{x.shape[2]}x{x.shape[3]} +stats"
     applied = C.c_int32(0)
@@ -207,21 +260,51 @@ def conv_fprop_stats(x, w_packed_xfold, bias, y, k: Sequence[int], sums: torch.T
     return bool(applied.value)
 
 
+_WGRAD_N = (256, 128, 64, 32, 16)        # output-channel widths of the tcgen05 weight-gradient kernels (one N tile each)
+
+
+def _wgrad_cuts(cout: int):
+    """Output-channel slices [(a, b), ...] that the tensor-core weight-gradient kernels take: Cout itself when it is one of their
+    N tiles, else a greedy cover by them (512 -> 256 + 256, 384 -> 256 + 128, 48 -> 32 + 16)."""
+    if cout in _WGRAD_N or cout % 16:
+        return [(0, cout)]
+    cuts, a = [], 0
+    while a < cout:
+        w = next(n for n in _WGRAD_N if n <= cout - a)
+        cuts.append((a, a + w))
+        a += w
+    return cuts
+
+
 def conv_wgrad(x, dy, cout: int, cin: int, k: Sequence[int], dw_out: torch.Tensor, dbias_out: Optional[torch.Tensor],
-               accumulate=False, impl=_lib.IMPL_AUTO):
-    """dw_out: (Cout, Cin, *k) fp32; dbias_out: (Cout,) fp32, must be zero-initialised unless accumulate."""
+               accumulate=False, impl=_lib.IMPL_AUTO, defer_unpack: bool = True):
+    """dw_out: (Cout, Cin, *k) fp32; dbias_out: (Cout,) fp32, must be zero-initialised unless accumulate.  Inside a Trainer pass
+    the un-pack of the gradient into `dw_out` is queued (`UNPACK_QUEUE`) unless `defer_unpack` is False."""
     taps = k[0] * k[1] * k[2]
     packed = zeros(cout * taps * cin, torch.float32, x.device)
-    label = flops = nbytes = None
-    if PROFILE is not None:
-        vox = x.shape[0] * x.shape[1] * x.shape[2] * x.shape[3]
-        flops = 2.0 * vox * cin * cout * taps
-        nbytes = vox * (cin + cout) * x.element_size()
-        label = "conv_wgrad_" + _impl_name(x, dy, k, True, impl)
-        if PROFILE_SHAPES:
-            label += f" {cin}->{cout} k{k[0]}{k[1]}{k[2]} @{x.shape[1]}x{x.shape[2]}x{x.shape[3]}"
-    _launch_timed(label, flops, nbytes, "b200_conv_wgrad", _ref(x), _ref(dy), _ptr(packed), _ptr(dbias_out), k[0], k[1], k[2], impl, stream_ptr())
-    _launch("b200_unpack_conv_wgrad", _ptr(packed), _ptr(dw_out), cout, cin, taps, 1 if accumulate else 0, stream_ptr())
+    cuts = [(0, cout)]
+    if impl == _lib.IMPL_AUTO and x.dtype != torch.float32 and conv_impl_query(x, dy, k, True) == _lib.IMPL_SIMT:
+        # Cout outside the kernels' N tiles (e.g. the 512-channel layers of BASELINE config[4]): one launch per slice of dy, each
+        # writing its own rows of the packed [Cout][tap][Cin] gradient -- instead of the CUDA-core fallback for the whole layer
+        c2 = _wgrad_cuts(cout)
+        if len(c2) > 1 and all(conv_impl_query(x, dy[..., a:b], k, True) != _lib.IMPL_SIMT for a, b in c2):
+            cuts = c2
+    for a, b in cuts:
+        dys = dy if len(cuts) == 1 else dy[..., a:b]
+        label = flops = nbytes = None
+        if PROFILE is not None:
+            vox = x.shape[0] * x.shape[1] * x.shape[2] * x.shape[3]
+            flops = 2.0 * vox * cin * (b - a) * taps
+            nbytes = vox * (cin + (b - a)) * x.element_size()
+            label = _family("wgrad", x, dys, k, True, impl)
+            if PROFILE_SHAPES:
+                label += f" {cin}->{b - a} k{k[0]}{k[1]}{k[2]} @{x.shape[1]}x{x.shape[2]}x{x.shape[3]}"
+        _launch_timed(label, flops, nbytes, "b200_conv_wgrad", _ref(x), _ref(dys), _ptr(packed[a * taps * cin:b * taps * cin]),
+                      _ptr(None if dbias_out is None else dbias_out[a:b]), k[0], k[1], k[2], impl, stream_ptr())
+    if defer_unpack and UNPACK_QUEUE is not None and dw_out.is_contiguous():
+        UNPACK_QUEUE.append((UNPACK_WGRAD, packed, dw_out, cout, cin, taps, 1, 1, 1 if accumulate else 0))
+    else:
+        _launch("b200_unpack_conv_wgrad", _ptr(packed), _ptr(dw_out), cout, cin, taps, 1 if accumulate else 0, stream_ptr())
 
 
 def convT_fprop(x, w, bias, y, s: Sequence[int]):
@@ -251,6 +334,8 @@ def pack_convT_weight(w: torch.Tensor, dtype: torch.dtype, for_dgrad: bool) -> t
     out = torch.empty(w.numel(), dtype=dtype, device=w.device)
     _launch("b200_pack_convT_weight", _ptr(w), _ptr(out), _lib.torch_dtype_code(dtype), cin, cout, taps, 1 if for_dgrad else 0,
             stream_ptr())
+    global LAST_PACK
+    LAST_PACK = (PACK_CONVT, w, out, cin, cout, taps, 1, 1, 1 if for_dgrad else 0)
     return out
 
 
@@ -277,7 +362,10 @@ def convT_wgrad_tc(x, dy, dw: torch.Tensor, dbias, s: Sequence[int], accumulate=
     packed = zeros(taps * cout * cin, torch.float32, x.device)
     _launch_timed("convT_wgrad_tc", _convT_work(x, cout, s) if PROFILE is not None else 0, 0,
                   "b200_convT_wgrad_tc", _ref(x), _ref(dy), _ptr(packed), _ptr(dbias), s[0], s[1], s[2], stream_ptr())
-    _launch("b200_unpack_convT_wgrad", _ptr(packed), _ptr(dw), cin, cout, taps, 1 if accumulate else 0, stream_ptr())
+    if UNPACK_QUEUE is not None and dw.is_contiguous():
+        UNPACK_QUEUE.append((UNPACK_CONVT_WGRAD, packed, dw, cin, cout, taps, 1, 1, 1 if accumulate else 0))
+    else:
+        _launch("b200_unpack_convT_wgrad", _ptr(packed), _ptr(dw), cin, cout, taps, 1 if accumulate else 0, stream_ptr())
 
 
 # ------------------------------------------------------------------------------------------------- dropout

@@ -361,6 +361,26 @@ int b200_softmax_ce(const b200_tensor* logits, const int64_t* target, double* su
 /* head activations (biapy/engine/base_workflow.py:1367-1470): sigmoid per channel or softmax over [c0, c1) */
 int b200_softmax_channels(const b200_tensor* x, const b200_tensor* y, int32_t c0, int32_t c1, void* stream);
 
+/* ------------------------------------------------------------------------------------ batched weight re-packing
+ * A training pass re-packs every fp32 master weight for the tensor-core kernels (b200_pack_conv_weight, _xfold, b200_pack_convT_weight:
+ * 66 launches for the config-[1] network) and un-packs every weight gradient (b200_unpack_conv_wgrad, b200_unpack_convT_wgrad: 32);
+ * b200_pack_batch runs any mix of those element mappings in ONE launch per 48 jobs.  `jobs` is a HOST array; src / dst are
+ * device pointers.  kind: 0 plain pack, 1 x-folded pack, 2 transposed-conv pack (flip = for_dgrad), 3 un-pack of a conv weight
+ * gradient, 4 un-pack of a transposed-conv weight gradient (flip = accumulate into dst); (cout, cin, kd, kh, kw) as in the
+ * single-job calls -- for kinds 2 / 4 `cout` carries the transposed conv's Cin and `cin` its Cout, the argument order of
+ * b200_pack_convT_weight(w, packed, dtype, cin, cout, taps, ...).  block_begin / n_blocks / total are filled in by the call. */
+typedef struct b200_pack_job {
+  const float* src;
+  void* dst;
+  int32_t kind;
+  int32_t cout, cin;
+  int32_t kd, kh, kw;
+  int32_t flip;
+  int32_t block_begin, n_blocks;
+  int64_t total;
+} b200_pack_job;
+int b200_pack_batch(const b200_pack_job* jobs, int32_t n_jobs, int32_t dtype, void* stream);
+
 /* --------------------------------------------------------------------------------------------- optimiser
  * AdamW / SGD on a flat fp32 buffer (replaces timm create_optimizer_v2 -> torch.optim, engine/__init__.py:62-68). */
 int b200_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,

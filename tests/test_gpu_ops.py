@@ -507,3 +507,50 @@ def test_dropout_mask_statistics_and_backward(dtype):
     dy = torch.randn_like(x)
     dx = ops.dropout(dy, torch.empty_like(x), p, seed, 0).float()
     assert torch.allclose(dx, dy.float() * (y_next != 0) / (1 - p), rtol=2e-2, atol=1e-3)
+
+
+def test_pack_batch_equals_the_single_job_kernels():
+    """b200_pack_batch (one launch for all weight packs / weight-gradient un-packs of a training pass) against the single-job
+    kernels it replaces, bit for bit, on a mixed job list long enough to need two launches (> 48 jobs)."""
+    from biapy_b200 import ops
+    g = torch.Generator().manual_seed(21)
+    jobs, want = [], []
+    for rep in range(6):
+        for cout, cin, k in ((16, 16, (3, 3, 3)), (32, 16, (3, 3, 3)), (16, 48, (1, 3, 3)), (64, 32, (1, 1, 1)), (16, 2, (3, 3, 3))):
+            w = torch.randn(cout, cin, *k, generator=g).cuda()
+            for flip in (False, True):
+                if cin % 16 == 0 or not flip:
+                    ref = ops.pack_conv_weight_xfold(w, torch.bfloat16, flip)
+                    jobs.append((ops.PACK_XFOLD, w, torch.zeros_like(ref), cout, cin, k[0], k[1], k[2], int(flip)))
+                    want.append(ref)
+                ref = ops.pack_conv_weight(w, torch.bfloat16, flip)
+                jobs.append((ops.PACK_PLAIN, w, torch.zeros_like(ref), cout, cin, k[0], k[1], k[2], int(flip)))
+                want.append(ref)
+        wt = torch.randn(32, 16, 2, 2, 2, generator=g).cuda()                    # transposed conv (Cin, Cout, *s)
+        for for_dgrad in (False, True):
+            ref = ops.pack_convT_weight(wt, torch.bfloat16, for_dgrad)
+            jobs.append((ops.PACK_CONVT, wt, torch.zeros_like(ref), 32, 16, 8, 1, 1, int(for_dgrad)))
+            want.append(ref)
+    assert len(jobs) > 48
+    n0 = ops.LAUNCHES
+    ops.pack_batch(jobs, torch.bfloat16)
+    assert ops.LAUNCHES - n0 == (len(jobs) + 47) // 48
+    for j, ref in zip(jobs, want):
+        assert torch.equal(j[2], ref), j[0]
+    # un-packs: queued by conv_wgrad / convT_wgrad_tc inside a Trainer pass, here driven directly
+    packed = torch.randn(16 * 27 * 32, generator=g).cuda()
+    dw0 = torch.randn(16, 32, 3, 3, 3, generator=g).cuda()
+    ref = dw0.clone()
+    ops._launch("b200_unpack_conv_wgrad", ops._ptr(packed), ops._ptr(ref), 16, 32, 27, 1, _stream())
+    got = dw0.clone()
+    ops.UNPACK_QUEUE = [(ops.UNPACK_WGRAD, packed, got, 16, 32, 27, 1, 1, 1)]
+    try:
+        ops.flush_unpacks()
+    finally:
+        ops.UNPACK_QUEUE = None
+    assert torch.equal(got, ref)
+
+
+def _stream():
+    from biapy_b200 import _lib
+    return _lib.stream_ptr()

@@ -99,6 +99,29 @@ WGRAD_CASES = [
     (2, 24, 32, 16, 16, 16, (3, 3, 3)),    # z-slab wgrad: several voxel tiles per CTA (ring wrap-around)
     (1, 16, 16, 16, 96, 16, (3, 3, 3)),    # z-slab wgrad: 54 slab atoms
 ]
+# Cout outside the kernels' N tiles: ops.conv_wgrad covers it with slices of dy (512 = 256 + 256, 384 = 256 + 128, 48 = 32 + 16)
+WGRAD_SPLIT_CASES = [(2, 1, 16, 16, 256, 512, (1, 3, 3)), (1, 4, 8, 8, 64, 384, (3, 3, 3)), (1, 8, 8, 8, 16, 48, (3, 3, 3))]
+
+
+@pytest.mark.parametrize("case", WGRAD_SPLIT_CASES)
+def test_conv_wgrad_cout_slices(case):
+    from biapy_b200 import _lib, ops
+    n, d, h, w, cin, cout, k = case
+    dtype = torch.bfloat16
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(n, cin, d, h, w, generator=g).to(dtype).float()
+    wt = torch.zeros(cout, cin, *k, requires_grad=True)
+    b = torch.zeros(cout, requires_grad=True)
+    gy = torch.randn(n, cout, d, h, w, generator=g).to(dtype).float()
+    F.conv3d(x, wt, b, padding=[kk // 2 for kk in k]).backward(gy)
+    assert len(ops._wgrad_cuts(cout)) > 1
+    dw = torch.empty(cout, cin, *k, device="cuda")
+    db = torch.zeros(cout, device="cuda")
+    n0 = ops.LAUNCHES
+    ops.conv_wgrad(cl(x).to(dtype), cl(gy).to(dtype), cout, cin, k, dw, db)          # AUTO: must not fall back to the CUDA cores
+    assert ops.LAUNCHES - n0 == len(ops._wgrad_cuts(cout)) + 1
+    torch.cuda.synchronize()
+    assert nerr(dw.cpu(), wt.grad) < 2e-3 and nerr(db.cpu(), b.grad) < 2e-3
 
 
 @pytest.mark.parametrize("case", WGRAD_CASES)
@@ -120,7 +143,8 @@ def test_conv_wgrad_umma(case, dtype):
     assert nerr(db.cpu(), b.grad) < 2e-3
 
 
-@pytest.mark.parametrize("shape", [(2, 4, 8, 8, 32, 32), (1, 8, 8, 8, 256, 256), (1, 4, 4, 16, 64, 64), (1, 3, 5, 12, 32, 16)])
+@pytest.mark.parametrize("shape", [(2, 4, 8, 8, 32, 32), (1, 8, 8, 8, 256, 256), (1, 4, 4, 16, 64, 64), (1, 3, 5, 12, 32, 16),
+                                   (2, 1, 16, 16, 512, 256)])       # Cin = 512: the bottleneck up-sampling of BASELINE config[4]
 @pytest.mark.parametrize("stride", [(2, 2, 2), (1, 2, 2)])
 def test_convT_tensor_core_route(shape, stride):
     """ConvTranspose(k = s): fprop / dgrad / wgrad through the tcgen05 kernels on strided sub-lattice views."""
