@@ -365,6 +365,36 @@ __global__ void __launch_bounds__(256) overlap_add_cover_kernel(const TI* __rest
 // 32-bit element offsets: the launcher checks n_patches * patch volume < 2^31.
 struct SlotRow { int n, off0, off1; float f0, f1; };      // covering patches of one coordinate (n > 2: walk), row offsets, weights
 
+// NZ x NY x (1 or 2) covering patches of one output element, in patch order (z-major, y, then x).  NZ / NY are compile-time (they
+// are the same for a whole warp), the second x slot is a per-thread predicate.  All loads are issued before the first add.
+template <typename TI, int NZ, int NY>
+__device__ __forceinline__ void slot_accumulate(const TI* __restrict__ b0, const TI* __restrict__ b1, bool two_x, const int (&zoff)[2],
+                                                const float (&fz)[2], const SlotRow& t, float fx0, float fx1, float& acc, float& wsum) {
+  float v0[NZ * NY], v1[NZ * NY];
+#pragma unroll
+  for (int kz = 0; kz < NZ; ++kz)
+#pragma unroll
+    for (int ky = 0; ky < NY; ++ky) {
+      const int o = zoff[kz] + (ky ? t.off1 : t.off0);
+      v0[kz * NY + ky] = to_f<TI>(b0[o]);
+      v1[kz * NY + ky] = two_x ? to_f<TI>(b1[o]) : 0.f;
+    }
+#pragma unroll
+  for (int kz = 0; kz < NZ; ++kz)
+#pragma unroll
+    for (int ky = 0; ky < NY; ++ky) {
+      const float fzy = __fmul_rn(fz[kz], ky ? t.f1 : t.f0);
+      const float w0 = __fmul_rn(fzy, fx0);
+      acc = __fadd_rn(acc, __fmul_rn(v0[kz * NY + ky], w0));
+      wsum = __fadd_rn(wsum, w0);
+      if (two_x) {
+        const float w1 = __fmul_rn(fzy, fx1);
+        acc = __fadd_rn(acc, __fmul_rn(v1[kz * NY + ky], w1));
+        wsum = __fadd_rn(wsum, w1);
+      }
+    }
+}
+
 template <typename TI, typename TO, int UNROLL>
 __global__ void __launch_bounds__(256) overlap_add_slot_kernel(const TI* __restrict__ patches, TO* __restrict__ out, MergeParams p,
                                          int z0, int nz_out, int rows_per_block,
@@ -425,36 +455,23 @@ __global__ void __launch_bounds__(256) overlap_add_slot_kernel(const TI* __restr
           ++nxc;
         }
       }
-      const bool zx_fast = nzc <= 2 && nxc <= 2;
+      const bool zx_fast = (nzc == 1 || nzc == 2) && (nxc == 1 || nxc == 2);
+      const bool two_x = nxc == 2;
+      const TI* b0 = patches + xoff[0];
+      const TI* b1 = patches + xoff[1];
       TO* op = out + ((int64_t)zl * H + y_begin) * row_el + e0;
 #pragma unroll UNROLL
       for (int r = 0; r < y_end - y_begin; ++r) {
         const SlotRow t = s_row[r];
         float acc = 0.f, wsum = 0.f;
-        if (zx_fast && t.n <= 2) {
-          float v[8];
-#pragma unroll
-          for (int kz = 0; kz < 2; ++kz)
-#pragma unroll
-            for (int ky = 0; ky < 2; ++ky)
-#pragma unroll
-              for (int kx = 0; kx < 2; ++kx) {
-                const bool on = kz < nzc && ky < t.n && kx < nxc;
-                v[kz * 4 + ky * 2 + kx] = on ? to_f<TI>(patches[zoff[kz] + (ky ? t.off1 : t.off0) + xoff[kx]]) : 0.f;
-              }
-#pragma unroll
-          for (int kz = 0; kz < 2; ++kz)
-#pragma unroll
-            for (int ky = 0; ky < 2; ++ky) {
-              const float fzy = __fmul_rn(fz[kz], ky ? t.f1 : t.f0);
-#pragma unroll
-              for (int kx = 0; kx < 2; ++kx)
-                if (kz < nzc && ky < t.n && kx < nxc) {
-                  const float w = __fmul_rn(fzy, fx[kx]);
-                  acc = __fadd_rn(acc, __fmul_rn(v[kz * 4 + ky * 2 + kx], w));
-                  wsum = __fadd_rn(wsum, w);
-                }
-            }
+        if (zx_fast && (t.n == 1 || t.n == 2)) {
+          if (nzc == 1) {
+            if (t.n == 1) slot_accumulate<TI, 1, 1>(b0, b1, two_x, zoff, fz, t, fx[0], fx[1], acc, wsum);
+            else slot_accumulate<TI, 1, 2>(b0, b1, two_x, zoff, fz, t, fx[0], fx[1], acc, wsum);
+          } else {
+            if (t.n == 1) slot_accumulate<TI, 2, 1>(b0, b1, two_x, zoff, fz, t, fx[0], fx[1], acc, wsum);
+            else slot_accumulate<TI, 2, 2>(b0, b1, two_x, zoff, fz, t, fx[0], fx[1], acc, wsum);
+          }
         } else {
           const int y = y_begin + r;
           for (int iz = 0; iz < nz; ++iz) {
