@@ -105,7 +105,8 @@ SIGNATURES = {
     "b200_norm_act_bwd_apply": (_I, [_T, _T, _I, _P, _T, _I, _P]),
     "b200_norm_silu_fast_ok": (_I, [_T, _T, _T]),
     "b200_scale_shift_silu_fast": (_I, [_T, _P, _P, _T, _P]),
-    "b200_norm_silu_bwd_reduce_g": (_I, [_T, _T, _P, _P, _I, _P, _P, _P, _P]),
+    "b200_norm_silu_bwd_reduce_g": (_I, [_T, _T, _P, _P, _I, _P, _P, _P, _I, _P]),
+    "b200_norm_silu_bwd_apply_fast": (_I, [_T, _T, _P, _T, _I, _P]),
     "b200_norm_bwd_apply_g": (_I, [_T, _T, _P, _T, _I, _P]),
     "b200_act_bwd": (_I, [_T, _T, _I, _T, _I, _P]),
     "b200_binary": (_I, [_T, _T, _T, _I, _P]),

@@ -65,7 +65,7 @@ __global__ void scale_shift_silu_rows_fast_kernel(View<const T> x, View<T> y, co
 // backward pass 1: sums (sum g, sum g * (x - mean)) per (n, c) AND g written over dy.  The sums take g before it is rounded to T
 // (they become dgamma / dbeta: on the emulator, sums of the rounded values were 0.3 % off on a 210-voxel tensor); the apply pass
 // then subtracts means that differ from those of the stored values by the mean rounding error, far below one T ulp.
-template <typename T, int VEC, int U, int MINB>
+template <typename T, int VEC, int U, int MINB, bool WRITE_G = true>
 __global__ void __launch_bounds__(256, MINB) norm_silu_bwd_reduce_g_kernel(View<const T> x, View<T> dy_g, const float* __restrict__ mean,
                                                                      const float* __restrict__ rstd, int groups,
                                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256, MINB) norm_silu_bwd_reduce_g_kernel(View<
             s[i] += g;
             s2[i] = fmaf(g, fx - mu_c[i], s2[i]);
           }
-          *reinterpret_cast<Pack<T, VEC>*>(db + (v + (int64_t)u * rows) * dy_g.ld) = pg;
+          if (WRITE_G) *reinterpret_cast<Pack<T, VEC>*>(db + (v + (int64_t)u * rows) * dy_g.ld) = pg;
         }
     }
     double* dst = s_red + ((int64_t)row * cv_count + cv) * VEC * 2;
@@ -170,6 +170,55 @@ __global__ void __launch_bounds__(256, MINB) norm_bwd_apply_g_rows_kernel(View<c
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
           float r = fmaf(to_f<T>(pg[u].v[i]), k0[i], -fmaf(to_f<T>(px[u].v[i]), kp[i], kq[i]));
+          if (accumulate) r += to_f<T>(po[u].v[i]);
+          out.v[i] = from_f<T>(r);
+        }
+        *reinterpret_cast<Pack<T, VEC>*>(ob + v * dx.ld) = out;
+      }
+    }
+  }
+}
+
+
+// backward pass 2 without the g hand-over: recomputes the derivative from (x, dy) with the one-MUFU sigmoid.  Pairs with
+// norm_silu_bwd_reduce_g_kernel<..., WRITE_G = false>: no extra write in pass 1, one more tanh per element here.
+template <typename T, int VEC, int U, int MINB>
+__global__ void __launch_bounds__(256, MINB) norm_silu_bwd_apply_fast_rows_kernel(View<const T> x, View<const T> dy, View<T> dx,
+                                                                            const float* __restrict__ coef, int accumulate, int cvn, int rows) {
+  const int n = blockIdx.y;
+  const int cv = threadIdx.x % cvn, row = threadIdx.x / cvn;
+  if (row >= rows) return;
+  float k0[VEC], kb[VEC], kp[VEC], kq[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const float* cf = coef + ((int64_t)n * x.c + cv * VEC + i) * 4;
+    k0[i] = cf[0]; kb[i] = cf[1]; kp[i] = cf[2]; kq[i] = cf[3];
+  }
+  const T* xb = x.p + (int64_t)n * x.spatial * x.ld + cv * VEC;
+  const T* db = dy.p + (int64_t)n * x.spatial * dy.ld + cv * VEC;
+  T* ob = dx.p + (int64_t)n * x.spatial * dx.ld + cv * VEC;
+  const int64_t stride = (int64_t)gridDim.x * rows;
+  for (int64_t v0 = (int64_t)blockIdx.x * rows + row; v0 < x.spatial; v0 += U * stride) {
+    Pack<T, VEC> px[U], pd[U], po[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = v0 + u * stride;
+      if (v < x.spatial) {
+        px[u] = *reinterpret_cast<const Pack<T, VEC>*>(xb + v * x.ld);
+        pd[u] = *reinterpret_cast<const Pack<T, VEC>*>(db + v * dy.ld);
+        if (accumulate) po[u] = *reinterpret_cast<const Pack<T, VEC>*>(ob + v * dx.ld);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = v0 + u * stride;
+      if (v < x.spatial) {
+        Pack<T, VEC> out;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          const float fx = to_f<T>(px[u].v[i]);
+          const float g = to_f<T>(pd[u].v[i]) * silu_grad_fast(fmaf(fx, k0[i], kb[i]));
+          float r = fmaf(g, k0[i], -fmaf(fx, kp[i], kq[i]));
           if (accumulate) r += to_f<T>(po[u].v[i]);
           out.v[i] = from_f<T>(r);
         }

@@ -1466,7 +1466,8 @@ B200_EXPORT int b200_scale_shift_silu_fast(const b200_tensor* x, const float* sc
 }
 
 B200_EXPORT int b200_norm_silu_bwd_reduce_g(const b200_tensor* x, const b200_tensor* dy_g, const float* mean, const float* rstd,
-                                            int32_t groups, const float* gamma, const float* beta, double* red, void* stream) {
+                                            int32_t groups, const float* gamma, const float* beta, double* red, int32_t write_g,
+                                            void* stream) {
   B200_CHECK_ARG(check_tensor(x, "reduce_g.x") && check_tensor(dy_g, "reduce_g.dy") && mean && rstd && red, "%s", b200_last_error());
   B200_CHECK_ARG(norm_fast_ok(x, dy_g, nullptr), "norm_silu_bwd_reduce_g: tensors do not qualify");
   B200_CHECK_ARG(groups > 0 && x->c % groups == 0, "norm_silu_bwd_reduce_g: bad groups");
@@ -1483,8 +1484,31 @@ B200_EXPORT int b200_norm_silu_bwd_reduce_g(const b200_tensor* x, const b200_ten
     if (chunks > cap) chunks = cap;
     if (chunks < 1) chunks = 1;
     const size_t smem = sizeof(double) * rows * cvn * V * 2;
-    norm_silu_bwd_reduce_g_kernel<T, V, 1, 4><<<dim3((unsigned)chunks, x->n), threads, smem, st>>>(xv, gv, mean, rstd, groups, gamma,
-                                                                                               beta, red, cvn, rows);
+    if (write_g)
+      norm_silu_bwd_reduce_g_kernel<T, V, 1, 4, true><<<dim3((unsigned)chunks, x->n), threads, smem, st>>>(xv, gv, mean, rstd, groups,
+                                                                                                       gamma, beta, red, cvn, rows);
+    else
+      norm_silu_bwd_reduce_g_kernel<T, V, 1, 4, false><<<dim3((unsigned)chunks, x->n), threads, smem, st>>>(xv, gv, mean, rstd, groups,
+                                                                                                        gamma, beta, red, cvn, rows);
+  });
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+B200_EXPORT int b200_norm_silu_bwd_apply_fast(const b200_tensor* x, const b200_tensor* dy, const float* coef, const b200_tensor* dx,
+                                              int32_t accumulate, void* stream) {
+  B200_CHECK_ARG(check_tensor(x, "apply_fast.x") && check_tensor(dy, "apply_fast.dy") && check_tensor(dx, "apply_fast.dx") && coef, "%s",
+                 b200_last_error());
+  B200_CHECK_ARG(norm_fast_ok(x, dy, dx), "norm_silu_bwd_apply_fast: tensors do not qualify");
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_DISPATCH_DTYPE16(x->dtype, T, {
+    constexpr int V = 8;
+    View<const T> xv = view<const T>(x);
+    View<const T> dv = view<const T>(dy);
+    View<T> ov = view<T>(dx);
+    int cvn = x->c / V, rows = 256 / cvn;
+    dim3 grid(rows_grid(xv.spatial, rows, x->n), x->n);
+    norm_silu_bwd_apply_fast_rows_kernel<T, V, 1, 4><<<grid, 256, 0, st>>>(xv, dv, ov, coef, accumulate, cvn, rows);
   });
   B200_LAUNCH_CHECK();
   return B200_OK;

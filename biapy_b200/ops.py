@@ -458,6 +458,9 @@ def bn_eval_stats(x, running_mean, running_var, gamma, beta, eps: float) -> Norm
 # relative error of 2^-11: below bf16's rounding step, comparable to fp16's -- the fp16 engine is the 1e-3 parity path and keeps
 # the exact exponential unless asked.
 NORM_FAST = os.environ.get("B200_NORM_FAST", "auto").lower()
+# backward form of the fast chain: 'g' = pass 1 leaves g = dy * act' in dy's place (needs dy_dead), 'recompute' = pass 2 evaluates
+# the derivative again with the one-MUFU sigmoid (no extra write in pass 1)
+NORM_BWD = os.environ.get("B200_NORM_BWD", "g").lower()
 
 
 def norm_fast_ok(x, dy=None, dx=None) -> bool:
@@ -479,10 +482,11 @@ def norm_act_bwd(x, dy, st: NormStats, gamma, beta, act: str, dx, dgamma, dbeta,
     whose reduce pass leaves g = dy * act'(z) in dy's place for the apply pass."""
     n, d, h, w, c = x.shape
     red = zeros(n * c * 2, torch.float64, x.device)
-    fast = dy_dead and act == "silu" and norm_fast_ok(x, dy, dx)
+    write_g = NORM_BWD != "recompute"
+    fast = (dy_dead or not write_g) and act == "silu" and norm_fast_ok(x, dy, dx)
     if fast:
         _launch("b200_norm_silu_bwd_reduce_g", _ref(x), _ref(dy), _ptr(st.mean), _ptr(st.rstd), st.groups, _ptr(gamma), _ptr(beta),
-                _ptr(red), stream_ptr(), shape=x.shape)
+                _ptr(red), 1 if write_g else 0, stream_ptr(), shape=x.shape)
     else:
         _launch("b200_norm_act_bwd_reduce", _ref(x), _ref(dy), _ptr(st.mean), _ptr(st.rstd), st.groups, _ptr(gamma), _ptr(beta),
                 ACT[act], _ptr(red), stream_ptr(), shape=x.shape)
@@ -501,8 +505,11 @@ def norm_act_bwd(x, dy, st: NormStats, gamma, beta, act: str, dx, dgamma, dbeta,
     _launch("b200_norm_bwd_finalize", _ptr(red), _ptr(st.mean), _ptr(st.rstd), _ptr(gamma), _ptr(beta), n, c, st.groups,
             d * h * w * world, 1 if st.batch_stats else 0, _ptr(coef), _ptr(dgamma), _ptr(dbeta), stream_ptr())
     if dx is not None:
-        if fast:
+        if fast and write_g:
             _launch("b200_norm_bwd_apply_g", _ref(x), _ref(dy), _ptr(coef), _ref(dx), 1 if accumulate else 0, stream_ptr(),
+                    shape=x.shape)
+        elif fast:
+            _launch("b200_norm_silu_bwd_apply_fast", _ref(x), _ref(dy), _ptr(coef), _ref(dx), 1 if accumulate else 0, stream_ptr(),
                     shape=x.shape)
         else:
             _launch("b200_norm_act_bwd_apply", _ref(x), _ref(dy), ACT[act], _ptr(coef), _ref(dx), 1 if accumulate else 0,

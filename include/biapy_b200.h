@@ -323,8 +323,12 @@ int b200_norm_act_bwd_apply(const b200_tensor* x, const b200_tensor* dy, int32_t
  * (bf16 / fp16, 8-channel vectors, <= 2048 channels); dy / dx may be null for the forward-only question. */
 int b200_norm_silu_fast_ok(const b200_tensor* x, const b200_tensor* dy, const b200_tensor* dx);
 int b200_scale_shift_silu_fast(const b200_tensor* x, const float* scale, const float* shift, const b200_tensor* y, void* stream);
+/* write_g = 0: dy is left alone and the apply pass is b200_norm_silu_bwd_apply_fast, which recomputes the derivative (no extra
+ * write in pass 1, one more MUFU per element in pass 2). */
 int b200_norm_silu_bwd_reduce_g(const b200_tensor* x, const b200_tensor* dy_g, const float* mean, const float* rstd,
-                                int32_t groups, const float* gamma, const float* beta, double* red, void* stream);
+                                int32_t groups, const float* gamma, const float* beta, double* red, int32_t write_g, void* stream);
+int b200_norm_silu_bwd_apply_fast(const b200_tensor* x, const b200_tensor* dy, const float* coef, const b200_tensor* dx,
+                                  int32_t accumulate, void* stream);
 int b200_norm_bwd_apply_g(const b200_tensor* x, const b200_tensor* g, const float* coef, const b200_tensor* dx,
                           int32_t accumulate, void* stream);
 /* activation only (norm == 'none'): dx (+)= dy * act'(x) */

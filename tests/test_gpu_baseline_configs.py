@@ -79,9 +79,15 @@ def test_full_size_config_forward_backward(arch, kw, batch, lowp):
 CFG1 = dict(image_shape=(128, 128, 128, 2), activation="silu", feature_maps=[16, 32, 64, 128, 256], drop_values=[0] * 5,
             normalization="gn", k_size=3, yx_down=[2] * 4, z_down=[2] * 4, isotropy=[True] * 5, larger_io=False,
             conv_layers=[2] * 5, output_channels=[1])
-# Bounds = 2x what the device run of this test measured (profiles/parity_cfg1_r2.json); rel-L2 for the 16-bit engines, whose
+# Bounds <= 2x what the device run of this test measured (profiles/parity_cfg1_r2.json); rel-L2 for the 16-bit engines, whose
 # per-element error is a rounding noise of the storage format, normalised max for fp32.  (dtype, y, dW, dx)
-CFG1_BOUNDS = {torch.float32: (1e-3, 1e-3, 5e-2), torch.float16: (5e-3, 2.5e-2, 5e-2), torch.bfloat16: (5e-2, 2.5e-1, 2.5e-1)}
+#   measured   fp32: 1.3e-6 / 6.5e-4 / 2.5e-2 (ATen's own fp32 vs float64: 6.5e-7 / 2.3e-4 / 1.3e-2; torch CUDA fp32: dx 1.1e-1)
+#              fp16: 6.1e-4 / 1.2e-2 / 2.4e-2 (torch.autocast fp16 on CUDA: 7.1e-4 / 1.2e-2 / 2.6e-2)
+#              bf16: 5.1e-3 / 3.5e-2 / 6.9e-2 (torch.autocast bf16 on CUDA: 5.8e-3 / 3.7e-2 / 7.3e-2)
+# The north-star bar (1e-3) is met by the fp32 engine for outputs and parameter gradients and by the fp16 engine for outputs; 16-bit
+# parameter gradients sit at the level PyTorch's own autocast reaches on the same graph: max-pool routing is discontinuous, a
+# rounding that flips an arg-max moves a whole gradient entry (error ~ sqrt(rounding step): bf16 / fp16 = 3.0, not 8).
+CFG1_BOUNDS = {torch.float32: (1e-3, 1e-3, 5e-2), torch.float16: (1e-3, 2.4e-2, 5e-2), torch.bfloat16: (1e-2, 7e-2, 1.4e-1)}
 
 
 def test_full_size_cfg1_resunet128():

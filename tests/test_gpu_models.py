@@ -47,7 +47,7 @@ FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "model_*.npz")))
 
 
 @pytest.mark.parametrize("path", FIXTURES)
-@pytest.mark.parametrize("dtype,tol_fwd,tol_bwd", [(torch.float32, 1e-3, 1e-3), (torch.bfloat16, 5e-2, 2.5e-1)])
+@pytest.mark.parametrize("dtype,tol_fwd,tol_bwd", [(torch.float32, 1e-3, 1e-3), (torch.float16, 1e-2, 1e-1), (torch.bfloat16, 5e-2, 2.5e-1)])
 def test_golden_forward_backward(path, dtype, tol_fwd, tol_bwd):
     z = np.load(path)
     kw = json.loads(str(z["kwargs_json"]))
@@ -74,6 +74,13 @@ def test_golden_forward_backward(path, dtype, tol_fwd, tol_bwd):
     l2_gx = l2err(x.grad.cpu(), torch.from_numpy(z["gx"]))
     print(f"\n[parity] {os.path.basename(path)} {dtype}: max-norm fwd {e_fwd:.2e} dx {e_gx:.2e} dparams {e_p:.2e} ({worst}); "
           f"rel-L2 fwd {l2_fwd:.2e} dx {l2_gx:.2e}")
+    try:                                # one line per case for profiles/parity_golden_r2.jsonl
+        os.makedirs("gpurun_out", exist_ok=True)
+        with open("gpurun_out/parity_golden.jsonl", "a") as f:
+            f.write(json.dumps({"fixture": os.path.basename(path), "dtype": str(dtype).replace("torch.", ""), "fwd_max": e_fwd, "dx_max": e_gx,
+                                "dparams_max": e_p, "fwd_l2": l2_fwd, "dx_l2": l2_gx}) + "\n")
+    except OSError:
+        pass
     if dtype == torch.float32:          # the 1e-3 parity bar of the north star
         assert e_fwd < tol_fwd and e_gx < tol_bwd and e_p < tol_bwd
     else:                               # bf16 storage: stated, looser bound on the relative L2 error

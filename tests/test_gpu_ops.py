@@ -246,11 +246,13 @@ def test_norm_act_fwd_bwd(kind, c, groups, act, dtype):
 
 @pytest.mark.parametrize("c,groups,pad", [(16, 8, 0), (48, 8, 16), (96, 8, 0)])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-def test_norm_silu_fast_chain(c, groups, pad, dtype, monkeypatch):
+@pytest.mark.parametrize("bwd", ["g", "recompute"])
+def test_norm_silu_fast_chain(c, groups, pad, dtype, bwd, monkeypatch):
     """The one-MUFU SiLU chain (norm_fast.cuh) against ATen in fp32 on operands rounded to the engine dtype: forward, dx (plain and
     accumulated into a channel slice), dgamma / dbeta; dy is overwritten by g = dy * silu'(z) as documented."""
     from biapy_b200 import ops
     monkeypatch.setattr(ops, "NORM_FAST", "1")
+    monkeypatch.setattr(ops, "NORM_BWD", bwd)
     n, d, h, w = 2, 6, 6, 10
     g = torch.Generator().manual_seed(3)
     x = (torch.randn(n, c, d, h, w, generator=g) * 1.7 + 0.4).to(dtype).float()
@@ -275,7 +277,7 @@ def test_norm_silu_fast_chain(c, groups, pad, dtype, monkeypatch):
         dx = dxbuf[..., pad:]
         dg, db = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
         ops.norm_act_bwd(xd, dy, st, gamma.cuda(), beta.cuda(), "silu", dx, dg, db, accumulate=accumulate, dy_dead=True)
-        assert not torch.equal(dy, dy0)                                   # g left in place of dy
+        assert torch.equal(dy, dy0) == (bwd == "recompute")             # 'g': g left in place of dy; 'recompute': dy untouched
         want = xr.grad + (1.0 if accumulate else 0.0)
         assert nerr(ncdhw(dx), want) < tol
         assert nerr(dg.cpu(), gr.grad) < tol and nerr(db.cpu(), br.grad) < tol
