@@ -395,8 +395,8 @@ __device__ __forceinline__ void slot_accumulate(const TI* __restrict__ b0, const
     }
 }
 
-template <typename TI, typename TO, int UNROLL>
-__global__ void __launch_bounds__(256) overlap_add_slot_kernel(const TI* __restrict__ patches, TO* __restrict__ out, MergeParams p,
+template <typename TI, typename TO, int UNROLL, int MINB>
+__global__ void __launch_bounds__(256, MINB) overlap_add_slot_kernel(const TI* __restrict__ patches, TO* __restrict__ out, MergeParams p,
                                          int z0, int nz_out, int rows_per_block,
                                          const int64_t* __restrict__ sz, const int64_t* __restrict__ sy,
                                          const int64_t* __restrict__ sx, const float* __restrict__ wz,
@@ -531,9 +531,10 @@ static int launch_overlap_add(const void* patches, void* out, const MergeParams&
       if (rpb > p.H) rpb = p.H;
       const dim3 g((unsigned)ceil_div(p.H, rpb), gy);
       const size_t smem = sizeof(SlotRow) * (size_t)rpb + sizeof(int) * (size_t)(p.nz + p.ny + p.nx) + 16;
-#define B200_SLOT(U) overlap_add_slot_kernel<TI, TO, U><<<g, threads, smem, st>>>((const TI*)patches, (TO*)out, p, (int)z0, (int)nz_out, \
-                                                                              (int)rpb, sz, sy, sx, wz, wy, wx)
-      if (unroll2 == 1) B200_SLOT(1); else if (unroll2 == 4) B200_SLOT(4); else B200_SLOT(2);
+      static const int occ6 = getenv("B200_MERGE_OCC") ? atoi(getenv("B200_MERGE_OCC")) == 6 : 0;   // 6 blocks / SM (40 registers, spills)
+#define B200_SLOT(U, MB) overlap_add_slot_kernel<TI, TO, U, MB><<<g, threads, smem, st>>>((const TI*)patches, (TO*)out, p, (int)z0, \
+                                                                                      (int)nz_out, (int)rpb, sz, sy, sx, wz, wy, wx)
+      if (occ6) B200_SLOT(2, 6); else if (unroll2 == 1) B200_SLOT(1, 5); else if (unroll2 == 4) B200_SLOT(4, 5); else B200_SLOT(2, 5);
 #undef B200_SLOT
       B200_LAUNCH_CHECK();
       return B200_OK;

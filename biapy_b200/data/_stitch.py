@@ -51,9 +51,21 @@ def identity_axis(n: int) -> Tuple[np.ndarray, np.ndarray]:
     return np.arange(n, dtype=np.int64), np.ones(1, dtype=np.float32)
 
 
+_DEV_TABLES: dict = {}
+
+
 def _dev(a: np.ndarray, device):
+    """Small host table (patch starts, spline windows) on the device; cached by content, so that the 54 crop / merge calls of a
+    volume (and every call of a benchmark loop) do not each pay six pageable host-to-device copies."""
     import torch
-    return torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    a = np.ascontiguousarray(a)
+    key = (str(device), a.dtype.str, a.shape, a.tobytes())
+    t = _DEV_TABLES.get(key)
+    if t is None:
+        if len(_DEV_TABLES) > 256:
+            _DEV_TABLES.clear()
+        t = _DEV_TABLES[key] = torch.from_numpy(a).to(device)
+    return t
 
 
 class VolumeShard:
