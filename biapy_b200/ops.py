@@ -460,7 +460,9 @@ def bn_eval_stats(x, running_mean, running_var, gamma, beta, eps: float) -> Norm
 NORM_FAST = os.environ.get("B200_NORM_FAST", "auto").lower()
 # backward form of the fast chain: 'g' = pass 1 leaves g = dy * act' in dy's place (needs dy_dead), 'recompute' = pass 2 evaluates
 # the derivative again with the one-MUFU sigmoid (no extra write in pass 1)
-NORM_BWD = os.environ.get("B200_NORM_BWD", "g").lower()
+# measured (config[1] step, profiles/README.md round 2): 'recompute' 14.79 ms, 'g' 14.83 ms -- the extra write of pass 1 costs what the
+# second derivative saves; 'recompute' is the default because it leaves dy alone
+NORM_BWD = os.environ.get("B200_NORM_BWD", "recompute").lower()
 
 
 def norm_fast_ok(x, dy=None, dx=None) -> bool:

@@ -139,3 +139,117 @@ def test_trainer_optimizer_state_interoperates_with_torch_adamw(tmp_path):
     torch.cuda.synchronize()
     for a, b in zip(tr.fp.params, tr2.fp.params):
         assert (a - b).abs().max().item() <= 1e-6 * max(1.0, a.abs().max().item())
+
+
+@pytest.mark.parametrize("opt_name", ["adam", "sgd"])
+def test_adam_and_timm_sgd_follow_torch(opt_name):
+    """TRAIN.OPTIMIZER = 'ADAM' (torch.optim.Adam, L2 decay) and 'SGD' (timm: momentum 0.9 + Nesterov) through the Trainer: 3 steps
+    with gradient clipping on the same batch against torch CPU on the oracle graph (fp32 engine)."""
+    from biapy_b200.engine.train import Trainer
+    m, sd = _model(torch.float32)
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 32, 32, 32, 2, generator=g)
+    t = (torch.rand(2, 32, 32, 32, 1, generator=g) < 0.3).float()
+    sd_r = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    if opt_name == "adam":
+        opt = torch.optim.Adam(list(sd_r.values()), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.02)
+        kw = dict(optimizer="adam", lr=1e-3, weight_decay=0.02)
+    else:
+        opt = torch.optim.SGD(list(sd_r.values()), lr=1e-2, momentum=0.9, nesterov=True, weight_decay=1e-3)
+        kw = dict(optimizer="sgd", lr=1e-2, weight_decay=1e-3, momentum=0.9, nesterov=True)
+    ref = []
+    for _ in range(3):
+        y = port_models.forward("resunet", sd_r, x.permute(0, 4, 1, 2, 3), training=True, **KW)
+        loss = port_models.bce_with_logits_loss(y, t.permute(0, 4, 1, 2, 3))
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(list(sd_r.values()), 0.5)
+        opt.step()
+        ref.append(loss.item())
+    m = m.cuda().set_engine(dtype=torch.float32)
+    tr = Trainer(m, loss="bce", clip_norm=0.5, **kw)
+    got = [tr.step(x.numpy(), t.numpy()).item() for _ in range(3)]
+    for a, b in zip(got, ref):
+        assert abs(a - b) < 2e-4 * max(1.0, abs(b)), (got, ref)
+    sd_t = tr.state_dict()
+    assert sd_t["param_groups"][0].get("nesterov", False) == (opt_name == "sgd") and tr.t == 3
+    now = m.state_dict()
+    num = sum(((now[k].cpu() - v.detach()).double() ** 2).sum().item() for k, v in sd_r.items())
+    den = sum((v.detach().double() ** 2).sum().item() for v in sd_r.values())
+    assert (num / den) ** 0.5 < (1e-3 if opt_name == "adam" else 1e-4)
+
+
+def test_fp16_engine_trains_with_loss_scaling_and_graph_handles_a_trailing_batch():
+    """fp16 engine: the Trainer propagates the gradient of the summed loss (no underflow) and divides in the optimiser kernel --
+    the 3-step loss trajectory follows the CPU oracle like bf16's does, no step is skipped; a CUDA-graphed Trainer falls back to
+    the eager pass for a trailing batch of another size instead of broadcasting or failing."""
+    from biapy_b200.engine.train import Trainer
+    m, sd = _model(torch.float16)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 32, 32, 32, 2, generator=g)
+    t = (torch.rand(2, 32, 32, 32, 1, generator=g) < 0.3).float()
+    sd_r = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    opt = torch.optim.AdamW(list(sd_r.values()), lr=1e-3, weight_decay=0.02)
+    ref = []
+    for _ in range(3):
+        y = port_models.forward("resunet", sd_r, x.permute(0, 4, 1, 2, 3), training=True, **KW)
+        loss = port_models.bce_with_logits_loss(y, t.permute(0, 4, 1, 2, 3))
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        ref.append(loss.item())
+    m = m.cuda().set_engine(dtype=torch.float16)
+    tr = Trainer(m, loss="bce", optimizer="adamw", lr=1e-3, weight_decay=0.02)
+    got = [tr.step(x.numpy(), t.numpy()).item() for _ in range(3)]
+    for a, b in zip(got, ref):
+        assert abs(a - b) < 1e-2 * max(1.0, abs(b)), (got, ref)
+    assert tr._opt_state.tolist() == [3, 0]
+    tr.enable_cuda_graph(x.cuda(), t.cuda())
+    l_full = tr.step(x.numpy(), t.numpy()).item()
+    l_tail = tr.step(x[:1].numpy(), t[:1].numpy()).item()           # trailing batch of 1: eager pass, not a broadcast
+    assert np.isfinite(l_full) and np.isfinite(l_tail) and tr._opt_state.tolist() == [5, 0]
+
+
+def test_cross_entropy_ignore_index_and_n2v_without_host_sync():
+    """CrossEntropyLoss(ignore_index) through the Trainer (mean over the counted voxels, divisor read on the device by the
+    optimiser) and the one-pass Noise2Void loss, each against torch CPU for one SGD step; an illegal label is reported."""
+    from biapy_b200.engine.train import Trainer
+    from biapy_b200.models.unet import U_Net
+    kw = dict(image_shape=(16, 16, 16, 1), activation="elu", feature_maps=[16, 32], drop_values=[0, 0], normalization="in", k_size=3,
+              yx_down=[2], z_down=[2], isotropy=[True] * 2, larger_io=False, conv_layers=[2] * 2)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(2, 16, 16, 16, 1, generator=g)
+    for loss_kind in ("ce", "n2v_mse"):
+        out_c = 3 if loss_kind == "ce" else 1
+        torch.manual_seed(0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = U_Net(output_channels=[out_c], **kw)
+        sd_r = {k: v.clone().requires_grad_(True) for k, v in m.state_dict().items()}
+        y = port_models.forward("unet", sd_r, x.permute(0, 4, 1, 2, 3), training=True, output_channels=[out_c], **kw)
+        if loss_kind == "ce":
+            cls = torch.randint(0, 3, (2, 16, 16, 16, 1), generator=g)
+            cls[:, :3] = -100
+            loss = torch.nn.functional.cross_entropy(y, cls[..., 0], ignore_index=-100)
+            target = cls.float()
+        else:
+            tgt = torch.randn(2, 16, 16, 16, 1, generator=g)
+            mask = (torch.rand(2, 16, 16, 16, 1, generator=g) < 0.05).float()
+            target = torch.cat([tgt, mask], -1)
+            yp = y.permute(0, 2, 3, 4, 1)
+            loss = torch.sum(torch.square(tgt - yp * mask)) / torch.sum(mask)
+        loss.backward()
+        m = m.cuda().set_engine(dtype=torch.float32)
+        p0 = {k: v.detach().clone() for k, v in m.named_parameters()}
+        tr = Trainer(m, loss=loss_kind, optimizer="sgd", lr=0.1)
+        got = tr.step(x.numpy(), target.numpy()).item()
+        assert abs(got - loss.item()) < 1e-5 * max(1.0, abs(loss.item())), (loss_kind, got, loss.item())
+        for k, p in m.named_parameters():                              # p = p0 - lr * grad
+            want = p0[k].cpu() - 0.1 * sd_r[k].grad
+            assert (p.detach().cpu() - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item()), (loss_kind, k)
+        if loss_kind == "ce":
+            tr.check_labels()
+            bad = target.clone()
+            bad[0, 5, 5, 5, 0] = 7
+            tr.step(x.numpy(), bad.numpy())
+            with pytest.raises(ValueError):
+                tr.check_labels()

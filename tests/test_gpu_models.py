@@ -4,7 +4,9 @@ the unmodified BiaPy classes on CPU) and against the CPU oracle at other sizes.
 Tolerance (BASELINE north_star): outputs and gradients within 1e-3 relative of the fp32 CPU reference.  The
 measure is the normalised max error  max|a-b| / max|b|  per tensor (per model for parameter gradients, because
 parameters in front of a norm layer have mathematically-zero gradients).  The fp32 engine must meet 1e-3; the
-bf16 storage path (the bench dtype) is held to a looser, stated bound and its error is printed."""
+16-bit storage engines are held to stated bounds <= 2x what the device measured on these fixtures (profiles/parity_golden_r2.jsonl:
+fp16 1.8e-3 forward / 9e-2 backward, bf16 1.5e-2 / 2.0e-1 -- tiny networks at tiny sizes, every max-pool arg-max flip is a
+visible fraction of the gradient; the full-size table is tests/test_gpu_baseline_configs.py)."""
 import contextlib
 import glob
 import io
@@ -47,7 +49,7 @@ FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "model_*.npz")))
 
 
 @pytest.mark.parametrize("path", FIXTURES)
-@pytest.mark.parametrize("dtype,tol_fwd,tol_bwd", [(torch.float32, 1e-3, 1e-3), (torch.float16, 1e-2, 1e-1), (torch.bfloat16, 5e-2, 2.5e-1)])
+@pytest.mark.parametrize("dtype,tol_fwd,tol_bwd", [(torch.float32, 1e-3, 1e-3), (torch.float16, 4e-3, 1.5e-1), (torch.bfloat16, 3e-2, 2.5e-1)])
 def test_golden_forward_backward(path, dtype, tol_fwd, tol_bwd):
     z = np.load(path)
     kw = json.loads(str(z["kwargs_json"]))
