@@ -657,12 +657,13 @@ __global__ void __launch_bounds__(256) conv1x1_cin_cv_kernel(const T* __restrict
   }
 }
 
-// dw[co][ci], dbias[co] for cout <= 2 and cin = 8 * CVN <= 32 (segmentation heads)
-template <typename T, int CVN>
+// dw[co][ci], dbias[co] for cout <= MAXCO (2: segmentation heads; 8: the F_int = 8 layers of the attention gates) and
+// cin = 8 * CVN <= 32
+template <typename T, int CVN, int MAXCO = 2>
 __global__ void __launch_bounds__(256) conv1x1_wgrad_head_cv_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy,
                                                                     int64_t lddy, float* __restrict__ dw, float* __restrict__ dbias,
                                                                     int cout, int64_t nvox) {
-  constexpr int kMaxCin = 32, kMaxCout = 2, cin = 8 * CVN;
+  constexpr int kMaxCin = 32, kMaxCout = MAXCO, cin = 8 * CVN;
   __shared__ float s_red[8][kMaxCout * (kMaxCin + 1)];
   const int cv = threadIdx.x & (CVN - 1);
   float acc[kMaxCout][8], bacc[kMaxCout];
@@ -673,7 +674,7 @@ __global__ void __launch_bounds__(256) conv1x1_wgrad_head_cv_kernel(const T* __r
     for (int k = 0; k < 8; ++k) acc[j][k] = 0.f;
   }
   const int64_t total = nvox * CVN, stride = (int64_t)gridDim.x * blockDim.x;
-  constexpr int U = 4;   // four voxel vectors in flight per thread (loads first, then the FMAs)
+  constexpr int U = MAXCO > 2 ? 2 : 4;   // voxel vectors in flight per thread (loads first, then the FMAs)
   for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += U * stride) {
     Pack<T, 8> px[U];
     float d[U][kMaxCout];
@@ -852,6 +853,12 @@ static void launch_wgrad_head_cv(const b200_tensor* x, const b200_tensor* dy, fl
   if (blocks < 1) blocks = 1;
   const T* xp = (const T*)x->data;
   const T* gp = (const T*)dy->data;
+  if (dy->c > 2) {
+    if (cvn == 1) conv1x1_wgrad_head_cv_kernel<T, 1, 8><<<(unsigned)blocks, 256, 0, st>>>(xp, x->ld, gp, dy->ld, dw, dbias, dy->c, nvox);
+    else if (cvn == 2) conv1x1_wgrad_head_cv_kernel<T, 2, 8><<<(unsigned)blocks, 256, 0, st>>>(xp, x->ld, gp, dy->ld, dw, dbias, dy->c, nvox);
+    else conv1x1_wgrad_head_cv_kernel<T, 4, 8><<<(unsigned)blocks, 256, 0, st>>>(xp, x->ld, gp, dy->ld, dw, dbias, dy->c, nvox);
+    return;
+  }
   if (cvn == 1) conv1x1_wgrad_head_cv_kernel<T, 1><<<(unsigned)blocks, 256, 0, st>>>(xp, x->ld, gp, dy->ld, dw, dbias, dy->c, nvox);
   else if (cvn == 2) conv1x1_wgrad_head_cv_kernel<T, 2><<<(unsigned)blocks, 256, 0, st>>>(xp, x->ld, gp, dy->ld, dw, dbias, dy->c, nvox);
   else conv1x1_wgrad_head_cv_kernel<T, 4><<<(unsigned)blocks, 256, 0, st>>>(xp, x->ld, gp, dy->ld, dw, dbias, dy->c, nvox);
@@ -931,7 +938,8 @@ int conv_fprop_simt(const b200_tensor* x, const void* w, const float* bias, cons
 
 int conv_wgrad_simt(const b200_tensor* x, const b200_tensor* dy, float* dw, float* dbias, int kd, int kh, int kw,
                     cudaStream_t st) {
-  if (small_pointwise(x, dy, kd, kh, kw) && dy->c <= 2 && x->c <= 32 && vec16(x)) {
+  const bool head8 = pw_coalesced_enabled() && dy->c <= 8 && (x->c == 8 || x->c == 16 || x->c == 32) && x->dtype != B200_F32;
+  if (small_pointwise(x, dy, kd, kh, kw) && (dy->c <= 2 || head8) && x->c <= 32 && vec16(x)) {
     const int64_t nvox = voxels(x);
     int64_t blocks = ceil_div(nvox, 256 * 8);
     if (blocks > (int64_t)sm_count() * 4) blocks = (int64_t)sm_count() * 4;
