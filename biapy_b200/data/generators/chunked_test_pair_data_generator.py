@@ -1,6 +1,8 @@
 """By-chunks tile generator on the B200: mirror of ``biapy.data.generators.chunked_test_pair_data_generator``
-(``biapy/data/generators/chunked_test_pair_data_generator.py``) for volumes that are resident in HBM (or numpy arrays that
-are uploaded once).
+(``biapy/data/generators/chunked_test_pair_data_generator.py``) for volumes that are resident in HBM (numpy arrays are uploaded
+once) AND for lazy array-likes -- anything with ``.shape`` and slice reads, i.e. a ``zarr.Array``, an ``h5py.Dataset`` or a
+``numpy.memmap`` -- from which every tile is read with its halo exactly like the reference's
+``extract_patch_from_efficient_file`` does (``biapy/data/data_3D_manipulation.py:179-351``): volumes larger than HBM stream through.
 
 Same grid attributes (``step_z``, ``vols_per_z``, ``z_vol_start`` ..., ``total_vols``, ``tile_ids``, ``patches_of_tile``),
 same methods (``_patch_coords``, ``tile_coords``, ``rank_workload``, ``extract_and_prepare_sample``,
@@ -9,8 +11,8 @@ over the sorted tile ids, ``:612-624``).  The integer bookkeeping runs in the C 
 ``b200_chunk_patch_coords``), the data movement in two CUDA kernels (``b200_chunk_extract`` / ``b200_chunk_insert``) that
 handle a whole batch of tiles per launch.
 
-Out of scope here (the reference's storage side, SURVEY 8 "next" rank 4): Zarr / H5 handles, axis orders other than
-``ZYXC``, ROI masks, sample filtering, normalisation modules -- they raise ``NotImplementedError``.
+Out of scope here: opening Zarr / H5 files (the caller hands over the opened dataset; neither package is needed by this module),
+axis orders other than ``ZYXC``, ROI masks, sample filtering, normalisation modules -- they raise ``NotImplementedError``.
 """
 from __future__ import annotations
 
@@ -39,17 +41,28 @@ class chunked_test_pair_data_generator:
         if roi_mask_path or convert_to_rgb or any(v for v in unsupported.values()):
             raise NotImplementedError(f"not implemented by the B200 by-chunks generator: roi_mask / convert_to_rgb / {sorted(unsupported)}")
         X = sample_to_process["X"]
-        if isinstance(X, np.ndarray):
+        self.lazy = None
+        if isinstance(X, np.ndarray) and not isinstance(X, np.memmap):
             if not torch.cuda.is_available():
                 raise _lib.B200Error("no CUDA device: biapy_b200 has no CPU path for by-chunks extraction")
             X = torch.from_numpy(np.ascontiguousarray(X)).cuda()
         if not isinstance(X, torch.Tensor):
-            raise NotImplementedError("Zarr / H5 inputs are not implemented: pass a numpy array or a CUDA tensor (Z, Y, X, C)")
-        _lib.require_cuda(X, "by-chunks volume")
-        if X.dim() != 4:
-            raise ValueError(f"expected a (Z, Y, X, C) volume, got shape {tuple(X.shape)}")
+            # lazy array-like (zarr.Array / h5py.Dataset / numpy.memmap): tiles are read one by one with their halo
+            if not (hasattr(X, "shape") and hasattr(X, "__getitem__")) or len(X.shape) != 4:
+                raise NotImplementedError("by-chunks input must be a numpy array, a CUDA tensor or a (Z, Y, X, C) array-like with "
+                                          "slice reads (zarr.Array, h5py.Dataset, numpy.memmap)")
+            if not torch.cuda.is_available():
+                raise _lib.B200Error("no CUDA device: biapy_b200 has no CPU path for by-chunks extraction")
+            self.lazy = X
+            self.device = torch.device("cuda", torch.cuda.current_device())
+            self.bytes_read = 0
+        else:
+            _lib.require_cuda(X, "by-chunks volume")
+            if X.dim() != 4:
+                raise ValueError(f"expected a (Z, Y, X, C) volume, got shape {tuple(X.shape)}")
+            self.device = X.device
         self.sample_to_process = sample_to_process
-        self.X_parallel_data = X.contiguous()
+        self.X_parallel_data = None if self.lazy is not None else X.contiguous()
         self.filename = sample_to_process.get("X_filename", "")
         self.norm_module = norm_module
         self.input_axes, self.mask_input_axes, self.out_data_order = input_axes, mask_input_axes, input_axes
@@ -60,7 +73,7 @@ class chunked_test_pair_data_generator:
 
         self.c = _lib.ChunkGrid()
         arr = lambda v: (C.c_int64 * 3)(*[int(t) for t in v[:3]])
-        st = _lib.lib().b200_chunk_grid_plan(arr(X.shape), arr(self.crop_shape), arr(self.padding), int(z_start), int(z_end), C.byref(self.c))
+        st = _lib.lib().b200_chunk_grid_plan(arr(tuple(X.shape)), arr(self.crop_shape), arr(self.padding), int(z_start), int(z_end), C.byref(self.c))
         if st != 0:
             raise ValueError(_lib.lib().b200_last_error().decode())           # the reference raises ValueError (:247-274)
         self.step_z, self.step_y, self.step_x = (int(v) for v in self.c.step)
@@ -139,14 +152,46 @@ class chunked_test_pair_data_generator:
         """-> (patches CUDA tensor (n, *crop_shape), added_pad list, real coords list) for a batch of tiles, one launch."""
         import torch
         raws = [self._raw(v) for v in vol_ids]
+        pads = [[[r[21], r[22]], [r[23], r[24]], [r[25], r[26]], [0, 0]] for r in raws]
+        if self.lazy is not None:
+            return self._extract_lazy(raws), pads, [_coords(r[9:15]) for r in raws]
         desc = np.array([[r[3], r[4] - r[3], r[15], r[5], r[6] - r[5], r[17], r[7], r[8] - r[7], r[19]] for r in raws], dtype=np.int64)
         X = self.X_parallel_data
         out = torch.empty((len(raws),) + self.crop_shape, dtype=X.dtype, device=X.device)
         d = torch.from_numpy(desc).to(X.device)
         _lib.call("b200_chunk_extract", X.data_ptr(), _lib.torch_dtype_code(X.dtype), self.z_dim, self.y_dim, self.x_dim, X.shape[3],
                   out.data_ptr(), len(raws), self.crop_shape[0], self.crop_shape[1], self.crop_shape[2], d.data_ptr(), _lib.stream_ptr())
-        pads = [[[r[21], r[22]], [r[23], r[24]], [r[25], r[26]], [0, 0]] for r in raws]
         return out, pads, [_coords(r[9:15]) for r in raws]
+
+    def _extract_lazy(self, raws):
+        """Tiles of a lazy volume: read the effective region of every tile (halo included, clipped at the volume border: what
+        ``extract_patch_from_efficient_file`` reads), upload it, and let the same extraction kernel reflect-pad it to the crop
+        shape -- the box plays the role of the volume, so its descriptor starts at 0."""
+        import torch
+        first = np.asarray(self.lazy[0:1, 0:1, 0:1])
+        tdt = torch.from_numpy(first).dtype
+        out = torch.empty((len(raws),) + self.crop_shape, dtype=tdt, device=self.device)
+        for j, r in enumerate(raws):
+            box = np.ascontiguousarray(self.lazy[r[3]:r[4], r[5]:r[6], r[7]:r[8]])
+            self.bytes_read += box.nbytes
+            bd = torch.from_numpy(box).to(self.device, non_blocking=True)
+            desc = torch.tensor([[0, r[4] - r[3], r[15], 0, r[6] - r[5], r[17], 0, r[8] - r[7], r[19]]], dtype=torch.int64, device=self.device)
+            _lib.call("b200_chunk_extract", bd.data_ptr(), _lib.torch_dtype_code(bd.dtype), box.shape[0], box.shape[1], box.shape[2],
+                      box.shape[3], out[j].data_ptr(), 1, self.crop_shape[0], self.crop_shape[1], self.crop_shape[2], desc.data_ptr(),
+                      _lib.stream_ptr())
+        return out
+
+    def write_batch(self, pred, pads: Sequence, coords: Sequence[PatchCoords], out):
+        """Lazy output (zarr.Array / h5py.Dataset / numpy.memmap, (Z, Y, X, C_out)): strip the padding of every predicted tile
+        and assign it to its region -- ``insert_patch_in_efficient_file`` (``data_3D_manipulation.py:265-351``); the storage
+        library does the chunking."""
+        host = pred.cpu().numpy()
+        for j, (c, p) in enumerate(zip(coords, pads)):
+            pz, py, px = host.shape[1:4]
+            tile = host[j, p[0][0]:pz - p[0][1], p[1][0]:py - p[1][1], p[2][0]:px - p[2][1]]
+            if tile.shape[:3] != (c.z_end - c.z_start, c.y_end - c.y_start, c.x_end - c.x_start):
+                raise ValueError("could not broadcast the stripped prediction into the output region")
+            out[c.z_start:c.z_end, c.y_start:c.y_end, c.x_start:c.x_end] = tile
 
     def extract_and_prepare_sample(self, z: int, y: int, x: int, patch_coords: PatchCoords, extract: str = "image"):
         """Reference signature (``:489-575``): one tile -> (numpy patch of ``crop_shape``, pad_to_add)."""
@@ -159,7 +204,7 @@ class chunked_test_pair_data_generator:
     def _ensure_out(self, channels: int, dtype):
         import torch
         if self.out_data is None:
-            self.out_data = torch.zeros((self.z_dim, self.y_dim, self.x_dim, channels), dtype=dtype, device=self.X_parallel_data.device)
+            self.out_data = torch.zeros((self.z_dim, self.y_dim, self.x_dim, channels), dtype=dtype, device=self.device)
         return self.out_data
 
     def insert_batch(self, pred, pads: Sequence, coords: Sequence[PatchCoords], mode: str = "replace", out=None):
@@ -186,6 +231,6 @@ class chunked_test_pair_data_generator:
         """Reference signature (``:802-832``): `patch` is the already stripped prediction (numpy or CUDA, (z, y, x, C))."""
         import torch
         if isinstance(patch, np.ndarray):
-            patch = torch.from_numpy(np.ascontiguousarray(patch)).to(self.X_parallel_data.device)
+            patch = torch.from_numpy(np.ascontiguousarray(patch)).to(self.device)
         zero = [[0, 0], [0, 0], [0, 0]]
         self.insert_batch(patch[None], [zero], [patch_coords], out=self._ensure_out(patch.shape[-1], patch.dtype))

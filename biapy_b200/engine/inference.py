@@ -199,8 +199,37 @@ def predict_by_chunks(model, vol, patch_shape: Sequence[int], padding=(0, 0, 0),
     without the halo.  Tiles are dealt to ranks exactly as the reference's ``DistributedSampler`` deals them; every rank
     writes only its own tiles (disjoint regions), so with ``reduce=True`` one NCCL all-reduce (sum of disjoint supports)
     leaves the full prediction on every rank -- the reference gets the same effect by writing into a shared Zarr file.
-    vol: (Z, Y, X, C) numpy array or CUDA tensor; returns (Z, Y, X, C_out) in the same container type."""
+    vol: (Z, Y, X, C) numpy array or CUDA tensor; returns (Z, Y, X, C_out) in the same container type.
+
+    Streaming: `vol` may be a lazy array-like -- ``zarr.Array``, ``h5py.Dataset``, ``numpy.memmap``: anything with
+    ``.shape`` and slice reads -- and `out` a writable one of shape (Z, Y, X, C_out).  Every tile is then read with its halo from
+    `vol`, predicted, stripped and assigned to its region of `out` (``extract_patch_from_efficient_file`` /
+    ``insert_patch_in_efficient_file``, ``data_3D_manipulation.py:179-351``): neither the volume nor the prediction is ever
+    resident as a whole, on the host or on the device, and the ranks write disjoint regions of the shared file (no collective).
+    Returns `out`."""
     from ..data.generators.chunked_test_pair_data_generator import chunked_test_pair_data_generator
+    lazy = not isinstance(vol, torch.Tensor) and (isinstance(vol, np.memmap) or not isinstance(vol, np.ndarray))
+    if lazy:
+        if out is None or isinstance(out, torch.Tensor):
+            raise ValueError("streaming by-chunks inference writes into `out`: pass a writable (Z, Y, X, C_out) array-like "
+                             "(zarr.Array, h5py.Dataset, numpy.memmap or numpy array)")
+        gen = chunked_test_pair_data_generator(dict(X=vol, Y=None, X_filename="", X_dir=""), None, "ZYXC", "ZYXC", tuple(patch_shape),
+                                               tuple(padding), z_start=z_start, z_end=z_end, patches_per_tile=patches_per_tile)
+        c_out = sum(model.output_channels)
+        acts = head_activations or ["linear"] * c_out
+        if tuple(out.shape) != (gen.z_dim, gen.y_dim, gen.x_dim, c_out):
+            raise ValueError(f"`out` must have shape {(gen.z_dim, gen.y_dim, gen.x_dim, c_out)}, got {tuple(out.shape)}")
+        todo = gen.rank_patches(world, rank, drop_repeats=True)
+        for k in range(0, len(todo), batch_size):
+            xb, pads, coords = gen.extract_batch(todo[k:k + batch_size])
+            y = model(xb.permute(0, 4, 1, 2, 3))
+            ycl = y.permute(0, 2, 3, 4, 1)
+            act = torch.empty(ycl.shape, dtype=out_dtype, device=ycl.device)
+            apply_head_activations(ycl, acts, act)
+            gen.write_batch(act, pads, coords, out)
+        if world > 1 and torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.barrier()                      # the reference's only synchronisation on this path (:2614)
+        return out
     is_np = isinstance(vol, np.ndarray)
     gen = chunked_test_pair_data_generator(dict(X=_stitch.to_device(vol), Y=None, X_filename="", X_dir=""), None, "ZYXC", "ZYXC",
                                            tuple(patch_shape), tuple(padding), z_start=z_start, z_end=z_end,

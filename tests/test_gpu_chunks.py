@@ -106,3 +106,66 @@ def test_chunk_errors_mirror_reference():
         G(dict(X=vol, Y=None), None, "ZYXC", "ZYXC", (32, 16, 16, 1), (0, 0, 0))
     with pytest.raises(ValueError, match="Padding"):
         G(dict(X=vol, Y=None), None, "ZYXC", "ZYXC", (16, 16, 16, 1), (8, 0, 0))
+
+
+class _CountingLazy:
+    """A lazy (Z, Y, X, C) volume as zarr / h5py hand it over: `.shape`, `.dtype`, slice reads only -- and a record of how much
+    was read at once, to show that the volume is never materialised."""
+
+    def __init__(self, arr):
+        self._a, self.shape, self.dtype, self.max_read, self.reads = arr, arr.shape, arr.dtype, 0, 0
+
+    def __getitem__(self, key):
+        out = self._a[key]
+        self.max_read = max(self.max_read, out.nbytes)
+        self.reads += 1
+        return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [c for c in CASES if c["arrays"]][:3], ids=lambda c: c["name"])
+def test_lazy_volume_tiles_equal_the_resident_path(case):
+    """Tiles extracted from a lazy array-like (one halo read per tile, reflect padding by the same kernel) are the bytes the
+    resident-volume path -- pinned to the reference's generator above -- extracts; an identity 'model' written back tile by tile
+    into a memmap reproduces the volume."""
+    vol = _vol(case)
+    res = _gen(case, vol)
+    lazy = _CountingLazy(vol)
+    g = _gen(case, lazy)
+    assert g.lazy is lazy and g.total_vols == res.total_vols
+    ids = list(range(g.total_vols))
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        out = np.lib.format.open_memmap(os.path.join(tmp, "out.npy"), mode="w+", dtype=np.float32, shape=vol.shape)
+        for k in range(0, len(ids), 7):
+            xa, pa, ca = g.extract_batch(ids[k:k + 7])
+            xb, pb, cb = res.extract_batch(ids[k:k + 7])
+            assert torch.equal(xa, xb) and pa == pb and ca == cb
+            g.write_batch(xa, pa, ca, out)
+        assert np.array_equal(np.asarray(out), vol)
+    tile_bytes = int(np.prod(case["crop"][:3])) * vol.shape[3] * 4
+    assert lazy.max_read <= tile_bytes and lazy.max_read < vol.nbytes        # one tile with its halo at a time
+
+
+@pytest.mark.gpu
+def test_streaming_by_chunks_inference_equals_the_resident_call(tmp_path):
+    """predict_by_chunks on a numpy.memmap volume, written into a memmap prediction, against the same call on the resident
+    volume (which tests/test_gpu_workflow.py and tools/dist_check.py hold to the oracle / to world 1)."""
+    import contextlib
+    import io
+    from biapy_b200.engine.inference import predict_by_chunks
+    from biapy_b200.models.resunet import ResUNet
+    kw = dict(image_shape=(32, 32, 32, 2), activation="silu", feature_maps=[16, 32, 64], drop_values=[0, 0, 0], normalization="gn",
+              k_size=3, yx_down=[2, 2], z_down=[2, 2], isotropy=[True] * 3, larger_io=False, conv_layers=[2] * 3, output_channels=[1])
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = ResUNet(**kw).cuda().set_engine(dtype=torch.float32).eval()
+    vol = np.random.default_rng(3).standard_normal((72, 64, 80, 2)).astype(np.float32)
+    np.save(tmp_path / "vol.npy", vol)
+    lazy = np.load(tmp_path / "vol.npy", mmap_mode="r")
+    out = np.lib.format.open_memmap(tmp_path / "pred.npy", mode="w+", dtype=np.float32, shape=(72, 64, 80, 1))
+    ref = predict_by_chunks(m, vol, (32, 32, 32, 2), padding=(4, 4, 4), batch_size=3, head_activations=["ce_sigmoid"])
+    got = predict_by_chunks(m, lazy, (32, 32, 32, 2), padding=(4, 4, 4), batch_size=3, head_activations=["ce_sigmoid"], out=out)
+    assert got is out and np.array_equal(np.asarray(out), ref)
+    with pytest.raises(ValueError):
+        predict_by_chunks(m, lazy, (32, 32, 32, 2), padding=(4, 4, 4), batch_size=3, head_activations=["ce_sigmoid"])

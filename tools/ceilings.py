@@ -85,7 +85,9 @@ def main(path):
             if m:
                 fam, c = m.group(1), int(m.group(2))
                 el = BATCH * int(m.group(3)) * int(m.group(4)) * int(m.group(5)) * c * n
-                per = {"channel_sums": 1, "scale_shift_act": 2, "norm_act_bwd_reduce": 2, "norm_act_bwd_apply": 3}.get(fam)
+                per = {"channel_sums": 1, "scale_shift_act": 2, "norm_act_bwd_reduce": 2, "norm_act_bwd_apply": 3,
+                       "scale_shift_silu_fast": 2, "norm_silu_bwd_reduce_g": 2, "norm_bwd_apply_g": 3,
+                       "norm_silu_bwd_apply_fast": 3}.get(fam)
                 if per:
                     byts = el * per * ELT
                     bound, ceil_ms, work = "hbm", byts / hbm * 1e3, f"{byts / 1e6:.0f} MB"
