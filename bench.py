@@ -500,7 +500,7 @@ def measure_inference(args, rank, world, local, peaks, dtype, steps, with_cpu=Fa
     out_h = torch.empty(z1 - z0, V, V, 1, dtype=torch.float32).pin_memory()
 
     def e2e_step(i):                                          # host volume planes in, host prediction slab out
-        r = predict_volume(model, _stitch.VolumeShard(vol_h.cuda(non_blocking=True), a, V), (P, P, P, 2), **pkw)
+        r = predict_volume(model, _stitch.VolumeShard(vol_h, a, V), (P, P, P, 2), **pkw)      # pinned planes: upload pipelined with the batches
         slab = r[0] if isinstance(r, tuple) else r
         out_h.copy_(slab, non_blocking=True)
 
@@ -557,7 +557,7 @@ def measure_inference(args, rank, world, local, peaks, dtype, steps, with_cpu=Fa
             "e2e": {"value": 216 / (ms_e2e / 1e3), "unit": "patches/s", "ms_per_volume": ms_e2e,
                     "h2d_bytes_per_step": vol_h.numel() * 2, "d2h_bytes_per_step": out_h.numel() * 4,
                     "api": "biapy_b200.engine.inference.predict_volume(VolumeShard(pinned host fp16 planes), rank, world, gather='none') "
-                           "-> pinned host fp32 slab (bytes are rank 0's)"},
+                           "-> pinned host fp32 slab (bytes are rank 0's; the upload is pipelined with the forward passes)"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
 
 

@@ -84,6 +84,36 @@ class _GraphedBatch:
         dst.copy_(self.out)
 
 
+class _PipelinedUpload:
+    """Host -> device copy of a pinned volume shard on a side stream, in plane order, cut where the batches of the sliding window
+    first need more planes: the forward passes of batch i run while the planes of batch i + 1 ... arrive."""
+
+    def __init__(self, shard: "_stitch.VolumeShard"):
+        self.host = shard.data
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.dev = torch.empty(self.host.shape, dtype=self.host.dtype, device=self.device)
+        self.shard = _stitch.VolumeShard(self.dev, shard.z0, shard.depth)
+        self.z0 = shard.z0
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.events = []
+
+    def start(self, z_hi_per_batch):
+        done = 0
+        nz = self.host.shape[0]
+        with torch.cuda.stream(self.stream):
+            for i, z_hi in enumerate(z_hi_per_batch):
+                hi = nz if i == len(z_hi_per_batch) - 1 else max(done, min(nz, int(z_hi) - self.z0))
+                if hi > done:
+                    self.dev[done:hi].copy_(self.host[done:hi], non_blocking=True)
+                    done = hi
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+                self.events.append(ev)
+
+    def wait(self, batch_index: int):
+        torch.cuda.current_stream(self.device).wait_event(self.events[batch_index])
+
+
 def _graphed_batch(model, xb: torch.Tensor, acts, out_dtype) -> Optional[_GraphedBatch]:
     if os.environ.get("B200_INFER_GRAPH", "1") == "0" or model.training or not hasattr(model, "engine_dtype"):
         return None
@@ -120,7 +150,15 @@ def predict_volume(model, vol, patch_shape: Sequence[int], overlap=(0, 0, 0), pa
     from . import dist as bd
     if gather not in ("all", "rank0", "none"):
         raise ValueError(f"gather must be 'all', 'rank0' or 'none', got {gather!r}")
-    if isinstance(vol, _stitch.VolumeShard):
+    upload = None
+    if (isinstance(vol, _stitch.VolumeShard) and isinstance(vol.data, torch.Tensor) and not vol.data.is_cuda and vol.data.is_pinned()
+            and torch.cuda.is_available()):
+        # pinned host planes: the upload is pipelined with the forward passes (see _PipelinedUpload); the result is a CUDA tensor
+        is_np = False
+        upload = _PipelinedUpload(vol)
+        dev_vol = upload.shard
+        device = dev_vol.data.device
+    elif isinstance(vol, _stitch.VolumeShard):
         is_np = isinstance(vol.data, np.ndarray)
         dev_vol = _stitch.VolumeShard(_stitch.to_device(vol.data), vol.z0, vol.depth)
         device = dev_vol.data.device
@@ -133,13 +171,26 @@ def predict_volume(model, vol, patch_shape: Sequence[int], overlap=(0, 0, 0), pa
     starts_c = [a.starts(0) for a in axes]
     n = len(starts_c[0]) * len(starts_c[1]) * len(starts_c[2])
     first, end = bd.deal_patch_range(n, rank, world)
-    patches = _stitch.crop_device(dev_vol, patch_shape[:3], starts_c, padding, pad_type, patch_range=(first, end))
+    n_yx = len(starts_c[1]) * len(starts_c[2])
+    if upload is None:
+        patches = _stitch.crop_device(dev_vol, patch_shape[:3], starts_c, padding, pad_type, patch_range=(first, end))
+    else:
+        # every copy is queued now, in plane order, on the copy stream; a batch waits only for the planes its patches read
+        upload.start([_stitch.planes_needed(Z, int(patch_shape[0]), int(padding[0]), starts_c[0], n_yx,
+                                            (first + k, min(first + k + batch_size, end)), pad_type)[1]
+                      for k in range(0, end - first, batch_size)])
+        patches = None
     c_out = sum(model.output_channels)
     acts = head_activations or ["linear"] * c_out
     # the full-grid array: this rank writes its own patches, the exchange fills in the pieces of the others it needs
-    pred = torch.empty((n,) + tuple(patches.shape[1:4]) + (c_out,), dtype=out_dtype, device=patches.device)
-    for k in range(0, end - first, batch_size):
-        xb = patches[k:k + batch_size]
+    pred = torch.empty((n,) + tuple(int(v) for v in patch_shape[:3]) + (c_out,), dtype=out_dtype, device=device)
+    for bi, k in enumerate(range(0, end - first, batch_size)):
+        if upload is None:
+            xb = patches[k:k + batch_size]
+        else:
+            upload.wait(bi)
+            xb = _stitch.crop_device(dev_vol, patch_shape[:3], starts_c, padding, pad_type,
+                                     patch_range=(first + k, min(first + k + batch_size, end)))
         dst = pred[first + k:first + k + xb.shape[0]]
         if tta:
             from ..data.post_processing.post_processing import ensemble_predictions

@@ -253,3 +253,28 @@ def test_cross_entropy_ignore_index_and_n2v_without_host_sync():
             tr.step(x.numpy(), bad.numpy())
             with pytest.raises(ValueError):
                 tr.check_labels()
+
+
+def test_pinned_host_shard_upload_is_pipelined_and_equal():
+    """predict_volume fed a pinned host VolumeShard (the upload runs on a copy stream, cut where the batches first need more
+    planes) returns what the device-resident call returns, bit for bit, for a whole volume and for a proper shard of it."""
+    from biapy_b200.data import _stitch
+    from biapy_b200.engine.inference import predict_volume, shard_planes
+    m, _ = _model(torch.float32)
+    m = m.cuda().set_engine(dtype=torch.float32).eval()
+    vol = torch.randn(72, 40, 48, 2, generator=torch.Generator().manual_seed(9))
+    patch, ov, pad = (32, 32, 32, 2), (0.25, 0.25, 0.25), (4, 0, 2)
+    kw = dict(overlap=ov, padding=pad, batch_size=3, head_activations=["ce_sigmoid"])
+    ref = predict_volume(m, vol.cuda(), patch, **kw)
+    got = predict_volume(m, _stitch.VolumeShard(vol.pin_memory(), 0, 72), patch, **kw)
+    assert got.is_cuda and torch.equal(got, ref)
+    # the planes one rank of three would read: crop from the shard == crop from the volume for that rank's patches
+    a, b = shard_planes(vol.shape, patch, ov, pad, "reflect", 1, 3)
+    assert 0 < a and b < 72
+    axes = [_stitch.Axis(vol.shape[i], patch[i], pad[i], ov[i]) for i in range(3)]
+    starts = [ax.starts(0) for ax in axes]
+    n = axes[0].n * axes[1].n * axes[2].n
+    rng = (n // 3, 2 * n // 3)
+    full = _stitch.crop_device(vol.cuda(), patch[:3], starts, pad, "reflect", patch_range=rng)
+    part = _stitch.crop_device(_stitch.VolumeShard(vol[a:b].contiguous().cuda(), a, 72), patch[:3], starts, pad, "reflect", patch_range=rng)
+    assert torch.equal(full, part)
