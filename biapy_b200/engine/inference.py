@@ -100,6 +100,10 @@ class _PipelinedUpload:
     def start(self, z_hi_per_batch):
         done = 0
         nz = self.host.shape[0]
+        # the buffer may be a block the main stream just released: order the copies behind the work queued there, and tell the
+        # allocator that the copy stream uses it
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        self.dev.record_stream(self.stream)
         with torch.cuda.stream(self.stream):
             for i, z_hi in enumerate(z_hi_per_batch):
                 hi = nz if i == len(z_hi_per_batch) - 1 else max(done, min(nz, int(z_hi) - self.z0))
