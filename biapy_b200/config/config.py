@@ -30,7 +30,8 @@ DEFAULTS: Dict[str, Any] = {
         "CONV_BLOCK_ORDER": "conv_norm_act", "LOAD_CHECKPOINT": False, "LOAD_CHECKPOINT_EPOCH": "best_on_val",
         "ITEMS_TO_LOAD_FROM_CHECKPOINT": ["model"], "SAVE_CKPT_FREQ": -1,
     },
-    "LOSS": {"TYPE": "", "CONTRAST": {"ENABLE": False, "PROJ_DIM": 256}},                    # :1916
+    "LOSS": {"TYPE": "", "CONTRAST": {"ENABLE": False, "PROJ_DIM": 256},                     # :1916
+             "CLASS_REBALANCE": "none", "CLASS_WEIGHTS": [], "IGNORE_INDEX": -1},            # :1925-1931
     "TRAIN": {"ENABLE": False, "OPTIMIZER": ["SGD"], "LR": [1.0e-4], "W_DECAY": 0.02, "OPT_BETAS": [[0.9, 0.999]],   # :1964-1990
               "BATCH_SIZE": 2, "GRADIENT_CLIP_NORM": 0.0, "EPOCHS": 360, "PATIENCE": -1, "VERBOSE": False,
               "LR_SCHEDULER": {"NAME": "", "MIN_LR": [-1.0], "REDUCEONPLATEAU_FACTOR": 0.5,                           # :2005-2031

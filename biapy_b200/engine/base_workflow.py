@@ -209,7 +209,8 @@ class Base_Workflow:
         sgd = dict(momentum=0.9, nesterov=True) if opt == "sgd" else {}      # timm's 'sgd' (see engine/__init__.py)
         self.trainer = Trainer(self.model, loss=self.loss_kind, optimizer=opt, lr=float(first(cfg.TRAIN.LR)),
                                betas=tuple(first(cfg.TRAIN.OPT_BETAS)), weight_decay=float(cfg.TRAIN.W_DECAY),
-                               clip_norm=float(cfg.TRAIN.GRADIENT_CLIP_NORM), **sgd)
+                               clip_norm=float(cfg.TRAIN.GRADIENT_CLIP_NORM), ignore_index=int(getattr(self, "ignore_index", -100)),
+                               **sgd)
         return self.trainer
 
     def train(self, train_generator, val_generator=None, cuda_graph: bool = False):
