@@ -203,6 +203,8 @@ class Base_Workflow:
     def prepare_trainer(self) -> Trainer:
         cfg = self.cfg
         assert self.model is not None, "call prepare_model() first"
+        if getattr(self, "unsupported_loss_options", None):
+            raise NotImplementedError(self.unsupported_loss_options)
         opt = str(first(cfg.TRAIN.OPTIMIZER)).lower()
         if opt not in ("adamw", "adam", "sgd"):
             raise NotImplementedError(f"TRAIN.OPTIMIZER={opt!r}: the fused optimiser kernels cover ADAMW, ADAM and SGD")

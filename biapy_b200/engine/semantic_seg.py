@@ -17,14 +17,14 @@ class Semantic_Segmentation_Workflow(Base_Workflow):
         self.loss_kind = "ce" if n > 2 else "bce"
         # CrossEntropyLoss_wrapper (reference metrics.py:493-586, built at semantic_seg.py:193-200): LOSS.IGNORE_INDEX -1 means
         # torch's default -100; class re-balancing (a weight tensor in the loss) is not in the fused loss kernels
+        # ('manual' is the only value the wrapper acts on, :540); refused when a Trainer is built, inference is unaffected
         loss_cfg = self.cfg.get("LOSS", {}) if hasattr(self.cfg, "get") else {}
-        if str(loss_cfg.get("CLASS_REBALANCE", "none")).lower() != "none" or list(loss_cfg.get("CLASS_WEIGHTS", []) or []):
-            raise NotImplementedError("LOSS.CLASS_REBALANCE / LOSS.CLASS_WEIGHTS are not implemented by the B200 loss kernels "
-                                      "(un-weighted BCEWithLogits / CrossEntropy only)")
+        self.unsupported_loss_options = None
+        if str(loss_cfg.get("CLASS_REBALANCE", "none")).lower() == "manual":
+            self.unsupported_loss_options = ("LOSS.CLASS_REBALANCE = 'manual' (class weights in the loss) is not implemented by the "
+                                             "B200 loss kernels: un-weighted BCEWithLogits / CrossEntropy only")
         ii = int(loss_cfg.get("IGNORE_INDEX", -1))
         self.ignore_index = -100 if ii == -1 else ii
-        if n <= 2 and ii != -1:
-            raise NotImplementedError("LOSS.IGNORE_INDEX with the binary (BCEWithLogits) loss is not implemented by the B200 engine")
         super().define_activations_and_channels()
 
     def after_merge_patches(self, pred, threshold=None):
