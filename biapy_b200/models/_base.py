@@ -34,6 +34,7 @@ class _NetFn(torch.autograd.Function):
         outs, tape, out_tts, x_tt = model._execute(x, record=True, x_requires_grad=x.requires_grad)
         ctx.tape, ctx.out_tts, ctx.x_tt, ctx.params = tape, out_tts, x_tt, params
         ctx.ndim = model.ndim
+        ctx.model_ref = model
         return tuple(outs)
 
     @staticmethod
@@ -64,7 +65,15 @@ class _NetFn(torch.autograd.Function):
                     gcl = gcl * scale
                 ops.convert(gcl, tt.grad())
             tt.mark_written()
-        tape.backward()
+        arena = None
+        if ops.ARENA is None and not torch.cuda.is_current_stream_capturing():
+            arena = ctx.model_ref.__dict__.setdefault("_arena_bwd", ops.ZeroArena())
+            arena.begin(ctx.x_tt.data.device)
+        try:
+            tape.backward()
+        finally:
+            if arena is not None:
+                arena.end()
         gx = None
         if ctx.x_tt.requires_grad:
             gx32 = torch.empty(ctx.x_tt.shape, dtype=torch.float32, device=ctx.x_tt.data.device)
@@ -304,7 +313,18 @@ class UNetFamily(nn.Module):
         else:
             x_tt = TT(torch.empty(xcl.shape, dtype=self.engine_dtype, device=x.device), requires_grad=x_requires_grad)
             ops.convert(xcl, x_tt.data)
-        pred, cls = self._run(tape, x_tt)
+        # the zero-initialised accumulators of the pass (channel sums ...) come out of ONE cleared buffer instead of a torch fill
+        # kernel each; they are all consumed before the forward returns.  Not inside a CUDA-graph capture of the caller (the
+        # arena may grow) and not nested inside a Trainer pass, which has its own.
+        arena = None
+        if ops.ARENA is None and not torch.cuda.is_current_stream_capturing():
+            arena = self.__dict__.setdefault("_arena_fwd", ops.ZeroArena())
+            arena.begin(x.device)
+        try:
+            pred, cls = self._run(tape, x_tt)
+        finally:
+            if arena is not None:
+                arena.end()
         outs, tts = [], []
         for t in (pred, cls):
             if t is None:
