@@ -90,6 +90,10 @@ struct FpropParams {
   // phase-gather mode (dgrad of a transposed convolution): tap t reads its A box through PhaseMaps::m[t] at unshifted
   // coordinates and its weights from rows [t * wrows, t * wrows + cout) of the packed matrix; kd = phases, kh = kw = 1
   int phases, wrows;
+  // transposed mode, TMA-store epilogue: PhaseMaps::m[t] describes output phase t of the fine tensor (box 16 channels x voxel
+  // tile); a (128 voxels x 16 channels) block is staged at epi_off (2 x 4 KB) and leaves with one bulk tensor store
+  int epi_tma;
+  uint32_t epi_off;
 };
 
 constexpr int kMaxStages = 12;
@@ -219,6 +223,7 @@ conv_fprop_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     const int row = q * 32 + lane;
     const int lx = row % p.bw, ly = (row / p.bw) % p.bh, lz = row / (p.bw * p.bh);
     int it = 0;
+    uint32_t up_box = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       int n, z0, y0, x0, n0;
@@ -228,6 +233,46 @@ conv_fprop_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
       const int gz = z0 + lz, gy = y0 + ly, gx = x0 + lx;
       const bool valid = gz < p.d && gy < p.h && gx < p.w;
       const bool up = p.usd != 0;
+      if (up && p.epi_tma) {
+        // Transposed convolution, TMA-store epilogue.  The direct path below has every thread store the 32-byte piece of its
+        // own coarse voxel: 32 pieces a fine-voxel pitch (or more) apart per warp instruction = 32 LSU wavefronts, and the
+        // kernel (K = Cin: two MMAs per tile) is nothing but its epilogue.  Here the 128 rows of a (phase, 16-channel) column
+        // block are staged as a dense 4 KB box and leave with ONE bulk tensor store through the map of that phase -- the
+        // strided sub-lattice of the fine tensor seen as a coarse tensor; partial tiles are clipped by the TMA unit.
+        const bool issuer = threadIdx.x == 64;
+        const uint32_t stage0 = smem0 + p.epi_off;
+        int ph_t = n0 / p.pcout, ph_co = n0 - ph_t * p.pcout;
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.nt);
+        for (int j0 = 0; j0 < p.nt && n0 + j0 < p.cout; j0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + j0, r);
+          tmem_ld_wait();
+          const float* brow = bias ? bias + ph_co : nullptr;
+          Pack<T, 8> w0, w1;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            w0.v[j] = from_f<T>(__uint_as_float(r[j]) + (brow ? __ldg(brow + j) : 0.f));
+            w1.v[j] = from_f<T>(__uint_as_float(r[8 + j]) + (brow ? __ldg(brow + 8 + j) : 0.f));
+          }
+          const uint32_t sbuf = stage0 + (up_box & 1u) * 4096u;
+          if (issuer) bulk_wait_group_read<1>();                 // the store that read this buffer two boxes ago is done with it
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          st_shared_v4(sbuf + (uint32_t)row * 32u, *reinterpret_cast<const uint4*>(&w0));
+          st_shared_v4(sbuf + (uint32_t)row * 32u + 16u, *reinterpret_cast<const uint4*>(&w1));
+          fence_proxy_async();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (issuer) {
+            tma_store_5d(&pm.m[ph_t], sbuf, ph_co, x0, y0, z0, n);
+            bulk_commit_group();
+          }
+          ++up_box;
+          ph_co += 16;
+          if (ph_co == p.pcout) { ph_co = 0; ++ph_t; }
+        }
+        tc_fence_before();
+        mbar_arrive(bar_tempty + 8 * buf);
+        continue;
+      }
       T* ybase = up ? y + (int64_t)n * p.ysn + (int64_t)gz * p.usd * p.ysd + (int64_t)gy * p.ush * p.ysh + (int64_t)gx * p.usw * p.ysw
                     : y + (int64_t)n * p.ysn + (int64_t)gz * p.ysd + (int64_t)gy * p.ysh + (int64_t)gx * p.ysw + n0;
       // transposed mode: running (phase, channel) of the current 16-column chunk
@@ -277,6 +322,7 @@ conv_fprop_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
       tc_fence_before();
       mbar_arrive(bar_tempty + 8 * buf);
     }
+    if (p.epi_tma && threadIdx.x == 64) bulk_wait_group_read<0>();       // the staging buffers must outlive their stores
   }
   tc_fence_before();
   __syncthreads();
@@ -1537,6 +1583,38 @@ static int conv_fprop_umma_impl(const ActView& xv, const void* w, const float* b
   memset(&pm, 0, sizeof(pm));
   int rc = make_act_tmap(&tx, *x, p.ck, p.bw, p.bh, p.bd);
   if (rc) return rc;
+  // transposed mode: TMA-store epilogue through one output map per phase (B200_CONVT_TMA=0: direct scatter stores)
+  static const int convt_tma_env = getenv("B200_CONVT_TMA") ? atoi(getenv("B200_CONVT_TMA")) : 1;
+  const int up_phases = up.sd * up.sh * up.sw;
+  if (up.sd && convt_tma_env && up_phases <= 8 && up.cout % 16 == 0 && !accumulate && aligned16(yv_in.data) && yv_in.sw % 8 == 0 &&
+      yv_in.sh % 8 == 0 && yv_in.sd % 8 == 0 && yv_in.sn % 8 == 0) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    int t = 0;
+    bool ok = fn != nullptr;
+    for (int a = 0; a < up.sd && ok; ++a)
+      for (int b = 0; b < up.sh && ok; ++b)
+        for (int c = 0; c < up.sw && ok; ++c, ++t) {
+          // phase (a, b, c) of the fine tensor as a coarse tensor: x's dims, strides times the up-sampling factors
+          char* base = (char*)yv_in.data + ((int64_t)a * yv_in.sd + (int64_t)b * yv_in.sh + (int64_t)c * yv_in.sw) * 2;
+          const cuuint64_t dims[5] = {(cuuint64_t)up.cout, (cuuint64_t)x->w, (cuuint64_t)x->h, (cuuint64_t)x->d, (cuuint64_t)x->n};
+          const cuuint64_t strides[4] = {(cuuint64_t)yv_in.sw * up.sw * 2, (cuuint64_t)yv_in.sh * up.sh * 2,
+                                         (cuuint64_t)yv_in.sd * up.sd * 2, (cuuint64_t)yv_in.sn * 2};
+          const cuuint32_t box[5] = {16, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bd, 1};
+          const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+          CUresult r = fn(&pm.m[t], tm_dtype(yv_in.dtype), 5, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          ok = r == CUDA_SUCCESS;
+        }
+    if (ok) {
+      int st2 = (int)((200u * 1024u - 8192u) / p.stage_bytes);
+      if (st2 > 8) st2 = 8;
+      if (st2 >= 2) {
+        p.stages = st2;
+        p.epi_tma = 1;
+        p.epi_off = (uint32_t)p.stages * p.stage_bytes;
+      }
+    }
+  }
   if (nphases) {
     for (int t = 0; t < nphases; ++t) {
       rc = make_act_tmap(&pm.m[t], phase_views[t], p.ck, p.bw, p.bh, p.bd);
@@ -1548,7 +1626,7 @@ static int conv_fprop_umma_impl(const ActView& xv, const void* w, const float* b
   }
   if (rc) return rc;
 
-  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + (p.epi_tma ? 8192 : 0);
   int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
   if (x->dtype == B200_BF16) {
     auto kern = conv_fprop_umma_kernel<__nv_bfloat16>;

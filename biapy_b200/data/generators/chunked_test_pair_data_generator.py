@@ -168,11 +168,11 @@ class chunked_test_pair_data_generator:
         ``extract_patch_from_efficient_file`` reads), upload it, and let the same extraction kernel reflect-pad it to the crop
         shape -- the box plays the role of the volume, so its descriptor starts at 0."""
         import torch
-        first = np.asarray(self.lazy[0:1, 0:1, 0:1])
+        first = np.array(self.lazy[0:1, 0:1, 0:1])                # a copy: memmaps opened read-only are not writable
         tdt = torch.from_numpy(first).dtype
         out = torch.empty((len(raws),) + self.crop_shape, dtype=tdt, device=self.device)
         for j, r in enumerate(raws):
-            box = np.ascontiguousarray(self.lazy[r[3]:r[4], r[5]:r[6], r[7]:r[8]])
+            box = np.array(self.lazy[r[3]:r[4], r[5]:r[6], r[7]:r[8]], order="C")
             self.bytes_read += box.nbytes
             bd = torch.from_numpy(box).to(self.device, non_blocking=True)
             desc = torch.tensor([[0, r[4] - r[3], r[15], 0, r[6] - r[5], r[17], 0, r[8] - r[7], r[19]]], dtype=torch.int64, device=self.device)
