@@ -94,6 +94,7 @@ struct FpropParams {
   // tile); a (128 voxels x 16 channels) block is staged at epi_off (2 x 4 KB) and leaves with one bulk tensor store
   int epi_tma;
   uint32_t epi_off;
+  int epi_cbox;                         // channels per output box: 64 / 32 / 16 (SWIZZLE_128B / 64B / none)
 };
 
 constexpr int kMaxStages = 12;
@@ -245,6 +246,12 @@ conv_fprop_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
         const uint32_t sbuf = smem0 + p.epi_off + (up_box & 1u) * (uint32_t)p.nt * 256u;
         const int ph_t0 = n0 / p.pcout, ph_co0 = n0 - ph_t0 * p.pcout;
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.nt);
+        // box = 128 rows x epi_cbox channels (row pitch = epi_cbox * 2 bytes) in the shared-memory layout of the map's swizzle:
+        // 16-byte piece c of row r sits at piece c ^ (r & 7) (128-byte rows), c ^ ((r >> 1) & 3) (64-byte rows), c (32-byte rows)
+        const uint32_t cps = (uint32_t)p.epi_cbox >> 4;          // 16-channel chunks per box: 4 / 2 / 1
+        const uint32_t pitch = (uint32_t)p.epi_cbox * 2u;
+        const uint32_t swz = cps == 4 ? ((uint32_t)row & 7u) : (cps == 2 ? (((uint32_t)row >> 1) & 3u) : 0u);
+        const uint32_t rbase = sbuf + (uint32_t)row * pitch;
         if (issuer) bulk_wait_group_read<1>();                   // the stores that read this buffer two tiles ago are done with it
         asm volatile("bar.sync 1, 128;" ::: "memory");
         int ph_co = ph_co0;
@@ -259,9 +266,11 @@ conv_fprop_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
             w0.v[j] = from_f<T>(__uint_as_float(r[j]) + (brow ? __ldg(brow + j) : 0.f));
             w1.v[j] = from_f<T>(__uint_as_float(r[8 + j]) + (brow ? __ldg(brow + 8 + j) : 0.f));
           }
-          const uint32_t dst = sbuf + (uint32_t)(j0 >> 4) * 4096u + (uint32_t)row * 32u;
-          st_shared_v4(dst, *reinterpret_cast<const uint4*>(&w0));
-          st_shared_v4(dst + 16u, *reinterpret_cast<const uint4*>(&w1));
+          const uint32_t chunk = (uint32_t)j0 >> 4;
+          const uint32_t box = chunk / cps, k = chunk - box * cps;
+          const uint32_t dst = rbase + box * 128u * pitch;
+          st_shared_v4(dst + ((2u * k) ^ swz) * 16u, *reinterpret_cast<const uint4*>(&w0));
+          st_shared_v4(dst + ((2u * k + 1u) ^ swz) * 16u, *reinterpret_cast<const uint4*>(&w1));
           ph_co += 16;
           if (ph_co == p.pcout) ph_co = 0;
         }
@@ -272,9 +281,9 @@ conv_fprop_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
         if (issuer) {
           int ph_t = ph_t0;
           ph_co = ph_co0;
-          for (int j0 = 0; j0 < p.nt && n0 + j0 < p.cout; j0 += 16) {
-            tma_store_5d(&pm.m[ph_t], sbuf + (uint32_t)(j0 >> 4) * 4096u, ph_co, x0, y0, z0, n);
-            ph_co += 16;
+          for (int j0 = 0; j0 < p.nt && n0 + j0 < p.cout; j0 += p.epi_cbox) {
+            tma_store_5d(&pm.m[ph_t], sbuf + (uint32_t)(j0 / p.epi_cbox) * 128u * pitch, ph_co, x0, y0, z0, n);
+            ph_co += p.epi_cbox;
             if (ph_co == p.pcout) { ph_co = 0; ++ph_t; }
           }
           bulk_commit_group();
@@ -1600,6 +1609,10 @@ static int conv_fprop_umma_impl(const ActView& xv, const void* w, const float* b
     EncodeTiledFn fn = encode_tiled_fn();
     int t = 0;
     bool ok = fn != nullptr;
+    // widest box the channel count allows: fewer, longer rows per bulk store (B200_CONVT_BOX caps it: 16 / 32 / 64)
+    static const int box_env = getenv("B200_CONVT_BOX") ? atoi(getenv("B200_CONVT_BOX")) : 64;
+    int cbox = (up.cout % 64 == 0 && p.nt % 64 == 0) ? 64 : ((up.cout % 32 == 0 && p.nt % 32 == 0) ? 32 : 16);
+    while (cbox > box_env && cbox > 16) cbox >>= 1;
     for (int a = 0; a < up.sd && ok; ++a)
       for (int b = 0; b < up.sh && ok; ++b)
         for (int c = 0; c < up.sw && ok; ++c, ++t) {
@@ -1608,10 +1621,11 @@ static int conv_fprop_umma_impl(const ActView& xv, const void* w, const float* b
           const cuuint64_t dims[5] = {(cuuint64_t)up.cout, (cuuint64_t)x->w, (cuuint64_t)x->h, (cuuint64_t)x->d, (cuuint64_t)x->n};
           const cuuint64_t strides[4] = {(cuuint64_t)yv_in.sw * up.sw * 2, (cuuint64_t)yv_in.sh * up.sh * 2,
                                          (cuuint64_t)yv_in.sd * up.sd * 2, (cuuint64_t)yv_in.sn * 2};
-          const cuuint32_t box[5] = {16, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bd, 1};
+          const cuuint32_t box[5] = {(cuuint32_t)cbox, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bd, 1};
           const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
           CUresult r = fn(&pm.m[t], tm_dtype(yv_in.dtype), 5, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          cbox == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (cbox == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
+                          CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
           ok = r == CUDA_SUCCESS;
         }
     const uint32_t epi_bytes = 2u * (uint32_t)p.nt * 256u;       // two staging buffers of nt / 16 boxes of 4 KB
@@ -1621,6 +1635,7 @@ static int conv_fprop_umma_impl(const ActView& xv, const void* w, const float* b
       p.stages = st2;
       p.epi_tma = 1;
       p.epi_off = (uint32_t)p.stages * p.stage_bytes;
+      p.epi_cbox = cbox;
     }
   }
   if (nphases) {
