@@ -92,6 +92,8 @@ SIGNATURES = {
     "b200_unpack_convT_wgrad": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "b200_maxpool_fwd": (_I, [_T, _T, _I, _I, _I, _P]),
     "b200_maxpool_bwd": (_I, [_T, _T, _T, _T, _I, _I, _I, _I, _P]),
+    "b200_maxpool_bwd_to_ok": (_I, [_T, _T, _T, _T, _I, _I, _I]),
+    "b200_maxpool_bwd_to": (_I, [_T, _T, _T, _T, _I, _I, _I, _P]),
     "b200_channel_sums": (_I, [_T, _P, _P]),
     "b200_norm_finalize": (_I, [_P, _I, _I, _I, _L, _I, _P, _P, _F, _P, _P, _P, _P, _P]),
     "b200_scale_shift_act": (_I, [_T, _P, _P, _I, _T, _P]),

@@ -249,9 +249,9 @@ conv_fprop_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
         // box = 128 rows x epi_cbox channels (row pitch = epi_cbox * 2 bytes) in the shared-memory layout of the map's swizzle:
         // 16-byte piece c of row r sits at piece c ^ (r & 7) (128-byte rows), c ^ ((r >> 1) & 3) (64-byte rows), c (32-byte rows)
         const uint32_t cps = (uint32_t)p.epi_cbox >> 4;          // 16-channel chunks per box: 4 / 2 / 1
-        const uint32_t pitch = (uint32_t)p.epi_cbox * 2u;
+        const uint32_t lg = cps == 4 ? 2u : (cps == 2 ? 1u : 0u);
         const uint32_t swz = cps == 4 ? ((uint32_t)row & 7u) : (cps == 2 ? (((uint32_t)row >> 1) & 3u) : 0u);
-        const uint32_t rbase = sbuf + (uint32_t)row * pitch;
+        const uint32_t rbase = sbuf + ((uint32_t)row << (5u + lg));          // row pitch = 32 << lg bytes
         if (issuer) bulk_wait_group_read<1>();                   // the stores that read this buffer two tiles ago are done with it
         asm volatile("bar.sync 1, 128;" ::: "memory");
         int ph_co = ph_co0;
@@ -267,10 +267,10 @@ conv_fprop_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
             w1.v[j] = from_f<T>(__uint_as_float(r[8 + j]) + (brow ? __ldg(brow + 8 + j) : 0.f));
           }
           const uint32_t chunk = (uint32_t)j0 >> 4;
-          const uint32_t box = chunk / cps, k = chunk - box * cps;
-          const uint32_t dst = rbase + box * 128u * pitch;
-          st_shared_v4(dst + ((2u * k) ^ swz) * 16u, *reinterpret_cast<const uint4*>(&w0));
-          st_shared_v4(dst + ((2u * k + 1u) ^ swz) * 16u, *reinterpret_cast<const uint4*>(&w1));
+          const uint32_t k2 = (chunk & (cps - 1u)) << 1;                      // first 16-byte piece of this chunk inside its row
+          const uint32_t dst = rbase + ((chunk >> lg) << (12u + lg));         // box = 128 rows x (32 << lg) bytes
+          st_shared_v4(dst + ((k2 ^ swz) << 4), *reinterpret_cast<const uint4*>(&w0));
+          st_shared_v4(dst + (((k2 + 1u) ^ swz) << 4), *reinterpret_cast<const uint4*>(&w1));
           ph_co += 16;
           if (ph_co == p.pcout) ph_co = 0;
         }
@@ -282,7 +282,7 @@ conv_fprop_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
           int ph_t = ph_t0;
           ph_co = ph_co0;
           for (int j0 = 0; j0 < p.nt && n0 + j0 < p.cout; j0 += p.epi_cbox) {
-            tma_store_5d(&pm.m[ph_t], sbuf + (uint32_t)(j0 / p.epi_cbox) * 128u * pitch, ph_co, x0, y0, z0, n);
+            tma_store_5d(&pm.m[ph_t], sbuf + (((uint32_t)j0 >> (4u + lg)) << (12u + lg)), ph_co, x0, y0, z0, n);
             ph_co += p.epi_cbox;
             if (ph_co == p.pcout) { ph_co = 0; ++ph_t; }
           }

@@ -637,7 +637,7 @@ __global__ void __launch_bounds__(256) maxpool_fwd_win_kernel(const T* __restric
 
 template <typename T, int VEC, int PD, int PH, int PW, bool ACC, typename IDX>
 __global__ void __launch_bounds__(256) maxpool_bwd_win_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy,
-                                                              int64_t lddy, T* __restrict__ dx, int64_t lddx, PoolGeom g) {
+                                                              int64_t lddy, T* dx, int64_t lddx, const T* dsrc, int64_t ldsrc, PoolGeom g) {
   constexpr int NW = PD * PH * PW;
   const IDX cvn = (IDX)(g.c / VEC);
   const IDX total = (IDX)((int64_t)g.n * g.od * g.oh * g.ow * (g.c / VEC));
@@ -652,6 +652,9 @@ __global__ void __launch_bounds__(256) maxpool_bwd_win_kernel(const T* __restric
     const int64_t vox0 = (((int64_t)n * g.d + oz * PD) * g.h + oy * PH) * g.w + ox * PW;
     const T* xb = x + vox0 * ldx + cv * VEC;
     T* db = dx + vox0 * lddx + cv * VEC;
+    // ACC: the routed gradient is added to `dsrc` (== dx for the in-place form; another tensor, possibly with another voxel pitch,
+    // when the sum is handed on as a dense tensor while the running gradient lives in a channel slice of a concat buffer)
+    const T* sb = ACC ? dsrc + vox0 * ldsrc + cv * VEC : nullptr;
     const int64_t ov = (((int64_t)n * g.od + oz) * g.oh + oy) * g.ow + ox;
     Pack<T, VEC> p[NW], old[NW];
 #pragma unroll
@@ -662,7 +665,7 @@ __global__ void __launch_bounds__(256) maxpool_bwd_win_kernel(const T* __restric
         for (int e = 0; e < PW; ++e) {
           const int64_t off = ((int64_t)a * g.h + b) * g.w + e;
           p[(a * PH + b) * PW + e] = *reinterpret_cast<const Pack<T, VEC>*>(xb + off * ldx);
-          if (ACC) old[(a * PH + b) * PW + e] = *reinterpret_cast<const Pack<T, VEC>*>(db + off * lddx);
+          if (ACC) old[(a * PH + b) * PW + e] = *reinterpret_cast<const Pack<T, VEC>*>(sb + off * ldsrc);
         }
     const Pack<T, VEC> pg = *reinterpret_cast<const Pack<T, VEC>*>(dy + ov * lddy + cv * VEC);
     float m[VEC];
@@ -701,29 +704,31 @@ static inline bool pool_win_enabled() {
 }
 
 template <typename T, int V, int PD, typename IDX>
-static void launch_pool_bwd_win2(const b200_tensor* x, const b200_tensor* dy, const b200_tensor* dx, const PoolGeom& g, int accumulate,
-                                 cudaStream_t st) {
+static void launch_pool_bwd_win2(const b200_tensor* x, const b200_tensor* dy, const b200_tensor* dx, const b200_tensor* dsrc,
+                                 const PoolGeom& g, int accumulate, cudaStream_t st) {
   const unsigned grid = grid_for(voxels(dy) * (x->c / V), 256);
   const T* xp = (const T*)x->data;
   const T* gp = (const T*)dy->data;
   T* dp = (T*)dx->data;
-  if (accumulate) maxpool_bwd_win_kernel<T, V, PD, 2, 2, true, IDX><<<grid, 256, 0, st>>>(xp, x->ld, gp, dy->ld, dp, dx->ld, g);
-  else maxpool_bwd_win_kernel<T, V, PD, 2, 2, false, IDX><<<grid, 256, 0, st>>>(xp, x->ld, gp, dy->ld, dp, dx->ld, g);
+  const T* sp = dsrc ? (const T*)dsrc->data : dp;
+  const int64_t lds = dsrc ? dsrc->ld : dx->ld;
+  if (accumulate) maxpool_bwd_win_kernel<T, V, PD, 2, 2, true, IDX><<<grid, 256, 0, st>>>(xp, x->ld, gp, dy->ld, dp, dx->ld, sp, lds, g);
+  else maxpool_bwd_win_kernel<T, V, PD, 2, 2, false, IDX><<<grid, 256, 0, st>>>(xp, x->ld, gp, dy->ld, dp, dx->ld, sp, lds, g);
 }
 
 // 32-bit index decode whenever the (thread count + one grid stride) stays below 2^31
 static inline bool pool_idx32(int64_t threads) { return threads + (int64_t)sm_count() * 8 * 256 < ((int64_t)1 << 31); }
 
 template <typename T, int V>
-static void launch_pool_bwd_win(const b200_tensor* x, const b200_tensor* dy, const b200_tensor* dx, const PoolGeom& g, int pd,
-                                int accumulate, cudaStream_t st) {
+static void launch_pool_bwd_win(const b200_tensor* x, const b200_tensor* dy, const b200_tensor* dx, const b200_tensor* dsrc,
+                                const PoolGeom& g, int pd, int accumulate, cudaStream_t st) {
   const bool small = pool_idx32(voxels(dy) * (x->c / V));
   if (pd == 2) {
-    if (small) launch_pool_bwd_win2<T, V, 2, uint32_t>(x, dy, dx, g, accumulate, st);
-    else launch_pool_bwd_win2<T, V, 2, int64_t>(x, dy, dx, g, accumulate, st);
+    if (small) launch_pool_bwd_win2<T, V, 2, uint32_t>(x, dy, dx, dsrc, g, accumulate, st);
+    else launch_pool_bwd_win2<T, V, 2, int64_t>(x, dy, dx, dsrc, g, accumulate, st);
   } else {
-    if (small) launch_pool_bwd_win2<T, V, 1, uint32_t>(x, dy, dx, g, accumulate, st);
-    else launch_pool_bwd_win2<T, V, 1, int64_t>(x, dy, dx, g, accumulate, st);
+    if (small) launch_pool_bwd_win2<T, V, 1, uint32_t>(x, dy, dx, dsrc, g, accumulate, st);
+    else launch_pool_bwd_win2<T, V, 1, int64_t>(x, dy, dx, dsrc, g, accumulate, st);
   }
 }
 
@@ -1600,7 +1605,7 @@ B200_EXPORT int b200_maxpool_bwd(const b200_tensor* x, const b200_tensor* y, con
     constexpr int V = VecOf<T>::n;
     if (divisible && vec_ok(x, V) && vec_ok(dy, V) && vec_ok(dx, V) && pool_win_enabled() && ph == 2 && pw == 2 &&
         (pd == 1 || pd == 2)) {
-      launch_pool_bwd_win<T, V>(x, dy, dx, g, pd, accumulate, (cudaStream_t)stream);
+      launch_pool_bwd_win<T, V>(x, dy, dx, nullptr, g, pd, accumulate, (cudaStream_t)stream);
     } else if (divisible && vec_ok(x, V) && vec_ok(dy, V) && vec_ok(dx, V))
       maxpool_bwd_vec_kernel<T, V, 8><<<grid_for(voxels(dy) * (x->c / V), 256), 256, 0, (cudaStream_t)stream>>>(
           (const T*)x->data, x->ld, (const T*)dy->data, dy->ld, (T*)dx->data, dx->ld, g, accumulate);
@@ -1608,6 +1613,33 @@ B200_EXPORT int b200_maxpool_bwd(const b200_tensor* x, const b200_tensor* y, con
       maxpool_bwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x->data, x->ld, (const T*)dy->data,
                                                                                   dy->ld, (T*)dx->data, dx->ld, g, accumulate);
   });
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+static bool pool_bwd_to_ok(const b200_tensor* x, const b200_tensor* dy, const b200_tensor* dx_in, const b200_tensor* dx_out, int pd, int ph,
+                           int pw) {
+  if (!x || !dy || !dx_out || x->dtype == B200_F32 || !pool_win_enabled() || ph != 2 || pw != 2 || (pd != 1 && pd != 2)) return false;
+  if (x->d % pd || x->h % ph || x->w % pw) return false;
+  if (!(vec_ok(x, 8) && vec_ok(dy, 8) && vec_ok(dx_out, 8))) return false;
+  if (dx_in && !(vec_ok(dx_in, 8) && dx_in->dtype == x->dtype && dx_in->c == x->c && same_spatial(x, dx_in))) return false;
+  return dy->dtype == x->dtype && dx_out->dtype == x->dtype && dx_out->c == x->c && same_spatial(x, dx_out);
+}
+
+B200_EXPORT int b200_maxpool_bwd_to_ok(const b200_tensor* x, const b200_tensor* dy, const b200_tensor* dx_in, const b200_tensor* dx_out,
+                                       int32_t pd, int32_t ph, int32_t pw) {
+  return pool_bwd_to_ok(x, dy, dx_in, dx_out, pd, ph, pw) ? 1 : 0;
+}
+
+B200_EXPORT int b200_maxpool_bwd_to(const b200_tensor* x, const b200_tensor* dy, const b200_tensor* dx_in, const b200_tensor* dx_out,
+                                    int32_t pd, int32_t ph, int32_t pw, void* stream) {
+  B200_CHECK_ARG(check_tensor(x, "maxpool_bwd_to.x") && check_tensor(dy, "maxpool_bwd_to.dy") && check_tensor(dx_out, "maxpool_bwd_to.dx_out"),
+                 "%s", b200_last_error());
+  B200_CHECK_ARG(pool_bwd_to_ok(x, dy, dx_in, dx_out, pd, ph, pw), "maxpool_bwd_to: operands not supported (query b200_maxpool_bwd_to_ok)");
+  PoolGeom g;
+  int st = pool_geom(x, dy, pd, ph, pw, &g);
+  if (st) return st;
+  B200_DISPATCH_DTYPE16(x->dtype, T, (launch_pool_bwd_win<T, 8>(x, dy, dx_out, dx_in, g, pd, dx_in ? 1 : 0, (cudaStream_t)stream)));
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

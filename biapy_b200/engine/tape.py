@@ -26,7 +26,7 @@ from .. import _lib, ops
 class TT:
     """A tensor on the tape: data + lazily allocated gradient; may be a channel slice of a parent buffer."""
 
-    __slots__ = ("data", "_grad", "_ready", "parent", "off", "requires_grad", "padded", "sums")
+    __slots__ = ("data", "_grad", "_ready", "parent", "off", "requires_grad", "padded", "sums", "dense_grad")
 
     def __init__(self, data: torch.Tensor, requires_grad: bool = True, parent: "Optional[TT]" = None, off: int = 0):
         self.data = data
@@ -37,6 +37,7 @@ class TT:
         self.requires_grad = requires_grad
         self.padded = None          # zero-padded 16-channel copy (network inputs with < 16 channels, see Tape.conv)
         self.sums = None            # (N, C, 2) float64 channel sums left by the producing convolution's epilogue (Tape.conv)
+        self.dense_grad = None      # slices only: the finished gradient as a dense tensor (left by Tape.maxpool's backward)
 
     @property
     def shape(self):
@@ -55,7 +56,10 @@ class TT:
         return self.parent.grad_ready if self.parent is not None else self._ready
 
     def grad(self) -> torch.Tensor:
-        """Gradient buffer (allocated on first use).  For slices: a view into the parent's gradient."""
+        """Gradient buffer (allocated on first use).  For slices: a view into the parent's gradient -- or, once the last writer
+        has handed the finished sum on as a dense tensor (Tape.maxpool), that tensor."""
+        if self.dense_grad is not None:
+            return self.dense_grad
         if self.parent is not None:
             return self.parent.grad()[..., self.off:self.off + self.c]
         if self._grad is None:
@@ -102,6 +106,7 @@ class Tape:
         self.use_xfold = os.environ.get("B200_XFOLD", "1") != "0"
         # conv -> norm: channel sums of the normalisation produced by the convolution epilogue (x-slab kernels)
         self.fuse_stats = os.environ.get("B200_FUSE_STATS", "1") != "0"
+        self.pool_dense = os.environ.get("B200_POOL_DENSE", "1") != "0"
         self.param_grads: Dict[torch.nn.Parameter, torch.Tensor] = {}
         # key -> (pack job, packed tensor) of every weight pack this pass launched on its own (Trainer: replayed as one launch)
         self.pack_record: Optional[Dict] = None
@@ -395,6 +400,15 @@ class Tape:
                 assert out.grad_ready
                 if x.requires_grad:
                     acc = x.prepare_accumulate()
+                    if x.parent is not None and acc and self.pool_dense and self.dtype != torch.float32:
+                        # The pooled path is the last writer of a skip tensor's gradient, which lives in a channel slice of the
+                        # concat buffer's gradient; the x-folded dgrad / wgrad of the producing block need it dense.  Write the
+                        # sum (slice + routed gradient) straight into a dense tensor and hand that on, instead of updating the
+                        # slice in place and copying it out afterwards (five strided copies per step, 0.28 ms).
+                        dense = torch.empty(x.shape, dtype=x.data.dtype, device=x.data.device)
+                        if ops.maxpool_bwd_to(x.data, out.grad(), x.grad(), dense, p):
+                            x.dense_grad = dense
+                            return
                     ops.maxpool_bwd(x.data, out.data, out.grad(), x.grad(), p, accumulate=acc)
             self.steps.append(bwd)
         return out

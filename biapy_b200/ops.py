@@ -396,6 +396,14 @@ def maxpool_bwd(x, y, dy, dx, p: Sequence[int], accumulate=False):
     _launch("b200_maxpool_bwd", _ref(x), _ref(y), _ref(dy), _ref(dx), p[0], p[1], p[2], 1 if accumulate else 0, stream_ptr())
 
 
+def maxpool_bwd_to(x, dy, dx_in, dx_out, p: Sequence[int]) -> bool:
+    """dx_out (dense) = (dx_in or 0) + routed dy; returns False (nothing launched) when the operands do not qualify."""
+    if not _lib.lib().b200_maxpool_bwd_to_ok(_ref(x), _ref(dy), _ref(dx_in), _ref(dx_out), p[0], p[1], p[2]):
+        return False
+    _launch("b200_maxpool_bwd_to", _ref(x), _ref(dy), _ref(dx_in), _ref(dx_out), p[0], p[1], p[2], stream_ptr())
+    return True
+
+
 # ------------------------------------------------------------------------------------- normalisation / act
 class NormStats:
     __slots__ = ("mean", "rstd", "scale", "shift", "groups", "batch_stats", "world", "sync_group")

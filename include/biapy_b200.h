@@ -273,6 +273,13 @@ int b200_unpack_convT_wgrad(const float* dw_packed, float* dw, int32_t cin, int3
 int b200_maxpool_fwd(const b200_tensor* x, const b200_tensor* y, int32_t pd, int32_t ph, int32_t pw, void* stream);
 int b200_maxpool_bwd(const b200_tensor* x, const b200_tensor* y, const b200_tensor* dy, const b200_tensor* dx,
                      int32_t pd, int32_t ph, int32_t pw, int32_t accumulate, void* stream);
+/* Out-of-place form for gradients that live in a channel slice of a concat buffer: dx_out = (dx_in ? dx_in : 0) + the routed dy,
+ * dx_out dense.  The max-pool backward is the last writer of a skip tensor's gradient, so handing the sum on as a dense tensor
+ * saves the strided-to-dense copy the x-folded dgrad / wgrad of the producing block would need.  2 x 2 (x 2) windows, 16-bit. */
+int b200_maxpool_bwd_to_ok(const b200_tensor* x, const b200_tensor* dy, const b200_tensor* dx_in, const b200_tensor* dx_out,
+                           int32_t pd, int32_t ph, int32_t pw);
+int b200_maxpool_bwd_to(const b200_tensor* x, const b200_tensor* dy, const b200_tensor* dx_in, const b200_tensor* dx_out,
+                        int32_t pd, int32_t ph, int32_t pw, void* stream);
 
 /* ------------------------------------------------------------------------------------ normalisation + activation
  * GroupNorm(8|16, C) / InstanceNorm(affine) / BatchNorm (biapy/models/blocks.py:2092-2165) as
