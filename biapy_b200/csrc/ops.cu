@@ -1807,7 +1807,7 @@ B200_EXPORT int b200_pack_batch(const b200_pack_job* jobs, int32_t n_jobs, int32
     int block = 0;
     for (int k = 0; k < n; ++k) {
       const b200_pack_job& s = jobs[j0 + k];
-      B200_CHECK_ARG(s.src && s.dst && s.kind >= 0 && s.kind <= 4 && s.cout > 0 && s.cin > 0 && s.kd > 0 && s.kh > 0 && s.kw > 0,
+      B200_CHECK_ARG(s.src && s.dst && s.kind >= 0 && s.kind <= 5 && s.cout > 0 && s.cin > 0 && s.kd > 0 && s.kh > 0 && s.kw > 0,
                      "pack_batch: bad job %d", j0 + k);
       PackJob& d = tab.j[k];
       d.src = s.src; d.dst = s.dst; d.kind = s.kind; d.cout = s.cout; d.cin = s.cin; d.kd = s.kd; d.kh = s.kh; d.kw = s.kw;
@@ -1818,6 +1818,11 @@ B200_EXPORT int b200_pack_batch(const b200_pack_job* jobs, int32_t n_jobs, int32
         int xoff = 0, kxp = 0;
         B200_CHECK_ARG(pack_xfold_geom(CI, s.kw, &xoff, &kxp), "pack_batch: job %d: x-folded packing needs Cin in (2, 4, 8) or a multiple of 16", j0 + k);
         total = (int64_t)4 * CO * s.kd * s.kh * kxp;
+      } else if (s.kind == PACK_XLINE) {
+        const int CO = s.flip ? s.cin : s.cout, CI = s.flip ? s.cout : s.cin;
+        B200_CHECK_ARG(CO == 16 && (CI == 16 || CI == 48) && s.kd == 3 && s.kh == 3 && s.kw == 3,
+                       "pack_batch: job %d: x-line packing takes 3x3x3 kernels with (Cout', Cin') = (16, 16 | 48)", j0 + k);
+        total = (int64_t)27 * (CI / 16) * 48 * 16;
       }
       d.total = total;
       // ~1 K elements per block, at most 512 blocks per job: the 1.8 M-element packs of the 256-channel layers must not become

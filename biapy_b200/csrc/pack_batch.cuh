@@ -10,7 +10,8 @@ enum PackKind : int32_t {
   PACK_XFOLD = 1,        // block-Toeplitz packing of the x-folded kernels in T
   PACK_CONVT = 2,        // (Cin,Cout,taps) fp32 -> [tap][Cout][Cin] (flip = for_dgrad: [tap][Cin][Cout]) in T
   UNPACK_WGRAD = 3,      // [Cout][tap][Cin] fp32 -> (Cout,Cin,taps) fp32, flip = accumulate
-  UNPACK_CONVT_WGRAD = 4 // [tap][Cout][Cin] fp32 -> (Cin,Cout,taps) fp32, flip = accumulate
+  UNPACK_CONVT_WGRAD = 4, // [tap][Cout][Cin] fp32 -> (Cin,Cout,taps) fp32, flip = accumulate
+  PACK_XLINE = 5         // rotated (48 x 16) SWIZZLE_32B tiles of the x-line kernel (conv_xline.cu: pack_weight_xline_kernel) in T
 };
 
 struct PackJob {
@@ -103,6 +104,28 @@ __device__ __forceinline__ void pack_batch_body(const PackJob* __restrict__ jobs
       const int ci = (int)(i / ((int64_t)taps * cout));
       const int64_t o = jb.flip ? (((int64_t)t * cin + ci) * cout + co) : (((int64_t)t * cout + co) * cin + ci);
       p[o] = from_f<T>(jb.src[i]);
+    }
+  } else if (jb.kind == PACK_XLINE) {
+    T* out = (T*)jb.dst;
+    const int CI = jb.flip ? jb.cout : jb.cin;
+    const int ks = CI / 16;
+    for (int64_t i = first; i < jb.total; i += stride) {
+      int t = (int)i;
+      const int kk = t % 16; t /= 16;
+      const int rr = t % 48; t /= 48;
+      const int k = t % ks; t /= ks;
+      const int dx = t % 3; t /= 3;
+      const int dy = t % 3; t /= 3;
+      const int r = t;
+      const int s = rr / 16, co = rr % 16;
+      const int dz = ((r + 1 - s) % 3 + 3) % 3;
+      const int ci = k * 16 + kk;
+      float v;
+      if (jb.flip) v = jb.src[((((int64_t)ci * jb.cin + co) * 3 + (2 - dz)) * 3 + (2 - dy)) * 3 + (2 - dx)];
+      else v = jb.src[((((int64_t)co * jb.cin + ci) * 3 + dz) * 3 + dy) * 3 + dx];
+      const int tile = ((r * 3 + dy) * 3 + dx) * ks + k;
+      const int off = rr * 16 + ((((kk >> 3) ^ ((rr >> 2) & 1))) << 3) + (kk & 7);
+      out[(int64_t)tile * (48 * 16) + off] = from_f<T>(v);
     }
   } else if (jb.kind == UNPACK_WGRAD) {
     float* dw = (float*)jb.dst;

@@ -109,7 +109,7 @@ class PackJob(C.Structure):
                 ("n_blocks", C.c_int32), ("total", C.c_int64)]
 
 
-PACK_PLAIN, PACK_XFOLD, PACK_CONVT, UNPACK_WGRAD, UNPACK_CONVT_WGRAD = 0, 1, 2, 3, 4
+PACK_PLAIN, PACK_XFOLD, PACK_CONVT, UNPACK_WGRAD, UNPACK_CONVT_WGRAD, PACK_XLINE = 0, 1, 2, 3, 4, 5
 # set by the single-job pack functions: (kind, src tensor, dst tensor, cout, cin, kd, kh, kw, flip) of the launch just made --
 # the Tape copies it into the Trainer's pack plan so that later passes replay all packs as one launch
 LAST_PACK = None
@@ -226,6 +226,52 @@ def pack_conv_weight_xfold(w: torch.Tensor, dtype: torch.dtype, flip_transpose: 
     global LAST_PACK
     LAST_PACK = (PACK_XFOLD, w, out, cout, cin, k[0], k[1], k[2], 1 if flip_transpose else 0)
     return out
+
+
+def conv_xline_supported(x, y, k) -> bool:
+    """True when the x-line kernel (csrc/conv_xline.cu) takes these operands: 3x3x3, W = 128, Cout = 16, Cin in (16, 48), dense
+    16-bit channels-last input, and B200_XLINE != 0."""
+    if x.dtype == torch.float32 or tuple(k) != (3, 3, 3):
+        return False
+    return bool(_lib.lib().b200_conv_xline_supported(_ref(x), _ref(y), 3, 3, 3))
+
+
+def pack_conv_weight_xline(w: torch.Tensor, dtype: torch.dtype, flip_transpose: bool) -> torch.Tensor:
+    """w: (Cout, Cin, 3, 3, 3) fp32 -> rotated (48 x 16) tiles of the x-line kernel (`b200_pack_conv_weight_xline`)."""
+    w = w.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    cout, cin = w.shape[:2]
+    ci_l = cout if flip_transpose else cin
+    out = torch.empty(27 * (ci_l // 16) * 48 * 16, dtype=dtype, device=w.device)
+    _launch("b200_pack_conv_weight_xline", _ptr(w), _ptr(out), _lib.torch_dtype_code(dtype), cout, cin, 1 if flip_transpose else 0,
+            stream_ptr())
+    global LAST_PACK
+    LAST_PACK = (PACK_XLINE, w, out, cout, cin, 3, 3, 3, 1 if flip_transpose else 0)
+    return out
+
+
+def conv_fprop_xline(x, w_packed_xline, bias, y, accumulate=False, scale=None, shift=None, fuse: int = 0, a_out=None, sums=None):
+    """x-line convolution; fuse = 1 / 2: silu(x * scale + shift) (exact / one-MUFU chain) applied to the input on the operand
+    path, `a_out` receives the activated input (`b200_conv_fprop_xline`)."""
+    label = flops = nbytes = None
+    if PROFILE is not None:
+        vox = x.shape[0] * x.shape[1] * x.shape[2] * x.shape[3]
+        flops = 2.0 * vox * x.shape[-1] * y.shape[-1] * 27
+        nbytes = vox * (x.shape[-1] * (2 if a_out is not None else 1) + y.shape[-1] * (2 if accumulate else 1)) * x.element_size()
+        label = "conv_fprop_xline" + ("_gn_silu" if fuse else "")
+        if PROFILE_SHAPES:
+            label += (f" {x.shape[-1]}->{y.shape[-1]} k333 @{x.shape[1]}x{x.shape[2]}x{x.shape[3]}"
+                      + (" +stats" if sums is not None else ""))
+    _launch_timed(label, flops, nbytes, "b200_conv_fprop_xline", _ref(x), _ptr(w_packed_xline), _ptr(bias), _ref(y),
+                  1 if accumulate else 0, _ptr(scale), _ptr(shift), int(fuse), _ref(a_out), _ptr(sums), stream_ptr())
+    return y
+
+
+def xline_selftest(verbose: int = 0) -> float:
+    err = C.c_double(0.0)
+    call("b200_xline_selftest", C.byref(err), int(verbose), stream_ptr())
+    return float(err.value)
 
 
 def conv_fprop(x, w_packed, bias, y, k: Sequence[int], residual=None, accumulate=False, impl=_lib.IMPL_AUTO):

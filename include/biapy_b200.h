@@ -233,6 +233,23 @@ int b200_conv_fprop_stats(const b200_tensor* x, const void* w_packed_xfold, cons
  * B200_IMPL_XFOLD in b200_conv_fprop; B200_IMPL_AUTO never selects it (the packing differs). */
 int b200_pack_conv_weight_xfold(const float* w, void* packed, int32_t dtype, int32_t cout, int32_t cin, int32_t kd,
                                 int32_t kh, int32_t kw, int32_t flip_transpose, void* stream);
+/* x-line kernel (csrc/conv_xline.cu): 3x3x3 convolution of the Cout = 16 layers at W = 128 (Cin = 16 or 48, dense channels-last
+ * input) with the operand in tensor memory, and -- the "Conv3D + GroupNorm + SiLU" fusion of the reference's pre-activation
+ * order GN(in) -> act -> conv (biapy/models/blocks.py:1304-1378) -- the normalisation-apply + activation of its INPUT on the
+ * operand path:  fuse = 0: y (+)= conv(x) + bias;  fuse = 1 / 2: a = silu(x * scale[n,c] + shift[n,c]) (arithmetic of
+ * b200_scale_shift_act / b200_scale_shift_silu_fast, rounded to the engine dtype exactly like their stored result),
+ * y (+)= conv(a) + bias, and a_out (nullable; dense, x's shape) receives a for the backward pass.  sums (nullable): double
+ * [N][16][2] += (sum y, sum y*y) of the stored output, as b200_conv_fprop_stats.  Weights: b200_pack_conv_weight_xline
+ * (27 * Cin/16 tiles of 48 x 16 elements: [r][dy][dx][k][(s, co)][ci] with tap dz = (r + 1 - s) mod 3; flip_transpose = 1 packs
+ * the dgrad operand).  b200_conv_xline_supported: 1 when (x, y, kernel) qualify and B200_XLINE != 0. */
+int b200_conv_xline_supported(const b200_tensor* x, const b200_tensor* y, int32_t kd, int32_t kh, int32_t kw);
+int b200_pack_conv_weight_xline(const float* w, void* packed, int32_t dtype, int32_t cout, int32_t cin, int32_t flip_transpose,
+                                void* stream);
+int b200_conv_fprop_xline(const b200_tensor* x, const void* w_packed, const float* bias, const b200_tensor* y, int32_t accumulate,
+                          const float* scale, const float* shift, int32_t fuse, const b200_tensor* a_out, double* sums,
+                          void* stream);
+/* one tcgen05.mma with the A operand in tensor memory against exact integers; *max_err = largest absolute deviation */
+int b200_xline_selftest(double* max_err, int32_t verbose, void* stream);
 /* best kernel family for these operands: B200_IMPL_XFOLD, B200_IMPL_UMMA or B200_IMPL_SIMT
  * (wgrad != 0: for b200_conv_wgrad with y = dy; never XFOLD) */
 int b200_conv_impl_query(const b200_tensor* x, const b200_tensor* y, int32_t kd, int32_t kh, int32_t kw, int32_t wgrad);
@@ -376,7 +393,7 @@ int b200_softmax_channels(const b200_tensor* x, const b200_tensor* y, int32_t c0
  * A training pass re-packs every fp32 master weight for the tensor-core kernels (b200_pack_conv_weight, _xfold, b200_pack_convT_weight:
  * 66 launches for the config-[1] network) and un-packs every weight gradient (b200_unpack_conv_wgrad, b200_unpack_convT_wgrad: 32);
  * b200_pack_batch runs any mix of those element mappings in ONE launch per 48 jobs.  `jobs` is a HOST array; src / dst are
- * device pointers.  kind: 0 plain pack, 1 x-folded pack, 2 transposed-conv pack (flip = for_dgrad), 3 un-pack of a conv weight
+ * device pointers.  kind: 0 plain pack, 1 x-folded pack, 2 transposed-conv pack (flip = for_dgrad), 3 un-pack of a conv weight (5: x-line pack, after 4)
  * gradient, 4 un-pack of a transposed-conv weight gradient (flip = accumulate into dst); (cout, cin, kd, kh, kw) as in the
  * single-job calls -- for kinds 2 / 4 `cout` carries the transposed conv's Cin and `cin` its Cout, the argument order of
  * b200_pack_convT_weight(w, packed, dtype, cin, cout, taps, ...).  block_begin / n_blocks / total are filled in by the call. */
