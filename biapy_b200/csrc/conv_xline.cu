@@ -75,6 +75,19 @@ __device__ __forceinline__ float xl_silu(float z) {
   return __fdividef(z, 1.f + __expf(-z));
 }
 
+// bounded wait without the printf path of mbar_wait (one call site of that costs ~25 instructions and a stack frame)
+__device__ __forceinline__ void xl_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 255u) == 0u) {
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > 4000000000LL) __trap();
+    }
+  }
+}
+
 struct XlineParams {
   int n, d, h;
   int bands, zchunks, zc, units;
@@ -83,6 +96,9 @@ struct XlineParams {
   long long ysw, ysh, ysd, ysn;    // element strides of the output
   int accumulate;
   uint32_t idesc;
+  int ablate;                      // B200_XL_ABLATE bits: 1 no MMA, 2 no activation math, 4 no operand stores, 8 no output,
+                                   // 16 no bulk copies, 32 no accumulator zeroing, 64 no operand loads (timing experiments only)
+  long long* dbg;                  // B200_XL_DBG: per-block cycle counters (tools/xline_probe.py)
 };
 
 constexpr uint32_t kXlTileBytes = 48u * 32u;   // one B tile: 48 rows (s, co) x 16 ci, SWIZZLE_32B K-major
@@ -90,32 +106,37 @@ constexpr uint32_t kXlTileBytes = 48u * 32u;   // one B tile: 48 rows (s, co) x 
 __device__ __forceinline__ int xl_mod3(int v) { return ((v % 3) + 3) % 3; }
 
 template <typename T, int KS, int BY, int FUSE>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(FUSE ? 448 : 320, 1)
 conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, const float* __restrict__ bias, T* __restrict__ y,
                         T* __restrict__ a_out, const float* __restrict__ scale, const float* __restrict__ shift,
                         double* __restrict__ stats, const XlineParams p) {
   constexpr int NR = KS == 1 ? 8 : 3;            // raw ring: slots of two lines
   constexpr int NA = KS == 1 ? 5 : 4;            // operand ring in tensor memory: slots of one line (three shifted copies)
   constexpr int PAIRS = (BY + 2) / 2;
+  constexpr int LB = KS == 1 ? 2 : 1;            // lines a staging iteration handles together
+  constexpr int G = 2;                           // output lines an epilogue iteration handles together
   constexpr uint32_t LINE = 4096u * KS;
+  constexpr uint32_t VOX = 32u * KS;             // bytes per voxel
   constexpr uint32_t ACOLS = 24u * KS;
   constexpr uint32_t ACC = (uint32_t)BY * 48u;
   constexpr uint32_t BBYTES = 27u * KS * kXlTileBytes;
   constexpr int W = 8 * KS;                      // 32-bit words per voxel
+  constexpr uint32_t CFB = 2u * 16u * KS * 4u;   // coefficient table per math warp: scale[Cin], shift[Cin]
   static_assert(BY % 2 == 0 && ACC + NA * ACOLS <= 512, "tensor memory budget");
 
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t s_bar[2 * NR + 2 * NA + 2 * BY + 1];
+  __shared__ uint64_t s_bar[3 * NR + 2 * NA + 2 * BY + 1];
   __shared__ uint32_t s_tmem;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sm_b = smem0, sm_raw = smem0 + BBYTES, sm_ex = sm_raw + NR * 2u * LINE;
+  const uint32_t sm_b = smem0, sm_raw = smem0 + BBYTES, sm_cf = sm_raw + NR * 2u * LINE;
   const uint32_t bar0 = smem_u32(s_bar);
-  const uint32_t raw_full = bar0, raw_free = raw_full + 8 * NR, a_full = raw_free + 8 * NR, a_free = a_full + 8 * NA,
-                 acc_full = a_free + 8 * NA, acc_free = acc_full + 8 * BY, w_full = acc_free + 8 * BY;
+  const uint32_t raw_full = bar0, raw_free = raw_full + 8 * NR, xf_full = raw_free + 8 * NR, a_full = xf_full + 8 * NR,
+                 a_free = a_full + 8 * NA, acc_full = a_free + 8 * NA, acc_free = acc_full + 8 * BY, w_full = acc_free + 8 * BY;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long* const dbg = p.dbg ? p.dbg + (long long)blockIdx.x * 16 : nullptr;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NR; ++i) { mbar_init(raw_full + 8 * i, 1); mbar_init(raw_free + 8 * i, 4); }
+    for (int i = 0; i < NR; ++i) { mbar_init(raw_full + 8 * i, 1); mbar_init(raw_free + 8 * i, 4); mbar_init(xf_full + 8 * i, 4); }
     for (int i = 0; i < NA; ++i) { mbar_init(a_full + 8 * i, 4); mbar_init(a_free + 8 * i, 1); }
     for (int i = 0; i < BY; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_free + 8 * i, 4); }
     mbar_init(w_full, 1);
@@ -136,10 +157,27 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
     z0 = zk * p.zc;
     zhi = z0 + p.zc < p.d ? z0 + p.zc : p.d;
   };
+  // valid lines [lo, hi) of pair pr in the band starting at y0
+  auto pair_range = [&](int y0, int pr, int& lo, int& hi) {
+    lo = 2 * pr; hi = 2 * pr + 2;
+    if ((unsigned)(y0 - 1 + lo) >= (unsigned)p.h) ++lo;
+    if ((unsigned)(y0 - 1 + hi - 1) >= (unsigned)p.h) --hi;
+  };
+  // bounded wait; with the debug buffer the cycles spent waiting are added to `acc` (a register of the calling thread)
+  auto wait_on = [&](uint32_t bar, uint32_t parity, long long& acc) {
+    if (dbg) {
+      const long long t0 = clock64();
+      xl_wait(bar, parity);
+      acc += clock64() - t0;
+    } else {
+      xl_wait(bar, parity);
+    }
+  };
 
   if (warp == 9) {
     // ===================================================================== bulk-copy issue
     if (elect_one()) {
+      long long w_free = 0;
       mbar_expect_tx(w_full, BBYTES);
       bulk_g2s(sm_b, wpk, BBYTES, w_full);
       int rs = 0;
@@ -153,60 +191,77 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
           const char* plane = xb + (long long)n * p.xsn_b + (long long)pz * p.xsd_b;
 #pragma unroll 1
           for (int pr = 0; pr < PAIRS; ++pr) {
-            int lo = 2 * pr, hi = 2 * pr + 2;
-            if ((unsigned)(y0 - 1 + lo) >= (unsigned)p.h) ++lo;
-            if ((unsigned)(y0 - 1 + hi - 1) >= (unsigned)p.h) --hi;
+            int lo, hi;
+            pair_range(y0, pr, lo, hi);
             if (lo >= hi) continue;
-            mbar_wait(raw_free + 8 * rs, rph ^ 1);
+            wait_on(raw_free + 8 * rs, rph ^ 1, w_free);
             const uint32_t bytes = (uint32_t)(hi - lo) * LINE;
-            mbar_expect_tx(raw_full + 8 * rs, bytes);
-            bulk_g2s(sm_raw + (uint32_t)rs * 2u * LINE + (uint32_t)(lo - 2 * pr) * LINE,
-                     plane + (long long)(y0 - 1 + lo) * p.xsh_b, bytes, raw_full + 8 * rs);
+            if (p.ablate & 16) {
+              mbar_arrive(raw_full + 8 * rs);
+            } else {
+              mbar_expect_tx(raw_full + 8 * rs, bytes);
+              bulk_g2s(sm_raw + (uint32_t)rs * 2u * LINE + (uint32_t)(lo - 2 * pr) * LINE,
+                       plane + (long long)(y0 - 1 + lo) * p.xsh_b, bytes, raw_full + 8 * rs);
+            }
             if (++rs == NR) { rs = 0; rph ^= 1; }
           }
         }
       }
+      if (dbg) dbg[9] = w_free;
     }
   } else if (warp == 8) {
     // ===================================================================== MMA issue
     if (elect_one()) {
+      const long long t_begin = dbg ? clock64() : 0;
+      long long w_acc = 0, w_a = 0, t_issue = 0;
       const uint32_t idesc = in_reg(p.idesc);
       const uint32_t b_hi = (256u >> 4) | (1u << 14) | ((uint32_t)kSwizzle32 << 29);
       const uint32_t b_lo0 = ((sm_b >> 4) & 0x3FFFu) | (1u << 16);
-      mbar_wait(w_full, 0);
+      const uint32_t tstep = kXlTileBytes >> 4;
+      xl_wait(w_full, 0);
       int slot = 0;
       uint32_t aph = 0, pc = 0;
+      long long nlines = 0;
       for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
         int n, z0, zhi, y0;
         decode(u, n, z0, zhi, y0);
         for (int pz = z0 - 1; pz <= zhi; ++pz, ++pc) {
           const bool pv = (unsigned)pz < (unsigned)p.d;
-          const uint32_t b_r = b_lo0 + (uint32_t)xl_mod3(pz) * (9u * KS * (kXlTileBytes >> 4));
-#pragma unroll
+          const uint32_t b_r = b_lo0 + (uint32_t)xl_mod3(pz) * (9u * KS * tstep);
+          // one compact body per input line (the fully unrolled form was 48 KB of straight-line code for this one thread)
+#pragma unroll 1
           for (int i = 0; i < BY + 2; ++i) {
             if (i < BY) {
-              mbar_wait(acc_free + 8 * i, pc & 1);
+              wait_on(acc_free + 8 * i, pc & 1, w_acc);
               tc_fence_after();
             }
             const bool lv = pv && (unsigned)(y0 - 1 + i) < (unsigned)p.h;
             if (lv) {
-              mbar_wait(a_full + 8 * slot, aph);
+              wait_on(a_full + 8 * slot, aph, w_a);
               tc_fence_after();
+              ++nlines;
+              const long long tm = dbg ? clock64() : 0;
               const uint32_t a_base = tmem + ACC + (uint32_t)slot * ACOLS;
+              const uint32_t d_i = tmem + (uint32_t)i * 48u;
+              if (!(p.ablate & 1)) {
+                if (i >= 2) {                      // last contribution (dy = 2) to output line i - 2
 #pragma unroll
-              for (int oo = i - 2; oo <= i; ++oo) {
-                if (oo < 0 || oo >= BY) continue;
-                const int dy = i - oo;
-                const uint32_t d_t = tmem + (uint32_t)oo * 48u;
+                  for (int t = 0; t < 3 * KS; ++t) umma_f16_ts(d_i - 96u, a_base + 8u * t, b_r + (uint32_t)(6 * KS + t) * tstep, b_hi, idesc, 1u);
+                }
+              }
+              if (i >= 2) umma_commit(acc_full + 8 * (i - 2));
+              if (!(p.ablate & 1)) {
+                if (i >= 1 && i <= BY) {
 #pragma unroll
-                for (int dx = 0; dx < 3; ++dx)
+                  for (int t = 0; t < 3 * KS; ++t) umma_f16_ts(d_i - 48u, a_base + 8u * t, b_r + (uint32_t)(3 * KS + t) * tstep, b_hi, idesc, 1u);
+                }
+                if (i < BY) {
 #pragma unroll
-                  for (int k = 0; k < KS; ++k)
-                    umma_f16_ts(d_t, a_base + (uint32_t)(dx * KS + k) * 8u,
-                                b_r + (uint32_t)((dy * 3 + dx) * KS + k) * (kXlTileBytes >> 4), b_hi, idesc, 1u);
-                if (oo == i - 2) umma_commit(acc_full + 8 * oo);
+                  for (int t = 0; t < 3 * KS; ++t) umma_f16_ts(d_i, a_base + 8u * t, b_r + (uint32_t)t * tstep, b_hi, idesc, 1u);
+                }
               }
               umma_commit(a_free + 8 * slot);
+              if (dbg) t_issue += clock64() - tm;
               if (++slot == NA) { slot = 0; aph ^= 1; }
             } else if (i >= 2) {
               umma_commit(acc_full + 8 * (i - 2));
@@ -214,119 +269,170 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
           }
         }
       }
+      if (dbg) { dbg[0] = clock64() - t_begin; dbg[1] = w_acc; dbg[2] = w_a; dbg[10] = nlines; dbg[15] = t_issue; }
     }
-  } else if (warp >= 4) {
-    // ===================================================================== transform: raw line -> three operand copies in TMEM
-    const int q = warp & 3;
-    const int xv = q * 32 + lane;
-    const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16) + ACC;
-    int rs = 0, slot = 0;
-    uint32_t rph = 0, aph = 0, par = 0;
-    float sc[KS == 1 ? 16 : 1], sh[KS == 1 ? 16 : 1];
-    const char* ab = reinterpret_cast<const char*>(a_out);
-    for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
-      int n, z0, zhi, y0;
-      decode(u, n, z0, zhi, y0);
-      if constexpr (FUSE != 0 && KS == 1) {
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          sc[c] = __ldg(scale + (long long)n * 16 + c);
-          sh[c] = __ldg(shift + (long long)n * 16 + c);
+  } else if (warp >= 10) {
+    // ===================================================================== activation (FUSE only): raw lines -> silu(x * scale + shift)
+    // in place in the raw ring, and the activated tensor for the backward pass
+    if constexpr (FUSE != 0) {
+      const int q = warp - 10;
+      const int xv = q * 32 + lane;
+      const uint32_t cf = sm_cf + (uint32_t)q * CFB;
+      const bool d0 = dbg != nullptr && threadIdx.x == 320;
+      const long long t_begin = d0 ? clock64() : 0;
+      long long w_raw = 0;
+      int rs = 0;
+      uint32_t rph = 0;
+      char* const ab = reinterpret_cast<char*>(a_out);
+      for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+        int n, z0, zhi, y0;
+        decode(u, n, z0, zhi, y0);
+        __syncwarp();
+        for (int c = lane; c < 16 * KS; c += 32) {
+          const float s = __ldg(scale + (long long)n * (16 * KS) + c), h = __ldg(shift + (long long)n * (16 * KS) + c);
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(cf + 4u * c), "f"(s) : "memory");
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(cf + 64u * KS + 4u * c), "f"(h) : "memory");
         }
-      }
-      for (int pz = z0 - 1; pz <= zhi; ++pz) {
-        if ((unsigned)pz >= (unsigned)p.d) continue;
+        __syncwarp();
+        for (int pz = z0 - 1; pz <= zhi; ++pz) {
+          if ((unsigned)pz >= (unsigned)p.d) continue;
+          const bool zown = a_out != nullptr && pz >= z0 && pz < zhi;
 #pragma unroll 1
-        for (int pr = 0; pr < PAIRS; ++pr) {
-          int lo = 2 * pr, hi = 2 * pr + 2;
-          if ((unsigned)(y0 - 1 + lo) >= (unsigned)p.h) ++lo;
-          if ((unsigned)(y0 - 1 + hi - 1) >= (unsigned)p.h) --hi;
-          if (lo >= hi) continue;
-          mbar_wait(raw_full + 8 * rs, rph);
-          for (int i = lo; i < hi; ++i) {
-            uint32_t v[W], lf[W], rt[W];
-            const uint32_t src = sm_raw + (uint32_t)rs * 2u * LINE + (uint32_t)(i - 2 * pr) * LINE + (uint32_t)xv * (32u * KS);
+          for (int pr = 0; pr < PAIRS; ++pr) {
+            int lo, hi;
+            pair_range(y0, pr, lo, hi);
+            if (lo >= hi) continue;
+            if (d0) wait_on(raw_full + 8 * rs, rph, w_raw); else xl_wait(raw_full + 8 * rs, rph);
+#pragma unroll 1
+            for (int i = lo; i < hi; ++i) {
+              const uint32_t src = sm_raw + (uint32_t)rs * 2u * LINE + (uint32_t)(i - 2 * pr) * LINE + (uint32_t)xv * VOX;
+              uint32_t v[W];
 #pragma unroll
-            for (int j = 0; j < W / 4; ++j)
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                           : "=r"(v[4 * j]), "=r"(v[4 * j + 1]), "=r"(v[4 * j + 2]), "=r"(v[4 * j + 3])
-                           : "r"(src + 16u * j));
-            if (FUSE) {
+              for (int j = 0; j < W / 4; ++j)
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(v[4 * j]), "=r"(v[4 * j + 1]), "=r"(v[4 * j + 2]), "=r"(v[4 * j + 3])
+                             : "r"(src + 16u * j));
+              if (!(p.ablate & 2)) {
 #pragma unroll
-              for (int j = 0; j < W; ++j) {
-                Pack<T, 2> e = *reinterpret_cast<Pack<T, 2>*>(&v[j]);
-                float s0, s1, h0, h1;
-                if constexpr (KS == 1) { s0 = sc[2 * j]; s1 = sc[2 * j + 1]; h0 = sh[2 * j]; h1 = sh[2 * j + 1]; }
-                else {
-                  s0 = __ldg(scale + (long long)n * (16 * KS) + 2 * j); s1 = __ldg(scale + (long long)n * (16 * KS) + 2 * j + 1);
-                  h0 = __ldg(shift + (long long)n * (16 * KS) + 2 * j); h1 = __ldg(shift + (long long)n * (16 * KS) + 2 * j + 1);
+                for (int m = 0; m < W / 2; ++m) {
+                  float4 s4, h4;
+                  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(s4.x), "=f"(s4.y), "=f"(s4.z), "=f"(s4.w) : "r"(cf + 16u * m));
+                  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                               : "=f"(h4.x), "=f"(h4.y), "=f"(h4.z), "=f"(h4.w)
+                               : "r"(cf + 64u * KS + 16u * m));
+                  Pack<T, 2> e0 = *reinterpret_cast<Pack<T, 2>*>(&v[2 * m]);
+                  Pack<T, 2> e1 = *reinterpret_cast<Pack<T, 2>*>(&v[2 * m + 1]);
+                  e0.v[0] = from_f<T>(xl_silu<FUSE>(fmaf(to_f<T>(e0.v[0]), s4.x, h4.x)));
+                  e0.v[1] = from_f<T>(xl_silu<FUSE>(fmaf(to_f<T>(e0.v[1]), s4.y, h4.y)));
+                  e1.v[0] = from_f<T>(xl_silu<FUSE>(fmaf(to_f<T>(e1.v[0]), s4.z, h4.z)));
+                  e1.v[1] = from_f<T>(xl_silu<FUSE>(fmaf(to_f<T>(e1.v[1]), s4.w, h4.w)));
+                  v[2 * m] = *reinterpret_cast<uint32_t*>(&e0);
+                  v[2 * m + 1] = *reinterpret_cast<uint32_t*>(&e1);
                 }
-                e.v[0] = from_f<T>(xl_silu<FUSE>(fmaf(to_f<T>(e.v[0]), s0, h0)));
-                e.v[1] = from_f<T>(xl_silu<FUSE>(fmaf(to_f<T>(e.v[1]), s1, h1)));
-                v[j] = *reinterpret_cast<uint32_t*>(&e);
               }
-              if (a_out != nullptr && i >= 1 && i <= BY && pz >= z0 && pz < zhi) {
-                char* dst = const_cast<char*>(ab) + (long long)n * p.asn_b + (long long)pz * p.asd_b +
-                            (long long)(y0 - 1 + i) * p.ash_b + (long long)xv * (32 * KS);
+#pragma unroll
+              for (int j = 0; j < W / 4; ++j) st_shared_v4(src + 16u * j, make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+              if (zown && i >= 1 && i <= BY) {
+                char* dst = ab + (long long)n * p.asn_b + (long long)pz * p.asd_b + (long long)(y0 - 1 + i) * p.ash_b + (long long)xv * VOX;
 #pragma unroll
                 for (int j = 0; j < W / 4; ++j)
                   *reinterpret_cast<uint4*>(dst + 16 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
               }
             }
-            // neighbours in x: lane - 1 / lane + 1, across warps through a 32-byte exchange, zeros at the line ends
-            const uint32_t ex = sm_ex + par * (8u * 4u * W) ;
-            if (lane == 0 || lane == 31) {
-              const uint32_t dst = ex + (uint32_t)(q * 2 + (lane == 31 ? 1 : 0)) * (4u * W);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(xf_full + 8 * rs);
+            if (++rs == NR) { rs = 0; rph ^= 1; }
+          }
+        }
+      }
+      if (d0) { dbg[11] = clock64() - t_begin; dbg[12] = w_raw; }
+    }
+  } else if (warp >= 4) {
+    // ===================================================================== staging: ring lines -> three operand copies in TMEM
+    // thread = voxel = TMEM lane: its own voxel and the two neighbours in x (zeros at the line ends = 'same' padding in x)
+    const int q = warp & 3;
+    const int xv = q * 32 + lane;
+    const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16) + ACC;
+    const uint32_t in_full = FUSE ? xf_full : raw_full;
+    const bool d0 = dbg != nullptr && threadIdx.x == 128;
+    const long long t_begin = d0 ? clock64() : 0;
+    long long w_in = 0, w_afree = 0, t_ld = 0, t_st = 0, t_arr = 0;
+    int rs = 0, slot = 0;
+    uint32_t rph = 0, aph = 0;
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+      int n, z0, zhi, y0;
+      decode(u, n, z0, zhi, y0);
+      for (int pz = z0 - 1; pz <= zhi; ++pz) {
+        if ((unsigned)pz >= (unsigned)p.d) continue;
+#pragma unroll 1
+        for (int pr = 0; pr < PAIRS; ++pr) {
+          int lo, hi;
+          pair_range(y0, pr, lo, hi);
+          if (lo >= hi) continue;
+          if (d0) wait_on(in_full + 8 * rs, rph, w_in); else xl_wait(in_full + 8 * rs, rph);
+#pragma unroll 1
+          for (int i0 = lo; i0 < hi; i0 += LB) {
+            const int nl = hi - i0 < LB ? hi - i0 : LB;
+            uint32_t v[LB][W], lf[LB][W], rt[LB][W];
+            long long ts = d0 ? clock64() : 0;
 #pragma unroll
-              for (int j = 0; j < W / 4; ++j) st_shared_v4(dst + 16u * j, make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
-            }
+            for (int l = 0; l < LB; ++l) {
+              if (l < nl && !(p.ablate & 64)) {
+                const uint32_t src = sm_raw + (uint32_t)rs * 2u * LINE + (uint32_t)(i0 + l - 2 * pr) * LINE + (uint32_t)xv * VOX;
 #pragma unroll
-            for (int j = 0; j < W; ++j) {
-              lf[j] = __shfl_up_sync(0xffffffffu, v[j], 1);
-              rt[j] = __shfl_down_sync(0xffffffffu, v[j], 1);
-            }
-            asm volatile("bar.sync 2, 128;" ::: "memory");
-            if (lane == 0) {
-              if (q == 0) {
-#pragma unroll
-                for (int j = 0; j < W; ++j) lf[j] = 0u;
-              } else {
-                const uint32_t s2 = ex + (uint32_t)((q - 1) * 2 + 1) * (4u * W);
-#pragma unroll
-                for (int j = 0; j < W / 4; ++j)
+                for (int j = 0; j < W / 4; ++j) {
                   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                               : "=r"(lf[4 * j]), "=r"(lf[4 * j + 1]), "=r"(lf[4 * j + 2]), "=r"(lf[4 * j + 3])
-                               : "r"(s2 + 16u * j));
+                               : "=r"(v[l][4 * j]), "=r"(v[l][4 * j + 1]), "=r"(v[l][4 * j + 2]), "=r"(v[l][4 * j + 3])
+                               : "r"(src + 16u * j));
+                  if (xv > 0)
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(lf[l][4 * j]), "=r"(lf[l][4 * j + 1]), "=r"(lf[l][4 * j + 2]), "=r"(lf[l][4 * j + 3])
+                                 : "r"(src - VOX + 16u * j));
+                  else lf[l][4 * j] = lf[l][4 * j + 1] = lf[l][4 * j + 2] = lf[l][4 * j + 3] = 0u;
+                  if (xv < 127)
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(rt[l][4 * j]), "=r"(rt[l][4 * j + 1]), "=r"(rt[l][4 * j + 2]), "=r"(rt[l][4 * j + 3])
+                                 : "r"(src + VOX + 16u * j));
+                  else rt[l][4 * j] = rt[l][4 * j + 1] = rt[l][4 * j + 2] = rt[l][4 * j + 3] = 0u;
+                }
               }
             }
-            if (lane == 31) {
-              if (q == 3) {
+            if (d0) { const long long t = clock64(); t_ld += t - ts; }
+            int sl[LB];
 #pragma unroll
-                for (int j = 0; j < W; ++j) rt[j] = 0u;
-              } else {
-                const uint32_t s2 = ex + (uint32_t)((q + 1) * 2) * (4u * W);
-#pragma unroll
-                for (int j = 0; j < W / 4; ++j)
-                  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                               : "=r"(rt[4 * j]), "=r"(rt[4 * j + 1]), "=r"(rt[4 * j + 2]), "=r"(rt[4 * j + 3])
-                               : "r"(s2 + 16u * j));
+            for (int l = 0; l < LB; ++l) {
+              sl[l] = slot;
+              if (l < nl) {
+                if (d0) wait_on(a_free + 8 * slot, aph ^ 1, w_afree); else xl_wait(a_free + 8 * slot, aph ^ 1);
+                if (++slot == NA) { slot = 0; aph ^= 1; }
               }
             }
-            par ^= 1u;
-            mbar_wait(a_free + 8 * slot, aph ^ 1);
+            if (d0) ts = clock64();
             tc_fence_after();
-            const uint32_t ta = t_lane + (uint32_t)slot * ACOLS;
+            if (!(p.ablate & 4)) {
 #pragma unroll
-            for (int k = 0; k < KS; ++k) {
-              tmem_st8(ta + (uint32_t)(0 * KS + k) * 8u, lf + 8 * k);
-              tmem_st8(ta + (uint32_t)(1 * KS + k) * 8u, v + 8 * k);
-              tmem_st8(ta + (uint32_t)(2 * KS + k) * 8u, rt + 8 * k);
+              for (int l = 0; l < LB; ++l) {
+                if (l < nl) {
+                  const uint32_t ta = t_lane + (uint32_t)sl[l] * ACOLS;
+#pragma unroll
+                  for (int k = 0; k < KS; ++k) {
+                    tmem_st8(ta + (uint32_t)(0 * KS + k) * 8u, lf[l] + 8 * k);
+                    tmem_st8(ta + (uint32_t)(1 * KS + k) * 8u, v[l] + 8 * k);
+                    tmem_st8(ta + (uint32_t)(2 * KS + k) * 8u, rt[l] + 8 * k);
+                  }
+                }
+              }
+              tmem_st_wait();
             }
-            tmem_st_wait();
+            if (d0) { const long long t = clock64(); t_st += t - ts; ts = t; }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(a_full + 8 * slot);
-            if (++slot == NA) { slot = 0; aph ^= 1; }
+            if (lane == 0) {
+#pragma unroll
+              for (int l = 0; l < LB; ++l)
+                if (l < nl) mbar_arrive(a_full + 8 * sl[l]);
+            }
+            if (d0) { const long long t = clock64(); t_arr += t - ts; }
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(raw_free + 8 * rs);
@@ -334,11 +440,14 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
         }
       }
     }
+    if (d0) { dbg[3] = clock64() - t_begin; dbg[4] = w_in; dbg[5] = w_afree; dbg[6] = t_ld; dbg[13] = t_st; dbg[14] = t_arr; }
   } else {
     // ===================================================================== epilogue
     const int q = warp;
     const int xv = q * 32 + lane;
     const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
+    const bool d0 = dbg != nullptr && threadIdx.x == 0;
+    long long w_full_acc = 0;
 #pragma unroll 1
     for (uint32_t c = 0; c < ACC; c += 16) tmem_st16_zero(t_lane + c);
     tmem_st_wait();
@@ -346,6 +455,7 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
     __syncwarp();
     if (lane == 0)
       for (int o = 0; o < BY; ++o) mbar_arrive(acc_free + 8 * o);
+    const long long t_begin = d0 ? clock64() : 0;
     float bs[16];
 #pragma unroll
     for (int c = 0; c < 16; ++c) bs[c] = bias ? __ldg(bias + c) : 0.f;
@@ -361,65 +471,97 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
         const bool sv = zo >= z0 && zo < zhi;
         const uint32_t cs = (uint32_t)xl_mod3(zo) * 16u;
         const bool last = pz == zhi;
+        T* const yplane = y + (long long)n * p.ysn + (long long)zo * p.ysd + (long long)xv * p.ysw;
 #pragma unroll 1
-        for (int o = 0; o < BY; ++o) {
-          mbar_wait(acc_full + 8 * o, pc & 1);
+        for (int g0 = 0; g0 < BY; g0 += G) {
+          uint32_t r[G][16];
+          uint4 old[G][2];
+          if (p.accumulate && sv) {
+#pragma unroll
+            for (int l = 0; l < G; ++l)
+              if (y0 + g0 + l < p.h) {
+                const T* yp = yplane + (long long)(y0 + g0 + l) * p.ysh;
+                old[l][0] = *reinterpret_cast<const uint4*>(yp);
+                old[l][1] = *reinterpret_cast<const uint4*>(yp + 8);
+              }
+          }
+#pragma unroll
+          for (int l = 0; l < G; ++l) {
+            if (d0) wait_on(acc_full + 8 * (g0 + l), pc & 1, w_full_acc); else xl_wait(acc_full + 8 * (g0 + l), pc & 1);
+          }
           tc_fence_after();
-          const uint32_t col = t_lane + (uint32_t)o * 48u;
-          const bool st = sv && y0 + o < p.h;
-          uint32_t r[16];
-          if (st) {
-            tmem_ld16(col + cs, r);
+          if (sv && !(p.ablate & 8)) {
+#pragma unroll
+            for (int l = 0; l < G; ++l)
+              if (y0 + g0 + l < p.h) tmem_ld16(t_lane + (uint32_t)(g0 + l) * 48u + cs, r[l]);
             tmem_ld_wait();
           }
-          if (last) {
-            tmem_st16_zero(col);
-            tmem_st16_zero(col + 16u);
-            tmem_st16_zero(col + 32u);
-          } else {
-            tmem_st16_zero(col + cs);
+#pragma unroll
+          for (int l = 0; l < G; ++l) {
+            if (p.ablate & 32) break;
+            const uint32_t col = t_lane + (uint32_t)(g0 + l) * 48u;
+            if (last) {
+              tmem_st16_zero(col);
+              tmem_st16_zero(col + 16u);
+              tmem_st16_zero(col + 32u);
+            } else {
+              tmem_st16_zero(col + cs);
+            }
           }
-          tmem_st_wait();
+          if (!(p.ablate & 32)) tmem_st_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(acc_free + 8 * o);
-          if (st) {
-            T* yp = y + (long long)n * p.ysn + (long long)zo * p.ysd + (long long)(y0 + o) * p.ysh + (long long)xv * p.ysw;
-            float f[16];
+          if (lane == 0) {
 #pragma unroll
-            for (int c = 0; c < 16; ++c) f[c] = __uint_as_float(r[c]) + bs[c];
-            if (p.accumulate) {
-              const Pack<T, 8> o0 = *reinterpret_cast<const Pack<T, 8>*>(yp);
-              const Pack<T, 8> o1 = *reinterpret_cast<const Pack<T, 8>*>(yp + 8);
+            for (int l = 0; l < G; ++l) mbar_arrive(acc_free + 8 * (g0 + l));
+          }
+          if (sv && !(p.ablate & 8)) {
 #pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                f[c] += to_f<T>(o0.v[c]);
-                f[8 + c] += to_f<T>(o1.v[c]);
-              }
-            }
-            Pack<T, 8> w0, w1;
+            for (int l = 0; l < G; ++l) {
+              if (y0 + g0 + l < p.h) {
+                T* yp = yplane + (long long)(y0 + g0 + l) * p.ysh;
+                float f[16];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              w0.v[c] = from_f<T>(f[c]);
-              w1.v[c] = from_f<T>(f[8 + c]);
-            }
-            *reinterpret_cast<Pack<T, 8>*>(yp) = w0;
-            *reinterpret_cast<Pack<T, 8>*>(yp + 8) = w1;
-            if (stats != nullptr) {
+                for (int c = 0; c < 16; ++c) f[c] = __uint_as_float(r[l][c]) + bs[c];
+                if (p.accumulate) {
+                  const Pack<T, 8> o0 = *reinterpret_cast<const Pack<T, 8>*>(&old[l][0]);
+                  const Pack<T, 8> o1 = *reinterpret_cast<const Pack<T, 8>*>(&old[l][1]);
 #pragma unroll
-              for (int c = 0; c < 16; ++c) {
-                const float vv = to_f<T>(c < 8 ? w0.v[c] : w1.v[c - 8]);
-                s1[c] += vv;
-                s2[c] = fmaf(vv, vv, s2[c]);
+                  for (int c = 0; c < 8; ++c) {
+                    f[c] += to_f<T>(o0.v[c]);
+                    f[8 + c] += to_f<T>(o1.v[c]);
+                  }
+                }
+                Pack<T, 8> w0, w1;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                  w0.v[c] = from_f<T>(f[c]);
+                  w1.v[c] = from_f<T>(f[8 + c]);
+                }
+                *reinterpret_cast<Pack<T, 8>*>(yp) = w0;
+                *reinterpret_cast<Pack<T, 8>*>(yp + 8) = w1;
+                if (stats != nullptr) {
+#pragma unroll
+                  for (int c = 0; c < 16; ++c) {
+                    const float vv = to_f<T>(c < 8 ? w0.v[c] : w1.v[c - 8]);
+                    s1[c] += vv;
+                    s2[c] = fmaf(vv, vv, s2[c]);
+                  }
+                }
               }
             }
           }
         }
       }
       if (stats != nullptr) {
-#pragma unroll
+#pragma unroll 1
         for (int c = 0; c < 16; ++c) {
-          const float a = warp_sum(s1[c]), b = warp_sum(s2[c]);
+          float a = 0.f, b = 0.f;
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            if (k == c) { a = s1[k]; b = s2[k]; }
+          a = warp_sum(a);
+          b = warp_sum(b);
           if (lane == 0) {
             atomicAdd(stats + ((long long)n * 16 + c) * 2, (double)a);
             atomicAdd(stats + ((long long)n * 16 + c) * 2 + 1, (double)b);
@@ -427,6 +569,7 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
         }
       }
     }
+    if (d0) { dbg[7] = clock64() - t_begin; dbg[8] = w_full_acc; }
   }
   tc_fence_before();
   __syncthreads();
@@ -500,7 +643,7 @@ __global__ void __launch_bounds__(128, 1) xline_selftest_kernel(float* __restric
     umma_f16_ts(tmem, tmem + 64u, b_lo, b_hi, idesc, 0u);
     umma_commit(smem_u32(&s_bar));
   }
-  mbar_wait(smem_u32(&s_bar), 0);
+  xl_wait(smem_u32(&s_bar), 0);
   tc_fence_after();
   for (int c0 = 0; c0 < 48; c0 += 16) {
     uint32_t r[16];
@@ -512,6 +655,48 @@ __global__ void __launch_bounds__(128, 1) xline_selftest_kernel(float* __restric
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+// Issue rate / execution time of tcgen05.mma (M = 128, K = 16, kind::f16) with the A operand in tensor memory (ts = 1) or in
+// shared memory (ts = 0): `count` MMAs back to back from one thread, then one commit; out[block] = cycles from the first issue to
+// the arrival of the commit, out[148 + block] = cycles the issuing thread spent issuing.
+__global__ void __launch_bounds__(128, 1) xline_rate_kernel(int n, int count, int ts, uint32_t idesc, long long* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t s_bar;
+  __shared__ uint32_t s_tmem;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&s_bar), 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 512);
+  for (uint32_t i = threadIdx.x; i < 48u * 1024u / 4u; i += 128) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0u;
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  if (warp == 0 && elect_one()) {
+    const uint32_t b_hi = (256u >> 4) | (1u << 14) | ((uint32_t)kSwizzle32 << 29);
+    const uint32_t b_lo = ((smem0 >> 4) & 0x3FFFu) | (1u << 16);
+    const uint32_t a_lo = (((smem0 + 16384u) >> 4) & 0x3FFFu) | (1u << 16);
+    const long long t0 = clock64();
+    for (int i = 0; i < count; i += 4) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (ts) umma_f16_ts(tmem, tmem + 256u + 8u * j, b_lo, b_hi, idesc, 1u);
+        else umma_f16_split(tmem, a_lo, b_hi, b_lo, b_hi, idesc, 1u);
+      }
+    }
+    const long long t1 = clock64();
+    umma_commit(smem_u32(&s_bar));
+    xl_wait(smem_u32(&s_bar), 0);
+    const long long t2 = clock64();
+    out[blockIdx.x] = t2 - t0;
+    out[148 + blockIdx.x] = t1 - t0;
+  }
+  (void)n;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 bool conv_xline_ok(const ActView& x, const ActView& y, int kd, int kh, int kw) {
@@ -539,7 +724,19 @@ template <typename T, int KS, int BY>
 static int launch_xline(const ActView& x, const void* w, const float* bias, const ActView& y, const ActView* a_out, const float* scale,
                         const float* shift, int fuse, double* stats, XlineParams p, cudaStream_t st) {
   constexpr int NR = KS == 1 ? 8 : 3;
-  const size_t smem = 27u * KS * kXlTileBytes + (size_t)NR * 2u * 4096u * KS + 2u * 8u * 32u * KS + 1024u;
+  const size_t smem = 27u * KS * kXlTileBytes + (size_t)NR * 2u * 4096u * KS + 4u * (2u * 64u * KS) + 1024u;
+  {
+    const char* e = getenv("B200_XL_ABLATE");
+    p.ablate = e ? atoi(e) : 0;
+    e = getenv("B200_XL_DBG");
+    p.dbg = nullptr;
+    if (e && atoi(e)) {
+      static long long* d_dbg = nullptr;
+      if (!d_dbg) B200_CUDA(cudaMalloc(&d_dbg, sizeof(long long) * 16 * 256));
+      B200_CUDA(cudaMemsetAsync(d_dbg, 0, sizeof(long long) * 16 * 256, st));
+      p.dbg = d_dbg;
+    }
+  }
   p.bands = (int)ceil_div(x.h, BY);
   {  // z chunks: whole waves of units over the SMs against the two halo planes every chunk re-reads
     double best = -1.0;
@@ -560,13 +757,27 @@ static int launch_xline(const ActView& x, const void* w, const float* bias, cons
   {                                                                                                                    \
     auto kern = conv_fprop_xline_kernel<T, KS, BY, F>;                                                                 \
     B200_CUDA(raise_dyn_smem_cap(kern));                                                                               \
-    kern<<<grid, 320, smem, st>>>((const T*)x.data, (const T*)w, bias, (T*)y.data, ap, scale, shift, stats, p);       \
+    kern<<<grid, F ? 448 : 320, smem, st>>>((const T*)x.data, (const T*)w, bias, (T*)y.data, ap, scale, shift, stats, p);       \
   }
   if (fuse == 0) XL_LAUNCH(0)
   else if (fuse == 1) XL_LAUNCH(1)
   else XL_LAUNCH(2)
 #undef XL_LAUNCH
   B200_LAUNCH_CHECK();
+  if (p.dbg) {
+    static long long h[16 * 256];
+    B200_CUDA(cudaMemcpyAsync(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    double a[16] = {0};
+    for (int b = 0; b < grid; ++b)
+      for (int k = 0; k < 16; ++k) a[k] += (double)h[b * 16 + k] / grid;
+    const double nl = a[10] > 0 ? a[10] : 1;
+    printf("xline dbg KS=%d BY=%d fuse=%d units=%d zc=%d grid=%d lines/CTA=%.0f | per line: mma total %.0f (wait acc_free %.0f, a_full %.0f) | "
+           "staging total %.0f (in_full %.0f, a_free %.0f; lds %.0f, sttm+wait %.0f, fence+arrive %.0f) | activation total %.0f (raw_full %.0f) | epilogue total %.0f (acc_full %.0f) | loader wait %.0f | mma issue section %.0f\n",
+           KS, BY, fuse, p.units, p.zc, grid, a[10], a[0] / nl, a[1] / nl, a[2] / nl, a[3] / nl, a[4] / nl, a[5] / nl, a[6] / nl,
+           a[13] / nl, a[14] / nl, a[11] / nl, a[12] / nl, a[7] / nl, a[8] / nl, a[9] / nl, a[15] / nl);
+    fflush(stdout);
+  }
   return B200_OK;
 }
 
@@ -627,6 +838,27 @@ B200_EXPORT int b200_xline_selftest(double* max_err, int32_t verbose, void* stre
       if (verbose > 1 && e > 0.5 && t < 4) printf("xline_selftest: row %d col %d got %g expected %g\n", t, rr, h[t * 48 + rr], ref);
     }
   if (verbose) { printf("xline_selftest: max abs error %g\n", worst); fflush(stdout); }
+  if (verbose > 2) {
+    long long* d_t = nullptr;
+    B200_CUDA(cudaMalloc(&d_t, sizeof(long long) * 296));
+    B200_CUDA(cudaFuncSetAttribute(sm100::xline_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    const int ns[8] = {16, 32, 48, 64, 96, 144, 192, 256};
+    for (int ts = 1; ts >= 0; --ts)
+      for (int ni = 0; ni < 8; ++ni) {
+        const int count = 4096;
+        sm100::xline_rate_kernel<<<148, 128, 64 * 1024, st>>>(ns[ni], count, ts, sm100::make_idesc(1, ns[ni], 0, 0), d_t);
+        B200_LAUNCH_CHECK();
+        long long ht[296];
+        B200_CUDA(cudaMemcpyAsync(ht, d_t, sizeof(ht), cudaMemcpyDeviceToHost, st));
+        B200_CUDA(cudaStreamSynchronize(st));
+        long long tot = 0, iss = 0;
+        for (int b = 0; b < 148; ++b) { if (ht[b] > tot) tot = ht[b]; if (ht[148 + b] > iss) iss = ht[148 + b]; }
+        printf("mma_rate A-in-%s N=%d: %.1f cycles/MMA to completion, %.1f cycles/MMA issue\n", ts ? "TMEM" : "smem", ns[ni],
+               (double)tot / count, (double)iss / count);
+      }
+    cudaFree(d_t);
+    fflush(stdout);
+  }
   if (max_err) *max_err = worst;
   return B200_OK;
 }

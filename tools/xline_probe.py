@@ -129,12 +129,43 @@ def timings(dtype):
             print(f"time {str(dtype)[6:]} {cin}->16 @128^3 x4 {name}: {ms:.4f} ms  {tf:.0f} TFLOP/s", flush=True)
 
 
+def diagnose(dtype, sweep=True):
+    """Per-role cycle counters (B200_XL_DBG) and ablation timings (B200_XL_ABLATE) of the full-size launches."""
+    dev = "cuda"
+    for cin in (16, 48):
+        x = torch.randn((4, 128, 128, 128, cin), device=dev).to(dtype)
+        w = torch.randn((16, cin, 3, 3, 3), device=dev) * 0.1
+        b = torch.randn(16, device=dev)
+        y = torch.zeros((4, 128, 128, 128, 16), device=dev, dtype=dtype)
+        scale = torch.rand((4, cin), device=dev) + 0.5
+        shift = torch.randn((4, cin), device=dev)
+        wl = ops.pack_conv_weight_xline(w, dtype, False)
+        fz = 2 if dtype == torch.bfloat16 else 1
+        variants = [("plain", dict()), ("acc", dict(accumulate=True)), (f"fuse{fz}", dict(scale=scale, shift=shift, fuse=fz))]
+        os.environ["B200_XL_DBG"] = "1"
+        for name, kw in variants:
+            print(f"dbg {str(dtype)[6:]} {cin}->16 {name}:", flush=True)
+            ops.conv_fprop_xline(x, wl, b, y, **kw)
+            torch.cuda.synchronize()
+        os.environ["B200_XL_DBG"] = "0"
+        for ab in ((0, 1, 4, 8, 5, 9, 12, 13, 2) if sweep else (0, 1, 13, 13 + 16, 13 + 32, 13 + 64, 13 + 16 + 32 + 64)):
+            os.environ["B200_XL_ABLATE"] = str(ab)
+            for name, kw in variants:
+                if ab == 2 and not name.startswith("fuse"):
+                    continue
+                ms = time_ms(lambda: ops.conv_fprop_xline(x, wl, b, y, **kw), reps=10)
+                print(f"ablate {ab:2d} {str(dtype)[6:]} {cin}->16 {name}: {ms:.4f} ms", flush=True)
+        os.environ["B200_XL_ABLATE"] = "0"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--time", action="store_true")
+    ap.add_argument("--diag", action="store_true")
+    ap.add_argument("--diag-quick", action="store_true")
     a = ap.parse_args()
-    err = ops.xline_selftest(verbose=2)
+    err = ops.xline_selftest(verbose=3 if (a.diag or a.diag_quick) else 2)
     print(f"selftest max abs error {err}", flush=True)
     ok = err == 0.0
     bf, hf = torch.bfloat16, torch.float16
@@ -158,6 +189,8 @@ def main():
     if a.time:
         timings(torch.float16)
         timings(torch.bfloat16)
+    if a.diag or a.diag_quick:
+        diagnose(torch.float16, sweep=not a.diag_quick)
     return 0 if ok else 1
 
 
