@@ -122,7 +122,7 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
   constexpr uint32_t BBYTES = 27u * KS * kXlTileBytes;
   constexpr int W = 8 * KS;                      // 32-bit words per voxel
   constexpr uint32_t CFB = 2u * 16u * KS * 4u;   // coefficient table per math warp: scale[Cin], shift[Cin]
-  static_assert(BY % 2 == 0 && ACC + NA * ACOLS <= 512, "tensor memory budget");
+  static_assert(BY % 2 == 0 && G == 2 && ACC + NA * ACOLS <= 512, "tensor memory budget / group barriers");
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t s_bar[3 * NR + 2 * NA + 2 * BY + 1];
@@ -143,9 +143,9 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
     fence_barrier_init();
   }
   if (warp == 8) tmem_alloc(smem_u32(&s_tmem), 512);
-  tc_fence_before();
+  if (!(p.ablate & 128)) tc_fence_before();
   __syncthreads();
-  tc_fence_after();
+  if (!(p.ablate & 128)) tc_fence_after();
   const uint32_t tmem = s_tmem;
 
   auto decode = [&](int u, int& n, int& z0, int& zhi, int& y0) {
@@ -231,14 +231,14 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
           // one compact body per input line (the fully unrolled form was 48 KB of straight-line code for this one thread)
 #pragma unroll 1
           for (int i = 0; i < BY + 2; ++i) {
-            if (i < BY) {
-              wait_on(acc_free + 8 * i, pc & 1, w_acc);
-              tc_fence_after();
+            if (i < BY && (i & 1) == 0) {           // first touch of the group (i, i + 1) of output lines in this plane
+              wait_on(acc_free + 8 * (i >> 1), pc & 1, w_acc);
+              if (!(p.ablate & 128)) tc_fence_after();
             }
             const bool lv = pv && (unsigned)(y0 - 1 + i) < (unsigned)p.h;
             if (lv) {
               wait_on(a_full + 8 * slot, aph, w_a);
-              tc_fence_after();
+              if (!(p.ablate & 128)) tc_fence_after();
               ++nlines;
               const long long tm = dbg ? clock64() : 0;
               const uint32_t a_base = tmem + ACC + (uint32_t)slot * ACOLS;
@@ -249,7 +249,7 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
                   for (int t = 0; t < 3 * KS; ++t) umma_f16_ts(d_i - 96u, a_base + 8u * t, b_r + (uint32_t)(6 * KS + t) * tstep, b_hi, idesc, 1u);
                 }
               }
-              if (i >= 2) umma_commit(acc_full + 8 * (i - 2));
+              if (i >= 3 && (i & 1)) umma_commit(acc_full + 8 * ((i - 3) >> 1));   // lines i - 3 and i - 2 are complete
               if (!(p.ablate & 1)) {
                 if (i >= 1 && i <= BY) {
 #pragma unroll
@@ -260,11 +260,11 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
                   for (int t = 0; t < 3 * KS; ++t) umma_f16_ts(d_i, a_base + 8u * t, b_r + (uint32_t)t * tstep, b_hi, idesc, 1u);
                 }
               }
-              umma_commit(a_free + 8 * slot);
+              if (p.ablate & 256) mbar_arrive(a_free + 8 * slot); else umma_commit(a_free + 8 * slot);
               if (dbg) t_issue += clock64() - tm;
               if (++slot == NA) { slot = 0; aph ^= 1; }
-            } else if (i >= 2) {
-              umma_commit(acc_full + 8 * (i - 2));
+            } else if (i >= 3 && (i & 1)) {
+              umma_commit(acc_full + 8 * ((i - 3) >> 1));
             }
           }
         }
@@ -302,7 +302,9 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
             int lo, hi;
             pair_range(y0, pr, lo, hi);
             if (lo >= hi) continue;
-            if (d0) wait_on(raw_full + 8 * rs, rph, w_raw); else xl_wait(raw_full + 8 * rs, rph);
+            if (lane == 0) wait_on(raw_full + 8 * rs, rph, w_raw);
+            __syncwarp();
+            (void)mbar_try_wait(raw_full + 8 * rs, rph);               // every lane observes the phase the bulk copy completed
 #pragma unroll 1
             for (int i = lo; i < hi; ++i) {
               const uint32_t src = sm_raw + (uint32_t)rs * 2u * LINE + (uint32_t)(i - 2 * pr) * LINE + (uint32_t)xv * VOX;
@@ -349,14 +351,18 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
     }
   } else if (warp >= 4) {
     // ===================================================================== staging: ring lines -> three operand copies in TMEM
-    // thread = voxel = TMEM lane: its own voxel and the two neighbours in x (zeros at the line ends = 'same' padding in x)
+    // thread = voxel = TMEM lane.  Its own voxel comes from shared memory (16-byte pieces in a lane-dependent order: lanes l and
+    // l + 4 sit 4 voxels = a whole number of bank rows apart and would collide), the neighbours in x from the adjacent lanes
+    // (shuffles), for the first / last lane of a warp from shared memory again; zeros at the line ends = 'same' padding in x.
     const int q = warp & 3;
     const int xv = q * 32 + lane;
     const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16) + ACC;
     const uint32_t in_full = FUSE ? xf_full : raw_full;
     const bool d0 = dbg != nullptr && threadIdx.x == 128;
     const long long t_begin = d0 ? clock64() : 0;
-    long long w_in = 0, w_afree = 0, t_ld = 0, t_st = 0, t_arr = 0;
+    long long w_in = 0, w_afree = 0;
+    const bool sw = ((lane >> 2) & 1) != 0;
+    constexpr int NCH = W / 4;                 // 16-byte pieces per voxel
     int rs = 0, slot = 0;
     uint32_t rph = 0, aph = 0;
     for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
@@ -369,46 +375,71 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
           int lo, hi;
           pair_range(y0, pr, lo, hi);
           if (lo >= hi) continue;
-          if (d0) wait_on(in_full + 8 * rs, rph, w_in); else xl_wait(in_full + 8 * rs, rph);
+          if (lane == 0) wait_on(in_full + 8 * rs, rph, w_in);
+          __syncwarp();
+          if (!FUSE) (void)mbar_try_wait(in_full + 8 * rs, rph);     // every lane observes the phase the bulk copy completed
 #pragma unroll 1
           for (int i0 = lo; i0 < hi; i0 += LB) {
             const int nl = hi - i0 < LB ? hi - i0 : LB;
             uint32_t v[LB][W], lf[LB][W], rt[LB][W];
-            long long ts = d0 ? clock64() : 0;
 #pragma unroll
             for (int l = 0; l < LB; ++l) {
               if (l < nl && !(p.ablate & 64)) {
                 const uint32_t src = sm_raw + (uint32_t)rs * 2u * LINE + (uint32_t)(i0 + l - 2 * pr) * LINE + (uint32_t)xv * VOX;
+                uint32_t t[W];
 #pragma unroll
-                for (int j = 0; j < W / 4; ++j) {
+                for (int j = 0; j < NCH; ++j) {
+                  const uint32_t piece = sw ? (uint32_t)((j + 1) % NCH) : (uint32_t)j;
                   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                               : "=r"(v[l][4 * j]), "=r"(v[l][4 * j + 1]), "=r"(v[l][4 * j + 2]), "=r"(v[l][4 * j + 3])
-                               : "r"(src + 16u * j));
-                  if (xv > 0)
-                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                                 : "=r"(lf[l][4 * j]), "=r"(lf[l][4 * j + 1]), "=r"(lf[l][4 * j + 2]), "=r"(lf[l][4 * j + 3])
-                                 : "r"(src - VOX + 16u * j));
-                  else lf[l][4 * j] = lf[l][4 * j + 1] = lf[l][4 * j + 2] = lf[l][4 * j + 3] = 0u;
-                  if (xv < 127)
-                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                                 : "=r"(rt[l][4 * j]), "=r"(rt[l][4 * j + 1]), "=r"(rt[l][4 * j + 2]), "=r"(rt[l][4 * j + 3])
-                                 : "r"(src + VOX + 16u * j));
-                  else rt[l][4 * j] = rt[l][4 * j + 1] = rt[l][4 * j + 2] = rt[l][4 * j + 3] = 0u;
+                               : "=r"(t[4 * j]), "=r"(t[4 * j + 1]), "=r"(t[4 * j + 2]), "=r"(t[4 * j + 3])
+                               : "r"(src + 16u * piece));
+                }
+#pragma unroll
+                for (int j = 0; j < NCH; ++j)
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) v[l][4 * j + e] = sw ? t[4 * ((j + NCH - 1) % NCH) + e] : t[4 * j + e];
+#pragma unroll
+                for (int j = 0; j < W; ++j) {
+                  lf[l][j] = __shfl_up_sync(0xffffffffu, v[l][j], 1);
+                  rt[l][j] = __shfl_down_sync(0xffffffffu, v[l][j], 1);
+                }
+                if (lane == 0) {
+                  if (q == 0) {
+#pragma unroll
+                    for (int j = 0; j < W; ++j) lf[l][j] = 0u;
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < NCH; ++j)
+                      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                   : "=r"(lf[l][4 * j]), "=r"(lf[l][4 * j + 1]), "=r"(lf[l][4 * j + 2]), "=r"(lf[l][4 * j + 3])
+                                   : "r"(src - VOX + 16u * j));
+                  }
+                }
+                if (lane == 31) {
+                  if (q == 3) {
+#pragma unroll
+                    for (int j = 0; j < W; ++j) rt[l][j] = 0u;
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < NCH; ++j)
+                      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                   : "=r"(rt[l][4 * j]), "=r"(rt[l][4 * j + 1]), "=r"(rt[l][4 * j + 2]), "=r"(rt[l][4 * j + 3])
+                                   : "r"(src + VOX + 16u * j));
+                  }
                 }
               }
             }
-            if (d0) { const long long t = clock64(); t_ld += t - ts; }
             int sl[LB];
 #pragma unroll
             for (int l = 0; l < LB; ++l) {
               sl[l] = slot;
               if (l < nl) {
-                if (d0) wait_on(a_free + 8 * slot, aph ^ 1, w_afree); else xl_wait(a_free + 8 * slot, aph ^ 1);
+                if (lane == 0) wait_on(a_free + 8 * slot, aph ^ 1, w_afree);
                 if (++slot == NA) { slot = 0; aph ^= 1; }
               }
             }
-            if (d0) ts = clock64();
-            tc_fence_after();
+            __syncwarp();
+            if (!(p.ablate & 128)) tc_fence_after();
             if (!(p.ablate & 4)) {
 #pragma unroll
               for (int l = 0; l < LB; ++l) {
@@ -424,15 +455,13 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
               }
               tmem_st_wait();
             }
-            if (d0) { const long long t = clock64(); t_st += t - ts; ts = t; }
-            tc_fence_before();
+            if (!(p.ablate & 128)) tc_fence_before();
             __syncwarp();
             if (lane == 0) {
 #pragma unroll
               for (int l = 0; l < LB; ++l)
                 if (l < nl) mbar_arrive(a_full + 8 * sl[l]);
             }
-            if (d0) { const long long t = clock64(); t_arr += t - ts; }
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(raw_free + 8 * rs);
@@ -440,7 +469,7 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
         }
       }
     }
-    if (d0) { dbg[3] = clock64() - t_begin; dbg[4] = w_in; dbg[5] = w_afree; dbg[6] = t_ld; dbg[13] = t_st; dbg[14] = t_arr; }
+    if (d0) { dbg[3] = clock64() - t_begin; dbg[4] = w_in; dbg[5] = w_afree; }
   } else {
     // ===================================================================== epilogue
     const int q = warp;
@@ -451,10 +480,10 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
 #pragma unroll 1
     for (uint32_t c = 0; c < ACC; c += 16) tmem_st16_zero(t_lane + c);
     tmem_st_wait();
-    tc_fence_before();
+    if (!(p.ablate & 128)) tc_fence_before();
     __syncwarp();
     if (lane == 0)
-      for (int o = 0; o < BY; ++o) mbar_arrive(acc_free + 8 * o);
+      for (int o = 0; o < BY / 2; ++o) mbar_arrive(acc_free + 8 * o);
     const long long t_begin = d0 ? clock64() : 0;
     float bs[16];
 #pragma unroll
@@ -485,11 +514,9 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
                 old[l][1] = *reinterpret_cast<const uint4*>(yp + 8);
               }
           }
-#pragma unroll
-          for (int l = 0; l < G; ++l) {
-            if (d0) wait_on(acc_full + 8 * (g0 + l), pc & 1, w_full_acc); else xl_wait(acc_full + 8 * (g0 + l), pc & 1);
-          }
-          tc_fence_after();
+          if (lane == 0) wait_on(acc_full + 8 * (g0 >> 1), pc & 1, w_full_acc);
+          __syncwarp();
+          if (!(p.ablate & 128)) tc_fence_after();
           if (sv && !(p.ablate & 8)) {
 #pragma unroll
             for (int l = 0; l < G; ++l)
@@ -509,12 +536,9 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
             }
           }
           if (!(p.ablate & 32)) tmem_st_wait();
-          tc_fence_before();
+          if (!(p.ablate & 128)) tc_fence_before();
           __syncwarp();
-          if (lane == 0) {
-#pragma unroll
-            for (int l = 0; l < G; ++l) mbar_arrive(acc_free + 8 * (g0 + l));
-          }
+          if (lane == 0) mbar_arrive(acc_free + 8 * (g0 >> 1));
           if (sv && !(p.ablate & 8)) {
 #pragma unroll
             for (int l = 0; l < G; ++l) {
@@ -571,7 +595,7 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
     }
     if (d0) { dbg[7] = clock64() - t_begin; dbg[8] = w_full_acc; }
   }
-  tc_fence_before();
+  if (!(p.ablate & 128)) tc_fence_before();
   __syncthreads();
   if (warp == 8) tmem_dealloc(tmem, 512);
 }
