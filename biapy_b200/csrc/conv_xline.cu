@@ -88,6 +88,20 @@ __device__ __forceinline__ void xl_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// wait of the roles with slack (epilogue, bulk-copy issue): back off between polls instead of hammering the barrier unit
+__device__ __forceinline__ void xl_wait_sleep(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(100);
+    if ((++spins & 255u) == 0u) {
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > 4000000000LL) __trap();
+    }
+  }
+}
+
 struct XlineParams {
   int n, d, h;
   int bands, zchunks, zc, units;
@@ -95,7 +109,7 @@ struct XlineParams {
   long long ash_b, asd_b, asn_b;   // same for the optional activated copy
   long long ysw, ysh, ysd, ysn;    // element strides of the output
   int accumulate;
-  uint32_t idesc;
+  uint32_t idesc, idesc96, idesc144;   // N = 48 / 96 / 144
   int ablate;                      // B200_XL_ABLATE bits: 1 no MMA, 2 no activation math, 4 no operand stores, 8 no output,
                                    // 16 no bulk copies, 32 no accumulator zeroing, 64 no operand loads (timing experiments only)
   long long* dbg;                  // B200_XL_DBG: per-block cycle counters (tools/xline_probe.py)
@@ -105,24 +119,43 @@ constexpr uint32_t kXlTileBytes = 48u * 32u;   // one B tile: 48 rows (s, co) x 
 
 __device__ __forceinline__ int xl_mod3(int v) { return ((v % 3) + 3) % 3; }
 
+__device__ __noinline__ void xl_wait_slow(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 255u) == 0u) {
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > 4000000000LL) __trap();
+    }
+  }
+}
+// wait of the MMA-issuing thread: two instructions on the path where the barrier has already flipped
+__device__ __forceinline__ void xl_wait_lean(uint32_t bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) xl_wait_slow(bar, parity);
+}
+
 template <typename T, int KS, int BY, int FUSE>
-__global__ void __launch_bounds__(FUSE ? 448 : 320, 1)
+__global__ void __launch_bounds__(FUSE ? 512 : 320, 1)
 conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, const float* __restrict__ bias, T* __restrict__ y,
                         T* __restrict__ a_out, const float* __restrict__ scale, const float* __restrict__ shift,
                         double* __restrict__ stats, const XlineParams p) {
   constexpr int NR = KS == 1 ? 8 : 3;            // raw ring: slots of two lines
-  constexpr int NA = KS == 1 ? 5 : 4;            // operand ring in tensor memory: slots of one line (three shifted copies)
-  constexpr int PAIRS = (BY + 2) / 2;
+  constexpr int NA = KS == 1 ? 5 : 3;            // operand ring in tensor memory: slots of one line (three shifted copies)
+  constexpr int NL = BY + 2;                     // input lines of a band
+  constexpr int PAIRS = NL / 2;
   constexpr int LB = KS == 1 ? 2 : 1;            // lines a staging iteration handles together
-  constexpr int G = 2;                           // output lines an epilogue iteration handles together
+  constexpr int G = 2;                           // output lines per accumulator barrier / epilogue iteration
   constexpr uint32_t LINE = 4096u * KS;
   constexpr uint32_t VOX = 32u * KS;             // bytes per voxel
   constexpr uint32_t ACOLS = 24u * KS;
   constexpr uint32_t ACC = (uint32_t)BY * 48u;
   constexpr uint32_t BBYTES = 27u * KS * kXlTileBytes;
+  constexpr uint32_t TSTEP = 3u * kXlTileBytes >> 4;   // one (r, dx, k) tile of 144 rows, in 16-byte units
   constexpr int W = 8 * KS;                      // 32-bit words per voxel
-  constexpr uint32_t CFB = 2u * 16u * KS * 4u;   // coefficient table per math warp: scale[Cin], shift[Cin]
-  static_assert(BY % 2 == 0 && G == 2 && ACC + NA * ACOLS <= 512, "tensor memory budget / group barriers");
+  constexpr uint32_t CFB = 2u * 16u * KS * 4u;   // coefficient table per activation warp: scale[Cin], shift[Cin]
+  // The operand slot of a line is its POSITION in the band modulo NA (lines outside the volume pass through as empty slots), so
+  // every tensor-memory address and barrier parity of the MMA thread is a compile-time constant of the unrolled line loop.
+  static_assert(BY % 2 == 0 && G == 2 && NL % NA == 0 && (NL / NA) % 2 == 0 && ACC + NA * ACOLS <= 512, "tensor memory budget / static slots");
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t s_bar[3 * NR + 2 * NA + 2 * BY + 1];
@@ -136,16 +169,16 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
   long long* const dbg = p.dbg ? p.dbg + (long long)blockIdx.x * 16 : nullptr;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NR; ++i) { mbar_init(raw_full + 8 * i, 1); mbar_init(raw_free + 8 * i, 4); mbar_init(xf_full + 8 * i, 4); }
+    for (int i = 0; i < NR; ++i) { mbar_init(raw_full + 8 * i, 1); mbar_init(raw_free + 8 * i, 4); mbar_init(xf_full + 8 * i, 6); }
     for (int i = 0; i < NA; ++i) { mbar_init(a_full + 8 * i, 4); mbar_init(a_free + 8 * i, 1); }
     for (int i = 0; i < BY; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_free + 8 * i, 4); }
     mbar_init(w_full, 1);
     fence_barrier_init();
   }
   if (warp == 8) tmem_alloc(smem_u32(&s_tmem), 512);
-  if (!(p.ablate & 128)) tc_fence_before();
+  tc_fence_before();
   __syncthreads();
-  if (!(p.ablate & 128)) tc_fence_after();
+  tc_fence_after();
   const uint32_t tmem = s_tmem;
 
   auto decode = [&](int u, int& n, int& z0, int& zhi, int& y0) {
@@ -194,7 +227,7 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
             int lo, hi;
             pair_range(y0, pr, lo, hi);
             if (lo >= hi) continue;
-            wait_on(raw_free + 8 * rs, rph ^ 1, w_free);
+            if (p.ablate & 512) xl_wait_sleep(raw_free + 8 * rs, rph ^ 1); else wait_on(raw_free + 8 * rs, rph ^ 1, w_free);
             const uint32_t bytes = (uint32_t)(hi - lo) * LINE;
             if (p.ablate & 16) {
               mbar_arrive(raw_full + 8 * rs);
@@ -211,89 +244,98 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
     }
   } else if (warp == 8) {
     // ===================================================================== MMA issue
+    // One thread; everything it touches per line is a constant offset from registers set up once per plane.  Input line i of the
+    // band feeds output lines i, i-1, i-2 (taps dy = 0, 1, 2), which sit in ascending column order (line o at (BY-1-o)*48), so ONE
+    // instruction per (dx, k) with N = 144 (96 / 48 at the band edges) covers the three taps.
     if (elect_one()) {
       const long long t_begin = dbg ? clock64() : 0;
-      long long w_acc = 0, w_a = 0, t_issue = 0;
-      const uint32_t idesc = in_reg(p.idesc);
+      const uint32_t id144 = in_reg(p.idesc144), id96 = in_reg(p.idesc96), id48 = in_reg(p.idesc);
       const uint32_t b_hi = (256u >> 4) | (1u << 14) | ((uint32_t)kSwizzle32 << 29);
       const uint32_t b_lo0 = ((sm_b >> 4) & 0x3FFFu) | (1u << 16);
-      const uint32_t tstep = kXlTileBytes >> 4;
+      const uint32_t abase0 = tmem + ACC;
       xl_wait(w_full, 0);
-      int slot = 0;
-      uint32_t aph = 0, pc = 0;
+      uint32_t pc = 0;
       long long nlines = 0;
       for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
         int n, z0, zhi, y0;
         decode(u, n, z0, zhi, y0);
+        uint32_t vmask = 0;
+#pragma unroll
+        for (int i = 0; i < NL; ++i) vmask |= ((unsigned)(y0 - 1 + i) < (unsigned)p.h ? 1u : 0u) << i;
         for (int pz = z0 - 1; pz <= zhi; ++pz, ++pc) {
-          const bool pv = (unsigned)pz < (unsigned)p.d;
-          const uint32_t b_r = b_lo0 + (uint32_t)xl_mod3(pz) * (9u * KS * tstep);
-          // one compact body per input line (the fully unrolled form was 48 KB of straight-line code for this one thread)
+          const uint32_t par = pc & 1u;
+          if ((unsigned)pz >= (unsigned)p.d) {      // plane outside the volume: nothing to add, the epilogue still turns the ring
 #pragma unroll 1
-          for (int i = 0; i < BY + 2; ++i) {
-            if (i < BY && (i & 1) == 0) {           // first touch of the group (i, i + 1) of output lines in this plane
-              wait_on(acc_free + 8 * (i >> 1), pc & 1, w_acc);
-              if (!(p.ablate & 128)) tc_fence_after();
+            for (int g = 0; g < BY / 2; ++g) {
+              xl_wait_lean(acc_free + 8 * g, par);
+              umma_commit(acc_full + 8 * g);
             }
-            const bool lv = pv && (unsigned)(y0 - 1 + i) < (unsigned)p.h;
-            if (lv) {
-              wait_on(a_full + 8 * slot, aph, w_a);
-              if (!(p.ablate & 128)) tc_fence_after();
+            continue;
+          }
+          const uint32_t b_r = b_lo0 + (uint32_t)xl_mod3(pz) * (3u * KS * TSTEP);
+          // The state of the NEXT line's barriers is sampled (test_wait: never blocks) before this line's MMAs are issued, so the
+          // ~100-cycle round trip of a barrier query hides behind the issue of the MMAs instead of preceding every line.
+          bool ok_a = mbar_test_wait(a_full, 0u);
+          bool ok_c = mbar_test_wait(acc_free, par);
+#pragma unroll
+          for (int i = 0; i < NL; ++i) {
+            const uint32_t slot = (uint32_t)(i % NA);
+            if (i < BY && (i & 1) == 0) {           // first touch of output lines (i, i + 1) in this plane
+              if (!ok_c) xl_wait_slow(acc_free + 8 * (i >> 1), par);
+            }
+            if (!ok_a) xl_wait_slow(a_full + 8 * slot, (uint32_t)((i / NA) & 1));
+            tc_fence_after();
+            if (i + 1 < NL) {
+              ok_a = mbar_test_wait(a_full + 8 * (uint32_t)((i + 1) % NA), (uint32_t)(((i + 1) / NA) & 1));
+              if (i + 1 < BY && ((i + 1) & 1) == 0) ok_c = mbar_test_wait(acc_free + 8 * ((i + 1) >> 1), par);
+            }
+            if ((vmask >> i) & 1u) {
               ++nlines;
-              const long long tm = dbg ? clock64() : 0;
-              const uint32_t a_base = tmem + ACC + (uint32_t)slot * ACOLS;
-              const uint32_t d_i = tmem + (uint32_t)i * 48u;
               if (!(p.ablate & 1)) {
-                if (i >= 2) {                      // last contribution (dy = 2) to output line i - 2
+                const uint32_t a_b = abase0 + slot * ACOLS;
+                const int o_hi = i < BY ? i : BY - 1;                 // highest output line this input line feeds
+                const uint32_t d_t = tmem + (uint32_t)(BY - 1 - o_hi) * 48u;
+                const uint32_t ro = i < BY ? 0u : (uint32_t)(i - BY + 1) * (kXlTileBytes >> 4);   // first B row = 48 * (i - o_hi)
+                const int o_lo = i >= 2 ? i - 2 : 0;
+                const int nrows = (o_hi - o_lo + 1) * 48;
+                const uint32_t idesc = nrows == 144 ? id144 : (nrows == 96 ? id96 : id48);
 #pragma unroll
-                  for (int t = 0; t < 3 * KS; ++t) umma_f16_ts(d_i - 96u, a_base + 8u * t, b_r + (uint32_t)(6 * KS + t) * tstep, b_hi, idesc, 1u);
-                }
+                for (int t = 0; t < 3 * KS; ++t) umma_f16_ts(d_t, a_b + 8u * t, b_r + (uint32_t)t * TSTEP + ro, b_hi, idesc, 1u);
               }
-              if (i >= 3 && (i & 1)) umma_commit(acc_full + 8 * ((i - 3) >> 1));   // lines i - 3 and i - 2 are complete
-              if (!(p.ablate & 1)) {
-                if (i >= 1 && i <= BY) {
-#pragma unroll
-                  for (int t = 0; t < 3 * KS; ++t) umma_f16_ts(d_i - 48u, a_base + 8u * t, b_r + (uint32_t)(3 * KS + t) * tstep, b_hi, idesc, 1u);
-                }
-                if (i < BY) {
-#pragma unroll
-                  for (int t = 0; t < 3 * KS; ++t) umma_f16_ts(d_i, a_base + 8u * t, b_r + (uint32_t)t * tstep, b_hi, idesc, 1u);
-                }
-              }
-              if (p.ablate & 256) mbar_arrive(a_free + 8 * slot); else umma_commit(a_free + 8 * slot);
-              if (dbg) t_issue += clock64() - tm;
-              if (++slot == NA) { slot = 0; aph ^= 1; }
-            } else if (i >= 3 && (i & 1)) {
-              umma_commit(acc_full + 8 * ((i - 3) >> 1));
             }
+            if (i >= 3 && (i & 1)) umma_commit(acc_full + 8 * ((i - 3) >> 1));   // output lines i - 3 and i - 2 are complete
+            umma_commit(a_free + 8 * slot);
           }
         }
       }
-      if (dbg) { dbg[0] = clock64() - t_begin; dbg[1] = w_acc; dbg[2] = w_a; dbg[10] = nlines; dbg[15] = t_issue; }
+      if (dbg) { dbg[0] = clock64() - t_begin; dbg[10] = nlines; }
     }
   } else if (warp >= 10) {
     // ===================================================================== activation (FUSE only): raw lines -> silu(x * scale + shift)
-    // in place in the raw ring, and the activated tensor for the backward pass
+    // in place in the raw ring, and the activated tensor for the backward pass.  Six warps; a thread walks the 16-byte pieces
+    // (8 channels) of the pair's two lines with stride 192 -- a multiple of the pieces per voxel, so its channel block and its 16
+    // coefficients never change -- consecutive threads touch consecutive pieces (no bank conflicts, coalesced a_out stores), and
+    // the independent pieces of a pair keep the MUFU pipe fed.
     if constexpr (FUSE != 0) {
-      const int q = warp - 10;
-      const int xv = q * 32 + lane;
-      const uint32_t cf = sm_cf + (uint32_t)q * CFB;
-      const bool d0 = dbg != nullptr && threadIdx.x == 320;
+      constexpr int NPC = 512 * KS;                           // pieces of a pair
+      constexpr int NIT = (NPC + 191) / 192;
+      const int tm = (int)threadIdx.x - 320;                  // 0 .. 191
+      const bool d0 = dbg != nullptr && tm == 0;
       const long long t_begin = d0 ? clock64() : 0;
       long long w_raw = 0;
       int rs = 0;
       uint32_t rph = 0;
       char* const ab = reinterpret_cast<char*>(a_out);
+      const int c8 = (tm % (2 * KS)) * 8;
       for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
         int n, z0, zhi, y0;
         decode(u, n, z0, zhi, y0);
-        __syncwarp();
-        for (int c = lane; c < 16 * KS; c += 32) {
-          const float s = __ldg(scale + (long long)n * (16 * KS) + c), h = __ldg(shift + (long long)n * (16 * KS) + c);
-          asm volatile("st.shared.f32 [%0], %1;" ::"r"(cf + 4u * c), "f"(s) : "memory");
-          asm volatile("st.shared.f32 [%0], %1;" ::"r"(cf + 64u * KS + 4u * c), "f"(h) : "memory");
+        float sc[8], sh[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          sc[e] = __ldg(scale + (long long)n * (16 * KS) + c8 + e);
+          sh[e] = __ldg(shift + (long long)n * (16 * KS) + c8 + e);
         }
-        __syncwarp();
         for (int pz = z0 - 1; pz <= zhi; ++pz) {
           if ((unsigned)pz >= (unsigned)p.d) continue;
           const bool zown = a_out != nullptr && pz >= z0 && pz < zhi;
@@ -302,43 +344,46 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
             int lo, hi;
             pair_range(y0, pr, lo, hi);
             if (lo >= hi) continue;
-            if (lane == 0) wait_on(raw_full + 8 * rs, rph, w_raw);
-            __syncwarp();
-            (void)mbar_try_wait(raw_full + 8 * rs, rph);               // every lane observes the phase the bulk copy completed
-#pragma unroll 1
-            for (int i = lo; i < hi; ++i) {
-              const uint32_t src = sm_raw + (uint32_t)rs * 2u * LINE + (uint32_t)(i - 2 * pr) * LINE + (uint32_t)xv * VOX;
-              uint32_t v[W];
+            if (d0) wait_on(raw_full + 8 * rs, rph, w_raw); else xl_wait(raw_full + 8 * rs, rph);
+            const uint32_t base = sm_raw + (uint32_t)rs * 2u * LINE;
+            uint32_t v[NIT][4];
+            bool on[NIT];
 #pragma unroll
-              for (int j = 0; j < W / 4; ++j)
+            for (int it = 0; it < NIT; ++it) {
+              const int pc = tm + 192 * it;
+              const int i = 2 * pr + pc / (256 * KS);
+              on[it] = pc < NPC && i >= lo && i < hi;
+              if (on[it])
                 asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(v[4 * j]), "=r"(v[4 * j + 1]), "=r"(v[4 * j + 2]), "=r"(v[4 * j + 3])
-                             : "r"(src + 16u * j));
-              if (!(p.ablate & 2)) {
+                             : "=r"(v[it][0]), "=r"(v[it][1]), "=r"(v[it][2]), "=r"(v[it][3])
+                             : "r"(base + 16u * (uint32_t)pc));
+            }
+            if (!(p.ablate & 2)) {
 #pragma unroll
-                for (int m = 0; m < W / 2; ++m) {
-                  float4 s4, h4;
-                  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(s4.x), "=f"(s4.y), "=f"(s4.z), "=f"(s4.w) : "r"(cf + 16u * m));
-                  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                               : "=f"(h4.x), "=f"(h4.y), "=f"(h4.z), "=f"(h4.w)
-                               : "r"(cf + 64u * KS + 16u * m));
-                  Pack<T, 2> e0 = *reinterpret_cast<Pack<T, 2>*>(&v[2 * m]);
-                  Pack<T, 2> e1 = *reinterpret_cast<Pack<T, 2>*>(&v[2 * m + 1]);
-                  e0.v[0] = from_f<T>(xl_silu<FUSE>(fmaf(to_f<T>(e0.v[0]), s4.x, h4.x)));
-                  e0.v[1] = from_f<T>(xl_silu<FUSE>(fmaf(to_f<T>(e0.v[1]), s4.y, h4.y)));
-                  e1.v[0] = from_f<T>(xl_silu<FUSE>(fmaf(to_f<T>(e1.v[0]), s4.z, h4.z)));
-                  e1.v[1] = from_f<T>(xl_silu<FUSE>(fmaf(to_f<T>(e1.v[1]), s4.w, h4.w)));
-                  v[2 * m] = *reinterpret_cast<uint32_t*>(&e0);
-                  v[2 * m + 1] = *reinterpret_cast<uint32_t*>(&e1);
+              for (int it = 0; it < NIT; ++it) {
+                if (on[it]) {
+#pragma unroll
+                  for (int w2 = 0; w2 < 4; ++w2) {
+                    Pack<T, 2> e = *reinterpret_cast<Pack<T, 2>*>(&v[it][w2]);
+                    e.v[0] = from_f<T>(xl_silu<FUSE>(fmaf(to_f<T>(e.v[0]), sc[2 * w2], sh[2 * w2])));
+                    e.v[1] = from_f<T>(xl_silu<FUSE>(fmaf(to_f<T>(e.v[1]), sc[2 * w2 + 1], sh[2 * w2 + 1])));
+                    v[it][w2] = *reinterpret_cast<uint32_t*>(&e);
+                  }
                 }
               }
+            }
 #pragma unroll
-              for (int j = 0; j < W / 4; ++j) st_shared_v4(src + 16u * j, make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
-              if (zown && i >= 1 && i <= BY) {
-                char* dst = ab + (long long)n * p.asn_b + (long long)pz * p.asd_b + (long long)(y0 - 1 + i) * p.ash_b + (long long)xv * VOX;
-#pragma unroll
-                for (int j = 0; j < W / 4; ++j)
-                  *reinterpret_cast<uint4*>(dst + 16 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int it = 0; it < NIT; ++it) {
+              if (on[it]) {
+                const int pc = tm + 192 * it;
+                const int l = pc / (256 * KS);
+                const int i = 2 * pr + l;
+                st_shared_v4(base + 16u * (uint32_t)pc, make_uint4(v[it][0], v[it][1], v[it][2], v[it][3]));
+                if (zown && i >= 1 && i <= BY) {
+                  char* dst = ab + (long long)n * p.asn_b + (long long)pz * p.asd_b + (long long)(y0 - 1 + i) * p.ash_b +
+                              16 * (pc - l * 256 * KS);
+                  *reinterpret_cast<uint4*>(dst) = make_uint4(v[it][0], v[it][1], v[it][2], v[it][3]);
+                }
               }
             }
             __syncwarp();
@@ -351,9 +396,7 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
     }
   } else if (warp >= 4) {
     // ===================================================================== staging: ring lines -> three operand copies in TMEM
-    // thread = voxel = TMEM lane.  Its own voxel comes from shared memory (16-byte pieces in a lane-dependent order: lanes l and
-    // l + 4 sit 4 voxels = a whole number of bank rows apart and would collide), the neighbours in x from the adjacent lanes
-    // (shuffles), for the first / last lane of a warp from shared memory again; zeros at the line ends = 'same' padding in x.
+    // thread = voxel = TMEM lane: its own voxel and the two neighbours in x (zeros at the line ends = 'same' padding in x)
     const int q = warp & 3;
     const int xv = q * 32 + lane;
     const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16) + ACC;
@@ -361,10 +404,8 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
     const bool d0 = dbg != nullptr && threadIdx.x == 128;
     const long long t_begin = d0 ? clock64() : 0;
     long long w_in = 0, w_afree = 0;
-    const bool sw = ((lane >> 2) & 1) != 0;
-    constexpr int NCH = W / 4;                 // 16-byte pieces per voxel
-    int rs = 0, slot = 0;
-    uint32_t rph = 0, aph = 0;
+    int rs = 0;
+    uint32_t rph = 0;
     for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
       int n, z0, zhi, y0;
       decode(u, n, z0, zhi, y0);
@@ -374,77 +415,52 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
         for (int pr = 0; pr < PAIRS; ++pr) {
           int lo, hi;
           pair_range(y0, pr, lo, hi);
-          if (lo >= hi) continue;
-          if (lane == 0) wait_on(in_full + 8 * rs, rph, w_in);
-          __syncwarp();
-          if (!FUSE) (void)mbar_try_wait(in_full + 8 * rs, rph);     // every lane observes the phase the bulk copy completed
+          const bool has = lo < hi;
+          if (has) { if (d0) wait_on(in_full + 8 * rs, rph, w_in); else xl_wait(in_full + 8 * rs, rph); }
 #pragma unroll 1
-          for (int i0 = lo; i0 < hi; i0 += LB) {
-            const int nl = hi - i0 < LB ? hi - i0 : LB;
+          for (int i0 = 2 * pr; i0 < 2 * pr + 2; i0 += LB) {
             uint32_t v[LB][W], lf[LB][W], rt[LB][W];
+            bool ok_f[LB];
+#pragma unroll
+            for (int l = 0; l < LB; ++l)      // sampled here, consumed after the loads: the query's latency overlaps them
+              ok_f[l] = mbar_test_wait(a_free + 8 * (uint32_t)((i0 + l) % NA), (uint32_t)((((i0 + l) / NA) & 1) ^ 1));
 #pragma unroll
             for (int l = 0; l < LB; ++l) {
-              if (l < nl && !(p.ablate & 64)) {
-                const uint32_t src = sm_raw + (uint32_t)rs * 2u * LINE + (uint32_t)(i0 + l - 2 * pr) * LINE + (uint32_t)xv * VOX;
-                uint32_t t[W];
+              const int i = i0 + l;
+              if (i >= lo && i < hi && !(p.ablate & 64)) {
+                const uint32_t src = sm_raw + (uint32_t)rs * 2u * LINE + (uint32_t)(i - 2 * pr) * LINE + (uint32_t)xv * VOX;
 #pragma unroll
-                for (int j = 0; j < NCH; ++j) {
-                  const uint32_t piece = sw ? (uint32_t)((j + 1) % NCH) : (uint32_t)j;
+                for (int j = 0; j < W / 4; ++j) {
                   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                               : "=r"(t[4 * j]), "=r"(t[4 * j + 1]), "=r"(t[4 * j + 2]), "=r"(t[4 * j + 3])
-                               : "r"(src + 16u * piece));
-                }
-#pragma unroll
-                for (int j = 0; j < NCH; ++j)
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) v[l][4 * j + e] = sw ? t[4 * ((j + NCH - 1) % NCH) + e] : t[4 * j + e];
-#pragma unroll
-                for (int j = 0; j < W; ++j) {
-                  lf[l][j] = __shfl_up_sync(0xffffffffu, v[l][j], 1);
-                  rt[l][j] = __shfl_down_sync(0xffffffffu, v[l][j], 1);
-                }
-                if (lane == 0) {
-                  if (q == 0) {
-#pragma unroll
-                    for (int j = 0; j < W; ++j) lf[l][j] = 0u;
-                  } else {
-#pragma unroll
-                    for (int j = 0; j < NCH; ++j)
-                      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                                   : "=r"(lf[l][4 * j]), "=r"(lf[l][4 * j + 1]), "=r"(lf[l][4 * j + 2]), "=r"(lf[l][4 * j + 3])
-                                   : "r"(src - VOX + 16u * j));
-                  }
-                }
-                if (lane == 31) {
-                  if (q == 3) {
-#pragma unroll
-                    for (int j = 0; j < W; ++j) rt[l][j] = 0u;
-                  } else {
-#pragma unroll
-                    for (int j = 0; j < NCH; ++j)
-                      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                                   : "=r"(rt[l][4 * j]), "=r"(rt[l][4 * j + 1]), "=r"(rt[l][4 * j + 2]), "=r"(rt[l][4 * j + 3])
-                                   : "r"(src + VOX + 16u * j));
-                  }
+                               : "=r"(v[l][4 * j]), "=r"(v[l][4 * j + 1]), "=r"(v[l][4 * j + 2]), "=r"(v[l][4 * j + 3])
+                               : "r"(src + 16u * j));
+                  if (xv > 0)
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(lf[l][4 * j]), "=r"(lf[l][4 * j + 1]), "=r"(lf[l][4 * j + 2]), "=r"(lf[l][4 * j + 3])
+                                 : "r"(src - VOX + 16u * j));
+                  else lf[l][4 * j] = lf[l][4 * j + 1] = lf[l][4 * j + 2] = lf[l][4 * j + 3] = 0u;
+                  if (xv < 127)
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(rt[l][4 * j]), "=r"(rt[l][4 * j + 1]), "=r"(rt[l][4 * j + 2]), "=r"(rt[l][4 * j + 3])
+                                 : "r"(src + VOX + 16u * j));
+                  else rt[l][4 * j] = rt[l][4 * j + 1] = rt[l][4 * j + 2] = rt[l][4 * j + 3] = 0u;
                 }
               }
             }
-            int sl[LB];
 #pragma unroll
             for (int l = 0; l < LB; ++l) {
-              sl[l] = slot;
-              if (l < nl) {
-                if (lane == 0) wait_on(a_free + 8 * slot, aph ^ 1, w_afree);
-                if (++slot == NA) { slot = 0; aph ^= 1; }
-              }
+              const int i = i0 + l;
+              const uint32_t fb = a_free + 8 * (uint32_t)(i % NA);
+              const uint32_t fp = (uint32_t)(((i / NA) & 1) ^ 1);
+              if (!ok_f[l]) { if (d0) wait_on(fb, fp, w_afree); else xl_wait(fb, fp); }
             }
-            __syncwarp();
-            if (!(p.ablate & 128)) tc_fence_after();
+            tc_fence_after();
             if (!(p.ablate & 4)) {
 #pragma unroll
               for (int l = 0; l < LB; ++l) {
-                if (l < nl) {
-                  const uint32_t ta = t_lane + (uint32_t)sl[l] * ACOLS;
+                const int i = i0 + l;
+                if (i >= lo && i < hi) {
+                  const uint32_t ta = t_lane + (uint32_t)(i % NA) * ACOLS;
 #pragma unroll
                   for (int k = 0; k < KS; ++k) {
                     tmem_st8(ta + (uint32_t)(0 * KS + k) * 8u, lf[l] + 8 * k);
@@ -455,17 +471,18 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
               }
               tmem_st_wait();
             }
-            if (!(p.ablate & 128)) tc_fence_before();
+            tc_fence_before();
             __syncwarp();
             if (lane == 0) {
 #pragma unroll
-              for (int l = 0; l < LB; ++l)
-                if (l < nl) mbar_arrive(a_full + 8 * sl[l]);
+              for (int l = 0; l < LB; ++l) mbar_arrive(a_full + 8 * (uint32_t)((i0 + l) % NA));
             }
           }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(raw_free + 8 * rs);
-          if (++rs == NR) { rs = 0; rph ^= 1; }
+          if (has) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(raw_free + 8 * rs);
+            if (++rs == NR) { rs = 0; rph ^= 1; }
+          }
         }
       }
     }
@@ -480,7 +497,7 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
 #pragma unroll 1
     for (uint32_t c = 0; c < ACC; c += 16) tmem_st16_zero(t_lane + c);
     tmem_st_wait();
-    if (!(p.ablate & 128)) tc_fence_before();
+    tc_fence_before();
     __syncwarp();
     if (lane == 0)
       for (int o = 0; o < BY / 2; ++o) mbar_arrive(acc_free + 8 * o);
@@ -514,19 +531,27 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
                 old[l][1] = *reinterpret_cast<const uint4*>(yp + 8);
               }
           }
-          if (lane == 0) wait_on(acc_full + 8 * (g0 >> 1), pc & 1, w_full_acc);
-          __syncwarp();
-          if (!(p.ablate & 128)) tc_fence_after();
+          if (p.ablate & 1024) {
+            if (lane == 0) xl_wait_sleep(acc_full + 8 * (g0 >> 1), pc & 1);
+            __syncwarp();
+          } else if (p.ablate & 512) {
+            xl_wait_sleep(acc_full + 8 * (g0 >> 1), pc & 1);
+          } else if (d0) {
+            wait_on(acc_full + 8 * (g0 >> 1), pc & 1, w_full_acc);
+          } else {
+            xl_wait(acc_full + 8 * (g0 >> 1), pc & 1);
+          }
+          tc_fence_after();
           if (sv && !(p.ablate & 8)) {
 #pragma unroll
             for (int l = 0; l < G; ++l)
-              if (y0 + g0 + l < p.h) tmem_ld16(t_lane + (uint32_t)(g0 + l) * 48u + cs, r[l]);
+              if (y0 + g0 + l < p.h) tmem_ld16(t_lane + (uint32_t)(BY - 1 - g0 - l) * 48u + cs, r[l]);
             tmem_ld_wait();
           }
 #pragma unroll
           for (int l = 0; l < G; ++l) {
             if (p.ablate & 32) break;
-            const uint32_t col = t_lane + (uint32_t)(g0 + l) * 48u;
+            const uint32_t col = t_lane + (uint32_t)(BY - 1 - g0 - l) * 48u;
             if (last) {
               tmem_st16_zero(col);
               tmem_st16_zero(col + 16u);
@@ -536,7 +561,7 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
             }
           }
           if (!(p.ablate & 32)) tmem_st_wait();
-          if (!(p.ablate & 128)) tc_fence_before();
+          tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(acc_free + 8 * (g0 >> 1));
           if (sv && !(p.ablate & 8)) {
@@ -595,37 +620,36 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
     }
     if (d0) { dbg[7] = clock64() - t_begin; dbg[8] = w_full_acc; }
   }
-  if (!(p.ablate & 128)) tc_fence_before();
+  tc_fence_before();
   __syncthreads();
   if (warp == 8) tmem_dealloc(tmem, 512);
 }
 
-// Weights of the x-line kernel: [r][dy][dx][k][row = s*16 + co][kk], ci = 16 k + kk, tap dz = (r + 1 - s) mod 3, each
-// (48 x 16) tile in the SWIZZLE_32B K-major shared-memory image (16-byte half kk >> 3 of row rr sits at half ^ ((rr >> 2) & 1)),
-// so the whole matrix is ONE linear bulk copy.  flip: dgrad operand W'[ci][co][2-dz][2-dy][2-dx].
+// Weights of the x-line kernel: [r][dx][k][row = dy*48 + s*16 + co][kk], ci = 16 k + kk, tap dz = (r + 1 - s) mod 3, each
+// (144 x 16) tile in the SWIZZLE_32B K-major shared-memory image (16-byte half kk >> 3 of row rr sits at half ^ ((rr >> 2) & 1)),
+// so the whole matrix is ONE linear bulk copy and the three dy taps of a (dx, k) pair are one N = 144 operand (48-row sub-ranges
+// at the band edges).  flip: dgrad operand W'[ci][co][2-dz][2-dy][2-dx].
 template <typename T>
 __global__ void pack_weight_xline_kernel(const float* __restrict__ w, T* __restrict__ out, int cout, int cin, int flip) {
-  const int CO = flip ? cin : cout, CI = flip ? cout : cin;   // CO == 16
+  const int CI = flip ? cout : cin;
   const int ks = CI / 16;
   const int total = 27 * ks * 48 * 16;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     int t = idx;
     const int kk = t % 16; t /= 16;
-    const int rr = t % 48; t /= 48;
+    const int rr = t % 144; t /= 144;
     const int k = t % ks; t /= ks;
     const int dx = t % 3; t /= 3;
-    const int dy = t % 3; t /= 3;
     const int r = t;
-    const int s = rr / 16, co = rr % 16;
+    const int dy = rr / 48, s = (rr % 48) / 16, co = rr % 16;
     const int dz = ((r + 1 - s) % 3 + 3) % 3;
     const int ci = k * 16 + kk;
     float v;
     if (flip) v = w[((((int64_t)ci * cin + co) * 3 + (2 - dz)) * 3 + (2 - dy)) * 3 + (2 - dx)];
     else v = w[((((int64_t)co * cin + ci) * 3 + dz) * 3 + dy) * 3 + dx];
-    (void)CO;
-    const int tile = ((r * 3 + dy) * 3 + dx) * ks + k;
+    const int tile = (r * 3 + dx) * ks + k;
     const int off = rr * 16 + ((((kk >> 3) ^ ((rr >> 2) & 1))) << 3) + (kk & 7);
-    out[(int64_t)tile * (48 * 16) + off] = from_f<T>(v);
+    out[(int64_t)tile * (144 * 16) + off] = from_f<T>(v);
   }
 }
 
@@ -781,7 +805,7 @@ static int launch_xline(const ActView& x, const void* w, const float* bias, cons
   {                                                                                                                    \
     auto kern = conv_fprop_xline_kernel<T, KS, BY, F>;                                                                 \
     B200_CUDA(raise_dyn_smem_cap(kern));                                                                               \
-    kern<<<grid, F ? 448 : 320, smem, st>>>((const T*)x.data, (const T*)w, bias, (T*)y.data, ap, scale, shift, stats, p);       \
+    kern<<<grid, F ? 512 : 320, smem, st>>>((const T*)x.data, (const T*)w, bias, (T*)y.data, ap, scale, shift, stats, p);       \
   }
   if (fuse == 0) XL_LAUNCH(0)
   else if (fuse == 1) XL_LAUNCH(1)
@@ -825,6 +849,8 @@ int conv_fprop_xline_v(const ActView& x, const void* w, const float* bias, const
   p.ysw = y.sw; p.ysh = y.sh; p.ysd = y.sd; p.ysn = y.sn;
   p.accumulate = accumulate;
   p.idesc = make_idesc(x.dtype == B200_BF16, 48, 0, 0);
+  p.idesc96 = make_idesc(x.dtype == B200_BF16, 96, 0, 0);
+  p.idesc144 = make_idesc(x.dtype == B200_BF16, 144, 0, 0);
   if (x.dtype == B200_BF16) {
     if (x.c == 16) return launch_xline<__nv_bfloat16, 1, 8>(x, w, bias, y, a_out, scale, shift, fuse, stats, p, st);
     return launch_xline<__nv_bfloat16, 3, 4>(x, w, bias, y, a_out, scale, shift, fuse, stats, p, st);

@@ -112,20 +112,19 @@ __device__ __forceinline__ void pack_batch_body(const PackJob* __restrict__ jobs
     for (int64_t i = first; i < jb.total; i += stride) {
       int t = (int)i;
       const int kk = t % 16; t /= 16;
-      const int rr = t % 48; t /= 48;
+      const int rr = t % 144; t /= 144;
       const int k = t % ks; t /= ks;
       const int dx = t % 3; t /= 3;
-      const int dy = t % 3; t /= 3;
       const int r = t;
-      const int s = rr / 16, co = rr % 16;
+      const int dy = rr / 48, s = (rr % 48) / 16, co = rr % 16;
       const int dz = ((r + 1 - s) % 3 + 3) % 3;
       const int ci = k * 16 + kk;
       float v;
       if (jb.flip) v = jb.src[((((int64_t)ci * jb.cin + co) * 3 + (2 - dz)) * 3 + (2 - dy)) * 3 + (2 - dx)];
       else v = jb.src[((((int64_t)co * jb.cin + ci) * 3 + dz) * 3 + dy) * 3 + dx];
-      const int tile = ((r * 3 + dy) * 3 + dx) * ks + k;
+      const int tile = (r * 3 + dx) * ks + k;
       const int off = rr * 16 + ((((kk >> 3) ^ ((rr >> 2) & 1))) << 3) + (kk & 7);
-      out[(int64_t)tile * (48 * 16) + off] = from_f<T>(v);
+      out[(int64_t)tile * (144 * 16) + off] = from_f<T>(v);
     }
   } else if (jb.kind == UNPACK_WGRAD) {
     float* dw = (float*)jb.dst;

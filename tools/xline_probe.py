@@ -148,7 +148,7 @@ def diagnose(dtype, sweep=True):
             ops.conv_fprop_xline(x, wl, b, y, **kw)
             torch.cuda.synchronize()
         os.environ["B200_XL_DBG"] = "0"
-        for ab in ((0, 1, 4, 8, 5, 9, 12, 13, 2) if sweep else (0, 128, 13, 125, 125 + 128, 125 + 256, 125 + 128 + 256)):
+        for ab in ((0, 1, 4, 8, 5, 9, 12, 13, 2) if sweep else (0, 512, 1024 + 512, 125, 125 + 512, 125 + 512 + 1024)):
             os.environ["B200_XL_ABLATE"] = str(ab)
             for name, kw in variants:
                 if ab == 2 and not name.startswith("fuse"):
