@@ -759,12 +759,8 @@ bool conv_xline_ok(const ActView& x, const ActView& y, int kd, int kh, int kw) {
 }
 
 static int xline_mode() {
-  static int m = -1;
-  if (m < 0) {
-    const char* e = getenv("B200_XLINE");
-    m = e ? atoi(e) : 1;
-  }
-  return m;
+  const char* e = getenv("B200_XLINE");     // read per call: the host side (engine/tape.py) re-reads it per pass as well
+  return e ? atoi(e) : 1;
 }
 bool conv_xline_enabled() { return xline_mode() != 0; }
 

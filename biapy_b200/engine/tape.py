@@ -26,10 +26,12 @@ from .. import _lib, ops
 class TT:
     """A tensor on the tape: data + lazily allocated gradient; may be a channel slice of a parent buffer."""
 
-    __slots__ = ("data", "_grad", "_ready", "parent", "off", "requires_grad", "padded", "sums", "dense_grad")
+    __slots__ = ("_data", "pending", "_meta", "_grad", "_ready", "parent", "off", "requires_grad", "padded", "sums", "dense_grad")
 
-    def __init__(self, data: torch.Tensor, requires_grad: bool = True, parent: "Optional[TT]" = None, off: int = 0):
-        self.data = data
+    def __init__(self, data: Optional[torch.Tensor], requires_grad: bool = True, parent: "Optional[TT]" = None, off: int = 0):
+        self._data = data
+        self.pending = None         # lazy act(norm(src)): (materialise callback) until a consumer needs the tensor (Tape.norm_act)
+        self._meta = None           # (shape, dtype, device) of a lazy tensor
         self._grad = None
         self._ready = False
         self.parent = parent
@@ -40,12 +42,25 @@ class TT:
         self.dense_grad = None      # slices only: the finished gradient as a dense tensor (left by Tape.maxpool's backward)
 
     @property
+    def data(self) -> torch.Tensor:
+        """The tensor.  A lazy normalisation + activation result (Tape.norm_act(lazy=True)) is written out on first access --
+        unless the consuming convolution applied it on its own operand path (Tape.conv, x-line kernel)."""
+        if self._data is None and self.pending is not None:
+            fn, self.pending = self.pending, None
+            self._data = fn()
+        return self._data
+
+    @property
+    def is_lazy(self) -> bool:
+        return self._data is None and self.pending is not None
+
+    @property
     def shape(self):
-        return self.data.shape
+        return self._meta[0] if self._data is None else self._data.shape
 
     @property
     def c(self) -> int:
-        return self.data.shape[-1]
+        return self.shape[-1]
 
     def slice(self, off: int, c: int) -> "TT":
         return TT(self.data[..., off:off + c], self.requires_grad, parent=self, off=off)
@@ -63,7 +78,11 @@ class TT:
         if self.parent is not None:
             return self.parent.grad()[..., self.off:self.off + self.c]
         if self._grad is None:
-            self._grad = torch.empty_like(self.data)
+            if self._data is None:
+                shape, dtype, device = self._meta
+                self._grad = torch.empty(shape, dtype=dtype, device=device)
+            else:
+                self._grad = torch.empty_like(self._data)
         return self._grad
 
     def mark_written(self):
@@ -107,6 +126,13 @@ class Tape:
         # conv -> norm: channel sums of the normalisation produced by the convolution epilogue (x-slab kernels)
         self.fuse_stats = os.environ.get("B200_FUSE_STATS", "1") != "0"
         self.pool_dense = os.environ.get("B200_POOL_DENSE", "1") != "0"
+        # x-line kernel (csrc/conv_xline.cu): B200_XLINE = 0 off, 1 (default) where it measured faster than the x-folded kernels
+        # (profiles/xline_probe_r2_*.log: Cin = 48 and non-accumulating Cin = 16 launches), 2 every launch it supports.
+        # B200_XLINE_FUSE = auto (default): GroupNorm-apply + SiLU on the operand path when the one-MUFU chain is the engine's
+        # chain (bf16: ops.norm_fast_ok); 1: also with the exact chain (fp16 -- measured slower than the two separate launches,
+        # the activation warps become the bottleneck); 0: never.
+        self.xline = int(os.environ.get("B200_XLINE", "1"))
+        self.xline_fuse = os.environ.get("B200_XLINE_FUSE", "auto").lower()
         self.param_grads: Dict[torch.nn.Parameter, torch.Tensor] = {}
         # key -> (pack job, packed tensor) of every weight pack this pass launched on its own (Trainer: replayed as one launch)
         self.pack_record: Optional[Dict] = None
@@ -170,6 +196,8 @@ class Tape:
         normalisation then runs the stand-alone reduction)."""
         impl = self.impl
         wkey = w if wkey is None else wkey
+        if self._xline_ok(x, y, k, accumulate):
+            return self._xline_launch(x, w, flip, bias, y, accumulate, wkey, stats)
         if impl == _lib.IMPL_AUTO and self.dtype != torch.float32 and self.use_xfold:
             x = self._dense_for_xfold(x, y.shape[4])
             if ops.conv_impl_query(x, y, k) == _lib.IMPL_XFOLD:
@@ -193,6 +221,32 @@ class Tape:
         ops.conv_fprop(x, wp, bias, y, k, accumulate=accumulate, impl=impl)
         return None
 
+    def _xline_ok(self, x: torch.Tensor, y: torch.Tensor, k, accumulate: bool, fused: bool = False) -> bool:
+        if (self.xline <= 0 or self.impl != _lib.IMPL_AUTO or self.dtype == torch.float32 or tuple(k) != (3, 3, 3)
+                or x.shape[3] != 128 or y.shape[4] != 16 or x.shape[4] not in (16, 48)):
+            return False
+        if self.xline == 1 and not fused and accumulate and x.shape[4] == 16:
+            return False        # 16 -> 16 with the residual add: the x-folded kernel's TMA element-wise add is faster
+        return ops.conv_xline_supported(x, y, k)
+
+    def _xline_launch(self, x, w, flip, bias, y, accumulate, wkey, stats, scale=None, shift=None, fuse=0, a_out=None):
+        wp = self._cached((id(wkey), flip, "xline"), w, lambda: ops.pack_conv_weight_xline(w, self.dtype, flip))
+        sums = None
+        if stats and self.fuse_stats and not accumulate:
+            sums = ops.zeros(y.shape[0] * y.shape[4] * 2, torch.float64, y.device)
+        ops.conv_fprop_xline(x, wp, bias, y, accumulate=accumulate, scale=scale, shift=shift, fuse=fuse, a_out=a_out, sums=sums)
+        return sums
+
+    def _fuse_mode(self, x: torch.Tensor) -> int:
+        """0 = keep normalisation-apply + SiLU as its own launch; 1 / 2 = apply it inside the x-line convolution with the exact /
+        one-MUFU chain -- always the chain `ops.scale_shift_act` would run for this tensor, so both routes store the same bits."""
+        if self.xline <= 0 or self.xline_fuse in ("0", "off") or self.dtype == torch.float32:
+            return 0
+        fast = ops.norm_fast_ok(x)
+        if fast:
+            return 2
+        return 1 if self.xline_fuse == "1" else 0
+
     @staticmethod
     def _k3(k) -> Tuple[int, int, int]:
         k = tuple(int(v) for v in k)
@@ -212,6 +266,10 @@ class Tape:
         k = self._k3(w.shape[2:])
         cout, cin = w.shape[0], w.shape[1]
         assert x.c == cin, (x.c, cin)
+        if x.is_lazy:
+            fused = self._conv_fused(x, mod, out, accumulate, stats, k, cout, cin)
+            if fused is not None:
+                return fused
         if out is None:
             out = self.new(x.data, cout)
         # image-fed layers (Cin = 2, 4, 8): the x-folded slab kernels take the narrow input as it is (3x3x3), the pointwise
@@ -223,17 +281,42 @@ class Tape:
             return self._conv_padded_input(x, mod, out, accumulate, k, cout, cin)
         out.sums = self._conv_launch(x.data, w, False, self._f32(b), out.data, k, accumulate, stats=stats and not accumulate)
         if self.training:
-            def bwd(x=x, out=out, w=w, b=b, k=k, cout=cout, cin=cin, narrow=narrow):
-                dy = out.grad() if (narrow and k == (1, 1, 1)) else self._dense_for_xfold(out.grad(), cin)
-                assert out.grad_ready, "conv output gradient was never produced"
-                if w.requires_grad:
-                    gb = self._pgrad(b) if (b is not None and b.requires_grad) else None
-                    first = w not in self.param_grads
-                    ops.conv_wgrad(x.data, dy, cout, cin, k, self._pgrad(w), gb, accumulate=not first, impl=self.impl)
-                if x.requires_grad:
-                    acc = x.prepare_accumulate()
-                    self._conv_launch(dy, w, True, None, x.grad(), k, acc)
-            self.steps.append(bwd)
+            self._conv_backward(x, out, w, b, k, cout, cin, narrow)
+        return out
+
+    def _conv_backward(self, x: TT, out: TT, w, b, k, cout: int, cin: int, narrow: bool):
+        def bwd(x=x, out=out, w=w, b=b, k=k, cout=cout, cin=cin, narrow=narrow):
+            dy = out.grad() if (narrow and k == (1, 1, 1)) else self._dense_for_xfold(out.grad(), cin)
+            assert out.grad_ready, "conv output gradient was never produced"
+            if w.requires_grad:
+                gb = self._pgrad(b) if (b is not None and b.requires_grad) else None
+                first = w not in self.param_grads
+                ops.conv_wgrad(x.data, dy, cout, cin, k, self._pgrad(w), gb, accumulate=not first, impl=self.impl)
+            if x.requires_grad:
+                acc = x.prepare_accumulate()
+                self._conv_launch(dy, w, True, None, x.grad(), k, acc)
+        self.steps.append(bwd)
+
+    def _conv_fused(self, x: TT, mod, out: Optional[TT], accumulate: bool, stats: bool, k, cout: int, cin: int) -> Optional[TT]:
+        """x is a lazy act(norm(src)) (Tape.norm_act): run the convolution on `src` with the normalisation-apply + SiLU on the
+        operand path of the x-line kernel -- the fused Conv3D + GroupNorm + SiLU launch.  In training the kernel also writes the
+        activated tensor (the weight gradient and nothing else reads it).  None when this convolution cannot take it."""
+        src, st, fuse = x._meta[3]
+        shape, dtype, device = x._meta[:3]
+        if cout != 16 or tuple(k) != (3, 3, 3) or self.xline <= 0:
+            return None
+        if out is None:
+            out = TT(torch.empty(tuple(shape[:4]) + (cout,), dtype=self.dtype, device=self.device))
+        if not self._xline_ok(src.data, out.data, k, accumulate, fused=True):
+            return None
+        w, b = mod.weight, mod.bias
+        a_buf = torch.empty(shape, dtype=dtype, device=device) if self.training else None
+        out.sums = self._xline_launch(src.data, w, False, self._f32(b), out.data, accumulate, w, stats and not accumulate,
+                                      scale=st.scale, shift=st.shift, fuse=fuse, a_out=a_buf)
+        x.pending = None
+        x._data = a_buf             # eval mode: the activated tensor never exists
+        if self.training:
+            self._conv_backward(x, out, w, b, k, cout, cin, narrow=False)
         return out
 
     def _conv_padded_input(self, x: TT, mod, out: TT, accumulate: bool, k, cout: int, cin: int) -> TT:
@@ -298,13 +381,21 @@ class Tape:
             self.steps.append(bwd)
         return out
 
-    def norm_act(self, x: TT, norm: Optional[torch.nn.Module], act: Optional[str], out: Optional[TT] = None) -> TT:
-        """out = act(norm(x)).  norm: GroupNorm / InstanceNorm(affine) parameter holder or None."""
+    def norm_act(self, x: TT, norm: Optional[torch.nn.Module], act: Optional[str], out: Optional[TT] = None,
+                 lazy: bool = False) -> TT:
+        """out = act(norm(x)).  norm: GroupNorm / InstanceNorm(affine) parameter holder or None.  `lazy`: the caller hands the
+        result straight to a convolution -- the statistics are computed now, the apply pass is left to the consumer (see TT.data)."""
         act = (act or "none").lower()
         if norm is None and act in ("none", "linear"):
             return x
         sums, x.sums = x.sums, None
-        if out is None:
+        # lazy route: GroupNorm / InstanceNorm + SiLU of a dense 16- or 48-channel tensor at W = 128 whose apply pass the x-line
+        # convolution can run on its operand path (chain chosen by _fuse_mode: the one scale_shift_act would run)
+        fuse = 0
+        if (lazy and out is None and norm is not None and act == "silu" and x.parent is None and x.shape[3] == 128
+                and x.c in (16, 48) and not isinstance(norm, torch.nn.modules.batchnorm._BatchNorm) and x.data.is_contiguous()):
+            fuse = self._fuse_mode(x.data)
+        if out is None and not fuse:
             out = self.new(x.data, x.c)
         if norm is None:
             ops.scale_shift_act(x.data, None, None, act, out.data)
@@ -342,7 +433,15 @@ class Tape:
                 st = ops.bn_eval_stats(x.data, norm.running_mean, norm.running_var, g32, b32, float(norm.eps))
         else:
             st = ops.norm_stats(x.data, groups, g32, b32, eps=float(norm.eps), sums=sums)
-        ops.scale_shift_act(x.data, st.scale, st.shift, act, out.data)
+        if fuse:
+            # the consumer decides: a 3x3x3 convolution into 16 channels applies scale / shift / SiLU on its own operand path
+            # (Tape._conv_fused); anything else reads `.data`, which runs the stand-alone launch first
+            out = TT(None)
+            out._meta = (tuple(x.shape), x.data.dtype, x.data.device, (x, st, fuse))
+            out.pending = lambda x=x, st=st, act=act, meta=out._meta: ops.scale_shift_act(
+                x.data, st.scale, st.shift, act, torch.empty(meta[0], dtype=meta[1], device=meta[2]))
+        else:
+            ops.scale_shift_act(x.data, st.scale, st.shift, act, out.data)
         if self.training and st.mean is not None:
             def bwd(x=x, out=out, st=st, gamma=gamma, beta=beta, g32=g32, b32=b32, act=act):
                 assert out.grad_ready

@@ -169,12 +169,13 @@ class ConvBlock(nn.Module):
         act = _act_name(b[self._act_idx]) if self._act_idx is not None else None
         return b[self._conv_idx], norm, act
 
-    def run(self, tape: Tape, x: TT, out: Optional[TT] = None, into: Optional[TT] = None) -> TT:
-        """`out`: write the block result there.  `into`: accumulate the (bare) final convolution into it."""
+    def run(self, tape: Tape, x: TT, out: Optional[TT] = None, into: Optional[TT] = None, lazy: bool = False) -> TT:
+        """`out`: write the block result there.  `into`: accumulate the (bare) final convolution into it.  `lazy`: the caller
+        feeds the result to a convolution and nothing else (Tape.norm_act)."""
         if self.nconvs > 1:
             for i, sub in enumerate(self.block):
                 last = i == self.nconvs - 1
-                x = sub.run(tape, x, out=out if last else None, into=into if last else None)
+                x = sub.run(tape, x, out=out if last else None, into=into if last else None, lazy=lazy if last else True)
             return x
         conv, norm, act = self._parts()
         if self.dropout_p > 0 and self.training:
@@ -189,7 +190,7 @@ class ConvBlock(nn.Module):
                 y = tape.norm_act(tape.conv(x, conv, stats=norm is not None), norm, act)
             return tape.dropout(y, self.dropout_p, out=out)
         if self.order == "norm_act_conv":
-            h = tape.norm_act(x, norm, act)
+            h = tape.norm_act(x, norm, act, lazy=True)      # consumed by the convolution only: fusable on its operand path
             if into is not None:
                 return tape.conv(h, conv, out=into, accumulate=True)
             return tape.conv(h, conv, out=out)
@@ -198,8 +199,9 @@ class ConvBlock(nn.Module):
                 return tape.conv(x, conv, out=into, accumulate=True)
             return tape.conv(x, conv, out=out)
         assert into is None, "only a bare convolution can be accumulated into a residual"
-        # conv -> norm: the channel sums of the normalisation come out of the convolution's epilogue when the kernel has one
-        return tape.norm_act(tape.conv(x, conv, stats=norm is not None), norm, act, out=out)
+        # conv -> norm: the channel sums of the normalisation come out of the convolution's epilogue when the kernel has one.
+        # `lazy`: inside a residual block the result only feeds the next convolution, which can apply norm + act on its operand path
+        return tape.norm_act(tape.conv(x, conv, stats=norm is not None), norm, act, out=out, lazy=lazy)
 
     @property
     def ends_with_bare_conv(self) -> bool:
@@ -367,7 +369,7 @@ class ResConvBlock(nn.Module):
         if self.order == "conv_norm_act" and (self._pre_norm_idx is not None or self._pre_act_idx is not None):
             norm = self.block[self._pre_norm_idx] if self._pre_norm_idx is not None else None
             act = _act_name(self.block[self._pre_act_idx]) if self._pre_act_idx is not None else None
-            h = tape.norm_act(x, norm, act)
+            h = tape.norm_act(x, norm, act, lazy=norm is not None)      # feeds the first convolution only
             first = max(i for i in (self._pre_norm_idx, self._pre_act_idx) if i is not None) + 1
             # inplace=True activation applied straight to the block input (no norm in front) also changes what the
             # shortcut sees in the reference (blocks.py:1458 evaluates block(x) first)
@@ -377,10 +379,10 @@ class ResConvBlock(nn.Module):
         res = tape.conv(shortcut_in, self.shortcut[0], out=out)
         if convs[-1].ends_with_bare_conv:
             for cb in convs[:-1]:
-                h = cb.run(tape, h)
+                h = cb.run(tape, h, lazy=True)
             return convs[-1].run(tape, h, into=res)
-        for cb in convs:
-            h = cb.run(tape, h)
+        for i, cb in enumerate(convs):
+            h = cb.run(tape, h, lazy=i + 1 < len(convs))
         return tape.add(h, res, out=res)
 
 
