@@ -26,7 +26,8 @@
 //     sums of the stored values for the following normalisation (conv -> norm, == b200_channel_sums of the output).
 //
 // Work unit = (sample, z chunk, band of BY output lines); planes z0-1 .. zhi and lines y0-1 .. y0+BY are read (halo).
-// Warps: 0-3 epilogue, 4-7 transform, 8 MMA issue (one elected lane), 9 bulk-copy issue (one elected lane).
+// Warps: 0-3 epilogue, 4-7 and 10-13 operand staging (two teams), 8 MMA issue (one elected lane), 9 bulk-copy issue (one
+// elected lane), 14-19 activation (fused launches only).
 #include "umma.cuh"
 
 namespace b200 {
@@ -135,7 +136,7 @@ __device__ __forceinline__ void xl_wait_lean(uint32_t bar, uint32_t parity) {
 }
 
 template <typename T, int KS, int BY, int FUSE>
-__global__ void __launch_bounds__(FUSE ? 512 : 320, 1)
+__global__ void __launch_bounds__(FUSE ? 640 : 448, 1)
 conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, const float* __restrict__ bias, T* __restrict__ y,
                         T* __restrict__ a_out, const float* __restrict__ scale, const float* __restrict__ shift,
                         double* __restrict__ stats, const XlineParams p) {
@@ -310,7 +311,7 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
       }
       if (dbg) { dbg[0] = clock64() - t_begin; dbg[10] = nlines; }
     }
-  } else if (warp >= 10) {
+  } else if (warp >= 14) {
     // ===================================================================== activation (FUSE only): raw lines -> silu(x * scale + shift)
     // in place in the raw ring, and the activated tensor for the backward pass.  Six warps; a thread walks the 16-byte pieces
     // (8 channels) of the pair's two lines with stride 192 -- a multiple of the pieces per voxel, so its channel block and its 16
@@ -319,7 +320,7 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
     if constexpr (FUSE != 0) {
       constexpr int NPC = 512 * KS;                           // pieces of a pair
       constexpr int NIT = (NPC + 191) / 192;
-      const int tm = (int)threadIdx.x - 320;                  // 0 .. 191
+      const int tm = (int)threadIdx.x - 448;                  // 0 .. 191
       const bool d0 = dbg != nullptr && tm == 0;
       const long long t_begin = d0 ? clock64() : 0;
       long long w_raw = 0;
@@ -397,7 +398,11 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
   } else if (warp >= 4) {
     // ===================================================================== staging: ring lines -> three operand copies in TMEM
     // thread = voxel = TMEM lane: its own voxel and the two neighbours in x (zeros at the line ends = 'same' padding in x)
+    // Two teams of four warps (4-7 and 10-13, one warp per lane quarter each) take alternate pairs: the chain wait -> loads ->
+    // tcgen05.st -> wait::st -> fence -> arrive of one pair overlaps the next pair's.
     const int q = warp & 3;
+    const uint32_t team = warp >= 10 ? 1u : 0u;
+    uint32_t cpair = 0;
     const int xv = q * 32 + lane;
     const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16) + ACC;
     const uint32_t in_full = FUSE ? xf_full : raw_full;
@@ -416,6 +421,10 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
           int lo, hi;
           pair_range(y0, pr, lo, hi);
           const bool has = lo < hi;
+          if (((cpair++) & 1u) != team) {            // the other team's pair
+            if (has && ++rs == NR) { rs = 0; rph ^= 1; }
+            continue;
+          }
           if (has) { if (d0) wait_on(in_full + 8 * rs, rph, w_in); else xl_wait(in_full + 8 * rs, rph); }
 #pragma unroll 1
           for (int i0 = 2 * pr; i0 < 2 * pr + 2; i0 += LB) {
@@ -801,7 +810,7 @@ static int launch_xline(const ActView& x, const void* w, const float* bias, cons
   {                                                                                                                    \
     auto kern = conv_fprop_xline_kernel<T, KS, BY, F>;                                                                 \
     B200_CUDA(raise_dyn_smem_cap(kern));                                                                               \
-    kern<<<grid, F ? 512 : 320, smem, st>>>((const T*)x.data, (const T*)w, bias, (T*)y.data, ap, scale, shift, stats, p);       \
+    kern<<<grid, F ? 640 : 448, smem, st>>>((const T*)x.data, (const T*)w, bias, (T*)y.data, ap, scale, shift, stats, p);       \
   }
   if (fuse == 0) XL_LAUNCH(0)
   else if (fuse == 1) XL_LAUNCH(1)
