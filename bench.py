@@ -366,10 +366,25 @@ def roofline_from_profile(prof, steps, peaks, timed_region_s, region):
     for name, recs in prof.items():
         t = sum(a.elapsed_time(b) for a, b, _, _ in recs)
         agg[name] = (t, sum(r[2] for r in recs), sum(r[3] for r in recs), len(recs))
-    # dominant family among the tensor-bound ones (conv1x1_* / conv_image_* are HBM streams: see ops._family)
-    tensor_fams = [k for k in agg if agg[k][1] > 0 and not k.startswith(("conv1x1_", "conv_image_"))]
-    top = max(tensor_fams or [k for k in agg if agg[k][1] > 0], key=lambda k: agg[k][0])
-    t, fl, by, cnt = agg[top]
+    # dominant family among the tensor-bound ones (conv1x1_* / conv_image_* are HBM streams: see ops._family).  The forward /
+    # input-gradient convolutions of the small-channel layers run on two kernel families since round 2 (x-folded: conv_umma.cu,
+    # x-line: conv_xline.cu, chosen per layer by engine/tape.py): they are ONE family for the roofline -- the same layers, the
+    # same algorithmic FLOPs -- with the per-kernel split kept in `all` and `members`.
+    def group_of(k):
+        fam = k.split(" ")[0]
+        return "conv_fprop" if fam.startswith("conv_fprop_") else fam
+    tensor_keys = [k for k in agg if agg[k][1] > 0 and not k.startswith(("conv1x1_", "conv_image_"))]
+    groups = {}
+    for k in tensor_keys or [k for k in agg if agg[k][1] > 0]:
+        g = groups.setdefault(group_of(k), [0.0, 0.0, 0.0, 0, {}])
+        g[0] += agg[k][0]; g[1] += agg[k][1]; g[2] += agg[k][2]; g[3] += agg[k][3]
+        fam = k.split(" ")[0]
+        m = g[4].setdefault(fam, [0.0, 0.0, 0])
+        m[0] += agg[k][0]; m[1] += agg[k][1]; m[2] += agg[k][3]
+    top = max(groups, key=lambda g: groups[g][0])
+    t, fl, by, cnt, members = groups[top]
+    members = {k: {"ms_per_step": round(v[0] / steps, 3), "TFLOP/s": round(v[1] / (v[0] / 1e3) / 1e12, 1), "launches": v[2] // steps}
+               for k, v in sorted(members.items(), key=lambda kv: -kv[1][0])}
     ach = fl / (t / 1e3) / 1e12
     # a short timed region runs at boost clocks: the burst figure is the like-for-like denominator; long runs settle at the sustained one
     burst = timed_region_s < 2.0
@@ -378,17 +393,19 @@ def roofline_from_profile(prof, steps, peaks, timed_region_s, region):
     for f in ("traffic_r2.json", "traffic_r1.json"):
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", f)))
-            fam = top.split(" ")[0]               # --detail labels carry the layer shape after the family name
-            if fam in tj:
+            fam = next((m for m in members if m in tj), None)      # ncu capture of the group's most expensive kernel family
+            if fam is not None:
                 traffic = tj[fam]["dram_bytes_per_launch"]
-                traffic_note = tj[fam]
+                traffic_note = dict(tj[fam], family=fam, other_captures={m: tj[m] for m in members if m in tj and m != fam})
                 break
         except (OSError, ValueError, KeyError):
             pass
+    if len(members) > 1:
+        top = top + " (" + " + ".join(members) + ")"
     total_flops = sum(v[1] for v in agg.values())
     return {"kernel": top, "region": region, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
             "frac": ach / peak, "frac_of_sustained": ach / peaks["tf_sust"], "frac_of_burst": ach / peaks["tf_burst"],
-            "traffic": traffic, "traffic_note": traffic_note, "launches": cnt, "ms_in_step": t / steps,
+            "traffic": traffic, "traffic_note": traffic_note, "launches": cnt, "ms_in_step": t / steps, "members": members,
             "peak_source": peaks["src"] + (", burst figure (timed region %.2f s, boost clocks)" % timed_region_s if burst
                                            else ", sustained figure (kernel timed inside a %.1f s region)" % timed_region_s),
             "algorithmic_gflop_per_step_from_events": total_flops / steps / 1e9,

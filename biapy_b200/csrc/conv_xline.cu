@@ -26,8 +26,8 @@
 //     sums of the stored values for the following normalisation (conv -> norm, == b200_channel_sums of the output).
 //
 // Work unit = (sample, z chunk, band of BY output lines); planes z0-1 .. zhi and lines y0-1 .. y0+BY are read (halo).
-// Warps: 0-3 epilogue, 4-7 and 10-13 operand staging (two teams), 8 MMA issue (one elected lane), 9 bulk-copy issue (one
-// elected lane), 14-19 activation (fused launches only).
+// Warps: 0-3 epilogue, 4-7 and 8-11 operand staging (two teams on alternate line pairs; in the fused launch they also apply the
+// normalisation + activation), 12 MMA issue (one elected lane), 13 bulk-copy issue (one elected lane).
 #include "umma.cuh"
 
 namespace b200 {
@@ -136,7 +136,7 @@ __device__ __forceinline__ void xl_wait_lean(uint32_t bar, uint32_t parity) {
 }
 
 template <typename T, int KS, int BY, int FUSE>
-__global__ void __launch_bounds__(FUSE ? 640 : 448, 1)
+__global__ void __launch_bounds__(448, 1)
 conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, const float* __restrict__ bias, T* __restrict__ y,
                         T* __restrict__ a_out, const float* __restrict__ scale, const float* __restrict__ shift,
                         double* __restrict__ stats, const XlineParams p) {
@@ -176,12 +176,11 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
     mbar_init(w_full, 1);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(smem_u32(&s_tmem), 512);
+  if (warp == 12) tmem_alloc(smem_u32(&s_tmem), 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s_tmem;
-
   auto decode = [&](int u, int& n, int& z0, int& zhi, int& y0) {
     const int band = u % p.bands;
     int t = u / p.bands;
@@ -208,7 +207,7 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
     }
   };
 
-  if (warp == 9) {
+  if (warp == 13) {
     // ===================================================================== bulk-copy issue
     if (elect_one()) {
       long long w_free = 0;
@@ -243,7 +242,7 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
       }
       if (dbg) dbg[9] = w_free;
     }
-  } else if (warp == 8) {
+  } else if (warp == 12) {
     // ===================================================================== MMA issue
     // One thread; everything it touches per line is a constant offset from registers set up once per plane.  Input line i of the
     // band feeds output lines i, i-1, i-2 (taps dy = 0, 1, 2), which sit in ascending column order (line o at (BY-1-o)*48), so ONE
@@ -311,101 +310,19 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
       }
       if (dbg) { dbg[0] = clock64() - t_begin; dbg[10] = nlines; }
     }
-  } else if (warp >= 14) {
-    // ===================================================================== activation (FUSE only): raw lines -> silu(x * scale + shift)
-    // in place in the raw ring, and the activated tensor for the backward pass.  Six warps; a thread walks the 16-byte pieces
-    // (8 channels) of the pair's two lines with stride 192 -- a multiple of the pieces per voxel, so its channel block and its 16
-    // coefficients never change -- consecutive threads touch consecutive pieces (no bank conflicts, coalesced a_out stores), and
-    // the independent pieces of a pair keep the MUFU pipe fed.
-    if constexpr (FUSE != 0) {
-      constexpr int NPC = 512 * KS;                           // pieces of a pair
-      constexpr int NIT = (NPC + 191) / 192;
-      const int tm = (int)threadIdx.x - 448;                  // 0 .. 191
-      const bool d0 = dbg != nullptr && tm == 0;
-      const long long t_begin = d0 ? clock64() : 0;
-      long long w_raw = 0;
-      int rs = 0;
-      uint32_t rph = 0;
-      char* const ab = reinterpret_cast<char*>(a_out);
-      const int c8 = (tm % (2 * KS)) * 8;
-      for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
-        int n, z0, zhi, y0;
-        decode(u, n, z0, zhi, y0);
-        float sc[8], sh[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          sc[e] = __ldg(scale + (long long)n * (16 * KS) + c8 + e);
-          sh[e] = __ldg(shift + (long long)n * (16 * KS) + c8 + e);
-        }
-        for (int pz = z0 - 1; pz <= zhi; ++pz) {
-          if ((unsigned)pz >= (unsigned)p.d) continue;
-          const bool zown = a_out != nullptr && pz >= z0 && pz < zhi;
-#pragma unroll 1
-          for (int pr = 0; pr < PAIRS; ++pr) {
-            int lo, hi;
-            pair_range(y0, pr, lo, hi);
-            if (lo >= hi) continue;
-            if (d0) wait_on(raw_full + 8 * rs, rph, w_raw); else xl_wait(raw_full + 8 * rs, rph);
-            const uint32_t base = sm_raw + (uint32_t)rs * 2u * LINE;
-            uint32_t v[NIT][4];
-            bool on[NIT];
-#pragma unroll
-            for (int it = 0; it < NIT; ++it) {
-              const int pc = tm + 192 * it;
-              const int i = 2 * pr + pc / (256 * KS);
-              on[it] = pc < NPC && i >= lo && i < hi;
-              if (on[it])
-                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(v[it][0]), "=r"(v[it][1]), "=r"(v[it][2]), "=r"(v[it][3])
-                             : "r"(base + 16u * (uint32_t)pc));
-            }
-            if (!(p.ablate & 2)) {
-#pragma unroll
-              for (int it = 0; it < NIT; ++it) {
-                if (on[it]) {
-#pragma unroll
-                  for (int w2 = 0; w2 < 4; ++w2) {
-                    Pack<T, 2> e = *reinterpret_cast<Pack<T, 2>*>(&v[it][w2]);
-                    e.v[0] = from_f<T>(xl_silu<FUSE>(fmaf(to_f<T>(e.v[0]), sc[2 * w2], sh[2 * w2])));
-                    e.v[1] = from_f<T>(xl_silu<FUSE>(fmaf(to_f<T>(e.v[1]), sc[2 * w2 + 1], sh[2 * w2 + 1])));
-                    v[it][w2] = *reinterpret_cast<uint32_t*>(&e);
-                  }
-                }
-              }
-            }
-#pragma unroll
-            for (int it = 0; it < NIT; ++it) {
-              if (on[it]) {
-                const int pc = tm + 192 * it;
-                const int l = pc / (256 * KS);
-                const int i = 2 * pr + l;
-                st_shared_v4(base + 16u * (uint32_t)pc, make_uint4(v[it][0], v[it][1], v[it][2], v[it][3]));
-                if (zown && i >= 1 && i <= BY) {
-                  char* dst = ab + (long long)n * p.asn_b + (long long)pz * p.asd_b + (long long)(y0 - 1 + i) * p.ash_b +
-                              16 * (pc - l * 256 * KS);
-                  *reinterpret_cast<uint4*>(dst) = make_uint4(v[it][0], v[it][1], v[it][2], v[it][3]);
-                }
-              }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(xf_full + 8 * rs);
-            if (++rs == NR) { rs = 0; rph ^= 1; }
-          }
-        }
-      }
-      if (d0) { dbg[11] = clock64() - t_begin; dbg[12] = w_raw; }
-    }
   } else if (warp >= 4) {
     // ===================================================================== staging: ring lines -> three operand copies in TMEM
     // thread = voxel = TMEM lane: its own voxel and the two neighbours in x (zeros at the line ends = 'same' padding in x)
-    // Two teams of four warps (4-7 and 10-13, one warp per lane quarter each) take alternate pairs: the chain wait -> loads ->
+    // Two teams of four warps (4-7 and 8-11, one warp per lane quarter each) take alternate pairs: the chain wait -> loads ->
     // tcgen05.st -> wait::st -> fence -> arrive of one pair overlaps the next pair's.
     const int q = warp & 3;
-    const uint32_t team = warp >= 10 ? 1u : 0u;
+    const uint32_t team = warp >= 8 ? 1u : 0u;
     uint32_t cpair = 0;
     const int xv = q * 32 + lane;
     const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16) + ACC;
-    const uint32_t in_full = FUSE ? xf_full : raw_full;
+    const uint32_t in_full = raw_full;
+    const uint32_t cf = sm_cf + (uint32_t)(warp - 4) * CFB;       // this warp's copy of scale[Cin], shift[Cin] (fused launches)
+    char* const ab = reinterpret_cast<char*>(a_out);
     const bool d0 = dbg != nullptr && threadIdx.x == 128;
     const long long t_begin = d0 ? clock64() : 0;
     long long w_in = 0, w_afree = 0;
@@ -414,8 +331,18 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
     for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
       int n, z0, zhi, y0;
       decode(u, n, z0, zhi, y0);
+      if constexpr (FUSE != 0) {
+        __syncwarp();
+        for (int c = lane; c < 16 * KS; c += 32) {
+          const float sv = __ldg(scale + (long long)n * (16 * KS) + c), hv = __ldg(shift + (long long)n * (16 * KS) + c);
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(cf + 4u * c), "f"(sv) : "memory");
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(cf + 64u * KS + 4u * c), "f"(hv) : "memory");
+        }
+        __syncwarp();
+      }
       for (int pz = z0 - 1; pz <= zhi; ++pz) {
         if ((unsigned)pz >= (unsigned)p.d) continue;
+        const bool zown = FUSE != 0 && a_out != nullptr && pz >= z0 && pz < zhi;
 #pragma unroll 1
         for (int pr = 0; pr < PAIRS; ++pr) {
           int lo, hi;
@@ -433,6 +360,83 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
 #pragma unroll
             for (int l = 0; l < LB; ++l)      // sampled here, consumed after the loads: the query's latency overlaps them
               ok_f[l] = mbar_test_wait(a_free + 8 * (uint32_t)((i0 + l) % NA), (uint32_t)((((i0 + l) / NA) & 1) ^ 1));
+            if constexpr (FUSE != 0) {
+              // fused GroupNorm-apply + SiLU: every thread activates its own voxel(s) in place in the ring (and stores them to
+              // a_out), the team meets at its own named barrier, then the neighbours are read like raw voxels
+#pragma unroll
+              for (int l = 0; l < LB; ++l) {
+                const int i = i0 + l;
+                if (i >= lo && i < hi) {
+                  const uint32_t src = sm_raw + (uint32_t)rs * 2u * LINE + (uint32_t)(i - 2 * pr) * LINE + (uint32_t)xv * VOX;
+#pragma unroll
+                  for (int j = 0; j < W / 4; ++j)
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(v[l][4 * j]), "=r"(v[l][4 * j + 1]), "=r"(v[l][4 * j + 2]), "=r"(v[l][4 * j + 3])
+                                 : "r"(src + 16u * j));
+                }
+              }
+              if (!(p.ablate & 2)) {
+#pragma unroll
+                for (int m = 0; m < W / 2; ++m) {
+                  float4 s4, h4;
+                  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(s4.x), "=f"(s4.y), "=f"(s4.z), "=f"(s4.w) : "r"(cf + 16u * m));
+                  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                               : "=f"(h4.x), "=f"(h4.y), "=f"(h4.z), "=f"(h4.w)
+                               : "r"(cf + 64u * KS + 16u * m));
+#pragma unroll
+                  for (int l = 0; l < LB; ++l) {
+                    const int i = i0 + l;
+                    if (i >= lo && i < hi) {
+                      Pack<T, 2> e0 = *reinterpret_cast<Pack<T, 2>*>(&v[l][2 * m]);
+                      Pack<T, 2> e1 = *reinterpret_cast<Pack<T, 2>*>(&v[l][2 * m + 1]);
+                      e0.v[0] = from_f<T>(xl_silu<FUSE>(fmaf(to_f<T>(e0.v[0]), s4.x, h4.x)));
+                      e0.v[1] = from_f<T>(xl_silu<FUSE>(fmaf(to_f<T>(e0.v[1]), s4.y, h4.y)));
+                      e1.v[0] = from_f<T>(xl_silu<FUSE>(fmaf(to_f<T>(e1.v[0]), s4.z, h4.z)));
+                      e1.v[1] = from_f<T>(xl_silu<FUSE>(fmaf(to_f<T>(e1.v[1]), s4.w, h4.w)));
+                      v[l][2 * m] = *reinterpret_cast<uint32_t*>(&e0);
+                      v[l][2 * m + 1] = *reinterpret_cast<uint32_t*>(&e1);
+                    }
+                  }
+                }
+              }
+#pragma unroll
+              for (int l = 0; l < LB; ++l) {
+                const int i = i0 + l;
+                if (i >= lo && i < hi) {
+                  const uint32_t src = sm_raw + (uint32_t)rs * 2u * LINE + (uint32_t)(i - 2 * pr) * LINE + (uint32_t)xv * VOX;
+#pragma unroll
+                  for (int j = 0; j < W / 4; ++j)
+                    st_shared_v4(src + 16u * j, make_uint4(v[l][4 * j], v[l][4 * j + 1], v[l][4 * j + 2], v[l][4 * j + 3]));
+                  if (zown && i >= 1 && i <= BY) {
+                    char* dst = ab + (long long)n * p.asn_b + (long long)pz * p.asd_b + (long long)(y0 - 1 + i) * p.ash_b + (long long)xv * VOX;
+#pragma unroll
+                    for (int j = 0; j < W / 4; ++j)
+                      *reinterpret_cast<uint4*>(dst + 16 * j) = make_uint4(v[l][4 * j], v[l][4 * j + 1], v[l][4 * j + 2], v[l][4 * j + 3]);
+                  }
+                }
+              }
+              if (team) asm volatile("bar.sync 2, 128;" ::: "memory"); else asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+              for (int l = 0; l < LB; ++l) {
+                const int i = i0 + l;
+                if (i >= lo && i < hi) {
+                  const uint32_t src = sm_raw + (uint32_t)rs * 2u * LINE + (uint32_t)(i - 2 * pr) * LINE + (uint32_t)xv * VOX;
+#pragma unroll
+                  for (int j = 0; j < W / 4; ++j) {
+                    if (xv > 0)
+                      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                   : "=r"(lf[l][4 * j]), "=r"(lf[l][4 * j + 1]), "=r"(lf[l][4 * j + 2]), "=r"(lf[l][4 * j + 3])
+                                   : "r"(src - VOX + 16u * j));
+                    else lf[l][4 * j] = lf[l][4 * j + 1] = lf[l][4 * j + 2] = lf[l][4 * j + 3] = 0u;
+                    if (xv < 127)
+                      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                   : "=r"(rt[l][4 * j]), "=r"(rt[l][4 * j + 1]), "=r"(rt[l][4 * j + 2]), "=r"(rt[l][4 * j + 3])
+                                   : "r"(src + VOX + 16u * j));
+                    else rt[l][4 * j] = rt[l][4 * j + 1] = rt[l][4 * j + 2] = rt[l][4 * j + 3] = 0u;
+                  }
+                }
+              }
+            } else {
 #pragma unroll
             for (int l = 0; l < LB; ++l) {
               const int i = i0 + l;
@@ -455,6 +459,7 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
                   else rt[l][4 * j] = rt[l][4 * j + 1] = rt[l][4 * j + 2] = rt[l][4 * j + 3] = 0u;
                 }
               }
+            }
             }
 #pragma unroll
             for (int l = 0; l < LB; ++l) {
@@ -631,7 +636,7 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, 512);
+  if (warp == 12) tmem_dealloc(tmem, 512);
 }
 
 // Weights of the x-line kernel: [r][dx][k][row = dy*48 + s*16 + co][kk], ci = 16 k + kk, tap dz = (r + 1 - s) mod 3, each
@@ -777,7 +782,7 @@ template <typename T, int KS, int BY>
 static int launch_xline(const ActView& x, const void* w, const float* bias, const ActView& y, const ActView* a_out, const float* scale,
                         const float* shift, int fuse, double* stats, XlineParams p, cudaStream_t st) {
   constexpr int NR = KS == 1 ? 8 : 3;
-  const size_t smem = 27u * KS * kXlTileBytes + (size_t)NR * 2u * 4096u * KS + 4u * (2u * 64u * KS) + 1024u;
+  const size_t smem = 27u * KS * kXlTileBytes + (size_t)NR * 2u * 4096u * KS + 8u * (2u * 64u * KS) + 1024u;
   {
     const char* e = getenv("B200_XL_ABLATE");
     p.ablate = e ? atoi(e) : 0;
@@ -810,7 +815,7 @@ static int launch_xline(const ActView& x, const void* w, const float* bias, cons
   {                                                                                                                    \
     auto kern = conv_fprop_xline_kernel<T, KS, BY, F>;                                                                 \
     B200_CUDA(raise_dyn_smem_cap(kern));                                                                               \
-    kern<<<grid, F ? 640 : 448, smem, st>>>((const T*)x.data, (const T*)w, bias, (T*)y.data, ap, scale, shift, stats, p);       \
+    kern<<<grid, 448, smem, st>>>((const T*)x.data, (const T*)w, bias, (T*)y.data, ap, scale, shift, stats, p);       \
   }
   if (fuse == 0) XL_LAUNCH(0)
   else if (fuse == 1) XL_LAUNCH(1)

@@ -128,11 +128,12 @@ class Tape:
         self.pool_dense = os.environ.get("B200_POOL_DENSE", "1") != "0"
         # x-line kernel (csrc/conv_xline.cu): B200_XLINE = 0 off, 1 (default) where it measured faster than the x-folded kernels
         # (profiles/xline_probe_r2_*.log: Cin = 48 and non-accumulating Cin = 16 launches), 2 every launch it supports.
-        # B200_XLINE_FUSE = auto (default): GroupNorm-apply + SiLU on the operand path when the one-MUFU chain is the engine's
-        # chain (bf16: ops.norm_fast_ok); 1: also with the exact chain (fp16 -- measured slower than the two separate launches,
-        # the activation warps become the bottleneck); 0: never.
+        # B200_XLINE_FUSE = 1: GroupNorm-apply + SiLU on the operand path of that convolution (the fused Conv3D + GN + SiLU launch).
+        # Off by default: measured on the B200 the fused launch costs what the plain launch + the stand-alone HBM-speed apply pass
+        # cost for 16 channels (0.31 vs 0.22 + 0.09 ms) and more for 48 (0.77 vs 0.40 + 0.28 ms) -- the activation arithmetic sits on
+        # the issue-bound staging warps and every input line is staged 1.4-1.7 times (band / z-chunk halo); DESIGN 3.2d.
         self.xline = int(os.environ.get("B200_XLINE", "1"))
-        self.xline_fuse = os.environ.get("B200_XLINE_FUSE", "auto").lower()
+        self.xline_fuse = os.environ.get("B200_XLINE_FUSE", "0").lower()
         self.param_grads: Dict[torch.nn.Parameter, torch.Tensor] = {}
         # key -> (pack job, packed tensor) of every weight pack this pass launched on its own (Trainer: replayed as one launch)
         self.pack_record: Optional[Dict] = None
@@ -240,12 +241,9 @@ class Tape:
     def _fuse_mode(self, x: torch.Tensor) -> int:
         """0 = keep normalisation-apply + SiLU as its own launch; 1 / 2 = apply it inside the x-line convolution with the exact /
         one-MUFU chain -- always the chain `ops.scale_shift_act` would run for this tensor, so both routes store the same bits."""
-        if self.xline <= 0 or self.xline_fuse in ("0", "off") or self.dtype == torch.float32:
+        if self.xline <= 0 or self.xline_fuse not in ("1", "on") or self.dtype == torch.float32:
             return 0
-        fast = ops.norm_fast_ok(x)
-        if fast:
-            return 2
-        return 1 if self.xline_fuse == "1" else 0
+        return 2 if ops.norm_fast_ok(x) else 1
 
     @staticmethod
     def _k3(k) -> Tuple[int, int, int]:

@@ -38,6 +38,7 @@ KERNELS = {
     "ends.cu": ["select_hist_kernel", "edge_hist_kernel"],
     "stitch.cu": ["overlap_add_kernel", "overlap_add_cover_kernel", "overlap_add_slot_kernel"],
     "conv_umma.cu": ["pack_weight_xfold_kernel", "pack_convT_weight_kernel", "unpack_convT_wgrad_kernel"],
+    "conv_xline.cu": ["pack_weight_xline_kernel"],
 }
 # helper definitions that sit right above a kernel and are cut out together with it
 PREAMBLE = {
