@@ -38,6 +38,21 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                ::"r"(dst), "l"((uint64_t)src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// global[dst .. dst + bytes) += shared[src ..) element-wise in the 16-bit type T, formed in L2 by the bulk-copy engine
+template <typename T>
+__device__ __forceinline__ void bulk_reduce_add(void* dst, uint32_t src, uint32_t bytes);
+template <>
+__device__ __forceinline__ void bulk_reduce_add<__half>(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.noftz.f16 [%0], [%1], %2;"
+               ::"l"((uint64_t)dst), "r"(src), "r"(bytes)
+               : "memory");
+}
+template <>
+__device__ __forceinline__ void bulk_reduce_add<__nv_bfloat16>(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.noftz.bf16 [%0], [%1], %2;"
+               ::"l"((uint64_t)dst), "r"(src), "r"(bytes)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
@@ -110,6 +125,7 @@ struct XlineParams {
   long long ash_b, asd_b, asn_b;   // same for the optional activated copy
   long long ysw, ysh, ysd, ysn;    // element strides of the output
   int accumulate;
+  int acc_bulk;                    // accumulate through the bulk-copy engine's element-wise add (dense output lines, no statistics)
   uint32_t idesc, idesc96, idesc144;   // N = 48 / 96 / 144
   int ablate;                      // B200_XL_ABLATE bits: 1 no MMA, 2 no activation math, 4 no operand stores, 8 no output,
                                    // 16 no bulk copies, 32 no accumulator zeroing, 64 no operand loads (timing experiments only)
@@ -162,7 +178,7 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
   __shared__ uint64_t s_bar[3 * NR + 2 * NA + 2 * BY + 1];
   __shared__ uint32_t s_tmem;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sm_b = smem0, sm_raw = smem0 + BBYTES, sm_cf = sm_raw + NR * 2u * LINE;
+  const uint32_t sm_b = smem0, sm_raw = smem0 + BBYTES, sm_cf = sm_raw + NR * 2u * LINE, sm_epi = sm_cf + 8u * CFB;
   const uint32_t bar0 = smem_u32(s_bar);
   const uint32_t raw_full = bar0, raw_free = raw_full + 8 * NR, xf_full = raw_free + 8 * NR, a_full = xf_full + 8 * NR,
                  a_free = a_full + 8 * NA, acc_full = a_free + 8 * NA, acc_free = acc_full + 8 * BY, w_full = acc_free + 8 * BY;
@@ -519,7 +535,7 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
     float bs[16];
 #pragma unroll
     for (int c = 0; c < 16; ++c) bs[c] = bias ? __ldg(bias + c) : 0.f;
-    uint32_t pc = 0;
+    uint32_t pc = 0, ebuf = 0;
     for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
       int n, z0, zhi, y0;
       decode(u, n, z0, zhi, y0);
@@ -536,7 +552,7 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
         for (int g0 = 0; g0 < BY; g0 += G) {
           uint32_t r[G][16];
           uint4 old[G][2];
-          if (p.accumulate && sv) {
+          if (p.accumulate && !p.acc_bulk && sv) {
 #pragma unroll
             for (int l = 0; l < G; ++l)
               if (y0 + g0 + l < p.h) {
@@ -578,6 +594,10 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(acc_free + 8 * (g0 >> 1));
+          if (p.acc_bulk && sv) {           // the adds that read this staging buffer two groups ago have finished reading it
+            if (lane == 0) bulk_wait_group_read<1>();
+            __syncwarp();
+          }
           if (sv && !(p.ablate & 8)) {
 #pragma unroll
             for (int l = 0; l < G; ++l) {
@@ -586,7 +606,7 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
                 float f[16];
 #pragma unroll
                 for (int c = 0; c < 16; ++c) f[c] = __uint_as_float(r[l][c]) + bs[c];
-                if (p.accumulate) {
+                if (p.accumulate && !p.acc_bulk) {
                   const Pack<T, 8> o0 = *reinterpret_cast<const Pack<T, 8>*>(&old[l][0]);
                   const Pack<T, 8> o1 = *reinterpret_cast<const Pack<T, 8>*>(&old[l][1]);
 #pragma unroll
@@ -601,8 +621,20 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
                   w0.v[c] = from_f<T>(f[c]);
                   w1.v[c] = from_f<T>(f[8 + c]);
                 }
-                *reinterpret_cast<Pack<T, 8>*>(yp) = w0;
-                *reinterpret_cast<Pack<T, 8>*>(yp + 8) = w1;
+                if (p.acc_bulk) {
+                  // residual / shared-gradient form on dense lines: the warp's 32 voxels (1 KB) are staged in shared memory and
+                  // leave as ONE element-wise add of the bulk-copy engine (the sum is formed in L2 on the rounded value, like the
+                  // x-slab kernel's TMA add): no read of the old value through the SM
+                  const uint32_t stg = sm_epi + ((uint32_t)(q * 2 + (int)ebuf) * G + (uint32_t)l) * 1024u;
+                  st_shared_v4(stg + (uint32_t)lane * 32u, *reinterpret_cast<const uint4*>(&w0));
+                  st_shared_v4(stg + (uint32_t)lane * 32u + 16u, *reinterpret_cast<const uint4*>(&w1));
+                  fence_proxy_async();
+                  __syncwarp();
+                  if (lane == 0) bulk_reduce_add<T>(yp - (long long)lane * p.ysw, stg, 1024u);
+                } else {
+                  *reinterpret_cast<Pack<T, 8>*>(yp) = w0;
+                  *reinterpret_cast<Pack<T, 8>*>(yp + 8) = w1;
+                }
                 if (stats != nullptr) {
 #pragma unroll
                   for (int c = 0; c < 16; ++c) {
@@ -613,6 +645,10 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
                 }
               }
             }
+          }
+          if (p.acc_bulk && sv) {
+            if (lane == 0) bulk_commit_group();
+            ebuf ^= 1u;
           }
         }
       }
@@ -632,6 +668,7 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
         }
       }
     }
+    if (p.acc_bulk && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the adds have been performed
     if (d0) { dbg[7] = clock64() - t_begin; dbg[8] = w_full_acc; }
   }
   tc_fence_before();
@@ -782,7 +819,7 @@ template <typename T, int KS, int BY>
 static int launch_xline(const ActView& x, const void* w, const float* bias, const ActView& y, const ActView* a_out, const float* scale,
                         const float* shift, int fuse, double* stats, XlineParams p, cudaStream_t st) {
   constexpr int NR = KS == 1 ? 8 : 3;
-  const size_t smem = 27u * KS * kXlTileBytes + (size_t)NR * 2u * 4096u * KS + 8u * (2u * 64u * KS) + 1024u;
+  const size_t smem = 27u * KS * kXlTileBytes + (size_t)NR * 2u * 4096u * KS + 8u * (2u * 64u * KS) + 16384u + 1024u;
   {
     const char* e = getenv("B200_XL_ABLATE");
     p.ablate = e ? atoi(e) : 0;
@@ -858,6 +895,10 @@ int conv_fprop_xline_v(const ActView& x, const void* w, const float* bias, const
   if (a_out) { p.ash_b = a_out->sh * 2; p.asd_b = a_out->sd * 2; p.asn_b = a_out->sn * 2; }
   p.ysw = y.sw; p.ysh = y.sh; p.ysd = y.sd; p.ysn = y.sn;
   p.accumulate = accumulate;
+  {
+    const char* e = getenv("B200_XL_ACC_BULK");
+    p.acc_bulk = accumulate && stats == nullptr && y.sw == 16 && (!e || atoi(e)) ? 1 : 0;
+  }
   p.idesc = make_idesc(x.dtype == B200_BF16, 48, 0, 0);
   p.idesc96 = make_idesc(x.dtype == B200_BF16, 96, 0, 0);
   p.idesc144 = make_idesc(x.dtype == B200_BF16, 144, 0, 0);

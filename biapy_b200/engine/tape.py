@@ -127,7 +127,7 @@ class Tape:
         self.fuse_stats = os.environ.get("B200_FUSE_STATS", "1") != "0"
         self.pool_dense = os.environ.get("B200_POOL_DENSE", "1") != "0"
         # x-line kernel (csrc/conv_xline.cu): B200_XLINE = 0 off, 1 (default) where it measured faster than the x-folded kernels
-        # (profiles/xline_probe_r2_*.log: Cin = 48 and non-accumulating Cin = 16 launches), 2 every launch it supports.
+        # (profiles/xline_probe_r2_*.log: the Cin = 48 launches, 0.39 vs 0.62 ms), 2 every launch it supports (Cin = 16 as well).
         # B200_XLINE_FUSE = 1: GroupNorm-apply + SiLU on the operand path of that convolution (the fused Conv3D + GN + SiLU launch).
         # Off by default: measured on the B200 the fused launch costs what the plain launch + the stand-alone HBM-speed apply pass
         # cost for 16 channels (0.31 vs 0.22 + 0.09 ms) and more for 48 (0.77 vs 0.40 + 0.28 ms) -- the activation arithmetic sits on
@@ -226,8 +226,8 @@ class Tape:
         if (self.xline <= 0 or self.impl != _lib.IMPL_AUTO or self.dtype == torch.float32 or tuple(k) != (3, 3, 3)
                 or x.shape[3] != 128 or y.shape[4] != 16 or x.shape[4] not in (16, 48)):
             return False
-        if self.xline == 1 and not fused and accumulate and x.shape[4] == 16:
-            return False        # 16 -> 16 with the residual add: the x-folded kernel's TMA element-wise add is faster
+        if self.xline == 1 and not fused and x.shape[4] == 16:
+            return False        # 16 -> 16: on a par with the x-slab kernel (0.22-0.28 vs 0.23-0.27 ms over five boxes); 48 -> 16: 1.6x faster
         return ops.conv_xline_supported(x, y, k)
 
     def _xline_launch(self, x, w, flip, bias, y, accumulate, wkey, stats, scale=None, shift=None, fuse=0, a_out=None):

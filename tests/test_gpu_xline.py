@@ -42,7 +42,11 @@ CASES = [
     (1, 6, 16, 16, torch.bfloat16, 2, False, True, True, False, None),
     (1, 6, 12, 48, torch.float16, 1, False, False, True, False, None),
     (2, 5, 12, 48, torch.bfloat16, 2, False, True, True, False, None),
-    (2, 5, 16, 16, torch.float16, 0, True, False, False, False, None),           # residual form
+    (2, 5, 16, 16, torch.float16, 0, True, False, False, False, None),           # residual form: bulk element-wise add in L2
+    (2, 9, 24, 16, torch.bfloat16, 0, True, False, False, False, None),
+    (1, 5, 16, 16, torch.float16, 0, True, True, False, False, None),            # residual form + statistics: read-add-write
+    (1, 5, 16, 16, torch.float16, 0, True, False, False, False, 48),             # residual form into a channel slice
+    (1, 6, 8, 48, torch.float16, 0, True, False, False, False, None),
     (1, 5, 16, 16, torch.float16, 1, True, False, True, False, None),            # fused + residual
     (1, 5, 16, 16, torch.float16, 0, False, False, False, True, None),           # dgrad packing
     (1, 5, 8, 48, torch.float16, 0, False, False, False, True, None),
@@ -86,6 +90,9 @@ def test_xline_against_aten(n, d, h, cin, dtype, fuse, accumulate, stats, a_out,
     if accumulate:
         old = torch.randn(y.shape, device=dev, generator=g).to(dtype)
         y.copy_(old)
+        if ld_y:
+            ybuf[..., :8] = 0
+            ybuf[..., 24:] = 0
     ao = torch.empty_like(x) if a_out else None
     sums = torch.zeros(n * 16 * 2, dtype=torch.float64, device=dev) if stats else None
     assert ops.conv_xline_supported(x, y, (3, 3, 3))
