@@ -234,14 +234,18 @@ int b200_conv_fprop_stats(const b200_tensor* x, const void* w_packed_xfold, cons
 int b200_pack_conv_weight_xfold(const float* w, void* packed, int32_t dtype, int32_t cout, int32_t cin, int32_t kd,
                                 int32_t kh, int32_t kw, int32_t flip_transpose, void* stream);
 /* x-line kernel (csrc/conv_xline.cu): 3x3x3 convolution of the Cout = 16 layers at W = 128 (Cin = 16 or 48, dense channels-last
- * input) with the operand in tensor memory, and -- the "Conv3D + GroupNorm + SiLU" fusion of the reference's pre-activation
- * order GN(in) -> act -> conv (biapy/models/blocks.py:1304-1378) -- the normalisation-apply + activation of its INPUT on the
- * operand path:  fuse = 0: y (+)= conv(x) + bias;  fuse = 1 / 2: a = silu(x * scale[n,c] + shift[n,c]) (arithmetic of
- * b200_scale_shift_act / b200_scale_shift_silu_fast, rounded to the engine dtype exactly like their stored result),
- * y (+)= conv(a) + bias, and a_out (nullable; dense, x's shape) receives a for the backward pass.  sums (nullable): double
- * [N][16][2] += (sum y, sum y*y) of the stored output, as b200_conv_fprop_stats.  Weights: b200_pack_conv_weight_xline
- * (27 * Cin/16 tiles of 48 x 16 elements: [r][dy][dx][k][(s, co)][ci] with tap dz = (r + 1 - s) mod 3; flip_transpose = 1 packs
- * the dgrad operand).  b200_conv_xline_supported: 1 when (x, y, kernel) qualify and B200_XLINE != 0. */
+ * input) -- one GEMM row per voxel, the A operand (a line and its two x-shifted copies) in tensor memory, no block-Toeplitz zeros
+ * -- and the "Conv3D + GroupNorm + SiLU" fusion of the reference's pre-activation order GN(in) -> act -> conv
+ * (biapy/models/blocks.py:1304-1378; conv -> norm -> act of blocks.py:148-160 is this launch's `sums` + the next one's `fuse`):
+ *   fuse = 0: y (+)= conv(x) + bias;
+ *   fuse = 1 / 2: a = silu(x * scale[n,c] + shift[n,c]) -- the arithmetic of b200_scale_shift_act (1) / b200_scale_shift_silu_fast
+ *     (2), rounded to the engine dtype exactly like their stored result -- then y (+)= conv(a) + bias; a_out (nullable; dense, x's
+ *     shape) receives a for the backward pass, bit-identical to the stand-alone launch.
+ * sums (nullable): double [N][16][2] += (sum y, sum y*y) of the stored output, as b200_conv_fprop_stats.  accumulate on dense
+ * output lines without sums is an element-wise add of the bulk-copy engine (formed in L2 on the rounded value).
+ * Weights: b200_pack_conv_weight_xline -- 9 * Cin/16 tiles [r][dx][k] of 144 x 16 elements, row dy*48 + s*16 + co, column ci - 16k,
+ * tap dz = (r + 1 - s) mod 3 (r = input plane mod 3, s = output plane mod 3), each tile in the SWIZZLE_32B K-major shared-memory
+ * image; flip_transpose = 1 packs the dgrad operand.  b200_conv_xline_supported: 1 when (x, y, kernel) qualify and B200_XLINE != 0. */
 int b200_conv_xline_supported(const b200_tensor* x, const b200_tensor* y, int32_t kd, int32_t kh, int32_t kw);
 int b200_pack_conv_weight_xline(const float* w, void* packed, int32_t dtype, int32_t cout, int32_t cin, int32_t flip_transpose,
                                 void* stream);
