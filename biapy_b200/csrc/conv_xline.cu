@@ -151,13 +151,13 @@ __device__ __forceinline__ void xl_wait_lean(uint32_t bar, uint32_t parity) {
   if (!mbar_try_wait(bar, parity)) xl_wait_slow(bar, parity);
 }
 
-template <typename T, int KS, int BY, int FUSE>
+template <typename T, int KS, int BY, int FUSE, int CO16>
 __global__ void __launch_bounds__(448, 1)
 conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, const float* __restrict__ bias, T* __restrict__ y,
                         T* __restrict__ a_out, const float* __restrict__ scale, const float* __restrict__ shift,
                         double* __restrict__ stats, const XlineParams p) {
   constexpr int NR = KS == 1 ? 8 : 3;            // raw ring: slots of two lines
-  constexpr int NA = KS == 1 ? 5 : 3;            // operand ring in tensor memory: slots of one line (three shifted copies)
+  constexpr int NA = KS == 1 ? (CO16 == 1 ? 5 : 4) : 3;   // operand ring in tensor memory: slots of one line (three shifted copies)
   constexpr int NL = BY + 2;                     // input lines of a band
   constexpr int PAIRS = NL / 2;
   constexpr int LB = KS == 1 ? 2 : 1;            // lines a staging iteration handles together
@@ -165,14 +165,17 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
   constexpr uint32_t LINE = 4096u * KS;
   constexpr uint32_t VOX = 32u * KS;             // bytes per voxel
   constexpr uint32_t ACOLS = 24u * KS;
-  constexpr uint32_t ACC = (uint32_t)BY * 48u;
-  constexpr uint32_t BBYTES = 27u * KS * kXlTileBytes;
+  constexpr uint32_t LBK = 48u * CO16;           // accumulator columns of one output line: 3 output planes x Cout
+  constexpr uint32_t ACC = (uint32_t)BY * LBK;
+  constexpr uint32_t BBYTES = 27u * KS * CO16 * kXlTileBytes;   // 9 KS (Cout 16) / 27 KS (Cout 48) tiles of 144 rows
   constexpr uint32_t TSTEP = 3u * kXlTileBytes >> 4;   // one (r, dx, k) tile of 144 rows, in 16-byte units
   constexpr int W = 8 * KS;                      // 32-bit words per voxel
   constexpr uint32_t CFB = 2u * 16u * KS * 4u;   // coefficient table per activation warp: scale[Cin], shift[Cin]
   // The operand slot of a line is its POSITION in the band modulo NA (lines outside the volume pass through as empty slots), so
   // every tensor-memory address and barrier parity of the MMA thread is a compile-time constant of the unrolled line loop.
-  static_assert(BY % 2 == 0 && G == 2 && NL % NA == 0 && (NL / NA) % 2 == 0 && ACC + NA * ACOLS <= 512, "tensor memory budget / static slots");
+  constexpr int TPP = NL / NA;                   // turns of the operand ring per plane: the barrier parity of line i in the vp-th
+  static_assert(BY % 2 == 0 && G == 2 && NL % NA == 0 && ACC + NA * ACOLS <= 512 && (CO16 == 1 || (CO16 == 3 && FUSE == 0)),   // processed plane is (vp * TPP + i / NA) & 1
+                "tensor memory budget / static slots");
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t s_bar[3 * NR + 2 * NA + 2 * BY + 1];
@@ -270,7 +273,7 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
       const uint32_t b_lo0 = ((sm_b >> 4) & 0x3FFFu) | (1u << 16);
       const uint32_t abase0 = tmem + ACC;
       xl_wait(w_full, 0);
-      uint32_t pc = 0;
+      uint32_t pc = 0, vp = 0;
       long long nlines = 0;
       for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
         int n, z0, zhi, y0;
@@ -288,10 +291,12 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
             }
             continue;
           }
-          const uint32_t b_r = b_lo0 + (uint32_t)xl_mod3(pz) * (3u * KS * TSTEP);
+          const uint32_t b_r = b_lo0 + (uint32_t)xl_mod3(pz) * (3u * KS * (CO16 == 1 ? 1u : 3u) * TSTEP);
+          const uint32_t podd = (TPP & 1) ? (vp & 1u) : 0u;
+          ++vp;
           // The state of the NEXT line's barriers is sampled (test_wait: never blocks) before this line's MMAs are issued, so the
           // ~100-cycle round trip of a barrier query hides behind the issue of the MMAs instead of preceding every line.
-          bool ok_a = mbar_test_wait(a_full, 0u);
+          bool ok_a = mbar_test_wait(a_full, podd);
           bool ok_c = mbar_test_wait(acc_free, par);
 #pragma unroll
           for (int i = 0; i < NL; ++i) {
@@ -299,24 +304,37 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
             if (i < BY && (i & 1) == 0) {           // first touch of output lines (i, i + 1) in this plane
               if (!ok_c) xl_wait_slow(acc_free + 8 * (i >> 1), par);
             }
-            if (!ok_a) xl_wait_slow(a_full + 8 * slot, (uint32_t)((i / NA) & 1));
+            if (!ok_a) xl_wait_slow(a_full + 8 * slot, podd ^ (uint32_t)((i / NA) & 1));
             tc_fence_after();
             if (i + 1 < NL) {
-              ok_a = mbar_test_wait(a_full + 8 * (uint32_t)((i + 1) % NA), (uint32_t)(((i + 1) / NA) & 1));
+              ok_a = mbar_test_wait(a_full + 8 * (uint32_t)((i + 1) % NA), podd ^ (uint32_t)(((i + 1) / NA) & 1));
               if (i + 1 < BY && ((i + 1) & 1) == 0) ok_c = mbar_test_wait(acc_free + 8 * ((i + 1) >> 1), par);
             }
             if ((vmask >> i) & 1u) {
               ++nlines;
               if (!(p.ablate & 1)) {
                 const uint32_t a_b = abase0 + slot * ACOLS;
-                const int o_hi = i < BY ? i : BY - 1;                 // highest output line this input line feeds
-                const uint32_t d_t = tmem + (uint32_t)(BY - 1 - o_hi) * 48u;
-                const uint32_t ro = i < BY ? 0u : (uint32_t)(i - BY + 1) * (kXlTileBytes >> 4);   // first B row = 48 * (i - o_hi)
-                const int o_lo = i >= 2 ? i - 2 : 0;
-                const int nrows = (o_hi - o_lo + 1) * 48;
-                const uint32_t idesc = nrows == 144 ? id144 : (nrows == 96 ? id96 : id48);
+                if constexpr (CO16 == 1) {
+                  const int o_hi = i < BY ? i : BY - 1;                 // highest output line this input line feeds
+                  const uint32_t d_t = tmem + (uint32_t)(BY - 1 - o_hi) * 48u;
+                  const uint32_t ro = i < BY ? 0u : (uint32_t)(i - BY + 1) * (kXlTileBytes >> 4);   // first B row = 48 * (i - o_hi)
+                  const int o_lo = i >= 2 ? i - 2 : 0;
+                  const int nrows = (o_hi - o_lo + 1) * 48;
+                  const uint32_t idesc = nrows == 144 ? id144 : (nrows == 96 ? id96 : id48);
 #pragma unroll
-                for (int t = 0; t < 3 * KS; ++t) umma_f16_ts(d_t, a_b + 8u * t, b_r + (uint32_t)t * TSTEP + ro, b_hi, idesc, 1u);
+                  for (int t = 0; t < 3 * KS; ++t) umma_f16_ts(d_t, a_b + 8u * t, b_r + (uint32_t)t * TSTEP + ro, b_hi, idesc, 1u);
+                } else {
+                  // Cout = 48: one output line is 144 columns (3 planes x 48 channels), one MMA per (dy, dx, k)
+#pragma unroll
+                  for (int dy = 0; dy < 3; ++dy) {
+                    const int o = i - dy;
+                    if (o < 0 || o >= BY) continue;
+                    const uint32_t d_t = tmem + (uint32_t)(BY - 1 - o) * LBK;
+#pragma unroll
+                    for (int t = 0; t < 3 * KS; ++t)
+                      umma_f16_ts(d_t, a_b + 8u * t, b_r + (uint32_t)(dy * 3 * KS + t) * TSTEP, b_hi, id144, 1u);
+                  }
+                }
               }
             }
             if (i >= 3 && (i & 1)) umma_commit(acc_full + 8 * ((i - 3) >> 1));   // output lines i - 3 and i - 2 are complete
@@ -343,7 +361,7 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
     const long long t_begin = d0 ? clock64() : 0;
     long long w_in = 0, w_afree = 0;
     int rs = 0;
-    uint32_t rph = 0;
+    uint32_t rph = 0, vp = 0;
     for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
       int n, z0, zhi, y0;
       decode(u, n, z0, zhi, y0);
@@ -359,6 +377,8 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
       for (int pz = z0 - 1; pz <= zhi; ++pz) {
         if ((unsigned)pz >= (unsigned)p.d) continue;
         const bool zown = FUSE != 0 && a_out != nullptr && pz >= z0 && pz < zhi;
+        const uint32_t podd = (TPP & 1) ? (vp & 1u) : 0u;
+        ++vp;
 #pragma unroll 1
         for (int pr = 0; pr < PAIRS; ++pr) {
           int lo, hi;
@@ -375,7 +395,7 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
             bool ok_f[LB];
 #pragma unroll
             for (int l = 0; l < LB; ++l)      // sampled here, consumed after the loads: the query's latency overlaps them
-              ok_f[l] = mbar_test_wait(a_free + 8 * (uint32_t)((i0 + l) % NA), (uint32_t)((((i0 + l) / NA) & 1) ^ 1));
+              ok_f[l] = mbar_test_wait(a_free + 8 * (uint32_t)((i0 + l) % NA), podd ^ (uint32_t)((((i0 + l) / NA) & 1) ^ 1));
             if constexpr (FUSE != 0) {
               // fused GroupNorm-apply + SiLU: every thread activates its own voxel(s) in place in the ring (and stores them to
               // a_out), the team meets at its own named barrier, then the neighbours are read like raw voxels
@@ -481,7 +501,7 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
             for (int l = 0; l < LB; ++l) {
               const int i = i0 + l;
               const uint32_t fb = a_free + 8 * (uint32_t)(i % NA);
-              const uint32_t fp = (uint32_t)(((i / NA) & 1) ^ 1);
+              const uint32_t fp = podd ^ (uint32_t)(((i / NA) & 1) ^ 1);
               if (!ok_f[l]) { if (d0) wait_on(fb, fp, w_afree); else xl_wait(fb, fp); }
             }
             tc_fence_after();
@@ -545,9 +565,53 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
       for (int pz = z0 - 1; pz <= zhi; ++pz, ++pc) {
         const int zo = pz - 1;
         const bool sv = zo >= z0 && zo < zhi;
-        const uint32_t cs = (uint32_t)xl_mod3(zo) * 16u;
+        const uint32_t cs = (uint32_t)xl_mod3(zo) * 16u * CO16;
         const bool last = pz == zhi;
         T* const yplane = y + (long long)n * p.ysn + (long long)zo * p.ysd + (long long)xv * p.ysw;
+        if constexpr (CO16 == 3) {
+          // Cout = 48 (input gradient of the 48 -> 16 layer): 48 columns per plane block, 96 bytes per voxel, line by line
+#pragma unroll 1
+          for (int g0 = 0; g0 < BY; g0 += G) {
+            if (d0) wait_on(acc_full + 8 * (g0 >> 1), pc & 1, w_full_acc); else xl_wait(acc_full + 8 * (g0 >> 1), pc & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int l = 0; l < G; ++l) {
+              const uint32_t col = t_lane + (uint32_t)(BY - 1 - g0 - l) * LBK;
+              const bool st = sv && y0 + g0 + l < p.h && !(p.ablate & 8);
+              uint32_t r[3][16];
+              if (st) {
+#pragma unroll
+                for (int cb = 0; cb < 3; ++cb) tmem_ld16(col + cs + 16u * cb, r[cb]);
+                tmem_ld_wait();
+              }
+              if (last) {
+#pragma unroll
+                for (int j = 0; j < 9; ++j) tmem_st16_zero(col + 16u * j);
+              } else {
+#pragma unroll
+                for (int cb = 0; cb < 3; ++cb) tmem_st16_zero(col + cs + 16u * cb);
+              }
+              if (st) {
+                T* yp = yplane + (long long)(y0 + g0 + l) * p.ysh;
+#pragma unroll
+                for (int cb = 0; cb < 3; ++cb) {
+                  Pack<T, 8> w0, w1;
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) {
+                    w0.v[c] = from_f<T>(__uint_as_float(r[cb][c]) + (bias ? __ldg(bias + cb * 16 + c) : 0.f));
+                    w1.v[c] = from_f<T>(__uint_as_float(r[cb][8 + c]) + (bias ? __ldg(bias + cb * 16 + 8 + c) : 0.f));
+                  }
+                  *reinterpret_cast<Pack<T, 8>*>(yp + cb * 16) = w0;
+                  *reinterpret_cast<Pack<T, 8>*>(yp + cb * 16 + 8) = w1;
+                }
+              }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_free + 8 * (g0 >> 1));
+          }
+        } else {
 #pragma unroll 1
         for (int g0 = 0; g0 < BY; g0 += G) {
           uint32_t r[G][16];
@@ -575,13 +639,13 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
           if (sv && !(p.ablate & 8)) {
 #pragma unroll
             for (int l = 0; l < G; ++l)
-              if (y0 + g0 + l < p.h) tmem_ld16(t_lane + (uint32_t)(BY - 1 - g0 - l) * 48u + cs, r[l]);
+              if (y0 + g0 + l < p.h) tmem_ld16(t_lane + (uint32_t)(BY - 1 - g0 - l) * LBK + cs, r[l]);
             tmem_ld_wait();
           }
 #pragma unroll
           for (int l = 0; l < G; ++l) {
             if (p.ablate & 32) break;
-            const uint32_t col = t_lane + (uint32_t)(BY - 1 - g0 - l) * 48u;
+            const uint32_t col = t_lane + (uint32_t)(BY - 1 - g0 - l) * LBK;
             if (last) {
               tmem_st16_zero(col);
               tmem_st16_zero(col + 16u);
@@ -652,6 +716,7 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
           }
         }
       }
+        }
       if (stats != nullptr) {
 #pragma unroll 1
         for (int c = 0; c < 16; ++c) {
@@ -676,31 +741,44 @@ conv_fprop_xline_kernel(const T* __restrict__ x, const T* __restrict__ wpk, cons
   if (warp == 12) tmem_dealloc(tmem, 512);
 }
 
-// Weights of the x-line kernel: [r][dx][k][row = dy*48 + s*16 + co][kk], ci = 16 k + kk, tap dz = (r + 1 - s) mod 3, each
-// (144 x 16) tile in the SWIZZLE_32B K-major shared-memory image (16-byte half kk >> 3 of row rr sits at half ^ ((rr >> 2) & 1)),
-// so the whole matrix is ONE linear bulk copy and the three dy taps of a (dx, k) pair are one N = 144 operand (48-row sub-ranges
-// at the band edges).  flip: dgrad operand W'[ci][co][2-dz][2-dy][2-dx].
+// Weights of the x-line kernel.  Cout' = 16: [r][dx][k][row = dy*48 + s*16 + co][kk]; Cout' = 48: [r][dy][dx][k][row = s*48 + co][kk];
+// ci = 16 k + kk, tap dz = (r + 1 - s) mod 3, each (144 x 16) tile in the SWIZZLE_32B K-major shared-memory image (16-byte half
+// kk >> 3 of row rr sits at half ^ ((rr >> 2) & 1)), so the whole matrix is ONE linear bulk copy; with 16 output channels the three
+// dy taps of a (dx, k) pair are one N = 144 operand (48-row sub-ranges at the band edges).  flip: dgrad operand
+// W'[ci][co][2-dz][2-dy][2-dx].
+__host__ __device__ inline void xline_pack_index(int64_t idx, int ks, int co_n, int* r, int* dy, int* dx, int* k, int* s, int* co, int* kk,
+                                                 int64_t* out) {
+  int64_t t = idx;
+  *kk = (int)(t % 16); t /= 16;
+  const int rr = (int)(t % 144); t /= 144;
+  *k = (int)(t % ks); t /= ks;
+  *dx = (int)(t % 3); t /= 3;
+  if (co_n == 16) {
+    *r = (int)t;
+    *dy = rr / 48; *s = (rr % 48) / 16; *co = rr % 16;
+  } else {
+    *dy = (int)(t % 3); t /= 3;
+    *r = (int)t;
+    *s = rr / 48; *co = rr % 48;
+  }
+  const int64_t tile = idx / (144 * 16);
+  *out = tile * (144 * 16) + rr * 16 + ((((*kk >> 3) ^ ((rr >> 2) & 1))) << 3) + (*kk & 7);
+}
 template <typename T>
 __global__ void pack_weight_xline_kernel(const float* __restrict__ w, T* __restrict__ out, int cout, int cin, int flip) {
-  const int CI = flip ? cout : cin;
+  const int CO = flip ? cin : cout, CI = flip ? cout : cin;
   const int ks = CI / 16;
-  const int total = 27 * ks * 48 * 16;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    int t = idx;
-    const int kk = t % 16; t /= 16;
-    const int rr = t % 144; t /= 144;
-    const int k = t % ks; t /= ks;
-    const int dx = t % 3; t /= 3;
-    const int r = t;
-    const int dy = rr / 48, s = (rr % 48) / 16, co = rr % 16;
+  const int64_t total = (int64_t)27 * ks * CO * 48;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    int r, dy, dx, k, s, co, kk;
+    int64_t o;
+    xline_pack_index(idx, ks, CO, &r, &dy, &dx, &k, &s, &co, &kk, &o);
     const int dz = ((r + 1 - s) % 3 + 3) % 3;
     const int ci = k * 16 + kk;
     float v;
     if (flip) v = w[((((int64_t)ci * cin + co) * 3 + (2 - dz)) * 3 + (2 - dy)) * 3 + (2 - dx)];
     else v = w[((((int64_t)co * cin + ci) * 3 + dz) * 3 + dy) * 3 + dx];
-    const int tile = (r * 3 + dx) * ks + k;
-    const int off = rr * 16 + ((((kk >> 3) ^ ((rr >> 2) & 1))) << 3) + (kk & 7);
-    out[(int64_t)tile * (144 * 16) + off] = from_f<T>(v);
+    out[o] = from_f<T>(v);
   }
 }
 
@@ -801,7 +879,7 @@ __global__ void __launch_bounds__(128, 1) xline_rate_kernel(int n, int count, in
 bool conv_xline_ok(const ActView& x, const ActView& y, int kd, int kh, int kw) {
   if (kd != 3 || kh != 3 || kw != 3) return false;
   if (x.dtype != y.dtype || (x.dtype != B200_BF16 && x.dtype != B200_F16)) return false;
-  if (x.w != 128 || y.c != 16 || (x.c != 16 && x.c != 48)) return false;
+  if (x.w != 128 || !((y.c == 16 && (x.c == 16 || x.c == 48)) || (y.c == 48 && x.c == 16))) return false;
   if (x.n != y.n || x.d != y.d || x.h != y.h || x.w != y.w) return false;
   if (x.sw != x.c || x.sh != (int64_t)x.w * x.c) return false;                  // dense lines, contiguous lines in a plane
   if (((uintptr_t)x.data & 15) || (x.sd * 2) % 16 || (x.sn * 2) % 16) return false;
@@ -815,11 +893,11 @@ static int xline_mode() {
 }
 bool conv_xline_enabled() { return xline_mode() != 0; }
 
-template <typename T, int KS, int BY>
+template <typename T, int KS, int BY, int CO16>
 static int launch_xline(const ActView& x, const void* w, const float* bias, const ActView& y, const ActView* a_out, const float* scale,
                         const float* shift, int fuse, double* stats, XlineParams p, cudaStream_t st) {
   constexpr int NR = KS == 1 ? 8 : 3;
-  const size_t smem = 27u * KS * kXlTileBytes + (size_t)NR * 2u * 4096u * KS + 8u * (2u * 64u * KS) + 16384u + 1024u;
+  const size_t smem = 27u * KS * CO16 * kXlTileBytes + (size_t)NR * 2u * 4096u * KS + 8u * (2u * 64u * KS) + 16384u + 1024u;
   {
     const char* e = getenv("B200_XL_ABLATE");
     p.ablate = e ? atoi(e) : 0;
@@ -850,13 +928,17 @@ static int launch_xline(const ActView& x, const void* w, const float* bias, cons
   T* ap = a_out ? (T*)a_out->data : nullptr;
 #define XL_LAUNCH(F)                                                                                                   \
   {                                                                                                                    \
-    auto kern = conv_fprop_xline_kernel<T, KS, BY, F>;                                                                 \
+    auto kern = conv_fprop_xline_kernel<T, KS, BY, F, CO16>;                                                           \
     B200_CUDA(raise_dyn_smem_cap(kern));                                                                               \
     kern<<<grid, 448, smem, st>>>((const T*)x.data, (const T*)w, bias, (T*)y.data, ap, scale, shift, stats, p);       \
   }
-  if (fuse == 0) XL_LAUNCH(0)
-  else if (fuse == 1) XL_LAUNCH(1)
-  else XL_LAUNCH(2)
+  if constexpr (CO16 == 3) {
+    XL_LAUNCH(0)
+  } else {
+    if (fuse == 0) XL_LAUNCH(0)
+    else if (fuse == 1) XL_LAUNCH(1)
+    else XL_LAUNCH(2)
+  }
 #undef XL_LAUNCH
   B200_LAUNCH_CHECK();
   if (p.dbg) {
@@ -883,6 +965,8 @@ int conv_fprop_xline_v(const ActView& x, const void* w, const float* bias, const
   B200_CHECK_ARG(conv_xline_ok(x, y, 3, 3, 3), "conv_fprop(xline): unsupported operands");
   B200_CHECK_ARG(fuse == 0 || (scale && shift), "conv_fprop(xline): fused normalisation needs scale and shift");
   B200_CHECK_ARG(fuse >= 0 && fuse <= 2, "conv_fprop(xline): bad fuse mode");
+  B200_CHECK_ARG(y.c == 16 || (fuse == 0 && !accumulate && stats == nullptr),
+                 "conv_fprop(xline): 48 output channels (the input gradient of the 48 -> 16 layer) come without fusion, accumulation or statistics");
   if (a_out) {
     B200_CHECK_ARG(fuse != 0, "conv_fprop(xline): a_out without a fused activation");
     B200_CHECK_ARG(a_out->dtype == x.dtype && a_out->n == x.n && a_out->d == x.d && a_out->h == x.h && a_out->w == x.w &&
@@ -903,11 +987,13 @@ int conv_fprop_xline_v(const ActView& x, const void* w, const float* bias, const
   p.idesc96 = make_idesc(x.dtype == B200_BF16, 96, 0, 0);
   p.idesc144 = make_idesc(x.dtype == B200_BF16, 144, 0, 0);
   if (x.dtype == B200_BF16) {
-    if (x.c == 16) return launch_xline<__nv_bfloat16, 1, 8>(x, w, bias, y, a_out, scale, shift, fuse, stats, p, st);
-    return launch_xline<__nv_bfloat16, 3, 4>(x, w, bias, y, a_out, scale, shift, fuse, stats, p, st);
+    if (y.c == 48) return launch_xline<__nv_bfloat16, 1, 2, 3>(x, w, bias, y, a_out, scale, shift, fuse, stats, p, st);
+    if (x.c == 16) return launch_xline<__nv_bfloat16, 1, 8, 1>(x, w, bias, y, a_out, scale, shift, fuse, stats, p, st);
+    return launch_xline<__nv_bfloat16, 3, 4, 1>(x, w, bias, y, a_out, scale, shift, fuse, stats, p, st);
   }
-  if (x.c == 16) return launch_xline<__half, 1, 8>(x, w, bias, y, a_out, scale, shift, fuse, stats, p, st);
-  return launch_xline<__half, 3, 4>(x, w, bias, y, a_out, scale, shift, fuse, stats, p, st);
+  if (y.c == 48) return launch_xline<__half, 1, 2, 3>(x, w, bias, y, a_out, scale, shift, fuse, stats, p, st);
+  if (x.c == 16) return launch_xline<__half, 1, 8, 1>(x, w, bias, y, a_out, scale, shift, fuse, stats, p, st);
+  return launch_xline<__half, 3, 4, 1>(x, w, bias, y, a_out, scale, shift, fuse, stats, p, st);
 }
 
 }  // namespace sm100
@@ -973,9 +1059,10 @@ B200_EXPORT int b200_pack_conv_weight_xline(const float* w, void* packed, int32_
                                             int32_t flip_transpose, void* stream) {
   B200_CHECK_ARG(w && packed, "pack_conv_weight_xline: null pointer");
   const int CO = flip_transpose ? cin : cout, CI = flip_transpose ? cout : cin;
-  B200_CHECK_ARG(CO == 16 && (CI == 16 || CI == 48), "pack_conv_weight_xline: (Cout', Cin') = (%d, %d) not supported", CO, CI);
+  B200_CHECK_ARG((CO == 16 && (CI == 16 || CI == 48)) || (CO == 48 && CI == 16),
+                 "pack_conv_weight_xline: (Cout', Cin') = (%d, %d) not supported", CO, CI);
   cudaStream_t st = (cudaStream_t)stream;
-  const int total = 27 * (CI / 16) * 48 * 16;
+  const int total = 27 * (CI / 16) * CO * 48;
   const unsigned blocks = (unsigned)ceil_div(total, 256);
   if (dtype == B200_BF16)
     sm100::pack_weight_xline_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w, (__nv_bfloat16*)packed, cout, cin, flip_transpose);

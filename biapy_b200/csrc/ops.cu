@@ -1820,9 +1820,9 @@ B200_EXPORT int b200_pack_batch(const b200_pack_job* jobs, int32_t n_jobs, int32
         total = (int64_t)4 * CO * s.kd * s.kh * kxp;
       } else if (s.kind == PACK_XLINE) {
         const int CO = s.flip ? s.cin : s.cout, CI = s.flip ? s.cout : s.cin;
-        B200_CHECK_ARG(CO == 16 && (CI == 16 || CI == 48) && s.kd == 3 && s.kh == 3 && s.kw == 3,
-                       "pack_batch: job %d: x-line packing takes 3x3x3 kernels with (Cout', Cin') = (16, 16 | 48)", j0 + k);
-        total = (int64_t)27 * (CI / 16) * 48 * 16;
+        B200_CHECK_ARG(((CO == 16 && (CI == 16 || CI == 48)) || (CO == 48 && CI == 16)) && s.kd == 3 && s.kh == 3 && s.kw == 3,
+                       "pack_batch: job %d: x-line packing takes 3x3x3 kernels with (Cout', Cin') = (16, 16 | 48) or (48, 16)", j0 + k);
+        total = (int64_t)27 * (CI / 16) * CO * 48;
       }
       d.total = total;
       // ~1 K elements per block, at most 512 blocks per job: the 1.8 M-element packs of the 256-channel layers must not become

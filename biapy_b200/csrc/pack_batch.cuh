@@ -107,24 +107,25 @@ __device__ __forceinline__ void pack_batch_body(const PackJob* __restrict__ jobs
     }
   } else if (jb.kind == PACK_XLINE) {
     T* out = (T*)jb.dst;
-    const int CI = jb.flip ? jb.cout : jb.cin;
+    const int CO = jb.flip ? jb.cin : jb.cout, CI = jb.flip ? jb.cout : jb.cin;
     const int ks = CI / 16;
     for (int64_t i = first; i < jb.total; i += stride) {
-      int t = (int)i;
-      const int kk = t % 16; t /= 16;
-      const int rr = t % 144; t /= 144;
-      const int k = t % ks; t /= ks;
-      const int dx = t % 3; t /= 3;
-      const int r = t;
-      const int dy = rr / 48, s = (rr % 48) / 16, co = rr % 16;
+      // index space and layout of pack_weight_xline_kernel (conv_xline.cu): Cout' = 16: [r][dx][k][dy*48 + s*16 + co][kk];
+      // Cout' = 48: [r][dy][dx][k][s*48 + co][kk]
+      int64_t t = i;
+      const int kk = (int)(t % 16); t /= 16;
+      const int rr = (int)(t % 144); t /= 144;
+      const int k = (int)(t % ks); t /= ks;
+      const int dx = (int)(t % 3); t /= 3;
+      int r, dy, s, co;
+      if (CO == 16) { r = (int)t; dy = rr / 48; s = (rr % 48) / 16; co = rr % 16; }
+      else { dy = (int)(t % 3); t /= 3; r = (int)t; s = rr / 48; co = rr % 48; }
       const int dz = ((r + 1 - s) % 3 + 3) % 3;
       const int ci = k * 16 + kk;
       float v;
       if (jb.flip) v = jb.src[((((int64_t)ci * jb.cin + co) * 3 + (2 - dz)) * 3 + (2 - dy)) * 3 + (2 - dx)];
       else v = jb.src[((((int64_t)co * jb.cin + ci) * 3 + dz) * 3 + dy) * 3 + dx];
-      const int tile = (r * 3 + dx) * ks + k;
-      const int off = rr * 16 + ((((kk >> 3) ^ ((rr >> 2) & 1))) << 3) + (kk & 7);
-      out[(int64_t)tile * (144 * 16) + off] = from_f<T>(v);
+      out[(i / (144 * 16)) * (144 * 16) + rr * 16 + ((((kk >> 3) ^ ((rr >> 2) & 1))) << 3) + (kk & 7)] = from_f<T>(v);
     }
   } else if (jb.kind == UNPACK_WGRAD) {
     float* dw = (float*)jb.dst;

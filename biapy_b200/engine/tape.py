@@ -197,7 +197,7 @@ class Tape:
         normalisation then runs the stand-alone reduction)."""
         impl = self.impl
         wkey = w if wkey is None else wkey
-        if self._xline_ok(x, y, k, accumulate):
+        if self._xline_ok(x, y, k, accumulate, stats=stats and self.fuse_stats and not accumulate):
             return self._xline_launch(x, w, flip, bias, y, accumulate, wkey, stats)
         if impl == _lib.IMPL_AUTO and self.dtype != torch.float32 and self.use_xfold:
             x = self._dense_for_xfold(x, y.shape[4])
@@ -222,11 +222,17 @@ class Tape:
         ops.conv_fprop(x, wp, bias, y, k, accumulate=accumulate, impl=impl)
         return None
 
-    def _xline_ok(self, x: torch.Tensor, y: torch.Tensor, k, accumulate: bool, fused: bool = False) -> bool:
+    def _xline_ok(self, x: torch.Tensor, y: torch.Tensor, k, accumulate: bool, fused: bool = False, stats: bool = False) -> bool:
         if (self.xline <= 0 or self.impl != _lib.IMPL_AUTO or self.dtype == torch.float32 or tuple(k) != (3, 3, 3)
-                or x.shape[3] != 128 or y.shape[4] != 16 or x.shape[4] not in (16, 48)):
+                or x.shape[3] != 128):
             return False
-        if self.xline == 1 and not fused and x.shape[4] == 16:
+        cin, cout = x.shape[4], y.shape[4]
+        if cout == 48:          # the input gradient of the 48 -> 16 layer: plain launches only
+            if cin != 16 or accumulate or fused or stats:
+                return False
+        elif cout != 16 or cin not in (16, 48):
+            return False
+        elif self.xline == 1 and not fused and cin == 16:
             return False        # 16 -> 16: on a par with the x-slab kernel (0.22-0.28 vs 0.23-0.27 ms over five boxes); 48 -> 16: 1.6x faster
         return ops.conv_xline_supported(x, y, k)
 

@@ -229,8 +229,8 @@ def pack_conv_weight_xfold(w: torch.Tensor, dtype: torch.dtype, flip_transpose: 
 
 
 def conv_xline_supported(x, y, k) -> bool:
-    """True when the x-line kernel (csrc/conv_xline.cu) takes these operands: 3x3x3, W = 128, Cout = 16, Cin in (16, 48), dense
-    16-bit channels-last input, and B200_XLINE != 0."""
+    """True when the x-line kernel (csrc/conv_xline.cu) takes these operands: 3x3x3, W = 128, (Cin, Cout) in (16 | 48, 16) or
+    (16, 48) -- the latter without accumulation, statistics or fusion -- dense 16-bit channels-last input, and B200_XLINE != 0."""
     if x.dtype == torch.float32 or tuple(k) != (3, 3, 3):
         return False
     return bool(_lib.lib().b200_conv_xline_supported(_ref(x), _ref(y), 3, 3, 3))
@@ -242,8 +242,8 @@ def pack_conv_weight_xline(w: torch.Tensor, dtype: torch.dtype, flip_transpose: 
     if w.dtype != torch.float32 or not w.is_contiguous():
         w = w.float().contiguous()
     cout, cin = w.shape[:2]
-    ci_l = cout if flip_transpose else cin
-    out = torch.empty(27 * (ci_l // 16) * 48 * 16, dtype=dtype, device=w.device)
+    co_l, ci_l = (cin, cout) if flip_transpose else (cout, cin)
+    out = torch.empty(27 * (ci_l // 16) * co_l * 48, dtype=dtype, device=w.device)
     _launch("b200_pack_conv_weight_xline", _ptr(w), _ptr(out), _lib.torch_dtype_code(dtype), cout, cin, 1 if flip_transpose else 0,
             stream_ptr())
     global LAST_PACK

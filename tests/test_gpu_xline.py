@@ -114,6 +114,32 @@ def test_xline_against_aten(n, d, h, cin, dtype, fuse, accumulate, stats, a_out,
         assert float(ybuf[..., :8].abs().max()) == 0.0 and float(ybuf[..., 24:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("n,d,h,dtype,flip", [(1, 3, 8, torch.float16, False), (2, 7, 10, torch.bfloat16, True), (1, 5, 3, torch.float16, True),
+                                               (1, 33, 128, torch.float16, True)])
+def test_xline_48_output_channels(n, d, h, dtype, flip):
+    """Cin = 16 -> Cout = 48: the input gradient of the 48 -> 16 layer (flip: the packing that launch uses)."""
+    from biapy_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(77 + n + d + h)
+    dev = "cuda"
+    x = torch.randn((n, d, h, 128, 16), device=dev, generator=g).to(dtype)
+    if flip:      # parameter of the forward layer: (Cout = 16, Cin = 48, 3, 3, 3); the launch computes conv(x, W') with 48 outputs
+        w = torch.randn((16, 48, 3, 3, 3), device=dev, generator=g) * 0.1
+        w_eff = w.permute(1, 0, 2, 3, 4).flip(2, 3, 4).contiguous()
+    else:
+        w = torch.randn((48, 16, 3, 3, 3), device=dev, generator=g) * 0.1
+        w_eff = w
+    wp = ops.pack_conv_weight_xline(w, dtype, flip)
+    y = torch.empty((n, d, h, 128, 48), device=dev, dtype=dtype)
+    assert ops.conv_xline_supported(x, y, (3, 3, 3))
+    ops.conv_fprop_xline(x, wp, None, y)
+    torch.cuda.synchronize()
+    e = _nmax(y, _ref_conv(x, w_eff.to(dtype).float(), None))
+    print(f"\n[xline 16->48] n{n} d{d} h{h} {dtype} flip{int(flip)}: normalised max error {e:.2e}")
+    assert e < (2e-2 if dtype == torch.bfloat16 else 3e-3)
+    with pytest.raises(Exception):
+        ops.conv_fprop_xline(x, wp, None, y, accumulate=True)
+
+
 def test_xline_rejects_what_it_cannot_take():
     from biapy_b200 import _lib, ops
     x = torch.zeros((1, 4, 8, 64, 16), device="cuda", dtype=torch.float16)

@@ -44,6 +44,7 @@ KERNELS = {
 PREAMBLE = {
     "select_hist_kernel": "template <typename S> __device__ __forceinline__ uint32_t select_key",
     "pack_weight_xfold_kernel": "__host__ __device__ inline bool xfold_geom",
+    "pack_weight_xline_kernel": "__host__ __device__ inline void xline_pack_index",
     "bce_logits_kernel": "__device__ __forceinline__ void block_atomic_add",
     "overlap_add_kernel": "struct MergeParams {",
     "overlap_add_slot_kernel": "struct SlotRow {",

@@ -129,6 +129,23 @@ def timings(dtype):
             print(f"time {str(dtype)[6:]} {cin}->16 @128^3 x4 {name}: {ms:.4f} ms  {tf:.0f} TFLOP/s", flush=True)
 
 
+def timings48(dtype):
+    """Cin = 16 -> Cout = 48 (the input gradient of the 48 -> 16 layer): x-folded against x-line."""
+    dev = "cuda"
+    x = torch.randn((4, 128, 128, 128, 16), device=dev).to(dtype)
+    w = torch.randn((48, 16, 3, 3, 3), device=dev) * 0.1
+    y = torch.empty((4, 128, 128, 128, 48), device=dev, dtype=dtype)
+    wl = ops.pack_conv_weight_xline(w, dtype, False)
+    wf = ops.pack_conv_weight_xfold(w, dtype, False)
+    gf = 2.0 * 4 * 128 ** 3 * 16 * 48 * 27 / 1e9
+    for name, fn in (("xfold", lambda: ops.conv_fprop(x, wf, None, y, (3, 3, 3), impl=_lib.IMPL_XFOLD)),
+                     ("xline", lambda: ops.conv_fprop_xline(x, wl, None, y)),
+                     ("xfold", lambda: ops.conv_fprop(x, wf, None, y, (3, 3, 3), impl=_lib.IMPL_XFOLD)),
+                     ("xline", lambda: ops.conv_fprop_xline(x, wl, None, y))):
+        ms = time_ms(fn)
+        print(f"time {str(dtype)[6:]} 16->48 @128^3 x4 {name}: {ms:.4f} ms  {gf / ms:.0f} TFLOP/s", flush=True)
+
+
 def diagnose(dtype, sweep=True):
     """Per-role cycle counters (B200_XL_DBG) and ablation timings (B200_XL_ABLATE) of the full-size launches."""
     dev = "cuda"
@@ -187,6 +204,8 @@ def main():
         ok &= case(1, 128, 128, 16, bf, fuse=2, seed=14)
     print("ALL OK" if ok else "SOME FAILED", flush=True)
     if a.time:
+        timings48(torch.float16)
+        timings48(torch.bfloat16)
         timings(torch.float16)
         timings(torch.bfloat16)
     if a.diag or a.diag_quick:
