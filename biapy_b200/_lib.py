@@ -84,6 +84,8 @@ SIGNATURES = {
     "b200_pack_conv_weight_xline": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "b200_conv_fprop_xline": (_I, [_T, _P, _P, _T, _I, _P, _P, _I, _T, _P, _P]),
     "b200_xline_selftest": (_I, [C.POINTER(_D), _I, _P]),
+    "b200_conv_wgrad_xline_supported": (_I, [_T, _T, _I, _I, _I]),
+    "b200_conv_wgrad_xline": (_I, [_T, _T, _P, _P, _P]),
     "b200_unpack_conv_wgrad": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "b200_convT_fprop": (_I, [_T, _P, _P, _T, _I, _I, _I, _P]),
     "b200_convT_dgrad": (_I, [_T, _P, _T, _I, _I, _I, _I, _P]),

@@ -1087,3 +1087,363 @@ B200_EXPORT int b200_conv_fprop_xline(const b200_tensor* x, const void* w_packed
   return sm100::conv_fprop_xline_v(sm100::view_of(x), w_packed, bias, sm100::view_of(y), accumulate, a_out ? &av : nullptr, scale,
                                    shift, fuse, sums, (cudaStream_t)stream);
 }
+
+namespace b200 {
+namespace sm100 {
+
+// ================================================================================================== x-line weight gradient
+// dW[co][tap][ci] += sum over voxels of dY[vox][co] * A[vox + off(tap)][ci] for the 16-output-channel 3x3x3 layers at W = 128 (the
+// layers whose x-folded weight gradient leaves 3/4 of its M = 128 operand to structural zeros).  The contraction index of one GEMM
+// is the 128 voxels of a LINE:
+//
+//   D[(dx, ci)][(dz, l, co)] += sum_x  A_dx^T[(dx, ci)][x] * dY^T[(plane z_in - dz + 1, line y_in - 1 + l), co][x]       l = 0..2 (dy = 2 - l)
+//
+// * A^T lives in TENSOR MEMORY: lane = (dx, ci) (48 of 128 lanes; the MMA's cost is N-bound, the idle lanes are free), column =
+//   two consecutive voxels; thread (dx, ci) of a staging team gathers its channel of the input line (shifted by dx - 1, zeros at
+//   the ends) from the raw line in shared memory and stores 64 columns.
+// * dY^T is the B operand: transposer warps scatter every dY line once into K-major SWIZZLE_32B tiles [k-step][line * 16 + co][16 x]
+//   of a four-plane ring; the three lines a tap row needs are 48 consecutive rows, so one N = 48 MMA per (dz, k-step): 24 MMAs of
+//   34 cycles per input line, all of them useful MACs.
+// * D = the complete 27-tap gradient block of this input-channel group, 48 lanes x 144 columns, stays in tensor memory for the
+//   whole launch and is added to dw with fp32 atomics once per CTA.
+// Warps: 0-3 dY transposers (and the final reduction), 4-5 / 8-9 two A staging teams on alternate lines, 6 MMA issue, 7 bulk copies.
+struct XwParams {
+  int n, d, h;
+  int bands, zchunks, zc, units;
+  long long ash_b, asd_b, asn_b;   // byte strides of the activation: line, plane, sample
+  int avox_b, aoff_b;              // bytes per voxel of the activation, byte offset of this launch's 16-channel group
+  long long gsh_b, gsd_b, gsn_b;   // byte strides of dY (dense 16-channel lines)
+  int cin_total, ci_off;
+  uint32_t idesc;                  // N = 48
+};
+
+template <typename T, int AL>      // AL = bytes of an activation line / 4096 (1: 16 channels per voxel, 3: 48)
+__global__ void __launch_bounds__(320, 1)
+conv_wgrad_xline_kernel(const T* __restrict__ a, const T* __restrict__ dy, float* __restrict__ dw, const XwParams p) {
+  constexpr int BYW = 4, DL = BYW + 2;          // input lines per band, dY lines per plane of the window
+  constexpr int NRD = 6, NRA = 4, NAW = 5;      // raw dY ring (lines), raw activation ring (lines), operand ring in TMEM (lines)
+  constexpr uint32_t ABYTES = 4096u * AL;
+  constexpr uint32_t PSLOT = 8u * (DL * 16u) * 32u;   // one transposed dY plane: 8 k-steps x 96 rows x 32 bytes
+  constexpr uint32_t KSTEP = (DL * 16u) * 32u;
+  constexpr uint32_t DCOLS = 144u, ACOL = DCOLS;      // accumulator columns, first operand column
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t s_bar[2 * NRD + 2 * NRA + 8 + 2 * NAW + 1];
+  __shared__ uint32_t s_tmem;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sm_t = smem0, sm_dyr = sm_t + 4u * PSLOT, sm_ar = sm_dyr + NRD * 4096u;
+  const uint32_t bar0 = smem_u32(s_bar);
+  const uint32_t dyr_full = bar0, dyr_free = dyr_full + 8 * NRD, ar_full = dyr_free + 8 * NRD, ar_free = ar_full + 8 * NRA,
+                 pl_full = ar_free + 8 * NRA, pl_free = pl_full + 32, a_full = pl_free + 32, a_free = a_full + 8 * NAW,
+                 done = a_free + 8 * NAW;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NRD; ++i) { mbar_init(dyr_full + 8 * i, 1); mbar_init(dyr_free + 8 * i, 4); }
+    for (int i = 0; i < NRA; ++i) { mbar_init(ar_full + 8 * i, 1); mbar_init(ar_free + 8 * i, 2); }
+    for (int i = 0; i < 4; ++i) { mbar_init(pl_full + 8 * i, 4); mbar_init(pl_free + 8 * i, 1); }
+    for (int i = 0; i < NAW; ++i) { mbar_init(a_full + 8 * i, 2); mbar_init(a_free + 8 * i, 1); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 6) tmem_alloc(smem_u32(&s_tmem), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  if (warp < 4) {                                   // accumulators and every lane of the operand ring start at zero
+    const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (uint32_t c = 0; c < DCOLS + NAW * 64u; c += 16) tmem_st16_zero(tl + c);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  auto decode = [&](int u, int& n, int& z0, int& zhi, int& y0) {
+    const int band = u % p.bands;
+    int t = u / p.bands;
+    const int zk = t % p.zchunks;
+    n = t / p.zchunks;
+    y0 = band * BYW;
+    z0 = zk * p.zc;
+    zhi = z0 + p.zc < p.d ? z0 + p.zc : p.d;
+  };
+
+  if (warp == 7) {
+    // ===================================================================== bulk copies: dY lines plane by plane, activation lines
+    if (elect_one()) {
+      int rd = 0, ra = 0;
+      uint32_t rdph = 0, raph = 0;
+      const char* ab = reinterpret_cast<const char*>(a);
+      const char* gb = reinterpret_cast<const char*>(dy);
+      for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+        int n, z0, zhi, y0;
+        decode(u, n, z0, zhi, y0);
+        for (int P = z0 - 1; P <= zhi; ++P) {
+          if ((unsigned)P < (unsigned)p.d) {
+#pragma unroll 1
+            for (int l = 0; l < DL; ++l) {
+              const int y = y0 - 1 + l;
+              if ((unsigned)y >= (unsigned)p.h) continue;
+              xl_wait(dyr_free + 8 * rd, rdph ^ 1);
+              mbar_expect_tx(dyr_full + 8 * rd, 4096u);
+              bulk_g2s(sm_dyr + (uint32_t)rd * 4096u, gb + (long long)n * p.gsn_b + (long long)P * p.gsd_b + (long long)y * p.gsh_b, 4096u,
+                       dyr_full + 8 * rd);
+              if (++rd == NRD) { rd = 0; rdph ^= 1; }
+            }
+          }
+          const int zin = P - 1;
+          if (zin >= z0 && zin < zhi) {
+#pragma unroll 1
+            for (int j = 0; j < BYW; ++j) {
+              const int y = y0 + j;
+              if (y >= p.h) continue;
+              xl_wait(ar_free + 8 * ra, raph ^ 1);
+              mbar_expect_tx(ar_full + 8 * ra, ABYTES);
+              bulk_g2s(sm_ar + (uint32_t)ra * ABYTES, ab + (long long)n * p.asn_b + (long long)zin * p.asd_b + (long long)y * p.ash_b, ABYTES,
+                       ar_full + 8 * ra);
+              if (++ra == NRA) { ra = 0; raph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 6) {
+    // ===================================================================== MMA issue
+    if (elect_one()) {
+      const uint32_t idesc = in_reg(p.idesc);
+      const uint32_t b_hi = (256u >> 4) | (1u << 14) | ((uint32_t)kSwizzle32 << 29);
+      uint32_t qbase = 0, lc = 0;
+      for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+        int n, z0, zhi, y0;
+        decode(u, n, z0, zhi, y0);
+        const int nplanes = zhi - z0 + 2;
+        int waited = -1;
+        for (int zin = z0; zin < zhi; ++zin) {
+          const int pic = zin - z0 + 1;             // window index of the centre plane (plane P = z0 - 1 + index)
+          while (waited < pic + 1) {
+            ++waited;
+            const uint32_t qq = qbase + (uint32_t)waited;
+            xl_wait(pl_full + 8 * (qq & 3u), (qq >> 2) & 1u);
+          }
+          tc_fence_after();
+#pragma unroll 1
+          for (int j = 0; j < BYW; ++j) {
+            if (y0 + j >= p.h) continue;
+            const uint32_t aslot = lc % NAW;
+            xl_wait(a_full + 8 * aslot, (lc / NAW) & 1u);
+            tc_fence_after();
+            const uint32_t a_t = tmem + ACOL + aslot * 64u;
+#pragma unroll
+            for (int dz = 0; dz < 3; ++dz) {
+              const uint32_t qq = qbase + (uint32_t)(pic - dz + 1);
+              const uint32_t b_lo = (((sm_t + (qq & 3u) * PSLOT + (uint32_t)j * 512u) >> 4) & 0x3FFFu) | (1u << 16);
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks)
+                umma_f16_ts(tmem + (uint32_t)dz * 48u, a_t + 8u * ks, b_lo + (uint32_t)ks * (KSTEP >> 4), b_hi, idesc, 1u);
+            }
+            umma_commit(a_free + 8 * aslot);
+            ++lc;
+          }
+          umma_commit(pl_free + 8 * ((qbase + (uint32_t)(pic - 1)) & 3u));      // the plane below the centre is not needed again
+        }
+        umma_commit(pl_free + 8 * ((qbase + (uint32_t)(nplanes - 2)) & 3u));
+        umma_commit(pl_free + 8 * ((qbase + (uint32_t)(nplanes - 1)) & 3u));
+        qbase += (uint32_t)nplanes;
+      }
+      umma_commit(done);
+    }
+  } else if (warp >= 4) {
+    // ===================================================================== activation staging: A^T of a line into tensor memory
+    const uint32_t team = warp >= 8 ? 1u : 0u;
+    const int L = (warp & 1) * 32 + lane;           // TMEM lane = (dx, ci)
+    const bool active = L < 48;
+    const int dx = L >> 4, ci = L & 15;
+    const uint32_t tl = tmem + ((uint32_t)((warp & 1) * 32) << 16) + ACOL;
+    int ra = 0;
+    uint32_t raph = 0, lc = 0;
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+      int n, z0, zhi, y0;
+      decode(u, n, z0, zhi, y0);
+      for (int zin = z0; zin < zhi; ++zin) {
+#pragma unroll 1
+        for (int j = 0; j < BYW; ++j) {
+          if (y0 + j >= p.h) continue;
+          if ((lc & 1u) == team) {
+            xl_wait(ar_full + 8 * ra, raph);
+            const uint32_t base = sm_ar + (uint32_t)ra * ABYTES + (uint32_t)p.aoff_b + (uint32_t)ci * 2u;
+            uint32_t r[64];
+#pragma unroll
+            for (int xp = 0; xp < 64; ++xp) {
+              const int x0 = 2 * xp + dx - 1;
+              uint32_t lo = 0, hi = 0;
+              if (active && x0 >= 0) {
+                uint16_t t16;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(t16) : "r"(base + (uint32_t)x0 * (uint32_t)p.avox_b));
+                lo = t16;
+              }
+              if (active && x0 + 1 < 128) {
+                uint16_t t16;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(t16) : "r"(base + (uint32_t)(x0 + 1) * (uint32_t)p.avox_b));
+                hi = t16;
+              }
+              r[xp] = lo | (hi << 16);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ar_free + 8 * ra);
+            const uint32_t aslot = lc % NAW;
+            xl_wait(a_free + 8 * aslot, ((lc / NAW) & 1u) ^ 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) tmem_st8(tl + aslot * 64u + 8u * ks, r + 8 * ks);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full + 8 * aslot);
+          }
+          if (++ra == NRA) { ra = 0; raph ^= 1; }
+          ++lc;
+        }
+      }
+    }
+  } else {
+    // ===================================================================== dY transposition, then the reduction of the accumulators
+    const int xv = warp * 32 + lane;
+    int rd = 0;
+    uint32_t rdph = 0, qn = 0;
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+      int n, z0, zhi, y0;
+      decode(u, n, z0, zhi, y0);
+      for (int P = z0 - 1; P <= zhi; ++P, ++qn) {
+        const uint32_t slot = qn & 3u;
+        xl_wait(pl_free + 8 * slot, ((qn >> 2) & 1u) ^ 1u);
+        const uint32_t tbase = sm_t + slot * PSLOT + (uint32_t)(xv >> 4) * KSTEP + (uint32_t)(xv & 7) * 2u;
+        const uint32_t half = (uint32_t)((xv >> 3) & 1);
+#pragma unroll 1
+        for (int l = 0; l < DL; ++l) {
+          const int y = y0 - 1 + l;
+          uint32_t v[8];
+          if ((unsigned)P < (unsigned)p.d && (unsigned)y < (unsigned)p.h) {
+            xl_wait(dyr_full + 8 * rd, rdph);
+            const uint32_t src = sm_dyr + (uint32_t)rd * 4096u + (uint32_t)xv * 32u;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(src));
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(src + 16u));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dyr_free + 8 * rd);
+            if (++rd == NRD) { rd = 0; rdph ^= 1; }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = 0u;
+          }
+#pragma unroll
+          for (int co = 0; co < 16; ++co) {
+            const uint32_t row = (uint32_t)(l * 16 + co);
+            const uint32_t addr = tbase + row * 32u + ((half ^ ((row >> 2) & 1u)) << 4);
+            const uint16_t hv = (uint16_t)((co & 1) ? (v[co >> 1] >> 16) : (v[co >> 1] & 0xffffu));
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(hv) : "memory");
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pl_full + 8 * slot);
+      }
+    }
+    xl_wait(done, 0);
+    tc_fence_after();
+    if (warp < 2) {
+      const int L = warp * 32 + lane;
+      const int dx = L >> 4, ci = L & 15;
+#pragma unroll 1
+      for (int c16 = 0; c16 < 9; ++c16) {
+        uint32_t r[16];
+        tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c16 * 16u, r);
+        tmem_ld_wait();
+        if (L < 48) {
+          const int dz = c16 / 3, dyt = 2 - (c16 % 3);
+          const int tap = (dz * 3 + dyt) * 3 + dx;
+#pragma unroll
+          for (int co = 0; co < 16; ++co)
+            atomicAdd(dw + ((long long)co * 27 + tap) * p.cin_total + p.ci_off + ci, __uint_as_float(r[co]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 6) tmem_dealloc(tmem, 512);
+}
+
+bool conv_wgrad_xline_ok(const ActView& x, const ActView& dy) {
+  if (x.dtype != dy.dtype || (x.dtype != B200_BF16 && x.dtype != B200_F16)) return false;
+  if (x.w != 128 || dy.c != 16 || (x.c != 16 && x.c != 48)) return false;
+  if (x.n != dy.n || x.d != dy.d || x.h != dy.h || x.w != dy.w) return false;
+  if (x.sw != x.c || x.sh != (int64_t)x.w * x.c || dy.sw != 16 || dy.sh != (int64_t)dy.w * 16) return false;
+  if (((uintptr_t)x.data & 15) || (x.sd * 2) % 16 || (x.sn * 2) % 16) return false;
+  if (((uintptr_t)dy.data & 15) || (dy.sd * 2) % 16 || (dy.sn * 2) % 16) return false;
+  return true;
+}
+
+template <typename T, int AL>
+static int launch_wgrad_xline(const ActView& x, const ActView& dy, float* dw, int ci_off, cudaStream_t st) {
+  XwParams p{};
+  p.n = x.n; p.d = x.d; p.h = x.h;
+  p.ash_b = x.sh * 2; p.asd_b = x.sd * 2; p.asn_b = x.sn * 2;
+  p.avox_b = x.c * 2; p.aoff_b = ci_off * 2;
+  p.gsh_b = dy.sh * 2; p.gsd_b = dy.sd * 2; p.gsn_b = dy.sn * 2;
+  p.cin_total = x.c; p.ci_off = ci_off;
+  p.idesc = make_idesc(x.dtype == B200_BF16, 48, 0, 0);
+  p.bands = (int)ceil_div(x.h, 4);
+  {
+    double best = -1.0;
+    const int kmax = x.d < 32 ? x.d : 32;
+    for (int k = 1; k <= kmax; ++k) {
+      const int zc = (int)ceil_div(x.d, k);
+      const int kk = (int)ceil_div(x.d, zc);
+      const int64_t units = (int64_t)x.n * p.bands * kk;
+      const int64_t waves = ceil_div(units, sm_count());
+      const double eff = (double)units / (double)(waves * sm_count()) * (double)zc / (double)(zc + 1);   // two extra dY planes cost about one input plane
+      if (eff > best + 1e-9) { best = eff; p.zc = zc; p.zchunks = kk; }
+    }
+  }
+  p.units = x.n * p.bands * p.zchunks;
+  const int grid = p.units < sm_count() ? p.units : sm_count();
+  const size_t smem = 4u * (8u * 96u * 32u) + 6u * 4096u + 4u * 4096u * AL + 1024u;
+  auto kern = conv_wgrad_xline_kernel<T, AL>;
+  B200_CUDA(raise_dyn_smem_cap(kern));
+  kern<<<grid, 320, smem, st>>>((const T*)x.data, (const T*)dy.data, dw, p);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+}  // namespace sm100
+int conv_bias_grad(const b200_tensor* dy, float* dbias, cudaStream_t st);   // conv_simt.cu
+}  // namespace b200
+
+B200_EXPORT int b200_conv_wgrad_xline_supported(const b200_tensor* x, const b200_tensor* dy, int32_t kd, int32_t kh, int32_t kw) {
+  if (!x || !dy || !x->data || !dy->data || kd != 3 || kh != 3 || kw != 3) return 0;
+  const char* e = getenv("B200_XLINE_WGRAD");
+  if (e && atoi(e) == 0) return 0;
+  return sm100::conv_wgrad_xline_ok(sm100::view_of(x), sm100::view_of(dy)) ? 1 : 0;
+}
+
+B200_EXPORT int b200_conv_wgrad_xline(const b200_tensor* x, const b200_tensor* dy, float* dw_packed, float* dbias, void* stream) {
+  B200_CHECK_ARG(x && dy && dw_packed, "conv_wgrad_xline: null pointer");
+  B200_CHECK_ARG(check_tensor(x, "conv_wgrad_xline.x") && check_tensor(dy, "conv_wgrad_xline.dy"), "%s", b200_last_error());
+  const sm100::ActView xv = sm100::view_of(x), gv = sm100::view_of(dy);
+  B200_CHECK_ARG(sm100::conv_wgrad_xline_ok(xv, gv), "conv_wgrad_xline: unsupported operands (3x3x3, W = 128, Cout = 16, Cin in (16, 48), dense 16-bit lines)");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int g = 0; g < x->c / 16; ++g) {
+    int rc;
+    if (x->dtype == B200_BF16)
+      rc = x->c == 16 ? sm100::launch_wgrad_xline<__nv_bfloat16, 1>(xv, gv, dw_packed, 16 * g, st)
+                      : sm100::launch_wgrad_xline<__nv_bfloat16, 3>(xv, gv, dw_packed, 16 * g, st);
+    else
+      rc = x->c == 16 ? sm100::launch_wgrad_xline<__half, 1>(xv, gv, dw_packed, 16 * g, st)
+                      : sm100::launch_wgrad_xline<__half, 3>(xv, gv, dw_packed, 16 * g, st);
+    if (rc) return rc;
+  }
+  if (dbias) return conv_bias_grad(dy, dbias, st);
+  return B200_OK;
+}

@@ -306,6 +306,9 @@ def conv_fprop_stats(x, w_packed_xfold, bias, y, k: Sequence[int], sums: torch.T
     return bool(applied.value)
 
 
+# B200_XLINE_WGRAD = 0 keeps the 16-output-channel 3x3x3 weight gradients at W = 128 on the x-folded kernels
+XLINE_WGRAD = os.environ.get("B200_XLINE_WGRAD", "1") != "0"
+
 _WGRAD_N = (256, 128, 64, 32, 16)        # output-channel widths of the tcgen05 weight-gradient kernels (one N tile each)
 
 
@@ -328,6 +331,27 @@ def conv_wgrad(x, dy, cout: int, cin: int, k: Sequence[int], dw_out: torch.Tenso
     the un-pack of the gradient into `dw_out` is queued (`UNPACK_QUEUE`) unless `defer_unpack` is False."""
     taps = k[0] * k[1] * k[2]
     packed = zeros(cout * taps * cin, torch.float32, x.device)
+    if (impl == _lib.IMPL_AUTO and XLINE_WGRAD and x.dtype != torch.float32 and cout == 16 and tuple(k) == (3, 3, 3)
+            and x.shape[3] == 128 and cin in (16, 48)
+            and _lib.lib().b200_conv_wgrad_xline_supported(_ref(x), _ref(dy), 3, 3, 3)):
+        # x-line weight gradient (csrc/conv_xline.cu): the contraction runs over the voxels of a line, the transposed activation
+        # line sits in tensor memory, the 27-tap block is accumulated in tensor memory for the whole launch
+        label = flops = nbytes = None
+        if PROFILE is not None:
+            vox = x.shape[0] * x.shape[1] * x.shape[2] * x.shape[3]
+            flops = 2.0 * vox * cin * cout * taps
+            nbytes = vox * (cin + cout) * x.element_size()
+            label = "conv_wgrad_xline"
+            if PROFILE_SHAPES:
+                label += f" {cin}->{cout} k333 @{x.shape[1]}x{x.shape[2]}x{x.shape[3]}"
+        _launch_timed(label, flops, nbytes, "b200_conv_wgrad_xline", _ref(x), _ref(dy), _ptr(packed), _ptr(dbias_out), stream_ptr())
+        global LAUNCHES
+        LAUNCHES += cin // 16 - 1 + (1 if dbias_out is not None else 0)
+        if defer_unpack and UNPACK_QUEUE is not None and dw_out.is_contiguous():
+            UNPACK_QUEUE.append((UNPACK_WGRAD, packed, dw_out, cout, cin, taps, 1, 1, 1 if accumulate else 0))
+        else:
+            _launch("b200_unpack_conv_wgrad", _ptr(packed), _ptr(dw_out), cout, cin, taps, 1 if accumulate else 0, stream_ptr())
+        return
     cuts = [(0, cout)]
     if impl == _lib.IMPL_AUTO and x.dtype != torch.float32 and conv_impl_query(x, dy, k, True) == _lib.IMPL_SIMT:
         # Cout outside the kernels' N tiles (e.g. the 512-channel layers of BASELINE config[4]): one launch per slice of dy, each

@@ -252,6 +252,13 @@ int b200_pack_conv_weight_xline(const float* w, void* packed, int32_t dtype, int
 int b200_conv_fprop_xline(const b200_tensor* x, const void* w_packed, const float* bias, const b200_tensor* y, int32_t accumulate,
                           const float* scale, const float* shift, int32_t fuse, const b200_tensor* a_out, double* sums,
                           void* stream);
+/* x-line weight gradient (csrc/conv_xline.cu): dw_packed[16][27][Cin] (fp32, zero-initialised or accumulated by the caller) +=
+ * sum_vox dy[vox][co] * x[vox + off(tap)][ci] for the 3x3x3 layers with 16 output channels at W = 128, Cin = 16 or 48, dense
+ * 16-bit lines; dbias (nullable) += sum_vox dy.  The contraction runs over the 128 voxels of a line with the transposed
+ * activation line in tensor memory and the transposed dY lines as the shared-memory operand; the 27-tap gradient block stays in
+ * tensor memory for the whole launch (one launch per 16 input channels).  Same contract as b200_conv_wgrad. */
+int b200_conv_wgrad_xline_supported(const b200_tensor* x, const b200_tensor* dy, int32_t kd, int32_t kh, int32_t kw);
+int b200_conv_wgrad_xline(const b200_tensor* x, const b200_tensor* dy, float* dw_packed, float* dbias, void* stream);
 /* one tcgen05.mma with the A operand in tensor memory against exact integers; *max_err = largest absolute deviation */
 int b200_xline_selftest(double* max_err, int32_t verbose, void* stream);
 /* best kernel family for these operands: B200_IMPL_XFOLD, B200_IMPL_UMMA or B200_IMPL_SIMT

@@ -140,6 +140,29 @@ def test_xline_48_output_channels(n, d, h, dtype, flip):
         ops.conv_fprop_xline(x, wp, None, y, accumulate=True)
 
 
+@pytest.mark.parametrize("n,d,h,cin,dtype", [(1, 3, 8, 16, torch.float16), (2, 5, 10, 16, torch.bfloat16), (1, 4, 8, 48, torch.float16),
+                                              (1, 1, 1, 16, torch.float16), (2, 19, 36, 16, torch.float16), (1, 9, 128, 48, torch.bfloat16)])
+def test_xline_wgrad_against_aten(n, d, h, cin, dtype):
+    """dW (and dbias) of a 3x3x3 convolution with 16 output channels at W = 128 against ATen's fp32 weight gradient on the operands
+    as stored; fp32 accumulation in tensor memory and fp32 atomics: the difference is summation order only."""
+    from biapy_b200 import _lib, ops
+    g = torch.Generator(device="cuda").manual_seed(4321 + n + d + h + cin)
+    dev = "cuda"
+    x = torch.randn((n, d, h, 128, cin), device=dev, generator=g).to(dtype)
+    dy = torch.randn((n, d, h, 128, 16), device=dev, generator=g).to(dtype)
+    assert _lib.lib().b200_conv_wgrad_xline_supported(ops._ref(x), ops._ref(dy), 3, 3, 3)
+    packed = torch.zeros(16 * 27 * cin, dtype=torch.float32, device=dev)
+    dbias = torch.zeros(16, dtype=torch.float32, device=dev)
+    _lib.call("b200_conv_wgrad_xline", ops._ref(x), ops._ref(dy), ops._ptr(packed), ops._ptr(dbias), ops.stream_ptr())
+    torch.cuda.synchronize()
+    want = torch.nn.grad.conv3d_weight(x.float().permute(0, 4, 1, 2, 3), (16, cin, 3, 3, 3), dy.float().permute(0, 4, 1, 2, 3), padding=1)
+    got = packed.view(16, 27, cin).permute(0, 2, 1).reshape(16, cin, 3, 3, 3)
+    e = _nmax(got, want)
+    eb = _nmax(dbias, dy.float().sum((0, 1, 2, 3)))
+    print(f"\n[xline wgrad] n{n} d{d} h{h} cin{cin} {dtype}: normalised max error dW {e:.2e} dbias {eb:.2e}")
+    assert e < 2e-3 and eb < 1e-3
+
+
 def test_xline_rejects_what_it_cannot_take():
     from biapy_b200 import _lib, ops
     x = torch.zeros((1, 4, 8, 64, 16), device="cuda", dtype=torch.float16)

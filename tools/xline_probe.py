@@ -146,6 +146,24 @@ def timings48(dtype):
         print(f"time {str(dtype)[6:]} 16->48 @128^3 x4 {name}: {ms:.4f} ms  {gf / ms:.0f} TFLOP/s", flush=True)
 
 
+def timings_wgrad(dtype):
+    """Weight gradient of the 16-output-channel layers at 128^3 x 4: x-folded kernels against the x-line form."""
+    dev = "cuda"
+    for cin in (16, 48):
+        x = torch.randn((4, 128, 128, 128, cin), device=dev).to(dtype)
+        dy = torch.randn((4, 128, 128, 128, 16), device=dev).to(dtype)
+        packed = torch.zeros(16 * 27 * cin, dtype=torch.float32, device=dev)
+        dbias = torch.zeros(16, dtype=torch.float32, device=dev)
+        gf = 2.0 * 4 * 128 ** 3 * cin * 16 * 27 / 1e9
+        rows = [("xfold", lambda: _lib.call("b200_conv_wgrad", ops._ref(x), ops._ref(dy), ops._ptr(packed), ops._ptr(dbias), 3, 3, 3,
+                                            _lib.IMPL_AUTO, ops.stream_ptr())),
+                ("xline", lambda: _lib.call("b200_conv_wgrad_xline", ops._ref(x), ops._ref(dy), ops._ptr(packed), ops._ptr(dbias),
+                                            ops.stream_ptr()))]
+        for name, fn in rows + rows:
+            ms = time_ms(fn, reps=10)
+            print(f"time {str(dtype)[6:]} wgrad {cin}->16 @128^3 x4 {name}: {ms:.4f} ms  {gf / ms:.0f} TFLOP/s", flush=True)
+
+
 def diagnose(dtype, sweep=True):
     """Per-role cycle counters (B200_XL_DBG) and ablation timings (B200_XL_ABLATE) of the full-size launches."""
     dev = "cuda"
@@ -180,6 +198,7 @@ def main():
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--time", action="store_true")
     ap.add_argument("--diag", action="store_true")
+    ap.add_argument("--wgrad", action="store_true")
     ap.add_argument("--diag-quick", action="store_true")
     a = ap.parse_args()
     err = ops.xline_selftest(verbose=3 if (a.diag or a.diag_quick) else 2)
@@ -203,6 +222,9 @@ def main():
         ok &= case(2, 40, 128, 16, hf, stats=True, seed=13)
         ok &= case(1, 128, 128, 16, bf, fuse=2, seed=14)
     print("ALL OK" if ok else "SOME FAILED", flush=True)
+    if a.wgrad:
+        timings_wgrad(torch.float16)
+        timings_wgrad(torch.bfloat16)
     if a.time:
         timings48(torch.float16)
         timings48(torch.bfloat16)
