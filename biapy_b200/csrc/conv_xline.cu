@@ -1094,19 +1094,21 @@ namespace sm100 {
 // ================================================================================================== x-line weight gradient
 // dW[co][tap][ci] += sum over voxels of dY[vox][co] * A[vox + off(tap)][ci] for the 16-output-channel 3x3x3 layers at W = 128 (the
 // layers whose x-folded weight gradient leaves 3/4 of its M = 128 operand to structural zeros).  The contraction index of one GEMM
-// is the 128 voxels of a LINE:
+// is the 128 voxels of a LINE, and one MMA set covers a PAIR of input lines (y, y + 1) of one plane z_in:
 //
-//   D[(dx, ci)][(dz, l, co)] += sum_x  A_dx^T[(dx, ci)][x] * dY^T[(plane z_in - dz + 1, line y_in - 1 + l), co][x]       l = 0..2 (dy = 2 - l)
+//   D[(line, dx, ci)][(dz, lb, co)] += sum_x  A^T[(line, dx, ci)][x] * dY^T[(plane z_in - dz + 1, row y - 1 + lb), co][x]      lb = 0..3
 //
-// * A^T lives in TENSOR MEMORY: lane = (dx, ci) (48 of 128 lanes; the MMA's cost is N-bound, the idle lanes are free), column =
-//   two consecutive voxels; thread (dx, ci) of a staging team gathers its channel of the input line (shifted by dx - 1, zeros at
-//   the ends) from the raw line in shared memory and stores 64 columns.
-// * dY^T is the B operand: transposer warps scatter every dY line once into K-major SWIZZLE_32B tiles [k-step][line * 16 + co][16 x]
-//   of a four-plane ring; the three lines a tap row needs are 48 consecutive rows, so one N = 48 MMA per (dz, k-step): 24 MMAs of
-//   34 cycles per input line, all of them useful MACs.
-// * D = the complete 27-tap gradient block of this input-channel group, 48 lanes x 144 columns, stays in tensor memory for the
-//   whole launch and is added to dw with fp32 atomics once per CTA.
-// Warps: 0-3 dY transposers (and the final reduction), 4-5 / 8-9 two A staging teams on alternate lines, 6 MMA issue, 7 bulk copies.
+// * A^T lives in TENSOR MEMORY: lane = (line of the pair, dx, ci) = 96 of 128 lanes, column = two consecutive voxels.  Scatter warps
+//   (thread = voxel) write every raw activation line as three x-shifted rows per channel into a padded row-major buffer
+//   [(dx, ci)][x] in shared memory (zeros at the line ends stay from the start); three staging warps read their lane's row with
+//   16-byte loads and store 64 columns (tcgen05.st).
+// * dY^T is the B operand: transposer warps scatter every dY line once into K-major SWIZZLE_32B tiles [k-step][row * 16 + co][16 x]
+//   of a four-plane ring; the four dY rows a pair touches are 64 consecutive tile rows: one N = 64 MMA per (dz, k-step), 24 MMAs of
+//   42 cycles per pair of input lines.  Line 0 of the pair uses column blocks lb = 0..2 (dy = 2 - lb), line 1 blocks 1..3 (dy = 3 - lb);
+//   the fourth block of each row group is never read.
+// * D = the complete 27-tap gradient block of this input-channel group, stays in tensor memory for the whole launch and is added
+//   to dw with fp32 atomics once per CTA.
+// Warps: 0-3 dY transposers (and the final reduction), 4-7 activation scatter, 8-10 operand staging, 11 MMA issue, 12 bulk copies.
 struct XwParams {
   int n, d, h;
   int bands, zchunks, zc, units;
@@ -1114,39 +1116,45 @@ struct XwParams {
   int avox_b, aoff_b;              // bytes per voxel of the activation, byte offset of this launch's 16-channel group
   long long gsh_b, gsd_b, gsn_b;   // byte strides of dY (dense 16-channel lines)
   int cin_total, ci_off;
-  uint32_t idesc;                  // N = 48
+  uint32_t idesc;                  // N = 64
 };
 
 template <typename T, int AL>      // AL = bytes of an activation line / 4096 (1: 16 channels per voxel, 3: 48)
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(416, 1)
 conv_wgrad_xline_kernel(const T* __restrict__ a, const T* __restrict__ dy, float* __restrict__ dw, const XwParams p) {
-  constexpr int BYW = 4, DL = BYW + 2;          // input lines per band, dY lines per plane of the window
-  constexpr int NRD = 6, NRA = 4, NAW = 5;      // raw dY ring (lines), raw activation ring (lines), operand ring in TMEM (lines)
+  constexpr int BYW = 4, DL = BYW + 2;          // input lines per band, dY rows per plane of the window
+  constexpr int NRD = 6, NRA = AL == 1 ? 4 : 3; // raw dY ring (lines), raw activation ring (lines)
+  constexpr int NAT = 2, NAW = 5;               // A^T pair buffers in shared memory, operand ring in TMEM (pairs)
   constexpr uint32_t ABYTES = 4096u * AL;
   constexpr uint32_t PSLOT = 8u * (DL * 16u) * 32u;   // one transposed dY plane: 8 k-steps x 96 rows x 32 bytes
   constexpr uint32_t KSTEP = (DL * 16u) * 32u;
-  constexpr uint32_t DCOLS = 144u, ACOL = DCOLS;      // accumulator columns, first operand column
+  constexpr uint32_t ATROW = 272u;                    // 128 voxels x 2 bytes + 16: consecutive rows start 4 banks apart
+  constexpr uint32_t ATLINE = 48u * ATROW, ATPAIR = 2u * ATLINE;
+  constexpr uint32_t DCOLS = 192u, ACOL = DCOLS;      // accumulator columns (3 dz x 4 rows x 16), first operand column
 
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t s_bar[2 * NRD + 2 * NRA + 8 + 2 * NAW + 1];
+  __shared__ uint64_t s_bar[2 * NRD + 2 * NRA + 8 + 2 * NAT + 2 * NAW + 1];
   __shared__ uint32_t s_tmem;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sm_t = smem0, sm_dyr = sm_t + 4u * PSLOT, sm_ar = sm_dyr + NRD * 4096u;
+  const uint32_t sm_t = smem0, sm_dyr = sm_t + 4u * PSLOT, sm_ar = sm_dyr + NRD * 4096u, sm_at = sm_ar + NRA * ABYTES;
   const uint32_t bar0 = smem_u32(s_bar);
   const uint32_t dyr_full = bar0, dyr_free = dyr_full + 8 * NRD, ar_full = dyr_free + 8 * NRD, ar_free = ar_full + 8 * NRA,
-                 pl_full = ar_free + 8 * NRA, pl_free = pl_full + 32, a_full = pl_free + 32, a_free = a_full + 8 * NAW,
-                 done = a_free + 8 * NAW;
+                 pl_full = ar_free + 8 * NRA, pl_free = pl_full + 32, at_full = pl_free + 32, at_free = at_full + 8 * NAT,
+                 a_full = at_free + 8 * NAT, a_free = a_full + 8 * NAW, done = a_free + 8 * NAW;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NRD; ++i) { mbar_init(dyr_full + 8 * i, 1); mbar_init(dyr_free + 8 * i, 4); }
-    for (int i = 0; i < NRA; ++i) { mbar_init(ar_full + 8 * i, 1); mbar_init(ar_free + 8 * i, 2); }
+    for (int i = 0; i < NRA; ++i) { mbar_init(ar_full + 8 * i, 1); mbar_init(ar_free + 8 * i, 4); }
     for (int i = 0; i < 4; ++i) { mbar_init(pl_full + 8 * i, 4); mbar_init(pl_free + 8 * i, 1); }
-    for (int i = 0; i < NAW; ++i) { mbar_init(a_full + 8 * i, 2); mbar_init(a_free + 8 * i, 1); }
+    for (int i = 0; i < NAT; ++i) { mbar_init(at_full + 8 * i, 4); mbar_init(at_free + 8 * i, 3); }
+    for (int i = 0; i < NAW; ++i) { mbar_init(a_full + 8 * i, 3); mbar_init(a_free + 8 * i, 1); }
     mbar_init(done, 1);
     fence_barrier_init();
   }
-  if (warp == 6) tmem_alloc(smem_u32(&s_tmem), 512);
+  if (warp == 11) tmem_alloc(smem_u32(&s_tmem), 512);
+  // the A^T buffers start at zero: the first column of the dx = 0 rows and the last column of the dx = 2 rows are never written
+  for (uint32_t o = threadIdx.x * 16u; o < NAT * ATPAIR; o += blockDim.x * 16u) st_shared_v4(sm_at + o, make_uint4(0u, 0u, 0u, 0u));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1154,7 +1162,7 @@ conv_wgrad_xline_kernel(const T* __restrict__ a, const T* __restrict__ dy, float
   if (warp < 4) {                                   // accumulators and every lane of the operand ring start at zero
     const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
-    for (uint32_t c = 0; c < DCOLS + NAW * 64u; c += 16) tmem_st16_zero(tl + c);
+    for (uint32_t c = 0; c < 512u; c += 16) tmem_st16_zero(tl + c);
     tmem_st_wait();
   }
   tc_fence_before();
@@ -1171,7 +1179,7 @@ conv_wgrad_xline_kernel(const T* __restrict__ a, const T* __restrict__ dy, float
     zhi = z0 + p.zc < p.d ? z0 + p.zc : p.d;
   };
 
-  if (warp == 7) {
+  if (warp == 12) {
     // ===================================================================== bulk copies: dY lines plane by plane, activation lines
     if (elect_one()) {
       int rd = 0, ra = 0;
@@ -1210,12 +1218,12 @@ conv_wgrad_xline_kernel(const T* __restrict__ a, const T* __restrict__ dy, float
         }
       }
     }
-  } else if (warp == 6) {
+  } else if (warp == 11) {
     // ===================================================================== MMA issue
     if (elect_one()) {
       const uint32_t idesc = in_reg(p.idesc);
       const uint32_t b_hi = (256u >> 4) | (1u << 14) | ((uint32_t)kSwizzle32 << 29);
-      uint32_t qbase = 0, lc = 0;
+      uint32_t qbase = 0, pc = 0;                   // planes produced before this unit, pairs consumed
       for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
         int n, z0, zhi, y0;
         decode(u, n, z0, zhi, y0);
@@ -1230,22 +1238,22 @@ conv_wgrad_xline_kernel(const T* __restrict__ a, const T* __restrict__ dy, float
           }
           tc_fence_after();
 #pragma unroll 1
-          for (int j = 0; j < BYW; ++j) {
-            if (y0 + j >= p.h) continue;
-            const uint32_t aslot = lc % NAW;
-            xl_wait(a_full + 8 * aslot, (lc / NAW) & 1u);
+          for (int t = 0; t < BYW / 2; ++t) {
+            if (y0 + 2 * t >= p.h) continue;
+            const uint32_t aslot = pc % NAW;
+            xl_wait(a_full + 8 * aslot, (pc / NAW) & 1u);
             tc_fence_after();
             const uint32_t a_t = tmem + ACOL + aslot * 64u;
 #pragma unroll
             for (int dz = 0; dz < 3; ++dz) {
               const uint32_t qq = qbase + (uint32_t)(pic - dz + 1);
-              const uint32_t b_lo = (((sm_t + (qq & 3u) * PSLOT + (uint32_t)j * 512u) >> 4) & 0x3FFFu) | (1u << 16);
+              const uint32_t b_lo = (((sm_t + (qq & 3u) * PSLOT + (uint32_t)t * 1024u) >> 4) & 0x3FFFu) | (1u << 16);
 #pragma unroll
               for (int ks = 0; ks < 8; ++ks)
-                umma_f16_ts(tmem + (uint32_t)dz * 48u, a_t + 8u * ks, b_lo + (uint32_t)ks * (KSTEP >> 4), b_hi, idesc, 1u);
+                umma_f16_ts(tmem + (uint32_t)dz * 64u, a_t + 8u * ks, b_lo + (uint32_t)ks * (KSTEP >> 4), b_hi, idesc, 1u);
             }
             umma_commit(a_free + 8 * aslot);
-            ++lc;
+            ++pc;
           }
           umma_commit(pl_free + 8 * ((qbase + (uint32_t)(pic - 1)) & 3u));      // the plane below the centre is not needed again
         }
@@ -1255,56 +1263,85 @@ conv_wgrad_xline_kernel(const T* __restrict__ a, const T* __restrict__ dy, float
       }
       umma_commit(done);
     }
-  } else if (warp >= 4) {
-    // ===================================================================== activation staging: A^T of a line into tensor memory
-    const uint32_t team = warp >= 8 ? 1u : 0u;
-    const int L = (warp & 1) * 32 + lane;           // TMEM lane = (dx, ci)
-    const bool active = L < 48;
-    const int dx = L >> 4, ci = L & 15;
-    const uint32_t tl = tmem + ((uint32_t)((warp & 1) * 32) << 16) + ACOL;
-    int ra = 0;
-    uint32_t raph = 0, lc = 0;
+  } else if (warp >= 8) {
+    // ===================================================================== operand staging: A^T rows of a pair -> tensor memory
+    const int q = warp - 8;                         // TMEM lane quarter 0..2: lanes (line, dx, ci) = 0..95
+    const int L = q * 32 + lane;
+    const uint32_t rowoff = (uint32_t)(L < 48 ? L : L - 48) * ATROW + (L < 48 ? 0u : ATLINE);
+    const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16) + ACOL;
+    uint32_t pc = 0;
     for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
       int n, z0, zhi, y0;
       decode(u, n, z0, zhi, y0);
       for (int zin = z0; zin < zhi; ++zin) {
 #pragma unroll 1
-        for (int j = 0; j < BYW; ++j) {
-          if (y0 + j >= p.h) continue;
-          if ((lc & 1u) == team) {
-            xl_wait(ar_full + 8 * ra, raph);
-            const uint32_t base = sm_ar + (uint32_t)ra * ABYTES + (uint32_t)p.aoff_b + (uint32_t)ci * 2u;
-            uint32_t r[64];
+        for (int t = 0; t < BYW / 2; ++t) {
+          if (y0 + 2 * t >= p.h) continue;
+          const uint32_t ats = pc % NAT, aslot = pc % NAW;
+          xl_wait(at_full + 8 * ats, (pc / NAT) & 1u);
+          uint32_t r[64];
+          const uint32_t src = sm_at + ats * ATPAIR + rowoff;
 #pragma unroll
-            for (int xp = 0; xp < 64; ++xp) {
-              const int x0 = 2 * xp + dx - 1;
-              uint32_t lo = 0, hi = 0;
-              if (active && x0 >= 0) {
-                uint16_t t16;
-                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(t16) : "r"(base + (uint32_t)x0 * (uint32_t)p.avox_b));
-                lo = t16;
-              }
-              if (active && x0 + 1 < 128) {
-                uint16_t t16;
-                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(t16) : "r"(base + (uint32_t)(x0 + 1) * (uint32_t)p.avox_b));
-                hi = t16;
-              }
-              r[xp] = lo | (hi << 16);
+          for (int j = 0; j < 16; ++j)
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(r[4 * j]), "=r"(r[4 * j + 1]), "=r"(r[4 * j + 2]), "=r"(r[4 * j + 3])
+                         : "r"(src + 16u * j));
+          __syncwarp();
+          if (lane == 0) mbar_arrive(at_free + 8 * ats);
+          xl_wait(a_free + 8 * aslot, ((pc / NAW) & 1u) ^ 1u);
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) tmem_st8(tl + aslot * 64u + 8u * ks, r + 8 * ks);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(a_full + 8 * aslot);
+          ++pc;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================================================== activation scatter: raw line -> three x-shifted rows per channel
+    const int xv = (warp - 4) * 32 + lane;
+    int ra = 0;
+    uint32_t raph = 0, pc = 0;
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+      int n, z0, zhi, y0;
+      decode(u, n, z0, zhi, y0);
+      for (int zin = z0; zin < zhi; ++zin) {
+#pragma unroll 1
+        for (int t = 0; t < BYW / 2; ++t) {
+          if (y0 + 2 * t >= p.h) continue;
+          const uint32_t ats = pc % NAT;
+          xl_wait(at_free + 8 * ats, ((pc / NAT) & 1u) ^ 1u);
+#pragma unroll 1
+          for (int ln = 0; ln < 2; ++ln) {
+            uint32_t v[8];
+            if (y0 + 2 * t + ln < p.h) {
+              xl_wait(ar_full + 8 * ra, raph);
+              const uint32_t src = sm_ar + (uint32_t)ra * ABYTES + (uint32_t)xv * (uint32_t)p.avox_b + (uint32_t)p.aoff_b;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(src));
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(src + 16u));
+              __syncwarp();
+              if (lane == 0) mbar_arrive(ar_free + 8 * ra);
+              if (++ra == NRA) { ra = 0; raph ^= 1; }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = 0u;                       // the pair's second line lies outside the volume
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(ar_free + 8 * ra);
-            const uint32_t aslot = lc % NAW;
-            xl_wait(a_free + 8 * aslot, ((lc / NAW) & 1u) ^ 1u);
-            tc_fence_after();
+            const uint32_t dst = sm_at + ats * ATPAIR + (uint32_t)ln * ATLINE + (uint32_t)xv * 2u;
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) tmem_st8(tl + aslot * 64u + 8u * ks, r + 8 * ks);
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(a_full + 8 * aslot);
+            for (int ci = 0; ci < 16; ++ci) {
+              const uint16_t hv = (uint16_t)((ci & 1) ? (v[ci >> 1] >> 16) : (v[ci >> 1] & 0xffffu));
+              // A_dx^T[(dx, ci)][x'] = a[x' + dx - 1][ci]: voxel xv lands at column xv - dx + 1
+              if (xv < 127) asm volatile("st.shared.u16 [%0], %1;" ::"r"(dst + (uint32_t)ci * ATROW + 2u), "h"(hv) : "memory");
+              asm volatile("st.shared.u16 [%0], %1;" ::"r"(dst + (uint32_t)(16 + ci) * ATROW), "h"(hv) : "memory");
+              if (xv > 0) asm volatile("st.shared.u16 [%0], %1;" ::"r"(dst + (uint32_t)(32 + ci) * ATROW - 2u), "h"(hv) : "memory");
+            }
           }
-          if (++ra == NRA) { ra = 0; raph ^= 1; }
-          ++lc;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(at_full + 8 * ats);
+          ++pc;
         }
       }
     }
@@ -1352,16 +1389,17 @@ conv_wgrad_xline_kernel(const T* __restrict__ a, const T* __restrict__ dy, float
     }
     xl_wait(done, 0);
     tc_fence_after();
-    if (warp < 2) {
-      const int L = warp * 32 + lane;
-      const int dx = L >> 4, ci = L & 15;
+    if (warp < 3) {
+      const int L = warp * 32 + lane;               // (line of the pair, dx, ci)
+      const int ln = L >= 48 ? 1 : 0, dx = (L - 48 * ln) >> 4, ci = L & 15;
 #pragma unroll 1
-      for (int c16 = 0; c16 < 9; ++c16) {
+      for (int c16 = 0; c16 < 12; ++c16) {
         uint32_t r[16];
         tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c16 * 16u, r);
         tmem_ld_wait();
-        if (L < 48) {
-          const int dz = c16 / 3, dyt = 2 - (c16 % 3);
+        const int dz = c16 >> 2, lb = c16 & 3;
+        const int dyt = 2 + ln - lb;                // line 0 of a pair: dy = 2 - lb, line 1: dy = 3 - lb
+        if (L < 96 && dyt >= 0 && dyt < 3) {
           const int tap = (dz * 3 + dyt) * 3 + dx;
 #pragma unroll
           for (int co = 0; co < 16; ++co)
@@ -1372,7 +1410,7 @@ conv_wgrad_xline_kernel(const T* __restrict__ a, const T* __restrict__ dy, float
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 6) tmem_dealloc(tmem, 512);
+  if (warp == 11) tmem_dealloc(tmem, 512);
 }
 
 bool conv_wgrad_xline_ok(const ActView& x, const ActView& dy) {
@@ -1393,7 +1431,7 @@ static int launch_wgrad_xline(const ActView& x, const ActView& dy, float* dw, in
   p.avox_b = x.c * 2; p.aoff_b = ci_off * 2;
   p.gsh_b = dy.sh * 2; p.gsd_b = dy.sd * 2; p.gsn_b = dy.sn * 2;
   p.cin_total = x.c; p.ci_off = ci_off;
-  p.idesc = make_idesc(x.dtype == B200_BF16, 48, 0, 0);
+  p.idesc = make_idesc(x.dtype == B200_BF16, 64, 0, 0);
   p.bands = (int)ceil_div(x.h, 4);
   {
     double best = -1.0;
@@ -1409,10 +1447,10 @@ static int launch_wgrad_xline(const ActView& x, const ActView& dy, float* dw, in
   }
   p.units = x.n * p.bands * p.zchunks;
   const int grid = p.units < sm_count() ? p.units : sm_count();
-  const size_t smem = 4u * (8u * 96u * 32u) + 6u * 4096u + 4u * 4096u * AL + 1024u;
+  const size_t smem = 4u * (8u * 96u * 32u) + 6u * 4096u + (size_t)(AL == 1 ? 4 : 3) * 4096u * AL + 2u * (2u * 48u * 272u) + 1024u;
   auto kern = conv_wgrad_xline_kernel<T, AL>;
   B200_CUDA(raise_dyn_smem_cap(kern));
-  kern<<<grid, 320, smem, st>>>((const T*)x.data, (const T*)dy.data, dw, p);
+  kern<<<grid, 416, smem, st>>>((const T*)x.data, (const T*)dy.data, dw, p);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

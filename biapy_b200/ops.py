@@ -308,6 +308,9 @@ def conv_fprop_stats(x, w_packed_xfold, bias, y, k: Sequence[int], sums: torch.T
 
 # B200_XLINE_WGRAD = 0 keeps the 16-output-channel 3x3x3 weight gradients at W = 128 on the x-folded kernels
 XLINE_WGRAD = os.environ.get("B200_XLINE_WGRAD", "1") != "0"
+# input-channel counts that take it: 16 -> 16 measured 0.32 ms against 0.38 x-folded (128^3 x 4); 48 -> 16 (three launches, one per
+# 16-channel group, each transposing dY again) 0.94-1.00 against 0.82-0.87, so it stays x-folded unless B200_XLINE_WGRAD_CIN lists it
+XLINE_WGRAD_CIN = tuple(int(v) for v in os.environ.get("B200_XLINE_WGRAD_CIN", "16").split(",") if v)
 
 _WGRAD_N = (256, 128, 64, 32, 16)        # output-channel widths of the tcgen05 weight-gradient kernels (one N tile each)
 
@@ -332,7 +335,7 @@ def conv_wgrad(x, dy, cout: int, cin: int, k: Sequence[int], dw_out: torch.Tenso
     taps = k[0] * k[1] * k[2]
     packed = zeros(cout * taps * cin, torch.float32, x.device)
     if (impl == _lib.IMPL_AUTO and XLINE_WGRAD and x.dtype != torch.float32 and cout == 16 and tuple(k) == (3, 3, 3)
-            and x.shape[3] == 128 and cin in (16, 48)
+            and x.shape[3] == 128 and cin in XLINE_WGRAD_CIN
             and _lib.lib().b200_conv_wgrad_xline_supported(_ref(x), _ref(dy), 3, 3, 3)):
         # x-line weight gradient (csrc/conv_xline.cu): the contraction runs over the voxels of a line, the transposed activation
         # line sits in tensor memory, the 27-tap block is accumulated in tensor memory for the whole launch
