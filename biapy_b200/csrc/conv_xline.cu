@@ -66,6 +66,18 @@ __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// four 8 x 8 matrices of 16-bit elements: lane 8 m + i gives the address of row i (16 bytes) of matrix m; loaded transposed
+// (register m of thread T = elements [2 (T % 4)][T / 4], [2 (T % 4) + 1][T / 4] of matrix m), stored as they sit in the registers
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t* r) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr)
+               : "memory");
+}
+__device__ __forceinline__ void stmatrix_x4(uint32_t addr, const uint32_t* r) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3])
+               : "memory");
+}
 
 // D[tmem] += A[tmem] * B[smem]: A = 128 lanes x 8 columns (16 K-elements of 16 bits, two per column)
 __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
@@ -1098,17 +1110,19 @@ namespace sm100 {
 //
 //   D[(line, dx, ci)][(dz, lb, co)] += sum_x  A^T[(line, dx, ci)][x] * dY^T[(plane z_in - dz + 1, row y - 1 + lb), co][x]      lb = 0..3
 //
-// * A^T lives in TENSOR MEMORY: lane = (line of the pair, dx, ci) = 96 of 128 lanes, column = two consecutive voxels.  Scatter warps
-//   (thread = voxel) write every raw activation line as three x-shifted rows per channel into a padded row-major buffer
-//   [(dx, ci)][x] in shared memory (zeros at the line ends stay from the start); three staging warps read their lane's row with
-//   16-byte loads and store 64 columns (tcgen05.st).
-// * dY^T is the B operand: transposer warps scatter every dY line once into K-major SWIZZLE_32B tiles [k-step][row * 16 + co][16 x]
+// * A^T lives in TENSOR MEMORY: lane = (line of the pair, dx, ci) = 96 of 128 lanes, column = two consecutive voxels.  Transposer
+//   warps turn every raw activation line [x][ci] into ONE row-major copy [ci][x] in shared memory (ldmatrix.trans + stmatrix, 8 x 8
+//   blocks; rows 272 bytes apart with a 16-byte zero pad between them); three staging warps read their lane's row with 16-byte
+//   loads, apply the x shift of their dx in registers (a 16-bit funnel shift across neighbouring words, the pads supply the zeros
+//   at the line ends) and store 64 columns (tcgen05.st).
+// * dY^T is the B operand: transposer warps turn every dY line once (ldmatrix.trans + stmatrix again: the first form, one 2-byte
+//   store per element, kept the shared-memory pipe 91 % busy) into K-major SWIZZLE_32B tiles [k-step][row * 16 + co][16 x]
 //   of a four-plane ring; the four dY rows a pair touches are 64 consecutive tile rows: one N = 64 MMA per (dz, k-step), 24 MMAs of
 //   42 cycles per pair of input lines.  Line 0 of the pair uses column blocks lb = 0..2 (dy = 2 - lb), line 1 blocks 1..3 (dy = 3 - lb);
 //   the fourth block of each row group is never read.
 // * D = the complete 27-tap gradient block of this input-channel group, stays in tensor memory for the whole launch and is added
 //   to dw with fp32 atomics once per CTA.
-// Warps: 0-3 dY transposers (and the final reduction), 4-7 activation scatter, 8-10 operand staging, 11 MMA issue, 12 bulk copies.
+// Warps: 0-3 dY transposers (and the final reduction), 4-7 activation transposers, 8-10 operand staging, 11 MMA issue, 12 bulk copies.
 struct XwParams {
   int n, d, h;
   int bands, zchunks, zc, units;
@@ -1123,20 +1137,20 @@ template <typename T, int AL>      // AL = bytes of an activation line / 4096 (1
 __global__ void __launch_bounds__(416, 1)
 conv_wgrad_xline_kernel(const T* __restrict__ a, const T* __restrict__ dy, float* __restrict__ dw, const XwParams p) {
   constexpr int BYW = 4, DL = BYW + 2;          // input lines per band, dY rows per plane of the window
-  constexpr int NRD = 6, NRA = AL == 1 ? 4 : 3; // raw dY ring (lines), raw activation ring (lines)
-  constexpr int NAT = 2, NAW = 5;               // A^T pair buffers in shared memory, operand ring in TMEM (pairs)
+  constexpr int NRD = 2, NRA = AL == 1 ? 4 : 2; // raw dY ring (windows of DL rows of one plane), raw activation ring (pairs of lines)
+  constexpr int NAT = AL == 1 ? 4 : 3, NAW = 5; // A^T pair buffers in shared memory, operand ring in TMEM (pairs)
   constexpr uint32_t ABYTES = 4096u * AL;
   constexpr uint32_t PSLOT = 8u * (DL * 16u) * 32u;   // one transposed dY plane: 8 k-steps x 96 rows x 32 bytes
   constexpr uint32_t KSTEP = (DL * 16u) * 32u;
-  constexpr uint32_t ATROW = 272u;                    // 128 voxels x 2 bytes + 16: consecutive rows start 4 banks apart
-  constexpr uint32_t ATLINE = 48u * ATROW, ATPAIR = 2u * ATLINE;
+  constexpr uint32_t ATROW = 272u;                    // 16 bytes of zeros + 128 voxels x 2 bytes: consecutive rows start 4 banks apart
+  constexpr uint32_t ATLINE = 16u * ATROW, ATPAIR = 2u * ATLINE + 16u;   // [line][ci] rows and the pad behind the last row
   constexpr uint32_t DCOLS = 192u, ACOL = DCOLS;      // accumulator columns (3 dz x 4 rows x 16), first operand column
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t s_bar[2 * NRD + 2 * NRA + 8 + 2 * NAT + 2 * NAW + 1];
   __shared__ uint32_t s_tmem;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sm_t = smem0, sm_dyr = sm_t + 4u * PSLOT, sm_ar = sm_dyr + NRD * 4096u, sm_at = sm_ar + NRA * ABYTES;
+  const uint32_t sm_t = smem0, sm_dyr = sm_t + 4u * PSLOT, sm_ar = sm_dyr + NRD * DL * 4096u, sm_at = sm_ar + NRA * 2u * ABYTES;
   const uint32_t bar0 = smem_u32(s_bar);
   const uint32_t dyr_full = bar0, dyr_free = dyr_full + 8 * NRD, ar_full = dyr_free + 8 * NRD, ar_free = ar_full + 8 * NRA,
                  pl_full = ar_free + 8 * NRA, pl_free = pl_full + 32, at_full = pl_free + 32, at_free = at_full + 8 * NAT,
@@ -1153,7 +1167,7 @@ conv_wgrad_xline_kernel(const T* __restrict__ a, const T* __restrict__ dy, float
     fence_barrier_init();
   }
   if (warp == 11) tmem_alloc(smem_u32(&s_tmem), 512);
-  // the A^T buffers start at zero: the first column of the dx = 0 rows and the last column of the dx = 2 rows are never written
+  // the A^T buffers start at zero: the pads between the rows are never written
   for (uint32_t o = threadIdx.x * 16u; o < NAT * ATPAIR; o += blockDim.x * 16u) st_shared_v4(sm_at + o, make_uint4(0u, 0u, 0u, 0u));
   tc_fence_before();
   __syncthreads();
@@ -1180,7 +1194,8 @@ conv_wgrad_xline_kernel(const T* __restrict__ a, const T* __restrict__ dy, float
   };
 
   if (warp == 12) {
-    // ===================================================================== bulk copies: dY lines plane by plane, activation lines
+    // ===================================================================== bulk copies: ONE copy per dY window of a plane (its rows are
+    // contiguous in a dense tensor) and ONE per pair of activation lines -- with a copy per line the issuing thread was the limit
     if (elect_one()) {
       int rd = 0, ra = 0;
       uint32_t rdph = 0, raph = 0;
@@ -1189,29 +1204,27 @@ conv_wgrad_xline_kernel(const T* __restrict__ a, const T* __restrict__ dy, float
       for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
         int n, z0, zhi, y0;
         decode(u, n, z0, zhi, y0);
+        const int ylo = y0 > 0 ? y0 - 1 : 0, yhi = y0 + BYW + 1 < p.h ? y0 + BYW + 1 : p.h;   // rows of the window inside the volume
+        const uint32_t dbytes = (uint32_t)(yhi - ylo) * 4096u;
+        const char* gn = gb + (long long)n * p.gsn_b + (long long)ylo * p.gsh_b;
+        const char* an = ab + (long long)n * p.asn_b;
         for (int P = z0 - 1; P <= zhi; ++P) {
           if ((unsigned)P < (unsigned)p.d) {
-#pragma unroll 1
-            for (int l = 0; l < DL; ++l) {
-              const int y = y0 - 1 + l;
-              if ((unsigned)y >= (unsigned)p.h) continue;
-              xl_wait(dyr_free + 8 * rd, rdph ^ 1);
-              mbar_expect_tx(dyr_full + 8 * rd, 4096u);
-              bulk_g2s(sm_dyr + (uint32_t)rd * 4096u, gb + (long long)n * p.gsn_b + (long long)P * p.gsd_b + (long long)y * p.gsh_b, 4096u,
-                       dyr_full + 8 * rd);
-              if (++rd == NRD) { rd = 0; rdph ^= 1; }
-            }
+            xl_wait(dyr_free + 8 * rd, rdph ^ 1);
+            mbar_expect_tx(dyr_full + 8 * rd, dbytes);
+            bulk_g2s(sm_dyr + (uint32_t)(rd * DL + (ylo - (y0 - 1))) * 4096u, gn + (long long)P * p.gsd_b, dbytes, dyr_full + 8 * rd);
+            if (++rd == NRD) { rd = 0; rdph ^= 1; }
           }
           const int zin = P - 1;
           if (zin >= z0 && zin < zhi) {
 #pragma unroll 1
-            for (int j = 0; j < BYW; ++j) {
-              const int y = y0 + j;
+            for (int t = 0; t < BYW / 2; ++t) {
+              const int y = y0 + 2 * t;
               if (y >= p.h) continue;
+              const uint32_t abytes = y + 1 < p.h ? 2u * ABYTES : ABYTES;
               xl_wait(ar_free + 8 * ra, raph ^ 1);
-              mbar_expect_tx(ar_full + 8 * ra, ABYTES);
-              bulk_g2s(sm_ar + (uint32_t)ra * ABYTES, ab + (long long)n * p.asn_b + (long long)zin * p.asd_b + (long long)y * p.ash_b, ABYTES,
-                       ar_full + 8 * ra);
+              mbar_expect_tx(ar_full + 8 * ra, abytes);
+              bulk_g2s(sm_ar + (uint32_t)ra * 2u * ABYTES, an + (long long)zin * p.asd_b + (long long)y * p.ash_b, abytes, ar_full + 8 * ra);
               if (++ra == NRA) { ra = 0; raph ^= 1; }
             }
           }
@@ -1267,7 +1280,9 @@ conv_wgrad_xline_kernel(const T* __restrict__ a, const T* __restrict__ dy, float
     // ===================================================================== operand staging: A^T rows of a pair -> tensor memory
     const int q = warp - 8;                         // TMEM lane quarter 0..2: lanes (line, dx, ci) = 0..95
     const int L = q * 32 + lane;
-    const uint32_t rowoff = (uint32_t)(L < 48 ? L : L - 48) * ATROW + (L < 48 ? 0u : ATLINE);
+    const int dx = ((L < 48 ? L : L - 48) >> 4);    // the fourth warp quarter (lanes 96..127) does not exist: 3 warps
+    const uint32_t rowoff = (uint32_t)(L & 15) * ATROW + (L < 48 ? 0u : ATLINE) + 16u;
+    const uint32_t sh = dx == 1 ? 0u : 16u;
     const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16) + ACOL;
     uint32_t pc = 0;
     for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
@@ -1279,15 +1294,21 @@ conv_wgrad_xline_kernel(const T* __restrict__ a, const T* __restrict__ dy, float
           if (y0 + 2 * t >= p.h) continue;
           const uint32_t ats = pc % NAT, aslot = pc % NAW;
           xl_wait(at_full + 8 * ats, (pc / NAT) & 1u);
-          uint32_t r[64];
+          uint32_t w[66], r[64];                    // w[1 + j] = voxels 2 j, 2 j + 1 of the row; w[0], w[65] = the pads (zeros)
           const uint32_t src = sm_at + ats * ATPAIR + rowoff;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w[0]) : "r"(src - 4u));
 #pragma unroll
           for (int j = 0; j < 16; ++j)
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(r[4 * j]), "=r"(r[4 * j + 1]), "=r"(r[4 * j + 2]), "=r"(r[4 * j + 3])
+                         : "=r"(w[1 + 4 * j]), "=r"(w[2 + 4 * j]), "=r"(w[3 + 4 * j]), "=r"(w[4 + 4 * j])
                          : "r"(src + 16u * j));
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w[65]) : "r"(src + 256u));
           __syncwarp();
           if (lane == 0) mbar_arrive(at_free + 8 * ats);
+          // A_dx^T[x'] = a[x' + dx - 1]: dx = 0 takes (a[2j - 1], a[2j]), dx = 1 the word as it is, dx = 2 (a[2j + 1], a[2j + 2])
+#pragma unroll
+          for (int j = 0; j < 64; ++j)
+            r[j] = __funnelshift_r(dx == 0 ? w[j] : w[j + 1], dx == 0 ? w[j + 1] : w[j + 2], sh);
           xl_wait(a_free + 8 * aslot, ((pc / NAW) & 1u) ^ 1u);
           tc_fence_after();
 #pragma unroll
@@ -1301,8 +1322,16 @@ conv_wgrad_xline_kernel(const T* __restrict__ a, const T* __restrict__ dy, float
       }
     }
   } else if (warp >= 4) {
-    // ===================================================================== activation scatter: raw line -> three x-shifted rows per channel
-    const int xv = (warp - 4) * 32 + lane;
+    // ===================================================================== activation lines [x][ci] -> rows [ci][x], 8 x 8 blocks
+    // warp w owns the voxel blocks xb = 4 w .. 4 w + 3; instruction k of a line moves xb = 4 w + 2 k + (m >> 1), channel block m & 1
+    const int m = lane >> 3, i = lane & 7;
+    uint32_t ld_off[2], st_off[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const uint32_t xb = (uint32_t)(4 * (warp - 4) + 2 * k + (m >> 1)), cb = (uint32_t)(m & 1);
+      ld_off[k] = (8u * xb + (uint32_t)i) * (uint32_t)p.avox_b + (uint32_t)p.aoff_b + 16u * cb;
+      st_off[k] = (8u * cb + (uint32_t)i) * ATROW + 16u + 16u * xb;
+    }
     int ra = 0;
     uint32_t raph = 0, pc = 0;
     for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
@@ -1314,30 +1343,26 @@ conv_wgrad_xline_kernel(const T* __restrict__ a, const T* __restrict__ dy, float
           if (y0 + 2 * t >= p.h) continue;
           const uint32_t ats = pc % NAT;
           xl_wait(at_free + 8 * ats, ((pc / NAT) & 1u) ^ 1u);
-#pragma unroll 1
+          uint32_t v[2][2][4];
+          xl_wait(ar_full + 8 * ra, raph);
+          const uint32_t src = sm_ar + (uint32_t)ra * 2u * ABYTES;
+          ldmatrix_x4_trans(src + ld_off[0], v[0][0]);
+          ldmatrix_x4_trans(src + ld_off[1], v[0][1]);
+          if (y0 + 2 * t + 1 < p.h) {
+            ldmatrix_x4_trans(src + ABYTES + ld_off[0], v[1][0]);
+            ldmatrix_x4_trans(src + ABYTES + ld_off[1], v[1][1]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[1][0][e] = v[1][1][e] = 0u;      // the pair's second line lies outside the volume
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(ar_free + 8 * ra);
+          if (++ra == NRA) { ra = 0; raph ^= 1; }
+          const uint32_t dst = sm_at + ats * ATPAIR;
+#pragma unroll
           for (int ln = 0; ln < 2; ++ln) {
-            uint32_t v[8];
-            if (y0 + 2 * t + ln < p.h) {
-              xl_wait(ar_full + 8 * ra, raph);
-              const uint32_t src = sm_ar + (uint32_t)ra * ABYTES + (uint32_t)xv * (uint32_t)p.avox_b + (uint32_t)p.aoff_b;
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(src));
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(src + 16u));
-              __syncwarp();
-              if (lane == 0) mbar_arrive(ar_free + 8 * ra);
-              if (++ra == NRA) { ra = 0; raph ^= 1; }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = 0u;                       // the pair's second line lies outside the volume
-            }
-            const uint32_t dst = sm_at + ats * ATPAIR + (uint32_t)ln * ATLINE + (uint32_t)xv * 2u;
-#pragma unroll
-            for (int ci = 0; ci < 16; ++ci) {
-              const uint16_t hv = (uint16_t)((ci & 1) ? (v[ci >> 1] >> 16) : (v[ci >> 1] & 0xffffu));
-              // A_dx^T[(dx, ci)][x'] = a[x' + dx - 1][ci]: voxel xv lands at column xv - dx + 1
-              if (xv < 127) asm volatile("st.shared.u16 [%0], %1;" ::"r"(dst + (uint32_t)ci * ATROW + 2u), "h"(hv) : "memory");
-              asm volatile("st.shared.u16 [%0], %1;" ::"r"(dst + (uint32_t)(16 + ci) * ATROW), "h"(hv) : "memory");
-              if (xv > 0) asm volatile("st.shared.u16 [%0], %1;" ::"r"(dst + (uint32_t)(32 + ci) * ATROW - 2u), "h"(hv) : "memory");
-            }
+            stmatrix_x4(dst + (uint32_t)ln * ATLINE + st_off[0], v[ln][0]);
+            stmatrix_x4(dst + (uint32_t)ln * ATLINE + st_off[1], v[ln][1]);
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(at_full + 8 * ats);
@@ -1347,7 +1372,16 @@ conv_wgrad_xline_kernel(const T* __restrict__ a, const T* __restrict__ dy, float
     }
   } else {
     // ===================================================================== dY transposition, then the reduction of the accumulators
-    const int xv = warp * 32 + lane;
+    // warp w owns the voxel blocks xb = 4 w .. 4 w + 3 of every line; instruction k moves xb = 4 w + 2 k + (m >> 1), channel block
+    // m & 1: rows co = 8 (m & 1) + i of tile row group l, k-step xb >> 1, 16-byte chunk (xb & 1) ^ (row bit 2) (SWIZZLE_32B)
+    const int m = lane >> 3, i = lane & 7;
+    uint32_t ld_off[2], st_off[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const uint32_t xb = (uint32_t)(4 * warp + 2 * k + (m >> 1)), cb = (uint32_t)(m & 1);
+      ld_off[k] = (8u * xb + (uint32_t)i) * 32u + 16u * cb;
+      st_off[k] = (xb >> 1) * KSTEP + (8u * cb + (uint32_t)i) * 32u + (((xb & 1u) ^ ((uint32_t)(i >> 2) & 1u)) << 4);
+    }
     int rd = 0;
     uint32_t rdph = 0, qn = 0;
     for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
@@ -1356,31 +1390,28 @@ conv_wgrad_xline_kernel(const T* __restrict__ a, const T* __restrict__ dy, float
       for (int P = z0 - 1; P <= zhi; ++P, ++qn) {
         const uint32_t slot = qn & 3u;
         xl_wait(pl_free + 8 * slot, ((qn >> 2) & 1u) ^ 1u);
-        const uint32_t tbase = sm_t + slot * PSLOT + (uint32_t)(xv >> 4) * KSTEP + (uint32_t)(xv & 7) * 2u;
-        const uint32_t half = (uint32_t)((xv >> 3) & 1);
-#pragma unroll 1
+        const uint32_t tbase = sm_t + slot * PSLOT;
+        const bool plane_in = (unsigned)P < (unsigned)p.d;
+        const uint32_t src = sm_dyr + (uint32_t)rd * (DL * 4096u);
+        if (plane_in) xl_wait(dyr_full + 8 * rd, rdph);
+#pragma unroll
         for (int l = 0; l < DL; ++l) {
           const int y = y0 - 1 + l;
-          uint32_t v[8];
-          if ((unsigned)P < (unsigned)p.d && (unsigned)y < (unsigned)p.h) {
-            xl_wait(dyr_full + 8 * rd, rdph);
-            const uint32_t src = sm_dyr + (uint32_t)rd * 4096u + (uint32_t)xv * 32u;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(src));
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(src + 16u));
+          uint32_t v[2][4];
+          if (plane_in && (unsigned)y < (unsigned)p.h) {
+            ldmatrix_x4_trans(src + (uint32_t)l * 4096u + ld_off[0], v[0]);
+            ldmatrix_x4_trans(src + (uint32_t)l * 4096u + ld_off[1], v[1]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[0][e] = v[1][e] = 0u;
+          }
+          if (l == DL - 1 && plane_in) {            // every row of the window sits in registers: hand the slot back
             __syncwarp();
             if (lane == 0) mbar_arrive(dyr_free + 8 * rd);
             if (++rd == NRD) { rd = 0; rdph ^= 1; }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = 0u;
           }
-#pragma unroll
-          for (int co = 0; co < 16; ++co) {
-            const uint32_t row = (uint32_t)(l * 16 + co);
-            const uint32_t addr = tbase + row * 32u + ((half ^ ((row >> 2) & 1u)) << 4);
-            const uint16_t hv = (uint16_t)((co & 1) ? (v[co >> 1] >> 16) : (v[co >> 1] & 0xffffu));
-            asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(hv) : "memory");
-          }
+          stmatrix_x4(tbase + (uint32_t)l * 512u + st_off[0], v[0]);
+          stmatrix_x4(tbase + (uint32_t)l * 512u + st_off[1], v[1]);
         }
         fence_proxy_async();
         __syncwarp();
@@ -1447,7 +1478,7 @@ static int launch_wgrad_xline(const ActView& x, const ActView& dy, float* dw, in
   }
   p.units = x.n * p.bands * p.zchunks;
   const int grid = p.units < sm_count() ? p.units : sm_count();
-  const size_t smem = 4u * (8u * 96u * 32u) + 6u * 4096u + (size_t)(AL == 1 ? 4 : 3) * 4096u * AL + 2u * (2u * 48u * 272u) + 1024u;
+  const size_t smem = 4u * (8u * 96u * 32u) + 2u * 6u * 4096u + (size_t)(AL == 1 ? 4 : 2) * 2u * 4096u * AL + (size_t)(AL == 1 ? 4 : 3) * (2u * 16u * 272u + 16u) + 1024u;
   auto kern = conv_wgrad_xline_kernel<T, AL>;
   B200_CUDA(raise_dyn_smem_cap(kern));
   kern<<<grid, 416, smem, st>>>((const T*)x.data, (const T*)dy.data, dw, p);

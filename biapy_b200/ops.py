@@ -308,9 +308,9 @@ def conv_fprop_stats(x, w_packed_xfold, bias, y, k: Sequence[int], sums: torch.T
 
 # B200_XLINE_WGRAD = 0 keeps the 16-output-channel 3x3x3 weight gradients at W = 128 on the x-folded kernels
 XLINE_WGRAD = os.environ.get("B200_XLINE_WGRAD", "1") != "0"
-# input-channel counts that take it: 16 -> 16 measured 0.32 ms against 0.38 x-folded (128^3 x 4); 48 -> 16 (three launches, one per
-# 16-channel group, each transposing dY again) 0.94-1.00 against 0.82-0.87, so it stays x-folded unless B200_XLINE_WGRAD_CIN lists it
-XLINE_WGRAD_CIN = tuple(int(v) for v in os.environ.get("B200_XLINE_WGRAD_CIN", "16").split(",") if v)
+# input-channel counts that take it (128^3 x 4, fp16): 16 -> 16 0.22 ms against 0.39 x-folded; 48 -> 16 (three launches, one per
+# 16-channel group, each transposing dY again) 0.65 against 0.85
+XLINE_WGRAD_CIN = tuple(int(v) for v in os.environ.get("B200_XLINE_WGRAD_CIN", "16,48").split(",") if v)
 
 _WGRAD_N = (256, 128, 64, 32, 16)        # output-channel widths of the tcgen05 weight-gradient kernels (one N tile each)
 
