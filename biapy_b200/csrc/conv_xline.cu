@@ -28,6 +28,8 @@
 // Work unit = (sample, z chunk, band of BY output lines); planes z0-1 .. zhi and lines y0-1 .. y0+BY are read (halo).
 // Warps: 0-3 epilogue, 4-7 and 8-11 operand staging (two teams on alternate line pairs; in the fused launch they also apply the
 // normalisation + activation), 12 MMA issue (one elected lane), 13 bulk-copy issue (one elected lane).
+#include <type_traits>
+
 #include "umma.cuh"
 
 namespace b200 {
@@ -1122,6 +1124,9 @@ namespace sm100 {
 //   the fourth block of each row group is never read.
 // * D = the complete 27-tap gradient block of this input-channel group, stays in tensor memory for the whole launch and is added
 //   to dw with fp32 atomics once per CTA.
+// * The bias gradient rides along: operand lane 96 holds ones in every ring slot, so accumulator lane 96 collects the column sums
+//   of dY^T; the blocks (dz = 1, lb = 1) and (dz = 1, lb = 2) -- the pair's own two rows of the centre plane -- count every voxel
+//   of the unit exactly once (an MMA costs the same with 97 lanes as with 96; the separate pass over dY is gone).
 // Warps: 0-3 dY transposers (and the final reduction), 4-7 activation transposers, 8-10 operand staging, 11 MMA issue, 12 bulk copies.
 struct XwParams {
   int n, d, h;
@@ -1135,7 +1140,8 @@ struct XwParams {
 
 template <typename T, int AL>      // AL = bytes of an activation line / 4096 (1: 16 channels per voxel, 3: 48)
 __global__ void __launch_bounds__(416, 1)
-conv_wgrad_xline_kernel(const T* __restrict__ a, const T* __restrict__ dy, float* __restrict__ dw, const XwParams p) {
+conv_wgrad_xline_kernel(const T* __restrict__ a, const T* __restrict__ dy, float* __restrict__ dw, float* __restrict__ dbias,
+                        const XwParams p) {
   constexpr int BYW = 4, DL = BYW + 2;          // input lines per band, dY rows per plane of the window
   constexpr int NRD = 2, NRA = AL == 1 ? 4 : 2; // raw dY ring (windows of DL rows of one plane), raw activation ring (pairs of lines)
   constexpr int NAT = AL == 1 ? 4 : 3, NAW = 5; // A^T pair buffers in shared memory, operand ring in TMEM (pairs)
@@ -1178,6 +1184,14 @@ conv_wgrad_xline_kernel(const T* __restrict__ a, const T* __restrict__ dy, float
 #pragma unroll 1
     for (uint32_t c = 0; c < 512u; c += 16) tmem_st16_zero(tl + c);
     tmem_st_wait();
+    if (warp == 3 && dbias) {                       // lane 96 of every operand slot: ones (1.0 twice per column)
+      uint32_t ones[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ones[e] = lane == 0 ? (std::is_same<T, __half>::value ? 0x3C003C00u : 0x3F803F80u) : 0u;
+#pragma unroll 1
+      for (uint32_t c = 0; c < NAW * 64u; c += 8) tmem_st8(tl + ACOL + c, ones);
+      tmem_st_wait();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -1437,6 +1451,15 @@ conv_wgrad_xline_kernel(const T* __restrict__ a, const T* __restrict__ dy, float
             atomicAdd(dw + ((long long)co * 27 + tap) * p.cin_total + p.ci_off + ci, __uint_as_float(r[co]));
         }
       }
+    } else if (dbias) {                             // warp 3: accumulator lane 96 = column sums of dY^T
+      uint32_t r1[16], r2[16];
+      tmem_ld16(tmem + (96u << 16) + 5u * 16u, r1);
+      tmem_ld16(tmem + (96u << 16) + 6u * 16u, r2);
+      tmem_ld_wait();
+      if (lane == 0) {
+#pragma unroll
+        for (int co = 0; co < 16; ++co) atomicAdd(dbias + co, __uint_as_float(r1[co]) + __uint_as_float(r2[co]));
+      }
     }
   }
   tc_fence_before();
@@ -1455,7 +1478,7 @@ bool conv_wgrad_xline_ok(const ActView& x, const ActView& dy) {
 }
 
 template <typename T, int AL>
-static int launch_wgrad_xline(const ActView& x, const ActView& dy, float* dw, int ci_off, cudaStream_t st) {
+static int launch_wgrad_xline(const ActView& x, const ActView& dy, float* dw, float* dbias, int ci_off, cudaStream_t st) {
   XwParams p{};
   p.n = x.n; p.d = x.d; p.h = x.h;
   p.ash_b = x.sh * 2; p.asd_b = x.sd * 2; p.asn_b = x.sn * 2;
@@ -1481,13 +1504,12 @@ static int launch_wgrad_xline(const ActView& x, const ActView& dy, float* dw, in
   const size_t smem = 4u * (8u * 96u * 32u) + 2u * 6u * 4096u + (size_t)(AL == 1 ? 4 : 2) * 2u * 4096u * AL + (size_t)(AL == 1 ? 4 : 3) * (2u * 16u * 272u + 16u) + 1024u;
   auto kern = conv_wgrad_xline_kernel<T, AL>;
   B200_CUDA(raise_dyn_smem_cap(kern));
-  kern<<<grid, 416, smem, st>>>((const T*)x.data, (const T*)dy.data, dw, p);
+  kern<<<grid, 416, smem, st>>>((const T*)x.data, (const T*)dy.data, dw, dbias, p);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
 
 }  // namespace sm100
-int conv_bias_grad(const b200_tensor* dy, float* dbias, cudaStream_t st);   // conv_simt.cu
 }  // namespace b200
 
 B200_EXPORT int b200_conv_wgrad_xline_supported(const b200_tensor* x, const b200_tensor* dy, int32_t kd, int32_t kh, int32_t kw) {
@@ -1506,13 +1528,12 @@ B200_EXPORT int b200_conv_wgrad_xline(const b200_tensor* x, const b200_tensor* d
   for (int g = 0; g < x->c / 16; ++g) {
     int rc;
     if (x->dtype == B200_BF16)
-      rc = x->c == 16 ? sm100::launch_wgrad_xline<__nv_bfloat16, 1>(xv, gv, dw_packed, 16 * g, st)
-                      : sm100::launch_wgrad_xline<__nv_bfloat16, 3>(xv, gv, dw_packed, 16 * g, st);
+      rc = x->c == 16 ? sm100::launch_wgrad_xline<__nv_bfloat16, 1>(xv, gv, dw_packed, g == 0 ? dbias : nullptr, 16 * g, st)
+                      : sm100::launch_wgrad_xline<__nv_bfloat16, 3>(xv, gv, dw_packed, g == 0 ? dbias : nullptr, 16 * g, st);
     else
-      rc = x->c == 16 ? sm100::launch_wgrad_xline<__half, 1>(xv, gv, dw_packed, 16 * g, st)
-                      : sm100::launch_wgrad_xline<__half, 3>(xv, gv, dw_packed, 16 * g, st);
+      rc = x->c == 16 ? sm100::launch_wgrad_xline<__half, 1>(xv, gv, dw_packed, g == 0 ? dbias : nullptr, 16 * g, st)
+                      : sm100::launch_wgrad_xline<__half, 3>(xv, gv, dw_packed, g == 0 ? dbias : nullptr, 16 * g, st);
     if (rc) return rc;
   }
-  if (dbias) return conv_bias_grad(dy, dbias, st);
   return B200_OK;
 }

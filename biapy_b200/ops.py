@@ -349,7 +349,7 @@ def conv_wgrad(x, dy, cout: int, cin: int, k: Sequence[int], dw_out: torch.Tenso
                 label += f" {cin}->{cout} k333 @{x.shape[1]}x{x.shape[2]}x{x.shape[3]}"
         _launch_timed(label, flops, nbytes, "b200_conv_wgrad_xline", _ref(x), _ref(dy), _ptr(packed), _ptr(dbias_out), stream_ptr())
         global LAUNCHES
-        LAUNCHES += cin // 16 - 1 + (1 if dbias_out is not None else 0)
+        LAUNCHES += cin // 16 - 1                     # the bias gradient rides in the first launch (a row of ones in the operand)
         if defer_unpack and UNPACK_QUEUE is not None and dw_out.is_contiguous():
             UNPACK_QUEUE.append((UNPACK_WGRAD, packed, dw_out, cout, cin, taps, 1, 1, 1 if accumulate else 0))
         else:

@@ -254,7 +254,8 @@ int b200_conv_fprop_xline(const b200_tensor* x, const void* w_packed, const floa
                           void* stream);
 /* x-line weight gradient (csrc/conv_xline.cu): dw_packed[16][27][Cin] (fp32, zero-initialised or accumulated by the caller) +=
  * sum_vox dy[vox][co] * x[vox + off(tap)][ci] for the 3x3x3 layers with 16 output channels at W = 128, Cin = 16 or 48, dense
- * 16-bit lines; dbias (nullable) += sum_vox dy.  The contraction runs over the 128 voxels of a line with the transposed
+ * 16-bit lines; dbias (nullable) += sum_vox dy (inside the same launch: a row of ones in the activation operand).  The contraction
+ * runs over the 128 voxels of a line with the transposed
  * activation line in tensor memory and the transposed dY lines as the shared-memory operand; the 27-tap gradient block stays in
  * tensor memory for the whole launch (one launch per 16 input channels).  Same contract as b200_conv_wgrad. */
 int b200_conv_wgrad_xline_supported(const b200_tensor* x, const b200_tensor* dy, int32_t kd, int32_t kh, int32_t kw);
