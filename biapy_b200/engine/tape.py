@@ -126,6 +126,7 @@ class Tape:
         # conv -> norm: channel sums of the normalisation produced by the convolution epilogue (x-slab kernels)
         self.fuse_stats = os.environ.get("B200_FUSE_STATS", "1") != "0"
         self.pool_dense = os.environ.get("B200_POOL_DENSE", "1") != "0"
+        self.dbias_share = os.environ.get("B200_DBIAS_SHARE", "1") != "0"
         # x-line kernel (csrc/conv_xline.cu): B200_XLINE = 0 off, 1 (default) where it measured faster than the x-folded kernels
         # (profiles/xline_probe_r2_*.log: the Cin = 48 launches, 0.39 vs 0.62 ms), 2 every launch it supports (Cin = 16 as well).
         # B200_XLINE_FUSE = 1: GroupNorm-apply + SiLU on the operand path of that convolution (the fused Conv3D + GN + SiLU launch).
@@ -139,6 +140,10 @@ class Tape:
         self.pack_record: Optional[Dict] = None
         self._packed: Dict[Tuple, torch.Tensor] = {}
         self._pad16: Dict[int, torch.Tensor] = {}
+        # convolutions that wrote the same output tensor (block(x) + shortcut(x): the accumulate epilogue) have the same bias
+        # gradient, the channel sums of that tensor's gradient: id(out) -> (out, bias gradient of the first one that ran)
+        self._dbias_memo: Dict[int, Tuple[TT, torch.Tensor]] = {}
+        self._dbias_touched: set = set()
 
     # ------------------------------------------------------------------------------------------ helpers
     def new(self, like: torch.Tensor, channels: int, spatial: Optional[Sequence[int]] = None) -> TT:
@@ -295,7 +300,18 @@ class Tape:
             if w.requires_grad:
                 gb = self._pgrad(b) if (b is not None and b.requires_grad) else None
                 first = w not in self.param_grads
-                ops.conv_wgrad(x.data, dy, cout, cin, k, self._pgrad(w), gb, accumulate=not first, impl=self.impl)
+                memo = self._dbias_memo.get(id(out)) if gb is not None else None
+                if memo is not None and memo[1].numel() == gb.numel():
+                    # second producer of `out`: its bias gradient is the first one's (copied with the batched un-packs)
+                    ops.conv_wgrad(x.data, dy, cout, cin, k, self._pgrad(w), None, accumulate=not first, impl=self.impl)
+                    ops.queue_float_add(memo[1], gb)
+                    self._dbias_touched.add(id(b))
+                else:
+                    ops.conv_wgrad(x.data, dy, cout, cin, k, self._pgrad(w), gb, accumulate=not first, impl=self.impl)
+                    if gb is not None and id(b) not in self._dbias_touched and self.dbias_share:
+                        self._dbias_memo[id(out)] = (out, gb)      # holds nothing but this layer's sums (zero before this pass)
+                    if gb is not None:
+                        self._dbias_touched.add(id(b))
             if x.requires_grad:
                 acc = x.prepare_accumulate()
                 self._conv_launch(dy, w, True, None, x.grad(), k, acc)

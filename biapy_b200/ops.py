@@ -138,6 +138,17 @@ def flush_unpacks():
         pack_batch([j[:9] for j in q], torch.bfloat16)      # fp32 -> fp32 jobs: the dtype only selects the (unused) pack type
 
 
+def queue_float_add(src: torch.Tensor, dst: torch.Tensor):
+    """dst += src (contiguous fp32 vectors, e.g. a bias gradient shared by two layers): rides in the batched un-pack launch of a
+    Trainer pass, a launch of its own otherwise."""
+    n = src.numel()
+    assert dst.numel() == n and src.dtype == dst.dtype == torch.float32 and src.is_contiguous() and dst.is_contiguous()
+    if UNPACK_QUEUE is not None:
+        UNPACK_QUEUE.append((UNPACK_WGRAD, src, dst, n, 1, 1, 1, 1, 1))
+    else:
+        _launch("b200_unpack_conv_wgrad", _ptr(src), _ptr(dst), n, 1, 1, 1, stream_ptr())
+
+
 def conv_impl_query(x, y, k, wgrad=False) -> int:
     """Best kernel family for these operands: IMPL_XFOLD / IMPL_UMMA / IMPL_SIMT."""
     return _lib.lib().b200_conv_impl_query(_ref(x), _ref(y), k[0], k[1], k[2], 1 if wgrad else 0)

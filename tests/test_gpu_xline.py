@@ -195,6 +195,7 @@ def test_resunet_level0_through_xline(dtype, monkeypatch):
     for mode in ("0", "2"):
         monkeypatch.setenv("B200_XLINE", mode)
         monkeypatch.setenv("B200_XLINE_FUSE", "1")
+        monkeypatch.setenv("B200_XLINE_WGRAD", "0" if mode == "0" else "1")      # the x-line weight gradient has its own switch
         model.zero_grad(set_to_none=True)
         ops.PROFILE, ops.PROFILE_SHAPES = {}, True
         xin = x.clone().requires_grad_(True)
@@ -207,6 +208,7 @@ def test_resunet_level0_through_xline(dtype, monkeypatch):
     assert not any("xline" in k for k in res["0"][3])
     assert any(k.startswith("conv_fprop_xline_gn_silu") for k in res["2"][3]), sorted(res["2"][3])
     assert any(k.startswith("conv_fprop_xline ") for k in res["2"][3]), sorted(res["2"][3])
+    assert any(k.startswith("conv_wgrad_xline") for k in res["2"][3]), sorted(res["2"][3])
     print("\n[xline labels]", sorted(k for k in res["2"][3] if "xline" in k or k.startswith("scale_shift")))
     # Both routes round every stored tensor to the engine dtype in different summation orders; the input gradient additionally
     # passes the max-pool arg-max, where one flipped maximum moves a whole gradient value (max-norm of dx between the two fp16
