@@ -110,6 +110,8 @@ SIGNATURES = {
     "b200_bn_update_running": (_I, [_P, _P, _F, _D, _F, _P, _P, _I, _P]),
     "b200_bn_eval_coeffs": (_I, [_P, _P, _P, _P, _F, _I, _I, _P, _P, _P]),
     "b200_norm_bwd_finalize": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _L, _I, _P, _P, _P, _P]),
+    "b200_norm_bwd_finalize_sums": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _L, _I, _P, _P, _P, _P, _P, _P]),
+    "b200_sums_through_pointwise": (_I, [_P, _P, _P, _I, _I, _P]),
     "b200_norm_act_bwd_apply": (_I, [_T, _T, _I, _P, _T, _I, _P]),
     "b200_norm_silu_fast_ok": (_I, [_T, _T, _T]),
     "b200_scale_shift_silu_fast": (_I, [_T, _P, _P, _T, _P]),

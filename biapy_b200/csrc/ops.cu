@@ -153,27 +153,35 @@ __global__ void norm_finalize_kernel(const double* __restrict__ sums, int n, int
                                      int batch_stats, const float* __restrict__ gamma, const float* __restrict__ beta,
                                      float eps, float* __restrict__ mean, float* __restrict__ rstd,
                                      float* __restrict__ scale, float* __restrict__ shift) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (n, g)
-  if (idx >= n * groups) return;
-  int ni = idx / groups, g = idx % groups;
-  int cpg = c / groups;
+  // one WARP per (n, g): the lanes stride over the group's channels (GroupNorm(8, C): up to 48 channels per group at the deep
+  // levels -- one thread walking them through dependent double-precision loads was a 5-15 us kernel 17 times per pass)
+  const int wid = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (wid >= n * groups) return;
+  const int ni = wid / groups, g = wid % groups;
+  const int cpg = c / groups;
   double s = 0.0, s2 = 0.0;
-  int n0 = batch_stats ? 0 : ni, n1 = batch_stats ? n : ni + 1;
+  const int n0 = batch_stats ? 0 : ni, n1 = batch_stats ? n : ni + 1;
   for (int nn = n0; nn < n1; ++nn)
-    for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) {
+    for (int cc = g * cpg + lane; cc < (g + 1) * cpg; cc += 32) {
       s += sums[((int64_t)nn * c + cc) * 2];
       s2 += sums[((int64_t)nn * c + cc) * 2 + 1];
     }
-  double m = (double)spatial * cpg * (n1 - n0);
-  double mu = s / m;
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  const double m = (double)spatial * cpg * (n1 - n0);
+  const double mu = s / m;
   double var = s2 / m - mu * mu;
   if (var < 0.0) var = 0.0;
-  float r = 1.0f / sqrtf((float)var + eps);
-  mean[idx] = (float)mu;
-  rstd[idx] = r;
-  for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) {
-    float ga = gamma ? gamma[cc] : 1.f, be = beta ? beta[cc] : 0.f;
-    float sc = r * ga;
+  const float r = 1.0f / sqrtf((float)var + eps);
+  if (lane == 0) {
+    mean[wid] = (float)mu;
+    rstd[wid] = r;
+  }
+  for (int cc = g * cpg + lane; cc < (g + 1) * cpg; cc += 32) {
+    const float ga = gamma ? gamma[cc] : 1.f, be = beta ? beta[cc] : 0.f;
+    const float sc = r * ga;
     scale[(int64_t)ni * c + cc] = sc;
     shift[(int64_t)ni * c + cc] = be - (float)mu * sc;
   }
@@ -279,34 +287,47 @@ __global__ void norm_bwd_finalize_kernel(const double* __restrict__ red, const f
                                          const float* __restrict__ rstd, const float* __restrict__ gamma,
                                          const float* __restrict__ beta, int n, int c, int groups, int64_t spatial,
                                          int batch_stats, float* __restrict__ coef, float* __restrict__ dgamma,
-                                         float* __restrict__ dbeta) {
+                                         float* __restrict__ dbeta, const double* __restrict__ xsums = nullptr,
+                                         float* __restrict__ dxsum = nullptr) {
   // red[n][c] = (S1 = sum g, Sgc = sum g*(x - mean));  S2 = sum g*xhat = rstd*Sgc
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  int cpg = c / groups;
-  if (idx < n * groups) {
-    int ni = idx / groups, g = idx % groups;
-    int n0 = batch_stats ? 0 : ni, n1 = batch_stats ? n : ni + 1;
+  // one WARP per (n, g) for the coefficients (lanes over the group's channels), one THREAD per channel for dgamma / dbeta
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int wid = idx >> 5, lane = threadIdx.x & 31;
+  const int cpg = c / groups;
+  if (wid < n * groups) {
+    const int ni = wid / groups, g = wid % groups;
+    const int n0 = batch_stats ? 0 : ni, n1 = batch_stats ? n : ni + 1;
     double a = 0.0, b = 0.0;
     for (int nn = n0; nn < n1; ++nn) {
       const double r = (double)rstd[(int64_t)nn * groups + g];
-      for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) {
-        double ga = gamma ? (double)gamma[cc] : 1.0;
-        double s1 = red[((int64_t)nn * c + cc) * 2], sgc = red[((int64_t)nn * c + cc) * 2 + 1];
+      for (int cc = g * cpg + lane; cc < (g + 1) * cpg; cc += 32) {
+        const double ga = gamma ? (double)gamma[cc] : 1.0;
+        const double s1 = red[((int64_t)nn * c + cc) * 2], sgc = red[((int64_t)nn * c + cc) * 2 + 1];
         a += ga * s1;
         b += ga * (r * sgc);
       }
     }
-    double m = (double)spatial * cpg * (n1 - n0);
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    const double m = (double)spatial * cpg * (n1 - n0);
     // with ypre = x*k0 + B and g = dy*act'(ypre):  dx = g*k0 - x*P - Q
-    float r = rstd[idx], mu = mean[idx];
-    float k1 = (float)(r * (a / m)), k2 = (float)(r * (b / m));
-    for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) {
-      float ga = gamma ? gamma[cc] : 1.f, be = beta ? beta[cc] : 0.f;
+    const float r = rstd[wid], mu = mean[wid];
+    const float k1 = (float)(r * (a / m)), k2 = (float)(r * (b / m));
+    for (int cc = g * cpg + lane; cc < (g + 1) * cpg; cc += 32) {
+      const float ga = gamma ? gamma[cc] : 1.f, be = beta ? beta[cc] : 0.f;
       float* o = coef + ((int64_t)ni * c + cc) * 4;
-      o[0] = r * ga;
+      const float k0 = r * ga, kp = r * k2, kq = k1 - mu * r * k2;
+      o[0] = k0;
       o[1] = be - mu * r * ga;
-      o[2] = r * k2;
-      o[3] = k1 - mu * r * k2;
+      o[2] = kp;
+      o[3] = kq;
+      // dxsum[c] += sum over this sample's voxels of dx = g*k0 - x*P - Q, from the sums alone (xsums[n][c][0] = sum x of the
+      // forward statistics): the bias gradient of a convolution whose output feeds this normalisation only -- no pass over dx
+      if (dxsum && xsums)
+        atomicAdd(&dxsum[cc], (float)((double)k0 * red[((int64_t)ni * c + cc) * 2] - (double)kp * xsums[((int64_t)ni * c + cc) * 2] -
+                                      (double)kq * (double)spatial));
     }
   }
   if (idx < c) {
@@ -321,6 +342,18 @@ __global__ void norm_bwd_finalize_kernel(const double* __restrict__ red, const f
     if (dgamma) dgamma[idx] += (float)sg;
     if (dbeta) dbeta[idx] += (float)sb;
   }
+}
+
+// xsum[ci] += sum_co w[co][ci] * dysum[co]: the channel sums of a gradient pass through a pointwise convolution's input
+// gradient as they are (dx = W^T dy voxel by voxel), so the sums of `x.grad` stay known after a 1x1 shortcut accumulates into it
+__global__ void sums_through_pointwise_kernel(const float* __restrict__ w, const float* __restrict__ dysum, float* __restrict__ xsum,
+                                              int cout, int cin) {
+  const int ci = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;   // one warp per input channel
+  if (ci >= cin) return;
+  double acc = 0.0;
+  for (int co = lane; co < cout; co += 32) acc += (double)w[(int64_t)co * cin + ci] * (double)dysum[co];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) xsum[ci] += (float)acc;
 }
 
 // element-wise fallback (any channel count): coefficients re-read per element
@@ -1106,7 +1139,7 @@ B200_EXPORT int b200_norm_finalize(const double* sums, int32_t n, int32_t c, int
                                    float* mean, float* rstd, float* scale, float* shift, void* stream) {
   B200_CHECK_ARG(sums && mean && rstd && scale && shift, "norm_finalize: null pointer");
   B200_CHECK_ARG(groups > 0 && c % groups == 0, "norm_finalize: channels %d not divisible by groups %d", c, groups);
-  int total = n * groups;
+  int total = n * groups * 32;                    // one warp per (n, g)
   norm_finalize_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, n, c, groups, spatial, batch_stats,
                                                                              gamma, beta, eps, mean, rstd, scale, shift);
   B200_LAUNCH_CHECK();
@@ -1199,9 +1232,28 @@ B200_EXPORT int b200_norm_bwd_finalize(const double* red, const float* mean, con
                                        const float* beta, int32_t n, int32_t c, int32_t groups, int64_t spatial,
                                        int32_t batch_stats, float* coef, float* dgamma, float* dbeta, void* stream) {
   B200_CHECK_ARG(red && mean && rstd && coef, "norm_bwd_finalize: null pointer");
-  int total = n * groups > c ? n * groups : c;
+  int total = n * groups * 32 > c ? n * groups * 32 : c;      // one warp per (n, g), one thread per channel
   norm_bwd_finalize_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(red, mean, rstd, gamma, beta, n, c, groups,
                                                                                  spatial, batch_stats, coef, dgamma, dbeta);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+B200_EXPORT int b200_norm_bwd_finalize_sums(const double* red, const float* mean, const float* rstd, const float* gamma,
+                                            const float* beta, int32_t n, int32_t c, int32_t groups, int64_t spatial,
+                                            int32_t batch_stats, float* coef, float* dgamma, float* dbeta, const double* xsums,
+                                            float* dxsum, void* stream) {
+  B200_CHECK_ARG(red && mean && rstd && coef && xsums && dxsum, "norm_bwd_finalize_sums: null pointer");
+  int total = n * groups * 32 > c ? n * groups * 32 : c;
+  norm_bwd_finalize_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(red, mean, rstd, gamma, beta, n, c, groups,
+                                                                                 spatial, batch_stats, coef, dgamma, dbeta, xsums, dxsum);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+B200_EXPORT int b200_sums_through_pointwise(const float* w, const float* dysum, float* xsum, int32_t cout, int32_t cin, void* stream) {
+  B200_CHECK_ARG(w && dysum && xsum && cout > 0 && cin > 0, "sums_through_pointwise: bad args");
+  sums_through_pointwise_kernel<<<(cin * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(w, dysum, xsum, cout, cin);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

@@ -23,10 +23,13 @@ import torch
 from .. import _lib, ops
 
 
+_DEBUG = os.environ.get("B200_TAPE_DEBUG", "0") != "0"
+
+
 class TT:
     """A tensor on the tape: data + lazily allocated gradient; may be a channel slice of a parent buffer."""
 
-    __slots__ = ("_data", "pending", "_meta", "_grad", "_ready", "parent", "off", "requires_grad", "padded", "sums", "dense_grad")
+    __slots__ = ("_data", "pending", "_meta", "_grad", "_ready", "parent", "off", "requires_grad", "padded", "sums", "dense_grad", "grad_sums")
 
     def __init__(self, data: Optional[torch.Tensor], requires_grad: bool = True, parent: "Optional[TT]" = None, off: int = 0):
         self._data = data
@@ -40,6 +43,10 @@ class TT:
         self.padded = None          # zero-padded 16-channel copy (network inputs with < 16 channels, see Tape.conv)
         self.sums = None            # (N, C, 2) float64 channel sums left by the producing convolution's epilogue (Tape.conv)
         self.dense_grad = None      # slices only: the finished gradient as a dense tensor (left by Tape.maxpool's backward)
+        # (C,) fp32 = sum over samples and voxels of this tensor's gradient, while every writer so far could state its share without
+        # a pass over the data (normalisation backward: from its reductions; pointwise input gradients: W^T sums); None otherwise.
+        # A convolution that produced the tensor takes its bias gradient from here (Tape._conv_backward, Tape.convT).
+        self.grad_sums = None
 
     @property
     def data(self) -> torch.Tensor:
@@ -102,9 +109,11 @@ class TT:
             if not root._ready:
                 root.grad().zero_()
                 root._ready = True
+            root.grad_sums = None                   # a writer into a channel slice: the root's sums are no longer known
             return True
         acc = self._ready
         self._ready = True
+        self.grad_sums = None                       # the writer restores it when it knows its share (see grad_sums)
         return acc
 
 
@@ -127,6 +136,8 @@ class Tape:
         self.fuse_stats = os.environ.get("B200_FUSE_STATS", "1") != "0"
         self.pool_dense = os.environ.get("B200_POOL_DENSE", "1") != "0"
         self.dbias_share = os.environ.get("B200_DBIAS_SHARE", "1") != "0"
+        # bias gradients from the normalisation backward's reductions instead of a pass over dy (TT.grad_sums)
+        self.dbias_analytic = os.environ.get("B200_DBIAS_ANALYTIC", "1") != "0"
         # x-line kernel (csrc/conv_xline.cu): B200_XLINE = 0 off, 1 (default) where it measured faster than the x-folded kernels
         # (profiles/xline_probe_r2_*.log: the Cin = 48 launches, 0.39 vs 0.62 ms), 2 every launch it supports (Cin = 16 as well).
         # B200_XLINE_FUSE = 1: GroupNorm-apply + SiLU on the operand path of that convolution (the fused Conv3D + GN + SiLU launch).
@@ -150,6 +161,17 @@ class Tape:
         n = like.shape[0]
         sp = tuple(spatial) if spatial is not None else tuple(like.shape[1:4])
         return TT(torch.empty((n,) + sp + (channels,), dtype=self.dtype, device=self.device))
+
+    @staticmethod
+    def _grad_sums_of(t: TT) -> Optional[torch.Tensor]:
+        """Channel sums of t's gradient if they are known (TT.grad_sums; for a channel slice: the slice of its parent's)."""
+        if t.dense_grad is not None:
+            return None
+        if t.parent is None:
+            return t.grad_sums
+        if t.parent.parent is None and t.parent.grad_sums is not None:
+            return t.parent.grad_sums[t.off:t.off + t.c]
+        return None
 
     def _pgrad(self, p: torch.nn.Parameter) -> torch.Tensor:
         g = self.param_grads.get(p)
@@ -300,21 +322,45 @@ class Tape:
             if w.requires_grad:
                 gb = self._pgrad(b) if (b is not None and b.requires_grad) else None
                 first = w not in self.param_grads
+                gs = self._grad_sums_of(out) if gb is not None else None
                 memo = self._dbias_memo.get(id(out)) if gb is not None else None
-                if memo is not None and memo[1].numel() == gb.numel():
+                if _DEBUG:
+                    print(f"[tape] conv bwd {cin}->{cout} k{k} @{tuple(x.shape[1:4])}: bias from "
+                          f"{'grad_sums' if gs is not None else 'memo' if memo is not None else 'pass over dy' if gb is not None else 'none'}"
+                          f" (out slice: {out.parent is not None}, dense_grad: {out.dense_grad is not None})")
+                dysum = None                        # a tensor that holds sum(dy) per channel at this point of the stream
+                if gs is not None:
+                    # every writer of out.grad stated its channel sums (normalisation backward): that IS the bias gradient
+                    ops.conv_wgrad(x.data, dy, cout, cin, k, self._pgrad(w), None, accumulate=not first, impl=self.impl)
+                    ops.queue_float_add(gs, gb)
+                    self._dbias_touched.add(id(b))
+                    dysum = gs
+                elif memo is not None and memo[1].numel() == gb.numel():
                     # second producer of `out`: its bias gradient is the first one's (copied with the batched un-packs)
                     ops.conv_wgrad(x.data, dy, cout, cin, k, self._pgrad(w), None, accumulate=not first, impl=self.impl)
                     ops.queue_float_add(memo[1], gb)
                     self._dbias_touched.add(id(b))
+                    dysum = memo[1]
                 else:
                     ops.conv_wgrad(x.data, dy, cout, cin, k, self._pgrad(w), gb, accumulate=not first, impl=self.impl)
-                    if gb is not None and id(b) not in self._dbias_touched and self.dbias_share:
-                        self._dbias_memo[id(out)] = (out, gb)      # holds nothing but this layer's sums (zero before this pass)
+                    if gb is not None and id(b) not in self._dbias_touched:
+                        dysum = gb                  # holds nothing but this layer's sums (zero before this pass)
+                        if self.dbias_share:
+                            self._dbias_memo[id(out)] = (out, gb)
                     if gb is not None:
                         self._dbias_touched.add(id(b))
+            else:
+                dysum = None
             if x.requires_grad:
+                # pointwise input gradient: dx = W^T dy voxel by voxel, so its channel sums are W^T sum(dy)
+                want_sums = self.dbias_analytic and tuple(k) == (1, 1, 1) and dysum is not None and x.parent is None
+                sums_prev = x.grad_sums
                 acc = x.prepare_accumulate()
                 self._conv_launch(dy, w, True, None, x.grad(), k, acc)
+                if want_sums and (not acc or sums_prev is not None):
+                    sums_x = sums_prev if acc else ops.zeros(cin, torch.float32, self.device)
+                    ops.sums_through_pointwise(self._f32(w).contiguous(), dysum, sums_x)
+                    x.grad_sums = sums_x
         self.steps.append(bwd)
 
     def _conv_fused(self, x: TT, mod, out: Optional[TT], accumulate: bool, stats: bool, k, cout: int, cin: int) -> Optional[TT]:
@@ -387,6 +433,13 @@ class Tape:
                 assert out.grad_ready
                 if w.requires_grad:
                     gb = self._pgrad(b) if (b is not None and b.requires_grad) else None
+                    gs = self._grad_sums_of(out) if (gb is not None and tc) else None
+                    if _DEBUG:
+                        print(f"[tape] convT bwd {cin}->{cout} @{tuple(x.shape[1:4])}: bias from {'grad_sums' if gs is not None else 'pass over dy'}"
+                              f" (out slice: {out.parent is not None}, parent sums: {out.parent is not None and out.parent.grad_sums is not None})")
+                    if gs is not None:              # the concat gradient's channel sums are known: no pass over dy for the bias
+                        ops.queue_float_add(gs, gb)
+                        gb = None
                     if tc:
                         ops.convT_wgrad_tc(x.data, dy, self._pgrad(w), gb, s, accumulate=True)
                     else:
@@ -467,11 +520,20 @@ class Tape:
                 assert out.grad_ready
                 dg = self._pgrad(gamma) if (gamma is not None and gamma.requires_grad) else None
                 db = self._pgrad(beta) if (beta is not None and beta.requires_grad) else None
-                dx, acc = None, False
+                dx, acc, gs = None, False, None
                 if x.requires_grad:
+                    gs_old = x.grad_sums
                     acc = x.prepare_accumulate()
                     dx = x.grad()
-                ops.norm_act_bwd(x.data, out.grad(), st, g32, b32, act, dx, dg, db, accumulate=acc, dy_dead=True)
+                    if (self.dbias_analytic and x.parent is None and getattr(st, "sums", None) is not None and (st.world or 1) == 1
+                            and (not acc or gs_old is not None)):
+                        gs = gs_old if acc else ops.zeros(x.c, torch.float32, self.device)
+                if _DEBUG:
+                    print(f"[tape] norm bwd c{x.c} @{tuple(x.shape[1:4])}: acc {acc}, sums {'yes' if gs is not None else 'no'} (slice: {x.parent is not None}, "
+                          f"st.sums: {getattr(st, 'sums', None) is not None})")
+                ops.norm_act_bwd(x.data, out.grad(), st, g32, b32, act, dx, dg, db, accumulate=acc, dy_dead=True, dx_sums=gs)
+                if gs is not None:
+                    x.grad_sums = gs
             self.steps.append(bwd)
         return out
 

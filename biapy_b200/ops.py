@@ -149,6 +149,13 @@ def queue_float_add(src: torch.Tensor, dst: torch.Tensor):
         _launch("b200_unpack_conv_wgrad", _ptr(src), _ptr(dst), n, 1, 1, 1, stream_ptr())
 
 
+def sums_through_pointwise(w: torch.Tensor, dysum: torch.Tensor, xsum: torch.Tensor):
+    """xsum (Cin,) += W^T dysum for the pointwise convolution weight W (Cout, Cin, 1, 1, 1) fp32."""
+    cout, cin = w.shape[0], w.shape[1]
+    assert w.is_contiguous() and w.dtype == torch.float32 and dysum.numel() == cout and xsum.numel() == cin
+    _launch("b200_sums_through_pointwise", _ptr(w), _ptr(dysum), _ptr(xsum), cout, cin, stream_ptr())
+
+
 def conv_impl_query(x, y, k, wgrad=False) -> int:
     """Best kernel family for these operands: IMPL_XFOLD / IMPL_UMMA / IMPL_SIMT."""
     return _lib.lib().b200_conv_impl_query(_ref(x), _ref(y), k[0], k[1], k[2], 1 if wgrad else 0)
@@ -490,7 +497,7 @@ def maxpool_bwd_to(x, dy, dx_in, dx_out, p: Sequence[int]) -> bool:
 
 # ------------------------------------------------------------------------------------- normalisation / act
 class NormStats:
-    __slots__ = ("mean", "rstd", "scale", "shift", "groups", "batch_stats", "world", "sync_group")
+    __slots__ = ("mean", "rstd", "scale", "shift", "groups", "batch_stats", "world", "sync_group", "sums")
 
 
 def _sync_world(sync_group) -> int:
@@ -519,6 +526,7 @@ def norm_stats(x, groups: int, gamma, beta, eps: float = 1e-5, batch_stats: bool
     st = NormStats()
     st.groups, st.batch_stats = groups, batch_stats
     st.world, st.sync_group = world, sync_group
+    st.sums = sums if world == 1 else None        # per-sample channel sums of x: the backward derives sum(dx) from them (norm_act_bwd)
     buf = torch.empty(2 * n * groups + 2 * n * c, dtype=torch.float32, device=x.device)
     st.mean, st.rstd = buf[: n * groups], buf[n * groups: 2 * n * groups]
     st.scale, st.shift = buf[2 * n * groups: 2 * n * groups + n * c], buf[2 * n * groups + n * c:]
@@ -538,6 +546,7 @@ def bn_eval_stats(x, running_mean, running_var, gamma, beta, eps: float) -> Norm
     n, c = x.shape[0], x.shape[-1]
     st = NormStats()
     st.groups, st.batch_stats, st.world, st.sync_group = c, True, 1, False
+    st.sums = None
     buf = torch.empty(2 * n * c, dtype=torch.float32, device=x.device)
     st.mean = st.rstd = None
     st.scale, st.shift = buf[: n * c], buf[n * c:]
@@ -571,9 +580,11 @@ def scale_shift_act(x, scale, shift, act: str, y):
     return y
 
 
-def norm_act_bwd(x, dy, st: NormStats, gamma, beta, act: str, dx, dgamma, dbeta, accumulate=False, dy_dead: bool = False):
+def norm_act_bwd(x, dy, st: NormStats, gamma, beta, act: str, dx, dgamma, dbeta, accumulate=False, dy_dead: bool = False,
+                 dx_sums: Optional[torch.Tensor] = None):
     """`dy_dead`: nothing reads dy after this call (true for the tape's activation gradients) -- allows the fast SiLU chain,
-    whose reduce pass leaves g = dy * act'(z) in dy's place for the apply pass."""
+    whose reduce pass leaves g = dy * act'(z) in dy's place for the apply pass.  `dx_sums`: (C,) fp32, += the sum over samples and
+    voxels of the dx this call produces (its own contribution when accumulating), derived from the reductions -- needs `st.sums`."""
     n, d, h, w, c = x.shape
     red = zeros(n * c * 2, torch.float64, x.device)
     write_g = NORM_BWD != "recompute"
@@ -596,8 +607,13 @@ def norm_act_bwd(x, dy, st: NormStats, gamma, beta, act: str, dx, dgamma, dbeta,
         red = torch.zeros_like(red)
         red.view(n, c * 2)[0] = tot
         dgamma = dbeta = None
-    _launch("b200_norm_bwd_finalize", _ptr(red), _ptr(st.mean), _ptr(st.rstd), _ptr(gamma), _ptr(beta), n, c, st.groups,
-            d * h * w * world, 1 if st.batch_stats else 0, _ptr(coef), _ptr(dgamma), _ptr(dbeta), stream_ptr())
+    if dx_sums is not None:
+        assert world == 1 and st.sums is not None and dx_sums.numel() == c
+        _launch("b200_norm_bwd_finalize_sums", _ptr(red), _ptr(st.mean), _ptr(st.rstd), _ptr(gamma), _ptr(beta), n, c, st.groups,
+                d * h * w, 1 if st.batch_stats else 0, _ptr(coef), _ptr(dgamma), _ptr(dbeta), _ptr(st.sums), _ptr(dx_sums), stream_ptr())
+    else:
+        _launch("b200_norm_bwd_finalize", _ptr(red), _ptr(st.mean), _ptr(st.rstd), _ptr(gamma), _ptr(beta), n, c, st.groups,
+                d * h * w * world, 1 if st.batch_stats else 0, _ptr(coef), _ptr(dgamma), _ptr(dbeta), stream_ptr())
     if dx is not None:
         if fast and write_g:
             _launch("b200_norm_bwd_apply_g", _ref(x), _ref(dy), _ptr(coef), _ref(dx), 1 if accumulate else 0, stream_ptr(),

@@ -349,6 +349,15 @@ int b200_norm_act_bwd_reduce(const b200_tensor* x, const b200_tensor* dy, const 
 int b200_norm_bwd_finalize(const double* red, const float* mean, const float* rstd, const float* gamma, const float* beta,
                            int32_t n, int32_t c, int32_t groups, int64_t spatial, int32_t batch_stats,
                            float* coef, float* dgamma, float* dbeta, void* stream);
+/* the same, and dxsum[C] += sum over samples and voxels of the dx the apply pass will write (not accumulated), from the sums alone:
+ * xsums[N][C][2] are the forward channel sums (b200_channel_sums / the convolution epilogue).  That is the bias gradient of a
+ * convolution whose output feeds this normalisation only (reference: autograd of blocks.py:148-160) -- no pass over dx.          */
+int b200_norm_bwd_finalize_sums(const double* red, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                                int32_t n, int32_t c, int32_t groups, int64_t spatial, int32_t batch_stats,
+                                float* coef, float* dgamma, float* dbeta, const double* xsums, float* dxsum, void* stream);
+/* xsum[Cin] += W^T dysum for a pointwise convolution W (Cout, Cin): channel sums of a gradient after a 1x1 layer's input gradient
+ * has been accumulated into it                                                                                                    */
+int b200_sums_through_pointwise(const float* w, const float* dysum, float* xsum, int32_t cout, int32_t cin, void* stream);
 /* pass 2: dx (+)= g*k0 - x*P - Q                                                                               */
 int b200_norm_act_bwd_apply(const b200_tensor* x, const b200_tensor* dy, int32_t act, const float* coef,
                             const b200_tensor* dx, int32_t accumulate, void* stream);
