@@ -910,6 +910,32 @@ __global__ void bce_logits_kernel(View<const T> z, const float* __restrict__ tar
   block_atomic_add(acc, loss_sum);
 }
 
+// the same on dense 16-bit tensors (ld == c, element count a multiple of 8): eight logits per 16-byte load, one exponential per
+// element (loss and sigmoid share exp(-|z|)), float partial sums per thread (a few dozen terms) folded in double
+template <typename T>
+__global__ void __launch_bounds__(256) bce_logits_dense_kernel(const T* __restrict__ z, const float* __restrict__ target,
+                                                               double* __restrict__ loss_sum, T* __restrict__ dz, float grad_scale,
+                                                               int64_t total8) {
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
+    const Pack<T, 8> pz = *reinterpret_cast<const Pack<T, 8>*>(z + i * 8);
+    const Pack<float, 4> t0 = *reinterpret_cast<const Pack<float, 4>*>(target + i * 8);
+    const Pack<float, 4> t1 = *reinterpret_cast<const Pack<float, 4>*>(target + i * 8 + 4);
+    const float t[8] = {t0.v[0], t0.v[1], t0.v[2], t0.v[3], t1.v[0], t1.v[1], t1.v[2], t1.v[3]};
+    Pack<T, 8> out;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float v = to_f<T>(pz.v[k]);
+      const float e = expf(-fabsf(v));
+      acc += fmaxf(v, 0.f) - v * t[k] + log1pf(e);            // max(z,0) - z*t + log1p(exp(-|z|))
+      const float s = (v >= 0.f ? 1.f : e) / (1.f + e);       // sigmoid(z)
+      out.v[k] = from_f<T>((s - t[k]) * grad_scale);
+    }
+    if (dz) *reinterpret_cast<Pack<T, 8>*>(dz + i * 8) = out;
+  }
+  block_atomic_add((double)acc, loss_sum);
+}
+
 // target dense (vox, 2C): first C = target, last C = mask
 template <typename T>
 __global__ void n2v_mse_kernel(View<const T> y, const float* __restrict__ target, double* __restrict__ sums,
@@ -1755,6 +1781,16 @@ B200_EXPORT int b200_bce_logits(const b200_tensor* logits, const float* target, 
   B200_CHECK_ARG(check_tensor(logits, "bce.logits") && target && loss_sum, "%s", b200_last_error());
   if (dlogits) B200_CHECK_ARG(check_tensor(dlogits, "bce.dlogits") && same_spatial(logits, dlogits) &&
                                   logits->c == dlogits->c && logits->dtype == dlogits->dtype, "bce: dlogits mismatch");
+  const int64_t total = voxels(logits) * logits->c;
+  if (logits->dtype != B200_F32 && logits->ld == logits->c && (!dlogits || dlogits->ld == dlogits->c) && total % 8 == 0 &&
+      (((uintptr_t)logits->data | (uintptr_t)target | (uintptr_t)(dlogits ? dlogits->data : nullptr)) & 15) == 0) {
+    B200_DISPATCH_DTYPE16(logits->dtype, T, {
+      bce_logits_dense_kernel<T><<<grid_for(total / 8, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+          (const T*)logits->data, target, loss_sum, dlogits ? (T*)dlogits->data : nullptr, grad_scale, total / 8);
+    });
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+  }
   B200_DISPATCH_DTYPE(logits->dtype, T, {
     View<T> dv{dlogits ? (T*)dlogits->data : nullptr, dlogits ? dlogits->ld : 0, logits->c, voxels(logits), 0};
     bce_logits_kernel<T><<<grid_for(voxels(logits) * logits->c, 256, 4), 256, 0, (cudaStream_t)stream>>>(

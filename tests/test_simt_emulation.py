@@ -34,7 +34,7 @@ KERNELS = {
     "ops.cu": ["maxpool_fwd_win_kernel", "maxpool_bwd_win_kernel", "channel_sums_kernel", "norm_finalize_kernel",
                "scale_shift_act_rows_kernel", "norm_act_bwd_reduce_kernel", "norm_bwd_finalize_kernel",
                "norm_act_bwd_apply_rows_kernel", "adamw_kernel", "adam_kernel", "sgd_kernel", "optim_prepare_kernel",
-               "optim_dev_kernel", "bce_logits_kernel", "n2v_mse_kernel", "softmax_ce_kernel"],
+               "optim_dev_kernel", "bce_logits_kernel", "bce_logits_dense_kernel", "n2v_mse_kernel", "softmax_ce_kernel"],
     "ends.cu": ["select_hist_kernel", "edge_hist_kernel"],
     "stitch.cu": ["overlap_add_kernel", "overlap_add_cover_kernel", "overlap_add_slot_kernel"],
     "conv_umma.cu": ["pack_weight_xfold_kernel", "pack_convT_weight_kernel", "unpack_convT_wgrad_kernel"],
