@@ -356,6 +356,10 @@ def measure_training(spec, dtype_name, args, rank, world, local, with_profile=Tr
         trainer._graph = g
         res["region"] = "separate eager pass of the same steps in this process (timed region replays a CUDA graph)"
     res["skipped_steps"] = int(trainer._opt_state[1].item())
+    res["allreduce"] = ("none (one rank)" if world == 1 else
+                        f"flat fp32 gradient; elements [{trainer._split[1]}, {trainer.fp.grad.numel()}) reduced on a side stream under the second "
+                        f"CUDA graph of the pass (backward steps below {trainer._split[0]}), the rest after it"
+                        if getattr(trainer, "_graph_b", None) is not None else "one all-reduce of the flat fp32 gradient after the pass")
     del trainer
     torch.cuda.empty_cache()
     return res
@@ -446,6 +450,7 @@ def run_train(args):
         "scaling": "weak", "vs_baseline": None, "dtype": dtype_name, "data": "synthetic",
         "config": {"workload": spec["label"],
                    "global_batch": n_units, "parallelism": f"dp{world}", "cuda_graph": bool(args.graph),
+                   "allreduce": main.get("allreduce"),
                    "l2": "per-step working set (activations + gradients, several GB) >> 126 MB L2; no explicit flush",
                    "algorithmic_gflop_per_step": step_gflop,
                    "dtype_note": "fp16 storage / fp32 accumulation (tcgen05 kind::f16): the 16-bit engine whose outputs meet the 1e-3 "

@@ -155,6 +155,9 @@ class Tape:
         # gradient, the channel sums of that tensor's gradient: id(out) -> (out, bias gradient of the first one that ran)
         self._dbias_memo: Dict[int, Tuple[TT, torch.Tensor]] = {}
         self._dbias_touched: set = set()
+        self.pgrad_log: Optional[list] = None        # [(step index, parameter)] of the backward pass when a list is put here
+        self._cur_step: Optional[int] = None
+        self.n_steps = 0
 
     # ------------------------------------------------------------------------------------------ helpers
     def new(self, like: torch.Tensor, channels: int, spatial: Optional[Sequence[int]] = None) -> TT:
@@ -174,6 +177,8 @@ class Tape:
         return None
 
     def _pgrad(self, p: torch.nn.Parameter) -> torch.Tensor:
+        if self.pgrad_log is not None and self._cur_step is not None:
+            self.pgrad_log.append((self._cur_step, p))          # which backward step touches which parameter gradient
         g = self.param_grads.get(p)
         if g is None:
             g = torch.zeros(p.shape, dtype=torch.float32, device=self.device)
@@ -656,9 +661,17 @@ class Tape:
         return out
 
     # ------------------------------------------------------------------------------------------ backward
-    def backward(self):
-        for step in reversed(self.steps):
-            step()
+    def backward(self, split_at: Optional[int] = None, on_split=None):
+        """Run the recorded steps in reverse.  `split_at` = M: `on_split()` is called once every step with index >= M has run (the
+        Trainer ends one CUDA graph there and starts the next, see Trainer.enable_cuda_graph)."""
+        n = len(self.steps)
+        for i in range(n - 1, -1, -1):
+            if on_split is not None and split_at is not None and i == split_at - 1:
+                on_split()
+            self._cur_step = i
+            self.steps[i]()
+        self._cur_step = None
+        self.n_steps = n
         self.steps = []
 
 

@@ -101,6 +101,11 @@ class Trainer:
         self.device = self.fp.flat.device
         self.ndim = model.ndim
         self._graph = None
+        self._graph_b = None           # second half of the captured pass when the gradient all-reduce overlaps it (enable_cuda_graph)
+        self._split = None             # (tape step index, flat offset): steps >= index finish every gradient at / after the offset
+        self._on_split = None
+        self._probe_log = None
+        self._tail_reduced = False
         self.graph_launches = 0
         self._arena = ops.ZeroArena()
         # device-resident optimiser inputs (ops.optim_step_dev): hyper-parameters, step counters, scratch, gradient norm
@@ -249,13 +254,82 @@ class Trainer:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         n0 = ops.LAUNCHES
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self._loss_static = self._forward_backward(self._x_static, self._t_static)
+        split = self._plan_allreduce_overlap() if self.world > 1 else None
+        if split is not None:
+            # Data-parallel run: the pass is captured as TWO graphs.  The first ends once backward has finished every gradient of
+            # the flat buffer's tail (everything but the first encoder levels, > 95 % of the bytes); its all-reduce then runs on a
+            # side stream under the second graph -- the expensive full-resolution encoder levels -- instead of after the pass.
+            import gc
+            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            self._split = split
+            cap = torch.cuda.Stream()
+            gc.collect()
+            torch.cuda.synchronize()
+            cap.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(cap):
+                ga.capture_begin()
+
+                def on_split():
+                    ops.flush_unpacks()                          # the weight gradients finished so far leave their packed form now
+                    ga.capture_end()
+                    gb.capture_begin(pool=ga.pool())
+
+                self._on_split = on_split
+                try:
+                    self._loss_static = self._forward_backward(self._x_static, self._t_static)
+                finally:
+                    self._on_split = None
+                gb.capture_end()
+            torch.cuda.current_stream().wait_stream(cap)
+            torch.cuda.synchronize()
+            self._graph, self._graph_b = ga, gb
+            self._comm_stream = torch.cuda.Stream()
+            self._split_event = torch.cuda.Event()
+        else:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._loss_static = self._forward_backward(self._x_static, self._t_static)
+            self._graph = g
         self.graph_launches = ops.LAUNCHES - n0
-        self._graph = g
         ops.PROFILE = prof
         return self
+
+    def _plan_allreduce_overlap(self):
+        """(M, off) or None.  One eager pass logs which backward step touches which parameter gradient; `off` is the largest
+        parameter boundary of the flat buffer with at most 5 % of the elements in front of it, M the lowest step index that touches a
+        gradient at or behind `off`: once the steps >= M have run, grad[off:] is final.  Only for the plain mean losses (no per-rank
+        device divisor in front of the reduction) and when at least a tenth of the backward steps remain to hide the collective.
+        `B200_OVERLAP_ALLREDUCE=0` keeps the single graph + all-reduce after the pass."""
+        import os
+        if os.environ.get("B200_OVERLAP_ALLREDUCE", "1") == "0" or self.loss_kind != "bce":
+            return None
+        self._probe_log = []
+        try:
+            self._forward_backward(self._x_static, self._t_static)
+        finally:
+            log, self._probe_log = self._probe_log, None
+        torch.cuda.synchronize()
+        n_steps = self._probe_nsteps
+        if not log or not n_steps:
+            return None
+        base = self.fp.grad.data_ptr()
+        first = {}
+        for i, p in log:
+            v = self.fp.grad_views.get(p)
+            if v is None:
+                return None                                      # a gradient outside the flat buffer: keep the simple form
+            o = (v.data_ptr() - base) // 4
+            first[o] = min(first.get(o, i), i)
+        total = self.fp.grad.numel()
+        offs = sorted(first)
+        cands = [o for o in offs if 0 < o <= total // 20]
+        if not cands:
+            return None
+        off = cands[-1]
+        m = min(i for o, i in first.items() if o >= off)
+        if m <= 0 or m >= n_steps or m < n_steps // 10:
+            return None
+        return (m, off)
 
     def _stage_host_batch(self, xs: torch.Tensor, ts: torch.Tensor):
         """Host batch -> device staging buffers on a dedicated copy stream (two slots), then a device-to-device copy
@@ -304,6 +378,16 @@ class Trainer:
             if ts.data_ptr() != self._t_static.data_ptr():
                 self._t_static.copy_(ts, non_blocking=True)
         self._graph.replay()
+        if self._graph_b is not None:
+            # grad[off:] is final: reduce it on the side stream while the second graph runs the rest of backward
+            main = torch.cuda.current_stream()
+            self._split_event.record(main)
+            with torch.cuda.stream(self._comm_stream):
+                self._comm_stream.wait_event(self._split_event)
+                torch.distributed.all_reduce(self.fp.grad[self._split[1]:], group=self.pg)
+            self._graph_b.replay()
+            main.wait_stream(self._comm_stream)
+            self._tail_reduced = True
         ops.LAUNCHES += self.graph_launches
         self._reduce_and_update()
         return self._loss_static
@@ -352,7 +436,13 @@ class Trainer:
         assert cls is None, "class heads are not part of the semantic-seg / denoising training step"
         loss = self._loss_and_grad(pred, td)
         pred.mark_written()
-        tape.backward()
+        if self._probe_log is not None:
+            tape.pgrad_log = self._probe_log
+        if self._on_split is not None and self._split is not None:
+            tape.backward(split_at=self._split[0], on_split=self._on_split)
+        else:
+            tape.backward()
+        self._probe_nsteps = tape.n_steps
         return loss
 
     def evaluate(self, x, target) -> torch.Tensor:
@@ -438,7 +528,12 @@ class Trainer:
             # DDP averages the gradients of the per-rank *mean* losses: divide by this rank's own count before the reduction
             ops.scale_by_dev(g, denom, unscale)
             unscale, denom = 1.0, None
-        scale = allreduce_mean_(g, self.pg)                      # one NCCL all-reduce over NVLink (no-op for 1 rank)
+        if self._tail_reduced:
+            # the tail went out under the second graph (_step_graphed); what is left are the first encoder levels' few parameters
+            self._tail_reduced = False
+            scale = allreduce_mean_(g[:self._split[1]], self.pg)
+        else:
+            scale = allreduce_mean_(g, self.pg)                  # one NCCL all-reduce over NVLink (no-op for 1 rank)
         clip = float(self.clip_norm) if self.clip_norm and self.clip_norm > 0 else 0.0
         need_gsq = clip > 0 or self.model.engine_dtype == torch.float16
         if need_gsq:

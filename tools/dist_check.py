@@ -79,6 +79,34 @@ same = bool(torch.equal(lo, hi))
 say(f"training: replicas built from seeds 10 + rank, 3 AdamW steps (bf16 engine), parameters identical on all {world} ranks: {same}; loss {loss.item():.4f}")
 ok &= same
 
+# the captured step (CUDA graph): with more than one rank the pass is two graphs and the all-reduce of the flat gradient's tail runs
+# under the second one (Trainer.enable_cuda_graph) -- the reduced gradient must be the eager step's, and replicas must stay identical
+m3 = build(ResUNet, 0, **KW).cuda().set_engine(dtype=torch.float32)
+tr3 = Trainer(m3, loss="bce", optimizer="sgd", lr=0.0)
+tr3.enable_cuda_graph(xs[rank].cuda(), ts[rank].cuda())
+for _ in range(2):
+    tr3.step(xs[rank].cuda(), ts[rank].cuda())
+torch.cuda.synchronize()
+err3 = ((tr3.fp.grad / world - tr1.fp.grad).norm() / tr1.fp.grad.norm()).item()
+say(f"training: captured step, split {tr3._split} (tape step, flat offset of {tr3.fp.grad.numel()}), two graphs: {tr3._graph_b is not None}; "
+    f"gradient vs single process: rel-L2 {err3:.2e}")
+ok &= err3 < 1e-5 and (tr3._graph_b is not None)
+m4 = build(ResUNet, 10 + rank, **KW).cuda().set_engine(dtype=torch.bfloat16)
+tr4 = Trainer(m4, loss="bce", optimizer="adamw", lr=1e-3, weight_decay=0.02)
+tr4.enable_cuda_graph(xs[rank].numpy(), ts[rank].numpy())
+for _ in range(3):
+    loss4 = tr4.step(xs[rank].numpy(), ts[rank].numpy())
+torch.cuda.synchronize()
+flat4 = tr4.fp.flat.clone()
+lo, hi = flat4.clone(), flat4.clone()
+dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+same4 = bool(torch.equal(lo, hi))
+d4 = ((flat4 - flat).norm() / flat.norm()).item()
+say(f"training: captured + overlapped, 3 AdamW steps (bf16 engine): parameters identical on all {world} ranks: {same4}; against the eager "
+    f"steps: rel-L2 {d4:.2e}; loss {loss4.item():.4f}")
+ok &= same4 and d4 < 1e-3
+
 # ---- 2. SyncBatchNorm --------------------------------------------------------------------------------------------
 KB = dict(image_shape=(32, 32, 1), activation="relu", feature_maps=[16, 32], drop_values=[0, 0], normalization="sync_bn", k_size=3,
           yx_down=[2], z_down=[2], isotropy=[True] * 2, larger_io=False, conv_layers=[2] * 2, output_channels=[1])
