@@ -133,6 +133,7 @@ SIGNATURES = {
     "b200_optim_step_dev": (_I, [_I, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P, _P]),
     "b200_sumsq": (_I, [_P, _L, _P, _P]),
     "b200_pack_batch": (_I, [_P, _I, _I, _P]),
+    "b200_memset_zero": (_I, [_P, _L, _P]),
     "b200_write_floats": (_I, [_P, C.POINTER(_F), _I, _P]),
     "b200_scale_by_dev": (_I, [_P, _L, _P, _F, _P]),
     "b200_umma_selftest": (_I, [_I, _P]),

@@ -1929,6 +1929,12 @@ B200_EXPORT int b200_pack_batch(const b200_pack_job* jobs, int32_t n_jobs, int32
   return B200_OK;
 }
 
+B200_EXPORT int b200_memset_zero(void* dst, int64_t bytes, void* stream) {
+  B200_CHECK_ARG(dst && bytes >= 0, "memset_zero: bad args");
+  if (bytes) B200_CUDA(cudaMemsetAsync(dst, 0, (size_t)bytes, (cudaStream_t)stream));
+  return B200_OK;
+}
+
 B200_EXPORT int b200_write_floats(float* dst, const float* values, int32_t n, void* stream) {
   B200_CHECK_ARG(dst && values && n > 0 && n <= 16, "write_floats: 1..16 values");
   FloatBlock b;

@@ -65,13 +65,18 @@ __device__ __forceinline__ void pack_batch_body(const PackJob* __restrict__ jobs
   const int64_t stride = (int64_t)jb.n_blocks * blockDim.x;
   const int taps = jb.kd * jb.kh * jb.kw;
   if (jb.kind == PACK_PLAIN) {
+    // walked by OUTPUT index: consecutive threads write consecutive elements (one 64-byte store per warp, not 32 scattered 2-byte
+    // stores), and a block owns ONE contiguous chunk of the output, so the strided reads of a (co) / (ci) slab of the source stay
+    // in L1 across its taps (27 * Cin * 4 bytes <= 41 KB)
     T* p = (T*)jb.dst;
-    for (int64_t i = first; i < jb.total; i += stride) {
-      const int t = (int)(i % taps);
-      const int ci = (int)((i / taps) % jb.cin);
-      const int co = (int)(i / ((int64_t)taps * jb.cin));
-      const int64_t o = jb.flip ? (((int64_t)ci * taps + (taps - 1 - t)) * jb.cout + co) : (((int64_t)co * taps + t) * jb.cin + ci);
-      p[o] = from_f<T>(jb.src[i]);
+    const uint32_t total = (uint32_t)jb.total, chunk = (total + jb.n_blocks - 1) / jb.n_blocks;
+    const uint32_t lo = (uint32_t)(blockIdx.x - jb.block_begin) * chunk, hi = lo + chunk < total ? lo + chunk : total;
+    const uint32_t cin = jb.cin, cout = jb.cout, tp = taps;
+    for (uint32_t o = lo + threadIdx.x; o < hi; o += blockDim.x) {
+      uint32_t co, ci, t;
+      if (!jb.flip) { ci = o % cin; t = (o / cin) % tp; co = o / (cin * tp); }            // [Cout][tap][Cin]
+      else { co = o % cout; t = tp - 1 - (o / cout) % tp; ci = o / (cout * tp); }         // [Cin][flipped tap][Cout]
+      p[o] = from_f<T>(jb.src[((size_t)co * cin + ci) * tp + t]);
     }
   } else if (jb.kind == PACK_XFOLD) {
     T* out = (T*)jb.dst;
@@ -97,13 +102,14 @@ __device__ __forceinline__ void pack_batch_body(const PackJob* __restrict__ jobs
     }
   } else if (jb.kind == PACK_CONVT) {
     T* p = (T*)jb.dst;
-    const int cin = jb.cout, cout = jb.cin;          // see PackJob: product argument order (cin, cout, taps)
-    for (int64_t i = first; i < jb.total; i += stride) {
-      const int t = (int)(i % taps);
-      const int co = (int)((i / taps) % cout);
-      const int ci = (int)(i / ((int64_t)taps * cout));
-      const int64_t o = jb.flip ? (((int64_t)t * cin + ci) * cout + co) : (((int64_t)t * cout + co) * cin + ci);
-      p[o] = from_f<T>(jb.src[i]);
+    const uint32_t cin = jb.cout, cout = jb.cin, tp = taps;          // see PackJob: product argument order (cin, cout, taps)
+    const uint32_t total = (uint32_t)jb.total, chunk = (total + jb.n_blocks - 1) / jb.n_blocks;
+    const uint32_t lo = (uint32_t)(blockIdx.x - jb.block_begin) * chunk, hi = lo + chunk < total ? lo + chunk : total;
+    for (uint32_t o = lo + threadIdx.x; o < hi; o += blockDim.x) {   // by output index, as PACK_PLAIN
+      uint32_t co, ci, t;
+      if (!jb.flip) { ci = o % cin; co = (o / cin) % cout; t = o / (cin * cout); }        // [tap][Cout][Cin]
+      else { co = o % cout; ci = (o / cout) % cin; t = o / (cout * cin); }                // [tap][Cin][Cout]
+      p[o] = from_f<T>(jb.src[((size_t)ci * cout + co) * tp + t]);
     }
   } else if (jb.kind == PACK_XLINE) {
     T* out = (T*)jb.dst;

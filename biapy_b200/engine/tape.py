@@ -107,7 +107,7 @@ class TT:
             while root.parent is not None:
                 root = root.parent
             if not root._ready:
-                root.grad().zero_()
+                ops.zero_(root.grad())
                 root._ready = True
             root.grad_sums = None                   # a writer into a channel slice: the root's sums are no longer known
             return True

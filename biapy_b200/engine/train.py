@@ -398,7 +398,7 @@ class Trainer:
         tape.param_grads = dict(self.fp.grad_views)           # gradients land directly in the flat buffer
         if model.training:
             tape.rng_seed = model.next_rng_seed(self.device)
-        self.fp.grad.zero_()
+        ops.zero_(self.fp.grad)
         self._arena.begin(self.device)            # one fill for all the accumulators of this pass
         # Weight packs: the first pass launches them one by one and records the jobs whose source is a view of the flat
         # parameter buffer (stable address, contents rewritten by the optimiser); every later pass replays them as ONE batched
@@ -537,7 +537,7 @@ class Trainer:
         clip = float(self.clip_norm) if self.clip_norm and self.clip_norm > 0 else 0.0
         need_gsq = clip > 0 or self.model.engine_dtype == torch.float16
         if need_gsq:
-            self._gsq.zero_()
+            ops.zero_(self._gsq)
             ops.sumsq(g, out=self._gsq)
         b1, b2 = self.betas
         hp = (float(self.lr), float(b1), float(b2), float(self.eps), float(self.wd), float(self.momentum),

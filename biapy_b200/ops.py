@@ -44,7 +44,7 @@ class ZeroArena:
                 self._retired.append(self.buf)
             self.buf = torch.empty(size, dtype=torch.uint8, device=device)
         if self.buf is not None:
-            self.buf.zero_()
+            zero_(self.buf)
         self.off = self.need = 0
         ARENA = self
 
@@ -63,6 +63,14 @@ class ZeroArena:
 
 
 ARENA: Optional[ZeroArena] = None      # the arena of the training pass in flight (set by ZeroArena.begin / end)
+
+
+def zero_(t: torch.Tensor) -> torch.Tensor:
+    """t[...] = 0 for a CUDA tensor whose elements are one contiguous block (cudaMemsetAsync on the current stream)."""
+    if not t.is_cuda or not t.is_contiguous():
+        return t.zero_()
+    call("b200_memset_zero", _ptr(t), t.numel() * t.element_size(), stream_ptr())      # a memset, not a kernel: not counted in LAUNCHES
+    return t
 
 
 def zeros(numel: int, dtype: torch.dtype, device) -> torch.Tensor:

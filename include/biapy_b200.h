@@ -451,6 +451,9 @@ int b200_optim_step_dev(int32_t kind, float* p, const float* g, float* m, float*
                         const double* gsq, const double* denom, int64_t* state, float* derived, void* stream);
 /* dst[0..n) = values[0..n) (n <= 16) in stream order: the values travel as kernel arguments, so the host array may be reused
  * at once (how per-iteration hyper-parameters reach b200_optim_step_dev without a pinned staging buffer). */
+/* dst[0 .. bytes) = 0 on the stream (cudaMemsetAsync: a memset node inside a captured graph): the gradient buffers and accumulators the
+ * engine clears once per pass (reference: optimizer.zero_grad(), train_engine.py:106-203)                                          */
+int b200_memset_zero(void* dst, int64_t bytes, void* stream);
 int b200_write_floats(float* dst, const float* values, int32_t n, void* stream);
 /* g *= mul / *denom with the divisor read on the device (per-rank mean of a masked loss before the gradient all-reduce). */
 int b200_scale_by_dev(float* g, int64_t n, const double* denom, float mul, void* stream);
