@@ -56,6 +56,21 @@ class FlatParams:
             p: self.grad[o:o + p.numel()].view(p.shape) for p, o in zip(params, offs)}
 
 
+def choose_allreduce_split(first: Dict[int, int], total: int, n_steps: int):
+    """`first`: flat offset of a parameter gradient -> lowest backward-step index that touches it; `total`: elements of the flat
+    buffer; `n_steps`: steps of the pass.  Returns (M, off) -- once the steps >= M have run, grad[off:] is final -- or None: `off` is
+    the largest parameter boundary with at most 5 % of the elements in front of it, and at least a tenth of the steps must remain
+    after the split to hide the collective."""
+    cands = [o for o in sorted(first) if 0 < o <= total // 20]
+    if not cands:
+        return None
+    off = cands[-1]
+    m = min(i for o, i in first.items() if o >= off)
+    if m <= 0 or m >= n_steps or m < n_steps // 10:
+        return None
+    return (m, off)
+
+
 class Trainer:
     """One object = model + loss + optimiser state; ``step(x, target)`` runs one training iteration.
 
@@ -320,16 +335,7 @@ class Trainer:
                 return None                                      # a gradient outside the flat buffer: keep the simple form
             o = (v.data_ptr() - base) // 4
             first[o] = min(first.get(o, i), i)
-        total = self.fp.grad.numel()
-        offs = sorted(first)
-        cands = [o for o in offs if 0 < o <= total // 20]
-        if not cands:
-            return None
-        off = cands[-1]
-        m = min(i for o, i in first.items() if o >= off)
-        if m <= 0 or m >= n_steps or m < n_steps // 10:
-            return None
-        return (m, off)
+        return choose_allreduce_split(first, self.fp.grad.numel(), n_steps)
 
     def _stage_host_batch(self, xs: torch.Tensor, ts: torch.Tensor):
         """Host batch -> device staging buffers on a dedicated copy stream (two slots), then a device-to-device copy

@@ -278,3 +278,36 @@ def test_pinned_host_shard_upload_is_pipelined_and_equal():
     full = _stitch.crop_device(vol.cuda(), patch[:3], starts, pad, "reflect", patch_range=rng)
     part = _stitch.crop_device(_stitch.VolumeShard(vol[a:b].contiguous().cuda(), a, 72), patch[:3], starts, pad, "reflect", patch_range=rng)
     assert torch.equal(full, part)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.float16, 2e-2)])
+def test_bias_gradients_without_a_pass_over_dy(dtype, tol, monkeypatch):
+    """The bias gradients taken from the normalisation backward's reductions / shared between the producers of one output / passed
+    through the pointwise shortcut (Tape: TT.grad_sums, _dbias_memo) against the plain form (one pass over dy per layer)."""
+    from biapy_b200.engine.train import Trainer
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 32, 32, 32, 2, generator=g)
+    t = (torch.rand(2, 32, 32, 32, 1, generator=g) < 0.3).float()
+    grads = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("B200_DBIAS_ANALYTIC", mode)
+        monkeypatch.setenv("B200_DBIAS_SHARE", mode)
+        m, _ = _model(dtype)
+        m = m.cuda().set_engine(dtype=dtype)
+        tr = Trainer(m, loss="bce", optimizer="sgd", lr=0.0)
+        tr.step(x.numpy(), t.numpy())
+        torch.cuda.synchronize()
+        grads[mode] = {n: tr.fp.grad_views[p].clone() for n, p in m.named_parameters()}
+    worst = ("", 0.0)
+    for n, a in grads["0"].items():
+        b = grads["1"][n]
+        if n.endswith(".bias") or n.endswith("bias"):
+            e = ((a - b).norm() / a.norm().clamp_min(1e-20)).item()
+            # a bias in front of a GroupNorm has a gradient that is the small difference of large sums: compare against the size
+            # of the weight gradient's entries of the same layer as well
+            if e > worst[1]:
+                worst = (n, e)
+            assert e < tol or (a - b).abs().max().item() < tol * grads["0"][n[:-4] + "weight"].abs().max().item(), (n, e)
+        else:
+            assert torch.equal(a, b) or ((a - b).norm() / a.norm().clamp_min(1e-20)).item() < 1e-5, n
+    print("\n[bias gradients] worst relative difference", worst)

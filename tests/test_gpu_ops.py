@@ -556,3 +556,17 @@ def test_pack_batch_equals_the_single_job_kernels():
 def _stream():
     from biapy_b200 import _lib
     return _lib.stream_ptr()
+
+
+def test_memset_zero_and_sums_through_pointwise():
+    """b200_memset_zero (cudaMemsetAsync behind the C ABI) and b200_sums_through_pointwise (xsum += W^T dysum)."""
+    from biapy_b200 import ops
+    t = torch.randn(1000, device="cuda")
+    ops.zero_(t[10:900])
+    assert t[10:900].abs().max().item() == 0.0 and t[:10].abs().min().item() > 0.0 and t[900:].abs().min().item() > 0.0
+    w = torch.randn(48, 200, 1, 1, 1, device="cuda")
+    dys = torch.randn(48, device="cuda")
+    xs = torch.randn(200, device="cuda")
+    want = xs.double() + w.view(48, 200).double().t() @ dys.double()
+    ops.sums_through_pointwise(w, dys, xs)
+    assert ((xs.double() - want).abs().max() / want.abs().max()).item() < 1e-6

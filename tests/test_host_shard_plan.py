@@ -58,3 +58,25 @@ def test_cfg2_grid_traffic():
     allgather = 189 * 128 * plane
     assert max(recv) < 0.25 * allgather
     print("bytes received per rank (fp32 predictions):", recv, "all-gather:", allgather)
+
+
+def test_allreduce_split_choice():
+    """Trainer.enable_cuda_graph (world > 1): where the captured pass is cut so that the tail of the flat gradient can be reduced under
+    the rest of backward.  Offsets in flat order = forward order; backward touches them from the last step down."""
+    from biapy_b200.engine.train import choose_allreduce_split
+    # ten parameters of growing size, parameter k first touched by backward step 10 * k (encoder first in the buffer, last in backward)
+    sizes = [10, 20, 40, 80, 1000, 2000, 4000, 8000, 16000, 32000]
+    offs, o = [], 0
+    for s in sizes:
+        offs.append(o)
+        o += s
+    first = {off: 10 * k + 5 for k, off in enumerate(offs)}
+    total, n_steps = o, 100
+    m, off = choose_allreduce_split(first, total, n_steps)
+    assert off == offs[6] and off <= total // 20          # 3150 of 63150 elements stay in front (the largest boundary within 5 %)
+    assert m == 65                                        # everything at / behind `off` is final once the steps >= 65 have run
+    assert all(i >= m for o_, i in first.items() if o_ >= off)
+    # nothing to hide the collective behind: the split would leave fewer than a tenth of the steps
+    assert choose_allreduce_split({0: 0, 10: 2, 20: 50}, 1000, 100) is None
+    # no parameter boundary inside the first 5 %
+    assert choose_allreduce_split({0: 3, 600: 40}, 1000, 100) is None
