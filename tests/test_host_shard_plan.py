@@ -77,6 +77,6 @@ def test_allreduce_split_choice():
     assert m == 65                                        # everything at / behind `off` is final once the steps >= 65 have run
     assert all(i >= m for o_, i in first.items() if o_ >= off)
     # nothing to hide the collective behind: the split would leave fewer than a tenth of the steps
-    assert choose_allreduce_split({0: 0, 10: 2, 20: 50}, 1000, 100) is None
+    assert choose_allreduce_split({0: 0, 10: 2, 600: 50}, 1000, 100) is None
     # no parameter boundary inside the first 5 %
     assert choose_allreduce_split({0: 3, 600: 40}, 1000, 100) is None
