@@ -563,9 +563,11 @@ def bn_eval_stats(x, running_mean, running_var, gamma, beta, eps: float) -> Norm
     return st
 
 
-# B200_NORM_FAST: 'auto' (default) = the one-MUFU SiLU chain for bf16 tensors, '1' = also fp16, '0' = off.  tanh.approx has a
-# relative error of 2^-11: below bf16's rounding step, comparable to fp16's -- the fp16 engine is the 1e-3 parity path and keeps
-# the exact exponential unless asked.
+# B200_NORM_FAST: 'auto' (default) = the one-MUFU SiLU chain for bf16 tensors and for the BACKWARD of fp16 tensors, '1' = fp16
+# forward as well, '0' = off, 'bf16' = bf16 only.  tanh.approx has a relative error of 2^-11: below bf16's rounding step, comparable
+# to fp16's -- the fp16 engine is the 1e-3 parity path for OUTPUTS and keeps the exact exponential in the forward pass; its
+# gradients carry the 16-bit storage error of the whole backward chain (1e-2), two orders above what the approximate
+# sigmoid of the derivative adds.
 NORM_FAST = os.environ.get("B200_NORM_FAST", "auto").lower()
 # backward form of the fast chain: 'g' = pass 1 leaves g = dy * act' in dy's place (needs dy_dead), 'recompute' = pass 2 evaluates
 # the derivative again with the one-MUFU sigmoid (no extra write in pass 1)
@@ -574,8 +576,10 @@ NORM_FAST = os.environ.get("B200_NORM_FAST", "auto").lower()
 NORM_BWD = os.environ.get("B200_NORM_BWD", "recompute").lower()
 
 
-def norm_fast_ok(x, dy=None, dx=None) -> bool:
-    if NORM_FAST in ("0", "off") or x.dtype == torch.float32 or (x.dtype == torch.float16 and NORM_FAST != "1"):
+def norm_fast_ok(x, dy=None, dx=None, backward: bool = False) -> bool:
+    if NORM_FAST in ("0", "off") or x.dtype == torch.float32:
+        return False
+    if x.dtype == torch.float16 and not (NORM_FAST == "1" or (backward and NORM_FAST == "auto")):
         return False
     return bool(_lib.lib().b200_norm_silu_fast_ok(_ref(x), _ref(dy), _ref(dx)))
 
@@ -596,7 +600,7 @@ def norm_act_bwd(x, dy, st: NormStats, gamma, beta, act: str, dx, dgamma, dbeta,
     n, d, h, w, c = x.shape
     red = zeros(n * c * 2, torch.float64, x.device)
     write_g = NORM_BWD != "recompute"
-    fast = (dy_dead or not write_g) and act == "silu" and norm_fast_ok(x, dy, dx)
+    fast = (dy_dead or not write_g) and act == "silu" and norm_fast_ok(x, dy, dx, backward=True)
     if fast:
         _launch("b200_norm_silu_bwd_reduce_g", _ref(x), _ref(dy), _ptr(st.mean), _ptr(st.rstd), st.groups, _ptr(gamma), _ptr(beta),
                 _ptr(red), 1 if write_g else 0, stream_ptr(), shape=x.shape)
