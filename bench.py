@@ -441,7 +441,7 @@ def run_train(args):
     step_gflop = spec["step_gflop"] or (roof["algorithmic_gflop_per_step_from_events"] if roof else None)
     parity = None
     try:
-        parity = json.load(open(os.path.join(ROOT, "profiles", "parity_cfg1_r2.json")))
+        parity = json.load(open(os.path.join(ROOT, "profiles", "parity_cfg1_r2e.json")))
     except (OSError, ValueError):
         pass
     out = {
@@ -456,7 +456,7 @@ def run_train(args):
                    "dtype_note": "fp16 storage / fp32 accumulation (tcgen05 kind::f16): the 16-bit engine whose outputs meet the 1e-3 "
                                  "tolerance; BASELINE's bf16 label is the other_dtype line (same kernels, bf16 storage)"
                                  if dtype_name == "fp16" else None,
-                   "parity": {"tolerance": "1e-3 rel (north_star)", "full_size_table": "profiles/parity_cfg1_r2.json "
+                   "parity": {"tolerance": "1e-3 rel (north_star)", "full_size_table": "profiles/parity_cfg1_r2e.json "
                               "(tests/test_gpu_baseline_configs.py::test_full_size_cfg1_resunet128)",
                               "meets_1e-3_on_outputs": ["float32", "float16"], "measured": parity}},
         "e2e": {"value": n_units / (main["ms_e2e"] / 1e3), "unit": spec["unit"], "ms_per_step": main["ms_e2e"],
