@@ -13,7 +13,9 @@ against straightforward loops / textbook formulas in double precision:
   (``pack_batch.cuh``) against them;
 * the loss kernels (BCE with logits, soft-max cross-entropy, Noise2Void masked MSE: sums and gradients) and the fused AdamW / Adam / SGD (+ Nesterov) kernels, by-value and device-hyper-parameter forms, against the torch.optim update rules in double precision;
 * the whole GroupNorm / InstanceNorm + activation chain: ``channel_sums`` -> ``norm_finalize`` -> ``scale_shift_act_rows`` and
-  ``norm_act_bwd_reduce`` -> ``norm_bwd_finalize`` -> ``norm_act_bwd_apply_rows`` (dx, dgamma, dbeta) on channel slices.
+  ``norm_act_bwd_reduce`` -> ``norm_bwd_finalize`` -> ``norm_act_bwd_apply_rows`` (dx, dgamma, dbeta) on channel slices, and the
+  channel sums of dx that ``norm_bwd_finalize`` derives from the reductions (the bias gradient of the convolution in front of the
+  normalisation) against the brute-force sum of the reference dx; ``sums_through_pointwise`` against W^T s.
 
 This is test infrastructure: it proves indexing, shuffle patterns, reduction layouts and formulas, not speed; the device run of
 the same kernels is covered by the ``-m gpu`` parity tests.  It is what lets a kernel be changed with no GPU at hand.
@@ -32,7 +34,7 @@ KERNELS = {
     "conv_simt.cu": ["conv1x1_cout_cv_kernel", "conv1x1_cin_cv_kernel", "conv1x1_wgrad_head_cv_kernel",
                      "conv1x1_wgrad_image_cv_kernel", "pack_weight_kernel", "unpack_wgrad_kernel"],
     "ops.cu": ["maxpool_fwd_win_kernel", "maxpool_bwd_win_kernel", "channel_sums_kernel", "norm_finalize_kernel",
-               "scale_shift_act_rows_kernel", "norm_act_bwd_reduce_kernel", "norm_bwd_finalize_kernel",
+               "scale_shift_act_rows_kernel", "norm_act_bwd_reduce_kernel", "norm_bwd_finalize_kernel", "sums_through_pointwise_kernel",
                "norm_act_bwd_apply_rows_kernel", "adamw_kernel", "adam_kernel", "sgd_kernel", "optim_prepare_kernel",
                "optim_dev_kernel", "bce_logits_kernel", "bce_logits_dense_kernel", "n2v_mse_kernel", "softmax_ce_kernel"],
     "ends.cu": ["select_hist_kernel", "edge_hist_kernel"],
